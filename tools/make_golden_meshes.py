@@ -1,0 +1,30 @@
+#!/usr/bin/env python3
+"""Dev-time: convert the reference's mesh fixtures into tests/golden/meshes/*.npz (nodes f8, cells i4).
+
+Sources: /root/reference/ressources/meshes/lightTri2.h5 (tests/unittests/solver/TestHDGSolver.cpp:16-24) and
+ressources/meshes/regression/regression_dim-{2,3}_h-*_ord-*.h5 (tests/regression/HDG/*.cpp).
+"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from mini_h5 import MiniH5
+
+REF = "/root/reference/ressources/meshes"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "meshes")
+os.makedirs(OUT, exist_ok=True)
+todo = ["lightTri2.h5", "lightTri.h5"]
+for h in ("3e-1", "2e-1", "1e-1"):
+    for o in range(1, 6):
+        if h == "1e-1" and o == 5:
+            continue
+        todo.append("regression/regression_dim-2_h-%s_ord-%d.h5" % (h, o))
+for o in range(1, 6):
+    todo.append("regression/regression_dim-3_h-3e-1_ord-%d.h5" % o)
+for o in range(1, 4):
+    todo.append("regression/regression_dim-3_h-2e-1_ord-%d.h5" % o)
+for t in todo:
+    f = MiniH5(os.path.join(REF, t))
+    nodes, cells = f.read("/Mesh/Nodes"), f.read("/Mesh/Cells")
+    name = os.path.basename(t)[:-3] + ".npz"
+    np.savez_compressed(os.path.join(OUT, name), nodes=nodes, cells=cells.astype(np.int32))
+    print(name, nodes.shape, cells.shape)

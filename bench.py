@@ -1,0 +1,315 @@
+#!/usr/bin/env python3
+"""bench.py -- HDG elements assembled+condensed per second at p=3 on 3-D tets (BASELINE.json metric).
+
+A "step" is one pass of the hot path (HDGSolver::assemble: geometry -> operator contractions -> static condensation ->
+Dirichlet masking -> scatter into the global trace CSR + RHS) over the whole synthetic mesh.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cubes N3]
+
+* default workload = BASELINE.json configs[2]: 3D Poisson HDG order 3 on a synthetic 1M-tet (55^3 x 6 Kuhn) mesh, one B200.
+* N > 1 (torchrun): the element set is split into N contiguous slabs, one per rank, no data-path collective
+  (assembly has none) -> "scaling": "strong".
+* `value`   : device-resident throughput (inputs in HBM, CUDA events on the library's stream, max over ranks).
+* `e2e`     : same metric through the reference-shaped API (hyperfox_b200.hfox.HDGSolver.assemble) with HOST fields:
+              H2D of the input fields and D2H of the assembled RHS checksum inside the timed region.
+* `roofline`: algorithmic FP64 flops (1,325,333 per p=3 element) / kernel time vs the DFMA peak
+              measured in this run (MEASURED_PEAKS.json holds no FP64 figure); HBM side reported alongside.
+* `cpu_baseline`: the oracle's C++ restatement of the reference path on all host cores, bounded sample.
+* --impl reference: the reference cannot be built here (Eigen/PETSc/MOAB/... absent) -> times the oracle port.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_ELEM = {1: 16610, 2: 201490, 3: 1325333, 4: 6220333, 5: 23364077}      # SURVEY.md section 8(d), tets
+BYTES_STORE = {1: 3136, 2: 13288, 3: 40256, 4: 99076, 5: 211696}
+
+
+def poisson_inputs(nodes, cells, order, dim=3):
+    from hyperfox_b200 import capi
+    tp = capi.host_compute_faces(dim, order, cells)
+    nF, nNf = tp["faces"].shape
+    ana = np.sin(nodes[:, 0]) * np.exp(nodes[:, 1])
+    dirv = np.zeros((nF, nNf))
+    b = tp["boundary"]
+    dirv[b] = ana[tp["faces"][b]]
+    tau = np.ones((nF, nNf))
+    return tp, tau, dirv
+
+
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu=0):
+        self.rows, self.proc, self.gpu = [], None, gpu
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_baseline(order, cores, target_s=12.0, dim=3):
+    """Oracle port of the reference path (HouseholderQR condensation as the reference) on `cores` workers."""
+    from hyperfox_b200 import meshgen
+    from oracle import lib as O
+    from oracle.mesh import compute_faces
+    from oracle.refel import ReferenceElement
+    per_core = {1: 60000.0, 2: 9000.0, 3: 1500.0, 4: 300.0, 5: 80.0}[order]   # rough el/s/core, only sizes the sample
+    want = max(cores * per_core * target_s, 6.0 * 8)
+    N = max(2, int(round((want / 6.0) ** (1.0 / 3.0))))
+    nodes, cells = meshgen.kuhn_mesh(N, order, dim)
+    re = ReferenceElement(dim, order)
+    topo = compute_faces(cells, re)
+    nF, nNf = topo["faces"].shape
+    ana = np.sin(nodes[:, 0]) * np.exp(nodes[:, 1])
+    dirv = np.zeros((nF, nNf, 1)); dirv[topo["boundary"], :, 0] = ana[topo["faces"][topo["boundary"]]]
+    h = O.HDGOracle(re, dict(nodes=nodes, cells=cells, **topo), O.make_model(1, O.OP_DIFFUSION), dict(Tau=np.ones((nF, nNf, 1)), Dirichlet=dirv))
+    h.pattern()
+    sec, _, _ = h.bench_assemble(cores, useLU=0)
+    return cells.shape[0] / sec, "Kuhn %d^3 x 6 = %d tets, order %d, %d threads, %.1f s" % (N, cells.shape[0], order, cores, sec), sec
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    vals = []
+    sample = ""
+    for i in range(args.warmup + args.steps):
+        v, sample, sec = cpu_baseline(args.order, cores, target_s=4.0)
+        if i >= args.warmup:
+            vals.append((v, sec))
+    v = float(np.mean([x[0] for x in vals]))
+    ms = float(np.mean([x[1] for x in vals])) * 1e3
+    line = {"impl": "reference", "metric": "HDG elements assembled+condensed/s (p=%d 3D tets)" % args.order, "value": v, "unit": "elements/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3D Poisson HDG order %d, oracle port of the reference CPU path (reference binary not buildable here: "
+                                   "needs Eigen/Boost/PETSc/MOAB/Zoltan/HDF5/MPI)" % args.order, "sample_per_step": sample},
+            "cpu_baseline": {"value": v, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native")
+    ap.add_argument("--cubes", type=int, default=55, help="N: the unit cube is split into N^3 hexes x 6 Kuhn tets")
+    ap.add_argument("--order", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from hyperfox_b200 import capi, hfox, meshgen
+    from hyperfox_b200.capi import check, lib, pd, pi
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); lrank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(lrank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dim, order, N = 3, args.order, args.cubes
+    t0 = time.time()
+    verts, lin = meshgen.kuhn_linear(N, dim)
+    nTot = lin.shape[0]
+    e0, e1 = nTot * rank // world, nTot * (rank + 1) // world     # contiguous slab per rank (RCB stand-in for Zoltan)
+    used = np.unique(lin[e0:e1])
+    remap = -np.ones(verts.shape[0], dtype=np.int64); remap[used] = np.arange(used.size)
+    nodes, cells = meshgen.high_order(verts[used], remap[lin[e0:e1]].astype(np.int32), order)
+    tp, tau, dirv = poisson_inputs(nodes, cells, order, dim)
+    # only faces on the true domain boundary carry the Dirichlet condition (slab cuts are interior faces of the global mesh)
+    fc = nodes[tp["faces"][tp["boundary"]]].reshape(tp["boundary"].size, -1, dim)
+    onb = np.zeros(tp["boundary"].size, dtype=bool)
+    for d in range(dim):
+        onb |= np.all(np.abs(fc[:, :, d]) < 1e-12, axis=1) | np.all(np.abs(fc[:, :, d] - 1.0) < 1e-12, axis=1)
+    bfaces = tp["boundary"][onb].astype(np.int32)
+    t_setup = time.time() - t0
+    nC, nF, nNf = cells.shape[0], tp["faces"].shape[0], tp["faces"].shape[1]
+
+    # ---- device-resident arm: C ABI directly, inputs already in HBM ---------------------------------------------------
+    L = lib()
+    h = C.c_void_p()
+    check(L.hfx_ctx_create(lrank, C.byref(h)))
+    check(L.hfx_refel_set(h, dim, order, 0), h)
+    check(L.hfx_mesh_set(h, nodes.shape[0], pd(nodes), nC, pi(cells)), h)
+    check(L.hfx_field_set(h, b"Tau", 2, nNf, 1, pd(tau), 0), h)
+    check(L.hfx_field_set(h, b"Dirichlet", 2, nNf, 1, pd(dirv), 0), h)
+    md = capi.ModelDesc(1, 1, 0, 0.0)
+    check(L.hfx_model_describe(h, C.byref(md)), h)
+    check(L.hfx_boundary_describe(h, 0, bfaces.size, pi(bfaces)), h)
+    check(L.hfx_allocate(h, 0), h)
+    nnz = C.c_longlong(0); nrows = C.c_longlong(0)
+    check(L.hfx_get_csr(h, C.byref(nrows), C.byref(nnz), None, None, None, None), h)
+
+    sampler = ClockSampler(lrank)
+    for _ in range(args.warmup):
+        check(L.hfx_assemble(h), h)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ms_tot, ms_k = [], []
+    a, b = C.c_float(0), C.c_float(0)
+    t1 = time.time()
+    for _ in range(args.steps):
+        check(L.hfx_assemble(h), h)
+        L.hfx_last_assemble_ms(h, C.byref(a), C.byref(b))
+        ms_tot.append(a.value); ms_k.append(b.value)
+    barrier()
+    wall_ms = (time.time() - t1) * 1e3 / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    my_ms = float(np.mean(ms_tot)); my_k = float(np.mean(ms_k))
+
+    # ---- end-to-end arm: reference-shaped API, host fields, H2D + D2H inside the timed region ---------------------------
+    e2e_ms = None
+    h2d = d2h = 0
+    if not args.no_e2e:
+        check(L.hfx_ctx_destroy(h)); h = None
+        m = hfox.Mesh(dim, order, "simplex")
+        m.nodes, m.cells = capi.f64(nodes), capi.i32(cells)
+        m.faces, m.cell2FaceMap, m.face2CellMap, m.boundaryFaces = tp["faces"], tp["cell2face"], tp["face2cell"], tp["boundary"]
+        re = m.getReferenceElement()
+        fm = {"Solution": hfox.Field(m, hfox.Cell, re.getNumNodes(), 1), "Flux": hfox.Field(m, hfox.Cell, re.getNumNodes(), dim),
+              "Trace": hfox.Field(m, hfox.Face, nNf, 1), "Tau": hfox.Field(m, hfox.Face, nNf, 1), "Dirichlet": hfox.Field(m, hfox.Face, nNf, 1)}
+        # pinned host storage for the fields that cross PCIe every step
+        pin = {k: torch.empty(fm[k].values.size, dtype=torch.float64).pin_memory() for k in ("Tau", "Dirichlet")}
+        for k, src in (("Tau", tau), ("Dirichlet", dirv)):
+            fm[k].values = pin[k].numpy()
+            fm[k].values[:] = src.ravel()
+        s = hfox.HDGSolver(device=lrank)
+        s.setMesh(m); s.setFieldMap(fm); s.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts(), device=lrank))
+        s.setModel(hfox.HDGLaplaceModel(re)); s.setBoundaryCondition(hfox.DirichletModel(re.getFaceElement()), bfaces.tolist())
+        s.initialize(); s.allocate()
+        status = np.zeros(4)
+        for _ in range(max(1, args.warmup)):
+            s.assemble()
+        barrier()
+        t2 = time.time()
+        for _ in range(args.steps):
+            s.assemble()                      # H2D: Tau + Dirichlet ; kernel ; D2H: status word (inside hfx_assemble)
+        barrier()
+        e2e_ms = (time.time() - t2) * 1e3 / args.steps
+        h2d = int(fm["Tau"].values.nbytes + fm["Dirichlet"].values.nbytes)
+        d2h = 4
+
+    # ---- max over ranks ---------------------------------------------------------------------------------------------
+    red = torch.tensor([my_ms, my_k, e2e_ms if e2e_ms is not None else 0.0, wall_ms], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(nC)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_step, ms_kernel, ms_e2e, ms_wall = [float(x) for x in red.cpu()]
+    nAll = float(tot.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak = fp64_peak(lrank)
+    flops = FLOPS_PER_ELEM[order] * nC
+    ach = flops / (my_k * 1e-3) / 1e12
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_ach = BYTES_STORE[order] * nC / (my_k * 1e-3) / 1e9
+    line = {
+        "metric": "HDG elements assembled+condensed/s (p=%d 3D tets)" % order,
+        "value": nAll / (ms_step * 1e-3), "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "3D Poisson HDG order %d, synthetic Kuhn mesh %d^3 x 6 = %d tets (BASELINE configs[2]), HDGLaplaceModel + DirichletModel, tau=1"
+                               % (order, N, nTot), "elements_per_rank": nC, "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
+                   "l2": "inputs+outputs per step (%.1f GB) far larger than the 126 MB L2" % ((BYTES_STORE[order] * nC) / 1e9),
+                   "timing": "CUDA events on the library stream around memset+kernel, max over ranks; wall-clock per step %.2f ms" % ms_wall,
+                   "setup_s": round(t_setup, 1)},
+        "roofline": {"bound": "fp64", "achieved": ach, "peak": peak["tflops"], "unit": "TFLOP/s", "frac": ach / peak["tflops"] if peak["tflops"] else None,
+                     "traffic": None, "peak_source": peak["how"], "kernel_ms": my_k,
+                     "algorithmic_flops_per_element": FLOPS_PER_ELEM[order],
+                     "hbm": {"achieved_GBs": hbm_ach, "peak_GBs": hbm_peak, "frac": hbm_ach / hbm_peak, "bytes_per_element": BYTES_STORE[order],
+                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+        "gpu_launches": 1 * args.steps,
+        "clocks": clocks,
+    }
+    if e2e_ms is not None:
+        line["e2e"] = {"value": nAll / (ms_e2e * 1e-3), "unit": "elements/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+                       "api": "hyperfox_b200.hfox.HDGSolver.assemble (host Fields, pinned Tau/Dirichlet)"}
+    if not args.no_cpu_baseline and world >= 1:
+        cores = os.cpu_count() or 1
+        v, sample, _ = cpu_baseline(order, cores)
+        line["cpu_baseline"] = {"value": v, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def fp64_peak(device):
+    """DFMA peak measured in this run by a register-resident FMA chain kernel (libhfx: hfx_fp64_peak)."""
+    from hyperfox_b200.capi import lib
+    L = lib()
+    try:
+        L.hfx_fp64_peak.restype = C.c_double
+        tf = L.hfx_fp64_peak(device)
+        if tf > 0:
+            return {"tflops": tf, "how": "measured in this run: DFMA chain microbenchmark (hfx_fp64_peak), best of 5"}
+    except Exception:
+        pass
+    return {"tflops": 37.0, "how": "fallback: nominal B200 FP64 (148 SM x 64 DFMA/clk x 1.965 GHz)"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,531 @@
+"""Host-side mirror (Python) of the reference's class surface for the HDG path, over the C ABI of libhfx.so.
+
+Same names, argument meaning and error behaviour as the reference C++ classes, so the parity tests read like the
+reference's own tests (tests/unittests/solver/TestHDGSolver.cpp, tests/regression/HDG/TestHDGLaplace.cpp):
+
+  ReferenceElement  <- src/element/ReferenceElement.h          Mesh   <- src/mesh/Mesh.h
+  Field             <- src/field/Field.h                        HDG*Model, DirichletModel <- src/model/*.h
+  PetscOpts         <- src/resolution/PetscOpts.h               HDGSolver <- src/solver/HDGSolver.h + Solver.h
+  CudaLinAlgebraInterface (replaces PetscInterface) <- src/resolution/LinAlgebraInterface.h:23-162
+  NonLinearWrapper  <- src/solver/NonLinearWrapper.h
+
+Host Fields hold the values (as in the reference); HDGSolver.assemble() copies the input fields to the GPU, HDGSolver.solve()
+copies Trace / Solution / Flux back.  The C++ mirror with the same names lives in include/hyperfox/.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import ErrorHandle, check, f64, i32, lcheck, lib, pd, pi
+
+Node, Cell, Face = 0, 1, 2      # FieldType (src/field/FieldTypes.h); C ABI: HFX_FIELD_NODE/CELL/FACE
+Add, Set = 0, 1                 # AssemblyType.h
+KSPGMRES, KSPCG = 0, 1
+PCNONE, PCJACOBI = 0, 1
+IMPLICIT = 0
+
+OP_DIFFUSION, OP_CONVECTION, OP_REACTION, OP_SOURCE, OP_UNABU = 1, 2, 4, 8, 16
+
+
+class ReferenceElement:
+    """ReferenceElement(dim, order, geom): tables come from the product's host builder (csrc/host/hfx_refel.cpp)."""
+
+    def __init__(self, dim, order, geom="simplex"):
+        if geom not in ("simplex", "orthotope", "quad", "hex"):
+            raise ErrorHandle("ReferenceElement : setGeometry : Element type %s is not yet supported." % geom)
+        self._geom = 0 if geom == "simplex" else 1
+        self.t = capi.host_refel_tables(dim, order, self._geom)
+        self.dim, self.order, self.geom = dim, order, geom
+        self._face = None
+
+    def getDimension(self): return self.dim
+    def getOrder(self): return self.order
+    def getNumNodes(self): return self.t["nN"]
+    def getNumIPs(self): return self.t["nIP"]
+    def getNumFaces(self): return self.t["nFc"]
+    def getNodes(self): return self.t["nodes"]
+    def getFaceNodes(self): return self.t["faceNodes"]
+    def getIPCoords(self): return self.t["ipCoords"]
+    def getIPWeights(self): return self.t["w"]
+    def getIPShapeFunctions(self): return self.t["shape"]
+    def getIPDerivShapeFunctions(self): return self.t["dshape"]
+
+    def getFaceElement(self):
+        if self._face is None and self.dim > 0:
+            self._face = ReferenceElement(self.dim - 1, self.order, self.geom)
+        return self._face
+
+
+class Mesh:
+    """Mesh(dim, order, geom) + setMesh(nodes, cells); faces/adjacency from the product's topology builder."""
+
+    def __init__(self, dim, order, geom="simplex"):
+        self.refEl = ReferenceElement(dim, order, geom)
+        self.dim, self.order = dim, order
+        self.nodes = self.cells = None
+        self.partitioner = None
+
+    def setMesh(self, nodes, cells):
+        self.nodes, self.cells = f64(nodes), i32(cells)
+        if self.cells.shape[1] != self.refEl.getNumNodes():
+            raise ErrorHandle("Mesh : setMesh : the connectivity does not match the reference element")
+        tp = capi.host_compute_faces(self.dim, self.order, self.cells, self.refEl._geom)
+        self.faces, self.cell2FaceMap, self.face2CellMap, self.boundaryFaces = tp["faces"], tp["cell2face"], tp["face2cell"], tp["boundary"]
+
+    def getReferenceElement(self): return self.refEl
+    def getNodeSpaceDimension(self): return self.nodes.shape[1]
+    def getNumberPoints(self): return self.nodes.shape[0]
+    def getNumberCells(self): return self.cells.shape[0]
+    def getNumberFaces(self): return self.faces.shape[0]
+    def getBoundaryFaces(self): return self.boundaryFaces
+    def getCell(self, i): return self.cells[i]
+    def getFace(self, i): return self.faces[i]
+    def getCell2Face(self, i): return self.cell2FaceMap[i]
+    def getFace2Cell(self, i): return self.face2CellMap[i][self.face2CellMap[i] >= 0]
+    def getPoint(self, i): return self.nodes[i]
+    def getSlicePoints(self, ids): return self.nodes[np.asarray(ids)]
+
+
+class Field:
+    """Field(mesh, type, nObjPerEnt, nValsPerObj): values[(ent*nObj + o)*nVals + v] (src/field/Field.cpp:41-61)."""
+
+    def __init__(self, mesh, ftype, nObjPerEnt, nValsPerObj):
+        self.mesh, self.type, self.nObj, self.nVals = mesh, ftype, nObjPerEnt, nValsPerObj
+        nEnt = {Node: mesh.getNumberPoints(), Cell: mesh.getNumberCells(), Face: mesh.getNumberFaces()}[ftype]
+        self.values = np.zeros(nEnt * nObjPerEnt * nValsPerObj)
+        self.doubleValued = False
+
+    def getValues(self): return self.values
+    def getFieldType(self): return self.type
+    def getNumObjPerEnt(self): return self.nObj
+    def getNumValsPerObj(self): return self.nVals
+    def setDoubleValued(self, b): self.doubleValued = bool(b)
+    def isDoubleValued(self): return self.doubleValued
+    def getLength(self): return self.values.size
+
+
+class Euler:
+    """TimeScheme: implicit Euler as coded in the reference (src/operator/Euler.cpp:18-37; the explicit flavour has no device kernel)."""
+
+    def __init__(self, refEl, isExplicit=False):
+        if isExplicit:
+            raise ErrorHandle("Euler : Euler : the explicit Euler scheme has no device kernel")
+        self.dt = 0.0
+
+    def setTimeStep(self, dt): self.dt = dt
+
+
+class _HDGModel:
+    opmask = 0
+    needsSource = False
+
+    def __init__(self, refEl):
+        self.refEl = refEl
+        self.allocated = False
+        self.timeScheme = None
+        self.sourceFunc = self.reactionFunc = None
+        self.nDOF = 1
+
+    def setTimeScheme(self, ts):
+        if self.allocated:
+            raise ErrorHandle("FEModel : setTimeScheme : the time scheme must be set before allocation or field setting")
+        self.timeScheme = ts
+
+    def allocate(self, nDOFsPerNode):
+        if nDOFsPerNode < 1:
+            raise ErrorHandle("HDGOperator : allocate : the number of DOFs per node must be at least one")
+        self.nDOF = nDOFsPerNode
+        self.allocated = True
+
+    def getAssemblyType(self): return (Add, Add)
+
+    def _mask(self, fieldNames, strict=True):
+        return self.opmask
+
+
+class HDGLaplaceModel(_HDGModel):
+    """Base + Diffusion(D = I) (src/model/HDGLaplaceModel.cpp:18-30)."""
+    opmask = OP_DIFFUSION
+
+    def _mask(self, fieldNames, strict=True):
+        return OP_DIFFUSION
+
+    usesDiffusionField = False
+
+
+class HDGDiffusionSource(_HDGModel):
+    """Base + Diffusion(DiffusionTensor field if given) ; rhs = Source (src/model/HDGDiffusionSource.cpp:43-85)."""
+    usesDiffusionField = True
+
+    def setSourceFunction(self, s):
+        if not self.allocated:
+            raise ErrorHandle("HDGDiffusionSource : setSourceFunction : the model must be allocated before setting the source function")
+        self.sourceFunc = s
+
+    def _mask(self, fieldNames, strict=True):
+        if self.sourceFunc is None and strict:   # computeLocalRHS always evaluates the source (HDGDiffusionSource.cpp:81-85)
+            raise ErrorHandle("Source : calcSource : must set a source function before calculating the source.")
+        return OP_DIFFUSION | (OP_SOURCE if self.sourceFunc is not None else 0)
+
+
+class HDGConvectionDiffusionReactionSource(_HDGModel):
+    """Base [+ Convection if Velocity] [+ Diffusion if DiffusionTensor] [+ Reaction] ; rhs = [Source]
+    (src/model/HDGConvectionDiffusionReactionSource.cpp:69-108)."""
+    usesDiffusionField = True
+
+    def setSourceFunction(self, s):
+        if not self.allocated:
+            raise ErrorHandle("HDGConvectionDiffusionReactionSource : setSourceFunction : the model must be allocated before setting the source function")
+        self.sourceFunc = s
+
+    def setReactionFunction(self, r):
+        if not self.allocated:
+            raise ErrorHandle("HDGConvectionDiffusionReactionSource : setReactionFunction : the model must be allocated before setting the reaction function")
+        self.reactionFunc = r
+
+    def _mask(self, fieldNames, strict=True):
+        if "Velocity" not in fieldNames and "DiffusionTensor" not in fieldNames:
+            raise ErrorHandle("HDGConvectionDiffusionReactionSource : setFieldMap : must provide at least either a Velocity field or a DiffusionTensor field")
+        m = 0
+        if "Velocity" in fieldNames: m |= OP_CONVECTION
+        if "DiffusionTensor" in fieldNames: m |= OP_DIFFUSION
+        if self.reactionFunc is not None: m |= OP_REACTION
+        if self.sourceFunc is not None: m |= OP_SOURCE
+        return m
+
+
+class DirichletModel:
+    """assembly = {Set, Set}, localMatrix = I, localRHS = Dirichlet (src/model/DirichletModel.cpp:19-44)."""
+    kind = 0
+
+    def __init__(self, faceRefEl):
+        self.refEl = faceRefEl
+
+    def allocate(self, nDOFsPerNode): pass
+    def getAssemblyType(self): return (Set, Set)
+
+
+class IntegratedDirichletModel(DirichletModel):
+    """localMatrix = face mass, localRHS = M g (src/model/IntegratedDirichletModel.cpp)."""
+    kind = 1
+
+
+class PetscOpts:
+    """Same defaults as src/resolution/PetscOpts.h:12-28."""
+
+    def __init__(self, solverType=KSPGMRES, preconditionnerType=PCJACOBI, rtol=1e-6, maxits=1000, verbose=False, restart=30):
+        self.solverType, self.preconditionnerType, self.rtol, self.maxits, self.verbose, self.restart = solverType, preconditionnerType, rtol, maxits, verbose, restart
+
+    def c(self):
+        return capi.SolveOpts(self.solverType, self.preconditionnerType, self.restart, self.maxits, self.rtol)
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        check(lib().hfx_ctx_create(device, C.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().hfx_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class CudaLinAlgebraInterface:
+    """Drop-in for PetscInterface behind LinAlgebraInterface (src/resolution/LinAlgebraInterface.h:23-162)."""
+
+    def __init__(self, options=None, context=None, device=0):
+        self.opts = options or PetscOpts()
+        self.ctx = context or Context(device)
+        self.h = C.c_void_p()
+        check(lib().hfx_lai_create(self.ctx.h, C.byref(self.h)))
+        o = self.opts.c()
+        lib().hfx_lai_set_opts(self.h, C.byref(o))
+        self.stats = capi.SolveStats()
+
+    def _c(self, rc): lcheck(rc, self.h)
+    def initialize(self): self._c(lib().hfx_lai_initialize(self.h))
+    def configure(self): self._c(lib().hfx_lai_configure(self.h))
+
+    def allocate(self, ndofs, diagSparsePattern=None, offSparsePattern=None):
+        self._c(lib().hfx_lai_allocate(self.h, int(ndofs), None, None))
+
+    def addValMatrix(self, i, j, val): self._c(lib().hfx_lai_add_val_matrix(self.h, int(i), int(j), float(val)))
+    def setValMatrix(self, i, j, val): self._c(lib().hfx_lai_set_val_matrix(self.h, int(i), int(j), float(val)))
+    def addValRHS(self, i, val): self._c(lib().hfx_lai_add_val_rhs(self.h, int(i), float(val)))
+    def setValRHS(self, i, val): self._c(lib().hfx_lai_set_val_rhs(self.h, int(i), float(val)))
+
+    def addValsMatrix(self, is_, js, vals):
+        is_, js, vals = i32(is_), i32(js), f64(vals)
+        self._c(lib().hfx_lai_add_vals_matrix(self.h, is_.size, pi(is_), js.size, pi(js), pd(vals)))
+
+    def setValsMatrix(self, is_, js, vals):
+        is_, js, vals = i32(is_), i32(js), f64(vals)
+        self._c(lib().hfx_lai_set_vals_matrix(self.h, is_.size, pi(is_), js.size, pi(js), pd(vals)))
+
+    def addValsRHS(self, is_, vals):
+        is_, vals = i32(is_), f64(vals)
+        self._c(lib().hfx_lai_add_vals_rhs(self.h, is_.size, pi(is_), pd(vals)))
+
+    def setValsRHS(self, is_, vals):
+        is_, vals = i32(is_), f64(vals)
+        self._c(lib().hfx_lai_set_vals_rhs(self.h, is_.size, pi(is_), pd(vals)))
+
+    def zeroOutRows(self, is_):
+        is_ = i32(is_)
+        self._c(lib().hfx_lai_zero_out_rows(self.h, is_.size, pi(is_)))
+
+    def assemble(self): self._c(lib().hfx_lai_assemble(self.h))
+    def assembleFlush(self): self._c(lib().hfx_lai_assemble_flush(self.h))
+    def clearSystem(self): self._c(lib().hfx_lai_clear_system(self.h))
+    def destroySystem(self): self._c(lib().hfx_lai_destroy_system(self.h))
+
+    def getNumDofs(self):
+        n = C.c_int(0)
+        lib().hfx_lai_get_num_dofs(self.h, C.byref(n))
+        return n.value
+
+    def getSolutionOwnership(self):
+        lo, hi = C.c_int(0), C.c_int(0)
+        self._c(lib().hfx_lai_get_solution_ownership(self.h, C.byref(lo), C.byref(hi)))
+        return list(range(lo.value, hi.value))
+
+    def solve(self, solution=None):
+        n = self.getNumDofs()
+        out = np.zeros(n)
+        self._c(lib().hfx_lai_solve(self.h, pd(out), C.byref(self.stats)))
+        if solution is not None:
+            solution.resize(n, refcheck=False)
+            solution[:] = out
+        return out
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().hfx_lai_destroy(self.h)
+        except Exception:
+            pass
+
+
+class HDGSolverOpts:
+    def __init__(self, type=IMPLICIT, verbosity=False):
+        self.type, self.verbosity = type, verbosity
+
+
+class HDGSolver:
+    """HDGSolver: set*/initialize/allocate/assemble/solve with the reference's call-order contract
+    (src/solver/Solver.h:35-88, src/solver/HDGSolver.cpp:5-106,166-174,677-779)."""
+
+    INPUT_FIELDS = ("Tau", "Dirichlet", "DiffusionTensor", "Velocity")
+
+    def __init__(self, device=0, keepLocalS=False):
+        self.myMesh = self.fieldMap = self.linSystem = self.model = None
+        self.boundaries = []
+        self.initialized = self.allocated = self.assembled = False
+        self.device = device
+        self.keepLocalS = keepLocalS
+        self.ctx = None
+        self.verbose = False
+        self.stats = capi.SolveStats()
+        self._meshUploaded = False
+
+    def setVerbosity(self, v): self.verbose = bool(v)
+    def setOptions(self, opts):
+        if opts.type != IMPLICIT:
+            raise ErrorHandle("HDGSolver : setOptions : only the IMPLICIT solver type has a device path")
+    def setMesh(self, m): self.myMesh = m; self._meshUploaded = False
+    def setFieldMap(self, fm): self.fieldMap = fm
+    def setLinSystem(self, lai): self.linSystem = lai
+    def setModel(self, m): self.model = m
+
+    def setBoundaryModel(self, bm):
+        if self.myMesh is None:
+            raise ErrorHandle("Solver : setBoundaryModel : must set the Mesh before the boundary model.")
+        self.boundaries.append((bm, None))
+
+    def setBoundaryCondition(self, bm, faces):
+        self.boundaries.append((bm, np.array(sorted(faces), dtype=np.int32)))
+
+    def initialize(self):
+        if self.linSystem is not None:
+            self.linSystem.destroySystem()
+            self.linSystem.initialize()
+            self.linSystem.configure()
+        self.initialized = True
+
+    def _h(self): return self.ctx.h
+
+    def _upload_field(self, name):
+        f = self.fieldMap[name]
+        v = f64(f.values)
+        check(lib().hfx_field_set(self._h(), name.encode(), f.type, f.nObj, f.nVals, pd(v), int(f.doubleValued)), self._h())
+
+    def allocate(self):
+        if not self.initialized:
+            raise ErrorHandle("HDGSolver : allocate : must initialize the solver before allocating.")
+        if self.myMesh is None:
+            raise ErrorHandle("HDGSolver : allocate : must set the Mesh before allocating.")
+        if self.linSystem is None:
+            raise ErrorHandle("HDGSolver : allocate : must set the linear system before allocating.")
+        if self.model is None:
+            raise ErrorHandle("HDGSolver : allocate : must set the model before allocating.")
+        if not self.boundaries:
+            raise ErrorHandle("HDGSolver : allocate : must set the boundary model before allocating.")
+        if not self.fieldMap:
+            raise ErrorHandle("HDGSolver : allocate : must set the fields before allocating.")
+        fm, mesh, re = self.fieldMap, self.myMesh, self.myMesh.getReferenceElement()
+        for nm, msg in (("Solution", "the field map must have a Solution field."), ("Flux", "the field map must have a Flux field."),
+                        ("Tau", "the field map must have a Tau field."), ("Trace", "the field map must have a Trace field.")):
+            if nm not in fm:
+                raise ErrorHandle("HDGSolver : allocate : " + msg)
+        sol = fm["Solution"]
+        if sol.type != Cell:
+            raise ErrorHandle("HDGSolver : allocate : the Solution field must be a cell field.")
+        if sol.nObj != re.getNumNodes():
+            raise ErrorHandle("HDGSolver : allocate : the Solution field must have an object per element node.")
+        self.nDOFsPerNode = sol.nVals
+        fl = fm["Flux"]
+        if fl.type != Cell or fl.nObj != re.getNumNodes() or fl.nVals != self.nDOFsPerNode * mesh.getNodeSpaceDimension():
+            raise ErrorHandle("HDGSolver : allocate : the Flux field must represent a spatial derivative of the Solution field.")
+        if fm["Trace"].type != Face or fm["Trace"].nVals != self.nDOFsPerNode:
+            raise ErrorHandle("HDGSolver : allocate : the Trace field must have the same number of values per object as the Solution field.")
+        self.ctx = getattr(self.linSystem, "ctx", None) or Context(self.device)
+        L, h = lib(), self._h()
+        if not self._meshUploaded:
+            check(L.hfx_refel_set(h, mesh.dim, mesh.order, re._geom), h)
+            check(L.hfx_mesh_set(h, mesh.getNumberPoints(), pd(mesh.nodes), mesh.getNumberCells(), pi(mesh.cells)), h)
+            self._meshUploaded = True
+        self.model.allocate(self.nDOFsPerNode)
+        for name in self._input_fields():
+            self._upload_field(name)
+        self._describe_model(strict=False)
+        for bm, faces in self.boundaries:
+            bm.allocate(self.nDOFsPerNode)
+            check(L.hfx_boundary_describe(h, bm.kind, 0 if faces is None else faces.size, None if faces is None else pi(faces)), h)
+        check(L.hfx_allocate(h, 1 if self.keepLocalS else 0), h)
+        self.allocated = True
+
+    def _input_fields(self):
+        names = [n for n in self.INPUT_FIELDS if n in self.fieldMap]
+        if not getattr(self.model, "usesDiffusionField", True) and "DiffusionTensor" in names:
+            names.remove("DiffusionTensor")   # HDGLaplaceModel never reads it (HDGLaplaceModel.cpp:18-30)
+        if self.model.timeScheme is not None and self.allocated:
+            names.append("Solution")
+        return names
+
+    def _describe_model(self, strict=True):
+        names = set(self._input_fields())
+        mask = self.model._mask(names, strict)
+        ts = 1 if self.model.timeScheme is not None else 0
+        md = capi.ModelDesc(self.nDOFsPerNode, mask, ts, self.model.timeScheme.dt if ts else 0.0)
+        check(lib().hfx_model_describe(self._h(), C.byref(md)), self._h())
+        self._mask = mask
+
+    def _eval_callbacks(self):
+        L, h, mesh = lib(), self._h(), self.myMesh
+        if self._mask & (OP_SOURCE | OP_REACTION):
+            nC, nIP, d = mesh.getNumberCells(), mesh.getReferenceElement().getNumIPs(), mesh.dim
+            if getattr(self, "_xip", None) is None:
+                self._xip = np.zeros((nC, nIP, d))
+                check(L.hfx_ip_coords(h, pd(self._xip)), h)
+            pts = self._xip.reshape(-1, d)
+            if self._mask & OP_SOURCE:
+                v = f64([self.model.sourceFunc(list(p)) for p in pts])
+                check(L.hfx_source_values(h, pd(v)), h)
+            if self._mask & OP_REACTION:
+                v = f64([self.model.reactionFunc(list(p)) for p in pts])
+                check(L.hfx_reaction_values(h, pd(v)), h)
+
+    def assemble(self):
+        if not (self.initialized and self.allocated):
+            raise ErrorHandle("HDGSolver : assemble : the solver must be initialized and allocated before assembling.")
+        for name in self._input_fields():
+            self._upload_field(name)
+        self._describe_model()
+        self._eval_callbacks()
+        check(lib().hfx_assemble(self._h()), self._h())
+        self.assembled = True
+
+    def solve(self):
+        if not self.assembled:
+            raise ErrorHandle("HDGSolver : solve : system must be assembled before solving")
+        o = self.linSystem.opts.c() if hasattr(self.linSystem, "opts") else PetscOpts().c()
+        check(lib().hfx_solve(self._h(), C.byref(o), C.byref(self.stats)), self._h())
+        for name in ("Trace", "Solution", "Flux"):
+            f = self.fieldMap[name]
+            check(lib().hfx_field_get(self._h(), name.encode(), pd(f.values)), self._h())
+
+    # ---- parity hooks -------------------------------------------------------------------------------------------
+    def getCSR(self, with_cols=True):
+        L, h = lib(), self._h()
+        n, nnz = C.c_longlong(0), C.c_longlong(0)
+        check(L.hfx_get_csr(h, C.byref(n), C.byref(nnz), None, None, None, None), h)
+        rowptr = np.zeros(n.value + 1, dtype=np.int64)
+        col = np.zeros(nnz.value, dtype=np.int32) if with_cols else None
+        vals = np.zeros(nnz.value); rhs = np.zeros(n.value)
+        check(L.hfx_get_csr(h, None, None, rowptr.ctypes.data_as(capi.lp), pi(col), pd(vals), pd(rhs)), h)
+        return rowptr, col, vals, rhs
+
+    def getLocal(self, iEl=0, nEl=None):
+        mesh, re = self.myMesh, self.myMesh.getReferenceElement()
+        nEl = mesh.getNumberCells() - iEl if nEl is None else nEl
+        nD = self.nDOFsPerNode
+        u = re.getNumNodes() * nD; q = u * mesh.dim; l = re.getNumFaces() * re.getFaceElement().getNumNodes() * nD
+        out = dict(U=np.zeros((nEl, u * l)), U0=np.zeros((nEl, u)), Q=np.zeros((nEl, q * l)), Q0=np.zeros((nEl, q)))
+        if self.keepLocalS:
+            out.update(S=np.zeros((nEl, l * l)), S0=np.zeros((nEl, l)))
+        check(lib().hfx_get_local(self._h(), iEl, nEl, pd(out.get("S")), pd(out.get("S0")), pd(out["U"]), pd(out["U0"]), pd(out["Q"]), pd(out["Q0"])), self._h())
+        return out
+
+    def getElemDofs(self):
+        mesh, re = self.myMesh, self.myMesh.getReferenceElement()
+        l = re.getNumFaces() * re.getFaceElement().getNumNodes() * self.nDOFsPerNode
+        out = np.zeros((mesh.getNumberCells(), l), dtype=np.int32)
+        check(lib().hfx_get_elem_dofs(self._h(), 0, mesh.getNumberCells(), pi(out)), self._h())
+        return out
+
+    def lastAssembleMs(self):
+        a, b = C.c_float(0), C.c_float(0)
+        lib().hfx_last_assemble_ms(self._h(), C.byref(a), C.byref(b))
+        return a.value, b.value
+
+
+class NonLinearWrapper:
+    """Fixed-point / Newton driver with damping (src/solver/NonLinearWrapper.cpp:41-79)."""
+
+    def __init__(self):
+        self.mySolver = self.currentSolution = self.previousSolution = None
+        self.resTol, self.maxIters, self.dampening, self.residual, self.verbose = 1e-6, 1000, 0.0, 0.0, False
+
+    def setSolver(self, s): self.mySolver = s
+    def setSolutionFields(self, cur, prev): self.currentSolution, self.previousSolution = cur, prev
+    def setMaxIterations(self, n): self.maxIters = n
+    def setResidualTolerance(self, t): self.resTol = t
+    def setDampening(self, d): self.dampening = d
+    def setVerbosity(self, v): self.verbose = v
+    def getResidual(self): return self.residual
+
+    def solve(self):
+        if self.mySolver is None:
+            raise ErrorHandle("NonLinearWrapper : solve : the Solver must be set before attempting to solve")
+        if self.currentSolution is None:
+            raise ErrorHandle("NonLinearWrapper : solve : the current and previous Solutions should be set before attempting to solve")
+        cur, prev = self.currentSolution.values, self.previousSolution.values
+        for _ in range(self.maxIters):
+            self.mySolver.assemble()
+            self.mySolver.solve()
+            diff, ref = float(np.sum((cur - prev) ** 2)), float(np.sum(prev ** 2))
+            self.residual = np.sqrt(diff / ref) if ref != 0 else np.sqrt(diff)
+            if self.residual < self.resTol:
+                break
+            val = (1.0 - self.dampening) * cur + self.dampening * prev
+            cur[:] = val
+            prev[:] = val

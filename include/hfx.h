@@ -1,0 +1,133 @@
+/* hfx.h -- C ABI of the B200-native HyperFox element-by-element HDG path (libhfx.so).
+ *
+ * The reference has no FFI: the path sits behind C++ classes.  Each entry point below names the reference
+ * interface it replaces (file:line under the reference tree).  The C++ mirror classes in include/hyperfox/
+ * (hfox::Mesh, Field, HDGSolver, HDGLaplaceModel, ..., CudaLinAlgebraInterface) call only these functions.
+ *
+ * Conventions: every function returns 0 on success, non-zero on error; hfx_last_error() then returns a message in
+ * the reference's ErrorHandle format "Class : function : message" (src/globals/ErrorHandle.cpp:5-7,41-44).
+ * Host buffers are caller-owned; device buffers are library-owned.  All reals are FP64, ids are 32-bit int
+ * (row pointers 64-bit).  Layouts are the reference's.
+ */
+#ifndef HFX_H
+#define HFX_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hfx_ctx hfx_ctx;
+
+/* ---- context ------------------------------------------------------------------------------------------------ */
+int hfx_ctx_create(int device, hfx_ctx** ctx);
+int hfx_ctx_destroy(hfx_ctx* ctx);
+const char* hfx_last_error(const hfx_ctx* ctx); /* ctx may be NULL: last error of a failed hfx_ctx_create */
+int hfx_device_count(void);                     /* 0 when no CUDA device is usable: the product has no CPU fallback */
+double hfx_fp64_peak(int device);               /* measured DFMA peak of the device in TFLOP/s (roofline denominator; <0 on error) */
+
+/* ---- reference element: ReferenceElement(dim, order, geom)  src/element/ReferenceElement.cpp:5-26 ------------ */
+enum { HFX_SIMPLEX = 0, HFX_ORTHOTOPE = 1 };
+int hfx_refel_set(hfx_ctx* ctx, int dim, int order, int geom);
+int hfx_refel_info(const hfx_ctx* ctx, int* nN, int* nNf, int* nFc, int* nIP, int* nIPf);
+/* getNodes/getFaceNodes/getIPCoords/getIPWeights/getIPShapeFunctions/getIPDerivShapeFunctions (ReferenceElement.cpp:499-540),
+   any pointer may be NULL.  Shapes: nodes[nN][dim], ipCoords[nIP][dim], w[nIP], shape[nIP][nN], dshape[nIP][nN][dim],
+   fshape[nIPf][nNf], fdshape[nIPf][nNf][dim-1], fw[nIPf], faceNodes[nFc][nNf]. */
+int hfx_refel_tables(const hfx_ctx* ctx, double* nodes, double* ipCoords, double* w, double* shape, double* dshape,
+                     double* fshape, double* fdshape, double* fw, int* faceNodes);
+/* stateless variant usable without a GPU (host table builder only) */
+int hfx_refel_host_tables(int dim, int order, int geom, int* sizes /*[5] nN,nNf,nFc,nIP,nIPf*/, double* nodes, double* ipCoords,
+                          double* w, double* shape, double* dshape, double* fshape, double* fdshape, double* fw, int* faceNodes);
+
+/* ---- mesh: Mesh::setMesh + computeFaces  src/mesh/Mesh.cpp:31-46,183-274 ------------------------------------- */
+int hfx_mesh_set(hfx_ctx* ctx, int nNodes, const double* nodes /*[nNodes][dim]*/, int nCells, const int* cells /*[nCells][nN]*/);
+/* optional: caller-supplied topology (e.g. MOAB's) instead of the built-in face builder */
+int hfx_mesh_set_topology(hfx_ctx* ctx, int nFaces, const int* faces, const int* cell2face, const int* face2cell);
+int hfx_mesh_sizes(const hfx_ctx* ctx, int* nNodes, int* nCells, int* nFaces, int* nBoundary);
+int hfx_mesh_get_topology(const hfx_ctx* ctx, int* faces, int* cell2face, int* face2cell, int* boundary);
+/* host-only variant of the face builder (no GPU needed): returns nFaces, fills caller arrays sized for the worst case
+   (nCells*nFc faces); pass NULL arrays to only count */
+int hfx_host_compute_faces(int dim, int order, int geom, int nCells, const int* cells, int* nFaces, int* faces, int* cell2face,
+                           int* face2cell, int* nBoundary, int* boundary);
+
+/* ---- fields: Field(mesh, type, nObjPerEnt, nValsPerObj)  src/field/Field.cpp:41-61 ---------------------------- */
+enum { HFX_FIELD_NODE = 0, HFX_FIELD_FACE = 2, HFX_FIELD_CELL = 1 };
+/* names with a meaning on the path: "Tau", "Dirichlet", "DiffusionTensor", "Velocity", "Solution", "Flux", "Trace",
+   "BufferSolution" (Solver.h:125-141, HDGSolver.cpp:24-73).  Copies host -> device. */
+int hfx_field_set(hfx_ctx* ctx, const char* name, int type, int nObjPerEnt, int nValsPerObj, const double* vals, int doubleValued);
+int hfx_field_get(hfx_ctx* ctx, const char* name, double* vals); /* device -> host */
+int hfx_field_size(const hfx_ctx* ctx, const char* name, long long* n);
+
+/* ---- model: the four HDG models as an operator descriptor  src/model/*.cpp (computeLocalMatrix/RHS) ----------- */
+enum { HFX_OP_DIFFUSION = 1, HFX_OP_CONVECTION = 2, HFX_OP_REACTION = 4, HFX_OP_SOURCE = 8, HFX_OP_UNABU = 16 };
+enum { HFX_TS_NONE = 0, HFX_TS_EULER_IMPLICIT = 1 };
+typedef struct {
+  int nDOF;       /* FEModel::allocate(nDOFsPerNode)                                   */
+  int opmask;     /* Base is always present (HDGModel.cpp:28-32)                       */
+  int timeScheme; /* FEModel::setTimeScheme (HDGModel.cpp:38-47, Euler.cpp:18-37)      */
+  double dt;
+} hfx_model_desc;
+int hfx_model_describe(hfx_ctx* ctx, const hfx_model_desc* md);
+/* std::function source/reaction callbacks (Source.h:36, Reaction.h:38) are evaluated by the host at x(IP):
+   hfx_ip_coords returns x(ip) = sum_i phi_i(ip) x_i (Source.cpp:5-22), [nCells][nIP][dim] */
+int hfx_ip_coords(hfx_ctx* ctx, double* xip);
+int hfx_source_values(hfx_ctx* ctx, const double* vals /*[nCells][nIP]*/);
+int hfx_reaction_values(hfx_ctx* ctx, const double* vals /*[nCells][nIP]*/);
+/* Solver::setBoundaryCondition(BoundaryModel*, faces)  Solver.h:41-48; DirichletModel / IntegratedDirichletModel */
+enum { HFX_BC_DIRICHLET = 0, HFX_BC_INTEGRATED_DIRICHLET = 1 };
+int hfx_boundary_describe(hfx_ctx* ctx, int kind, int nFaces, const int* faceIds /* NULL: mesh boundary */);
+
+/* ---- solver: HDGSolver::allocate / assemble / solve  src/solver/HDGSolver.cpp:5-106,166-174,677-779 ----------- */
+enum { HFX_KEEP_LOCAL_S = 1 }; /* also store the per-element S,S0 Fields the reference keeps (HDGSolver.cpp:101-104) */
+int hfx_allocate(hfx_ctx* ctx, int flags);
+int hfx_assemble(hfx_ctx* ctx);
+typedef struct {
+  int ksp;       /* 0 GMRES (PetscOpts.h:14) ; 1 CG                                   */
+  int pc;        /* 0 none, 1 point Jacobi (PetscOpts.h:16), 2 face-block Jacobi       */
+  int restart;   /* 30 = PETSc default                                                  */
+  int maxits;    /* PetscOpts.h:24: 1000                                                */
+  double rtol;   /* PetscOpts.h:20: 1e-6                                                */
+} hfx_solve_opts;
+typedef struct { int iterations; double resnorm; double bnorm; int converged; } hfx_solve_stats;
+int hfx_solve(hfx_ctx* ctx, const hfx_solve_opts* opts, hfx_solve_stats* stats); /* Trace <- solution; then recovery */
+int hfx_recover(hfx_ctx* ctx);                                                    /* HDGSolver.cpp:741-775 */
+int hfx_sync(hfx_ctx* ctx);
+/* timing of the last hfx_assemble (CUDA events on the library's stream), milliseconds */
+int hfx_last_assemble_ms(const hfx_ctx* ctx, float* msTotal, float* msKernel);
+
+/* ---- parity hooks ----------------------------------------------------------------------------------------------- */
+/* CSR of the global trace system: sorted columns, explicit zeros (PetscInterface.cpp:99-103).  nnz query with NULLs. */
+int hfx_get_csr(hfx_ctx* ctx, long long* nrows, long long* nnz, long long* rowptr, int* colidx, double* vals, double* rhs);
+/* per-element condensed blocks, column-major as the reference stores them (HDGSolver.cpp:336-341); any may be NULL */
+int hfx_get_local(hfx_ctx* ctx, int iEl, int nEl, double* S, double* S0, double* U, double* U0, double* Q, double* Q0);
+/* element -> global trace dof ids (matRowCols, HDGSolver.cpp:596) */
+int hfx_get_elem_dofs(hfx_ctx* ctx, int iEl, int nEl, int* dofs);
+
+/* ---- LinAlgebraInterface mirror  src/resolution/LinAlgebraInterface.h:23-162, PetscInterface.cpp ----------------- */
+typedef struct hfx_lai hfx_lai;
+int hfx_lai_create(hfx_ctx* ctx, hfx_lai** lai);
+int hfx_lai_destroy(hfx_lai* lai);
+const char* hfx_lai_last_error(const hfx_lai* lai);
+int hfx_lai_set_opts(hfx_lai* lai, const hfx_solve_opts* opts);
+int hfx_lai_initialize(hfx_lai* lai);
+int hfx_lai_configure(hfx_lai* lai);
+int hfx_lai_allocate(hfx_lai* lai, int ndofs, const int* diagPattern, const int* offPattern);
+int hfx_lai_add_val_matrix(hfx_lai* lai, int i, int j, double val);
+int hfx_lai_add_vals_matrix(hfx_lai* lai, int ni, const int* is, int nj, const int* js, const double* vals /*row-major ni x nj*/);
+int hfx_lai_add_val_rhs(hfx_lai* lai, int i, double val);
+int hfx_lai_add_vals_rhs(hfx_lai* lai, int ni, const int* is, const double* vals);
+int hfx_lai_set_val_matrix(hfx_lai* lai, int i, int j, double val);
+int hfx_lai_set_vals_matrix(hfx_lai* lai, int ni, const int* is, int nj, const int* js, const double* vals);
+int hfx_lai_set_val_rhs(hfx_lai* lai, int i, double val);
+int hfx_lai_set_vals_rhs(hfx_lai* lai, int ni, const int* is, const double* vals);
+int hfx_lai_zero_out_rows(hfx_lai* lai, int ni, const int* is);
+int hfx_lai_assemble(hfx_lai* lai);
+int hfx_lai_assemble_flush(hfx_lai* lai);
+int hfx_lai_solve(hfx_lai* lai, double* solution /*[ndofs]*/, hfx_solve_stats* stats);
+int hfx_lai_get_solution_ownership(hfx_lai* lai, int* lo, int* hi);
+int hfx_lai_clear_system(hfx_lai* lai);
+int hfx_lai_destroy_system(hfx_lai* lai);
+int hfx_lai_get_num_dofs(const hfx_lai* lai, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HFX_H */

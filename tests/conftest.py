@@ -1,0 +1,34 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_mesh(name):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "meshes", name + ".npz"))
+    return z["nodes"], z["cells"]
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    from oracle import lib as O
+    O.lib()
+    return O
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    # the C-ABI library must exist for both CPU (symbol / host-table tests) and GPU tests
+    so = os.path.join(ROOT, "hyperfox_b200", "libhfx.so")
+    if not os.path.exists(so):
+        import __graft_entry__ as g
+        g.build()

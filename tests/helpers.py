@@ -1,0 +1,146 @@
+"""Shared problem set-ups for the parity tests: the same inputs go to the oracle (CPU restatement of the reference)
+and to the CUDA path through the reference-shaped API (hyperfox_b200.hfox)."""
+import numpy as np
+
+from hyperfox_b200 import hfox, meshgen
+from oracle import lib as O
+from oracle.mesh import compute_faces
+from oracle.refel import ReferenceElement as OracleRefEl
+from tests.conftest import load_mesh
+
+
+def sin_exp(x):
+    return np.sin(x[0]) * np.exp(x[1])
+
+
+def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="dirichlet", tau_double=False, diff="none", seed=0):
+    """Returns dict with numpy inputs in the reference's Field layouts."""
+    rng = np.random.default_rng(seed)
+    if mesh == "kuhn":
+        nodes, cells = meshgen.kuhn_mesh(N, order, dim, perturb=perturb)
+    else:
+        nodes, cells = load_mesh(mesh)
+    ore = OracleRefEl(dim, order)
+    topo = compute_faces(cells, ore)
+    nF, nNf, nN = topo["faces"].shape[0], ore.faceElement.nNodes, ore.nNodes
+    ana = np.sin(nodes[:, 0]) * np.exp(nodes[:, 1])
+    dirv = np.zeros((nF, nNf, 1))
+    b = topo["boundary"]
+    dirv[b, :, 0] = ana[topo["faces"][b]]
+    case = dict(dim=dim, order=order, nodes=nodes, cells=cells, topo=topo, ore=ore, ana=ana, model=model, bc=bc)
+    fields = {"Dirichlet": dirv}
+    if tau_double:
+        fields["Tau"] = 0.5 + rng.random((nF, nNf, 2))
+    else:
+        fields["Tau"] = np.ones((nF, nNf, 1)) if model == "laplace" else 0.5 + rng.random((nF, nNf, 1))
+    if diff == "scalar":
+        fields["DiffusionTensor"] = 0.5 + rng.random((nodes.shape[0], 1))
+    elif diff == "tensor":
+        A = rng.standard_normal((nodes.shape[0], dim, dim)) * 0.2
+        D = np.eye(dim)[None] + A @ A.transpose(0, 2, 1) + 0.1 * A    # not symmetric on purpose: exercises the col-major layout
+        fields["DiffusionTensor"] = D.transpose(0, 2, 1).reshape(nodes.shape[0], dim * dim)   # col-major per node
+    if model == "cdrs":
+        c = nodes - 0.5
+        vel = np.zeros_like(nodes)
+        vel[:, 0], vel[:, 1] = -4 * c[:, 1], 4 * c[:, 0]
+        fields["Velocity"] = vel
+    case["fields"] = fields
+    case["source"] = (lambda x: np.exp(-10 * sum((xi - 0.5) ** 2 for xi in x))) if model in ("diffsrc", "cdrs", "euler") else None
+    case["reaction"] = (lambda x: 1.0 + x[0]) if model == "cdrs" else None
+    if model == "euler":
+        case["solOld"] = rng.random((cells.shape[0], nN))
+    return case
+
+
+def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
+    ore, topo = case["ore"], case["topo"]
+    rc = O.RefElC(ore)
+    model = case["model"]
+    f = dict(case["fields"])
+    mask, diffComps, ts = O.OP_DIFFUSION, 0, O.TS_NONE
+    if model == "laplace":
+        f.pop("DiffusionTensor", None)
+    if "DiffusionTensor" in f:
+        diffComps = f["DiffusionTensor"].shape[1]
+    if model == "cdrs":
+        mask = O.OP_CONVECTION | (O.OP_DIFFUSION if "DiffusionTensor" in f else 0)
+    xip = np.einsum("pi,cid->cpd", ore.ipShape, case["nodes"][case["cells"]])
+    if case["source"] is not None:
+        mask |= O.OP_SOURCE
+        f["srcIP"] = np.array([[case["source"](p) for p in el] for el in xip])
+    if case["reaction"] is not None:
+        mask |= O.OP_REACTION
+        f["reacIP"] = np.array([[case["reaction"](p) for p in el] for el in xip])
+    if model == "euler":
+        ts = O.TS_EULER_IMPLICIT
+        f["solOld"] = case["solOld"]
+    md = O.make_model(1, mask, diffComps, ts, 0.1)
+    mesh = dict(nodes=case["nodes"], cells=case["cells"], **topo)
+    h = O.HDGOracle(rc, mesh, md, f, bcKind=O.BC_DIRICHLET if case["bc"] == "dirichlet" else O.BC_INTEGRATED_DIRICHLET, useLU=useLU)
+    h.assemble()
+    if solve:
+        h.solve(rtol=rtol, maxits=maxits)
+    return h
+
+
+def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True):
+    dim, order = case["dim"], case["order"]
+    m = hfox.Mesh(dim, order, "simplex")
+    m.setMesh(case["nodes"], case["cells"])
+    re = m.getReferenceElement()
+    nN, nNf = re.getNumNodes(), re.getFaceElement().getNumNodes()
+    fm = {}
+    fm["Solution"] = hfox.Field(m, hfox.Cell, nN, 1)
+    fm["Flux"] = hfox.Field(m, hfox.Cell, nN, dim)
+    fm["Trace"] = hfox.Field(m, hfox.Face, nNf, 1)
+    tau = case["fields"]["Tau"]
+    fm["Tau"] = hfox.Field(m, hfox.Face, nNf, tau.shape[2])
+    fm["Tau"].values[:] = tau.ravel()
+    if tau.shape[2] == 2:
+        fm["Tau"].setDoubleValued(True)
+    fm["Dirichlet"] = hfox.Field(m, hfox.Face, nNf, 1)
+    fm["Dirichlet"].values[:] = case["fields"]["Dirichlet"].ravel()
+    if "DiffusionTensor" in case["fields"]:
+        d = case["fields"]["DiffusionTensor"]
+        fm["DiffusionTensor"] = hfox.Field(m, hfox.Node, 1, d.shape[1])
+        fm["DiffusionTensor"].values[:] = d.ravel()
+    if "Velocity" in case["fields"]:
+        fm["Velocity"] = hfox.Field(m, hfox.Node, 1, dim)
+        fm["Velocity"].values[:] = case["fields"]["Velocity"].ravel()
+    model = case["model"]
+    if model == "laplace":
+        mod = hfox.HDGLaplaceModel(re)
+    elif model in ("diffsrc", "euler"):
+        mod = hfox.HDGDiffusionSource(re)
+    else:
+        mod = hfox.HDGConvectionDiffusionReactionSource(re)
+    if model == "euler":
+        ts = hfox.Euler(re)
+        ts.setTimeStep(0.1)
+        mod.setTimeScheme(ts)
+        fm["Solution"].values[:] = case["solOld"].ravel()
+    bm = hfox.DirichletModel(re.getFaceElement()) if case["bc"] == "dirichlet" else hfox.IntegratedDirichletModel(re.getFaceElement())
+    opts = hfox.PetscOpts(rtol=rtol, maxits=maxits, verbose=False)
+    lai = hfox.CudaLinAlgebraInterface(opts)
+    s = hfox.HDGSolver(keepLocalS=keepS)
+    s.setVerbosity(False)
+    s.setMesh(m)
+    s.setFieldMap(fm)
+    s.setLinSystem(lai)
+    s.setModel(mod)
+    s.setBoundaryModel(bm)
+    s.initialize()
+    s.allocate()
+    if case["source"] is not None:
+        mod.setSourceFunction(case["source"])
+    if case["reaction"] is not None:
+        mod.setReactionFunction(case["reaction"])
+    s.assemble()
+    if solve:
+        s.solve()
+    return s, fm, m
+
+
+def rel_err(a, b):
+    sc = np.abs(b).max()
+    return np.abs(a - b).max() / (sc if sc > 0 else 1.0)

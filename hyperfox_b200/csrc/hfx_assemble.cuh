@@ -9,17 +9,22 @@
 // Structure exploited (valid for every in-scope model, checked numerically against the oracle in tests/):
 //   S_qq = M (x) I_dim        (HDGBase.cpp:152; no other operator writes the q rows)      -> one nN x nN inverse W = M^-1
 //   q-rows / l-rows couple to u,q only through the face nodes                              -> t x t weighted face mass matrices
-// All local matrices are column-major ("row index contiguous").
+//
+// Shared-memory layout rule: matrices read as the LEFT operand of a product are column-major (row index contiguous), matrices
+// read as the RIGHT operand are row-major (column index contiguous); leading dimensions are even so that every register tile
+// is fetched with 128-bit shared loads.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 
 namespace hfx {
 
 struct AsmParams {
   int nCells;
   // mesh
-  const double* nodes; const int* cells; const int* cell2face;
-  // per-element maps built on device by build_elem_maps (hfx_allocate)
+  const double* elemX;        // [nCells][nN*DIM] element-major node coordinates (gathered once at allocate)
+  const int* cells; const int* cell2face;
+  // per-element maps built on device by elem_maps_kernel (hfx_allocate)
   const uint8_t* fperm;       // [nCells][nFc*nNf] position in faces[F] of element-local face node (HDGSolver.cpp:258-275)
   const uint8_t* tauSide;     // [nCells][nFc]     0 if this cell is face2Cell[F][0] (HDGSolver.cpp:290-293)
   const uint8_t* elemPos;     // [nCells][nFc*nFc] position of face f2 in the sorted neighbour list of face f
@@ -46,6 +51,7 @@ struct AsmParams {
   double* U; double* Q; double* U0; double* Q0; double* S; double* S0;  // S,S0 may be NULL
   double* vals; double* rhs;
   int* status;                // bit 0: (near) zero pivot met in a local inverse
+  long long* prof;            // optional [16] per-phase cycle counters (block 0 only), NULL in production
 };
 
 template <int DIM, int P> struct ElemCfg;
@@ -65,54 +71,55 @@ HFX_CFG(3, 5, 56, 21, 81, 25)
 #undef HFX_CFG
 
 constexpr int kAsmThreads = 256;
+#define HFX_PROF(i) do { if (p.prof && blockIdx.x == 0 && tid == 0) { long long c_ = clock64(); p.prof[i] += c_ - tprev; tprev = c_; } } while (0)
 
-// ---- register-tiled batched GEMM on shared-memory operands -----------------------------------------------------------
-// C_b(m,n) = sum_k A_b(m,k) * B_b(k,n) for b<BATCH, m<M, n<N; fa(b,m,k)/fb(b,k,n) are loaders, fs(b,m,n,acc) the epilogue.
-// Tiles are dealt to `nt` threads; consecutive threads take consecutive m-tiles so that column-major A operands are read
-// conflict-free and B operands are warp-broadcasts.
-template <int BATCH, int M, int N, int K, int TM, int TN, class FA, class FB, class FS>
-__device__ __forceinline__ void tile_gemm(int tid, int nt, FA fa, FB fb, FS fs) {
-  constexpr int MT = (M + TM - 1) / TM, NTT = (N + TN - 1) / TN;
-  for (int tile = tid; tile < BATCH * MT * NTT; tile += nt) {
-    const int bt = tile / (MT * NTT), tl = tile % (MT * NTT);
-    const int m0 = (tl % MT) * TM, n0 = (tl / MT) * TN;
-    double acc[TM][TN];
+__host__ __device__ constexpr int ev(int x) { return (x + 1) & ~1; }
+
+// ---- register-tile micro kernel ------------------------------------------------------------------------------------------
+// acc[i][j] += A[i] * B[j] over one k: A column-major (16-byte aligned, TM even), B row-major (TN even) => 128-bit shared loads.
+template <int TM, int TN>
+__device__ __forceinline__ void mk_step(double (&acc)[TM][TN], const double* __restrict__ a, const double* __restrict__ b) {
+  double av[TM], bv[TN];
 #pragma unroll
-    for (int i = 0; i < TM; i++)
+  for (int i = 0; i < TM; i += 2) { const double2 v = *reinterpret_cast<const double2*>(a + i); av[i] = v.x; av[i + 1] = v.y; }
 #pragma unroll
-      for (int j = 0; j < TN; j++) acc[i][j] = 0.0;
+  for (int j = 0; j < TN; j += 2) { const double2 v = *reinterpret_cast<const double2*>(b + j); bv[j] = v.x; bv[j + 1] = v.y; }
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+}
+template <int TM, int TN, int K>
+__device__ __forceinline__ void mk(double (&acc)[TM][TN], const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb) {
+  if (K <= 24) {
+#pragma unroll
+    for (int k = 0; k < K; k++) mk_step<TM, TN>(acc, A + lda * k, B + ldb * k);
+  } else {
 #pragma unroll 4
-    for (int k = 0; k < K; k++) {
-      double a[TM], b[TN];
-#pragma unroll
-      for (int i = 0; i < TM; i++) a[i] = (M % TM == 0 || m0 + i < M) ? fa(bt, m0 + i, k) : 0.0;
-#pragma unroll
-      for (int j = 0; j < TN; j++) b[j] = (N % TN == 0 || n0 + j < N) ? fb(bt, k, n0 + j) : 0.0;
-#pragma unroll
-      for (int i = 0; i < TM; i++)
-#pragma unroll
-        for (int j = 0; j < TN; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-    }
-#pragma unroll
-    for (int i = 0; i < TM; i++)
-#pragma unroll
-      for (int j = 0; j < TN; j++)
-        if ((M % TM == 0 || m0 + i < M) && (N % TN == 0 || n0 + j < N)) fs(bt, m0 + i, n0 + j, acc[i][j]);
+    for (int k = 0; k < K; k++) mk_step<TM, TN>(acc, A + lda * k, B + ldb * k);
   }
 }
+template <int TM, int TN>
+__device__ __forceinline__ void zero_acc(double (&acc)[TM][TN]) {
+#pragma unroll
+  for (int i = 0; i < TM; i++)
+#pragma unroll
+    for (int j = 0; j < TN; j++) acc[i][j] = 0.0;
+}
 
-// ---- in-register Gauss-Jordan inverse by one warp ----------------------------------------------------------------------
-// Lane r holds rows r, r+32, ... of the n x n matrix (column-major in shared memory, leading dimension n); unpivoted
-// (the local matrices M and K are definite for a coercive HDG local problem); *flag |= 1 if a pivot underflows.
+// ---- Gauss-Jordan inverse by one warp --------------------------------------------------------------------------------------
+// Lane r owns rows r, r+32, ... in registers; the pivot row of each step is published in a scratch line in shared memory and read
+// back as a broadcast, so no shuffles.  Unpivoted (M and K are definite for a coercive local problem); a vanishing pivot raises
+// bit 0 of *flag.  src/dst are column-major with leading dimension ld (src may equal dst).
 template <int n>
-__device__ __forceinline__ void warp_invert(const double* __restrict__ src, double* __restrict__ dst, int lane, int* flag) {
-  constexpr int R = (n + 31) / 32;
+__device__ __forceinline__ void warp_invert(const double* src, double* dst, int ld, double* scratch /*[2*ev(n)]*/, int lane, int* flag) {
+  constexpr int R = (n + 31) / 32, np = ev(n);
   double row[R][n];
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int i = lane + 32 * r;
 #pragma unroll
-    for (int j = 0; j < n; j++) row[r][j] = (i < n) ? src[i + n * j] : ((i == j) ? 1.0 : 0.0);
+    for (int j = 0; j < n; j++) row[r][j] = (i < n) ? src[i + ld * j] : 0.0;
   }
   double scale = 0.0;
 #pragma unroll
@@ -122,35 +129,124 @@ __device__ __forceinline__ void warp_invert(const double* __restrict__ src, doub
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, o));
   bool bad = false;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < n; j++) scratch[j] = row[0][j];
+  }
+  __syncwarp();
 #pragma unroll
   for (int k = 0; k < n; k++) {
-    const int kl = k & 31, kr = k >> 5;
-    double piv = __shfl_sync(0xffffffffu, row[kr][k], kl);
+    const double* pr = scratch + (k & 1) * np;     // pivot row before the update
+    double* nx = scratch + ((k + 1) & 1) * np;
+    const double piv = pr[k];
     if (!(fabs(piv) > 1e-14 * scale)) bad = true;
     const double ip = 1.0 / piv;
-    double f[R];
 #pragma unroll
-    for (int r = 0; r < R; r++) f[r] = row[r][k] * ip;
+    for (int r = 0; r < R; r++) {
+      const bool isPivotRow = (lane + 32 * r) == k;
+      const double f = row[r][k] * ip;
 #pragma unroll
-    for (int j = 0; j < n; j++) {
-      const double pj = __shfl_sync(0xffffffffu, row[kr][j], kl);  // pivot row entry (before update)
+      for (int j = 0; j < n; j++) {
+        const double pj = pr[j];
+        if (j == k) row[r][j] = isPivotRow ? ip : -f;
+        else row[r][j] = isPivotRow ? pj * ip : fma(-f, pj, row[r][j]);
+      }
+      if (k + 1 < n && (lane + 32 * r) == k + 1) {
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        const bool isPivotRow = (r == kr) && (lane == kl);
-        if (j == k) row[r][j] = isPivotRow ? ip : -f[r];
-        else row[r][j] = isPivotRow ? pj * ip : fma(-f[r], pj, row[r][j]);
+        for (int j = 0; j < n; j++) nx[j] = row[r][j];
       }
     }
+    __syncwarp();
   }
 #pragma unroll
   for (int r = 0; r < R; r++) {
     const int i = lane + 32 * r;
     if (i < n) {
 #pragma unroll
-      for (int j = 0; j < n; j++) dst[i + n * j] = row[r][j];
+      for (int j = 0; j < n; j++) dst[i + ld * j] = row[r][j];
     }
   }
   if (bad && lane == 0) atomicOr(flag, 1);
+}
+
+// ---- small device helpers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rcp(double x) {   // MUFU seed + two Newton steps: full double precision, no slow path
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// warp-granular dynamic tile queue: every call hands the warp the next 32 consecutive tile ids
+__device__ __forceinline__ int grab32(int* ctr, int lane) {
+  int v = 0;
+  if (lane == 0) v = atomicAdd(ctr, 32);
+  return __shfl_sync(0xffffffffu, v, 0) + lane;
+}
+
+// ---- Gauss-Jordan inverse by a group of kGJThreads threads (warps 0..3, named barrier 1) ---------------------------------
+// 2x2 block pivots: half the serial depth of the scalar algorithm (the pivot chain, not the flops, is what costs: ~300-450
+// cycles per barrier step on B200, see tools/ubench/gj2.cu).  Ping-pong between two column-major buffers with even leading
+// dimension ld: a step reads one buffer and writes the other, so one barrier per pivot block suffices.  Each thread owns 2x1
+// strips aligned with the pivot pairs; branch-free.  Unpivoted (M and K are definite for a coercive local problem); a vanishing
+// pivot block raises bit 0 of *flag.  np = n rounded up to even: the caller provides pad row/column = 0, pad diagonal = 1.
+// The inverse ends in ((np/2) odd ? b1 : b0).
+constexpr int kGJThreads = 128;
+template <int np, int ld>
+__device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* flag) {
+  // not inlined on purpose: inside the big kernel the register allocator rematerialises every address of this latency-bound loop
+  constexpr int MT = np / 2, NS = MT * np, NQ = (NS + kGJThreads - 1) / kGJThreads;
+  const double s0 = b0[0];
+  const double scale = s0 * s0;
+  bool bad = false;
+  const double* src = b0;
+  double* dst = b1;
+#pragma unroll 1
+  for (int k = 0; k < np; k += 2) {
+    const double2 pc0 = *reinterpret_cast<const double2*>(src + k + ld * k);         // pivot block, column 0
+    const double2 pc1 = *reinterpret_cast<const double2*>(src + k + ld * (k + 1));   // pivot block, column 1
+    double2 a[NQ], c0[NQ], c1[NQ], pj[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      const int s2 = tid + q * kGJThreads;
+      if (s2 < NS) {
+        const int i0 = (s2 % MT) * 2, j = s2 / MT;
+        a[q] = *reinterpret_cast<const double2*>(src + i0 + ld * j);
+        c0[q] = *reinterpret_cast<const double2*>(src + i0 + ld * k);
+        c1[q] = *reinterpret_cast<const double2*>(src + i0 + ld * (k + 1));
+        pj[q] = *reinterpret_cast<const double2*>(src + k + ld * j);
+      }
+    }
+    const double det = fma(pc0.x, pc1.y, -pc1.x * pc0.y);
+    if (!(fabs(det) > 1e-28 * scale)) bad = true;
+    const double id = fast_rcp(det);
+    const double i00 = pc1.y * id, i01 = -pc1.x * id, i10 = -pc0.y * id, i11 = pc0.x * id;   // inverse of the pivot block
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      const int s2 = tid + q * kGJThreads;
+      if (s2 < NS) {
+        const int i0 = (s2 % MT) * 2, j = s2 / MT;
+        const bool inK = (j == k) || (j == k + 1);
+        double v0 = fma(i00, pj[q].x, i01 * pj[q].y), v1 = fma(i10, pj[q].x, i11 * pj[q].y);   // P^-1 A[K,j]
+        if (j == k) { v0 = i00; v1 = i10; }
+        if (j == k + 1) { v0 = i01; v1 = i11; }
+        const double ax = inK ? 0.0 : a[q].x, ay = inK ? 0.0 : a[q].y;
+        double r0 = fma(-c0[q].x, v0, fma(-c1[q].x, v1, ax));
+        double r1 = fma(-c0[q].y, v0, fma(-c1[q].y, v1, ay));
+        if (i0 == k) { r0 = v0; r1 = v1; }
+        *reinterpret_cast<double2*>(dst + i0 + ld * j) = make_double2(r0, r1);
+      }
+    }
+    bar_sync_named(1, kGJThreads);
+    const double* tsw = dst; dst = const_cast<double*>(src); src = tsw;
+  }
+  if (bad) atomicOr(flag, 1);
 }
 
 __device__ __forceinline__ void det_inv(const double (&J)[2][2], double& det, double (&I)[2][2]) {
@@ -171,50 +267,70 @@ template <int DIM, int P>
 struct AsmSmem {
   using C = ElemCfg<DIM, P>;
   static constexpr int nN = C::nN, t = C::nNf, nFc = C::nFc, nIP = C::nIP, nIPf = C::nIPf;
-  static constexpr int l = nFc * t, l1 = l + 1, NW = 3 + 2 * DIM;  // face weight kinds: tau, n_d, (Dn)_d, v.n, 1
-  // offsets in doubles
-  static constexpr int oX = 0;                               // coords [nN][DIM]
-  static constexpr int oIJ = oX + nN * DIM;                  // dV * invJ  [nIP][DIM*DIM]  (m,r)
-  static constexpr int oDV = oIJ + nIP * DIM * DIM;          // dV [nIP]
-  static constexpr int oDIP = oDV + nIP;                     // D at bulk IPs [nIP][DIM*DIM] col-major
-  static constexpr int oVIP = oDIP + nIP * DIM * DIM;        // v at bulk IPs [nIP][DIM]
-  static constexpr int oLW = oVIP + nIP * DIM;               // (reac*dV + euler*dV) [nIP], src*dV [nIP]
-  static constexpr int oFWT = oLW + 2 * nIP;                 // face IP weights [nFc*nIPf][NW]
-  static constexpr int oTAU = oFWT + nFc * nIPf * NW;        // tau at element-local face nodes [l]
-  static constexpr int oDN = oTAU + l;                       // D at nodes [nN][DIM*DIM]
-  static constexpr int oVN = oDN + nN * DIM * DIM;           // v at nodes [nN][DIM]
-  static constexpr int oG = oVN + nN * DIM;                  // g [nIP][DIM][nN]   -> later A_d [DIM][nN x nN]
-  static constexpr int szG = (nIP * DIM * nN > DIM * nN * nN) ? nIP * DIM * nN : DIM * nN * nN;
-  static constexpr int oCG = oG + szG;                       // suu left operand [nIP][nN]
-  static constexpr int oM = oCG + nIP * nN;                  // M
-  static constexpr int oW = oM + nN * nN;                    // W = M^-1
-  static constexpr int oSQU = oW + nN * nN;                  // Squ_d [DIM][nN x nN] -> later U [nN x l1]
-  static constexpr int szSQU = (DIM * nN * nN > nN * l1) ? DIM * nN * nN : nN * l1;
-  static constexpr int oSUQ = oSQU + szSQU;                  // Suq_d [DIM][nN x nN]
-  static constexpr int oSUU = oSUQ + DIM * nN * nN;          // Suu -> K -> K^-1
-  static constexpr int oFW = oSUU + nN * nN;                 // weighted face mass matrices [nFc][NW][t x t]
-  static constexpr int oB = oFW + nFc * NW * t * t;          // B_d [DIM][nN x l1] -> Q_d
-  static constexpr int oR = oB + DIM * nN * l1;              // R [nN x l1]
-  static constexpr int oFU = oR + nN * l1;                   // Fu [nN]
-  static constexpr int oEnd = oFU + nN;
+  static constexpr int l = nFc * t, NW = 3 + 2 * DIM;   // face weight kinds: tau, n_d, (Dn)_d, v.n, 1
+  static constexpr int nNp = ev(nN), tp = ev(t), ldc = ev(l + 1) + 2, nJ = nIP + nFc * nIPf;
+  static constexpr int ldg = ev(DIM * nN);              // leading dimension of the g rows (one row per ip)
+  static constexpr int ldw = ((nFc * NW + 3) / 4) * 4;
+  // offsets in doubles (all even => 16-byte aligned)
+  static constexpr int oPHI = 0;                             // shape table, row-major [nIP][nNp]
+  static constexpr int oWQ = oPHI + nIP * nNp;               // cubature weights [nIP] then face weights [nIPf] (resident)
+  static constexpr int oX = oWQ + ev(nIP + nIPf);            // coords [nN][DIM]
+  static constexpr int oIJ = oX + ev(nN * DIM);              // dV * invJ  [nIP][DIM*DIM]  (m,r)
+  static constexpr int oDV = oIJ + ev(nIP * DIM * DIM);      // dV [nIP]
+  static constexpr int oDIP = oDV + ev(nIP);                 // D at bulk IPs [nIP][DIM*DIM] col-major
+  static constexpr int oVIP = oDIP + ev(nIP * DIM * DIM);    // v at bulk IPs [nIP][DIM]
+  static constexpr int oLW = oVIP + ev(nIP * DIM);           // (reac*dV + euler*dV) [nIP], src*dV [nIP]
+  static constexpr int oFWT = oLW + ev(2 * nIP);             // face IP weights, row-major [nIPf][ldw], column (f,kind)
+  static constexpr int oTAU = oFWT + nIPf * ldw;             // tau at element-local face nodes [l]
+  static constexpr int oDN = oTAU + ev(l);                   // D at nodes [nN][DIM*DIM]
+  static constexpr int oVN = oDN + ev(nN * DIM * DIM);       // v at nodes [nN][DIM]
+  static constexpr int oG = oVN + ev(nN * DIM);              // g rows [nIP][ldg], entry (d,i) -> later A_d [DIM][nNp x nN] col-major
+  static constexpr int szG0 = (nIP * ldg > DIM * nNp * nN) ? nIP * ldg : DIM * nNp * nN;
+  static constexpr int szG = (szG0 > nJ * DIM * DIM) ? szG0 : nJ * DIM * DIM;   // also hosts the raw Jacobians [nJ][DIM*DIM] (dead before g is formed)
+  static constexpr int oJ = oG;
+  static constexpr int oM = oG + ev(szG) + 4;                // M, col-major ld nNp
+  static constexpr int oW = oM + nNp * nNp;                  // W = M^-1 (nNp columns: the block Gauss-Jordan works on the even-padded matrix)
+  static constexpr int oSQU = oW + nNp * nNp;                // Squ_d row-major [DIM][nN][nNp] -> later U row-major [nN][ldc]
+  static constexpr int szSQU = (DIM * nN * nNp > nN * ldc) ? DIM * nN * nNp : nN * ldc;
+  static constexpr int oSUQ = oSQU + szSQU;                  // Suq_d col-major [DIM][nNp x nN]
+  static constexpr int oSUU = oSUQ + DIM * nNp * nN;         // Suu -> K -> K^-1, col-major ld nNp
+  static constexpr int oFW = oSUU + nNp * nNp;               // weighted face mass matrices [nFc][NW][tp x t] (symmetric)
+  static constexpr int oB = oFW + nFc * NW * tp * t;         // B_d row-major [DIM][nN][ldc] -> Q_d
+  static constexpr int oR = oB + DIM * nN * ldc;             // R row-major [nN][ldc]; before P6 it hosts the suu left operand cg [nIP][nNp]
+  static constexpr int szR = (nN * ldc > nIP * nNp) ? nN * ldc : nIP * nNp;
+  static constexpr int oCG = oR;
+  // Per-element staging of the read-only tables (with ~227 KB of shared memory carved out the L1 is ~1 KB, so __ldg would go to L2):
+  //   dshape | fdshape | fshape at the start of the FW region (all three are consumed before the face matrices are formed),
+  //   ffs (phi_a phi_b of the face element) at the end of the B region (consumed while FW is written, before B is).
+  static constexpr int nDSH = ev(nIP * nN * DIM), nFDS = ev(nIPf * t * (DIM - 1)), nFSH = ev(nIPf * t), nFFS = ev(nIPf * t * t);
+  static constexpr int oDSH = oFW, oFDS = oDSH + nDSH, oFSH = oFDS + nFDS, oFFS = oR - nFFS;
+  static_assert(oFSH + nFSH <= oFFS, "staged tables do not fit in the FW+B regions");
+  static_assert(oFFS >= oB, "ffs staging must not overlap the face matrices");
+  static constexpr int oFU = oR + szR;                       // Fu [nN]
+  static constexpr int oSCR = oFU + ev(nN);                  // Gauss-Jordan pivot-row scratch [2*nNp]
+  static constexpr int oEnd = oSCR + 2 * nNp;
   static constexpr int nDoubles = oEnd;
   // after the doubles: row starts (nFc x int64) then a small int area
-  static constexpr int nInts = 8 + 2 * nFc * t + nFc * nN + nFc * nFc + 3 * nFc + 8;
+  static constexpr int nInts = 8 + 2 * nFc * t + nFc * nN + nFc * nFc + 5 * nFc + 8;
   static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * nFc + 4 * (size_t)nInts;
 };
 
 template <int DIM, int P>
 __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmParams p) {
   using L = AsmSmem<DIM, P>;
-  constexpr int nN = L::nN, t = L::t, nFc = L::nFc, nIP = L::nIP, nIPf = L::nIPf, l = L::l, l1 = L::l1, NW = L::NW;
+  constexpr int nN = L::nN, t = L::t, nFc = L::nFc, nIP = L::nIP, nIPf = L::nIPf, l = L::l, NW = L::NW;
+  constexpr int nNp = L::nNp, tp = L::tp, ldc = L::ldc, ldg = L::ldg, ldw = L::ldw, nJ = L::nJ;
   constexpr int D2 = DIM * DIM, NT = kAsmThreads;
   constexpr int kTau = 0, kN = 1, kDN = 1 + DIM, kC = 1 + 2 * DIM, kOne = 2 + 2 * DIM;
-  extern __shared__ double sm[];
-  double* X = sm + L::oX; double* IJ = sm + L::oIJ; double* DV = sm + L::oDV; double* DIP = sm + L::oDIP; double* VIP = sm + L::oVIP;
-  double* LW = sm + L::oLW; double* FWT = sm + L::oFWT; double* TAU = sm + L::oTAU; double* DN = sm + L::oDN; double* VN = sm + L::oVN;
-  double* G = sm + L::oG; double* CG = sm + L::oCG; double* Mm = sm + L::oM; double* W = sm + L::oW; double* SQU = sm + L::oSQU;
-  double* SUQ = sm + L::oSUQ; double* SUU = sm + L::oSUU; double* FW = sm + L::oFW; double* B = sm + L::oB; double* R = sm + L::oR;
-  double* FU = sm + L::oFU;
+  constexpr int FWS = tp * t;   // stride between face matrices
+  constexpr bool kPrefetch = (nN * DIM <= 64) && (l <= 128) && (nFc * nFc <= 32);
+  extern __shared__ __align__(16) double sm[];
+  double* PHI = sm + L::oPHI; double* X = sm + L::oX; double* JR = sm + L::oJ; double* IJ = sm + L::oIJ; double* DV = sm + L::oDV;
+  double* DIP = sm + L::oDIP; double* VIP = sm + L::oVIP; double* LW = sm + L::oLW; double* FWT = sm + L::oFWT; double* TAU = sm + L::oTAU;
+  double* DN = sm + L::oDN; double* VN = sm + L::oVN; double* G = sm + L::oG; double* CG = sm + L::oCG; double* Mm = sm + L::oM;
+  double* Wb = sm + L::oW; double* SQU = sm + L::oSQU; double* SUQ = sm + L::oSUQ; double* SUU = sm + L::oSUU; double* FW = sm + L::oFW;
+  double* B = sm + L::oB; double* R = sm + L::oR; double* FU = sm + L::oFU;
+  double* WQ = sm + L::oWQ; double* DSH = sm + L::oDSH; double* FDS = sm + L::oFDS; double* FSH = sm + L::oFSH; double* FFS = sm + L::oFFS;
   long long* ROWS = reinterpret_cast<long long*>(sm + L::nDoubles);   // [nFc] first entry of row (F,0) in vals
   int* ISM = reinterpret_cast<int*>(ROWS + nFc);                      // [nFc] global face ids
   int* FN = ISM + 8;                                                  // [nFc*t] faceNodes
@@ -224,6 +340,8 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   int* RLEN = POS + nFc * nFc;                                        // [nFc] row length
   int* BCF = RLEN + nFc;                                              // [nFc] boundary kind
   int* INTF = BCF + nFc;                                              // [nFc] interior flag
+  int* OPP = INTF + nFc;                                              // [nFc] first node not on the face (orientation test)
+  int* QCTR = OPP + nFc;                                              // [4] dynamic tile-queue counters
   double* A = G;    // A_d aliases g (dead after the contractions)
   double* Um = SQU; // U aliases Squ (dead after A)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -231,31 +349,69 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   const bool euler = p.timeScheme == 1;
   const bool diffField = hasDiff && p.diffComps > 0 && p.diff;
 
+  // ---- once per CTA: constant tables; padding lanes must hold finite numbers --------------------------------------------
+  for (int i = tid; i < L::nDoubles; i += NT) sm[i] = 0.0;
+  __syncthreads();
   for (int i = tid; i < nFc * t; i += NT) FN[i] = p.faceNodes[i];
   for (int i = tid; i < nFc * nN; i += NT) NIF[i] = p.nodeInFace[i];
+  for (int i = tid; i < nIP * nN; i += NT) PHI[(i / nN) * nNp + (i % nN)] = p.shape[i];
+  for (int i = tid; i < nIP + nIPf; i += NT) WQ[i] = i < nIP ? p.w[i] : p.fw[i - nIP];
+  if (tid < nFc) { int vn = 0; for (int kk = 0; kk < nN; kk++) if (p.nodeInFace[tid * nN + kk] < 0) { vn = kk; break; } OPP[tid] = vn; }
   __syncthreads();
 
-  for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
-    // ---- P0: gather ------------------------------------------------------------------------------------------------
-    const int* cell = p.cells + (size_t)e * nN;
-    for (int i = tid; i < nN * DIM; i += NT) X[i] = p.nodes[(size_t)cell[i / DIM] * DIM + (i % DIM)];
-    if (tid < nFc) {
-      const int F = p.cell2face[(size_t)e * nFc + tid];
-      ISM[tid] = F;
-      ROWS[tid] = p.faceRowStart[F];
-      RLEN[tid] = (int)p.faceNnb[F] * t;
-      BCF[tid] = p.faceBC[F];
-      INTF[tid] = p.faceInterior[F];
-    }
-    for (int i = tid; i < nFc * nFc; i += NT) POS[i] = p.elemPos[(size_t)e * nFc * nFc + i];
-    for (int i = tid; i < l; i += NT) {
-      const int f = i / t;
+  // ---- software prefetch of the next element's gather (registers) ------------------------------------------------------
+  double pfX = 0.0, pfTau = 0.0;
+  int pfF = 0, pfPerm = 0, pfPos = 0, pfRlen = 0, pfBc = 0, pfInt = 0;
+  long long pfRow = 0;
+  auto prefetch = [&](int e) {
+    if (!kPrefetch || e >= p.nCells) return;
+    if (tid < nN * DIM) pfX = p.elemX[(size_t)e * nN * DIM + tid];
+    if (tid >= 64 && tid < 64 + l) {
+      const int i = tid - 64, f = i / t;
       const int F = p.cell2face[(size_t)e * nFc + f];
-      const int pos = p.fperm[(size_t)e * l + i];
-      PERM[i] = pos;
+      pfPerm = p.fperm[(size_t)e * l + i];
       const int side = (p.tauVals == 2) ? p.tauSide[(size_t)e * nFc + f] : 0;
-      TAU[i] = p.tau[((size_t)F * t + pos) * p.tauVals + side];
+      pfTau = p.tau[((size_t)F * t + pfPerm) * p.tauVals + side];
     }
+    if (tid >= 192 && tid < 192 + nFc) {
+      const int F = p.cell2face[(size_t)e * nFc + (tid - 192)];
+      pfF = F; pfRow = p.faceRowStart[F]; pfRlen = (int)p.faceNnb[F] * t; pfBc = p.faceBC[F]; pfInt = p.faceInterior[F];
+    }
+    if (tid >= 224 && tid < 224 + nFc * nFc) pfPos = p.elemPos[(size_t)e * nFc * nFc + (tid - 224)];
+  };
+  prefetch(blockIdx.x);
+
+  long long tprev = clock64();
+  for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
+    // ---- P0: commit the prefetched gather -----------------------------------------------------------------------------------
+    if (kPrefetch) {
+      if (tid < nN * DIM) X[tid] = pfX;
+      if (tid >= 64 && tid < 64 + l) { TAU[tid - 64] = pfTau; PERM[tid - 64] = pfPerm; }
+      if (tid >= 192 && tid < 192 + nFc) { const int f = tid - 192; ISM[f] = pfF; ROWS[f] = pfRow; RLEN[f] = pfRlen; BCF[f] = pfBc; INTF[f] = pfInt; }
+      if (tid >= 224 && tid < 224 + nFc * nFc) POS[tid - 224] = pfPos;
+    } else {   // large elements: direct gather
+      for (int i = tid; i < nN * DIM; i += NT) X[i] = p.elemX[(size_t)e * nN * DIM + i];
+      for (int i = tid; i < l; i += NT) {
+        const int f = i / t;
+        const int F = p.cell2face[(size_t)e * nFc + f];
+        const int pos = p.fperm[(size_t)e * l + i];
+        PERM[i] = pos;
+        const int side = (p.tauVals == 2) ? p.tauSide[(size_t)e * nFc + f] : 0;
+        TAU[i] = p.tau[((size_t)F * t + pos) * p.tauVals + side];
+      }
+      if (tid < nFc) {
+        const int F = p.cell2face[(size_t)e * nFc + tid];
+        ISM[tid] = F; ROWS[tid] = p.faceRowStart[F]; RLEN[tid] = (int)p.faceNnb[F] * t; BCF[tid] = p.faceBC[F]; INTF[tid] = p.faceInterior[F];
+      }
+      for (int i = tid; i < nFc * nFc; i += NT) POS[i] = p.elemPos[(size_t)e * nFc * nFc + i];
+    }
+    if (tid == NT - 1) { QCTR[0] = 0; QCTR[1] = 0; QCTR[2] = 0; QCTR[3] = 0; }
+    // stage the read-only tables of this element pass (L2 -> shared, asynchronous 16-byte copies)
+    for (int i = tid; i < L::nDSH / 2; i += NT) cp_async16(DSH + 2 * i, p.dshape + 2 * i);
+    for (int i = tid; i < L::nFDS / 2; i += NT) cp_async16(FDS + 2 * i, p.fdshape + 2 * i);
+    for (int i = tid; i < L::nFSH / 2; i += NT) cp_async16(FSH + 2 * i, p.fshape + 2 * i);
+    for (int i = tid; i < L::nFFS / 2; i += NT) cp_async16(FFS + 2 * i, p.ffs + 2 * i);
+    const int* cell = p.cells + (size_t)e * nN;
     if (diffField) {
       for (int i = tid; i < nN * D2; i += NT) {
         const int nd = i / D2, c = i % D2;
@@ -267,29 +423,47 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
     }
     if (hasConv) for (int i = tid; i < nN * DIM; i += NT) VN[i] = p.vel[(size_t)cell[i / DIM] * DIM + (i % DIM)];
+    cp_async_wait_all();
     __syncthreads();
+    HFX_PROF(0);
 
-    // ---- P1: geometry at bulk and face integration points (Operator.cpp:14-84, HDGModel.cpp:53-85, HDGBase.cpp:18-65) --
-    for (int k = tid; k < nIP + nFc * nIPf; k += NT) {
+    // ---- P1a: raw Jacobians, one entry per thread (Operator.cpp:14-39) --------------------------------------------------------
+    for (int idx = tid; idx < nIP * D2 + nFc * nIPf * (DIM - 1) * DIM; idx += NT) {
+      if (idx < nIP * D2) {
+        const int ip = idx / D2, r = (idx % D2) / DIM, m = idx % DIM;
+        const double* d = DSH + ip * nN * DIM + r;
+        double s = 0.0;
+#pragma unroll 4
+        for (int i = 0; i < nN; i++) s = fma(d[i * DIM], X[i * DIM + m], s);
+        JR[ip * D2 + r * DIM + m] = s;
+      } else {
+        const int k2 = idx - nIP * D2;
+        const int fi = k2 / ((DIM - 1) * DIM), rm = k2 % ((DIM - 1) * DIM), r = rm / DIM, m = rm % DIM;
+        const int f = fi / nIPf, ip = fi % nIPf;
+        const int* fn = FN + f * t;
+        const double* d = FDS + ip * t * (DIM - 1) + r;
+        double s = 0.0;
+#pragma unroll 2
+        for (int a = 0; a < t; a++) s = fma(d[a * (DIM - 1)], X[fn[a] * DIM + m], s);
+        JR[(nIP + fi) * D2 + r * DIM + m] = s;
+      }
+    }
+    __syncthreads();
+    // the next element's gather flies while this element is computed
+    prefetch(e + gridDim.x);
+
+    // ---- P1b: measures, inverses, normals, coefficient interpolation (Operator.cpp:41-84, HDGModel.cpp:53-85, HDGBase.cpp:18-65) --
+    for (int k = tid; k < nJ; k += NT) {
       if (k < nIP) {
         const int ip = k;
         double J[DIM][DIM];
 #pragma unroll
         for (int r = 0; r < DIM; r++)
 #pragma unroll
-          for (int m = 0; m < DIM; m++) J[r][m] = 0.0;
-        for (int i = 0; i < nN; i++) {
-          const double* d = p.dshape + ((size_t)ip * nN + i) * DIM;
-#pragma unroll
-          for (int r = 0; r < DIM; r++) {
-            const double dr = __ldg(d + r);
-#pragma unroll
-            for (int m = 0; m < DIM; m++) J[r][m] = fma(dr, X[i * DIM + m], J[r][m]);
-          }
-        }
+          for (int m = 0; m < DIM; m++) J[r][m] = JR[ip * D2 + r * DIM + m];
         double det, I[DIM][DIM];
         det_inv(J, det, I);
-        const double dv = __ldg(p.w + ip) * det;
+        const double dv = WQ[ip] * det;
         DV[ip] = dv;
 #pragma unroll
         for (int m = 0; m < DIM; m++)
@@ -300,7 +474,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
           for (int c = 0; c < D2; c++) Dc[c] = 0.0;
           for (int i = 0; i < nN; i++) {
-            const double s = __ldg(p.shape + (size_t)ip * nN + i);
+            const double s = PHI[ip * nNp + i];
 #pragma unroll
             for (int c = 0; c < D2; c++) Dc[c] = fma(s, DN[i * D2 + c], Dc[c]);
           }
@@ -312,7 +486,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
           for (int d = 0; d < DIM; d++) v[d] = 0.0;
           for (int i = 0; i < nN; i++) {
-            const double s = __ldg(p.shape + (size_t)ip * nN + i);
+            const double s = PHI[ip * nNp + i];
 #pragma unroll
             for (int d = 0; d < DIM; d++) v[d] = fma(s, VN[i * DIM + d], v[d]);
           }
@@ -323,7 +497,14 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         if (hasReac) lw += p.reacIP[(size_t)e * nIP + ip] * dv;
         if (euler) lw += dv;
         LW[ip] = lw;
-        LW[nIP + ip] = hasSrc ? p.srcIP[(size_t)e * nIP + ip] * dv : 0.0;
+        double rw = hasSrc ? p.srcIP[(size_t)e * nIP + ip] * dv : 0.0;
+        if (euler) {   // Mass * Solution_old = sum_ip dV phi_i(ip) u_old(ip)
+          const double* so = p.solOld + (size_t)e * nN;
+          double uo = 0.0;
+          for (int i = 0; i < nN; i++) uo = fma(PHI[ip * nNp + i], so[i], uo);
+          rw = fma(dv, uo, rw);
+        }
+        LW[nIP + ip] = rw;
       } else {
         const int fi = k - nIP, f = fi / nIPf, ip = fi % nIPf;
         const int* fn = FN + f * t;
@@ -331,7 +512,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
         for (int r = 0; r < DIM - 1; r++)
 #pragma unroll
-          for (int m = 0; m < DIM; m++) J[r][m] = 0.0;
+          for (int m = 0; m < DIM; m++) J[r][m] = JR[(nIP + fi) * D2 + r * DIM + m];
         double tauip = 0.0, Dc[D2], v[DIM];
 #pragma unroll
         for (int c = 0; c < D2; c++) Dc[c] = 0.0;
@@ -339,14 +520,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         for (int d = 0; d < DIM; d++) v[d] = 0.0;
         for (int a = 0; a < t; a++) {
           const int nd = fn[a];
-          const double* d = p.fdshape + ((size_t)ip * t + a) * (DIM - 1);
-          const double s = __ldg(p.fshape + (size_t)ip * t + a);
-#pragma unroll
-          for (int r = 0; r < DIM - 1; r++) {
-            const double dr = __ldg(d + r);
-#pragma unroll
-            for (int m = 0; m < DIM; m++) J[r][m] = fma(dr, X[nd * DIM + m], J[r][m]);
-          }
+          const double s = FSH[ip * t + a];
           tauip = fma(s, TAU[f * t + a], tauip);
           if (diffField) {
 #pragma unroll
@@ -377,17 +551,17 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         nrm = sqrt(nrm);
         // outward orientation: (x_opposite - x_v0) . n <= 0   (HDGBase.cpp:43-62)
         const int v0 = fn[0];
-        int vn = 0;
-        for (int kk = 0; kk < nN; kk++) if (NIF[f * nN + kk] < 0) { vn = kk; break; }
+        const int vn = OPP[f];
+        const double inrm = 1.0 / nrm;
         double prod = 0.0;
 #pragma unroll
-        for (int m = 0; m < DIM; m++) { nv[m] /= nrm; prod = fma(X[vn * DIM + m] - X[v0 * DIM + m], nv[m], prod); }
+        for (int m = 0; m < DIM; m++) { nv[m] *= inrm; prod = fma(X[vn * DIM + m] - X[v0 * DIM + m], nv[m], prod); }
         if (prod > 0.0) {
 #pragma unroll
           for (int m = 0; m < DIM; m++) nv[m] = -nv[m];
         }
-        const double dvf = __ldg(p.fw + ip) * area;
-        double* wt = FWT + (size_t)fi * NW;
+        const double dvf = WQ[nIP + ip] * area;
+        double* wt = FWT + (size_t)ip * ldw + f * NW;
         wt[kTau] = dvf * tauip;
         double vdn = 0.0;
 #pragma unroll
@@ -407,74 +581,156 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
     }
     __syncthreads();
+    HFX_PROF(1);
 
-    // ---- P2: g[ip][d][i] = dV (J^-1 grad_ref phi_i)_d ; cg = suu left operand ----------------------------------------
+    // ---- P2: g[ip][(d,i)] = dV (J^-1 grad_ref phi_i)_d ; cg = suu left operand ----------------------------------------
     for (int idx = tid; idx < nIP * nN; idx += NT) {
       const int ip = idx / nN, i = idx % nN;
-      const double* d = p.dshape + ((size_t)ip * nN + i) * DIM;
+      const double* d = DSH + (ip * nN + i) * DIM;
       double dr[DIM], gg[DIM];
 #pragma unroll
-      for (int r = 0; r < DIM; r++) dr[r] = __ldg(d + r);
+      for (int r = 0; r < DIM; r++) dr[r] = d[r];
 #pragma unroll
       for (int m = 0; m < DIM; m++) {
         double s = 0.0;
 #pragma unroll
         for (int r = 0; r < DIM; r++) s = fma(IJ[ip * D2 + m * DIM + r], dr[r], s);
         gg[m] = s;
-        G[(ip * DIM + m) * nN + i] = s;
+        G[ip * ldg + m * nN + i] = s;
       }
-      double c = LW[ip] * __ldg(p.shape + (size_t)ip * nN + i);
+      double c = LW[ip] * PHI[ip * nNp + i];
       if (hasConv) {
 #pragma unroll
         for (int m = 0; m < DIM; m++) c = fma(-VIP[ip * DIM + m], gg[m], c);
       }
-      CG[ip * nN + i] = c;
+      CG[ip * nNp + i] = c;
     }
     __syncthreads();
+    HFX_PROF(2);
 
-    // ---- P3a: M = sum_ip dV phi phi^T ---------------------------------------------------------------------------------
-    tile_gemm<1, nN, nN, nIP, 2, 1>(tid, NT,
-        [&](int, int m, int k) { return DV[k] * __ldg(p.shape + (size_t)k * nN + m); },
-        [&](int, int k, int n) { return __ldg(p.shape + (size_t)k * nN + n); },
-        [&](int, int m, int n, double v) { Mm[m + nN * n] = v; });
-    __syncthreads();
-
-    // ---- P3b: warp 0 inverts M while the other warps do the remaining contractions ---------------------------------
-    if (warp == 0) {
-      warp_invert<nN>(Mm, W, lane, p.status);
-    } else {
-      const int t2 = tid - 32, nt2 = NT - 32;
-      // Squ_d[k][j] = sum_ip g[ip][d][k] phi[ip][j]     rows m = (d,k)   (HDGBase.cpp:150)
-      tile_gemm<1, DIM * nN, nN, nIP, 2, 2>(t2, nt2,
-          [&](int, int m, int k) { return G[k * DIM * nN + m]; },
-          [&](int, int k, int n) { return __ldg(p.shape + (size_t)k * nN + n); },
-          [&](int, int m, int n, double v) { const int d = m / nN, kk = m % nN; SQU[(d * nN + n) * nN + kk] = v; });
-      // Suu (bulk part): -C^T (Convection.cpp:5-49) + reaction mass + Euler mass
-      tile_gemm<1, nN, nN, nIP, 2, 2>(t2, nt2,
-          [&](int, int m, int k) { return CG[k * nN + m]; },
-          [&](int, int k, int n) { return __ldg(p.shape + (size_t)k * nN + n); },
-          [&](int, int m, int n, double v) { SUU[m + nN * n] = v; });
-      // weighted face mass matrices FW[f][kind][a + t b] = sum_ip wt[f][ip][kind] phi_a phi_b
-      tile_gemm<1, t * t, nFc * NW, nIPf, 2, 2>(t2, nt2,
-          [&](int, int m, int k) { return __ldg(p.ffs + (size_t)k * t * t + m); },
-          [&](int, int k, int n) { const int f = n / NW, kind = n % NW; return FWT[(size_t)(f * nIPf + k) * NW + kind]; },
-          [&](int, int m, int n, double v) { FW[(size_t)n * t * t + m] = v; });
-      // Fu = source (Source.cpp:24-48)
-      for (int i = t2; i < nN; i += nt2) {
-        double s = 0.0;
-        if (hasSrc) for (int ip = 0; ip < nIP; ip++) s = fma(__ldg(p.shape + (size_t)ip * nN + i), LW[nIP + ip], s);
-        FU[i] = s;
+    // ---- P3a: M = sum_ip dV phi phi^T (2x2 tiles; the left operand dV*phi is formed on the fly) --------------------------
+    {
+      constexpr int MT = nNp / 2, NTT = nNp / 2;
+      for (int tile = tid; tile < MT * NTT; tile += NT) {
+        const int m0 = (tile % MT) * 2, n0 = (tile / MT) * 2;
+        double acc[2][2];
+        zero_acc(acc);
+#pragma unroll 4
+        for (int k = 0; k < nIP; k++) {
+          const double2 a = *reinterpret_cast<const double2*>(PHI + k * nNp + m0);
+          const double2 b = *reinterpret_cast<const double2*>(PHI + k * nNp + n0);
+          const double dv = DV[k];
+          const double ax = a.x * dv, ay = a.y * dv;
+          acc[0][0] = fma(ax, b.x, acc[0][0]); acc[0][1] = fma(ax, b.y, acc[0][1]);
+          acc[1][0] = fma(ay, b.x, acc[1][0]); acc[1][1] = fma(ay, b.y, acc[1][1]);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int j = 0; j < 2; j++) if (m0 + i < nN && n0 + j < nN) Mm[(m0 + i) + nNp * (n0 + j)] = acc[i][j];
+      }
+      if ((nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal for the 2x2-block Gauss-Jordan (pad row/column are zero)
+        for (int j = 0; j < nN; j++) { Mm[nN + nNp * j] = 0.0; Mm[j + nNp * nN] = 0.0; }
+        Mm[nN + nNp * nN] = 1.0;
       }
     }
     __syncthreads();
+    HFX_PROF(3);
 
-    // ---- P3c: Suq bulk part (HDGDiffusion.cpp:130-144).  D = I: identical to Squ; no diffusion: zero ---------------------
+    // ---- P3b: W = M^-1 by warps 0-3 (Gauss-Jordan, named barrier) while a dynamic tile queue feeds the remaining contractions
+    //            (Squ, Suu, face matrices, Fu) to every warp that is free ----------------------------------------------------
+    double* const W = ((nNp / 2) & 1) ? Wb : Mm;
+    if (tid < kGJThreads) group_invert<nNp, nNp>(Mm, Wb, tid, p.status);
+    if (p.opmask & (1 << 30)) __syncthreads();   // experiment: exclusive inversion
+    HFX_PROF(14);
+    {
+      constexpr int MROWS = DIM * nN, SQ_MT = ev(MROWS) / 2, SQ_NT = (nN + 3) / 4, T_SQU = SQ_MT * SQ_NT;       // 2x4 tiles
+      constexpr int UU_MT = nNp / 2, T_SUU = UU_MT * UU_MT;                                                       // 2x2 tiles
+      constexpr int MR = t * t, FW_MT = (MR + 3) / 4, NC = nFc * NW, FW_NT = (NC + 3) / 4, T_FW = FW_MT * FW_NT;  // 4x4 tiles
+      static_assert(4 * FW_NT <= ldw + 2, "face weight rows too short");
+      constexpr int T_ALL = T_SQU + T_SUU + T_FW + nN;
+      for (;;) {
+        int tile = grab32(&QCTR[0], lane);
+        if (tile - lane >= T_ALL) break;
+        if (tile < T_SQU) {
+          // Squ_d[k][j] = sum_ip g[ip][(d,k)] phi[ip][j]  (HDGBase.cpp:150); with D = I the same numbers are Suq_d[k][j] (HDGDiffusion.cpp:130-144)
+          const int m0 = (tile % SQ_MT) * 2, n0 = (tile / SQ_MT) * 4;
+          double acc[2][4];
+          zero_acc(acc);
+          mk<2, 4, nIP>(acc, G + m0, ldg, PHI + n0, nNp);
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const int m = m0 + i;
+            if (m < MROWS) {
+              const int d = m / nN, kk = m % nN;
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const int n = n0 + j;
+                if (n < nN) {
+                  SQU[(d * nN + kk) * nNp + n] = acc[i][j];                                      // row-major (right operand of A = W Squ)
+                  if (!diffField) SUQ[(d * nN + n) * nNp + kk] = hasDiff ? acc[i][j] : 0.0;      // col-major (left operand of K, R)
+                }
+              }
+            }
+          }
+        } else if (tile < T_SQU + T_SUU) {
+          // Suu (bulk part): -C^T (Convection.cpp:5-49) + reaction mass + Euler mass
+          tile -= T_SQU;
+          const int m0 = (tile % UU_MT) * 2, n0 = (tile / UU_MT) * 2;
+          double acc[2][2];
+          zero_acc(acc);
+          mk<2, 2, nIP>(acc, CG + m0, nNp, PHI + n0, nNp);
+#pragma unroll
+          for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 2; j++) if (m0 + i < nN && n0 + j < nN) SUU[(m0 + i) + nNp * (n0 + j)] = acc[i][j];
+        } else if (tile < T_SQU + T_SUU + T_FW) {
+          // weighted face mass matrices FW[f][kind][a + tp b] = sum_ip wt[ip][(f,kind)] phi_a phi_b
+          tile -= T_SQU + T_SUU;
+          const int m0 = (tile % FW_MT) * 4, n0 = (tile / FW_MT) * 4;
+          double acc[4][4];
+          zero_acc(acc);
+#pragma unroll 2
+          for (int k = 0; k < nIPf; k++) {
+            double av[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) av[i] = (m0 + i < MR) ? FFS[k * MR + m0 + i] : 0.0;
+            const double2 b0 = *reinterpret_cast<const double2*>(FWT + k * ldw + n0);
+            const double2 b1 = *reinterpret_cast<const double2*>(FWT + k * ldw + n0 + 2);
+            const double bv[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+              for (int j = 0; j < 4; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int m = m0 + i;
+            if (m < MR) {
+              const int a = m % t, b = m / t;
+#pragma unroll
+              for (int j = 0; j < 4; j++) if (n0 + j < NC) FW[(n0 + j) * FWS + a + tp * b] = acc[i][j];
+            }
+          }
+        } else if (tile < T_ALL) {
+          // Fu = source (Source.cpp:24-48) + Euler mass * Solution_old (Euler.cpp:29-30), both as sum_ip phi_i(ip) * weight(ip)
+          const int i = tile - (T_SQU + T_SUU + T_FW);
+          double s2 = 0.0;
+          if (hasSrc || euler) for (int ip = 0; ip < nIP; ip++) s2 = fma(PHI[ip * nNp + i], LW[nIP + ip], s2);
+          FU[i] = s2;
+        }
+      }
+    }
+    __syncthreads();
+    HFX_PROF(4);
+
+    // ---- P3c: Suq bulk part with a diffusion field (HDGDiffusion.cpp:31-72,130-144) ----------------------------------------
     if (diffField) {
       for (int idx = tid; idx < nIP * nN; idx += NT) {   // g <- D g in place
         const int ip = idx / nN, i = idx % nN;
         double gg[DIM], o[DIM];
 #pragma unroll
-        for (int m = 0; m < DIM; m++) gg[m] = G[(ip * DIM + m) * nN + i];
+        for (int m = 0; m < DIM; m++) gg[m] = G[ip * ldg + m * nN + i];
 #pragma unroll
         for (int a = 0; a < DIM; a++) {
           double s = 0.0;
@@ -483,157 +739,280 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           o[a] = s;
         }
 #pragma unroll
-        for (int m = 0; m < DIM; m++) G[(ip * DIM + m) * nN + i] = o[m];
+        for (int m = 0; m < DIM; m++) G[ip * ldg + m * nN + i] = o[m];
       }
       __syncthreads();
-      tile_gemm<1, DIM * nN, nN, nIP, 2, 2>(tid, NT,
-          [&](int, int m, int k) { return G[k * DIM * nN + m]; },
-          [&](int, int k, int n) { return __ldg(p.shape + (size_t)k * nN + n); },
-          [&](int, int m, int n, double v) { const int d = m / nN, i = m % nN; SUQ[(d * nN + n) * nN + i] = v; });
-    } else {
-      // Suq_d[i][j] (bulk) equals Squ_d[i][j] entry by entry when D = I
-      for (int idx = tid; idx < DIM * nN * nN; idx += NT) SUQ[idx] = hasDiff ? SQU[idx] : 0.0;
-    }
-    // Euler: Fu += Mass * Solution_old (Euler.cpp:29-30)
-    if (euler && tid < nN) {
-      double s = FU[tid];
-      const double* so = p.solOld + (size_t)e * nN;
-      for (int j = 0; j < nN; j++) s = fma(Mm[tid + nN * j], so[j], s);
-      FU[tid] = s;
+      constexpr int MROWS = DIM * nN, MT = ev(MROWS) / 2, NTT = nNp / 2;
+      for (int tile = tid; tile < MT * NTT; tile += NT) {
+        const int m0 = (tile % MT) * 2, n0 = (tile / MT) * 2;
+        double acc[2][2];
+        zero_acc(acc);
+        mk<2, 2, nIP>(acc, G + m0, ldg, PHI + n0, nNp);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int m = m0 + i;
+          if (m < MROWS) {
+            const int d = m / nN, kk = m % nN;
+#pragma unroll
+            for (int j = 0; j < 2; j++) if (n0 + j < nN) SUQ[(d * nN + n0 + j) * nNp + kk] = acc[i][j];
+          }
+        }
+      }
     }
     __syncthreads();
+    HFX_PROF(6);
     // face parts of Suu (+tau mass, HDGBase.cpp:128) and Suq (-(Dn) mass, HDGDiffusion.cpp:121), gather form
     for (int idx = tid; idx < nN * nN; idx += NT) {
       const int i = idx % nN, j = idx / nN;
-      double suu = SUU[idx], suq[DIM];
+      double suu = SUU[i + nNp * j], suq[DIM];
 #pragma unroll
-      for (int d = 0; d < DIM; d++) suq[d] = SUQ[d * nN * nN + idx];
+      for (int d = 0; d < DIM; d++) suq[d] = SUQ[(d * nN + j) * nNp + i];
       for (int f = 0; f < nFc; f++) {
         const int a = NIF[f * nN + i], b = NIF[f * nN + j];
         if (a >= 0 && b >= 0) {
-          const double* fw = FW + (size_t)f * NW * t * t + a + t * b;
-          suu += fw[kTau * t * t];
+          const double* fw = FW + (size_t)f * NW * FWS + a + tp * b;
+          suu += fw[kTau * FWS];
 #pragma unroll
-          for (int d = 0; d < DIM; d++) suq[d] -= fw[(kDN + d) * t * t];
+          for (int d = 0; d < DIM; d++) suq[d] -= fw[(kDN + d) * FWS];
         }
       }
-      SUU[idx] = suu;
+      SUU[i + nNp * j] = suu;
 #pragma unroll
-      for (int d = 0; d < DIM; d++) SUQ[d * nN * nN + idx] = suq[d];
+      for (int d = 0; d < DIM; d++) SUQ[(d * nN + j) * nNp + i] = suq[d];
+    }
+    if ((nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal of K for the 2x2-block Gauss-Jordan
+      for (int j = 0; j < nN; j++) { SUU[nN + nNp * j] = 0.0; SUU[j + nNp * nN] = 0.0; }
+      SUU[nN + nNp * nN] = 1.0;
     }
     __syncthreads();
+    HFX_PROF(7);
 
-    // ---- P4: A_d = W Squ_d ;  B_d = W Sql_d with Sql[(fn_f(a),d),(f,b)] = -N_fd[a][b] (HDGBase.cpp:134) -----------------
-    tile_gemm<1, nN, DIM * nN, nN, 2, 3>(tid, NT,
-        [&](int, int m, int k) { return W[m + nN * k]; },
-        [&](int, int k, int n) { return SQU[n * nN + k]; },          // n = (d,j)
-        [&](int, int m, int n, double v) { A[n * nN + m] = v; });    // A[(d*nN + j)*nN + i] = A_d[i][j]
-    tile_gemm<nFc, nN, DIM * t, t, 2, (t % 5 == 0 ? 5 : (t % 3 == 0 ? 3 : (t % 2 == 0 ? 2 : 1)))>(tid, NT,
-        [&](int f, int m, int k) { return W[m + nN * FN[f * t + k]]; },
-        [&](int f, int k, int n) { const int d = n / t, b = n % t; return FW[((size_t)f * NW + kN + d) * t * t + k + t * b]; },
-        [&](int f, int m, int n, double v) { const int d = n / t, b = n % t; B[(size_t)d * nN * l1 + m + nN * (f * t + b)] = -v; });
-    for (int idx = tid; idx < DIM * nN; idx += NT) B[(size_t)(idx / nN) * nN * l1 + (idx % nN) + nN * l] = 0.0;  // Q0 column
-    __syncthreads();
-
-    // ---- P5: K = Suu - sum_d Suq_d A_d  (HDGSolver.cpp:335) ------------------------------------------------------------
-    tile_gemm<1, nN, nN, DIM * nN, 2, 1>(tid, NT,
-        [&](int, int m, int k) { return SUQ[k * nN + m]; },                                   // k = (d,k')
-        [&](int, int k, int n) { const int d = k / nN, kk = k % nN; return A[(d * nN + n) * nN + kk]; },
-        [&](int, int m, int n, double v) { SUU[m + nN * n] -= v; });
-    __syncthreads();
-
-    // ---- P6: warp 0 inverts K in place; the others form R = Sul - sum_d Suq_d B_d, last column -Fu (:342-343) ----------
-    if (warp == 0) {
-      warp_invert<nN>(SUU, SUU, lane, p.status);
-    } else {
-      const int t2 = tid - 32, nt2 = NT - 32;
-      tile_gemm<1, nN, l, DIM * nN, 2, 2>(t2, nt2,
-          [&](int, int m, int k) { return SUQ[k * nN + m]; },
-          [&](int, int k, int n) { const int d = k / nN, j = k % nN; return B[(size_t)d * nN * l1 + j + nN * n]; },
-          [&](int, int m, int n, double v) {
-            const int f = n / t, b = n % t, a = NIF[f * nN + m];
-            double sul = 0.0;
-            if (a >= 0) { const double* fw = FW + (size_t)f * NW * t * t + a + t * b; sul = fw[kC * t * t] - fw[kTau * t * t]; }
-            R[m + nN * n] = sul - v;
-          });
-      for (int i = t2; i < nN; i += nt2) R[i + nN * l] = -FU[i];
+    // ---- P4: A_d = W Squ_d (col-major out) ;  B_d = W Sql_d with Sql[(fn_f(a),d),(f,b)] = -N_fd[a][b] (HDGBase.cpp:134) ------
+    {
+      constexpr int MT = nNp / 2, NTT = (nN + 3) / 4;
+      for (int tile = tid; tile < DIM * MT * NTT; tile += NT) {
+        const int d = tile / (MT * NTT), tl = tile % (MT * NTT);
+        const int m0 = (tl % MT) * 2, n0 = (tl / MT) * 4;
+        double acc[2][4];
+        zero_acc(acc);
+        mk<2, 4, nN>(acc, W + m0, nNp, SQU + d * nN * nNp + n0, nNp);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+          if (n0 + j < nN) *reinterpret_cast<double2*>(A + (d * nN + n0 + j) * nNp + m0) = make_double2(acc[0][j], acc[1][j]);
+      }
+      // B: per (f, d): (nN x t) = W[:, fn_f] (nN x t) * N_fd (t x t), one full row of N_fd per register tile when it fits
+      constexpr int TNB = (tp <= 16) ? tp : 2, NTB = tp / TNB;
+      for (int tile = tid; tile < nFc * DIM * MT * NTB; tile += NT) {
+        const int fd = tile / (MT * NTB), tl = tile % (MT * NTB);
+        const int f = fd / DIM, d = fd % DIM;
+        const int m0 = (tl % MT) * 2, n0 = (tl / MT) * TNB;
+        const double* fw = FW + (f * NW + kN + d) * FWS + n0;   // symmetric: row a is contiguous over b
+        const int* fn = FN + f * t;
+        double acc[2][TNB];
+        zero_acc(acc);
+#pragma unroll
+        for (int a = 0; a < t; a++) mk_step<2, TNB>(acc, W + m0 + nNp * fn[a], fw + tp * a);
+#pragma unroll
+        for (int i = 0; i < 2; i++)
+#pragma unroll
+          for (int j = 0; j < TNB; j++)
+            if (m0 + i < nN && n0 + j < t) B[(d * nN + m0 + i) * ldc + f * t + n0 + j] = -acc[i][j];
+      }
+      for (int idx = tid; idx < DIM * nN; idx += NT) { B[idx * ldc + l] = 0.0; B[idx * ldc + l + 1] = 0.0; }  // Q0 column
     }
     __syncthreads();
+    HFX_PROF(8);
 
-    // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu ------------------------------------------------------------------------------
+    // ---- P5: one queued phase: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335) and R = Sul - sum_d Suq_d B_d, column l = -Fu (:342-343)
+    {
+      constexpr int MT = nNp / 2, T_K = MT * nN, R_NT = ev(l) / 2, T_R = MT * R_NT, T_ALL = T_K + T_R + nN;
+      for (;;) {
+        int tile = grab32(&QCTR[1], lane);
+        if (tile - lane >= T_ALL) break;
+        if (tile < T_K) {   // right operand A is column-major => scalar loads, 2x1 strips
+          const int m0 = (tile % MT) * 2, n = tile / MT;
+          double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+          for (int d = 0; d < DIM; d++) {
+            const double* sq = SUQ + d * nN * nNp + m0;
+            const double* ac = A + (d * nN + n) * nNp;
+#pragma unroll 4
+            for (int k = 0; k < nN; k++) {
+              const double2 s2 = *reinterpret_cast<const double2*>(sq + nNp * k);
+              const double b = ac[k];
+              a0 = fma(s2.x, b, a0); a1 = fma(s2.y, b, a1);
+            }
+          }
+          SUU[m0 + nNp * n] -= a0;
+          if (m0 + 1 < nN) SUU[m0 + 1 + nNp * n] -= a1;
+        } else if (tile < T_K + T_R) {
+          tile -= T_K;
+          const int m0 = (tile % MT) * 2, n0 = (tile / MT) * 2;
+          double acc[2][2];
+          zero_acc(acc);
+#pragma unroll
+          for (int d = 0; d < DIM; d++) mk<2, 2, nN>(acc, SUQ + d * nN * nNp + m0, nNp, B + d * nN * ldc + n0, ldc);
+#pragma unroll
+          for (int i = 0; i < 2; i++) {
+            const int m = m0 + i;
+            if (m < nN) {
+#pragma unroll
+              for (int j = 0; j < 2; j++) {
+                const int n = n0 + j;
+                if (n < l) {
+                  const int f = n / t, b = n % t, a = NIF[f * nN + m];
+                  double sul = 0.0;
+                  if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = fw[kC * FWS] - fw[kTau * FWS]; }
+                  R[m * ldc + n] = sul - acc[i][j];
+                }
+              }
+            }
+          }
+        } else if (tile < T_ALL) {
+          const int i = tile - (T_K + T_R);
+          R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0;
+        }
+      }
+    }
+    __syncthreads();
+    HFX_PROF(9);
+
+    // ---- P6: K^-1 by warps 0-3 (Gauss-Jordan) ---------------------------------------------------------------------------------
+    double* const KB = (W == Mm) ? Wb : Mm;          // the buffer that does not hold W
+    double* const KI = ((nNp / 2) & 1) ? KB : SUU;
+    if (tid < kGJThreads) group_invert<nNp, nNp>(SUU, KB, tid, p.status);
+    __syncthreads();
+    HFX_PROF(10);
+
+    // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu (column l) ------------------------------------------------------------------------
     {
       double* gU = p.U + (size_t)e * nN * l;
       double* gU0 = p.U0 + (size_t)e * nN;
-      tile_gemm<1, nN, l1, nN, 2, 2>(tid, NT,
-          [&](int, int m, int k) { return SUU[m + nN * k]; },
-          [&](int, int k, int n) { return R[k + nN * n]; },
-          [&](int, int m, int n, double v) {
-            Um[m + nN * n] = -v;
-            if (n < l) gU[m + nN * n] = -v; else gU0[m] = -v;
-          });
+      constexpr int MT = nNp / 2, NTT = ev(l + 1) / 2;
+      for (int tile = tid; tile < MT * NTT; tile += NT) {
+        const int m0 = (tile % MT) * 2, n0 = (tile / MT) * 2;
+        double acc[2][2];
+        zero_acc(acc);
+        mk<2, 2, nN>(acc, KI + m0, nNp, R + n0, ldc);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int m = m0 + i;
+          if (m < nN) {
+#pragma unroll
+            for (int j = 0; j < 2; j++) {
+              const int n = n0 + j;
+              const double v = -acc[i][j];
+              Um[m * ldc + n] = v;
+              if (n < l) gU[m + nN * n] = v; else if (n == l) gU0[m] = v;
+            }
+          }
+        }
+      }
     }
     __syncthreads();
+    HFX_PROF(11);
 
     // ---- P8: Q_d = -A_d U - B_d ; Q0_d = -A_d U0  (:344-345) -----------------------------------------------------------
     {
       double* gQ = p.Q + (size_t)e * (DIM * nN) * l;
       double* gQ0 = p.Q0 + (size_t)e * (DIM * nN);
-      tile_gemm<DIM, nN, l1, nN, 2, 4>(tid, NT,
-          [&](int d, int m, int k) { return A[(d * nN + k) * nN + m]; },
-          [&](int, int k, int n) { return Um[k + nN * n]; },
-          [&](int d, int m, int n, double v) {
-            double* bq = B + (size_t)d * nN * l1 + m + nN * n;
-            const double qv = -v - *bq;
-            *bq = qv;
-            if (n < l) gQ[(m * DIM + d) + (size_t)(DIM * nN) * n] = qv; else gQ0[m * DIM + d] = qv;
-          });
+      constexpr int MT = (nN + 3) / 4, NTT = (l + 1 + 3) / 4;   // 4 x 4 tiles
+      for (int tile = tid; tile < DIM * MT * NTT; tile += NT) {
+        const int d = tile / (MT * NTT), tl = tile % (MT * NTT);
+        const int m0 = (tl % MT) * 4, n0 = (tl / MT) * 4;
+        double acc[4][4];
+        zero_acc(acc);
+        mk<4, 4, nN>(acc, A + d * nN * nNp + m0, nNp, Um + n0, ldc);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const int m = m0 + i;
+          if (m < nN) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const int n = n0 + j;
+              if (n <= l) {
+                double* bq = B + (d * nN + m) * ldc + n;
+                const double qv = -acc[i][j] - *bq;
+                *bq = qv;
+                if (n < l) gQ[(m * DIM + d) + (DIM * nN) * n] = qv; else gQ0[m * DIM + d] = qv;
+              }
+            }
+          }
+        }
+      }
     }
     __syncthreads();
+    HFX_PROF(12);
 
     // ---- P9: S = Slu U + Slq Q + Sll ; S0 = Fl - Slu U0 - Slq Q0 (:347-348); Dirichlet rows (:489-501); scatter (:596-618) --
     {
       double* gS = p.S ? p.S + (size_t)e * l * l : nullptr;
       double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
-      tile_gemm<nFc, t, l1, (1 + DIM) * t, 2, 2>(tid, NT,
-          [&](int f, int m, int k) {
-            const int kind = k / t, b = k % t;
-            const double* fw = FW + (size_t)f * NW * t * t + m + t * b;
-            return kind == 0 ? fw[kTau * t * t] : -fw[(kDN + kind - 1) * t * t];
-          },
-          [&](int f, int k, int n) {
-            const int kind = k / t, b = k % t, nd = FN[f * t + b];
-            return kind == 0 ? Um[nd + nN * n] : B[(size_t)(kind - 1) * nN * l1 + nd + nN * n];
-          },
-          [&](int f, int a, int n, double v) {
-            const int F = ISM[f], bc = BCF[f];
-            const bool inter = INTF[f];
-            const int rowDof = F * t + PERM[f * t + a];
+      constexpr int MT = tp / 2, NTT = (l + 1 + 3) / 4;   // per face: (t x (l+1)) in 2 x 4 tiles
+      for (int tile = tid; tile < nFc * MT * NTT; tile += NT) {
+        const int f = tile / (MT * NTT), tl = tile % (MT * NTT);
+        const int a0 = (tl % MT) * 2, n0 = (tl / MT) * 4;
+        const int* fn = FN + f * t;
+        const double* fwf = FW + f * NW * FWS;
+        double acc[2][4];
+        zero_acc(acc);
+        // Slu = +tau mass on the face nodes of U (HDGBase.cpp:126)
+#pragma unroll
+        for (int b = 0; b < t; b++) mk_step<2, 4>(acc, fwf + kTau * FWS + a0 + tp * b, Um + fn[b] * ldc + n0);
+        if (hasDiff) {   // Slq = -(D n) mass on the face nodes of Q_d (HDGDiffusion.cpp:120)
+          double acc2[2][4];
+          zero_acc(acc2);
+#pragma unroll
+          for (int d = 0; d < DIM; d++)
+#pragma unroll
+            for (int b = 0; b < t; b++) mk_step<2, 4>(acc2, fwf + (kDN + d) * FWS + a0 + tp * b, B + (d * nN + fn[b]) * ldc + n0);
+#pragma unroll
+          for (int i = 0; i < 2; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[i][j] -= acc2[i][j];
+        }
+        const int F = ISM[f], bc = BCF[f];
+        const bool inter = INTF[f];
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int a = a0 + i;
+          if (a >= t) continue;
+          const int rowDof = F * t + PERM[f * t + a];
+          double* rowp = p.vals + ROWS[f] + (long long)PERM[f * t + a] * RLEN[f];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int n = n0 + j;
+            if (n > l) continue;
+            const double v = acc[i][j];
             if (n == l) {   // S0
               double s0 = -v;
               if (bc == 1) s0 = p.dirichlet[(size_t)F * t + a];
               else if (bc == 2) {
                 s0 = 0.0;
-                for (int b = 0; b < t; b++) s0 = fma(FW[((size_t)f * NW + kOne) * t * t + a + t * b], p.dirichlet[(size_t)F * t + b], s0);
+                for (int b = 0; b < t; b++) s0 = fma(fwf[kOne * FWS + a + tp * b], p.dirichlet[(size_t)F * t + b], s0);
               }
               if (gS0) gS0[f * t + a] = s0;
               if (inter) atomicAdd(p.rhs + rowDof, s0); else p.rhs[rowDof] = s0;
-              return;
+              continue;
             }
             const int f2 = n / t, b2 = n % t;
             double sv = v;
-            if (f2 == f) { const double* fw = FW + (size_t)f * NW * t * t + a + t * b2; sv += fw[kC * t * t] - fw[kTau * t * t]; }
+            if (f2 == f) sv += fwf[kC * FWS + a + tp * b2] - fwf[kTau * FWS + a + tp * b2];
             if (bc == 1) sv = (f2 == f && b2 == a) ? 1.0 : 0.0;
-            else if (bc == 2) sv = (f2 == f) ? FW[((size_t)f * NW + kOne) * t * t + a + t * b2] : 0.0;
+            else if (bc == 2) sv = (f2 == f) ? fwf[kOne * FWS + a + tp * b2] : 0.0;
             if (gS) gS[(f * t + a) + (size_t)l * n] = sv;
-            double* dst = p.vals + ROWS[f] + (long long)PERM[f * t + a] * RLEN[f] + POS[f * nFc + f2] * t + PERM[f2 * t + b2];
+            double* dst = rowp + POS[f * nFc + f2] * t + PERM[f2 * t + b2];
             if (f2 == f && inter) atomicAdd(dst, sv); else *dst = sv;
-          });
+          }
+        }
+      }
     }
     __syncthreads();
+    HFX_PROF(13);
   }
 }
 
-// host-side launch helper: returns false if (dim, order) has no shared-memory-resident instantiation
+// host-side launch helper
 template <int DIM, int P>
 inline cudaError_t launch_assemble_t(const AsmParams& p, int nSM, cudaStream_t st) {
   using L = AsmSmem<DIM, P>;
@@ -646,6 +1025,7 @@ inline cudaError_t launch_assemble_t(const AsmParams& p, int nSM, cudaStream_t s
   int perSM = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_assemble_kernel<DIM, P>, kAsmThreads, L::bytes);
   if (perSM < 1) perSM = 1;
+  if (const char* ev_ = getenv("HFX_CTAS_PER_SM")) { int v = atoi(ev_); if (v >= 1 && v < perSM) perSM = v; }   // experiments only
   long long grid = (long long)nSM * perSM;
   if (grid > p.nCells) grid = p.nCells;
   if (grid < 1) grid = 1;

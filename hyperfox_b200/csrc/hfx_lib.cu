@@ -117,6 +117,14 @@ __global__ void elem_maps_kernel(int nCells, int nN, int nFc, int t, const int* 
   }
 }
 
+// element-major copy of the node coordinates: the fused kernel streams them with coalesced loads instead of a two-level gather
+__global__ void elem_coords_kernel(long long n, int nN, int dim, const double* __restrict__ nodes, const int* __restrict__ cells, double* __restrict__ elemX) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const long long ei = idx / dim; const int m = (int)(idx % dim);
+  elemX[idx] = nodes[(size_t)cells[ei] * dim + m];
+}
+
 __global__ void ip_coords_kernel(int nCells, int nN, int nIP, int dim, const double* __restrict__ nodes, const int* __restrict__ cells,
                                  const double* __restrict__ shape, double* __restrict__ xip) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -442,7 +450,7 @@ struct hfx_ctx {
   // mesh
   int nNodes = 0, nCells = 0, nFaces = 0;
   std::vector<int> hFaces, hC2F, hF2C, hBoundary;
-  DBuf<double> dNodes; DBuf<int> dCells, dFaces, dC2F, dF2C;
+  DBuf<double> dNodes, dElemX; DBuf<int> dCells, dFaces, dC2F, dF2C;
   bool meshSet = false, topoSet = false;
   // fields
   std::map<std::string, DField> fields;
@@ -458,6 +466,7 @@ struct hfx_ctx {
   long long nnz = 0;
   DBuf<double> dU, dQ, dU0, dQ0, dS, dS0, dVals, dRhs;
   DBuf<int> dStatus;
+  DBuf<long long> dProf; bool profOn = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   float msTotal = 0, msKernel = 0;
   Krylov krylov;
@@ -629,13 +638,14 @@ int hfx_refel_set(hfx_ctx* c, int dim, int order, int geom) {
     const RefElement& re = *c->re;
     const RefElement* fe = re.faceElement();
     c->dim = dim; c->order = order; c->nN = re.numNodes(); c->nNf = fe->numNodes(); c->nFc = re.numFaces(); c->nIP = re.numIPs(); c->nIPf = fe->numIPs();
-    c->dShape.upload(re.ipShape(), c->st); c->dDShape.upload(re.ipDShape(), c->st); c->dW.upload(re.ipWeights(), c->st);
-    c->dFShape.upload(fe->ipShape(), c->st); c->dFDShape.upload(fe->ipDShape(), c->st); c->dFW.upload(fe->ipWeights(), c->st);
+    auto padded = [](std::vector<double> v) { v.resize(v.size() + 2, 0.0); return v; };   // the kernel stages tables in 16-byte chunks
+    c->dShape.upload(padded(re.ipShape()), c->st); c->dDShape.upload(padded(re.ipDShape()), c->st); c->dW.upload(padded(re.ipWeights()), c->st);
+    c->dFShape.upload(padded(fe->ipShape()), c->st); c->dFDShape.upload(padded(fe->ipDShape()), c->st); c->dFW.upload(padded(fe->ipWeights()), c->st);
     c->dFaceNodes.upload(re.faceNodes(), c->st);
     const int t = c->nNf;
     std::vector<double> ffs((size_t)c->nIPf * t * t);
     for (int ip = 0; ip < c->nIPf; ip++) for (int b = 0; b < t; b++) for (int a = 0; a < t; a++) ffs[((size_t)ip * t + b) * t + a] = fe->ipShape()[(size_t)ip * t + a] * fe->ipShape()[(size_t)ip * t + b];
-    c->dFFS.upload(ffs, c->st);
+    c->dFFS.upload(padded(ffs), c->st);
     std::vector<int8_t> nif((size_t)c->nFc * c->nN, -1);
     for (int f = 0; f < c->nFc; f++) for (int a = 0; a < t; a++) nif[(size_t)f * c->nN + re.faceNodes()[(size_t)f * t + a]] = (int8_t)a;
     c->dNodeInFace.upload(nif, c->st);
@@ -819,6 +829,9 @@ int hfx_allocate(hfx_ctx* c, int flags) {
     int status = 0;
     c->dStatus.download(&status, 1, c->st);
     need(!(status & 2), "HDGSolver", "calcElementalMatrices", "couldn't find cell node in face.");
+    c->dElemX.alloc((size_t)nC * c->nN * c->dim);
+    elem_coords_kernel<<<nblk((long long)nC * c->nN * c->dim, 256), 256, 0, c->st>>>((long long)nC * c->nN * c->dim, c->nN, c->dim, c->dNodes.p, c->dCells.p, c->dElemX.p);
+    HFX_CUDA(cudaGetLastError());
     // element blocks (HDGSolver.cpp:93-104) and the global system (linSystem->allocate :81)
     c->dU.alloc((size_t)nC * u * l); c->dQ.alloc((size_t)nC * q * l); c->dU0.alloc((size_t)nC * u); c->dQ0.alloc((size_t)nC * q);
     if (c->keepS) { c->dS.alloc((size_t)nC * l * l); c->dS0.alloc((size_t)nC * l); } else { c->dS.release(); c->dS0.release(); }
@@ -833,7 +846,7 @@ int hfx_assemble(hfx_ctx* c) {
     need(c->allocated, "HDGSolver", "assemble", "the solver must be initialized and allocated before assembling.");
     AsmParams p{};
     p.nCells = c->nCells;
-    p.nodes = c->dNodes.p; p.cells = c->dCells.p; p.cell2face = c->dC2F.p;
+    p.elemX = c->dElemX.p; p.cells = c->dCells.p; p.cell2face = c->dC2F.p;
     p.fperm = c->dFperm.p; p.tauSide = c->dTauSide.p; p.elemPos = c->dElemPos.p;
     p.faceRowStart = c->dFaceRowStart.p; p.faceNnb = c->dNnb.p; p.faceBC = c->dFaceBC.p; p.faceInterior = c->dInterior.p;
     DField* tau = find_field(c, "Tau");
@@ -860,6 +873,7 @@ int hfx_assemble(hfx_ctx* c) {
     p.faceNodes = c->dFaceNodes.p; p.nodeInFace = c->dNodeInFace.p;
     p.U = c->dU.p; p.Q = c->dQ.p; p.U0 = c->dU0.p; p.Q0 = c->dQ0.p; p.S = c->dS.p; p.S0 = c->dS0.p;
     p.vals = c->dVals.p; p.rhs = c->dRhs.p; p.status = c->dStatus.p;
+    p.prof = c->profOn ? c->dProf.p : nullptr;
     HFX_CUDA(cudaEventRecord(c->ev0, c->st));
     // linSystem->clearSystem() (HDGSolver.cpp:532-536): entries with two contributors are accumulated on zeroed storage
     c->dVals.zero(c->st); c->dRhs.zero(c->st); c->dStatus.zero(c->st);
@@ -875,6 +889,15 @@ int hfx_assemble(hfx_ctx* c) {
     need(!(status & 1), "HDGSolver", "calcElementalMatrices", "singular local matrix met during static condensation");
     c->assembled = true;
   });
+}
+
+int hfx_assemble_profile(hfx_ctx* c, long long* cycles16) {   // dev aid: per-phase clock64 deltas of CTA 0 (see hfx_assemble.cuh HFX_PROF)
+  int rc = guard(c, [&] { HFX_CUDA(cudaSetDevice(c->device)); c->dProf.alloc(16); c->dProf.zero(c->st); c->profOn = true; });
+  if (rc) return rc;
+  rc = hfx_assemble(c);
+  c->profOn = false;
+  if (rc) return rc;
+  return guard(c, [&] { c->dProf.download(cycles16, 16, c->st); });
 }
 
 int hfx_last_assemble_ms(const hfx_ctx* c, float* msTotal, float* msKernel) {

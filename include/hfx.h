@@ -92,6 +92,8 @@ int hfx_recover(hfx_ctx* ctx);                                                  
 int hfx_sync(hfx_ctx* ctx);
 /* timing of the last hfx_assemble (CUDA events on the library's stream), milliseconds */
 int hfx_last_assemble_ms(const hfx_ctx* ctx, float* msTotal, float* msKernel);
+/* development aid: one assemble with per-phase clock64 counters of CTA 0 (cycles16[16]) */
+int hfx_assemble_profile(hfx_ctx* ctx, long long* cycles16);
 
 /* ---- parity hooks ----------------------------------------------------------------------------------------------- */
 /* CSR of the global trace system: sorted columns, explicit zeros (PetscInterface.cpp:99-103).  nnz query with NULLs. */

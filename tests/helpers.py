@@ -13,13 +13,20 @@ def sin_exp(x):
     return np.sin(x[0]) * np.exp(x[1])
 
 
-def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="dirichlet", tau_double=False, diff="none", seed=0):
-    """Returns dict with numpy inputs in the reference's Field layouts."""
+def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="dirichlet", tau_double=False, diff="none", seed=0, curved=0.0):
+    """Returns dict with numpy inputs in the reference's Field layouts.  curved > 0 displaces every non-vertex node by
+    curved*h*U(-1,1)^dim: genuinely curved (non-affine) elements, Jacobians and normals vary from cubature point to point."""
     rng = np.random.default_rng(seed)
     if mesh == "kuhn":
         nodes, cells = meshgen.kuhn_mesh(N, order, dim, perturb=perturb)
     else:
         nodes, cells = load_mesh(mesh)
+    if curved > 0.0 and order > 1:
+        isv = np.zeros(nodes.shape[0], dtype=bool)
+        isv[np.unique(cells[:, :dim + 1])] = True
+        h = np.linalg.norm(nodes[cells[:, 1]] - nodes[cells[:, 0]], axis=1).min()
+        nodes = nodes.copy()
+        nodes[~isv] += curved * h * np.random.default_rng(seed + 77).uniform(-1, 1, size=(int((~isv).sum()), dim))
     ore = OracleRefEl(dim, order)
     topo = compute_faces(cells, ore)
     nF, nNf, nN = topo["faces"].shape[0], ore.faceElement.nNodes, ore.nNodes

@@ -10,7 +10,9 @@ from tests import helpers as H
 
 pytestmark = pytest.mark.gpu
 
-TOL_ENTRIES = 1e-12
+TOL_ENTRIES = 1e-12      # assembled entries: per-element S, S0 and the global CSR values / RHS
+TOL_RECOVERY = 2e-11     # local recovery operators U, Q, U0, Q0 = K^-1(...): conditioning-limited (the oracle's own QR and LU variants
+                         # differ by up to ~5e-12 at order 5); they only feed Solution/Flux, whose bar is 1e-10
 TOL_SOLUTION = 1e-10
 
 
@@ -29,7 +31,7 @@ def compare(case, solve=True):
     loc = s.getLocal()
     for name, ref in (("U", o.U), ("Q", o.Q), ("S", o.S), ("U0", o.U0), ("Q0", o.Q0), ("S0", o.S0)):
         e = H.rel_err(loc[name], ref)
-        assert e < TOL_ENTRIES, (name, e)
+        assert e < (TOL_ENTRIES if name in ("S", "S0") else TOL_RECOVERY), (name, e)
     assert H.rel_err(vals, o.vals) < TOL_ENTRIES
     assert H.rel_err(rhs, o.rhs) < TOL_ENTRIES
     if solve:
@@ -43,6 +45,13 @@ def compare(case, solve=True):
 @pytest.mark.parametrize("dim,order", [(2, 1), (2, 2), (2, 3), (2, 4), (2, 5), (3, 1), (3, 2), (3, 3)])
 def test_laplace_kuhn_perturbed(dim, order):
     compare(H.make_case(dim, order, N=3 if dim == 3 else 4, perturb=0.15))
+
+
+@pytest.mark.parametrize("dim,order,model", [(2, 2, "laplace"), (2, 4, "cdrs"), (3, 2, "diffsrc"), (3, 3, "laplace"), (3, 3, "cdrs")])
+def test_curved_elements(dim, order, model):
+    """Non-affine geometry: every non-vertex node displaced, so det J, J^-1 and the normals vary over the element."""
+    compare(H.make_case(dim, order, N=3, model=model, diff="scalar" if model != "laplace" else "none", tau_double=model != "laplace",
+                        curved=0.04, seed=11))
 
 
 @pytest.mark.parametrize("name,dim,order", [("regression_dim-2_h-1e-1_ord-2", 2, 2), ("regression_dim-3_h-2e-1_ord-3", 3, 3),

@@ -190,6 +190,54 @@ __device__ __forceinline__ int grab32(int* ctr, int lane) {
   return __shfl_sync(0xffffffffu, v, 0) + lane;
 }
 
+// ---- FP64 tensor-core building blocks (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4) --------------------------------------------
+// Measured on B200 (tools/ubench/dmma.cu): 16 cycles per DMMA per SM sub-partition (same 37 TFLOP/s peak as the DFMA pipe, which it
+// shares), latency 26 cycles.  What it buys here is operand traffic: one 64-bit shared load per lane feeds 8 FMAs per lane, where a
+// 2x2 CUDA-core register tile needs 8 bytes of shared-memory traffic per FMA and saturates the 128 B/clk shared pipe at 25% of peak.
+// Fragment layout: lane = 4*lr + lc;  A[m0+lr][k0+lc], B[k0+lc][n0+lr], C[m0+lr][n0+2*lc+{0,1}].
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+// One warp task: rows [8*mt, 8*mt+8) x NTW column tiles starting at column tile nt0, K = 4*KS.
+// fa(m, k), fb(k, n) return operand entries (they own all range handling: k beyond the true K must give an exact zero product);
+// fs(m, n, v0, v1) receives C[m][n], C[m][n+1] (n even).
+template <int NTW, int KS, class FA, class FB, class FS>
+__device__ __forceinline__ void mma_task(int mt, int nt0, int lane, FA fa, FB fb, FS fs) {
+  const int lr = lane >> 2, lc = lane & 3;
+  const int m = mt * 8 + lr;
+  double c[NTW][2];
+#pragma unroll
+  for (int j = 0; j < NTW; j++) { c[j][0] = 0.0; c[j][1] = 0.0; }
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) {
+    const int k = ks * 4 + lc;
+    const double a = fa(m, k);
+#pragma unroll
+    for (int j = 0; j < NTW; j++) dmma(c[j], a, fb(k, (nt0 + j) * 8 + lr));
+  }
+#pragma unroll
+  for (int j = 0; j < NTW; j++) fs(m, (nt0 + j) * 8 + 2 * lc, c[j][0], c[j][1]);
+}
+// single output tile with the K loop split over two accumulators (dependent DMMA chains would otherwise be latency bound)
+template <int KS, class FA, class FB, class FS>
+__device__ __forceinline__ void mma_task_splitk(int mt, int nt, int lane, FA fa, FB fb, FS fs) {
+  const int lr = lane >> 2, lc = lane & 3;
+  const int m = mt * 8 + lr, n = nt * 8 + lr;
+  double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+#pragma unroll
+  for (int ks = 0; ks < KS; ks += 2) {
+    const int k = ks * 4 + lc;
+    dmma(c0, fa(m, k), fb(k, n));
+    if (ks + 1 < KS) dmma(c1, fa(m, k + 4), fb(k + 4, n));
+  }
+  fs(m, nt * 8 + 2 * lc, c0[0] + c1[0], c0[1] + c1[1]);
+}
+__device__ __forceinline__ int grab1(int* ctr, int lane) {   // warp-granular dynamic task queue
+  int v = 0;
+  if (lane == 0) v = atomicAdd(ctr, 1);
+  return __shfl_sync(0xffffffffu, v, 0);
+}
+
 // ---- Gauss-Jordan inverse by a group of kGJThreads threads (warps 0..3, named barrier 1) ---------------------------------
 // 2x2 block pivots: half the serial depth of the scalar algorithm (the pivot chain, not the flops, is what costs: ~300-450
 // cycles per barrier step on B200, see tools/ubench/gj2.cu).  Ping-pong between two column-major buffers with even leading
@@ -449,6 +497,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
     }
     __syncthreads();
+    HFX_PROF(5);
     // the next element's gather flies while this element is computed
     prefetch(e + gridDim.x);
 
@@ -608,116 +657,88 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     __syncthreads();
     HFX_PROF(2);
 
-    // ---- P3a: M = sum_ip dV phi phi^T (2x2 tiles; the left operand dV*phi is formed on the fly) --------------------------
-    {
-      constexpr int MT = nNp / 2, NTT = nNp / 2;
-      for (int tile = tid; tile < MT * NTT; tile += NT) {
-        const int m0 = (tile % MT) * 2, n0 = (tile / MT) * 2;
-        double acc[2][2];
-        zero_acc(acc);
-#pragma unroll 4
-        for (int k = 0; k < nIP; k++) {
-          const double2 a = *reinterpret_cast<const double2*>(PHI + k * nNp + m0);
-          const double2 b = *reinterpret_cast<const double2*>(PHI + k * nNp + n0);
-          const double dv = DV[k];
-          const double ax = a.x * dv, ay = a.y * dv;
-          acc[0][0] = fma(ax, b.x, acc[0][0]); acc[0][1] = fma(ax, b.y, acc[0][1]);
-          acc[1][0] = fma(ay, b.x, acc[1][0]); acc[1][1] = fma(ay, b.y, acc[1][1]);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; i++)
-#pragma unroll
-          for (int j = 0; j < 2; j++) if (m0 + i < nN && n0 + j < nN) Mm[(m0 + i) + nNp * (n0 + j)] = acc[i][j];
-      }
-      if ((nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal for the 2x2-block Gauss-Jordan (pad row/column are zero)
-        for (int j = 0; j < nN; j++) { Mm[nN + nNp * j] = 0.0; Mm[j + nNp * nN] = 0.0; }
-        Mm[nN + nNp * nN] = 1.0;
-      }
+    // =====================================================================================================================
+    // From here on every product runs on the FP64 tensor cores: a phase is a list of warp tasks (8 output rows x up to 3 column
+    // tiles of 8), operands are fetched from shared memory one 64-bit word per lane.
+    constexpr int MTN = (nN + 7) / 8;           // 8-row tiles over the element nodes
+    constexpr int NWARP = NT / 32;
+    constexpr int KS_IP = (nIP + 3) / 4, KS_IPF = (nIPf + 3) / 4, KS_N = (nN + 3) / 4, KS_T = (t + 3) / 4, KS_QN = (DIM * nN + 3) / 4;
+
+    // ---- P3a: M = sum_ip dV phi phi^T (Mass.cpp:5-38 / HDGBase.cpp:152) ------------------------------------------------------
+    for (int task = warp; task < MTN * ((MTN + 2) / 3); task += NWARP) {
+      const int mt = task % MTN, ng = task / MTN;
+      mma_task<3, KS_IP>(mt, ng * 3, lane,
+          [&](int m, int k) { return (k < nIP && m < nN) ? DV[k] * PHI[k * nNp + m] : 0.0; },
+          [&](int k, int n) { return (k < nIP && n < nN) ? PHI[k * nNp + n] : 0.0; },
+          [&](int m, int n, double v0, double v1) {
+            if (m < nN) { if (n < nN) Mm[m + nNp * n] = v0; if (n + 1 < nN) Mm[m + nNp * (n + 1)] = v1; }
+          });
+    }
+    if ((nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal for the 2x2-block Gauss-Jordan (pad row/column are zero)
+      for (int j = 0; j < nN; j++) { Mm[nN + nNp * j] = 0.0; Mm[j + nNp * nN] = 0.0; }
+      Mm[nN + nNp * nN] = 1.0;
     }
     __syncthreads();
     HFX_PROF(3);
 
-    // ---- P3b: W = M^-1 by warps 0-3 (Gauss-Jordan, named barrier) while a dynamic tile queue feeds the remaining contractions
-    //            (Squ, Suu, face matrices, Fu) to every warp that is free ----------------------------------------------------
+    // ---- P3b: W = M^-1 by warps 0-3 (block Gauss-Jordan, named barrier) while a dynamic task queue feeds the remaining
+    //            contractions (Squ, Suu, face matrices, Fu) to every warp that is free -------------------------------------------
     double* const W = ((nNp / 2) & 1) ? Wb : Mm;
     if (tid < kGJThreads) group_invert<nNp, nNp>(Mm, Wb, tid, p.status);
-    if (p.opmask & (1 << 30)) __syncthreads();   // experiment: exclusive inversion
     HFX_PROF(14);
     {
-      constexpr int MROWS = DIM * nN, SQ_MT = ev(MROWS) / 2, SQ_NT = (nN + 3) / 4, T_SQU = SQ_MT * SQ_NT;       // 2x4 tiles
-      constexpr int UU_MT = nNp / 2, T_SUU = UU_MT * UU_MT;                                                       // 2x2 tiles
-      constexpr int MR = t * t, FW_MT = (MR + 3) / 4, NC = nFc * NW, FW_NT = (NC + 3) / 4, T_FW = FW_MT * FW_NT;  // 4x4 tiles
-      static_assert(4 * FW_NT <= ldw + 2, "face weight rows too short");
-      constexpr int T_ALL = T_SQU + T_SUU + T_FW + nN;
+      constexpr int MROWS = DIM * nN, SQ_MT = (MROWS + 7) / 8, NG_N = (MTN + 2) / 3;   // column groups of 3 tiles over nN
+      constexpr int T_SQU = SQ_MT * NG_N, T_SUU = MTN * NG_N;
+      constexpr int MR = t * t, FW_MT = (MR + 7) / 8, NC = nFc * NW, FW_NG = ((NC + 7) / 8 + 2) / 3, T_FW = FW_MT * FW_NG;
+      constexpr int T_ALL = T_SQU + T_SUU + T_FW + 1;
       for (;;) {
-        int tile = grab32(&QCTR[0], lane);
-        if (tile - lane >= T_ALL) break;
-        if (tile < T_SQU) {
+        int task = grab1(&QCTR[0], lane);
+        if (task >= T_ALL) break;
+        if (task < T_SQU) {
           // Squ_d[k][j] = sum_ip g[ip][(d,k)] phi[ip][j]  (HDGBase.cpp:150); with D = I the same numbers are Suq_d[k][j] (HDGDiffusion.cpp:130-144)
-          const int m0 = (tile % SQ_MT) * 2, n0 = (tile / SQ_MT) * 4;
-          double acc[2][4];
-          zero_acc(acc);
-          mk<2, 4, nIP>(acc, G + m0, ldg, PHI + n0, nNp);
-#pragma unroll
-          for (int i = 0; i < 2; i++) {
-            const int m = m0 + i;
-            if (m < MROWS) {
-              const int d = m / nN, kk = m % nN;
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                const int n = n0 + j;
-                if (n < nN) {
-                  SQU[(d * nN + kk) * nNp + n] = acc[i][j];                                      // row-major (right operand of A = W Squ)
-                  if (!diffField) SUQ[(d * nN + n) * nNp + kk] = hasDiff ? acc[i][j] : 0.0;      // col-major (left operand of K, R)
+          mma_task<3, KS_IP>(task % SQ_MT, (task / SQ_MT) * 3, lane,
+              [&](int m, int k) { return (k < nIP && m < MROWS) ? G[k * ldg + m] : 0.0; },
+              [&](int k, int n) { return (k < nIP && n < nN) ? PHI[k * nNp + n] : 0.0; },
+              [&](int m, int n, double v0, double v1) {
+                if (m < MROWS && n < nN) {
+                  const int d = m / nN, kk = m % nN;
+                  SQU[(d * nN + kk) * nNp + n] = v0;
+                  if (n + 1 < nN) SQU[(d * nN + kk) * nNp + n + 1] = v1;
+                  if (!diffField) {
+                    SUQ[(d * nN + n) * nNp + kk] = hasDiff ? v0 : 0.0;
+                    if (n + 1 < nN) SUQ[(d * nN + n + 1) * nNp + kk] = hasDiff ? v1 : 0.0;
+                  }
                 }
-              }
-            }
-          }
-        } else if (tile < T_SQU + T_SUU) {
+              });
+        } else if (task < T_SQU + T_SUU) {
           // Suu (bulk part): -C^T (Convection.cpp:5-49) + reaction mass + Euler mass
-          tile -= T_SQU;
-          const int m0 = (tile % UU_MT) * 2, n0 = (tile / UU_MT) * 2;
-          double acc[2][2];
-          zero_acc(acc);
-          mk<2, 2, nIP>(acc, CG + m0, nNp, PHI + n0, nNp);
-#pragma unroll
-          for (int i = 0; i < 2; i++)
-#pragma unroll
-            for (int j = 0; j < 2; j++) if (m0 + i < nN && n0 + j < nN) SUU[(m0 + i) + nNp * (n0 + j)] = acc[i][j];
-        } else if (tile < T_SQU + T_SUU + T_FW) {
-          // weighted face mass matrices FW[f][kind][a + tp b] = sum_ip wt[ip][(f,kind)] phi_a phi_b
-          tile -= T_SQU + T_SUU;
-          const int m0 = (tile % FW_MT) * 4, n0 = (tile / FW_MT) * 4;
-          double acc[4][4];
-          zero_acc(acc);
-#pragma unroll 2
-          for (int k = 0; k < nIPf; k++) {
-            double av[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) av[i] = (m0 + i < MR) ? FFS[k * MR + m0 + i] : 0.0;
-            const double2 b0 = *reinterpret_cast<const double2*>(FWT + k * ldw + n0);
-            const double2 b1 = *reinterpret_cast<const double2*>(FWT + k * ldw + n0 + 2);
-            const double bv[4] = {b0.x, b0.y, b1.x, b1.y};
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-#pragma unroll
-              for (int j = 0; j < 4; j++) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-          }
-#pragma unroll
-          for (int i = 0; i < 4; i++) {
-            const int m = m0 + i;
-            if (m < MR) {
-              const int a = m % t, b = m / t;
-#pragma unroll
-              for (int j = 0; j < 4; j++) if (n0 + j < NC) FW[(n0 + j) * FWS + a + tp * b] = acc[i][j];
-            }
-          }
-        } else if (tile < T_ALL) {
+          task -= T_SQU;
+          mma_task<3, KS_IP>(task % MTN, (task / MTN) * 3, lane,
+              [&](int m, int k) { return (k < nIP && m < nN) ? CG[k * nNp + m] : 0.0; },
+              [&](int k, int n) { return (k < nIP && n < nN) ? PHI[k * nNp + n] : 0.0; },
+              [&](int m, int n, double v0, double v1) {
+                if (m < nN) { if (n < nN) SUU[m + nNp * n] = v0; if (n + 1 < nN) SUU[m + nNp * (n + 1)] = v1; }
+              });
+        } else if (task < T_SQU + T_SUU + T_FW) {
+          // weighted face mass matrices FW[(f,kind)][a + tp b] = sum_ip wt[ip][(f,kind)] phi_a phi_b
+          task -= T_SQU + T_SUU;
+          mma_task<3, KS_IPF>(task % FW_MT, (task / FW_MT) * 3, lane,
+              [&](int m, int k) { return (k < nIPf && m < MR) ? FFS[k * MR + m] : 0.0; },
+              [&](int k, int n) { return (k < nIPf && n < NC) ? FWT[k * ldw + n] : 0.0; },
+              [&](int m, int n, double v0, double v1) {
+                if (m < MR) {
+                  const int a = m % t, b = m / t;
+                  if (n < NC) FW[n * FWS + a + tp * b] = v0;
+                  if (n + 1 < NC) FW[(n + 1) * FWS + a + tp * b] = v1;
+                }
+              });
+        } else {
           // Fu = source (Source.cpp:24-48) + Euler mass * Solution_old (Euler.cpp:29-30), both as sum_ip phi_i(ip) * weight(ip)
-          const int i = tile - (T_SQU + T_SUU + T_FW);
-          double s2 = 0.0;
-          if (hasSrc || euler) for (int ip = 0; ip < nIP; ip++) s2 = fma(PHI[ip * nNp + i], LW[nIP + ip], s2);
-          FU[i] = s2;
+          for (int i = lane; i < nN; i += 32) {
+            double s2 = 0.0;
+            if (hasSrc || euler) for (int ip = 0; ip < nIP; ip++) s2 = fma(PHI[ip * nNp + i], LW[nIP + ip], s2);
+            FU[i] = s2;
+          }
         }
       }
     }
@@ -733,33 +754,30 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         for (int m = 0; m < DIM; m++) gg[m] = G[ip * ldg + m * nN + i];
 #pragma unroll
         for (int a = 0; a < DIM; a++) {
-          double s = 0.0;
+          double s2 = 0.0;
 #pragma unroll
-          for (int b = 0; b < DIM; b++) s = fma(DIP[ip * D2 + b * DIM + a], gg[b], s);
-          o[a] = s;
+          for (int b = 0; b < DIM; b++) s2 = fma(DIP[ip * D2 + b * DIM + a], gg[b], s2);
+          o[a] = s2;
         }
 #pragma unroll
         for (int m = 0; m < DIM; m++) G[ip * ldg + m * nN + i] = o[m];
       }
       __syncthreads();
-      constexpr int MROWS = DIM * nN, MT = ev(MROWS) / 2, NTT = nNp / 2;
-      for (int tile = tid; tile < MT * NTT; tile += NT) {
-        const int m0 = (tile % MT) * 2, n0 = (tile / MT) * 2;
-        double acc[2][2];
-        zero_acc(acc);
-        mk<2, 2, nIP>(acc, G + m0, ldg, PHI + n0, nNp);
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          const int m = m0 + i;
-          if (m < MROWS) {
-            const int d = m / nN, kk = m % nN;
-#pragma unroll
-            for (int j = 0; j < 2; j++) if (n0 + j < nN) SUQ[(d * nN + n0 + j) * nNp + kk] = acc[i][j];
-          }
-        }
+      constexpr int MROWS = DIM * nN, SQ_MT = (MROWS + 7) / 8, NG_N = (MTN + 2) / 3;
+      for (int task = warp; task < SQ_MT * NG_N; task += NWARP) {
+        mma_task<3, KS_IP>(task % SQ_MT, (task / SQ_MT) * 3, lane,
+            [&](int m, int k) { return (k < nIP && m < MROWS) ? G[k * ldg + m] : 0.0; },
+            [&](int k, int n) { return (k < nIP && n < nN) ? PHI[k * nNp + n] : 0.0; },
+            [&](int m, int n, double v0, double v1) {
+              if (m < MROWS && n < nN) {
+                const int d = m / nN, kk = m % nN;
+                SUQ[(d * nN + n) * nNp + kk] = v0;
+                if (n + 1 < nN) SUQ[(d * nN + n + 1) * nNp + kk] = v1;
+              }
+            });
       }
+      __syncthreads();
     }
-    __syncthreads();
     HFX_PROF(6);
     // face parts of Suu (+tau mass, HDGBase.cpp:128) and Suq (-(Dn) mass, HDGDiffusion.cpp:121), gather form
     for (int idx = tid; idx < nN * nN; idx += NT) {
@@ -770,7 +788,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       for (int f = 0; f < nFc; f++) {
         const int a = NIF[f * nN + i], b = NIF[f * nN + j];
         if (a >= 0 && b >= 0) {
-          const double* fw = FW + (size_t)f * NW * FWS + a + tp * b;
+          const double* fw = FW + f * NW * FWS + a + tp * b;
           suu += fw[kTau * FWS];
 #pragma unroll
           for (int d = 0; d < DIM; d++) suq[d] -= fw[(kDN + d) * FWS];
@@ -789,95 +807,76 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
     // ---- P4: A_d = W Squ_d (col-major out) ;  B_d = W Sql_d with Sql[(fn_f(a),d),(f,b)] = -N_fd[a][b] (HDGBase.cpp:134) ------
     {
-      constexpr int MT = nNp / 2, NTT = (nN + 3) / 4;
-      for (int tile = tid; tile < DIM * MT * NTT; tile += NT) {
-        const int d = tile / (MT * NTT), tl = tile % (MT * NTT);
-        const int m0 = (tl % MT) * 2, n0 = (tl / MT) * 4;
-        double acc[2][4];
-        zero_acc(acc);
-        mk<2, 4, nN>(acc, W + m0, nNp, SQU + d * nN * nNp + n0, nNp);
-#pragma unroll
-        for (int j = 0; j < 4; j++)
-          if (n0 + j < nN) *reinterpret_cast<double2*>(A + (d * nN + n0 + j) * nNp + m0) = make_double2(acc[0][j], acc[1][j]);
-      }
-      // B: per (f, d): (nN x t) = W[:, fn_f] (nN x t) * N_fd (t x t), one full row of N_fd per register tile when it fits
-      constexpr int TNB = (tp <= 16) ? tp : 2, NTB = tp / TNB;
-      for (int tile = tid; tile < nFc * DIM * MT * NTB; tile += NT) {
-        const int fd = tile / (MT * NTB), tl = tile % (MT * NTB);
-        const int f = fd / DIM, d = fd % DIM;
-        const int m0 = (tl % MT) * 2, n0 = (tl / MT) * TNB;
-        const double* fw = FW + (f * NW + kN + d) * FWS + n0;   // symmetric: row a is contiguous over b
-        const int* fn = FN + f * t;
-        double acc[2][TNB];
-        zero_acc(acc);
-#pragma unroll
-        for (int a = 0; a < t; a++) mk_step<2, TNB>(acc, W + m0 + nNp * fn[a], fw + tp * a);
-#pragma unroll
-        for (int i = 0; i < 2; i++)
-#pragma unroll
-          for (int j = 0; j < TNB; j++)
-            if (m0 + i < nN && n0 + j < t) B[(d * nN + m0 + i) * ldc + f * t + n0 + j] = -acc[i][j];
+      constexpr int NG_N = (MTN + 2) / 3, T_A = DIM * MTN * NG_N;
+      constexpr int NB = DIM * t, NG_B = ((NB + 7) / 8 + 2) / 3, T_B = nFc * MTN * NG_B;
+      for (int task = warp; task < T_A + T_B; task += NWARP) {
+        if (task < T_A) {
+          const int d = task / (MTN * NG_N), r = task % (MTN * NG_N);
+          mma_task<3, KS_N>(r % MTN, (r / MTN) * 3, lane,
+              [&](int m, int k) { return (k < nN && m < nN) ? W[m + nNp * k] : 0.0; },
+              [&](int k, int n) { return (k < nN && n < nN) ? SQU[(d * nN + k) * nNp + n] : 0.0; },
+              [&](int m, int n, double v0, double v1) {
+                if (m < nN) { if (n < nN) A[(d * nN + n) * nNp + m] = v0; if (n + 1 < nN) A[(d * nN + n + 1) * nNp + m] = v1; }
+              });
+        } else {
+          const int tb = task - T_A, f = tb / (MTN * NG_B), r = tb % (MTN * NG_B);
+          const int* fn = FN + f * t;
+          mma_task<3, KS_T>(r % MTN, (r / MTN) * 3, lane,
+              [&](int m, int k) { return (k < t && m < nN) ? W[m + nNp * fn[k]] : 0.0; },
+              [&](int k, int n) { return (k < t && n < NB) ? FW[(f * NW + kN + n / t) * FWS + k + tp * (n % t)] : 0.0; },   // n = (d, b)
+              [&](int m, int n, double v0, double v1) {
+                if (m < nN) {
+                  if (n < NB) B[((n / t) * nN + m) * ldc + f * t + (n % t)] = -v0;
+                  if (n + 1 < NB) B[(((n + 1) / t) * nN + m) * ldc + f * t + ((n + 1) % t)] = -v1;
+                }
+              });
+        }
       }
       for (int idx = tid; idx < DIM * nN; idx += NT) { B[idx * ldc + l] = 0.0; B[idx * ldc + l + 1] = 0.0; }  // Q0 column
     }
     __syncthreads();
     HFX_PROF(8);
 
-    // ---- P5: one queued phase: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335) and R = Sul - sum_d Suq_d B_d, column l = -Fu (:342-343)
+    // ---- P5: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335) and R = Sul - sum_d Suq_d B_d, column l = -Fu (:342-343) -------------
     {
-      constexpr int MT = nNp / 2, T_K = MT * nN, R_NT = ev(l) / 2, T_R = MT * R_NT, T_ALL = T_K + T_R + nN;
-      for (;;) {
-        int tile = grab32(&QCTR[1], lane);
-        if (tile - lane >= T_ALL) break;
-        if (tile < T_K) {   // right operand A is column-major => scalar loads, 2x1 strips
-          const int m0 = (tile % MT) * 2, n = tile / MT;
-          double a0 = 0.0, a1 = 0.0;
+      constexpr int LT = (l + 7) / 8, T_K = MTN * MTN, T_R = MTN * LT;
+      for (int task = warp; task < T_K + T_R + 1; task += NWARP) {
+        if (task < T_K) {
+          mma_task_splitk<KS_QN>(task % MTN, task / MTN, lane,
+              [&](int m, int k) { return (k < DIM * nN && m < nN) ? SUQ[k * nNp + m] : 0.0; },                        // k = (d, k')
+              [&](int k, int n) { return (k < DIM * nN && n < nN) ? A[((k / nN) * nN + n) * nNp + (k % nN)] : 0.0; },
+              [&](int m, int n, double v0, double v1) {
+                if (m < nN) { if (n < nN) SUU[m + nNp * n] -= v0; if (n + 1 < nN) SUU[m + nNp * (n + 1)] -= v1; }
+              });
+        } else if (task < T_K + T_R) {
+          const int r = task - T_K;
+          mma_task_splitk<KS_QN>(r % MTN, r / MTN, lane,
+              [&](int m, int k) { return (k < DIM * nN && m < nN) ? SUQ[k * nNp + m] : 0.0; },
+              [&](int k, int n) { return (k < DIM * nN && n < l) ? B[k * ldc + n] : 0.0; },
+              [&](int m, int n, double v0, double v1) {
+                if (m < nN) {
+                  double vv[2] = {v0, v1};
 #pragma unroll
-          for (int d = 0; d < DIM; d++) {
-            const double* sq = SUQ + d * nN * nNp + m0;
-            const double* ac = A + (d * nN + n) * nNp;
-#pragma unroll 4
-            for (int k = 0; k < nN; k++) {
-              const double2 s2 = *reinterpret_cast<const double2*>(sq + nNp * k);
-              const double b = ac[k];
-              a0 = fma(s2.x, b, a0); a1 = fma(s2.y, b, a1);
-            }
-          }
-          SUU[m0 + nNp * n] -= a0;
-          if (m0 + 1 < nN) SUU[m0 + 1 + nNp * n] -= a1;
-        } else if (tile < T_K + T_R) {
-          tile -= T_K;
-          const int m0 = (tile % MT) * 2, n0 = (tile / MT) * 2;
-          double acc[2][2];
-          zero_acc(acc);
-#pragma unroll
-          for (int d = 0; d < DIM; d++) mk<2, 2, nN>(acc, SUQ + d * nN * nNp + m0, nNp, B + d * nN * ldc + n0, ldc);
-#pragma unroll
-          for (int i = 0; i < 2; i++) {
-            const int m = m0 + i;
-            if (m < nN) {
-#pragma unroll
-              for (int j = 0; j < 2; j++) {
-                const int n = n0 + j;
-                if (n < l) {
-                  const int f = n / t, b = n % t, a = NIF[f * nN + m];
-                  double sul = 0.0;
-                  if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = fw[kC * FWS] - fw[kTau * FWS]; }
-                  R[m * ldc + n] = sul - acc[i][j];
+                  for (int j = 0; j < 2; j++) {
+                    const int c = n + j;
+                    if (c < l) {
+                      const int f = c / t, b = c % t, a = NIF[f * nN + m];
+                      double sul = 0.0;
+                      if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = fw[kC * FWS] - fw[kTau * FWS]; }
+                      R[m * ldc + c] = sul - vv[j];
+                    }
+                  }
                 }
-              }
-            }
-          }
-        } else if (tile < T_ALL) {
-          const int i = tile - (T_K + T_R);
-          R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0;
+              });
+        } else {
+          for (int i = lane; i < nN; i += 32) { R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0; }
         }
       }
     }
     __syncthreads();
     HFX_PROF(9);
 
-    // ---- P6: K^-1 by warps 0-3 (Gauss-Jordan) ---------------------------------------------------------------------------------
+    // ---- P6: K^-1 by warps 0-3 (block Gauss-Jordan) ----------------------------------------------------------------------------
     double* const KB = (W == Mm) ? Wb : Mm;          // the buffer that does not hold W
     double* const KI = ((nNp / 2) & 1) ? KB : SUU;
     if (tid < kGJThreads) group_invert<nNp, nNp>(SUU, KB, tid, p.status);
@@ -888,25 +887,17 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     {
       double* gU = p.U + (size_t)e * nN * l;
       double* gU0 = p.U0 + (size_t)e * nN;
-      constexpr int MT = nNp / 2, NTT = ev(l + 1) / 2;
-      for (int tile = tid; tile < MT * NTT; tile += NT) {
-        const int m0 = (tile % MT) * 2, n0 = (tile / MT) * 2;
-        double acc[2][2];
-        zero_acc(acc);
-        mk<2, 2, nN>(acc, KI + m0, nNp, R + n0, ldc);
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          const int m = m0 + i;
-          if (m < nN) {
-#pragma unroll
-            for (int j = 0; j < 2; j++) {
-              const int n = n0 + j;
-              const double v = -acc[i][j];
-              Um[m * ldc + n] = v;
-              if (n < l) gU[m + nN * n] = v; else if (n == l) gU0[m] = v;
-            }
-          }
-        }
+      constexpr int L1T = (l + 1 + 7) / 8, NG = (L1T + 2) / 3;
+      for (int task = warp; task < MTN * NG; task += NWARP) {
+        mma_task<3, KS_N>(task % MTN, (task / MTN) * 3, lane,
+            [&](int m, int k) { return (k < nN && m < nN) ? KI[m + nNp * k] : 0.0; },
+            [&](int k, int n) { return (k < nN && n <= l) ? R[k * ldc + n] : 0.0; },
+            [&](int m, int n, double v0, double v1) {
+              if (m < nN) {
+                if (n <= l) { Um[m * ldc + n] = -v0; if (n < l) gU[m + nN * n] = -v0; else gU0[m] = -v0; }
+                if (n + 1 <= l) { Um[m * ldc + n + 1] = -v1; if (n + 1 < l) gU[m + nN * (n + 1)] = -v1; else gU0[m] = -v1; }
+              }
+            });
       }
     }
     __syncthreads();
@@ -916,29 +907,27 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     {
       double* gQ = p.Q + (size_t)e * (DIM * nN) * l;
       double* gQ0 = p.Q0 + (size_t)e * (DIM * nN);
-      constexpr int MT = (nN + 3) / 4, NTT = (l + 1 + 3) / 4;   // 4 x 4 tiles
-      for (int tile = tid; tile < DIM * MT * NTT; tile += NT) {
-        const int d = tile / (MT * NTT), tl = tile % (MT * NTT);
-        const int m0 = (tl % MT) * 4, n0 = (tl / MT) * 4;
-        double acc[4][4];
-        zero_acc(acc);
-        mk<4, 4, nN>(acc, A + d * nN * nNp + m0, nNp, Um + n0, ldc);
+      constexpr int L1T = (l + 1 + 7) / 8, NG = (L1T + 2) / 3;
+      for (int task = warp; task < DIM * MTN * NG; task += NWARP) {
+        const int d = task / (MTN * NG), r = task % (MTN * NG);
+        mma_task<3, KS_N>(r % MTN, (r / MTN) * 3, lane,
+            [&](int m, int k) { return (k < nN && m < nN) ? A[(d * nN + k) * nNp + m] : 0.0; },
+            [&](int k, int n) { return (k < nN && n <= l) ? Um[k * ldc + n] : 0.0; },
+            [&](int m, int n, double v0, double v1) {
+              if (m < nN) {
+                double vv[2] = {v0, v1};
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const int m = m0 + i;
-          if (m < nN) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const int n = n0 + j;
-              if (n <= l) {
-                double* bq = B + (d * nN + m) * ldc + n;
-                const double qv = -acc[i][j] - *bq;
-                *bq = qv;
-                if (n < l) gQ[(m * DIM + d) + (DIM * nN) * n] = qv; else gQ0[m * DIM + d] = qv;
+                for (int j = 0; j < 2; j++) {
+                  const int c = n + j;
+                  if (c <= l) {
+                    double* bq = B + (d * nN + m) * ldc + c;
+                    const double qv = -vv[j] - *bq;
+                    *bq = qv;
+                    if (c < l) gQ[(m * DIM + d) + (DIM * nN) * c] = qv; else gQ0[m * DIM + d] = qv;
+                  }
+                }
               }
-            }
-          }
-        }
+            });
       }
     }
     __syncthreads();
@@ -948,63 +937,55 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     {
       double* gS = p.S ? p.S + (size_t)e * l * l : nullptr;
       double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
-      constexpr int MT = tp / 2, NTT = (l + 1 + 3) / 4;   // per face: (t x (l+1)) in 2 x 4 tiles
-      for (int tile = tid; tile < nFc * MT * NTT; tile += NT) {
-        const int f = tile / (MT * NTT), tl = tile % (MT * NTT);
-        const int a0 = (tl % MT) * 2, n0 = (tl / MT) * 4;
+      constexpr int TT = (t + 7) / 8, L1T = (l + 1 + 7) / 8, NG = (L1T + 2) / 3;
+      constexpr int KTOT = (1 + DIM) * t, KS_S = (KTOT + 3) / 4;   // k = (kind, b): kind 0 -> Slu (tau mass on U), kind 1+d -> Slq_d (-(Dn)_d mass on Q_d)
+      for (int task = warp; task < nFc * TT * NG; task += NWARP) {
+        const int f = task / (TT * NG), r = task % (TT * NG);
         const int* fn = FN + f * t;
         const double* fwf = FW + f * NW * FWS;
-        double acc[2][4];
-        zero_acc(acc);
-        // Slu = +tau mass on the face nodes of U (HDGBase.cpp:126)
-#pragma unroll
-        for (int b = 0; b < t; b++) mk_step<2, 4>(acc, fwf + kTau * FWS + a0 + tp * b, Um + fn[b] * ldc + n0);
-        if (hasDiff) {   // Slq = -(D n) mass on the face nodes of Q_d (HDGDiffusion.cpp:120)
-          double acc2[2][4];
-          zero_acc(acc2);
-#pragma unroll
-          for (int d = 0; d < DIM; d++)
-#pragma unroll
-            for (int b = 0; b < t; b++) mk_step<2, 4>(acc2, fwf + (kDN + d) * FWS + a0 + tp * b, B + (d * nN + fn[b]) * ldc + n0);
-#pragma unroll
-          for (int i = 0; i < 2; i++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[i][j] -= acc2[i][j];
-        }
         const int F = ISM[f], bc = BCF[f];
         const bool inter = INTF[f];
+        mma_task<3, KS_S>(r % TT, (r / TT) * 3, lane,
+            [&](int a, int k) {
+              if (k >= KTOT || a >= t) return 0.0;
+              const int kind = k / t, b = k % t;
+              return kind == 0 ? fwf[kTau * FWS + a + tp * b] : (hasDiff ? -fwf[(kDN + kind - 1) * FWS + a + tp * b] : 0.0);
+            },
+            [&](int k, int n) {
+              if (k >= KTOT || n > l) return 0.0;
+              const int kind = k / t, nd = fn[k % t];
+              return kind == 0 ? Um[nd * ldc + n] : B[((kind - 1) * nN + nd) * ldc + n];
+            },
+            [&](int a, int n, double v0, double v1) {
+              if (a >= t) return;
+              const int rowDof = F * t + PERM[f * t + a];
+              double* rowp = p.vals + ROWS[f] + (long long)PERM[f * t + a] * RLEN[f];
+              double vv[2] = {v0, v1};
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
-          const int a = a0 + i;
-          if (a >= t) continue;
-          const int rowDof = F * t + PERM[f * t + a];
-          double* rowp = p.vals + ROWS[f] + (long long)PERM[f * t + a] * RLEN[f];
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const int n = n0 + j;
-            if (n > l) continue;
-            const double v = acc[i][j];
-            if (n == l) {   // S0
-              double s0 = -v;
-              if (bc == 1) s0 = p.dirichlet[(size_t)F * t + a];
-              else if (bc == 2) {
-                s0 = 0.0;
-                for (int b = 0; b < t; b++) s0 = fma(fwf[kOne * FWS + a + tp * b], p.dirichlet[(size_t)F * t + b], s0);
+              for (int j = 0; j < 2; j++) {
+                const int c = n + j;
+                if (c > l) continue;
+                if (c == l) {   // S0
+                  double s0 = -vv[j];
+                  if (bc == 1) s0 = p.dirichlet[(size_t)F * t + a];
+                  else if (bc == 2) {
+                    s0 = 0.0;
+                    for (int b = 0; b < t; b++) s0 = fma(fwf[kOne * FWS + a + tp * b], p.dirichlet[(size_t)F * t + b], s0);
+                  }
+                  if (gS0) gS0[f * t + a] = s0;
+                  if (inter) atomicAdd(p.rhs + rowDof, s0); else p.rhs[rowDof] = s0;
+                  continue;
+                }
+                const int f2 = c / t, b2 = c % t;
+                double sv = vv[j];
+                if (f2 == f) sv += fwf[kC * FWS + a + tp * b2] - fwf[kTau * FWS + a + tp * b2];
+                if (bc == 1) sv = (f2 == f && b2 == a) ? 1.0 : 0.0;
+                else if (bc == 2) sv = (f2 == f) ? fwf[kOne * FWS + a + tp * b2] : 0.0;
+                if (gS) gS[(f * t + a) + (size_t)l * c] = sv;
+                double* dst = rowp + POS[f * nFc + f2] * t + PERM[f2 * t + b2];
+                if (f2 == f && inter) atomicAdd(dst, sv); else *dst = sv;
               }
-              if (gS0) gS0[f * t + a] = s0;
-              if (inter) atomicAdd(p.rhs + rowDof, s0); else p.rhs[rowDof] = s0;
-              continue;
-            }
-            const int f2 = n / t, b2 = n % t;
-            double sv = v;
-            if (f2 == f) sv += fwf[kC * FWS + a + tp * b2] - fwf[kTau * FWS + a + tp * b2];
-            if (bc == 1) sv = (f2 == f && b2 == a) ? 1.0 : 0.0;
-            else if (bc == 2) sv = (f2 == f) ? fwf[kOne * FWS + a + tp * b2] : 0.0;
-            if (gS) gS[(f * t + a) + (size_t)l * n] = sv;
-            double* dst = rowp + POS[f * nFc + f2] * t + PERM[f2 * t + b2];
-            if (f2 == f && inter) atomicAdd(dst, sv); else *dst = sv;
-          }
-        }
+            });
       }
     }
     __syncthreads();

@@ -47,6 +47,7 @@ struct AsmParams {
   const double* ffs;          // [nIPf][nNf*nNf] phi_a*phi_b products of the face element
   const int* faceNodes;       // [nFc][nNf]
   const int8_t* nodeInFace;   // [nFc][nN] inverse of faceNodes (-1 if not on the face)
+  const double* mhinv;        // inverse of the reference mass matrix, column-major [ev(nN)][ev(nN)] (unit pad diagonal)
   // outputs
   double* U; double* Q; double* U0; double* Q0; double* S; double* S0;  // S,S0 may be NULL
   double* vals; double* rhs;
@@ -232,6 +233,38 @@ __device__ __forceinline__ void mma_task_splitk(int mt, int nt, int lane, FA fa,
   }
   fs(m, nt * 8 + 2 * lc, c0[0] + c1[0], c0[1] + c1[1]);
 }
+// Lean variant for operands that are affine in k (pointer + stride): no index arithmetic or range predicates in the k loop.
+// pa -> A[m][0] with stride lda between consecutive k; pb[j] -> B[0][n_j] with stride ldb.  Rows / columns beyond the matrix
+// are clamped by the caller (their results are discarded); k beyond the true K contributes an exact zero (a = 0, b finite).
+template <int NTW, int K>
+__device__ __forceinline__ void mma_affine(double (&c)[NTW][2], const double* __restrict__ pa, int lda,
+                                           const double* const (&pb)[NTW], int ldb, int lc) {
+  constexpr int KS = (K + 3) / 4;
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++) {
+    const int k = ks * 4 + lc;
+    double a, b[NTW];
+    if (ks * 4 + 3 < K) {
+      a = pa[k * lda];
+#pragma unroll
+      for (int j = 0; j < NTW; j++) b[j] = pb[j][k * ldb];
+    } else {
+      const int kk = k < K ? k : K - 1;
+      a = k < K ? pa[kk * lda] : 0.0;
+#pragma unroll
+      for (int j = 0; j < NTW; j++) b[j] = pb[j][kk * ldb];
+    }
+#pragma unroll
+    for (int j = 0; j < NTW; j++) dmma(c[j], a, b[j]);
+  }
+}
+template <int NTW>
+__device__ __forceinline__ void zero_c(double (&c)[NTW][2]) {
+#pragma unroll
+  for (int j = 0; j < NTW; j++) { c[j][0] = 0.0; c[j][1] = 0.0; }
+}
+__device__ __forceinline__ int imin(int a, int b) { return a < b ? a : b; }
+
 __device__ __forceinline__ int grab1(int* ctr, int lane) {   // warp-granular dynamic task queue
   int v = 0;
   if (lane == 0) v = atomicAdd(ctr, 1);
@@ -246,10 +279,10 @@ __device__ __forceinline__ int grab1(int* ctr, int lane) {   // warp-granular dy
 // pivot block raises bit 0 of *flag.  np = n rounded up to even: the caller provides pad row/column = 0, pad diagonal = 1.
 // The inverse ends in ((np/2) odd ? b1 : b0).
 constexpr int kGJThreads = 128;
-template <int np, int ld>
+template <int np, int ld, int GT>
 __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* flag) {
   // not inlined on purpose: inside the big kernel the register allocator rematerialises every address of this latency-bound loop
-  constexpr int MT = np / 2, NS = MT * np, NQ = (NS + kGJThreads - 1) / kGJThreads;
+  constexpr int MT = np / 2, NS = MT * np, NQ = (NS + GT - 1) / GT;
   const double s0 = b0[0];
   const double scale = s0 * s0;
   bool bad = false;
@@ -262,7 +295,7 @@ __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* 
     double2 a[NQ], c0[NQ], c1[NQ], pj[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-      const int s2 = tid + q * kGJThreads;
+      const int s2 = tid + q * GT;
       if (s2 < NS) {
         const int i0 = (s2 % MT) * 2, j = s2 / MT;
         a[q] = *reinterpret_cast<const double2*>(src + i0 + ld * j);
@@ -277,7 +310,7 @@ __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* 
     const double i00 = pc1.y * id, i01 = -pc1.x * id, i10 = -pc0.y * id, i11 = pc0.x * id;   // inverse of the pivot block
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-      const int s2 = tid + q * kGJThreads;
+      const int s2 = tid + q * GT;
       if (s2 < NS) {
         const int i0 = (s2 % MT) * 2, j = s2 / MT;
         const bool inK = (j == k) || (j == k + 1);
@@ -291,7 +324,7 @@ __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* 
         *reinterpret_cast<double2*>(dst + i0 + ld * j) = make_double2(r0, r1);
       }
     }
-    bar_sync_named(1, kGJThreads);
+    if (GT == kAsmThreads) __syncthreads(); else bar_sync_named(1, GT);
     const double* tsw = dst; dst = const_cast<double*>(src); src = tsw;
   }
   if (bad) atomicOr(flag, 1);
@@ -355,7 +388,7 @@ struct AsmSmem {
   static_assert(oFSH + nFSH <= oFFS, "staged tables do not fit in the FW+B regions");
   static_assert(oFFS >= oB, "ffs staging must not overlap the face matrices");
   static constexpr int oFU = oR + szR;                       // Fu [nN]
-  static constexpr int oSCR = oFU + ev(nN);                  // Gauss-Jordan pivot-row scratch [2*nNp]
+  static constexpr int oSCR = oFU + ev(nN) + 2;              // (FU[ev(nN)] holds 1/detJ of the first cubature point)
   static constexpr int oEnd = oSCR + 2 * nNp;
   static constexpr int nDoubles = oEnd;
   // after the doubles: row starts (nFc x int64) then a small int area
@@ -406,6 +439,15 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   for (int i = tid; i < nIP + nIPf; i += NT) WQ[i] = i < nIP ? p.w[i] : p.fw[i - nIP];
   if (tid < nFc) { int vn = 0; for (int kk = 0; kk < nN; kk++) if (p.nodeInFace[tid * nN + kk] < 0) { vn = kk; break; } OPP[tid] = vn; }
   __syncthreads();
+
+  // reference-mass inverse: each thread keeps its share in registers for the whole kernel (constant-detJ shortcut for M^-1)
+  constexpr int NMH = (nNp * nNp + NT - 1) / NT;
+  constexpr bool kMHReg = NMH <= 2;
+  double mh[kMHReg ? NMH : 1];
+  if (kMHReg) {
+#pragma unroll
+    for (int q = 0; q < NMH; q++) mh[q] = (tid + q * NT < nNp * nNp) ? p.mhinv[tid + q * NT] : 0.0;
+  }
 
   // ---- software prefetch of the next element's gather (registers) ------------------------------------------------------
   double pfX = 0.0, pfTau = 0.0;
@@ -512,6 +554,16 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           for (int m = 0; m < DIM; m++) J[r][m] = JR[ip * D2 + r * DIM + m];
         double det, I[DIM][DIM];
         det_inv(J, det, I);
+        {   // is det J constant over the element?  (then M = det J * reference mass exactly, whatever the geometry does otherwise)
+          double J0[DIM][DIM], det0, I0[DIM][DIM];
+#pragma unroll
+          for (int r = 0; r < DIM; r++)
+#pragma unroll
+            for (int m = 0; m < DIM; m++) J0[r][m] = JR[r * DIM + m];
+          det_inv(J0, det0, I0);
+          if (!(fabs(det - det0) <= 1e-13 * fabs(det0))) QCTR[3] = 1;
+          if (ip == 0) FU[ev(nN)] = 1.0 / det0;
+        }
         const double dv = WQ[ip] * det;
         DV[ip] = dv;
 #pragma unroll
@@ -665,7 +717,20 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     constexpr int KS_IP = (nIP + 3) / 4, KS_IPF = (nIPf + 3) / 4, KS_N = (nN + 3) / 4, KS_T = (t + 3) / 4, KS_QN = (DIM * nN + 3) / 4;
 
     // ---- P3a: M = sum_ip dV phi phi^T (Mass.cpp:5-38 / HDGBase.cpp:152) ------------------------------------------------------
-    for (int task = warp; task < MTN * ((MTN + 2) / 3); task += NWARP) {
+    // If det J is constant over the element (every straight-sided simplex), M = det J * M_ref exactly and W = M_ref^-1 / det J:
+    // no contraction and no inversion.  Curved elements take the general path.
+    const bool constDet = (QCTR[3] == 0);
+    double* const W = ((nNp / 2) & 1) ? Wb : Mm;
+    if (constDet) {
+      const double rdet = FU[ev(nN)];
+      if (kMHReg) {
+#pragma unroll
+        for (int q = 0; q < NMH; q++) if (tid + q * NT < nNp * nNp) W[tid + q * NT] = mh[q] * rdet;
+      } else {
+        for (int i = tid; i < nNp * nNp; i += NT) W[i] = p.mhinv[i] * rdet;
+      }
+    }
+    if (!constDet) for (int task = warp; task < MTN * ((MTN + 2) / 3); task += NWARP) {
       const int mt = task % MTN, ng = task / MTN;
       mma_task<3, KS_IP>(mt, ng * 3, lane,
           [&](int m, int k) { return (k < nIP && m < nN) ? DV[k] * PHI[k * nNp + m] : 0.0; },
@@ -674,64 +739,80 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
             if (m < nN) { if (n < nN) Mm[m + nNp * n] = v0; if (n + 1 < nN) Mm[m + nNp * (n + 1)] = v1; }
           });
     }
-    if ((nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal for the 2x2-block Gauss-Jordan (pad row/column are zero)
+    if (!constDet && (nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal for the 2x2-block Gauss-Jordan (pad row/column are zero)
       for (int j = 0; j < nN; j++) { Mm[nN + nNp * j] = 0.0; Mm[j + nNp * nN] = 0.0; }
       Mm[nN + nNp * nN] = 1.0;
     }
     __syncthreads();
     HFX_PROF(3);
 
-    // ---- P3b: W = M^-1 by warps 0-3 (block Gauss-Jordan, named barrier) while a dynamic task queue feeds the remaining
-    //            contractions (Squ, Suu, face matrices, Fu) to every warp that is free -------------------------------------------
-    double* const W = ((nNp / 2) & 1) ? Wb : Mm;
-    if (tid < kGJThreads) group_invert<nNp, nNp>(Mm, Wb, tid, p.status);
+    // ---- P3b: (general path only: W = M^-1 by warps 0-3, block Gauss-Jordan) ; contractions Squ, Suu, face matrices, Fu as
+    //            warp tasks: dynamic queue when the inversion runs beside them, static round-robin otherwise ------------------
+    if (!constDet && tid < kGJThreads) group_invert<nNp, nNp, kGJThreads>(Mm, Wb, tid, p.status);
     HFX_PROF(14);
     {
+      const int lr = lane >> 2, lc = lane & 3;
       constexpr int MROWS = DIM * nN, SQ_MT = (MROWS + 7) / 8, NG_N = (MTN + 2) / 3;   // column groups of 3 tiles over nN
       constexpr int T_SQU = SQ_MT * NG_N, T_SUU = MTN * NG_N;
       constexpr int MR = t * t, FW_MT = (MR + 7) / 8, NC = nFc * NW, FW_NG = ((NC + 7) / 8 + 2) / 3, T_FW = FW_MT * FW_NG;
       constexpr int T_ALL = T_SQU + T_SUU + T_FW + 1;
-      for (;;) {
-        int task = grab1(&QCTR[0], lane);
-        if (task >= T_ALL) break;
-        if (task < T_SQU) {
-          // Squ_d[k][j] = sum_ip g[ip][(d,k)] phi[ip][j]  (HDGBase.cpp:150); with D = I the same numbers are Suq_d[k][j] (HDGDiffusion.cpp:130-144)
-          mma_task<3, KS_IP>(task % SQ_MT, (task / SQ_MT) * 3, lane,
-              [&](int m, int k) { return (k < nIP && m < MROWS) ? G[k * ldg + m] : 0.0; },
-              [&](int k, int n) { return (k < nIP && n < nN) ? PHI[k * nNp + n] : 0.0; },
-              [&](int m, int n, double v0, double v1) {
-                if (m < MROWS && n < nN) {
-                  const int d = m / nN, kk = m % nN;
-                  SQU[(d * nN + kk) * nNp + n] = v0;
-                  if (n + 1 < nN) SQU[(d * nN + kk) * nNp + n + 1] = v1;
-                  if (!diffField) {
-                    SUQ[(d * nN + n) * nNp + kk] = hasDiff ? v0 : 0.0;
-                    if (n + 1 < nN) SUQ[(d * nN + n + 1) * nNp + kk] = hasDiff ? v1 : 0.0;
+      int task = constDet ? warp : grab1(&QCTR[0], lane);
+      while (task < T_ALL) {
+        if (task < T_SQU + T_SUU) {
+          // Squ_d[k][j] = sum_ip g[ip][(d,k)] phi[ip][j]  (HDGBase.cpp:150; with D = I also Suq_d, HDGDiffusion.cpp:130-144)
+          // Suu (bulk part) = sum_ip cg[ip][i] phi[ip][j]: -C^T (Convection.cpp:5-49) + reaction mass + Euler mass
+          const bool isSqu = task < T_SQU;
+          const int tk = isSqu ? task : task - T_SQU;
+          const int mt = isSqu ? tk % SQ_MT : tk % MTN, ng = isSqu ? tk / SQ_MT : tk / MTN;
+          const int m = mt * 8 + lr, mrows = isSqu ? MROWS : nN;
+          const double* pa = (isSqu ? G : CG) + imin(m, mrows - 1);
+          const double* pb[3];
+#pragma unroll
+          for (int j = 0; j < 3; j++) pb[j] = PHI + imin((ng * 3 + j) * 8 + lr, nN - 1);
+          double c[3][2];
+          zero_c(c);
+          mma_affine<3, nIP>(c, pa, isSqu ? ldg : nNp, pb, nNp, lc);
+          if (m < mrows) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int n = (ng * 3 + j) * 8 + 2 * lc + h;
+                if (n < nN) {
+                  if (isSqu) {
+                    const int d = m / nN, kk = m % nN;
+                    SQU[(d * nN + kk) * nNp + n] = c[j][h];                               // right operand of A = W Squ
+                    if (!diffField) SUQ[(d * nN + n) * nNp + kk] = hasDiff ? c[j][h] : 0.0;   // left operand of K, R
+                  } else {
+                    SUU[m + nNp * n] = c[j][h];
                   }
                 }
-              });
-        } else if (task < T_SQU + T_SUU) {
-          // Suu (bulk part): -C^T (Convection.cpp:5-49) + reaction mass + Euler mass
-          task -= T_SQU;
-          mma_task<3, KS_IP>(task % MTN, (task / MTN) * 3, lane,
-              [&](int m, int k) { return (k < nIP && m < nN) ? CG[k * nNp + m] : 0.0; },
-              [&](int k, int n) { return (k < nIP && n < nN) ? PHI[k * nNp + n] : 0.0; },
-              [&](int m, int n, double v0, double v1) {
-                if (m < nN) { if (n < nN) SUU[m + nNp * n] = v0; if (n + 1 < nN) SUU[m + nNp * (n + 1)] = v1; }
-              });
+              }
+            }
+          }
         } else if (task < T_SQU + T_SUU + T_FW) {
           // weighted face mass matrices FW[(f,kind)][a + tp b] = sum_ip wt[ip][(f,kind)] phi_a phi_b
-          task -= T_SQU + T_SUU;
-          mma_task<3, KS_IPF>(task % FW_MT, (task / FW_MT) * 3, lane,
-              [&](int m, int k) { return (k < nIPf && m < MR) ? FFS[k * MR + m] : 0.0; },
-              [&](int k, int n) { return (k < nIPf && n < NC) ? FWT[k * ldw + n] : 0.0; },
-              [&](int m, int n, double v0, double v1) {
-                if (m < MR) {
-                  const int a = m % t, b = m / t;
-                  if (n < NC) FW[n * FWS + a + tp * b] = v0;
-                  if (n + 1 < NC) FW[(n + 1) * FWS + a + tp * b] = v1;
-                }
-              });
+          const int tk = task - (T_SQU + T_SUU);
+          const int mt = tk % FW_MT, ng = tk / FW_MT;
+          const int m = mt * 8 + lr;
+          const double* pa = FFS + imin(m, MR - 1);
+          const double* pb[3];
+#pragma unroll
+          for (int j = 0; j < 3; j++) pb[j] = FWT + imin((ng * 3 + j) * 8 + lr, NC - 1);
+          double c[3][2];
+          zero_c(c);
+          mma_affine<3, nIPf>(c, pa, MR, pb, ldw, lc);
+          if (m < MR) {
+            double* dstm = FW + (m % t) + tp * (m / t);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int n = (ng * 3 + j) * 8 + 2 * lc + h;
+                if (n < NC) dstm[n * FWS] = c[j][h];
+              }
+            }
+          }
         } else {
           // Fu = source (Source.cpp:24-48) + Euler mass * Solution_old (Euler.cpp:29-30), both as sum_ip phi_i(ip) * weight(ip)
           for (int i = lane; i < nN; i += 32) {
@@ -740,6 +821,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
             FU[i] = s2;
           }
         }
+        task = constDet ? task + NWARP : grab1(&QCTR[0], lane);
       }
     }
     __syncthreads();
@@ -807,29 +889,60 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
     // ---- P4: A_d = W Squ_d (col-major out) ;  B_d = W Sql_d with Sql[(fn_f(a),d),(f,b)] = -N_fd[a][b] (HDGBase.cpp:134) ------
     {
+      const int lr = lane >> 2, lc = lane & 3;
       constexpr int NG_N = (MTN + 2) / 3, T_A = DIM * MTN * NG_N;
-      constexpr int NB = DIM * t, NG_B = ((NB + 7) / 8 + 2) / 3, T_B = nFc * MTN * NG_B;
+      constexpr int NB = DIM * t, NBT = (NB + 7) / 8, NG_B = (NBT + 2) / 3, T_B = nFc * MTN * NG_B;
       for (int task = warp; task < T_A + T_B; task += NWARP) {
         if (task < T_A) {
           const int d = task / (MTN * NG_N), r = task % (MTN * NG_N);
-          mma_task<3, KS_N>(r % MTN, (r / MTN) * 3, lane,
-              [&](int m, int k) { return (k < nN && m < nN) ? W[m + nNp * k] : 0.0; },
-              [&](int k, int n) { return (k < nN && n < nN) ? SQU[(d * nN + k) * nNp + n] : 0.0; },
-              [&](int m, int n, double v0, double v1) {
-                if (m < nN) { if (n < nN) A[(d * nN + n) * nNp + m] = v0; if (n + 1 < nN) A[(d * nN + n + 1) * nNp + m] = v1; }
-              });
+          const int m = (r % MTN) * 8 + lr, ng = r / MTN;
+          const double* pa = W + imin(m, nN - 1);
+          const double* pb[3];
+#pragma unroll
+          for (int j = 0; j < 3; j++) pb[j] = SQU + d * nN * nNp + imin((ng * 3 + j) * 8 + lr, nN - 1);
+          double c[3][2];
+          zero_c(c);
+          mma_affine<3, nN>(c, pa, nNp, pb, nNp, lc);
+          if (m < nN) {
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int n = (ng * 3 + j) * 8 + 2 * lc + h;
+                if (n < nN) A[(d * nN + n) * nNp + m] = c[j][h];
+              }
+          }
         } else {
           const int tb = task - T_A, f = tb / (MTN * NG_B), r = tb % (MTN * NG_B);
+          const int m = (r % MTN) * 8 + lr, ng = r / MTN;
           const int* fn = FN + f * t;
-          mma_task<3, KS_T>(r % MTN, (r / MTN) * 3, lane,
-              [&](int m, int k) { return (k < t && m < nN) ? W[m + nNp * fn[k]] : 0.0; },
-              [&](int k, int n) { return (k < t && n < NB) ? FW[(f * NW + kN + n / t) * FWS + k + tp * (n % t)] : 0.0; },   // n = (d, b)
-              [&](int m, int n, double v0, double v1) {
-                if (m < nN) {
-                  if (n < NB) B[((n / t) * nN + m) * ldc + f * t + (n % t)] = -v0;
-                  if (n + 1 < NB) B[(((n + 1) / t) * nN + m) * ldc + f * t + ((n + 1) % t)] = -v1;
-                }
-              });
+          // left operand: gathered columns W[:, fn_f(k)] ; right operand: N_fd[k][b] = FW[(f,kN+d)][k + tp b], column n = (d, b)
+          const double* wrow = W + imin(m, nN - 1);
+          const double* pb[3];
+#pragma unroll
+          for (int j = 0; j < 3; j++) {
+            const int n = imin((ng * 3 + j) * 8 + lr, NB - 1);
+            pb[j] = FW + (f * NW + kN + n / t) * FWS + tp * (n % t);
+          }
+          double c[3][2];
+          zero_c(c);
+          constexpr int KS = (t + 3) / 4;
+#pragma unroll
+          for (int ks = 0; ks < KS; ks++) {
+            const int k = ks * 4 + lc, kk = k < t ? k : t - 1;
+            const double a = k < t ? wrow[nNp * fn[kk]] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 3; j++) if ((ng * 3 + j) < NBT) dmma(c[j], a, pb[j][kk]);
+          }
+          if (m < nN) {
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int n = (ng * 3 + j) * 8 + 2 * lc + h;
+                if (n < NB) B[((n / t) * nN + m) * ldc + f * t + (n % t)] = -c[j][h];
+              }
+          }
         }
       }
       for (int idx = tid; idx < DIM * nN; idx += NT) { B[idx * ldc + l] = 0.0; B[idx * ldc + l + 1] = 0.0; }  // Q0 column
@@ -839,35 +952,54 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
     // ---- P5: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335) and R = Sul - sum_d Suq_d B_d, column l = -Fu (:342-343) -------------
     {
-      constexpr int LT = (l + 7) / 8, T_K = MTN * MTN, T_R = MTN * LT;
+      const int lr = lane >> 2, lc = lane & 3;
+      constexpr int LT = (l + 7) / 8, NG_N = (MTN + 2) / 3, NG_L = (LT + 1) / 2, T_K = MTN * NG_N, T_R = MTN * NG_L;
       for (int task = warp; task < T_K + T_R + 1; task += NWARP) {
         if (task < T_K) {
-          mma_task_splitk<KS_QN>(task % MTN, task / MTN, lane,
-              [&](int m, int k) { return (k < DIM * nN && m < nN) ? SUQ[k * nNp + m] : 0.0; },                        // k = (d, k')
-              [&](int k, int n) { return (k < DIM * nN && n < nN) ? A[((k / nN) * nN + n) * nNp + (k % nN)] : 0.0; },
-              [&](int m, int n, double v0, double v1) {
-                if (m < nN) { if (n < nN) SUU[m + nNp * n] -= v0; if (n + 1 < nN) SUU[m + nNp * (n + 1)] -= v1; }
-              });
+          const int m = (task % MTN) * 8 + lr, ng = task / MTN;
+          double c[3][2];
+          zero_c(c);
+#pragma unroll
+          for (int d = 0; d < DIM; d++) {   // right operand A_d[k][n] is column-major: stride 1 in k
+            const double* pa = SUQ + d * nN * nNp + imin(m, nN - 1);
+            const double* pb[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++) pb[j] = A + (d * nN + imin((ng * 3 + j) * 8 + lr, nN - 1)) * nNp;
+            mma_affine<3, nN>(c, pa, nNp, pb, 1, lc);
+          }
+          if (m < nN) {
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int n = (ng * 3 + j) * 8 + 2 * lc + h;
+                if (n < nN) SUU[m + nNp * n] -= c[j][h];
+              }
+          }
         } else if (task < T_K + T_R) {
           const int r = task - T_K;
-          mma_task_splitk<KS_QN>(r % MTN, r / MTN, lane,
-              [&](int m, int k) { return (k < DIM * nN && m < nN) ? SUQ[k * nNp + m] : 0.0; },
-              [&](int k, int n) { return (k < DIM * nN && n < l) ? B[k * ldc + n] : 0.0; },
-              [&](int m, int n, double v0, double v1) {
-                if (m < nN) {
-                  double vv[2] = {v0, v1};
+          const int m = (r % MTN) * 8 + lr, ng = r / MTN;
+          double c[2][2];
+          zero_c(c);
+          const double* pa = SUQ + imin(m, nN - 1);           // k = (d, k') runs over the rows of [B_0; B_1; ...] contiguously
+          const double* pb[2];
 #pragma unroll
-                  for (int j = 0; j < 2; j++) {
-                    const int c = n + j;
-                    if (c < l) {
-                      const int f = c / t, b = c % t, a = NIF[f * nN + m];
-                      double sul = 0.0;
-                      if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = fw[kC * FWS] - fw[kTau * FWS]; }
-                      R[m * ldc + c] = sul - vv[j];
-                    }
-                  }
+          for (int j = 0; j < 2; j++) pb[j] = B + imin((ng * 2 + j) * 8 + lr, l);
+          mma_affine<2, DIM * nN>(c, pa, nNp, pb, ldc, lc);
+          if (m < nN) {
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int cc = (ng * 2 + j) * 8 + 2 * lc + h;
+                if (cc < l) {
+                  const int f = cc / t, b = cc % t, a = NIF[f * nN + m];
+                  double sul = 0.0;
+                  if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = fw[kC * FWS] - fw[kTau * FWS]; }
+                  R[m * ldc + cc] = sul - c[j][h];
                 }
-              });
+              }
+          }
         } else {
           for (int i = lane; i < nN; i += 32) { R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0; }
         }
@@ -876,28 +1008,36 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     __syncthreads();
     HFX_PROF(9);
 
-    // ---- P6: K^-1 by warps 0-3 (block Gauss-Jordan) ----------------------------------------------------------------------------
+    // ---- P6: K^-1 (block Gauss-Jordan) ---------------------------------------------------------------------------------------
     double* const KB = (W == Mm) ? Wb : Mm;          // the buffer that does not hold W
     double* const KI = ((nNp / 2) & 1) ? KB : SUU;
-    if (tid < kGJThreads) group_invert<nNp, nNp>(SUU, KB, tid, p.status);
-    __syncthreads();
+    group_invert<nNp, nNp, NT>(SUU, KB, tid, p.status);   // nothing else can run here: all eight warps share the pivot steps
     HFX_PROF(10);
 
     // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu (column l) ------------------------------------------------------------------------
     {
+      const int lr = lane >> 2, lc = lane & 3;
       double* gU = p.U + (size_t)e * nN * l;
       double* gU0 = p.U0 + (size_t)e * nN;
       constexpr int L1T = (l + 1 + 7) / 8, NG = (L1T + 2) / 3;
       for (int task = warp; task < MTN * NG; task += NWARP) {
-        mma_task<3, KS_N>(task % MTN, (task / MTN) * 3, lane,
-            [&](int m, int k) { return (k < nN && m < nN) ? KI[m + nNp * k] : 0.0; },
-            [&](int k, int n) { return (k < nN && n <= l) ? R[k * ldc + n] : 0.0; },
-            [&](int m, int n, double v0, double v1) {
-              if (m < nN) {
-                if (n <= l) { Um[m * ldc + n] = -v0; if (n < l) gU[m + nN * n] = -v0; else gU0[m] = -v0; }
-                if (n + 1 <= l) { Um[m * ldc + n + 1] = -v1; if (n + 1 < l) gU[m + nN * (n + 1)] = -v1; else gU0[m] = -v1; }
-              }
-            });
+        const int m = (task % MTN) * 8 + lr, ng = task / MTN;
+        const double* pa = KI + imin(m, nN - 1);
+        const double* pb[3];
+#pragma unroll
+        for (int j = 0; j < 3; j++) pb[j] = R + imin((ng * 3 + j) * 8 + lr, l);
+        double c[3][2];
+        zero_c(c);
+        mma_affine<3, nN>(c, pa, nNp, pb, ldc, lc);
+        if (m < nN) {
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int n = (ng * 3 + j) * 8 + 2 * lc + h;
+              if (n <= l) { const double v = -c[j][h]; Um[m * ldc + n] = v; if (n < l) gU[m + nN * n] = v; else gU0[m] = v; }
+            }
+        }
       }
     }
     __syncthreads();
@@ -905,29 +1045,34 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
     // ---- P8: Q_d = -A_d U - B_d ; Q0_d = -A_d U0  (:344-345) -----------------------------------------------------------
     {
+      const int lr = lane >> 2, lc = lane & 3;
       double* gQ = p.Q + (size_t)e * (DIM * nN) * l;
       double* gQ0 = p.Q0 + (size_t)e * (DIM * nN);
       constexpr int L1T = (l + 1 + 7) / 8, NG = (L1T + 2) / 3;
       for (int task = warp; task < DIM * MTN * NG; task += NWARP) {
         const int d = task / (MTN * NG), r = task % (MTN * NG);
-        mma_task<3, KS_N>(r % MTN, (r / MTN) * 3, lane,
-            [&](int m, int k) { return (k < nN && m < nN) ? A[(d * nN + k) * nNp + m] : 0.0; },
-            [&](int k, int n) { return (k < nN && n <= l) ? Um[k * ldc + n] : 0.0; },
-            [&](int m, int n, double v0, double v1) {
-              if (m < nN) {
-                double vv[2] = {v0, v1};
+        const int m = (r % MTN) * 8 + lr, ng = r / MTN;
+        const double* pa = A + d * nN * nNp + imin(m, nN - 1);     // A_d[m][k], column-major
+        const double* pb[3];
 #pragma unroll
-                for (int j = 0; j < 2; j++) {
-                  const int c = n + j;
-                  if (c <= l) {
-                    double* bq = B + (d * nN + m) * ldc + c;
-                    const double qv = -vv[j] - *bq;
-                    *bq = qv;
-                    if (c < l) gQ[(m * DIM + d) + (DIM * nN) * c] = qv; else gQ0[m * DIM + d] = qv;
-                  }
-                }
+        for (int j = 0; j < 3; j++) pb[j] = Um + imin((ng * 3 + j) * 8 + lr, l);
+        double c[3][2];
+        zero_c(c);
+        mma_affine<3, nN>(c, pa, nNp, pb, ldc, lc);
+        if (m < nN) {
+          double* brow = B + (d * nN + m) * ldc;
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int n = (ng * 3 + j) * 8 + 2 * lc + h;
+              if (n <= l) {
+                const double qv = -c[j][h] - brow[n];
+                brow[n] = qv;
+                if (n < l) gQ[(m * DIM + d) + (DIM * nN) * n] = qv; else gQ0[m * DIM + d] = qv;
               }
-            });
+            }
+        }
       }
     }
     __syncthreads();

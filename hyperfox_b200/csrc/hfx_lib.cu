@@ -445,7 +445,7 @@ struct hfx_ctx {
   // reference element
   std::unique_ptr<RefElement> re;
   int dim = 0, order = 0, nN = 0, nNf = 0, nFc = 0, nIP = 0, nIPf = 0;
-  DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS;
+  DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv;
   DBuf<int> dFaceNodes; DBuf<int8_t> dNodeInFace;
   // mesh
   int nNodes = 0, nCells = 0, nFaces = 0;
@@ -646,6 +646,23 @@ int hfx_refel_set(hfx_ctx* c, int dim, int order, int geom) {
     std::vector<double> ffs((size_t)c->nIPf * t * t);
     for (int ip = 0; ip < c->nIPf; ip++) for (int b = 0; b < t; b++) for (int a = 0; a < t; a++) ffs[((size_t)ip * t + b) * t + a] = fe->ipShape()[(size_t)ip * t + a] * fe->ipShape()[(size_t)ip * t + b];
     c->dFFS.upload(padded(ffs), c->st);
+    {   // inverse of the reference mass matrix (column-major, even-padded with a unit diagonal): W = M_ref^-1 / detJ when detJ is constant
+      const int n = c->nN, np = (n + 1) & ~1, nip = c->nIP;
+      std::vector<double> M((size_t)n * n, 0.0), I((size_t)n * n, 0.0);
+      for (int ip = 0; ip < nip; ip++) for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) M[(size_t)i * n + j] += re.ipWeights()[ip] * re.ipShape()[(size_t)ip * n + i] * re.ipShape()[(size_t)ip * n + j];
+      for (int i = 0; i < n; i++) I[(size_t)i * n + i] = 1.0;
+      for (int k = 0; k < n; k++) {   // Gauss-Jordan with partial pivoting (host, once per reference element)
+        int pv = k; for (int i = k + 1; i < n; i++) if (std::fabs(M[(size_t)i * n + k]) > std::fabs(M[(size_t)pv * n + k])) pv = i;
+        if (pv != k) for (int j = 0; j < n; j++) { std::swap(M[(size_t)k * n + j], M[(size_t)pv * n + j]); std::swap(I[(size_t)k * n + j], I[(size_t)pv * n + j]); }
+        const double d = 1.0 / M[(size_t)k * n + k];
+        for (int j = 0; j < n; j++) { M[(size_t)k * n + j] *= d; I[(size_t)k * n + j] *= d; }
+        for (int i = 0; i < n; i++) if (i != k) { const double f = M[(size_t)i * n + k]; if (f != 0.0) for (int j = 0; j < n; j++) { M[(size_t)i * n + j] -= f * M[(size_t)k * n + j]; I[(size_t)i * n + j] -= f * I[(size_t)k * n + j]; } }
+      }
+      std::vector<double> mh((size_t)np * np, 0.0);
+      for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) mh[(size_t)i + (size_t)np * j] = I[(size_t)i * n + j];
+      if (np > n) mh[(size_t)n + (size_t)np * n] = 1.0;
+      c->dMHInv.upload(mh, c->st);
+    }
     std::vector<int8_t> nif((size_t)c->nFc * c->nN, -1);
     for (int f = 0; f < c->nFc; f++) for (int a = 0; a < t; a++) nif[(size_t)f * c->nN + re.faceNodes()[(size_t)f * t + a]] = (int8_t)a;
     c->dNodeInFace.upload(nif, c->st);
@@ -870,7 +887,7 @@ int hfx_assemble(hfx_ctx* c) {
     if (p.timeScheme == HFX_TS_EULER_IMPLICIT) p.solOld = find_field(c, "Solution")->d.p;
     p.dirichlet = find_field(c, "Dirichlet")->d.p;
     p.shape = c->dShape.p; p.dshape = c->dDShape.p; p.w = c->dW.p; p.fshape = c->dFShape.p; p.fdshape = c->dFDShape.p; p.fw = c->dFW.p; p.ffs = c->dFFS.p;
-    p.faceNodes = c->dFaceNodes.p; p.nodeInFace = c->dNodeInFace.p;
+    p.faceNodes = c->dFaceNodes.p; p.nodeInFace = c->dNodeInFace.p; p.mhinv = c->dMHInv.p;
     p.U = c->dU.p; p.Q = c->dQ.p; p.U0 = c->dU0.p; p.Q0 = c->dQ0.p; p.S = c->dS.p; p.S0 = c->dS0.p;
     p.vals = c->dVals.p; p.rhs = c->dRhs.p; p.status = c->dStatus.p;
     p.prof = c->profOn ? c->dProf.p : nullptr;

@@ -390,7 +390,11 @@ struct AsmSmem {
   static constexpr int oFU = oR + szR;                       // Fu [nN]
   static constexpr int oSCR = oFU + ev(nN) + 2;              // (FU[ev(nN)] holds 1/detJ of the first cubature point)
   static constexpr int oEnd = oSCR + 2 * nNp;
-  static constexpr int nDoubles = oEnd;
+  // S staging [l][ldc] for the coalesced write-out: reuses the dead g/A + M + W span when it is large enough (large elements),
+  // otherwise gets its own area (small elements, where shared memory is not the limit)
+  static constexpr bool stFits = (oSQU - oG) >= l * ldc;
+  static constexpr int oST = stFits ? oG : oEnd;
+  static constexpr int nDoubles = stFits ? oEnd : oEnd + l * ldc;
   // after the doubles: row starts (nFc x int64) then a small int area
   static constexpr int nInts = 8 + 2 * nFc * t + nFc * nN + nFc * nFc + 5 * nFc + 8;
   static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * nFc + 4 * (size_t)nInts;
@@ -424,6 +428,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   int* OPP = INTF + nFc;                                              // [nFc] first node not on the face (orientation test)
   int* QCTR = OPP + nFc;                                              // [4] dynamic tile-queue counters
   double* A = G;    // A_d aliases g (dead after the contractions)
+  double* ST = sm + L::oST;   // S staging [l][ldc] for the coalesced write-out
   double* Um = SQU; // U aliases Squ (dead after A)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool hasDiff = p.opmask & 1, hasConv = p.opmask & 2, hasReac = (p.opmask & 4) && p.reacIP, hasSrc = (p.opmask & 8) && p.srcIP;
@@ -951,54 +956,39 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     HFX_PROF(8);
 
     // ---- P5: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335) and R = Sul - sum_d Suq_d B_d, column l = -Fu (:342-343) -------------
+    //      one output tile per warp task, K loop split over two accumulators (long dependent DMMA chains are latency bound)
     {
       const int lr = lane >> 2, lc = lane & 3;
-      constexpr int LT = (l + 7) / 8, NG_N = (MTN + 2) / 3, NG_L = (LT + 1) / 2, T_K = MTN * NG_N, T_R = MTN * NG_L;
+      constexpr int LT = (l + 7) / 8, T_K = MTN * MTN, T_R = MTN * LT, KQ = DIM * nN, KSQ = (KQ + 3) / 4;
       for (int task = warp; task < T_K + T_R + 1; task += NWARP) {
-        if (task < T_K) {
-          const int m = (task % MTN) * 8 + lr, ng = task / MTN;
-          double c[3][2];
-          zero_c(c);
+        if (task < T_K + T_R) {
+          const bool isK = task < T_K;
+          const int r = isK ? task : task - T_K;
+          const int m = (r % MTN) * 8 + lr, nt = r / MTN;
+          const int ncl = imin(nt * 8 + lr, isK ? nN - 1 : l);
+          const double* pa = SUQ + imin(m, nN - 1);            // Suq[m][(d,k')], stride nNp in k = (d,k')
+          double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
 #pragma unroll
-          for (int d = 0; d < DIM; d++) {   // right operand A_d[k][n] is column-major: stride 1 in k
-            const double* pa = SUQ + d * nN * nNp + imin(m, nN - 1);
-            const double* pb[3];
-#pragma unroll
-            for (int j = 0; j < 3; j++) pb[j] = A + (d * nN + imin((ng * 3 + j) * 8 + lr, nN - 1)) * nNp;
-            mma_affine<3, nN>(c, pa, nNp, pb, 1, lc);
+          for (int ks = 0; ks < KSQ; ks++) {
+            const int k = ks * 4 + lc, kk = k < KQ ? k : KQ - 1;
+            const double a = k < KQ ? pa[kk * nNp] : 0.0;
+            // right operand: K: A_d[k'][n] (column-major per d) ; R: B[(d,k')][n] (row-major, rows stacked over d)
+            const double b = isK ? A[((kk / nN) * nN + ncl) * nNp + (kk % nN)] : B[kk * ldc + ncl];
+            if (ks & 1) dmma(c1, a, b); else dmma(c0, a, b);
           }
           if (m < nN) {
 #pragma unroll
-            for (int j = 0; j < 3; j++)
-#pragma unroll
-              for (int h = 0; h < 2; h++) {
-                const int n = (ng * 3 + j) * 8 + 2 * lc + h;
-                if (n < nN) SUU[m + nNp * n] -= c[j][h];
+            for (int h = 0; h < 2; h++) {
+              const int cc = nt * 8 + 2 * lc + h;
+              const double v = (h ? c0[1] + c1[1] : c0[0] + c1[0]);
+              if (isK) { if (cc < nN) SUU[m + nNp * cc] -= v; }
+              else if (cc < l) {
+                const int f = cc / t, b = cc % t, a = NIF[f * nN + m];
+                double sul = 0.0;
+                if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = fw[kC * FWS] - fw[kTau * FWS]; }
+                R[m * ldc + cc] = sul - v;
               }
-          }
-        } else if (task < T_K + T_R) {
-          const int r = task - T_K;
-          const int m = (r % MTN) * 8 + lr, ng = r / MTN;
-          double c[2][2];
-          zero_c(c);
-          const double* pa = SUQ + imin(m, nN - 1);           // k = (d, k') runs over the rows of [B_0; B_1; ...] contiguously
-          const double* pb[2];
-#pragma unroll
-          for (int j = 0; j < 2; j++) pb[j] = B + imin((ng * 2 + j) * 8 + lr, l);
-          mma_affine<2, DIM * nN>(c, pa, nNp, pb, ldc, lc);
-          if (m < nN) {
-#pragma unroll
-            for (int j = 0; j < 2; j++)
-#pragma unroll
-              for (int h = 0; h < 2; h++) {
-                const int cc = (ng * 2 + j) * 8 + 2 * lc + h;
-                if (cc < l) {
-                  const int f = cc / t, b = cc % t, a = NIF[f * nN + m];
-                  double sul = 0.0;
-                  if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = fw[kC * FWS] - fw[kTau * FWS]; }
-                  R[m * ldc + cc] = sul - c[j][h];
-                }
-              }
+            }
           }
         } else {
           for (int i = lane; i < nN; i += 32) { R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0; }
@@ -1017,25 +1007,23 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu (column l) ------------------------------------------------------------------------
     {
       const int lr = lane >> 2, lc = lane & 3;
-      double* gU = p.U + (size_t)e * nN * l;
-      double* gU0 = p.U0 + (size_t)e * nN;
-      constexpr int L1T = (l + 1 + 7) / 8, NG = (L1T + 2) / 3;
+      constexpr int L1T = (l + 1 + 7) / 8, NG = (L1T + 1) / 2;
       for (int task = warp; task < MTN * NG; task += NWARP) {
         const int m = (task % MTN) * 8 + lr, ng = task / MTN;
         const double* pa = KI + imin(m, nN - 1);
-        const double* pb[3];
+        const double* pb[2];
 #pragma unroll
-        for (int j = 0; j < 3; j++) pb[j] = R + imin((ng * 3 + j) * 8 + lr, l);
-        double c[3][2];
+        for (int j = 0; j < 2; j++) pb[j] = R + imin((ng * 2 + j) * 8 + lr, l);
+        double c[2][2];
         zero_c(c);
-        mma_affine<3, nN>(c, pa, nNp, pb, ldc, lc);
+        mma_affine<2, nN>(c, pa, nNp, pb, ldc, lc);
         if (m < nN) {
 #pragma unroll
-          for (int j = 0; j < 3; j++)
+          for (int j = 0; j < 2; j++)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-              const int n = (ng * 3 + j) * 8 + 2 * lc + h;
-              if (n <= l) { const double v = -c[j][h]; Um[m * ldc + n] = v; if (n < l) gU[m + nN * n] = v; else gU0[m] = v; }
+              const int n = (ng * 2 + j) * 8 + 2 * lc + h;
+              if (n <= l) Um[m * ldc + n] = -c[j][h];
             }
         }
       }
@@ -1046,8 +1034,6 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     // ---- P8: Q_d = -A_d U - B_d ; Q0_d = -A_d U0  (:344-345) -----------------------------------------------------------
     {
       const int lr = lane >> 2, lc = lane & 3;
-      double* gQ = p.Q + (size_t)e * (DIM * nN) * l;
-      double* gQ0 = p.Q0 + (size_t)e * (DIM * nN);
       constexpr int L1T = (l + 1 + 7) / 8, NG = (L1T + 2) / 3;
       for (int task = warp; task < DIM * MTN * NG; task += NWARP) {
         const int d = task / (MTN * NG), r = task % (MTN * NG);
@@ -1067,9 +1053,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
             for (int h = 0; h < 2; h++) {
               const int n = (ng * 3 + j) * 8 + 2 * lc + h;
               if (n <= l) {
-                const double qv = -c[j][h] - brow[n];
-                brow[n] = qv;
-                if (n < l) gQ[(m * DIM + d) + (DIM * nN) * n] = qv; else gQ0[m * DIM + d] = qv;
+                brow[n] = -c[j][h] - brow[n];
               }
             }
         }
@@ -1080,61 +1064,87 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
     // ---- P9: S = Slu U + Slq Q + Sll ; S0 = Fl - Slu U0 - Slq Q0 (:347-348); Dirichlet rows (:489-501); scatter (:596-618) --
     {
-      double* gS = p.S ? p.S + (size_t)e * l * l : nullptr;
-      double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
-      constexpr int TT = (t + 7) / 8, L1T = (l + 1 + 7) / 8, NG = (L1T + 2) / 3;
+      const int lr = lane >> 2, lc = lane & 3;
+      constexpr int TT = (t + 7) / 8, L1T = (l + 1 + 7) / 8, NTW9 = (L1T <= 6 ? L1T : 4), NG = (L1T + NTW9 - 1) / NTW9;   // one gather of the left operand feeds a whole row of column tiles
       constexpr int KTOT = (1 + DIM) * t, KS_S = (KTOT + 3) / 4;   // k = (kind, b): kind 0 -> Slu (tau mass on U), kind 1+d -> Slq_d (-(Dn)_d mass on Q_d)
       for (int task = warp; task < nFc * TT * NG; task += NWARP) {
         const int f = task / (TT * NG), r = task % (TT * NG);
+        const int a = (r % TT) * 8 + lr, ng = r / TT;
         const int* fn = FN + f * t;
         const double* fwf = FW + f * NW * FWS;
-        const int F = ISM[f], bc = BCF[f];
-        const bool inter = INTF[f];
-        mma_task<3, KS_S>(r % TT, (r / TT) * 3, lane,
-            [&](int a, int k) {
-              if (k >= KTOT || a >= t) return 0.0;
-              const int kind = k / t, b = k % t;
-              return kind == 0 ? fwf[kTau * FWS + a + tp * b] : (hasDiff ? -fwf[(kDN + kind - 1) * FWS + a + tp * b] : 0.0);
-            },
-            [&](int k, int n) {
-              if (k >= KTOT || n > l) return 0.0;
-              const int kind = k / t, nd = fn[k % t];
-              return kind == 0 ? Um[nd * ldc + n] : B[((kind - 1) * nN + nd) * ldc + n];
-            },
-            [&](int a, int n, double v0, double v1) {
-              if (a >= t) return;
-              const int rowDof = F * t + PERM[f * t + a];
-              double* rowp = p.vals + ROWS[f] + (long long)PERM[f * t + a] * RLEN[f];
-              double vv[2] = {v0, v1};
+        const int acl = imin(a, t - 1);
+        int ncl[NTW9];
 #pragma unroll
-              for (int j = 0; j < 2; j++) {
-                const int c = n + j;
-                if (c > l) continue;
-                if (c == l) {   // S0
-                  double s0 = -vv[j];
-                  if (bc == 1) s0 = p.dirichlet[(size_t)F * t + a];
-                  else if (bc == 2) {
-                    s0 = 0.0;
-                    for (int b = 0; b < t; b++) s0 = fma(fwf[kOne * FWS + a + tp * b], p.dirichlet[(size_t)F * t + b], s0);
-                  }
-                  if (gS0) gS0[f * t + a] = s0;
-                  if (inter) atomicAdd(p.rhs + rowDof, s0); else p.rhs[rowDof] = s0;
-                  continue;
-                }
-                const int f2 = c / t, b2 = c % t;
-                double sv = vv[j];
-                if (f2 == f) sv += fwf[kC * FWS + a + tp * b2] - fwf[kTau * FWS + a + tp * b2];
-                if (bc == 1) sv = (f2 == f && b2 == a) ? 1.0 : 0.0;
-                else if (bc == 2) sv = (f2 == f) ? fwf[kOne * FWS + a + tp * b2] : 0.0;
-                if (gS) gS[(f * t + a) + (size_t)l * c] = sv;
-                double* dst = rowp + POS[f * nFc + f2] * t + PERM[f2 * t + b2];
-                if (f2 == f && inter) atomicAdd(dst, sv); else *dst = sv;
-              }
-            });
+        for (int j = 0; j < NTW9; j++) ncl[j] = imin((ng * NTW9 + j) * 8 + lr, l);
+        double c[NTW9][2];
+        zero_c(c);
+#pragma unroll
+        for (int ks = 0; ks < KS_S; ks++) {
+          const int k = ks * 4 + lc, kk = k < KTOT ? k : KTOT - 1;
+          const int kind = kk / t, b = kk % t, nd = fn[b];
+          double av = kind == 0 ? fwf[kTau * FWS + acl + tp * b] : (hasDiff ? -fwf[(kDN + kind - 1) * FWS + acl + tp * b] : 0.0);
+          if (k >= KTOT) av = 0.0;
+          const double* brow = kind == 0 ? Um + nd * ldc : B + ((kind - 1) * nN + nd) * ldc;
+#pragma unroll
+          for (int j = 0; j < NTW9; j++) dmma(c[j], av, brow[ncl[j]]);
+        }
+        if (a < t) {
+          double* strow = ST + (f * t + a) * ldc;
+#pragma unroll
+          for (int j = 0; j < NTW9; j++) {
+            const int cc = (ng * NTW9 + j) * 8 + 2 * lc;
+            if (cc <= l) *reinterpret_cast<double2*>(strow + cc) = make_double2(c[j][0], c[j][1]);
+          }
+        }
       }
     }
     __syncthreads();
     HFX_PROF(13);
+
+    // ---- P10: write-out.  Every global store of the element happens here, from shared memory, with consecutive threads on
+    //      consecutive addresses: U, Q (column-major, contiguous per element) and the CSR rows of S in t-long segments ----------
+    {
+      double* gU = p.U + (size_t)e * nN * l;
+      for (int idx = tid; idx < nN * l; idx += NT) gU[idx] = Um[(idx % nN) * ldc + idx / nN];
+      if (tid < nN) p.U0[(size_t)e * nN + tid] = Um[tid * ldc + l];
+      constexpr int q = DIM * nN;
+      double* gQ = p.Q + (size_t)e * q * l;
+      for (int idx = tid; idx < q * l; idx += NT) {
+        const int rq = idx % q, c = idx / q;
+        gQ[idx] = B[((rq % DIM) * nN + rq / DIM) * ldc + c];
+      }
+      if (tid < q) p.Q0[(size_t)e * q + tid] = B[((tid % DIM) * nN + tid / DIM) * ldc + l];
+      double* gS = p.S ? p.S + (size_t)e * l * l : nullptr;
+      double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
+      for (int idx = tid; idx < l * l; idx += NT) {
+        const int r = idx / l, cc = idx % l;
+        const int f = r / t, a = r % t, f2 = cc / t, b2 = cc % t;
+        const double* fwf = FW + f * NW * FWS;
+        const int bc = BCF[f];
+        double sv = ST[r * ldc + cc];
+        if (f2 == f) sv += fwf[kC * FWS + a + tp * b2] - fwf[kTau * FWS + a + tp * b2];   // Sll = -tau mass + (v.n) mass
+        if (bc == 1) sv = (f2 == f && b2 == a) ? 1.0 : 0.0;                                 // DirichletModel row (Set)
+        else if (bc == 2) sv = (f2 == f) ? fwf[kOne * FWS + a + tp * b2] : 0.0;             // IntegratedDirichletModel row
+        if (gS) gS[r + (size_t)l * cc] = sv;
+        const int prow = PERM[r];
+        double* dst = p.vals + ROWS[f] + (long long)prow * RLEN[f] + POS[f * nFc + f2] * t + PERM[f2 * t + b2];
+        if (f2 == f && INTF[f]) atomicAdd(dst, sv); else *dst = sv;
+      }
+      if (tid < l) {
+        const int r = tid, f = r / t, a = r % t, F = ISM[f], bc = BCF[f];
+        const double* fwf = FW + f * NW * FWS;
+        double s0 = -ST[r * ldc + l];
+        if (bc == 1) s0 = p.dirichlet[(size_t)F * t + a];
+        else if (bc == 2) {
+          s0 = 0.0;
+          for (int b = 0; b < t; b++) s0 = fma(fwf[kOne * FWS + a + tp * b], p.dirichlet[(size_t)F * t + b], s0);
+        }
+        if (gS0) gS0[r] = s0;
+        const int rowDof = F * t + PERM[r];
+        if (INTF[f]) atomicAdd(p.rhs + rowDof, s0); else p.rhs[rowDof] = s0;
+      }
+    }
+    __syncthreads();
   }
 }
 

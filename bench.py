@@ -164,12 +164,12 @@ def main():
 
     dim, order, N = 3, args.order, args.cubes
     t0 = time.time()
+    from hyperfox_b200 import partition
     verts, lin = meshgen.kuhn_linear(N, dim)
     nTot = lin.shape[0]
-    e0, e1 = nTot * rank // world, nTot * (rank + 1) // world     # contiguous slab per rank (RCB stand-in for Zoltan)
-    used = np.unique(lin[e0:e1])
-    remap = -np.ones(verts.shape[0], dtype=np.int64); remap[used] = np.arange(used.size)
-    nodes, cells = meshgen.high_order(verts[used], remap[lin[e0:e1]].astype(np.int32), order)
+    e0, e1 = partition.slab_range(nTot, rank, world)              # contiguous slab per rank (stand-in for the Zoltan partition)
+    lverts, lcells, _ = partition.extract_submesh(verts, lin, np.arange(e0, e1))
+    nodes, cells = meshgen.high_order(lverts, lcells, order)
     tp, tau, dirv = poisson_inputs(nodes, cells, order, dim)
     # only faces on the true domain boundary carry the Dirichlet condition (slab cuts are interior faces of the global mesh)
     fc = nodes[tp["faces"][tp["boundary"]]].reshape(tp["boundary"].size, -1, dim)

@@ -33,6 +33,9 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_ELEM = {1: 16610, 2: 201490, 3: 1325333, 4: 6220333, 5: 23364077}      # SURVEY.md section 8(d), tets
 BYTES_STORE = {1: 3136, 2: 13288, 3: 40256, 4: 99076, 5: 211696}
+# dram__bytes_read.sum + dram__bytes_write.sum of hdg_assemble_kernel per element, from the committed `ncu --set full` capture
+# (profiles/r1_assemble_p3_ncu_full_summary.txt: 3.4738 GB for 82,944 p=3 tets); per-launch traffic = this x elements of the launch
+NCU_TRAFFIC_PER_ELEM = {3: (347.069952e6 + 3.126732e9) / 82944.0}
 
 
 def poisson_inputs(nodes, cells, order, dim=3):
@@ -277,8 +280,10 @@ def main():
                    "l2": "inputs+outputs per step (%.1f GB) far larger than the 126 MB L2" % ((BYTES_STORE[order] * nC) / 1e9),
                    "timing": "CUDA events on the library stream around memset+kernel, max over ranks; wall-clock per step %.2f ms" % ms_wall,
                    "setup_s": round(t_setup, 1)},
-        "roofline": {"bound": "fp64", "achieved": ach, "peak": peak["tflops"], "unit": "TFLOP/s", "frac": ach / peak["tflops"] if peak["tflops"] else None,
-                     "traffic": None, "peak_source": peak["how"], "kernel_ms": my_k,
+        "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4 + DFMA share one 64 FMA/clk/SM pipe; tcgen05 has no FP64 kind)", "achieved": ach, "peak": peak["tflops"], "unit": "TFLOP/s", "frac": ach / peak["tflops"] if peak["tflops"] else None,
+                     "traffic": (NCU_TRAFFIC_PER_ELEM[order] * nC if order in NCU_TRAFFIC_PER_ELEM else None),
+                     "traffic_source": "ncu --set full capture at 82,944 tets scaled per element (profiles/r1_assemble_p3_ncu_full_summary.txt); algorithmic bytes %d/element" % BYTES_STORE[order],
+                     "peak_source": peak["how"], "kernel_ms": my_k,
                      "algorithmic_flops_per_element": FLOPS_PER_ELEM[order],
                      "hbm": {"achieved_GBs": hbm_ach, "peak_GBs": hbm_peak, "frac": hbm_ach / hbm_peak, "bytes_per_element": BYTES_STORE[order],
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},

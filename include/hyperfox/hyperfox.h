@@ -1,0 +1,740 @@
+/* hyperfox.h -- C++ host mirror of the reference's class surface for the element-by-element HDG path, over the C ABI
+ * of libhfx.so (include/hfx.h).  Header-only; link with -lhfx.
+ *
+ * Same class names, method names, argument meaning and error behaviour (hfox::ErrorHandle, "Class : function : message") as
+ * the reference, so code written against the reference's headers compiles against these after swapping the include path
+ * and PetscInterface -> CudaLinAlgebraInterface:
+ *
+ *   ErrorHandle                <- src/globals/ErrorHandle.h             ReferenceElement <- src/element/ReferenceElement.h
+ *   Mesh                       <- src/mesh/Mesh.h                       Field, FieldType <- src/field/Field.h, FieldTypes.h
+ *   PetscOpts                  <- src/resolution/PetscOpts.h            LinAlgebraInterface <- src/resolution/LinAlgebraInterface.h:23-162
+ *   CudaLinAlgebraInterface    (replaces PetscInterface, src/resolution/PetscInterface.cpp)
+ *   TimeScheme, Euler, RungeKutta  <- src/operator/{TimeScheme,Euler,RungeKutta}.h
+ *   FEModel, HDGModel, HDGLaplaceModel, HDGDiffusionSource, HDGConvectionDiffusionReactionSource, HDGBurgersModel,
+ *   BoundaryModel, DirichletModel, IntegratedDirichletModel  <- src/model/*.h
+ *   Solver, HDGSolver, HDGSolverOpts  <- src/solver/{Solver,HDGSolver,HDGSolverOpts}.h
+ *   NonLinearWrapper           <- src/solver/NonLinearWrapper.h
+ *
+ * What differs by design: models are operator *descriptors* (the per-element virtual compute() of the reference cannot run on
+ * the device; std::function source/reaction callbacks are evaluated by the host at x(IP) and uploaded); Fields stay host-side
+ * std::vector<double> (as in the reference) and are copied to / from HBM by HDGSolver::assemble / solve.  There is no CPU
+ * fallback: without a CUDA device every compute call throws ErrorHandle.
+ */
+#ifndef HYPERFOX_B200_HYPERFOX_H
+#define HYPERFOX_B200_HYPERFOX_H
+
+#include <algorithm>
+#include <cmath>
+#include <exception>
+#include <functional>
+#include <iostream>
+#include <map>
+#include <set>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../hfx.h"
+
+namespace hfox {
+
+// ---- src/globals/ErrorHandle.h ------------------------------------------------------------------------------------------
+class ErrorHandle : public std::exception {
+ public:
+  ErrorHandle() {}
+  explicit ErrorHandle(const std::string& full) : message(full) {}
+  ErrorHandle(const std::string& cls, const std::string& fn, const std::string& msg) : message(cls + " : " + fn + " : " + msg) {}
+  const char* what() const noexcept override { return message.c_str(); }
+
+ protected:
+  std::string message;
+};
+
+namespace detail {
+inline void check(int rc, const hfx_ctx* c) { if (rc != 0) { const char* m = hfx_last_error(c); throw ErrorHandle(m && *m ? m : "hfx : call : unknown error"); } }
+inline void lcheck(int rc, const hfx_lai* l) { if (rc != 0) { const char* m = hfx_lai_last_error(l); throw ErrorHandle(m && *m ? m : "hfx : call : unknown error"); } }
+// one device context shared by the solver and its linear system
+class Context {
+ public:
+  explicit Context(int device = 0) { detail::check(hfx_ctx_create(device, &h), nullptr); }
+  ~Context() { if (h) hfx_ctx_destroy(h); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  hfx_ctx* h = nullptr;
+};
+}  // namespace detail
+
+// ---- src/field/FieldTypes.h, src/model/AssemblyType.h ------------------------------------------------------------------
+enum FieldType : int { None = -1, Node = 0, Edge = 1, Face = 2, Cell = 3 };
+enum UnitAssemblyType { NoAssembly, Add, Set };
+struct AssemblyType { UnitAssemblyType matrix; UnitAssemblyType rhs; };
+
+// ---- src/element/ReferenceElement.h ------------------------------------------------------------------------------------
+enum elementGeometry { simplex, orthotope };
+
+class ReferenceElement {
+ public:
+  ReferenceElement(int dim, int ord, std::string geom) : dimension(dim), order(ord) {
+    if (geom == "simplex") geometry = simplex;
+    else if (geom == "orthotope") geometry = orthotope;
+    else throw ErrorHandle("ReferenceElement", "setGeometry", "Element type " + geom + " is not yet supported.");
+    geomName = geom;
+    if (dim < 0) throw ErrorHandle("ReferenceElement", "setDim", "Dimension must be positive.");
+    if (dim == 0) { nNodes = 1; nFaces = 0; nodes.assign(1, std::vector<double>()); ipShapeFunctions.assign(1, std::vector<double>(1, 1.0)); ipWeights.assign(1, 1.0); ipCoords.assign(1, std::vector<double>()); return; }
+    int sz[5] = {0, 0, 0, 0, 0};
+    detail::check(hfx_refel_host_tables(dim, ord, geometry == simplex ? HFX_SIMPLEX : HFX_ORTHOTOPE, sz, 0, 0, 0, 0, 0, 0, 0, 0, 0), nullptr);
+    const int nN = sz[0], nNf = sz[1], nFc = sz[2], nIP = sz[3], nIPf = sz[4];
+    std::vector<double> nd((size_t)nN * dim), ipc((size_t)nIP * dim), w(nIP), sh((size_t)nIP * nN), dsh((size_t)nIP * nN * dim), fsh((size_t)nIPf * nNf),
+        fdsh((size_t)nIPf * nNf * std::max(dim - 1, 1)), fw(nIPf);
+    std::vector<int> fn((size_t)nFc * nNf);
+    detail::check(hfx_refel_host_tables(dim, ord, geometry == simplex ? HFX_SIMPLEX : HFX_ORTHOTOPE, sz, nd.data(), ipc.data(), w.data(), sh.data(), dsh.data(),
+                                        fsh.data(), fdsh.data(), fw.data(), fn.data()), nullptr);
+    nNodes = nN; nFaces = nFc;
+    nodes.assign(nN, std::vector<double>(dim));
+    for (int i = 0; i < nN; i++) for (int d = 0; d < dim; d++) nodes[i][d] = nd[(size_t)i * dim + d];
+    ipCoords.assign(nIP, std::vector<double>(dim));
+    for (int i = 0; i < nIP; i++) for (int d = 0; d < dim; d++) ipCoords[i][d] = ipc[(size_t)i * dim + d];
+    ipWeights = w;
+    ipShapeFunctions.assign(nIP, std::vector<double>(nN));
+    ipDerivShapeFunctions.assign(nIP, std::vector<std::vector<double> >(nN, std::vector<double>(dim)));
+    for (int ip = 0; ip < nIP; ip++) for (int i = 0; i < nN; i++) {
+      ipShapeFunctions[ip][i] = sh[(size_t)ip * nN + i];
+      for (int d = 0; d < dim; d++) ipDerivShapeFunctions[ip][i][d] = dsh[((size_t)ip * nN + i) * dim + d];
+    }
+    faceNodes.assign(nFc, std::vector<int>(nNf));
+    for (int f = 0; f < nFc; f++) for (int j = 0; j < nNf; j++) faceNodes[f][j] = fn[(size_t)f * nNf + j];
+    faceElement = new ReferenceElement(dim - 1, ord, geom);
+  }
+  ~ReferenceElement() { delete faceElement; }
+  ReferenceElement(const ReferenceElement&) = delete;
+  ReferenceElement& operator=(const ReferenceElement&) = delete;
+  int getDimension() const { return dimension; }
+  int getOrder() const { return order; }
+  elementGeometry getGeometry() const { return geometry; }
+  const std::string& getGeometryName() const { return geomName; }
+  int getNumNodes() const { return nNodes; }
+  int getNumIPs() const { return (int)ipWeights.size(); }
+  int getNumFaces() const { return nFaces; }
+  const std::vector<std::vector<double> >* getNodes() const { return &nodes; }
+  const std::vector<std::vector<int> >* getFaceNodes() const { return &faceNodes; }
+  const std::vector<std::vector<double> >* getIPCoords() const { return &ipCoords; }
+  const std::vector<double>* getIPWeights() const { return &ipWeights; }
+  const std::vector<std::vector<double> >* getIPShapeFunctions() const { return &ipShapeFunctions; }
+  const std::vector<std::vector<std::vector<double> > >* getIPDerivShapeFunctions() const { return &ipDerivShapeFunctions; }
+  const ReferenceElement* getFaceElement() const { return faceElement; }
+
+ protected:
+  int dimension, order, nNodes = 0, nFaces = 0;
+  elementGeometry geometry = simplex;
+  std::string geomName;
+  std::vector<std::vector<double> > nodes, ipCoords, ipShapeFunctions;
+  std::vector<double> ipWeights;
+  std::vector<std::vector<std::vector<double> > > ipDerivShapeFunctions;
+  std::vector<std::vector<int> > faceNodes;
+  ReferenceElement* faceElement = nullptr;
+};
+
+// ---- src/mesh/Mesh.h -----------------------------------------------------------------------------------------------------
+class Partitioner;
+class Mesh {
+ public:
+  Mesh() {}
+  Mesh(int dim, int order, std::string geom) { setReferenceElement(dim, order, geom); }
+  Mesh(int dim, int order, std::string geom, int dimPointSpace, std::vector<double>& points, std::vector<int>& connectivity) {
+    setReferenceElement(dim, order, geom);
+    setMesh(dimPointSpace, points, connectivity);
+  }
+  ~Mesh() { delete refElement; }
+  Mesh(const Mesh&) = delete;
+  Mesh& operator=(const Mesh&) = delete;
+  void setReferenceElement(int dim, int order, std::string geom) {
+    delete refElement;
+    refElement = new ReferenceElement(dim, order, geom);
+    nNodesPerCell = refElement->getNumNodes();
+    nNodesPerFace = refElement->getFaceElement()->getNumNodes();
+    nFacesPerCell = refElement->getNumFaces();
+  }
+  // src/mesh/Mesh.cpp:31-46: copies the candidates, then computeFaces()
+  void setMesh(int dimPointSpace, std::vector<double>& points_candidate, std::vector<int>& connectivity_candidate) {
+    if (!refElement) throw ErrorHandle("Mesh", "setMesh", "the reference element must be set before the mesh");
+    if (dimPointSpace <= 0 || points_candidate.size() % dimPointSpace != 0) throw ErrorHandle("Mesh", "setMesh", "the points are not consistent with the dimension of the point space");
+    if (connectivity_candidate.size() % nNodesPerCell != 0) throw ErrorHandle("Mesh", "setMesh", "the connectivity is not consistent with the reference element");
+    dimNodeSpace = dimPointSpace;
+    nodes = points_candidate; cells = connectivity_candidate;
+    nNodes = (int)nodes.size() / dimNodeSpace; nCells = (int)cells.size() / nNodesPerCell;
+    computeFaces();
+  }
+  void setPartitioner(Partitioner* p) { part = p; }
+  Partitioner* getPartitioner() { return part; }
+  const std::vector<double>* getPoints() const { return &nodes; }
+  const std::vector<int>* getCells() const { return &cells; }
+  const std::vector<int>* getFaces() const { return &faces; }
+  void getPoint(int i, std::vector<double>* p) const { p->assign(nodes.begin() + (size_t)i * dimNodeSpace, nodes.begin() + (size_t)(i + 1) * dimNodeSpace); }
+  void getCell(int i, std::vector<int>* c) const { c->assign(cells.begin() + (size_t)i * nNodesPerCell, cells.begin() + (size_t)(i + 1) * nNodesPerCell); }
+  void getFace(int i, std::vector<int>* f) const { f->assign(faces.begin() + (size_t)i * nNodesPerFace, faces.begin() + (size_t)(i + 1) * nNodesPerFace); }
+  void getSlicePoints(const std::vector<int>& slice, std::vector<std::vector<double> >* pts) const {
+    pts->resize(slice.size());
+    for (size_t k = 0; k < slice.size(); k++) getPoint(slice[k], &(*pts)[k]);
+  }
+  void getSliceCells(const std::vector<int>& slice, std::vector<std::vector<int> >* out) const {
+    out->resize(slice.size());
+    for (size_t k = 0; k < slice.size(); k++) getCell(slice[k], &(*out)[k]);
+  }
+  void getSliceFaces(const std::vector<int>& slice, std::vector<std::vector<int> >* out) const {
+    out->resize(slice.size());
+    for (size_t k = 0; k < slice.size(); k++) getFace(slice[k], &(*out)[k]);
+  }
+  const ReferenceElement* getReferenceElement() const { return refElement; }
+  int getNumberPoints() const { return nNodes; }
+  int getNumberCells() const { return nCells; }
+  int getNumberFaces() const { return nFaces; }
+  int getDimension() const { return refElement->getDimension(); }
+  int getNodeSpaceDimension() const { return dimNodeSpace; }
+  int getNumFacesPerCell() const { return nFacesPerCell; }
+  const std::vector<int>* getCell2FaceMap() const { return &cell2FaceMap; }
+  void getCell2Face(int i, std::vector<int>* c2f) const { c2f->assign(cell2FaceMap.begin() + (size_t)i * nFacesPerCell, cell2FaceMap.begin() + (size_t)(i + 1) * nFacesPerCell); }
+  const std::vector<int>* getFace2CellMap() const { return &face2CellMap; }
+  void getFace2Cell(int i, std::vector<int>* f2c) const {   // src/mesh/Mesh.cpp: boundary faces list one cell only
+    f2c->clear();
+    for (int k = 0; k < 2; k++) if (face2CellMap[(size_t)2 * i + k] >= 0) f2c->push_back(face2CellMap[(size_t)2 * i + k]);
+  }
+  std::set<int>* getBoundaryFaces() { return &boundaryFaces; }
+
+ protected:
+  // src/mesh/Mesh.cpp:183-274,377-537 (MOAB) -> the product's host topology builder
+  void computeFaces() {
+    const int dim = refElement->getDimension(), order = refElement->getOrder(), geom = refElement->getGeometry() == simplex ? HFX_SIMPLEX : HFX_ORTHOTOPE;
+    int nF = 0, nB = 0;
+    detail::check(hfx_host_compute_faces(dim, order, geom, nCells, cells.data(), &nF, 0, 0, 0, &nB, 0), nullptr);
+    faces.assign((size_t)nF * nNodesPerFace, 0); cell2FaceMap.assign((size_t)nCells * nFacesPerCell, 0); face2CellMap.assign((size_t)nF * 2, -1);
+    std::vector<int> b(nB);
+    detail::check(hfx_host_compute_faces(dim, order, geom, nCells, cells.data(), &nF, faces.data(), cell2FaceMap.data(), face2CellMap.data(), &nB, b.data()), nullptr);
+    nFaces = nF;
+    boundaryFaces = std::set<int>(b.begin(), b.end());
+  }
+  std::vector<double> nodes;
+  std::vector<int> cells, faces, face2CellMap, cell2FaceMap;
+  int dimNodeSpace = 0, nNodes = 0, nCells = 0, nFaces = 0, nNodesPerCell = 0, nNodesPerFace = 0, nFacesPerCell = 0;
+  ReferenceElement* refElement = nullptr;
+  Partitioner* part = nullptr;
+  std::set<int> boundaryFaces;
+};
+
+// ---- src/field/Field.h ---------------------------------------------------------------------------------------------------
+class Field {
+ public:
+  Field() {}
+  explicit Field(Mesh* mesh) : pmesh(mesh) {}
+  Field(Mesh* mesh, FieldType t, int nObjPerEnt, int nValPerObj) : pmesh(mesh), type(t), numObjPerEnt(nObjPerEnt), numValsPerObj(nValPerObj) { allocate(); }
+  virtual ~Field() {}
+  Mesh* getMesh() const { return pmesh; }
+  void setMesh(Mesh* m) { pmesh = m; }
+  int getLength() const { return (int)values.size(); }
+  void computeNumEntities() {   // src/field/Field.cpp:25-39
+    switch (type) {
+      case Node: numEntities = pmesh->getNumberPoints(); break;
+      case Face: numEntities = pmesh->getNumberFaces(); break;
+      case Cell: numEntities = pmesh->getNumberCells(); break;
+      default: throw ErrorHandle("Field", "computeNumEntities", "the field type is not supported");
+    }
+  }
+  void allocate() { computeNumEntities(); values.assign((size_t)numEntities * numObjPerEnt * numValsPerObj, 0.0); }
+  std::vector<double>* getValues() { return &values; }
+  FieldType* getFieldType() { return &type; }
+  int* getNumEntities() { return &numEntities; }
+  int* getNumObjPerEnt() { return &numObjPerEnt; }
+  int* getNumValsPerObj() { return &numValsPerObj; }
+  void getValues(int i, std::vector<double>* vals) {
+    const size_t n = (size_t)numObjPerEnt * numValsPerObj;
+    vals->assign(values.begin() + i * n, values.begin() + (i + 1) * n);
+  }
+  void getSliceValues(std::vector<int>& is, std::vector<double>* vals) {
+    const size_t n = (size_t)numObjPerEnt * numValsPerObj;
+    vals->resize(is.size() * n);
+    for (size_t k = 0; k < is.size(); k++) std::copy(values.begin() + is[k] * n, values.begin() + (is[k] + 1) * n, vals->begin() + k * n);
+  }
+  void setDoubleValued(bool d) { doubleValued = d; }
+  bool isDoubleValued() { return doubleValued; }
+
+ protected:
+  std::vector<double> values;
+  Mesh* pmesh = nullptr;
+  FieldType type = None;
+  int numEntities = 0, numObjPerEnt = 0, numValsPerObj = 0;
+  bool doubleValued = false;
+};
+
+// ---- src/resolution/PetscOpts.h ------------------------------------------------------------------------------------------
+typedef const char* KSPType;
+typedef const char* PCType;
+#ifndef KSPGMRES
+#define KSPGMRES "gmres"
+#define KSPCG "cg"
+#define PCNONE "none"
+#define PCJACOBI "jacobi"
+#define PCBJACOBI "bjacobi"
+#endif
+struct PetscOpts {
+  KSPType solverType{KSPGMRES};
+  PCType preconditionnerType{PCJACOBI};
+  double rtol{1e-6};
+  int maxits{1000};
+  bool verbose{1};
+};
+
+// ---- src/resolution/LinAlgebraInterface.h:23-162 -------------------------------------------------------------------------
+class LinAlgebraInterface {
+ public:
+  virtual ~LinAlgebraInterface() {}
+  virtual void initialize() = 0;
+  virtual void configure() = 0;
+  virtual void allocate(int ndofs, const std::vector<int>* diagSparsePattern = NULL, const std::vector<int>* offSparsePattern = NULL) = 0;
+  virtual void addValMatrix(int i, int j, const double& val) = 0;
+  virtual void addValsMatrix(std::vector<int>& is, std::vector<int>& js, const double* vals) = 0;   // vals row-major |is| x |js|
+  virtual void addValRHS(int i, const double& val) = 0;
+  virtual void addValsRHS(std::vector<int>& is, const double* vals) = 0;
+  virtual void setValMatrix(int i, int j, const double& val) = 0;
+  virtual void setValsMatrix(std::vector<int>& is, std::vector<int>& js, const double* vals) = 0;
+  virtual void setValRHS(int i, const double& val) = 0;
+  virtual void setValsRHS(std::vector<int>& is, const double* vals) = 0;
+  virtual void zeroOutRows(std::vector<int>& is) = 0;
+  virtual void assemble() = 0;
+  virtual void assembleFlush() = 0;
+  virtual void solve(std::vector<double>* solution) = 0;
+  virtual void getSolutionOwnership(std::vector<int>* ownership) = 0;
+  virtual void clearSystem() = 0;
+  virtual void destroySystem() = 0;
+  virtual int getNumDofs() const = 0;
+};
+
+// Drop-in for PetscInterface: device CSR + GMRES(30)/CG with Jacobi (src/resolution/PetscInterface.cpp:60-265)
+class CudaLinAlgebraInterface : public LinAlgebraInterface {
+ public:
+  explicit CudaLinAlgebraInterface(PetscOpts options = PetscOpts(), int device = 0) : myOptions(options), dev(device) {}
+  ~CudaLinAlgebraInterface() { if (lai) hfx_lai_destroy(lai); delete ctx; }
+  void setOptions(PetscOpts options) { myOptions = options; if (lai) pushOpts(); }
+  void initialize() override { ensure(); detail::lcheck(hfx_lai_initialize(lai), lai); }
+  void configure() override { ensure(); pushOpts(); detail::lcheck(hfx_lai_configure(lai), lai); }
+  void allocate(int ndofs, const std::vector<int>* diag = NULL, const std::vector<int>* off = NULL) override {
+    ensure();
+    detail::lcheck(hfx_lai_allocate(lai, ndofs, diag ? diag->data() : NULL, off ? off->data() : NULL), lai);
+  }
+  void addValMatrix(int i, int j, const double& val) override { ensure(); detail::lcheck(hfx_lai_add_val_matrix(lai, i, j, val), lai); }
+  void addValsMatrix(std::vector<int>& is, std::vector<int>& js, const double* vals) override { ensure(); detail::lcheck(hfx_lai_add_vals_matrix(lai, (int)is.size(), is.data(), (int)js.size(), js.data(), vals), lai); }
+  void addValRHS(int i, const double& val) override { ensure(); detail::lcheck(hfx_lai_add_val_rhs(lai, i, val), lai); }
+  void addValsRHS(std::vector<int>& is, const double* vals) override { ensure(); detail::lcheck(hfx_lai_add_vals_rhs(lai, (int)is.size(), is.data(), vals), lai); }
+  void setValMatrix(int i, int j, const double& val) override { ensure(); detail::lcheck(hfx_lai_set_val_matrix(lai, i, j, val), lai); }
+  void setValsMatrix(std::vector<int>& is, std::vector<int>& js, const double* vals) override { ensure(); detail::lcheck(hfx_lai_set_vals_matrix(lai, (int)is.size(), is.data(), (int)js.size(), js.data(), vals), lai); }
+  void setValRHS(int i, const double& val) override { ensure(); detail::lcheck(hfx_lai_set_val_rhs(lai, i, val), lai); }
+  void setValsRHS(std::vector<int>& is, const double* vals) override { ensure(); detail::lcheck(hfx_lai_set_vals_rhs(lai, (int)is.size(), is.data(), vals), lai); }
+  void zeroOutRows(std::vector<int>& is) override { ensure(); detail::lcheck(hfx_lai_zero_out_rows(lai, (int)is.size(), is.data()), lai); }
+  void assemble() override { ensure(); detail::lcheck(hfx_lai_assemble(lai), lai); }
+  void assembleFlush() override { ensure(); detail::lcheck(hfx_lai_assemble_flush(lai), lai); }
+  void solve(std::vector<double>* solution) override {
+    ensure();
+    int n = 0;
+    hfx_lai_get_num_dofs(lai, &n);
+    solution->resize(n);
+    detail::lcheck(hfx_lai_solve(lai, solution->data(), &stats), lai);
+  }
+  void getSolutionOwnership(std::vector<int>* own) override {
+    ensure();
+    int lo = 0, hi = 0;
+    detail::lcheck(hfx_lai_get_solution_ownership(lai, &lo, &hi), lai);
+    own->resize(hi - lo);
+    for (int i = lo; i < hi; i++) (*own)[i - lo] = i;
+  }
+  void clearSystem() override { ensure(); detail::lcheck(hfx_lai_clear_system(lai), lai); }
+  void destroySystem() override { ensure(); detail::lcheck(hfx_lai_destroy_system(lai), lai); }
+  int getNumDofs() const override { int n = 0; if (lai) hfx_lai_get_num_dofs(lai, &n); return n; }
+  // device plumbing shared with HDGSolver
+  hfx_ctx* context() { ensure(); return ctx->h; }
+  hfx_solve_opts cOpts() const {
+    hfx_solve_opts o;
+    o.ksp = std::string(myOptions.solverType) == KSPCG ? 1 : 0;
+    const std::string pc(myOptions.preconditionnerType);
+    o.pc = pc == PCNONE ? 0 : (pc == PCBJACOBI ? 2 : 1);
+    o.restart = 30; o.maxits = myOptions.maxits; o.rtol = myOptions.rtol;
+    return o;
+  }
+  const hfx_solve_stats& getStats() const { return stats; }
+  hfx_solve_stats stats{0, 0.0, 0.0, 0};
+
+ protected:
+  void ensure() {
+    if (!ctx) ctx = new detail::Context(dev);
+    if (!lai) detail::check(hfx_lai_create(ctx->h, &lai), ctx->h);
+  }
+  void pushOpts() { hfx_solve_opts o = cOpts(); hfx_lai_set_opts(lai, &o); }
+  PetscOpts myOptions;
+  int dev = 0;
+  detail::Context* ctx = nullptr;
+  hfx_lai* lai = nullptr;
+};
+
+// ---- src/operator/TimeScheme.h, Euler.h --------------------------------------------------------------------------------------
+class TimeScheme {
+ public:
+  explicit TimeScheme(const ReferenceElement* re) : refEl(re) {}
+  virtual ~TimeScheme() {}
+  void setTimeStep(double timeStep) { deltat = timeStep; }
+  double getTimeStep() const { return deltat; }
+  virtual int cKind() const = 0;
+
+ protected:
+  const ReferenceElement* refEl;
+  double deltat = 0.0;
+};
+class Euler : public TimeScheme {
+ public:
+  Euler(const ReferenceElement* re, bool isExplicitUser = false) : TimeScheme(re), isExplicit(isExplicitUser) {
+    if (isExplicit) throw ErrorHandle("Euler", "Euler", "the explicit Euler scheme has no device kernel");
+  }
+  int cKind() const override { return HFX_TS_EULER_IMPLICIT; }
+
+ protected:
+  bool isExplicit = false;
+};
+
+// ---- src/model/FEModel.h, HDGModel.h, the HDG models ----------------------------------------------------------------------------
+class FEModel {
+ public:
+  explicit FEModel(const ReferenceElement* re) : refEl(re) {}
+  virtual ~FEModel() {}
+  virtual void allocate(int nDOFsPerNode) = 0;
+  void setTimeScheme(TimeScheme* ts) {   // src/model/FEModel.cpp:15-20
+    if (allocated) throw ErrorHandle("FEModel", "setTimeScheme", "the time scheme must be set before allocation or field setting");
+    timeScheme = ts;
+  }
+  virtual const AssemblyType* getAssemblyType() const { return &assembly; }
+  const ReferenceElement* getReferenceElement() const { return refEl; }
+  TimeScheme* getTimeScheme() const { return timeScheme; }
+  typedef std::function<double(const std::vector<double>&)> ScalarFunction;
+
+ protected:
+  const ReferenceElement* refEl;
+  TimeScheme* timeScheme = NULL;
+  bool allocated = 0;
+  AssemblyType assembly{Add, Add};
+};
+
+class HDGModel : public FEModel {
+ public:
+  using FEModel::FEModel;
+  void allocate(int nDOFsPerNode) override {
+    if (nDOFsPerNode < 1) throw ErrorHandle("HDGOperator", "allocate", "the number of DOFs per node must be at least one");
+    nDOFsPNode = nDOFsPerNode; allocated = 1;
+  }
+  // operator descriptor for the device (Base is always present, src/model/HDGModel.cpp:28-32); fieldNames = names in the solver's field map
+  virtual int opmask(const std::set<std::string>& fieldNames, bool strict) const = 0;
+  virtual bool usesDiffusionField() const { return true; }
+  const ScalarFunction& sourceFunction() const { return source; }
+  const ScalarFunction& reactionFunction() const { return reaction; }
+  int getNumDOFsPerNode() const { return nDOFsPNode; }
+
+ protected:
+  int nDOFsPNode = 1;
+  ScalarFunction source, reaction;
+};
+
+class HDGLaplaceModel : public HDGModel {   // Base + Diffusion(D = I)  (src/model/HDGLaplaceModel.cpp:18-30)
+ public:
+  using HDGModel::HDGModel;
+  int opmask(const std::set<std::string>&, bool) const override { return HFX_OP_DIFFUSION; }
+  bool usesDiffusionField() const override { return false; }
+};
+
+class HDGDiffusionSource : public HDGModel {   // Base + Diffusion(DiffusionTensor) ; rhs = Source  (src/model/HDGDiffusionSource.cpp:43-85)
+ public:
+  using HDGModel::HDGModel;
+  void setSourceFunction(ScalarFunction s) {
+    if (!allocated) throw ErrorHandle("HDGDiffusionSource", "setSourceFunction", "the model must be allocated before setting the source function");
+    source = s;
+  }
+  int opmask(const std::set<std::string>&, bool strict) const override {
+    if (!source && strict) throw ErrorHandle("Source", "calcSource", "must set a source function before calculating the source.");
+    return HFX_OP_DIFFUSION | (source ? HFX_OP_SOURCE : 0);
+  }
+};
+
+class HDGConvectionDiffusionReactionSource : public HDGModel {   // src/model/HDGConvectionDiffusionReactionSource.cpp:69-108
+ public:
+  using HDGModel::HDGModel;
+  void setSourceFunction(ScalarFunction s) {
+    if (!allocated) throw ErrorHandle("HDGConvectionDiffusionReactionSource", "setSourceFunction", "the model must be allocated before setting the source function");
+    source = s;
+  }
+  void setReactionFunction(ScalarFunction r) {
+    if (!allocated) throw ErrorHandle("HDGConvectionDiffusionReactionSource", "setReactionFunction", "the model must be allocated before setting the reaction function");
+    reaction = r;
+  }
+  int opmask(const std::set<std::string>& names, bool) const override {
+    const bool v = names.count("Velocity"), d = names.count("DiffusionTensor");
+    if (!v && !d) throw ErrorHandle("HDGConvectionDiffusionReactionSource", "setFieldMap", "must provide at least either a Velocity field or a DiffusionTensor field");
+    return (v ? HFX_OP_CONVECTION : 0) | (d ? HFX_OP_DIFFUSION : 0) | (reaction ? HFX_OP_REACTION : 0) | (source ? HFX_OP_SOURCE : 0);
+  }
+};
+
+enum BoundaryModelType { CGType, HDGType };
+class BoundaryModel : public FEModel {
+ public:
+  using FEModel::FEModel;
+  BoundaryModelType getBoundaryModelType() const { return myType; }
+  virtual int cKind() const = 0;
+
+ protected:
+  BoundaryModelType myType = CGType;
+};
+class DirichletModel : public BoundaryModel {   // assembly = {Set, Set}, I, g  (src/model/DirichletModel.cpp:19-44)
+ public:
+  explicit DirichletModel(const ReferenceElement* re) : BoundaryModel(re) { assembly.matrix = Set; assembly.rhs = Set; }
+  void allocate(int) override { allocated = 1; }
+  int cKind() const override { return HFX_BC_DIRICHLET; }
+};
+class IntegratedDirichletModel : public BoundaryModel {   // face mass, M g  (src/model/IntegratedDirichletModel.cpp)
+ public:
+  explicit IntegratedDirichletModel(const ReferenceElement* re) : BoundaryModel(re) { assembly.matrix = Set; assembly.rhs = Set; }
+  void allocate(int) override { allocated = 1; }
+  int cKind() const override { return HFX_BC_INTEGRATED_DIRICHLET; }
+};
+
+// ---- src/solver/Solver.h, HDGSolverOpts.h, HDGSolver.h ------------------------------------------------------------------------
+enum HDGSolverType { IMPLICIT, WEXPLICIT, SEXPLICIT };
+struct HDGSolverOpts { HDGSolverType type = IMPLICIT; bool verbosity = 1; };
+
+class Solver {
+ public:
+  Solver() {}
+  virtual ~Solver() {}
+  virtual void setModel(FEModel* m) { model = m; }
+  virtual void setBoundaryModel(BoundaryModel* m) {
+    if (myMesh == NULL) throw ErrorHandle("Solver", "setBoundaryModel", "must set the Mesh before the boundary model.");
+    boundaryList.push_back(std::make_tuple(m, myMesh->getBoundaryFaces()));
+  }
+  virtual void setBoundaryCondition(BoundaryModel* m, std::set<int>* faces) { boundaryList.push_back(std::make_tuple(m, faces)); }
+  virtual void setLinSystem(LinAlgebraInterface* lai) { linSystem = lai; }
+  virtual void setFieldMap(std::map<std::string, Field*>* fm) { fieldMap = fm; }
+  virtual void setMesh(Mesh* m) { myMesh = m; meshUploaded = false; }
+  virtual void setVerbosity(bool v) { verbose = v; }
+  virtual void initialize() {   // src/solver/Solver.cpp:5-12
+    if (linSystem != NULL) { linSystem->destroySystem(); linSystem->initialize(); linSystem->configure(); }
+    initialized = 1;
+  }
+  virtual void allocate() = 0;
+  virtual void assemble() = 0;
+  virtual void solve() = 0;
+
+ protected:
+  LinAlgebraInterface* linSystem = NULL;
+  FEModel* model = NULL;
+  std::vector<std::tuple<BoundaryModel*, std::set<int>*> > boundaryList;
+  std::map<std::string, Field*>* fieldMap = NULL;
+  Mesh* myMesh = NULL;
+  int nDOFsPerNode = 1;
+  bool initialized = 0, allocated = 0, assembled = 0, verbose = 1, meshUploaded = false;
+};
+
+class HDGSolver : public Solver {
+ public:
+  using Solver::Solver;
+  ~HDGSolver() { delete ownCtx; }
+  void setOptions(HDGSolverOpts opts) {
+    if (opts.type != IMPLICIT) throw ErrorHandle("HDGSolver", "setOptions", "only the IMPLICIT solver type has a device path");
+    myOpts = opts;
+  }
+  void setDevice(int d) { device = d; }
+  void keepLocalS(bool k) { keepS = k; }
+
+  void allocate() override {   // src/solver/HDGSolver.cpp:5-106
+    if (!initialized) throw ErrorHandle("HDGSolver", "allocate", "must initialize the solver before allocating.");
+    if (myMesh == NULL) throw ErrorHandle("HDGSolver", "allocate", "must set the Mesh before allocating.");
+    if (linSystem == NULL) throw ErrorHandle("HDGSolver", "allocate", "must set the linear system before allocating.");
+    if (model == NULL) throw ErrorHandle("HDGSolver", "allocate", "must set the model before allocating.");
+    if (boundaryList.empty()) throw ErrorHandle("HDGSolver", "allocate", "must set the boundary model before allocating.");
+    if (fieldMap == NULL || fieldMap->size() == 0) throw ErrorHandle("HDGSolver", "allocate", "must set the fields before allocating.");
+    const ReferenceElement* re = myMesh->getReferenceElement();
+    const int nN = re->getNumNodes(), nNf = re->getFaceElement()->getNumNodes();
+    Field* f = need("Solution");
+    if (*f->getFieldType() != Cell) throw ErrorHandle("HDGSolver", "allocate", "the Solution field must be a cell field.");
+    if (*f->getNumObjPerEnt() != nN) throw ErrorHandle("HDGSolver", "allocate", "the Solution field must have an object per element node.");
+    nDOFsPerNode = *f->getNumValsPerObj();
+    f = need("Flux");
+    if (*f->getFieldType() != Cell) throw ErrorHandle("HDGSolver", "allocate", "the Flux field must be a cell field.");
+    if (*f->getNumObjPerEnt() != nN) throw ErrorHandle("HDGSolver", "allocate", "the Flux field must have an object per element node.");
+    if (*f->getNumValsPerObj() != nDOFsPerNode * myMesh->getNodeSpaceDimension()) throw ErrorHandle("HDGSolver", "allocate", "the Flux field must represent a spatial derivative of the Solution field.");
+    f = need("Tau");
+    if (*f->getFieldType() != Face) throw ErrorHandle("HDGSolver", "allocate", "the Tau field must be a face field.");
+    if (*f->getNumObjPerEnt() != nNf) throw ErrorHandle("HDGSolver", "allocate", "the Tau field must have an object per element node.");
+    if (*f->getNumValsPerObj() != nDOFsPerNode * nDOFsPerNode && *f->getNumValsPerObj() != 2 * nDOFsPerNode * nDOFsPerNode)
+      throw ErrorHandle("HDGSolver", "allocate", "the Tau field must have the same or twice the number of values per object as the Solution field.");
+    f = need("Trace");
+    if (*f->getFieldType() != Face) throw ErrorHandle("HDGSolver", "allocate", "the Trace field must be a face field.");
+    if (*f->getNumObjPerEnt() != nNf) throw ErrorHandle("HDGSolver", "allocate", "the Trace field must have an object per element node.");
+    if (*f->getNumValsPerObj() != nDOFsPerNode) throw ErrorHandle("HDGSolver", "allocate", "the Trace field must have the same number of values per object as the Solution field.");
+    hfx_ctx* h = ctx();
+    if (!meshUploaded) {
+      detail::check(hfx_refel_set(h, re->getDimension(), re->getOrder(), re->getGeometry() == simplex ? HFX_SIMPLEX : HFX_ORTHOTOPE), h);
+      detail::check(hfx_mesh_set(h, myMesh->getNumberPoints(), myMesh->getPoints()->data(), myMesh->getNumberCells(), myMesh->getCells()->data()), h);
+      detail::check(hfx_mesh_set_topology(h, myMesh->getNumberFaces(), myMesh->getFaces()->data(), myMesh->getCell2FaceMap()->data(), myMesh->getFace2CellMap()->data()), h);
+      meshUploaded = true;
+      xip.clear();
+    }
+    model->allocate(nDOFsPerNode);
+    uploadInputs();
+    describeModel(false);
+    for (size_t i = 0; i < boundaryList.size(); i++) {
+      BoundaryModel* bm = std::get<0>(boundaryList[i]);
+      bm->allocate(nDOFsPerNode);
+      if (bm->getBoundaryModelType() != CGType) throw ErrorHandle("HDGSolver", "applyBoundaryConditions", "only CGType boundary models have a device path");
+      std::vector<int> ids(std::get<1>(boundaryList[i])->begin(), std::get<1>(boundaryList[i])->end());
+      static const int none = 0;
+      detail::check(hfx_boundary_describe(h, bm->cKind(), (int)ids.size(), ids.empty() ? &none : ids.data()), h);
+    }
+    detail::check(hfx_allocate(h, keepS ? HFX_KEEP_LOCAL_S : 0), h);
+    allocated = 1;
+  }
+
+  void assemble() override {   // src/solver/HDGSolver.cpp:166-174
+    if (!(initialized && allocated)) throw ErrorHandle("HDGSolver", "assemble", "the solver must be initialized and allocated before assembling.");
+    uploadInputs();
+    describeModel(true);
+    evalCallbacks();
+    detail::check(hfx_assemble(ctx()), ctx());
+    assembled = 1;
+  }
+
+  void solve() override {   // src/solver/HDGSolver.cpp:677-779: linSystem->solve(Trace) + local recovery
+    if (!assembled) throw ErrorHandle("HDGSolver", "solve", "system must be assembled before solving");
+    hfx_solve_opts o{0, 1, 30, 1000, 1e-6};
+    CudaLinAlgebraInterface* cl = dynamic_cast<CudaLinAlgebraInterface*>(linSystem);
+    if (cl) o = cl->cOpts();
+    detail::check(hfx_solve(ctx(), &o, &stats), ctx());
+    if (cl) cl->stats = stats;
+    const char* out[3] = {"Trace", "Solution", "Flux"};
+    for (int k = 0; k < 3; k++) detail::check(hfx_field_get(ctx(), out[k], fieldMap->at(out[k])->getValues()->data()), ctx());
+  }
+
+  // parity hooks
+  void getCSR(std::vector<long long>* rowptr, std::vector<int>* colidx, std::vector<double>* vals, std::vector<double>* rhs) {
+    long long n = 0, nnz = 0;
+    detail::check(hfx_get_csr(ctx(), &n, &nnz, 0, 0, 0, 0), ctx());
+    if (rowptr) rowptr->resize(n + 1);
+    if (colidx) colidx->resize(nnz);
+    if (vals) vals->resize(nnz);
+    if (rhs) rhs->resize(n);
+    detail::check(hfx_get_csr(ctx(), 0, 0, rowptr ? rowptr->data() : 0, colidx ? colidx->data() : 0, vals ? vals->data() : 0, rhs ? rhs->data() : 0), ctx());
+  }
+  const hfx_solve_stats& getStats() const { return stats; }
+  hfx_ctx* context() { return ctx(); }
+
+ protected:
+  Field* need(const char* name) {
+    std::map<std::string, Field*>::iterator it = fieldMap->find(name);
+    if (it == fieldMap->end()) throw ErrorHandle("HDGSolver", "allocate", std::string("the field map must have a ") + name + " field.");
+    return it->second;
+  }
+  hfx_ctx* ctx() {
+    CudaLinAlgebraInterface* cl = dynamic_cast<CudaLinAlgebraInterface*>(linSystem);
+    if (cl) return cl->context();
+    if (!ownCtx) ownCtx = new detail::Context(device);
+    return ownCtx->h;
+  }
+  static int cType(FieldType t) { return t == Node ? HFX_FIELD_NODE : (t == Face ? HFX_FIELD_FACE : HFX_FIELD_CELL); }
+  std::set<std::string> inputNames() const {
+    static const char* in[] = {"Tau", "Dirichlet", "DiffusionTensor", "Velocity"};
+    std::set<std::string> s;
+    for (int k = 0; k < 4; k++) if (fieldMap->count(in[k])) s.insert(in[k]);
+    const HDGModel* hm = dynamic_cast<const HDGModel*>(model);
+    if (hm && !hm->usesDiffusionField()) s.erase("DiffusionTensor");   // HDGLaplaceModel never reads it
+    if (model->getTimeScheme() && allocated) s.insert("Solution");
+    return s;
+  }
+  void uploadInputs() {
+    const std::set<std::string> names = inputNames();
+    for (std::set<std::string>::const_iterator it = names.begin(); it != names.end(); ++it) {
+      Field* f = fieldMap->at(*it);
+      detail::check(hfx_field_set(ctx(), it->c_str(), cType(*f->getFieldType()), *f->getNumObjPerEnt(), *f->getNumValsPerObj(), f->getValues()->data(), f->isDoubleValued() ? 1 : 0), ctx());
+    }
+  }
+  void describeModel(bool strict) {
+    const HDGModel* hm = dynamic_cast<const HDGModel*>(model);
+    if (!hm) throw ErrorHandle("HDGSolver", "allocate", "the model must be an HDGModel");
+    hfx_model_desc md;
+    md.nDOF = nDOFsPerNode; md.opmask = hm->opmask(inputNames(), strict);
+    TimeScheme* ts = model->getTimeScheme();
+    md.timeScheme = ts ? ts->cKind() : HFX_TS_NONE; md.dt = ts ? ts->getTimeStep() : 0.0;
+    detail::check(hfx_model_describe(ctx(), &md), ctx());
+    mask = md.opmask;
+  }
+  void evalCallbacks() {   // std::function callbacks run on the host at x(IP) (Source.cpp:5-22, Reaction.cpp:5-22)
+    if (!(mask & (HFX_OP_SOURCE | HFX_OP_REACTION))) return;
+    const HDGModel* hm = static_cast<const HDGModel*>(model);
+    const int nC = myMesh->getNumberCells(), nIP = myMesh->getReferenceElement()->getNumIPs(), d = myMesh->getNodeSpaceDimension();
+    if (xip.empty()) { xip.resize((size_t)nC * nIP * d); detail::check(hfx_ip_coords(ctx(), xip.data()), ctx()); }
+    std::vector<double> v((size_t)nC * nIP), pt(d);
+    for (int pass = 0; pass < 2; pass++) {
+      const bool src = pass == 0;
+      if (!(mask & (src ? HFX_OP_SOURCE : HFX_OP_REACTION))) continue;
+      const FEModel::ScalarFunction& fn = src ? hm->sourceFunction() : hm->reactionFunction();
+      for (size_t k = 0; k < v.size(); k++) { pt.assign(xip.begin() + k * d, xip.begin() + (k + 1) * d); v[k] = fn(pt); }
+      detail::check(src ? hfx_source_values(ctx(), v.data()) : hfx_reaction_values(ctx(), v.data()), ctx());
+    }
+  }
+  HDGSolverOpts myOpts;
+  detail::Context* ownCtx = nullptr;
+  int device = 0, mask = 0;
+  bool keepS = false;
+  std::vector<double> xip;
+  hfx_solve_stats stats{0, 0.0, 0.0, 0};
+};
+
+// ---- src/solver/NonLinearWrapper.h / .cpp:41-79 -----------------------------------------------------------------------------
+class NonLinearWrapper {
+ public:
+  NonLinearWrapper() : mySolver(NULL), previousSolution(NULL), currentSolution(NULL), residual(0.0) {
+    residualComputer = vanillaResidualComputer;
+    linearizedSolver = vanillaLinearizedSolver;
+  }
+  void solve() {
+    if (mySolver == NULL) throw ErrorHandle("NonLinearWrapper", "solve", "the Solver must be set before attempting to solve");
+    if (currentSolution == NULL || previousSolution == NULL) throw ErrorHandle("NonLinearWrapper", "solve", "the current and previous Solutions should be set before attempting to solve");
+    std::vector<double>* cur = currentSolution->getValues();
+    std::vector<double>* prev = previousSolution->getValues();
+    for (int it = 0; it < maxIters; it++) {
+      linearizedSolver(mySolver);
+      residual = residualComputer(currentSolution, previousSolution);
+      if (verbose) std::cout << "Non-linear iteration " << it << " : residual = " << residual << std::endl;
+      if (residual < resTol) break;
+      for (size_t k = 0; k < cur->size(); k++) { const double v = (1.0 - dampening) * (*cur)[k] + dampening * (*prev)[k]; (*cur)[k] = v; (*prev)[k] = v; }
+    }
+  }
+  double getResidual() { return residual; }
+  void setResidualTolerance(double tol) { resTol = tol; }
+  void setMaxIterations(int iters) { maxIters = iters; }
+  void setVerbosity(bool v) { verbose = v; }
+  void setSolutionFields(Field* currentSol, Field* prevSol) { currentSolution = currentSol; previousSolution = prevSol; }
+  void setSolver(Solver* solver) { mySolver = solver; }
+  void setResidualComputer(std::function<double(Field*, Field*)> rc) { residualComputer = rc; }
+  void setLinearizedSolver(std::function<void(Solver*)> sc) { linearizedSolver = sc; }
+  void setDampening(double damp) { dampening = damp; }
+
+ protected:
+  static double vanillaResidualComputer(Field* cur, Field* prev) {   // relative l2 change (NonLinearWrapper.cpp:12-39)
+    double diff = 0.0, ref = 0.0;
+    const std::vector<double>&c = *cur->getValues(), &p = *prev->getValues();
+    for (size_t k = 0; k < c.size(); k++) { diff += (c[k] - p[k]) * (c[k] - p[k]); ref += p[k] * p[k]; }
+    return ref != 0.0 ? std::sqrt(diff / ref) : std::sqrt(diff);
+  }
+  static void vanillaLinearizedSolver(Solver* s) { s->assemble(); s->solve(); }
+  std::function<void(Solver*)> linearizedSolver;
+  Solver* mySolver;
+  Field* previousSolution;
+  Field* currentSolution;
+  std::function<double(Field*, Field*)> residualComputer;
+  double residual, resTol = 1e-6, dampening = 0.0;
+  int maxIters = 1000;   // the constructor overrides the header default of 20 (NonLinearWrapper.cpp:5)
+  bool verbose = true;
+};
+
+}  // namespace hfox
+#endif

@@ -1,0 +1,268 @@
+// The reference's own solver / linear-algebra tests rewritten against the C++ mirror (include/hyperfox/) of its class surface:
+//   tests/unittests/solver/TestHDGSolver.cpp:16-100            (call-order contract + constant solution on lightTri2)
+//   tests/unittests/resolution/TestLinAlgebraInterfaces.cpp:29-170 (state machine + three stock systems)
+//   tests/regression/HDG/TestHDGLaplace.cpp:110-139            (u = sin x e^y on the reference's regression meshes, l2 ceiling 1e-2)
+//   tests/regression/HDG/TestHDGDiffusionSource.cpp            (HDGDiffusionSource + source callback: manufactured Poisson)
+// Only differences: meshes come from text exports of the reference's .h5 fixtures (HDF5Io is out of scope), PetscInterface ->
+// CudaLinAlgebraInterface, Catch2's CHECK -> the four-line macros below.
+// usage: test_hdg_path <mesh dir> [section]   sections: contract | solver | lai | laplace | diffsrc
+#include <cstdio>
+#include <fstream>
+#include <numeric>
+
+#include "DirichletModel.h"
+#include "CudaLinAlgebraInterface.h"
+#include "Field.h"
+#include "HDGDiffusionSource.h"
+#include "HDGLaplaceModel.h"
+#include "HDGSolver.h"
+#include "Mesh.h"
+
+using namespace hfox;
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(cond) do { g_checks++; if (!(cond)) { g_fail++; std::printf("FAILED %s:%d  %s\n", __FILE__, __LINE__, #cond); } } while (0)
+#define CHECK_THROWS(expr) do { g_checks++; bool th_ = false; try { expr; } catch (const ErrorHandle&) { th_ = true; } if (!th_) { g_fail++; std::printf("FAILED %s:%d  no throw: %s\n", __FILE__, __LINE__, #expr); } } while (0)
+#define CHECK_NOTHROW(expr) do { g_checks++; try { expr; } catch (const std::exception& e_) { g_fail++; std::printf("FAILED %s:%d  threw (%s): %s\n", __FILE__, __LINE__, e_.what(), #expr); } } while (0)
+
+static void loadMesh(const std::string& path, Mesh* m, int dim) {
+  std::ifstream in(path.c_str());
+  if (!in) throw ErrorHandle("Test", "loadMesh", "cannot open " + path);
+  int nNodes, d, nCells, nN;
+  in >> nNodes >> d >> nCells >> nN;
+  std::vector<double> pts((size_t)nNodes * d);
+  std::vector<int> cells((size_t)nCells * nN);
+  for (size_t i = 0; i < pts.size(); i++) in >> pts[i];
+  for (size_t i = 0; i < cells.size(); i++) in >> cells[i];
+  (void)dim;
+  m->setMesh(d, pts, cells);
+}
+
+// tests/unittests/solver/TestHDGSolver.cpp
+static void testHDGSolver(const std::string& dir, bool compute) {
+  Mesh m(2, 2, "simplex");
+  loadMesh(dir + "/lightTri2.txt", &m, 2);
+  std::map<std::string, Field*> fieldMap;
+  Field sol(&m, Cell, m.getReferenceElement()->getNumNodes(), 1);
+  Field flux(&m, Cell, m.getReferenceElement()->getNumNodes(), 2);
+  Field dir_(&m, Face, m.getReferenceElement()->getFaceElement()->getNumNodes(), 1);
+  Field lambda(&m, Face, m.getReferenceElement()->getFaceElement()->getNumNodes(), 1);
+  Field tau(&m, Face, m.getReferenceElement()->getFaceElement()->getNumNodes(), 1);
+  std::fill(dir_.getValues()->begin(), dir_.getValues()->end(), 3.0);
+  std::fill(tau.getValues()->begin(), tau.getValues()->end(), 1.0);
+  DirichletModel dirMod(m.getReferenceElement()->getFaceElement());
+  HDGLaplaceModel hdgLapMod(m.getReferenceElement());
+  PetscOpts myOpts;
+  myOpts.rtol = 1e-12;
+  myOpts.verbose = false;
+  CudaLinAlgebraInterface petscIFace(myOpts);
+  HDGSolver hdgSolve;
+  CHECK_NOTHROW(hdgSolve.setVerbosity(0));
+  CHECK_THROWS(hdgSolve.solve());
+  CHECK_THROWS(hdgSolve.assemble());
+  CHECK_THROWS(hdgSolve.allocate());
+  CHECK_NOTHROW(hdgSolve.setMesh(&m));
+  CHECK_THROWS(hdgSolve.solve());
+  CHECK_THROWS(hdgSolve.assemble());
+  CHECK_THROWS(hdgSolve.allocate());
+  fieldMap["Solution"] = &sol;
+  fieldMap["Flux"] = &flux;
+  fieldMap["Trace"] = &lambda;
+  fieldMap["Dirichlet"] = &dir_;
+  fieldMap["Tau"] = &tau;
+  CHECK_NOTHROW(hdgSolve.setFieldMap(&fieldMap));
+  CHECK_THROWS(hdgSolve.solve());
+  CHECK_THROWS(hdgSolve.assemble());
+  CHECK_THROWS(hdgSolve.allocate());
+  CHECK_NOTHROW(hdgSolve.setLinSystem(&petscIFace));
+  CHECK_THROWS(hdgSolve.solve());
+  CHECK_THROWS(hdgSolve.assemble());
+  CHECK_THROWS(hdgSolve.allocate());
+  CHECK_NOTHROW(hdgSolve.setModel(&hdgLapMod));
+  CHECK_THROWS(hdgSolve.solve());
+  CHECK_THROWS(hdgSolve.assemble());
+  CHECK_THROWS(hdgSolve.allocate());
+  CHECK_NOTHROW(hdgSolve.setBoundaryModel(&dirMod));
+  CHECK_THROWS(hdgSolve.solve());
+  CHECK_THROWS(hdgSolve.assemble());
+  CHECK_THROWS(hdgSolve.allocate());
+  CHECK_THROWS(hdgSolve.solve());
+  if (!compute) return;   // everything below needs the GPU
+  CHECK_NOTHROW(hdgSolve.initialize());
+  CHECK_NOTHROW(hdgSolve.allocate());
+  CHECK_THROWS(hdgSolve.solve());
+  CHECK_NOTHROW(hdgSolve.assemble());
+  CHECK_NOTHROW(hdgSolve.solve());
+  const std::vector<double>*solVals = sol.getValues(), *fluxVals = flux.getValues(), *traceVals = lambda.getValues();
+  int nNodesPerEl = m.getReferenceElement()->getNumNodes();
+  int nNodesPerFc = m.getReferenceElement()->getFaceElement()->getNumNodes();
+  for (int i = 0; i < m.getNumberCells(); i++) {
+    for (int j = 0; j < nNodesPerEl; j++) {
+      CHECK(std::fabs((*solVals)[i * nNodesPerEl + j] - 3.0) < 1e-12);
+      for (int k = 0; k < 2; k++) CHECK(std::fabs((*fluxVals)[(i * nNodesPerEl + j) * 2 + k]) < 1e-12);
+    }
+  }
+  for (int i = 0; i < m.getNumberFaces(); i++)
+    for (int j = 0; j < nNodesPerFc; j++) CHECK(std::fabs((*traceVals)[i * nNodesPerFc + j] - 3.0) < 1e-12);
+}
+
+// tests/unittests/resolution/TestLinAlgebraInterfaces.cpp
+static void testLinAlgebraInterface() {
+  PetscOpts o;
+  o.rtol = 1e-16;
+  o.maxits = 1000;
+  o.verbose = false;
+  {   // every step throws before its prerequisite (:29-67)
+    CudaLinAlgebraInterface a(o);
+    LinAlgebraInterface* lai = &a;
+    CHECK_THROWS(lai->configure());
+    CHECK_THROWS(lai->allocate(3));
+    CHECK_THROWS(lai->addValMatrix(0, 0, 1.0));
+    CHECK_THROWS(lai->assemble());
+    std::vector<double> x;
+    CHECK_THROWS(lai->solve(&x));
+    CHECK_NOTHROW(lai->initialize());
+    CHECK_THROWS(lai->allocate(3));
+    CHECK_NOTHROW(lai->configure());
+    CHECK_THROWS(lai->addValMatrix(0, 0, 1.0));
+    CHECK_NOTHROW(lai->allocate(3));
+    CHECK_THROWS(lai->solve(&x));
+  }
+  const int sizes[] = {1, 2, 5, 10, 100};
+  for (int s = 0; s < 5; s++) {
+    const int n = sizes[s];
+    CudaLinAlgebraInterface a(o);
+    LinAlgebraInterface* lai = &a;
+    std::vector<int> rows(n);
+    std::iota(rows.begin(), rows.end(), 0);
+    std::vector<double> b(n), x;
+    for (int i = 0; i < n; i++) b[i] = 0.25 + 0.5 * ((i * 7919) % 101) / 101.0;
+    // identity (:70-100)
+    lai->initialize(); lai->configure(); lai->allocate(n);
+    for (int i = 0; i < n; i++) { lai->addValMatrix(i, i, 1.0); lai->addValRHS(i, b[i]); }
+    lai->assemble();
+    lai->solve(&x);
+    CHECK((int)x.size() == n);
+    for (int i = 0; i < n; i++) CHECK(std::fabs(x[i] - b[i]) < 1e-12);
+    // lower triangular ones, rhs = 1..n  => x = 1 (:101-135); vals row-major |is| x |js| (TestPetscInterface.cpp:57-63)
+    lai->destroySystem(); lai->initialize(); lai->configure(); lai->allocate(n);
+    std::vector<double> T((size_t)n * n, 0.0), rhs(n);
+    for (int i = 0; i < n; i++) { rhs[i] = i + 1.0; for (int j = 0; j <= i; j++) T[(size_t)i * n + j] = 1.0; }
+    lai->addValsMatrix(rows, rows, T.data());
+    lai->addValsRHS(rows, rhs.data());
+    lai->assemble();
+    lai->solve(&x);
+    for (int i = 0; i < n; i++) CHECK(std::fabs(x[i] - 1.0) < 1e-10);
+    // "hinge": 2 on the diagonal, -1 below (:136-170), INSERT mode after clearSystem
+    lai->clearSystem();
+    std::vector<double> H((size_t)n * n, 0.0), xs(n), hb(n, 0.0);
+    for (int i = 0; i < n; i++) { H[(size_t)i * n + i] = 2.0; if (i > 0) H[(size_t)i * n + i - 1] = -1.0; xs[i] = b[n - 1 - i]; }
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) hb[i] += H[(size_t)i * n + j] * xs[j];
+    lai->setValsMatrix(rows, rows, H.data());
+    lai->setValsRHS(rows, hb.data());
+    lai->assemble();
+    lai->solve(&x);
+    for (int i = 0; i < n; i++) CHECK(std::fabs(x[i] - xs[i]) < 1e-10);
+  }
+}
+
+static double anaLaplace(const std::vector<double>& x) { return std::sin(x[0]) * std::exp(x[1]); }   // TestHDGLaplace.cpp:20-28
+
+// tests/regression/HDG/TestHDGLaplace.cpp:30-139 (one mesh per call)
+static void testLaplace(const std::string& path, int dim, int order) {
+  Mesh m(dim, order, "simplex");
+  loadMesh(path, &m, dim);
+  const int nN = m.getReferenceElement()->getNumNodes(), nNf = m.getReferenceElement()->getFaceElement()->getNumNodes();
+  Field sol(&m, Cell, nN, 1), flux(&m, Cell, nN, dim), dirichlet(&m, Face, nNf, 1), trace(&m, Face, nNf, 1), tau(&m, Face, nNf, 1);
+  std::fill(tau.getValues()->begin(), tau.getValues()->end(), 1.0);
+  std::vector<int> face;
+  std::vector<double> pt;
+  for (std::set<int>::const_iterator it = m.getBoundaryFaces()->begin(); it != m.getBoundaryFaces()->end(); ++it) {
+    m.getFace(*it, &face);
+    for (int j = 0; j < nNf; j++) { m.getPoint(face[j], &pt); (*dirichlet.getValues())[(size_t)*it * nNf + j] = anaLaplace(pt); }
+  }
+  std::map<std::string, Field*> fieldMap;
+  fieldMap["Solution"] = &sol; fieldMap["Flux"] = &flux; fieldMap["Dirichlet"] = &dirichlet; fieldMap["Trace"] = &trace; fieldMap["Tau"] = &tau;
+  PetscOpts myOpts;
+  myOpts.maxits = 20000; myOpts.rtol = 1e-12; myOpts.verbose = false;
+  CudaLinAlgebraInterface lai(myOpts);
+  HDGLaplaceModel model(m.getReferenceElement());
+  DirichletModel dirMod(m.getReferenceElement()->getFaceElement());
+  HDGSolver solver;
+  solver.setVerbosity(false);
+  solver.setMesh(&m); solver.setFieldMap(&fieldMap); solver.setLinSystem(&lai); solver.setModel(&model); solver.setBoundaryModel(&dirMod);
+  solver.initialize(); solver.allocate(); solver.assemble(); solver.solve();
+  CHECK(solver.getStats().converged == 1);
+  double num = 0.0, den = 0.0;
+  std::vector<int> cell;
+  for (int c = 0; c < m.getNumberCells(); c++) {
+    m.getCell(c, &cell);
+    for (int i = 0; i < nN; i++) { m.getPoint(cell[i], &pt); const double a = anaLaplace(pt), e = (*sol.getValues())[(size_t)c * nN + i] - a; num += e * e; den += a * a; }
+  }
+  const double l2 = std::sqrt(num / den);
+  std::printf("  laplace %s: %d cells, gmres its %d, nodal relative l2 error %.3e\n", path.c_str(), m.getNumberCells(), solver.getStats().iterations, l2);
+  CHECK(l2 < 1e-2);
+}
+
+// HDGDiffusionSource with a std::function source: -lap u = f, u = sin(pi x) sin(pi y) (manufactured), homogeneous Dirichlet data from u
+static void testDiffusionSource(const std::string& path) {
+  const double pi = 3.14159265358979323846;
+  Mesh m(2, 3, "simplex");
+  loadMesh(path, &m, 2);
+  const int nN = m.getReferenceElement()->getNumNodes(), nNf = m.getReferenceElement()->getFaceElement()->getNumNodes();
+  Field sol(&m, Cell, nN, 1), flux(&m, Cell, nN, 2), dirichlet(&m, Face, nNf, 1), trace(&m, Face, nNf, 1), tau(&m, Face, nNf, 1), D(&m, Node, 1, 1);
+  std::fill(tau.getValues()->begin(), tau.getValues()->end(), 1.0);
+  std::fill(D.getValues()->begin(), D.getValues()->end(), 1.0);
+  auto ana = [pi](const std::vector<double>& x) { return std::sin(pi * x[0]) * std::sin(pi * x[1]); };
+  std::vector<int> face;
+  std::vector<double> pt;
+  for (std::set<int>::const_iterator it = m.getBoundaryFaces()->begin(); it != m.getBoundaryFaces()->end(); ++it) {
+    m.getFace(*it, &face);
+    for (int j = 0; j < nNf; j++) { m.getPoint(face[j], &pt); (*dirichlet.getValues())[(size_t)*it * nNf + j] = ana(pt); }
+  }
+  std::map<std::string, Field*> fieldMap;
+  fieldMap["Solution"] = &sol; fieldMap["Flux"] = &flux; fieldMap["Dirichlet"] = &dirichlet; fieldMap["Trace"] = &trace; fieldMap["Tau"] = &tau;
+  fieldMap["DiffusionTensor"] = &D;
+  PetscOpts myOpts;
+  myOpts.maxits = 20000; myOpts.rtol = 1e-12; myOpts.verbose = false;
+  CudaLinAlgebraInterface lai(myOpts);
+  HDGDiffusionSource model(m.getReferenceElement());
+  DirichletModel dirMod(m.getReferenceElement()->getFaceElement());
+  HDGSolver solver;
+  solver.setVerbosity(false);
+  solver.setMesh(&m); solver.setFieldMap(&fieldMap); solver.setLinSystem(&lai); solver.setModel(&model); solver.setBoundaryModel(&dirMod);
+  solver.initialize(); solver.allocate();
+  CHECK_THROWS(solver.assemble());   // Source::calcSource: no source function yet
+  model.setSourceFunction([pi, ana](const std::vector<double>& x) { return 2.0 * pi * pi * ana(x); });
+  solver.assemble(); solver.solve();
+  CHECK(solver.getStats().converged == 1);
+  double num = 0.0, den = 0.0;
+  std::vector<int> cell;
+  for (int c = 0; c < m.getNumberCells(); c++) {
+    m.getCell(c, &cell);
+    for (int i = 0; i < nN; i++) { m.getPoint(cell[i], &pt); const double a = ana(pt), e = (*sol.getValues())[(size_t)c * nN + i] - a; num += e * e; den += a * a; }
+  }
+  const double l2 = std::sqrt(num / den);
+  std::printf("  diffusion-source %s: nodal relative l2 error %.3e\n", path.c_str(), l2);
+  CHECK(l2 < 1e-2);
+}
+
+int main(int argc, char** argv) {
+  if (argc < 2) { std::printf("usage: %s <mesh dir> [contract|solver|lai|laplace|diffsrc]\n", argv[0]); return 2; }
+  const std::string dir = argv[1], sec = argc > 2 ? argv[2] : "all";
+  try {
+    if (sec == "contract") testHDGSolver(dir, false);
+    if (sec == "solver" || sec == "all") testHDGSolver(dir, true);
+    if (sec == "lai" || sec == "all") testLinAlgebraInterface();
+    if (sec == "laplace" || sec == "all") {
+      testLaplace(dir + "/regression_dim-2_h-1e-1_ord-2.txt", 2, 2);
+      testLaplace(dir + "/regression_dim-3_h-2e-1_ord-3.txt", 3, 3);
+    }
+    if (sec == "diffsrc" || sec == "all") testDiffusionSource(dir + "/regression_dim-2_h-1e-1_ord-3.txt");
+  } catch (const std::exception& e) {
+    std::printf("FAILED: uncaught exception: %s\n", e.what());
+    g_fail++;
+  }
+  std::printf("%d checks, %d failed\n", g_checks, g_fail);
+  return g_fail ? 1 : 0;
+}

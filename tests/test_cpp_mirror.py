@@ -1,0 +1,54 @@
+"""The C++ host mirror (include/hyperfox/*.h) of the reference's class surface, driven by the reference's own solver tests
+rewritten against it (tests/cpp/test_hdg_path.cpp).  CPU: it compiles, links against libhfx.so and honours the call-order
+contract without a device.  GPU: the full known-answer cases."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "test_hdg_path.cpp")
+BIN = os.path.join(ROOT, "tests", "cpp", "test_hdg_path")
+MESHES = ["lightTri2", "regression_dim-2_h-1e-1_ord-2", "regression_dim-3_h-2e-1_ord-3", "regression_dim-2_h-1e-1_ord-3"]
+
+
+def build_cpp_test():
+    deps = [SRC, os.path.join(ROOT, "include", "hyperfox", "hyperfox.h"), os.path.join(ROOT, "include", "hfx.h"), os.path.join(ROOT, "hyperfox_b200", "libhfx.so")]
+    if os.path.exists(BIN) and all(os.path.getmtime(BIN) >= os.path.getmtime(d) for d in deps):
+        return BIN
+    libdir = os.path.join(ROOT, "hyperfox_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(ROOT, "include", "hyperfox"), SRC, "-o", BIN,
+                           "-L", libdir, "-lhfx", "-Wl,-rpath," + libdir, "-Wl,-rpath,/usr/local/cuda/lib64"])
+    return BIN
+
+
+@pytest.fixture(scope="module")
+def mesh_dir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("meshes")
+    for name in MESHES:
+        z = np.load(os.path.join(ROOT, "tests", "golden", "meshes", name + ".npz"))
+        nodes, cells = z["nodes"], z["cells"]
+        with open(os.path.join(d, name + ".txt"), "w") as f:
+            f.write("%d %d %d %d\n" % (nodes.shape[0], nodes.shape[1], cells.shape[0], cells.shape[1]))
+            np.savetxt(f, nodes, fmt="%.17g")
+            np.savetxt(f, cells, fmt="%d")
+    return str(d)
+
+
+def run(mesh_dir, section):
+    p = subprocess.run([build_cpp_test(), mesh_dir, section], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return p.stdout
+
+
+def test_cpp_mirror_builds_and_call_order_contract(mesh_dir):
+    """TestHDGSolver.cpp:37-80: every step throws before its prerequisite (no device needed up to initialize())."""
+    out = run(mesh_dir, "contract")
+    assert " 0 failed" in out
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_reference_tests(mesh_dir):
+    out = run(mesh_dir, "all")
+    assert " 0 failed" in out, out

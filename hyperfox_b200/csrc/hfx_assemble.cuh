@@ -330,15 +330,20 @@ __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* 
   if (bad) atomicOr(flag, 1);
 }
 
+__device__ __forceinline__ double det_only(const double (&J)[2][2]) { return J[0][0] * J[1][1] - J[0][1] * J[1][0]; }
+__device__ __forceinline__ double det_only(const double (&J)[3][3]) {
+  const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+  return J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+}
 __device__ __forceinline__ void det_inv(const double (&J)[2][2], double& det, double (&I)[2][2]) {
   det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
-  const double id = 1.0 / det;
+  const double id = fast_rcp(det);
   I[0][0] = J[1][1] * id; I[0][1] = -J[0][1] * id; I[1][0] = -J[1][0] * id; I[1][1] = J[0][0] * id;
 }
 __device__ __forceinline__ void det_inv(const double (&J)[3][3], double& det, double (&I)[3][3]) {
   const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
   det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
-  const double id = 1.0 / det;
+  const double id = fast_rcp(det);
   I[0][0] = c00 * id; I[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id; I[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
   I[1][0] = c01 * id; I[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id; I[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
   I[2][0] = c02 * id; I[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id; I[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
@@ -396,8 +401,10 @@ struct AsmSmem {
   static constexpr int oST = stFits ? oG : oEnd;
   static constexpr int nDoubles = stFits ? oEnd : oEnd + l * ldc;
   // after the doubles: row starts (nFc x int64) then a small int area
-  static constexpr int nInts = 8 + 2 * nFc * t + nFc * nN + nFc * nFc + 5 * nFc + 8;
-  static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * nFc + 4 * (size_t)nInts;
+  static constexpr int nNLUT = ((DIM * t + 7) / 8) * 8;              // column (d,b) of B_d -> offset of row block d + b
+  static constexpr int nKLUT = (((1 + DIM) * t + 3) / 4) * 4;        // P9 reduction index (kind,b) -> operand offsets
+  static constexpr int nInts = 8 + 2 * nFc * t + nFc * nN + nFc * nFc + 5 * nFc + 8 + nNLUT + 2 * nKLUT + nFc * l;
+  static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * (nFc + l) + 4 * (size_t)nInts;
 };
 
 template <int DIM, int P>
@@ -405,7 +412,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   using L = AsmSmem<DIM, P>;
   constexpr int nN = L::nN, t = L::t, nFc = L::nFc, nIP = L::nIP, nIPf = L::nIPf, l = L::l, NW = L::NW;
   constexpr int nNp = L::nNp, tp = L::tp, ldc = L::ldc, ldg = L::ldg, ldw = L::ldw, nJ = L::nJ;
-  constexpr int D2 = DIM * DIM, NT = kAsmThreads;
+  constexpr int D2 = DIM * DIM, NT = kAsmThreads, NWARP = NT / 32;
   constexpr int kTau = 0, kN = 1, kDN = 1 + DIM, kC = 1 + 2 * DIM, kOne = 2 + 2 * DIM;
   constexpr int FWS = tp * t;   // stride between face matrices
   constexpr bool kPrefetch = (nN * DIM <= 64) && (l <= 128) && (nFc * nFc <= 32);
@@ -417,7 +424,8 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   double* B = sm + L::oB; double* R = sm + L::oR; double* FU = sm + L::oFU;
   double* WQ = sm + L::oWQ; double* DSH = sm + L::oDSH; double* FDS = sm + L::oFDS; double* FSH = sm + L::oFSH; double* FFS = sm + L::oFFS;
   long long* ROWS = reinterpret_cast<long long*>(sm + L::nDoubles);   // [nFc] first entry of row (F,0) in vals
-  int* ISM = reinterpret_cast<int*>(ROWS + nFc);                      // [nFc] global face ids
+  long long* RBASE = ROWS + nFc;                                      // [l] first entry of the CSR row of element-local trace row r
+  int* ISM = reinterpret_cast<int*>(RBASE + l);                       // [nFc] global face ids
   int* FN = ISM + 8;                                                  // [nFc*t] faceNodes
   int* PERM = FN + nFc * t;                                           // [nFc*t] element-local -> face-node position
   int* NIF = PERM + nFc * t;                                          // [nFc*nN] node -> position in face (or -1)
@@ -427,6 +435,9 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   int* INTF = BCF + nFc;                                              // [nFc] interior flag
   int* OPP = INTF + nFc;                                              // [nFc] first node not on the face (orientation test)
   int* QCTR = OPP + nFc;                                              // [4] dynamic tile-queue counters
+  int* NLUT = QCTR + 8;                                               // [nNLUT]
+  int* KLUT = NLUT + L::nNLUT;                                        // [nKLUT][2]
+  int* POSROW = KLUT + 2 * L::nKLUT;                                  // [nFc][l] column offset of element-local column cc inside a row of face f
   double* A = G;    // A_d aliases g (dead after the contractions)
   double* ST = sm + L::oST;   // S staging [l][ldc] for the coalesced write-out
   double* Um = SQU; // U aliases Squ (dead after A)
@@ -434,6 +445,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   const bool hasDiff = p.opmask & 1, hasConv = p.opmask & 2, hasReac = (p.opmask & 4) && p.reacIP, hasSrc = (p.opmask & 8) && p.srcIP;
   const bool euler = p.timeScheme == 1;
   const bool diffField = hasDiff && p.diffComps > 0 && p.diff;
+  const bool needSuu = hasConv || hasReac || euler;   // bulk part of Suu: -C^T, reaction mass, Euler mass
 
   // ---- once per CTA: constant tables; padding lanes must hold finite numbers --------------------------------------------
   for (int i = tid; i < L::nDoubles; i += NT) sm[i] = 0.0;
@@ -443,6 +455,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   for (int i = tid; i < nIP * nN; i += NT) PHI[(i / nN) * nNp + (i % nN)] = p.shape[i];
   for (int i = tid; i < nIP + nIPf; i += NT) WQ[i] = i < nIP ? p.w[i] : p.fw[i - nIP];
   if (tid < nFc) { int vn = 0; for (int kk = 0; kk < nN; kk++) if (p.nodeInFace[tid * nN + kk] < 0) { vn = kk; break; } OPP[tid] = vn; }
+  for (int n = tid; n < L::nNLUT; n += NT) { const int nn = n < DIM * t ? n : DIM * t - 1; NLUT[n] = (nn / t) * nN * ldc + (nn % t); }
   __syncthreads();
 
   // reference-mass inverse: each thread keeps its share in registers for the whole kernel (constant-detJ shortcut for M^-1)
@@ -458,23 +471,44 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   double pfX = 0.0, pfTau = 0.0;
   int pfF = 0, pfPerm = 0, pfPos = 0, pfRlen = 0, pfBc = 0, pfInt = 0;
   long long pfRow = 0;
-  auto prefetch = [&](int e) {
+  // two stages: the second one's addresses depend on values loaded by the first (face ids), so it is issued a few phases later --
+  // issuing both back to back parks the issuing warps on the first loads' DRAM latency in the middle of the geometry phase
+  int pfSide = 0;
+  auto prefetchA = [&](int e) {
     if (!kPrefetch || e >= p.nCells) return;
     if (tid < nN * DIM) pfX = p.elemX[(size_t)e * nN * DIM + tid];
     if (tid >= 64 && tid < 64 + l) {
       const int i = tid - 64, f = i / t;
-      const int F = p.cell2face[(size_t)e * nFc + f];
+      pfF = p.cell2face[(size_t)e * nFc + f];
       pfPerm = p.fperm[(size_t)e * l + i];
-      const int side = (p.tauVals == 2) ? p.tauSide[(size_t)e * nFc + f] : 0;
-      pfTau = p.tau[((size_t)F * t + pfPerm) * p.tauVals + side];
+      pfSide = (p.tauVals == 2) ? p.tauSide[(size_t)e * nFc + f] : 0;
     }
-    if (tid >= 192 && tid < 192 + nFc) {
-      const int F = p.cell2face[(size_t)e * nFc + (tid - 192)];
-      pfF = F; pfRow = p.faceRowStart[F]; pfRlen = (int)p.faceNnb[F] * t; pfBc = p.faceBC[F]; pfInt = p.faceInterior[F];
-    }
+    if (tid >= 192 && tid < 192 + nFc) pfF = p.cell2face[(size_t)e * nFc + (tid - 192)];
     if (tid >= 224 && tid < 224 + nFc * nFc) pfPos = p.elemPos[(size_t)e * nFc * nFc + (tid - 224)];
   };
-  prefetch(blockIdx.x);
+  auto prefetchB = [&](int e) {
+    if (!kPrefetch || e >= p.nCells) return;
+    if (tid >= 64 && tid < 64 + l) pfTau = p.tau[((size_t)pfF * t + pfPerm) * p.tauVals + pfSide];
+    if (tid >= 192 && tid < 192 + nFc) { const int F = pfF; pfRow = p.faceRowStart[F]; pfRlen = (int)p.faceNnb[F] * t; pfBc = p.faceBC[F]; pfInt = p.faceInterior[F]; }
+  };
+  prefetchA(blockIdx.x);
+  prefetchB(blockIdx.x);
+
+  // column tiles (8 columns, kind-major) of the weighted face mass contraction that this model needs
+  constexpr int NCT = (nFc * NW + 7) / 8;
+  unsigned baseNeed = 0, intNeed = 0;
+#pragma unroll
+  for (int T = 0; T < NCT; T++) {
+#pragma unroll
+    for (int cidx = 8 * T; cidx < 8 * T + 8; cidx++) {
+      if (cidx < nFc * NW) {
+        const int kind = cidx / nFc;
+        if (kind <= DIM || (kind < kC && diffField) || (kind == kC && hasConv)) baseNeed |= 1u << T;
+        if (kind == kOne) intNeed |= 1u << T;
+      }
+    }
+  }
+  const int kDNe = diffField ? kDN : kN;   // D = I (HDGDiffusion.cpp:102-105): (Dn)_d mass = n_d mass
 
   long long tprev = clock64();
   for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
@@ -521,32 +555,59 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     cp_async_wait_all();
     __syncthreads();
     HFX_PROF(0);
+    unsigned tileNeed = baseNeed;
+#pragma unroll
+    for (int f = 0; f < nFc; f++) if (BCF[f] == 2) tileNeed |= intNeed;
+    // scatter maps of this element (HDGSolver.cpp:596: matRowCols), consumed by the write-out
+    for (int i = tid; i < nFc * l; i += NT) { const int f = i / l, cc = i - f * l; POSROW[i] = POS[f * nFc + cc / t] * t + PERM[cc]; }
+    if (tid < l) { const int f = tid / t; RBASE[tid] = ROWS[f] + (long long)PERM[tid] * RLEN[f]; }
 
-    // ---- P1a: raw Jacobians, one entry per thread (Operator.cpp:14-39) --------------------------------------------------------
-    for (int idx = tid; idx < nIP * D2 + nFc * nIPf * (DIM - 1) * DIM; idx += NT) {
-      if (idx < nIP * D2) {
-        const int ip = idx / D2, r = (idx % D2) / DIM, m = idx % DIM;
-        const double* d = DSH + ip * nN * DIM + r;
-        double s = 0.0;
-#pragma unroll 4
-        for (int i = 0; i < nN; i++) s = fma(d[i * DIM], X[i * DIM + m], s);
-        JR[ip * D2 + r * DIM + m] = s;
-      } else {
-        const int k2 = idx - nIP * D2;
-        const int fi = k2 / ((DIM - 1) * DIM), rm = k2 % ((DIM - 1) * DIM), r = rm / DIM, m = rm % DIM;
-        const int f = fi / nIPf, ip = fi % nIPf;
-        const int* fn = FN + f * t;
-        const double* d = FDS + ip * t * (DIM - 1) + r;
-        double s = 0.0;
-#pragma unroll 2
-        for (int a = 0; a < t; a++) s = fma(d[a * (DIM - 1)], X[fn[a] * DIM + m], s);
-        JR[(nIP + fi) * D2 + r * DIM + m] = s;
+    // ---- P1a: raw Jacobians (Operator.cpp:14-39) as two small tensor-core products: rows (ip, r), reduction over the nodes,
+    //      columns = the DIM coordinates (one 8-wide tile, DIM columns used) ------------------------------------------------------
+    {
+      const int lr = lane >> 2, lc = lane & 3;
+      constexpr int MB = nIP * DIM, MBT = (MB + 7) / 8, MF = nIPf * (DIM - 1), MFT = (MF + 7) / 8;
+      constexpr int KSB = (nN + 3) / 4, KSF1 = (t + 3) / 4;
+      const int mcol = imin(lr, DIM - 1);   // B-operand column held by this lane
+      for (int task = warp; task < MBT + nFc * MFT; task += NWARP) {
+        double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+        if (task < MBT) {
+          const int row = task * 8 + lr, rc = imin(row, MB - 1);
+          const double* pa = DSH + (rc / DIM) * nN * DIM + (rc % DIM);     // dshape[ip][i][r], stride DIM in i
+#pragma unroll
+          for (int ks = 0; ks < KSB; ks++) {
+            const int k = ks * 4 + lc, kk = imin(k, nN - 1);
+            const double a = k < nN ? pa[kk * DIM] : 0.0;
+            const double b = X[kk * DIM + mcol];
+            if (ks & 1) dmma(c1, a, b); else dmma(c0, a, b);
+          }
+          if (row < MB) {
+            if (2 * lc < DIM) JR[row * DIM + 2 * lc] = c0[0] + c1[0];
+            if (2 * lc + 1 < DIM) JR[row * DIM + 2 * lc + 1] = c0[1] + c1[1];
+          }
+        } else {
+          const int tf = task - MBT, f = tf / MFT, row = (tf % MFT) * 8 + lr, rc = imin(row, MF - 1);
+          const int* fn = FN + f * t;
+          const double* pa = FDS + (rc / (DIM - 1)) * t * (DIM - 1) + (rc % (DIM - 1));   // fdshape[ip][a][r], stride DIM-1 in a
+#pragma unroll
+          for (int ks = 0; ks < KSF1; ks++) {
+            const int k = ks * 4 + lc, kk = imin(k, t - 1);
+            const double a = k < t ? pa[kk * (DIM - 1)] : 0.0;
+            const double b = X[fn[kk] * DIM + mcol];
+            if (ks & 1) dmma(c1, a, b); else dmma(c0, a, b);
+          }
+          if (row < MF) {
+            double* dst = JR + (nIP + f * nIPf + row / (DIM - 1)) * D2 + (row % (DIM - 1)) * DIM;
+            if (2 * lc < DIM) dst[2 * lc] = c0[0] + c1[0];
+            if (2 * lc + 1 < DIM) dst[2 * lc + 1] = c0[1] + c1[1];
+          }
+        }
       }
     }
     __syncthreads();
     HFX_PROF(5);
     // the next element's gather flies while this element is computed
-    prefetch(e + gridDim.x);
+    prefetchA(e + gridDim.x);
 
     // ---- P1b: measures, inverses, normals, coefficient interpolation (Operator.cpp:41-84, HDGModel.cpp:53-85, HDGBase.cpp:18-65) --
     for (int k = tid; k < nJ; k += NT) {
@@ -560,14 +621,14 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         double det, I[DIM][DIM];
         det_inv(J, det, I);
         {   // is det J constant over the element?  (then M = det J * reference mass exactly, whatever the geometry does otherwise)
-          double J0[DIM][DIM], det0, I0[DIM][DIM];
+          double J0[DIM][DIM];
 #pragma unroll
           for (int r = 0; r < DIM; r++)
 #pragma unroll
             for (int m = 0; m < DIM; m++) J0[r][m] = JR[r * DIM + m];
-          det_inv(J0, det0, I0);
+          const double det0 = det_only(J0);
           if (!(fabs(det - det0) <= 1e-13 * fabs(det0))) QCTR[3] = 1;
-          if (ip == 0) FU[ev(nN)] = 1.0 / det0;
+          if (ip == 0) FU[ev(nN)] = fast_rcp(det0);
         }
         const double dv = WQ[ip] * det;
         DV[ip] = dv;
@@ -651,14 +712,11 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           const double g01 = J[0][0] * J[DIM - 2][0] + J[0][1] * J[DIM - 2][1] + J[0][2 % DIM] * J[DIM - 2][2 % DIM];
           area = sqrt(g00 * g11 - g01 * g01);
         }
-        double nrm = 0.0;
-#pragma unroll
-        for (int m = 0; m < DIM; m++) nrm = fma(nv[m], nv[m], nrm);
-        nrm = sqrt(nrm);
+        // |J_0 x J_1| = sqrt(det(J J^T)) (2D: |tangent|): the norm of the un-normalised normal is the face measure
         // outward orientation: (x_opposite - x_v0) . n <= 0   (HDGBase.cpp:43-62)
         const int v0 = fn[0];
         const int vn = OPP[f];
-        const double inrm = 1.0 / nrm;
+        const double inrm = fast_rcp(area);
         double prod = 0.0;
 #pragma unroll
         for (int m = 0; m < DIM; m++) { nv[m] *= inrm; prod = fma(X[vn * DIM + m] - X[v0 * DIM + m], nv[m], prod); }
@@ -667,23 +725,23 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           for (int m = 0; m < DIM; m++) nv[m] = -nv[m];
         }
         const double dvf = WQ[nIP + ip] * area;
-        double* wt = FWT + (size_t)ip * ldw + f * NW;
-        wt[kTau] = dvf * tauip;
+        double* wt = FWT + (size_t)ip * ldw + f;          // column (kind, f), kind-major: whole column tiles of unused kinds are skipped
+        wt[kTau * nFc] = dvf * tauip;
         double vdn = 0.0;
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
-          wt[kN + d] = dvf * nv[d];
+          wt[(kN + d) * nFc] = -dvf * nv[d];            // the n_d and (Dn)_d mass matrices are stored NEGATED: that is how Sql, Slq, Suq use them
           double dn = nv[d];
           if (diffField) {
             dn = 0.0;
 #pragma unroll
             for (int b = 0; b < DIM; b++) dn = fma(Dc[b * DIM + d], nv[b], dn);  // (D n)_d, D col-major
           }
-          wt[kDN + d] = hasDiff ? dvf * dn : 0.0;
+          wt[(kDN + d) * nFc] = hasDiff ? -dvf * dn : 0.0;
           vdn = fma(v[d], nv[d], vdn);
         }
-        wt[kC] = hasConv ? dvf * vdn : 0.0;
-        wt[kOne] = dvf;
+        wt[kC * nFc] = hasConv ? dvf * vdn : 0.0;
+        wt[kOne * nFc] = dvf;
       }
     }
     __syncthreads();
@@ -718,7 +776,6 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     // From here on every product runs on the FP64 tensor cores: a phase is a list of warp tasks (8 output rows x up to 3 column
     // tiles of 8), operands are fetched from shared memory one 64-bit word per lane.
     constexpr int MTN = (nN + 7) / 8;           // 8-row tiles over the element nodes
-    constexpr int NWARP = NT / 32;
     constexpr int KS_IP = (nIP + 3) / 4, KS_IPF = (nIPf + 3) / 4, KS_N = (nN + 3) / 4, KS_T = (t + 3) / 4, KS_QN = (DIM * nN + 3) / 4;
 
     // ---- P3a: M = sum_ip dV phi phi^T (Mass.cpp:5-38 / HDGBase.cpp:152) ------------------------------------------------------
@@ -776,7 +833,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           for (int j = 0; j < 3; j++) pb[j] = PHI + imin((ng * 3 + j) * 8 + lr, nN - 1);
           double c[3][2];
           zero_c(c);
-          mma_affine<3, nIP>(c, pa, isSqu ? ldg : nNp, pb, nNp, lc);
+          if (isSqu || needSuu) mma_affine<3, nIP>(c, pa, isSqu ? ldg : nNp, pb, nNp, lc);   // Laplace-type models: bulk Suu = 0
           if (m < mrows) {
 #pragma unroll
             for (int j = 0; j < 3; j++) {
@@ -800,21 +857,31 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           const int tk = task - (T_SQU + T_SUU);
           const int mt = tk % FW_MT, ng = tk / FW_MT;
           const int m = mt * 8 + lr;
-          const double* pa = FFS + imin(m, MR - 1);
-          const double* pb[3];
+          const unsigned need3 = (tileNeed >> (ng * 3)) & 7u;   // column tiles of kinds no operator of this model reads are skipped
+          if (need3) {
+            const double* pa = FFS + imin(m, MR - 1);
+            const double* pb[3];
 #pragma unroll
-          for (int j = 0; j < 3; j++) pb[j] = FWT + imin((ng * 3 + j) * 8 + lr, NC - 1);
-          double c[3][2];
-          zero_c(c);
-          mma_affine<3, nIPf>(c, pa, MR, pb, ldw, lc);
-          if (m < MR) {
-            double* dstm = FW + (m % t) + tp * (m / t);
+            for (int j = 0; j < 3; j++) pb[j] = FWT + imin((ng * 3 + j) * 8 + lr, NC - 1);
+            double c[3][2];
+            zero_c(c);
+            constexpr int KSF = (nIPf + 3) / 4;
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
+            for (int ks = 0; ks < KSF; ks++) {
+              const int k = ks * 4 + lc, kk = k < nIPf ? k : nIPf - 1;
+              const double a = k < nIPf ? pa[kk * MR] : 0.0;
 #pragma unroll
-              for (int h = 0; h < 2; h++) {
-                const int n = (ng * 3 + j) * 8 + 2 * lc + h;
-                if (n < NC) dstm[n * FWS] = c[j][h];
+              for (int j = 0; j < 3; j++) if (need3 & (1u << j)) dmma(c[j], a, pb[j][kk * ldw]);
+            }
+            if (m < MR) {
+              double* dstm = FW + (m % t) + tp * (m / t);
+#pragma unroll
+              for (int j = 0; j < 3; j++) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                  const int n = (ng * 3 + j) * 8 + 2 * lc + h;
+                  if (n < NC && (need3 & (1u << j))) dstm[((n % nFc) * NW + n / nFc) * FWS] = c[j][h];
+                }
               }
             }
           }
@@ -831,6 +898,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     }
     __syncthreads();
     HFX_PROF(4);
+    prefetchB(e + gridDim.x);
 
     // ---- P3c: Suq bulk part with a diffusion field (HDGDiffusion.cpp:31-72,130-144) ----------------------------------------
     if (diffField) {
@@ -878,7 +946,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           const double* fw = FW + f * NW * FWS + a + tp * b;
           suu += fw[kTau * FWS];
 #pragma unroll
-          for (int d = 0; d < DIM; d++) suq[d] -= fw[(kDN + d) * FWS];
+          for (int d = 0; d < DIM; d++) suq[d] += hasDiff ? fw[(kDNe + d) * FWS] : 0.0;
         }
       }
       SUU[i + nNp * j] = suu;
@@ -921,7 +989,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           const int tb = task - T_A, f = tb / (MTN * NG_B), r = tb % (MTN * NG_B);
           const int m = (r % MTN) * 8 + lr, ng = r / MTN;
           const int* fn = FN + f * t;
-          // left operand: gathered columns W[:, fn_f(k)] ; right operand: N_fd[k][b] = FW[(f,kN+d)][k + tp b], column n = (d, b)
+          // left operand: gathered columns W[:, fn_f(k)] ; right operand: -N_fd[k][b] = FW[(f,kN+d)][k + tp b], column n = (d, b)
           const double* wrow = W + imin(m, nN - 1);
           const double* pb[3];
 #pragma unroll
@@ -945,7 +1013,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
               for (int h = 0; h < 2; h++) {
                 const int n = (ng * 3 + j) * 8 + 2 * lc + h;
-                if (n < NB) B[((n / t) * nN + m) * ldc + f * t + (n % t)] = -c[j][h];
+                if (n < NB) B[NLUT[n] + m * ldc + f * t] = c[j][h];
               }
           }
         }
@@ -955,53 +1023,57 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     __syncthreads();
     HFX_PROF(8);
 
-    // ---- P5: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335) and R = Sul - sum_d Suq_d B_d, column l = -Fu (:342-343) -------------
-    //      one output tile per warp task, K loop split over two accumulators (long dependent DMMA chains are latency bound)
+    // ---- P5: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335), R = Sul - sum_d Suq_d B_d with column l = -Fu (:342-343).
+    //      One output tile per warp task, reduction split over two accumulators (long dependent DMMA chains are latency bound).
+    double* const KB = (W == Mm) ? Wb : Mm;          // the buffer that does not hold W (W is dead once A and B exist)
+    double* const KI = ((nNp / 2) & 1) ? KB : SUU;
     {
       const int lr = lane >> 2, lc = lane & 3;
-      constexpr int LT = (l + 7) / 8, T_K = MTN * MTN, T_R = MTN * LT, KQ = DIM * nN, KSQ = (KQ + 3) / 4;
-      for (int task = warp; task < T_K + T_R + 1; task += NWARP) {
-        if (task < T_K + T_R) {
-          const bool isK = task < T_K;
-          const int r = isK ? task : task - T_K;
-          const int m = (r % MTN) * 8 + lr, nt = r / MTN;
-          const int ncl = imin(nt * 8 + lr, isK ? nN - 1 : l);
-          const double* pa = SUQ + imin(m, nN - 1);            // Suq[m][(d,k')], stride nNp in k = (d,k')
-          double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+      constexpr int LT = (l + 7) / 8, T_K = MTN * MTN, T_R = MTN * LT + 1;
+      auto kr_task = [&](bool isK, int r) {
+        if (!isK && r == T_R - 1) {
+          for (int i = lane; i < nN; i += 32) { R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0; }
+          return;
+        }
+        const int m = (r % MTN) * 8 + lr, nt = r / MTN;
+        const int ncl = imin(nt * 8 + lr, isK ? nN - 1 : l);
+        const double* pa = SUQ + imin(m, nN - 1);                                  // Suq[m][(d,k')]: stride nNp in k'
+        const double* pb = isK ? A + ncl * nNp : B + ncl;                          // K: A_d[k'][n] column-major ; R: B_d[k'][n] row-major
+        const int sb = isK ? 1 : ldc, sd = isK ? nN * nNp : nN * ldc;
+        double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
 #pragma unroll
-          for (int ks = 0; ks < KSQ; ks++) {
-            const int k = ks * 4 + lc, kk = k < KQ ? k : KQ - 1;
-            const double a = k < KQ ? pa[kk * nNp] : 0.0;
-            // right operand: K: A_d[k'][n] (column-major per d) ; R: B[(d,k')][n] (row-major, rows stacked over d)
-            const double b = isK ? A[((kk / nN) * nN + ncl) * nNp + (kk % nN)] : B[kk * ldc + ncl];
-            if (ks & 1) dmma(c1, a, b); else dmma(c0, a, b);
+        for (int d = 0; d < DIM; d++) {
+#pragma unroll
+          for (int ks = 0; ks < KS_N; ks++) {
+            const int k = ks * 4 + lc, kk = (ks * 4 + 3 < nN) ? k : imin(k, nN - 1);
+            double a = pa[(d * nN + kk) * nNp];
+            if (ks * 4 + 3 >= nN && k >= nN) a = 0.0;
+            const double b = pb[d * sd + kk * sb];
+            if ((d * KS_N + ks) & 1) dmma(c1, a, b); else dmma(c0, a, b);
           }
-          if (m < nN) {
+        }
+        if (m < nN) {
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const int cc = nt * 8 + 2 * lc + h;
-              const double v = (h ? c0[1] + c1[1] : c0[0] + c1[0]);
-              if (isK) { if (cc < nN) SUU[m + nNp * cc] -= v; }
-              else if (cc < l) {
-                const int f = cc / t, b = cc % t, a = NIF[f * nN + m];
-                double sul = 0.0;
-                if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = fw[kC * FWS] - fw[kTau * FWS]; }
-                R[m * ldc + cc] = sul - v;
-              }
+          for (int h = 0; h < 2; h++) {
+            const int cc = nt * 8 + 2 * lc + h;
+            const double v = (h ? c0[1] + c1[1] : c0[0] + c1[0]);
+            if (isK) { if (cc < nN) SUU[m + nNp * cc] -= v; }
+            else if (cc < l) {
+              const int f = cc / t, b = cc % t, a = NIF[f * nN + m];
+              double sul = 0.0;
+              if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = (hasConv ? fw[kC * FWS] : 0.0) - fw[kTau * FWS]; }
+              R[m * ldc + cc] = sul - v;
             }
           }
-        } else {
-          for (int i = lane; i < nN; i += 32) { R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0; }
         }
-      }
+      };
+      for (int task = warp; task < T_K + T_R; task += NWARP) { if (task < T_K) kr_task(true, task); else kr_task(false, task - T_K); }
     }
     __syncthreads();
     HFX_PROF(9);
-
-    // ---- P6: K^-1 (block Gauss-Jordan) ---------------------------------------------------------------------------------------
-    double* const KB = (W == Mm) ? Wb : Mm;          // the buffer that does not hold W
-    double* const KI = ((nNp / 2) & 1) ? KB : SUU;
-    group_invert<nNp, nNp, NT>(SUU, KB, tid, p.status);   // nothing else can run here: all eight warps share the pivot steps
+    // ---- P6: K^-1 (2x2-block-pivot Gauss-Jordan on all eight warps: the pivot chain is serial, measured variants that ran it on
+    //      four warps or on one warp beside the R tiles were slower) ------------------------------------------------
+    group_invert<nNp, nNp, NT>(SUU, KB, tid, p.status);
     HFX_PROF(10);
 
     // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu (column l) ------------------------------------------------------------------------
@@ -1082,7 +1154,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         for (int ks = 0; ks < KS_S; ks++) {
           const int k = ks * 4 + lc, kk = k < KTOT ? k : KTOT - 1;
           const int kind = kk / t, b = kk % t, nd = fn[b];
-          double av = kind == 0 ? fwf[kTau * FWS + acl + tp * b] : (hasDiff ? -fwf[(kDN + kind - 1) * FWS + acl + tp * b] : 0.0);
+          double av = kind == 0 ? fwf[kTau * FWS + acl + tp * b] : (hasDiff ? fwf[(kDNe + kind - 1) * FWS + acl + tp * b] : 0.0);
           if (k >= KTOT) av = 0.0;
           const double* brow = kind == 0 ? Um + nd * ldc : B + ((kind - 1) * nN + nd) * ldc;
 #pragma unroll
@@ -1101,34 +1173,86 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     __syncthreads();
     HFX_PROF(13);
 
-    // ---- P10: write-out.  Every global store of the element happens here, from shared memory, with consecutive threads on
-    //      consecutive addresses: U, Q (column-major, contiguous per element) and the CSR rows of S in t-long segments ----------
+    // ---- P10: write-out.  Every global store of the element happens here, from shared memory.  U/Q: a lane owns one output row
+    //      (consecutive lanes -> consecutive addresses), a warp owns column pairs.  S: a warp owns rows, a lane owns columns
+    //      (consecutive lanes -> consecutive, permuted, CSR entries of one row).  All loops have compile-time trip counts and are
+    //      unrolled with the shared-memory loads batched ahead of the stores: this phase is latency-, not bandwidth-bound. -----
     {
-      double* gU = p.U + (size_t)e * nN * l;
-      for (int idx = tid; idx < nN * l; idx += NT) gU[idx] = Um[(idx % nN) * ldc + idx / nN];
-      if (tid < nN) p.U0[(size_t)e * nN + tid] = Um[tid * ldc + l];
       constexpr int q = DIM * nN;
+      constexpr int NPAIR = (l + 1) / 2, CPW = (NPAIR + NWARP - 1) / NWARP;
+      double* gU = p.U + (size_t)e * nN * l;
+#pragma unroll
+      for (int h = 0; h < (nN + 31) / 32; h++) {
+        const int r = lane + 32 * h;
+        if (r < nN) {
+          const double* src = Um + r * ldc;
+          double2 v[CPW];
+#pragma unroll
+          for (int i = 0; i < CPW; i++) { const int c = 2 * (warp + NWARP * i); v[i] = (c < l) ? *reinterpret_cast<const double2*>(src + c) : make_double2(0.0, 0.0); }
+#pragma unroll
+          for (int i = 0; i < CPW; i++) {
+            const int c = 2 * (warp + NWARP * i);
+            if (c < l) gU[(size_t)c * nN + r] = v[i].x;
+            if (c + 1 < l) gU[(size_t)(c + 1) * nN + r] = v[i].y;
+          }
+        }
+      }
+      if (tid < nN) p.U0[(size_t)e * nN + tid] = Um[tid * ldc + l];
       double* gQ = p.Q + (size_t)e * q * l;
-      for (int idx = tid; idx < q * l; idx += NT) {
-        const int rq = idx % q, c = idx / q;
-        gQ[idx] = B[((rq % DIM) * nN + rq / DIM) * ldc + c];
+#pragma unroll
+      for (int h = 0; h < (q + 31) / 32; h++) {
+        const int rq = lane + 32 * h;
+        if (rq < q) {
+          const double* src = B + ((rq % DIM) * nN + rq / DIM) * ldc;
+          double2 v[CPW];
+#pragma unroll
+          for (int i = 0; i < CPW; i++) { const int c = 2 * (warp + NWARP * i); v[i] = (c < l) ? *reinterpret_cast<const double2*>(src + c) : make_double2(0.0, 0.0); }
+#pragma unroll
+          for (int i = 0; i < CPW; i++) {
+            const int c = 2 * (warp + NWARP * i);
+            if (c < l) gQ[(size_t)c * q + rq] = v[i].x;
+            if (c + 1 < l) gQ[(size_t)(c + 1) * q + rq] = v[i].y;
+          }
+        }
       }
       if (tid < q) p.Q0[(size_t)e * q + tid] = B[((tid % DIM) * nN + tid / DIM) * ldc + l];
       double* gS = p.S ? p.S + (size_t)e * l * l : nullptr;
       double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
-      for (int idx = tid; idx < l * l; idx += NT) {
-        const int r = idx / l, cc = idx % l;
-        const int f = r / t, a = r % t, f2 = cc / t, b2 = cc % t;
-        const double* fwf = FW + f * NW * FWS;
-        const int bc = BCF[f];
-        double sv = ST[r * ldc + cc];
-        if (f2 == f) sv += fwf[kC * FWS + a + tp * b2] - fwf[kTau * FWS + a + tp * b2];   // Sll = -tau mass + (v.n) mass
-        if (bc == 1) sv = (f2 == f && b2 == a) ? 1.0 : 0.0;                                 // DirichletModel row (Set)
-        else if (bc == 2) sv = (f2 == f) ? fwf[kOne * FWS + a + tp * b2] : 0.0;             // IntegratedDirichletModel row
-        if (gS) gS[r + (size_t)l * cc] = sv;
-        const int prow = PERM[r];
-        double* dst = p.vals + ROWS[f] + (long long)prow * RLEN[f] + POS[f * nFc + f2] * t + PERM[f2 * t + b2];
-        if (f2 == f && INTF[f]) atomicAdd(dst, sv); else *dst = sv;
+      constexpr int RPW = (l + NWARP - 1) / NWARP;
+#pragma unroll
+      for (int h = 0; h < (l + 31) / 32; h++) {
+        const int cc = lane + 32 * h;
+        if (cc < l) {
+          const int f2 = cc / t, b2 = cc - f2 * t;
+          double sv[RPW];
+          int off[RPW];
+#pragma unroll
+          for (int i = 0; i < RPW; i++) {
+            const int r = warp + NWARP * i;
+            if (r < l) {
+              const int f = r / t, a = r - f * t, bc = BCF[f];
+              const double* fwd = FW + f * NW * FWS + a + tp * b2;
+              const bool diag = (f2 == f);
+              double v = ST[r * ldc + cc];
+              const double dterm = (hasConv ? fwd[kC * FWS] : 0.0) - fwd[kTau * FWS];   // Sll = -tau mass + (v.n) mass
+              v += diag ? dterm : 0.0;
+              if (bc == 1) v = (diag && b2 == a) ? 1.0 : 0.0;                            // DirichletModel row (Set)
+              else if (bc == 2) v = diag ? fwd[kOne * FWS] : 0.0;                        // IntegratedDirichletModel row
+              sv[i] = v;
+              off[i] = POSROW[f * l + cc];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < RPW; i++) {
+            const int r = warp + NWARP * i;
+            if (r < l) {
+              const int f = r / t;
+              if (gS) gS[r + (size_t)l * cc] = sv[i];
+              double* dst = p.vals + RBASE[r] + off[i];
+              if (f2 == f && INTF[f]) atomicAdd(dst, sv[i]); else *dst = sv[i];
+            }
+          }
+        }
       }
       if (tid < l) {
         const int r = tid, f = r / t, a = r % t, F = ISM[f], bc = BCF[f];
@@ -1145,6 +1269,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
     }
     __syncthreads();
+    HFX_PROF(15);
   }
 }
 

@@ -8,14 +8,14 @@ hdr = None; cur = None; curfile = ""
 per = collections.OrderedDict()
 for r in rows:
     if len(r) == 2 and r[0] == "File Path": curfile = r[1].split("/")[-1]; continue
-    if len(r) > 5 and r[0] == "Line No": hdr = r; iI = hdr.index("Instructions Executed"); iS = hdr.index("# Samples"); iW = hdr.index("L1 Wavefronts Shared"); continue
+    if len(r) > 5 and r[0] == "Line No": hdr = r; iI = hdr.index("Instructions Executed"); iS = hdr.index("# Samples"); iW = hdr.index("L1 Wavefronts Shared"); iX = hdr.index("L1 Wavefronts Shared Excessive"); continue
     if hdr is None or len(r) < len(hdr): continue
     if r[0] != "":
-        cur = (curfile, int(r[0]), r[1].strip()); per.setdefault(cur, [0, 0, 0, collections.Counter()]); continue
+        cur = (curfile, int(r[0]), r[1].strip()); per.setdefault(cur, [0, 0, 0, collections.Counter(), 0]); continue
     if cur is None: continue
-    try: ins = int(r[iI]); smp = int(r[iS]); wv = int(r[iW])
+    try: ins = int(r[iI]); smp = int(r[iS]); wv = int(r[iW]); xs = int(r[iX])
     except ValueError: continue
-    a = per[cur]; a[0] += ins; a[1] += smp; a[2] += wv
+    a = per[cur]; a[0] += ins; a[1] += smp; a[2] += wv; a[4] += xs
     op = r[3].split()[0] if not r[3].strip().startswith("@") else r[3].split()[1]
     a[3][op.split(".")[0]] += ins
 totI = sum(v[0] for v in per.values()); totS = sum(v[1] for v in per.values()); totW = sum(v[2] for v in per.values())
@@ -45,3 +45,8 @@ for p, a in agg.items(): print("%-18s %8.1f %8.1f %8.1f" % (p, 100.0 * a[0] / to
 print("\ntop lines by samples:")
 for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])[:top]:
     print("%5d %5.1f%% smp %5.1f%% ins %5.1f%% wf | %s | %s" % (k[1], 100.0 * v[1] / max(totS, 1), 100.0 * v[0] / totI, 100.0 * v[2] / max(totW, 1), k[2][:90], dict(v[3].most_common(4))))
+
+totX = sum(v[4] for v in per.values())
+print("\ntop lines by shared-memory wavefronts (excessive = beyond the conflict-free minimum; total excessive %.1f%% of all):" % (100.0 * totX / max(totW, 1)))
+for k, v in sorted(per.items(), key=lambda kv: -kv[1][2])[:top]:
+    print("%5d %5.1f%% wf (%5.1f%% of them excessive) %5.1f%% ins | %s" % (k[1], 100.0 * v[2] / max(totW, 1), 100.0 * v[4] / max(v[2], 1), 100.0 * v[0] / totI, k[2][:100]))

@@ -40,7 +40,7 @@ struct AsmParams {
   const double* srcIP; const double* reacIP;
   const double* solOld;
   const double* dirichlet;
-  int opmask; int timeScheme;
+  int opmask; int timeScheme; double dt;
   // tables (device global, read-only)
   const double* shape; const double* dshape; const double* w;
   const double* fshape; const double* fdshape; const double* fw;
@@ -444,6 +444,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool hasDiff = p.opmask & 1, hasConv = p.opmask & 2, hasReac = (p.opmask & 4) && p.reacIP, hasSrc = (p.opmask & 8) && p.srcIP;
   const bool euler = p.timeScheme == 1;
+  const double ts = euler ? p.dt : 1.0;   // Euler::apply scales the u rows (Su, Fu) by dt before adding the mass terms (Euler.cpp:28-32)
   const bool diffField = hasDiff && p.diffComps > 0 && p.diff;
   const bool needSuu = hasConv || hasReac || euler;   // bulk part of Suu: -C^T, reaction mass, Euler mass
 
@@ -661,10 +662,10 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           for (int d = 0; d < DIM; d++) VIP[ip * DIM + d] = v[d];
         }
         double lw = 0.0;
-        if (hasReac) lw += p.reacIP[(size_t)e * nIP + ip] * dv;
+        if (hasReac) lw += ts * p.reacIP[(size_t)e * nIP + ip] * dv;
         if (euler) lw += dv;
         LW[ip] = lw;
-        double rw = hasSrc ? p.srcIP[(size_t)e * nIP + ip] * dv : 0.0;
+        double rw = hasSrc ? ts * p.srcIP[(size_t)e * nIP + ip] * dv : 0.0;
         if (euler) {   // Mass * Solution_old = sum_ip dV phi_i(ip) u_old(ip)
           const double* so = p.solOld + (size_t)e * nN;
           double uo = 0.0;
@@ -765,7 +766,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       double c = LW[ip] * PHI[ip * nNp + i];
       if (hasConv) {
 #pragma unroll
-        for (int m = 0; m < DIM; m++) c = fma(-VIP[ip * DIM + m], gg[m], c);
+        for (int m = 0; m < DIM; m++) c = fma(-ts * VIP[ip * DIM + m], gg[m], c);
       }
       CG[ip * nNp + i] = c;
     }
@@ -944,14 +945,14 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         const int a = NIF[f * nN + i], b = NIF[f * nN + j];
         if (a >= 0 && b >= 0) {
           const double* fw = FW + f * NW * FWS + a + tp * b;
-          suu += fw[kTau * FWS];
+          suu += ts * fw[kTau * FWS];
 #pragma unroll
           for (int d = 0; d < DIM; d++) suq[d] += hasDiff ? fw[(kDNe + d) * FWS] : 0.0;
         }
       }
       SUU[i + nNp * j] = suu;
 #pragma unroll
-      for (int d = 0; d < DIM; d++) SUQ[(d * nN + j) * nNp + i] = suq[d];
+      for (int d = 0; d < DIM; d++) SUQ[(d * nN + j) * nNp + i] = ts * suq[d];
     }
     if ((nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal of K for the 2x2-block Gauss-Jordan
       for (int j = 0; j < nN; j++) { SUU[nN + nNp * j] = 0.0; SUU[j + nNp * nN] = 0.0; }
@@ -1061,7 +1062,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
             else if (cc < l) {
               const int f = cc / t, b = cc % t, a = NIF[f * nN + m];
               double sul = 0.0;
-              if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = (hasConv ? fw[kC * FWS] : 0.0) - fw[kTau * FWS]; }
+              if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = ts * ((hasConv ? fw[kC * FWS] : 0.0) - fw[kTau * FWS]); }
               R[m * ldc + cc] = sul - v;
             }
           }

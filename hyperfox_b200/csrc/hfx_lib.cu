@@ -13,6 +13,7 @@
 
 #include "../../include/hfx.h"
 #include "hfx_assemble.cuh"
+#include "hfx_generic.cuh"
 #include "host/hfx_refel.h"
 #include "host/hfx_topology.h"
 
@@ -233,14 +234,14 @@ __global__ void scale_copy_kernel(long long n, const double* __restrict__ src, d
 }
 
 // recovery (HDGSolver.cpp:741-775): one CTA per element, thread per output row; U,Q column-major => coalesced
-__global__ void recover_kernel(int nCells, int u, int q, int l, int nFc, int t, const int* __restrict__ cell2face, const uint8_t* __restrict__ fperm,
+__global__ void recover_kernel(int nCells, int u, int q, int l, int nFc, int nNf, int nD, const int* __restrict__ cell2face, const uint8_t* __restrict__ fperm,
                                const double* __restrict__ trace, const double* __restrict__ U, const double* __restrict__ Q,
                                const double* __restrict__ U0, const double* __restrict__ Q0, double* __restrict__ sol, double* __restrict__ flux) {
   extern __shared__ double lam[];
   for (int e = blockIdx.x; e < nCells; e += gridDim.x) {
-    for (int i = threadIdx.x; i < l; i += blockDim.x) {
-      const int f = i / t;
-      lam[i] = trace[(size_t)cell2face[(size_t)e * nFc + f] * t + fperm[(size_t)e * l + i]];
+    for (int i = threadIdx.x; i < l; i += blockDim.x) {   // lambda_e[(f*nNf+j)*nD+k] = Trace[(face_f*nNf + pos)*nD + k]  (:752-766)
+      const int fa = i / nD, k = i - fa * nD, f = fa / nNf;
+      lam[i] = trace[((size_t)cell2face[(size_t)e * nFc + f] * nNf + fperm[(size_t)e * nFc * nNf + fa]) * nD + k];
     }
     __syncthreads();
     for (int r = threadIdx.x; r < u + q; r += blockDim.x) {
@@ -454,7 +455,8 @@ struct hfx_ctx {
   bool meshSet = false, topoSet = false;
   // fields
   std::map<std::string, DField> fields;
-  DBuf<double> dSrc, dReac;
+  DBuf<double> dSrc, dReac; int nSrc = 1;
+  DBuf<double> dGenWs; int genGrid = 0; long long genStride = 0;
   // model / boundary
   hfx_model_desc md{1, HFX_OP_DIFFUSION, HFX_TS_NONE, 0.0};
   bool modelSet = false, bcSet = false;
@@ -767,8 +769,12 @@ int hfx_field_size(const hfx_ctx* c, const char* name, long long* n) {
 int hfx_model_describe(hfx_ctx* c, const hfx_model_desc* md) {
   return guard(c, [&] {
     need(md->nDOF >= 1, "HDGModel", "allocate", "the number of DOFs per node must be at least one");
-    need(md->nDOF == 1, "HDGModel", "allocate", "device kernels for nDOFsPerNode > 1 (HDGBurgersModel) are not built yet");
-    need(!(md->opmask & HFX_OP_UNABU), "HDGModel", "allocate", "the HDGUNabU operator has no device kernel yet");
+    need(md->nDOF <= 3, "HDGModel", "allocate", "the device kernels support at most 3 DOFs per node");
+    if (md->opmask & HFX_OP_UNABU) {
+      need(c->re && md->nDOF == c->dim, "HDGUNabU", "allocate", "the number of degrees of freedom per node must be equal to the dimension of the element for the UNabU operator");
+      need(!(md->opmask & HFX_OP_CONVECTION), "HDGModel", "allocate", "no model combines HDGUNabU with HDGConvection");
+    }
+    if ((md->opmask & HFX_OP_SOURCE) && md->nDOF > 1) need(md->opmask & HFX_OP_UNABU, "Source", "assemble", "a scalar Source operator needs nDOFsPerNode == 1 (Source.cpp:40-47)");
     need(md->timeScheme == HFX_TS_NONE || md->timeScheme == HFX_TS_EULER_IMPLICIT, "HDGModel", "setTimeScheme", "unsupported time scheme");
     if (c->modelSet && c->md.nDOF != md->nDOF) c->allocated = false;   // block sizes change with nDOF only
     c->md = *md; c->modelSet = true; c->assembled = false;
@@ -786,9 +792,16 @@ int hfx_ip_coords(hfx_ctx* c, double* xip) {
   });
 }
 
-int hfx_source_values(hfx_ctx* c, const double* vals) {
-  return guard(c, [&] { HFX_CUDA(cudaSetDevice(c->device)); need(c->meshSet, "Source", "setSourceFunction", "the mesh must be set"); c->dSrc.upload(vals, (size_t)c->nCells * c->nIP, c->st); HFX_CUDA(cudaStreamSynchronize(c->st)); });
+int hfx_source_values_n(hfx_ctx* c, int nComp, const double* vals) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    need(c->meshSet, "Source", "setSourceFunction", "the mesh must be set");
+    need(nComp >= 1 && nComp <= 3, "Source", "setSourceFunction", "between one and three source components");
+    c->dSrc.upload(vals, (size_t)c->nCells * c->nIP * nComp, c->st); c->nSrc = nComp;
+    HFX_CUDA(cudaStreamSynchronize(c->st));
+  });
 }
+int hfx_source_values(hfx_ctx* c, const double* vals) { return hfx_source_values_n(c, 1, vals); }
 int hfx_reaction_values(hfx_ctx* c, const double* vals) {
   return guard(c, [&] { HFX_CUDA(cudaSetDevice(c->device)); need(c->meshSet, "Reaction", "setReactionFunction", "the mesh must be set"); c->dReac.upload(vals, (size_t)c->nCells * c->nIP, c->st); HFX_CUDA(cudaStreamSynchronize(c->st)); });
 }
@@ -868,7 +881,8 @@ int hfx_assemble(hfx_ctx* c) {
     p.faceRowStart = c->dFaceRowStart.p; p.faceNnb = c->dNnb.p; p.faceBC = c->dFaceBC.p; p.faceInterior = c->dInterior.p;
     DField* tau = find_field(c, "Tau");
     p.tau = tau->d.p; p.tauVals = tau->nVal;
-    p.opmask = c->md.opmask; p.timeScheme = c->md.timeScheme;
+    p.opmask = c->md.opmask; p.timeScheme = c->md.timeScheme; p.dt = c->md.dt;
+    if (p.timeScheme != HFX_TS_NONE) need(c->md.dt != 0.0, "Euler", "apply", "the time step needs to be set before applying and it should not be 0");
     DField* diff = find_field(c, "DiffusionTensor");
     if ((p.opmask & HFX_OP_DIFFUSION) && diff) {
       need(diff->type == HFX_FIELD_NODE || diff->type == HFX_FIELD_CELL, "HDGDiffusionSource", "parseDiffusionVals", "the DiffusionTensor must be a node or a cell field");
@@ -895,9 +909,40 @@ int hfx_assemble(hfx_ctx* c) {
     // linSystem->clearSystem() (HDGSolver.cpp:532-536): entries with two contributors are accumulated on zeroed storage
     c->dVals.zero(c->st); c->dRhs.zero(c->st); c->dStatus.zero(c->st);
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
-    bool supported = true;
-    HFX_CUDA(launch_assemble(c->dim, c->order, p, c->nSM, c->st, &supported));
-    need(supported, "HDGSolver", "assemble", "no device kernel instantiated for this (dimension, order)");
+    bool fused = c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && !getenv("HFX_FORCE_GENERIC");
+    if (fused) {
+      bool supported = true;
+      HFX_CUDA(launch_assemble(c->dim, c->order, p, c->nSM, c->st, &supported));
+      fused = supported;
+    }
+    if (!fused) {   // general kernel: 3-D orders 4-5, nDOFsPerNode > 1, HDGUNabU
+      GenParams g{};
+      g.a = p; g.dim = c->dim; g.nN = c->nN; g.nNf = c->nNf; g.nFc = c->nFc; g.nIP = c->nIP; g.nIPf = c->nIPf; g.nD = c->md.nDOF;
+      g.nSrc = 1;
+      if (p.opmask & HFX_OP_UNABU) {
+        DField* bs = find_field(c, "BufferSolution");
+        need(bs && bs->type == HFX_FIELD_CELL && bs->nObj == c->nN && bs->nVal == g.nD, "HDGBurgersModel", "setFieldMap", "need to give a field named BufferSolution to the HDGBurgersModel");
+        g.bufSol = bs->d.p; g.tracePrev = find_field(c, "Trace")->d.p;
+        g.nSrc = c->dim;
+      }
+      if (p.opmask & HFX_OP_SOURCE) need(c->nSrc == g.nSrc, "Source", "calcSource", "the number of source components does not match the model");
+      const int uu = c->nN * g.nD;
+      need(uu <= 96, "HDGSolver", "assemble", "the general device kernel supports local solution blocks of at most 96 unknowns");
+      const GenWs z(g.dim, g.nN, g.nNf, g.nFc, g.nIP, g.nIPf, g.nD);
+      const size_t smem = gen_smem_bytes(g.nN, g.nNf, g.nFc, g.nD);
+      static size_t smemSet = 0;
+      if (smem > smemSet) { HFX_CUDA(cudaFuncSetAttribute(hdg_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smemSet = smem; }
+      int perSM = 1;
+      HFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_generic_kernel, kGenThreads, smem));
+      if (perSM < 1) perSM = 1;
+      if (perSM > 4) perSM = 4;
+      long long grid = std::min<long long>((long long)c->nSM * perSM, c->nCells);
+      if (grid < 1) grid = 1;
+      if (c->genGrid != grid || c->genStride != z.total) { c->dGenWs.alloc((size_t)grid * z.total); c->genGrid = (int)grid; c->genStride = z.total; }
+      g.ws = c->dGenWs.p; g.wsStride = z.total;
+      hdg_generic_kernel<<<(int)grid, kGenThreads, smem, c->st>>>(g);
+      HFX_CUDA(cudaGetLastError());
+    }
     HFX_CUDA(cudaEventRecord(c->ev2, c->st));
     int status = 0;
     c->dStatus.download(&status, 1, c->st);
@@ -931,7 +976,8 @@ int hfx_recover(hfx_ctx* c) {
     const int nD = c->md.nDOF, t = c->nNf * nD, u = c->nN * nD, q = u * c->dim, l = c->nFc * t;
     int grid = std::min(c->nCells, c->nSM * 16);
     int bs = ((u + q + 31) / 32) * 32; if (bs > 256) bs = 256;
-    recover_kernel<<<grid, bs, l * sizeof(double), c->st>>>(c->nCells, u, q, l, c->nFc, t, c->dC2F.p, c->dFperm.p, find_field(c, "Trace")->d.p,
+    (void)t;
+    recover_kernel<<<grid, bs, l * sizeof(double), c->st>>>(c->nCells, u, q, l, c->nFc, c->nNf, nD, c->dC2F.p, c->dFperm.p, find_field(c, "Trace")->d.p,
                                                             c->dU.p, c->dQ.p, c->dU0.p, c->dQ0.p, find_field(c, "Solution")->d.p, find_field(c, "Flux")->d.p);
     HFX_CUDA(cudaGetLastError());
     HFX_CUDA(cudaStreamSynchronize(c->st));

@@ -195,6 +195,32 @@ class HDGConvectionDiffusionReactionSource(_HDGModel):
         return m
 
 
+class HDGBurgersModel(_HDGModel):
+    """Base + HDGUNabU (Newton-linearised convection, needs BufferSolution and Trace) [+ Diffusion if DiffusionTensor] ; rhs = UNabU
+    rhs [+ one scalar Source per component]  (src/model/HDGBurgersModel.cpp:5-124)."""
+    usesDiffusionField = True
+    isBurgers = True
+
+    def allocate(self, nDOFsPerNode):
+        if nDOFsPerNode != self.refEl.getDimension():
+            raise ErrorHandle("HDGBurgersModel : allocate : the number of DOFs per node must be equal to the number of spatial dimensions for the Burgers equation")
+        _HDGModel.allocate(self, nDOFsPerNode)
+
+    def setSourceFunction(self, s):
+        """s(x, i): source of component i (std::function<double(const std::vector<double>&, int)>)."""
+        if not self.allocated:
+            raise ErrorHandle("HDGBurgersModel : setSourceFunction : the model must be allocated before setting the source function")
+        self.sourceFunc = s
+
+    def _mask(self, fieldNames, strict=True):
+        if "BufferSolution" not in fieldNames:
+            raise ErrorHandle("HDGBurgersModel : setFieldMap : must provide a BufferSolution field for the Newton-Raphson iterations")
+        m = OP_UNABU
+        if "DiffusionTensor" in fieldNames: m |= OP_DIFFUSION
+        if self.sourceFunc is not None: m |= OP_SOURCE
+        return m
+
+
 class DirichletModel:
     """assembly = {Set, Set}, localMatrix = I, localRHS = Dirichlet (src/model/DirichletModel.cpp:19-44)."""
     kind = 0
@@ -419,6 +445,8 @@ class HDGSolver:
             names.remove("DiffusionTensor")   # HDGLaplaceModel never reads it (HDGLaplaceModel.cpp:18-30)
         if self.model.timeScheme is not None and self.allocated:
             names.append("Solution")
+        if getattr(self.model, "isBurgers", False):
+            names += [n for n in ("BufferSolution", "Trace") if n in self.fieldMap]
         return names
 
     def _describe_model(self, strict=True):
@@ -438,8 +466,12 @@ class HDGSolver:
                 check(L.hfx_ip_coords(h, pd(self._xip)), h)
             pts = self._xip.reshape(-1, d)
             if self._mask & OP_SOURCE:
-                v = f64([self.model.sourceFunc(list(p)) for p in pts])
-                check(L.hfx_source_values(h, pd(v)), h)
+                if getattr(self.model, "isBurgers", False):   # one scalar Source per component (HDGBurgersModel.cpp:51-56,112-122)
+                    v = f64([[[self.model.sourceFunc(list(p), c) for p in el] for c in range(d)] for el in self._xip])
+                    check(L.hfx_source_values_n(h, d, pd(v)), h)
+                else:
+                    v = f64([self.model.sourceFunc(list(p)) for p in pts])
+                    check(L.hfx_source_values(h, pd(v)), h)
             if self._mask & OP_REACTION:
                 v = f64([self.model.reactionFunc(list(p)) for p in pts])
                 check(L.hfx_reaction_values(h, pd(v)), h)

@@ -70,6 +70,8 @@ int hfx_model_describe(hfx_ctx* ctx, const hfx_model_desc* md);
    hfx_ip_coords returns x(ip) = sum_i phi_i(ip) x_i (Source.cpp:5-22), [nCells][nIP][dim] */
 int hfx_ip_coords(hfx_ctx* ctx, double* xip);
 int hfx_source_values(hfx_ctx* ctx, const double* vals /*[nCells][nIP]*/);
+/* per-component sources of the Burgers model (HDGBurgersModel.cpp:51-56,112-122: one scalar Source per component), [nCells][nComp][nIP] */
+int hfx_source_values_n(hfx_ctx* ctx, int nComp, const double* vals);
 int hfx_reaction_values(hfx_ctx* ctx, const double* vals /*[nCells][nIP]*/);
 /* Solver::setBoundaryCondition(BoundaryModel*, faces)  Solver.h:41-48; DirichletModel / IntegratedDirichletModel */
 enum { HFX_BC_DIRICHLET = 0, HFX_BC_INTEGRATED_DIRICHLET = 1 };

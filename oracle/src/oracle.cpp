@@ -457,13 +457,19 @@ void local_system(const orc_refel* re, const orc_model* md, const orc_elfields* 
     Mat M(z.u, z.u);
     for (int i = 0; i < z.nN; i++) for (int j = 0; j < z.nN; j++) for (int k = 0; k < z.nDOF; k++) M(i * z.nDOF + k, j * z.nDOF + k) = M1(i, j);
     const int u = z.u, n = z.n;
-    if (md->timeScheme == ORC_TS_EULER_IMPLICIT) {          // Euler.cpp:28-30
+    if (md->timeScheme == ORC_TS_EULER_IMPLICIT || md->timeScheme == ORC_TS_EULER_EXPLICIT) {   // Euler.cpp:28-29: Su *= dt; Fu *= dt
+      for (int i = 0; i < u; i++) {
+        for (int j = 0; j < n; j++) A(i, j) *= md->dt;
+        F[i] *= md->dt;
+      }
+    }
+    if (md->timeScheme == ORC_TS_EULER_IMPLICIT) {          // Euler.cpp:30-32
       for (int i = 0; i < u; i++) {
         double s = 0;
         for (int j = 0; j < u; j++) { A(i, j) += M(i, j); s += M(i, j) * f->solOld[j]; }
         F[i] += s;
       }
-    } else if (md->timeScheme == ORC_TS_EULER_EXPLICIT) {   // Euler.cpp:31-34
+    } else if (md->timeScheme == ORC_TS_EULER_EXPLICIT) {   // Euler.cpp:33-36
       for (int i = 0; i < u; i++) {
         double s = 0;
         for (int j = 0; j < u; j++) s += (M(i, j) - A(i, j)) * f->solOld[j];

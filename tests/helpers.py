@@ -31,12 +31,22 @@ def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="di
     topo = compute_faces(cells, ore)
     nF, nNf, nN = topo["faces"].shape[0], ore.faceElement.nNodes, ore.nNodes
     ana = np.sin(nodes[:, 0]) * np.exp(nodes[:, 1])
-    dirv = np.zeros((nF, nNf, 1))
+    nD = dim if model == "burgers" else 1
+    dirv = np.zeros((nF, nNf, nD))
     b = topo["boundary"]
     dirv[b, :, 0] = ana[topo["faces"][b]]
-    case = dict(dim=dim, order=order, nodes=nodes, cells=cells, topo=topo, ore=ore, ana=ana, model=model, bc=bc)
+    if nD > 1:
+        dirv[b, :, 1] = (np.cos(nodes[:, 0]) * np.exp(-nodes[:, 1]))[topo["faces"][b]]
+        if nD > 2:
+            dirv[b, :, 2] = (nodes[:, 2] * nodes[:, 0])[topo["faces"][b]]
+    case = dict(dim=dim, order=order, nodes=nodes, cells=cells, topo=topo, ore=ore, ana=ana, model=model, bc=bc, nD=nD)
     fields = {"Dirichlet": dirv}
-    if tau_double:
+    if nD > 1:     # tau is a full nDOF x nDOF matrix per face node (col-major), HDGBase.cpp:18-32
+        blk = 2.0 * np.eye(nD)[None, None] + 0.3 * rng.random((nF, nNf, nD, nD))
+        fields["Tau"] = np.concatenate([blk.reshape(nF, nNf, nD * nD), (blk + 0.2).reshape(nF, nNf, nD * nD)], axis=2) if tau_double else blk.reshape(nF, nNf, nD * nD)
+        fields["BufferSolution"] = 0.3 * rng.standard_normal((cells.shape[0], nN, nD))
+        fields["Trace"] = 0.3 * rng.standard_normal((nF, nNf, nD))
+    elif tau_double:
         fields["Tau"] = 0.5 + rng.random((nF, nNf, 2))
     else:
         fields["Tau"] = np.ones((nF, nNf, 1)) if model == "laplace" else 0.5 + rng.random((nF, nNf, 1))
@@ -53,6 +63,8 @@ def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="di
         fields["Velocity"] = vel
     case["fields"] = fields
     case["source"] = (lambda x: np.exp(-10 * sum((xi - 0.5) ** 2 for xi in x))) if model in ("diffsrc", "cdrs", "euler") else None
+    if model == "burgers":
+        case["source"] = lambda x, c: (c + 1.0) * np.exp(-3 * sum((xi - 0.4) ** 2 for xi in x))
     case["reaction"] = (lambda x: 1.0 + x[0]) if model == "cdrs" else None
     if model == "euler":
         case["solOld"] = rng.random((cells.shape[0], nN))
@@ -72,7 +84,11 @@ def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
     if model == "cdrs":
         mask = O.OP_CONVECTION | (O.OP_DIFFUSION if "DiffusionTensor" in f else 0)
     xip = np.einsum("pi,cid->cpd", ore.ipShape, case["nodes"][case["cells"]])
-    if case["source"] is not None:
+    nD = case.get("nD", 1)
+    if model == "burgers":
+        mask = O.OP_UNABU | (O.OP_DIFFUSION if "DiffusionTensor" in f else 0) | O.OP_SOURCE
+        f["srcIP"] = np.array([[[case["source"](p, c) for p in el] for c in range(case["dim"])] for el in xip])
+    elif case["source"] is not None:
         mask |= O.OP_SOURCE
         f["srcIP"] = np.array([[case["source"](p) for p in el] for el in xip])
     if case["reaction"] is not None:
@@ -81,7 +97,7 @@ def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
     if model == "euler":
         ts = O.TS_EULER_IMPLICIT
         f["solOld"] = case["solOld"]
-    md = O.make_model(1, mask, diffComps, ts, 0.1)
+    md = O.make_model(nD, mask, diffComps, ts, 0.1)
     mesh = dict(nodes=case["nodes"], cells=case["cells"], **topo)
     h = O.HDGOracle(rc, mesh, md, f, bcKind=O.BC_DIRICHLET if case["bc"] == "dirichlet" else O.BC_INTEGRATED_DIRICHLET, useLU=useLU)
     h.assemble()
@@ -97,15 +113,20 @@ def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True):
     re = m.getReferenceElement()
     nN, nNf = re.getNumNodes(), re.getFaceElement().getNumNodes()
     fm = {}
-    fm["Solution"] = hfox.Field(m, hfox.Cell, nN, 1)
-    fm["Flux"] = hfox.Field(m, hfox.Cell, nN, dim)
-    fm["Trace"] = hfox.Field(m, hfox.Face, nNf, 1)
+    nD = case.get("nD", 1)
+    fm["Solution"] = hfox.Field(m, hfox.Cell, nN, nD)
+    fm["Flux"] = hfox.Field(m, hfox.Cell, nN, dim * nD)
+    fm["Trace"] = hfox.Field(m, hfox.Face, nNf, nD)
     tau = case["fields"]["Tau"]
     fm["Tau"] = hfox.Field(m, hfox.Face, nNf, tau.shape[2])
     fm["Tau"].values[:] = tau.ravel()
-    if tau.shape[2] == 2:
+    if tau.shape[2] == 2 * nD * nD:
         fm["Tau"].setDoubleValued(True)
-    fm["Dirichlet"] = hfox.Field(m, hfox.Face, nNf, 1)
+    if "BufferSolution" in case["fields"]:
+        fm["BufferSolution"] = hfox.Field(m, hfox.Cell, nN, nD)
+        fm["BufferSolution"].values[:] = case["fields"]["BufferSolution"].ravel()
+        fm["Trace"].values[:] = case["fields"]["Trace"].ravel()
+    fm["Dirichlet"] = hfox.Field(m, hfox.Face, nNf, nD)
     fm["Dirichlet"].values[:] = case["fields"]["Dirichlet"].ravel()
     if "DiffusionTensor" in case["fields"]:
         d = case["fields"]["DiffusionTensor"]
@@ -119,6 +140,8 @@ def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True):
         mod = hfox.HDGLaplaceModel(re)
     elif model in ("diffsrc", "euler"):
         mod = hfox.HDGDiffusionSource(re)
+    elif model == "burgers":
+        mod = hfox.HDGBurgersModel(re)
     else:
         mod = hfox.HDGConvectionDiffusionReactionSource(re)
     if model == "euler":

@@ -171,3 +171,27 @@ def test_lai_stock_systems(n):
     a.setValsRHS(rows, M @ xs)
     a.assemble()
     assert np.abs(a.solve() - xs).max() < 1e-10
+
+
+# ---- general kernel (hfx_generic.cuh): 3-D orders 4-5, nDOFsPerNode > 1, HDGUNabU --------------------------------------------
+@pytest.mark.parametrize("dim,order,model,diff,bc", [(2, 2, "cdrs", "scalar", "dirichlet"), (3, 2, "diffsrc", "tensor", "dirichlet"),
+                                                     (3, 3, "laplace", "none", "dirichlet"), (2, 3, "euler", "scalar", "dirichlet"),
+                                                     (3, 2, "laplace", "none", "integrated"), (3, 3, "cdrs", "scalar", "dirichlet")])
+def test_general_kernel_matches_oracle_and_fused(dim, order, model, diff, bc, monkeypatch):
+    """The general kernel forced on configurations the fused kernel also covers: same parity bars against the oracle."""
+    monkeypatch.setenv("HFX_FORCE_GENERIC", "1")
+    compare(H.make_case(dim, order, N=3, model=model, diff=diff, bc=bc, tau_double=model != "laplace", seed=13, curved=0.03 if model == "cdrs" else 0.0))
+
+
+@pytest.mark.parametrize("order,model", [(4, "laplace"), (5, "laplace"), (4, "cdrs")])
+def test_3d_orders_4_and_5(order, model):
+    """BASELINE.json configs[3]/[4]: order 4 (convection-diffusion) and the order sweep up to the reference's maximum (5) on tets."""
+    compare(H.make_case(3, order, N=2, perturb=0.1, model=model, diff="scalar" if model == "cdrs" else "none", tau_double=model == "cdrs", seed=17))
+
+
+@pytest.mark.parametrize("dim,order,diff,tau_double", [(2, 1, "scalar", False), (2, 2, "scalar", True), (2, 3, "tensor", False), (2, 4, "scalar", True),
+                                                       (3, 2, "scalar", False)])
+def test_burgers_model_one_newton_linearisation(dim, order, diff, tau_double):
+    """HDGBurgersModel (nDOFsPerNode = dim): Base + HDGUNabU + Diffusion with per-component sources, linearised about a random
+    previous iterate (BufferSolution, Trace) -- BASELINE.json configs[1] at every order of its sweep."""
+    compare(H.make_case(dim, order, N=3, model="burgers", diff=diff, tau_double=tau_double, seed=19))

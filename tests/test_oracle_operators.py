@@ -130,14 +130,17 @@ def test_models_are_sums_of_operators_and_structure(dim, order):
     ref[:nN, :nN] += R
     assert ((A - ref) ** 2).sum() < 1e-12
     assert np.abs(F[:nN] - re.ipShape.T @ (src * dV[:rc.nIP])).max() < 1e-13 and np.abs(F[nN:]).max() == 0
-    # implicit Euler as coded (Euler.cpp:28-30): Suu += M, Fu += M u_old
-    mdE = O.make_model(1, O.OP_DIFFUSION | O.OP_SOURCE, diffComps=1, timeScheme=O.TS_EULER_IMPLICIT, dt=0.1)
+    # implicit Euler as coded (Euler.cpp:18-37, hook HDGModel.cpp:38-47): the u rows Su, Fu are scaled by dt, then Suu += M, Fu += M u_old
+    # (TestEuler.cpp:70-76: backEuler.apply(conv, 1) == mass + dt*conv, mass*sol + dt*1)
+    dt = 0.1
+    mdE = O.make_model(1, O.OP_DIFFUSION | O.OP_SOURCE, diffComps=1, timeScheme=O.TS_EULER_IMPLICIT, dt=dt)
     AE, FE = O.local_system(rc, mdE, nodes=nodes, tau=tau, diff=diff, srcIP=src, solOld=sold)
     M = O.op_mass(re.ipShape, dV[:rc.nIP])
     refE = base + dif
+    refE[:nN, :] *= dt
     refE[:nN, :nN] += M
     assert ((AE - refE) ** 2).sum() < 1e-12
-    assert np.abs(FE[:nN] - (re.ipShape.T @ (src * dV[:rc.nIP]) + M @ sold)).max() < 1e-12
+    assert np.abs(FE[:nN] - (dt * (re.ipShape.T @ (src * dV[:rc.nIP])) + M @ sold)).max() < 1e-12 and np.abs(FE[nN:]).max() == 0
     # structure
     sQ, sL = nN, nN * (dim + 1)
     assert np.abs(A[sQ:sL, sQ:sL] - np.kron(O.op_mass(re.ipShape, dV[:rc.nIP]), np.eye(dim))).max() < 1e-13

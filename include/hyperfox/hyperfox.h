@@ -428,6 +428,7 @@ class HDGModel : public FEModel {
   // operator descriptor for the device (Base is always present, src/model/HDGModel.cpp:28-32); fieldNames = names in the solver's field map
   virtual int opmask(const std::set<std::string>& fieldNames, bool strict) const = 0;
   virtual bool usesDiffusionField() const { return true; }
+  virtual bool isBurgers() const { return false; }
   const ScalarFunction& sourceFunction() const { return source; }
   const ScalarFunction& reactionFunction() const { return reaction; }
   int getNumDOFsPerNode() const { return nDOFsPNode; }
@@ -473,6 +474,31 @@ class HDGConvectionDiffusionReactionSource : public HDGModel {   // src/model/HD
     if (!v && !d) throw ErrorHandle("HDGConvectionDiffusionReactionSource", "setFieldMap", "must provide at least either a Velocity field or a DiffusionTensor field");
     return (v ? HFX_OP_CONVECTION : 0) | (d ? HFX_OP_DIFFUSION : 0) | (reaction ? HFX_OP_REACTION : 0) | (source ? HFX_OP_SOURCE : 0);
   }
+};
+
+// Base + HDGUNabU [+ Diffusion if DiffusionTensor] ; rhs = UNabU rhs [+ one scalar Source per component]  (src/model/HDGBurgersModel.cpp:5-124)
+class HDGBurgersModel : public HDGModel {
+ public:
+  using HDGModel::HDGModel;
+  typedef std::function<double(const std::vector<double>&, int)> ComponentFunction;
+  void allocate(int nDOFsPerNodeUser) override {
+    if (nDOFsPerNodeUser != refEl->getDimension())
+      throw ErrorHandle("HDGBurgersModel", "allocate", "the number of DOFs per node must be equal to the number of spatial dimensions for the Burgers equation");
+    HDGModel::allocate(nDOFsPerNodeUser);
+  }
+  void setSourceFunction(ComponentFunction s) {
+    if (!allocated) throw ErrorHandle("HDGBurgersModel", "setSourceFunction", "the model must be allocated before setting the source function");
+    componentSource = s;
+  }
+  const ComponentFunction& componentSourceFunction() const { return componentSource; }
+  bool isBurgers() const override { return true; }
+  int opmask(const std::set<std::string>& names, bool) const override {
+    if (!names.count("BufferSolution")) throw ErrorHandle("HDGBurgersModel", "setFieldMap", "must provide a BufferSolution field for the Newton-Raphson iterations");
+    return HFX_OP_UNABU | (names.count("DiffusionTensor") ? HFX_OP_DIFFUSION : 0) | (componentSource ? HFX_OP_SOURCE : 0);
+  }
+
+ protected:
+  ComponentFunction componentSource;
 };
 
 enum BoundaryModelType { CGType, HDGType };
@@ -647,6 +673,7 @@ class HDGSolver : public Solver {
     const HDGModel* hm = dynamic_cast<const HDGModel*>(model);
     if (hm && !hm->usesDiffusionField()) s.erase("DiffusionTensor");   // HDGLaplaceModel never reads it
     if (model->getTimeScheme() && allocated) s.insert("Solution");
+    if (hm && hm->isBurgers()) { if (fieldMap->count("BufferSolution")) s.insert("BufferSolution"); s.insert("Trace"); }
     return s;
   }
   void uploadInputs() {
@@ -672,6 +699,17 @@ class HDGSolver : public Solver {
     const int nC = myMesh->getNumberCells(), nIP = myMesh->getReferenceElement()->getNumIPs(), d = myMesh->getNodeSpaceDimension();
     if (xip.empty()) { xip.resize((size_t)nC * nIP * d); detail::check(hfx_ip_coords(ctx(), xip.data()), ctx()); }
     std::vector<double> v((size_t)nC * nIP), pt(d);
+    if (hm->isBurgers()) {   // one scalar Source per component, [nCells][dim][nIP] (HDGBurgersModel.cpp:51-56,112-122)
+      const HDGBurgersModel::ComponentFunction& fn = static_cast<const HDGBurgersModel*>(hm)->componentSourceFunction();
+      std::vector<double> vc((size_t)nC * d * nIP);
+      for (int e = 0; e < nC; e++) for (int c = 0; c < d; c++) for (int ip = 0; ip < nIP; ip++) {
+        const size_t k = (size_t)e * nIP + ip;
+        pt.assign(xip.begin() + k * d, xip.begin() + (k + 1) * d);
+        vc[((size_t)e * d + c) * nIP + ip] = fn(pt, c);
+      }
+      detail::check(hfx_source_values_n(ctx(), d, vc.data()), ctx());
+      return;
+    }
     for (int pass = 0; pass < 2; pass++) {
       const bool src = pass == 0;
       if (!(mask & (src ? HFX_OP_SOURCE : HFX_OP_REACTION))) continue;

@@ -195,3 +195,71 @@ def test_burgers_model_one_newton_linearisation(dim, order, diff, tau_double):
     """HDGBurgersModel (nDOFsPerNode = dim): Base + HDGUNabU + Diffusion with per-component sources, linearised about a random
     previous iterate (BufferSolution, Trace) -- BASELINE.json configs[1] at every order of its sweep."""
     compare(H.make_case(dim, order, N=3, model="burgers", diff=diff, tau_double=tau_double, seed=19))
+
+
+def _burgers_stat_analytic(x, D=1.0, A=0.5, x0=(1.0, 0.0)):
+    """tests/regression/HDG/TestHDGBurgersStat.cpp:46-90: Cole-Hopf solution u = -2 D grad(phi) / phi."""
+    ex, em = np.exp(A * (x[:, 0] - x0[0])), np.exp(-A * (x[:, 0] - x0[0]))
+    cy, sy = np.cos(A * (x[:, 1] - x0[1])), np.sin(A * (x[:, 1] - x0[1]))
+    pot = 0.001 * A * np.exp((1 + x0[0]) * A) * (1 + x[:, 0]) + (ex + em) * cy
+    g0 = 0.001 * A * np.exp((1 + x0[0]) * A) + A * (ex - em) * cy
+    g1 = -A * (ex + em) * sy
+    return np.stack([g0, g1], axis=1) * (-2.0 * D / pot)[:, None]
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_burgers_stationary_newton_regression(order):
+    """BASELINE.json configs[1] = tests/regression/HDG/TestHDGBurgersStat.cpp: HDGBurgersModel + IntegratedDirichletModel on
+    regression_dim-2_h-2e-1_ord-p, D = 1, tau = (2D/h) I on both sides, NonLinearWrapper(<= 10 iterations, tol 1e-6) from a zero state.
+    The device Newton loop must (i) converge to the Cole-Hopf solution and (ii) follow the oracle's Newton iterates."""
+    from hyperfox_b200 import hfox
+    from oracle import lib as O
+    from oracle.mesh import compute_faces
+    from oracle.refel import ReferenceElement as OracleRefEl
+    from tests.conftest import load_mesh
+    dim, D, h = 2, 1.0, 0.2
+    nodes, cells = load_mesh("regression_dim-2_h-2e-1_ord-%d" % order)
+    m = hfox.Mesh(dim, order, "simplex")
+    m.setMesh(nodes, cells)
+    re = m.getReferenceElement()
+    nN, nNf, nF, nC = re.getNumNodes(), re.getFaceElement().getNumNodes(), m.getNumberFaces(), m.getNumberCells()
+    ana = _burgers_stat_analytic(nodes, D)
+    fm = {"Solution": hfox.Field(m, hfox.Cell, nN, dim), "BufferSolution": hfox.Field(m, hfox.Cell, nN, dim), "Flux": hfox.Field(m, hfox.Cell, nN, dim * dim),
+          "Trace": hfox.Field(m, hfox.Face, nNf, dim), "Tau": hfox.Field(m, hfox.Face, nNf, 2 * dim * dim), "Dirichlet": hfox.Field(m, hfox.Face, nNf, dim),
+          "DiffusionTensor": hfox.Field(m, hfox.Node, 1, 1)}
+    fm["Tau"].setDoubleValued(True)
+    tau = np.zeros((nF, nNf, 2, dim, dim)); tau[..., 0, 0] = tau[..., 1, 1] = 2.0 * D / h
+    fm["Tau"].values[:] = tau.ravel()
+    fm["DiffusionTensor"].values[:] = D
+    dirv = np.zeros((nF, nNf, dim)); b = m.boundaryFaces
+    dirv[b] = ana[m.faces[b]]
+    fm["Dirichlet"].values[:] = dirv.ravel()
+    mod = hfox.HDGBurgersModel(re)
+    s = hfox.HDGSolver()
+    s.setMesh(m); s.setFieldMap(fm); s.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts(rtol=1e-14, maxits=10000)))
+    s.setModel(mod); s.setBoundaryModel(hfox.IntegratedDirichletModel(re.getFaceElement()))
+    s.initialize(); s.allocate()
+    w = hfox.NonLinearWrapper()
+    w.setMaxIterations(10); w.setResidualTolerance(1e-6); w.setSolutionFields(fm["Solution"], fm["BufferSolution"]); w.setSolver(s)
+    w.solve()
+    assert w.getResidual() < 1e-6
+    sol = fm["Solution"].values.reshape(nC, nN, dim)
+    err = np.sqrt(((sol - ana[cells]) ** 2).sum() / (ana[cells] ** 2).sum())
+    assert err < [3e-2, 2e-3, 3e-4, 5e-5][order - 1], err      # reference ceiling: l2Err < 1 (TestHDGBurgersStat.cpp:363)
+    # the same Newton loop on the oracle
+    ore = OracleRefEl(dim, order)
+    topo = compute_faces(cells, ore)
+    f = {"Tau": tau.reshape(nF, nNf, 2 * dim * dim), "Dirichlet": dirv, "DiffusionTensor": np.full((nodes.shape[0], 1), D),
+         "BufferSolution": np.zeros((nC, nN, dim)), "Trace": np.zeros((nF, nNf, dim))}
+    o = O.HDGOracle(O.RefElC(ore), dict(nodes=nodes, cells=cells, **topo), O.make_model(dim, O.OP_UNABU | O.OP_DIFFUSION, 1), f, bcKind=O.BC_INTEGRATED_DIRICHLET)
+    cur, prev = np.zeros((nC, nN * dim)), np.zeros((nC, nN * dim))
+    for _ in range(10):
+        f["BufferSolution"] = prev.reshape(nC, nN, dim)
+        o.set_fields(f); o.assemble(); o.solve(rtol=1e-14, maxits=10000)
+        cur = o.sol.copy(); f["Trace"] = o.trace.reshape(nF, nNf, dim)
+        diff, ref = ((cur - prev) ** 2).sum(), (prev ** 2).sum()
+        res = np.sqrt(diff / ref) if ref != 0 else np.sqrt(diff)
+        if res < 1e-6:
+            break
+        prev = cur.copy()
+    assert H.rel_err(fm["Solution"].values, cur.ravel()) < 1e-8

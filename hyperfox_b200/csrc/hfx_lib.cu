@@ -1,5 +1,7 @@
 // libhfx.so -- C ABI (include/hfx.h) over the sm_100a kernels.  No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is loaded with dlopen so that libhfx.so has no link-time NCCL dependency
 
 #include <algorithm>
 #include <cmath>
@@ -140,11 +142,13 @@ __global__ void ip_coords_kernel(int nCells, int nN, int nIP, int dim, const dou
 
 // y = A x on the face-block CSR layout: row (F,a) = nnb(F) contiguous t-blocks, one warp per row.
 __global__ void spmv_face_kernel(int nFaces, int t, int nFc2, const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
-                                 const int* __restrict__ nbr, const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y) {
+                                 const int* __restrict__ nbr, const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
+                                 const uint8_t* __restrict__ owned /*NULL: all rows*/) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= (long long)nFaces * t) return;
   const int F = (int)(row / t), a = (int)(row % t);
+  if (owned && !owned[F]) { if (lane == 0) y[row] = 0.0; return; }   // rows of ghost faces belong to another rank
   const int m = nnb[F], len = m * t;
   const double* v = vals + rowStart[F] + (long long)a * len;
   double s = 0.0;
@@ -297,6 +301,96 @@ __global__ void dfma_peak_kernel(int iters, double* out) {
 static inline int nblk(long long n, int bs) { return (int)((n + bs - 1) / bs); }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// NCCL over NVLink: trace-halo exchange + dot-product all-reduce of the distributed Krylov solve (replaces the MPI ghost exchange
+// of src/parallel/Partitioner.cpp:565-826 and PETSc's VecScatter / MPI_Allreduce inside KSPSolve)
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  static NcclApi& get() {
+    static NcclApi a;
+    if (!a.h) {
+      const char* names[] = {getenv("HFX_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+      for (const char* nm : names) { if (nm && (a.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL))) break; }
+      if (!a.h) throw Err("hfx", "comm", "cannot load libnccl.so.2 (set HFX_NCCL_LIB)");
+      auto sym = [&](const char* n) { void* p = dlsym(a.h, n); if (!p) throw Err("hfx", "comm", std::string("missing NCCL symbol ") + n); return p; };
+      a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId"); a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+      a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy"); a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+      a.Send = (decltype(a.Send))sym("ncclSend"); a.Recv = (decltype(a.Recv))sym("ncclRecv");
+      a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart"); a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+      a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    }
+    return a;
+  }
+};
+#define HFX_NCCL(call)                                                                                                   \
+  do {                                                                                                                   \
+    ncclResult_t r_ = (call);                                                                                            \
+    if (r_ != ncclSuccess) throw hfx::Err("hfx", __func__, std::string("NCCL error: ") + NcclApi::get().GetErrorString(r_)); \
+  } while (0)
+
+// one neighbour = one contiguous slice of the packed send / receive buffers
+struct Halo {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nRanks = 1;
+  bool planned = false;
+  std::vector<int> nbr, sendOff, recvOff;   // offsets in faces, size nNbr + 1
+  DBuf<int> dSend, dRecv;                   // local face ids
+  DBuf<double> sbuf, rbuf;
+  DBuf<uint8_t> dOwned;                     // [nFaces] 1 if this rank owns the face (its trace rows)
+  DBuf<uint8_t> dCanon;                     // [nFaces][nNf] canonical position of every local face node
+  long long nOwnedFaces = 0;
+};
+
+// Blocks travel in a rank-independent node order: canon[F][a] = position of local face node a in the canonical order of face F (the
+// face-element node order induced by sorting the face's vertices by global vertex id).  The local order of a face comes from its
+// first LOCAL cell, which differs between the owner and a rank that sees the face as a ghost.
+__global__ void halo_pack_kernel(long long n, int nNf, int nD, const int* __restrict__ faces, const uint8_t* __restrict__ canon, const double* __restrict__ x,
+                                 double* __restrict__ buf) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = nNf * nD;
+  const long long slot = i / t; const int r = (int)(i % t), a = r / nD, k = r - a * nD, F = faces[slot];
+  buf[slot * t + canon[(size_t)F * nNf + a] * nD + k] = x[(size_t)F * t + r];
+}
+__global__ void halo_unpack_kernel(long long n, int nNf, int nD, const int* __restrict__ faces, const uint8_t* __restrict__ canon, const double* __restrict__ buf,
+                                   double* __restrict__ x) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = nNf * nD;
+  const long long slot = i / t; const int r = (int)(i % t), a = r / nD, k = r - a * nD, F = faces[slot];
+  x[(size_t)F * t + r] = buf[slot * t + canon[(size_t)F * nNf + a] * nD + k];
+}
+__global__ void mask_rows_kernel(long long n, int t, const uint8_t* __restrict__ owned, const double* __restrict__ src, double* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = owned[i / t] ? src[i] : 0.0;
+}
+
+// ghost-face blocks of x <- their owners' values (one grouped send/recv round over NVLink)
+inline void halo_exchange(Halo& H, int nNf, int nD, double* x, cudaStream_t st) {
+  if (!H.comm || !H.planned) return;
+  NcclApi& N = NcclApi::get();
+  const int t = nNf * nD;
+  const long long ns = (long long)H.sendOff.back() * t, nr = (long long)H.recvOff.back() * t;
+  if (ns) halo_pack_kernel<<<nblk(ns, 256), 256, 0, st>>>(ns, nNf, nD, H.dSend.p, H.dCanon.p, x, H.sbuf.p);
+  HFX_NCCL(N.GroupStart());
+  for (size_t k = 0; k < H.nbr.size(); k++) {
+    const size_t sc = (size_t)(H.sendOff[k + 1] - H.sendOff[k]) * t, rc = (size_t)(H.recvOff[k + 1] - H.recvOff[k]) * t;
+    if (sc) HFX_NCCL(N.Send(H.sbuf.p + (size_t)H.sendOff[k] * t, sc, ncclDouble, H.nbr[k], H.comm, st));
+    if (rc) HFX_NCCL(N.Recv(H.rbuf.p + (size_t)H.recvOff[k] * t, rc, ncclDouble, H.nbr[k], H.comm, st));
+  }
+  HFX_NCCL(N.GroupEnd());
+  if (nr) halo_unpack_kernel<<<nblk(nr, 256), 256, 0, st>>>(nr, nNf, nD, H.dRecv.p, H.dCanon.p, H.rbuf.p, x);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Krylov solver on an abstract operator
 struct LinOp {
   long long n = 0;
@@ -308,12 +402,14 @@ struct LinOp {
 struct Krylov {
   DBuf<double> V, w, tmp, dinv, partial, hdev, z, pvec;
   double* hpin = nullptr;
+  Halo* halo = nullptr;   // set for a distributed solve: dots are summed over the ranks (vectors are zero on non-owned rows)
   ~Krylov() { if (hpin) cudaFreeHost(hpin); }
   void dots(long long n, int nv, const double* Vp, long long ldv, const double* wv, cudaStream_t st, double* out_host) {
     partial.alloc((size_t)nv * kDotBlocks);
     hdev.alloc(64);
     multi_dot_kernel<<<kDotBlocks, 256, 256 * sizeof(double), st>>>(n, nv, Vp, ldv, wv, partial.p);
     dot_final_kernel<<<nv, 256, 0, st>>>(nv, kDotBlocks, partial.p, hdev.p);
+    if (halo && halo->comm) HFX_NCCL(NcclApi::get().AllReduce(hdev.p, hdev.p, nv, ncclDouble, ncclSum, halo->comm, st));
     HFX_CUDA(cudaMemcpyAsync(out_host, hdev.p, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     HFX_CUDA(cudaStreamSynchronize(st));
   }
@@ -472,6 +568,8 @@ struct hfx_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
   float msTotal = 0, msKernel = 0;
   Krylov krylov;
+  Halo halo;
+  DBuf<double> dXh, dBm;   // distributed solve: halo-extended input vector of the SpMV, right-hand side restricted to the owned rows
 };
 
 namespace {
@@ -487,7 +585,15 @@ struct FaceOp : LinOp {
   hfx_ctx* c;
   explicit FaceOp(hfx_ctx* c_) : c(c_) { n = (long long)c->nFaces * c->nNf * c->md.nDOF; }
   void apply(const double* x, double* y, cudaStream_t st) override {
-    spmv_face_kernel<<<nblk(n * 32, 256), 256, 0, st>>>(c->nFaces, c->nNf * c->md.nDOF, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y);
+    const int t = c->nNf * c->md.nDOF;
+    const uint8_t* owned = nullptr;
+    if (c->halo.comm && c->halo.planned) {   // owned rows only; ghost-face blocks of the input come from their owners (NCCL over NVLink)
+      c->dXh.alloc((size_t)n);
+      HFX_CUDA(cudaMemcpyAsync(c->dXh.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      halo_exchange(c->halo, c->nNf, c->md.nDOF, c->dXh.p, st);
+      x = c->dXh.p; owned = c->halo.dOwned.p;
+    }
+    spmv_face_kernel<<<nblk(n * 32, 256), 256, 0, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
   }
   void diag_inverse(double* dinv, cudaStream_t st) override {
     diag_face_kernel<<<nblk(n, 256), 256, 0, st>>>(c->nFaces, c->nNf * c->md.nDOF, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, dinv);
@@ -590,6 +696,7 @@ int hfx_ctx_destroy(hfx_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
+  if (c->halo.comm) { try { NcclApi::get().CommDestroy(c->halo.comm); } catch (...) {} c->halo.comm = nullptr; }
   cudaStream_t st = c->st;
   delete c;
   if (st) cudaStreamDestroy(st);
@@ -991,10 +1098,73 @@ int hfx_solve(hfx_ctx* c, const hfx_solve_opts* opts, hfx_solve_stats* stats) {
     hfx_solve_opts o = opts ? *opts : hfx_solve_opts{0, 1, 30, 1000, 1e-6};
     need(o.pc == 0 || o.pc == 1, "hfx", "solve", "only point-Jacobi or no preconditioner are available for the trace system");
     FaceOp A(c);
-    c->krylov.solve(A, c->dRhs.p, find_field(c, "Trace")->d.p, o, stats, c->st);
+    const double* b = c->dRhs.p;
+    double* x = find_field(c, "Trace")->d.p;
+    const bool dist = c->halo.comm && c->halo.planned;
+    c->krylov.halo = dist ? &c->halo : nullptr;
+    if (dist) {   // every Krylov vector is zero on the rows this rank does not own, so plain dots + all-reduce give the global dots
+      const int t = c->nNf * c->md.nDOF;
+      c->dBm.alloc((size_t)A.n);
+      mask_rows_kernel<<<nblk(A.n, 256), 256, 0, c->st>>>(A.n, t, c->halo.dOwned.p, b, c->dBm.p);
+      b = c->dBm.p;
+    }
+    c->krylov.solve(A, b, x, o, stats, c->st);
+    if (dist) { halo_exchange(c->halo, c->nNf, c->md.nDOF, x, c->st); HFX_CUDA(cudaStreamSynchronize(c->st)); }   // recovery needs the ghost traces (HDGSolver.cpp:730-732)
   });
   if (rc) return rc;
   return hfx_recover(c);
+}
+
+int hfx_comm_unique_id(char* id128) {
+  return guard(nullptr, [&] { ncclUniqueId id; HFX_NCCL(NcclApi::get().GetUniqueId(&id)); std::memcpy(id128, id.internal, NCCL_UNIQUE_ID_BYTES); });
+}
+
+int hfx_comm_init(hfx_ctx* c, int nRanks, int rank, const char* id128) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    need(nRanks >= 1 && rank >= 0 && rank < nRanks, "hfx", "comm_init", "invalid rank / number of ranks");
+    if (c->halo.comm) { NcclApi::get().CommDestroy(c->halo.comm); c->halo.comm = nullptr; }
+    ncclUniqueId id;
+    std::memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
+    HFX_NCCL(NcclApi::get().CommInitRank(&c->halo.comm, nRanks, id, rank));
+    c->halo.rank = rank; c->halo.nRanks = nRanks;
+  });
+}
+
+int hfx_comm_set_halo(hfx_ctx* c, int nNbr, const int* nbrRank, const int* sendCount, const int* sendFaces, const int* recvCount, const int* recvFaces,
+                      const unsigned char* ownedFace, const unsigned char* canonPos) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    need(c->topoSet, "Partitioner", "computeSharedFaces", "the mesh must be set before the halo plan");
+    Halo& H = c->halo;
+    H.nbr.assign(nbrRank, nbrRank + nNbr);
+    H.sendOff.assign(1, 0); H.recvOff.assign(1, 0);
+    for (int k = 0; k < nNbr; k++) { H.sendOff.push_back(H.sendOff.back() + sendCount[k]); H.recvOff.push_back(H.recvOff.back() + recvCount[k]); }
+    for (int i = 0; i < H.sendOff.back(); i++) need(sendFaces[i] >= 0 && sendFaces[i] < c->nFaces && ownedFace[sendFaces[i]], "Partitioner", "computeSharedFaces", "a face to send is not an owned local face");
+    for (int i = 0; i < H.recvOff.back(); i++) need(recvFaces[i] >= 0 && recvFaces[i] < c->nFaces && !ownedFace[recvFaces[i]], "Partitioner", "computeSharedFaces", "a face to receive is not a ghost local face");
+    H.dSend.upload(sendFaces, (size_t)H.sendOff.back(), c->st); H.dRecv.upload(recvFaces, (size_t)H.recvOff.back(), c->st);
+    H.dOwned.upload(ownedFace, (size_t)c->nFaces, c->st);
+    for (size_t i = 0; i < (size_t)c->nFaces * c->nNf; i++) need(canonPos[i] < c->nNf, "Partitioner", "computeSharedFaces", "canonical face-node position out of range");
+    H.dCanon.upload(canonPos, (size_t)c->nFaces * c->nNf, c->st);
+    H.nOwnedFaces = 0;
+    for (int F = 0; F < c->nFaces; F++) H.nOwnedFaces += ownedFace[F] ? 1 : 0;
+    const int tmax = c->nNf * 3;
+    H.sbuf.alloc((size_t)std::max(1, H.sendOff.back()) * tmax); H.rbuf.alloc((size_t)std::max(1, H.recvOff.back()) * tmax);
+    HFX_CUDA(cudaStreamSynchronize(c->st));
+    H.planned = true;
+  });
+}
+
+int hfx_comm_halo_field(hfx_ctx* c, const char* name) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    DField* f = find_field(c, name);
+    need(f && f->type == HFX_FIELD_FACE, "Partitioner", "updateSharedInformation", "no such face field");
+    need(c->halo.comm && c->halo.planned, "Partitioner", "updateSharedInformation", "the communicator and the halo plan must be set first");
+    need(f->nObj == c->nNf, "Partitioner", "updateSharedInformation", "the face field must have one object per face node");
+    halo_exchange(c->halo, c->nNf, f->nVal, f->d.p, c->st);
+    HFX_CUDA(cudaStreamSynchronize(c->st));
+  });
 }
 
 int hfx_get_csr(hfx_ctx* c, long long* nrows, long long* nnz, long long* rowptr, int* colidx, double* vals, double* rhs) {

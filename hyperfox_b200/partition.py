@@ -57,3 +57,117 @@ def shared_faces(lin_cells, part, rank, dim):
     mine = cut & ((a == rank) | (b == rank))
     other = np.where(a[mine] == rank, b[mine], a[mine])
     return uniq[two][mine], other
+
+
+# ---- distributed trace solve: ownership + halo plan (the reference's ZoltanPartitioner.cpp:83-133 + Partitioner.cpp:42-107) --------
+def global_linear_topology(lin_cells, dim):
+    """Global face numbering of the linear skeleton (MOAB convention restated in csrc/host/hfx_topology.cpp): c2f [nC,nFc], f2c [nF,2]."""
+    from . import capi
+    tp = capi.host_compute_faces(dim, 1, lin_cells)
+    return tp["cell2face"], tp["face2cell"]
+
+
+def face_owner(f2c, part):
+    """A face travels with its first adjacent cell (the lowest global cell id): every face is owned by exactly one rank."""
+    return part[f2c[:, 0]]
+
+
+def rank_cells(c2f, f2c, part, rank):
+    """Owned cells of `rank` + the ghost cells across the faces it owns (overlap-1: the owner recomputes the neighbour's element)."""
+    owned = np.flatnonzero(part == rank)
+    own_face = face_owner(f2c, part) == rank
+    second = f2c[own_face, 1]
+    second = second[second >= 0]
+    ghosts = np.unique(second[part[second] != rank])
+    return owned, ghosts
+
+
+def rank_problem(verts, lin_cells, part, rank, dim, c2f=None, f2c=None):
+    """Everything rank `rank` needs, computed from the global linear mesh without communication (it is deterministic, so every rank
+    derives the same plan): local cells (owned first, then ghosts), the global id and owner of every local face, and the halo lists in
+    LOCAL face ids ordered by global face id.  Returns a dict."""
+    if c2f is None:
+        c2f, f2c = global_linear_topology(lin_cells, dim)
+    owner = face_owner(f2c, part)
+    world = int(part.max()) + 1
+    owned, ghosts = rank_cells(c2f, f2c, part, rank)
+    cells_g = np.concatenate([owned, ghosts])
+    lverts, lcells, vids = extract_submesh(verts, lin_cells, cells_g)
+    from . import capi
+    ltp = capi.host_compute_faces(dim, 1, lcells)                      # local face numbering (same local face order as the global one)
+    nFl = ltp["faces"].shape[0]
+    gface = np.full(nFl, -1, dtype=np.int64)
+    gface[ltp["cell2face"].ravel()] = c2f[cells_g].ravel()
+    fowner = owner[gface]
+    mine = fowner == rank
+    # faces each rank holds as ghosts (its non-owned local faces), by global id
+    need = {}
+    for r in range(world):
+        if r == rank:
+            gf = gface
+        else:
+            o_r, g_r = rank_cells(c2f, f2c, part, r)
+            gf = np.unique(c2f[np.concatenate([o_r, g_r])].ravel())
+        need[r] = np.sort(gf[owner[gf] != r])
+    order = np.argsort(gface)
+    sorted_g = gface[order]
+
+    def to_local(gids):
+        pos = np.searchsorted(sorted_g, gids)
+        assert np.array_equal(sorted_g[pos], gids)
+        return order[pos].astype(np.int32)
+
+    nbrs, send, recv = [], [], []
+    for r in range(world):
+        if r == rank:
+            continue
+        s = need[r][owner[need[r]] == rank]          # my owned faces that r sees as ghosts
+        rr = need[rank][owner[need[rank]] == r]      # my ghosts owned by r
+        if s.size or rr.size:
+            nbrs.append(r); send.append(to_local(s)); recv.append(to_local(rr))
+    return dict(owned_cells=owned, ghost_cells=ghosts, cells_global=cells_g, verts=lverts, lin_cells=lcells, vertex_ids=vids,
+                face_global=gface, face_owner=fowner.astype(np.int32), owned_face=mine.astype(np.uint8), nbrs=np.array(nbrs, dtype=np.int32),
+                send=send, recv=recv, local_topology=ltp)
+
+
+def face_canonical_positions(dim, order, faces, node_vertex_gid):
+    """canon[F][a] = position of local face node a of face F in the rank-independent order of that face: the face-element node order
+    obtained when the face's vertices are taken in ascending global vertex id.  faces: [nF, nNf] local high-order face connectivity
+    (vertices first, in face-element vertex order); node_vertex_gid[node] = global vertex id of a vertex node."""
+    import itertools
+    from . import capi
+    nF, nNf = faces.shape
+    nv = dim                                                     # vertices of a face
+    if order == 1:
+        ranks = np.argsort(np.argsort(node_vertex_gid[faces[:, :nv]], axis=1), axis=1)
+        return ranks.astype(np.uint8)
+    ref = capi.host_refel_tables(dim - 1, order)["nodes"]        # [nNf, dim-1] on [-1,1]^(dim-1)
+    lam = np.concatenate([(1.0 - 0.5 * (ref + 1.0).sum(1))[:, None], 0.5 * (ref + 1.0)], axis=1)   # barycentric wrt the face-element vertices
+    table = {}
+    for rho in itertools.permutations(range(nv)):                # rho[k] = rank of local vertex k in the sorted order
+        lam_c = np.zeros_like(lam)
+        for k in range(nv):
+            lam_c[:, rho[k]] = lam[:, k]
+        d = np.abs(lam_c[:, None, :] - lam[None, :, :]).max(axis=2)
+        pos = d.argmin(axis=1)
+        assert d[np.arange(nNf), pos].max() < 1e-10 and np.unique(pos).size == nNf
+        table[rho] = pos
+    ranks = np.argsort(np.argsort(node_vertex_gid[faces[:, :nv]], axis=1), axis=1)
+    out = np.zeros((nF, nNf), dtype=np.uint8)
+    for rho, pos in table.items():
+        sel = np.all(ranks == np.array(rho)[None, :], axis=1)
+        out[sel] = pos[None, :]
+    return out
+
+
+def set_halo(ctx_handle, prob, canon):
+    """Hand the halo plan of rank_problem() and the canonical face-node positions to the library (hfx_comm_set_halo)."""
+    from . import capi
+    from .capi import check, lib, pi
+    import ctypes as C
+    sc = np.array([a.size for a in prob["send"]], dtype=np.int32); rc = np.array([a.size for a in prob["recv"]], dtype=np.int32)
+    sf = np.concatenate(prob["send"]).astype(np.int32) if prob["send"] else np.zeros(0, dtype=np.int32)
+    rf = np.concatenate(prob["recv"]).astype(np.int32) if prob["recv"] else np.zeros(0, dtype=np.int32)
+    own = np.ascontiguousarray(prob["owned_face"], dtype=np.uint8)
+    check(lib().hfx_comm_set_halo(ctx_handle, int(prob["nbrs"].size), pi(prob["nbrs"]), pi(sc), pi(np.ascontiguousarray(sf)), pi(rc), pi(np.ascontiguousarray(rf)),
+                                  own.ctypes.data_as(C.POINTER(C.c_ubyte)), np.ascontiguousarray(canon, dtype=np.uint8).ctypes.data_as(C.POINTER(C.c_ubyte))), ctx_handle)

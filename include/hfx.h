@@ -97,6 +97,21 @@ int hfx_last_assemble_ms(const hfx_ctx* ctx, float* msTotal, float* msKernel);
 /* development aid: one assemble with per-phase clock64 counters of CTA 0 (cycles16[16]) */
 int hfx_assemble_profile(hfx_ctx* ctx, long long* cycles16);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink  (replaces src/parallel/Partitioner.cpp:42-107,565-826 for this path) -------- */
+/* Every rank holds its owned cells plus the ghost cells across the faces it owns (overlap-1 recompute: assembly needs no exchange).
+   The owner of a face assembles and solves its t trace rows; the other rank sees the face as a ghost column.  Per Krylov iteration:
+   one grouped ncclSend/ncclRecv of the packed ghost-face blocks + one ncclAllReduce of the Gram-Schmidt dots; one more halo exchange of
+   Trace before the local recovery (HDGSolver.cpp:730-732). */
+int hfx_comm_unique_id(char* id128 /*[128] ncclUniqueId, created by rank 0 and broadcast by the host program*/);
+int hfx_comm_init(hfx_ctx* ctx, int nRanks, int rank, const char* id128);
+/* halo plan in LOCAL face ids: for neighbour k, sendFaces = owned faces that are ghosts on nbrRank[k] and recvFaces = ghost faces owned
+   by nbrRank[k], both ordered by global face id (the sharedFaceList contract of Partitioner.h:223); ownedFace[nFaces] = 1 if owned;
+   canonPos[nFaces][nNf] = position of each local face node in the rank-independent node order of its face (blocks travel in that
+   order: the local order of a face comes from its first LOCAL cell and differs between ranks) */
+int hfx_comm_set_halo(hfx_ctx* ctx, int nNbr, const int* nbrRank, const int* sendCount, const int* sendFaces, const int* recvCount,
+                      const int* recvFaces, const unsigned char* ownedFace, const unsigned char* canonPos);
+int hfx_comm_halo_field(hfx_ctx* ctx, const char* faceFieldName); /* Partitioner::updateSharedInformation for one face field */
+
 /* ---- parity hooks ----------------------------------------------------------------------------------------------- */
 /* CSR of the global trace system: sorted columns, explicit zeros (PetscInterface.cpp:99-103).  nnz query with NULLs. */
 int hfx_get_csr(hfx_ctx* ctx, long long* nrows, long long* nnz, long long* rowptr, int* colidx, double* vals, double* rhs);

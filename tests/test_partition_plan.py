@@ -1,0 +1,57 @@
+"""Host logic of the multi-GPU path, on CPU: face ownership, overlap-1 ghost cells, halo send/recv lists and
+the rank-independent face-node order in which trace blocks travel."""
+import numpy as np
+import pytest
+
+from hyperfox_b200 import capi, meshgen, partition as P
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ownership_and_halo_lists_are_consistent(world):
+    v, c = meshgen.kuhn_linear(4, 3)
+    part = P.partition_vector(c.shape[0], world)
+    c2f, f2c = P.global_linear_topology(c, 3)
+    probs = [P.rank_problem(v, c, part, r, 3, c2f, f2c) for r in range(world)]
+    # every face is owned by exactly one rank (ZoltanPartitioner.cpp:83-133: the face travels with one of its cells)
+    owned = np.concatenate([p["face_global"][p["owned_face"] == 1] for p in probs])
+    assert np.array_equal(np.sort(owned), np.arange(f2c.shape[0]))
+    for r, p in enumerate(probs):
+        # rows of owned faces are complete: both adjacent cells are local
+        loc_cells = set(p["cells_global"].tolist())
+        for F in p["face_global"][p["owned_face"] == 1]:
+            assert all(int(cc) in loc_cells for cc in f2c[F] if cc >= 0)
+        # what r sends to s is exactly what s receives from r, in the same (global id) order: the sharedFaceList contract
+        for k, s in enumerate(p["nbrs"]):
+            q = probs[s]
+            ks = list(q["nbrs"]).index(r)
+            assert np.array_equal(p["face_global"][p["send"][k]], q["face_global"][q["recv"][ks]])
+            assert np.all(p["owned_face"][p["send"][k]] == 1) and np.all(p["owned_face"][p["recv"][k]] == 0)
+        # every ghost face is received from exactly one neighbour
+        ghosts = np.flatnonzero(p["owned_face"] == 0)
+        recv = np.concatenate(p["recv"]) if p["recv"] else np.zeros(0, dtype=int)
+        assert np.array_equal(np.sort(recv), ghosts)
+
+
+@pytest.mark.parametrize("dim,order", [(2, 2), (2, 4), (3, 1), (3, 2), (3, 3), (3, 4)])
+def test_canonical_face_node_order_is_rank_independent(dim, order):
+    """The two cells of a face order its nodes differently; the canonical positions must map the same physical node to the same slot."""
+    v, c = meshgen.kuhn_linear(2, dim)
+    nodes, cells = meshgen.high_order(v, c, order)
+    tp = capi.host_compute_faces(dim, order, cells)
+    gv = np.full(nodes.shape[0], -1, dtype=np.int64)
+    gv[cells[:, :dim + 1]] = c
+    fn = capi.host_refel_tables(dim, order)["faceNodes"]
+    canon1 = P.face_canonical_positions(dim, order, tp["faces"], gv)
+    checked = 0
+    for F in range(tp["faces"].shape[0]):
+        c2 = tp["face2cell"][F, 1]
+        if c2 < 0:
+            continue
+        k = list(tp["cell2face"][c2]).index(F)
+        f2 = cells[c2][fn[k]][None, :]
+        canon2 = P.face_canonical_positions(dim, order, f2, gv)[0]
+        a = np.empty(f2.shape[1], dtype=int); a[canon1[F]] = tp["faces"][F]
+        b = np.empty(f2.shape[1], dtype=int); b[canon2] = f2[0]
+        assert np.array_equal(a, b)
+        checked += 1
+    assert checked > 0

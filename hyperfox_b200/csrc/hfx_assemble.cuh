@@ -48,6 +48,12 @@ struct AsmParams {
   const int* faceNodes;       // [nFc][nNf]
   const int8_t* nodeInFace;   // [nFc][nN] inverse of faceNodes (-1 if not on the face)
   const double* mhinv;        // inverse of the reference mass matrix, column-major [ev(nN)][ev(nN)] (unit pad diagonal)
+  // straight-sided elements: reference matrices of the purely geometric blocks (built by hfx_refel_set) and the per-element flag
+  const double* sref;         // S^_r [DIM][nN][ev(nN)]: Squ_d = sum_r detJ Jinv(d,r) S^_r
+  const double* aref;         // A^_r [DIM][ev(nN) x nN] column-major: A_d = sum_r Jinv(d,r) A^_r          (A^_r = M_ref^-1 S^_r)
+  const double* mfref;        // M^f [ev(t) x t]: face reference mass
+  const double* bref;         // B^_f [nFc][nN][t] = M_ref^-1[:, faceNodes_f] M^f: W Sql_d = -(area n_d / detJ) B^_f
+  const uint8_t* affine;      // [nCells] or NULL (shortcut disabled)
   // outputs
   double* U; double* Q; double* U0; double* Q0; double* S; double* S0;  // S,S0 may be NULL
   double* vals; double* rhs;
@@ -394,7 +400,8 @@ struct AsmSmem {
   static_assert(oFFS >= oB, "ffs staging must not overlap the face matrices");
   static constexpr int oFU = oR + szR;                       // Fu [nN]
   static constexpr int oSCR = oFU + ev(nN) + 2;              // (FU[ev(nN)] holds 1/detJ of the first cubature point)
-  static constexpr int oEnd = oSCR + 2 * nNp;
+  static constexpr int oGEO = oSCR + 2 * nNp;                // constant geometry of a straight-sided element: Jinv [DIM*DIM], det, per face n[DIM], area
+  static constexpr int oEnd = oGEO + ev(DIM * DIM + 1 + nFc * (DIM + 1));
   // S staging [l][ldc] for the coalesced write-out: reuses the dead g/A + M + W span when it is large enough (large elements),
   // otherwise gets its own area (small elements, where shared memory is not the limit)
   static constexpr bool stFits = (oSQU - oG) >= l * ldc;
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   double* DIP = sm + L::oDIP; double* VIP = sm + L::oVIP; double* LW = sm + L::oLW; double* FWT = sm + L::oFWT; double* TAU = sm + L::oTAU;
   double* DN = sm + L::oDN; double* VN = sm + L::oVN; double* G = sm + L::oG; double* CG = sm + L::oCG; double* Mm = sm + L::oM;
   double* Wb = sm + L::oW; double* SQU = sm + L::oSQU; double* SUQ = sm + L::oSUQ; double* SUU = sm + L::oSUU; double* FW = sm + L::oFW;
-  double* B = sm + L::oB; double* R = sm + L::oR; double* FU = sm + L::oFU;
+  double* B = sm + L::oB; double* R = sm + L::oR; double* FU = sm + L::oFU; double* GEO = sm + L::oGEO;
   double* WQ = sm + L::oWQ; double* DSH = sm + L::oDSH; double* FDS = sm + L::oFDS; double* FSH = sm + L::oFSH; double* FFS = sm + L::oFFS;
   long long* ROWS = reinterpret_cast<long long*>(sm + L::nDoubles);   // [nFc] first entry of row (F,0) in vals
   long long* RBASE = ROWS + nFc;                                      // [l] first entry of the CSR row of element-local trace row r
@@ -474,9 +481,10 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   long long pfRow = 0;
   // two stages: the second one's addresses depend on values loaded by the first (face ids), so it is issued a few phases later --
   // issuing both back to back parks the issuing warps on the first loads' DRAM latency in the middle of the geometry phase
-  int pfSide = 0;
+  int pfSide = 0, pfAff = 0;
   auto prefetchA = [&](int e) {
     if (!kPrefetch || e >= p.nCells) return;
+    pfAff = p.affine ? p.affine[e] : 0;   // every thread: warp-uniform control flow later, no shared-memory round trip
     if (tid < nN * DIM) pfX = p.elemX[(size_t)e * nN * DIM + tid];
     if (tid >= 64 && tid < 64 + l) {
       const int i = tid - 64, f = i / t;
@@ -497,7 +505,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
   // column tiles (8 columns, kind-major) of the weighted face mass contraction that this model needs
   constexpr int NCT = (nFc * NW + 7) / 8;
-  unsigned baseNeed = 0, intNeed = 0;
+  unsigned baseNeed = 0, intNeed = 0, affNeed = 0;   // affNeed: straight-sided elements take the n_d kinds from the reference face mass
 #pragma unroll
   for (int T = 0; T < NCT; T++) {
 #pragma unroll
@@ -505,6 +513,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       if (cidx < nFc * NW) {
         const int kind = cidx / nFc;
         if (kind <= DIM || (kind < kC && diffField) || (kind == kC && hasConv)) baseNeed |= 1u << T;
+        if (kind == 0 || (kind > DIM && kind < kC && diffField) || (kind == kC && hasConv)) affNeed |= 1u << T;
         if (kind == kOne) intNeed |= 1u << T;
       }
     }
@@ -536,9 +545,14 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       for (int i = tid; i < nFc * nFc; i += NT) POS[i] = p.elemPos[(size_t)e * nFc * nFc + i];
     }
     if (tid == NT - 1) { QCTR[0] = 0; QCTR[1] = 0; QCTR[2] = 0; QCTR[3] = 0; }
+    // straight-sided element (flag computed once at allocate): constant Jacobians straight from the vertices, and the purely geometric
+    // blocks Squ, A = Sqq^-1 Squ, B = Sqq^-1 Sql and the n_d face matrices are scalar combinations of reference matrices
+    const bool aff = (kPrefetch ? pfAff : (p.affine ? (int)p.affine[e] : 0)) != 0;
+    const bool affAB = aff && !diffField;              // with a diffusion field g (which A aliases) is still live when the tables are applied
+    const bool needG = !aff || hasConv || diffField;   // the gradient rows g are only needed by the convection / diffusion-field contractions
     // stage the read-only tables of this element pass (L2 -> shared, asynchronous 16-byte copies)
-    for (int i = tid; i < L::nDSH / 2; i += NT) cp_async16(DSH + 2 * i, p.dshape + 2 * i);
-    for (int i = tid; i < L::nFDS / 2; i += NT) cp_async16(FDS + 2 * i, p.fdshape + 2 * i);
+    if (needG) for (int i = tid; i < L::nDSH / 2; i += NT) cp_async16(DSH + 2 * i, p.dshape + 2 * i);
+    if (!aff) for (int i = tid; i < L::nFDS / 2; i += NT) cp_async16(FDS + 2 * i, p.fdshape + 2 * i);
     for (int i = tid; i < L::nFSH / 2; i += NT) cp_async16(FSH + 2 * i, p.fshape + 2 * i);
     for (int i = tid; i < L::nFFS / 2; i += NT) cp_async16(FFS + 2 * i, p.ffs + 2 * i);
     const int* cell = p.cells + (size_t)e * nN;
@@ -556,7 +570,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     cp_async_wait_all();
     __syncthreads();
     HFX_PROF(0);
-    unsigned tileNeed = baseNeed;
+    unsigned tileNeed = aff ? affNeed : baseNeed;
 #pragma unroll
     for (int f = 0; f < nFc; f++) if (BCF[f] == 2) tileNeed |= intNeed;
     // scatter maps of this element (HDGSolver.cpp:596: matRowCols), consumed by the write-out
@@ -565,7 +579,19 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
     // ---- P1a: raw Jacobians (Operator.cpp:14-39) as two small tensor-core products: rows (ip, r), reduction over the nodes,
     //      columns = the DIM coordinates (one 8-wide tile, DIM columns used) ------------------------------------------------------
-    {
+    if (aff) {
+      for (int idx = tid; idx < nIP * D2 + nFc * nIPf * (DIM - 1) * DIM; idx += NT) {
+        if (idx < nIP * D2) {
+          const int rm = idx % D2, r = rm / DIM, m = rm % DIM;
+          JR[idx] = 0.5 * (X[(r + 1) * DIM + m] - X[m]);
+        } else {
+          const int k2 = idx - nIP * D2;
+          const int fi = k2 / ((DIM - 1) * DIM), rm = k2 % ((DIM - 1) * DIM), r = rm / DIM, m = rm % DIM, f = fi / nIPf;
+          const int* fn = FN + f * t;
+          JR[(nIP + fi) * D2 + r * DIM + m] = 0.5 * (X[fn[r + 1] * DIM + m] - X[fn[0] * DIM + m]);
+        }
+      }
+    } else {
       const int lr = lane >> 2, lc = lane & 3;
       constexpr int MB = nIP * DIM, MBT = (MB + 7) / 8, MF = nIPf * (DIM - 1), MFT = (MF + 7) / 8;
       constexpr int KSB = (nN + 3) / 4, KSF1 = (t + 3) / 4;
@@ -629,7 +655,14 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
             for (int m = 0; m < DIM; m++) J0[r][m] = JR[r * DIM + m];
           const double det0 = det_only(J0);
           if (!(fabs(det - det0) <= 1e-13 * fabs(det0))) QCTR[3] = 1;
-          if (ip == 0) FU[ev(nN)] = fast_rcp(det0);
+          if (ip == 0) {
+            FU[ev(nN)] = fast_rcp(det0);
+#pragma unroll
+            for (int m = 0; m < DIM; m++)
+#pragma unroll
+              for (int r = 0; r < DIM; r++) GEO[m * DIM + r] = I[m][r];
+            GEO[D2] = det;
+          }
         }
         const double dv = WQ[ip] * det;
         DV[ip] = dv;
@@ -725,6 +758,11 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
           for (int m = 0; m < DIM; m++) nv[m] = -nv[m];
         }
+        if (ip == 0) {
+#pragma unroll
+          for (int m = 0; m < DIM; m++) GEO[D2 + 1 + f * (DIM + 1) + m] = nv[m];
+          GEO[D2 + 1 + f * (DIM + 1) + DIM] = area;
+        }
         const double dvf = WQ[nIP + ip] * area;
         double* wt = FWT + (size_t)ip * ldw + f;          // column (kind, f), kind-major: whole column tiles of unused kinds are skipped
         wt[kTau * nFc] = dvf * tauip;
@@ -749,7 +787,9 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     HFX_PROF(1);
 
     // ---- P2: g[ip][(d,i)] = dV (J^-1 grad_ref phi_i)_d ; cg = suu left operand ----------------------------------------
-    for (int idx = tid; idx < nIP * nN; idx += NT) {
+    if (!needG) {
+      if (needSuu) for (int idx = tid; idx < nIP * nN; idx += NT) { const int ip = idx / nN, i = idx % nN; CG[ip * nNp + i] = LW[ip] * PHI[ip * nNp + i]; }
+    } else for (int idx = tid; idx < nIP * nN; idx += NT) {
       const int ip = idx / nN, i = idx % nN;
       const double* d = DSH + (ip * nN + i) * DIM;
       double dr[DIM], gg[DIM];
@@ -784,7 +824,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     // no contraction and no inversion.  Curved elements take the general path.
     const bool constDet = (QCTR[3] == 0);
     double* const W = ((nNp / 2) & 1) ? Wb : Mm;
-    if (constDet) {
+    if (constDet && !affAB) {
       const double rdet = FU[ev(nN)];
       if (kMHReg) {
 #pragma unroll
@@ -819,7 +859,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       constexpr int T_SQU = SQ_MT * NG_N, T_SUU = MTN * NG_N;
       constexpr int MR = t * t, FW_MT = (MR + 7) / 8, NC = nFc * NW, FW_NG = ((NC + 7) / 8 + 2) / 3, T_FW = FW_MT * FW_NG;
       constexpr int T_ALL = T_SQU + T_SUU + T_FW + 1;
-      int task = constDet ? warp : grab1(&QCTR[0], lane);
+      int task = constDet ? warp + (aff ? T_SQU : 0) : grab1(&QCTR[0], lane);   // straight-sided: Squ comes from the reference matrices below
       while (task < T_ALL) {
         if (task < T_SQU + T_SUU) {
           // Squ_d[k][j] = sum_ip g[ip][(d,k)] phi[ip][j]  (HDGBase.cpp:150; with D = I also Suq_d, HDGDiffusion.cpp:130-144)
@@ -881,7 +921,8 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                   const int n = (ng * 3 + j) * 8 + 2 * lc + h;
-                  if (n < NC && (need3 & (1u << j))) dstm[((n % nFc) * NW + n / nFc) * FWS] = c[j][h];
+                  const bool nKind = aff && (n / nFc) >= kN && (n / nFc) < kN + DIM;   // written from the reference face mass instead
+                  if (n < NC && (need3 & (1u << j)) && !nKind) dstm[((n % nFc) * NW + n / nFc) * FWS] = c[j][h];
                 }
               }
             }
@@ -895,6 +936,37 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           }
         }
         task = constDet ? task + NWARP : grab1(&QCTR[0], lane);
+      }
+    }
+    if (aff) {
+      // straight-sided element: Squ_d = detJ sum_r Jinv(d,r) S^_r, A_d = sum_r Jinv(d,r) A^_r, B_d = -(area n_d / detJ) B^_f,
+      // n_d face matrices = -area n_d M^f (stored negated like the contraction does).  Reference matrices are read from L2.
+      const double det = GEO[D2];
+      double Ji[D2];
+#pragma unroll
+      for (int c2 = 0; c2 < D2; c2++) Ji[c2] = GEO[c2];
+      for (int idx = tid; idx < nN * nNp; idx += NT) {
+        double sr[DIM], ar[DIM];
+#pragma unroll
+        for (int r = 0; r < DIM; r++) { sr[r] = __ldg(p.sref + r * nN * nNp + idx); ar[r] = __ldg(p.aref + r * nN * nNp + idx); }
+        const int k = idx / nNp, n = idx - k * nNp;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+          double vs = 0.0, va = 0.0;
+#pragma unroll
+          for (int r = 0; r < DIM; r++) { vs = fma(Ji[d * DIM + r], sr[r], vs); va = fma(Ji[d * DIM + r], ar[r], va); }
+          vs *= det;
+          SQU[(d * nN + k) * nNp + n] = vs;                                             // Squ_d[k][n] (only feeds P3c / parity of layout)
+          if (!diffField && n < nN) SUQ[(d * nN + n) * nNp + k] = hasDiff ? vs : 0.0;   // Suq_d bulk part with D = I
+          if (affAB) A[d * nN * nNp + idx] = va;                                        // A_d column-major: idx = n * nNp + m
+        }
+      }
+      for (int idx = tid; idx < nFc * FWS; idx += NT) {
+        const int f = idx / FWS, ab = idx - f * FWS;
+        const double* gf = GEO + D2 + 1 + f * (DIM + 1);
+        const double sc = -gf[DIM] * __ldg(p.mfref + ab);
+#pragma unroll
+        for (int d = 0; d < DIM; d++) FW[(f * NW + kN + d) * FWS + ab] = sc * gf[d];
       }
     }
     __syncthreads();
@@ -966,7 +1038,17 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       const int lr = lane >> 2, lc = lane & 3;
       constexpr int NG_N = (MTN + 2) / 3, T_A = DIM * MTN * NG_N;
       constexpr int NB = DIM * t, NBT = (NB + 7) / 8, NG_B = (NBT + 2) / 3, T_B = nFc * MTN * NG_B;
-      for (int task = warp; task < T_A + T_B; task += NWARP) {
+      if (affAB) {   // B_d = -(area n_d / detJ) B^_f  (here, not beside the face contraction: the staged phi_a phi_b table lives in the B region)
+        const double rdet = FU[ev(nN)];
+        for (int idx = tid; idx < nFc * nN * t; idx += NT) {
+          const int f = idx / (nN * t), rem = idx - f * nN * t, m = rem / t, b = rem - m * t;
+          const double* gf = GEO + D2 + 1 + f * (DIM + 1);
+          const double sc = -gf[DIM] * rdet * __ldg(p.bref + idx);
+#pragma unroll
+          for (int d = 0; d < DIM; d++) B[(d * nN + m) * ldc + f * t + b] = sc * gf[d];
+        }
+      }
+      if (!affAB) for (int task = warp; task < T_A + T_B; task += NWARP) {
         if (task < T_A) {
           const int d = task / (MTN * NG_N), r = task % (MTN * NG_N);
           const int m = (r % MTN) * 8 + lr, ng = r / MTN;

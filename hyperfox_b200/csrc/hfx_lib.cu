@@ -128,6 +128,24 @@ __global__ void elem_coords_kernel(long long n, int nN, int dim, const double* _
   elemX[idx] = nodes[(size_t)cells[ei] * dim + m];
 }
 
+// 1 if every node of the element sits at the affine image of its reference position (straight-sided simplex): the Jacobian is then
+// constant over the element and the fused kernel takes the reference-matrix shortcut for the purely geometric blocks
+__global__ void elem_affine_kernel(int nCells, int nN, int dim, const double* __restrict__ elemX, const double* __restrict__ bary, uint8_t* __restrict__ affine) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nCells) return;
+  const double* X = elemX + (size_t)e * nN * dim;
+  double h = 0.0;
+  for (int v = 1; v <= dim; v++) for (int m = 0; m < dim; m++) h = fmax(h, fabs(X[v * dim + m] - X[m]));
+  bool ok = true;
+  for (int i = dim + 1; i < nN && ok; i++)
+    for (int m = 0; m < dim; m++) {
+      double s = 0.0;
+      for (int v = 0; v <= dim; v++) s = fma(bary[i * (dim + 1) + v], X[v * dim + m], s);
+      if (!(fabs(s - X[i * dim + m]) <= 1e-13 * h)) ok = false;
+    }
+  affine[e] = ok ? 1 : 0;
+}
+
 __global__ void ip_coords_kernel(int nCells, int nN, int nIP, int dim, const double* __restrict__ nodes, const int* __restrict__ cells,
                                  const double* __restrict__ shape, double* __restrict__ xip) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -542,7 +560,8 @@ struct hfx_ctx {
   // reference element
   std::unique_ptr<RefElement> re;
   int dim = 0, order = 0, nN = 0, nNf = 0, nFc = 0, nIP = 0, nIPf = 0;
-  DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv;
+  DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv, dSRef, dARef, dMFRef, dBRef, dBary;
+  DBuf<uint8_t> dAffine;
   DBuf<int> dFaceNodes; DBuf<int8_t> dNodeInFace;
   // mesh
   int nNodes = 0, nCells = 0, nFaces = 0;
@@ -771,6 +790,42 @@ int hfx_refel_set(hfx_ctx* c, int dim, int order, int geom) {
       for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) mh[(size_t)i + (size_t)np * j] = I[(size_t)i * n + j];
       if (np > n) mh[(size_t)n + (size_t)np * n] = 1.0;
       c->dMHInv.upload(mh, c->st);
+      // Straight-sided (affine) elements: J is constant, so the bulk blocks are scalar combinations of reference matrices.
+      //   S^_r[k][j] = sum_ip w dphi_k/dxi_r phi_j ;  A^_r = M_ref^-1 S^_r ;  M^f = face reference mass ;  B^_f = M_ref^-1[:, faceNodes_f] M^f
+      const int dim = c->dim, t = c->nNf, tp = (t + 1) & ~1, nipf = c->nIPf;
+      std::vector<double> sref((size_t)dim * n * np, 0.0), aref((size_t)dim * np * n, 0.0), mf((size_t)tp * t, 0.0), bref((size_t)c->nFc * n * t, 0.0);
+      for (int r = 0; r < dim; r++)
+        for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) {
+          double s2 = 0.0;
+          for (int ip = 0; ip < nip; ip++) s2 += re.ipWeights()[ip] * re.ipDShape()[((size_t)ip * n + k) * dim + r] * re.ipShape()[(size_t)ip * n + j];
+          sref[((size_t)r * n + k) * np + j] = s2;
+        }
+      for (int r = 0; r < dim; r++)
+        for (int m = 0; m < n; m++) for (int j = 0; j < n; j++) {
+          double s2 = 0.0;
+          for (int k = 0; k < n; k++) s2 += I[(size_t)m * n + k] * sref[((size_t)r * n + k) * np + j];
+          aref[((size_t)r * n + j) * np + m] = s2;   // column-major like A_d
+        }
+      for (int a = 0; a < t; a++) for (int b = 0; b < t; b++) {
+        double s2 = 0.0;
+        for (int ip = 0; ip < nipf; ip++) s2 += fe->ipWeights()[ip] * fe->ipShape()[(size_t)ip * t + a] * fe->ipShape()[(size_t)ip * t + b];
+        mf[(size_t)a + (size_t)tp * b] = s2;
+      }
+      for (int f = 0; f < c->nFc; f++)
+        for (int m = 0; m < n; m++) for (int b = 0; b < t; b++) {
+          double s2 = 0.0;
+          for (int a = 0; a < t; a++) s2 += I[(size_t)m * n + re.faceNodes()[(size_t)f * t + a]] * mf[(size_t)a + (size_t)tp * b];
+          bref[((size_t)f * n + m) * t + b] = s2;
+        }
+      c->dSRef.upload(padded(sref), c->st); c->dARef.upload(padded(aref), c->st); c->dMFRef.upload(padded(mf), c->st); c->dBRef.upload(padded(bref), c->st);
+      // barycentric coordinates of the reference nodes (affinity test of the physical elements at allocate)
+      std::vector<double> bary((size_t)n * (dim + 1));
+      for (int i = 0; i < n; i++) {
+        double s0 = 1.0;
+        for (int d = 0; d < dim; d++) { const double lam = 0.5 * (re.nodes()[(size_t)i * dim + d] + 1.0); bary[(size_t)i * (dim + 1) + d + 1] = lam; s0 -= lam; }
+        bary[(size_t)i * (dim + 1)] = s0;
+      }
+      c->dBary.upload(bary, c->st);
     }
     std::vector<int8_t> nif((size_t)c->nFc * c->nN, -1);
     for (int f = 0; f < c->nFc; f++) for (int a = 0; a < t; a++) nif[(size_t)f * c->nN + re.faceNodes()[(size_t)f * t + a]] = (int8_t)a;
@@ -969,6 +1024,9 @@ int hfx_allocate(hfx_ctx* c, int flags) {
     c->dElemX.alloc((size_t)nC * c->nN * c->dim);
     elem_coords_kernel<<<nblk((long long)nC * c->nN * c->dim, 256), 256, 0, c->st>>>((long long)nC * c->nN * c->dim, c->nN, c->dim, c->dNodes.p, c->dCells.p, c->dElemX.p);
     HFX_CUDA(cudaGetLastError());
+    c->dAffine.alloc(nC);
+    elem_affine_kernel<<<nblk(nC, 128), 128, 0, c->st>>>(nC, c->nN, c->dim, c->dElemX.p, c->dBary.p, c->dAffine.p);
+    HFX_CUDA(cudaGetLastError());
     // element blocks (HDGSolver.cpp:93-104) and the global system (linSystem->allocate :81)
     c->dU.alloc((size_t)nC * u * l); c->dQ.alloc((size_t)nC * q * l); c->dU0.alloc((size_t)nC * u); c->dQ0.alloc((size_t)nC * q);
     if (c->keepS) { c->dS.alloc((size_t)nC * l * l); c->dS0.alloc((size_t)nC * l); } else { c->dS.release(); c->dS0.release(); }
@@ -1009,6 +1067,8 @@ int hfx_assemble(hfx_ctx* c) {
     p.dirichlet = find_field(c, "Dirichlet")->d.p;
     p.shape = c->dShape.p; p.dshape = c->dDShape.p; p.w = c->dW.p; p.fshape = c->dFShape.p; p.fdshape = c->dFDShape.p; p.fw = c->dFW.p; p.ffs = c->dFFS.p;
     p.faceNodes = c->dFaceNodes.p; p.nodeInFace = c->dNodeInFace.p; p.mhinv = c->dMHInv.p;
+    p.sref = c->dSRef.p; p.aref = c->dARef.p; p.mfref = c->dMFRef.p; p.bref = c->dBRef.p;
+    p.affine = getenv("HFX_NO_AFFINE") ? nullptr : c->dAffine.p;
     p.U = c->dU.p; p.Q = c->dQ.p; p.U0 = c->dU0.p; p.Q0 = c->dQ0.p; p.S = c->dS.p; p.S0 = c->dS0.p;
     p.vals = c->dVals.p; p.rhs = c->dRhs.p; p.status = c->dStatus.p;
     p.prof = c->profOn ? c->dProf.p : nullptr;

@@ -579,19 +579,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
     // ---- P1a: raw Jacobians (Operator.cpp:14-39) as two small tensor-core products: rows (ip, r), reduction over the nodes,
     //      columns = the DIM coordinates (one 8-wide tile, DIM columns used) ------------------------------------------------------
-    if (aff) {
-      for (int idx = tid; idx < nIP * D2 + nFc * nIPf * (DIM - 1) * DIM; idx += NT) {
-        if (idx < nIP * D2) {
-          const int rm = idx % D2, r = rm / DIM, m = rm % DIM;
-          JR[idx] = 0.5 * (X[(r + 1) * DIM + m] - X[m]);
-        } else {
-          const int k2 = idx - nIP * D2;
-          const int fi = k2 / ((DIM - 1) * DIM), rm = k2 % ((DIM - 1) * DIM), r = rm / DIM, m = rm % DIM, f = fi / nIPf;
-          const int* fn = FN + f * t;
-          JR[(nIP + fi) * D2 + r * DIM + m] = 0.5 * (X[fn[r + 1] * DIM + m] - X[fn[0] * DIM + m]);
-        }
-      }
-    } else {
+    if (!aff) {
       const int lr = lane >> 2, lc = lane & 3;
       constexpr int MB = nIP * DIM, MBT = (MB + 7) / 8, MF = nIPf * (DIM - 1), MFT = (MF + 7) / 8;
       constexpr int KSB = (nN + 3) / 4, KSF1 = (t + 3) / 4;
@@ -631,7 +619,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         }
       }
     }
-    __syncthreads();
+    if (!aff) __syncthreads();   // (straight-sided elements read their constant Jacobians straight from the vertices: no P1a, no barrier)
     HFX_PROF(5);
     // the next element's gather flies while this element is computed
     prefetchA(e + gridDim.x);
@@ -644,7 +632,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
         for (int r = 0; r < DIM; r++)
 #pragma unroll
-          for (int m = 0; m < DIM; m++) J[r][m] = JR[ip * D2 + r * DIM + m];
+          for (int m = 0; m < DIM; m++) J[r][m] = aff ? 0.5 * (X[(r + 1) * DIM + m] - X[m]) : JR[ip * D2 + r * DIM + m];
         double det, I[DIM][DIM];
         det_inv(J, det, I);
         {   // is det J constant over the element?  (then M = det J * reference mass exactly, whatever the geometry does otherwise)
@@ -652,8 +640,8 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
           for (int r = 0; r < DIM; r++)
 #pragma unroll
-            for (int m = 0; m < DIM; m++) J0[r][m] = JR[r * DIM + m];
-          const double det0 = det_only(J0);
+            for (int m = 0; m < DIM; m++) J0[r][m] = aff ? J[r][m] : JR[r * DIM + m];
+          const double det0 = aff ? det : det_only(J0);
           if (!(fabs(det - det0) <= 1e-13 * fabs(det0))) QCTR[3] = 1;
           if (ip == 0) {
             FU[ev(nN)] = fast_rcp(det0);
@@ -713,7 +701,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
         for (int r = 0; r < DIM - 1; r++)
 #pragma unroll
-          for (int m = 0; m < DIM; m++) J[r][m] = JR[(nIP + fi) * D2 + r * DIM + m];
+          for (int m = 0; m < DIM; m++) J[r][m] = aff ? 0.5 * (X[fn[r + 1] * DIM + m] - X[fn[0] * DIM + m]) : JR[(nIP + fi) * D2 + r * DIM + m];
         double tauip = 0.0, Dc[D2], v[DIM];
 #pragma unroll
         for (int c = 0; c < D2; c++) Dc[c] = 0.0;
@@ -783,6 +771,36 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         wt[kOne * nFc] = dvf;
       }
     }
+    if (aff) {
+      // Straight-sided element, beside the per-point work above (done by the first warps only): the purely geometric bulk blocks as
+      // scalar combinations of reference matrices (read from L2; their latency hides behind the serial chains of the geometry):
+      //   Squ_d = detJ sum_r Jinv(d,r) S^_r  (-> Suq_d bulk part when D = I),   A_d = Sqq^-1 Squ_d = sum_r Jinv(d,r) A^_r.
+      constexpr int TOFF = (((nJ + 31) / 32) * 32 <= NT - 64) ? ((nJ + 31) / 32) * 32 : 0;
+      if (tid >= TOFF) {
+        double J[DIM][DIM], det, Ii[DIM][DIM];
+#pragma unroll
+        for (int r = 0; r < DIM; r++)
+#pragma unroll
+          for (int m = 0; m < DIM; m++) J[r][m] = 0.5 * (X[(r + 1) * DIM + m] - X[m]);
+        det_inv(J, det, Ii);
+        for (int idx = tid - TOFF; idx < nN * nNp; idx += NT - TOFF) {
+          double sr[DIM], ar[DIM];
+#pragma unroll
+          for (int r = 0; r < DIM; r++) { sr[r] = __ldg(p.sref + r * nN * nNp + idx); ar[r] = affAB ? __ldg(p.aref + r * nN * nNp + idx) : 0.0; }
+          const int k = idx / nNp, n = idx - k * nNp;
+#pragma unroll
+          for (int d = 0; d < DIM; d++) {
+            double vs = 0.0, va = 0.0;
+#pragma unroll
+            for (int r = 0; r < DIM; r++) { vs = fma(Ii[d][r], sr[r], vs); va = fma(Ii[d][r], ar[r], va); }
+            vs *= det;
+            if (!affAB) SQU[(d * nN + k) * nNp + n] = vs;                                 // right operand of A = W Squ (general P4 path)
+            if (!diffField && n < nN) SUQ[(d * nN + n) * nNp + k] = hasDiff ? vs : 0.0;   // Suq_d bulk part with D = I
+            if (affAB) A[d * nN * nNp + idx] = va;                                        // A_d column-major: idx = n * nNp + m
+          }
+        }
+      }
+    }
     __syncthreads();
     HFX_PROF(1);
 
@@ -801,7 +819,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
         for (int r = 0; r < DIM; r++) s = fma(IJ[ip * D2 + m * DIM + r], dr[r], s);
         gg[m] = s;
-        G[ip * ldg + m * nN + i] = s;
+        if (!aff || diffField) G[ip * ldg + m * nN + i] = s;   // straight-sided: A (which aliases g) is already in place
       }
       double c = LW[ip] * PHI[ip * nNp + i];
       if (hasConv) {
@@ -939,28 +957,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
     }
     if (aff) {
-      // straight-sided element: Squ_d = detJ sum_r Jinv(d,r) S^_r, A_d = sum_r Jinv(d,r) A^_r, B_d = -(area n_d / detJ) B^_f,
-      // n_d face matrices = -area n_d M^f (stored negated like the contraction does).  Reference matrices are read from L2.
-      const double det = GEO[D2];
-      double Ji[D2];
-#pragma unroll
-      for (int c2 = 0; c2 < D2; c2++) Ji[c2] = GEO[c2];
-      for (int idx = tid; idx < nN * nNp; idx += NT) {
-        double sr[DIM], ar[DIM];
-#pragma unroll
-        for (int r = 0; r < DIM; r++) { sr[r] = __ldg(p.sref + r * nN * nNp + idx); ar[r] = __ldg(p.aref + r * nN * nNp + idx); }
-        const int k = idx / nNp, n = idx - k * nNp;
-#pragma unroll
-        for (int d = 0; d < DIM; d++) {
-          double vs = 0.0, va = 0.0;
-#pragma unroll
-          for (int r = 0; r < DIM; r++) { vs = fma(Ji[d * DIM + r], sr[r], vs); va = fma(Ji[d * DIM + r], ar[r], va); }
-          vs *= det;
-          SQU[(d * nN + k) * nNp + n] = vs;                                             // Squ_d[k][n] (only feeds P3c / parity of layout)
-          if (!diffField && n < nN) SUQ[(d * nN + n) * nNp + k] = hasDiff ? vs : 0.0;   // Suq_d bulk part with D = I
-          if (affAB) A[d * nN * nNp + idx] = va;                                        // A_d column-major: idx = n * nNp + m
-        }
-      }
+      // straight-sided element: n_d face matrices = -area n_d M^f (stored negated like the contraction does)
       for (int idx = tid; idx < nFc * FWS; idx += NT) {
         const int f = idx / FWS, ab = idx - f * FWS;
         const double* gf = GEO + D2 + 1 + f * (DIM + 1);
@@ -1007,6 +1004,25 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       __syncthreads();
     }
     HFX_PROF(6);
+    if (affAB) {   // B_d = -(area n_d / detJ) B^_f  (after the face contraction: the staged phi_a phi_b table lives in the B region)
+      const double rdet = FU[ev(nN)];
+      constexpr int NIB = (nFc * nN * t + NT - 1) / NT;
+      double bv[NIB];
+#pragma unroll
+      for (int it = 0; it < NIB; it++) { const int idx = tid + it * NT; bv[it] = idx < nFc * nN * t ? __ldg(p.bref + idx) : 0.0; }
+#pragma unroll
+      for (int it = 0; it < NIB; it++) {
+        const int idx = tid + it * NT;
+        if (idx < nFc * nN * t) {
+          const int f = idx / (nN * t), rem = idx - f * nN * t, m = rem / t, b = rem - m * t;
+          const double* gf = GEO + D2 + 1 + f * (DIM + 1);
+          const double sc = -gf[DIM] * rdet * bv[it];
+#pragma unroll
+          for (int d = 0; d < DIM; d++) B[(d * nN + m) * ldc + f * t + b] = sc * gf[d];
+        }
+      }
+      for (int idx = tid; idx < DIM * nN; idx += NT) { B[idx * ldc + l] = 0.0; B[idx * ldc + l + 1] = 0.0; }  // Q0 column
+    }
     // face parts of Suu (+tau mass, HDGBase.cpp:128) and Suq (-(Dn) mass, HDGDiffusion.cpp:121), gather form
     for (int idx = tid; idx < nN * nN; idx += NT) {
       const int i = idx % nN, j = idx / nN;
@@ -1038,16 +1054,6 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       const int lr = lane >> 2, lc = lane & 3;
       constexpr int NG_N = (MTN + 2) / 3, T_A = DIM * MTN * NG_N;
       constexpr int NB = DIM * t, NBT = (NB + 7) / 8, NG_B = (NBT + 2) / 3, T_B = nFc * MTN * NG_B;
-      if (affAB) {   // B_d = -(area n_d / detJ) B^_f  (here, not beside the face contraction: the staged phi_a phi_b table lives in the B region)
-        const double rdet = FU[ev(nN)];
-        for (int idx = tid; idx < nFc * nN * t; idx += NT) {
-          const int f = idx / (nN * t), rem = idx - f * nN * t, m = rem / t, b = rem - m * t;
-          const double* gf = GEO + D2 + 1 + f * (DIM + 1);
-          const double sc = -gf[DIM] * rdet * __ldg(p.bref + idx);
-#pragma unroll
-          for (int d = 0; d < DIM; d++) B[(d * nN + m) * ldc + f * t + b] = sc * gf[d];
-        }
-      }
       if (!affAB) for (int task = warp; task < T_A + T_B; task += NWARP) {
         if (task < T_A) {
           const int d = task / (MTN * NG_N), r = task % (MTN * NG_N);
@@ -1101,9 +1107,9 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           }
         }
       }
-      for (int idx = tid; idx < DIM * nN; idx += NT) { B[idx * ldc + l] = 0.0; B[idx * ldc + l + 1] = 0.0; }  // Q0 column
+      if (!affAB) for (int idx = tid; idx < DIM * nN; idx += NT) { B[idx * ldc + l] = 0.0; B[idx * ldc + l + 1] = 0.0; }  // Q0 column
     }
-    __syncthreads();
+    if (!affAB) __syncthreads();
     HFX_PROF(8);
 
     // ---- P5: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335), R = Sul - sum_d Suq_d B_d with column l = -Fu (:342-343).

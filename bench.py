@@ -224,6 +224,17 @@ def main():
     wall_ms = (time.time() - t1) * 1e3 / args.steps
     clocks = sampler.stop() if rank == 0 else None
     my_ms = float(np.mean(ms_tot)); my_k = float(np.mean(ms_k))
+    # transparency: the same workload through the GENERAL path of the fused kernel (what curved elements / diffusion-field models take):
+    # the straight-sided shortcut is switched off for three untimed-in-the-headline steps
+    os.environ["HFX_NO_AFFINE"] = "1"
+    gen_k = []
+    for i in range(3):
+        check(L.hfx_assemble(h), h)
+        L.hfx_last_assemble_ms(h, C.byref(a), C.byref(b))
+        if i > 0:
+            gen_k.append(a.value)
+    del os.environ["HFX_NO_AFFINE"]
+    general_ms = float(np.mean(gen_k))
 
     # ---- end-to-end arm: reference-shaped API, host fields, H2D + D2H inside the timed region ---------------------------
     e2e_ms = None
@@ -288,7 +299,10 @@ def main():
                                % (order, N, nTot), "elements_per_rank": nC, "owned_elements_rank0": nOwned, "partition": ("slabs of the lexicographic Kuhn mesh, overlap-1 ghost cells recomputed by the face owner" if world > 1 else "single rank"), "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
                    "l2": "inputs+outputs per step (%.1f GB) far larger than the 126 MB L2" % ((BYTES_STORE[order] * nC) / 1e9),
                    "timing": "CUDA events on the library stream around memset+kernel, max over ranks; wall-clock per step %.2f ms" % ms_wall,
-                   "setup_s": round(t_setup, 1)},
+                   "setup_s": round(t_setup, 1),
+                   "straight_sided_shortcut": "every element of this mesh is affine and takes the reference-matrix shortcut for the purely geometric blocks "
+                                              "(DESIGN.md 4.1); with the shortcut disabled (general path, as for curved elements) rank 0 runs at %.3g elements/s"
+                                              % (nC / (general_ms * 1e-3))},
         "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4 + DFMA share one 64 FMA/clk/SM pipe; tcgen05 has no FP64 kind)", "achieved": ach, "peak": peak["tflops"], "unit": "TFLOP/s", "frac": ach / peak["tflops"] if peak["tflops"] else None,
                      "traffic": (NCU_TRAFFIC_PER_ELEM[order] * nC if order in NCU_TRAFFIC_PER_ELEM else None),
                      "traffic_source": "ncu --set full capture at 82,944 tets scaled per element (profiles/r1_assemble_p3_ncu_full_summary.txt); algorithmic bytes %d/element" % BYTES_STORE[order],

@@ -81,7 +81,7 @@ __device__ inline void cta_invert(double* aug, int n, double* scr, int* ipiv, in
   }
 }
 
-__global__ void __launch_bounds__(kGenThreads) hdg_generic_kernel(const GenParams P) {
+__global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenParams P) {
   const AsmParams& p = P.a;
   const int dim = P.dim, nN = P.nN, nNf = P.nNf, nFc = P.nFc, nIP = P.nIP, nIPf = P.nIPf, nD = P.nD;
   const GenWs z(dim, nN, nNf, nFc, nIP, nIPf, nD);

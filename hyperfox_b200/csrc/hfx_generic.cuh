@@ -24,6 +24,11 @@ struct GenParams {
   int nSrc;                  // source components: 1, or dim for the Burgers model (HDGBurgersModel.cpp:112-122)
   double* ws;                // per-CTA scratch
   long long wsStride;        // doubles per CTA
+  // RungeKutta::apply (src/operator/RungeKutta.cpp:90-143), auxiliary fields {Flux, Trace}: time scheme code 2
+  int rkStage, rkNumStages;
+  double rkRow[8];           // Butcher row of the current stage (a_s0 .. a_s,nStages-1)
+  const double* oldSol; const double* oldFlux; const double* oldTrace;          // OldSolution / OldFlux (cell), OldTrace (face)
+  const double* rkSol[8]; const double* rkFlux[8]; const double* rkTrace[8];   // RKStage_k, RKStage_Flux_k (cell), RKStage_Trace_k (face)
 };
 
 // scratch layout (offsets in doubles), identical on host and device
@@ -386,6 +391,39 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         double s = 0.0;
         for (int j = 0; j < nN; j++) s = fma(MM[i * nN + j], SOLD[j * nD + k], s);
         Fv[r] = fma(Fv[r], p.dt, s);
+      }
+      __syncthreads();
+    }
+
+    if (p.timeScheme == 2) {   // RungeKutta::apply on the u rows (stiffness = Su [u x n], columns [Solution | Flux | Trace])
+      // UJ = dt sum_{s < stage} a_s [RKStage_s ; RKStage_Flux_s ; RKStage_Trace_s] + UT,  UT = [OldSolution ; OldFlux ; OldTrace]   (element-local order)
+      double* UT = Bq; double* UJ = Bq + n;     // Bq [q x (l+1)] >= 2n doubles is free until the condensation
+      for (int j = tid; j < n; j += NT) {
+        double ut, uj = 0.0;
+        if (j < u) { ut = P.oldSol[(size_t)e * u + j]; for (int s2 = 0; s2 < P.rkStage; s2++) uj = fma(P.rkRow[s2], P.rkSol[s2][(size_t)e * u + j], uj); }
+        else if (j < sL) { const int jq = j - u; ut = P.oldFlux[(size_t)e * q + jq]; for (int s2 = 0; s2 < P.rkStage; s2++) uj = fma(P.rkRow[s2], P.rkFlux[s2][(size_t)e * q + jq], uj); }
+        else {
+          const int jl = j - sL, fa = jl / nD, k = jl - fa * nD, f = fa / nNf;
+          const size_t g = ((size_t)FACE[f] * nNf + PERM[fa]) * nD + k;
+          ut = P.oldTrace[g];
+          for (int s2 = 0; s2 < P.rkStage; s2++) uj = fma(P.rkRow[s2], P.rkTrace[s2][g], uj);
+        }
+        UT[j] = ut; UJ[j] = fma(uj, p.dt, ut);
+      }
+      __syncthreads();
+      const double ass = P.rkRow[P.rkStage];
+      for (int r = tid; r < u; r += NT) {   // s <- dt s - (dt Su) uj ; Su <- a_ss dt Su + [M 0 0] ; s += Su ut
+        const int i = r / nD, k = r - i * nD;
+        double ex = 0.0, im = 0.0;
+        for (int j = 0; j < n; j++) {
+          double v = Lm[(size_t)r + (size_t)n * j] * p.dt;
+          ex = fma(v, UJ[j], ex);
+          v *= ass;
+          if (j < u && (j % nD) == k) v += MM[i * nN + j / nD];
+          Lm[(size_t)r + (size_t)n * j] = v;
+          im = fma(v, UT[j], im);
+        }
+        Fv[r] = fma(Fv[r], p.dt, -ex) + im;
       }
       __syncthreads();
     }

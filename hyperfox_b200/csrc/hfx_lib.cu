@@ -572,6 +572,7 @@ struct hfx_ctx {
   std::map<std::string, DField> fields;
   DBuf<double> dSrc, dReac; int nSrc = 1;
   DBuf<double> dGenWs; int genGrid = 0; long long genStride = 0;
+  int rkStage = 0, rkNumStages = 0; double rkRow[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // model / boundary
   hfx_model_desc md{1, HFX_OP_DIFFUSION, HFX_TS_NONE, 0.0};
   bool modelSet = false, bcSet = false;
@@ -937,9 +938,19 @@ int hfx_model_describe(hfx_ctx* c, const hfx_model_desc* md) {
       need(!(md->opmask & HFX_OP_CONVECTION), "HDGModel", "allocate", "no model combines HDGUNabU with HDGConvection");
     }
     if ((md->opmask & HFX_OP_SOURCE) && md->nDOF > 1) need(md->opmask & HFX_OP_UNABU, "Source", "assemble", "a scalar Source operator needs nDOFsPerNode == 1 (Source.cpp:40-47)");
-    need(md->timeScheme == HFX_TS_NONE || md->timeScheme == HFX_TS_EULER_IMPLICIT, "HDGModel", "setTimeScheme", "unsupported time scheme");
+    need(md->timeScheme == HFX_TS_NONE || md->timeScheme == HFX_TS_EULER_IMPLICIT || md->timeScheme == HFX_TS_RUNGE_KUTTA, "HDGModel", "setTimeScheme", "unsupported time scheme");
     if (c->modelSet && c->md.nDOF != md->nDOF) c->allocated = false;   // block sizes change with nDOF only
     c->md = *md; c->modelSet = true; c->assembled = false;
+  });
+}
+
+int hfx_time_scheme_rk(hfx_ctx* c, int stage, int nStages, const double* row) {
+  return guard(c, [&] {
+    need(nStages >= 1 && nStages <= 8 && stage >= 0 && stage < nStages, "RungeKutta", "apply", "between 1 and 8 stages, 0 <= stage < stages");
+    for (int k = stage + 1; k < nStages; k++) need(row[k] == 0.0, "RungeKutta", "setButcherTable", "the upper triangular part of the Butcher table should be null (no fully implicit implementation as of yet)");
+    c->rkStage = stage; c->rkNumStages = nStages;
+    for (int k = 0; k < 8; k++) c->rkRow[k] = k < nStages ? row[k] : 0.0;
+    c->assembled = false;
   });
 }
 
@@ -1076,7 +1087,7 @@ int hfx_assemble(hfx_ctx* c) {
     // linSystem->clearSystem() (HDGSolver.cpp:532-536): entries with two contributors are accumulated on zeroed storage
     c->dVals.zero(c->st); c->dRhs.zero(c->st); c->dStatus.zero(c->st);
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
-    bool fused = c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && !getenv("HFX_FORCE_GENERIC");
+    bool fused = c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
     if (fused) {
       bool supported = true;
       HFX_CUDA(launch_assemble(c->dim, c->order, p, c->nSM, c->st, &supported));
@@ -1093,6 +1104,27 @@ int hfx_assemble(hfx_ctx* c) {
         g.nSrc = c->dim;
       }
       if (p.opmask & HFX_OP_SOURCE) need(c->nSrc == g.nSrc, "Source", "calcSource", "the number of source components does not match the model");
+      if (p.timeScheme == HFX_TS_RUNGE_KUTTA) {   // RungeKutta::setFieldMap checks (RungeKutta.cpp:44-88), auxiliary fields {Flux, Trace}
+        need(c->rkNumStages >= 1, "RungeKutta", "apply", "the Butcher row of the stage must be set (hfx_time_scheme_rk) before assembling");
+        const int uq = c->nN * g.nD, qq = uq * c->dim;
+        auto cellf = [&](const std::string& nm, int vals) -> const double* {
+          DField* f = find_field(c, nm.c_str());
+          need(f && f->type == HFX_FIELD_CELL && f->nObj * f->nVal == vals, "RungeKutta", "setFieldMap", ("the field map must provide the field " + nm).c_str());
+          return f->d.p;
+        };
+        auto facef = [&](const std::string& nm) -> const double* {
+          DField* f = find_field(c, nm.c_str());
+          need(f && f->type == HFX_FIELD_FACE && f->nObj == c->nNf && f->nVal == g.nD, "RungeKutta", "setFieldMap", ("the field map must provide the field " + nm).c_str());
+          return f->d.p;
+        };
+        g.oldSol = cellf("OldSolution", uq); g.oldFlux = cellf("OldFlux", qq); g.oldTrace = facef("OldTrace");
+        g.rkStage = c->rkStage; g.rkNumStages = c->rkNumStages;
+        for (int k = 0; k < 8; k++) g.rkRow[k] = c->rkRow[k];
+        for (int k = 0; k < c->rkStage; k++) {
+          g.rkSol[k] = cellf("RKStage_" + std::to_string(k), uq); g.rkFlux[k] = cellf("RKStage_Flux_" + std::to_string(k), qq);
+          g.rkTrace[k] = facef("RKStage_Trace_" + std::to_string(k));
+        }
+      }
       const int uu = c->nN * g.nD;
       need(uu <= 96, "HDGSolver", "assemble", "the general device kernel supports local solution blocks of at most 96 unknowns");
       const GenWs z(g.dim, g.nN, g.nNf, g.nFc, g.nIP, g.nIPf, g.nD);

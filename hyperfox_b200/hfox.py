@@ -116,6 +116,80 @@ class Euler:
     def setTimeStep(self, dt): self.dt = dt
 
 
+# RKType (src/operator/RKType.h) and the Butcher tables of RungeKutta::setUpDB (src/operator/RungeKutta.cpp:215-291): row s < nStages =
+# [c_s | a_s0 .. a_s,nStages-1], last row = [0 | b_0 .. b_nStages-1]
+FEuler, EMidpoint, Heun, Kutta3, Heun3, SSPRK3, RK4, BEuler, IMidpoint, CrankNicolson, KS2, QZ2, ALX2, RK43 = range(14)
+_g = 1.0 - np.sqrt(2.0) / 2.0
+BUTCHER = {
+    FEuler: [[0, 0], [0, 1]],
+    EMidpoint: [[0, 0, 0], [0.5, 0.5, 0], [0, 0, 1]],
+    Heun: [[0, 0, 0], [1, 1, 0], [0, 0.5, 0.5]],
+    Kutta3: [[0, 0, 0, 0], [0.5, 0.5, 0, 0], [1, -1, 2, 0], [0, 1 / 6, 2 / 3, 1 / 6]],
+    Heun3: [[0, 0, 0, 0], [1 / 3, 1 / 3, 0, 0], [2 / 3, 0, 2 / 3, 0], [0, 1 / 4, 0, 3 / 4]],
+    SSPRK3: [[0, 0, 0, 0], [1, 1, 0, 0], [0.5, 0.25, 0.25, 0], [0, 1 / 6, 1 / 6, 2 / 3]],
+    RK4: [[0, 0, 0, 0, 0], [0.5, 0.5, 0, 0, 0], [0.5, 0, 0.5, 0, 0], [1, 0, 0, 1, 0], [0, 1 / 6, 1 / 3, 1 / 3, 1 / 6]],
+    BEuler: [[1, 1], [0, 1]],
+    IMidpoint: [[0.5, 0.5], [0, 1]],
+    CrankNicolson: [[0, 0, 0], [1, 0.5, 0.5], [0, 0.5, 0.5]],
+    KS2: [[0.5, 0.5, 0], [1.5, -0.5, 2], [0, -0.5, 1.5]],
+    QZ2: [[0.25, 0.25, 0], [0.75, 0.5, 0.25], [0, 0.5, 0.5]],
+    ALX2: [[_g, _g, 0], [1, 1 - _g, _g], [0, 1 - _g, _g]],
+    RK43: [[0.5, 0.5, 0, 0, 0], [2 / 3, 1 / 6, 0.5, 0, 0], [0.5, -0.5, 0.5, 0.5, 0], [1, 1.5, -1.5, 0.5, 0.5], [0, 1.5, -1.5, 0.5, 0.5]],
+}
+
+
+class RungeKutta:
+    """TimeScheme: RungeKutta(refEl, type, auxiliaryFields) (src/operator/RungeKutta.cpp).  apply() runs inside the device assembly
+    (hfx_time_scheme_rk); computeStage / computeSolution are the reference's field updates (:145-213) on the host Fields."""
+    isRK = True
+
+    def __init__(self, refEl, type=CrankNicolson, fields=()):
+        self.setButcherTable(type)
+        self.auxiliaryFields = list(fields)
+        self.stageCounter = 0
+        self.dt = 0.0
+
+    def setButcherTable(self, t):
+        tab = np.array(BUTCHER[t] if not isinstance(t, (list, np.ndarray)) else t, dtype=float)
+        if tab.shape[0] != tab.shape[1]:
+            raise ErrorHandle("RungeKutta : setButcherTable : the Butcher table should be square")
+        if np.any(np.triu(tab[:-1, 1:], 1) != 0):
+            raise ErrorHandle("RungeKutta : setButcherTable : the upper triangular part of the Butcher table should be null (no fully implicit implementation as of yet)")
+        self.bTable = tab
+
+    def setTimeStep(self, dt): self.dt = dt
+    def getStage(self): return self.stageCounter
+    def getNumStages(self): return self.bTable.shape[1] - 1
+    def stageRow(self): return np.ascontiguousarray(self.bTable[self.stageCounter, 1:])
+
+    def fieldNames(self):
+        """Everything RungeKutta::setFieldMap requires (:44-88) for the current stage."""
+        names = ["OldSolution"] + ["Old" + a for a in self.auxiliaryFields]
+        for k in range(self.stageCounter):
+            names += ["RKStage_%d" % k] + ["RKStage_%s_%d" % (a, k) for a in self.auxiliaryFields]
+        return names
+
+    def computeStage(self, fm):
+        if self.stageCounter >= self.getNumStages():
+            raise ErrorHandle("RungeKutta : computeStage : cannot compute more stages than the method allows, think about computing the solution")
+        row, s = self.bTable[self.stageCounter, 1:], self.stageCounter
+        for base in ["Solution"] + self.auxiliaryFields:
+            stage = lambda k: fm["RKStage_%d" % k if base == "Solution" else "RKStage_%s_%d" % (base, k)]
+            sol, old = fm[base].values, fm["Old" + base].values
+            stage(s).values[:] = (sol - old) / self.dt
+            sol[:] = old + self.dt * sum(row[j] * stage(j).values for j in range(s + 1))
+        self.stageCounter += 1
+
+    def computeSolution(self, fm):
+        if self.stageCounter != self.getNumStages():
+            raise ErrorHandle("RungeKutta : computeSolution : all stages must be computed before computing the solution")
+        bs = self.bTable[self.stageCounter, 1:]
+        for base in ["Solution"] + self.auxiliaryFields:
+            stage = lambda k: fm["RKStage_%d" % k if base == "Solution" else "RKStage_%s_%d" % (base, k)]
+            fm[base].values[:] = fm["Old" + base].values + self.dt * sum(bs[k] * stage(k).values for k in range(self.getNumStages()))
+        self.stageCounter = 0
+
+
 class _HDGModel:
     opmask = 0
     needsSource = False
@@ -443,7 +517,11 @@ class HDGSolver:
         names = [n for n in self.INPUT_FIELDS if n in self.fieldMap]
         if not getattr(self.model, "usesDiffusionField", True) and "DiffusionTensor" in names:
             names.remove("DiffusionTensor")   # HDGLaplaceModel never reads it (HDGLaplaceModel.cpp:18-30)
-        if self.model.timeScheme is not None and self.allocated:
+        ts = self.model.timeScheme
+        if ts is not None and getattr(ts, "isRK", False):
+            if self.allocated:
+                names += [n for n in ts.fieldNames() if n in self.fieldMap]
+        elif ts is not None and self.allocated:
             names.append("Solution")
         if getattr(self.model, "isBurgers", False):
             names += [n for n in ("BufferSolution", "Trace") if n in self.fieldMap]
@@ -452,9 +530,19 @@ class HDGSolver:
     def _describe_model(self, strict=True):
         names = set(self._input_fields())
         mask = self.model._mask(names, strict)
-        ts = 1 if self.model.timeScheme is not None else 0
-        md = capi.ModelDesc(self.nDOFsPerNode, mask, ts, self.model.timeScheme.dt if ts else 0.0)
+        tso = self.model.timeScheme
+        ts = 0 if tso is None else (2 if getattr(tso, "isRK", False) else 1)
+        md = capi.ModelDesc(self.nDOFsPerNode, mask, ts, tso.dt if ts else 0.0)
         check(lib().hfx_model_describe(self._h(), C.byref(md)), self._h())
+        if ts == 2:
+            if sorted(tso.auxiliaryFields) != ["Flux", "Trace"]:
+                raise ErrorHandle("RungeKutta : apply : the stiffness matrix does not have the correct dimensions (the HDG path needs the auxiliary fields Flux and Trace)")
+            if strict:
+                for n in tso.fieldNames():
+                    if n not in self.fieldMap:
+                        raise ErrorHandle("RungeKutta : setFieldMap : the field map must provide the field " + n)
+            row = tso.stageRow() if tso.getStage() < tso.getNumStages() else np.zeros(tso.getNumStages())
+            check(lib().hfx_time_scheme_rk(self._h(), min(tso.getStage(), tso.getNumStages() - 1), tso.getNumStages(), pd(row)), self._h())
         self._mask = mask
 
     def _eval_callbacks(self):

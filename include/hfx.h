@@ -58,7 +58,7 @@ int hfx_field_size(const hfx_ctx* ctx, const char* name, long long* n);
 
 /* ---- model: the four HDG models as an operator descriptor  src/model/*.cpp (computeLocalMatrix/RHS) ----------- */
 enum { HFX_OP_DIFFUSION = 1, HFX_OP_CONVECTION = 2, HFX_OP_REACTION = 4, HFX_OP_SOURCE = 8, HFX_OP_UNABU = 16 };
-enum { HFX_TS_NONE = 0, HFX_TS_EULER_IMPLICIT = 1 };
+enum { HFX_TS_NONE = 0, HFX_TS_EULER_IMPLICIT = 1, HFX_TS_RUNGE_KUTTA = 2 };
 typedef struct {
   int nDOF;       /* FEModel::allocate(nDOFsPerNode)                                   */
   int opmask;     /* Base is always present (HDGModel.cpp:28-32)                       */
@@ -66,6 +66,10 @@ typedef struct {
   double dt;
 } hfx_model_desc;
 int hfx_model_describe(hfx_ctx* ctx, const hfx_model_desc* md);
+/* RungeKutta::apply (src/operator/RungeKutta.cpp:90-143) with auxiliary fields {Flux, Trace}: Butcher row a_s0..a_s,nStages-1 of the current
+   stage (lower triangular tables only).  Fields read at assemble: OldSolution, OldFlux (cell), OldTrace (face), and for k < stage
+   RKStage_k, RKStage_Flux_k (cell), RKStage_Trace_k (face) -- the reference's names (RungeKutta.cpp:44-88) */
+int hfx_time_scheme_rk(hfx_ctx* ctx, int stage, int nStages, const double* row);
 /* std::function source/reaction callbacks (Source.h:36, Reaction.h:38) are evaluated by the host at x(IP):
    hfx_ip_coords returns x(ip) = sum_i phi_i(ip) x_i (Source.cpp:5-22), [nCells][nIP][dim] */
 int hfx_ip_coords(hfx_ctx* ctx, double* xip);

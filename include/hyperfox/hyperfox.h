@@ -396,6 +396,92 @@ class Euler : public TimeScheme {
   bool isExplicit = false;
 };
 
+// ---- src/operator/RKType.h, RungeKutta.h -------------------------------------------------------------------------------------------
+enum RKType { FEuler, EMidpoint, Heun, Kutta3, Heun3, SSPRK3, RK4, BEuler, IMidpoint, CrankNicolson, KS2, QZ2, ALX2, RK43 };
+class RungeKutta : public TimeScheme {
+ public:
+  RungeKutta(const ReferenceElement* re, RKType type = CrankNicolson, std::vector<std::string> fields = std::vector<std::string>()) : TimeScheme(re) {
+    setButcherTable(type);
+    auxiliaryFields = fields;
+    stageCounter = 0;
+  }
+  int cKind() const override { return HFX_TS_RUNGE_KUTTA; }
+  // RungeKutta::setUpDB (RungeKutta.cpp:215-291): row s < nStages = [c_s | a_s0 .. a_s,nStages-1], last row = [0 | b]
+  void setButcherTable(RKType type) {
+    const double g = 1.0 - std::sqrt(2.0) / 2.0;
+    switch (type) {
+      case FEuler: tab(2, {0, 0, 0, 1}); break;
+      case EMidpoint: tab(3, {0, 0, 0, 0.5, 0.5, 0, 0, 0, 1}); break;
+      case Heun: tab(3, {0, 0, 0, 1, 1, 0, 0, 0.5, 0.5}); break;
+      case Kutta3: tab(4, {0, 0, 0, 0, 0.5, 0.5, 0, 0, 1, -1, 2, 0, 0, 1.0 / 6, 2.0 / 3, 1.0 / 6}); break;
+      case Heun3: tab(4, {0, 0, 0, 0, 1.0 / 3, 1.0 / 3, 0, 0, 2.0 / 3, 0, 2.0 / 3, 0, 0, 0.25, 0, 0.75}); break;
+      case SSPRK3: tab(4, {0, 0, 0, 0, 1, 1, 0, 0, 0.5, 0.25, 0.25, 0, 0, 1.0 / 6, 1.0 / 6, 2.0 / 3}); break;
+      case RK4: tab(5, {0, 0, 0, 0, 0, 0.5, 0.5, 0, 0, 0, 0.5, 0, 0.5, 0, 0, 1, 0, 0, 1, 0, 0, 1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6}); break;
+      case BEuler: tab(2, {1, 1, 0, 1}); break;
+      case IMidpoint: tab(2, {0.5, 0.5, 0, 1}); break;
+      case CrankNicolson: tab(3, {0, 0, 0, 1, 0.5, 0.5, 0, 0.5, 0.5}); break;
+      case KS2: tab(3, {0.5, 0.5, 0, 1.5, -0.5, 2, 0, -0.5, 1.5}); break;
+      case QZ2: tab(3, {0.25, 0.25, 0, 0.75, 0.5, 0.25, 0, 0.5, 0.5}); break;
+      case ALX2: tab(3, {g, g, 0, 1, 1 - g, g, 0, 1 - g, g}); break;
+      case RK43: tab(5, {0.5, 0.5, 0, 0, 0, 2.0 / 3, 1.0 / 6, 0.5, 0, 0, 0.5, -0.5, 0.5, 0.5, 0, 1, 1.5, -1.5, 0.5, 0.5, 0, 1.5, -1.5, 0.5, 0.5}); break;
+    }
+  }
+  void setAuxiliaryFields(std::vector<std::string> fields) { auxiliaryFields = fields; }
+  const std::vector<std::string>& getAuxiliaryFields() const { return auxiliaryFields; }
+  int getStage() const { return stageCounter; }
+  int getNumStages() const { return nT - 1; }
+  std::vector<double> stageRow() const { return std::vector<double>(bTable.begin() + stageCounter * nT + 1, bTable.begin() + (stageCounter + 1) * nT); }
+  // every field RungeKutta::setFieldMap requires for the current stage (:44-88)
+  std::vector<std::string> fieldNames() const {
+    std::vector<std::string> n(1, "OldSolution");
+    for (size_t a = 0; a < auxiliaryFields.size(); a++) n.push_back("Old" + auxiliaryFields[a]);
+    for (int k = 0; k < stageCounter; k++) {
+      n.push_back("RKStage_" + std::to_string(k));
+      for (size_t a = 0; a < auxiliaryFields.size(); a++) n.push_back("RKStage_" + auxiliaryFields[a] + "_" + std::to_string(k));
+    }
+    return n;
+  }
+  void computeStage(std::map<std::string, Field*>* fm) {   // RungeKutta.cpp:145-180
+    if (stageCounter >= getNumStages()) throw ErrorHandle("RungeKutta", "computeStage", "cannot compute more stages than the method allows, think about computing the solution");
+    const double invdt = 1.0 / deltat;
+    for (size_t b = 0; b <= auxiliaryFields.size(); b++) {
+      const std::string base = b == 0 ? "Solution" : auxiliaryFields[b - 1];
+      std::vector<double>& sol = *fm->at(base)->getValues();
+      const std::vector<double>& old = *fm->at("Old" + base)->getValues();
+      std::vector<double>& rk = *fm->at(stageName(base, stageCounter))->getValues();
+      for (size_t i = 0; i < sol.size(); i++) {
+        rk[i] = invdt * (sol[i] - old[i]);
+        double buffer = 0.0;
+        for (int j = 0; j < stageCounter + 1; j++) buffer += bTable[stageCounter * nT + 1 + j] * (*fm->at(stageName(base, j))->getValues())[i];
+        sol[i] = old[i] + deltat * buffer;
+      }
+    }
+    stageCounter += 1;
+  }
+  void computeSolution(std::map<std::string, Field*>* fm) {   // RungeKutta.cpp:182-213
+    if (stageCounter != getNumStages()) throw ErrorHandle("RungeKutta", "computeSolution", "all stages must be computed before computing the solution");
+    for (size_t b = 0; b <= auxiliaryFields.size(); b++) {
+      const std::string base = b == 0 ? "Solution" : auxiliaryFields[b - 1];
+      std::vector<double>& sol = *fm->at(base)->getValues();
+      sol = *fm->at("Old" + base)->getValues();
+      for (int k = 0; k < getNumStages(); k++) {
+        const double bkdt = bTable[stageCounter * nT + 1 + k] * deltat;
+        const std::vector<double>& rk = *fm->at(stageName(base, k))->getValues();
+        for (size_t i = 0; i < rk.size(); i++) sol[i] += bkdt * rk[i];
+      }
+    }
+    stageCounter = 0;
+  }
+
+ protected:
+  static std::string stageName(const std::string& base, int k) { return base == "Solution" ? "RKStage_" + std::to_string(k) : "RKStage_" + base + "_" + std::to_string(k); }
+  void tab(int n, std::initializer_list<double> v) { nT = n; bTable.assign(v.begin(), v.end()); }
+  std::vector<double> bTable;
+  int nT = 0;
+  std::vector<std::string> auxiliaryFields;
+  int stageCounter = 0;
+};
+
 // ---- src/model/FEModel.h, HDGModel.h, the HDG models ----------------------------------------------------------------------------
 class FEModel {
  public:
@@ -672,7 +758,9 @@ class HDGSolver : public Solver {
     for (int k = 0; k < 4; k++) if (fieldMap->count(in[k])) s.insert(in[k]);
     const HDGModel* hm = dynamic_cast<const HDGModel*>(model);
     if (hm && !hm->usesDiffusionField()) s.erase("DiffusionTensor");   // HDGLaplaceModel never reads it
-    if (model->getTimeScheme() && allocated) s.insert("Solution");
+    if (RungeKutta* rk = dynamic_cast<RungeKutta*>(model->getTimeScheme())) {
+      if (allocated) { const std::vector<std::string> nm = rk->fieldNames(); for (size_t k = 0; k < nm.size(); k++) if (fieldMap->count(nm[k])) s.insert(nm[k]); }
+    } else if (model->getTimeScheme() && allocated) s.insert("Solution");
     if (hm && hm->isBurgers()) { if (fieldMap->count("BufferSolution")) s.insert("BufferSolution"); s.insert("Trace"); }
     return s;
   }
@@ -691,6 +779,16 @@ class HDGSolver : public Solver {
     TimeScheme* ts = model->getTimeScheme();
     md.timeScheme = ts ? ts->cKind() : HFX_TS_NONE; md.dt = ts ? ts->getTimeStep() : 0.0;
     detail::check(hfx_model_describe(ctx(), &md), ctx());
+    if (RungeKutta* rk = dynamic_cast<RungeKutta*>(ts)) {   // RungeKutta::apply runs inside the device assembly
+      std::vector<std::string> aux = rk->getAuxiliaryFields();
+      std::sort(aux.begin(), aux.end());
+      if (aux.size() != 2 || aux[0] != "Flux" || aux[1] != "Trace")
+        throw ErrorHandle("RungeKutta", "apply", "the stiffness matrix does not have the correct dimensions (the HDG path needs the auxiliary fields Flux and Trace)");
+      if (strict) { const std::vector<std::string> nm = rk->fieldNames(); for (size_t k = 0; k < nm.size(); k++) if (!fieldMap->count(nm[k])) throw ErrorHandle("RungeKutta", "setFieldMap", "the field map must provide the field " + nm[k]); }
+      const int nSt = rk->getNumStages(), st = std::min(rk->getStage(), nSt - 1);
+      std::vector<double> row = rk->getStage() < nSt ? rk->stageRow() : std::vector<double>(nSt, 0.0);
+      detail::check(hfx_time_scheme_rk(ctx(), st, nSt, row.data()), ctx());
+    }
     mask = md.opmask;
   }
   void evalCallbacks() {   // std::function callbacks run on the host at x(IP) (Source.cpp:5-22, Reaction.cpp:5-22)

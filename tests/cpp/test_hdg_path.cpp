@@ -5,7 +5,7 @@
 //   tests/regression/HDG/TestHDGDiffusionSource.cpp            (HDGDiffusionSource + source callback: manufactured Poisson)
 // Only differences: meshes come from text exports of the reference's .h5 fixtures (HDF5Io is out of scope), PetscInterface ->
 // CudaLinAlgebraInterface, Catch2's CHECK -> the four-line macros below.
-// usage: test_hdg_path <mesh dir> [section]   sections: contract | solver | lai | laplace | diffsrc
+// usage: test_hdg_path <mesh dir> [section]   sections: contract | solver | lai | laplace | diffsrc | rk
 #include <cstdio>
 #include <fstream>
 #include <numeric>
@@ -17,6 +17,7 @@
 #include "HDGLaplaceModel.h"
 #include "HDGSolver.h"
 #include "Mesh.h"
+#include "RungeKutta.h"
 
 using namespace hfox;
 
@@ -247,6 +248,66 @@ static void testDiffusionSource(const std::string& path) {
   CHECK(l2 < 1e-2);
 }
 
+// tests/regression/HDG/TestHDGDiffusionSource.cpp:23-47,200-252: HDGDiffusionSource + RungeKutta(BEuler, {Flux, Trace}), the reference's time loop
+static double anaDiffSrc(double t, const std::vector<double>& v) {
+  const double pi = 3.14159265358979323846;
+  double res = 0.0, arg = 0.0;
+  for (size_t i = 0; i < v.size(); i++) { const double a = v[i] - 0.5; res += a * std::erf(a) + std::exp(-a * a) / std::sqrt(pi); arg += pi / 2.0 * v[i]; }
+  return res + std::exp(-(double)v.size() * (pi / 2.0) * (pi / 2.0) * t) * std::cos(arg);
+}
+static void testDiffusionSourceRK(const std::string& path) {
+  const double pi = 3.14159265358979323846, dt = 1e-2;
+  Mesh m(2, 2, "simplex");
+  loadMesh(path, &m, 2);
+  const ReferenceElement* re = m.getReferenceElement();
+  const int nN = re->getNumNodes(), nNf = re->getFaceElement()->getNumNodes();
+  RungeKutta ts(re, BEuler, {"Flux", "Trace"});
+  ts.setTimeStep(dt);
+  Field sol(&m, Cell, nN, 1), flux(&m, Cell, nN, 2), trace(&m, Face, nNf, 1), tau(&m, Face, nNf, 1), dirichlet(&m, Face, nNf, 1), D(&m, Node, 1, 1);
+  Field oldSol(&m, Cell, nN, 1), oldFlux(&m, Cell, nN, 2), oldTrace(&m, Face, nNf, 1), rk0(&m, Cell, nN, 1), rkF0(&m, Cell, nN, 2), rkT0(&m, Face, nNf, 1);
+  std::fill(tau.getValues()->begin(), tau.getValues()->end(), 1.0 / std::sqrt(dt));
+  std::fill(D.getValues()->begin(), D.getValues()->end(), 1.0);
+  std::map<std::string, Field*> fm;
+  fm["Solution"] = &sol; fm["Flux"] = &flux; fm["Trace"] = &trace; fm["Tau"] = &tau; fm["Dirichlet"] = &dirichlet; fm["DiffusionTensor"] = &D;
+  fm["OldSolution"] = &oldSol; fm["OldFlux"] = &oldFlux; fm["OldTrace"] = &oldTrace;
+  fm["RKStage_0"] = &rk0; fm["RKStage_Flux_0"] = &rkF0; fm["RKStage_Trace_0"] = &rkT0;
+  std::vector<int> cell, face;
+  std::vector<double> pt;
+  for (int c = 0; c < m.getNumberCells(); c++) { m.getCell(c, &cell); for (int i = 0; i < nN; i++) { m.getPoint(cell[i], &pt); (*sol.getValues())[(size_t)c * nN + i] = anaDiffSrc(0.0, pt); } }
+  for (int f = 0; f < m.getNumberFaces(); f++) { m.getFace(f, &face); for (int j = 0; j < nNf; j++) { m.getPoint(face[j], &pt); (*trace.getValues())[(size_t)f * nNf + j] = anaDiffSrc(0.0, pt); } }
+  PetscOpts myOpts;
+  myOpts.maxits = 20000; myOpts.rtol = 1e-12; myOpts.verbose = false;
+  CudaLinAlgebraInterface lai(myOpts);
+  HDGDiffusionSource model(re);
+  model.setTimeScheme(&ts);
+  DirichletModel dirMod(re->getFaceElement());
+  HDGSolver solver;
+  solver.setVerbosity(false);
+  solver.setMesh(&m); solver.setFieldMap(&fm); solver.setLinSystem(&lai); solver.setModel(&model); solver.setBoundaryModel(&dirMod);
+  solver.initialize(); solver.allocate();
+  CHECK_THROWS(model.setTimeScheme(&ts));   // FEModel.cpp:15-20: not after allocation
+  model.setSourceFunction([pi](const std::vector<double>& x) { double r = 0.0; for (size_t i = 0; i < x.size(); i++) r -= 2.0 / std::sqrt(pi) * std::exp(-(x[i] - 0.5) * (x[i] - 0.5)); return r; });
+  double t = 0.0;
+  for (int it = 0; it < 5; it++) {
+    t += dt;
+    for (std::set<int>::const_iterator b = m.getBoundaryFaces()->begin(); b != m.getBoundaryFaces()->end(); ++b) {
+      m.getFace(*b, &face);
+      for (int j = 0; j < nNf; j++) { m.getPoint(face[j], &pt); (*dirichlet.getValues())[(size_t)*b * nNf + j] = anaDiffSrc(t, pt); }
+    }
+    *oldSol.getValues() = *sol.getValues(); *oldFlux.getValues() = *flux.getValues(); *oldTrace.getValues() = *trace.getValues();
+    for (int k = 0; k < ts.getNumStages(); k++) { solver.assemble(); solver.solve(); ts.computeStage(&fm); }
+    ts.computeSolution(&fm);
+  }
+  double num = 0.0, den = 0.0;
+  for (int c = 0; c < m.getNumberCells(); c++) {
+    m.getCell(c, &cell);
+    for (int i = 0; i < nN; i++) { m.getPoint(cell[i], &pt); const double a = anaDiffSrc(t, pt), e = (*sol.getValues())[(size_t)c * nN + i] - a; num += e * e; den += a * a; }
+  }
+  const double l2 = std::sqrt(num / den);
+  std::printf("  diffusion-source RungeKutta(BEuler) %s: 5 steps of dt=1e-2, nodal relative l2 error %.3e\n", path.c_str(), l2);
+  CHECK(l2 < 1e-2);
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { std::printf("usage: %s <mesh dir> [contract|solver|lai|laplace|diffsrc]\n", argv[0]); return 2; }
   const std::string dir = argv[1], sec = argc > 2 ? argv[2] : "all";
@@ -259,6 +320,7 @@ int main(int argc, char** argv) {
       testLaplace(dir + "/regression_dim-3_h-2e-1_ord-3.txt", 3, 3);
     }
     if (sec == "diffsrc" || sec == "all") testDiffusionSource(dir + "/regression_dim-2_h-1e-1_ord-3.txt");
+    if (sec == "rk" || sec == "all") testDiffusionSourceRK(dir + "/regression_dim-2_h-2e-1_ord-2.txt");
   } catch (const std::exception& e) {
     std::printf("FAILED: uncaught exception: %s\n", e.what());
     g_fail++;

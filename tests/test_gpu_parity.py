@@ -285,3 +285,88 @@ def test_distributed_solve_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
     _run_dist(2, cubes=4)
+
+
+def _diffsrc_analytic(t, x):
+    """tests/regression/HDG/TestHDGDiffusionSource.cpp:32-47 (analyticalDiffSrc) and :23-30 (gaussianSrc)."""
+    from scipy.special import erf
+    a = x - 0.5
+    res = (a * erf(a) + np.exp(-a ** 2) / np.sqrt(np.pi)).sum(axis=1)
+    return res + np.exp(-x.shape[1] * (np.pi / 2) ** 2 * t) * np.cos(np.pi / 2 * x.sum(axis=1))
+
+
+@pytest.mark.parametrize("rk", ["BEuler", "CrankNicolson", "QZ2"])
+def test_diffusion_source_runge_kutta_time_loop(rk):
+    """BASELINE.json configs[0] = tests/regression/HDG/TestHDGDiffusionSource.cpp: HDGDiffusionSource + RungeKutta(type, {Flux, Trace}) +
+    DirichletModel on regression_dim-2_h-2e-1_ord-2, tau = 1/sqrt(dt), gaussian source, dt = 1e-2 -- the reference's time loop
+    (OldX <- X; per stage: assemble, solve, computeStage; computeSolution).  Device vs the oracle running the same loop, and vs the
+    analytic solution."""
+    from hyperfox_b200 import hfox
+    from oracle import lib as O
+    from oracle.mesh import compute_faces
+    from oracle.refel import ReferenceElement as OracleRefEl
+    from tests.conftest import load_mesh
+    dim, order, dt, nSteps = 2, 2, 1e-2, 6
+    nodes, cells = load_mesh("regression_dim-2_h-2e-1_ord-2")
+    m = hfox.Mesh(dim, order, "simplex"); m.setMesh(nodes, cells)
+    re = m.getReferenceElement()
+    nN, nNf, nF, nC = re.getNumNodes(), re.getFaceElement().getNumNodes(), m.getNumberFaces(), m.getNumberCells()
+    ts = hfox.RungeKutta(re, getattr(hfox, rk), ["Flux", "Trace"]); ts.setTimeStep(dt)
+    nSt = ts.getNumStages()
+    fm = {"Solution": hfox.Field(m, hfox.Cell, nN, 1), "Flux": hfox.Field(m, hfox.Cell, nN, dim), "Trace": hfox.Field(m, hfox.Face, nNf, 1),
+          "Tau": hfox.Field(m, hfox.Face, nNf, 1), "Dirichlet": hfox.Field(m, hfox.Face, nNf, 1), "DiffusionTensor": hfox.Field(m, hfox.Node, 1, 1),
+          "OldSolution": hfox.Field(m, hfox.Cell, nN, 1), "OldFlux": hfox.Field(m, hfox.Cell, nN, dim), "OldTrace": hfox.Field(m, hfox.Face, nNf, 1)}
+    for k in range(nSt):
+        fm["RKStage_%d" % k] = hfox.Field(m, hfox.Cell, nN, 1); fm["RKStage_Flux_%d" % k] = hfox.Field(m, hfox.Cell, nN, dim)
+        fm["RKStage_Trace_%d" % k] = hfox.Field(m, hfox.Face, nNf, 1)
+    fm["Tau"].values[:] = 1.0 / np.sqrt(dt); fm["DiffusionTensor"].values[:] = 1.0
+    fm["Solution"].values[:] = _diffsrc_analytic(0.0, nodes)[cells].ravel()
+    fm["Trace"].values[:] = _diffsrc_analytic(0.0, nodes)[m.faces].ravel()
+    src = lambda x: -2.0 / np.sqrt(np.pi) * sum(np.exp(-(xi - 0.5) ** 2) for xi in x)
+    mod = hfox.HDGDiffusionSource(re); mod.setTimeScheme(ts)
+    s = hfox.HDGSolver()
+    s.setMesh(m); s.setFieldMap(fm); s.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts(rtol=1e-13, maxits=20000)))
+    s.setModel(mod); s.setBoundaryModel(hfox.DirichletModel(re.getFaceElement()))
+    s.initialize(); s.allocate()
+    mod.setSourceFunction(src)
+    # oracle twin
+    ore = OracleRefEl(dim, order); topo = compute_faces(cells, ore)
+    xip = np.einsum("pi,cid->cpd", ore.ipShape, nodes[cells])
+    of = {"Tau": np.full((nF, nNf, 1), 1.0 / np.sqrt(dt)), "DiffusionTensor": np.ones((nodes.shape[0], 1)), "Dirichlet": np.zeros((nF, nNf, 1)),
+          "srcIP": np.array([[src(p) for p in el] for el in xip])}
+    osol = fm["Solution"].values.reshape(nC, nN).copy(); oflux = np.zeros((nC, nN * dim)); otr = fm["Trace"].values.reshape(nF, nNf).copy()
+    b = m.boundaryFaces
+    t = 0.0
+    for step in range(nSteps):
+        t += dt
+        dirv = np.zeros((nF, nNf)); dirv[b] = _diffsrc_analytic(t, nodes)[m.faces[b]]
+        fm["Dirichlet"].values[:] = dirv.ravel()
+        for a in ("Solution", "Flux", "Trace"):
+            fm["Old" + a].values[:] = fm[a].values
+        for k in range(nSt):
+            s.assemble(); s.solve(); ts.computeStage(fm)
+        ts.computeSolution(fm)
+        # oracle: same loop (RungeKutta.cpp:90-213)
+        of["Dirichlet"] = dirv.reshape(nF, nNf, 1)
+        old = dict(Solution=osol.copy(), Flux=oflux.copy(), Trace=otr.copy())
+        cur = dict(Solution=osol, Flux=oflux, Trace=otr)
+        st = {a: [] for a in cur}
+        tab = ts.bTable
+        for k in range(nSt):
+            row = tab[k, 1:]
+            of.update(solOld=old["Solution"], fluxOld=old["Flux"], traceOld=old["Trace"].reshape(nF, nNf, 1))
+            if k > 0:
+                of.update(rkSol=np.array(st["Solution"]), rkFlux=np.array(st["Flux"]), rkTrace=np.array(st["Trace"]).reshape(k, nF, nNf, 1))
+            o = O.HDGOracle(O.RefElC(ore), dict(nodes=nodes, cells=cells, **topo), O.make_model(1, O.OP_DIFFUSION | O.OP_SOURCE, 1, O.TS_RK, dt, k, row), of)
+            o.assemble(); o.solve(rtol=1e-13, maxits=20000)
+            new = dict(Solution=o.sol, Flux=o.flux, Trace=o.trace.reshape(nF, nNf))
+            for a in cur:
+                st[a].append((new[a] - old[a]) / dt)
+                cur[a] = old[a] + dt * sum(row[j] * st[a][j] for j in range(k + 1))
+        bs = tab[nSt, 1:]
+        osol, oflux, otr = (old[a] + dt * sum(bs[k] * st[a][k] for k in range(nSt)) for a in ("Solution", "Flux", "Trace"))
+    assert H.rel_err(fm["Solution"].values, osol.ravel()) < 1e-9
+    assert H.rel_err(fm["Flux"].values, oflux.ravel()) < 1e-8
+    ana = _diffsrc_analytic(t, nodes)[cells]
+    sol = fm["Solution"].values.reshape(nC, nN)
+    assert np.sqrt(((sol - ana) ** 2).sum() / (ana ** 2).sum()) < 1e-2     # reference ceiling on the time-integrated l2 error (TestHDGDiffusionSource.cpp)

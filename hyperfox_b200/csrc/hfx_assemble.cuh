@@ -410,7 +410,8 @@ struct AsmSmem {
   // after the doubles: row starts (nFc x int64) then a small int area
   static constexpr int nNLUT = ((DIM * t + 7) / 8) * 8;              // column (d,b) of B_d -> offset of row block d + b
   static constexpr int nKLUT = (((1 + DIM) * t + 3) / 4) * 4;        // P9 reduction index (kind,b) -> operand offsets
-  static constexpr int nInts = 8 + 2 * nFc * t + nFc * nN + nFc * nFc + 5 * nFc + 8 + nNLUT + 2 * nKLUT + nFc * l;
+  static constexpr int nInts = 8 + 2 * nFc * t + nFc * nN + nFc * nFc + 5 * nFc + 8 + nNLUT + nFc * nKLUT + nFc * l;   // (KLUT: two 16-bit offsets per entry)
+  static_assert(nDoubles < 65536, "16-bit operand offsets");
   static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * (nFc + l) + 4 * (size_t)nInts;
 };
 
@@ -443,8 +444,8 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   int* OPP = INTF + nFc;                                              // [nFc] first node not on the face (orientation test)
   int* QCTR = OPP + nFc;                                              // [4] dynamic tile-queue counters
   int* NLUT = QCTR + 8;                                               // [nNLUT]
-  int* KLUT = NLUT + L::nNLUT;                                        // [nKLUT][2]
-  int* POSROW = KLUT + 2 * L::nKLUT;                                  // [nFc][l] column offset of element-local column cc inside a row of face f
+  unsigned short* KLUT = reinterpret_cast<unsigned short*>(NLUT + L::nNLUT);   // [nFc][nKLUT][2] 16-bit operand offsets of the P9 reduction index k = (kind, b)
+  int* POSROW = NLUT + L::nNLUT + nFc * L::nKLUT;                                  // [nFc][l] column offset of element-local column cc inside a row of face f
   double* A = G;    // A_d aliases g (dead after the contractions)
   double* ST = sm + L::oST;   // S staging [l][ldc] for the coalesced write-out
   double* Um = SQU; // U aliases Squ (dead after A)
@@ -519,6 +520,15 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     }
   }
   const int kDNe = diffField ? kDN : kN;   // D = I (HDGDiffusion.cpp:102-105): (Dn)_d mass = n_d mass
+  // P9 reduction index k = (kind, b): kind 0 -> Slu (tau mass on U), kind 1+d -> Slq_d ((Dn)_d mass, stored negated, on Q_d):
+  // offset of the left operand inside the face's weighted mass matrices, offset of the right operand's row (U or Q_d, node fn_f(b))
+  for (int i = tid; i < nFc * L::nKLUT; i += NT) {
+    const int f = i / L::nKLUT, k = i - f * L::nKLUT, kk = k < (1 + DIM) * t ? k : (1 + DIM) * t - 1;
+    const int kind = kk / t, b = kk - kind * t, nd = FN[f * t + b];
+    KLUT[2 * i] = (unsigned short)((kind == 0 ? kTau : kDNe + kind - 1) * FWS + tp * b);
+    KLUT[2 * i + 1] = (unsigned short)(kind == 0 ? L::oSQU + nd * ldc : L::oB + ((kind - 1) * nN + nd) * ldc);
+  }
+  __syncthreads();
 
   long long tprev = clock64();
   for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
@@ -1224,37 +1234,49 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     HFX_PROF(12);
 
     // ---- P9: S = Slu U + Slq Q + Sll ; S0 = Fl - Slu U0 - Slq Q0 (:347-348); Dirichlet rows (:489-501); scatter (:596-618) --
+    //      a warp task = all row tiles of one face x three column tiles: one gathered right-operand load feeds every row tile
     {
       const int lr = lane >> 2, lc = lane & 3;
-      constexpr int TT = (t + 7) / 8, L1T = (l + 1 + 7) / 8, NTW9 = (L1T <= 6 ? L1T : 4), NG = (L1T + NTW9 - 1) / NTW9;   // one gather of the left operand feeds a whole row of column tiles
-      constexpr int KTOT = (1 + DIM) * t, KS_S = (KTOT + 3) / 4;   // k = (kind, b): kind 0 -> Slu (tau mass on U), kind 1+d -> Slq_d (-(Dn)_d mass on Q_d)
-      for (int task = warp; task < nFc * TT * NG; task += NWARP) {
-        const int f = task / (TT * NG), r = task % (TT * NG);
-        const int a = (r % TT) * 8 + lr, ng = r / TT;
-        const int* fn = FN + f * t;
+      constexpr int TT = (t + 7) / 8, L1T = (l + 1 + 7) / 8, NTW9 = 3, NG = (L1T + NTW9 - 1) / NTW9;
+      constexpr int KTOT = (1 + DIM) * t, KS_S = (KTOT + 3) / 4;
+      for (int task = warp; task < nFc * NG; task += NWARP) {
+        const int f = task / NG, ng = task - f * NG;
         const double* fwf = FW + f * NW * FWS;
-        const int acl = imin(a, t - 1);
-        int ncl[NTW9];
+        const unsigned short* klut = KLUT + 2 * f * L::nKLUT;
+        int acl[TT], ncl[NTW9];
+#pragma unroll
+        for (int i = 0; i < TT; i++) acl[i] = imin(i * 8 + lr, t - 1);
 #pragma unroll
         for (int j = 0; j < NTW9; j++) ncl[j] = imin((ng * NTW9 + j) * 8 + lr, l);
-        double c[NTW9][2];
-        zero_c(c);
+        double c[TT][NTW9][2];
+#pragma unroll
+        for (int i = 0; i < TT; i++) zero_c(c[i]);
 #pragma unroll
         for (int ks = 0; ks < KS_S; ks++) {
-          const int k = ks * 4 + lc, kk = k < KTOT ? k : KTOT - 1;
-          const int kind = kk / t, b = kk % t, nd = fn[b];
-          double av = kind == 0 ? fwf[kTau * FWS + acl + tp * b] : (hasDiff ? fwf[(kDNe + kind - 1) * FWS + acl + tp * b] : 0.0);
-          if (k >= KTOT) av = 0.0;
-          const double* brow = kind == 0 ? Um + nd * ldc : B + ((kind - 1) * nN + nd) * ldc;
+          const int k = ks * 4 + lc;
+          const int2 off = make_int2((int)klut[2 * k], (int)klut[2 * k + 1]);
+          const bool live = (k < KTOT) && (k < t || hasDiff);
+          double av[TT], bv[NTW9];
 #pragma unroll
-          for (int j = 0; j < NTW9; j++) dmma(c[j], av, brow[ncl[j]]);
+          for (int i = 0; i < TT; i++) av[i] = live ? fwf[off.x + acl[i]] : 0.0;
+          const double* brow = sm + off.y;
+#pragma unroll
+          for (int j = 0; j < NTW9; j++) bv[j] = brow[ncl[j]];
+#pragma unroll
+          for (int i = 0; i < TT; i++)
+#pragma unroll
+            for (int j = 0; j < NTW9; j++) dmma(c[i][j], av[i], bv[j]);
         }
-        if (a < t) {
-          double* strow = ST + (f * t + a) * ldc;
 #pragma unroll
-          for (int j = 0; j < NTW9; j++) {
-            const int cc = (ng * NTW9 + j) * 8 + 2 * lc;
-            if (cc <= l) *reinterpret_cast<double2*>(strow + cc) = make_double2(c[j][0], c[j][1]);
+        for (int i = 0; i < TT; i++) {
+          const int a = i * 8 + lr;
+          if (a < t) {
+            double* strow = ST + (f * t + a) * ldc;
+#pragma unroll
+            for (int j = 0; j < NTW9; j++) {
+              const int cc = (ng * NTW9 + j) * 8 + 2 * lc;
+              if (cc <= l) *reinterpret_cast<double2*>(strow + cc) = make_double2(c[i][j][0], c[i][j][1]);
+            }
           }
         }
       }

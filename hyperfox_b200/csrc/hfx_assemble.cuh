@@ -50,6 +50,8 @@ struct AsmParams {
   const double* mhinv;        // inverse of the reference mass matrix, column-major [ev(nN)][ev(nN)] (unit pad diagonal)
   // straight-sided elements: reference matrices of the purely geometric blocks (built by hfx_refel_set) and the per-element flag
   const double* sref;         // S^_r [DIM][nN][ev(nN)]: Squ_d = sum_r detJ Jinv(d,r) S^_r
+  const double* srefT;        // S^_r transposed [DIM][nN][ev(nN)]: entry (r, j, k) = S^_r[k][j], the layout of the Suq_d left operand
+  int noRef;                  // experiments: disable the all-reference path
   const double* aref;         // A^_r [DIM][ev(nN) x nN] column-major: A_d = sum_r Jinv(d,r) A^_r          (A^_r = M_ref^-1 S^_r)
   const double* mfref;        // M^f [ev(t) x t]: face reference mass
   const double* bref;         // B^_f [nFc][nN][t] = M_ref^-1[:, faceNodes_f] M^f: W Sql_d = -(area n_d / detJ) B^_f
@@ -401,7 +403,9 @@ struct AsmSmem {
   static constexpr int oFU = oR + szR;                       // Fu [nN]
   static constexpr int oSCR = oFU + ev(nN) + 2;              // (FU[ev(nN)] holds 1/detJ of the first cubature point)
   static constexpr int oGEO = oSCR + 2 * nNp;                // constant geometry of a straight-sided element: Jinv [DIM*DIM], det, per face n[DIM], area
-  static constexpr int oEnd = oGEO + ev(DIM * DIM + 1 + nFc * (DIM + 1));
+  static constexpr int oGEOR = oGEO + ev(DIM * DIM + 1 + nFc * (DIM + 1));   // all-reference path, per face: -area n_d [DIM], tau area, area
+  static constexpr int oEnd = oGEOR + ev(nFc * (DIM + 2));
+  static_assert(ev(nFc * nN * t) <= szR && tp * t <= nNp * nNp, "reference tables are staged in the R and M regions");
   // S staging [l][ldc] for the coalesced write-out: reuses the dead g/A + M + W span when it is large enough (large elements),
   // otherwise gets its own area (small elements, where shared memory is not the limit)
   static constexpr bool stFits = (oSQU - oG) >= l * ldc;
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   double* DIP = sm + L::oDIP; double* VIP = sm + L::oVIP; double* LW = sm + L::oLW; double* FWT = sm + L::oFWT; double* TAU = sm + L::oTAU;
   double* DN = sm + L::oDN; double* VN = sm + L::oVN; double* G = sm + L::oG; double* CG = sm + L::oCG; double* Mm = sm + L::oM;
   double* Wb = sm + L::oW; double* SQU = sm + L::oSQU; double* SUQ = sm + L::oSUQ; double* SUU = sm + L::oSUU; double* FW = sm + L::oFW;
-  double* B = sm + L::oB; double* R = sm + L::oR; double* FU = sm + L::oFU; double* GEO = sm + L::oGEO;
+  double* B = sm + L::oB; double* R = sm + L::oR; double* FU = sm + L::oFU; double* GEO = sm + L::oGEO; double* GEOR = sm + L::oGEOR;
   double* WQ = sm + L::oWQ; double* DSH = sm + L::oDSH; double* FDS = sm + L::oFDS; double* FSH = sm + L::oFSH; double* FFS = sm + L::oFFS;
   long long* ROWS = reinterpret_cast<long long*>(sm + L::nDoubles);   // [nFc] first entry of row (F,0) in vals
   long long* RBASE = ROWS + nFc;                                      // [l] first entry of the CSR row of element-local trace row r
@@ -455,6 +459,11 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   const double ts = euler ? p.dt : 1.0;   // Euler::apply scales the u rows (Su, Fu) by dt before adding the mass terms (Euler.cpp:28-32)
   const bool diffField = hasDiff && p.diffComps > 0 && p.diff;
   const bool needSuu = hasConv || hasReac || euler;   // bulk part of Suu: -C^T, reaction mass, Euler mass
+  // All-reference path: a straight-sided element of a Laplace-type model (no convection / reaction / time scheme / diffusion field)
+  // whose tau is constant on each face has EVERY block of its local matrix as a scalar combination of reference matrices
+  // (tau mass = tau_f area_f M^f as well), so no cubature-point work is left at all.
+  const bool refModel = !diffField && !needSuu && !p.noRef && p.srefT;
+  constexpr bool kRefSrcPf = kPrefetch && nIP <= 64;
 
   // ---- once per CTA: constant tables; padding lanes must hold finite numbers --------------------------------------------
   for (int i = tid; i < L::nDoubles; i += NT) sm[i] = 0.0;
@@ -477,7 +486,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   }
 
   // ---- software prefetch of the next element's gather (registers) ------------------------------------------------------
-  double pfX = 0.0, pfTau = 0.0;
+  double pfX = 0.0, pfTau = 0.0, pfSrc = 0.0;
   int pfF = 0, pfPerm = 0, pfPos = 0, pfRlen = 0, pfBc = 0, pfInt = 0;
   long long pfRow = 0;
   // two stages: the second one's addresses depend on values loaded by the first (face ids), so it is issued a few phases later --
@@ -495,6 +504,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     }
     if (tid >= 192 && tid < 192 + nFc) pfF = p.cell2face[(size_t)e * nFc + (tid - 192)];
     if (tid >= 224 && tid < 224 + nFc * nFc) pfPos = p.elemPos[(size_t)e * nFc * nFc + (tid - 224)];
+    if (kRefSrcPf && refModel && hasSrc && tid >= 128 && tid < 128 + nIP) pfSrc = p.srcIP[(size_t)e * nIP + (tid - 128)];
   };
   auto prefetchB = [&](int e) {
     if (!kPrefetch || e >= p.nCells) return;
@@ -560,11 +570,25 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     const bool aff = (kPrefetch ? pfAff : (p.affine ? (int)p.affine[e] : 0)) != 0;
     const bool affAB = aff && !diffField;              // with a diffusion field g (which A aliases) is still live when the tables are applied
     const bool needG = !aff || hasConv || diffField;   // the gradient rows g are only needed by the convection / diffusion-field contractions
+    const bool refCand = aff && refModel;              // all-reference path if, in addition, tau is constant on each face (checked below)
     // stage the read-only tables of this element pass (L2 -> shared, asynchronous 16-byte copies)
-    if (needG) for (int i = tid; i < L::nDSH / 2; i += NT) cp_async16(DSH + 2 * i, p.dshape + 2 * i);
-    if (!aff) for (int i = tid; i < L::nFDS / 2; i += NT) cp_async16(FDS + 2 * i, p.fdshape + 2 * i);
-    for (int i = tid; i < L::nFSH / 2; i += NT) cp_async16(FSH + 2 * i, p.fshape + 2 * i);
-    for (int i = tid; i < L::nFFS / 2; i += NT) cp_async16(FFS + 2 * i, p.ffs + 2 * i);
+    auto stageStd = [&]() {
+      if (needG) for (int i = tid; i < L::nDSH / 2; i += NT) cp_async16(DSH + 2 * i, p.dshape + 2 * i);
+      if (!aff) for (int i = tid; i < L::nFDS / 2; i += NT) cp_async16(FDS + 2 * i, p.fdshape + 2 * i);
+      for (int i = tid; i < L::nFSH / 2; i += NT) cp_async16(FSH + 2 * i, p.fshape + 2 * i);
+      for (int i = tid; i < L::nFFS / 2; i += NT) cp_async16(FFS + 2 * i, p.ffs + 2 * i);
+    };
+    if (refCand) {
+      // reference matrices, staged where their combinations end up (A^_r -> A_d and S^_r^T -> Suq_d are combined in place) or in
+      // regions that are idle until the condensation (B^_f in R, M^f in M)
+      for (int i = tid; i < DIM * nN * nNp / 2; i += NT) { cp_async16(A + 2 * i, p.aref + 2 * i); cp_async16(SUQ + 2 * i, p.srefT + 2 * i); }
+      for (int i = tid; i < ev(nFc * nN * t) / 2; i += NT) cp_async16(R + 2 * i, p.bref + 2 * i);
+      for (int i = tid; i < FWS / 2; i += NT) cp_async16(Mm + 2 * i, p.mfref + 2 * i);
+      if (hasSrc) {   // source values times the cubature weights (scaled by det J later)
+        if (kRefSrcPf) { if (tid >= 128 && tid < 128 + nIP) LW[nIP + tid - 128] = ts * pfSrc * WQ[tid - 128]; }
+        else for (int i = tid; i < nIP; i += NT) LW[nIP + i] = ts * p.srcIP[(size_t)e * nIP + i] * WQ[i];
+      }
+    } else stageStd();
     const int* cell = p.cells + (size_t)e * nN;
     if (diffField) {
       for (int i = tid; i < nN * D2; i += NT) {
@@ -577,7 +601,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
     }
     if (hasConv) for (int i = tid; i < nN * DIM; i += NT) VN[i] = p.vel[(size_t)cell[i / DIM] * DIM + (i % DIM)];
-    cp_async_wait_all();
+    if (!refCand) cp_async_wait_all();
     __syncthreads();
     HFX_PROF(0);
     unsigned tileNeed = aff ? affNeed : baseNeed;
@@ -587,6 +611,148 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     for (int i = tid; i < nFc * l; i += NT) { const int f = i / l, cc = i - f * l; POSROW[i] = POS[f * nFc + cc / t] * t + PERM[cc]; }
     if (tid < l) { const int f = tid / t; RBASE[tid] = ROWS[f] + (long long)PERM[tid] * RLEN[f]; }
 
+    // ---- all-reference path, stage G: constant geometry (one thread per face + one for the bulk Jacobian), tau check ----------
+    bool ref = false;
+    if (refCand) {
+      int bad = 0;
+      if (tid < nFc) {
+        const int f = tid;
+        const int* fn = FN + f * t;
+        double J[DIM - 1][DIM];
+#pragma unroll
+        for (int r = 0; r < DIM - 1; r++)
+#pragma unroll
+          for (int m = 0; m < DIM; m++) J[r][m] = 0.5 * (X[fn[r + 1] * DIM + m] - X[fn[0] * DIM + m]);
+        double nv[DIM], area;
+        if (DIM == 2) {
+          nv[0] = -J[0][1]; nv[1] = J[0][0];
+          area = sqrt(J[0][0] * J[0][0] + J[0][1] * J[0][1]);
+        } else {
+          nv[0] = J[0][1] * J[DIM - 2][2 % DIM] - J[0][2 % DIM] * J[DIM - 2][1];
+          nv[1] = J[0][2 % DIM] * J[DIM - 2][0] - J[0][0] * J[DIM - 2][2 % DIM];
+          nv[DIM - 1] = J[0][0] * J[DIM - 2][1] - J[0][1] * J[DIM - 2][0];
+          const double g00 = J[0][0] * J[0][0] + J[0][1] * J[0][1] + J[0][2 % DIM] * J[0][2 % DIM];
+          const double g11 = J[DIM - 2][0] * J[DIM - 2][0] + J[DIM - 2][1] * J[DIM - 2][1] + J[DIM - 2][2 % DIM] * J[DIM - 2][2 % DIM];
+          const double g01 = J[0][0] * J[DIM - 2][0] + J[0][1] * J[DIM - 2][1] + J[0][2 % DIM] * J[DIM - 2][2 % DIM];
+          area = sqrt(g00 * g11 - g01 * g01);   // sqrt(det(J J^T)) (Operator.cpp:66-69)
+        }
+        const int v0 = fn[0], vn = OPP[f];
+        const double inrm = fast_rcp(area);
+        double prod = 0.0;
+#pragma unroll
+        for (int m = 0; m < DIM; m++) { nv[m] *= inrm; prod = fma(X[vn * DIM + m] - X[v0 * DIM + m], nv[m], prod); }   // outward (HDGBase.cpp:43-62)
+        if (prod > 0.0) {
+#pragma unroll
+          for (int m = 0; m < DIM; m++) nv[m] = -nv[m];
+        }
+        double* gf = GEO + D2 + 1 + f * (DIM + 1);
+        double* gr = GEOR + f * (DIM + 2);
+#pragma unroll
+        for (int m = 0; m < DIM; m++) { gf[m] = nv[m]; gr[m] = -area * nv[m]; }
+        gf[DIM] = area;
+        gr[DIM] = TAU[f * t] * area;
+        gr[DIM + 1] = area;
+      } else if (tid == 32) {
+        double J[DIM][DIM], det, I[DIM][DIM];
+#pragma unroll
+        for (int r = 0; r < DIM; r++)
+#pragma unroll
+          for (int m = 0; m < DIM; m++) J[r][m] = 0.5 * (X[(r + 1) * DIM + m] - X[m]);
+        det_inv(J, det, I);
+#pragma unroll
+        for (int m = 0; m < DIM; m++)
+#pragma unroll
+          for (int r = 0; r < DIM; r++) GEO[m * DIM + r] = I[m][r];
+        GEO[D2] = det;
+        FU[ev(nN)] = fast_rcp(det);
+      } else if (tid >= 64) {
+        for (int i = tid - 64; i < l; i += NT - 64) bad |= (TAU[i] != TAU[(i / t) * t]);
+      }
+      cp_async_wait_all();
+      ref = !__syncthreads_or(bad);
+      HFX_PROF(5);
+      prefetchA(e + gridDim.x);
+      if (!ref) {   // tau varies on a face: the general straight-sided path needs its own tables
+        stageStd();
+        cp_async_wait_all();
+        __syncthreads();
+      }
+    }
+    if (ref) {
+      // ---- stage R: every block from the staged reference matrices ---------------------------------------------------------------
+      //   A_d = sum_r Jinv(d,r) A^_r ;  Suq_d = detJ sum_r Jinv(d,r) S^_r^T - (area n_d) face mass ;  Suu = tau area face mass
+      //   B_d = -(area n_d / detJ) B^_f ;  face matrices tau area M^f, -area n_d M^f, area M^f
+      const double det = GEO[D2], rdet = FU[ev(nN)];
+      double Ii[DIM][DIM];
+#pragma unroll
+      for (int m = 0; m < DIM; m++)
+#pragma unroll
+        for (int r = 0; r < DIM; r++) Ii[m][r] = GEO[m * DIM + r];
+      for (int idx = tid; idx < nN * nNp; idx += NT) {
+        const int j = idx / nNp, i = idx - j * nNp;
+        double ar[DIM], sr[DIM], fq[DIM], suu = 0.0;
+#pragma unroll
+        for (int r = 0; r < DIM; r++) { ar[r] = A[r * nN * nNp + idx]; sr[r] = SUQ[r * nN * nNp + idx]; fq[r] = 0.0; }
+        if (i < nN) {
+#pragma unroll
+          for (int f = 0; f < nFc; f++) {
+            const int a = NIF[f * nN + i], b = NIF[f * nN + j];
+            if (a >= 0 && b >= 0) {
+              const double mv = Mm[a + tp * b];
+              const double* gr = GEOR + f * (DIM + 2);
+              suu = fma(gr[DIM], mv, suu);
+#pragma unroll
+              for (int d = 0; d < DIM; d++) fq[d] = fma(gr[d], mv, fq[d]);
+            }
+          }
+          SUU[i + nNp * j] = ts * suu;
+        }
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+          double va = 0.0, vs = 0.0;
+#pragma unroll
+          for (int r = 0; r < DIM; r++) { va = fma(Ii[d][r], ar[r], va); vs = fma(Ii[d][r], sr[r], vs); }
+          A[d * nN * nNp + idx] = va;
+          SUQ[d * nN * nNp + idx] = hasDiff ? ts * fma(det, vs, fq[d]) : 0.0;
+        }
+      }
+      if ((nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal of K for the 2x2-block Gauss-Jordan
+        for (int j = 0; j < nN; j++) { SUU[nN + nNp * j] = 0.0; SUU[j + nNp * nN] = 0.0; }
+        SUU[nN + nNp * nN] = 1.0;
+      }
+      for (int idx = tid; idx < nFc * nN * t; idx += NT) {
+        const int f = idx / (nN * t), rem = idx - f * nN * t, m = rem / t, b = rem - m * t;
+        const double* gr = GEOR + f * (DIM + 2);
+        const double sc = rdet * R[idx];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) B[(d * nN + m) * ldc + f * t + b] = sc * gr[d];
+      }
+      for (int idx = tid; idx < DIM * nN; idx += NT) { B[idx * ldc + l] = 0.0; B[idx * ldc + l + 1] = 0.0; }  // Q0 column
+      for (int idx = tid; idx < nFc * FWS; idx += NT) {
+        const int f = idx / FWS, ab = idx - f * FWS;
+        const double mv = Mm[ab];
+        const double* gr = GEOR + f * (DIM + 2);
+        double* fw = FW + f * NW * FWS + ab;
+        fw[kTau * FWS] = gr[DIM] * mv;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) fw[(kN + d) * FWS] = gr[d] * mv;
+        fw[kOne * FWS] = gr[DIM + 1] * mv;
+      }
+      if (tid >= NT - 32) {   // Fu = source (Source.cpp:24-48)
+        for (int i = tid - (NT - 32); i < nN; i += 32) {
+          double s2 = 0.0;
+          if (hasSrc) for (int ip = 0; ip < nIP; ip++) s2 = fma(PHI[ip * nNp + i], LW[nIP + ip], s2);
+          FU[i] = s2 * det;
+        }
+      }
+      __syncthreads();
+      HFX_PROF(1);
+      prefetchB(e + gridDim.x);
+    }
+    double* const W = ((nNp / 2) & 1) ? Wb : Mm;
+    constexpr int MTN = (nN + 7) / 8;           // 8-row tiles over the element nodes
+    constexpr int KS_IP = (nIP + 3) / 4, KS_N = (nN + 3) / 4;
+    if (!ref) {
     // ---- P1a: raw Jacobians (Operator.cpp:14-39) as two small tensor-core products: rows (ip, r), reduction over the nodes,
     //      columns = the DIM coordinates (one 8-wide tile, DIM columns used) ------------------------------------------------------
     if (!aff) {
@@ -632,7 +798,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     if (!aff) __syncthreads();   // (straight-sided elements read their constant Jacobians straight from the vertices: no P1a, no barrier)
     HFX_PROF(5);
     // the next element's gather flies while this element is computed
-    prefetchA(e + gridDim.x);
+    if (!refCand) prefetchA(e + gridDim.x);
 
     // ---- P1b: measures, inverses, normals, coefficient interpolation (Operator.cpp:41-84, HDGModel.cpp:53-85, HDGBase.cpp:18-65) --
     for (int k = tid; k < nJ; k += NT) {
@@ -844,14 +1010,11 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     // =====================================================================================================================
     // From here on every product runs on the FP64 tensor cores: a phase is a list of warp tasks (8 output rows x up to 3 column
     // tiles of 8), operands are fetched from shared memory one 64-bit word per lane.
-    constexpr int MTN = (nN + 7) / 8;           // 8-row tiles over the element nodes
-    constexpr int KS_IP = (nIP + 3) / 4, KS_IPF = (nIPf + 3) / 4, KS_N = (nN + 3) / 4, KS_T = (t + 3) / 4, KS_QN = (DIM * nN + 3) / 4;
 
     // ---- P3a: M = sum_ip dV phi phi^T (Mass.cpp:5-38 / HDGBase.cpp:152) ------------------------------------------------------
     // If det J is constant over the element (every straight-sided simplex), M = det J * M_ref exactly and W = M_ref^-1 / det J:
     // no contraction and no inversion.  Curved elements take the general path.
     const bool constDet = (QCTR[3] == 0);
-    double* const W = ((nNp / 2) & 1) ? Wb : Mm;
     if (constDet && !affAB) {
       const double rdet = FU[ev(nN)];
       if (kMHReg) {
@@ -1121,6 +1284,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     }
     if (!affAB) __syncthreads();
     HFX_PROF(8);
+    }   // !ref
 
     // ---- P5: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335), R = Sul - sum_d Suq_d B_d with column l = -Fu (:342-343).
     //      One output tile per warp task, reduction split over two accumulators (long dependent DMMA chains are latency bound).

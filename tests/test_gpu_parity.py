@@ -95,6 +95,26 @@ def test_integrated_dirichlet(dim, order):
     compare(H.make_case(dim, order, N=3, bc="integrated", seed=9))
 
 
+@pytest.mark.parametrize("dim,order,model,bc,mixed", [(3, 3, "laplace", "dirichlet", False), (3, 3, "diffsrc", "dirichlet", False), (3, 2, "diffsrc", "integrated", False),
+                                                       (2, 3, "diffsrc", "dirichlet", False), (2, 5, "laplace", "integrated", False), (3, 3, "diffsrc", "dirichlet", True),
+                                                       (3, 1, "laplace", "dirichlet", False)])
+def test_all_reference_path(dim, order, model, bc, mixed, monkeypatch):
+    """Straight-sided elements of a Laplace-type model whose tau is constant on each face (a different value per face and per side)
+    take every block from reference matrices; `mixed` makes tau vary along some faces, so both paths meet inside one mesh.
+    The same inputs with the path disabled (HFX_NO_REFPATH) must give the same condensed blocks."""
+    case = H.make_case(dim, order, N=3, perturb=0.12, model=model, bc=bc, tau_double=True, seed=21)
+    tau = case["fields"]["Tau"]
+    rng = np.random.default_rng(5)
+    keep = rng.random(tau.shape[0]) < 0.5 if mixed else np.zeros(tau.shape[0], dtype=bool)
+    tau[~keep] = tau[~keep][:, :1, :]          # constant along the face, one value per side
+    o, s, fm = compare(case)
+    monkeypatch.setenv("HFX_NO_REFPATH", "1")
+    s2, fm2, _ = H.run_device(case)
+    a, b = s.getLocal(), s2.getLocal()
+    for name in ("S", "S0", "U", "Q", "U0", "Q0"):
+        assert H.rel_err(a[name], b[name]) < TOL_ENTRIES, name
+
+
 def test_reassembly_is_bit_reproducible():
     """Deterministic scatter: two assemblies of the same inputs give bit-identical CSR values (<= 2 contributors per entry)."""
     case = H.make_case(3, 3, N=3, model="cdrs", diff="scalar", tau_double=True)

@@ -190,6 +190,18 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
 }
+// bulk asynchronous copies shared -> global (TMA, SASS UBLKCP / UBLKRED): sizes and both addresses are multiples of 16 bytes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, int bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_add_f64(double* gdst, const double* ssrc, int bytes) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // warp-granular dynamic tile queue: every call hands the warp the next 32 consecutive tile ids
@@ -427,6 +439,8 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   constexpr int D2 = DIM * DIM, NT = kAsmThreads, NWARP = NT / 32;
   constexpr int kTau = 0, kN = 1, kDN = 1 + DIM, kC = 1 + 2 * DIM, kOne = 2 + 2 * DIM;
   constexpr int FWS = tp * t;   // stride between face matrices
+  constexpr bool kBulkUQ = (l % 2) == 0;   // rows of U, Q are multiples of 16 bytes: bulk copies
+  constexpr bool kBulkS = (t % 2) == 0;    // (row, face block) pieces of S are multiples of 16 bytes: bulk copies / reduce-adds
   constexpr bool kPrefetch = (nN * DIM <= 64) && (l <= 128) && (nFc * nFc <= 32);
   extern __shared__ __align__(16) double sm[];
   double* PHI = sm + L::oPHI; double* X = sm + L::oX; double* JR = sm + L::oJ; double* IJ = sm + L::oIJ; double* DV = sm + L::oDV;
@@ -449,6 +463,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   int* QCTR = OPP + nFc;                                              // [4] dynamic tile-queue counters
   int* NLUT = QCTR + 8;                                               // [nNLUT]
   unsigned short* KLUT = reinterpret_cast<unsigned short*>(NLUT + L::nNLUT);   // [nFc][nKLUT][2] 16-bit operand offsets of the P9 reduction index k = (kind, b)
+  int* CMAP = NLUT + L::nNLUT + nFc * L::nKLUT;                                    // (bulk write-out) [l+1], shares the POSROW area
   int* POSROW = NLUT + L::nNLUT + nFc * L::nKLUT;                                  // [nFc][l] column offset of element-local column cc inside a row of face f
   double* A = G;    // A_d aliases g (dead after the contractions)
   double* ST = sm + L::oST;   // S staging [l][ldc] for the coalesced write-out
@@ -608,8 +623,14 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
     for (int f = 0; f < nFc; f++) if (BCF[f] == 2) tileNeed |= intNeed;
     // scatter maps of this element (HDGSolver.cpp:596: matRowCols), consumed by the write-out
-    for (int i = tid; i < nFc * l; i += NT) { const int f = i / l, cc = i - f * l; POSROW[i] = POS[f * nFc + cc / t] * t + PERM[cc]; }
-    if (tid < l) { const int f = tid / t; RBASE[tid] = ROWS[f] + (long long)PERM[tid] * RLEN[f]; }
+    // Global storage: per face F its nnb(F) neighbour blocks, each a contiguous row-major t x t block in face-node order (block CSR).
+    if (kBulkS) {   // staging already is in face-node order: CMAP[position] = element-local trace index
+      if (tid < l) CMAP[(tid / t) * t + PERM[tid]] = tid;
+      if (tid == l) CMAP[l] = l;
+    } else {
+      for (int i = tid; i < nFc * l; i += NT) { const int f = i / l, cc = i - f * l; POSROW[i] = POS[f * nFc + cc / t] * t * t + PERM[cc]; }
+      if (tid < l) { const int f = tid / t; RBASE[tid] = ROWS[f] + (long long)PERM[tid] * t; }
+    }
 
     // ---- all-reference path, stage G: constant geometry (one thread per face + one for the bulk Jacobian), tau check ----------
     bool ref = false;
@@ -1394,8 +1415,21 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         }
       }
     }
+    if (kBulkUQ) fence_proxy_async();
     __syncthreads();
     HFX_PROF(12);
+    // U, Q leave as whole rows (row-major per element in HBM): one bulk copy per row, issued here so that they fly during P9
+    if (kBulkUQ) {
+      constexpr int q = DIM * nN;
+      constexpr int RPWQ = (nN + q + NWARP - 1) / NWARP;   // a warp issues its copies one after the other: spread them evenly
+      static_assert(RPWQ <= 32, "rows per warp");
+      const int row = warp * RPWQ + lane;
+      if (lane < RPWQ && row < nN + q) {
+        if (row < nN) bulk_store(p.U + ((size_t)e * nN + row) * l, Um + row * ldc, l * 8);
+        else { const int rq = row - nN; bulk_store(p.Q + ((size_t)e * q + rq) * l, B + ((rq % DIM) * nN + rq / DIM) * ldc, l * 8); }
+        bulk_commit();
+      }
+    }
 
     // ---- P9: S = Slu U + Slq Q + Sll ; S0 = Fl - Slu U0 - Slq Q0 (:347-348); Dirichlet rows (:489-501); scatter (:596-618) --
     //      a warp task = all row tiles of one face x three column tiles: one gathered right-operand load feeds every row tile
@@ -1407,11 +1441,12 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         const int f = task / NG, ng = task - f * NG;
         const double* fwf = FW + f * NW * FWS;
         const unsigned short* klut = KLUT + 2 * f * L::nKLUT;
+        // bulk write-out: output rows / columns are face-node POSITIONS; the operands are fetched at the element-local indices they map to
         int acl[TT], ncl[NTW9];
 #pragma unroll
-        for (int i = 0; i < TT; i++) acl[i] = imin(i * 8 + lr, t - 1);
+        for (int i = 0; i < TT; i++) { acl[i] = imin(i * 8 + lr, t - 1); if (kBulkS) acl[i] = CMAP[f * t + acl[i]] - f * t; }
 #pragma unroll
-        for (int j = 0; j < NTW9; j++) ncl[j] = imin((ng * NTW9 + j) * 8 + lr, l);
+        for (int j = 0; j < NTW9; j++) { ncl[j] = imin((ng * NTW9 + j) * 8 + lr, l); if (kBulkS) ncl[j] = CMAP[ncl[j]]; }
         double c[TT][NTW9][2];
 #pragma unroll
         for (int i = 0; i < TT; i++) zero_c(c[i]);
@@ -1426,113 +1461,128 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           const double* brow = sm + off.y;
 #pragma unroll
           for (int j = 0; j < NTW9; j++) bv[j] = brow[ncl[j]];
+          if (kBulkS && ks * 4 < t) {   // Sll = -tau mass (HDGBase.cpp:125) rides on the tau-mass steps: tau mass (U - I)
+#pragma unroll
+            for (int j = 0; j < NTW9; j++) bv[j] -= (k < t && ncl[j] == f * t + k) ? 1.0 : 0.0;
+          }
 #pragma unroll
           for (int i = 0; i < TT; i++)
 #pragma unroll
             for (int j = 0; j < NTW9; j++) dmma(c[i][j], av[i], bv[j]);
         }
+        const int bcf = BCF[f];
 #pragma unroll
         for (int i = 0; i < TT; i++) {
           const int a = i * 8 + lr;
           if (a < t) {
-            double* strow = ST + (f * t + a) * ldc;
+            if (!kBulkS) {
+              double* strow = ST + (f * t + a) * ldc;
 #pragma unroll
-            for (int j = 0; j < NTW9; j++) {
-              const int cc = (ng * NTW9 + j) * 8 + 2 * lc;
-              if (cc <= l) *reinterpret_cast<double2*>(strow + cc) = make_double2(c[i][j][0], c[i][j][1]);
+              for (int j = 0; j < NTW9; j++) {
+                const int cc = (ng * NTW9 + j) * 8 + 2 * lc;
+                if (cc <= l) *reinterpret_cast<double2*>(strow + cc) = make_double2(c[i][j][0], c[i][j][1]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < NTW9; j++) {
+                const int cp = (ng * NTW9 + j) * 8 + 2 * lc;   // (a, cp): positions
+                if (cp < l) {
+                  const int f2 = cp / t, pb = cp - f2 * t;
+                  double v0 = c[i][j][0], v1 = c[i][j][1];
+                  if (hasConv || bcf) {   // convection part of Sll (HDGConvection.cpp:96), boundary rows (HDGSolver.cpp:489-501)
+                    const double* fwd = FW + f * NW * FWS + acl[i];
+                    const int b0 = CMAP[cp] - f2 * t, b1 = CMAP[cp + 1] - f2 * t;
+                    if (f2 == f) {
+                      if (hasConv) { v0 += fwd[kC * FWS + tp * b0]; v1 += fwd[kC * FWS + tp * b1]; }
+                      if (bcf == 2) { v0 = fwd[kOne * FWS + tp * b0]; v1 = fwd[kOne * FWS + tp * b1]; }   // IntegratedDirichletModel row
+                    } else if (bcf == 2) { v0 = 0.0; v1 = 0.0; }
+                    if (bcf == 1) { v0 = (f2 == f && pb == a) ? 1.0 : 0.0; v1 = (f2 == f && pb + 1 == a) ? 1.0 : 0.0; }   // DirichletModel row (Set)
+                  }
+                  *reinterpret_cast<double2*>(ST + ((f * nFc + f2) * t + a) * t + pb) = make_double2(v0, v1);
+                } else if (cp == l) ST[l * l + f * t + a] = c[i][j][0];
+              }
             }
           }
         }
       }
     }
+    if (kBulkS) fence_proxy_async();
     __syncthreads();
     HFX_PROF(13);
 
-    // ---- P10: write-out.  Every global store of the element happens here, from shared memory.  U/Q: a lane owns one output row
-    //      (consecutive lanes -> consecutive addresses), a warp owns column pairs.  S: a warp owns rows, a lane owns columns
-    //      (consecutive lanes -> consecutive, permuted, CSR entries of one row).  All loops have compile-time trip counts and are
-    //      unrolled with the shared-memory loads batched ahead of the stores: this phase is latency-, not bandwidth-bound. -----
+    // ---- P10: write-out.  S: every (row, neighbour-face block) of the element is t contiguous entries of the global face-block CSR,
+    //      already final and in row order in the staging area: one bulk copy each, a bulk reduce-add (f64) where the second element of
+    //      an interior face adds to the same diagonal block (two contributors, zeroed storage: the sum is order independent).
+    //      U, Q rows left after P8.  Elements whose sizes break the 16-byte granularity take the per-entry path.
     {
       constexpr int q = DIM * nN;
-      constexpr int NPAIR = (l + 1) / 2, CPW = (NPAIR + NWARP - 1) / NWARP;
-      double* gU = p.U + (size_t)e * nN * l;
+      if (!kBulkUQ) {
+        double* gU = p.U + (size_t)e * nN * l;
+        for (int idx = tid; idx < nN * l; idx += NT) { const int r = idx / l, c = idx - r * l; gU[idx] = Um[r * ldc + c]; }
+        double* gQ = p.Q + (size_t)e * q * l;
+        for (int idx = tid; idx < q * l; idx += NT) { const int rq = idx / l, c = idx - rq * l; gQ[idx] = B[((rq % DIM) * nN + rq / DIM) * ldc + c]; }
+      }
+      double* gS = p.S ? p.S + (size_t)e * l * l : nullptr;
+      double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
+      if (kBulkS) {
+        constexpr int OPW = (nFc * nFc + NWARP - 1) / NWARP;
+        const int k = warp * OPW + lane;
+        if (lane < OPW && k < nFc * nFc) {
+          const int f = k / nFc, f2 = k - f * nFc;
+          const double* src = ST + k * t * t;
+          double* dst = p.vals + ROWS[f] + (long long)POS[k] * t * t;
+          if (f2 == f && INTF[f]) bulk_add_f64(dst, src, t * t * 8); else bulk_store(dst, src, t * t * 8);
+          bulk_commit();
+        }
+        if (gS) for (int idx = tid; idx < l * l; idx += NT) {
+          const int cc = idx / l, r = idx - cc * l, f = r / t, f2 = cc / t;
+          gS[idx] = ST[((f * nFc + f2) * t + PERM[r]) * t + PERM[cc]];
+        }
+      } else {
+        constexpr int RPW = (l + NWARP - 1) / NWARP;
 #pragma unroll
-      for (int h = 0; h < (nN + 31) / 32; h++) {
-        const int r = lane + 32 * h;
-        if (r < nN) {
-          const double* src = Um + r * ldc;
-          double2 v[CPW];
+        for (int h = 0; h < (l + 31) / 32; h++) {
+          const int cc = lane + 32 * h;
+          if (cc < l) {
+            const int f2 = cc / t, b2 = cc - f2 * t;
+            double sv[RPW];
+            int off[RPW];
 #pragma unroll
-          for (int i = 0; i < CPW; i++) { const int c = 2 * (warp + NWARP * i); v[i] = (c < l) ? *reinterpret_cast<const double2*>(src + c) : make_double2(0.0, 0.0); }
+            for (int i = 0; i < RPW; i++) {
+              const int r = warp + NWARP * i;
+              if (r < l) {
+                const int f = r / t, a = r - f * t, bc = BCF[f];
+                const double* fwd = FW + f * NW * FWS + a + tp * b2;
+                const bool diag = (f2 == f);
+                double v = ST[r * ldc + cc];
+                const double dterm = (hasConv ? fwd[kC * FWS] : 0.0) - fwd[kTau * FWS];   // Sll = -tau mass + (v.n) mass
+                v += diag ? dterm : 0.0;
+                if (bc == 1) v = (diag && b2 == a) ? 1.0 : 0.0;                            // DirichletModel row (Set)
+                else if (bc == 2) v = diag ? fwd[kOne * FWS] : 0.0;                        // IntegratedDirichletModel row
+                sv[i] = v;
+                off[i] = POSROW[f * l + cc];
+              }
+            }
 #pragma unroll
-          for (int i = 0; i < CPW; i++) {
-            const int c = 2 * (warp + NWARP * i);
-            if (c < l) gU[(size_t)c * nN + r] = v[i].x;
-            if (c + 1 < l) gU[(size_t)(c + 1) * nN + r] = v[i].y;
+            for (int i = 0; i < RPW; i++) {
+              const int r = warp + NWARP * i;
+              if (r < l) {
+                const int f = r / t;
+                if (gS) gS[r + (size_t)l * cc] = sv[i];
+                double* dst = p.vals + RBASE[r] + off[i];
+                if (f2 == f && INTF[f]) atomicAdd(dst, sv[i]); else *dst = sv[i];
+              }
+            }
           }
         }
       }
       if (tid < nN) p.U0[(size_t)e * nN + tid] = Um[tid * ldc + l];
-      double* gQ = p.Q + (size_t)e * q * l;
-#pragma unroll
-      for (int h = 0; h < (q + 31) / 32; h++) {
-        const int rq = lane + 32 * h;
-        if (rq < q) {
-          const double* src = B + ((rq % DIM) * nN + rq / DIM) * ldc;
-          double2 v[CPW];
-#pragma unroll
-          for (int i = 0; i < CPW; i++) { const int c = 2 * (warp + NWARP * i); v[i] = (c < l) ? *reinterpret_cast<const double2*>(src + c) : make_double2(0.0, 0.0); }
-#pragma unroll
-          for (int i = 0; i < CPW; i++) {
-            const int c = 2 * (warp + NWARP * i);
-            if (c < l) gQ[(size_t)c * q + rq] = v[i].x;
-            if (c + 1 < l) gQ[(size_t)(c + 1) * q + rq] = v[i].y;
-          }
-        }
-      }
-      if (tid < q) p.Q0[(size_t)e * q + tid] = B[((tid % DIM) * nN + tid / DIM) * ldc + l];
-      double* gS = p.S ? p.S + (size_t)e * l * l : nullptr;
-      double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
-      constexpr int RPW = (l + NWARP - 1) / NWARP;
-#pragma unroll
-      for (int h = 0; h < (l + 31) / 32; h++) {
-        const int cc = lane + 32 * h;
-        if (cc < l) {
-          const int f2 = cc / t, b2 = cc - f2 * t;
-          double sv[RPW];
-          int off[RPW];
-#pragma unroll
-          for (int i = 0; i < RPW; i++) {
-            const int r = warp + NWARP * i;
-            if (r < l) {
-              const int f = r / t, a = r - f * t, bc = BCF[f];
-              const double* fwd = FW + f * NW * FWS + a + tp * b2;
-              const bool diag = (f2 == f);
-              double v = ST[r * ldc + cc];
-              const double dterm = (hasConv ? fwd[kC * FWS] : 0.0) - fwd[kTau * FWS];   // Sll = -tau mass + (v.n) mass
-              v += diag ? dterm : 0.0;
-              if (bc == 1) v = (diag && b2 == a) ? 1.0 : 0.0;                            // DirichletModel row (Set)
-              else if (bc == 2) v = diag ? fwd[kOne * FWS] : 0.0;                        // IntegratedDirichletModel row
-              sv[i] = v;
-              off[i] = POSROW[f * l + cc];
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < RPW; i++) {
-            const int r = warp + NWARP * i;
-            if (r < l) {
-              const int f = r / t;
-              if (gS) gS[r + (size_t)l * cc] = sv[i];
-              double* dst = p.vals + RBASE[r] + off[i];
-              if (f2 == f && INTF[f]) atomicAdd(dst, sv[i]); else *dst = sv[i];
-            }
-          }
-        }
-      }
+      if (tid >= 64 && tid < 64 + q) { const int rq = tid - 64; p.Q0[(size_t)e * q + rq] = B[((rq % DIM) * nN + rq / DIM) * ldc + l]; }
+      if (q > NT - 64) for (int rq = NT - 64 + tid; rq < q; rq += NT) p.Q0[(size_t)e * q + rq] = B[((rq % DIM) * nN + rq / DIM) * ldc + l];
       if (tid < l) {
         const int r = tid, f = r / t, a = r % t, F = ISM[f], bc = BCF[f];
         const double* fwf = FW + f * NW * FWS;
-        double s0 = -ST[r * ldc + l];
+        double s0 = kBulkS ? -ST[l * l + f * t + PERM[r]] : -ST[r * ldc + l];
         if (bc == 1) s0 = p.dirichlet[(size_t)F * t + a];
         else if (bc == 2) {
           s0 = 0.0;
@@ -1542,6 +1592,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         const int rowDof = F * t + PERM[r];
         if (INTF[f]) atomicAdd(p.rhs + rowDof, s0); else p.rhs[rowDof] = s0;
       }
+      if (kBulkUQ || kBulkS) bulk_wait_read();   // the staging areas are rewritten by the next element pass
     }
     __syncthreads();
     HFX_PROF(15);

@@ -482,9 +482,9 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       Qm[idx] = -s - Bq[idx];
     }
     __syncthreads();
-    // write U, Q, U0, Q0 (column-major per element, HDGSolver.cpp:336-341)
-    for (long long idx = tid; idx < (long long)u * l; idx += NT) p.U[(size_t)e * u * l + idx] = Um[idx];
-    for (long long idx = tid; idx < (long long)q * l; idx += NT) p.Q[(size_t)e * q * l + idx] = Qm[idx];
+    // write U, Q, U0, Q0 (HDGSolver.cpp:336-341; kept row-major per element on the device, see recover_kernel)
+    for (long long idx = tid; idx < (long long)u * l; idx += NT) { const int r = (int)(idx / l), cc = (int)(idx - (long long)r * l); p.U[(size_t)e * u * l + idx] = Um[(size_t)r + (size_t)u * cc]; }
+    for (long long idx = tid; idx < (long long)q * l; idx += NT) { const int r = (int)(idx / l), cc = (int)(idx - (long long)r * l); p.Q[(size_t)e * q * l + idx] = Qm[(size_t)r + (size_t)q * cc]; }
     for (int i = tid; i < u; i += NT) p.U0[(size_t)e * u + i] = Um[(size_t)u * l + i];
     for (int i = tid; i < q; i += NT) p.Q0[(size_t)e * q + i] = Qm[(size_t)q * l + i];
     // S = Slu U + Slq Q + Sll ; S0 = Fl - Slu U0 - Slq Q0 ; boundary rows (:489-501) ; scatter (:596-618)
@@ -497,13 +497,13 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       for (int j = 0; j < u; j++) s = fma(lrow[(size_t)n * j], Um[(size_t)j + (size_t)u * c], s);
       for (int rq = 0; rq < q; rq++) s = fma(lrow[(size_t)n * (sQ + rq)], Qm[(size_t)rq + (size_t)q * c], s);
       const int f = r / t, rr = r - f * t, a = rr / nD, k1 = rr - a * nD, F = FACE[f], bc = BCF[f];
-      const long long rowOff = ROWS[f] + (long long)(PERM[f * nNf + a] * nD + k1) * RLEN[f];
+      const long long rowOff = ROWS[f] + (long long)(PERM[f * nNf + a] * nD + k1) * t;   // block CSR: row inside each t x t neighbour block
       if (c < l) {
         const int f2 = c / t, cc = c - f2 * t, b = cc / nD, k2 = cc - b * nD;
         if (bc == 1) s = (r == c) ? 1.0 : 0.0;                                                       // DirichletModel: identity row
         else if (bc == 2) s = (f2 == f && k1 == k2) ? FONE[f * nNf * nNf + a * nNf + b] : 0.0;       // IntegratedDirichletModel: face mass (x) I
         if (gS) gS[(size_t)r + (size_t)l * c] = s;
-        double* dst = p.vals + rowOff + POS[f * nFc + f2] * t + PERM[f2 * nNf + b] * nD + k2;
+        double* dst = p.vals + rowOff + (long long)POS[f * nFc + f2] * t * t + PERM[f2 * nNf + b] * nD + k2;
         if (f2 == f && INTF[f]) atomicAdd(dst, s); else *dst = s;
       } else {
         double s0 = Fv[sL + r] - s;

@@ -158,9 +158,10 @@ __global__ void ip_coords_kernel(int nCells, int nN, int nIP, int dim, const dou
   }
 }
 
-// y = A x on the face-block CSR layout.  One warp per FACE: the t rows of a face are contiguous in vals (t * len doubles, len = nnb * t)
-// and share their column set, so the warp streams one contiguous 5.6 KB block (p=3 tets) and gathers the len entries of x once into
-// registers instead of once per row.  HBM-bound: 8 B of matrix per FMA.
+// y = A x on the block CSR layout: per face F its nnb(F) neighbour blocks (sorted neighbour faces = PETSc AIJ column order), each a
+// contiguous row-major t x t block.  One warp per FACE: the face's data is one contiguous run of t * len doubles (len = nnb * t;
+// 5.6 KB at p=3 tets) and its t rows share their column set, so the warp gathers the len entries of x once into registers instead
+// of once per row.  No column indices are read.  HBM-bound: 8 B of matrix per FMA.
 template <int MAXK>
 __global__ void spmv_face_kernel(int nFaces, int t, int nFc2, const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
                                  const int* __restrict__ nbr, const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
@@ -171,20 +172,22 @@ __global__ void spmv_face_kernel(int nFaces, int t, int nFc2, const long long* _
   if (owned && !owned[F]) { for (int a = lane; a < t; a += 32) y[(size_t)F * t + a] = 0.0; return; }   // rows of ghost faces belong to another rank
   const int m = nnb[F], len = m * t;
   double xr[MAXK];
+  int offk[MAXK];   // entry (row a, column k = g t + b) sits at g t^2 + a t + b
 #pragma unroll
   for (int q = 0; q < MAXK; q++) {
     const int k = lane + 32 * q;
     double xv = 0.0;
-    if (k < len) { const int g = k / t, b = k - g * t; xv = x[(size_t)nbr[(size_t)F * nFc2 + g] * t + b]; }
-    xr[q] = xv;
+    int o = 0;
+    if (k < len) { const int g = k / t, b = k - g * t; xv = x[(size_t)nbr[(size_t)F * nFc2 + g] * t + b]; o = g * t * t + b; }
+    xr[q] = xv; offk[q] = o;
   }
   const double* v = vals + rowStart[F];
   double keep = 0.0;
   for (int a = 0; a < t; a++) {
     double s = 0.0;
 #pragma unroll
-    for (int q = 0; q < MAXK; q++) { const int k = lane + 32 * q; if (k < len) s = fma(v[k], xr[q], s); }
-    v += len;
+    for (int q = 0; q < MAXK; q++) { const int k = lane + 32 * q; if (k < len) s = fma(v[offk[q]], xr[q], s); }
+    v += t;
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((a & 31) == lane) keep = s;
     if ((a & 31) == 31 || a == t - 1) { const int a0 = a & ~31; if (a0 + lane <= a) y[(size_t)F * t + a0 + lane] = keep; }
@@ -211,7 +214,7 @@ __global__ void diag_face_kernel(int nFaces, int t, int nFc2, const long long* _
   const int m = nnb[F];
   int g = 0;
   for (int k = 0; k < m; k++) if (nbr[(size_t)F * nFc2 + k] == F) g = k;
-  const double d = vals[rowStart[F] + (long long)a * m * t + g * t + a];
+  const double d = vals[rowStart[F] + ((long long)g * t + a) * t + a];
   dinv[row] = d != 0.0 ? 1.0 / d : 1.0;
 }
 __global__ void diag_csr_kernel(long long n, const long long* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals, double* __restrict__ dinv) {
@@ -269,31 +272,50 @@ __global__ void scale_copy_kernel(long long n, const double* __restrict__ src, d
 }
 
 // recovery (HDGSolver.cpp:741-775): one CTA per element, thread per output row; U,Q column-major => coalesced
+// U, Q are kept row-major per element ([u][l], [q][l]: the transpose of the reference's column-major storage, HDGSolver.cpp:336-341)
+// so that the assemble kernel writes whole rows with bulk copies and this kernel streams them: one warp per row, lanes along the row.
 __global__ void recover_kernel(int nCells, int u, int q, int l, int nFc, int nNf, int nD, const int* __restrict__ cell2face, const uint8_t* __restrict__ fperm,
                                const double* __restrict__ trace, const double* __restrict__ U, const double* __restrict__ Q,
-                               const double* __restrict__ U0, const double* __restrict__ Q0, double* __restrict__ sol, double* __restrict__ flux) {
-  extern __shared__ double lam[];
+                               const double* __restrict__ U0, const double* __restrict__ Q0, double* __restrict__ sol, double* __restrict__ flux, int chunkRows) {
+  extern __shared__ double lam[];   // [l] lambda_e, then [chunkRows * l / 2] partial products
+  double* part = lam + ((l + 1) & ~1);
+  const int tid = threadIdx.x, bs = blockDim.x, h = l >> 1;
   for (int e = blockIdx.x; e < nCells; e += gridDim.x) {
-    for (int i = threadIdx.x; i < l; i += blockDim.x) {   // lambda_e[(f*nNf+j)*nD+k] = Trace[(face_f*nNf + pos)*nD + k]  (:752-766)
+    for (int i = tid; i < l; i += bs) {   // lambda_e[(f*nNf+j)*nD+k] = Trace[(face_f*nNf + pos)*nD + k]  (:752-766)
       const int fa = i / nD, k = i - fa * nD, f = fa / nNf;
       lam[i] = trace[((size_t)cell2face[(size_t)e * nFc + f] * nNf + fperm[(size_t)e * nFc * nNf + fa]) * nD + k];
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < u + q; r += blockDim.x) {
-      if (r < u) {
-        const double* Ue = U + (size_t)e * u * l + r;
-        double s = U0[(size_t)e * u + r];
-        for (int c = 0; c < l; c++) s = fma(Ue[(size_t)c * u], lam[c], s);
-        sol[(size_t)e * u + r] = s;
+    const double* Ue = U + (size_t)e * u * l;   // rows 0..u-1 of U then rows 0..q-1 of Q: two contiguous streams
+    const double* Qe = Q + (size_t)e * q * l;
+    for (int r0 = 0; r0 < u + q; r0 += chunkRows) {
+      const int nr = min(chunkRows, u + q - r0);
+      if ((l & 1) == 0) {   // 16-byte loads, fully coalesced; a thread's pair never straddles a row
+        for (int i = tid; i < nr * h; i += bs) {
+          const int r = r0 + i / h, c = 2 * (i % h);
+          const double2 v = *reinterpret_cast<const double2*>((r < u ? Ue + (size_t)r * l : Qe + (size_t)(r - u) * l) + c);
+          part[i] = fma(v.x, lam[c], v.y * lam[c + 1]);
+        }
+        __syncthreads();
+        for (int i = tid; i < nr; i += bs) {
+          const int r = r0 + i;
+          double s2 = 0.0;
+          for (int k = 0; k < h; k++) s2 += part[i * h + k];
+          if (r < u) sol[(size_t)e * u + r] = s2 + U0[(size_t)e * u + r];
+          else flux[(size_t)e * q + (r - u)] = s2 + Q0[(size_t)e * q + (r - u)];
+        }
       } else {
-        const int rr = r - u;
-        const double* Qe = Q + (size_t)e * q * l + rr;
-        double s = Q0[(size_t)e * q + rr];
-        for (int c = 0; c < l; c++) s = fma(Qe[(size_t)c * q], lam[c], s);
-        flux[(size_t)e * q + rr] = s;
+        for (int i = tid; i < nr; i += bs) {
+          const int r = r0 + i;
+          const double* row = r < u ? Ue + (size_t)r * l : Qe + (size_t)(r - u) * l;
+          double s2 = 0.0;
+          for (int c = 0; c < l; c++) s2 = fma(row[c], lam[c], s2);
+          if (r < u) sol[(size_t)e * u + r] = s2 + U0[(size_t)e * u + r];
+          else flux[(size_t)e * q + (r - u)] = s2 + Q0[(size_t)e * q + (r - u)];
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
 
@@ -313,6 +335,17 @@ __global__ void expand_csr_kernel(int nFaces, int t, int nFc2, const long long* 
   rowptr[row] = s;
   if (colidx) for (int g = 0; g < m; g++) for (int b = 0; b < t; b++) colidx[s + g * t + b] = nbr[(size_t)F * nFc2 + g] * t + b;
   if (row == (long long)nFaces * t - 1) rowptr[row + 1] = s + (long long)m * t;
+}
+
+// values of the block layout in the order of the expanded CSR (parity hook only)
+__global__ void block_vals_to_csr_kernel(int nFaces, int t, const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
+                                         const double* __restrict__ vals, double* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= (long long)nFaces * t) return;
+  const int F = (int)(row / t), a = (int)(row % t);
+  const int m = nnb[F];
+  const long long s0 = rowStart[F];
+  for (int g = 0; g < m; g++) for (int b = 0; b < t; b++) out[s0 + (long long)a * m * t + g * t + b] = vals[s0 + ((long long)g * t + a) * t + b];
 }
 
 // FP64 FMA peak probe: 8 independent register-resident DFMA chains per thread
@@ -1194,10 +1227,12 @@ int hfx_recover(hfx_ctx* c) {
     need(c->assembled, "HDGSolver", "solve", "system must be assembled before solving");
     const int nD = c->md.nDOF, t = c->nNf * nD, u = c->nN * nD, q = u * c->dim, l = c->nFc * t;
     int grid = std::min(c->nCells, c->nSM * 16);
-    int bs = ((u + q + 31) / 32) * 32; if (bs > 256) bs = 256;
+    int bs = 256;
     (void)t;
-    recover_kernel<<<grid, bs, l * sizeof(double), c->st>>>(c->nCells, u, q, l, c->nFc, c->nNf, nD, c->dC2F.p, c->dFperm.p, find_field(c, "Trace")->d.p,
-                                                            c->dU.p, c->dQ.p, c->dU0.p, c->dQ0.p, find_field(c, "Solution")->d.p, find_field(c, "Flux")->d.p);
+    const int chunkRows = std::max(1, std::min(u + q, 4096 / std::max(1, l / 2)));
+    const size_t shm = ((size_t)((l + 1) & ~1) + (size_t)chunkRows * (l / 2)) * sizeof(double);
+    recover_kernel<<<grid, bs, shm, c->st>>>(c->nCells, u, q, l, c->nFc, c->nNf, nD, c->dC2F.p, c->dFperm.p, find_field(c, "Trace")->d.p,
+                                             c->dU.p, c->dQ.p, c->dU0.p, c->dQ0.p, find_field(c, "Solution")->d.p, find_field(c, "Flux")->d.p, chunkRows);
     HFX_CUDA(cudaGetLastError());
     HFX_CUDA(cudaStreamSynchronize(c->st));
   });
@@ -1295,7 +1330,12 @@ int hfx_get_csr(hfx_ctx* c, long long* nrows, long long* nnz, long long* rowptr,
       if (rowptr) drp.download(rowptr, n + 1, c->st);
       if (colidx) dci.download(colidx, (size_t)c->nnz, c->st);
     }
-    if (vals) c->dVals.download(vals, (size_t)c->nnz, c->st);
+    if (vals) {
+      DBuf<double> dv; dv.alloc((size_t)c->nnz);
+      block_vals_to_csr_kernel<<<nblk(n, 256), 256, 0, c->st>>>(c->nFaces, t, c->dFaceRowStart.p, c->dNnb.p, c->dVals.p, dv.p);
+      HFX_CUDA(cudaGetLastError());
+      dv.download(vals, (size_t)c->nnz, c->st);
+    }
     if (rhs) c->dRhs.download(rhs, (size_t)n, c->st);
   });
 }
@@ -1309,9 +1349,17 @@ int hfx_get_local(hfx_ctx* c, int iEl, int nEl, double* S, double* S0, double* U
     if (S || S0) need(c->keepS, "hfx", "get_local", "allocate with HFX_KEEP_LOCAL_S to keep the per-element S, S0 blocks");
     if (S) c->dS.download(S, (size_t)nEl * l * l, c->st, (size_t)iEl * l * l);
     if (S0) c->dS0.download(S0, (size_t)nEl * l, c->st, (size_t)iEl * l);
-    if (U) c->dU.download(U, (size_t)nEl * u * l, c->st, (size_t)iEl * u * l);
+    // U, Q live row-major on the device; the caller gets the reference's column-major blocks (HDGSolver.cpp:336-341)
+    auto fetchT = [&](DBuf<double>& d, double* out, int rows) {
+      std::vector<double> tmp((size_t)nEl * rows * l);
+      d.download(tmp.data(), tmp.size(), c->st, (size_t)iEl * rows * l);
+      for (int e = 0; e < nEl; e++)
+        for (int r = 0; r < rows; r++)
+          for (int cc = 0; cc < l; cc++) out[(size_t)e * rows * l + (size_t)cc * rows + r] = tmp[(size_t)e * rows * l + (size_t)r * l + cc];
+    };
+    if (U) fetchT(c->dU, U, u);
     if (U0) c->dU0.download(U0, (size_t)nEl * u, c->st, (size_t)iEl * u);
-    if (Q) c->dQ.download(Q, (size_t)nEl * q * l, c->st, (size_t)iEl * q * l);
+    if (Q) fetchT(c->dQ, Q, q);
     if (Q0) c->dQ0.download(Q0, (size_t)nEl * q, c->st, (size_t)iEl * q);
   });
 }

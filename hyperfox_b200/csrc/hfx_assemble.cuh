@@ -50,6 +50,7 @@ struct AsmParams {
   const double* mhinv;        // inverse of the reference mass matrix, column-major [ev(nN)][ev(nN)] (unit pad diagonal)
   // straight-sided elements: reference matrices of the purely geometric blocks (built by hfx_refel_set) and the per-element flag
   const double* sref;         // S^_r [DIM][nN][ev(nN)]: Squ_d = sum_r detJ Jinv(d,r) S^_r
+  const double* eref;         // E_f [nFc][nN][ev(nN)]: reference face mass scattered to the element nodes, entry (f, j, i) = M^f[a_f(i)][a_f(j)] or 0
   const double* srefT;        // S^_r transposed [DIM][nN][ev(nN)]: entry (r, j, k) = S^_r[k][j], the layout of the Suq_d left operand
   int noRef;                  // experiments: disable the all-reference path
   const double* aref;         // A^_r [DIM][ev(nN) x nN] column-major: A_d = sum_r Jinv(d,r) A^_r          (A^_r = M_ref^-1 S^_r)
@@ -418,6 +419,7 @@ struct AsmSmem {
   static constexpr int oGEOR = oGEO + ev(DIM * DIM + 1 + nFc * (DIM + 1));   // all-reference path, per face: -area n_d [DIM], tau area, area
   static constexpr int oEnd = oGEOR + ev(nFc * (DIM + 2));
   static_assert(ev(nFc * nN * t) <= szR && tp * t <= nNp * nNp, "reference tables are staged in the R and M regions");
+  static_assert(nFc * nN * nNp <= nNp * nNp + szSQU, "node-scattered face masses are staged in the W + Squ regions");
   // S staging [l][ldc] for the coalesced write-out: reuses the dead g/A + M + W span when it is large enough (large elements),
   // otherwise gets its own area (small elements, where shared memory is not the limit)
   static constexpr bool stFits = (oSQU - oG) >= l * ldc;
@@ -599,6 +601,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       for (int i = tid; i < DIM * nN * nNp / 2; i += NT) { cp_async16(A + 2 * i, p.aref + 2 * i); cp_async16(SUQ + 2 * i, p.srefT + 2 * i); }
       for (int i = tid; i < ev(nFc * nN * t) / 2; i += NT) cp_async16(R + 2 * i, p.bref + 2 * i);
       for (int i = tid; i < FWS / 2; i += NT) cp_async16(Mm + 2 * i, p.mfref + 2 * i);
+      for (int i = tid; i < nFc * nN * nNp / 2; i += NT) cp_async16(Wb + 2 * i, p.eref + 2 * i);   // E_f spans the W and Squ regions
       if (hasSrc) {   // source values times the cubature weights (scaled by det J later)
         if (kRefSrcPf) { if (tid >= 128 && tid < 128 + nIP) LW[nIP + tid - 128] = ts * pfSrc * WQ[tid - 128]; }
         else for (int i = tid; i < nIP; i += NT) LW[nIP + i] = ts * p.srcIP[(size_t)e * nIP + i] * WQ[i];
@@ -709,56 +712,82 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       for (int m = 0; m < DIM; m++)
 #pragma unroll
         for (int r = 0; r < DIM; r++) Ii[m][r] = GEO[m * DIM + r];
-      for (int idx = tid; idx < nN * nNp; idx += NT) {
-        const int j = idx / nNp, i = idx - j * nNp;
-        double ar[DIM], sr[DIM], fq[DIM], suu = 0.0;
+      // One list of independent work items spread round-robin over the threads (16-byte shared-memory accesses):
+      //   [A] A_d pairs, [S] Suq_d / Suu pairs (face parts from the node-scattered face masses E_f), [B] B_d, [F] face matrices.
+      constexpr int NA2 = nN * nNp / 2, NF2 = nFc * FWS / 2;
+      constexpr bool kVecT = (t % 2) == 0;
+      constexpr int NB = kVecT ? nFc * nN * t / 2 : nFc * nN * t;
+      constexpr int I_S = NA2, I_B = 2 * NA2, I_F = I_B + NB, I_END = I_F + NF2;
+      double2* const A2 = reinterpret_cast<double2*>(A);
+      double2* const SUQ2 = reinterpret_cast<double2*>(SUQ);
+      const double2* const E2 = reinterpret_cast<const double2*>(Wb);
+      for (int item = tid; item < I_END; item += NT) {
+        if (item < I_S) {
+          const int idx2 = item;
+          double2 ar[DIM];
 #pragma unroll
-        for (int r = 0; r < DIM; r++) { ar[r] = A[r * nN * nNp + idx]; sr[r] = SUQ[r * nN * nNp + idx]; fq[r] = 0.0; }
-        if (i < nN) {
+          for (int r = 0; r < DIM; r++) ar[r] = A2[r * NA2 + idx2];
+#pragma unroll
+          for (int d = 0; d < DIM; d++) {
+            double2 va = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int r = 0; r < DIM; r++) { va.x = fma(Ii[d][r], ar[r].x, va.x); va.y = fma(Ii[d][r], ar[r].y, va.y); }
+            A2[d * NA2 + idx2] = va;
+          }
+        } else if (item < I_B) {
+          const int idx2 = item - I_S;
+          double2 sr[DIM], fq[DIM], suu = make_double2(0.0, 0.0);
+#pragma unroll
+          for (int r = 0; r < DIM; r++) { sr[r] = SUQ2[r * NA2 + idx2]; fq[r] = make_double2(0.0, 0.0); }
 #pragma unroll
           for (int f = 0; f < nFc; f++) {
-            const int a = NIF[f * nN + i], b = NIF[f * nN + j];
-            if (a >= 0 && b >= 0) {
-              const double mv = Mm[a + tp * b];
-              const double* gr = GEOR + f * (DIM + 2);
-              suu = fma(gr[DIM], mv, suu);
+            const double2 ev2 = E2[f * NA2 + idx2];
+            const double* gr = GEOR + f * (DIM + 2);
+            suu.x = fma(gr[DIM], ev2.x, suu.x); suu.y = fma(gr[DIM], ev2.y, suu.y);
 #pragma unroll
-              for (int d = 0; d < DIM; d++) fq[d] = fma(gr[d], mv, fq[d]);
-            }
+            for (int d = 0; d < DIM; d++) { fq[d].x = fma(gr[d], ev2.x, fq[d].x); fq[d].y = fma(gr[d], ev2.y, fq[d].y); }
           }
-          SUU[i + nNp * j] = ts * suu;
-        }
+          *reinterpret_cast<double2*>(SUU + 2 * idx2) = make_double2(ts * suu.x, ts * suu.y);   // index i + nNp j = 2 idx2 (pad rows: zeros)
 #pragma unroll
-        for (int d = 0; d < DIM; d++) {
-          double va = 0.0, vs = 0.0;
+          for (int d = 0; d < DIM; d++) {
+            double2 vs = make_double2(0.0, 0.0);
 #pragma unroll
-          for (int r = 0; r < DIM; r++) { va = fma(Ii[d][r], ar[r], va); vs = fma(Ii[d][r], sr[r], vs); }
-          A[d * nN * nNp + idx] = va;
-          SUQ[d * nN * nNp + idx] = hasDiff ? ts * fma(det, vs, fq[d]) : 0.0;
+            for (int r = 0; r < DIM; r++) { vs.x = fma(Ii[d][r], sr[r].x, vs.x); vs.y = fma(Ii[d][r], sr[r].y, vs.y); }
+            SUQ2[d * NA2 + idx2] = hasDiff ? make_double2(ts * fma(det, vs.x, fq[d].x), ts * fma(det, vs.y, fq[d].y)) : make_double2(0.0, 0.0);
+          }
+        } else if (item < I_F) {
+          const int ib = item - I_B;
+          if (kVecT) {
+            constexpr int t2 = kVecT ? t / 2 : 1;
+            const int f = ib / (nN * t2), rem = ib - f * nN * t2, m = rem / t2, b = 2 * (rem - m * t2);
+            const double* gr = GEOR + f * (DIM + 2);
+            const double2 rv = reinterpret_cast<const double2*>(R)[ib];
+            const double s0 = rdet * rv.x, s1 = rdet * rv.y;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) *reinterpret_cast<double2*>(B + (d * nN + m) * ldc + f * t + b) = make_double2(s0 * gr[d], s1 * gr[d]);
+          } else {
+            const int f = ib / (nN * t), rem = ib - f * nN * t, m = rem / t, b = rem - m * t;
+            const double* gr = GEOR + f * (DIM + 2);
+            const double sc = rdet * R[ib];
+#pragma unroll
+            for (int d = 0; d < DIM; d++) B[(d * nN + m) * ldc + f * t + b] = sc * gr[d];
+          }
+        } else {
+          const int i2 = item - I_F, f = i2 / (FWS / 2), ab2 = i2 - f * (FWS / 2);
+          const double2 mv = reinterpret_cast<const double2*>(Mm)[ab2];
+          const double* gr = GEOR + f * (DIM + 2);
+          double2* fw2 = reinterpret_cast<double2*>(FW + f * NW * FWS) + ab2;
+          fw2[kTau * FWS / 2] = make_double2(gr[DIM] * mv.x, gr[DIM] * mv.y);
+#pragma unroll
+          for (int d = 0; d < DIM; d++) fw2[(kN + d) * FWS / 2] = make_double2(gr[d] * mv.x, gr[d] * mv.y);
+          fw2[kOne * FWS / 2] = make_double2(gr[DIM + 1] * mv.x, gr[DIM + 1] * mv.y);
         }
       }
-      if ((nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal of K for the 2x2-block Gauss-Jordan
-        for (int j = 0; j < nN; j++) { SUU[nN + nNp * j] = 0.0; SUU[j + nNp * nN] = 0.0; }
+      if ((nN & 1) && tid == NT - 1) {   // odd size: unit pad diagonal of K for the 2x2-block Gauss-Jordan (the pad row already holds zeros)
+        for (int j = 0; j < nN; j++) SUU[j + nNp * nN] = 0.0;
         SUU[nN + nNp * nN] = 1.0;
       }
-      for (int idx = tid; idx < nFc * nN * t; idx += NT) {
-        const int f = idx / (nN * t), rem = idx - f * nN * t, m = rem / t, b = rem - m * t;
-        const double* gr = GEOR + f * (DIM + 2);
-        const double sc = rdet * R[idx];
-#pragma unroll
-        for (int d = 0; d < DIM; d++) B[(d * nN + m) * ldc + f * t + b] = sc * gr[d];
-      }
       for (int idx = tid; idx < DIM * nN; idx += NT) { B[idx * ldc + l] = 0.0; B[idx * ldc + l + 1] = 0.0; }  // Q0 column
-      for (int idx = tid; idx < nFc * FWS; idx += NT) {
-        const int f = idx / FWS, ab = idx - f * FWS;
-        const double mv = Mm[ab];
-        const double* gr = GEOR + f * (DIM + 2);
-        double* fw = FW + f * NW * FWS + ab;
-        fw[kTau * FWS] = gr[DIM] * mv;
-#pragma unroll
-        for (int d = 0; d < DIM; d++) fw[(kN + d) * FWS] = gr[d] * mv;
-        fw[kOne * FWS] = gr[DIM + 1] * mv;
-      }
       if (tid >= NT - 32) {   // Fu = source (Source.cpp:24-48)
         for (int i = tid - (NT - 32); i < nN; i += 32) {
           double s2 = 0.0;

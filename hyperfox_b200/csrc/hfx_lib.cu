@@ -606,7 +606,7 @@ struct hfx_ctx {
   // reference element
   std::unique_ptr<RefElement> re;
   int dim = 0, order = 0, nN = 0, nNf = 0, nFc = 0, nIP = 0, nIPf = 0;
-  DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv, dSRef, dSRefT, dARef, dMFRef, dBRef, dBary;
+  DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv, dSRef, dSRefT, dERef, dARef, dMFRef, dBRef, dBary;
   DBuf<uint8_t> dAffine;
   DBuf<int> dFaceNodes; DBuf<int8_t> dNodeInFace;
   // mesh
@@ -871,6 +871,13 @@ int hfx_refel_set(hfx_ctx* c, int dim, int order, int geom) {
       std::vector<double> srefT((size_t)dim * n * np, 0.0);
       for (int r = 0; r < dim; r++) for (int k = 0; k < n; k++) for (int j = 0; j < n; j++) srefT[((size_t)r * n + j) * np + k] = sref[((size_t)r * n + k) * np + j];
       c->dSRefT.upload(padded(srefT), c->st);
+      std::vector<double> eref((size_t)c->nFc * n * np, 0.0);   // face mass scattered to the element nodes (Suu / Suq face parts)
+      for (int f = 0; f < c->nFc; f++)
+        for (int a = 0; a < t; a++) for (int b = 0; b < t; b++) {
+          const int i = re.faceNodes()[(size_t)f * t + a], j = re.faceNodes()[(size_t)f * t + b];
+          eref[((size_t)f * n + j) * np + i] = mf[(size_t)a + (size_t)tp * b];
+        }
+      c->dERef.upload(padded(eref), c->st);
       c->dSRef.upload(padded(sref), c->st); c->dARef.upload(padded(aref), c->st); c->dMFRef.upload(padded(mf), c->st); c->dBRef.upload(padded(bref), c->st);
       // barycentric coordinates of the reference nodes (affinity test of the physical elements at allocate)
       std::vector<double> bary((size_t)n * (dim + 1));
@@ -1131,7 +1138,7 @@ int hfx_assemble(hfx_ctx* c) {
     p.dirichlet = find_field(c, "Dirichlet")->d.p;
     p.shape = c->dShape.p; p.dshape = c->dDShape.p; p.w = c->dW.p; p.fshape = c->dFShape.p; p.fdshape = c->dFDShape.p; p.fw = c->dFW.p; p.ffs = c->dFFS.p;
     p.faceNodes = c->dFaceNodes.p; p.nodeInFace = c->dNodeInFace.p; p.mhinv = c->dMHInv.p;
-    p.sref = c->dSRef.p; p.srefT = c->dSRefT.p; p.noRef = getenv("HFX_NO_REFPATH") ? 1 : 0; p.aref = c->dARef.p; p.mfref = c->dMFRef.p; p.bref = c->dBRef.p;
+    p.sref = c->dSRef.p; p.srefT = c->dSRefT.p; p.eref = c->dERef.p; p.noRef = getenv("HFX_NO_REFPATH") ? 1 : 0; p.aref = c->dARef.p; p.mfref = c->dMFRef.p; p.bref = c->dBRef.p;
     p.affine = getenv("HFX_NO_AFFINE") ? nullptr : c->dAffine.p;
     p.U = c->dU.p; p.Q = c->dQ.p; p.U0 = c->dU0.p; p.Q0 = c->dQ0.p; p.S = c->dS.p; p.S0 = c->dS0.p;
     p.vals = c->dVals.p; p.rhs = c->dRhs.p; p.status = c->dStatus.p;

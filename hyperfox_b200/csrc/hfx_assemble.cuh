@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       if (tid < l) { const int f = tid / t; RBASE[tid] = ROWS[f] + (long long)PERM[tid] * t; }
     }
 
-    // ---- all-reference path, stage G: constant geometry (one thread per face + one for the bulk Jacobian), tau check ----------
+    // ---- PG (all-reference path, stage G): constant geometry (one thread per face + one for the bulk Jacobian), tau check ----------
     bool ref = false;
     if (refCand) {
       int bad = 0;
@@ -703,7 +703,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
     }
     if (ref) {
-      // ---- stage R: every block from the staged reference matrices ---------------------------------------------------------------
+      // ---- PR (all-reference path, stage R): every block from the staged reference matrices ---------------------------------------------------------------
       //   A_d = sum_r Jinv(d,r) A^_r ;  Suq_d = detJ sum_r Jinv(d,r) S^_r^T - (area n_d) face mass ;  Suu = tau area face mass
       //   B_d = -(area n_d / detJ) B^_f ;  face matrices tau area M^f, -area n_d M^f, area M^f
       const double det = GEO[D2], rdet = FU[ev(nN)];
@@ -1337,50 +1337,55 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     }   // !ref
 
     // ---- P5: K = Suu - sum_d Suq_d A_d (HDGSolver.cpp:335), R = Sul - sum_d Suq_d B_d with column l = -Fu (:342-343).
-    //      One output tile per warp task, reduction split over two accumulators (long dependent DMMA chains are latency bound).
+    //      A warp task = one column tile x every row tile: the right operand is fetched once per reduction step and feeds MTN
+    //      independent accumulator chains (operand traffic, not the DMMA pipe, is what limits these skinny products).
     double* const KB = (W == Mm) ? Wb : Mm;          // the buffer that does not hold W (W is dead once A and B exist)
     double* const KI = ((nNp / 2) & 1) ? KB : SUU;
     {
       const int lr = lane >> 2, lc = lane & 3;
-      constexpr int LT = (l + 7) / 8, T_K = MTN * MTN, T_R = MTN * LT + 1;
-      auto kr_task = [&](bool isK, int r) {
-        if (!isK && r == T_R - 1) {
-          for (int i = lane; i < nN; i += 32) { R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0; }
-          return;
-        }
-        const int m = (r % MTN) * 8 + lr, nt = r / MTN;
+      constexpr int LT = (l + 7) / 8, T_K = MTN, T_R = LT;
+      for (int task = warp; task < T_K + T_R; task += NWARP) {
+        const bool isK = task < T_K;
+        const int nt = isK ? task : task - T_K;
         const int ncl = imin(nt * 8 + lr, isK ? nN - 1 : l);
-        const double* pa = SUQ + imin(m, nN - 1);                                  // Suq[m][(d,k')]: stride nNp in k'
         const double* pb = isK ? A + ncl * nNp : B + ncl;                          // K: A_d[k'][n] column-major ; R: B_d[k'][n] row-major
         const int sb = isK ? 1 : ldc, sd = isK ? nN * nNp : nN * ldc;
-        double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};
+        const double* pa[MTN];
+#pragma unroll
+        for (int i = 0; i < MTN; i++) pa[i] = SUQ + imin(i * 8 + lr, nN - 1);     // Suq[m][(d,k')]: stride nNp in k'
+        double c[MTN][2];
+        zero_c(c);
 #pragma unroll
         for (int d = 0; d < DIM; d++) {
 #pragma unroll
           for (int ks = 0; ks < KS_N; ks++) {
             const int k = ks * 4 + lc, kk = (ks * 4 + 3 < nN) ? k : imin(k, nN - 1);
-            double a = pa[(d * nN + kk) * nNp];
-            if (ks * 4 + 3 >= nN && k >= nN) a = 0.0;
+            const bool dead = (ks * 4 + 3 >= nN) && k >= nN;
             const double b = pb[d * sd + kk * sb];
-            if ((d * KS_N + ks) & 1) dmma(c1, a, b); else dmma(c0, a, b);
+#pragma unroll
+            for (int i = 0; i < MTN; i++) { const double a = pa[i][(d * nN + kk) * nNp]; dmma(c[i], dead ? 0.0 : a, b); }
           }
         }
-        if (m < nN) {
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int cc = nt * 8 + 2 * lc + h;
-            const double v = (h ? c0[1] + c1[1] : c0[0] + c1[0]);
-            if (isK) { if (cc < nN) SUU[m + nNp * cc] -= v; }
-            else if (cc < l) {
-              const int f = cc / t, b = cc % t, a = NIF[f * nN + m];
-              double sul = 0.0;
-              if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = ts * ((hasConv ? fw[kC * FWS] : 0.0) - fw[kTau * FWS]); }
-              R[m * ldc + cc] = sul - v;
+        for (int i = 0; i < MTN; i++) {
+          const int m = i * 8 + lr;
+          if (m < nN) {
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int cc = nt * 8 + 2 * lc + h;
+              const double v = c[i][h];
+              if (isK) { if (cc < nN) SUU[m + nNp * cc] -= v; }
+              else if (cc < l) {
+                const int f = cc / t, b = cc % t, a = NIF[f * nN + m];
+                double sul = 0.0;
+                if (a >= 0) { const double* fw = FW + f * NW * FWS + a + tp * b; sul = ts * ((hasConv ? fw[kC * FWS] : 0.0) - fw[kTau * FWS]); }
+                R[m * ldc + cc] = sul - v;
+              }
             }
           }
         }
-      };
-      for (int task = warp; task < T_K + T_R; task += NWARP) { if (task < T_K) kr_task(true, task); else kr_task(false, task - T_K); }
+      }
+      for (int i = tid; i < nN; i += NT) { R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0; }
     }
     __syncthreads();
     HFX_PROF(9);
@@ -1392,24 +1397,26 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu (column l) ------------------------------------------------------------------------
     {
       const int lr = lane >> 2, lc = lane & 3;
-      constexpr int L1T = (l + 1 + 7) / 8, NG = (L1T + 1) / 2;
-      for (int task = warp; task < MTN * NG; task += NWARP) {
-        const int m = (task % MTN) * 8 + lr, ng = task / MTN;
-        const double* pa = KI + imin(m, nN - 1);
-        const double* pb[2];
+      constexpr int L1T = (l + 1 + 7) / 8;
+      for (int task = warp; task < L1T; task += NWARP) {
+        const double* pb = R + imin(task * 8 + lr, l);
+        const double* pa[MTN];
 #pragma unroll
-        for (int j = 0; j < 2; j++) pb[j] = R + imin((ng * 2 + j) * 8 + lr, l);
-        double c[2][2];
+        for (int i = 0; i < MTN; i++) pa[i] = KI + imin(i * 8 + lr, nN - 1);
+        double c[MTN][2];
         zero_c(c);
-        mma_affine<2, nN>(c, pa, nNp, pb, ldc, lc);
-        if (m < nN) {
 #pragma unroll
-          for (int j = 0; j < 2; j++)
+        for (int ks = 0; ks < KS_N; ks++) {
+          const int k = ks * 4 + lc, kk = (ks * 4 + 3 < nN) ? k : imin(k, nN - 1);
+          const bool dead = (ks * 4 + 3 >= nN) && k >= nN;
+          const double b = pb[kk * ldc];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const int n = (ng * 2 + j) * 8 + 2 * lc + h;
-              if (n <= l) Um[m * ldc + n] = -c[j][h];
-            }
+          for (int i = 0; i < MTN; i++) { const double a = pa[i][kk * nNp]; dmma(c[i], dead ? 0.0 : a, b); }
+        }
+#pragma unroll
+        for (int i = 0; i < MTN; i++) {
+          const int m = i * 8 + lr, n = task * 8 + 2 * lc;
+          if (m < nN && n <= l) *reinterpret_cast<double2*>(Um + m * ldc + n) = make_double2(-c[i][0], -c[i][1]);
         }
       }
     }
@@ -1417,32 +1424,38 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     HFX_PROF(11);
 
     // ---- P8: Q_d = -A_d U - B_d ; Q0_d = -A_d U0  (:344-345) -----------------------------------------------------------
+    //      warp task = (d, column tile) x every row tile; the tasks of the last, partial round are split into single tiles
     {
       const int lr = lane >> 2, lc = lane & 3;
-      constexpr int L1T = (l + 1 + 7) / 8, NG = (L1T + 2) / 3;
-      for (int task = warp; task < DIM * MTN * NG; task += NWARP) {
-        const int d = task / (MTN * NG), r = task % (MTN * NG);
-        const int m = (r % MTN) * 8 + lr, ng = r / MTN;
-        const double* pa = A + d * nN * nNp + imin(m, nN - 1);     // A_d[m][k], column-major
-        const double* pb[3];
+      constexpr int L1T = (l + 1 + 7) / 8, NT8 = DIM * L1T, NFULL = (NT8 / NWARP) * NWARP, NREM = NT8 - NFULL;
+      auto q_task = [&](int tk, int iBeg, int iEnd) {
+        const int d = tk / L1T, nt = tk - d * L1T;
+        const double* pb = Um + imin(nt * 8 + lr, l);
+        const double* pa[MTN];
 #pragma unroll
-        for (int j = 0; j < 3; j++) pb[j] = Um + imin((ng * 3 + j) * 8 + lr, l);
-        double c[3][2];
+        for (int i = 0; i < MTN; i++) pa[i] = A + d * nN * nNp + imin(i * 8 + lr, nN - 1);     // A_d[m][k], column-major
+        double c[MTN][2];
         zero_c(c);
-        mma_affine<3, nN>(c, pa, nNp, pb, ldc, lc);
-        if (m < nN) {
-          double* brow = B + (d * nN + m) * ldc;
 #pragma unroll
-          for (int j = 0; j < 3; j++)
+        for (int ks = 0; ks < KS_N; ks++) {
+          const int k = ks * 4 + lc, kk = (ks * 4 + 3 < nN) ? k : imin(k, nN - 1);
+          const bool dead = (ks * 4 + 3 >= nN) && k >= nN;
+          const double b = pb[kk * ldc];
 #pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const int n = (ng * 3 + j) * 8 + 2 * lc + h;
-              if (n <= l) {
-                brow[n] = -c[j][h] - brow[n];
-              }
-            }
+          for (int i = 0; i < MTN; i++) if (i >= iBeg && i < iEnd) { const double a = pa[i][kk * nNp]; dmma(c[i], dead ? 0.0 : a, b); }
         }
-      }
+#pragma unroll
+        for (int i = 0; i < MTN; i++) {
+          const int m = i * 8 + lr, n = nt * 8 + 2 * lc;
+          if (i >= iBeg && i < iEnd && m < nN && n <= l) {
+            double2* bq = reinterpret_cast<double2*>(B + (d * nN + m) * ldc + n);
+            const double2 o = *bq;
+            *bq = make_double2(-c[i][0] - o.x, -c[i][1] - o.y);
+          }
+        }
+      };
+      for (int task = warp; task < NFULL; task += NWARP) q_task(task, 0, MTN);
+      if (NREM > 0) for (int st = warp; st < NREM * MTN; st += NWARP) q_task(NFULL + st / MTN, st % MTN, st % MTN + 1);
     }
     if (kBulkUQ) fence_proxy_async();
     __syncthreads();

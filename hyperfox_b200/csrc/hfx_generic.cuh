@@ -54,6 +54,32 @@ struct GenWs {
 };
 
 constexpr int kGenThreads = 256;
+#define HFX_GPROF(i) do { if (p.prof && blockIdx.x == 0 && tid == 0) { long long c_ = clock64(); p.prof[i] += c_ - tprev; tprev = c_; } } while (0)
+
+// Warp task on the FP64 tensor cores with a run-time reduction length: rows [8 mt, 8 mt + 8) x NTW column tiles of 8 starting at tile
+// nt0.  fa(m, k) / fb(k, n) return operand entries and own every range check (out of range = exact zero); fs(m, n, v0, v1) receives
+// C[m][n], C[m][n+1] (n even).  Operands come straight from the per-CTA scratch (L2): four reduction steps of loads are in flight
+// before the first DMMA of a group, and one 64-bit load per lane feeds 8 FMAs per lane.
+template <int NTW, class FA, class FB, class FS>
+__device__ __forceinline__ void mma_task_rt(int mt, int nt0, int lane, int K, FA fa, FB fb, FS fs) {
+  const int lr = lane >> 2, lc = lane & 3;
+  const int m = mt * 8 + lr;
+  double c[NTW][2];
+#pragma unroll
+  for (int j = 0; j < NTW; j++) { c[j][0] = 0.0; c[j][1] = 0.0; }
+#pragma unroll 4
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    const int k = k0 + lc;
+    const double a = fa(m, k);
+    double b[NTW];
+#pragma unroll
+    for (int j = 0; j < NTW; j++) b[j] = fb(k, (nt0 + j) * 8 + lr);
+#pragma unroll
+    for (int j = 0; j < NTW; j++) dmma(c[j], a, b[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < NTW; j++) fs(m, (nt0 + j) * 8 + 2 * lc, c[j][0], c[j][1]);
+}
 
 // Gauss-Jordan inverse with partial pivoting of the left half of the row-major n x 2n matrix aug (right half = identity on entry,
 // inverse on exit).  Whole CTA.  scr: n + 2n doubles; ipiv: 1 int in shared memory.
@@ -86,6 +112,37 @@ __device__ inline void cta_invert(double* aug, int n, double* scr, int* ipiv, in
   }
 }
 
+// Unpivoted in-place-style Gauss-Jordan inverse of a row-major n x n matrix, ping-pong between two buffers, one barrier per step, no
+// integer division.  For the definite blocks (mass matrix; K of the linear models, as the fused kernel does); a vanishing pivot raises
+// bit 0 of *status.  Returns the buffer that holds the inverse.
+__device__ inline double* cta_invert_np(double* b0, double* b1, int n, int* status) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* src = b0; double* dst = b1;
+  const double scale = fabs(b0[0]);
+  bool bad = false;
+  for (int k = 0; k < n; k++) {
+    const double piv = src[(size_t)k * n + k];
+    if (!(fabs(piv) > 1e-14 * scale)) bad = true;
+    const double ip = 1.0 / piv;
+    const double* __restrict__ sp = src; double* __restrict__ dp = dst;   // distinct buffers: loads of all rows may run ahead of the stores
+    for (int j = lane; j < n; j += 32) {
+      const double pkj = sp[(size_t)k * n + j];
+#pragma unroll 4
+      for (int i = warp; i < n; i += nw) {
+        const double fik = sp[(size_t)i * n + k] * ip;
+        double v;
+        if (i == k) v = (j == k) ? ip : pkj * ip;
+        else v = (j == k) ? -fik : fma(-fik, pkj, sp[(size_t)i * n + j]);
+        dp[(size_t)i * n + j] = v;
+      }
+    }
+    __syncthreads();
+    double* tsw = dst; dst = src; src = tsw;
+  }
+  if (bad && threadIdx.x == 0) atomicOr(status, 1);
+  return src;
+}
+
 __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenParams P) {
   const AsmParams& p = P.a;
   const int dim = P.dim, nN = P.nN, nNf = P.nNf, nFc = P.nFc, nIP = P.nIP, nIPf = P.nIPf, nD = P.nD;
@@ -96,8 +153,8 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
   const bool euler = p.timeScheme == 1;
   const bool diffField = hasDiff && p.diffComps > 0 && p.diff;
   double* ws = P.ws + (size_t)blockIdx.x * P.wsStride;
-  double* Lm = ws + z.oLm; double* Fv = ws + z.oF; double* GM = ws + z.oGM; double* DV = ws + z.oDV; double* IJ = ws + z.oIJ; double* NRM = ws + z.oNRM;
-  double* TAUS = ws + z.oTAUS; double* DIP = ws + z.oDIP; double* VIP = ws + z.oVIP; double* VDN = ws + z.oVDN; double* FS = ws + z.oFS; double* TDN = ws + z.oTDN;
+  double* Lm = ws + z.oLm; double* Fv = ws + z.oF; double* GM = ws + z.oGM; double* DV = ws + z.oDV; double* IJ = ws + z.oIJ; double* NRM;
+  double* TAUS; double* DIP = ws + z.oDIP; double* VIP = ws + z.oVIP; double* VDN; double* FS; double* TDN;
   double* SIP = ws + z.oSIP; double* DIVS = ws + z.oDIVS; double* X = ws + z.oX; double* TAUn = ws + z.oTAUn; double* DN = ws + z.oDN; double* VN = ws + z.oVN;
   double* SOL = ws + z.oSOL; double* TR = ws + z.oTR; double* SOLD = ws + z.oSOLD; double* MM = ws + z.oMM; double* W = ws + z.oW; double* FT = ws + z.oFT;
   double* FCN = ws + z.oFCN; double* FNd = ws + z.oFNd; double* FDN = ws + z.oFDN; double* FONE = ws + z.oFONE; double* BUU = ws + z.oBUU; double* Aq = ws + z.oAq;
@@ -107,7 +164,15 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
   const int nmax = u > nN ? u : nN;
   double* AUG = gsm;                                 // [nmax][2 nmax]
   double* SCR = AUG + (size_t)nmax * 2 * nmax;       // [3 nmax]
-  long long* ROWS = reinterpret_cast<long long*>(SCR + 3 * nmax + 2);   // [nFc] first entry of row (F,0) in vals
+  // per-face-cubature-point weights and the face shape table: read nNf^2 times each by the face-matrix loop
+  double* FSHs = SCR + 3 * nmax + 2;                 // [nIPf][nNf]
+  double* DVF = FSHs + ((nIPf * nNf + 1) & ~1);      // [nFf] dV
+  VDN = DVF + nFf; TDN = VDN + nFf;                  // [nFf] dV v.n ; [nFf] dV (trace . n)
+  NRM = TDN + nFf;                                   // [nFf][dim]
+  double* DNV = NRM + nFf * dim;                     // [nFf][dim] (D n)
+  TAUS = DNV + nFf * dim;                            // [nFf][nD*nD]
+  FS = TAUS + nFf * sT;                              // [nFf][nD]
+  long long* ROWS = reinterpret_cast<long long*>(FS + ((nFf * nD + 1) & ~1));   // [nFc] first entry of row (F,0) in vals
   int* PERM = reinterpret_cast<int*>(ROWS + nFc);    // [nFc*nNf]
   int* NIF = PERM + nFc * nNf;                       // [nFc*nN]
   int* FNo = NIF + nFc * nN;                         // [nFc*nNf]
@@ -115,11 +180,13 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
   int* BCF = FACE + nFc; int* INTF = BCF + nFc; int* POS = INTF + nFc;   // [nFc], [nFc], [nFc*nFc]
   int* RLEN = POS + nFc * nFc; int* OPP = RLEN + nFc; int* IPIV = OPP + nFc;
 
+  for (int i = tid; i < nIPf * nNf; i += NT) FSHs[i] = p.fshape[i];
   for (int i = tid; i < nFc * nNf; i += NT) FNo[i] = p.faceNodes[i];
   for (int i = tid; i < nFc * nN; i += NT) NIF[i] = p.nodeInFace[i];
   if (tid < nFc) { int vn = 0; for (int kk = 0; kk < nN; kk++) if (p.nodeInFace[tid * nN + kk] < 0) { vn = kk; break; } OPP[tid] = vn; }
   __syncthreads();
 
+  long long tprev = clock64();
   for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
     // ---- gather (HDGSolver.cpp:231-326) ----------------------------------------------------------------------------------------
     const int* cell = p.cells + (size_t)e * nN;
@@ -151,12 +218,16 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     for (int i = tid; i < n; i += NT) Fv[i] = 0.0;
     __syncthreads();
 
+    HFX_GPROF(0);
+    const bool affE = p.affine && p.affine[e];
     // ---- geometry and coefficients at the cubature points -------------------------------------------------------------------------
     for (int k = tid; k < nJ; k += NT) {
       if (k < nIP) {
         const int ip = k;
         double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-        for (int i = 0; i < nN; i++) {
+        if (affE) {   // straight-sided element: constant Jacobian straight from the vertices
+          for (int r = 0; r < dim; r++) for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (X[(r + 1) * dim + m] - X[m]);
+        } else for (int i = 0; i < nN; i++) {
           const double* d = p.dshape + ((size_t)ip * nN + i) * dim;
           for (int r = 0; r < dim; r++) for (int m = 0; m < dim; m++) J[r][m] = fma(d[r], X[i * dim + m], J[r][m]);
         }
@@ -188,7 +259,9 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         const int fi = k - nIP, f = fi / nIPf, ip = fi - f * nIPf;
         const int* fn = FNo + f * nNf;
         double J[2][3] = {{0, 0, 0}, {0, 0, 0}};
-        for (int a = 0; a < nNf; a++) {
+        if (affE) {
+          for (int r = 0; r < dim - 1; r++) for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (X[fn[r + 1] * dim + m] - X[fn[0] * dim + m]);
+        } else for (int a = 0; a < nNf; a++) {
           const double* d = p.fdshape + ((size_t)ip * nNf + a) * (dim - 1);
           for (int r = 0; r < dim - 1; r++) for (int m = 0; m < dim; m++) J[r][m] = fma(d[r], X[fn[a] * dim + m], J[r][m]);
         }
@@ -207,22 +280,27 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         for (int m = 0; m < dim; m++) { nv[m] /= nrm; prod = fma(X[OPP[f] * dim + m] - X[fn[0] * dim + m], nv[m], prod); }   // HDGBase.cpp:43-62
         if (prod > 0.0) for (int m = 0; m < dim; m++) nv[m] = -nv[m];
         const double dvf = p.fw[ip] * area;
-        DV[nIP + fi] = dvf;
+        DV[nIP + fi] = dvf; DVF[fi] = dvf;
         for (int m = 0; m < dim; m++) NRM[fi * dim + m] = nv[m];
-        for (int c = 0; c < sT; c++) { double s = 0.0; for (int a = 0; a < nNf; a++) s = fma(TAUn[(f * nNf + a) * sT + c], p.fshape[(size_t)ip * nNf + a], s); TAUS[fi * sT + c] = s; }
+        for (int c = 0; c < sT; c++) { double s = 0.0; for (int a = 0; a < nNf; a++) s = fma(TAUn[(f * nNf + a) * sT + c], FSHs[ip * nNf + a], s); TAUS[fi * sT + c] = s; }
         for (int c = 0; c < dd; c++) {
           double s = ((c / dim) == (c % dim)) ? 1.0 : 0.0;
-          if (diffField) { s = 0.0; for (int a = 0; a < nNf; a++) s = fma(p.fshape[(size_t)ip * nNf + a], DN[fn[a] * dd + c], s); }
+          if (diffField) { s = 0.0; for (int a = 0; a < nNf; a++) s = fma(FSHs[ip * nNf + a], DN[fn[a] * dd + c], s); }
           DIP[(nIP + fi) * dd + c] = s;
         }
         double vdn = 0.0;
-        if (hasConv) for (int d = 0; d < dim; d++) { double s = 0.0; for (int a = 0; a < nNf; a++) s = fma(p.fshape[(size_t)ip * nNf + a], VN[fn[a] * dim + d], s); vdn = fma(s, nv[d], vdn); }
+        if (hasConv) for (int d = 0; d < dim; d++) { double s = 0.0; for (int a = 0; a < nNf; a++) s = fma(FSHs[ip * nNf + a], VN[fn[a] * dim + d], s); vdn = fma(s, nv[d], vdn); }
         VDN[fi] = dvf * vdn;
+        for (int d = 0; d < dim; d++) {   // (D n)_d, D col-major
+          double dn = 0.0;
+          for (int b2 = 0; b2 < dim; b2++) dn = fma(DIP[(nIP + fi) * dd + b2 * dim + d], nv[b2], dn);
+          DNV[fi * dim + d] = dn;
+        }
         if (hasUN) {   // HDGUNabU.cpp:107-124
           double tdn = 0.0;
           for (int d = 0; d < dim; d++) {
             double tr = 0.0, fs = 0.0;
-            for (int a = 0; a < nNf; a++) { tr = fma(TR[(f * nNf + a) * nD + d], p.fshape[(size_t)ip * nNf + a], tr); fs = fma(SOL[fn[a] * nD + d], p.fshape[(size_t)ip * nNf + a], fs); }
+            for (int a = 0; a < nNf; a++) { tr = fma(TR[(f * nNf + a) * nD + d], FSHs[ip * nNf + a], tr); fs = fma(SOL[fn[a] * nD + d], FSHs[ip * nNf + a], fs); }
             tdn = fma(tr, nv[d], tdn);
             FS[fi * nD + d] = fs;
           }
@@ -231,6 +309,7 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       }
     }
     __syncthreads();
+    HFX_GPROF(1);
     // physical gradients gm(d,i) = (J^-1 grad_ref phi_i)_d at the bulk points
     for (int idx = tid; idx < nIP * nN; idx += NT) {
       const int ip = idx / nN, i = idx - ip * nN;
@@ -250,14 +329,12 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       for (int c = 0; c < sT; c++) { tt[c] = 0.0; fsn[c] = 0.0; }
       for (int ip = 0; ip < nIPf; ip++) {
         const int fi = f * nIPf + ip;
-        const double ss = p.fshape[(size_t)ip * nNf + a] * p.fshape[(size_t)ip * nNf + b], dv = DV[nIP + fi], w = dv * ss;
+        const double ss = FSHs[ip * nNf + a] * FSHs[ip * nNf + b], dv = DVF[fi], w = dv * ss;
         one += w;
         cn = fma(VDN[fi], ss, cn);
         for (int d = 0; d < dim; d++) {
           nd3[d] = fma(w, NRM[fi * dim + d], nd3[d]);
-          double dn = 0.0;
-          for (int b2 = 0; b2 < dim; b2++) dn = fma(DIP[(nIP + fi) * dd + b2 * dim + d], NRM[fi * dim + b2], dn);   // (D n)_d, D col-major
-          dn3[d] = fma(w, dn, dn3[d]);
+          dn3[d] = fma(w, DNV[fi * dim + d], dn3[d]);
         }
         for (int c = 0; c < sT; c++) tt[c] = fma(w, TAUS[fi * sT + c], tt[c]);
         if (hasUN) {
@@ -273,22 +350,28 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         FCN[o] = (k1 == k2 ? (hasConv ? cn : 0.0) + tdn : 0.0) + fsn[k2 * nD + k1];   // convection (diag in dofs) + UNabU face block
       }
     }
-    // reference-to-physical mass matrix
-    for (int idx = tid; idx < nN * nN; idx += NT) {
-      const int i = idx / nN, j = idx - i * nN;
-      double s = 0.0;
-      for (int ip = 0; ip < nIP; ip++) s = fma(p.shape[(size_t)ip * nN + i] * p.shape[(size_t)ip * nN + j], DV[ip], s);
-      MM[idx] = s;
+    // reference-to-physical mass matrix (Mass.cpp:5-38): read by the time schemes and, for curved elements, inverted for Sqq^-1 = M^-1 (x) I;
+    // a straight-sided element without time scheme never reads it (Sqq itself is not stored: the condensation only needs W)
+    const bool affW = affE && p.mhinv;
+    if (!affW || euler || p.timeScheme == 2) {
+      const int lane = tid & 31, warp = tid >> 5, NWARP = NT / 32, MT = (nN + 7) / 8, NG = (nN + 23) / 24;
+      for (int task = warp; task < MT * NG; task += NWARP) {
+        mma_task_rt<3>(task % MT, (task / MT) * 3, lane, nIP,
+            [&](int i, int ip) { return (i < nN && ip < nIP) ? p.shape[(size_t)ip * nN + i] * DV[ip] : 0.0; },
+            [&](int ip, int j) { return (ip < nIP && j < nN) ? p.shape[(size_t)ip * nN + j] : 0.0; },
+            [&](int i, int j, double v0, double v1) { if (i < nN) { if (j < nN) MM[i * nN + j] = v0; if (j + 1 < nN) MM[i * nN + j + 1] = v1; } });
+      }
     }
     __syncthreads();
 
+    HFX_GPROF(2);
     // ---- local matrix, block by block ------------------------------------------------------------------------------------------------
     // uu
     for (int idx = tid; idx < nN * nN; idx += NT) {
       const int i = idx / nN, j = idx - i * nN;
       double sc = 0.0, un_same = 0.0, un[9];
       for (int c = 0; c < sT; c++) un[c] = 0.0;
-      for (int ip = 0; ip < nIP; ip++) {
+      if (hasReac || hasConv || hasUN) for (int ip = 0; ip < nIP; ip++) {
         const double pi_ = p.shape[(size_t)ip * nN + i], pj = p.shape[(size_t)ip * nN + j], dv = DV[ip];
         const double* gi = GM + ((size_t)ip * nN + i) * dim; const double* gj = GM + ((size_t)ip * nN + j) * dim;
         sc = fma(LW[ip] * pi_, pj, sc);                                                      // Reaction.cpp:24-36
@@ -312,26 +395,49 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         Lm[(size_t)(i * nD + k1) + (size_t)n * (j * nD + k2)] = (k1 == k2 ? sc : 0.0) + bu + ft[k2 * nD + k1];
       }
     }
-    // uq (HDGDiffusion bulk + faces) and qu (HDGBase bulk)
-    for (int idx = tid; idx < nN * nN * dim; idx += NT) {
-      const int i = idx / (nN * dim), jd = idx - i * nN * dim, j = jd / dim, d = jd - j * dim;
-      double suq = 0.0, squ = 0.0;
-      for (int ip = 0; ip < nIP; ip++) {
-        const double dv = DV[ip];
-        const double* gi = GM + ((size_t)ip * nN + i) * dim;
-        if (hasDiff) { double dg = 0.0; for (int b2 = 0; b2 < dim; b2++) dg = fma(DIP[ip * dd + b2 * dim + d], gi[b2], dg); suq = fma(dg * dv, p.shape[(size_t)ip * nN + j], suq); }
-        squ = fma(gi[d] * dv, p.shape[(size_t)ip * nN + j], squ);
-      }
-      if (hasDiff) for (int f = 0; f < nFc; f++) {
-        const int a = NIF[f * nN + i], b = NIF[f * nN + j];
-        if (a >= 0 && b >= 0) suq -= FDN[((size_t)f * dim + d) * nNf * nNf + a * nNf + b];
-      }
-      for (int k = 0; k < nD; k++) {
-        Lm[(size_t)(i * nD + k) + (size_t)n * (sQ + (j * dim + d) * nD + k)] = suq;     // Suq[(i,k),(j,d,k)]
-        Lm[(size_t)(sQ + (i * dim + d) * nD + k) + (size_t)n * (j * nD + k)] = squ;     // Squ[(i,d,k),(j,k)]
-        Lm[(size_t)(sQ + (i * dim + d) * nD + k) + (size_t)n * (sQ + (j * dim + d) * nD + k)] = MM[i * nN + j];   // Sqq = M (x) I
+    // uq (HDGDiffusion bulk + faces) and qu (HDGBase bulk): C[(i,d)][j] = sum_ip (g_i)_d dV phi_j on the tensor cores; with a diffusion
+    // field a second pass contracts (D g_i)_d for Suq (HDGDiffusion.cpp:130-144), otherwise Suq's bulk part equals Squ's
+    {
+      const int lane = tid & 31, warp = tid >> 5, NWARP = NT / 32;
+      const int Mr = nN * dim, MT = (Mr + 7) / 8, NG = (nN + 23) / 24;
+      const int npass = (hasDiff && diffField) ? 2 : 1;
+      for (int task = warp; task < npass * MT * NG; task += NWARP) {
+        const int pass = task / (MT * NG), r = task - pass * (MT * NG), mt = r % MT, ng = r / MT;
+        mma_task_rt<3>(mt, ng * 3, lane, nIP,
+            [&](int m, int ip) {
+              if (m >= Mr || ip >= nIP) return 0.0;
+              const int i = m / dim, d = m - i * dim;
+              const double* gi = GM + ((size_t)ip * nN + i) * dim;
+              double g = gi[d];
+              if (pass == 1) { g = 0.0; for (int b2 = 0; b2 < dim; b2++) g = fma(DIP[ip * dd + b2 * dim + d], gi[b2], g); }
+              return g * DV[ip];
+            },
+            [&](int ip, int j) { return (ip < nIP && j < nN) ? p.shape[(size_t)ip * nN + j] : 0.0; },
+            [&](int m, int j0, double v0, double v1) {
+              if (m >= Mr) return;
+              const int i = m / dim, d = m - i * dim;
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int j = j0 + h;
+                if (j >= nN) continue;
+                const double v = h ? v1 : v0;
+                const bool writeSuq = (pass == 1) || !diffField;
+                double suq = hasDiff ? v : 0.0;
+                if (writeSuq && hasDiff) for (int f = 0; f < nFc; f++) {
+                  const int a = NIF[f * nN + i], b = NIF[f * nN + j];
+                  if (a >= 0 && b >= 0) suq -= FDN[((size_t)f * dim + d) * nNf * nNf + a * nNf + b];
+                }
+                for (int k = 0; k < nD; k++) {
+                  if (writeSuq) Lm[(size_t)(i * nD + k) + (size_t)n * (sQ + (j * dim + d) * nD + k)] = suq;     // Suq[(i,k),(j,d,k)]
+                  if (pass == 0) {
+                    Lm[(size_t)(sQ + (i * dim + d) * nD + k) + (size_t)n * (j * nD + k)] = v;                   // Squ[(i,d,k),(j,k)]
+                  }
+                }
+              }
+            });
       }
     }
+    HFX_GPROF(3);
     // ul, lu, ql, lq, ll
     for (int idx = tid; idx < nN * nFc * nNf; idx += NT) {
       const int i = idx / (nFc * nNf), fb = idx - i * nFc * nNf, f = fb / nNf, b = fb - f * nNf;
@@ -362,6 +468,7 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       Fv[i * nD + c] = s;
     }
     __syncthreads();
+    HFX_GPROF(4);
     if (hasUN) {   // rhs = 1/2 op [u0; lambda0] on the u and lambda segments (HDGUNabU.cpp:178-190); op = the UNabU blocks only
       for (int r = tid; r < u + l; r += NT) {
         double s = 0.0;
@@ -428,60 +535,99 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       __syncthreads();
     }
 
+    HFX_GPROF(5);
     // ---- static condensation (HDGSolver.cpp:331-348) -------------------------------------------------------------------------------
-    for (int idx = tid; idx < nN * 2 * nN; idx += NT) { const int i = idx / (2 * nN), j = idx - i * 2 * nN; AUG[idx] = j < nN ? MM[i * nN + j] : (j - nN == i ? 1.0 : 0.0); }
-    __syncthreads();
-    cta_invert(AUG, nN, SCR, IPIV, p.status);
-    for (int idx = tid; idx < nN * nN; idx += NT) { const int i = idx / nN, j = idx - i * nN; W[idx] = AUG[(size_t)i * 2 * nN + nN + j]; }
-    __syncthreads();
-    {   // A = Sqq^-1 Squ, B = Sqq^-1 Sql (last column of B = 0)
-      const int sd = dim * nD;
-      for (long long idx = tid; idx < (long long)q * (u + l + 1); idx += NT) {
-        const int rq = (int)(idx % q); const int c = (int)(idx / q);
-        const int i = rq / sd, s2 = rq - i * sd;
-        double s = 0.0;
-        if (c < u + l) {
-          const double* col = Lm + (size_t)n * (c < u ? c : sL + (c - u)) + sQ + s2;
-          for (int j = 0; j < nN; j++) s = fma(W[i * nN + j], col[(size_t)j * sd], s);
-        }
-        if (c < u) Aq[(size_t)rq + (size_t)q * c] = s; else Bq[(size_t)rq + (size_t)q * (c - u)] = s;
+    // W = M^-1: a straight-sided element has M = det J * M_ref (constant det J), so W = M_ref^-1 / det J comes from the reference table;
+    // curved elements invert M (definite: unpivoted Gauss-Jordan)
+    const double* WI; int ldW; double wscale = 1.0;
+    if (affW) { WI = p.mhinv; ldW = (nN + 1) & ~1; wscale = p.w[0] / DV[0]; }
+    else {
+      for (int idx = tid; idx < nN * nN; idx += NT) AUG[idx] = MM[idx];
+      __syncthreads();
+      WI = cta_invert_np(AUG, AUG + (size_t)nN * nN, nN, p.status); ldW = nN;
+    }
+    HFX_GPROF(6);
+    const int lane = tid & 31, warp = tid >> 5, NWARP = NT / 32;
+    {   // A = Sqq^-1 Squ, B = Sqq^-1 Sql (last column of B = 0): one nN x (u+l) x nN product per (direction, dof) slot s2 of the q rows
+      const int sd = dim * nD, NC1 = u + l + 1, MT = (nN + 7) / 8, NG = (NC1 + 23) / 24;
+      for (int task = warp; task < sd * MT * NG; task += NWARP) {
+        const int s2 = task / (MT * NG), r = task - s2 * (MT * NG), mt = r % MT, ng = r / MT;
+        mma_task_rt<3>(mt, ng * 3, lane, nN,
+            [&](int i, int j) { return (i < nN && j < nN) ? WI[(size_t)i * ldW + j] * wscale : 0.0; },
+            [&](int j, int c) { return (j < nN && c < u + l) ? Lm[(size_t)(sQ + j * sd + s2) + (size_t)n * (c < u ? c : sL + (c - u))] : 0.0; },
+            [&](int i, int c, double v0, double v1) {
+              if (i < nN) {
+                const size_t rq = (size_t)i * sd + s2;
+                if (c < u) Aq[rq + (size_t)q * c] = v0; else if (c < NC1) Bq[rq + (size_t)q * (c - u)] = v0;
+                if (c + 1 < u) Aq[rq + (size_t)q * (c + 1)] = v1; else if (c + 1 < NC1) Bq[rq + (size_t)q * (c + 1 - u)] = v1;
+              }
+            });
       }
     }
     __syncthreads();
-    // K = Suu - Suq A (into the augmented shared matrix) ; R = [Sul - Suq B | -Fu]
-    for (long long idx = tid; idx < (long long)u * (u + l + 1); idx += NT) {
-      const int r = (int)(idx % u); const int c = (int)(idx / u);
-      double s;
-      if (c < u) {
-        s = Lm[(size_t)r + (size_t)n * c];
-        for (int rq = 0; rq < q; rq++) s = fma(-Lm[(size_t)r + (size_t)n * (sQ + rq)], Aq[(size_t)rq + (size_t)q * c], s);
-        AUG[(size_t)r * 2 * u + c] = s;
-        AUG[(size_t)r * 2 * u + u + c] = (r == c) ? 1.0 : 0.0;
-      } else {
-        const int cl = c - u;
-        s = cl < l ? Lm[(size_t)r + (size_t)n * (sL + cl)] : -Fv[r];
-        if (cl < l) for (int rq = 0; rq < q; rq++) s = fma(-Lm[(size_t)r + (size_t)n * (sQ + rq)], Bq[(size_t)rq + (size_t)q * cl], s);
-        Rm[(size_t)r + (size_t)u * cl] = s;
+    HFX_GPROF(7);
+    const bool pivK = hasUN;   // the Newton-linearised convection block can make K indefinite: partial pivoting there, definite otherwise
+    {   // K = Suu - Suq A (into the augmented shared matrix) ; R = [Sul - Suq B | -Fu]
+      const int MT = (u + 7) / 8, NC = u + l, NG = (NC + 23) / 24;
+      for (int task = warp; task < MT * NG; task += NWARP) {
+        const int mt = task % MT, ng = task / MT;
+        mma_task_rt<3>(mt, ng * 3, lane, q,
+            [&](int r, int rq) { return (r < u && rq < q) ? Lm[(size_t)r + (size_t)n * (sQ + rq)] : 0.0; },
+            [&](int rq, int c) { return (rq < q && c < NC) ? (c < u ? Aq[(size_t)rq + (size_t)q * c] : Bq[(size_t)rq + (size_t)q * (c - u)]) : 0.0; },
+            [&](int r, int c, double v0, double v1) {
+              if (r < u) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                  const int cc = c + h; const double v = h ? v1 : v0;
+                  if (cc < u) {
+                    const double kv = Lm[(size_t)r + (size_t)n * cc] - v;
+                    if (pivK) { AUG[(size_t)r * 2 * u + cc] = kv; AUG[(size_t)r * 2 * u + u + cc] = (r == cc) ? 1.0 : 0.0; }
+                    else AUG[(size_t)r * u + cc] = kv;
+                  }
+                  else if (cc < NC) Rm[(size_t)r + (size_t)u * (cc - u)] = Lm[(size_t)r + (size_t)n * (sL + cc - u)] - v;
+                }
+              }
+            });
+      }
+      for (int r = tid; r < u; r += NT) Rm[(size_t)r + (size_t)u * l] = -Fv[r];
+    }
+    __syncthreads();
+    HFX_GPROF(8);
+    const double* KI; int ldK;
+    if (pivK) { cta_invert(AUG, u, SCR, IPIV, p.status); KI = AUG + u; ldK = 2 * u; }
+    else { KI = cta_invert_np(AUG, AUG + (size_t)u * u, u, p.status); ldK = u; }
+    HFX_GPROF(9);
+    {   // U = -K^-1 R (column l: U0 = K^-1 Fu)
+      const int MT = (u + 7) / 8, NG = (l + 1 + 15) / 16;
+      for (int task = warp; task < MT * NG; task += NWARP) {
+        const int mt = task % MT, ng = task / MT;
+        mma_task_rt<2>(mt, ng * 2, lane, u,
+            [&](int r, int j) { return (r < u && j < u) ? KI[(size_t)r * ldK + j] : 0.0; },
+            [&](int j, int c) { return (j < u && c <= l) ? Rm[(size_t)j + (size_t)u * c] : 0.0; },
+            [&](int r, int c, double v0, double v1) {
+              if (r < u) { if (c <= l) Um[(size_t)r + (size_t)u * c] = -v0; if (c + 1 <= l) Um[(size_t)r + (size_t)u * (c + 1)] = -v1; }
+            });
       }
     }
     __syncthreads();
-    cta_invert(AUG, u, SCR, IPIV, p.status);
-    // U = -K^-1 R (column l: U0 = K^-1 Fu)
-    for (long long idx = tid; idx < (long long)u * (l + 1); idx += NT) {
-      const int r = (int)(idx % u); const int c = (int)(idx / u);
-      double s = 0.0;
-      for (int j = 0; j < u; j++) s = fma(AUG[(size_t)r * 2 * u + u + j], Rm[(size_t)j + (size_t)u * c], s);
-      Um[idx] = -s;
+    HFX_GPROF(10);
+    {   // Q = -A U - B (column l: Q0 = -A U0)
+      const int MT = (q + 7) / 8, NG = (l + 1 + 23) / 24;
+      for (int task = warp; task < MT * NG; task += NWARP) {
+        const int mt = task % MT, ng = task / MT;
+        mma_task_rt<3>(mt, ng * 3, lane, u,
+            [&](int rq, int j) { return (rq < q && j < u) ? Aq[(size_t)rq + (size_t)q * j] : 0.0; },
+            [&](int j, int c) { return (j < u && c <= l) ? Um[(size_t)j + (size_t)u * c] : 0.0; },
+            [&](int rq, int c, double v0, double v1) {
+              if (rq < q) {
+                if (c <= l) Qm[(size_t)rq + (size_t)q * c] = -v0 - Bq[(size_t)rq + (size_t)q * c];
+                if (c + 1 <= l) Qm[(size_t)rq + (size_t)q * (c + 1)] = -v1 - Bq[(size_t)rq + (size_t)q * (c + 1)];
+              }
+            });
+      }
     }
     __syncthreads();
-    // Q = -A U - B (column l: Q0 = -A U0)
-    for (long long idx = tid; idx < (long long)q * (l + 1); idx += NT) {
-      const int rq = (int)(idx % q); const int c = (int)(idx / q);
-      double s = 0.0;
-      for (int j = 0; j < u; j++) s = fma(Aq[(size_t)rq + (size_t)q * j], Um[(size_t)j + (size_t)u * c], s);
-      Qm[idx] = -s - Bq[idx];
-    }
-    __syncthreads();
+    HFX_GPROF(11);
     // write U, Q, U0, Q0 (HDGSolver.cpp:336-341; kept row-major per element on the device, see recover_kernel)
     for (long long idx = tid; idx < (long long)u * l; idx += NT) { const int r = (int)(idx / l), cc = (int)(idx - (long long)r * l); p.U[(size_t)e * u * l + idx] = Um[(size_t)r + (size_t)u * cc]; }
     for (long long idx = tid; idx < (long long)q * l; idx += NT) { const int r = (int)(idx / l), cc = (int)(idx - (long long)r * l); p.Q[(size_t)e * q * l + idx] = Qm[(size_t)r + (size_t)q * cc]; }
@@ -490,15 +636,12 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     // S = Slu U + Slq Q + Sll ; S0 = Fl - Slu U0 - Slq Q0 ; boundary rows (:489-501) ; scatter (:596-618)
     double* gS = p.S ? p.S + (size_t)e * l * l : nullptr;
     double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
-    for (long long idx = tid; idx < (long long)l * (l + 1); idx += NT) {
-      const int r = (int)(idx % l); const int c = (int)(idx / l);
-      const double* lrow = Lm + sL + r;
-      double s = c < l ? lrow[(size_t)n * (sL + c)] : 0.0;
-      for (int j = 0; j < u; j++) s = fma(lrow[(size_t)n * j], Um[(size_t)j + (size_t)u * c], s);
-      for (int rq = 0; rq < q; rq++) s = fma(lrow[(size_t)n * (sQ + rq)], Qm[(size_t)rq + (size_t)q * c], s);
+    HFX_GPROF(12);
+    auto emitS = [&](int r, int c, double s) {
       const int f = r / t, rr = r - f * t, a = rr / nD, k1 = rr - a * nD, F = FACE[f], bc = BCF[f];
       const long long rowOff = ROWS[f] + (long long)(PERM[f * nNf + a] * nD + k1) * t;   // block CSR: row inside each t x t neighbour block
       if (c < l) {
+        s += Lm[(size_t)(sL + r) + (size_t)n * (sL + c)];
         const int f2 = c / t, cc = c - f2 * t, b = cc / nD, k2 = cc - b * nD;
         if (bc == 1) s = (r == c) ? 1.0 : 0.0;                                                       // DirichletModel: identity row
         else if (bc == 2) s = (f2 == f && k1 == k2) ? FONE[f * nNf * nNf + a * nNf + b] : 0.0;       // IntegratedDirichletModel: face mass (x) I
@@ -513,14 +656,28 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         double* dst = p.rhs + ((size_t)F * nNf + PERM[f * nNf + a]) * nD + k1;
         if (INTF[f]) atomicAdd(dst, s0); else *dst = s0;
       }
+    };
+    {
+      const int MT = (l + 7) / 8, NG = (l + 1 + 23) / 24;
+      for (int task = warp; task < MT * NG; task += NWARP) {
+        const int mt = task % MT, ng = task / MT;
+        mma_task_rt<3>(mt, ng * 3, lane, u + q,
+            [&](int r, int k) { return (r < l && k < u + q) ? Lm[(size_t)(sL + r) + (size_t)n * k] : 0.0; },
+            [&](int k, int c) { return (c <= l && k < u + q) ? (k < u ? Um[(size_t)k + (size_t)u * c] : Qm[(size_t)(k - u) + (size_t)q * c]) : 0.0; },
+            [&](int r, int c, double v0, double v1) {
+              if (r < l) { if (c <= l) emitS(r, c, v0); if (c + 1 <= l) emitS(r, c + 1, v1); }
+            });
+      }
     }
     __syncthreads();
+    HFX_GPROF(13);
   }
 }
 
-inline size_t gen_smem_bytes(int nN, int nNf, int nFc, int nD) {
-  const int u = nN * nD, nmax = u > nN ? u : nN;
+inline size_t gen_smem_bytes(int nN, int nNf, int nFc, int nD, int dim, int nIPf) {
+  const int u = nN * nD, nmax = u > nN ? u : nN, nFf = nFc * nIPf;
   size_t doubles = (size_t)nmax * 2 * nmax + 3 * nmax + 2;
+  doubles += (size_t)((nIPf * nNf + 1) & ~1) + 3 * (size_t)nFf + 2 * (size_t)nFf * dim + (size_t)nFf * nD * nD + (size_t)((nFf * nD + 1) & ~1) + 2;
   size_t ints = (size_t)nFc * nNf * 2 + (size_t)nFc * nN + (size_t)nFc * 5 + (size_t)nFc * nFc + 2;
   ints = (ints + 1) & ~(size_t)1;
   return doubles * 8 + ints * 4 + 8 * (size_t)nFc + 16;

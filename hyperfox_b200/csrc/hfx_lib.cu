@@ -1188,7 +1188,7 @@ int hfx_assemble(hfx_ctx* c) {
       const int uu = c->nN * g.nD;
       need(uu <= 96, "HDGSolver", "assemble", "the general device kernel supports local solution blocks of at most 96 unknowns");
       const GenWs z(g.dim, g.nN, g.nNf, g.nFc, g.nIP, g.nIPf, g.nD);
-      const size_t smem = gen_smem_bytes(g.nN, g.nNf, g.nFc, g.nD);
+      const size_t smem = gen_smem_bytes(g.nN, g.nNf, g.nFc, g.nD, g.dim, g.nIPf);
       static size_t smemSet = 0;
       if (smem > smemSet) { HFX_CUDA(cudaFuncSetAttribute(hdg_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smemSet = smem; }
       int perSM = 1;

@@ -22,6 +22,7 @@ struct GenParams {
   const double* bufSol;      // BufferSolution, cell field [nCells][nN][nD]        (HDGBurgersModel.cpp:87-124)
   const double* tracePrev;   // Trace of the previous iterate, face field [nFaces][nNf][nD]
   int nSrc;                  // source components: 1, or dim for the Burgers model (HDGBurgersModel.cpp:112-122)
+  int smOpt[6];              // offsets (doubles, from the optional area) of Um, Rm, Aq, Bq, shape table, GM when they live in shared memory; -1: global scratch
   double* ws;                // per-CTA scratch
   long long wsStride;        // doubles per CTA
   // RungeKutta::apply (src/operator/RungeKutta.cpp:90-143), auxiliary fields {Flux, Trace}: time scheme code 2
@@ -56,26 +57,36 @@ struct GenWs {
 constexpr int kGenThreads = 256;
 #define HFX_GPROF(i) do { if (p.prof && blockIdx.x == 0 && tid == 0) { long long c_ = clock64(); p.prof[i] += c_ - tprev; tprev = c_; } } while (0)
 
-// Warp task on the FP64 tensor cores with a run-time reduction length: rows [8 mt, 8 mt + 8) x NTW column tiles of 8 starting at tile
-// nt0.  fa(m, k) / fb(k, n) return operand entries and own every range check (out of range = exact zero); fs(m, n, v0, v1) receives
-// C[m][n], C[m][n+1] (n even).  Operands come straight from the per-CTA scratch (L2): four reduction steps of loads are in flight
-// before the first DMMA of a group, and one 64-bit load per lane feeds 8 FMAs per lane.
+// Warp task on the FP64 tensor cores with run-time sizes: rows [8 mt, 8 mt + 8) x NTW column tiles of 8 starting at tile nt0 of the
+// M x N product with reduction length K.  fa(m, k) / fb(k, n) return operand entries and are only called with IN-RANGE indices
+// (rows / columns / reduction steps beyond the matrix are clamped here; a clamped reduction step gets an exact zero left operand),
+// so they are straight-line loads: the operands of four reduction steps are in flight before the first DMMA of a group, which is
+// what hides the L2 latency of operands that live in the per-CTA scratch.  fs(m, n, v0, v1) receives C[m][n], C[m][n+1] (n even)
+// and does its own range checks.
 template <int NTW, class FA, class FB, class FS>
-__device__ __forceinline__ void mma_task_rt(int mt, int nt0, int lane, int K, FA fa, FB fb, FS fs) {
+__device__ __forceinline__ void mma_task_rt(int mt, int nt0, int lane, int M, int N, int K, FA fa, FB fb, FS fs) {
   const int lr = lane >> 2, lc = lane & 3;
-  const int m = mt * 8 + lr;
+  const int m = mt * 8 + lr, mc = m < M ? m : M - 1;
+  int nc[NTW];
+#pragma unroll
+  for (int j = 0; j < NTW; j++) { const int nn = (nt0 + j) * 8 + lr; nc[j] = nn < N ? nn : N - 1; }
   double c[NTW][2];
 #pragma unroll
   for (int j = 0; j < NTW; j++) { c[j][0] = 0.0; c[j][1] = 0.0; }
-#pragma unroll 4
-  for (int k0 = 0; k0 < K; k0 += 4) {
-    const int k = k0 + lc;
-    const double a = fa(m, k);
-    double b[NTW];
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    double a[4], b[4][NTW];
 #pragma unroll
-    for (int j = 0; j < NTW; j++) b[j] = fb(k, (nt0 + j) * 8 + lr);
+    for (int s = 0; s < 4; s++) {
+      const int k = k0 + 4 * s + lc, kc = k < K ? k : K - 1;
+      const double av = fa(mc, kc);
+      a[s] = k < K ? av : 0.0;
 #pragma unroll
-    for (int j = 0; j < NTW; j++) dmma(c[j], a, b[j]);
+      for (int j = 0; j < NTW; j++) b[s][j] = fb(kc, nc[j]);
+    }
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+      for (int j = 0; j < NTW; j++) dmma(c[j], a[s], b[s][j]);
   }
 #pragma unroll
   for (int j = 0; j < NTW; j++) fs(m, (nt0 + j) * 8 + 2 * lc, c[j][0], c[j][1]);
@@ -158,7 +169,7 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
   double* SIP = ws + z.oSIP; double* DIVS = ws + z.oDIVS; double* X = ws + z.oX; double* TAUn = ws + z.oTAUn; double* DN = ws + z.oDN; double* VN = ws + z.oVN;
   double* SOL = ws + z.oSOL; double* TR = ws + z.oTR; double* SOLD = ws + z.oSOLD; double* MM = ws + z.oMM; double* W = ws + z.oW; double* FT = ws + z.oFT;
   double* FCN = ws + z.oFCN; double* FNd = ws + z.oFNd; double* FDN = ws + z.oFDN; double* FONE = ws + z.oFONE; double* BUU = ws + z.oBUU; double* Aq = ws + z.oAq;
-  double* Bq = ws + z.oBq; double* Rm = ws + z.oRm; double* Um = ws + z.oUm; double* Qm = ws + z.oQm; double* LW = ws + z.oLW;
+  double* Bq = ws + z.oBq; double* Rm = ws + z.oRm; double* Um = ws + z.oUm; double* LW = ws + z.oLW;
   // shared: augmented matrix for the two inverses, scratch rows, integer maps
   extern __shared__ __align__(16) double gsm[];
   const int nmax = u > nN ? u : nN;
@@ -179,6 +190,18 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
   int* FACE = FNo + nFc * nNf;                       // [nFc] global face ids
   int* BCF = FACE + nFc; int* INTF = BCF + nFc; int* POS = INTF + nFc;   // [nFc], [nFc], [nFc*nFc]
   int* RLEN = POS + nFc * nFc; int* OPP = RLEN + nFc; int* IPIV = OPP + nFc;
+  int* COLOFF = IPIV + 2;                            // [nFc][l] offset of element-local column c inside the block row of face f
+  long long* ROWOFF = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(COLOFF + nFc * l) + 15) & ~(uintptr_t)15);   // [l] first entry of element-local trace row r
+  // the big operands of the condensation products live in shared memory when they fit (decided on the host, largest benefit first)
+  double* OPT = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(ROWOFF + l) + 15) & ~(uintptr_t)15);
+  if (P.smOpt[0] >= 0) Um = OPT + P.smOpt[0];
+  if (P.smOpt[1] >= 0) Rm = OPT + P.smOpt[1];
+  if (P.smOpt[2] >= 0) Aq = OPT + P.smOpt[2];
+  if (P.smOpt[3] >= 0) Bq = OPT + P.smOpt[3];
+  double* const Qm = Bq;                             // Q = -A U - B overwrites B entry by entry
+  const double* SHP = p.shape;
+  if (P.smOpt[4] >= 0) { double* d = OPT + P.smOpt[4]; for (int i = tid; i < nIP * nN; i += NT) d[i] = p.shape[i]; SHP = d; }
+  if (P.smOpt[5] >= 0) GM = OPT + P.smOpt[5];
 
   for (int i = tid; i < nIPf * nNf; i += NT) FSHs[i] = p.fshape[i];
   for (int i = tid; i < nFc * nNf; i += NT) FNo[i] = p.faceNodes[i];
@@ -198,6 +221,11 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     }
     for (int i = tid; i < nFc * nFc; i += NT) POS[i] = p.elemPos[(size_t)e * nFc * nFc + i];
     __syncthreads();
+    for (int i = tid; i < nFc * l; i += NT) {   // block CSR: neighbour block of face f2 in the row of face f, column inside the t x t block
+      const int f = i / l, c = i - f * l, f2 = c / t, cc = c - f2 * t, b = cc / nD, k2 = cc - b * nD;
+      COLOFF[i] = POS[f * nFc + f2] * t * t + PERM[f2 * nNf + b] * nD + k2;
+    }
+    for (int r = tid; r < l; r += NT) { const int f = r / t, rr = r - f * t, a = rr / nD, k1 = rr - a * nD; ROWOFF[r] = ROWS[f] + (long long)(PERM[f * nNf + a] * nD + k1) * t; }
     for (int i = tid; i < nFc * nNf * sT; i += NT) {   // Tau: side selection :277-304 then permutation :306-326
       const int fa = i / sT, c = i - fa * sT, f = fa / nNf;
       const int side = (p.tauVals == 2 * sT) ? p.tauSide[(size_t)e * nFc + f] : 0;
@@ -356,9 +384,9 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     if (!affW || euler || p.timeScheme == 2) {
       const int lane = tid & 31, warp = tid >> 5, NWARP = NT / 32, MT = (nN + 7) / 8, NG = (nN + 23) / 24;
       for (int task = warp; task < MT * NG; task += NWARP) {
-        mma_task_rt<3>(task % MT, (task / MT) * 3, lane, nIP,
-            [&](int i, int ip) { return (i < nN && ip < nIP) ? p.shape[(size_t)ip * nN + i] * DV[ip] : 0.0; },
-            [&](int ip, int j) { return (ip < nIP && j < nN) ? p.shape[(size_t)ip * nN + j] : 0.0; },
+        mma_task_rt<3>(task % MT, (task / MT) * 3, lane, nN, nN, nIP,
+            [&](int i, int ip) { return SHP[ip * nN + i] * DV[ip]; },
+            [&](int ip, int j) { return SHP[ip * nN + j]; },
             [&](int i, int j, double v0, double v1) { if (i < nN) { if (j < nN) MM[i * nN + j] = v0; if (j + 1 < nN) MM[i * nN + j + 1] = v1; } });
       }
     }
@@ -403,16 +431,15 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       const int npass = (hasDiff && diffField) ? 2 : 1;
       for (int task = warp; task < npass * MT * NG; task += NWARP) {
         const int pass = task / (MT * NG), r = task - pass * (MT * NG), mt = r % MT, ng = r / MT;
-        mma_task_rt<3>(mt, ng * 3, lane, nIP,
+        mma_task_rt<3>(mt, ng * 3, lane, Mr, nN, nIP,
             [&](int m, int ip) {
-              if (m >= Mr || ip >= nIP) return 0.0;
               const int i = m / dim, d = m - i * dim;
               const double* gi = GM + ((size_t)ip * nN + i) * dim;
               double g = gi[d];
               if (pass == 1) { g = 0.0; for (int b2 = 0; b2 < dim; b2++) g = fma(DIP[ip * dd + b2 * dim + d], gi[b2], g); }
               return g * DV[ip];
             },
-            [&](int ip, int j) { return (ip < nIP && j < nN) ? p.shape[(size_t)ip * nN + j] : 0.0; },
+            [&](int ip, int j) { return SHP[ip * nN + j]; },
             [&](int m, int j0, double v0, double v1) {
               if (m >= Mr) return;
               const int i = m / dim, d = m - i * dim;
@@ -552,14 +579,14 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       const int sd = dim * nD, NC1 = u + l + 1, MT = (nN + 7) / 8, NG = (NC1 + 23) / 24;
       for (int task = warp; task < sd * MT * NG; task += NWARP) {
         const int s2 = task / (MT * NG), r = task - s2 * (MT * NG), mt = r % MT, ng = r / MT;
-        mma_task_rt<3>(mt, ng * 3, lane, nN,
-            [&](int i, int j) { return (i < nN && j < nN) ? WI[(size_t)i * ldW + j] * wscale : 0.0; },
-            [&](int j, int c) { return (j < nN && c < u + l) ? Lm[(size_t)(sQ + j * sd + s2) + (size_t)n * (c < u ? c : sL + (c - u))] : 0.0; },
+        mma_task_rt<3>(mt, ng * 3, lane, nN, u + l, nN,
+            [&](int i, int j) { return WI[(size_t)i * ldW + j] * wscale; },
+            [&](int j, int c) { return Lm[(size_t)(sQ + j * sd + s2) + (size_t)n * (c < u ? c : sL + (c - u))]; },
             [&](int i, int c, double v0, double v1) {
               if (i < nN) {
                 const size_t rq = (size_t)i * sd + s2;
-                if (c < u) Aq[rq + (size_t)q * c] = v0; else if (c < NC1) Bq[rq + (size_t)q * (c - u)] = v0;
-                if (c + 1 < u) Aq[rq + (size_t)q * (c + 1)] = v1; else if (c + 1 < NC1) Bq[rq + (size_t)q * (c + 1 - u)] = v1;
+                if (c < u) Aq[rq + (size_t)q * c] = v0; else if (c < NC1) Bq[rq + (size_t)q * (c - u)] = c < u + l ? v0 : 0.0;
+                if (c + 1 < u) Aq[rq + (size_t)q * (c + 1)] = v1; else if (c + 1 < NC1) Bq[rq + (size_t)q * (c + 1 - u)] = c + 1 < u + l ? v1 : 0.0;
               }
             });
       }
@@ -571,9 +598,9 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       const int MT = (u + 7) / 8, NC = u + l, NG = (NC + 23) / 24;
       for (int task = warp; task < MT * NG; task += NWARP) {
         const int mt = task % MT, ng = task / MT;
-        mma_task_rt<3>(mt, ng * 3, lane, q,
-            [&](int r, int rq) { return (r < u && rq < q) ? Lm[(size_t)r + (size_t)n * (sQ + rq)] : 0.0; },
-            [&](int rq, int c) { return (rq < q && c < NC) ? (c < u ? Aq[(size_t)rq + (size_t)q * c] : Bq[(size_t)rq + (size_t)q * (c - u)]) : 0.0; },
+        mma_task_rt<3>(mt, ng * 3, lane, u, NC, q,
+            [&](int r, int rq) { return Lm[(size_t)r + (size_t)n * (sQ + rq)]; },
+            [&](int rq, int c) { const double* pc = c < u ? Aq + (size_t)q * c : Bq + (size_t)q * (c - u); return pc[rq]; },
             [&](int r, int c, double v0, double v1) {
               if (r < u) {
 #pragma unroll
@@ -601,9 +628,9 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       const int MT = (u + 7) / 8, NG = (l + 1 + 15) / 16;
       for (int task = warp; task < MT * NG; task += NWARP) {
         const int mt = task % MT, ng = task / MT;
-        mma_task_rt<2>(mt, ng * 2, lane, u,
-            [&](int r, int j) { return (r < u && j < u) ? KI[(size_t)r * ldK + j] : 0.0; },
-            [&](int j, int c) { return (j < u && c <= l) ? Rm[(size_t)j + (size_t)u * c] : 0.0; },
+        mma_task_rt<2>(mt, ng * 2, lane, u, l + 1, u,
+            [&](int r, int j) { return KI[(size_t)r * ldK + j]; },
+            [&](int j, int c) { return Rm[(size_t)j + (size_t)u * c]; },
             [&](int r, int c, double v0, double v1) {
               if (r < u) { if (c <= l) Um[(size_t)r + (size_t)u * c] = -v0; if (c + 1 <= l) Um[(size_t)r + (size_t)u * (c + 1)] = -v1; }
             });
@@ -615,9 +642,9 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       const int MT = (q + 7) / 8, NG = (l + 1 + 23) / 24;
       for (int task = warp; task < MT * NG; task += NWARP) {
         const int mt = task % MT, ng = task / MT;
-        mma_task_rt<3>(mt, ng * 3, lane, u,
-            [&](int rq, int j) { return (rq < q && j < u) ? Aq[(size_t)rq + (size_t)q * j] : 0.0; },
-            [&](int j, int c) { return (j < u && c <= l) ? Um[(size_t)j + (size_t)u * c] : 0.0; },
+        mma_task_rt<3>(mt, ng * 3, lane, q, l + 1, u,
+            [&](int rq, int j) { return Aq[(size_t)rq + (size_t)q * j]; },
+            [&](int j, int c) { return Um[(size_t)j + (size_t)u * c]; },
             [&](int rq, int c, double v0, double v1) {
               if (rq < q) {
                 if (c <= l) Qm[(size_t)rq + (size_t)q * c] = -v0 - Bq[(size_t)rq + (size_t)q * c];
@@ -638,17 +665,20 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
     HFX_GPROF(12);
     auto emitS = [&](int r, int c, double s) {
-      const int f = r / t, rr = r - f * t, a = rr / nD, k1 = rr - a * nD, F = FACE[f], bc = BCF[f];
-      const long long rowOff = ROWS[f] + (long long)(PERM[f * nNf + a] * nD + k1) * t;   // block CSR: row inside each t x t neighbour block
+      const int f = r / t, bc = BCF[f];
       if (c < l) {
         s += Lm[(size_t)(sL + r) + (size_t)n * (sL + c)];
-        const int f2 = c / t, cc = c - f2 * t, b = cc / nD, k2 = cc - b * nD;
-        if (bc == 1) s = (r == c) ? 1.0 : 0.0;                                                       // DirichletModel: identity row
-        else if (bc == 2) s = (f2 == f && k1 == k2) ? FONE[f * nNf * nNf + a * nNf + b] : 0.0;       // IntegratedDirichletModel: face mass (x) I
+        const int f2 = c / t;
+        if (bc) {
+          const int rr = r - f * t, a = rr / nD, k1 = rr - a * nD, cc = c - f2 * t, b = cc / nD, k2 = cc - b * nD;
+          if (bc == 1) s = (r == c) ? 1.0 : 0.0;                                                       // DirichletModel: identity row
+          else s = (f2 == f && k1 == k2) ? FONE[f * nNf * nNf + a * nNf + b] : 0.0;                    // IntegratedDirichletModel: face mass (x) I
+        }
         if (gS) gS[(size_t)r + (size_t)l * c] = s;
-        double* dst = p.vals + rowOff + (long long)POS[f * nFc + f2] * t * t + PERM[f2 * nNf + b] * nD + k2;
+        double* dst = p.vals + ROWOFF[r] + COLOFF[f * l + c];
         if (f2 == f && INTF[f]) atomicAdd(dst, s); else *dst = s;
       } else {
+        const int rr = r - f * t, a = rr / nD, k1 = rr - a * nD, F = FACE[f];
         double s0 = Fv[sL + r] - s;
         if (bc == 1) s0 = p.dirichlet[((size_t)F * nNf + a) * nD + k1];
         else if (bc == 2) { s0 = 0.0; for (int b = 0; b < nNf; b++) s0 = fma(FONE[f * nNf * nNf + a * nNf + b], p.dirichlet[((size_t)F * nNf + b) * nD + k1], s0); }
@@ -661,9 +691,9 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       const int MT = (l + 7) / 8, NG = (l + 1 + 23) / 24;
       for (int task = warp; task < MT * NG; task += NWARP) {
         const int mt = task % MT, ng = task / MT;
-        mma_task_rt<3>(mt, ng * 3, lane, u + q,
-            [&](int r, int k) { return (r < l && k < u + q) ? Lm[(size_t)(sL + r) + (size_t)n * k] : 0.0; },
-            [&](int k, int c) { return (c <= l && k < u + q) ? (k < u ? Um[(size_t)k + (size_t)u * c] : Qm[(size_t)(k - u) + (size_t)q * c]) : 0.0; },
+        mma_task_rt<3>(mt, ng * 3, lane, l, l + 1, u + q,
+            [&](int r, int k) { return Lm[(size_t)(sL + r) + (size_t)n * k]; },
+            [&](int k, int c) { const double* pc = k < u ? Um + (size_t)u * c + k : Qm + (size_t)q * c + (k - u); return *pc; },
             [&](int r, int c, double v0, double v1) {
               if (r < l) { if (c <= l) emitS(r, c, v0); if (c + 1 <= l) emitS(r, c + 1, v1); }
             });
@@ -679,8 +709,21 @@ inline size_t gen_smem_bytes(int nN, int nNf, int nFc, int nD, int dim, int nIPf
   size_t doubles = (size_t)nmax * 2 * nmax + 3 * nmax + 2;
   doubles += (size_t)((nIPf * nNf + 1) & ~1) + 3 * (size_t)nFf + 2 * (size_t)nFf * dim + (size_t)nFf * nD * nD + (size_t)((nFf * nD + 1) & ~1) + 2;
   size_t ints = (size_t)nFc * nNf * 2 + (size_t)nFc * nN + (size_t)nFc * 5 + (size_t)nFc * nFc + 2;
-  ints = (ints + 1) & ~(size_t)1;
-  return doubles * 8 + ints * 4 + 8 * (size_t)nFc + 16;
+  const int l = nFc * nNf * nD;
+  ints += 2 + (size_t)((nFc * l + 1) & ~1);   // IPIV pad, COLOFF
+  ints = (ints + 3) & ~(size_t)3;
+  return doubles * 8 + ints * 4 + 8 * (size_t)nFc + 8 * (size_t)l + 64;
+}
+// Optional shared-memory residents (Um, Rm, Aq, Bq, shape, GM) within `budget` bytes, in that order of priority; returns the extra bytes.
+inline size_t gen_smem_optional(int dim, int nN, int nNf, int nFc, int nIP, int nD, size_t budget, int (&off)[6]) {
+  const size_t u = (size_t)nN * nD, q = u * dim, l = (size_t)nFc * nNf * nD;
+  const size_t need[6] = {u * (l + 1), u * (l + 1), q * u, q * (l + 1), (size_t)nIP * nN, (size_t)nIP * nN * dim};
+  size_t used = 0;
+  for (int k = 0; k < 6; k++) {
+    const size_t nd = (need[k] + 1) & ~(size_t)1;
+    if ((used + nd) * 8 <= budget) { off[k] = (int)used; used += nd; } else off[k] = -1;
+  }
+  return used * 8;
 }
 
 }  // namespace hfx

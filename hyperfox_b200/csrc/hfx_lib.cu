@@ -1188,7 +1188,11 @@ int hfx_assemble(hfx_ctx* c) {
       const int uu = c->nN * g.nD;
       need(uu <= 96, "HDGSolver", "assemble", "the general device kernel supports local solution blocks of at most 96 unknowns");
       const GenWs z(g.dim, g.nN, g.nNf, g.nFc, g.nIP, g.nIPf, g.nD);
-      const size_t smem = gen_smem_bytes(g.nN, g.nNf, g.nFc, g.nD, g.dim, g.nIPf);
+      const size_t smemBase = gen_smem_bytes(g.nN, g.nNf, g.nFc, g.nD, g.dim, g.nIPf);
+      // the operands of the condensation products move into shared memory as far as one CTA per SM allows (small elements keep several CTAs per SM)
+      const size_t smemCap = (getenv("HFX_GEN_ONE_CTA") ? 226 : 112) * 1024;   // default: two CTAs per SM stay resident
+      const size_t smem = smemBase + (getenv("HFX_GEN_NO_SMEM_OPERANDS") ? (std::fill(g.smOpt, g.smOpt + 6, -1), (size_t)0)
+                                                                        : gen_smem_optional(g.dim, g.nN, g.nNf, g.nFc, g.nIP, g.nD, smemCap > smemBase ? smemCap - smemBase : 0, g.smOpt));
       static size_t smemSet = 0;
       if (smem > smemSet) { HFX_CUDA(cudaFuncSetAttribute(hdg_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smemSet = smem; }
       int perSM = 1;

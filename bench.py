@@ -34,8 +34,8 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_ELEM = {1: 16610, 2: 201490, 3: 1325333, 4: 6220333, 5: 23364077}      # SURVEY.md section 8(d), tets
 BYTES_STORE = {1: 3136, 2: 13288, 3: 40256, 4: 99076, 5: 211696}
 # dram__bytes_read.sum + dram__bytes_write.sum of hdg_assemble_kernel per element, from the committed `ncu --set full` capture
-# (profiles/r1_assemble_p3_ncu_full_summary.txt: 3.4694 GB for 82,944 p=3 tets); per-launch traffic = this x elements of the launch
-NCU_TRAFFIC_PER_ELEM = {3: (350.986240e6 + 3.118447e9) / 82944.0}
+# (profiles/r1_assemble_p3_ncu_full_summary.txt: 3.3439 GB for 82,944 p=3 tets); per-launch traffic = this x elements of the launch
+NCU_TRAFFIC_PER_ELEM = {3: (247.53792e6 + 3.096336e9) / 82944.0}
 
 
 def poisson_inputs(nodes, cells, order, dim=3):
@@ -225,17 +225,21 @@ def main():
     wall_ms = (time.time() - t1) * 1e3 / args.steps
     clocks = sampler.stop() if rank == 0 else None
     my_ms = float(np.mean(ms_tot)); my_k = float(np.mean(ms_k))
-    # transparency: the same workload through the GENERAL path of the fused kernel (what curved elements / diffusion-field models take):
-    # the straight-sided shortcut is switched off for three untimed-in-the-headline steps
-    os.environ["HFX_NO_AFFINE"] = "1"
-    gen_k = []
-    for i in range(3):
-        check(L.hfx_assemble(h), h)
-        L.hfx_last_assemble_ms(h, C.byref(a), C.byref(b))
-        if i > 0:
-            gen_k.append(a.value)
-    del os.environ["HFX_NO_AFFINE"]
-    general_ms = float(np.mean(gen_k))
+    # transparency: the same workload through the two slower paths of the fused kernel, three steps each outside the headline:
+    #   HFX_NO_REFPATH: straight-sided path (what affine elements with a tau that varies along a face, or a convection / reaction /
+    #                   time-scheme model, take);  HFX_NO_AFFINE: general path (curved elements)
+    def other_path(var):
+        os.environ[var] = "1"
+        ks = []
+        for i in range(3):
+            check(L.hfx_assemble(h), h)
+            L.hfx_last_assemble_ms(h, C.byref(a), C.byref(b))
+            if i > 0:
+                ks.append(a.value)
+        del os.environ[var]
+        return float(np.mean(ks))
+    straight_ms = other_path("HFX_NO_REFPATH")
+    general_ms = other_path("HFX_NO_AFFINE")
     # the two other kernels of the path, timed separately from the headline: one GMRES(30) cycle on the assembled trace system
     # (not to convergence: 30 iterations, wall clock incl. the host-side Hessenberg updates) and the local recovery
     extra = {}
@@ -320,9 +324,10 @@ def main():
                    "l2": "inputs+outputs per step (%.1f GB) far larger than the 126 MB L2" % ((BYTES_STORE[order] * nC) / 1e9),
                    "timing": "CUDA events on the library stream around memset+kernel, max over ranks; wall-clock per step %.2f ms" % ms_wall,
                    "setup_s": round(t_setup, 1),
-                   "straight_sided_shortcut": "every element of this mesh is affine and takes the reference-matrix shortcut for the purely geometric blocks "
-                                              "(DESIGN.md 4.1); with the shortcut disabled (general path, as for curved elements) rank 0 runs at %.3g elements/s"
-                                              % (nC / (general_ms * 1e-3))},
+                   "element_paths": "every element of this mesh is straight-sided with a face-constant tau and takes the all-reference path "
+                                    "(every block from staged reference matrices, DESIGN.md 4.1); the same mesh through the straight-sided path "
+                                    "(tau varying along faces / other operators) runs at %.3g elements/s and through the general path "
+                                    "(curved elements) at %.3g elements/s on rank 0" % (nC / (straight_ms * 1e-3), nC / (general_ms * 1e-3))},
         "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4 + DFMA share one 64 FMA/clk/SM pipe; tcgen05 has no FP64 kind)", "achieved": ach, "peak": peak["tflops"], "unit": "TFLOP/s", "frac": ach / peak["tflops"] if peak["tflops"] else None,
                      "traffic": (NCU_TRAFFIC_PER_ELEM[order] * nC if order in NCU_TRAFFIC_PER_ELEM else None),
                      "traffic_source": "ncu --set full capture at 82,944 tets scaled per element (profiles/r1_assemble_p3_ncu_full_summary.txt); algorithmic bytes %d/element" % BYTES_STORE[order],

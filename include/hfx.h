@@ -119,7 +119,8 @@ int hfx_comm_halo_field(hfx_ctx* ctx, const char* faceFieldName); /* Partitioner
 /* ---- parity hooks ----------------------------------------------------------------------------------------------- */
 /* CSR of the global trace system: sorted columns, explicit zeros (PetscInterface.cpp:99-103).  nnz query with NULLs. */
 int hfx_get_csr(hfx_ctx* ctx, long long* nrows, long long* nnz, long long* rowptr, int* colidx, double* vals, double* rhs);
-/* per-element condensed blocks, column-major as the reference stores them (HDGSolver.cpp:336-341); any may be NULL */
+/* per-element condensed blocks, column-major as the reference stores them (HDGSolver.cpp:336-341; the device keeps U, Q row-major and
+   transposes here); any may be NULL */
 int hfx_get_local(hfx_ctx* ctx, int iEl, int nEl, double* S, double* S0, double* U, double* U0, double* Q, double* Q0);
 /* element -> global trace dof ids (matRowCols, HDGSolver.cpp:596) */
 int hfx_get_elem_dofs(hfx_ctx* ctx, int iEl, int nEl, int* dofs);

@@ -35,21 +35,21 @@ struct GenParams {
 // scratch layout (offsets in doubles), identical on host and device
 struct GenWs {
   int u, q, l, n, t, nJ, nFf, dd, sQ, sL;
-  long long oLm, oF, oGM, oDV, oIJ, oNRM, oTAUS, oDIP, oVIP, oVDN, oFS, oTDN, oSIP, oDIVS, oX, oTAUn, oDN, oVN, oSOL, oTR, oSOLD, oMM, oW, oFT, oFCN,
+  int oLm, oF, oGM, oDV, oIJ, oNRM, oTAUS, oDIP, oVIP, oVDN, oFS, oTDN, oSIP, oDIVS, oX, oTAUn, oDN, oVN, oSOL, oTR, oSOLD, oMM, oW, oFT, oFCN,
       oFNd, oFDN, oFONE, oBUU, oAq, oBq, oRm, oUm, oQm, oLW, total;
   __host__ __device__ GenWs(int dim, int nN, int nNf, int nFc, int nIP, int nIPf, int nD) {
     u = nN * nD; q = u * dim; t = nNf * nD; l = nFc * t; n = u + q + l; nJ = nIP + nFc * nIPf; nFf = nFc * nIPf; dd = dim * dim; sQ = u; sL = u + q;
-    long long o = 0;
-    auto take = [&](long long k) { long long r = o; o += (k + 1) & ~1LL; return r; };
-    oLm = take((long long)n * n); oF = take(n); oGM = take((long long)nIP * nN * dim); oDV = take(nJ); oIJ = take((long long)nIP * dd);
-    oNRM = take((long long)nFf * dim); oTAUS = take((long long)nFf * nD * nD); oDIP = take((long long)nJ * dd); oVIP = take((long long)nIP * dim);
-    oVDN = take(nFf); oFS = take((long long)nFf * nD); oTDN = take(nFf); oSIP = take((long long)nIP * nD); oDIVS = take(nIP);
-    oX = take((long long)nN * dim); oTAUn = take((long long)nFc * nNf * nD * nD); oDN = take((long long)nN * dd); oVN = take((long long)nN * dim);
-    oSOL = take(u); oTR = take(l); oSOLD = take(u); oMM = take((long long)nN * nN); oW = take((long long)nN * nN);
-    oFT = take((long long)nFc * t * t); oFCN = take((long long)nFc * t * t); oFNd = take((long long)nFc * dim * nNf * nNf);
-    oFDN = take((long long)nFc * dim * nNf * nNf); oFONE = take((long long)nFc * nNf * nNf); oBUU = take((long long)u * u);
-    oAq = take((long long)q * u); oBq = take((long long)q * (l + 1)); oRm = take((long long)u * (l + 1)); oUm = take((long long)u * (l + 1));
-    oQm = take((long long)q * (l + 1)); oLW = take(2LL * nIP + (long long)nIP * nD);
+    int o = 0;
+    auto take = [&](int k) { int r = o; o += (k + 1) & ~1; return r; };
+    oLm = take(n * n); oF = take(n); oGM = take(nIP * nN * dim); oDV = take(nJ); oIJ = take(nIP * dd);
+    oNRM = take(nFf * dim); oTAUS = take(nFf * nD * nD); oDIP = take(nJ * dd); oVIP = take(nIP * dim);
+    oVDN = take(nFf); oFS = take(nFf * nD); oTDN = take(nFf); oSIP = take(nIP * nD); oDIVS = take(nIP);
+    oX = take(nN * dim); oTAUn = take(nFc * nNf * nD * nD); oDN = take(nN * dd); oVN = take(nN * dim);
+    oSOL = take(u); oTR = take(l); oSOLD = take(u); oMM = take(nN * nN); oW = take(nN * nN);
+    oFT = take(nFc * t * t); oFCN = take(nFc * t * t); oFNd = take(nFc * dim * nNf * nNf);
+    oFDN = take(nFc * dim * nNf * nNf); oFONE = take(nFc * nNf * nNf); oBUU = take(u * u);
+    oAq = take(q * u); oBq = take(q * (l + 1)); oRm = take(u * (l + 1)); oUm = take(u * (l + 1));
+    oQm = take(q * (l + 1)); oLW = take(2 * nIP + nIP * nD);
     total = o;
   }
 };
@@ -100,7 +100,7 @@ __device__ inline void cta_invert(double* aug, int n, double* scr, int* ipiv, in
   for (int k = 0; k < n; k++) {
     if (tid < 32) {   // pivot search by warp 0
       double best = -1.0; int bi = k;
-      for (int i = k + tid; i < n; i += 32) { const double v = fabs(aug[(size_t)i * n2 + k]); if (v > best) { best = v; bi = i; } }
+      for (int i = k + tid; i < n; i += 32) { const double v = fabs(aug[i * n2 + k]); if (v > best) { best = v; bi = i; } }
       for (int o = 16; o > 0; o >>= 1) {
         const double ob = __shfl_xor_sync(0xffffffffu, best, o); const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
@@ -109,11 +109,11 @@ __device__ inline void cta_invert(double* aug, int n, double* scr, int* ipiv, in
     }
     __syncthreads();
     const int pv = *ipiv;
-    if (pv != k) for (int j = tid; j < n2; j += NT) { const double a = aug[(size_t)k * n2 + j]; aug[(size_t)k * n2 + j] = aug[(size_t)pv * n2 + j]; aug[(size_t)pv * n2 + j] = a; }
+    if (pv != k) for (int j = tid; j < n2; j += NT) { const double a = aug[k * n2 + j]; aug[k * n2 + j] = aug[pv * n2 + j]; aug[pv * n2 + j] = a; }
     __syncthreads();
-    const double ip = 1.0 / aug[(size_t)k * n2 + k];
-    for (int j = tid; j < n2; j += NT) rk[j] = aug[(size_t)k * n2 + j] * ip;
-    for (int i = tid; i < n; i += NT) fac[i] = aug[(size_t)i * n2 + k];
+    const double ip = 1.0 / aug[k * n2 + k];
+    for (int j = tid; j < n2; j += NT) rk[j] = aug[k * n2 + j] * ip;
+    for (int i = tid; i < n; i += NT) fac[i] = aug[i * n2 + k];
     __syncthreads();
     for (int idx = tid; idx < n * n2; idx += NT) {
       const int i = idx / n2, j = idx - i * n2;
@@ -127,25 +127,23 @@ __device__ inline void cta_invert(double* aug, int n, double* scr, int* ipiv, in
 // integer division.  For the definite blocks (mass matrix; K of the linear models, as the fused kernel does); a vanishing pivot raises
 // bit 0 of *status.  Returns the buffer that holds the inverse.
 __device__ inline double* cta_invert_np(double* b0, double* b1, int n, int* status) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   double* src = b0; double* dst = b1;
   const double scale = fabs(b0[0]);
+  const float rn = 1.0f / (float)n;
   bool bad = false;
   for (int k = 0; k < n; k++) {
-    const double piv = src[(size_t)k * n + k];
+    const double piv = src[k * n + k];
     if (!(fabs(piv) > 1e-14 * scale)) bad = true;
     const double ip = 1.0 / piv;
-    const double* __restrict__ sp = src; double* __restrict__ dp = dst;   // distinct buffers: loads of all rows may run ahead of the stores
-    for (int j = lane; j < n; j += 32) {
-      const double pkj = sp[(size_t)k * n + j];
-#pragma unroll 4
-      for (int i = warp; i < n; i += nw) {
-        const double fik = sp[(size_t)i * n + k] * ip;
-        double v;
-        if (i == k) v = (j == k) ? ip : pkj * ip;
-        else v = (j == k) ? -fik : fma(-fik, pkj, sp[(size_t)i * n + j]);
-        dp[(size_t)i * n + j] = v;
-      }
+    const double* __restrict__ sp = src; double* __restrict__ dp = dst;   // distinct buffers: the loads of all entries may run ahead of the stores
+#pragma unroll 2
+    for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+      const int i = __float2int_rd(((float)idx + 0.5f) * rn), j = idx - i * n;   // exact for idx < 2^22
+      const double pkj = sp[k * n + j], fik = sp[i * n + k] * ip;
+      double v;
+      if (i == k) v = (j == k) ? ip : pkj * ip;
+      else v = (j == k) ? -fik : fma(-fik, pkj, sp[idx]);
+      dp[idx] = v;
     }
     __syncthreads();
     double* tsw = dst; dst = src; src = tsw;
@@ -242,7 +240,14 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       for (int i = tid; i < l; i += NT) { const int fa = i / nD, k = i - fa * nD, f = fa / nNf; TR[i] = P.tracePrev[((size_t)FACE[f] * nNf + PERM[fa]) * nD + k]; }
     }
     if (euler) for (int i = tid; i < u; i += NT) SOLD[i] = p.solOld[(size_t)e * u + i];
-    for (long long i = tid; i < (long long)n * n; i += NT) Lm[i] = 0.0;
+    {   // zero the blocks of the local matrix that are read later (column-major, leading dimension n); the Sqq block is neither stored nor read
+      const int lane_ = tid & 31, warp_ = tid >> 5, nw_ = NT / 32;
+      for (int c = warp_; c < n; c += nw_) {
+        double* col = Lm + n * c;
+        const bool qcol = c >= sQ && c < sL;
+        for (int r = lane_; r < n; r += 32) if (!(qcol && r >= sQ && r < sL)) col[r] = 0.0;
+      }
+    }
     for (int i = tid; i < n; i += NT) Fv[i] = 0.0;
     __syncthreads();
 
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         if (affE) {   // straight-sided element: constant Jacobian straight from the vertices
           for (int r = 0; r < dim; r++) for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (X[(r + 1) * dim + m] - X[m]);
         } else for (int i = 0; i < nN; i++) {
-          const double* d = p.dshape + ((size_t)ip * nN + i) * dim;
+          const double* d = p.dshape + (ip * nN + i) * dim;
           for (int r = 0; r < dim; r++) for (int m = 0; m < dim; m++) J[r][m] = fma(d[r], X[i * dim + m], J[r][m]);
         }
         double det, I[3][3];
@@ -277,11 +282,11 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         for (int m = 0; m < dim; m++) for (int r = 0; r < dim; r++) IJ[ip * dd + m * dim + r] = I[m][r];   // invJ(m,r): x_m <- xi_r
         for (int c = 0; c < dd; c++) {
           double s = ((c / dim) == (c % dim)) ? 1.0 : 0.0;
-          if (diffField) { s = 0.0; for (int i = 0; i < nN; i++) s = fma(p.shape[(size_t)ip * nN + i], DN[i * dd + c], s); }
+          if (diffField) { s = 0.0; for (int i = 0; i < nN; i++) s = fma(p.shape[ip * nN + i], DN[i * dd + c], s); }
           DIP[ip * dd + c] = s;
         }
-        if (hasConv) for (int d = 0; d < dim; d++) { double s = 0.0; for (int i = 0; i < nN; i++) s = fma(p.shape[(size_t)ip * nN + i], VN[i * dim + d], s); VIP[ip * dim + d] = s; }
-        if (hasUN) for (int k2 = 0; k2 < nD; k2++) { double s = 0.0; for (int i = 0; i < nN; i++) s = fma(SOL[i * nD + k2], p.shape[(size_t)ip * nN + i], s); SIP[ip * nD + k2] = s; }
+        if (hasConv) for (int d = 0; d < dim; d++) { double s = 0.0; for (int i = 0; i < nN; i++) s = fma(p.shape[ip * nN + i], VN[i * dim + d], s); VIP[ip * dim + d] = s; }
+        if (hasUN) for (int k2 = 0; k2 < nD; k2++) { double s = 0.0; for (int i = 0; i < nN; i++) s = fma(SOL[i * nD + k2], p.shape[ip * nN + i], s); SIP[ip * nD + k2] = s; }
         LW[ip] = hasReac ? p.reacIP[(size_t)e * nIP + ip] * dv : 0.0;
       } else {
         const int fi = k - nIP, f = fi / nIPf, ip = fi - f * nIPf;
@@ -290,7 +295,7 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         if (affE) {
           for (int r = 0; r < dim - 1; r++) for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (X[fn[r + 1] * dim + m] - X[fn[0] * dim + m]);
         } else for (int a = 0; a < nNf; a++) {
-          const double* d = p.fdshape + ((size_t)ip * nNf + a) * (dim - 1);
+          const double* d = p.fdshape + (ip * nNf + a) * (dim - 1);
           for (int r = 0; r < dim - 1; r++) for (int m = 0; m < dim; m++) J[r][m] = fma(d[r], X[fn[a] * dim + m], J[r][m]);
         }
         double nv[3] = {0, 0, 0}, area;
@@ -341,13 +346,13 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     // physical gradients gm(d,i) = (J^-1 grad_ref phi_i)_d at the bulk points
     for (int idx = tid; idx < nIP * nN; idx += NT) {
       const int ip = idx / nN, i = idx - ip * nN;
-      const double* dp = p.dshape + ((size_t)ip * nN + i) * dim;
-      for (int d = 0; d < dim; d++) { double s = 0.0; for (int r = 0; r < dim; r++) s = fma(IJ[ip * dd + d * dim + r], dp[r], s); GM[((size_t)ip * nN + i) * dim + d] = s; }
+      const double* dp = p.dshape + (ip * nN + i) * dim;
+      for (int d = 0; d < dim; d++) { double s = 0.0; for (int r = 0; r < dim; r++) s = fma(IJ[ip * dd + d * dim + r], dp[r], s); GM[(ip * nN + i) * dim + d] = s; }
     }
     __syncthreads();
     if (hasUN) for (int ip = tid; ip < nIP; ip += NT) {   // div of the previous iterate (HDGUNabU.cpp:153-165)
       double dv = 0.0;
-      for (int i = 0; i < nN; i++) for (int d = 0; d < dim; d++) dv = fma(GM[((size_t)ip * nN + i) * dim + d], SOL[i * nD + d], dv);
+      for (int i = 0; i < nN; i++) for (int d = 0; d < dim; d++) dv = fma(GM[(ip * nN + i) * dim + d], SOL[i * nD + d], dv);
       DIVS[ip] = dv;
     }
     // ---- weighted face matrices (gather form of the face loops of HDGBase / HDGDiffusion / HDGConvection / HDGUNabU) -----------
@@ -371,9 +376,9 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         }
       }
       FONE[idx] = one;
-      for (int d = 0; d < dim; d++) { FNd[((size_t)f * dim + d) * nNf * nNf + ab] = nd3[d]; FDN[((size_t)f * dim + d) * nNf * nNf + ab] = dn3[d]; }
+      for (int d = 0; d < dim; d++) { FNd[(f * dim + d) * nNf * nNf + ab] = nd3[d]; FDN[(f * dim + d) * nNf * nNf + ab] = dn3[d]; }
       for (int k1 = 0; k1 < nD; k1++) for (int k2 = 0; k2 < nD; k2++) {   // row dof k1, column dof k2
-        const size_t o = (size_t)f * t * t + (size_t)(a * nD + k1) + (size_t)t * (b * nD + k2);
+        const size_t o = f * t * t + (a * nD + k1) + t * (b * nD + k2);
         FT[o] = tt[k2 * nD + k1];                                                   // tau(nd, md) stored col-major nD x nD: index md*nD + nd
         FCN[o] = (k1 == k2 ? (hasConv ? cn : 0.0) + tdn : 0.0) + fsn[k2 * nD + k1];   // convection (diag in dofs) + UNabU face block
       }
@@ -400,8 +405,8 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       double sc = 0.0, un_same = 0.0, un[9];
       for (int c = 0; c < sT; c++) un[c] = 0.0;
       if (hasReac || hasConv || hasUN) for (int ip = 0; ip < nIP; ip++) {
-        const double pi_ = p.shape[(size_t)ip * nN + i], pj = p.shape[(size_t)ip * nN + j], dv = DV[ip];
-        const double* gi = GM + ((size_t)ip * nN + i) * dim; const double* gj = GM + ((size_t)ip * nN + j) * dim;
+        const double pi_ = p.shape[ip * nN + i], pj = p.shape[ip * nN + j], dv = DV[ip];
+        const double* gi = GM + (ip * nN + i) * dim; const double* gj = GM + (ip * nN + j) * dim;
         sc = fma(LW[ip] * pi_, pj, sc);                                                      // Reaction.cpp:24-36
         if (hasConv) { double vg = 0.0; for (int d = 0; d < dim; d++) vg = fma(VIP[ip * dim + d], gi[d], vg); sc = fma(-dv * vg, pj, sc); }   // -C^T
         if (hasUN) {   // HDGUNabU.cpp:153-177
@@ -415,12 +420,12 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       for (int c = 0; c < sT; c++) ft[c] = 0.0;
       for (int f = 0; f < nFc; f++) {
         const int a = NIF[f * nN + i], b = NIF[f * nN + j];
-        if (a >= 0 && b >= 0) for (int k1 = 0; k1 < nD; k1++) for (int k2 = 0; k2 < nD; k2++) ft[k2 * nD + k1] += FT[(size_t)f * t * t + (a * nD + k1) + (size_t)t * (b * nD + k2)];
+        if (a >= 0 && b >= 0) for (int k1 = 0; k1 < nD; k1++) for (int k2 = 0; k2 < nD; k2++) ft[k2 * nD + k1] += FT[f * t * t + (a * nD + k1) + t * (b * nD + k2)];
       }
       for (int k1 = 0; k1 < nD; k1++) for (int k2 = 0; k2 < nD; k2++) {
         const double bu = hasUN ? un[k2 * nD + k1] + (k1 == k2 ? un_same : 0.0) : 0.0;
-        if (hasUN) BUU[(size_t)(i * nD + k1) + (size_t)u * (j * nD + k2)] = bu;
-        Lm[(size_t)(i * nD + k1) + (size_t)n * (j * nD + k2)] = (k1 == k2 ? sc : 0.0) + bu + ft[k2 * nD + k1];
+        if (hasUN) BUU[(i * nD + k1) + u * (j * nD + k2)] = bu;
+        Lm[(i * nD + k1) + n * (j * nD + k2)] = (k1 == k2 ? sc : 0.0) + bu + ft[k2 * nD + k1];
       }
     }
     // uq (HDGDiffusion bulk + faces) and qu (HDGBase bulk): C[(i,d)][j] = sum_ip (g_i)_d dV phi_j on the tensor cores; with a diffusion
@@ -434,7 +439,7 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         mma_task_rt<3>(mt, ng * 3, lane, Mr, nN, nIP,
             [&](int m, int ip) {
               const int i = m / dim, d = m - i * dim;
-              const double* gi = GM + ((size_t)ip * nN + i) * dim;
+              const double* gi = GM + (ip * nN + i) * dim;
               double g = gi[d];
               if (pass == 1) { g = 0.0; for (int b2 = 0; b2 < dim; b2++) g = fma(DIP[ip * dd + b2 * dim + d], gi[b2], g); }
               return g * DV[ip];
@@ -452,12 +457,12 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
                 double suq = hasDiff ? v : 0.0;
                 if (writeSuq && hasDiff) for (int f = 0; f < nFc; f++) {
                   const int a = NIF[f * nN + i], b = NIF[f * nN + j];
-                  if (a >= 0 && b >= 0) suq -= FDN[((size_t)f * dim + d) * nNf * nNf + a * nNf + b];
+                  if (a >= 0 && b >= 0) suq -= FDN[(f * dim + d) * nNf * nNf + a * nNf + b];
                 }
                 for (int k = 0; k < nD; k++) {
-                  if (writeSuq) Lm[(size_t)(i * nD + k) + (size_t)n * (sQ + (j * dim + d) * nD + k)] = suq;     // Suq[(i,k),(j,d,k)]
+                  if (writeSuq) Lm[(i * nD + k) + n * (sQ + (j * dim + d) * nD + k)] = suq;     // Suq[(i,k),(j,d,k)]
                   if (pass == 0) {
-                    Lm[(size_t)(sQ + (i * dim + d) * nD + k) + (size_t)n * (j * nD + k)] = v;                   // Squ[(i,d,k),(j,k)]
+                    Lm[(sQ + (i * dim + d) * nD + k) + n * (j * nD + k)] = v;                   // Squ[(i,d,k),(j,k)]
                   }
                 }
               }
@@ -472,26 +477,26 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       if (a < 0) continue;
       for (int k1 = 0; k1 < nD; k1++) {
         for (int k2 = 0; k2 < nD; k2++) {
-          const size_t o = (size_t)f * t * t + (a * nD + k1) + (size_t)t * (b * nD + k2);
-          Lm[(size_t)(i * nD + k1) + (size_t)n * (sL + (f * nNf + b) * nD + k2)] = -FT[o] + FCN[o];        // Sul[(fn_a,k1),(f,b,k2)]
-          const size_t ot = (size_t)f * t * t + (b * nD + k1) + (size_t)t * (a * nD + k2);
-          Lm[(size_t)(sL + (f * nNf + b) * nD + k1) + (size_t)n * (i * nD + k2)] = FT[ot];                // Slu[(f,b,k1),(fn_a,k2)]
+          const size_t o = f * t * t + (a * nD + k1) + t * (b * nD + k2);
+          Lm[(i * nD + k1) + n * (sL + (f * nNf + b) * nD + k2)] = -FT[o] + FCN[o];        // Sul[(fn_a,k1),(f,b,k2)]
+          const size_t ot = f * t * t + (b * nD + k1) + t * (a * nD + k2);
+          Lm[(sL + (f * nNf + b) * nD + k1) + n * (i * nD + k2)] = FT[ot];                // Slu[(f,b,k1),(fn_a,k2)]
         }
         for (int d = 0; d < dim; d++) {
-          Lm[(size_t)(sQ + (i * dim + d) * nD + k1) + (size_t)n * (sL + (f * nNf + b) * nD + k1)] = -FNd[((size_t)f * dim + d) * nNf * nNf + a * nNf + b];   // Sql
-          if (hasDiff) Lm[(size_t)(sL + (f * nNf + b) * nD + k1) + (size_t)n * (sQ + (i * dim + d) * nD + k1)] = -FDN[((size_t)f * dim + d) * nNf * nNf + b * nNf + a];   // Slq
+          Lm[(sQ + (i * dim + d) * nD + k1) + n * (sL + (f * nNf + b) * nD + k1)] = -FNd[(f * dim + d) * nNf * nNf + a * nNf + b];   // Sql
+          if (hasDiff) Lm[(sL + (f * nNf + b) * nD + k1) + n * (sQ + (i * dim + d) * nD + k1)] = -FDN[(f * dim + d) * nNf * nNf + b * nNf + a];   // Slq
         }
       }
     }
     for (int idx = tid; idx < nFc * t * t; idx += NT) {
       const int f = idx / (t * t), rc = idx - f * t * t, r = rc % t, c = rc / t;
-      Lm[(size_t)(sL + f * t + r) + (size_t)n * (sL + f * t + c)] = -FT[idx] + FCN[idx];   // Sll
+      Lm[(sL + f * t + r) + n * (sL + f * t + c)] = -FT[idx] + FCN[idx];   // Sll
     }
     // right-hand side: Source.cpp:24-48 (per component for the Burgers model)
     if (hasSrc) for (int idx = tid; idx < nN * P.nSrc; idx += NT) {
       const int i = idx / P.nSrc, c = idx - i * P.nSrc;
       double s = 0.0;
-      for (int ip = 0; ip < nIP; ip++) s = fma(p.shape[(size_t)ip * nN + i], p.srcIP[((size_t)e * P.nSrc + c) * nIP + ip] * DV[ip], s);
+      for (int ip = 0; ip < nIP; ip++) s = fma(p.shape[ip * nN + i], p.srcIP[((size_t)e * P.nSrc + c) * nIP + ip] * DV[ip], s);
       Fv[i * nD + c] = s;
     }
     __syncthreads();
@@ -501,15 +506,15 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         double s = 0.0;
         if (r < u) {
           const int i = r / nD, k1 = r - i * nD;
-          for (int j = 0; j < u; j++) s = fma(BUU[(size_t)r + (size_t)u * j], 0.5 * SOL[j], s);
+          for (int j = 0; j < u; j++) s = fma(BUU[r + u * j], 0.5 * SOL[j], s);
           for (int f = 0; f < nFc; f++) {
             const int a = NIF[f * nN + i];
-            if (a >= 0) for (int c = 0; c < t; c++) s = fma(FCN[(size_t)f * t * t + (a * nD + k1) + (size_t)t * c], 0.5 * TR[f * t + c], s);   // (no model combines HDGUNabU with HDGConvection: FCN is the UNabU block)
+            if (a >= 0) for (int c = 0; c < t; c++) s = fma(FCN[f * t * t + (a * nD + k1) + t * c], 0.5 * TR[f * t + c], s);   // (no model combines HDGUNabU with HDGConvection: FCN is the UNabU block)
           }
           Fv[r] += s;
         } else {
           const int rl = r - u, f = rl / t, rr = rl - f * t;
-          for (int c = 0; c < t; c++) s = fma(FCN[(size_t)f * t * t + rr + (size_t)t * c], 0.5 * TR[f * t + c], s);
+          for (int c = 0; c < t; c++) s = fma(FCN[f * t * t + rr + t * c], 0.5 * TR[f * t + c], s);
           Fv[sL + rl] += s;
         }
       }
@@ -517,9 +522,9 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     }
     // time scheme: Euler.cpp:18-37 on the u rows (hook HDGModel.cpp:38-47)
     if (euler) {
-      for (long long idx = tid; idx < (long long)u * n; idx += NT) { const int r = (int)(idx % u); const long long c = idx / u; Lm[(size_t)r + (size_t)n * c] *= p.dt; }
+      for (int idx = tid; idx < u * n; idx += NT) { const int c = idx / u, r = idx - c * u; Lm[r + n * c] *= p.dt; }
       __syncthreads();
-      for (int idx = tid; idx < nN * nN; idx += NT) { const int i = idx / nN, j = idx - i * nN; for (int k = 0; k < nD; k++) Lm[(size_t)(i * nD + k) + (size_t)n * (j * nD + k)] += MM[idx]; }
+      for (int idx = tid; idx < nN * nN; idx += NT) { const int i = idx / nN, j = idx - i * nN; for (int k = 0; k < nD; k++) Lm[(i * nD + k) + n * (j * nD + k)] += MM[idx]; }
       for (int r = tid; r < u; r += NT) {
         const int i = r / nD, k = r - i * nD;
         double s = 0.0;
@@ -550,11 +555,11 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
         const int i = r / nD, k = r - i * nD;
         double ex = 0.0, im = 0.0;
         for (int j = 0; j < n; j++) {
-          double v = Lm[(size_t)r + (size_t)n * j] * p.dt;
+          double v = Lm[r + n * j] * p.dt;
           ex = fma(v, UJ[j], ex);
           v *= ass;
           if (j < u && (j % nD) == k) v += MM[i * nN + j / nD];
-          Lm[(size_t)r + (size_t)n * j] = v;
+          Lm[r + n * j] = v;
           im = fma(v, UT[j], im);
         }
         Fv[r] = fma(Fv[r], p.dt, -ex) + im;
@@ -571,7 +576,7 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     else {
       for (int idx = tid; idx < nN * nN; idx += NT) AUG[idx] = MM[idx];
       __syncthreads();
-      WI = cta_invert_np(AUG, AUG + (size_t)nN * nN, nN, p.status); ldW = nN;
+      WI = cta_invert_np(AUG, AUG + nN * nN, nN, p.status); ldW = nN;
     }
     HFX_GPROF(6);
     const int lane = tid & 31, warp = tid >> 5, NWARP = NT / 32;
@@ -580,13 +585,13 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       for (int task = warp; task < sd * MT * NG; task += NWARP) {
         const int s2 = task / (MT * NG), r = task - s2 * (MT * NG), mt = r % MT, ng = r / MT;
         mma_task_rt<3>(mt, ng * 3, lane, nN, u + l, nN,
-            [&](int i, int j) { return WI[(size_t)i * ldW + j] * wscale; },
-            [&](int j, int c) { return Lm[(size_t)(sQ + j * sd + s2) + (size_t)n * (c < u ? c : sL + (c - u))]; },
+            [&](int i, int j) { return WI[i * ldW + j] * wscale; },
+            [&](int j, int c) { return Lm[(sQ + j * sd + s2) + n * (c < u ? c : sL + (c - u))]; },
             [&](int i, int c, double v0, double v1) {
               if (i < nN) {
-                const size_t rq = (size_t)i * sd + s2;
-                if (c < u) Aq[rq + (size_t)q * c] = v0; else if (c < NC1) Bq[rq + (size_t)q * (c - u)] = c < u + l ? v0 : 0.0;
-                if (c + 1 < u) Aq[rq + (size_t)q * (c + 1)] = v1; else if (c + 1 < NC1) Bq[rq + (size_t)q * (c + 1 - u)] = c + 1 < u + l ? v1 : 0.0;
+                const size_t rq = i * sd + s2;
+                if (c < u) Aq[rq + q * c] = v0; else if (c < NC1) Bq[rq + q * (c - u)] = c < u + l ? v0 : 0.0;
+                if (c + 1 < u) Aq[rq + q * (c + 1)] = v1; else if (c + 1 < NC1) Bq[rq + q * (c + 1 - u)] = c + 1 < u + l ? v1 : 0.0;
               }
             });
       }
@@ -599,40 +604,40 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       for (int task = warp; task < MT * NG; task += NWARP) {
         const int mt = task % MT, ng = task / MT;
         mma_task_rt<3>(mt, ng * 3, lane, u, NC, q,
-            [&](int r, int rq) { return Lm[(size_t)r + (size_t)n * (sQ + rq)]; },
-            [&](int rq, int c) { const double* pc = c < u ? Aq + (size_t)q * c : Bq + (size_t)q * (c - u); return pc[rq]; },
+            [&](int r, int rq) { return Lm[r + n * (sQ + rq)]; },
+            [&](int rq, int c) { const double* pc = c < u ? Aq + q * c : Bq + q * (c - u); return pc[rq]; },
             [&](int r, int c, double v0, double v1) {
               if (r < u) {
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                   const int cc = c + h; const double v = h ? v1 : v0;
                   if (cc < u) {
-                    const double kv = Lm[(size_t)r + (size_t)n * cc] - v;
-                    if (pivK) { AUG[(size_t)r * 2 * u + cc] = kv; AUG[(size_t)r * 2 * u + u + cc] = (r == cc) ? 1.0 : 0.0; }
-                    else AUG[(size_t)r * u + cc] = kv;
+                    const double kv = Lm[r + n * cc] - v;
+                    if (pivK) { AUG[r * 2 * u + cc] = kv; AUG[r * 2 * u + u + cc] = (r == cc) ? 1.0 : 0.0; }
+                    else AUG[r * u + cc] = kv;
                   }
-                  else if (cc < NC) Rm[(size_t)r + (size_t)u * (cc - u)] = Lm[(size_t)r + (size_t)n * (sL + cc - u)] - v;
+                  else if (cc < NC) Rm[r + u * (cc - u)] = Lm[r + n * (sL + cc - u)] - v;
                 }
               }
             });
       }
-      for (int r = tid; r < u; r += NT) Rm[(size_t)r + (size_t)u * l] = -Fv[r];
+      for (int r = tid; r < u; r += NT) Rm[r + u * l] = -Fv[r];
     }
     __syncthreads();
     HFX_GPROF(8);
     const double* KI; int ldK;
     if (pivK) { cta_invert(AUG, u, SCR, IPIV, p.status); KI = AUG + u; ldK = 2 * u; }
-    else { KI = cta_invert_np(AUG, AUG + (size_t)u * u, u, p.status); ldK = u; }
+    else { KI = cta_invert_np(AUG, AUG + u * u, u, p.status); ldK = u; }
     HFX_GPROF(9);
     {   // U = -K^-1 R (column l: U0 = K^-1 Fu)
       const int MT = (u + 7) / 8, NG = (l + 1 + 15) / 16;
       for (int task = warp; task < MT * NG; task += NWARP) {
         const int mt = task % MT, ng = task / MT;
         mma_task_rt<2>(mt, ng * 2, lane, u, l + 1, u,
-            [&](int r, int j) { return KI[(size_t)r * ldK + j]; },
-            [&](int j, int c) { return Rm[(size_t)j + (size_t)u * c]; },
+            [&](int r, int j) { return KI[r * ldK + j]; },
+            [&](int j, int c) { return Rm[j + u * c]; },
             [&](int r, int c, double v0, double v1) {
-              if (r < u) { if (c <= l) Um[(size_t)r + (size_t)u * c] = -v0; if (c + 1 <= l) Um[(size_t)r + (size_t)u * (c + 1)] = -v1; }
+              if (r < u) { if (c <= l) Um[r + u * c] = -v0; if (c + 1 <= l) Um[r + u * (c + 1)] = -v1; }
             });
       }
     }
@@ -643,12 +648,12 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       for (int task = warp; task < MT * NG; task += NWARP) {
         const int mt = task % MT, ng = task / MT;
         mma_task_rt<3>(mt, ng * 3, lane, q, l + 1, u,
-            [&](int rq, int j) { return Aq[(size_t)rq + (size_t)q * j]; },
-            [&](int j, int c) { return Um[(size_t)j + (size_t)u * c]; },
+            [&](int rq, int j) { return Aq[rq + q * j]; },
+            [&](int j, int c) { return Um[j + u * c]; },
             [&](int rq, int c, double v0, double v1) {
               if (rq < q) {
-                if (c <= l) Qm[(size_t)rq + (size_t)q * c] = -v0 - Bq[(size_t)rq + (size_t)q * c];
-                if (c + 1 <= l) Qm[(size_t)rq + (size_t)q * (c + 1)] = -v1 - Bq[(size_t)rq + (size_t)q * (c + 1)];
+                if (c <= l) Qm[rq + q * c] = -v0 - Bq[rq + q * c];
+                if (c + 1 <= l) Qm[rq + q * (c + 1)] = -v1 - Bq[rq + q * (c + 1)];
               }
             });
       }
@@ -656,10 +661,16 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     __syncthreads();
     HFX_GPROF(11);
     // write U, Q, U0, Q0 (HDGSolver.cpp:336-341; kept row-major per element on the device, see recover_kernel)
-    for (long long idx = tid; idx < (long long)u * l; idx += NT) { const int r = (int)(idx / l), cc = (int)(idx - (long long)r * l); p.U[(size_t)e * u * l + idx] = Um[(size_t)r + (size_t)u * cc]; }
-    for (long long idx = tid; idx < (long long)q * l; idx += NT) { const int r = (int)(idx / l), cc = (int)(idx - (long long)r * l); p.Q[(size_t)e * q * l + idx] = Qm[(size_t)r + (size_t)q * cc]; }
-    for (int i = tid; i < u; i += NT) p.U0[(size_t)e * u + i] = Um[(size_t)u * l + i];
-    for (int i = tid; i < q; i += NT) p.Q0[(size_t)e * q + i] = Qm[(size_t)q * l + i];
+    {   // one warp per row: consecutive lanes -> consecutive addresses of the row-major global block
+      const int lane_ = tid & 31, warp_ = tid >> 5, nw_ = NT / 32;
+      double* gU = p.U + (size_t)e * u * l; double* gQ = p.Q + (size_t)e * q * l;
+      for (int r = warp_; r < u + q; r += nw_) {
+        if (r < u) for (int cc = lane_; cc < l; cc += 32) gU[r * l + cc] = Um[r + u * cc];
+        else { const int rq = r - u; for (int cc = lane_; cc < l; cc += 32) gQ[rq * l + cc] = Qm[rq + q * cc]; }
+      }
+    }
+    for (int i = tid; i < u; i += NT) p.U0[(size_t)e * u + i] = Um[u * l + i];
+    for (int i = tid; i < q; i += NT) p.Q0[(size_t)e * q + i] = Qm[q * l + i];
     // S = Slu U + Slq Q + Sll ; S0 = Fl - Slu U0 - Slq Q0 ; boundary rows (:489-501) ; scatter (:596-618)
     double* gS = p.S ? p.S + (size_t)e * l * l : nullptr;
     double* gS0 = p.S0 ? p.S0 + (size_t)e * l : nullptr;
@@ -667,14 +678,14 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
     auto emitS = [&](int r, int c, double s) {
       const int f = r / t, bc = BCF[f];
       if (c < l) {
-        s += Lm[(size_t)(sL + r) + (size_t)n * (sL + c)];
+        s += Lm[(sL + r) + n * (sL + c)];
         const int f2 = c / t;
         if (bc) {
           const int rr = r - f * t, a = rr / nD, k1 = rr - a * nD, cc = c - f2 * t, b = cc / nD, k2 = cc - b * nD;
           if (bc == 1) s = (r == c) ? 1.0 : 0.0;                                                       // DirichletModel: identity row
           else s = (f2 == f && k1 == k2) ? FONE[f * nNf * nNf + a * nNf + b] : 0.0;                    // IntegratedDirichletModel: face mass (x) I
         }
-        if (gS) gS[(size_t)r + (size_t)l * c] = s;
+        if (gS) gS[r + l * c] = s;
         double* dst = p.vals + ROWOFF[r] + COLOFF[f * l + c];
         if (f2 == f && INTF[f]) atomicAdd(dst, s); else *dst = s;
       } else {
@@ -692,8 +703,8 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       for (int task = warp; task < MT * NG; task += NWARP) {
         const int mt = task % MT, ng = task / MT;
         mma_task_rt<3>(mt, ng * 3, lane, l, l + 1, u + q,
-            [&](int r, int k) { return Lm[(size_t)(sL + r) + (size_t)n * k]; },
-            [&](int k, int c) { const double* pc = k < u ? Um + (size_t)u * c + k : Qm + (size_t)q * c + (k - u); return *pc; },
+            [&](int r, int k) { return Lm[(sL + r) + n * k]; },
+            [&](int k, int c) { const double* pc = k < u ? Um + u * c + k : Qm + q * c + (k - u); return *pc; },
             [&](int r, int c, double v0, double v1) {
               if (r < l) { if (c <= l) emitS(r, c, v0); if (c + 1 <= l) emitS(r, c + 1, v1); }
             });

@@ -356,6 +356,41 @@ __global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenPa
       DIVS[ip] = dv;
     }
     // ---- weighted face matrices (gather form of the face loops of HDGBase / HDGDiffusion / HDGConvection / HDGUNabU) -----------
+    // scalar problems without the Newton-linearised block: one tensor-core product, rows = node pairs (a,b), reduction over the face
+    // cubature points, columns = (face, weight kind): 1, v.n, n_d, (D n)_d, tau
+    if (nD == 1 && !hasUN) {
+      const int lane = tid & 31, warp = tid >> 5, NWARP = NT / 32;
+      const int NK = 3 + 2 * dim, NCOL = nFc * NK, MR = nNf * nNf, MT = (MR + 7) / 8, NG = (NCOL + 23) / 24;
+      for (int task = warp; task < MT * NG; task += NWARP) {
+        mma_task_rt<3>(task % MT, (task / MT) * 3, lane, MR, NCOL, nIPf,
+            [&](int m, int ip) { const int a = m / nNf, b = m - a * nNf; return FSHs[ip * nNf + a] * FSHs[ip * nNf + b]; },
+            [&](int ip, int c) {
+              const int f = c / NK, kind = c - f * NK, fi = f * nIPf + ip;
+              const double dv = DVF[fi];
+              if (kind == 0) return dv;
+              if (kind == 1) return VDN[fi];
+              if (kind < 2 + dim) return dv * NRM[fi * dim + kind - 2];
+              if (kind < 2 + 2 * dim) return dv * DNV[fi * dim + kind - 2 - dim];
+              return dv * TAUS[fi];
+            },
+            [&](int m, int c0, double v0, double v1) {
+              if (m >= MR) return;
+              const int a = m / nNf, b = m - a * nNf;
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                const int c = c0 + h;
+                if (c >= NCOL) continue;
+                const double v = h ? v1 : v0;
+                const int f = c / NK, kind = c - f * NK;
+                if (kind == 0) FONE[f * MR + m] = v;
+                else if (kind == 1) FCN[f * t * t + a + t * b] = hasConv ? v : 0.0;
+                else if (kind < 2 + dim) FNd[(f * dim + kind - 2) * MR + m] = v;
+                else if (kind < 2 + 2 * dim) FDN[(f * dim + kind - 2 - dim) * MR + m] = v;
+                else FT[f * t * t + a + t * b] = v;
+              }
+            });
+      }
+    } else
     for (int idx = tid; idx < nFc * nNf * nNf; idx += NT) {
       const int f = idx / (nNf * nNf), ab = idx - f * nNf * nNf, a = ab / nNf, b = ab - a * nNf;
       double one = 0.0, cn = 0.0, tdn = 0.0, nd3[3] = {0, 0, 0}, dn3[3] = {0, 0, 0}, tt[9], fsn[9];

@@ -81,7 +81,7 @@ HFX_CFG(3, 5, 56, 21, 81, 25)
 #undef HFX_CFG
 
 constexpr int kAsmThreads = 256;
-#define HFX_PROF(i) do { if (p.prof && blockIdx.x == 0 && tid == 0) { long long c_ = clock64(); p.prof[i] += c_ - tprev; tprev = c_; } } while (0)
+#define HFX_PROF(i) do { if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) { long long c_ = clock64(); p.prof[i] += c_ - tprev; tprev = c_; } } while (0)
 
 __host__ __device__ constexpr int ev(int x) { return (x + 1) & ~1; }
 
@@ -301,7 +301,7 @@ __device__ __forceinline__ int grab1(int* ctr, int lane) {   // warp-granular dy
 // The inverse ends in ((np/2) odd ? b1 : b0).
 constexpr int kGJThreads = 128;
 template <int np, int ld, int GT>
-__device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* flag) {
+__device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* flag, int barId) {
   // not inlined on purpose: inside the big kernel the register allocator rematerialises every address of this latency-bound loop
   constexpr int MT = np / 2, NS = MT * np, NQ = (NS + GT - 1) / GT;
   const double s0 = b0[0];
@@ -345,7 +345,7 @@ __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* 
         *reinterpret_cast<double2*>(dst + i0 + ld * j) = make_double2(r0, r1);
       }
     }
-    if (GT == kAsmThreads) __syncthreads(); else bar_sync_named(1, GT);
+    if (GT == kAsmThreads) __syncthreads(); else if (GT == 32) __syncwarp(); else bar_sync_named(barId, GT);
     const double* tsw = dst; dst = const_cast<double*>(src); src = tsw;
   }
   if (bad) atomicOr(flag, 1);
@@ -431,20 +431,35 @@ struct AsmSmem {
   static constexpr int nInts = 8 + 2 * nFc * t + nFc * nN + nFc * nFc + 5 * nFc + 8 + nNLUT + nFc * nKLUT + nFc * l;   // (KLUT: two 16-bit offsets per entry)
   static_assert(nDoubles < 65536, "16-bit operand offsets");
   static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * (nFc + l) + 4 * (size_t)nInts;
+  static constexpr size_t gbytes = (bytes + 15) & ~(size_t)15;   // per element group
 };
 
-template <int DIM, int P>
+// TPE = threads per element: the CTA's 256 threads form 256 / TPE independent groups, each with its own shared-memory image and its
+// own element stream (group-local barriers only).  One CTA-wide group for p=3 tets, one warp per element for the linear elements.
+template <int DIM, int P, int TPE>
 __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmParams p) {
   using L = AsmSmem<DIM, P>;
   constexpr int nN = L::nN, t = L::t, nFc = L::nFc, nIP = L::nIP, nIPf = L::nIPf, l = L::l, NW = L::NW;
   constexpr int nNp = L::nNp, tp = L::tp, ldc = L::ldc, ldg = L::ldg, ldw = L::ldw, nJ = L::nJ;
-  constexpr int D2 = DIM * DIM, NT = kAsmThreads, NWARP = NT / 32;
+  constexpr int D2 = DIM * DIM, NT = TPE, NWARP = NT / 32, NGRP = kAsmThreads / TPE;
+  static_assert(TPE == 32 || TPE == 64 || TPE == 128 || TPE == 256, "group size");
+  static_assert(l < NT && nFc * nFc <= NT, "one thread per trace row");
   constexpr int kTau = 0, kN = 1, kDN = 1 + DIM, kC = 1 + 2 * DIM, kOne = 2 + 2 * DIM;
   constexpr int FWS = tp * t;   // stride between face matrices
   constexpr bool kBulkUQ = (l % 2) == 0;   // rows of U, Q are multiples of 16 bytes: bulk copies
   constexpr bool kBulkS = (t % 2) == 0;    // (row, face block) pieces of S are multiples of 16 bytes: bulk copies / reduce-adds
-  constexpr bool kPrefetch = (nN * DIM <= 64) && (l <= 128) && (nFc * nFc <= 32);
-  extern __shared__ __align__(16) double sm[];
+  constexpr bool kPrefetch = (TPE == 256) && (nN * DIM <= 64) && (l <= 128) && (nFc * nFc <= 32);
+  extern __shared__ __align__(16) double sm_all[];
+  const int grp = threadIdx.x / TPE;
+  double* const sm = sm_all + (size_t)grp * (L::gbytes / 8);
+  auto gsync = [&]() { if (TPE == kAsmThreads) __syncthreads(); else if (TPE == 32) __syncwarp(); else bar_sync_named(1 + grp, TPE); };
+  auto gsync_or = [&](int pred) -> int {
+    if (TPE == kAsmThreads) return __syncthreads_or(pred);
+    if (TPE == 32) { __syncwarp(); return __any_sync(0xffffffffu, pred); }
+    unsigned r;
+    asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; barrier.cta.red.or.pred q, %2, %3, p; selp.u32 %0, 1, 0, q; }" : "=r"(r) : "r"(pred), "r"(1 + grp), "r"(TPE) : "memory");
+    return (int)r;
+  };
   double* PHI = sm + L::oPHI; double* X = sm + L::oX; double* JR = sm + L::oJ; double* IJ = sm + L::oIJ; double* DV = sm + L::oDV;
   double* DIP = sm + L::oDIP; double* VIP = sm + L::oVIP; double* LW = sm + L::oLW; double* FWT = sm + L::oFWT; double* TAU = sm + L::oTAU;
   double* DN = sm + L::oDN; double* VN = sm + L::oVN; double* G = sm + L::oG; double* CG = sm + L::oCG; double* Mm = sm + L::oM;
@@ -470,7 +485,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   double* A = G;    // A_d aliases g (dead after the contractions)
   double* ST = sm + L::oST;   // S staging [l][ldc] for the coalesced write-out
   double* Um = SQU; // U aliases Squ (dead after A)
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x & (TPE - 1), lane = tid & 31, warp = tid >> 5;
   const bool hasDiff = p.opmask & 1, hasConv = p.opmask & 2, hasReac = (p.opmask & 4) && p.reacIP, hasSrc = (p.opmask & 8) && p.srcIP;
   const bool euler = p.timeScheme == 1;
   const double ts = euler ? p.dt : 1.0;   // Euler::apply scales the u rows (Su, Fu) by dt before adding the mass terms (Euler.cpp:28-32)
@@ -484,14 +499,14 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
   // ---- once per CTA: constant tables; padding lanes must hold finite numbers --------------------------------------------
   for (int i = tid; i < L::nDoubles; i += NT) sm[i] = 0.0;
-  __syncthreads();
+  gsync();
   for (int i = tid; i < nFc * t; i += NT) FN[i] = p.faceNodes[i];
   for (int i = tid; i < nFc * nN; i += NT) NIF[i] = p.nodeInFace[i];
   for (int i = tid; i < nIP * nN; i += NT) PHI[(i / nN) * nNp + (i % nN)] = p.shape[i];
   for (int i = tid; i < nIP + nIPf; i += NT) WQ[i] = i < nIP ? p.w[i] : p.fw[i - nIP];
   if (tid < nFc) { int vn = 0; for (int kk = 0; kk < nN; kk++) if (p.nodeInFace[tid * nN + kk] < 0) { vn = kk; break; } OPP[tid] = vn; }
   for (int n = tid; n < L::nNLUT; n += NT) { const int nn = n < DIM * t ? n : DIM * t - 1; NLUT[n] = (nn / t) * nN * ldc + (nn % t); }
-  __syncthreads();
+  gsync();
 
   // reference-mass inverse: each thread keeps its share in registers for the whole kernel (constant-detJ shortcut for M^-1)
   constexpr int NMH = (nNp * nNp + NT - 1) / NT;
@@ -528,8 +543,9 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     if (tid >= 64 && tid < 64 + l) pfTau = p.tau[((size_t)pfF * t + pfPerm) * p.tauVals + pfSide];
     if (tid >= 192 && tid < 192 + nFc) { const int F = pfF; pfRow = p.faceRowStart[F]; pfRlen = (int)p.faceNnb[F] * t; pfBc = p.faceBC[F]; pfInt = p.faceInterior[F]; }
   };
-  prefetchA(blockIdx.x);
-  prefetchB(blockIdx.x);
+  const int e0 = blockIdx.x * NGRP + grp, eStride = gridDim.x * NGRP;
+  prefetchA(e0);
+  prefetchB(e0);
 
   // column tiles (8 columns, kind-major) of the weighted face mass contraction that this model needs
   constexpr int NCT = (nFc * NW + 7) / 8;
@@ -555,10 +571,10 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     KLUT[2 * i] = (unsigned short)((kind == 0 ? kTau : kDNe + kind - 1) * FWS + tp * b);
     KLUT[2 * i + 1] = (unsigned short)(kind == 0 ? L::oSQU + nd * ldc : L::oB + ((kind - 1) * nN + nd) * ldc);
   }
-  __syncthreads();
+  gsync();
 
   long long tprev = clock64();
-  for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
+  for (int e = e0; e < p.nCells; e += eStride) {
     // ---- P0: commit the prefetched gather -----------------------------------------------------------------------------------
     if (kPrefetch) {
       if (tid < nN * DIM) X[tid] = pfX;
@@ -620,7 +636,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     }
     if (hasConv) for (int i = tid; i < nN * DIM; i += NT) VN[i] = p.vel[(size_t)cell[i / DIM] * DIM + (i % DIM)];
     if (!refCand) cp_async_wait_all();
-    __syncthreads();
+    gsync();
     HFX_PROF(0);
     unsigned tileNeed = aff ? affNeed : baseNeed;
 #pragma unroll
@@ -629,7 +645,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     // Global storage: per face F its nnb(F) neighbour blocks, each a contiguous row-major t x t block in face-node order (block CSR).
     if (kBulkS) {   // staging already is in face-node order: CMAP[position] = element-local trace index
       if (tid < l) CMAP[(tid / t) * t + PERM[tid]] = tid;
-      if (tid == l) CMAP[l] = l;
+      if (tid == l) CMAP[l] = l;   // (l < NT)
     } else {
       for (int i = tid; i < nFc * l; i += NT) { const int f = i / l, cc = i - f * l; POSROW[i] = POS[f * nFc + cc / t] * t * t + PERM[cc]; }
       if (tid < l) { const int f = tid / t; RBASE[tid] = ROWS[f] + (long long)PERM[tid] * t; }
@@ -676,7 +692,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         gf[DIM] = area;
         gr[DIM] = TAU[f * t] * area;
         gr[DIM + 1] = area;
-      } else if (tid == 32) {
+      } else if (tid == (NT > 32 ? 32 : nFc)) {
         double J[DIM][DIM], det, I[DIM][DIM];
 #pragma unroll
         for (int r = 0; r < DIM; r++)
@@ -689,17 +705,18 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           for (int r = 0; r < DIM; r++) GEO[m * DIM + r] = I[m][r];
         GEO[D2] = det;
         FU[ev(nN)] = fast_rcp(det);
-      } else if (tid >= 64) {
+      } else if (NT > 64 && tid >= 64) {
         for (int i = tid - 64; i < l; i += NT - 64) bad |= (TAU[i] != TAU[(i / t) * t]);
       }
+      if (NT <= 64) for (int i = tid; i < l; i += NT) bad |= (TAU[i] != TAU[(i / t) * t]);
       cp_async_wait_all();
-      ref = !__syncthreads_or(bad);
+      ref = !gsync_or(bad);
       HFX_PROF(5);
-      prefetchA(e + gridDim.x);
+      prefetchA(e + eStride);
       if (!ref) {   // tau varies on a face: the general straight-sided path needs its own tables
         stageStd();
         cp_async_wait_all();
-        __syncthreads();
+        gsync();
       }
     }
     if (ref) {
@@ -795,9 +812,9 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           FU[i] = s2 * det;
         }
       }
-      __syncthreads();
+      gsync();
       HFX_PROF(1);
-      prefetchB(e + gridDim.x);
+      prefetchB(e + eStride);
     }
     double* const W = ((nNp / 2) & 1) ? Wb : Mm;
     constexpr int MTN = (nN + 7) / 8;           // 8-row tiles over the element nodes
@@ -845,10 +862,10 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         }
       }
     }
-    if (!aff) __syncthreads();   // (straight-sided elements read their constant Jacobians straight from the vertices: no P1a, no barrier)
+    if (!aff) gsync();   // (straight-sided elements read their constant Jacobians straight from the vertices: no P1a, no barrier)
     HFX_PROF(5);
     // the next element's gather flies while this element is computed
-    if (!refCand) prefetchA(e + gridDim.x);
+    if (!refCand) prefetchA(e + eStride);
 
     // ---- P1b: measures, inverses, normals, coefficient interpolation (Operator.cpp:41-84, HDGModel.cpp:53-85, HDGBase.cpp:18-65) --
     for (int k = tid; k < nJ; k += NT) {
@@ -1027,7 +1044,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         }
       }
     }
-    __syncthreads();
+    gsync();
     HFX_PROF(1);
 
     // ---- P2: g[ip][(d,i)] = dV (J^-1 grad_ref phi_i)_d ; cg = suu left operand ----------------------------------------
@@ -1054,7 +1071,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
       CG[ip * nNp + i] = c;
     }
-    __syncthreads();
+    gsync();
     HFX_PROF(2);
 
     // =====================================================================================================================
@@ -1087,12 +1104,13 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       for (int j = 0; j < nN; j++) { Mm[nN + nNp * j] = 0.0; Mm[j + nNp * nN] = 0.0; }
       Mm[nN + nNp * nN] = 1.0;
     }
-    __syncthreads();
+    gsync();
     HFX_PROF(3);
 
     // ---- P3b: (general path only: W = M^-1 by warps 0-3, block Gauss-Jordan) ; contractions Squ, Suu, face matrices, Fu as
     //            warp tasks: dynamic queue when the inversion runs beside them, static round-robin otherwise ------------------
-    if (!constDet && tid < kGJThreads) group_invert<nNp, nNp, kGJThreads>(Mm, Wb, tid, p.status);
+    if (TPE == kAsmThreads) { if (!constDet && tid < kGJThreads) group_invert<nNp, nNp, kGJThreads>(Mm, Wb, tid, p.status, 1); }
+    else if (!constDet) group_invert<nNp, nNp, (TPE < kAsmThreads ? TPE : 32)>(Mm, Wb, tid, p.status, 1 + grp);
     HFX_PROF(14);
     {
       const int lr = lane >> 2, lc = lane & 3;
@@ -1189,9 +1207,9 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         for (int d = 0; d < DIM; d++) FW[(f * NW + kN + d) * FWS + ab] = sc * gf[d];
       }
     }
-    __syncthreads();
+    gsync();
     HFX_PROF(4);
-    prefetchB(e + gridDim.x);
+    prefetchB(e + eStride);
 
     // ---- P3c: Suq bulk part with a diffusion field (HDGDiffusion.cpp:31-72,130-144) ----------------------------------------
     if (diffField) {
@@ -1210,7 +1228,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
         for (int m = 0; m < DIM; m++) G[ip * ldg + m * nN + i] = o[m];
       }
-      __syncthreads();
+      gsync();
       constexpr int MROWS = DIM * nN, SQ_MT = (MROWS + 7) / 8, NG_N = (MTN + 2) / 3;
       for (int task = warp; task < SQ_MT * NG_N; task += NWARP) {
         mma_task<3, KS_IP>(task % SQ_MT, (task / SQ_MT) * 3, lane,
@@ -1224,7 +1242,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
               }
             });
       }
-      __syncthreads();
+      gsync();
     }
     HFX_PROF(6);
     if (affAB) {   // B_d = -(area n_d / detJ) B^_f  (after the face contraction: the staged phi_a phi_b table lives in the B region)
@@ -1269,7 +1287,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       for (int j = 0; j < nN; j++) { SUU[nN + nNp * j] = 0.0; SUU[j + nNp * nN] = 0.0; }
       SUU[nN + nNp * nN] = 1.0;
     }
-    __syncthreads();
+    gsync();
     HFX_PROF(7);
 
     // ---- P4: A_d = W Squ_d (col-major out) ;  B_d = W Sql_d with Sql[(fn_f(a),d),(f,b)] = -N_fd[a][b] (HDGBase.cpp:134) ------
@@ -1332,7 +1350,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
       if (!affAB) for (int idx = tid; idx < DIM * nN; idx += NT) { B[idx * ldc + l] = 0.0; B[idx * ldc + l + 1] = 0.0; }  // Q0 column
     }
-    if (!affAB) __syncthreads();
+    if (!affAB) gsync();
     HFX_PROF(8);
     }   // !ref
 
@@ -1387,11 +1405,11 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
       for (int i = tid; i < nN; i += NT) { R[i * ldc + l] = -FU[i]; R[i * ldc + l + 1] = 0.0; }
     }
-    __syncthreads();
+    gsync();
     HFX_PROF(9);
     // ---- P6: K^-1 (2x2-block-pivot Gauss-Jordan on all eight warps: the pivot chain is serial, measured variants that ran it on
     //      four warps or on one warp beside the R tiles were slower) ------------------------------------------------
-    group_invert<nNp, nNp, NT>(SUU, KB, tid, p.status);
+    group_invert<nNp, nNp, NT>(SUU, KB, tid, p.status, 1 + grp);
     HFX_PROF(10);
 
     // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu (column l) ------------------------------------------------------------------------
@@ -1420,7 +1438,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         }
       }
     }
-    __syncthreads();
+    gsync();
     HFX_PROF(11);
 
     // ---- P8: Q_d = -A_d U - B_d ; Q0_d = -A_d U0  (:344-345) -----------------------------------------------------------
@@ -1458,18 +1476,20 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       if (NREM > 0) for (int st = warp; st < NREM * MTN; st += NWARP) q_task(NFULL + st / MTN, st % MTN, st % MTN + 1);
     }
     if (kBulkUQ) fence_proxy_async();
-    __syncthreads();
+    gsync();
     HFX_PROF(12);
     // U, Q leave as whole rows (row-major per element in HBM): one bulk copy per row, issued here so that they fly during P9
     if (kBulkUQ) {
       constexpr int q = DIM * nN;
       constexpr int RPWQ = (nN + q + NWARP - 1) / NWARP;   // a warp issues its copies one after the other: spread them evenly
-      static_assert(RPWQ <= 32, "rows per warp");
-      const int row = warp * RPWQ + lane;
-      if (lane < RPWQ && row < nN + q) {
-        if (row < nN) bulk_store(p.U + ((size_t)e * nN + row) * l, Um + row * ldc, l * 8);
-        else { const int rq = row - nN; bulk_store(p.Q + ((size_t)e * q + rq) * l, B + ((rq % DIM) * nN + rq / DIM) * ldc, l * 8); }
-        bulk_commit();
+#pragma unroll
+      for (int r0 = 0; r0 < RPWQ; r0 += 32) {
+        const int row = warp * RPWQ + r0 + lane;
+        if (r0 + lane < RPWQ && row < nN + q) {
+          if (row < nN) bulk_store(p.U + ((size_t)e * nN + row) * l, Um + row * ldc, l * 8);
+          else { const int rq = row - nN; bulk_store(p.Q + ((size_t)e * q + rq) * l, B + ((rq % DIM) * nN + rq / DIM) * ldc, l * 8); }
+          bulk_commit();
+        }
       }
     }
 
@@ -1549,7 +1569,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
     }
     if (kBulkS) fence_proxy_async();
-    __syncthreads();
+    gsync();
     HFX_PROF(13);
 
     // ---- P10: write-out.  S: every (row, neighbour-face block) of the element is t contiguous entries of the global face-block CSR,
@@ -1619,8 +1639,10 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         }
       }
       if (tid < nN) p.U0[(size_t)e * nN + tid] = Um[tid * ldc + l];
-      if (tid >= 64 && tid < 64 + q) { const int rq = tid - 64; p.Q0[(size_t)e * q + rq] = B[((rq % DIM) * nN + rq / DIM) * ldc + l]; }
-      if (q > NT - 64) for (int rq = NT - 64 + tid; rq < q; rq += NT) p.Q0[(size_t)e * q + rq] = B[((rq % DIM) * nN + rq / DIM) * ldc + l];
+      if (NT > 64) {
+        if (tid >= 64 && tid < 64 + q) { const int rq = tid - 64; p.Q0[(size_t)e * q + rq] = B[((rq % DIM) * nN + rq / DIM) * ldc + l]; }
+        if (q > NT - 64) for (int rq = NT - 64 + tid; rq < q; rq += NT) p.Q0[(size_t)e * q + rq] = B[((rq % DIM) * nN + rq / DIM) * ldc + l];
+      } else for (int rq = tid; rq < q; rq += NT) p.Q0[(size_t)e * q + rq] = B[((rq % DIM) * nN + rq / DIM) * ldc + l];
       if (tid < l) {
         const int r = tid, f = r / t, a = r % t, F = ISM[f], bc = BCF[f];
         const double* fwf = FW + f * NW * FWS;
@@ -1636,30 +1658,42 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       }
       if (kBulkUQ || kBulkS) bulk_wait_read();   // the staging areas are rewritten by the next element pass
     }
-    __syncthreads();
+    gsync();
     HFX_PROF(15);
   }
 }
 
 // host-side launch helper
-template <int DIM, int P>
-inline cudaError_t launch_assemble_t(const AsmParams& p, int nSM, cudaStream_t st) {
+template <int DIM, int P, int TPE>
+inline cudaError_t launch_assemble_tpe(const AsmParams& p, int nSM, cudaStream_t st) {
   using L = AsmSmem<DIM, P>;
+  constexpr int NGRP = kAsmThreads / TPE;
+  constexpr size_t bytes = L::gbytes * NGRP;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(hdg_assemble_kernel<DIM, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+    cudaError_t e = cudaFuncSetAttribute(hdg_assemble_kernel<DIM, P, TPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
     attr = true;
   }
   int perSM = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_assemble_kernel<DIM, P>, kAsmThreads, L::bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_assemble_kernel<DIM, P, TPE>, kAsmThreads, bytes);
   if (perSM < 1) perSM = 1;
   if (const char* ev_ = getenv("HFX_CTAS_PER_SM")) { int v = atoi(ev_); if (v >= 1 && v < perSM) perSM = v; }   // experiments only
   long long grid = (long long)nSM * perSM;
-  if (grid > p.nCells) grid = p.nCells;
+  const long long need = ((long long)p.nCells + NGRP - 1) / NGRP;
+  if (grid > need) grid = need;
   if (grid < 1) grid = 1;
-  hdg_assemble_kernel<DIM, P><<<(int)grid, kAsmThreads, L::bytes, st>>>(p);
+  hdg_assemble_kernel<DIM, P, TPE><<<(int)grid, kAsmThreads, bytes, st>>>(p);
   return cudaGetLastError();
+}
+// Threads per element by element size: a 4-node element does not feed 256 threads; the linear elements get one warp each.
+template <int DIM, int P>
+inline cudaError_t launch_assemble_t(const AsmParams& p, int nSM, cudaStream_t st) {
+  using C = ElemCfg<DIM, P>;
+  constexpr int nN = C::nN;
+  constexpr int TPE = nN <= 6 ? 32 : nN <= 10 ? (DIM == 3 ? 128 : 64) : nN <= 15 ? 128 : 256;
+  if (getenv("HFX_ONE_GROUP")) return launch_assemble_tpe<DIM, P, 256>(p, nSM, st);   // experiments / A-B comparison
+  return launch_assemble_tpe<DIM, P, TPE>(p, nSM, st);
 }
 
 }  // namespace hfx

@@ -21,6 +21,7 @@ namespace hfx {
 
 struct AsmParams {
   int nCells;
+  int eBegin, eEnd;           // element range of this launch (a pipelined assemble launches one range per upload piece)
   // mesh
   const double* elemX;        // [nCells][nN*DIM] element-major node coordinates (gathered once at allocate)
   const int* cells; const int* cell2face;
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   // issuing both back to back parks the issuing warps on the first loads' DRAM latency in the middle of the geometry phase
   int pfSide = 0, pfAff = 0;
   auto prefetchA = [&](int e) {
-    if (!kPrefetch || e >= p.nCells) return;
+    if (!kPrefetch || e >= p.eEnd) return;
     pfAff = p.affine ? p.affine[e] : 0;   // every thread: warp-uniform control flow later, no shared-memory round trip
     if (tid < nN * DIM) pfX = p.elemX[(size_t)e * nN * DIM + tid];
     if (tid >= 64 && tid < 64 + l) {
@@ -539,11 +540,11 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     if (kRefSrcPf && refModel && hasSrc && tid >= 128 && tid < 128 + nIP) pfSrc = p.srcIP[(size_t)e * nIP + (tid - 128)];
   };
   auto prefetchB = [&](int e) {
-    if (!kPrefetch || e >= p.nCells) return;
+    if (!kPrefetch || e >= p.eEnd) return;
     if (tid >= 64 && tid < 64 + l) pfTau = p.tau[((size_t)pfF * t + pfPerm) * p.tauVals + pfSide];
     if (tid >= 192 && tid < 192 + nFc) { const int F = pfF; pfRow = p.faceRowStart[F]; pfRlen = (int)p.faceNnb[F] * t; pfBc = p.faceBC[F]; pfInt = p.faceInterior[F]; }
   };
-  const int e0 = blockIdx.x * NGRP + grp, eStride = gridDim.x * NGRP;
+  const int e0 = p.eBegin + blockIdx.x * NGRP + grp, eStride = gridDim.x * NGRP;
   prefetchA(e0);
   prefetchB(e0);
 
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   gsync();
 
   long long tprev = clock64();
-  for (int e = e0; e < p.nCells; e += eStride) {
+  for (int e = e0; e < p.eEnd; e += eStride) {
     // ---- P0: commit the prefetched gather -----------------------------------------------------------------------------------
     if (kPrefetch) {
       if (tid < nN * DIM) X[tid] = pfX;
@@ -1680,7 +1681,7 @@ inline cudaError_t launch_assemble_tpe(const AsmParams& p, int nSM, cudaStream_t
   if (perSM < 1) perSM = 1;
   if (const char* ev_ = getenv("HFX_CTAS_PER_SM")) { int v = atoi(ev_); if (v >= 1 && v < perSM) perSM = v; }   // experiments only
   long long grid = (long long)nSM * perSM;
-  const long long need = ((long long)p.nCells + NGRP - 1) / NGRP;
+  const long long need = ((long long)(p.eEnd - p.eBegin) + NGRP - 1) / NGRP;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
   hdg_assemble_kernel<DIM, P, TPE><<<(int)grid, kAsmThreads, bytes, st>>>(p);

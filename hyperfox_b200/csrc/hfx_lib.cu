@@ -50,7 +50,8 @@ struct DBuf {  // device buffer
   DBuf& operator=(const DBuf&) = delete;
 };
 
-struct DField { int type = 0, nObj = 0, nVal = 0, dbl = 0; DBuf<double> d; };
+struct DField { int type = 0, nObj = 0, nVal = 0, dbl = 0; DBuf<double> d;
+                std::vector<cudaEvent_t> ev; int pendingPieces = 0; /* asynchronous upload in flight: events per piece */ };
 
 // ---------------------------------------------------------------------------------------------------------------------
 // device kernels other than the fused assembly
@@ -602,6 +603,8 @@ using namespace hfx;
 struct hfx_ctx {
   int device = 0, nSM = 148;
   cudaStream_t st = nullptr;
+  cudaStream_t stCopy[2] = {nullptr, nullptr}; int copyRR = 0;   // asynchronous field uploads (hfx_field_set_async)
+  std::vector<int> chunkCellEnd, chunkFaceEnd;                   // element chunks of a pipelined assemble and the face-id prefix each one needs
   std::string err;
   // reference element
   std::unique_ptr<RefElement> re;
@@ -752,6 +755,7 @@ int hfx_ctx_create(int device, hfx_ctx** out) {
     HFX_CUDA(cudaGetDeviceProperties(&prop, device));
     c->nSM = prop.multiProcessorCount;
     HFX_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    HFX_CUDA(cudaStreamCreateWithFlags(&c->stCopy[0], cudaStreamNonBlocking)); HFX_CUDA(cudaStreamCreateWithFlags(&c->stCopy[1], cudaStreamNonBlocking));
     HFX_CUDA(cudaEventCreate(&c->ev0)); HFX_CUDA(cudaEventCreate(&c->ev1)); HFX_CUDA(cudaEventCreate(&c->ev2));
     c->dStatus.alloc(1); c->dStatus.zero(c->st);
     *out = c.release();
@@ -762,6 +766,8 @@ int hfx_ctx_destroy(hfx_ctx* c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
+  for (int k = 0; k < 2; k++) if (c->stCopy[k]) { cudaStreamSynchronize(c->stCopy[k]); cudaStreamDestroy(c->stCopy[k]); }
+  for (auto& kv : c->fields) for (cudaEvent_t e : kv.second.ev) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
@@ -973,6 +979,34 @@ int hfx_field_set(hfx_ctx* c, const char* name, int type, int nObj, int nVal, co
   });
 }
 
+// Asynchronous variant: enqueues the host -> device copy on a copy stream and returns.  `vals` (pinned memory for a real overlap) must stay
+// unchanged until the next hfx_assemble / hfx_sync returns.  Face fields are copied in pieces along the face-id prefixes of the element
+// chunks, so that hfx_assemble can start the first chunk of elements while the rest of the field is still crossing PCIe.
+int hfx_field_set_async(hfx_ctx* c, const char* name, int type, int nObj, int nVal, const double* vals, int dbl) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    need(c->topoSet, "Field", "Field", "the mesh must be set before creating fields");
+    need(type == HFX_FIELD_NODE || type == HFX_FIELD_CELL || type == HFX_FIELD_FACE, "Field", "Field", "unknown field type");
+    DField& f = c->fields[name];
+    f.type = type; f.nObj = nObj; f.nVal = nVal; f.dbl = dbl;
+    const size_t n = (size_t)field_len(c, f);
+    if (f.d.n != n || !f.d.p) { HFX_CUDA(cudaStreamSynchronize(c->st)); f.d.alloc(n); }
+    const bool pieces = type == HFX_FIELD_FACE && c->allocated && !c->chunkFaceEnd.empty() && c->chunkFaceEnd.back() == c->nFaces;
+    const int K = pieces ? (int)c->chunkFaceEnd.size() : 1;
+    while ((int)f.ev.size() < K) { cudaEvent_t e; HFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); f.ev.push_back(e); }
+    cudaStream_t cs = c->stCopy[c->copyRR]; c->copyRR ^= 1;
+    const size_t per = (size_t)nObj * nVal;
+    size_t b = 0;
+    for (int k = 0; k < K; k++) {
+      const size_t e = pieces ? (size_t)c->chunkFaceEnd[k] * per : n;
+      if (e > b) HFX_CUDA(cudaMemcpyAsync(f.d.p + b, vals + b, (e - b) * sizeof(double), cudaMemcpyHostToDevice, cs));
+      HFX_CUDA(cudaEventRecord(f.ev[k], cs));
+      b = e;
+    }
+    f.pendingPieces = K;
+  });
+}
+
 int hfx_field_get(hfx_ctx* c, const char* name, double* vals) {
   return guard(c, [&] {
     HFX_CUDA(cudaSetDevice(c->device));
@@ -1102,6 +1136,17 @@ int hfx_allocate(hfx_ctx* c, int flags) {
     c->dU.alloc((size_t)nC * u * l); c->dQ.alloc((size_t)nC * q * l); c->dU0.alloc((size_t)nC * u); c->dQ0.alloc((size_t)nC * q);
     if (c->keepS) { c->dS.alloc((size_t)nC * l * l); c->dS0.alloc((size_t)nC * l); } else { c->dS.release(); c->dS0.release(); }
     c->dVals.alloc((size_t)c->nnz); c->dRhs.alloc((size_t)nF * t);
+    {   // element chunks for the pipelined assemble (hfx_field_set_async): faces are numbered in order of first appearance over ascending
+        // cell ids (Mesh.cpp:183-274), so the cells [0, e) only touch the face-id prefix [0, 1 + max face id of those cells)
+      const int K = 8;
+      c->chunkCellEnd.assign(K, c->nCells); c->chunkFaceEnd.assign(K, c->nFaces);
+      int mx = -1; size_t pos = 0;
+      for (int k = 0; k < K; k++) {
+        const int ce = (int)((long long)c->nCells * (k + 1) / K);
+        for (; pos < (size_t)ce * c->nFc; pos++) mx = std::max(mx, c->hC2F[pos]);
+        c->chunkCellEnd[k] = ce; c->chunkFaceEnd[k] = k == K - 1 ? c->nFaces : mx + 1;
+      }
+    }
     c->allocated = true; c->assembled = false;
   });
 }
@@ -1148,11 +1193,30 @@ int hfx_assemble(hfx_ctx* c) {
     c->dVals.zero(c->st); c->dRhs.zero(c->st); c->dStatus.zero(c->st);
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
     bool fused = c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
+    // fields still crossing PCIe (hfx_field_set_async): the element chunks start as their face-id prefix has arrived
+    std::vector<DField*> pend;
+    for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) pend.push_back(&kv.second);
+    auto waitPieces = [&](int k, int K) {
+      for (DField* f : pend) {
+        const int piece = f->pendingPieces == K ? k : f->pendingPieces - 1;   // unpieced fields: everything must have arrived
+        HFX_CUDA(cudaStreamWaitEvent(c->st, f->ev[piece], 0));
+      }
+    };
+    p.eBegin = 0; p.eEnd = c->nCells;
     if (fused) {
       bool supported = true;
-      HFX_CUDA(launch_assemble(c->dim, c->order, p, c->nSM, c->st, &supported));
+      const int K = (!pend.empty() && !c->profOn) ? (int)c->chunkCellEnd.size() : 1;
+      for (int k = 0; k < K && supported; k++) {
+        if (!pend.empty()) waitPieces(K == 1 ? 0 : k, K == 1 ? -1 : K);
+        p.eBegin = (K == 1 || k == 0) ? 0 : c->chunkCellEnd[k - 1];
+        p.eEnd = K == 1 ? c->nCells : c->chunkCellEnd[k];
+        if (p.eEnd > p.eBegin) HFX_CUDA(launch_assemble(c->dim, c->order, p, c->nSM, c->st, &supported));
+      }
+      p.eBegin = 0; p.eEnd = c->nCells;
       fused = supported;
     }
+    if (!fused && !pend.empty()) waitPieces(0, -1);
+    for (DField* f : pend) f->pendingPieces = 0;
     if (!fused) {   // general kernel: 3-D orders 4-5, nDOFsPerNode > 1, HDGUNabU
       GenParams g{};
       g.a = p; g.dim = c->dim; g.nN = c->nN; g.nNf = c->nNf; g.nFc = c->nFc; g.nIP = c->nIP; g.nIPf = c->nIPf; g.nD = c->md.nDOF;
@@ -1230,7 +1294,7 @@ int hfx_last_assemble_ms(const hfx_ctx* c, float* msTotal, float* msKernel) {
   return 0;
 }
 
-int hfx_sync(hfx_ctx* c) { return guard(c, [&] { HFX_CUDA(cudaSetDevice(c->device)); HFX_CUDA(cudaStreamSynchronize(c->st)); }); }
+int hfx_sync(hfx_ctx* c) { return guard(c, [&] { HFX_CUDA(cudaSetDevice(c->device)); for (int k = 0; k < 2; k++) HFX_CUDA(cudaStreamSynchronize(c->stCopy[k])); HFX_CUDA(cudaStreamSynchronize(c->st)); }); }
 
 int hfx_recover(hfx_ctx* c) {
   return guard(c, [&] {

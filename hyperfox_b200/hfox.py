@@ -463,10 +463,14 @@ class HDGSolver:
 
     def _h(self): return self.ctx.h
 
-    def _upload_field(self, name):
+    def _upload_field(self, name, asynchronous=False):
         f = self.fieldMap[name]
         v = f64(f.values)
-        check(lib().hfx_field_set(self._h(), name.encode(), f.type, f.nObj, f.nVals, pd(v), int(f.doubleValued)), self._h())
+        if asynchronous:   # the copy overlaps the assembly; the field's storage is not touched before hfx_assemble returns
+            self._keep = getattr(self, "_keep", {}); self._keep[name] = v
+            check(lib().hfx_field_set_async(self._h(), name.encode(), f.type, f.nObj, f.nVals, pd(v), int(f.doubleValued)), self._h())
+        else:
+            check(lib().hfx_field_set(self._h(), name.encode(), f.type, f.nObj, f.nVals, pd(v), int(f.doubleValued)), self._h())
 
     def allocate(self):
         if not self.initialized:
@@ -568,7 +572,7 @@ class HDGSolver:
         if not (self.initialized and self.allocated):
             raise ErrorHandle("HDGSolver : assemble : the solver must be initialized and allocated before assembling.")
         for name in self._input_fields():
-            self._upload_field(name)
+            self._upload_field(name, asynchronous=True)
         self._describe_model()
         self._eval_callbacks()
         check(lib().hfx_assemble(self._h()), self._h())

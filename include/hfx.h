@@ -53,6 +53,9 @@ enum { HFX_FIELD_NODE = 0, HFX_FIELD_FACE = 2, HFX_FIELD_CELL = 1 };
 /* names with a meaning on the path: "Tau", "Dirichlet", "DiffusionTensor", "Velocity", "Solution", "Flux", "Trace",
    "BufferSolution" (Solver.h:125-141, HDGSolver.cpp:24-73).  Copies host -> device. */
 int hfx_field_set(hfx_ctx* ctx, const char* name, int type, int nObjPerEnt, int nValsPerObj, const double* vals, int doubleValued);
+/* Same, asynchronous: returns once the copy is enqueued; `vals` (pinned memory for a real overlap) must stay unchanged until the next
+   hfx_assemble / hfx_sync returns.  hfx_assemble starts on the first elements while the rest of a Face field is still in flight. */
+int hfx_field_set_async(hfx_ctx* ctx, const char* name, int type, int nObjPerEnt, int nValsPerObj, const double* vals, int doubleValued);
 int hfx_field_get(hfx_ctx* ctx, const char* name, double* vals); /* device -> host */
 int hfx_field_size(const hfx_ctx* ctx, const char* name, long long* n);
 

@@ -195,6 +195,50 @@ __global__ void spmv_face_kernel(int nFaces, int t, int nFc2, const long long* _
   }
 }
 
+// Streaming variant for block rows of at most kSpmvStage doubles (p <= 3 tets, every 2-D order): the warp first copies the face's whole
+// contiguous run into shared memory with 16-byte asynchronous copies -- every byte of the matrix crosses the SM exactly once, fully
+// coalesced, with the whole run in flight per warp -- then a few lanes per row reduce it against the gathered x.
+constexpr int kSpmvStage = 768, kSpmvMaxLen = 80;
+__global__ void __launch_bounds__(256) spmv_block_kernel(int nFaces, int t, int nFc2, const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
+                                                         const int* __restrict__ nbr, const double* __restrict__ vals, const double* __restrict__ x,
+                                                         double* __restrict__ y, const uint8_t* __restrict__ owned /*NULL: all rows*/) {
+  extern __shared__ __align__(16) double spmv_sm[];
+  double (*sv)[kSpmvStage] = reinterpret_cast<double (*)[kSpmvStage]>(spmv_sm);
+  double (*sx)[kSpmvMaxLen] = reinterpret_cast<double (*)[kSpmvMaxLen]>(spmv_sm + 8 * kSpmvStage);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int LPR = t > 16 ? 1 : (t > 8 ? 2 : (t > 4 ? 4 : 8));   // lanes per row (power of two), 32 / LPR rows per pass
+  const int a = lane / LPR, part = lane - a * LPR;
+  for (int F = blockIdx.x * 8 + w; F < nFaces; F += gridDim.x * 8) {
+    if (owned && !owned[F]) { for (int r = lane; r < t; r += 32) y[(size_t)F * t + r] = 0.0; continue; }   // rows of ghost faces belong to another rank
+    const int m = nnb[F], len = m * t, tot = len * t;
+    const double* v = vals + rowStart[F];
+    const bool al = ((rowStart[F] & 1) == 0);
+    const int n2 = al ? tot >> 1 : 0;
+    for (int i = lane; i < n2; i += 32) {
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(&sv[w][2 * i]);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(v + 2 * i) : "memory");
+    }
+    for (int i = 2 * n2 + lane; i < tot; i += 32) sv[w][i] = v[i];
+    for (int k = lane; k < len; k += 32) { const int g = k / t, b = k - g * t; sx[w][k] = x[(size_t)nbr[(size_t)F * nFc2 + g] * t + b]; }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    for (int a0 = 0; a0 < t; a0 += 32 / LPR) {
+      const int row = a0 + a;
+      double s = 0.0;
+      if (row < t) {
+        for (int g = 0; g < m; g++) {
+          const double* vr = &sv[w][(g * t + row) * t];
+          const double* xr = &sx[w][g * t];
+          for (int b = part; b < t; b += LPR) s = fma(vr[b], xr[b], s);
+        }
+      }
+      for (int o = 1; o < LPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (row < t && part == 0) y[(size_t)F * t + row] = s;
+    }
+    __syncwarp();
+  }
+}
+
 // generic CSR SpMV (LinAlgebraInterface mirror)
 __global__ void spmv_csr_kernel(long long n, const long long* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
                                 const double* __restrict__ x, double* __restrict__ y) {
@@ -663,7 +707,13 @@ struct FaceOp : LinOp {
       x = c->dXh.p; owned = c->halo.dOwned.p;
     }
     const int len = 2 * c->nFc * t, nb = nblk((long long)c->nFaces * 32, 256);   // at most 2 nFc - 1 neighbour faces per row
-    if (len <= 96) spmv_face_kernel<3><<<nb, 256, 0, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
+    const int lenMax = (2 * c->nFc - 1) * t;   // a face has at most 2 nFc - 1 neighbour faces (itself included)
+    if (lenMax * t <= kSpmvStage && lenMax <= kSpmvMaxLen && !getenv("HFX_SPMV_V1")) {
+      constexpr int shm = 8 * (kSpmvStage + kSpmvMaxLen) * (int)sizeof(double);
+      static bool attr = false;
+      if (!attr) { HFX_CUDA(cudaFuncSetAttribute(spmv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shm)); attr = true; }
+      spmv_block_kernel<<<std::min(nblk(c->nFaces, 8), c->nSM * 4), 256, shm, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
+    } else if (len <= 96) spmv_face_kernel<3><<<nb, 256, 0, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
     else if (len <= 256) spmv_face_kernel<8><<<nb, 256, 0, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
     else spmv_face_kernel<16><<<nb, 256, 0, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
   }

@@ -308,47 +308,52 @@ __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* 
   const double s0 = b0[0];
   const double scale = s0 * s0;
   bool bad = false;
-  const double* src = b0;
-  double* dst = b1;
-#pragma unroll 1
-  for (int k = 0; k < np; k += 2) {
-    const double2 pc0 = *reinterpret_cast<const double2*>(src + k + ld * k);         // pivot block, column 0
-    const double2 pc1 = *reinterpret_cast<const double2*>(src + k + ld * (k + 1));   // pivot block, column 1
+  // per-thread strip offsets, computed once: strip (rows i0, i0+1 ; column j)
+  int offA[NQ], offI[NQ], offJ[NQ], jq[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int s2 = tid + q * GT, sc = s2 < NS ? s2 : 0;
+    const int i0 = (sc % MT) * 2, j = sc / MT;
+    offI[q] = i0; offJ[q] = ld * j; offA[q] = i0 + ld * j; jq[q] = s2 < NS ? j : -8;
+  }
+  // one step: reads src, writes dst (distinct buffers), one barrier.  The update is written with the adjugate, P^-1 = adj(P) / det: every
+  // product is formed while the reciprocal of det is still in flight and 1/det enters in the last FMA only.
+  auto step = [&](const double* __restrict__ src, double* __restrict__ dst, int k) {
+    const double* colk = src + ld * k;
+    const double2 pc0 = *reinterpret_cast<const double2*>(colk + k);          // pivot block, column 0
+    const double2 pc1 = *reinterpret_cast<const double2*>(colk + ld + k);     // pivot block, column 1
     double2 a[NQ], c0[NQ], c1[NQ], pj[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-      const int s2 = tid + q * GT;
-      if (s2 < NS) {
-        const int i0 = (s2 % MT) * 2, j = s2 / MT;
-        a[q] = *reinterpret_cast<const double2*>(src + i0 + ld * j);
-        c0[q] = *reinterpret_cast<const double2*>(src + i0 + ld * k);
-        c1[q] = *reinterpret_cast<const double2*>(src + i0 + ld * (k + 1));
-        pj[q] = *reinterpret_cast<const double2*>(src + k + ld * j);
-      }
+      a[q] = *reinterpret_cast<const double2*>(src + offA[q]);
+      c0[q] = *reinterpret_cast<const double2*>(colk + offI[q]);
+      c1[q] = *reinterpret_cast<const double2*>(colk + ld + offI[q]);
+      pj[q] = *reinterpret_cast<const double2*>(src + offJ[q] + k);
     }
     const double det = fma(pc0.x, pc1.y, -pc1.x * pc0.y);
     if (!(fabs(det) > 1e-28 * scale)) bad = true;
     const double id = fast_rcp(det);
-    const double i00 = pc1.y * id, i01 = -pc1.x * id, i10 = -pc0.y * id, i11 = pc0.x * id;   // inverse of the pivot block
+    const double j00 = pc1.y, j01 = -pc1.x, j10 = -pc0.y, j11 = pc0.x;   // adj(P)
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
-      const int s2 = tid + q * GT;
-      if (s2 < NS) {
-        const int i0 = (s2 % MT) * 2, j = s2 / MT;
+      if (jq[q] >= 0) {
+        const int j = jq[q];
         const bool inK = (j == k) || (j == k + 1);
-        double v0 = fma(i00, pj[q].x, i01 * pj[q].y), v1 = fma(i10, pj[q].x, i11 * pj[q].y);   // P^-1 A[K,j]
-        if (j == k) { v0 = i00; v1 = i10; }
-        if (j == k + 1) { v0 = i01; v1 = i11; }
+        double v0 = fma(j00, pj[q].x, j01 * pj[q].y), v1 = fma(j10, pj[q].x, j11 * pj[q].y);   // adj(P) A[K,j]
+        if (j == k) { v0 = j00; v1 = j10; }
+        if (j == k + 1) { v0 = j01; v1 = j11; }
+        const double x0 = fma(c0[q].x, v0, c1[q].x * v1), x1 = fma(c0[q].y, v0, c1[q].y * v1);
         const double ax = inK ? 0.0 : a[q].x, ay = inK ? 0.0 : a[q].y;
-        double r0 = fma(-c0[q].x, v0, fma(-c1[q].x, v1, ax));
-        double r1 = fma(-c0[q].y, v0, fma(-c1[q].y, v1, ay));
-        if (i0 == k) { r0 = v0; r1 = v1; }
-        *reinterpret_cast<double2*>(dst + i0 + ld * j) = make_double2(r0, r1);
+        double r0 = fma(-x0, id, ax), r1 = fma(-x1, id, ay);
+        if (offI[q] == k) { r0 = v0 * id; r1 = v1 * id; }
+        *reinterpret_cast<double2*>(dst + offA[q]) = make_double2(r0, r1);
       }
     }
     if (GT == kAsmThreads) __syncthreads(); else if (GT == 32) __syncwarp(); else bar_sync_named(barId, GT);
-    const double* tsw = dst; dst = const_cast<double*>(src); src = tsw;
-  }
+  };
+#pragma unroll 1
+  for (int k = 0; k + 2 < np; k += 4) { step(b0, b1, k); step(b1, b0, k + 2); }
+  if ((np / 2) & 1) step(b0, b1, np - 2);
   if (bad) atomicOr(flag, 1);
 }
 

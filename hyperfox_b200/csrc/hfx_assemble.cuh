@@ -1699,6 +1699,7 @@ inline cudaError_t launch_assemble_t(const AsmParams& p, int nSM, cudaStream_t s
   constexpr int nN = C::nN;
   constexpr int TPE = nN <= 6 ? 32 : nN <= 10 ? (DIM == 3 ? 128 : 64) : nN <= 15 ? 128 : 256;
   if (getenv("HFX_ONE_GROUP")) return launch_assemble_tpe<DIM, P, 256>(p, nSM, st);   // experiments / A-B comparison
+  if (DIM == 3 && P == 2 && getenv("HFX_TPE64")) return launch_assemble_tpe<DIM, P, (DIM == 3 && P == 2) ? 64 : TPE>(p, nSM, st);
   return launch_assemble_tpe<DIM, P, TPE>(p, nSM, st);
 }
 

@@ -1023,6 +1023,7 @@ int hfx_field_set(hfx_ctx* c, const char* name, int type, int nObj, int nVal, co
     need(c->topoSet, "Field", "Field", "the mesh must be set before creating fields");
     need(type == HFX_FIELD_NODE || type == HFX_FIELD_CELL || type == HFX_FIELD_FACE, "Field", "Field", "unknown field type");
     DField& f = c->fields[name];
+    if (f.pendingPieces > 0) { for (int k = 0; k < 2; k++) HFX_CUDA(cudaStreamSynchronize(c->stCopy[k])); f.pendingPieces = 0; }   // an asynchronous upload of the same field is superseded
     f.type = type; f.nObj = nObj; f.nVal = nVal; f.dbl = dbl;
     f.d.upload(vals, (size_t)field_len(c, f), c->st);
     HFX_CUDA(cudaStreamSynchronize(c->st));

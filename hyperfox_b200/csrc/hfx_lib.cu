@@ -1352,8 +1352,8 @@ int hfx_recover(hfx_ctx* c) {
     HFX_CUDA(cudaSetDevice(c->device));
     need(c->assembled, "HDGSolver", "solve", "system must be assembled before solving");
     const int nD = c->md.nDOF, t = c->nNf * nD, u = c->nN * nD, q = u * c->dim, l = c->nFc * t;
-    int grid = std::min(c->nCells, c->nSM * 16);
-    int bs = 256;
+    int grid = std::min(c->nCells, c->nSM * 32);
+    int bs = getenv("HFX_REC_BS") ? atoi(getenv("HFX_REC_BS")) : 128;   // 128 threads: 16 elements in flight per SM (thread- and shared-memory-limited)
     (void)t;
     const int chunkRows = std::max(1, std::min(u + q, 4096 / std::max(1, l / 2)));
     const size_t shm = ((size_t)((l + 1) & ~1) + (size_t)chunkRows * (l / 2)) * sizeof(double);

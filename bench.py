@@ -176,7 +176,8 @@ def main():
     # the throughput counts OWNED cells only, the ghost layer is overhead.
     nOwned = nTot
     if world > 1:
-        part = partition.partition_vector(nTot, world)
+        part = partition.partition_vector(nTot, world)   # (box_partition_vector has the smaller cut, but 55 is odd: its 28^3 / 27^3 boxes
+                                                         #  are 5.5 % out of balance, more than the slabs' extra ghost layer costs)
         prob = partition.rank_problem(verts, lin, part, rank, dim)
         lverts, lcells, nOwned = prob["verts"], prob["lin_cells"], int(prob["owned_cells"].size)
     else:

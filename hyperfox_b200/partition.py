@@ -2,7 +2,8 @@
 
 The reference partitions cells with Zoltan GRAPH/PHG (src/parallel/ZoltanPartitioner.cpp:14-32,42-56); Zoltan is not available here
 and its output is not pinned by any reference test, so the harness uses a deterministic stand-in: contiguous element ranges of the
-lexicographically numbered Kuhn mesh (= coordinate slabs), or any externally supplied partition vector.  Global ids are assigned
+lexicographically numbered Kuhn mesh (= coordinate slabs; `box_partition_vector` gives 2/4/8 coordinate boxes), or any externally supplied
+partition vector.  Global ids are assigned
 before partitioning, as in the reference (Partitioner.cpp:13-36), so assembled entries do not depend on the partition.
 Assembly needs no exchange; the faces shared between ranks are what a trace halo exchange would carry.
 """
@@ -19,6 +20,28 @@ def partition_vector(n_total, world):
         e0, e1 = slab_range(n_total, r, world)
         p[e0:e1] = r
     return p
+
+
+def box_partition_vector(N, world, dim=3):
+    """Coordinate boxes of the N^dim Kuhn mesh (cell id = cube id * dim! + k, cube id lexicographic with x fastest): the stand-in for a
+    graph partition with a small cut (recursive coordinate bisection into 2/4/8 boxes).  world = 2^a is split
+    along z, then y, then x, one bisection per axis in turn; any other world size falls back to slabs."""
+    import math
+    a = int(round(math.log2(world))) if world > 0 else 0
+    fact = {2: 2, 3: 6}[dim]
+    if world < 1 or (1 << a) != world:
+        return partition_vector(N ** dim * fact, world)
+    p = [1] * dim                                  # boxes per axis (x, y[, z])
+    for k in range(a):
+        p[dim - 1 - (k % dim)] *= 2
+    ci = np.arange(N)
+    if dim == 3:
+        kk, jj, ii = np.meshgrid(ci, ci, ci, indexing="ij")
+        b = ((kk * p[2] // N) * p[1] + (jj * p[1] // N)) * p[0] + (ii * p[0] // N)
+    else:
+        jj, ii = np.meshgrid(ci, ci, indexing="ij")
+        b = (jj * p[1] // N) * p[0] + (ii * p[0] // N)
+    return np.repeat(b.ravel().astype(np.int32), fact)
 
 
 def extract_submesh(verts, lin_cells, owned):

@@ -6,10 +6,11 @@ import pytest
 from hyperfox_b200 import capi, meshgen, partition as P
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_ownership_and_halo_lists_are_consistent(world):
+@pytest.mark.parametrize("world,boxes", [(2, False), (4, False), (8, False), (2, True), (4, True), (8, True)])
+def test_ownership_and_halo_lists_are_consistent(world, boxes):
     v, c = meshgen.kuhn_linear(4, 3)
-    part = P.partition_vector(c.shape[0], world)
+    part = P.box_partition_vector(4, world, 3) if boxes else P.partition_vector(c.shape[0], world)
+    assert part.shape[0] == c.shape[0] and np.array_equal(np.bincount(part, minlength=world), np.full(world, c.shape[0] // world))
     c2f, f2c = P.global_linear_topology(c, 3)
     probs = [P.rank_problem(v, c, part, r, 3, c2f, f2c) for r in range(world)]
     # every face is owned by exactly one rank (ZoltanPartitioner.cpp:83-133: the face travels with one of its cells)

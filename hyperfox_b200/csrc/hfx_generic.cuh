@@ -152,7 +152,10 @@ __device__ inline double* cta_invert_np(double* b0, double* b1, int n, int* stat
   return src;
 }
 
-__global__ void __launch_bounds__(kGenThreads, 2) hdg_generic_kernel(const GenParams P) {
+#ifndef HFX_GEN_MINBLOCKS
+#define HFX_GEN_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_kernel(const GenParams P) {
   const AsmParams& p = P.a;
   const int dim = P.dim, nN = P.nN, nNf = P.nNf, nFc = P.nFc, nIP = P.nIP, nIPf = P.nIPf, nD = P.nD;
   const GenWs z(dim, nN, nNf, nFc, nIP, nIPf, nD);

@@ -1305,7 +1305,7 @@ int hfx_assemble(hfx_ctx* c) {
       const GenWs z(g.dim, g.nN, g.nNf, g.nFc, g.nIP, g.nIPf, g.nD);
       const size_t smemBase = gen_smem_bytes(g.nN, g.nNf, g.nFc, g.nD, g.dim, g.nIPf);
       // the operands of the condensation products move into shared memory as far as one CTA per SM allows (small elements keep several CTAs per SM)
-      const size_t smemCap = (getenv("HFX_GEN_ONE_CTA") ? 226 : 112) * 1024;   // default: two CTAs per SM stay resident
+      const size_t smemCap = (getenv("HFX_GEN_ONE_CTA") ? 226 : (HFX_GEN_MINBLOCKS == 3 ? 74 : 112)) * 1024;   // default: two CTAs per SM stay resident
       const size_t smem = smemBase + (getenv("HFX_GEN_NO_SMEM_OPERANDS") ? (std::fill(g.smOpt, g.smOpt + 6, -1), (size_t)0)
                                                                         : gen_smem_optional(g.dim, g.nN, g.nNf, g.nFc, g.nIP, g.nD, smemCap > smemBase ? smemCap - smemBase : 0, g.smOpt));
       static size_t smemSet = 0;

@@ -37,6 +37,7 @@ struct AsmParams {
   // fields
   const double* tau; int tauVals;
   const double* diff; int diffComps; int diffIsCell;
+  double diffConst;           // D = diffConst * I when there is no diffusion field (1, or the value of a scalar DiffusionTensor that is constant over the mesh)
   const double* vel;
   const double* srcIP; const double* reacIP;
   const double* solOld;
@@ -496,6 +497,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   const bool euler = p.timeScheme == 1;
   const double ts = euler ? p.dt : 1.0;   // Euler::apply scales the u rows (Su, Fu) by dt before adding the mass terms (Euler.cpp:28-32)
   const bool diffField = hasDiff && p.diffComps > 0 && p.diff;
+  const double dsc = hasDiff ? (diffField ? 1.0 : p.diffConst) : 0.0;   // scale of the D = c I blocks (Suq, Slq)
   const bool needSuu = hasConv || hasReac || euler;   // bulk part of Suu: -C^T, reaction mass, Euler mass
   // All-reference path: a straight-sided element of a Laplace-type model (no convection / reaction / time scheme / diffusion field)
   // whose tau is constant on each face has EVERY block of its local matrix as a scalar combination of reference matrices
@@ -776,7 +778,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
             double2 vs = make_double2(0.0, 0.0);
 #pragma unroll
             for (int r = 0; r < DIM; r++) { vs.x = fma(Ii[d][r], sr[r].x, vs.x); vs.y = fma(Ii[d][r], sr[r].y, vs.y); }
-            SUQ2[d * NA2 + idx2] = hasDiff ? make_double2(ts * fma(det, vs.x, fq[d].x), ts * fma(det, vs.y, fq[d].y)) : make_double2(0.0, 0.0);
+            SUQ2[d * NA2 + idx2] = make_double2(ts * dsc * fma(det, vs.x, fq[d].x), ts * dsc * fma(det, vs.y, fq[d].y));
           }
         } else if (item < I_F) {
           const int ib = item - I_B;
@@ -1044,7 +1046,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
             for (int r = 0; r < DIM; r++) { vs = fma(Ii[d][r], sr[r], vs); va = fma(Ii[d][r], ar[r], va); }
             vs *= det;
             if (!affAB) SQU[(d * nN + k) * nNp + n] = vs;                                 // right operand of A = W Squ (general P4 path)
-            if (!diffField && n < nN) SUQ[(d * nN + n) * nNp + k] = hasDiff ? vs : 0.0;   // Suq_d bulk part with D = I
+            if (!diffField && n < nN) SUQ[(d * nN + n) * nNp + k] = dsc * vs;   // Suq_d bulk part with D = c I
             if (affAB) A[d * nN * nNp + idx] = va;                                        // A_d column-major: idx = n * nNp + m
           }
         }
@@ -1150,7 +1152,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
                   if (isSqu) {
                     const int d = m / nN, kk = m % nN;
                     SQU[(d * nN + kk) * nNp + n] = c[j][h];                               // right operand of A = W Squ
-                    if (!diffField) SUQ[(d * nN + n) * nNp + kk] = hasDiff ? c[j][h] : 0.0;   // left operand of K, R
+                    if (!diffField) SUQ[(d * nN + n) * nNp + kk] = dsc * c[j][h];   // left operand of K, R (D = c I)
                   } else {
                     SUU[m + nNp * n] = c[j][h];
                   }
@@ -1282,7 +1284,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           const double* fw = FW + f * NW * FWS + a + tp * b;
           suu += ts * fw[kTau * FWS];
 #pragma unroll
-          for (int d = 0; d < DIM; d++) suq[d] += hasDiff ? fw[(kDNe + d) * FWS] : 0.0;
+          for (int d = 0; d < DIM; d++) suq[d] += dsc * fw[(kDNe + d) * FWS];
         }
       }
       SUU[i + nNp * j] = suu;
@@ -1525,7 +1527,9 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
           const bool live = (k < KTOT) && (k < t || hasDiff);
           double av[TT], bv[NTW9];
 #pragma unroll
-          for (int i = 0; i < TT; i++) av[i] = live ? fwf[off.x + acl[i]] : 0.0;
+          const double asc = k < t ? 1.0 : dsc;   // Slq = -(D n) mass: the n_d masses scaled by c when D = c I
+#pragma unroll
+          for (int i = 0; i < TT; i++) av[i] = live ? asc * fwf[off.x + acl[i]] : 0.0;
           const double* brow = sm + off.y;
 #pragma unroll
           for (int j = 0; j < NTW9; j++) bv[j] = brow[ncl[j]];

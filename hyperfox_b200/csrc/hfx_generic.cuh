@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
         DV[ip] = dv;
         for (int m = 0; m < dim; m++) for (int r = 0; r < dim; r++) IJ[ip * dd + m * dim + r] = I[m][r];   // invJ(m,r): x_m <- xi_r
         for (int c = 0; c < dd; c++) {
-          double s = ((c / dim) == (c % dim)) ? 1.0 : 0.0;
+          double s = ((c / dim) == (c % dim)) ? (diffField ? 1.0 : p.diffConst) : 0.0;
           if (diffField) { s = 0.0; for (int i = 0; i < nN; i++) s = fma(p.shape[ip * nN + i], DN[i * dd + c], s); }
           DIP[ip * dd + c] = s;
         }
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
         for (int m = 0; m < dim; m++) NRM[fi * dim + m] = nv[m];
         for (int c = 0; c < sT; c++) { double s = 0.0; for (int a = 0; a < nNf; a++) s = fma(TAUn[(f * nNf + a) * sT + c], FSHs[ip * nNf + a], s); TAUS[fi * sT + c] = s; }
         for (int c = 0; c < dd; c++) {
-          double s = ((c / dim) == (c % dim)) ? 1.0 : 0.0;
+          double s = ((c / dim) == (c % dim)) ? (diffField ? 1.0 : p.diffConst) : 0.0;
           if (diffField) { s = 0.0; for (int a = 0; a < nNf; a++) s = fma(FSHs[ip * nNf + a], DN[fn[a] * dd + c], s); }
           DIP[(nIP + fi) * dd + c] = s;
         }
@@ -492,7 +492,7 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
                 if (j >= nN) continue;
                 const double v = h ? v1 : v0;
                 const bool writeSuq = (pass == 1) || !diffField;
-                double suq = hasDiff ? v : 0.0;
+                double suq = hasDiff ? (diffField ? v : p.diffConst * v) : 0.0;
                 if (writeSuq && hasDiff) for (int f = 0; f < nFc; f++) {
                   const int a = NIF[f * nN + i], b = NIF[f * nN + j];
                   if (a >= 0 && b >= 0) suq -= FDN[(f * dim + d) * nNf * nNf + a * nNf + b];

@@ -393,6 +393,15 @@ __global__ void block_vals_to_csr_kernel(int nFaces, int t, const long long* __r
   for (int g = 0; g < m; g++) for (int b = 0; b < t; b++) out[s0 + (long long)a * m * t + g * t + b] = vals[s0 + ((long long)g * t + a) * t + b];
 }
 
+// is a scalar coefficient field constant?  out[0] = v[0], out[1] != 0 if some entry differs from it
+__global__ void field_is_const_kernel(long long n, const double* __restrict__ v, double* __restrict__ out) {
+  const double v0 = v[0];
+  bool diff = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) diff |= (v[i] != v0);
+  if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = v0;
+  if (__syncthreads_or(diff) && threadIdx.x == 0) out[1] = 1.0;   // (benign race: every writer stores the same value)
+}
+
 // FP64 FMA peak probe: 8 independent register-resident DFMA chains per thread
 __global__ void dfma_peak_kernel(int iters, double* out) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -675,7 +684,7 @@ struct hfx_ctx {
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
   DBuf<long long> dFaceRowStart, dBlockCount, dTotal;
   long long nnz = 0;
-  DBuf<double> dU, dQ, dU0, dQ0, dS, dS0, dVals, dRhs;
+  DBuf<double> dU, dQ, dU0, dQ0, dS, dS0, dVals, dRhs, dMinMax;
   DBuf<int> dStatus;
   DBuf<long long> dProf; bool profOn = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -1207,7 +1216,7 @@ int hfx_assemble(hfx_ctx* c) {
     HFX_CUDA(cudaSetDevice(c->device));
     need(c->allocated, "HDGSolver", "assemble", "the solver must be initialized and allocated before assembling.");
     AsmParams p{};
-    p.nCells = c->nCells;
+    p.nCells = c->nCells; p.diffConst = 1.0;
     p.elemX = c->dElemX.p; p.cells = c->dCells.p; p.cell2face = c->dC2F.p;
     p.fperm = c->dFperm.p; p.tauSide = c->dTauSide.p; p.elemPos = c->dElemPos.p;
     p.faceRowStart = c->dFaceRowStart.p; p.faceNnb = c->dNnb.p; p.faceBC = c->dFaceBC.p; p.faceInterior = c->dInterior.p;
@@ -1221,6 +1230,14 @@ int hfx_assemble(hfx_ctx* c) {
       const int comps = diff->type == HFX_FIELD_NODE ? diff->nObj * diff->nVal : diff->nVal;
       need(comps == 1 || comps == c->dim * c->dim, "HDGDiffusionSource", "parseDiffusionVals", "the dimension of the diffusion tensor vales are not correct, they should be either scalar or tensor of the dimension of the reference element");
       p.diff = diff->d.p; p.diffComps = comps; p.diffIsCell = diff->type == HFX_FIELD_CELL;
+      if (comps == 1 && !getenv("HFX_NO_CONST_DIFF")) {   // a scalar diffusion field that is constant over the mesh is D = c I: no field work in the kernels
+        if (diff->pendingPieces > 0) { for (int k = 0; k < 2; k++) HFX_CUDA(cudaStreamSynchronize(c->stCopy[k])); }
+        c->dMinMax.alloc(2); c->dMinMax.zero(c->st);
+        field_is_const_kernel<<<c->nSM * 4, 256, 0, c->st>>>((long long)diff->d.n, diff->d.p, c->dMinMax.p);
+        double mm[2] = {0.0, 1.0};
+        c->dMinMax.download(mm, 2, c->st);
+        if (mm[1] == 0.0) { p.diff = nullptr; p.diffComps = 0; p.diffConst = mm[0]; }
+      }
     }
     if (p.opmask & HFX_OP_CONVECTION) {
       DField* vel = find_field(c, "Velocity");

@@ -50,7 +50,9 @@ def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="di
         fields["Tau"] = 0.5 + rng.random((nF, nNf, 2))
     else:
         fields["Tau"] = np.ones((nF, nNf, 1)) if model == "laplace" else 0.5 + rng.random((nF, nNf, 1))
-    if diff == "scalar":
+    if diff == "const":      # a scalar diffusion field that happens to be constant: D = c I (the kernels then skip all field work)
+        fields["DiffusionTensor"] = np.full((nodes.shape[0], 1), 0.37)
+    elif diff == "scalar":
         fields["DiffusionTensor"] = 0.5 + rng.random((nodes.shape[0], 1))
     elif diff == "tensor":
         A = rng.standard_normal((nodes.shape[0], dim, dim)) * 0.2

@@ -115,6 +115,21 @@ def test_all_reference_path(dim, order, model, bc, mixed, monkeypatch):
         assert H.rel_err(a[name], b[name]) < TOL_ENTRIES, name
 
 
+@pytest.mark.parametrize("dim,order,model", [(3, 3, "diffsrc"), (2, 2, "diffsrc"), (3, 3, "cdrs"), (2, 4, "cdrs"), (3, 4, "cdrs"), (3, 2, "euler")])
+def test_constant_scalar_diffusion_field(dim, order, model, monkeypatch):
+    """A scalar DiffusionTensor field that is constant over the mesh is D = c I: the kernels scale the D = I blocks instead of
+    interpolating the field (and a Laplace-type model stays on the all-reference path).  Same result as the field path."""
+    case = H.make_case(dim, order, N=2 if order == 4 and dim == 3 else 3, perturb=0.1, model=model, diff="const", tau_double=model != "euler", seed=31)
+    if model == "diffsrc":
+        case["fields"]["Tau"][:] = case["fields"]["Tau"][:, :1, :]      # face-constant tau: all-reference path with c != 1
+    o, s, fm = compare(case)
+    monkeypatch.setenv("HFX_NO_CONST_DIFF", "1")
+    s2, fm2, _ = H.run_device(case)
+    a, b = s.getLocal(), s2.getLocal()
+    for name in ("S", "S0", "U", "Q", "U0", "Q0"):
+        assert H.rel_err(a[name], b[name]) < TOL_RECOVERY, name
+
+
 def test_reassembly_is_bit_reproducible():
     """Deterministic scatter: two assemblies of the same inputs give bit-identical CSR values (<= 2 contributors per entry)."""
     case = H.make_case(3, 3, N=3, model="cdrs", diff="scalar", tau_double=True)

@@ -630,7 +630,15 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         if (kRefSrcPf) { if (tid >= 128 && tid < 128 + nIP) LW[nIP + tid - 128] = ts * pfSrc * WQ[tid - 128]; }
         else for (int i = tid; i < nIP; i += NT) LW[nIP + i] = ts * p.srcIP[(size_t)e * nIP + i] * WQ[i];
       }
-    } else stageStd();
+    } else {
+      stageStd();
+      if (affAB) {   // straight-sided element of any other model: the geometric blocks still come from staged reference matrices (B^_f in the idle Squ region)
+        for (int i = tid; i < DIM * nN * nNp / 2; i += NT) { cp_async16(A + 2 * i, p.aref + 2 * i); cp_async16(SUQ + 2 * i, p.srefT + 2 * i); }
+        for (int i = tid; i < ev(nFc * nN * t) / 2; i += NT) cp_async16(SQU + 2 * i, p.bref + 2 * i);
+        for (int i = tid; i < FWS / 2; i += NT) cp_async16(Mm + 2 * i, p.mfref + 2 * i);
+      }
+    }
+    const double* const brefS = refCand ? R : SQU;   // where the staged B^_f sits
     const int* cell = p.cells + (size_t)e * nN;
     if (diffField) {
       for (int i = tid; i < nN * D2; i += NT) {
@@ -1034,6 +1042,28 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
           for (int m = 0; m < DIM; m++) J[r][m] = 0.5 * (X[(r + 1) * DIM + m] - X[m]);
         det_inv(J, det, Ii);
+        if (affAB && p.srefT) {
+          // staged reference matrices, combined in place: A^_r -> A_d, S^_r^T -> Suq_d bulk part (D = c I)
+          constexpr int NA2 = nN * nNp / 2;
+          double2* const A2 = reinterpret_cast<double2*>(A);
+          double2* const SUQ2 = reinterpret_cast<double2*>(SUQ);
+          for (int idx2 = tid - TOFF; idx2 < NA2; idx2 += NT - TOFF) {
+            double2 ar[DIM], sr[DIM];
+#pragma unroll
+            for (int r = 0; r < DIM; r++) { ar[r] = A2[r * NA2 + idx2]; sr[r] = SUQ2[r * NA2 + idx2]; }
+#pragma unroll
+            for (int d = 0; d < DIM; d++) {
+              double2 va = make_double2(0.0, 0.0), vs = make_double2(0.0, 0.0);
+#pragma unroll
+              for (int r = 0; r < DIM; r++) {
+                va.x = fma(Ii[d][r], ar[r].x, va.x); va.y = fma(Ii[d][r], ar[r].y, va.y);
+                vs.x = fma(Ii[d][r], sr[r].x, vs.x); vs.y = fma(Ii[d][r], sr[r].y, vs.y);
+              }
+              A2[d * NA2 + idx2] = va;
+              SUQ2[d * NA2 + idx2] = make_double2(dsc * det * vs.x, dsc * det * vs.y);
+            }
+          }
+        } else
         for (int idx = tid - TOFF; idx < nN * nNp; idx += NT - TOFF) {
           double sr[DIM], ar[DIM];
 #pragma unroll
@@ -1210,7 +1240,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       for (int idx = tid; idx < nFc * FWS; idx += NT) {
         const int f = idx / FWS, ab = idx - f * FWS;
         const double* gf = GEO + D2 + 1 + f * (DIM + 1);
-        const double sc = -gf[DIM] * __ldg(p.mfref + ab);
+        const double sc = -gf[DIM] * ((affAB && p.srefT) ? Mm[ab] : __ldg(p.mfref + ab));
 #pragma unroll
         for (int d = 0; d < DIM; d++) FW[(f * NW + kN + d) * FWS + ab] = sc * gf[d];
       }
@@ -1258,7 +1288,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
       constexpr int NIB = (nFc * nN * t + NT - 1) / NT;
       double bv[NIB];
 #pragma unroll
-      for (int it = 0; it < NIB; it++) { const int idx = tid + it * NT; bv[it] = idx < nFc * nN * t ? __ldg(p.bref + idx) : 0.0; }
+      for (int it = 0; it < NIB; it++) { const int idx = tid + it * NT; bv[it] = idx < nFc * nN * t ? (p.srefT ? brefS[idx] : __ldg(p.bref + idx)) : 0.0; }
 #pragma unroll
       for (int it = 0; it < NIB; it++) {
         const int idx = tid + it * NT;

@@ -51,7 +51,7 @@ struct DBuf {  // device buffer
 };
 
 struct DField { int type = 0, nObj = 0, nVal = 0, dbl = 0; DBuf<double> d;
-                std::vector<cudaEvent_t> ev; int pendingPieces = 0; /* asynchronous upload in flight: events per piece */ };
+                std::vector<cudaEvent_t> ev; int pendingPieces = 0; int copyStream = -1; /* asynchronous upload in flight: events per piece; a field keeps its copy stream */ };
 
 // ---------------------------------------------------------------------------------------------------------------------
 // device kernels other than the fused assembly
@@ -1054,7 +1054,8 @@ int hfx_field_set_async(hfx_ctx* c, const char* name, int type, int nObj, int nV
     const bool pieces = type == HFX_FIELD_FACE && c->allocated && !c->chunkFaceEnd.empty() && c->chunkFaceEnd.back() == c->nFaces;
     const int K = pieces ? (int)c->chunkFaceEnd.size() : 1;
     while ((int)f.ev.size() < K) { cudaEvent_t e; HFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); f.ev.push_back(e); }
-    cudaStream_t cs = c->stCopy[c->copyRR]; c->copyRR ^= 1;
+    if (f.copyStream < 0) { f.copyStream = c->copyRR; c->copyRR ^= 1; }   // successive uploads of one field stay ordered on one stream
+    cudaStream_t cs = c->stCopy[f.copyStream];
     const size_t per = (size_t)nObj * nVal;
     size_t b = 0;
     for (int k = 0; k < K; k++) {

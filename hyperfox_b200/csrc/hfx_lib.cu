@@ -270,6 +270,58 @@ __global__ void diag_csr_kernel(long long n, const long long* __restrict__ rowpt
   dinv[row] = d != 0.0 ? 1.0 / d : 1.0;
 }
 
+// Face-block Jacobi (pc = 2): inverse of the t x t diagonal block of every face, one warp per face, unpivoted Gauss-Jordan in the warp's
+// slice of shared memory (the diagonal blocks of the trace matrix are definite, or the identity on Dirichlet faces).  The inverse is
+// stored TRANSPOSED (column-major) so that the application reads it coalesced.  t <= 32.
+__global__ void block_diag_inverse_kernel(int nFaces, int t, int nFc2, const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
+                                          const int* __restrict__ nbr, const double* __restrict__ vals, double* __restrict__ dinvT) {
+  extern __shared__ double bsm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* A = bsm + (size_t)w * t * t;
+  for (int F = blockIdx.x * nw + w; F < nFaces; F += gridDim.x * nw) {
+    const int m = nnb[F];
+    int g = 0;
+    for (int k = 0; k < m; k++) if (nbr[(size_t)F * nFc2 + k] == F) g = k;
+    const double* blk = vals + rowStart[F] + (long long)g * t * t;
+    for (int i = lane; i < t * t; i += 32) A[i] = blk[i];
+    __syncwarp();
+    for (int k = 0; k < t; k++) {
+      const double piv = A[k * t + k];
+      const double ip = piv != 0.0 ? 1.0 / piv : 1.0;
+      __syncwarp();
+      if (lane < t) A[k * t + lane] = lane == k ? ip : A[k * t + lane] * ip;
+      __syncwarp();
+      const double rk = lane < t ? A[k * t + lane] : 0.0;
+      for (int i = 0; i < t; i++) {
+        if (i == k) continue;
+        const double f = A[i * t + k];
+        __syncwarp();
+        if (lane < t) A[i * t + lane] = lane == k ? -f * ip : fma(-f, rk, A[i * t + lane]);
+      }
+      __syncwarp();
+    }
+    double* out = dinvT + (size_t)F * t * t;
+    for (int i = lane; i < t * t; i += 32) { const int a = i / t, b = i - a * t; out[b * t + a] = A[i]; }
+    __syncwarp();
+  }
+}
+// z_F = D_F^-1 r_F with r = b - y or y; one warp per face, lane a owns row a
+__global__ void block_pc_apply_kernel(int nFaces, int t, const double* __restrict__ dinvT, const double* __restrict__ y, const double* __restrict__ b,
+                                      double* __restrict__ z) {
+  const int F = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (F >= nFaces) return;
+  const size_t o = (size_t)F * t;
+  double r = 0.0;
+  if (lane < t) r = b ? b[o + lane] - y[o + lane] : y[o + lane];
+  const double* D = dinvT + (size_t)F * t * t;
+  double acc = 0.0;
+  for (int k = 0; k < t; k++) {
+    const double rk = __shfl_sync(0xffffffffu, r, k);
+    if (lane < t) acc = fma(D[k * t + lane], rk, acc);
+  }
+  if (lane < t) z[o + lane] = acc;
+}
+
 // z = dinv .* (b - y)  or z = dinv .* y
 __global__ void pc_apply_kernel(long long n, const double* __restrict__ dinv, const double* __restrict__ y, const double* __restrict__ b, double* __restrict__ z, int usePC) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -514,6 +566,9 @@ struct LinOp {
   long long n = 0;
   virtual void apply(const double* x, double* y, cudaStream_t st) = 0;
   virtual void diag_inverse(double* dinv, cudaStream_t st) = 0;
+  virtual bool has_block_pc() const { return false; }
+  virtual void block_pc_setup(cudaStream_t) {}
+  virtual void block_pc_apply(const double*, const double*, double*, cudaStream_t) {}   // z = D^-1 (b - y) or D^-1 y
   virtual ~LinOp() {}
 };
 
@@ -540,11 +595,16 @@ struct Krylov {
     V.alloc((size_t)(m + 1) * n); w.alloc(n); tmp.alloc(n); dinv.alloc(n);
     if (!hpin) HFX_CUDA(cudaMallocHost(&hpin, 64 * sizeof(double)));
     const int usePC = o.pc != 0;
-    if (usePC) A.diag_inverse(dinv.p, st);
+    const bool blockPC = o.pc == 2;
+    if (blockPC && !A.has_block_pc()) throw Err("Krylov", "gmres", "the face-block Jacobi preconditioner needs the block-CSR trace operator");
+    if (blockPC) A.block_pc_setup(st); else if (usePC) A.diag_inverse(dinv.p, st);
     const int bs = 256, nb = nblk(n, bs);
+    auto pc_apply = [&](const double* yv, const double* bv, double* zv) {
+      if (blockPC) A.block_pc_apply(yv, bv, zv, st); else pc_apply_kernel<<<nb, bs, 0, st>>>(n, dinv.p, yv, bv, zv, usePC);
+    };
     HFX_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), st));
     // ||M^-1 b||
-    pc_apply_kernel<<<nb, bs, 0, st>>>(n, dinv.p, b, nullptr, w.p, usePC);
+    pc_apply(b, nullptr, w.p);
     dots(n, 1, w.p, n, w.p, st, hpin);
     const double bnorm = std::sqrt(hpin[0]);
     const double tol = std::max(o.rtol * bnorm, 1e-50);
@@ -554,7 +614,7 @@ struct Krylov {
     bool conv = res <= tol;
     while (!conv && its < o.maxits) {
       A.apply(x, tmp.p, st);
-      pc_apply_kernel<<<nb, bs, 0, st>>>(n, dinv.p, tmp.p, b, V.p, usePC);
+      pc_apply(tmp.p, b, V.p);
       dots(n, 1, V.p, n, V.p, st, hpin);
       const double beta = std::sqrt(hpin[0]);
       res = beta;
@@ -565,7 +625,7 @@ struct Krylov {
       int k = 0;
       for (; k < m && its < o.maxits; k++) {
         A.apply(V.p + (size_t)k * n, tmp.p, st);
-        pc_apply_kernel<<<nb, bs, 0, st>>>(n, dinv.p, tmp.p, nullptr, w.p, usePC);
+        pc_apply(tmp.p, nullptr, w.p);
         dots(n, k + 1, V.p, n, w.p, st, hpin);
         for (int j = 0; j <= k; j++) hcol[j] = hpin[j];
         HFX_CUDA(cudaMemcpyAsync(hdev.p + 32, hpin, (k + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -684,7 +744,7 @@ struct hfx_ctx {
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
   DBuf<long long> dFaceRowStart, dBlockCount, dTotal;
   long long nnz = 0;
-  DBuf<double> dU, dQ, dU0, dQ0, dS, dS0, dVals, dRhs, dMinMax;
+  DBuf<double> dU, dQ, dU0, dQ0, dS, dS0, dVals, dRhs, dMinMax, dBlockInv;
   DBuf<int> dStatus;
   DBuf<long long> dProf; bool profOn = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
@@ -728,6 +788,16 @@ struct FaceOp : LinOp {
   }
   void diag_inverse(double* dinv, cudaStream_t st) override {
     diag_face_kernel<<<nblk(n, 256), 256, 0, st>>>(c->nFaces, c->nNf * c->md.nDOF, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, dinv);
+  }
+  bool has_block_pc() const override { return c->nNf * c->md.nDOF <= 32; }
+  void block_pc_setup(cudaStream_t st) override {
+    const int t = c->nNf * c->md.nDOF;
+    c->dBlockInv.alloc((size_t)c->nFaces * t * t);
+    const size_t shm = (size_t)8 * t * t * sizeof(double);
+    block_diag_inverse_kernel<<<std::min(nblk(c->nFaces, 8), c->nSM * 8), 256, shm, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, c->dBlockInv.p);
+  }
+  void block_pc_apply(const double* y, const double* b, double* z, cudaStream_t st) override {
+    block_pc_apply_kernel<<<nblk((long long)c->nFaces * 32, 256), 256, 0, st>>>(c->nFaces, c->nNf * c->md.nDOF, c->dBlockInv.p, y, b, z);
   }
 };
 
@@ -1387,7 +1457,8 @@ int hfx_solve(hfx_ctx* c, const hfx_solve_opts* opts, hfx_solve_stats* stats) {
     HFX_CUDA(cudaSetDevice(c->device));
     need(c->assembled, "HDGSolver", "solve", "system must be assembled before solving");
     hfx_solve_opts o = opts ? *opts : hfx_solve_opts{0, 1, 30, 1000, 1e-6};
-    need(o.pc == 0 || o.pc == 1, "hfx", "solve", "only point-Jacobi or no preconditioner are available for the trace system");
+    need(o.pc == 0 || o.pc == 1 || o.pc == 2, "hfx", "solve", "preconditioners of the trace system: none (0), point Jacobi (1), face-block Jacobi (2)");
+    if (o.pc == 2 && (o.ksp == 1 || c->nNf * c->md.nDOF > 32)) o.pc = 1;   // CG and blocks beyond one warp keep point Jacobi
     FaceOp A(c);
     const double* b = c->dRhs.p;
     double* x = find_field(c, "Trace")->d.p;

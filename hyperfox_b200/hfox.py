@@ -22,7 +22,7 @@ from .capi import ErrorHandle, check, f64, i32, lcheck, lib, pd, pi
 Node, Cell, Face = 0, 1, 2      # FieldType (src/field/FieldTypes.h); C ABI: HFX_FIELD_NODE/CELL/FACE
 Add, Set = 0, 1                 # AssemblyType.h
 KSPGMRES, KSPCG = 0, 1
-PCNONE, PCJACOBI = 0, 1
+PCNONE, PCJACOBI, PCBJACOBI = 0, 1, 2   # PCBJACOBI: Jacobi on the t x t diagonal blocks of the faces (the block structure of the trace system)
 IMPLICIT = 0
 
 OP_DIFFUSION, OP_CONVECTION, OP_REACTION, OP_SOURCE, OP_UNABU = 1, 2, 4, 8, 16

@@ -1284,11 +1284,11 @@ int hfx_allocate(hfx_ctx* c, int flags) {
     c->dVals.alloc((size_t)c->nnz); c->dRhs.alloc((size_t)nF * t); c->valsCleared = false;
     {   // element chunks for the pipelined assemble (hfx_field_set_async): faces are numbered in order of first appearance over ascending
         // cell ids (Mesh.cpp:183-274), so the cells [0, e) only touch the face-id prefix [0, 1 + max face id of those cells)
-      const int K = 8;
+      const int K = 3;   // chunks 1/16, 3/16, 3/4 of the cells: a short first piece, few launches (each chunk's data is there long before the kernel gets to it)
       c->chunkCellEnd.assign(K, c->nCells); c->chunkFaceEnd.assign(K, c->nFaces);
       int mx = -1; size_t pos = 0;
       for (int k = 0; k < K; k++) {
-        const int ce = (int)((long long)c->nCells * (k + 1) / K);
+        const int ce = k == K - 1 ? c->nCells : (int)((long long)c->nCells >> (k == 0 ? 4 : 2));
         for (; pos < (size_t)ce * c->nFc; pos++) mx = std::max(mx, c->hC2F[pos]);
         c->chunkCellEnd[k] = ce; c->chunkFaceEnd[k] = k == K - 1 ? c->nFaces : mx + 1;
       }

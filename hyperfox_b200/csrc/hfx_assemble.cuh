@@ -1,5 +1,6 @@
 // Fused per-element HDG kernel for sm_100a: geometry -> operator contractions -> structured static condensation ->
-// Dirichlet masking -> deterministic scatter into the global trace matrix, one CTA per element, everything in shared memory.
+// Dirichlet masking -> deterministic scatter into the global trace matrix (block CSR), one thread group per element (32..256 threads
+// by element size), everything in shared memory, the results leave as bulk asynchronous copies.
 //
 // Replaces, per element, the reference's HDGSolver::calcElementalMatrices (src/solver/HDGSolver.cpp:176-359) with
 // Model::compute (src/model/HDG*.cpp), the operators (src/operator/HDGBase.cpp:67-158, HDGDiffusion.cpp:74-145,
@@ -427,7 +428,7 @@ struct AsmSmem {
   static constexpr int oEnd = oGEOR + ev(nFc * (DIM + 2));
   static_assert(ev(nFc * nN * t) <= szR && tp * t <= nNp * nNp, "reference tables are staged in the R and M regions");
   static_assert(nFc * nN * nNp <= nNp * nNp + szSQU, "node-scattered face masses are staged in the W + Squ regions");
-  // S staging [l][ldc] for the coalesced write-out: reuses the dead g/A + M + W span when it is large enough (large elements),
+  // S staging ([l][ldc], or the 16 t x t blocks of the bulk write-out): reuses the dead g/A + M + W span when it is large enough (large elements),
   // otherwise gets its own area (small elements, where shared memory is not the limit)
   static constexpr bool stFits = (oSQU - oG) >= l * ldc;
   static constexpr int oST = stFits ? oG : oEnd;
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   int* CMAP = NLUT + L::nNLUT + nFc * L::nKLUT;                                    // (bulk write-out) [l+1], shares the POSROW area
   int* POSROW = NLUT + L::nNLUT + nFc * L::nKLUT;                                  // [nFc][l] column offset of element-local column cc inside a row of face f
   double* A = G;    // A_d aliases g (dead after the contractions)
-  double* ST = sm + L::oST;   // S staging [l][ldc] for the coalesced write-out
+  double* ST = sm + L::oST;   // S staging for the write-out
   double* Um = SQU; // U aliases Squ (dead after A)
   const int tid = threadIdx.x & (TPE - 1), lane = tid & 31, warp = tid >> 5;
   const bool hasDiff = p.opmask & 1, hasConv = p.opmask & 2, hasReac = (p.opmask & 4) && p.reacIP, hasSrc = (p.opmask & 8) && p.srcIP;
@@ -1663,8 +1664,8 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     gsync();
     HFX_PROF(13);
 
-    // ---- P10: write-out.  S: every (row, neighbour-face block) of the element is t contiguous entries of the global face-block CSR,
-    //      already final and in row order in the staging area: one bulk copy each, a bulk reduce-add (f64) where the second element of
+    // ---- P10: write-out.  S: every (face, neighbour face) block of the element is one contiguous t x t block of the global block CSR,
+    //      already final and in face-node order in the staging area: one bulk copy each, a bulk reduce-add (f64) where the second element of
     //      an interior face adds to the same diagonal block (two contributors, zeroed storage: the sum is order independent).
     //      U, Q rows left after P8.  Elements whose sizes break the 16-byte granularity take the per-entry path.
     {

@@ -206,6 +206,21 @@ __device__ __forceinline__ void bulk_add_f64(double* gdst, const double* ssrc, i
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// bulk asynchronous copies global -> shared (TMA, SASS UBLKCP.S.G) completing on an mbarrier
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* sdst, const void* gsrc, int bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  asm volatile("{\n\t.reg .pred p;\n\tMBAR_WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra MBAR_WAIT_%=;\n\t}"
+               ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(phase) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void bar_sync_named(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 // warp-granular dynamic tile queue: every call hands the warp the next 32 consecutive tile ids
@@ -438,7 +453,7 @@ struct AsmSmem {
   static constexpr int nKLUT = (((1 + DIM) * t + 3) / 4) * 4;        // P9 reduction index (kind,b) -> operand offsets
   static constexpr int nInts = 8 + 2 * nFc * t + nFc * nN + nFc * nFc + 5 * nFc + 8 + nNLUT + nFc * nKLUT + nFc * l;   // (KLUT: two 16-bit offsets per entry)
   static_assert(nDoubles < 65536, "16-bit operand offsets");
-  static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * (nFc + l) + 4 * (size_t)nInts;
+  static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * (nFc + l + 1) + 4 * (size_t)nInts;   // (+1: the mbarrier of the bulk loads)
   static constexpr size_t gbytes = (bytes + 15) & ~(size_t)15;   // per element group
 };
 
@@ -476,7 +491,8 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   double* WQ = sm + L::oWQ; double* DSH = sm + L::oDSH; double* FDS = sm + L::oFDS; double* FSH = sm + L::oFSH; double* FFS = sm + L::oFFS;
   long long* ROWS = reinterpret_cast<long long*>(sm + L::nDoubles);   // [nFc] first entry of row (F,0) in vals
   long long* RBASE = ROWS + nFc;                                      // [l] first entry of the CSR row of element-local trace row r
-  int* ISM = reinterpret_cast<int*>(RBASE + l);                       // [nFc] global face ids
+  unsigned long long* MBAR = reinterpret_cast<unsigned long long*>(RBASE + l);   // completion barrier of the bulk loads of the reference matrices
+  int* ISM = reinterpret_cast<int*>(RBASE + l + 1);                   // [nFc] global face ids
   int* FN = ISM + 8;                                                  // [nFc*t] faceNodes
   int* PERM = FN + nFc * t;                                           // [nFc*t] element-local -> face-node position
   int* NIF = PERM + nFc * t;                                          // [nFc*nN] node -> position in face (or -1)
@@ -508,6 +524,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 
   // ---- once per CTA: constant tables; padding lanes must hold finite numbers --------------------------------------------
   for (int i = tid; i < L::nDoubles; i += NT) sm[i] = 0.0;
+  if (tid == 0) { mbar_init(MBAR, 1); fence_proxy_async(); }
   gsync();
   for (int i = tid; i < nFc * t; i += NT) FN[i] = p.faceNodes[i];
   for (int i = tid; i < nFc * nN; i += NT) NIF[i] = p.nodeInFace[i];
@@ -582,6 +599,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
   }
   gsync();
 
+  unsigned mphase = 0;
   long long tprev = clock64();
   for (int e = e0; e < p.eEnd; e += eStride) {
     // ---- P0: commit the prefetched gather -----------------------------------------------------------------------------------
@@ -623,10 +641,14 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     if (refCand) {
       // reference matrices, staged where their combinations end up (A^_r -> A_d and S^_r^T -> Suq_d are combined in place) or in
       // regions that are idle until the condensation (B^_f in R, M^f in M)
-      for (int i = tid; i < DIM * nN * nNp / 2; i += NT) { cp_async16(A + 2 * i, p.aref + 2 * i); cp_async16(SUQ + 2 * i, p.srefT + 2 * i); }
-      for (int i = tid; i < ev(nFc * nN * t) / 2; i += NT) cp_async16(R + 2 * i, p.bref + 2 * i);
-      for (int i = tid; i < FWS / 2; i += NT) cp_async16(Mm + 2 * i, p.mfref + 2 * i);
-      for (int i = tid; i < nFc * nN * nNp / 2; i += NT) cp_async16(Wb + 2 * i, p.eref + 2 * i);   // E_f spans the W and Squ regions
+      // five bulk copies (TMA) issued by one thread, completing on the group's mbarrier: 39 KB at p=3 without a single per-thread copy instruction
+      if (tid == 0) {
+        constexpr int szA = DIM * nN * nNp * 8, szB = ev(nFc * nN * t) * 8, szM = FWS * 8, szE = nFc * nN * nNp * 8;
+        mbar_expect_tx(MBAR, 2 * szA + szB + szM + szE);
+        bulk_load(A, p.aref, szA, MBAR); bulk_load(SUQ, p.srefT, szA, MBAR);
+        bulk_load(R, p.bref, szB, MBAR); bulk_load(Mm, p.mfref, szM, MBAR);
+        bulk_load(Wb, p.eref, szE, MBAR);   // E_f spans the W and Squ regions
+      }
       if (hasSrc) {   // source values times the cubature weights (scaled by det J later)
         if (kRefSrcPf) { if (tid >= 128 && tid < 128 + nIP) LW[nIP + tid - 128] = ts * pfSrc * WQ[tid - 128]; }
         else for (int i = tid; i < nIP; i += NT) LW[nIP + i] = ts * p.srcIP[(size_t)e * nIP + i] * WQ[i];
@@ -726,7 +748,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         for (int i = tid - 64; i < l; i += NT - 64) bad |= (TAU[i] != TAU[(i / t) * t]);
       }
       if (NT <= 64) for (int i = tid; i < l; i += NT) bad |= (TAU[i] != TAU[(i / t) * t]);
-      cp_async_wait_all();
+      mbar_wait(MBAR, mphase); mphase ^= 1;   // the staged reference matrices have landed
       ref = !gsync_or(bad);
       HFX_PROF(5);
       prefetchA(e + eStride);

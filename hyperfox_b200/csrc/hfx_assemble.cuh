@@ -190,6 +190,14 @@ __device__ __forceinline__ double fast_rcp(double x) {   // MUFU seed + two Newt
   r = fma(fma(-x, r, 1.0), r, r);
   return r;
 }
+__device__ __forceinline__ double fast_rsqrt(double x) {   // MUFU seed (2^-22) + two Newton steps: 1/sqrt(x) to ~1 ulp without the sqrt + rcp chain
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  const double h = 0.5 * x;
+  r = fma(fma(-h * r, r, 0.5), r, r);
+  r = fma(fma(-h * r, r, 0.5), r, r);
+  return r;
+}
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gsrc) : "memory");
@@ -705,18 +713,18 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         double nv[DIM], area;
         if (DIM == 2) {
           nv[0] = -J[0][1]; nv[1] = J[0][0];
-          area = sqrt(J[0][0] * J[0][0] + J[0][1] * J[0][1]);
         } else {
           nv[0] = J[0][1] * J[DIM - 2][2 % DIM] - J[0][2 % DIM] * J[DIM - 2][1];
           nv[1] = J[0][2 % DIM] * J[DIM - 2][0] - J[0][0] * J[DIM - 2][2 % DIM];
           nv[DIM - 1] = J[0][0] * J[DIM - 2][1] - J[0][1] * J[DIM - 2][0];
-          const double g00 = J[0][0] * J[0][0] + J[0][1] * J[0][1] + J[0][2 % DIM] * J[0][2 % DIM];
-          const double g11 = J[DIM - 2][0] * J[DIM - 2][0] + J[DIM - 2][1] * J[DIM - 2][1] + J[DIM - 2][2 % DIM] * J[DIM - 2][2 % DIM];
-          const double g01 = J[0][0] * J[DIM - 2][0] + J[0][1] * J[DIM - 2][1] + J[0][2 % DIM] * J[DIM - 2][2 % DIM];
-          area = sqrt(g00 * g11 - g01 * g01);   // sqrt(det(J J^T)) (Operator.cpp:66-69)
         }
+        // |J_0 x J_1| = sqrt(det(J J^T)) (Operator.cpp:66-69; 2-D: |tangent|): the norm of the un-normalised normal is the face measure
+        double nn = 0.0;
+#pragma unroll
+        for (int m = 0; m < DIM; m++) nn = fma(nv[m], nv[m], nn);
+        const double inrm = fast_rsqrt(nn);
+        area = nn * inrm;
         const int v0 = fn[0], vn = OPP[f];
-        const double inrm = fast_rcp(area);
         double prod = 0.0;
 #pragma unroll
         for (int m = 0; m < DIM; m++) { nv[m] *= inrm; prod = fma(X[vn * DIM + m] - X[v0 * DIM + m], nv[m], prod); }   // outward (HDGBase.cpp:43-62)

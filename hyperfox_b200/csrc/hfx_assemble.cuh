@@ -724,18 +724,16 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
         for (int m = 0; m < DIM; m++) nn = fma(nv[m], nv[m], nn);
         const double inrm = fast_rsqrt(nn);
         area = nn * inrm;
+        // outward orientation (HDGBase.cpp:43-62) from the un-normalised normal, beside the rsqrt chain; area * n = the oriented un-normalised normal
         const int v0 = fn[0], vn = OPP[f];
         double prod = 0.0;
 #pragma unroll
-        for (int m = 0; m < DIM; m++) { nv[m] *= inrm; prod = fma(X[vn * DIM + m] - X[v0 * DIM + m], nv[m], prod); }   // outward (HDGBase.cpp:43-62)
-        if (prod > 0.0) {
-#pragma unroll
-          for (int m = 0; m < DIM; m++) nv[m] = -nv[m];
-        }
+        for (int m = 0; m < DIM; m++) prod = fma(X[vn * DIM + m] - X[v0 * DIM + m], nv[m], prod);
+        const double sg = prod > 0.0 ? -1.0 : 1.0;
         double* gf = GEO + D2 + 1 + f * (DIM + 1);
         double* gr = GEOR + f * (DIM + 2);
 #pragma unroll
-        for (int m = 0; m < DIM; m++) { gf[m] = nv[m]; gr[m] = -area * nv[m]; }
+        for (int m = 0; m < DIM; m++) { gr[m] = -sg * nv[m]; gf[m] = sg * nv[m] * inrm; }
         gf[DIM] = area;
         gr[DIM] = TAU[f * t] * area;
         gr[DIM + 1] = area;

@@ -34,8 +34,8 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_ELEM = {1: 16610, 2: 201490, 3: 1325333, 4: 6220333, 5: 23364077}      # SURVEY.md section 8(d), tets
 BYTES_STORE = {1: 3136, 2: 13288, 3: 40256, 4: 99076, 5: 211696}
 # dram__bytes_read.sum + dram__bytes_write.sum of hdg_assemble_kernel per element, from the committed `ncu --set full` capture
-# (profiles/r1_assemble_p3_ncu_full_summary.txt: 3.3474 GB for 82,944 p=3 tets); per-launch traffic = this x elements of the launch
-NCU_TRAFFIC_PER_ELEM = {3: (250170624.0 + 3097262000.0) / 82944.0}
+# (profiles/r1_assemble_p3_ncu_full_summary.txt: 3.3439 GB for 82,944 p=3 tets); per-launch traffic = this x elements of the launch
+NCU_TRAFFIC_PER_ELEM = {3: (248216832.0 + 3095666000.0) / 82944.0}
 
 
 def poisson_inputs(nodes, cells, order, dim=3):

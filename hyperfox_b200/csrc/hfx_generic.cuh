@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
   double* Lm = ws + z.oLm; double* Fv = ws + z.oF; double* GM = ws + z.oGM; double* DV = ws + z.oDV; double* IJ = ws + z.oIJ; double* NRM;
   double* TAUS; double* DIP = ws + z.oDIP; double* VIP = ws + z.oVIP; double* VDN; double* FS; double* TDN;
   double* SIP = ws + z.oSIP; double* DIVS = ws + z.oDIVS; double* X = ws + z.oX; double* TAUn = ws + z.oTAUn; double* DN = ws + z.oDN; double* VN = ws + z.oVN;
-  double* SOL = ws + z.oSOL; double* TR = ws + z.oTR; double* SOLD = ws + z.oSOLD; double* MM = ws + z.oMM; double* W = ws + z.oW; double* FT = ws + z.oFT;
+  double* SOL = ws + z.oSOL; double* TR = ws + z.oTR; double* SOLD = ws + z.oSOLD; double* MM = ws + z.oMM; double* FT = ws + z.oFT;
   double* FCN = ws + z.oFCN; double* FNd = ws + z.oFNd; double* FDN = ws + z.oFDN; double* FONE = ws + z.oFONE; double* BUU = ws + z.oBUU; double* Aq = ws + z.oAq;
   double* Bq = ws + z.oBq; double* Rm = ws + z.oRm; double* Um = ws + z.oUm; double* LW = ws + z.oLW;
   // shared: augmented matrix for the two inverses, scratch rows, integer maps

@@ -1,4 +1,4 @@
-// General per-element HDG kernel (runtime sizes): any simplex dimension / order the reference element supports, any number of
+// General per-element HDG kernel (runtime sizes): any simplex or orthotope dimension / order the reference element supports, any number of
 // DOFs per node, every in-scope operator including the Newton-linearised HDGUNabU (HDGBurgersModel).  It covers what the fused
 // shared-memory kernel (hfx_assemble.cuh) has no instantiation for: 3-D orders 4-5, nDOFsPerNode > 1, HDGUNabU.
 //

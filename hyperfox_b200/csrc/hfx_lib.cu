@@ -736,7 +736,7 @@ struct hfx_ctx {
   std::string err;
   // reference element
   std::unique_ptr<RefElement> re;
-  int dim = 0, order = 0, nN = 0, nNf = 0, nFc = 0, nIP = 0, nIPf = 0;
+  int dim = 0, order = 0, geom = HFX_SIMPLEX, nN = 0, nNf = 0, nFc = 0, nIP = 0, nIPf = 0;
   DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv, dSRef, dSRefT, dERef, dARef, dMFRef, dBRef, dBary;
   DBuf<uint8_t> dAffine;
   DBuf<int> dFaceNodes; DBuf<int8_t> dNodeInFace;
@@ -960,9 +960,10 @@ int hfx_host_compute_faces(int dim, int order, int geom, int nCells, const int* 
 int hfx_refel_set(hfx_ctx* c, int dim, int order, int geom) {
   return guard(c, [&] {
     HFX_CUDA(cudaSetDevice(c->device));
-    need(geom == HFX_SIMPLEX, "ReferenceElement", "setGeometry", "only simplex elements have device kernels in this build");
+    need(geom == HFX_SIMPLEX || geom == HFX_ORTHOTOPE, "ReferenceElement", "setGeometry", "Element type is not yet supported.");
     need(dim == 2 || dim == 3, "ReferenceElement", "setDim", "the device path supports spatial dimensions 2 and 3");
-    c->re.reset(new RefElement(dim, order, kSimplex));
+    c->re.reset(new RefElement(dim, order, geom == HFX_SIMPLEX ? kSimplex : kOrthotope));
+    c->geom = geom;
     const RefElement& re = *c->re;
     const RefElement* fe = re.faceElement();
     c->dim = dim; c->order = order; c->nN = re.numNodes(); c->nNf = fe->numNodes(); c->nFc = re.numFaces(); c->nIP = re.numIPs(); c->nIPf = fe->numIPs();
@@ -1276,7 +1277,8 @@ int hfx_allocate(hfx_ctx* c, int flags) {
     elem_coords_kernel<<<nblk((long long)nC * c->nN * c->dim, 256), 256, 0, c->st>>>((long long)nC * c->nN * c->dim, c->nN, c->dim, c->dNodes.p, c->dCells.p, c->dElemX.p);
     HFX_CUDA(cudaGetLastError());
     c->dAffine.alloc(nC);
-    elem_affine_kernel<<<nblk(nC, 128), 128, 0, c->st>>>(nC, c->nN, c->dim, c->dElemX.p, c->dBary.p, c->dAffine.p);
+    if (c->geom == HFX_SIMPLEX) elem_affine_kernel<<<nblk(nC, 128), 128, 0, c->st>>>(nC, c->nN, c->dim, c->dElemX.p, c->dBary.p, c->dAffine.p);
+    else c->dAffine.zero(c->st);   // quads / hexes: multilinear geometry, Jacobians evaluated at the cubature points (general kernel)
     HFX_CUDA(cudaGetLastError());
     // element blocks (HDGSolver.cpp:93-104) and the global system (linSystem->allocate :81)
     c->dU.alloc((size_t)nC * u * l); c->dQ.alloc((size_t)nC * q * l); c->dU0.alloc((size_t)nC * u); c->dQ0.alloc((size_t)nC * q);
@@ -1351,7 +1353,7 @@ int hfx_assemble(hfx_ctx* c) {
     }
     c->dRhs.zero(c->st); c->dStatus.zero(c->st);
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
-    bool fused = c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
+    bool fused = c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
     // fields still crossing PCIe (hfx_field_set_async): the element chunks start as their face-id prefix has arrived
     std::vector<DField*> pend;
     for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) pend.push_back(&kv.second);

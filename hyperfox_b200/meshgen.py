@@ -106,3 +106,54 @@ def high_order(verts, cells, order, perturb=0.0, seed=20240229):
 def kuhn_mesh(N, order, dim=3, perturb=0.0):
     v, c = kuhn_linear(N, dim)
     return high_order(v, c, order, perturb)
+
+
+def box_mesh(N, order, dim=3, perturb=0.0, seed=20240229):
+    """Structured orthotope mesh of [0,1]^dim ("Hex variant: the N^3 hexes directly"): N^dim quads / hexes of
+    order p, cell id lexicographic (x fastest).  The order-p nodes are the multilinear image of the reference orthotope nodes
+    (ReferenceElement.cpp:885-1004: tensor products of the 1-D Lobatto points); shared nodes are identified through their integer
+    position on the global Lobatto lattice ((N p + 1)^dim points), numbered by first appearance over ascending cell ids.
+    perturb > 0 displaces the interior lattice VERTICES by perturb*h*U(-1,1)^dim before the high-order nodes are placed, which makes
+    the cells genuinely multilinear (non-constant Jacobians)."""
+    t = capi.host_refel_tables(dim, order, 1)
+    ref = t["nodes"]                                    # [nN, dim] in [-1,1]^dim
+    nN = ref.shape[0]
+    lob = np.unique(np.round(ref.ravel(), 12))          # the p+1 1-D Lobatto points
+    assert lob.size == order + 1
+    loc = np.argmin(np.abs(ref[:, :, None] - lob[None, None, :]), axis=2)   # [nN, dim] local lattice index of every reference node
+    ci = np.arange(N)
+    grids = np.meshgrid(*([ci] * dim), indexing="ij")   # slowest axis first
+    cell_ijk = np.stack([g.ravel() for g in grids[::-1]], axis=1)           # [nC, dim], x fastest
+    nC = cell_ijk.shape[0]
+    L = N * order + 1
+    lat = cell_ijk[:, None, :] * order + loc[None, :, :]                    # [nC, nN, dim] global lattice index
+    flat = np.zeros((nC, nN), dtype=np.int64)
+    for d in range(dim - 1, -1, -1):
+        flat = flat * L + lat[..., d]
+    uniq, first, inv = np.unique(flat.ravel(), return_index=True, return_inverse=True)
+    rank = np.empty(uniq.size, dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(uniq.size)
+    cells = rank[inv.reshape(-1)].reshape(nC, nN).astype(np.int32)
+    # vertex lattice (optionally perturbed), then the multilinear map of every cell
+    ax = np.arange(N + 1) / N
+    vg = np.meshgrid(*([ax] * dim), indexing="ij")
+    verts = np.stack([g.ravel() for g in vg[::-1]], axis=1)                 # x fastest: id = sum_d i_d (N+1)^d
+    if perturb > 0.0:
+        rng = np.random.default_rng(seed)
+        interior = np.all((verts > 1e-12) & (verts < 1 - 1e-12), axis=1)
+        verts[interior] += perturb / N * rng.uniform(-1, 1, size=(int(interior.sum()), dim))
+    nodes = np.zeros((uniq.size, dim))
+    xi = 0.5 * (ref + 1.0)                                                  # [nN, dim] in [0,1]
+    for corner in itertools.product((0, 1), repeat=dim):
+        wgt = np.ones(nN)
+        vid = np.zeros(nC, dtype=np.int64)
+        for d in range(dim - 1, -1, -1):
+            wgt = wgt * (xi[:, d] if corner[d] else 1.0 - xi[:, d])
+            vid = vid * (N + 1) + cell_ijk[:, d] + corner[d]
+        contrib = wgt[None, :, None] * verts[vid][:, None, :]               # [nC, nN, dim]
+        if corner == (0,) * dim:
+            acc = contrib
+        else:
+            acc = acc + contrib
+    nodes[cells.ravel()] = acc.reshape(-1, dim)         # shared nodes receive the same value from every cell (same multilinear edge/face map)
+    return nodes, cells

@@ -13,21 +13,23 @@ def sin_exp(x):
     return np.sin(x[0]) * np.exp(x[1])
 
 
-def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="dirichlet", tau_double=False, diff="none", seed=0, curved=0.0):
+def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="dirichlet", tau_double=False, diff="none", seed=0, curved=0.0, geom="simplex"):
     """Returns dict with numpy inputs in the reference's Field layouts.  curved > 0 displaces every non-vertex node by
     curved*h*U(-1,1)^dim: genuinely curved (non-affine) elements, Jacobians and normals vary from cubature point to point."""
     rng = np.random.default_rng(seed)
-    if mesh == "kuhn":
+    if geom == "orthotope":     # structured quads / hexes (the reference's orthotope elements: ReferenceElement.cpp:885-1004)
+        nodes, cells = meshgen.box_mesh(N, order, dim, perturb=perturb)
+    elif mesh == "kuhn":
         nodes, cells = meshgen.kuhn_mesh(N, order, dim, perturb=perturb)
     else:
         nodes, cells = load_mesh(mesh)
     if curved > 0.0 and order > 1:
         isv = np.zeros(nodes.shape[0], dtype=bool)
-        isv[np.unique(cells[:, :dim + 1])] = True
+        isv[np.unique(cells[:, :(2 ** dim if geom == "orthotope" else dim + 1)])] = True
         h = np.linalg.norm(nodes[cells[:, 1]] - nodes[cells[:, 0]], axis=1).min()
         nodes = nodes.copy()
         nodes[~isv] += curved * h * np.random.default_rng(seed + 77).uniform(-1, 1, size=(int((~isv).sum()), dim))
-    ore = OracleRefEl(dim, order)
+    ore = OracleRefEl(dim, order, geom)
     topo = compute_faces(cells, ore)
     nF, nNf, nN = topo["faces"].shape[0], ore.faceElement.nNodes, ore.nNodes
     ana = np.sin(nodes[:, 0]) * np.exp(nodes[:, 1])
@@ -39,7 +41,7 @@ def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="di
         dirv[b, :, 1] = (np.cos(nodes[:, 0]) * np.exp(-nodes[:, 1]))[topo["faces"][b]]
         if nD > 2:
             dirv[b, :, 2] = (nodes[:, 2] * nodes[:, 0])[topo["faces"][b]]
-    case = dict(dim=dim, order=order, nodes=nodes, cells=cells, topo=topo, ore=ore, ana=ana, model=model, bc=bc, nD=nD)
+    case = dict(dim=dim, order=order, geom=geom, nodes=nodes, cells=cells, topo=topo, ore=ore, ana=ana, model=model, bc=bc, nD=nD)
     fields = {"Dirichlet": dirv}
     if nD > 1:     # tau is a full nDOF x nDOF matrix per face node (col-major), HDGBase.cpp:18-32
         blk = 2.0 * np.eye(nD)[None, None] + 0.3 * rng.random((nF, nNf, nD, nD))
@@ -110,7 +112,7 @@ def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
 
 def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True):
     dim, order = case["dim"], case["order"]
-    m = hfox.Mesh(dim, order, "simplex")
+    m = hfox.Mesh(dim, order, case.get("geom", "simplex"))
     m.setMesh(case["nodes"], case["cells"])
     re = m.getReferenceElement()
     nN, nNf = re.getNumNodes(), re.getFaceElement().getNumNodes()

@@ -75,3 +75,45 @@ def test_qr_and_lu_condensation_agree_on_hexes():
     case = H.make_case(3, 2, N=2, perturb=0.15, model="cdrs", diff="tensor", tau_double=True, geom="orthotope", seed=5)
     a, b = H.run_oracle(case, useLU=0, solve=False), H.run_oracle(case, useLU=1, solve=False)
     assert H.rel_err(a.S, b.S) < 1e-12 and H.rel_err(a.vals, b.vals) < 1e-12
+
+
+def _both_topologies(dim, order, cells):
+    """Oracle (numpy) and product (host C++ behind the C ABI: hfx_host_compute_faces) topology of the same cells."""
+    from hyperfox_b200 import capi
+    cells = np.asarray(cells, dtype=np.int32)
+    o = H.compute_faces(cells, ReferenceElement(dim, order, "orthotope"))
+    p = capi.host_compute_faces(dim, order, cells, 1)
+    for k in ("faces", "cell2face", "face2cell", "boundary"):
+        assert np.array_equal(np.asarray(o[k]).reshape(-1), np.asarray(p[k]).reshape(-1)), k
+    return o
+
+
+def test_reference_quad_mesh_known_answers():
+    """tests/unittests/mesh/TestMesh.cpp:20-69,194-312 (four linear quads around node 4) and :314-420 (one order-2 quad): face counts,
+    face membership, face-to-cell adjacency and the boundary set, for the oracle and for the product's host topology builder."""
+    quads = [[0, 5, 4, 8], [1, 6, 4, 5], [2, 7, 4, 6], [3, 8, 4, 7]]
+    t = _both_topologies(2, 1, quads)
+    assert t["faces"].shape == (12, 2) and t["boundary"].size == 8
+    expected = [{0, 5}, {5, 1}, {1, 6}, {6, 2}, {2, 7}, {7, 3}, {3, 8}, {8, 0}, {5, 4}, {6, 4}, {7, 4}, {8, 4}]
+    got = [set(f) for f in t["faces"].tolist()]
+    assert sorted(map(sorted, got)) == sorted(map(sorted, expected))
+    boundary_nodes = {0, 1, 2, 3, 5, 6, 7, 8}
+    for F in t["boundary"]:
+        assert set(t["faces"][F].tolist()) <= boundary_nodes
+    for F, (c0, c1) in enumerate(t["face2cell"].tolist()):     # interior faces carry node 4 and two ascending cells
+        assert (c1 >= 0) == (4 in got[F])
+        if c1 >= 0:
+            assert c0 < c1 and all(set(got[F]) <= set(quads[c]) for c in (c0, c1))
+    for c in range(4):
+        for f in range(4):
+            assert set(got[t["cell2face"][c, f]]) <= set(quads[c])
+    # order 2: one 9-node quad, faces {0,1,5}, {1,2,6}, {2,3,7}, {3,0,8}, all on the boundary, all adjacent to cell 0 only
+    t2 = _both_topologies(2, 2, [[0, 1, 2, 3, 5, 6, 7, 8, 4]])
+    assert sorted(map(sorted, t2["faces"].tolist())) == sorted(map(sorted, [[0, 1, 5], [1, 2, 6], [2, 3, 7], [3, 0, 8]]))
+    assert t2["boundary"].size == 4 and (t2["face2cell"][:, 0] == 0).all() and (t2["face2cell"][:, 1] == -1).all()
+
+
+@pytest.mark.parametrize("dim,order", [(2, 3), (3, 2)])
+def test_box_mesh_topology_matches_between_oracle_and_product(dim, order):
+    nodes, cells = meshgen.box_mesh(3, order, dim)
+    _both_topologies(dim, order, cells)

@@ -1,0 +1,69 @@
+"""Gmsh reader + straight-sided order-p mesh generation (hyperfox_b200.meshio) against the reference's own
+fixtures: every ressources/meshes/regression/regression_dim-D_h-H_ord-P.h5 was produced by the reference's tools/convertGmsh2H5HO from
+regression_dim-D_h-H.msh (ressources/meshes/regression/generateH5FromMsh.py).  Regenerating them pins
+
+  * the generator (cells bit-exact, node coordinates to rounding), and with it
+  * the MOAB numbering convention the topology builders restate (first appearance over ascending cell ids, MBCN canonical sub-entity
+    order, entities of the input file first): the node numbering of an order >= 2 (edges) / >= 3 (faces) mesh depends on the relative
+    ids of the edges / faces of every cell, so a different convention gives different cells (checked below).
+
+Fixtures: tests/golden/meshes/*.npz (converted .h5) and tests/golden/meshes/msh/*.msh (verbatim), both by tools/make_golden_meshes.py."""
+import os
+
+import numpy as np
+import pytest
+
+from hyperfox_b200 import meshio
+from tests.conftest import load_mesh
+
+MSH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", "msh")
+CASES = [(2, "3e-1", o) for o in range(1, 6)] + [(2, "2e-1", o) for o in range(1, 6)] + [(2, "1e-1", o) for o in range(1, 5)] + \
+        [(3, "3e-1", o) for o in range(1, 6)] + [(3, "2e-1", o) for o in range(1, 4)]
+
+
+@pytest.mark.parametrize("dim,h,order", CASES)
+def test_regenerates_reference_fixture(dim, h, order):
+    nodes, cells = load_mesh("regression_dim-%d_h-%s_ord-%d" % (dim, h, order))
+    n, c = meshio.high_order_from_msh(os.path.join(MSH, "regression_dim-%d_h-%s.msh" % (dim, h)), dim, order)
+    assert c.shape == cells.shape and np.array_equal(c, cells)
+    assert n.shape == nodes.shape and np.abs(n - nodes).max() < 1e-15
+
+
+def test_read_msh_counts():
+    nodes, el = meshio.read_msh(os.path.join(MSH, "regression_dim-3_h-3e-1.msh"))
+    assert el[3].shape == (340, 4) and el[2].shape == (240, 3) and 1 not in el      # tets + the boundary triangles of the file
+    assert nodes.shape[1] == 3 and el[3].min() == 0 and el[3].max() == nodes.shape[0] - 1
+    nodes, el = meshio.read_msh(os.path.join(MSH, "regression_dim-2_h-3e-1.msh"))
+    assert el[2].shape == (52, 3) and nodes.shape == (35, 3) and np.all(nodes[:, 2] == 0.0)
+
+
+def test_fixture_pins_the_numbering_convention(monkeypatch):
+    """Any other order of the tet faces / edges inside a cell, or another starting vertex of a face, fails to reproduce the fixture."""
+    path = os.path.join(MSH, "regression_dim-3_h-3e-1.msh")
+    g4 = load_mesh("regression_dim-3_h-3e-1_ord-4")[1]
+    g2 = load_mesh("regression_dim-3_h-3e-1_ord-2")[1]
+    faces, edges = list(meshio._TET_FACES), list(meshio._EDGES[3])
+    for perm in ([1, 0, 2, 3], [0, 1, 3, 2], [3, 2, 1, 0], [0, 2, 1, 3]):
+        monkeypatch.setattr(meshio, "_TET_FACES", [faces[i] for i in perm])
+        assert not np.array_equal(meshio.high_order_from_msh(path, 3, 4)[1], g4)
+    monkeypatch.setattr(meshio, "_TET_FACES", [f[1:] + f[:1] for f in faces])
+    assert not np.array_equal(meshio.high_order_from_msh(path, 3, 4)[1], g4)
+    monkeypatch.setattr(meshio, "_TET_FACES", faces)
+    for perm in ([1, 0, 2, 3, 4, 5], [0, 1, 2, 4, 3, 5], [5, 4, 3, 2, 1, 0]):
+        monkeypatch.setitem(meshio._EDGES, 3, [edges[i] for i in perm])
+        assert not np.array_equal(meshio.high_order_from_msh(path, 3, 2)[1], g2)
+    monkeypatch.setitem(meshio._EDGES, 3, edges)
+    assert np.array_equal(meshio.high_order_from_msh(path, 3, 4)[1], g4)
+
+
+def test_topology_builder_uses_the_pinned_convention():
+    """The face numbering of the product's topology builder (hfx_host_compute_faces) is the same walk: faces by first appearance over
+    ascending cells in the canonical face order.  Cross-check: number the faces of the linear tets with meshio's sub-entity walk (no
+    pre-existing entities, as in Mesh::computeFaces where the mesh comes from the .h5 file) and compare cell2face."""
+    from hyperfox_b200 import capi
+    nodes, cells = load_mesh("regression_dim-3_h-3e-1_ord-1")
+    conn, adj = meshio._sub_entities(3, cells.astype(np.int64), {})
+    tp = capi.host_compute_faces(3, 1, cells)
+    assert tp["faces"].shape[0] == conn[2].shape[0]
+    assert np.array_equal(np.sort(np.asarray(tp["cell2face"]).reshape(-1, 4), axis=1), adj[2])
+    assert np.array_equal(np.sort(np.asarray(tp["faces"]).reshape(-1, 3), axis=1), np.sort(conn[2], axis=1))

@@ -28,3 +28,11 @@ for t in todo:
     name = os.path.basename(t)[:-3] + ".npz"
     np.savez_compressed(os.path.join(OUT, name), nodes=nodes, cells=cells.astype(np.int32))
     print(name, nodes.shape, cells.shape)
+
+# the Gmsh sources of the regression fixtures (inputs of tools/convertGmsh2H5HO in the reference): small ones only, copied verbatim as
+# test data so that tests/test_meshio.py can regenerate the .h5 fixtures above from them
+import shutil
+os.makedirs(os.path.join(OUT, "msh"), exist_ok=True)
+for t in ("regression_dim-2_h-3e-1", "regression_dim-2_h-2e-1", "regression_dim-2_h-1e-1", "regression_dim-3_h-3e-1", "regression_dim-3_h-2e-1"):
+    shutil.copyfile(os.path.join(REF, "regression", t + ".msh"), os.path.join(OUT, "msh", t + ".msh"))
+    print("msh/" + t + ".msh")

@@ -18,6 +18,7 @@
 #include "hfx_generic.cuh"
 #include "host/hfx_refel.h"
 #include "host/hfx_topology.h"
+#include "host/hfx_meshio.h"
 
 namespace hfx {
 
@@ -954,6 +955,33 @@ int hfx_host_compute_faces(int dim, int order, int geom, int nCells, const int* 
     if (cell2face) std::copy(tp.cell2face.begin(), tp.cell2face.end(), cell2face);
     if (face2cell) std::copy(tp.face2cell.begin(), tp.face2cell.end(), face2cell);
     if (boundary) std::copy(tp.boundary.begin(), tp.boundary.end(), boundary);
+  });
+}
+
+int hfx_host_read_msh(const char* path, int* nNodes, int counts[4], double* nodes, int* elems1, int* elems2, int* elems3) {
+  return guard(nullptr, [&] {
+    MshFile m;
+    read_msh(path ? path : "", &m);
+    if (nNodes) *nNodes = (int)(m.nodes.size() / 3);
+    if (counts) { counts[0] = 0; for (int k = 1; k <= 3; k++) counts[k] = (int)(m.elems[k].size() / (k + 1)); }
+    if (nodes) std::copy(m.nodes.begin(), m.nodes.end(), nodes);
+    int* dst[4] = {nullptr, elems1, elems2, elems3};
+    for (int k = 1; k <= 3; k++) if (dst[k]) std::copy(m.elems[k].begin(), m.elems[k].end(), dst[k]);
+  });
+}
+
+int hfx_host_high_order_mesh(int dim, int order, int nLin, const double* lin, int nCells, const int* cells, int nExisting1, const int* existing1,
+                             int nExisting2, const int* existing2, int* nNodesOut, double* nodesOut, int* cellsOut) {
+  return guard(nullptr, [&] {
+    std::vector<int> existing[4];
+    if (existing1 && nExisting1 > 0) existing[1].assign(existing1, existing1 + (size_t)nExisting1 * 2);
+    if (existing2 && nExisting2 > 0) existing[2].assign(existing2, existing2 + (size_t)nExisting2 * 3);
+    std::vector<double> nodes;
+    std::vector<int> ho;
+    high_order_mesh(dim, order, nLin, lin, nCells, cells, existing, &nodes, &ho);
+    if (nNodesOut) *nNodesOut = (int)(nodes.size() / dim);
+    if (nodesOut) std::copy(nodes.begin(), nodes.end(), nodesOut);
+    if (cellsOut) std::copy(ho.begin(), ho.end(), cellsOut);
   });
 }
 

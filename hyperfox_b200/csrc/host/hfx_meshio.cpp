@@ -1,0 +1,203 @@
+// Gmsh reader + order-p mesh generation without MOAB.  Reference: tools/convertGmsh2H5HO.cpp:117-257 (generateHigherOrderMesh),
+// :259-363 (readMesh), :366-397 (generateCellNodes).  Numbering convention of the intermediate entities (what MOAB decides there):
+//   * entities present in the input file come first, in file order and with the file's vertex order;
+//   * the missing sub-entities are created while walking the cells in ascending id and, inside a cell, the sub-entities in the
+//     canonical order below; a new one takes the next id and the vertex order of that first appearance;
+//   * the sub-entities adjacent to a cell are visited in ascending id.
+#include "hfx_meshio.h"
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <fstream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+
+#include "hfx_refel.h"
+
+namespace hfx {
+
+namespace {
+const int kEdges2[3][2] = {{0, 1}, {1, 2}, {2, 0}};
+const int kEdges3[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
+const int kTetFaces[4][3] = {{0, 1, 3}, {1, 2, 3}, {0, 3, 2}, {0, 2, 1}};
+
+[[noreturn]] void fail(const char* fn, const std::string& msg) { throw std::runtime_error(std::string("MeshIo : ") + fn + " : " + msg); }
+
+// inverse of a small (n <= 3) row-major matrix by Gauss-Jordan with partial pivoting
+void small_inverse(int n, const double* a, double* inv) {
+  double m[3][6];
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) { m[i][j] = a[i * n + j]; m[i][n + j] = i == j ? 1.0 : 0.0; }
+  for (int k = 0; k < n; k++) {
+    int pv = k;
+    for (int i = k + 1; i < n; i++) if (std::fabs(m[i][k]) > std::fabs(m[pv][k])) pv = i;
+    if (m[pv][k] == 0.0) fail("generateCellNodes", "degenerate cell");
+    if (pv != k) for (int j = 0; j < 2 * n; j++) std::swap(m[k][j], m[pv][j]);
+    const double d = 1.0 / m[k][k];
+    for (int j = 0; j < 2 * n; j++) m[k][j] *= d;
+    for (int i = 0; i < n; i++) if (i != k) { const double f = m[i][k]; for (int j = 0; j < 2 * n; j++) m[i][j] -= f * m[k][j]; }
+  }
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) inv[i * n + j] = m[i][n + j];
+}
+
+// generateCellNodes: node = T (xi - xi_0) + x_0 with T = [x_i - x_0] [xi_i - xi_0]^-1
+void cell_nodes(const RefElement& re, int dim, const double* lin /*[td+1][dim]*/, std::vector<double>* out) {
+  const int td = re.dim(), nN = re.numNodes();
+  const std::vector<double>& ref = re.nodes();
+  double locT[9], locTi[9], X[9], T[9];
+  for (int i = 0; i < td; i++) for (int j = 0; j < td; j++) locT[j * td + i] = ref[(size_t)(i + 1) * td + j] - ref[j];
+  small_inverse(td, locT, locTi);
+  for (int i = 0; i < td; i++) for (int j = 0; j < dim; j++) X[j * td + i] = lin[(i + 1) * dim + j] - lin[j];
+  for (int j = 0; j < dim; j++) for (int r = 0; r < td; r++) { double s = 0.0; for (int k = 0; k < td; k++) s += X[j * td + k] * locTi[k * td + r]; T[j * td + r] = s; }
+  out->resize((size_t)nN * dim);
+  for (int i = 0; i < nN; i++)
+    for (int j = 0; j < dim; j++) {
+      double s = 0.0;
+      for (int r = 0; r < td; r++) s += T[j * td + r] * (ref[(size_t)i * td + r] - ref[r]);
+      (*out)[(size_t)i * dim + j] = s + lin[j];
+    }
+}
+}  // namespace
+
+void read_msh(const std::string& path, MshFile* out) {
+  std::ifstream f(path);
+  if (!f) fail("readMsh", "could not load mesh file: " + path);
+  std::string line;
+  std::vector<long long> tags;
+  std::vector<double> raw;
+  std::vector<long long> el[4];
+  auto trimmed = [](std::string s) { while (!s.empty() && (s.back() == '\r' || s.back() == ' ')) s.pop_back(); return s; };
+  while (std::getline(f, line)) {
+    line = trimmed(line);
+    if (line == "$MeshFormat") {
+      std::getline(f, line);
+      std::istringstream is(line);
+      std::string ver; int type = -1;
+      is >> ver >> type;
+      if (ver.empty() || ver[0] != '2' || type != 0) fail("readMsh", "only the Gmsh 2.x ASCII format is supported");
+    } else if (line == "$Nodes") {
+      long long n = 0;
+      f >> n;
+      tags.resize((size_t)n); raw.resize((size_t)n * 3);
+      for (long long k = 0; k < n; k++) f >> tags[(size_t)k] >> raw[(size_t)k * 3] >> raw[(size_t)k * 3 + 1] >> raw[(size_t)k * 3 + 2];
+      if (!f) fail("readMsh", "truncated $Nodes section");
+    } else if (line == "$Elements") {
+      long long n = 0;
+      f >> n;
+      for (long long k = 0; k < n; k++) {
+        long long id; int ty, ntags;
+        f >> id >> ty >> ntags;
+        for (int t = 0; t < ntags; t++) { long long tag; f >> tag; }
+        int td = -1;
+        if (ty == 15) td = 0; else if (ty == 1) td = 1; else if (ty == 2) td = 2; else if (ty == 4) td = 3;
+        if (td < 0) fail("readMsh", "element type " + std::to_string(ty) + " is not supported (linear simplices only)");
+        for (int v = 0; v <= td; v++) { long long nd; f >> nd; if (td > 0) el[td].push_back(nd); }
+      }
+      if (!f) fail("readMsh", "truncated $Elements section");
+    }
+  }
+  if (tags.empty()) fail("readMsh", "no $Nodes section in " + path);
+  std::vector<size_t> order(tags.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return tags[a] < tags[b]; });
+  std::map<long long, int> remap;
+  out->nodes.resize(raw.size());
+  for (size_t i = 0; i < order.size(); i++) {
+    remap[tags[order[i]]] = (int)i;
+    for (int d = 0; d < 3; d++) out->nodes[i * 3 + d] = raw[order[i] * 3 + d];
+  }
+  for (int k = 1; k <= 3; k++) {
+    out->elems[k].resize(el[k].size());
+    for (size_t i = 0; i < el[k].size(); i++) {
+      auto it = remap.find(el[k][i]);
+      if (it == remap.end()) fail("readMsh", "an element refers to an unknown node tag");
+      out->elems[k][i] = it->second;
+    }
+  }
+}
+
+void high_order_mesh(int dim, int order, int nLin, const double* lin, int nCells, const int* cells, const std::vector<int> (&existing)[4],
+                     std::vector<double>* nodes, std::vector<int>* hoCells) {
+  if (dim != 2 && dim != 3) fail("generateHigherOrderMesh", "dimension must be 2 or 3");
+  // sub-entities of every topological dimension k < dim: connectivity + ascending ids per cell
+  std::vector<int> conn[4];
+  std::vector<int> adj[4];
+  int nSub[4] = {0, 0, 0, 0};
+  for (int k = 1; k < dim; k++) {
+    const int nv = k + 1;
+    const int ns = k == 1 ? (dim == 2 ? 3 : 6) : 4;
+    nSub[k] = ns;
+    std::map<std::array<int, 3>, int> ids;
+    auto key = [&](const int* v) { std::array<int, 3> a = {-1, -1, -1}; for (int i = 0; i < nv; i++) a[i] = v[i]; std::sort(a.begin(), a.begin() + nv); return a; };
+    conn[k] = existing[k];
+    for (size_t e = 0; e * nv < existing[k].size(); e++) ids.emplace(key(&existing[k][e * nv]), (int)e);
+    adj[k].resize((size_t)nCells * ns);
+    for (int c = 0; c < nCells; c++) {
+      for (int s = 0; s < ns; s++) {
+        int v[3];
+        for (int i = 0; i < nv; i++) {
+          const int loc = k == 1 ? (dim == 2 ? kEdges2[s][i] : kEdges3[s][i]) : kTetFaces[s][i];
+          v[i] = cells[(size_t)c * (dim + 1) + loc];
+        }
+        auto ins = ids.emplace(key(v), (int)(conn[k].size() / nv));
+        if (ins.second) conn[k].insert(conn[k].end(), v, v + nv);
+        adj[k][(size_t)c * ns + s] = ins.first->second;
+      }
+      std::sort(adj[k].begin() + (size_t)c * ns, adj[k].begin() + (size_t)(c + 1) * ns);
+    }
+  }
+  conn[dim].assign(cells, cells + (size_t)nCells * (dim + 1));
+  nSub[dim] = 1;
+  adj[dim].resize(nCells);
+  for (int c = 0; c < nCells; c++) adj[dim][c] = c;
+
+  std::vector<std::unique_ptr<RefElement>> re(dim + 1);
+  for (int k = 1; k <= dim; k++) re[k].reset(new RefElement(k, order, kSimplex));
+  const int nN = re[dim]->numNodes();
+  nodes->clear();
+  hoCells->assign((size_t)nCells * nN, -1);
+  std::vector<int> vertId(nLin, -1);
+  std::vector<std::vector<int>> entFirst(dim + 1);     // first generated node of an entity, -1 if not generated yet
+  for (int k = 1; k <= dim; k++) entFirst[k].assign(conn[k].size() / (k + 1), -1);
+  std::vector<double> elNodes, subNodes, linEl((size_t)(dim + 1) * dim), linSub((size_t)(dim + 1) * dim);
+  int next = 0;
+  for (int e = 0; e < nCells; e++) {
+    for (int i = 0; i <= dim; i++) {
+      const int v = cells[(size_t)e * (dim + 1) + i];
+      if (v < 0 || v >= nLin) fail("generateHigherOrderMesh", "cell refers to a vertex outside the node list");
+      for (int d = 0; d < dim; d++) linEl[(size_t)i * dim + d] = lin[(size_t)v * dim + d];
+      if (vertId[v] < 0) { vertId[v] = next++; nodes->insert(nodes->end(), &lin[(size_t)v * dim], &lin[(size_t)v * dim] + dim); }
+      (*hoCells)[(size_t)e * nN + i] = vertId[v];
+    }
+    cell_nodes(*re[dim], dim, linEl.data(), &elNodes);
+    for (int k = 1; k <= dim; k++) {
+      const std::vector<int>& inner = re[k]->innerNodes();
+      const int nIn = (int)inner.size();
+      if (nIn == 0) continue;
+      for (int s = 0; s < nSub[k]; s++) {
+        const int cid = adj[k][(size_t)e * nSub[k] + s];
+        if (entFirst[k][cid] < 0) {
+          for (int i = 0; i <= k; i++) for (int d = 0; d < dim; d++) linSub[(size_t)i * dim + d] = lin[(size_t)conn[k][(size_t)cid * (k + 1) + i] * dim + d];
+          cell_nodes(*re[k], dim, linSub.data(), &subNodes);
+          entFirst[k][cid] = next;
+          for (int l = 0; l < nIn; l++) { nodes->insert(nodes->end(), &subNodes[(size_t)inner[l] * dim], &subNodes[(size_t)inner[l] * dim] + dim); next++; }
+        }
+        for (int l = 0; l < nIn; l++) {
+          const int nid = entFirst[k][cid] + l;
+          int hit = -1;
+          for (int n = 0; n < nN && hit < 0; n++) {
+            bool eq = true;
+            for (int d = 0; d < dim && eq; d++) eq = std::fabs((*nodes)[(size_t)nid * dim + d] - elNodes[(size_t)n * dim + d]) < 1e-8;
+            if (eq) hit = n;
+          }
+          if (hit < 0) fail("generateHigherOrderMesh", "one of the cell nodes could not be found in element");
+          (*hoCells)[(size_t)e * nN + hit] = nid;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace hfx

@@ -1,0 +1,23 @@
+// Host-side mesh input of the product (C++17, no dependencies): Gmsh 2.2 ASCII reader and the straight-sided order-p mesh generator.
+// What the reference does with MOAB in tools/convertGmsh2H5HO.cpp:117-397; same node numbering (pinned by the reference's own
+// .msh -> .h5 fixture pairs, tests/test_meshio.py).
+#pragma once
+#include <string>
+#include <vector>
+
+namespace hfx {
+
+struct MshFile {
+  std::vector<double> nodes;            // [nNodes][3], ascending node tag
+  std::vector<int> elems[4];            // elems[k]: [m][k+1] linear simplices of topological dimension k (k = 1..3), file order, 0-based
+};
+
+// Throws std::runtime_error("MeshIo : readMsh : ...").
+void read_msh(const std::string& path, MshFile* out);
+
+// lin: [nLin][dim]; cells: [nCells][dim+1]; existing[k] (k = 1..dim-1): lower-dimensional entities already present in the input file.
+// Returns nodes [N][dim] and cells [nCells][nN] of the order-p mesh.
+void high_order_mesh(int dim, int order, int nLin, const double* lin, int nCells, const int* cells, const std::vector<int> (&existing)[4],
+                     std::vector<double>* nodes, std::vector<int>* hoCells);
+
+}  // namespace hfx

@@ -48,6 +48,17 @@ int hfx_mesh_get_topology(const hfx_ctx* ctx, int* faces, int* cell2face, int* f
 int hfx_host_compute_faces(int dim, int order, int geom, int nCells, const int* cells, int* nFaces, int* faces, int* cell2face,
                            int* face2cell, int* nBoundary, int* boundary);
 
+/* ---- mesh input, host only (no GPU needed): what tools/convertGmsh2H5HO.cpp:117-397 does through MOAB ------------- */
+/* Gmsh 2.2 ASCII file (linear simplices).  First call with NULL arrays to get the sizes: nNodes and counts[k] = number of entities of
+   topological dimension k (k = 1..3; counts[0] unused); then with nodes[nNodes][3] (ascending node tag) and elemsK[counts[K]][K+1]
+   (0-based vertex ids, file order; any pointer may be NULL). */
+int hfx_host_read_msh(const char* path, int* nNodes, int counts[4], double* nodes, int* elems1, int* elems2, int* elems3);
+/* generateHigherOrderMesh (convertGmsh2H5HO.cpp:117-257): straight-sided order-p simplex mesh from a linear one, the reference's node
+   numbering.  lin[nLin][dim], cells[nCells][dim+1]; existing1 / existing2: edges / triangles already present in the input file
+   (they precede the generated ones, as in MOAB).  Pass NULL output arrays to only count; nodesOut[nNodesOut][dim], cellsOut[nCells][nN]. */
+int hfx_host_high_order_mesh(int dim, int order, int nLin, const double* lin, int nCells, const int* cells, int nExisting1,
+                             const int* existing1, int nExisting2, const int* existing2, int* nNodesOut, double* nodesOut, int* cellsOut);
+
 /* ---- fields: Field(mesh, type, nObjPerEnt, nValsPerObj)  src/field/Field.cpp:41-61 ---------------------------- */
 enum { HFX_FIELD_NODE = 0, HFX_FIELD_FACE = 2, HFX_FIELD_CELL = 1 };
 /* names with a meaning on the path: "Tau", "Dirichlet", "DiffusionTensor", "Velocity", "Solution", "Flux", "Trace",

@@ -8,8 +8,10 @@ section 8c): `get_adjacencies(cells, dim-1, create=true, UNION)` creates faces w
 ascending id and, inside a cell, the local faces in the reference element's face order (same vertex sets as MBCN's
 canonical sides); a face seen for the first time gets the next id.  face2Cell lists adjacent cells in ascending id,
 second entry -1 on the boundary; a face's node list is taken from its lowest-id cell through the order-p faceNodes.
-No reference test pins the numbering itself (TestMesh.cpp checks membership only): "parity unpinned" for the ids,
-pinned for everything invariant under face renumbering.
+No reference test pins the numbering itself (TestMesh.cpp checks membership only), but the reference's mesh fixtures do: the
+.h5 regression meshes were generated from the .msh files by tools/convertGmsh2H5HO, whose node numbering depends on the relative
+MOAB ids of the faces of every cell; tests/test_meshio.py regenerates them bit-exactly with this convention (and with no other
+order of the local faces) and checks that this builder and the product's number the faces by the same walk.
 """
 import numpy as np
 

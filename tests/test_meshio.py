@@ -1,4 +1,5 @@
-"""Gmsh reader + straight-sided order-p mesh generation (hyperfox_b200.meshio) against the reference's own
+"""Gmsh reader + straight-sided order-p mesh generation (product: hyperfox_b200.meshio = host C++ behind the C ABI; oracle:
+oracle.meshio = numpy restatement) against the reference's own
 fixtures: every ressources/meshes/regression/regression_dim-D_h-H_ord-P.h5 was produced by the reference's tools/convertGmsh2H5HO from
 regression_dim-D_h-H.msh (ressources/meshes/regression/generateH5FromMsh.py).  Regenerating them pins
 
@@ -13,7 +14,8 @@ import os
 import numpy as np
 import pytest
 
-from hyperfox_b200 import meshio
+from hyperfox_b200 import meshio as product
+from oracle import meshio
 from tests.conftest import load_mesh
 
 MSH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", "msh")
@@ -21,15 +23,18 @@ CASES = [(2, "3e-1", o) for o in range(1, 6)] + [(2, "2e-1", o) for o in range(1
         [(3, "3e-1", o) for o in range(1, 6)] + [(3, "2e-1", o) for o in range(1, 4)]
 
 
+@pytest.mark.parametrize("impl", ["product", "oracle"])
 @pytest.mark.parametrize("dim,h,order", CASES)
-def test_regenerates_reference_fixture(dim, h, order):
+def test_regenerates_reference_fixture(dim, h, order, impl):
     nodes, cells = load_mesh("regression_dim-%d_h-%s_ord-%d" % (dim, h, order))
-    n, c = meshio.high_order_from_msh(os.path.join(MSH, "regression_dim-%d_h-%s.msh" % (dim, h)), dim, order)
+    n, c = (product if impl == "product" else meshio).high_order_from_msh(os.path.join(MSH, "regression_dim-%d_h-%s.msh" % (dim, h)), dim, order)
     assert c.shape == cells.shape and np.array_equal(c, cells)
     assert n.shape == nodes.shape and np.abs(n - nodes).max() < 1e-15
 
 
-def test_read_msh_counts():
+@pytest.mark.parametrize("impl", ["product", "oracle"])
+def test_read_msh_counts(impl):
+    meshio = product if impl == "product" else globals()["meshio"]
     nodes, el = meshio.read_msh(os.path.join(MSH, "regression_dim-3_h-3e-1.msh"))
     assert el[3].shape == (340, 4) and el[2].shape == (240, 3) and 1 not in el      # tets + the boundary triangles of the file
     assert nodes.shape[1] == 3 and el[3].min() == 0 and el[3].max() == nodes.shape[0] - 1
@@ -67,3 +72,23 @@ def test_topology_builder_uses_the_pinned_convention():
     assert tp["faces"].shape[0] == conn[2].shape[0]
     assert np.array_equal(np.sort(np.asarray(tp["cell2face"]).reshape(-1, 4), axis=1), adj[2])
     assert np.array_equal(np.sort(np.asarray(tp["faces"]).reshape(-1, 3), axis=1), np.sort(conn[2], axis=1))
+
+
+def test_product_reader_errors():
+    from hyperfox_b200.capi import ErrorHandle
+    with pytest.raises(ErrorHandle, match="MeshIo : readMsh : could not load mesh file"):
+        product.read_msh(os.path.join(MSH, "does_not_exist.msh"))
+    nodes, el = product.read_msh(os.path.join(MSH, "regression_dim-2_h-3e-1.msh"))
+    bad = el[2].copy()
+    bad[0, 0] = nodes.shape[0] + 5
+    with pytest.raises(ErrorHandle, match="generateHigherOrderMesh"):
+        product.high_order_from_linear(2, 2, nodes, bad)
+
+
+def test_product_and_oracle_agree_on_a_kuhn_mesh():
+    """A mesh without pre-existing lower-dimensional entities (the synthetic meshes of the benchmarks)."""
+    from hyperfox_b200 import meshgen
+    for dim, order in ((2, 4), (3, 3)):
+        v, c = meshgen.kuhn_linear(2, dim)
+        a, b = product.high_order_from_linear(dim, order, v, c), meshio.high_order_from_linear(dim, order, v, c)
+        assert np.array_equal(a[1], b[1]) and np.abs(a[0] - b[0]).max() < 1e-15

@@ -142,6 +142,8 @@ def main():
     ap.add_argument("--impl", default="native")
     ap.add_argument("--cubes", type=int, default=55, help="N: the unit cube is split into N^3 hexes x 6 Kuhn tets")
     ap.add_argument("--order", type=int, default=3)
+    ap.add_argument("--partition-file", default=None, help="cell partition vector (.npy or text, one rank id per cell of the global mesh), "
+                    "e.g. a Zoltan partition; default: contiguous slabs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
@@ -176,7 +178,8 @@ def main():
     # the throughput counts OWNED cells only, the ghost layer is overhead.
     nOwned = nTot
     if world > 1:
-        part = partition.partition_vector(nTot, world)   # (box_partition_vector has the smaller cut, but 55 is odd: its 28^3 / 27^3 boxes
+        part = partition.load_partition_vector(args.partition_file, nTot, world) if args.partition_file else \
+            partition.partition_vector(nTot, world)      # (box_partition_vector has the smaller cut, but 55 is odd: its 28^3 / 27^3 boxes
                                                          #  are 5.5 % out of balance, more than the slabs' extra ghost layer costs)
         prob = partition.rank_problem(verts, lin, part, rank, dim)
         lverts, lcells, nOwned = prob["verts"], prob["lin_cells"], int(prob["owned_cells"].size)
@@ -326,7 +329,7 @@ def main():
         "value": nAll / (ms_step * 1e-3), "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "3D Poisson HDG order %d, synthetic Kuhn mesh %d^3 x 6 = %d tets (BASELINE configs[2]), HDGLaplaceModel + DirichletModel, tau=1"
-                               % (order, N, nTot), "elements_per_rank": nC, "owned_elements_rank0": nOwned, "partition": ("slabs of the lexicographic Kuhn mesh, overlap-1 ghost cells recomputed by the face owner" if world > 1 else "single rank"), "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
+                               % (order, N, nTot), "elements_per_rank": nC, "owned_elements_rank0": nOwned, "partition": ((("file " + os.path.basename(args.partition_file)) if args.partition_file else "slabs of the lexicographic Kuhn mesh") + ", overlap-1 ghost cells recomputed by the face owner" if world > 1 else "single rank"), "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
                    "l2": "inputs+outputs per step (%.1f GB) far larger than the 126 MB L2" % ((BYTES_STORE[order] * nC) / 1e9),
                    "timing": "CUDA events on the library stream around memset+kernel, max over ranks; wall-clock per step %.2f ms" % ms_wall,
                    "setup_s": round(t_setup, 1),

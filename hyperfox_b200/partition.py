@@ -22,6 +22,20 @@ def partition_vector(n_total, world):
     return p
 
 
+def load_partition_vector(path, n_total, world):
+    """An externally supplied cell partition (one rank id per cell, global cell order): what the reference gets from Zoltan
+    (ZoltanPartitioner.cpp:35-167) and what SURVEY.md section 8e asks the harness to accept.  `.npy`, or text with one integer per cell."""
+    p = np.load(path) if str(path).endswith(".npy") else np.loadtxt(path, dtype=np.int64, ndmin=1)
+    p = np.asarray(p).reshape(-1)
+    if p.size != n_total:
+        raise ValueError("Partitioner : computePartition : the partition file holds %d entries for %d cells" % (p.size, n_total))
+    if p.min() < 0 or p.max() >= world:
+        raise ValueError("Partitioner : computePartition : rank ids must lie in [0, %d)" % world)
+    if np.unique(p).size != world:
+        raise ValueError("Partitioner : computePartition : every rank must own at least one cell")
+    return p.astype(np.int32)
+
+
 def box_partition_vector(N, world, dim=3):
     """Coordinate boxes of the N^dim Kuhn mesh (cell id = cube id * dim! + k, cube id lexicographic with x fastest): the stand-in for a
     graph partition with a small cut (recursive coordinate bisection into 2/4/8 boxes).  world = 2^a is split

@@ -56,3 +56,26 @@ def test_canonical_face_node_order_is_rank_independent(dim, order):
         assert np.array_equal(a, b)
         checked += 1
     assert checked > 0
+
+
+def test_supplied_partition_vector(tmp_path):
+    """An arbitrary (non-contiguous, graph-partitioner-like) partition vector from a file gives a consistent plan too, and the
+    assembled system does not depend on it: ownership covers every face exactly once."""
+    v, c = meshgen.kuhn_linear(3, 3)
+    rng = np.random.default_rng(5)
+    part = rng.integers(0, 3, size=c.shape[0]).astype(np.int32)
+    np.save(tmp_path / "part.npy", part)
+    np.savetxt(tmp_path / "part.txt", part, fmt="%d")
+    for f in ("part.npy", "part.txt"):
+        assert np.array_equal(P.load_partition_vector(str(tmp_path / f), c.shape[0], 3), part)
+    with pytest.raises(ValueError, match="holds"):
+        P.load_partition_vector(str(tmp_path / "part.npy"), c.shape[0] + 1, 3)
+    with pytest.raises(ValueError, match="rank ids"):
+        P.load_partition_vector(str(tmp_path / "part.npy"), c.shape[0], 2)
+    with pytest.raises(ValueError, match="at least one cell"):
+        P.load_partition_vector(str(tmp_path / "part.npy"), c.shape[0], 4)      # rank 3 owns nothing
+    c2f, f2c = P.global_linear_topology(c, 3)
+    probs = [P.rank_problem(v, c, part, r, 3, c2f, f2c) for r in range(3)]
+    owned = np.concatenate([p["face_global"][p["owned_face"] == 1] for p in probs])
+    assert np.array_equal(np.sort(owned), np.arange(f2c.shape[0]))
+    assert sum(int(p["owned_cells"].size) for p in probs) == c.shape[0]

@@ -220,6 +220,57 @@ class Mesh {
   std::set<int> boundaryFaces;
 };
 
+// ---- src/io/Io.h + tools/convertGmsh2H5HO.cpp ------------------------------------------------------------------------------
+// The reference's Io interface (load / write / setMesh / setField) for the one input format the path's callers start from: a Gmsh
+// 2.2 file of linear simplices, raised to the order of the mesh's reference element exactly as tools/convertGmsh2H5HO does
+// (generateHigherOrderMesh, :117-257) -- same node numbering, without MOAB (host C++ inside libhfx).
+class Field;
+class Io {
+ public:
+  virtual ~Io() {}
+  virtual void load(std::string filename) = 0;
+  virtual void write(std::string filename) = 0;
+  virtual void setMesh(Mesh* mesh) { myMesh = mesh; }
+  virtual void setField(std::string name, Field* field) { fieldMap[name] = field; }
+
+ protected:
+  static std::string getExtension(std::string filename) {
+    const size_t p = filename.find_last_of('.');
+    return p == std::string::npos ? std::string() : filename.substr(p);
+  }
+  Mesh* myMesh = nullptr;
+  std::map<std::string, Field*> fieldMap;
+};
+
+class GmshIo : public Io {
+ public:
+  GmshIo() {}
+  explicit GmshIo(Mesh* mesh) { setMesh(mesh); }
+  void load(std::string filename) override {
+    if (!myMesh) throw ErrorHandle("GmshIo", "load", "the mesh must be set before loading");
+    if (!myMesh->getReferenceElement()) throw ErrorHandle("GmshIo", "load", "the mesh needs a reference element (dimension and order) before loading");
+    if (getExtension(filename) != ".msh") throw ErrorHandle("GmshIo", "load", "the file extension must be .msh");
+    if (myMesh->getReferenceElement()->getGeometry() != simplex) throw ErrorHandle("GmshIo", "load", "only simplex meshes can be generated from a Gmsh file");
+    const int dim = myMesh->getDimension(), order = myMesh->getReferenceElement()->getOrder();
+    int nLin = 0, counts[4] = {0, 0, 0, 0};
+    detail::check(hfx_host_read_msh(filename.c_str(), &nLin, counts, 0, 0, 0, 0), nullptr);
+    std::vector<double> raw((size_t)nLin * 3), lin((size_t)nLin * dim);
+    std::vector<int> el[4];
+    for (int k = 1; k <= 3; k++) el[k].resize((size_t)counts[k] * (k + 1));
+    detail::check(hfx_host_read_msh(filename.c_str(), &nLin, counts, raw.data(), el[1].data(), el[2].data(), el[3].data()), nullptr);
+    if (counts[dim] == 0) throw ErrorHandle("GmshIo", "load", "the file holds no cells of the dimension of the mesh");
+    for (int i = 0; i < nLin; i++) for (int d = 0; d < dim; d++) lin[(size_t)i * dim + d] = raw[(size_t)i * 3 + d];
+    const int nEx2 = dim == 3 ? counts[2] : 0;
+    int nNodes = 0;
+    detail::check(hfx_host_high_order_mesh(dim, order, nLin, lin.data(), counts[dim], el[dim].data(), counts[1], el[1].data(), nEx2, el[2].data(), &nNodes, 0, 0), nullptr);
+    std::vector<double> pts((size_t)nNodes * dim);
+    std::vector<int> cells((size_t)counts[dim] * myMesh->getReferenceElement()->getNumNodes());
+    detail::check(hfx_host_high_order_mesh(dim, order, nLin, lin.data(), counts[dim], el[dim].data(), counts[1], el[1].data(), nEx2, el[2].data(), &nNodes, pts.data(), cells.data()), nullptr);
+    myMesh->setMesh(dim, pts, cells);
+  }
+  void write(std::string) override { throw ErrorHandle("GmshIo", "write", "writing Gmsh files is not supported"); }
+};
+
 // ---- src/field/Field.h ---------------------------------------------------------------------------------------------------
 class Field {
  public:

@@ -15,6 +15,7 @@
 #include "Field.h"
 #include "HDGDiffusionSource.h"
 #include "HDGLaplaceModel.h"
+#include "GmshIo.h"
 #include "HDGSolver.h"
 #include "Mesh.h"
 #include "RungeKutta.h"
@@ -308,11 +309,38 @@ static void testDiffusionSourceRK(const std::string& path) {
   CHECK(l2 < 1e-2);
 }
 
+// tools/convertGmsh2H5HO.cpp through the Io mirror: <dir>/<name>.msh raised to order p must equal the reference's own .h5 fixture
+// (<dir>/<name>_ord-p.txt): cells bit-exact, coordinates to rounding.  Host only.
+static void testGmshIo(const std::string& dir, const std::string& name, int dim, int order) {
+  Mesh fixture(dim, order, "simplex"), generated(dim, order, "simplex");
+  loadMesh(dir + "/" + name + "_ord-" + std::to_string(order) + ".txt", &fixture, dim);
+  GmshIo io(&generated);
+  CHECK_NOTHROW(io.load(dir + "/" + name + ".msh"));
+  CHECK(generated.getNumberPoints() == fixture.getNumberPoints());
+  CHECK(generated.getNumberCells() == fixture.getNumberCells());
+  CHECK(generated.getNumberFaces() == fixture.getNumberFaces());
+  CHECK(*generated.getCells() == *fixture.getCells());
+  CHECK(*generated.getFaces() == *fixture.getFaces());
+  double err = 0.0;
+  if (generated.getPoints()->size() == fixture.getPoints()->size())
+    for (size_t i = 0; i < fixture.getPoints()->size(); i++) err = std::max(err, std::fabs((*generated.getPoints())[i] - (*fixture.getPoints())[i]));
+  CHECK(err < 1e-15);
+  CHECK_THROWS(io.load(dir + "/" + name + ".h5"));
+  CHECK_THROWS(io.load(dir + "/missing.msh"));
+  CHECK_THROWS(io.write(dir + "/out.msh"));
+  GmshIo unset;
+  CHECK_THROWS(unset.load(dir + "/" + name + ".msh"));
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { std::printf("usage: %s <mesh dir> [contract|solver|lai|laplace|diffsrc]\n", argv[0]); return 2; }
+  if (argc < 2) { std::printf("usage: %s <mesh dir> [contract|meshio|solver|lai|laplace|diffsrc|rk]\n", argv[0]); return 2; }
   const std::string dir = argv[1], sec = argc > 2 ? argv[2] : "all";
   try {
     if (sec == "contract") testHDGSolver(dir, false);
+    if (sec == "meshio" || sec == "all") {
+      testGmshIo(dir, "regression_dim-2_h-2e-1", 2, 2);
+      testGmshIo(dir, "regression_dim-3_h-2e-1", 3, 3);
+    }
     if (sec == "solver" || sec == "all") testHDGSolver(dir, true);
     if (sec == "lai" || sec == "all") testLinAlgebraInterface();
     if (sec == "laplace" || sec == "all") {

@@ -33,6 +33,9 @@ def mesh_dir(tmp_path_factory):
             f.write("%d %d %d %d\n" % (nodes.shape[0], nodes.shape[1], cells.shape[0], cells.shape[1]))
             np.savetxt(f, nodes, fmt="%.17g")
             np.savetxt(f, cells, fmt="%d")
+    import shutil
+    for name in ("regression_dim-2_h-2e-1", "regression_dim-3_h-2e-1"):
+        shutil.copyfile(os.path.join(ROOT, "tests", "golden", "meshes", "msh", name + ".msh"), os.path.join(d, name + ".msh"))
     return str(d)
 
 
@@ -46,6 +49,12 @@ def test_cpp_mirror_builds_and_call_order_contract(mesh_dir):
     """TestHDGSolver.cpp:37-80: every step throws before its prerequisite (no device needed up to initialize())."""
     out = run(mesh_dir, "contract")
     assert " 0 failed" in out
+
+
+def test_cpp_mirror_gmsh_io_regenerates_reference_fixtures(mesh_dir):
+    """GmshIo (Io mirror) -> hfx_host_read_msh / hfx_host_high_order_mesh: the reference's .h5 fixtures from their .msh sources (host only)."""
+    out = run(mesh_dir, "meshio")
+    assert " 0 failed" in out, out
 
 
 @pytest.mark.gpu

@@ -26,6 +26,8 @@ double hfx_fp64_peak(int device);               /* measured DFMA peak of the dev
 
 /* ---- reference element: ReferenceElement(dim, order, geom)  src/element/ReferenceElement.cpp:5-26 ------------ */
 enum { HFX_SIMPLEX = 0, HFX_ORTHOTOPE = 1 };
+/* dim 2 or 3.  Simplices: orders 1-5 (fused kernel for triangles of every order and tets of order <= 3 with one DOF per node, general kernel otherwise);
+   orthotopes (ReferenceElement.cpp:624-627): quads of order 1-5, hexes of order 1-2, general kernel, multilinear geometry. */
 int hfx_refel_set(hfx_ctx* ctx, int dim, int order, int geom);
 int hfx_refel_info(const hfx_ctx* ctx, int* nN, int* nNf, int* nFc, int* nIP, int* nIPf);
 /* getNodes/getFaceNodes/getIPCoords/getIPWeights/getIPShapeFunctions/getIPDerivShapeFunctions (ReferenceElement.cpp:499-540),

@@ -21,6 +21,8 @@ struct GenParams {
   int dim, nN, nNf, nFc, nIP, nIPf, nD;
   const double* bufSol;      // BufferSolution, cell field [nCells][nN][nD]        (HDGBurgersModel.cpp:87-124)
   const double* tracePrev;   // Trace of the previous iterate, face field [nFaces][nNf][nD]
+  int frameV[4];             // local ids of the vertices spanning the affine frame of a straight-sided element (and, first dim of them, of a face):
+                             // 0,1,2,3 for simplices, 0,1,3,4 for orthotopes (ReferenceElement.cpp:885-943)
   int nSrc;                  // source components: 1, or dim for the Burgers model (HDGBurgersModel.cpp:112-122)
   int smOpt[6];              // offsets (doubles, from the optional area) of Um, Rm, Aq, Bq, shape table, GM when they live in shared memory; -1: global scratch
   double* ws;                // per-CTA scratch
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
         const int ip = k;
         double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
         if (affE) {   // straight-sided element: constant Jacobian straight from the vertices
-          for (int r = 0; r < dim; r++) for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (X[(r + 1) * dim + m] - X[m]);
+          for (int r = 0; r < dim; r++) for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (X[P.frameV[r + 1] * dim + m] - X[P.frameV[0] * dim + m]);
         } else for (int i = 0; i < nN; i++) {
           const double* d = p.dshape + (ip * nN + i) * dim;
           for (int r = 0; r < dim; r++) for (int m = 0; m < dim; m++) J[r][m] = fma(d[r], X[i * dim + m], J[r][m]);
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
         const int* fn = FNo + f * nNf;
         double J[2][3] = {{0, 0, 0}, {0, 0, 0}};
         if (affE) {
-          for (int r = 0; r < dim - 1; r++) for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (X[fn[r + 1] * dim + m] - X[fn[0] * dim + m]);
+          for (int r = 0; r < dim - 1; r++) for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (X[fn[P.frameV[r + 1]] * dim + m] - X[fn[P.frameV[0]] * dim + m]);
         } else for (int a = 0; a < nNf; a++) {
           const double* d = p.fdshape + (ip * nNf + a) * (dim - 1);
           for (int r = 0; r < dim - 1; r++) for (int m = 0; m < dim; m++) J[r][m] = fma(d[r], X[fn[a] * dim + m], J[r][m]);

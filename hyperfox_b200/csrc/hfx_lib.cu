@@ -130,19 +130,23 @@ __global__ void elem_coords_kernel(long long n, int nN, int dim, const double* _
   elemX[idx] = nodes[(size_t)cells[ei] * dim + m];
 }
 
-// 1 if every node of the element sits at the affine image of its reference position (straight-sided simplex): the Jacobian is then
-// constant over the element and the fused kernel takes the reference-matrix shortcut for the purely geometric blocks
-__global__ void elem_affine_kernel(int nCells, int nN, int dim, const double* __restrict__ elemX, const double* __restrict__ bary, uint8_t* __restrict__ affine) {
+// 1 if every node of the element sits at the affine image of its reference position (straight-sided simplex, parallelogram /
+// parallelepiped orthotope): the Jacobian is then constant over the element and the kernels take the reference-matrix shortcuts.
+// fv0..fv3: element-local ids of the vertices that span the affine frame (origin + one per reference axis): 0,1,..,dim for a simplex,
+// 0,1,3,4 for an orthotope (vertex order of ReferenceElement.cpp:885-943); bary: weights of every reference node on those vertices.
+__global__ void elem_affine_kernel(int nCells, int nN, int dim, int fv0, int fv1, int fv2, int fv3, const double* __restrict__ elemX,
+                                   const double* __restrict__ bary, uint8_t* __restrict__ affine) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= nCells) return;
+  const int fv[4] = {fv0, fv1, fv2, fv3};
   const double* X = elemX + (size_t)e * nN * dim;
   double h = 0.0;
-  for (int v = 1; v <= dim; v++) for (int m = 0; m < dim; m++) h = fmax(h, fabs(X[v * dim + m] - X[m]));
+  for (int v = 1; v <= dim; v++) for (int m = 0; m < dim; m++) h = fmax(h, fabs(X[fv[v] * dim + m] - X[fv[0] * dim + m]));
   bool ok = true;
-  for (int i = dim + 1; i < nN && ok; i++)
+  for (int i = 0; i < nN && ok; i++)
     for (int m = 0; m < dim; m++) {
       double s = 0.0;
-      for (int v = 0; v <= dim; v++) s = fma(bary[i * (dim + 1) + v], X[v * dim + m], s);
+      for (int v = 0; v <= dim; v++) s = fma(bary[i * (dim + 1) + v], X[fv[v] * dim + m], s);
       if (!(fabs(s - X[i * dim + m]) <= 1e-13 * h)) ok = false;
     }
   affine[e] = ok ? 1 : 0;
@@ -1305,8 +1309,10 @@ int hfx_allocate(hfx_ctx* c, int flags) {
     elem_coords_kernel<<<nblk((long long)nC * c->nN * c->dim, 256), 256, 0, c->st>>>((long long)nC * c->nN * c->dim, c->nN, c->dim, c->dNodes.p, c->dCells.p, c->dElemX.p);
     HFX_CUDA(cudaGetLastError());
     c->dAffine.alloc(nC);
-    if (c->geom == HFX_SIMPLEX) elem_affine_kernel<<<nblk(nC, 128), 128, 0, c->st>>>(nC, c->nN, c->dim, c->dElemX.p, c->dBary.p, c->dAffine.p);
-    else c->dAffine.zero(c->st);   // quads / hexes: multilinear geometry, Jacobians evaluated at the cubature points (general kernel)
+    {   // quads / hexes that are not parallelograms / parallelepipeds have a multilinear geometry: flag 0, Jacobians at every cubature point
+      const bool sx = c->geom == HFX_SIMPLEX;
+      elem_affine_kernel<<<nblk(nC, 128), 128, 0, c->st>>>(nC, c->nN, c->dim, 0, 1, sx ? 2 : 3, sx ? 3 : 4, c->dElemX.p, c->dBary.p, c->dAffine.p);
+    }
     HFX_CUDA(cudaGetLastError());
     // element blocks (HDGSolver.cpp:93-104) and the global system (linSystem->allocate :81)
     c->dU.alloc((size_t)nC * u * l); c->dQ.alloc((size_t)nC * q * l); c->dU0.alloc((size_t)nC * u); c->dQ0.alloc((size_t)nC * q);
@@ -1410,6 +1416,7 @@ int hfx_assemble(hfx_ctx* c) {
       GenParams g{};
       g.a = p; g.dim = c->dim; g.nN = c->nN; g.nNf = c->nNf; g.nFc = c->nFc; g.nIP = c->nIP; g.nIPf = c->nIPf; g.nD = c->md.nDOF;
       g.nSrc = 1;
+      g.frameV[0] = 0; g.frameV[1] = 1; g.frameV[2] = c->geom == HFX_SIMPLEX ? 2 : 3; g.frameV[3] = c->geom == HFX_SIMPLEX ? 3 : 4;
       if (p.opmask & HFX_OP_UNABU) {
         DField* bs = find_field(c, "BufferSolution");
         need(bs && bs->type == HFX_FIELD_CELL && bs->nObj == c->nN && bs->nVal == g.nD, "HDGBurgersModel", "setFieldMap", "need to give a field named BufferSolution to the HDGBurgersModel");

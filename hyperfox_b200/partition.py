@@ -2,8 +2,8 @@
 
 The reference partitions cells with Zoltan GRAPH/PHG (src/parallel/ZoltanPartitioner.cpp:14-32,42-56); Zoltan is not available here
 and its output is not pinned by any reference test, so the harness uses a deterministic stand-in: contiguous element ranges of the
-lexicographically numbered Kuhn mesh (= coordinate slabs; `box_partition_vector` gives 2/4/8 coordinate boxes), or any externally supplied
-partition vector.  Global ids are assigned
+lexicographically numbered Kuhn mesh (= coordinate slabs; `box_partition_vector` gives 2/4/8 coordinate boxes), recursive coordinate
+bisection of the cell centroids for any mesh (`rcb_partition_vector`), or any externally supplied partition vector (`load_partition_vector`).  Global ids are assigned
 before partitioning, as in the reference (Partitioner.cpp:13-36), so assembled entries do not depend on the partition.
 Assembly needs no exchange; the faces shared between ranks are what a trace halo exchange would carry.
 """
@@ -20,6 +20,29 @@ def partition_vector(n_total, world):
         e0, e1 = slab_range(n_total, r, world)
         p[e0:e1] = r
     return p
+
+
+def rcb_partition_vector(verts, lin_cells, world):
+    """Recursive coordinate bisection of the cell centroids (the deterministic stand-in for the Zoltan partition on
+    ANY mesh, structured or not).  A set of cells that has to feed k ranks is cut perpendicular to the longest axis of its bounding box
+    into floor(k/2) : ceil(k/2) parts by cell count (ties broken by cell id), so every world size is balanced to within one cell."""
+    verts = np.asarray(verts, dtype=np.float64)
+    cen = verts[np.asarray(lin_cells)].mean(axis=1)
+    part = np.zeros(cen.shape[0], dtype=np.int32)
+    stack = [(np.arange(cen.shape[0]), 0, int(world))]
+    while stack:
+        ids, r0, k = stack.pop()
+        if k == 1:
+            part[ids] = r0
+            continue
+        c = cen[ids]
+        ax = int(np.argmax(c.max(axis=0) - c.min(axis=0)))
+        kl = k // 2
+        nl = (ids.size * kl + k // 2) // k          # nearest integer to ids.size * kl / k
+        order = np.lexsort((ids, c[:, ax]))
+        stack.append((np.sort(ids[order[:nl]]), r0, kl))
+        stack.append((np.sort(ids[order[nl:]]), r0 + kl, k - kl))
+    return part
 
 
 def load_partition_vector(path, n_total, world):

@@ -79,3 +79,29 @@ def test_supplied_partition_vector(tmp_path):
     owned = np.concatenate([p["face_global"][p["owned_face"] == 1] for p in probs])
     assert np.array_equal(np.sort(owned), np.arange(f2c.shape[0]))
     assert sum(int(p["owned_cells"].size) for p in probs) == c.shape[0]
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_rcb_on_an_unstructured_reference_mesh(world):
+    """Recursive coordinate bisection on the reference's Gmsh tet mesh regression_dim-3_h-2e-1 (729 cells): balanced
+    to within one cell per bisection level, every face owned once, halo lists symmetric, and a cut much smaller than a random partition's."""
+    from tests.conftest import load_mesh
+    nodes, cells = load_mesh("regression_dim-3_h-2e-1_ord-1")
+    part = P.rcb_partition_vector(nodes, cells, world)
+    counts = np.bincount(part, minlength=world)
+    assert counts.sum() == cells.shape[0] and counts.max() - counts.min() <= 3
+    assert np.array_equal(part, P.rcb_partition_vector(nodes, cells, world))           # deterministic
+    c2f, f2c = P.global_linear_topology(cells, 3)
+    interior = f2c[:, 1] >= 0
+    cut = int((part[f2c[interior, 0]] != part[f2c[interior, 1]]).sum())
+    rnd = np.random.default_rng(1).integers(0, world, size=cells.shape[0])
+    cut_rnd = int((rnd[f2c[interior, 0]] != rnd[f2c[interior, 1]]).sum())
+    assert cut < 0.45 * cut_rnd
+    probs = [P.rank_problem(nodes[:, :3], cells, part, r, 3, c2f, f2c) for r in range(world)]
+    owned = np.concatenate([p["face_global"][p["owned_face"] == 1] for p in probs])
+    assert np.array_equal(np.sort(owned), np.arange(f2c.shape[0]))
+    for r, p in enumerate(probs):
+        for k, s in enumerate(p["nbrs"]):
+            q = probs[s]
+            ks = list(q["nbrs"]).index(r)
+            assert np.array_equal(p["face_global"][p["send"][k]], q["face_global"][q["recv"][ks]])

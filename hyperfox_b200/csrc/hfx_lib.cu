@@ -152,6 +152,26 @@ __global__ void elem_affine_kernel(int nCells, int nN, int dim, int fv0, int fv1
   affine[e] = ok ? 1 : 0;
 }
 
+// sum (b - y)^2 and sum b^2 (parity hook hfx_residual): grid-stride, warp + block reduction, one atomic pair per block
+__global__ void residual_sq_kernel(long long n, const double* __restrict__ b, const double* __restrict__ y, double* __restrict__ out) {
+  double r2 = 0.0, b2 = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double bi = b[i], d = bi - y[i];
+    r2 = fma(d, d, r2); b2 = fma(bi, bi, b2);
+  }
+  for (int o = 16; o > 0; o >>= 1) { r2 += __shfl_xor_sync(0xffffffffu, r2, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o); }
+  __shared__ double sr[32], sb[32];
+  const int w = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  if (ln == 0) { sr[w] = r2; sb[w] = b2; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    r2 = ln < nw ? sr[ln] : 0.0; b2 = ln < nw ? sb[ln] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) { r2 += __shfl_xor_sync(0xffffffffu, r2, o); b2 += __shfl_xor_sync(0xffffffffu, b2, o); }
+    if (ln == 0) { atomicAdd(out, r2); atomicAdd(out + 1, b2); }
+  }
+}
+
 __global__ void ip_coords_kernel(int nCells, int nN, int nIP, int dim, const double* __restrict__ nodes, const int* __restrict__ cells,
                                  const double* __restrict__ shape, double* __restrict__ xip) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1532,6 +1552,25 @@ int hfx_solve(hfx_ctx* c, const hfx_solve_opts* opts, hfx_solve_stats* stats) {
   });
   if (rc) return rc;
   return hfx_recover(c);
+}
+
+int hfx_residual(hfx_ctx* c, double* rnorm, double* bnorm) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    need(c->assembled, "HDGSolver", "solve", "system must be assembled before solving");
+    need(!(c->halo.comm && c->halo.planned), "hfx", "residual", "the residual hook works on the rank-local system only");
+    FaceOp A(c);
+    DBuf<double> y, acc;
+    y.alloc((size_t)A.n); acc.alloc(2); acc.zero(c->st);
+    A.apply(find_field(c, "Trace")->d.p, y.p, c->st);
+    residual_sq_kernel<<<(int)std::min<long long>(nblk(A.n, 256), (long long)c->nSM * 8), 256, 0, c->st>>>(A.n, c->dRhs.p, y.p, acc.p);
+    HFX_CUDA(cudaGetLastError());
+    double h[2] = {0.0, 0.0};
+    acc.download(h, 2, c->st);
+    HFX_CUDA(cudaStreamSynchronize(c->st));
+    if (rnorm) *rnorm = std::sqrt(h[0]);
+    if (bnorm) *bnorm = std::sqrt(h[1]);
+  });
 }
 
 int hfx_comm_unique_id(char* id128) {

@@ -137,6 +137,9 @@ int hfx_comm_halo_field(hfx_ctx* ctx, const char* faceFieldName); /* Partitioner
 int hfx_get_csr(hfx_ctx* ctx, long long* nrows, long long* nnz, long long* rowptr, int* colidx, double* vals, double* rhs);
 /* per-element condensed blocks, column-major as the reference stores them (HDGSolver.cpp:336-341; the device keeps U, Q row-major and
    transposes here); any may be NULL */
+/* parity hook: || rhs - A * Trace ||_2 and || rhs ||_2 of the assembled trace system with the current "Trace" field (one SpMV on the
+   device; lets a test check the global system at sizes where hfx_get_csr is too large to bring back) */
+int hfx_residual(hfx_ctx* ctx, double* rnorm, double* bnorm);
 int hfx_get_local(hfx_ctx* ctx, int iEl, int nEl, double* S, double* S0, double* U, double* U0, double* Q, double* Q0);
 /* element -> global trace dof ids (matRowCols, HDGSolver.cpp:596) */
 int hfx_get_elem_dofs(hfx_ctx* ctx, int iEl, int nEl, int* dofs);

@@ -92,3 +92,25 @@ def test_product_and_oracle_agree_on_a_kuhn_mesh():
         v, c = meshgen.kuhn_linear(2, dim)
         a, b = product.high_order_from_linear(dim, order, v, c), meshio.high_order_from_linear(dim, order, v, c)
         assert np.array_equal(a[1], b[1]) and np.abs(a[0] - b[0]).max() < 1e-15
+
+
+@pytest.mark.parametrize("impl", ["product", "oracle"])
+def test_reader_rejects_what_the_generator_cannot_raise(tmp_path, impl):
+    """Binary files, other format versions and non-simplex elements are refused with a message instead of being misread."""
+    m = product if impl == "product" else meshio
+    err = Exception if impl == "product" else ValueError
+    quad = "$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n4\n1 0 0 0\n2 1 0 0\n3 1 1 0\n4 0 1 0\n$EndNodes\n$Elements\n1\n1 3 2 1 1 1 2 3 4\n$EndElements\n"
+    (tmp_path / "quad.msh").write_text(quad)
+    with pytest.raises(err, match="not supported"):
+        m.read_msh(str(tmp_path / "quad.msh"))
+    (tmp_path / "bin.msh").write_text(quad.replace("2.2 0 8", "2.2 1 8"))
+    with pytest.raises(err, match="ASCII"):
+        m.read_msh(str(tmp_path / "bin.msh"))
+    (tmp_path / "v4.msh").write_text(quad.replace("2.2 0 8", "4.1 0 8"))
+    with pytest.raises(err, match="2.x"):
+        m.read_msh(str(tmp_path / "v4.msh"))
+    # node tags need not be contiguous or sorted: they are compacted in ascending tag order
+    tri = "$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n3\n30 0 1 0\n10 0 0 0\n20 1 0 0\n$EndNodes\n$Elements\n2\n1 15 2 0 1 10\n2 2 2 0 1 10 20 30\n$EndElements\n"
+    (tmp_path / "tri.msh").write_text(tri)
+    nodes, el = m.read_msh(str(tmp_path / "tri.msh"))
+    assert np.array_equal(nodes[:, :2], [[0, 0], [1, 0], [0, 1]]) and np.array_equal(el[2], [[0, 1, 2]]) and list(el) == [2]

@@ -994,6 +994,19 @@ int hfx_host_read_msh(const char* path, int* nNodes, int counts[4], double* node
   });
 }
 
+int hfx_host_read_h5_mesh(const char* path, int* nNodes, int* dimNodeSpace, int* nCells, int* nodesPerCell, double* nodes, int* cells) {
+  return guard(nullptr, [&] {
+    H5Mesh m;
+    read_h5_mesh(path ? path : "", &m);
+    if (dimNodeSpace) *dimNodeSpace = m.dimNodeSpace;
+    if (nodesPerCell) *nodesPerCell = m.nodesPerCell;
+    if (nNodes) *nNodes = m.dimNodeSpace ? (int)(m.nodes.size() / m.dimNodeSpace) : 0;
+    if (nCells) *nCells = m.nodesPerCell ? (int)(m.cells.size() / m.nodesPerCell) : 0;
+    if (nodes) std::copy(m.nodes.begin(), m.nodes.end(), nodes);
+    if (cells) std::copy(m.cells.begin(), m.cells.end(), cells);
+  });
+}
+
 int hfx_host_high_order_mesh(int dim, int order, int nLin, const double* lin, int nCells, const int* cells, int nExisting1, const int* existing1,
                              int nExisting2, const int* existing2, int* nNodesOut, double* nodesOut, int* cellsOut) {
   return guard(nullptr, [&] {

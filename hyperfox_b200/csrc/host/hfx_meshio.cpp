@@ -9,6 +9,9 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <iterator>
 #include <fstream>
 #include <map>
 #include <memory>
@@ -198,6 +201,125 @@ void high_order_mesh(int dim, int order, int nLin, const double* lin, int nCells
       }
     }
   }
+}
+
+// ---- HDF5 subset reader -------------------------------------------------------------------------------------------------------
+namespace {
+struct H5File {
+  std::vector<unsigned char> b;
+  [[noreturn]] static void bad(const std::string& m) { throw std::runtime_error("HDF5Io : loadMesh : " + m); }
+  uint64_t u(size_t off, int n) const {
+    if (off + n > b.size()) bad("truncated file");
+    uint64_t v = 0;
+    for (int i = n - 1; i >= 0; i--) v = (v << 8) | b[off + i];
+    return v;
+  }
+  bool tag(size_t off, const char* t) const { return off + 4 <= b.size() && std::equal(t, t + 4, b.begin() + off); }
+  struct Entry { uint64_t nameOff = 0, ohdr = 0, btree = 0, heap = 0; bool cached = false; };
+  struct Msg { int type; size_t data, size; };
+  Entry entry(size_t off) const {
+    Entry e;
+    e.nameOff = u(off, 8); e.ohdr = u(off + 8, 8);
+    if (u(off + 16, 4) == 1) { e.cached = true; e.btree = u(off + 24, 8); e.heap = u(off + 32, 8); }
+    return e;
+  }
+  std::vector<Msg> messages(size_t ohdr) const {
+    if (u(ohdr, 1) != 1) bad("only version-1 object headers are supported");
+    const size_t nmsg = u(ohdr + 2, 2);
+    std::vector<std::pair<size_t, size_t>> blocks = {{ohdr + 16, (size_t)u(ohdr + 8, 4)}};
+    std::vector<Msg> out;
+    for (size_t bi = 0; bi < blocks.size() && out.size() < nmsg; bi++) {
+      size_t off = blocks[bi].first;
+      const size_t end = off + blocks[bi].second;
+      while (off + 8 <= end && out.size() < nmsg) {
+        const int type = (int)u(off, 2);
+        const size_t sz = u(off + 2, 2), data = off + 8;
+        if (type == 0x10) blocks.push_back({(size_t)u(data, 8), (size_t)u(data + 8, 8)});   // continuation block
+        out.push_back({type, data, sz});
+        off = data + sz;
+      }
+    }
+    return out;
+  }
+  void walk(size_t node, size_t heapData, std::map<std::string, Entry>* out, int depth) const {
+    if (!tag(node, "TREE") || depth > 16) bad("corrupt group B-tree");
+    const int level = (int)u(node + 5, 1), nent = (int)u(node + 6, 2);
+    const size_t p = node + 8 + 16;
+    for (int i = 0; i < nent; i++) {
+      const size_t child = u(p + 8 + (size_t)i * 16, 8);
+      if (level > 0) { walk(child, heapData, out, depth + 1); continue; }
+      if (!tag(child, "SNOD")) bad("corrupt symbol table node");
+      const int ns = (int)u(child + 6, 2);
+      for (int k = 0; k < ns; k++) {
+        const Entry e = entry(child + 8 + (size_t)k * 40);
+        size_t s = heapData + e.nameOff;
+        std::string name;
+        while (s < b.size() && b[s]) name.push_back((char)b[s++]);
+        (*out)[name] = e;
+      }
+    }
+  }
+  std::map<std::string, Entry> children(Entry g) const {
+    if (!g.cached) for (const Msg& m : messages(g.ohdr)) if (m.type == 0x11) { g.btree = u(m.data, 8); g.heap = u(m.data + 8, 8); g.cached = true; }
+    if (!g.cached || !tag(g.heap, "HEAP")) bad("not a symbol-table group");
+    std::map<std::string, Entry> out;
+    walk(g.btree, u(g.heap + 8 + 16, 8), &out, 0);
+    return out;
+  }
+  // dataset -> shape, element class (0 integer, 1 float), element size, address of the contiguous data
+  void dataset(const Entry& d, std::vector<uint64_t>* shape, int* cls, int* size, size_t* addr) const {
+    bool haveS = false, haveT = false, haveL = false;
+    for (const Msg& m : messages(d.ohdr)) {
+      if (m.type == 0x1) {
+        const int v = (int)u(m.data, 1), rank = (int)u(m.data + 1, 1);
+        const size_t base = v == 1 ? m.data + 8 : m.data + 4;
+        shape->clear();
+        for (int i = 0; i < rank; i++) shape->push_back(u(base + 8 * (size_t)i, 8));
+        haveS = true;
+      } else if (m.type == 0x3) {
+        *cls = (int)(u(m.data, 1) & 0x0F); *size = (int)u(m.data + 4, 4); haveT = true;
+      } else if (m.type == 0x8) {
+        if (u(m.data, 1) != 3 || u(m.data + 1, 1) != 1) bad("only contiguous dataset layouts are supported");
+        *addr = (size_t)u(m.data + 2, 8); haveL = true;
+      }
+    }
+    if (!haveS || !haveT || !haveL) bad("incomplete dataset header");
+  }
+};
+}  // namespace
+
+void read_h5_mesh(const std::string& path, H5Mesh* out) {
+  H5File f;
+  {
+    std::ifstream in(path, std::ios::binary);
+    if (!in) H5File::bad("could not open " + path);
+    f.b.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+  }
+  static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+  if (f.b.size() < 96 || !std::equal(sig, sig + 8, f.b.begin())) H5File::bad(path + " is not an HDF5 file");
+  if (f.b[8] != 0 || f.b[13] != 8 || f.b[14] != 8) H5File::bad("only superblock version 0 with 8-byte offsets is supported");
+  const H5File::Entry root = f.entry(24 + 4 * 8);
+  auto top = f.children(root);
+  if (!top.count("Mesh")) H5File::bad("the file has no Mesh group");
+  auto mesh = f.children(top["Mesh"]);
+  if (!mesh.count("Nodes") || !mesh.count("Cells")) H5File::bad("the Mesh group must hold the Nodes and Cells datasets");
+  std::vector<uint64_t> shape;
+  int cls = -1, size = 0;
+  size_t addr = 0;
+  f.dataset(mesh["Nodes"], &shape, &cls, &size, &addr);
+  if (shape.size() != 2 || cls != 1 || size != 8) H5File::bad("Nodes must be a two-dimensional float64 dataset");
+  const size_t nn = (size_t)(shape[0] * shape[1]);
+  if (addr + nn * 8 > f.b.size()) H5File::bad("truncated Nodes dataset");
+  out->dimNodeSpace = (int)shape[1];
+  out->nodes.resize(nn);
+  std::memcpy(out->nodes.data(), f.b.data() + addr, nn * 8);
+  f.dataset(mesh["Cells"], &shape, &cls, &size, &addr);
+  if (shape.size() != 2 || cls != 0 || (size != 4 && size != 8)) H5File::bad("Cells must be a two-dimensional integer dataset");
+  const size_t nc = (size_t)(shape[0] * shape[1]);
+  if (addr + nc * size > f.b.size()) H5File::bad("truncated Cells dataset");
+  out->nodesPerCell = (int)shape[1];
+  out->cells.resize(nc);
+  for (size_t i = 0; i < nc; i++) out->cells[i] = (int)(int64_t)f.u(addr + i * size, size);
 }
 
 }  // namespace hfx

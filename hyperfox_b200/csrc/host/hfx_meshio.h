@@ -20,4 +20,14 @@ void read_msh(const std::string& path, MshFile* out);
 void high_order_mesh(int dim, int order, int nLin, const double* lin, int nCells, const int* cells, const std::vector<int> (&existing)[4],
                      std::vector<double>* nodes, std::vector<int>* hoCells);
 
+// HDF5 mesh file of the reference (HDF5Io::loadMesh, src/io/HDF5Io.cpp:111-152): datasets /Mesh/Nodes (f8, [nNodes][dimNodeSpace]) and
+// /Mesh/Cells (i4 or i8, [nCells][nN]).  Dependency-free reader of the subset of the format those files use: superblock version 0,
+// symbol-table groups, version-1 object headers, contiguous layout.  Throws std::runtime_error("HDF5Io : loadMesh : ...").
+struct H5Mesh {
+  int dimNodeSpace = 0, nodesPerCell = 0;
+  std::vector<double> nodes;
+  std::vector<int> cells;
+};
+void read_h5_mesh(const std::string& path, H5Mesh* out);
+
 }  // namespace hfx

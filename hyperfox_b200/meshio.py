@@ -1,6 +1,7 @@
 """Mesh input of the path's callers: Gmsh 2.2 ASCII reader and the straight-sided order-p mesh
 generator of the reference's tools/convertGmsh2H5HO.cpp:117-397, without MOAB.  The implementation is host C++
-(csrc/host/hfx_meshio.cpp) behind the C ABI (hfx_host_read_msh, hfx_host_high_order_mesh); this module is the ctypes wrapper.
+(csrc/host/hfx_meshio.cpp) behind the C ABI (hfx_host_read_msh, hfx_host_high_order_mesh, hfx_host_read_h5_mesh: the reference's .h5 mesh
+files without libhdf5); this module is the ctypes wrapper.
 The generated meshes carry the reference's node numbering: tests/test_meshio.py regenerates the reference's .h5 regression fixtures
 from their .msh sources, cells bit-exact."""
 import ctypes as C
@@ -41,3 +42,14 @@ def high_order_from_linear(dim, order, lin_nodes, cells, existing=None):
 def high_order_from_msh(path, dim, order):
     nodes, elems = read_msh(path)
     return high_order_from_linear(dim, order, nodes, elems[dim], {k: v for k, v in elems.items() if k < dim})
+
+
+def read_h5_mesh(path):
+    """HDF5Io::loadMesh (src/io/HDF5Io.cpp:111-152) without libhdf5: (nodes [nNodes, dimNodeSpace], cells [nCells, nN]) of a mesh file of
+    the reference (ressources/meshes/**/*.h5)."""
+    L = lib()
+    nn, d, nc, npc = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+    check(L.hfx_host_read_h5_mesh(str(path).encode(), C.byref(nn), C.byref(d), C.byref(nc), C.byref(npc), None, None))
+    nodes, cells = np.zeros((nn.value, d.value)), np.zeros((nc.value, npc.value), dtype=np.int32)
+    check(L.hfx_host_read_h5_mesh(str(path).encode(), C.byref(nn), C.byref(d), C.byref(nc), C.byref(npc), pd(nodes), pi(cells)))
+    return nodes, cells

@@ -55,6 +55,10 @@ int hfx_host_compute_faces(int dim, int order, int geom, int nCells, const int* 
    topological dimension k (k = 1..3; counts[0] unused); then with nodes[nNodes][3] (ascending node tag) and elemsK[counts[K]][K+1]
    (0-based vertex ids, file order; any pointer may be NULL). */
 int hfx_host_read_msh(const char* path, int* nNodes, int counts[4], double* nodes, int* elems1, int* elems2, int* elems3);
+/* HDF5Io::loadMesh (src/io/HDF5Io.cpp:111-152) without libhdf5: /Mesh/Nodes [nNodes][dimNodeSpace] (f8) and /Mesh/Cells
+   [nCells][nodesPerCell] (i4 / i8) of the reference's mesh files (superblock 0, symbol-table groups, contiguous datasets).  First call
+   with NULL arrays for the sizes. */
+int hfx_host_read_h5_mesh(const char* path, int* nNodes, int* dimNodeSpace, int* nCells, int* nodesPerCell, double* nodes, int* cells);
 /* generateHigherOrderMesh (convertGmsh2H5HO.cpp:117-257): straight-sided order-p simplex mesh from a linear one, the reference's node
    numbering.  lin[nLin][dim], cells[nCells][dim+1]; existing1 / existing2: edges / triangles already present in the input file
    (they precede the generated ones, as in MOAB).  Pass NULL output arrays to only count; nodesOut[nNodesOut][dim], cellsOut[nCells][nN]. */

@@ -242,6 +242,26 @@ class Io {
   std::map<std::string, Field*> fieldMap;
 };
 
+// src/io/HDF5Io.h: load() of the mesh part (loadMesh, HDF5Io.cpp:111-152) without libhdf5; field I/O and write() are out of scope.
+class HDF5Io : public Io {
+ public:
+  HDF5Io() {}
+  explicit HDF5Io(Mesh* mesh) { setMesh(mesh); }
+  void load(std::string filename) override {
+    if (!myMesh) throw ErrorHandle("HDF5Io", "load", "the mesh must be set before loading");
+    if (getExtension(filename) != ".h5") throw ErrorHandle("HDF5Io", "load", "the file extension must be .h5");
+    int nNodes = 0, dimSpace = 0, nCells = 0, nPerCell = 0;
+    detail::check(hfx_host_read_h5_mesh(filename.c_str(), &nNodes, &dimSpace, &nCells, &nPerCell, 0, 0), nullptr);
+    if (!myMesh->getReferenceElement() || myMesh->getReferenceElement()->getNumNodes() != nPerCell)
+      throw ErrorHandle("HDF5Io", "loadMesh", "the cells of the file do not have the number of nodes of the reference element of the mesh");
+    std::vector<double> pts((size_t)nNodes * dimSpace);
+    std::vector<int> cells((size_t)nCells * nPerCell);
+    detail::check(hfx_host_read_h5_mesh(filename.c_str(), &nNodes, &dimSpace, &nCells, &nPerCell, pts.data(), cells.data()), nullptr);
+    myMesh->setMesh(dimSpace, pts, cells);
+  }
+  void write(std::string) override { throw ErrorHandle("HDF5Io", "write", "writing HDF5 files is not supported by this build"); }
+};
+
 class GmshIo : public Io {
  public:
   GmshIo() {}

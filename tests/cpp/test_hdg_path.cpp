@@ -16,6 +16,7 @@
 #include "HDGDiffusionSource.h"
 #include "HDGLaplaceModel.h"
 #include "GmshIo.h"
+#include "HDF5Io.h"
 #include "HDGSolver.h"
 #include "Mesh.h"
 #include "RungeKutta.h"
@@ -330,6 +331,18 @@ static void testGmshIo(const std::string& dir, const std::string& name, int dim,
   CHECK_THROWS(io.write(dir + "/out.msh"));
   GmshIo unset;
   CHECK_THROWS(unset.load(dir + "/" + name + ".msh"));
+  // HDF5Io::load of the reference's own .h5 file (verbatim copy) gives the same mesh as the converted text fixture
+  Mesh fromH5(dim, order, "simplex");
+  HDF5Io h5(&fromH5);
+  CHECK_NOTHROW(h5.load(dir + "/" + name + "_ord-" + std::to_string(order) + ".h5"));
+  CHECK(*fromH5.getCells() == *fixture.getCells());
+  CHECK(*fromH5.getPoints() == *fixture.getPoints());
+  CHECK(*fromH5.getFaces() == *fixture.getFaces());
+  Mesh wrongOrder(dim, order + 1, "simplex");
+  HDF5Io h5w(&wrongOrder);
+  CHECK_THROWS(h5w.load(dir + "/" + name + "_ord-" + std::to_string(order) + ".h5"));
+  CHECK_THROWS(h5.load(dir + "/" + name + ".msh"));
+  CHECK_THROWS(h5.load(dir + "/missing.h5"));
 }
 
 int main(int argc, char** argv) {

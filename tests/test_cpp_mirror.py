@@ -36,6 +36,8 @@ def mesh_dir(tmp_path_factory):
     import shutil
     for name in ("regression_dim-2_h-2e-1", "regression_dim-3_h-2e-1"):
         shutil.copyfile(os.path.join(ROOT, "tests", "golden", "meshes", "msh", name + ".msh"), os.path.join(d, name + ".msh"))
+    for name in ("regression_dim-2_h-2e-1_ord-2", "regression_dim-3_h-2e-1_ord-3"):
+        shutil.copyfile(os.path.join(ROOT, "tests", "golden", "meshes", "h5", name + ".h5"), os.path.join(d, name + ".h5"))
     return str(d)
 
 

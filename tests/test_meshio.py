@@ -114,3 +114,37 @@ def test_reader_rejects_what_the_generator_cannot_raise(tmp_path, impl):
     (tmp_path / "tri.msh").write_text(tri)
     nodes, el = m.read_msh(str(tmp_path / "tri.msh"))
     assert np.array_equal(nodes[:, :2], [[0, 0], [1, 0], [0, 1]]) and np.array_equal(el[2], [[0, 1, 2]]) and list(el) == [2]
+
+
+H5 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", "h5")
+
+
+@pytest.mark.parametrize("name", ["lightTri2", "regression_dim-2_h-2e-1_ord-2", "regression_dim-3_h-2e-1_ord-3", "regression_dim-3_h-3e-1_ord-5"])
+def test_h5_mesh_reader_on_reference_files(name):
+    """hfx_host_read_h5_mesh (HDF5Io::loadMesh without libhdf5) on verbatim copies of the reference's mesh files.  The content is known
+    independently of any HDF5 reader: the regression files are regenerated bit-exactly from their .msh sources above, and lightTri2 is
+    written out in tests/unittests/solver/TestHDGSolver.cpp / SURVEY.md section 8c (cells [[0,1,3,5,4,8],[3,1,2,4,6,7]], 9 nodes)."""
+    nodes, cells = product.read_h5_mesh(os.path.join(H5, name + ".h5"))
+    gn, gc = load_mesh(name)
+    assert nodes.shape == gn.shape and cells.shape == gc.shape
+    assert np.array_equal(nodes, gn) and np.array_equal(cells, gc)
+    if name == "lightTri2":
+        assert cells.tolist() == [[0, 1, 3, 5, 4, 8], [3, 1, 2, 4, 6, 7]] and nodes.shape == (9, 2)
+    elif "h-3e-1" in name or "h-2e-1" in name:
+        dim, order = int(name.split("dim-")[1][0]), int(name[-1])
+        h = name.split("_h-")[1].split("_")[0]
+        n, c = product.high_order_from_msh(os.path.join(MSH, "regression_dim-%d_h-%s.msh" % (dim, h)), dim, order)
+        assert np.array_equal(c, cells) and np.abs(n - nodes).max() < 1e-15
+
+
+def test_h5_mesh_reader_errors(tmp_path):
+    from hyperfox_b200.capi import ErrorHandle
+    with pytest.raises(ErrorHandle, match="HDF5Io : loadMesh : could not open"):
+        product.read_h5_mesh(str(tmp_path / "missing.h5"))
+    (tmp_path / "not.h5").write_bytes(b"\x89HDX" + bytes(200))
+    with pytest.raises(ErrorHandle, match="not an HDF5 file"):
+        product.read_h5_mesh(str(tmp_path / "not.h5"))
+    raw = open(os.path.join(H5, "lightTri2.h5"), "rb").read()
+    (tmp_path / "cut.h5").write_bytes(raw[:1500])
+    with pytest.raises(ErrorHandle, match="HDF5Io : loadMesh"):
+        product.read_h5_mesh(str(tmp_path / "cut.h5"))

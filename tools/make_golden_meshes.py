@@ -36,3 +36,9 @@ os.makedirs(os.path.join(OUT, "msh"), exist_ok=True)
 for t in ("regression_dim-2_h-3e-1", "regression_dim-2_h-2e-1", "regression_dim-2_h-1e-1", "regression_dim-3_h-3e-1", "regression_dim-3_h-2e-1"):
     shutil.copyfile(os.path.join(REF, "regression", t + ".msh"), os.path.join(OUT, "msh", t + ".msh"))
     print("msh/" + t + ".msh")
+
+# a few of the reference's .h5 files verbatim (test data for the dependency-free HDF5 reader of the product, hfx_host_read_h5_mesh)
+os.makedirs(os.path.join(OUT, "h5"), exist_ok=True)
+for t in ("lightTri2.h5", "regression/regression_dim-2_h-2e-1_ord-2.h5", "regression/regression_dim-3_h-2e-1_ord-3.h5", "regression/regression_dim-3_h-3e-1_ord-5.h5"):
+    shutil.copyfile(os.path.join(REF, t), os.path.join(OUT, "h5", os.path.basename(t)))
+    print("h5/" + os.path.basename(t))

@@ -87,6 +87,47 @@ class Mesh:
     def getSlicePoints(self, ids): return self.nodes[np.asarray(ids)]
 
 
+class Io:
+    """src/io/Io.h: load / write / setMesh / setField."""
+
+    def __init__(self, mesh=None):
+        self.myMesh, self.fieldMap = mesh, {}
+
+    def setMesh(self, mesh): self.myMesh = mesh
+    def setField(self, name, field): self.fieldMap[name] = field
+    def load(self, filename): raise NotImplementedError
+    def write(self, filename): raise ErrorHandle("%s : write : writing is not supported by this build" % type(self).__name__)
+
+    def _need_mesh(self, filename, ext):
+        if self.myMesh is None:
+            raise ErrorHandle("%s : load : the mesh must be set before loading" % type(self).__name__)
+        if not str(filename).endswith(ext):
+            raise ErrorHandle("%s : load : the file extension must be %s" % (type(self).__name__, ext))
+
+
+class HDF5Io(Io):
+    """HDF5Io::load, mesh part (src/io/HDF5Io.cpp:111-152), without libhdf5 (hfx_host_read_h5_mesh)."""
+
+    def load(self, filename):
+        from . import meshio
+        self._need_mesh(filename, ".h5")
+        nodes, cells = meshio.read_h5_mesh(filename)
+        self.myMesh.setMesh(nodes, cells)
+
+
+class GmshIo(Io):
+    """A Gmsh 2.2 file of linear simplices raised to the order of the mesh's reference element with the node numbering of the
+    reference's tools/convertGmsh2H5HO.cpp:117-257 (hfx_host_read_msh + hfx_host_high_order_mesh)."""
+
+    def load(self, filename):
+        from . import meshio
+        self._need_mesh(filename, ".msh")
+        if self.myMesh.refEl.geom != "simplex":
+            raise ErrorHandle("GmshIo : load : only simplex meshes can be generated from a Gmsh file")
+        nodes, cells = meshio.high_order_from_msh(filename, self.myMesh.dim, self.myMesh.order)
+        self.myMesh.setMesh(nodes, cells)
+
+
 class Field:
     """Field(mesh, type, nObjPerEnt, nValsPerObj): values[(ent*nObj + o)*nVals + v] (src/field/Field.cpp:41-61)."""
 

@@ -148,3 +148,24 @@ def test_h5_mesh_reader_errors(tmp_path):
     (tmp_path / "cut.h5").write_bytes(raw[:1500])
     with pytest.raises(ErrorHandle, match="HDF5Io : loadMesh"):
         product.read_h5_mesh(str(tmp_path / "cut.h5"))
+
+
+def test_python_io_mirrors():
+    """hfox.HDF5Io / hfox.GmshIo (the reference's Io interface): both routes give the same Mesh, faces included."""
+    from hyperfox_b200 import hfox
+    a, b = hfox.Mesh(3, 3, "simplex"), hfox.Mesh(3, 3, "simplex")
+    hfox.HDF5Io(a).load(os.path.join(H5, "regression_dim-3_h-2e-1_ord-3.h5"))
+    io = hfox.GmshIo()
+    io.setMesh(b)
+    io.load(os.path.join(MSH, "regression_dim-3_h-2e-1.msh"))
+    assert a.getNumberCells() == b.getNumberCells() == 729 and a.getNumberPoints() == b.getNumberPoints() == 4249
+    assert np.array_equal(a.cells, b.cells) and np.array_equal(a.faces, b.faces) and np.array_equal(a.face2CellMap, b.face2CellMap)
+    assert np.abs(a.nodes - b.nodes).max() < 1e-15
+    with pytest.raises(hfox.ErrorHandle, match="extension"):
+        hfox.HDF5Io(a).load(os.path.join(MSH, "regression_dim-3_h-2e-1.msh"))
+    with pytest.raises(hfox.ErrorHandle, match="mesh must be set"):
+        hfox.GmshIo().load(os.path.join(MSH, "regression_dim-3_h-2e-1.msh"))
+    with pytest.raises(hfox.ErrorHandle, match="connectivity does not match"):
+        hfox.HDF5Io(hfox.Mesh(3, 2, "simplex")).load(os.path.join(H5, "regression_dim-3_h-2e-1_ord-3.h5"))
+    with pytest.raises(hfox.ErrorHandle, match="write"):
+        hfox.HDF5Io(a).write("out.h5")

@@ -163,3 +163,39 @@ def test_condensation_qr_vs_lu_and_direct(dim, order):
     S = D - C @ X
     assert np.abs(S - qr[2]).max() < 1e-11 * np.abs(S).max()
     assert np.abs(-X[:u] - qr[0]).max() < 1e-10 * np.abs(X).max() and np.abs(-X[u:] - qr[1]).max() < 1e-10 * np.abs(X).max()
+
+
+def _unabu_forms(dim, order, power):
+    """u = (x^power, 0, ..) on the reference element, trace = u on the faces: (u^T A_uu u + u^T A_ul t, rhs_u . u) of HDGUNabU."""
+    re = ReferenceElement(dim, order)
+    rc = O.RefElC(re)
+    nN, nD = re.nNodes, dim
+    sol = np.zeros((nN, nD))
+    sol[:, 0] = re.nodes[:, 0] ** power
+    trace = sol[np.asarray(re.faceNodes)]                       # [nFc, nNf, nD]
+    A, r = O.op_unabu(rc, nD, re.nodes, sol, trace)
+    u_len = nN * nD
+    u, t = sol.reshape(-1), trace.reshape(-1)
+    sL = u_len * (dim + 1)                                      # the trace block starts after the u and q blocks (TestHDGUNabU.cpp:98)
+    return float(u @ A[:u_len, :u_len] @ u + u @ A[:u_len, sL:sL + t.size] @ t), float(r[:u_len] @ u)
+
+
+def _intx2n(dim, k):
+    """tests/TestUtils.h.in:88-96: closed form of the integral the reference compares with."""
+    return 2.0 / (2.0 * k + 1) if dim < 3 else 1.0 / (2.0 * k + 3.0) + 1.0 / (2.0 * k + 1.0)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_hdg_unabu_closed_forms(dim, order):
+    """tests/unittests/operator/TestHDGUNabU.cpp:31-105 (u = x^(n+1) e_0, odd n+1, closed-form integrals, margin 1e-12) and :107-170
+    (a constant state gives zero for both forms)."""
+    for n in range(0, 2 * (order - 1) // 3):
+        if (n + 1) % 2 == 0:
+            continue
+        quad, lin = _unabu_forms(dim, order, n + 1)
+        ref = _intx2n(dim, (3 * n + 2) // 2)
+        assert abs(quad / (2.0 * (n + 1)) - ref) < 1e-12, (n, quad, ref)
+        assert abs(lin / (1.0 * (n + 1)) - ref) < 1e-12, (n, lin, ref)
+    quad, lin = _unabu_forms(dim, order, 0)                      # constant solution (1, 0, ..)
+    assert quad < 1e-12 and lin < 1e-12

@@ -101,3 +101,37 @@ def test_gmres_stock_systems_oracle():
             x = np.zeros(n); res = C.c_double(0)
             O.lib().orc_gmres(n, rowptr.ctypes.data_as(O._lp), O._i(colidx), O._d(vals), O._d(b), O._d(x), 30, 1, 1, 1e-16, 1000, C.byref(res))
             assert np.abs(x - xs).max() < 1e-10, (n, kind)
+
+
+@pytest.mark.parametrize("dim,order", [(2, 2), (2, 3), (3, 2)])
+@pytest.mark.parametrize("bc", ["dirichlet", "integrated"])
+def test_boundary_model_rows_of_the_global_system(dim, order, bc):
+    """tests/unittests/model/TestDirichletModel.cpp (local matrix = identity, rhs = the Dirichlet values, assembly type Set) and
+    TestIntegratedDirichletModel.cpp:46-54 (local matrix = face mass, rhs = mass x values), seen where they end up: the rows of the
+    boundary faces in the assembled trace system (HDGSolver.cpp:361-529: Set semantics, every other entry of those rows is zero)."""
+    import scipy.sparse as sp
+    from oracle.refel import ReferenceElement
+    case = H.make_case(dim, order, N=2, perturb=0.0, bc=bc, model="diffsrc", seed=2)
+    o = H.run_oracle(case, solve=False)
+    topo, nodes = case["topo"], case["nodes"]
+    faces, bnd = topo["faces"], topo["boundary"]
+    t = faces.shape[1]
+    A = sp.csr_matrix((o.vals, o.colidx, o.rowptr))
+    g = case["fields"]["Dirichlet"][:, :, 0]
+    fe = ReferenceElement(dim - 1, order)
+    Mref = np.einsum("p,pi,pj->ij", fe.ipWeights, fe.ipShape, fe.ipShape)
+    for F in bnd:
+        rows = A[F * t:(F + 1) * t].toarray()
+        diag = rows[:, F * t:(F + 1) * t]
+        off = rows.copy()
+        off[:, F * t:(F + 1) * t] = 0.0
+        assert np.abs(off).max() == 0.0
+        if bc == "dirichlet":
+            assert np.array_equal(diag, np.eye(t))
+            assert np.array_equal(o.rhs[F * t:(F + 1) * t], g[F])
+        else:
+            x = nodes[faces[F][:dim]]                                       # vertices of the straight-sided face
+            meas = np.linalg.norm(x[1] - x[0]) if dim == 2 else 0.5 * np.linalg.norm(np.cross(x[1] - x[0], x[2] - x[0]))
+            M = Mref * meas / 2.0                                           # reference measure of the face element: 2 (segment and triangle)
+            assert np.abs(diag - M).max() < 1e-13 * np.abs(M).max()
+            assert np.abs(o.rhs[F * t:(F + 1) * t] - M @ g[F]).max() < 1e-13 * max(1.0, np.abs(g[F]).max()) * np.abs(M).max() * t

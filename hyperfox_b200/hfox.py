@@ -669,6 +669,20 @@ class NonLinearWrapper:
     def __init__(self):
         self.mySolver = self.currentSolution = self.previousSolution = None
         self.resTol, self.maxIters, self.dampening, self.residual, self.verbose = 1e-6, 1000, 0.0, 0.0, False
+        self.linearizedSolver, self.residualComputer = self.vanillaLinearizedSolver, self.vanillaResidualComputer
+
+    @staticmethod
+    def vanillaLinearizedSolver(solver):          # NonLinearWrapper.cpp:36-39
+        solver.assemble()
+        solver.solve()
+
+    @staticmethod
+    def vanillaResidualComputer(cur, prev):       # NonLinearWrapper.cpp:12-34 (single process: the two all-reduces are identities)
+        diff, ref = float(np.sum((cur.values - prev.values) ** 2)), float(np.sum(prev.values ** 2))
+        return np.sqrt(diff / ref) if ref != 0 else np.sqrt(diff)
+
+    def setLinearizedSolver(self, f): self.linearizedSolver = f
+    def setResidualComputer(self, f): self.residualComputer = f
 
     def setSolver(self, s): self.mySolver = s
     def setSolutionFields(self, cur, prev): self.currentSolution, self.previousSolution = cur, prev
@@ -685,10 +699,8 @@ class NonLinearWrapper:
             raise ErrorHandle("NonLinearWrapper : solve : the current and previous Solutions should be set before attempting to solve")
         cur, prev = self.currentSolution.values, self.previousSolution.values
         for _ in range(self.maxIters):
-            self.mySolver.assemble()
-            self.mySolver.solve()
-            diff, ref = float(np.sum((cur - prev) ** 2)), float(np.sum(prev ** 2))
-            self.residual = np.sqrt(diff / ref) if ref != 0 else np.sqrt(diff)
+            self.linearizedSolver(self.mySolver)
+            self.residual = self.residualComputer(self.currentSolution, self.previousSolution)
             if self.residual < self.resTol:
                 break
             val = (1.0 - self.dampening) * cur + self.dampening * prev

@@ -58,3 +58,56 @@ def test_world_size_2_partition():
         assert out.stdout.count("ok") == 2
     finally:
         os.remove(script)
+
+
+HALO_WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from hyperfox_b200 import partition
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+z = np.load(os.path.join(%r, "tests", "golden", "meshes", "regression_dim-3_h-2e-1_ord-1.npz"))
+nodes, cells = z["nodes"], z["cells"]
+part = partition.rcb_partition_vector(nodes, cells, world)
+prob = partition.rank_problem(nodes[:, :3], cells, part, rank, 3)
+gface = prob["face_global"]
+# the exchange hfx_solve does per Krylov iteration (grouped ncclSend/ncclRecv of the packed ghost-face blocks), emulated with the
+# global face id as payload: what arrives in my ghost slots must be the ids of exactly those faces, in order
+trace = np.where(prob["owned_face"] == 1, gface, -1).astype(np.int64)       # owners know their values, ghosts do not yet
+reqs, bufs = [], []
+for k, nb in enumerate(prob["nbrs"].tolist()):
+    if prob["send"][k].size:
+        reqs.append(dist.isend(torch.from_numpy(trace[prob["send"][k]].copy()), dst=nb))
+    if prob["recv"][k].size:
+        b = torch.zeros(prob["recv"][k].size, dtype=torch.int64)
+        bufs.append((k, b)); reqs.append(dist.irecv(b, src=nb))
+for r in reqs:
+    r.wait()
+for k, b in bufs:
+    trace[prob["recv"][k]] = b.numpy()
+assert np.array_equal(trace, gface), "halo exchange did not fill every ghost face with its owner's value"
+# dots over owned rows + all-reduce = global dots (what the distributed GMRES relies on): every global face counted exactly once
+s = torch.tensor([float(gface[prob["owned_face"] == 1].sum()), float((prob["owned_face"] == 1).sum()), float(prob["owned_cells"].size)], dtype=torch.float64)
+dist.all_reduce(s)
+nF = int(s[1].item())
+assert s[0].item() == nF * (nF - 1) / 2 and int(s[2].item()) == cells.shape[0], s
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_world_size_2_halo_exchange_plan_on_an_unstructured_mesh():
+    """The send/recv lists of rank_problem() driven through real point-to-point messages between two processes (gloo standing in for
+    NCCL), recursive-coordinate-bisection partition of the reference's Gmsh tet mesh."""
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29535")
+    script = os.path.join(ROOT, "tests", "_gloo_halo_worker.py")
+    open(script, "w").write(HALO_WORKER % (ROOT, ROOT))
+    try:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+               "--master-port", "29535", script]
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+        assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+        assert out.stdout.count("ok") == 2
+    finally:
+        os.remove(script)

@@ -345,11 +345,41 @@ static void testGmshIo(const std::string& dir, const std::string& name, int dim,
   CHECK_THROWS(h5.load(dir + "/missing.h5"));
 }
 
+// tests/unittests/solver/TestNonLinearWrapper.cpp:11-46: Newton on x^2 = 0 through setLinearizedSolver, Node fields on lightTri.  Host only.
+static void testNonLinearWrapper(const std::string& dir) {
+  Mesh m(2, 1, "simplex");
+  loadMesh(dir + "/lightTri.txt", &m, 2);
+  Field sol(&m, Node, 1, 1);
+  Field interSol(&m, Node, 1, 1);
+  HDGSolver anySolver;   // never assembled: the linearized solver replaces assemble + solve (the reference passes a CGSolver)
+  const double startingVals[6] = {1.0, 2.0, -1.0, 0.25, 42.0, 1e-8};
+  CHECK_NOTHROW(NonLinearWrapper());
+  NonLinearWrapper wrap;
+  CHECK_THROWS(wrap.solve());
+  CHECK_NOTHROW(wrap.setVerbosity(0));
+  CHECK_NOTHROW(wrap.setSolutionFields(&sol, &interSol));
+  CHECK_THROWS(wrap.solve());
+  CHECK_NOTHROW(wrap.setSolver(&anySolver));
+  CHECK_NOTHROW(wrap.setLinearizedSolver([&sol, &interSol](Solver*) {
+    for (size_t i = 0; i < sol.getValues()->size(); i++) {
+      const double p = interSol.getValues()->at(i);
+      sol.getValues()->at(i) = p - p * p / (2.0 * p);
+    }
+  }));
+  for (int i = 0; i < 6; i++) {
+    for (size_t k = 0; k < interSol.getValues()->size(); k++) { interSol.getValues()->at(k) = startingVals[i]; sol.getValues()->at(k) = 0.0; }
+    CHECK_NOTHROW(wrap.solve());
+    CHECK(wrap.getResidual() < 1e-6);
+    for (size_t k = 0; k < interSol.getValues()->size(); k++) CHECK(std::fabs(interSol.getValues()->at(k)) < 1e-4);
+  }
+}
+
 int main(int argc, char** argv) {
-  if (argc < 2) { std::printf("usage: %s <mesh dir> [contract|meshio|solver|lai|laplace|diffsrc|rk]\n", argv[0]); return 2; }
+  if (argc < 2) { std::printf("usage: %s <mesh dir> [contract|meshio|nlw|solver|lai|laplace|diffsrc|rk]\n", argv[0]); return 2; }
   const std::string dir = argv[1], sec = argc > 2 ? argv[2] : "all";
   try {
     if (sec == "contract") testHDGSolver(dir, false);
+    if (sec == "nlw" || sec == "all") testNonLinearWrapper(dir);
     if (sec == "meshio" || sec == "all") {
       testGmshIo(dir, "regression_dim-2_h-2e-1", 2, 2);
       testGmshIo(dir, "regression_dim-3_h-2e-1", 3, 3);

@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "tests", "cpp", "test_hdg_path.cpp")
 BIN = os.path.join(ROOT, "tests", "cpp", "test_hdg_path")
-MESHES = ["lightTri2", "regression_dim-2_h-1e-1_ord-2", "regression_dim-3_h-2e-1_ord-3", "regression_dim-2_h-1e-1_ord-3", "regression_dim-2_h-2e-1_ord-2"]
+MESHES = ["lightTri", "lightTri2", "regression_dim-2_h-1e-1_ord-2", "regression_dim-3_h-2e-1_ord-3", "regression_dim-2_h-1e-1_ord-3", "regression_dim-2_h-2e-1_ord-2"]
 
 
 def build_cpp_test():
@@ -56,6 +56,12 @@ def test_cpp_mirror_builds_and_call_order_contract(mesh_dir):
 def test_cpp_mirror_gmsh_io_regenerates_reference_fixtures(mesh_dir):
     """GmshIo (Io mirror) -> hfx_host_read_msh / hfx_host_high_order_mesh: the reference's .h5 fixtures from their .msh sources (host only)."""
     out = run(mesh_dir, "meshio")
+    assert " 0 failed" in out, out
+
+
+def test_cpp_mirror_non_linear_wrapper(mesh_dir):
+    """TestNonLinearWrapper.cpp restated against the C++ mirror (host only)."""
+    out = run(mesh_dir, "nlw")
     assert " 0 failed" in out, out
 
 

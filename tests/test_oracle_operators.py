@@ -199,3 +199,42 @@ def test_hdg_unabu_closed_forms(dim, order):
         assert abs(lin / (1.0 * (n + 1)) - ref) < 1e-12, (n, lin, ref)
     quad, lin = _unabu_forms(dim, order, 0)                      # constant solution (1, 0, ..)
     assert quad < 1e-12 and lin < 1e-12
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_burgers_model_is_the_sum_of_its_operators(dim, order):
+    """tests/unittests/model/TestHDGBurgersModel.cpp:105-138: HDGBurgersModel (nDOF = dim) = HDGBase + HDGUNabU + HDGDiffusion, local
+    right-hand side = the HDGUNabU one; with Euler the u-rows are scaled by dt and the mass matrix enters (the same fields as the
+    reference's test: tau = I, D = 3 I, Solution = BufferSolution = Trace = 2)."""
+    re = ReferenceElement(dim, order)
+    rc = O.RefElC(re)
+    nN, nD, nFc, nNf = re.nNodes, dim, re.nFaces, re.faceElement.nNodes
+    u, q, l, n = O.sizes(rc, nD)
+    tau = np.tile(np.eye(nD).reshape(-1), (nFc, nNf, 1))                     # [nFc, nNf, nD*nD], col-major per node
+    diff = np.tile((3.0 * np.eye(dim)).reshape(-1), (nN, 1))                 # [nN, dim*dim]
+    sol = np.full((nN, nD), 2.0)
+    trace = np.full((nFc, nNf, nD), 2.0)
+    base = O.op_base(rc, nD, re.nodes, tau)
+    conv, rhs = O.op_unabu(rc, nD, re.nodes, sol, trace)
+    dif = O.op_diffusion(rc, nD, re.nodes, diff, dim * dim)
+    f = dict(nodes=re.nodes, tau=tau, diff=diff, bufSol=sol, trace=trace)
+    mask = O.OP_UNABU | O.OP_DIFFUSION
+    A, F = O.local_system(rc, O.make_model(nD, mask, dim * dim), **f)
+    ana = base + conv + dif
+    assert ((ana - A) ** 2).sum() < 1e-12 and ((rhs - F) ** 2).sum() < 1e-12
+    # Euler (TestHDGBurgersModel.cpp:117-138, Euler.cpp:28-32)
+    dt = 1e-2
+    A2, F2 = O.local_system(rc, O.make_model(nD, mask, dim * dim, O.TS_EULER_IMPLICIT, dt), solOld=sol.reshape(-1), **f)
+    jac, inv, dV, nrm = O.element_geometry(rc, re.nodes)
+    M1 = O.op_mass(re.ipShape, dV[:re.nIP])
+    M = np.kron(M1, np.eye(nD))
+    ana2 = ana.copy()
+    ana2[:u] *= dt
+    ana2[:u, :u] += M
+    assert ((ana2 - A2) ** 2).sum() < 1e-12
+    exp = rhs.copy()
+    exp[:u] = dt * rhs[:u] + M @ sol.reshape(-1)
+    assert ((exp - F2) ** 2).sum() < 1e-12
+    # the reference's test compares the u-segment with M sol alone: true because the HDGUNabU right-hand side of a constant state vanishes
+    assert np.abs(rhs[:u]).max() < 1e-12

@@ -191,10 +191,13 @@ class RungeKutta:
         self.dt = 0.0
 
     def setButcherTable(self, t):
-        tab = np.array(BUTCHER[t] if not isinstance(t, (list, np.ndarray)) else t, dtype=float)
-        if tab.shape[0] != tab.shape[1]:
+        if not isinstance(t, (list, np.ndarray)):          # RKType: straight from the database (RungeKutta.cpp:15-17)
+            self.bTable = np.array(BUTCHER[t], dtype=float)
+            return
+        tab = np.array(t, dtype=float)                     # explicit table: the reference's checks, RungeKutta.cpp:19-32 -- the strict upper
+        if tab.ndim != 2 or tab.shape[0] != tab.shape[1]:  # triangle of the WHOLE [c | a ; 0 | b] table must vanish (followed as coded)
             raise ErrorHandle("RungeKutta : setButcherTable : the Butcher table should be square")
-        if np.any(np.triu(tab[:-1, 1:], 1) != 0):
+        if np.any(np.triu(tab, 1) != 0):
             raise ErrorHandle("RungeKutta : setButcherTable : the upper triangular part of the Butcher table should be null (no fully implicit implementation as of yet)")
         self.bTable = tab
 

@@ -64,3 +64,58 @@ def test_non_linear_wrapper_contract_and_dampening():
     calls.clear()
     wrap.solve()
     assert len(calls) == 1
+
+
+class _F:
+    def __init__(self, v):
+        self.values = np.array(v, dtype=float)
+
+
+@pytest.mark.parametrize("rk,nst", [("BEuler", 1), ("FEuler", 1), ("CrankNicolson", 2), ("RK4", 4)])
+def test_runge_kutta_stage_bookkeeping(rk, nst):
+    """tests/unittests/operator/TestRungeKutta.cpp:32-43 (Butcher table characteristics) and :112-123, :190-201, :271-300 (computeStage
+    stores (Solution - OldSolution)/dt, advances the stage counter, computeSolution = OldSolution + dt sum b_k RKStage_k and resets)."""
+    re = hfox.ReferenceElement(2, 2, "simplex")
+    ts = hfox.RungeKutta(re, getattr(hfox, rk))
+    assert ts.getNumStages() == nst and ts.getStage() == 0
+    dt, n = 1e-1, re.getNumNodes()
+    ts.setTimeStep(dt)
+    fm = {"Solution": _F(np.full(n, 1.0)), "OldSolution": _F(np.full(n, 2.0))}
+    for k in range(nst):
+        fm["RKStage_%d" % k] = _F(np.full(n, 3.0 + k))
+    with pytest.raises(hfox.ErrorHandle, match="all stages must be computed"):
+        ts.computeSolution(fm)
+    stages = []
+    for k in range(nst):
+        before = fm["Solution"].values.copy()
+        ts.computeStage(fm)
+        assert ts.getStage() == k + 1
+        stages.append((before - 2.0) / dt)
+        assert np.array_equal(fm["RKStage_%d" % k].values, stages[-1])          # TestRungeKutta.cpp:115-118: exactly (1 - 2)/dt at stage 0
+        row = ts.bTable[k, 1:]
+        assert np.allclose(fm["Solution"].values, 2.0 + dt * sum(row[j] * stages[j] for j in range(k + 1)), rtol=0, atol=1e-14)
+        fm["Solution"].values[:] = 1.0 + 0.1 * (k + 1)                          # the next stage solve would overwrite Solution
+    with pytest.raises(hfox.ErrorHandle, match="cannot compute more stages"):
+        ts.computeStage(fm)
+    ts.computeSolution(fm)
+    assert ts.getStage() == 0
+    bs = ts.bTable[nst, 1:]
+    assert np.abs(fm["Solution"].values - (2.0 + dt * sum(bs[k] * stages[k] for k in range(nst)))).max() < 1e-12
+
+
+def test_runge_kutta_butcher_table_checks():
+    """TestRungeKutta.cpp:32-43, same calls: a 2x2 table of ones and a 3x2 table are refused, the 3x3 identity and RK4 are accepted."""
+    re = hfox.ReferenceElement(2, 1, "simplex")
+    ts = hfox.RungeKutta(re, hfox.CrankNicolson)
+    assert ts.getNumStages() == 2 and ts.getStage() == 0
+    with pytest.raises(hfox.ErrorHandle, match="upper triangular"):
+        ts.setButcherTable(np.ones((2, 2)))
+    with pytest.raises(hfox.ErrorHandle, match="square"):
+        ts.setButcherTable(np.eye(3)[:, :2])
+    ts.setButcherTable(np.eye(3))
+    ts.setButcherTable(hfox.RK4)
+    assert ts.getNumStages() == 4
+    for t in range(14):                                     # every table of the database loads (RungeKutta.cpp:215-291)
+        ts.setButcherTable(t)
+        assert ts.bTable.shape[0] == ts.bTable.shape[1] and np.all(ts.bTable[-1, 0] == 0) and np.all(np.triu(ts.bTable[:-1, 1:], 1) == 0)
+        assert abs(ts.bTable[-1, 1:].sum() - 1.0) < 1e-14  # consistency: sum b = 1

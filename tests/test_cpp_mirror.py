@@ -34,10 +34,11 @@ def mesh_dir(tmp_path_factory):
             np.savetxt(f, nodes, fmt="%.17g")
             np.savetxt(f, cells, fmt="%d")
     import shutil
+    from tests.conftest import unpacked_fixtures
     for name in ("regression_dim-2_h-2e-1", "regression_dim-3_h-2e-1"):
-        shutil.copyfile(os.path.join(ROOT, "tests", "golden", "meshes", "msh", name + ".msh"), os.path.join(d, name + ".msh"))
+        shutil.copyfile(os.path.join(unpacked_fixtures("msh"), name + ".msh"), os.path.join(d, name + ".msh"))
     for name in ("regression_dim-2_h-2e-1_ord-2", "regression_dim-3_h-2e-1_ord-3"):
-        shutil.copyfile(os.path.join(ROOT, "tests", "golden", "meshes", "h5", name + ".h5"), os.path.join(d, name + ".h5"))
+        shutil.copyfile(os.path.join(unpacked_fixtures("h5"), name + ".h5"), os.path.join(d, name + ".h5"))
     return str(d)
 
 

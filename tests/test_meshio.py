@@ -8,7 +8,8 @@ regression_dim-D_h-H.msh (ressources/meshes/regression/generateH5FromMsh.py).  R
     order, entities of the input file first): the node numbering of an order >= 2 (edges) / >= 3 (faces) mesh depends on the relative
     ids of the edges / faces of every cell, so a different convention gives different cells (checked below).
 
-Fixtures: tests/golden/meshes/*.npz (converted .h5) and tests/golden/meshes/msh/*.msh (verbatim), both by tools/make_golden_meshes.py."""
+Fixtures: tests/golden/meshes/*.npz (converted .h5) and tests/golden/meshes/msh/*.msh.gz (the reference's files, gzip-compressed), both by
+tools/make_golden_meshes.py."""
 import os
 
 import numpy as np
@@ -16,9 +17,9 @@ import pytest
 
 from hyperfox_b200 import meshio as product
 from oracle import meshio
-from tests.conftest import load_mesh
+from tests.conftest import load_mesh, unpacked_fixtures
 
-MSH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", "msh")
+MSH = unpacked_fixtures("msh")
 CASES = [(2, "3e-1", o) for o in range(1, 6)] + [(2, "2e-1", o) for o in range(1, 6)] + [(2, "1e-1", o) for o in range(1, 5)] + \
         [(3, "3e-1", o) for o in range(1, 6)] + [(3, "2e-1", o) for o in range(1, 4)]
 
@@ -116,7 +117,7 @@ def test_reader_rejects_what_the_generator_cannot_raise(tmp_path, impl):
     assert np.array_equal(nodes[:, :2], [[0, 0], [1, 0], [0, 1]]) and np.array_equal(el[2], [[0, 1, 2]]) and list(el) == [2]
 
 
-H5 = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "meshes", "h5")
+H5 = unpacked_fixtures("h5")
 
 
 @pytest.mark.parametrize("name", ["lightTri2", "regression_dim-2_h-2e-1_ord-2", "regression_dim-3_h-2e-1_ord-3", "regression_dim-3_h-3e-1_ord-5"])

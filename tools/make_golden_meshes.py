@@ -29,16 +29,19 @@ for t in todo:
     np.savez_compressed(os.path.join(OUT, name), nodes=nodes, cells=cells.astype(np.int32))
     print(name, nodes.shape, cells.shape)
 
-# the Gmsh sources of the regression fixtures (inputs of tools/convertGmsh2H5HO in the reference): small ones only, copied verbatim as
+# the Gmsh sources of the regression fixtures (inputs of tools/convertGmsh2H5HO in the reference): small ones only, stored gzip-compressed as
 # test data so that tests/test_meshio.py can regenerate the .h5 fixtures above from them
+import gzip
 import shutil
 os.makedirs(os.path.join(OUT, "msh"), exist_ok=True)
 for t in ("regression_dim-2_h-3e-1", "regression_dim-2_h-2e-1", "regression_dim-2_h-1e-1", "regression_dim-3_h-3e-1", "regression_dim-3_h-2e-1"):
-    shutil.copyfile(os.path.join(REF, "regression", t + ".msh"), os.path.join(OUT, "msh", t + ".msh"))
-    print("msh/" + t + ".msh")
+    with open(os.path.join(REF, "regression", t + ".msh"), "rb") as i, gzip.GzipFile(os.path.join(OUT, "msh", t + ".msh.gz"), "wb", mtime=0) as o:
+        shutil.copyfileobj(i, o)
+    print("msh/" + t + ".msh.gz")
 
-# a few of the reference's .h5 files verbatim (test data for the dependency-free HDF5 reader of the product, hfx_host_read_h5_mesh)
+# a few of the reference's .h5 files, gzip-compressed (test data for the dependency-free HDF5 reader of the product, hfx_host_read_h5_mesh)
 os.makedirs(os.path.join(OUT, "h5"), exist_ok=True)
 for t in ("lightTri2.h5", "regression/regression_dim-2_h-2e-1_ord-2.h5", "regression/regression_dim-3_h-2e-1_ord-3.h5", "regression/regression_dim-3_h-3e-1_ord-5.h5"):
-    shutil.copyfile(os.path.join(REF, t), os.path.join(OUT, "h5", os.path.basename(t)))
-    print("h5/" + os.path.basename(t))
+    with open(os.path.join(REF, t), "rb") as i, gzip.GzipFile(os.path.join(OUT, "h5", os.path.basename(t) + ".gz"), "wb", mtime=0) as o:
+        shutil.copyfileobj(i, o)
+    print("h5/" + os.path.basename(t) + ".gz")

@@ -170,3 +170,19 @@ def test_python_io_mirrors():
         hfox.HDF5Io(hfox.Mesh(3, 2, "simplex")).load(os.path.join(H5, "regression_dim-3_h-2e-1_ord-3.h5"))
     with pytest.raises(hfox.ErrorHandle, match="write"):
         hfox.HDF5Io(a).write("out.h5")
+
+
+@pytest.mark.parametrize("dim,order,N", [(2, 5, 6), (3, 3, 5), (3, 4, 3)])
+def test_generator_agrees_with_the_synthetic_mesh_generator(dim, order, N):
+    """The order-p Kuhn meshes of the benchmarks (hyperfox_b200.meshgen, barycentric construction) and the reference-numbered generator
+    place the same nodes in every cell (same element geometry to rounding, same node set); only the global numbering differs."""
+    from hyperfox_b200 import meshgen
+    v, c = meshgen.kuhn_linear(N, dim)
+    n1, c1 = product.high_order_from_linear(dim, order, v, c)
+    n2, c2 = meshgen.high_order(v, c, order)
+    assert n1.shape == n2.shape and c1.shape == c2.shape
+    assert np.abs(n1[c1] - n2[c2]).max() < 1e-15
+    # the two numberings are related by one global permutation
+    perm = np.full(n1.shape[0], -1, dtype=np.int64)
+    perm[c1.ravel()] = c2.ravel()
+    assert perm.min() >= 0 and np.unique(perm).size == perm.size and np.array_equal(perm[c1], c2)

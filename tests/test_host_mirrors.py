@@ -119,3 +119,24 @@ def test_runge_kutta_butcher_table_checks():
         ts.setButcherTable(t)
         assert ts.bTable.shape[0] == ts.bTable.shape[1] and np.all(ts.bTable[-1, 0] == 0) and np.all(np.triu(ts.bTable[:-1, 1:], 1) == 0)
         assert abs(ts.bTable[-1, 1:].sum() - 1.0) < 1e-14  # consistency: sum b = 1
+
+
+def test_host_builders_edge_cases():
+    """Empty meshes, a single cell (every face on the boundary) and a non-manifold input through the host C ABI (no GPU)."""
+    from hyperfox_b200 import capi, meshio
+    tp = capi.host_compute_faces(3, 2, np.zeros((0, 10), dtype=np.int32))
+    assert tp["faces"].shape == (0, 6) and tp["cell2face"].shape == (0, 4) and tp["boundary"].size == 0
+    n, c = meshio.high_order_from_linear(3, 2, np.zeros((0, 3)), np.zeros((0, 4), dtype=np.int32))
+    assert n.shape == (0, 3) and c.shape == (0, 10)
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]])
+    n, h = meshio.high_order_from_linear(3, 4, v, np.array([[0, 1, 2, 3]], dtype=np.int32))
+    assert n.shape == (35, 3) and np.array_equal(np.sort(h.ravel()), np.arange(35))
+    tp = capi.host_compute_faces(3, 4, h)
+    assert tp["faces"].shape == (4, 15) and tp["boundary"].tolist() == [0, 1, 2, 3] and np.array_equal(tp["face2cell"], [[0, -1]] * 4)
+    with pytest.raises(capi.ErrorHandle, match="shared by more than two cells"):
+        capi.host_compute_faces(3, 1, np.array([[0, 1, 2, 3], [0, 1, 2, 4], [0, 1, 2, 5]], dtype=np.int32))
+    m = hfox.Mesh(3, 2, "simplex")
+    with pytest.raises(hfox.ErrorHandle, match="connectivity does not match"):
+        m.setMesh(v, np.array([[0, 1, 2, 3]], dtype=np.int32))          # 4 nodes per cell for an order-2 reference element (10)
+    with pytest.raises(hfox.ErrorHandle, match="not yet supported"):
+        hfox.ReferenceElement(3, 2, "prism")

@@ -140,3 +140,15 @@ def test_host_builders_edge_cases():
         m.setMesh(v, np.array([[0, 1, 2, 3]], dtype=np.int32))          # 4 nodes per cell for an order-2 reference element (10)
     with pytest.raises(hfox.ErrorHandle, match="not yet supported"):
         hfox.ReferenceElement(3, 2, "prism")
+
+
+@pytest.mark.parametrize("dim,order,geom,msg", [(3, 3, 1, "interpolation order 3 is not yet supported for dimension 3"),
+                                                (3, 6, 0, "interpolation order 6 is not yet supported"),
+                                                (2, 6, 1, "interpolation order 6 is not yet supported"),
+                                                (4, 1, 0, "spatial dimension 4 is not yet supported")])
+def test_reference_element_limits(dim, order, geom, msg):
+    """ReferenceElement.cpp:614-634 (maximum orders: 5, hexes 2) and the constructor's checks, TestReferenceElement.cpp:24-44: same
+    refusals, same "Class : function : message" text, from the product's host builder."""
+    from hyperfox_b200 import capi
+    with pytest.raises(capi.ErrorHandle, match=msg):
+        capi.host_refel_tables(dim, order, geom)

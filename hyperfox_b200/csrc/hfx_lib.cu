@@ -16,6 +16,7 @@
 #include "../../include/hfx.h"
 #include "hfx_assemble.cuh"
 #include "hfx_generic.cuh"
+#include "hfx_krylov.cuh"
 #include "host/hfx_refel.h"
 #include "host/hfx_topology.h"
 #include "host/hfx_meshio.h"
@@ -189,13 +190,14 @@ __global__ void ip_coords_kernel(int nCells, int nN, int nIP, int dim, const dou
 // 5.6 KB at p=3 tets) and its t rows share their column set, so the warp gathers the len entries of x once into registers instead
 // of once per row.  No column indices are read.  HBM-bound: 8 B of matrix per FMA.
 template <int MAXK>
-__global__ void spmv_face_kernel(int nFaces, int t, int nFc2, const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
-                                 const int* __restrict__ nbr, const double* __restrict__ vals, const double* __restrict__ x, double* __restrict__ y,
-                                 const uint8_t* __restrict__ owned /*NULL: all rows*/) {
-  const int F = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+__global__ void spmv_face_kernel(int nList, const int* __restrict__ faceList /*NULL: faces 0..nList-1*/, int t, int nFc2, const long long* __restrict__ rowStart,
+                                 const uint8_t* __restrict__ nnb, const int* __restrict__ nbr, const double* __restrict__ vals, const double* __restrict__ x,
+                                 double* __restrict__ y, const double* __restrict__ dinv /*NULL or row scaling (Jacobi)*/, const int* __restrict__ done) {
+  if (done && *done) return;
+  const int li = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (F >= nFaces) return;
-  if (owned && !owned[F]) { for (int a = lane; a < t; a += 32) y[(size_t)F * t + a] = 0.0; return; }   // rows of ghost faces belong to another rank
+  if (li >= nList) return;
+  const int F = faceList ? faceList[li] : li;
   const int m = nnb[F], len = m * t;
   double xr[MAXK];
   int offk[MAXK];   // entry (row a, column k = g t + b) sits at g t^2 + a t + b
@@ -216,7 +218,10 @@ __global__ void spmv_face_kernel(int nFaces, int t, int nFc2, const long long* _
     v += t;
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((a & 31) == lane) keep = s;
-    if ((a & 31) == 31 || a == t - 1) { const int a0 = a & ~31; if (a0 + lane <= a) y[(size_t)F * t + a0 + lane] = keep; }
+    if ((a & 31) == 31 || a == t - 1) {
+      const int a0 = a & ~31;
+      if (a0 + lane <= a) { const size_t r = (size_t)F * t + a0 + lane; y[r] = dinv ? dinv[r] * keep : keep; }
+    }
   }
 }
 
@@ -224,17 +229,20 @@ __global__ void spmv_face_kernel(int nFaces, int t, int nFc2, const long long* _
 // contiguous run into shared memory with 16-byte asynchronous copies -- every byte of the matrix crosses the SM exactly once, fully
 // coalesced, with the whole run in flight per warp -- then a few lanes per row reduce it against the gathered x.
 constexpr int kSpmvStage = 768, kSpmvMaxLen = 80;
-__global__ void __launch_bounds__(256) spmv_block_kernel(int nFaces, int t, int nFc2, const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
+__global__ void __launch_bounds__(256) spmv_block_kernel(int nList, const int* __restrict__ faceList /*NULL: faces 0..nList-1*/, int t, int nFc2,
+                                                         const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
                                                          const int* __restrict__ nbr, const double* __restrict__ vals, const double* __restrict__ x,
-                                                         double* __restrict__ y, const uint8_t* __restrict__ owned /*NULL: all rows*/) {
+                                                         double* __restrict__ y, const double* __restrict__ dinv /*NULL or row scaling (Jacobi)*/,
+                                                         const int* __restrict__ done) {
+  if (done && *done) return;
   extern __shared__ __align__(16) double spmv_sm[];
   double (*sv)[kSpmvStage] = reinterpret_cast<double (*)[kSpmvStage]>(spmv_sm);
   double (*sx)[kSpmvMaxLen] = reinterpret_cast<double (*)[kSpmvMaxLen]>(spmv_sm + 8 * kSpmvStage);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int LPR = t > 16 ? 1 : (t > 8 ? 2 : (t > 4 ? 4 : 8));   // lanes per row (power of two), 32 / LPR rows per pass
   const int a = lane / LPR, part = lane - a * LPR;
-  for (int F = blockIdx.x * 8 + w; F < nFaces; F += gridDim.x * 8) {
-    if (owned && !owned[F]) { for (int r = lane; r < t; r += 32) y[(size_t)F * t + r] = 0.0; continue; }   // rows of ghost faces belong to another rank
+  for (int li = blockIdx.x * 8 + w; li < nList; li += gridDim.x * 8) {
+    const int F = faceList ? faceList[li] : li;
     const int m = nnb[F], len = m * t, tot = len * t;
     const double* v = vals + rowStart[F];
     const bool al = ((rowStart[F] & 1) == 0);
@@ -258,7 +266,7 @@ __global__ void __launch_bounds__(256) spmv_block_kernel(int nFaces, int t, int 
         }
       }
       for (int o = 1; o < LPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (row < t && part == 0) y[(size_t)F * t + row] = s;
+      if (row < t && part == 0) { const size_t r = (size_t)F * t + row; y[r] = dinv ? dinv[r] * s : s; }
     }
     __syncwarp();
   }
@@ -266,14 +274,15 @@ __global__ void __launch_bounds__(256) spmv_block_kernel(int nFaces, int t, int 
 
 // generic CSR SpMV (LinAlgebraInterface mirror)
 __global__ void spmv_csr_kernel(long long n, const long long* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
-                                const double* __restrict__ x, double* __restrict__ y) {
+                                const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ dinv, const int* __restrict__ done) {
+  if (done && *done) return;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
   double s = 0.0;
   for (long long k = rowptr[row] + lane; k < rowptr[row + 1]; k += 32) s = fma(vals[k], x[colidx[k]], s);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) y[row] = s;
+  if (lane == 0) y[row] = dinv ? dinv[row] * s : s;
 }
 
 __global__ void diag_face_kernel(int nFaces, int t, int nFc2, const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
@@ -370,7 +379,6 @@ __global__ void pc_apply_kernel(long long n, const double* __restrict__ dinv, co
 }
 
 // deterministic two-stage dots: out[j] = sum_i w[i] * V[j][i], j < nv   (classical Gram-Schmidt: all dots of one step at once)
-constexpr int kDotBlocks = 592;  // 4 x 148
 __global__ void multi_dot_kernel(long long n, int nv, const double* __restrict__ V, long long ldv, const double* __restrict__ w, double* __restrict__ partial) {
   extern __shared__ double red[];
   const int tid = threadIdx.x;
@@ -555,7 +563,14 @@ struct Halo {
   DBuf<double> sbuf, rbuf;
   DBuf<uint8_t> dOwned;                     // [nFaces] 1 if this rank owns the face (its trace rows)
   DBuf<uint8_t> dCanon;                     // [nFaces][nNf] canonical position of every local face node
+  DBuf<uint8_t> dDofMask; int maskT = 0;    // [nFaces * t] owned flag per trace dof (Gram-Schmidt passes of the distributed solve)
+  // owned faces split by what their rows read: `interior` rows only touch owned faces and are multiplied while the halo is in flight,
+  // `boundary` rows read at least one ghost face and wait for it
+  DBuf<int> dInterior, dBoundary; int nInterior = 0, nBoundary = 0;
   long long nOwnedFaces = 0;
+  cudaStream_t stComm = nullptr;            // the exchange runs beside the interior rows
+  cudaEvent_t evPack = nullptr, evHalo = nullptr;
+  long long bytesPerExchangePerDof = 0;     // (send + recv faces) * 8: bytes per exchange = this * t
 };
 
 // Blocks travel in a rank-independent node order: canon[F][a] = position of local face node a in the canonical order of face F (the
@@ -581,43 +596,65 @@ __global__ void mask_rows_kernel(long long n, int t, const uint8_t* __restrict__
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = owned[i / t] ? src[i] : 0.0;
 }
+__global__ void expand_mask_kernel(long long n, int t, const uint8_t* __restrict__ owned, uint8_t* __restrict__ dofMask) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dofMask[i] = owned[i / t];
+}
 
-// ghost-face blocks of x <- their owners' values (one grouped send/recv round over NVLink)
-inline void halo_exchange(Halo& H, int nNf, int nD, double* x, cudaStream_t st) {
+// ghost-face blocks of x <- their owners' values: pack on `st`, one grouped send/recv round over NVLink and the unpack on the halo's own
+// stream; halo_end makes `st` wait for the ghost values.  Work queued on `st` between the two calls overlaps the exchange.
+inline void halo_begin(Halo& H, int nNf, int nD, double* x, cudaStream_t st) {
   if (!H.comm || !H.planned) return;
   NcclApi& N = NcclApi::get();
   const int t = nNf * nD;
   const long long ns = (long long)H.sendOff.back() * t, nr = (long long)H.recvOff.back() * t;
   if (ns) halo_pack_kernel<<<nblk(ns, 256), 256, 0, st>>>(ns, nNf, nD, H.dSend.p, H.dCanon.p, x, H.sbuf.p);
+  HFX_CUDA(cudaEventRecord(H.evPack, st));
+  HFX_CUDA(cudaStreamWaitEvent(H.stComm, H.evPack, 0));
   HFX_NCCL(N.GroupStart());
   for (size_t k = 0; k < H.nbr.size(); k++) {
     const size_t sc = (size_t)(H.sendOff[k + 1] - H.sendOff[k]) * t, rc = (size_t)(H.recvOff[k + 1] - H.recvOff[k]) * t;
-    if (sc) HFX_NCCL(N.Send(H.sbuf.p + (size_t)H.sendOff[k] * t, sc, ncclDouble, H.nbr[k], H.comm, st));
-    if (rc) HFX_NCCL(N.Recv(H.rbuf.p + (size_t)H.recvOff[k] * t, rc, ncclDouble, H.nbr[k], H.comm, st));
+    if (sc) HFX_NCCL(N.Send(H.sbuf.p + (size_t)H.sendOff[k] * t, sc, ncclDouble, H.nbr[k], H.comm, H.stComm));
+    if (rc) HFX_NCCL(N.Recv(H.rbuf.p + (size_t)H.recvOff[k] * t, rc, ncclDouble, H.nbr[k], H.comm, H.stComm));
   }
   HFX_NCCL(N.GroupEnd());
-  if (nr) halo_unpack_kernel<<<nblk(nr, 256), 256, 0, st>>>(nr, nNf, nD, H.dRecv.p, H.dCanon.p, H.rbuf.p, x);
+  if (nr) halo_unpack_kernel<<<nblk(nr, 256), 256, 0, H.stComm>>>(nr, nNf, nD, H.dRecv.p, H.dCanon.p, H.rbuf.p, x);
+  HFX_CUDA(cudaEventRecord(H.evHalo, H.stComm));
 }
+inline void halo_end(Halo& H, cudaStream_t st) {
+  if (!H.comm || !H.planned) return;
+  HFX_CUDA(cudaStreamWaitEvent(st, H.evHalo, 0));
+}
+inline void halo_exchange(Halo& H, int nNf, int nD, double* x, cudaStream_t st) { halo_begin(H, nNf, nD, x, st); halo_end(H, st); }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Krylov solver on an abstract operator
 struct LinOp {
   long long n = 0;
-  virtual void apply(const double* x, double* y, cudaStream_t st) = 0;
+  // y = A x on the rows this rank owns (other rows of y are left untouched), optionally scaled row-wise by dinv (the Jacobi preconditioner
+  // rides in the SpMV epilogue).  A distributed operator first refreshes the ghost rows of x IN PLACE from their owners.  `done`: device
+  // flag, the kernels return at once when it is set (NULL: always run).
+  virtual void apply(double* x, double* y, const double* dinv, const int* done, cudaStream_t st) = 0;
   virtual void diag_inverse(double* dinv, cudaStream_t st) = 0;
   virtual bool has_block_pc() const { return false; }
   virtual void block_pc_setup(cudaStream_t) {}
   virtual void block_pc_apply(const double*, const double*, double*, cudaStream_t) {}   // z = D^-1 (b - y) or D^-1 y
+  virtual const uint8_t* dof_mask() { return nullptr; }   // distributed: 1 on the trace dofs this rank owns
   virtual ~LinOp() {}
 };
 
 struct Krylov {
-  DBuf<double> V, w, tmp, dinv, partial, hdev, z, pvec;
+  DBuf<double> V, w, tmp, dinv, partial, npart, red, hdev, z, pvec;
+  DBuf<GmresDev> state;
   double* hpin = nullptr;
+  GmresDev* hstate = nullptr;   // pinned copy of the device state, read once per restart cycle
+  int* hdone = nullptr;         // pinned ring of done flags (single-GPU early exit from a cycle)
+  cudaEvent_t evDone[kMaxRestart + 1] = {};
   Halo* halo = nullptr;   // set for a distributed solve: dots are summed over the ranks (vectors are zero on non-owned rows)
-  ~Krylov() { if (hpin) cudaFreeHost(hpin); }
+  float msPerIteration = 0.f; long long allReduces = 0, haloExchanges = 0;
+  ~Krylov() { if (hpin) cudaFreeHost(hpin); if (hstate) cudaFreeHost(hstate); if (hdone) cudaFreeHost(hdone); for (auto e : evDone) if (e) cudaEventDestroy(e); }
   void dots(long long n, int nv, const double* Vp, long long ldv, const double* wv, cudaStream_t st, double* out_host) {
-    partial.alloc((size_t)nv * kDotBlocks);
+    if (partial.n < (size_t)(kMaxRestart + 2) * kDotBlocks) partial.alloc((size_t)(kMaxRestart + 2) * kDotBlocks);
     hdev.alloc(64);
     multi_dot_kernel<<<kDotBlocks, 256, 256 * sizeof(double), st>>>(n, nv, Vp, ldv, wv, partial.p);
     dot_final_kernel<<<nv, 256, 0, st>>>(nv, kDotBlocks, partial.p, hdev.p);
@@ -625,78 +662,113 @@ struct Krylov {
     HFX_CUDA(cudaMemcpyAsync(out_host, hdev.p, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     HFX_CUDA(cudaStreamSynchronize(st));
   }
-  // GMRES(restart), left preconditioning, classical Gram-Schmidt, zero initial guess, test on the preconditioned residual:
-  // what PETSc's KSPGMRES does with the reference's settings (PetscInterface.cpp:60-82,222-247; PetscOpts.h:12-24).
+  template <int NV>
+  void launch_dots(long long n, int nv, const double* Vp, long long ldv, const double* zv, double* part, const int* done, cudaStream_t st) {
+    kry_dots_kernel<NV><<<kDotBlocks, 256, 0, st>>>(n, nv, Vp, ldv, zv, part, done);
+  }
+  void dots_dev(long long n, int nv, const double* Vp, long long ldv, const double* zv, double* part, const int* done, cudaStream_t st) {
+    if (nv <= 4) launch_dots<4>(n, nv, Vp, ldv, zv, part, done, st);
+    else if (nv <= 8) launch_dots<8>(n, nv, Vp, ldv, zv, part, done, st);
+    else if (nv <= 16) launch_dots<16>(n, nv, Vp, ldv, zv, part, done, st);
+    else launch_dots<32>(n, nv, Vp, ldv, zv, part, done, st);
+  }
+  void lincomb_dev(long long n, int nv, const double* Vp, long long ldv, const double* base, const double* coef, double sign, double* out,
+                   const uint8_t* mask, double* np, const int* done, cudaStream_t st) {
+    const int g = kDotBlocks;
+    if (nv <= 4) kry_lincomb_kernel<4><<<g, 256, 0, st>>>(n, nv, Vp, ldv, base, coef, sign, out, mask, np, done);
+    else if (nv <= 8) kry_lincomb_kernel<8><<<g, 256, 0, st>>>(n, nv, Vp, ldv, base, coef, sign, out, mask, np, done);
+    else if (nv <= 16) kry_lincomb_kernel<16><<<g, 256, 0, st>>>(n, nv, Vp, ldv, base, coef, sign, out, mask, np, done);
+    else kry_lincomb_kernel<32><<<g, 256, 0, st>>>(n, nv, Vp, ldv, base, coef, sign, out, mask, np, done);
+  }
+  // GMRES(restart): see hfx_krylov.cuh.  What PETSc's KSPGMRES does with the reference's settings (PetscInterface.cpp:60-82,222-247;
+  // PetscOpts.h:12-24), with the Hessenberg / Givens / convergence bookkeeping on the device and one host synchronisation per cycle.
   void gmres(LinOp& A, const double* b, double* x, const hfx_solve_opts& o, hfx_solve_stats* st_out, cudaStream_t st) {
-    const long long n = A.n;
+    const long long n = A.n, ldv = (n + 1) & ~1LL;
     const int m = o.restart > 0 ? o.restart : 30;
-    if (m > 30) throw Err("Krylov", "gmres", "restart larger than 30 is not supported");
-    V.alloc((size_t)(m + 1) * n); w.alloc(n); tmp.alloc(n); dinv.alloc(n);
-    if (!hpin) HFX_CUDA(cudaMallocHost(&hpin, 64 * sizeof(double)));
+    if (m > kMaxRestart) throw Err("Krylov", "gmres", "restart larger than 30 is not supported");
+    if (V.n != (size_t)(m + 1) * ldv) { V.alloc((size_t)(m + 1) * ldv); V.zero(st); }
+    w.alloc(n); tmp.alloc(n); dinv.alloc(n);
+    if (partial.n < (size_t)(kMaxRestart + 2) * kDotBlocks) partial.alloc((size_t)(kMaxRestart + 2) * kDotBlocks);
+    npart.alloc(kDotBlocks); red.alloc(kMaxRestart + 4); state.alloc(1);
+    if (!hstate) HFX_CUDA(cudaMallocHost(&hstate, sizeof(GmresDev)));
+    if (!hdone) HFX_CUDA(cudaMallocHost(&hdone, (kMaxRestart + 1) * sizeof(int)));
+    for (auto& e : evDone) if (!e) HFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const int usePC = o.pc != 0;
     const bool blockPC = o.pc == 2;
     if (blockPC && !A.has_block_pc()) throw Err("Krylov", "gmres", "the face-block Jacobi preconditioner needs the block-CSR trace operator");
     if (blockPC) A.block_pc_setup(st); else if (usePC) A.diag_inverse(dinv.p, st);
+    const double* dv = (usePC && !blockPC) ? dinv.p : nullptr;   // point Jacobi rides in the SpMV epilogue
+    const uint8_t* mask = A.dof_mask();
+    const bool dist = halo && halo->comm;
     const int bs = 256, nb = nblk(n, bs);
-    auto pc_apply = [&](const double* yv, const double* bv, double* zv) {
-      if (blockPC) A.block_pc_apply(yv, bv, zv, st); else pc_apply_kernel<<<nb, bs, 0, st>>>(n, dinv.p, yv, bv, zv, usePC);
-    };
+    std::memset(hstate, 0, sizeof(GmresDev));
+    hstate->rtol = o.rtol; hstate->first = 1; hstate->maxits = o.maxits; hstate->tol = 0.0;
+    HFX_CUDA(cudaMemcpyAsync(state.p, hstate, sizeof(GmresDev), cudaMemcpyHostToDevice, st));
     HFX_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), st));
-    // ||M^-1 b||
-    pc_apply(b, nullptr, w.p);
-    dots(n, 1, w.p, n, w.p, st, hpin);
-    const double bnorm = std::sqrt(hpin[0]);
-    const double tol = std::max(o.rtol * bnorm, 1e-50);
-    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m), sn(m), gg(m + 1), hcol(m + 2), y(m);
+    HFX_CUDA(cudaMemsetAsync(w.p, 0, n * sizeof(double), st));
+    HFX_CUDA(cudaMemsetAsync(tmp.p, 0, n * sizeof(double), st));
+    const int* done = &state.p->done;
+    auto all_reduce = [&](int cnt) { if (dist) { HFX_NCCL(NcclApi::get().AllReduce(red.p, red.p, cnt, ncclDouble, ncclSum, halo->comm, st)); allReduces++; } };
+    // z = M^-1 A v: point Jacobi inside the SpMV; face-block Jacobi as its own pass
+    auto op = [&](double* v, double* zv) {
+      if (blockPC) { A.apply(v, tmp.p, nullptr, done, st); A.block_pc_apply(tmp.p, nullptr, zv, st); }
+      else A.apply(v, zv, dv, done, st);
+    };
     int its = 0;
-    double res = bnorm;
-    bool conv = res <= tol;
-    while (!conv && its < o.maxits) {
-      A.apply(x, tmp.p, st);
-      pc_apply(tmp.p, b, V.p);
-      dots(n, 1, V.p, n, V.p, st, hpin);
-      const double beta = std::sqrt(hpin[0]);
-      res = beta;
-      if (res <= tol) { conv = true; break; }
-      scale_copy_kernel<<<nb, bs, 0, st>>>(n, V.p, 1.0 / beta, V.p);
-      std::fill(gg.begin(), gg.end(), 0.0);
-      gg[0] = beta;
+    bool finished = o.maxits <= 0;
+    bool firstCycle = true;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    HFX_CUDA(cudaEventCreate(&t0)); HFX_CUDA(cudaEventCreate(&t1));
+    HFX_CUDA(cudaEventRecord(t0, st));
+    while (!finished) {
+      // V_0 = M^-1 (b - A x)   (first cycle: x = 0)
+      if (firstCycle) {
+        if (blockPC) A.block_pc_apply(b, nullptr, V.p, st);
+        else kry_pc_kernel<<<nb, bs, 0, st>>>(n, dv, nullptr, b, V.p, mask);
+      } else {
+        A.apply(x, tmp.p, nullptr, nullptr, st);
+        if (blockPC) A.block_pc_apply(tmp.p, b, V.p, st);
+        else kry_pc_kernel<<<nb, bs, 0, st>>>(n, dv, tmp.p, b, V.p, mask);
+      }
+      firstCycle = false;
+      dots_dev(n, 1, V.p, ldv, V.p, npart.p, nullptr, st);   // ||V_0||^2 partial sums (nv = 1: partial[0 * grid + block] = npart layout)
+      const int mm = std::min(m, o.maxits - its);
       int k = 0;
-      for (; k < m && its < o.maxits; k++) {
-        A.apply(V.p + (size_t)k * n, tmp.p, st);
-        pc_apply(tmp.p, nullptr, w.p);
-        dots(n, k + 1, V.p, n, w.p, st, hpin);
-        for (int j = 0; j <= k; j++) hcol[j] = hpin[j];
-        HFX_CUDA(cudaMemcpyAsync(hdev.p + 32, hpin, (k + 1) * sizeof(double), cudaMemcpyHostToDevice, st));
-        multi_axpy_kernel<<<nb, bs, 0, st>>>(n, k + 1, V.p, n, hdev.p + 32, w.p, -1.0);
-        dots(n, 1, w.p, n, w.p, st, hpin + 40);
-        const double hn = std::sqrt(hpin[40]);
-        hcol[k + 1] = hn;
-        if (hn != 0.0) scale_copy_kernel<<<nb, bs, 0, st>>>(n, w.p, 1.0 / hn, V.p + (size_t)(k + 1) * n);
-        for (int j = 0; j < k; j++) { const double a = cs[j] * hcol[j] + sn[j] * hcol[j + 1]; hcol[j + 1] = -sn[j] * hcol[j] + cs[j] * hcol[j + 1]; hcol[j] = a; }
-        double dn = std::sqrt(hcol[k] * hcol[k] + hcol[k + 1] * hcol[k + 1]);
-        if (dn == 0.0) dn = 1e-300;
-        cs[k] = hcol[k] / dn; sn[k] = hcol[k + 1] / dn;
-        hcol[k] = dn; hcol[k + 1] = 0.0;
-        gg[k + 1] = -sn[k] * gg[k]; gg[k] = cs[k] * gg[k];
-        for (int j = 0; j <= k; j++) H[(size_t)j * m + k] = hcol[j];
-        its++;
-        res = std::fabs(gg[k + 1]);
-        if (res <= tol || hn == 0.0) { k++; break; }
+      for (; k < mm; k++) {
+        if (!dist && k >= 3) {   // single GPU: leave the cycle as soon as the device has been seen to converge (a few launches late)
+          if (cudaEventQuery(evDone[k - 3]) == cudaSuccess && hdone[k - 3]) break;
+        }
+        double* vk = V.p + (size_t)k * ldv;
+        op(vk, w.p);
+        dots_dev(n, k + 1, V.p, ldv, w.p, partial.p, done, st);
+        kry_reduce_kernel<<<k + 2, 256, 0, st>>>(k + 1, kDotBlocks, partial.p, npart.p, red.p, done);
+        all_reduce(k + 2);
+        kry_step_kernel<<<1, 32, 0, st>>>(state.p, k, k + 1, 0, red.p);
+        lincomb_dev(n, k + 1, V.p, ldv, w.p, state.p->c, -1.0, V.p + (size_t)(k + 1) * ldv, mask, npart.p, done, st);
+        if (!dist) {
+          HFX_CUDA(cudaMemcpyAsync(hdone + k, done, sizeof(int), cudaMemcpyDeviceToHost, st));
+          HFX_CUDA(cudaEventRecord(evDone[k], st));
+        }
       }
-      for (int i = k - 1; i >= 0; i--) {
-        double s = gg[i];
-        for (int j = i + 1; j < k; j++) s -= H[(size_t)i * m + j] * y[j];
-        y[i] = s / H[(size_t)i * m + i];
-      }
-      for (int j = 0; j < k; j++) hpin[j] = y[j];
-      HFX_CUDA(cudaMemcpyAsync(hdev.p + 32, hpin, k * sizeof(double), cudaMemcpyHostToDevice, st));
-      multi_axpy_kernel<<<nb, bs, 0, st>>>(n, k, V.p, n, hdev.p + 32, x, 1.0);
+      // tail: close the last column (needs ||V_mm||), solve the small triangular system, update x
+      kry_reduce_kernel<<<1, 256, 0, st>>>(0, kDotBlocks, partial.p, npart.p, red.p, done);
+      all_reduce(1);
+      kry_step_kernel<<<1, 32, 0, st>>>(state.p, k, 0, 1, red.p);
+      kry_backsolve_kernel<<<1, 32, 0, st>>>(state.p);
+      lincomb_dev(n, m, V.p, ldv, x, state.p->c, 1.0, x, nullptr, nullptr, nullptr, st);
+      HFX_CUDA(cudaMemcpyAsync(hstate, state.p, sizeof(GmresDev), cudaMemcpyDeviceToHost, st));
       HFX_CUDA(cudaStreamSynchronize(st));
-      if (res <= tol) conv = true;
+      its = hstate->its;
+      if (hstate->done || its >= o.maxits) finished = true;
     }
+    HFX_CUDA(cudaEventRecord(t1, st));
+    HFX_CUDA(cudaEventSynchronize(t1));
+    float ms = 0.f;
+    HFX_CUDA(cudaEventElapsedTime(&ms, t0, t1));
+    cudaEventDestroy(t0); cudaEventDestroy(t1);
+    msPerIteration = its > 0 ? ms / its : 0.f;
     HFX_CUDA(cudaGetLastError());
-    if (st_out) { st_out->iterations = its; st_out->resnorm = res; st_out->bnorm = bnorm; st_out->converged = conv ? 1 : 0; }
+    if (st_out) { st_out->iterations = its; st_out->resnorm = hstate->res; st_out->bnorm = hstate->bnorm; st_out->converged = hstate->converged; }
   }
   // Jacobi-preconditioned CG (valid only for symmetric systems; GMRES is the parity solver)
   void cg(LinOp& A, const double* b, double* x, const hfx_solve_opts& o, hfx_solve_stats* st_out, cudaStream_t st) {
@@ -707,6 +779,7 @@ struct Krylov {
     if (usePC) A.diag_inverse(dinv.p, st);
     const int bs = 256, nb = nblk(n, bs);
     HFX_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), st));
+    HFX_CUDA(cudaMemsetAsync(tmp.p, 0, n * sizeof(double), st));   // rows of ghost faces are never written by the SpMV
     HFX_CUDA(cudaMemcpyAsync(w.p, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));  // r = b
     pc_apply_kernel<<<nb, bs, 0, st>>>(n, dinv.p, w.p, nullptr, z.p, usePC);
     HFX_CUDA(cudaMemcpyAsync(pvec.p, z.p, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -718,7 +791,7 @@ struct Krylov {
     int its = 0;
     bool conv = res <= tol;
     while (!conv && its < o.maxits) {
-      A.apply(pvec.p, tmp.p, st);
+      A.apply(pvec.p, tmp.p, nullptr, nullptr, st);
       dots(n, 1, pvec.p, n, tmp.p, st, hpin);
       const double alpha = rz / hpin[0];
       hpin[1] = alpha;
@@ -806,25 +879,42 @@ int guard(hfx_ctx* c, F f) {
 struct FaceOp : LinOp {
   hfx_ctx* c;
   explicit FaceOp(hfx_ctx* c_) : c(c_) { n = (long long)c->nFaces * c->nNf * c->md.nDOF; }
-  void apply(const double* x, double* y, cudaStream_t st) override {
+  bool dist() const { return c->halo.comm && c->halo.planned; }
+  void spmv(int nList, const int* list, const double* x, double* y, const double* dinv, const int* done, cudaStream_t st) {
+    if (nList <= 0) return;
     const int t = c->nNf * c->md.nDOF;
-    const uint8_t* owned = nullptr;
-    if (c->halo.comm && c->halo.planned) {   // owned rows only; ghost-face blocks of the input come from their owners (NCCL over NVLink)
-      c->dXh.alloc((size_t)n);
-      HFX_CUDA(cudaMemcpyAsync(c->dXh.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-      halo_exchange(c->halo, c->nNf, c->md.nDOF, c->dXh.p, st);
-      x = c->dXh.p; owned = c->halo.dOwned.p;
-    }
-    const int len = 2 * c->nFc * t, nb = nblk((long long)c->nFaces * 32, 256);   // at most 2 nFc - 1 neighbour faces per row
+    const int len = 2 * c->nFc * t, nb = nblk((long long)nList * 32, 256);   // at most 2 nFc - 1 neighbour faces per row
     const int lenMax = (2 * c->nFc - 1) * t;   // a face has at most 2 nFc - 1 neighbour faces (itself included)
     if (lenMax * t <= kSpmvStage && lenMax <= kSpmvMaxLen && !getenv("HFX_SPMV_V1")) {
       constexpr int shm = 8 * (kSpmvStage + kSpmvMaxLen) * (int)sizeof(double);
-      static bool attr = false;
-      if (!attr) { HFX_CUDA(cudaFuncSetAttribute(spmv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shm)); attr = true; }
-      spmv_block_kernel<<<std::min(nblk(c->nFaces, 8), c->nSM * 4), 256, shm, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
-    } else if (len <= 96) spmv_face_kernel<3><<<nb, 256, 0, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
-    else if (len <= 256) spmv_face_kernel<8><<<nb, 256, 0, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
-    else spmv_face_kernel<16><<<nb, 256, 0, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, owned);
+      HFX_CUDA(cudaFuncSetAttribute(spmv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shm));   // per device: set every time (cheap)
+      spmv_block_kernel<<<std::min(nblk(nList, 8), c->nSM * 4), 256, shm, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);
+    } else if (len <= 96) spmv_face_kernel<3><<<nb, 256, 0, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);
+    else if (len <= 256) spmv_face_kernel<8><<<nb, 256, 0, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);
+    else spmv_face_kernel<16><<<nb, 256, 0, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);
+  }
+  void apply(double* x, double* y, const double* dinv, const int* done, cudaStream_t st) override {
+    if (dist()) {
+      // owned rows only.  The ghost-face blocks of x come from their owners (NCCL over NVLink, on the halo's stream) while the rows that
+      // read owned faces only are multiplied; the rows along the partition cut wait for the exchange.
+      Halo& H = c->halo;
+      halo_begin(H, c->nNf, c->md.nDOF, x, st);
+      c->krylov.haloExchanges++;
+      spmv(H.nInterior, H.dInterior.p, x, y, dinv, done, st);
+      halo_end(H, st);
+      spmv(H.nBoundary, H.dBoundary.p, x, y, dinv, done, st);
+    } else spmv(c->nFaces, nullptr, x, y, dinv, done, st);
+  }
+  const uint8_t* dof_mask() override {
+    if (!dist()) return nullptr;
+    Halo& H = c->halo;
+    const int t = c->nNf * c->md.nDOF;
+    if (H.maskT != t || H.dDofMask.n != (size_t)n) {
+      H.dDofMask.alloc((size_t)n);
+      expand_mask_kernel<<<nblk(n, 256), 256, 0, c->st>>>(n, t, H.dOwned.p, H.dDofMask.p);
+      H.maskT = t;
+    }
+    return H.dDofMask.p;
   }
   void diag_inverse(double* dinv, cudaStream_t st) override {
     diag_face_kernel<<<nblk(n, 256), 256, 0, st>>>(c->nFaces, c->nNf * c->md.nDOF, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, dinv);
@@ -833,8 +923,13 @@ struct FaceOp : LinOp {
   void block_pc_setup(cudaStream_t st) override {
     const int t = c->nNf * c->md.nDOF;
     c->dBlockInv.alloc((size_t)c->nFaces * t * t);
-    const size_t shm = (size_t)8 * t * t * sizeof(double);
-    block_diag_inverse_kernel<<<std::min(nblk(c->nFaces, 8), c->nSM * 8), 256, shm, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, c->dBlockInv.p);
+    // one t x t block per warp in shared memory: as many warps per CTA as fit (t = 30: 7.2 KB per warp)
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * t * t * sizeof(double) > 96 * 1024) warps >>= 1;
+    const size_t shm = (size_t)warps * t * t * sizeof(double);
+    HFX_CUDA(cudaFuncSetAttribute(block_diag_inverse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    block_diag_inverse_kernel<<<std::min(nblk(c->nFaces, warps), c->nSM * 8), warps * 32, shm, st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, c->dBlockInv.p);
+    HFX_CUDA(cudaGetLastError());
   }
   void block_pc_apply(const double* y, const double* b, double* z, cudaStream_t st) override {
     block_pc_apply_kernel<<<nblk((long long)c->nFaces * 32, 256), 256, 0, st>>>(c->nFaces, c->nNf * c->md.nDOF, c->dBlockInv.p, y, b, z);
@@ -941,6 +1036,7 @@ int hfx_ctx_destroy(hfx_ctx* c) {
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
   if (c->halo.comm) { try { NcclApi::get().CommDestroy(c->halo.comm); } catch (...) {} c->halo.comm = nullptr; }
+  if (c->halo.stComm) { cudaStreamSynchronize(c->halo.stComm); cudaStreamDestroy(c->halo.stComm); cudaEventDestroy(c->halo.evPack); cudaEventDestroy(c->halo.evHalo); }
   cudaStream_t st = c->st;
   delete c;
   if (st) cudaStreamDestroy(st);
@@ -1560,11 +1656,25 @@ int hfx_solve(hfx_ctx* c, const hfx_solve_opts* opts, hfx_solve_stats* stats) {
       mask_rows_kernel<<<nblk(A.n, 256), 256, 0, c->st>>>(A.n, t, c->halo.dOwned.p, b, c->dBm.p);
       b = c->dBm.p;
     }
+    c->krylov.allReduces = 0; c->krylov.haloExchanges = 0;
     c->krylov.solve(A, b, x, o, stats, c->st);
     if (dist) { halo_exchange(c->halo, c->nNf, c->md.nDOF, x, c->st); HFX_CUDA(cudaStreamSynchronize(c->st)); }   // recovery needs the ghost traces (HDGSolver.cpp:730-732)
   });
   if (rc) return rc;
   return hfx_recover(c);
+}
+
+int hfx_solve_info(const hfx_ctx* c, hfx_solve_info_t* info) {
+  if (!c || !info) return 1;
+  const Halo& H = c->halo;
+  const int t = c->nNf * c->md.nDOF;
+  info->msPerIteration = c->krylov.msPerIteration;
+  info->allReduces = c->krylov.allReduces; info->haloExchanges = c->krylov.haloExchanges;
+  info->haloBytesPerExchange = H.planned ? H.bytesPerExchangePerDof * t : 0;
+  info->ownedFaces = H.planned ? H.nOwnedFaces : c->nFaces;
+  info->interiorFaces = H.planned ? H.nInterior : c->nFaces; info->boundaryFaces = H.planned ? H.nBoundary : 0;
+  info->nNeighbours = H.planned ? (int)H.nbr.size() : 0;
+  return 0;
 }
 
 int hfx_residual(hfx_ctx* c, double* rnorm, double* bnorm) {
@@ -1575,7 +1685,7 @@ int hfx_residual(hfx_ctx* c, double* rnorm, double* bnorm) {
     FaceOp A(c);
     DBuf<double> y, acc;
     y.alloc((size_t)A.n); acc.alloc(2); acc.zero(c->st);
-    A.apply(find_field(c, "Trace")->d.p, y.p, c->st);
+    A.apply(find_field(c, "Trace")->d.p, y.p, nullptr, nullptr, c->st);
     residual_sq_kernel<<<(int)std::min<long long>(nblk(A.n, 256), (long long)c->nSM * 8), 256, 0, c->st>>>(A.n, c->dRhs.p, y.p, acc.p);
     HFX_CUDA(cudaGetLastError());
     double h[2] = {0.0, 0.0};
@@ -1599,6 +1709,11 @@ int hfx_comm_init(hfx_ctx* c, int nRanks, int rank, const char* id128) {
     std::memcpy(id.internal, id128, NCCL_UNIQUE_ID_BYTES);
     HFX_NCCL(NcclApi::get().CommInitRank(&c->halo.comm, nRanks, id, rank));
     c->halo.rank = rank; c->halo.nRanks = nRanks;
+    if (!c->halo.stComm) {
+      HFX_CUDA(cudaStreamCreateWithFlags(&c->halo.stComm, cudaStreamNonBlocking));
+      HFX_CUDA(cudaEventCreateWithFlags(&c->halo.evPack, cudaEventDisableTiming));
+      HFX_CUDA(cudaEventCreateWithFlags(&c->halo.evHalo, cudaEventDisableTiming));
+    }
   });
 }
 
@@ -1621,6 +1736,23 @@ int hfx_comm_set_halo(hfx_ctx* c, int nNbr, const int* nbrRank, const int* sendC
     for (int F = 0; F < c->nFaces; F++) H.nOwnedFaces += ownedFace[F] ? 1 : 0;
     const int tmax = c->nNf * 3;
     H.sbuf.alloc((size_t)std::max(1, H.sendOff.back()) * tmax); H.rbuf.alloc((size_t)std::max(1, H.recvOff.back()) * tmax);
+    {   // owned faces whose rows read owned faces only / at least one ghost face (the columns of a row: every face of the face's cells)
+      std::vector<int> inter, bnd;
+      for (int F = 0; F < c->nFaces; F++) {
+        if (!ownedFace[F]) continue;
+        bool ghost = false;
+        for (int s2 = 0; s2 < 2 && !ghost; s2++) {
+          const int cell = c->hF2C[(size_t)2 * F + s2];
+          if (cell < 0) continue;
+          for (int k = 0; k < c->nFc; k++) if (!ownedFace[c->hC2F[(size_t)cell * c->nFc + k]]) { ghost = true; break; }
+        }
+        (ghost ? bnd : inter).push_back(F);
+      }
+      H.nInterior = (int)inter.size(); H.nBoundary = (int)bnd.size();
+      H.dInterior.upload(inter, c->st); H.dBoundary.upload(bnd, c->st);
+    }
+    H.maskT = 0;
+    H.bytesPerExchangePerDof = 8LL * ((long long)H.sendOff.back() + H.recvOff.back());
     HFX_CUDA(cudaStreamSynchronize(c->st));
     H.planned = true;
   });

@@ -115,6 +115,10 @@ typedef struct {
 typedef struct { int iterations; double resnorm; double bnorm; int converged; } hfx_solve_stats;
 int hfx_solve(hfx_ctx* ctx, const hfx_solve_opts* opts, hfx_solve_stats* stats); /* Trace <- solution; then recovery */
 int hfx_recover(hfx_ctx* ctx);                                                    /* HDGSolver.cpp:741-775 */
+/* what the last hfx_solve cost: device time per Krylov iteration (CUDA events around the whole solve / iterations), and on several GPUs the
+   collectives it issued (replaces the MPI_Allreduce / VecScatter counts of KSPSolve's -log_view) */
+typedef struct { float msPerIteration; long long allReduces, haloExchanges, haloBytesPerExchange, ownedFaces, interiorFaces, boundaryFaces; int nNeighbours; } hfx_solve_info_t;
+int hfx_solve_info(const hfx_ctx* ctx, hfx_solve_info_t* info);
 int hfx_sync(hfx_ctx* ctx);
 /* timing of the last hfx_assemble (CUDA events on the library's stream), milliseconds */
 int hfx_last_assemble_ms(const hfx_ctx* ctx, float* msTotal, float* msKernel);

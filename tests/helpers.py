@@ -13,9 +13,12 @@ def sin_exp(x):
     return np.sin(x[0]) * np.exp(x[1])
 
 
-def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="dirichlet", tau_double=False, diff="none", seed=0, curved=0.0, geom="simplex"):
+def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="dirichlet", tau_double=False, diff="none", seed=0, curved=0.0, geom="simplex",
+              scale=1.0):
     """Returns dict with numpy inputs in the reference's Field layouts.  curved > 0 displaces every non-vertex node by
-    curved*h*U(-1,1)^dim: genuinely curved (non-affine) elements, Jacobians and normals vary from cubature point to point."""
+    curved*h*U(-1,1)^dim: genuinely curved (non-affine) elements, Jacobians and normals vary from cubature point to point.
+    scale shrinks the whole mesh (scale = 3/55 turns the N = 3 Kuhn cube into elements of the benchmark's h = 1/55).
+    model "cd": HDGConvectionDiffusionReactionSource with Velocity + DiffusionTensor only (BASELINE configs[3])."""
     rng = np.random.default_rng(seed)
     if geom == "orthotope":     # structured quads / hexes (the reference's orthotope elements: ReferenceElement.cpp:885-1004)
         nodes, cells = meshgen.box_mesh(N, order, dim, perturb=perturb)
@@ -23,6 +26,8 @@ def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="di
         nodes, cells = meshgen.kuhn_mesh(N, order, dim, perturb=perturb)
     else:
         nodes, cells = load_mesh(mesh)
+    if scale != 1.0:
+        nodes = nodes * scale
     if curved > 0.0 and order > 1:
         isv = np.zeros(nodes.shape[0], dtype=bool)
         isv[np.unique(cells[:, :(2 ** dim if geom == "orthotope" else dim + 1)])] = True
@@ -60,7 +65,7 @@ def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="di
         A = rng.standard_normal((nodes.shape[0], dim, dim)) * 0.2
         D = np.eye(dim)[None] + A @ A.transpose(0, 2, 1) + 0.1 * A    # not symmetric on purpose: exercises the col-major layout
         fields["DiffusionTensor"] = D.transpose(0, 2, 1).reshape(nodes.shape[0], dim * dim)   # col-major per node
-    if model == "cdrs":
+    if model in ("cdrs", "cd"):
         c = nodes - 0.5
         vel = np.zeros_like(nodes)
         vel[:, 0], vel[:, 1] = -4 * c[:, 1], 4 * c[:, 0]
@@ -75,6 +80,26 @@ def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="di
     return case
 
 
+def config4_fields(case, D=1e-2, dt=1e-2):
+    """BASELINE configs[3] (tests/parallel/TestParHDGConvectionDiffusionReactionSource.cpp): D = 1e-2 scalar Node field,
+    v = 4(-(y-1/2), x-1/2, 0), Tau = |v.n| + D / sqrt(D dt) on both sides of every face (double valued)."""
+    nodes, topo, dim = case["nodes"], case["topo"], case["dim"]
+    faces = topo["faces"]
+    vel = case["fields"]["Velocity"]
+    fx = nodes[faces[:, :dim]]                       # the face's vertices come first in its node list
+    if dim == 2:
+        tvec = fx[:, 1] - fx[:, 0]
+        nrm = np.stack([tvec[:, 1], -tvec[:, 0]], axis=1)
+    else:
+        nrm = np.cross(fx[:, 1] - fx[:, 0], fx[:, 2] - fx[:, 0])
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    vdn = np.abs(np.einsum("fad,fd->fa", vel[faces], nrm))
+    tau = vdn + D / np.sqrt(D * dt)
+    case["fields"]["Tau"] = np.stack([tau, tau], axis=2)
+    case["fields"]["DiffusionTensor"] = np.full((nodes.shape[0], 1), D)
+    return case
+
+
 def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
     ore, topo = case["ore"], case["topo"]
     rc = O.RefElC(ore)
@@ -85,7 +110,7 @@ def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
         f.pop("DiffusionTensor", None)
     if "DiffusionTensor" in f:
         diffComps = f["DiffusionTensor"].shape[1]
-    if model == "cdrs":
+    if model in ("cdrs", "cd"):
         mask = O.OP_CONVECTION | (O.OP_DIFFUSION if "DiffusionTensor" in f else 0)
     xip = np.einsum("pi,cid->cpd", ore.ipShape, case["nodes"][case["cells"]])
     nD = case.get("nD", 1)

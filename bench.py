@@ -92,8 +92,8 @@ class ClockSampler:
 
 def cpu_baseline(order, cores, target_s=12.0, dim=3):
     """Oracle port of the reference path (HouseholderQR condensation as the reference) on `cores` workers."""
-    from hyperfox_b200 import meshgen
     from oracle import lib as O
+    from oracle import meshgen          # the oracle's own mesh generator: this leg never touches the product package
     from oracle.mesh import compute_faces
     from oracle.refel import ReferenceElement
     per_core = {1: 60000.0, 2: 9000.0, 3: 1500.0, 4: 300.0, 5: 80.0}[order]   # rough el/s/core, only sizes the sample
@@ -109,6 +109,62 @@ def cpu_baseline(order, cores, target_s=12.0, dim=3):
     h.pattern()
     sec, _, _ = h.bench_assemble(cores, useLU=0)
     return cells.shape[0] / sec, "Kuhn %d^3 x 6 = %d tets, order %d, %d threads, %.1f s" % (N, cells.shape[0], order, cores, sec), sec
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Libraries print to fd 1 (NCCL's version banner, for one): everything but the JSON line goes to stderr."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
+def workload_name(order, N):
+    return "3D Poisson HDG order %d, synthetic Kuhn mesh %d^3 x 6 = %d tets (BASELINE configs[2]), HDGLaplaceModel + DirichletModel, tau=1" % (order, N, 6 * N ** 3)
+
+
+def nAll_owned(nOwned, world, torch, dist):
+    t = torch.tensor([float(nOwned)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def dist_gate(rank, world, lrank):
+    """Multi-GPU parity gate: the distributed product solve (NCCL halo + all-reduce inside libhfx.so) of the 1296-tet order-3 Poisson problem
+    of tests/dist_solve_check.py against the committed ORACLE solution tests/golden/dist_gate_kuhn6_p3.npz (tools/make_dist_golden.py).
+    Returns a dict; "ok" only if every owned cell of every rank agrees to 1e-10."""
+    import torch.distributed as dist
+    from hyperfox_b200 import partition
+    from hyperfox_b200.dist import DistributedPoisson
+    g = np.load(os.path.join(ROOT, "tests", "golden", "dist_gate_kuhn6_p3.npz"))
+    verts, lin, order = g["verts"], g["lin"], int(g["order"])
+    part = partition.rcb_partition_vector(verts, lin, world) if world > 1 else np.zeros(lin.shape[0], dtype=np.int32)
+    dp = DistributedPoisson(verts, lin, part, rank, world, order, device=lrank, rtol=1e-13)
+    dp.assemble(); dp.solve()
+    ids, sol = dp.owned_solution()
+    out = [None] * world
+    if world > 1:
+        dist.all_gather_object(out, (ids, sol, int(dp.solver.stats.iterations), int(dp.solver.stats.converged)))
+    else:
+        out = [(ids, sol, int(dp.solver.stats.iterations), int(dp.solver.stats.converged))]
+    full = np.zeros_like(g["solution"]); seen = np.zeros(lin.shape[0], dtype=int)
+    for ids_r, sol_r, _, _ in out:
+        full[ids_r] = sol_r; seen[ids_r] += 1
+    err = float(np.abs(full - g["solution"]).max() / np.abs(g["solution"]).max())
+    its = [x[2] for x in out]
+    ok = bool(np.all(seen == 1) and err < 1e-10 and all(x[3] == 1 for x in out) and len(set(its)) == 1)
+    return {"ok": ok, "status": "DIST_OK" if ok else "DIST_FAILED", "max_rel_err_vs_oracle": err, "gmres_iterations": its[0], "oracle_gmres_iterations": int(g["iterations"]),
+            "mesh": "Kuhn 6^3 x 6 = 1296 perturbed tets, order 3", "partition": "recursive coordinate bisection, %d ranks" % world}
 
 
 def run_reference(args):
@@ -127,11 +183,13 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "HDG elements assembled+condensed/s (p=%d 3D tets)" % args.order, "value": v, "unit": "elements/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3D Poisson HDG order %d, oracle port of the reference CPU path (reference binary not buildable here: "
-                                   "needs Eigen/Boost/PETSc/MOAB/Zoltan/HDF5/MPI)" % args.order, "sample_per_step": sample},
+            "config": {"workload": workload_name(args.order, args.cubes), "sample_per_step": sample,
+                       "implementation": "oracle port of the reference CPU path, all host cores (the reference binary is not buildable here: it needs "
+                                         "Eigen/Boost/PETSc/MOAB/Zoltan/HDF5/MPI); each step assembles+condenses a bounded sample of the workload's "
+                                         "elements (same element type, order, model, fields), elements/s does not depend on the sample size"},
             "cpu_baseline": {"value": v, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -143,11 +201,13 @@ def main():
     ap.add_argument("--cubes", type=int, default=55, help="N: the unit cube is split into N^3 hexes x 6 Kuhn tets")
     ap.add_argument("--order", type=int, default=3)
     ap.add_argument("--partition-file", default=None, help="cell partition vector (.npy or text, one rank id per cell of the global mesh), "
-                    "e.g. a Zoltan partition; default: contiguous slabs")
+                    "e.g. a Zoltan partition; default: recursive coordinate bisection")
+    ap.add_argument("--partition", default="rcb", choices=("rcb", "slabs"), help="built-in stand-in for the Zoltan partition")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -178,9 +238,9 @@ def main():
     # the throughput counts OWNED cells only, the ghost layer is overhead.
     nOwned = nTot
     if world > 1:
+        # recursive coordinate bisection of the cell centroids, balanced by cell count (a third of the slabs' cut at 8 ranks)
         part = partition.load_partition_vector(args.partition_file, nTot, world) if args.partition_file else \
-            partition.partition_vector(nTot, world)      # (box_partition_vector has the smaller cut, but 55 is odd: its 28^3 / 27^3 boxes
-                                                         #  are 5.5 % out of balance, more than the slabs' extra ghost layer costs)
+            (partition.rcb_partition_vector(verts, lin, world) if args.partition == "rcb" else partition.partition_vector(nTot, world))
         prob = partition.rank_problem(verts, lin, part, rank, dim)
         lverts, lcells, nOwned = prob["verts"], prob["lin_cells"], int(prob["owned_cells"].size)
     else:
@@ -244,30 +304,53 @@ def main():
         return float(np.mean(ks))
     straight_ms = other_path("HFX_NO_REFPATH")
     general_ms = other_path("HFX_NO_AFFINE")
-    # the two other kernels of the path, timed separately from the headline: one GMRES(30) cycle on the assembled trace system
-    # (not to convergence: 30 iterations, wall clock incl. the host-side Hessenberg updates) and the local recovery
+    # the two other kernels of the path, timed separately from the headline: GMRES(30) on the assembled trace system (not to
+    # convergence: the difference of a 90- and a 30-iteration solve, device time from CUDA events inside hfx_solve) and the local recovery.
+    # On several GPUs this is the product's distributed solve: ghost-face trace blocks over NCCL send/recv overlapped with the interior rows
+    # of the SpMV, one ncclAllReduce per iteration -- after a parity gate against the committed oracle solution.
     extra = {}
+    gate = None
     if not args.no_solve:
-        check(L.hfx_assemble(h), h)
+        gate = dist_gate(rank, world, lrank)
+        if world > 1 and gate["ok"]:
+            from hyperfox_b200.dist import broadcast_unique_id
+            uid = broadcast_unique_id(rank, world)
+            check(L.hfx_comm_init(h, world, rank, uid), h)
+            gv = np.full(nodes.shape[0], -1, dtype=np.int64)      # global vertex id of the vertex nodes of the local high-order mesh
+            gv[cells[:, :dim + 1]] = prob["vertex_ids"][prob["lin_cells"]]
+            canon = partition.face_canonical_positions(dim, order, tp["faces"], gv)
+            partition.set_halo(h, prob, canon)
+        if world == 1 or gate["ok"]:
+            check(L.hfx_assemble(h), h)
+            info = capi.SolveInfo()
 
-        def timed_solve(its):
-            so = capi.SolveOpts(0, 1, 30, its, 1e-30)
-            stt = capi.SolveStats()
+            def timed_solve(its):
+                so = capi.SolveOpts(0, 1, 30, its, 1e-30)
+                stt = capi.SolveStats()
+                barrier()
+                check(L.hfx_solve(h, C.byref(so), C.byref(stt)), h)
+                check(L.hfx_solve_info(h, C.byref(info)), h)
+                return info.msPerIteration * stt.iterations * 1e-3, stt.iterations
+            timed_solve(30)                      # first call: Krylov basis allocation
+            t30, i30 = timed_solve(30)
+            t90, i90 = timed_solve(90)           # difference of two solves: per-iteration time free of the fixed costs (set-up, first residual)
+            t_it = (t90 - t30) / max(i90 - i30, 1)
             check(L.hfx_sync(h), h)
-            ts0 = time.time()
-            check(L.hfx_solve(h, C.byref(so), C.byref(stt)), h)
-            check(L.hfx_sync(h), h)
-            return time.time() - ts0, stt.iterations
-        timed_solve(30)                      # first call: Krylov basis allocation
-        t30, i30 = timed_solve(30)
-        t90, i90 = timed_solve(90)           # difference of two solves: per-iteration time free of the fixed costs (recovery, set-up)
-        t_it = (t90 - t30) / max(i90 - i30, 1)
-        tr0 = time.time()
-        for _ in range(3):
-            check(L.hfx_recover(h), h)
-        t_rec = (time.time() - tr0) / 3
-        extra = {"gmres_ms_per_iteration": t_it * 1e3, "gmres_iterations_timed": i90 - i30,
-                 "spmv_matrix_GBs_lower_bound": 8.0 * nnz.value / t_it / 1e9, "recovery_elements_per_s": nC / t_rec}
+            tr0 = time.time()
+            for _ in range(3):
+                check(L.hfx_recover(h), h)
+            t_rec = (time.time() - tr0) / 3
+            red_s = torch.tensor([t_it, t_rec], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(red_s, op=dist.ReduceOp.MAX)
+            t_it_max, t_rec_max = [float(x) for x in red_s.cpu()]
+            extra = {"gmres_ms_per_iteration": t_it_max * 1e3, "gmres_ms_per_iteration_rank0": t_it * 1e3, "gmres_iterations_timed": i90 - i30,
+                     "timing": "CUDA events around hfx_solve on the library stream, (90-iteration solve - 30-iteration solve) / 60, max over ranks",
+                     "all_reduces_per_iteration": (info.allReduces / max(i90, 1)) if world > 1 else 0,
+                     "halo_exchanges_per_iteration": (info.haloExchanges / max(i90, 1)) if world > 1 else 0,
+                     "halo_bytes_per_exchange_rank0": int(info.haloBytesPerExchange), "neighbours_rank0": int(info.nNeighbours),
+                     "owned_faces_rank0": int(info.ownedFaces), "rows_overlapped_with_halo_rank0": int(info.interiorFaces), "rows_waiting_for_halo_rank0": int(info.boundaryFaces),
+                     "spmv_matrix_GBs_lower_bound_rank0": 8.0 * nnz.value / t_it / 1e9, "recovery_elements_per_s": nAll_owned(nOwned, world, torch, dist) / t_rec_max}
 
     # ---- end-to-end arm: reference-shaped API, host fields, H2D + D2H inside the timed region ---------------------------
     e2e_ms = None
@@ -328,8 +411,7 @@ def main():
         "metric": "HDG elements assembled+condensed/s (p=%d 3D tets)" % order,
         "value": nAll / (ms_step * 1e-3), "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "3D Poisson HDG order %d, synthetic Kuhn mesh %d^3 x 6 = %d tets (BASELINE configs[2]), HDGLaplaceModel + DirichletModel, tau=1"
-                               % (order, N, nTot), "elements_per_rank": nC, "owned_elements_rank0": nOwned, "partition": ((("file " + os.path.basename(args.partition_file)) if args.partition_file else "slabs of the lexicographic Kuhn mesh") + ", overlap-1 ghost cells recomputed by the face owner" if world > 1 else "single rank"), "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
+        "config": {"workload": workload_name(order, N), "elements_per_rank": nC, "owned_elements_rank0": nOwned, "partition": ((("file " + os.path.basename(args.partition_file)) if args.partition_file else ("recursive coordinate bisection of the cell centroids" if args.partition == "rcb" else "slabs of the lexicographic Kuhn mesh")) + ", overlap-1 ghost cells recomputed by the face owner" if world > 1 else "single rank"), "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
                    "l2": "inputs+outputs per step (%.1f GB) far larger than the 126 MB L2" % ((BYTES_STORE[order] * nC) / 1e9),
                    "timing": "CUDA events on the library stream around memset+kernel, max over ranks; wall-clock per step %.2f ms" % ms_wall,
                    "setup_s": round(t_setup, 1),
@@ -344,7 +426,8 @@ def main():
                      "algorithmic_flops_per_element": FLOPS_PER_ELEM[order],
                      "hbm": {"achieved_GBs": hbm_ach, "peak_GBs": hbm_peak, "frac": hbm_ach / hbm_peak, "bytes_per_element": BYTES_STORE[order],
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
-        "solve_and_recovery_rank0": extra,
+        "solve_and_recovery": extra,
+        "dist_gate": gate,
         "gpu_launches": 1 * args.steps,
         "clocks": clocks,
     }
@@ -355,7 +438,7 @@ def main():
         cores = os.cpu_count() or 1
         v, sample, _ = cpu_baseline(order, cores)
         line["cpu_baseline"] = {"value": v, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

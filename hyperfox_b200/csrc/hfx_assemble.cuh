@@ -1789,11 +1789,9 @@ inline cudaError_t launch_assemble_tpe(const AsmParams& p, int nSM, cudaStream_t
   using L = AsmSmem<DIM, P>;
   constexpr int NGRP = kAsmThreads / TPE;
   constexpr size_t bytes = L::gbytes * NGRP;
-  static bool attr = false;
-  if (!attr) {
+  {   // the attribute is per device (a process may hold contexts on several GPUs): set on every launch, it costs microseconds
     cudaError_t e = cudaFuncSetAttribute(hdg_assemble_kernel<DIM, P, TPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   int perSM = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_assemble_kernel<DIM, P, TPE>, kAsmThreads, bytes);

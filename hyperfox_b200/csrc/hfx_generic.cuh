@@ -23,6 +23,7 @@ struct GenParams {
   const double* tracePrev;   // Trace of the previous iterate, face field [nFaces][nNf][nD]
   int frameV[4];             // local ids of the vertices spanning the affine frame of a straight-sided element (and, first dim of them, of a face):
                              // 0,1,2,3 for simplices, 0,1,3,4 for orthotopes (ReferenceElement.cpp:885-943)
+  int forcePivot;            // partial pivoting in K^-1 whatever the model (fallback after a vanishing pivot in the unpivoted path)
   int nSrc;                  // source components: 1, or dim for the Burgers model (HDGBurgersModel.cpp:112-122)
   int smOpt[6];              // offsets (doubles, from the optional area) of Um, Rm, Aq, Bq, shape table, GM when they live in shared memory; -1: global scratch
   double* ws;                // per-CTA scratch
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
     }
     __syncthreads();
     HFX_GPROF(7);
-    const bool pivK = hasUN;   // the Newton-linearised convection block can make K indefinite: partial pivoting there, definite otherwise
+    const bool pivK = hasUN || P.forcePivot;   // the Newton-linearised convection block can make K indefinite: partial pivoting there, definite otherwise
     {   // K = Suu - Suq A (into the augmented shared matrix) ; R = [Sul - Suq B | -Fu]
       const int MT = (u + 7) / 8, NC = u + l, NG = (NC + 23) / 24;
       for (int task = warp; task < MT * NG; task += NWARP) {

@@ -33,11 +33,16 @@ struct GmresDev {
   int its, done, kc, first, maxits, converged;
 };
 
-// partial[j * gridDim.x + block] = sum over the block's share of z[i] * V[j][i], j < nv <= NV.  z is read once.
+// partial[j * gridDim.x + block] = sum over the block's share of z[i] * V[j][i] for the NV vectors j = NV blockIdx.y + (0..NV-1), j < nv.
+// A block column handles NV = 8 vectors: 38 registers, every SM full of warps that each keep eight 16-byte loads in flight (measured
+// 6.5 TB/s on the B200; with all 30 accumulators in one thread the kernel needs 154 registers and drops to 4 TB/s).  z is re-read once per
+// block column: 1/8 more traffic.
 template <int NV>
 __global__ void __launch_bounds__(256) kry_dots_kernel(long long n, int nv, const double* __restrict__ V, long long ldv, const double* __restrict__ z,
                                                        double* __restrict__ partial, const int* __restrict__ done) {
   if (done && *done) return;
+  const int j0 = blockIdx.y * NV;
+  V += (size_t)j0 * ldv; nv -= j0;
   double acc[NV];
 #pragma unroll
   for (int j = 0; j < NV; j++) acc[j] = 0.0;
@@ -64,33 +69,36 @@ __global__ void __launch_bounds__(256) kry_dots_kernel(long long n, int nv, cons
     if (lane == 0) red[w][j] = v;
   }
   __syncthreads();
-  if (threadIdx.x < nv) {
+  if (threadIdx.x < NV && (int)threadIdx.x < nv) {
     double s = 0.0;
     for (int k = 0; k < 8; k++) s += red[k][threadIdx.x];
-    partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;
+    partial[(size_t)(j0 + threadIdx.x) * gridDim.x + blockIdx.x] = s;
   }
 }
 
-// out[i] = base[i] + sign * sum_j coef[j] V[j][i] on the rows of `mask` (NULL: all rows); npart[block] = partial sum of out[i]^2 (NULL: none).
-// coef lives on the device.
-template <int NV>
+// out[i] = base[i] + sum_j coef[j] V[j][i] on the rows of `mask` (NULL: all rows); npart[block] = partial sum of out[i]^2 (NULL: none).
+// The coefficients (sign * coef[j], coef on the device) sit in shared memory and the vectors are consumed eight at a time, so the kernel
+// keeps ~40 registers whatever nv is.
 __global__ void __launch_bounds__(256) kry_lincomb_kernel(long long n, int nv, const double* __restrict__ V, long long ldv, const double* base,
                                                           const double* __restrict__ coef, double sign, double* out,
                                                           const uint8_t* __restrict__ mask, double* __restrict__ npart, const int* __restrict__ done) {
   if (done && *done) return;
-  double cj[NV];
-#pragma unroll
-  for (int j = 0; j < NV; j++) cj[j] = j < nv ? sign * coef[j] : 0.0;
+  __shared__ double cj[kMaxRestart + 2];
+  __shared__ double red[8];
+  if (threadIdx.x < kMaxRestart + 2) cj[threadIdx.x] = (int)threadIdx.x < nv ? sign * coef[threadIdx.x] : 0.0;
+  __syncthreads();
   double nrm = 0.0;
   const long long n2 = n >> 1;
+  const int nv8 = (nv + 7) & ~7;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     double2 s = reinterpret_cast<const double2*>(base)[i];
+    for (int j0 = 0; j0 < nv8; j0 += 8) {
+      double2 v[8];
 #pragma unroll
-    for (int j = 0; j < NV; j++)
-      if (j < nv) {
-        const double2 v = *reinterpret_cast<const double2*>(V + (size_t)j * ldv + 2 * i);
-        s.x = fma(cj[j], v.x, s.x); s.y = fma(cj[j], v.y, s.y);
-      }
+      for (int j = 0; j < 8; j++) v[j] = (j0 + j < nv) ? *reinterpret_cast<const double2*>(V + (size_t)(j0 + j) * ldv + 2 * i) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < 8; j++) { const double c = cj[(j0 + j) < kMaxRestart + 2 ? j0 + j : 0]; s.x = fma(c, v[j].x, s.x); s.y = fma(c, v[j].y, s.y); }
+    }
     if (mask) {
       const uchar2 m = reinterpret_cast<const uchar2*>(mask)[i];
       if (m.x) { out[2 * i] = s.x; nrm = fma(s.x, s.x, nrm); }
@@ -102,12 +110,10 @@ __global__ void __launch_bounds__(256) kry_lincomb_kernel(long long n, int nv, c
   }
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0 && (!mask || mask[n - 1])) {
     double s = base[n - 1];
-#pragma unroll
-    for (int j = 0; j < NV; j++) if (j < nv) s = fma(cj[j], V[(size_t)j * ldv + n - 1], s);
+    for (int j = 0; j < nv; j++) s = fma(cj[j], V[(size_t)j * ldv + n - 1], s);
     out[n - 1] = s; nrm = fma(s, s, nrm);
   }
   if (npart) {
-    __shared__ double red[8];
     for (int o = 16; o > 0; o >>= 1) nrm += __shfl_xor_sync(0xffffffffu, nrm, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nrm;
     __syncthreads();

@@ -662,23 +662,12 @@ struct Krylov {
     HFX_CUDA(cudaMemcpyAsync(out_host, hdev.p, nv * sizeof(double), cudaMemcpyDeviceToHost, st));
     HFX_CUDA(cudaStreamSynchronize(st));
   }
-  template <int NV>
-  void launch_dots(long long n, int nv, const double* Vp, long long ldv, const double* zv, double* part, const int* done, cudaStream_t st) {
-    kry_dots_kernel<NV><<<kDotBlocks, 256, 0, st>>>(n, nv, Vp, ldv, zv, part, done);
-  }
   void dots_dev(long long n, int nv, const double* Vp, long long ldv, const double* zv, double* part, const int* done, cudaStream_t st) {
-    if (nv <= 4) launch_dots<4>(n, nv, Vp, ldv, zv, part, done, st);
-    else if (nv <= 8) launch_dots<8>(n, nv, Vp, ldv, zv, part, done, st);
-    else if (nv <= 16) launch_dots<16>(n, nv, Vp, ldv, zv, part, done, st);
-    else launch_dots<32>(n, nv, Vp, ldv, zv, part, done, st);
+    kry_dots_kernel<8><<<dim3(kDotBlocks, (nv + 7) / 8), 256, 0, st>>>(n, nv, Vp, ldv, zv, part, done);
   }
   void lincomb_dev(long long n, int nv, const double* Vp, long long ldv, const double* base, const double* coef, double sign, double* out,
                    const uint8_t* mask, double* np, const int* done, cudaStream_t st) {
-    const int g = kDotBlocks;
-    if (nv <= 4) kry_lincomb_kernel<4><<<g, 256, 0, st>>>(n, nv, Vp, ldv, base, coef, sign, out, mask, np, done);
-    else if (nv <= 8) kry_lincomb_kernel<8><<<g, 256, 0, st>>>(n, nv, Vp, ldv, base, coef, sign, out, mask, np, done);
-    else if (nv <= 16) kry_lincomb_kernel<16><<<g, 256, 0, st>>>(n, nv, Vp, ldv, base, coef, sign, out, mask, np, done);
-    else kry_lincomb_kernel<32><<<g, 256, 0, st>>>(n, nv, Vp, ldv, base, coef, sign, out, mask, np, done);
+    kry_lincomb_kernel<<<kDotBlocks, 256, 0, st>>>(n, nv, Vp, ldv, base, coef, sign, out, mask, np, done);
   }
   // GMRES(restart): see hfx_krylov.cuh.  What PETSc's KSPGMRES does with the reference's settings (PetscInterface.cpp:60-82,222-247;
   // PetscOpts.h:12-24), with the Hessenberg / Givens / convergence bookkeeping on the device and one host synchronisation per cycle.
@@ -853,7 +842,7 @@ struct hfx_ctx {
   bool modelSet = false, bcSet = false;
   DBuf<uint8_t> dFaceBC;
   // allocation
-  bool allocated = false, assembled = false, keepS = false;
+  bool allocated = false, assembled = false, keepS = false, pivotFallback = false;
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
   DBuf<long long> dFaceRowStart, dBlockCount, dTotal;
   long long nnz = 0;
@@ -1421,6 +1410,21 @@ int hfx_allocate(hfx_ctx* c, int flags) {
     need(dir->type == HFX_FIELD_FACE && dir->nObj == c->nNf && dir->nVal == nD, "DirichletModel", "setFieldMap", "the Dirichlet field must be a face field with one object per face node");
     c->keepS = flags & HFX_KEEP_LOCAL_S;
     const int nF = c->nFaces, nC = c->nCells;
+    // The scatter stores every off-diagonal (face, neighbour face) block with a plain copy: a block must have ONE contributing element, i.e.
+    // two cells may share at most one face and a cell may not list a face twice (true for every conforming mesh; checked, not assumed).
+    for (int e = 0; e < nC; e++) {
+      int other[8];
+      for (int f = 0; f < c->nFc; f++) {
+        const int F = c->hC2F[(size_t)e * c->nFc + f];
+        need(F >= 0 && F < nF, "Mesh", "computeFaces", "cell2face refers to a face outside the face list");
+        const int c0 = c->hF2C[(size_t)2 * F], c1 = c->hF2C[(size_t)2 * F + 1];
+        other[f] = c0 == e ? c1 : c0;
+        for (int g = 0; g < f; g++) {
+          need(c->hC2F[(size_t)e * c->nFc + g] != F, "Mesh", "computeFaces", "a cell lists the same face twice");
+          need(other[f] < 0 || other[g] != other[f], "Mesh", "computeFaces", "two cells share more than one face: the block scatter needs a conforming mesh");
+        }
+      }
+    }
     // sparsity pattern + scatter maps, on device (HDGSolver::calcSparsityPattern :117-164)
     c->dNbr.alloc((size_t)nF * 2 * c->nFc); c->dNnb.alloc(nF); c->dInterior.alloc(nF); c->dBlockCount.alloc(nF); c->dFaceRowStart.alloc(nF); c->dTotal.alloc(1);
     face_pattern_kernel<<<nblk(nF, 256), 256, 0, c->st>>>(nF, c->nFc, t, c->dF2C.p, c->dC2F.p, c->dNbr.p, c->dNnb.p, c->dInterior.p, c->dBlockCount.p);
@@ -1509,12 +1513,15 @@ int hfx_assemble(hfx_ctx* c) {
     p.prof = c->profOn ? c->dProf.p : nullptr;
     HFX_CUDA(cudaEventRecord(c->ev0, c->st));
     // linSystem->clearSystem() (HDGSolver.cpp:532-536): entries with two contributors are accumulated on zeroed storage
-    if (!c->valsCleared || getenv("HFX_FULL_MEMSET")) { c->dVals.zero(c->st); c->valsCleared = true; }   // first assemble after allocate: everything
-    else {
-      const int t = c->nNf * c->md.nDOF;
-      zero_diag_blocks_kernel<<<nblk((long long)c->nFaces * 32, 256), 256, 0, c->st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dInterior.p, c->dVals.p);
-    }
-    c->dRhs.zero(c->st); c->dStatus.zero(c->st);
+    auto clearSystem = [&]() {
+      if (!c->valsCleared || getenv("HFX_FULL_MEMSET")) { c->dVals.zero(c->st); c->valsCleared = true; }   // first assemble after allocate: everything
+      else {
+        const int t = c->nNf * c->md.nDOF;
+        zero_diag_blocks_kernel<<<nblk((long long)c->nFaces * 32, 256), 256, 0, c->st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dInterior.p, c->dVals.p);
+      }
+      c->dRhs.zero(c->st); c->dStatus.zero(c->st);
+    };
+    clearSystem();
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
     bool fused = c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
     // fields still crossing PCIe (hfx_field_set_async): the element chunks start as their face-id prefix has arrived
@@ -1541,8 +1548,9 @@ int hfx_assemble(hfx_ctx* c) {
     }
     if (!fused && !pend.empty()) waitPieces(0, -1);
     for (DField* f : pend) f->pendingPieces = 0;
-    if (!fused) {   // general kernel: 3-D orders 4-5, nDOFsPerNode > 1, HDGUNabU
+    auto launchGeneric = [&](bool pivot) {   // general kernel: 3-D orders 4-5, nDOFsPerNode > 1, HDGUNabU, orthotopes; pivot: partial pivoting in K^-1
       GenParams g{};
+      g.forcePivot = pivot ? 1 : 0;
       g.a = p; g.dim = c->dim; g.nN = c->nN; g.nNf = c->nNf; g.nFc = c->nFc; g.nIP = c->nIP; g.nIPf = c->nIPf; g.nD = c->md.nDOF;
       g.nSrc = 1;
       g.frameV[0] = 0; g.frameV[1] = 1; g.frameV[2] = c->geom == HFX_SIMPLEX ? 2 : 3; g.frameV[3] = c->geom == HFX_SIMPLEX ? 3 : 4;
@@ -1582,8 +1590,7 @@ int hfx_assemble(hfx_ctx* c) {
       const size_t smemCap = (getenv("HFX_GEN_ONE_CTA") ? 226 : (HFX_GEN_MINBLOCKS == 3 ? 74 : 112)) * 1024;   // default: two CTAs per SM stay resident
       const size_t smem = smemBase + (getenv("HFX_GEN_NO_SMEM_OPERANDS") ? (std::fill(g.smOpt, g.smOpt + 6, -1), (size_t)0)
                                                                         : gen_smem_optional(g.dim, g.nN, g.nNf, g.nFc, g.nIP, g.nD, smemCap > smemBase ? smemCap - smemBase : 0, g.smOpt));
-      static size_t smemSet = 0;
-      if (smem > smemSet) { HFX_CUDA(cudaFuncSetAttribute(hdg_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smemSet = smem; }
+      HFX_CUDA(cudaFuncSetAttribute(hdg_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every launch
       int perSM = 1;
       HFX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_generic_kernel, kGenThreads, smem));
       if (perSM < 1) perSM = 1;
@@ -1594,10 +1601,22 @@ int hfx_assemble(hfx_ctx* c) {
       g.ws = c->dGenWs.p; g.wsStride = z.total;
       hdg_generic_kernel<<<(int)grid, kGenThreads, smem, c->st>>>(g);
       HFX_CUDA(cudaGetLastError());
-    }
+    };
+    if (!fused) launchGeneric(getenv("HFX_FORCE_PIVOT") != nullptr);
     HFX_CUDA(cudaEventRecord(c->ev2, c->st));
     int status = 0;
     c->dStatus.download(&status, 1, c->st);
+    c->pivotFallback = false;
+    if (getenv("HFX_DEBUG_RAISE_STATUS")) status |= 1;   // test hook: take the fallback below as if a pivot had vanished
+    if ((status & 1) && c->nN * c->md.nDOF <= 96 && !(c->md.opmask & HFX_OP_UNABU)) {
+      // A vanishing pivot in the UNPIVOTED Gauss-Jordan of some element's K (convection-dominated local problems are not definite): the
+      // reference's HouseholderQR would have gone through.  Redo the assembly with the general kernel's partially pivoted inverse.
+      clearSystem();
+      launchGeneric(true);
+      HFX_CUDA(cudaEventRecord(c->ev2, c->st));
+      c->dStatus.download(&status, 1, c->st);
+      c->pivotFallback = true;
+    }
     HFX_CUDA(cudaEventElapsedTime(&c->msTotal, c->ev0, c->ev2));
     HFX_CUDA(cudaEventElapsedTime(&c->msKernel, c->ev1, c->ev2));
     need(!(status & 1), "HDGSolver", "calcElementalMatrices", "singular local matrix met during static condensation");

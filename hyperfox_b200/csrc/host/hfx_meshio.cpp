@@ -208,13 +208,17 @@ namespace {
 struct H5File {
   std::vector<unsigned char> b;
   [[noreturn]] static void bad(const std::string& m) { throw std::runtime_error("HDF5Io : loadMesh : " + m); }
+  // every offset / size below comes from the (untrusted) file: range checks are written so that they cannot wrap around
+  bool inside(uint64_t off, uint64_t n) const { return off <= b.size() && n <= b.size() - off; }
+  mutable size_t visited = 0;
+  void visit() const { if (++visited > 1000000) bad("corrupt file (cyclic or oversized header structure)"); }
   uint64_t u(size_t off, int n) const {
-    if (off + n > b.size()) bad("truncated file");
+    if (!inside(off, (uint64_t)n)) bad("truncated file");
     uint64_t v = 0;
     for (int i = n - 1; i >= 0; i--) v = (v << 8) | b[off + i];
     return v;
   }
-  bool tag(size_t off, const char* t) const { return off + 4 <= b.size() && std::equal(t, t + 4, b.begin() + off); }
+  bool tag(size_t off, const char* t) const { return inside(off, 4) && std::equal(t, t + 4, b.begin() + off); }
   struct Entry { uint64_t nameOff = 0, ohdr = 0, btree = 0, heap = 0; bool cached = false; };
   struct Msg { int type; size_t data, size; };
   Entry entry(size_t off) const {
@@ -229,11 +233,15 @@ struct H5File {
     std::vector<std::pair<size_t, size_t>> blocks = {{ohdr + 16, (size_t)u(ohdr + 8, 4)}};
     std::vector<Msg> out;
     for (size_t bi = 0; bi < blocks.size() && out.size() < nmsg; bi++) {
+      visit();
       size_t off = blocks[bi].first;
+      if (!inside(off, blocks[bi].second)) bad("object header block outside the file");
       const size_t end = off + blocks[bi].second;
       while (off + 8 <= end && out.size() < nmsg) {
+        visit();
         const int type = (int)u(off, 2);
         const size_t sz = u(off + 2, 2), data = off + 8;
+        if (!inside(data, sz)) bad("object header message outside the file");
         if (type == 0x10) blocks.push_back({(size_t)u(data, 8), (size_t)u(data + 8, 8)});   // continuation block
         out.push_back({type, data, sz});
         off = data + sz;
@@ -242,6 +250,7 @@ struct H5File {
     return out;
   }
   void walk(size_t node, size_t heapData, std::map<std::string, Entry>* out, int depth) const {
+    visit();
     if (!tag(node, "TREE") || depth > 16) bad("corrupt group B-tree");
     const int level = (int)u(node + 5, 1), nent = (int)u(node + 6, 2);
     const size_t p = node + 8 + 16;
@@ -251,7 +260,9 @@ struct H5File {
       if (!tag(child, "SNOD")) bad("corrupt symbol table node");
       const int ns = (int)u(child + 6, 2);
       for (int k = 0; k < ns; k++) {
+        visit();
         const Entry e = entry(child + 8 + (size_t)k * 40);
+        if (!inside(heapData, e.nameOff)) bad("symbol name outside the file");
         size_t s = heapData + e.nameOff;
         std::string name;
         while (s < b.size() && b[s]) name.push_back((char)b[s++]);
@@ -281,6 +292,7 @@ struct H5File {
       } else if (m.type == 0x8) {
         if (u(m.data, 1) != 3 || u(m.data + 1, 1) != 1) bad("only contiguous dataset layouts are supported");
         *addr = (size_t)u(m.data + 2, 8); haveL = true;
+        if (u(m.data + 2, 8) == UINT64_MAX) bad("dataset without allocated storage (HADDR_UNDEF)");
       }
     }
     if (!haveS || !haveT || !haveL) bad("incomplete dataset header");
@@ -308,15 +320,17 @@ void read_h5_mesh(const std::string& path, H5Mesh* out) {
   size_t addr = 0;
   f.dataset(mesh["Nodes"], &shape, &cls, &size, &addr);
   if (shape.size() != 2 || cls != 1 || size != 8) H5File::bad("Nodes must be a two-dimensional float64 dataset");
+  if (shape[1] == 0 || shape[1] > 3 || shape[0] > f.b.size() / (8 * shape[1])) H5File::bad("truncated Nodes dataset");
   const size_t nn = (size_t)(shape[0] * shape[1]);
-  if (addr + nn * 8 > f.b.size()) H5File::bad("truncated Nodes dataset");
+  if (!f.inside(addr, (uint64_t)nn * 8)) H5File::bad("truncated Nodes dataset");
   out->dimNodeSpace = (int)shape[1];
   out->nodes.resize(nn);
   std::memcpy(out->nodes.data(), f.b.data() + addr, nn * 8);
   f.dataset(mesh["Cells"], &shape, &cls, &size, &addr);
   if (shape.size() != 2 || cls != 0 || (size != 4 && size != 8)) H5File::bad("Cells must be a two-dimensional integer dataset");
+  if (shape[1] == 0 || shape[1] > 4096 || shape[0] > f.b.size() / ((uint64_t)size * shape[1])) H5File::bad("truncated Cells dataset");
   const size_t nc = (size_t)(shape[0] * shape[1]);
-  if (addr + nc * size > f.b.size()) H5File::bad("truncated Cells dataset");
+  if (!f.inside(addr, (uint64_t)nc * size)) H5File::bad("truncated Cells dataset");
   out->nodesPerCell = (int)shape[1];
   out->cells.resize(nc);
   for (size_t i = 0; i < nc; i++) out->cells[i] = (int)(int64_t)f.u(addr + i * size, size);

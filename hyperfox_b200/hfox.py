@@ -70,6 +70,10 @@ class Mesh:
         self.nodes, self.cells = f64(nodes), i32(cells)
         if self.cells.shape[1] != self.refEl.getNumNodes():
             raise ErrorHandle("Mesh : setMesh : the connectivity does not match the reference element")
+        if self.nodes.ndim != 2 or self.nodes.shape[1] != self.dim:
+            # the device path reads nodes with stride dim (hfx_mesh_set): a node space of another dimension would be mis-strided silently
+            raise ErrorHandle("Mesh : setMesh : the device path needs dimNodeSpace == dimension of the reference element (%d coordinates per node given, %d expected)"
+                              % (self.nodes.shape[1] if self.nodes.ndim == 2 else -1, self.dim))
         tp = capi.host_compute_faces(self.dim, self.order, self.cells, self.refEl._geom)
         self.faces, self.cell2FaceMap, self.face2CellMap, self.boundaryFaces = tp["faces"], tp["cell2face"], tp["face2cell"], tp["boundary"]
 

@@ -151,6 +151,31 @@ def test_h5_mesh_reader_errors(tmp_path):
         product.read_h5_mesh(str(tmp_path / "cut.h5"))
 
 
+def test_h5_mesh_reader_survives_corrupt_offsets(tmp_path):
+    """Mesh files are untrusted input: every 8-byte word of a reference file replaced in turn by values that wrap around a 64-bit sum
+    (2^64-8, 2^64-1 = HADDR_UNDEF, 2^63) or point far outside the file.  The reader must either raise its ErrorHandle or return the
+    untouched mesh -- never read outside the buffer (`off + n > size` overflowed)."""
+    from hyperfox_b200.capi import ErrorHandle
+    raw = bytearray(open(os.path.join(H5, "lightTri2.h5"), "rb").read())
+    gn, gc = load_mesh("lightTri2")
+    path = str(tmp_path / "fuzz.h5")
+    rejected = 0
+    for off in range(8, min(len(raw) - 8, 4096), 8):
+        for val in (2 ** 64 - 8, 2 ** 64 - 1, 2 ** 63, len(raw) - 4, 2 ** 40):
+            b = bytearray(raw)
+            b[off:off + 8] = int(val).to_bytes(8, "little")
+            open(path, "wb").write(b)
+            try:
+                nodes, cells = product.read_h5_mesh(path)
+            except ErrorHandle:
+                rejected += 1
+                continue
+            assert nodes.shape[0] < 10 ** 6 and cells.shape[0] < 10 ** 6
+            if nodes.shape == gn.shape and cells.shape == gc.shape and off < 2048:
+                pass    # a word the reader does not interpret (or padding): the mesh may or may not be the original, but it came from inside the file
+    assert rejected > 20
+
+
 def test_python_io_mirrors():
     """hfox.HDF5Io / hfox.GmshIo (the reference's Io interface): both routes give the same Mesh, faces included."""
     from hyperfox_b200 import hfox

@@ -652,7 +652,10 @@ struct Krylov {
   cudaEvent_t evDone[kMaxRestart + 1] = {};
   Halo* halo = nullptr;   // set for a distributed solve: dots are summed over the ranks (vectors are zero on non-owned rows)
   float msPerIteration = 0.f; long long allReduces = 0, haloExchanges = 0;
-  ~Krylov() { if (hpin) cudaFreeHost(hpin); if (hstate) cudaFreeHost(hstate); if (hdone) cudaFreeHost(hdone); for (auto e : evDone) if (e) cudaEventDestroy(e); }
+  // phase timeline of the last solve (CUDA events on the solver's stream): operator (SpMV + halo + preconditioner), dots, reduction (+ all-reduce) + step, Gram-Schmidt update
+  cudaEvent_t evPh[kMaxRestart][5] = {};
+  float msPhase[4] = {0, 0, 0, 0}; long long phaseIts = 0;
+  ~Krylov() { if (hpin) cudaFreeHost(hpin); if (hstate) cudaFreeHost(hstate); if (hdone) cudaFreeHost(hdone); for (auto e : evDone) if (e) cudaEventDestroy(e); for (auto& r : evPh) for (auto e : r) if (e) cudaEventDestroy(e); }
   void dots(long long n, int nv, const double* Vp, long long ldv, const double* wv, cudaStream_t st, double* out_host) {
     if (partial.n < (size_t)(kMaxRestart + 2) * kDotBlocks) partial.alloc((size_t)(kMaxRestart + 2) * kDotBlocks);
     hdev.alloc(64);
@@ -682,6 +685,9 @@ struct Krylov {
     if (!hstate) HFX_CUDA(cudaMallocHost(&hstate, sizeof(GmresDev)));
     if (!hdone) HFX_CUDA(cudaMallocHost(&hdone, (kMaxRestart + 1) * sizeof(int)));
     for (auto& e : evDone) if (!e) HFX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& r : evPh) for (auto& e : r) if (!e) HFX_CUDA(cudaEventCreate(&e));
+    for (float& v : msPhase) v = 0.f;
+    phaseIts = 0;
     const int usePC = o.pc != 0;
     const bool blockPC = o.pc == 2;
     if (blockPC && !A.has_block_pc()) throw Err("Krylov", "gmres", "the face-block Jacobi preconditioner needs the block-CSR trace operator");
@@ -728,12 +734,17 @@ struct Krylov {
           if (cudaEventQuery(evDone[k - 3]) == cudaSuccess && hdone[k - 3]) break;
         }
         double* vk = V.p + (size_t)k * ldv;
+        HFX_CUDA(cudaEventRecord(evPh[k][0], st));
         op(vk, w.p);
+        HFX_CUDA(cudaEventRecord(evPh[k][1], st));
         dots_dev(n, k + 1, V.p, ldv, w.p, partial.p, done, st);
+        HFX_CUDA(cudaEventRecord(evPh[k][2], st));
         kry_reduce_kernel<<<k + 2, 256, 0, st>>>(k + 1, kDotBlocks, partial.p, npart.p, red.p, done);
         all_reduce(k + 2);
         kry_step_kernel<<<1, 32, 0, st>>>(state.p, k, k + 1, 0, red.p);
+        HFX_CUDA(cudaEventRecord(evPh[k][3], st));
         lincomb_dev(n, k + 1, V.p, ldv, w.p, state.p->c, -1.0, V.p + (size_t)(k + 1) * ldv, mask, npart.p, done, st);
+        HFX_CUDA(cudaEventRecord(evPh[k][4], st));
         if (!dist) {
           HFX_CUDA(cudaMemcpyAsync(hdone + k, done, sizeof(int), cudaMemcpyDeviceToHost, st));
           HFX_CUDA(cudaEventRecord(evDone[k], st));
@@ -747,6 +758,9 @@ struct Krylov {
       lincomb_dev(n, m, V.p, ldv, x, state.p->c, 1.0, x, nullptr, nullptr, nullptr, st);
       HFX_CUDA(cudaMemcpyAsync(hstate, state.p, sizeof(GmresDev), cudaMemcpyDeviceToHost, st));
       HFX_CUDA(cudaStreamSynchronize(st));
+      for (int kk = 0; kk < k; kk++)
+        for (int ph = 0; ph < 4; ph++) { float ms1 = 0.f; if (cudaEventElapsedTime(&ms1, evPh[kk][ph], evPh[kk][ph + 1]) == cudaSuccess) msPhase[ph] += ms1; }
+      phaseIts += k;
       its = hstate->its;
       if (hstate->done || its >= o.maxits) finished = true;
     }
@@ -1693,6 +1707,7 @@ int hfx_solve_info(const hfx_ctx* c, hfx_solve_info_t* info) {
   info->ownedFaces = H.planned ? H.nOwnedFaces : c->nFaces;
   info->interiorFaces = H.planned ? H.nInterior : c->nFaces; info->boundaryFaces = H.planned ? H.nBoundary : 0;
   info->nNeighbours = H.planned ? (int)H.nbr.size() : 0;
+  for (int ph = 0; ph < 4; ph++) info->msPhase[ph] = c->krylov.phaseIts > 0 ? c->krylov.msPhase[ph] / (float)c->krylov.phaseIts : 0.f;
   return 0;
 }
 

@@ -117,7 +117,8 @@ int hfx_solve(hfx_ctx* ctx, const hfx_solve_opts* opts, hfx_solve_stats* stats);
 int hfx_recover(hfx_ctx* ctx);                                                    /* HDGSolver.cpp:741-775 */
 /* what the last hfx_solve cost: device time per Krylov iteration (CUDA events around the whole solve / iterations), and on several GPUs the
    collectives it issued (replaces the MPI_Allreduce / VecScatter counts of KSPSolve's -log_view) */
-typedef struct { float msPerIteration; long long allReduces, haloExchanges, haloBytesPerExchange, ownedFaces, interiorFaces, boundaryFaces; int nNeighbours; } hfx_solve_info_t;
+typedef struct { float msPerIteration; long long allReduces, haloExchanges, haloBytesPerExchange, ownedFaces, interiorFaces, boundaryFaces; int nNeighbours;
+                 float msPhase[4]; /* mean ms per iteration: operator (SpMV + halo + preconditioner), dots, reduction (+ all-reduce) + Hessenberg step, Gram-Schmidt update */ } hfx_solve_info_t;
 int hfx_solve_info(const hfx_ctx* ctx, hfx_solve_info_t* info);
 int hfx_sync(hfx_ctx* ctx);
 /* timing of the last hfx_assemble (CUDA events on the library's stream), milliseconds */

@@ -42,7 +42,7 @@ def main():
         st = capi.SolveStats()
         check(L.hfx_solve(h, C.byref(so), C.byref(st)), h)
         check(L.hfx_solve_info(h, C.byref(info)), h)
-        print("solve: %d iterations, %.3f ms / iteration (device)" % (st.iterations, info.msPerIteration), flush=True)
+        print("solve: %d iterations, %.3f ms / iteration (device); phases op %.3f dots %.3f reduce+step %.3f update %.3f" % ((st.iterations, info.msPerIteration) + tuple(info.msPhase)), flush=True)
 
 
 if __name__ == "__main__":

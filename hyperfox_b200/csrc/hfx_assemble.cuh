@@ -1426,6 +1426,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     //      independent accumulator chains (operand traffic, not the DMMA pipe, is what limits these skinny products).
     double* const KB = (W == Mm) ? Wb : Mm;          // the buffer that does not hold W (W is dead once A and B exist)
     double* const KI = ((nNp / 2) & 1) ? KB : SUU;
+    double* const KC = W;                            // copy of K for the refinement step of U (P7r); the Gauss-Jordan consumes SUU and KB
     {
       const int lr = lane >> 2, lc = lane & 3;
       constexpr int LT = (l + 7) / 8, T_K = MTN, T_R = LT;
@@ -1459,7 +1460,7 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
             for (int h = 0; h < 2; h++) {
               const int cc = nt * 8 + 2 * lc + h;
               const double v = c[i][h];
-              if (isK) { if (cc < nN) SUU[m + nNp * cc] -= v; }
+              if (isK) { if (cc < nN) { const double kv = SUU[m + nNp * cc] - v; SUU[m + nNp * cc] = kv; KC[m + nNp * cc] = kv; } }
               else if (cc < l) {
                 const int f = cc / t, b = cc % t, a = NIF[f * nN + m];
                 double sul = 0.0;
@@ -1479,15 +1480,20 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     group_invert<nNp, nNp, NT>(SUU, KB, tid, p.status, 1 + grp);
     HFX_PROF(10);
 
-    // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu (column l) ------------------------------------------------------------------------
+    // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu (column l), then one step of iterative refinement, U <- U - K^-1 (K U + R).
+    //      U = -K^-1 R through an EXPLICIT inverse carries a forward error of eps cond(K) ||K^-1|| ||R||, and ||K^-1|| ||R|| / ||U|| ~ 1 / h on
+    //      fine meshes (K^-1 is dominated by the constant mode, which R barely excites); the refined U has the eps cond(K) ||U|| of the
+    //      reference's triangular solves (HDGSolver.cpp:331-343, HouseholderQR).  A warp owns one column tile through all three products
+    //      (a column of U depends on the same column of R only), so the steps are separated by warp barriers, not block barriers.
     {
       const int lr = lane >> 2, lc = lane & 3;
       constexpr int L1T = (l + 1 + 7) / 8;
-      for (int task = warp; task < L1T; task += NWARP) {
-        const double* pb = R + imin(task * 8 + lr, l);
+      // Cm[:, tile] = beta * Cm[:, tile] + sgn * Am * Bm[:, tile]
+      auto col_task = [&](int task, const double* Am, const double* Bm, double* Cm, double sgn, double beta) {
+        const double* pb = Bm + imin(task * 8 + lr, l);
         const double* pa[MTN];
 #pragma unroll
-        for (int i = 0; i < MTN; i++) pa[i] = KI + imin(i * 8 + lr, nN - 1);
+        for (int i = 0; i < MTN; i++) pa[i] = Am + imin(i * 8 + lr, nN - 1);
         double c[MTN][2];
         zero_c(c);
 #pragma unroll
@@ -1501,8 +1507,19 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
 #pragma unroll
         for (int i = 0; i < MTN; i++) {
           const int m = i * 8 + lr, n = task * 8 + 2 * lc;
-          if (m < nN && n <= l) *reinterpret_cast<double2*>(Um + m * ldc + n) = make_double2(-c[i][0], -c[i][1]);
+          if (m < nN && n <= l) {
+            double2* d2 = reinterpret_cast<double2*>(Cm + m * ldc + n);
+            const double2 o = beta != 0.0 ? *d2 : make_double2(0.0, 0.0);
+            *d2 = make_double2(fma(sgn, c[i][0], o.x), fma(sgn, c[i][1], o.y));
+          }
         }
+      };
+      for (int task = warp; task < L1T; task += NWARP) {
+        col_task(task, KI, R, Um, -1.0, 0.0);    // U = -K^-1 R
+        __syncwarp();
+        col_task(task, KC, Um, R, 1.0, 1.0);     // V = R + K U   (in place over the tile's columns of R)
+        __syncwarp();
+        col_task(task, KI, R, Um, -1.0, 1.0);    // U -= K^-1 V
       }
     }
     gsync();

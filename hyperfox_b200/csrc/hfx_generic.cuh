@@ -654,6 +654,7 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
                   const int cc = c + h; const double v = h ? v1 : v0;
                   if (cc < u) {
                     const double kv = Lm[r + n * cc] - v;
+                    BUU[r * u + cc] = kv;   // copy of K for the refinement of U (BUU is dead once the UNabU right-hand side is formed)
                     if (pivK) { AUG[r * 2 * u + cc] = kv; AUG[r * 2 * u + u + cc] = (r == cc) ? 1.0 : 0.0; }
                     else AUG[r * u + cc] = kv;
                   }
@@ -683,6 +684,29 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
       }
     }
     __syncthreads();
+    {   // one step of iterative refinement, U <- U - K^-1 (K U + R): the explicit inverse alone loses a factor ~ 1 / h on fine meshes (see hfx_assemble.cuh P7r)
+      const int MT = (u + 7) / 8, NG = (l + 1 + 15) / 16;
+      for (int task = warp; task < MT * NG; task += NWARP) {
+        const int mt = task % MT, ng = task / MT;
+        mma_task_rt<2>(mt, ng * 2, lane, u, l + 1, u,
+            [&](int r, int j) { return BUU[r * u + j]; },
+            [&](int j, int c) { return Um[j + u * c]; },
+            [&](int r, int c, double v0, double v1) {
+              if (r < u) { if (c <= l) Rm[r + u * c] += v0; if (c + 1 <= l) Rm[r + u * (c + 1)] += v1; }
+            });
+      }
+      __syncthreads();
+      for (int task = warp; task < MT * NG; task += NWARP) {
+        const int mt = task % MT, ng = task / MT;
+        mma_task_rt<2>(mt, ng * 2, lane, u, l + 1, u,
+            [&](int r, int j) { return KI[r * ldK + j]; },
+            [&](int j, int c) { return Rm[j + u * c]; },
+            [&](int r, int c, double v0, double v1) {
+              if (r < u) { if (c <= l) Um[r + u * c] -= v0; if (c + 1 <= l) Um[r + u * (c + 1)] -= v1; }
+            });
+      }
+      __syncthreads();
+    }
     HFX_GPROF(10);
     {   // Q = -A U - B (column l: Q0 = -A U0)
       const int MT = (q + 7) / 8, NG = (l + 1 + 23) / 24;

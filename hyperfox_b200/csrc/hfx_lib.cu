@@ -16,6 +16,7 @@
 #include "../../include/hfx.h"
 #include "hfx_assemble.cuh"
 #include "hfx_generic.cuh"
+#include "hfx_big.cuh"
 #include "hfx_krylov.cuh"
 #include "host/hfx_refel.h"
 #include "host/hfx_topology.h"
@@ -839,7 +840,7 @@ struct hfx_ctx {
   std::unique_ptr<RefElement> re;
   int dim = 0, order = 0, geom = HFX_SIMPLEX, nN = 0, nNf = 0, nFc = 0, nIP = 0, nIPf = 0;
   DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv, dSRef, dSRefT, dERef, dARef, dMFRef, dBRef, dBary;
-  DBuf<uint8_t> dAffine;
+  DBuf<uint8_t> dAffine; long long nNonAffine = 0;   // cells that are not the affine image of the reference element (curved / multilinear)
   DBuf<int> dFaceNodes; DBuf<int8_t> dNodeInFace;
   // mesh
   int nNodes = 0, nCells = 0, nFaces = 0;
@@ -856,7 +857,7 @@ struct hfx_ctx {
   bool modelSet = false, bcSet = false;
   DBuf<uint8_t> dFaceBC;
   // allocation
-  bool allocated = false, assembled = false, keepS = false, pivotFallback = false;
+  bool allocated = false, assembled = false, keepS = false, pivotFallback = false; int lastKernel = 0;
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
   DBuf<long long> dFaceRowStart, dBlockCount, dTotal;
   long long nnz = 0;
@@ -1461,6 +1462,12 @@ int hfx_allocate(hfx_ctx* c, int flags) {
       elem_affine_kernel<<<nblk(nC, 128), 128, 0, c->st>>>(nC, c->nN, c->dim, 0, 1, sx ? 2 : 3, sx ? 3 : 4, c->dElemX.p, c->dBary.p, c->dAffine.p);
     }
     HFX_CUDA(cudaGetLastError());
+    {   // how many cells are not affine: the large-element kernel (hfx_big.cuh) serves meshes of straight-sided cells only
+      std::vector<uint8_t> aff((size_t)nC);
+      c->dAffine.download(aff.data(), aff.size(), c->st);
+      long long na = 0; for (uint8_t v : aff) na += v ? 0 : 1;
+      c->nNonAffine = na;
+    }
     // element blocks (HDGSolver.cpp:93-104) and the global system (linSystem->allocate :81)
     c->dU.alloc((size_t)nC * u * l); c->dQ.alloc((size_t)nC * q * l); c->dU0.alloc((size_t)nC * u); c->dQ0.alloc((size_t)nC * q);
     if (c->keepS) { c->dS.alloc((size_t)nC * l * l); c->dS0.alloc((size_t)nC * l); } else { c->dS.release(); c->dS0.release(); }
@@ -1560,7 +1567,15 @@ int hfx_assemble(hfx_ctx* c) {
       p.eBegin = 0; p.eEnd = c->nCells;
       fused = supported;
     }
-    if (!fused && !pend.empty()) waitPieces(0, -1);
+    // 3-D order 4: the large-element kernel (one 512-thread CTA per SM, operands resident in shared memory) when every cell is straight-sided and D = c I
+    bool big = false;
+    if (!fused && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA
+        && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_BIG")) {
+      if (!pend.empty()) waitPieces(0, -1);
+      HFX_CUDA((launch_big<3, 4>(p, c->nSM, c->st)));
+      big = true;
+    }
+    if (!fused && !big && !pend.empty()) waitPieces(0, -1);
     for (DField* f : pend) f->pendingPieces = 0;
     auto launchGeneric = [&](bool pivot) {   // general kernel: 3-D orders 4-5, nDOFsPerNode > 1, HDGUNabU, orthotopes; pivot: partial pivoting in K^-1
       GenParams g{};
@@ -1616,7 +1631,8 @@ int hfx_assemble(hfx_ctx* c) {
       hdg_generic_kernel<<<(int)grid, kGenThreads, smem, c->st>>>(g);
       HFX_CUDA(cudaGetLastError());
     };
-    if (!fused) launchGeneric(getenv("HFX_FORCE_PIVOT") != nullptr);
+    if (!fused && !big) launchGeneric(getenv("HFX_FORCE_PIVOT") != nullptr);
+    c->lastKernel = fused ? 0 : (big ? 2 : 1);
     HFX_CUDA(cudaEventRecord(c->ev2, c->st));
     int status = 0;
     c->dStatus.download(&status, 1, c->st);
@@ -1629,7 +1645,7 @@ int hfx_assemble(hfx_ctx* c) {
       launchGeneric(true);
       HFX_CUDA(cudaEventRecord(c->ev2, c->st));
       c->dStatus.download(&status, 1, c->st);
-      c->pivotFallback = true;
+      c->pivotFallback = true; c->lastKernel = 1;
     }
     HFX_CUDA(cudaEventElapsedTime(&c->msTotal, c->ev0, c->ev2));
     HFX_CUDA(cudaEventElapsedTime(&c->msKernel, c->ev1, c->ev2));
@@ -1645,6 +1661,11 @@ int hfx_assemble_profile(hfx_ctx* c, long long* cycles16) {   // dev aid: per-ph
   c->profOn = false;
   if (rc) return rc;
   return guard(c, [&] { c->dProf.download(cycles16, 16, c->st); });
+}
+
+int hfx_last_assemble_kernel(const hfx_ctx* c, int* kernel, int* pivotFallback) {
+  if (kernel) *kernel = c->lastKernel; if (pivotFallback) *pivotFallback = c->pivotFallback ? 1 : 0;
+  return 0;
 }
 
 int hfx_last_assemble_ms(const hfx_ctx* c, float* msTotal, float* msKernel) {

@@ -669,6 +669,12 @@ class HDGSolver:
         lib().hfx_last_assemble_ms(self._h(), C.byref(a), C.byref(b))
         return a.value, b.value
 
+    def lastAssembleKernel(self):
+        """Which device kernel served the last assemble: "fused" (hfx_assemble.cuh), "general" (hfx_generic.cuh) or "big" (hfx_big.cuh)."""
+        k, pf = C.c_int(0), C.c_int(0)
+        lib().hfx_last_assemble_kernel(self._h(), C.byref(k), C.byref(pf))
+        return ("fused", "general", "big")[k.value]
+
 
 class NonLinearWrapper:
     """Fixed-point / Newton driver with damping (src/solver/NonLinearWrapper.cpp:41-79)."""

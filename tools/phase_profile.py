@@ -35,6 +35,12 @@ per = nC / grid
 names = ["P0 commit gather", "P1b per-IP geometry (+prefetch issue)", "P2 g", "P3a M", "P3b contractions", "P1a raw jacobians", "P3c Suq(D)", "P3d faceparts", "P4 A,B", "P5 K", "P6b invK (CTA)", "P7 U", "P8 Q", "P9 S+scatter", "P3b0 invM (CTA)", "P10 write-out"]
 if order >= 4 or os.environ.get("HFX_FORCE_GENERIC"):
     names = ["gather+zero Lm", "geometry @ IPs", "gradients, face matrices, M", "uu,uq,qu blocks", "ul,lu,ql,lq,ll + src", "UNabU rhs / time scheme", "invert M", "A,B = W [Squ|Sql]", "K, R", "invert K", "U", "Q", "write U,Q", "S + scatter", "-", "-"]
+kk = C.c_int(0)
+L.hfx_last_assemble_kernel(h, C.byref(kk), None)
+if kk.value == 2:
+    names = ["P0 gather", "PG geometry", "PA SJ + point weights", "PB face masses / CG", "PC Suu, Fu", "PD K, R", "PE invert K", "PF U + refinement", "PQ Q", "PZ Zq (+ U,Q bulk stores)", "PS S", "PW write-out", "-", "-", "-", "-"]
+    grid = min(nC, 148)
+    per = nC / grid
 tot = cyc.sum()
 print("elements %d, kernel %.3f ms -> %.2f M el/s ; CTA0 handled ~%.1f elements, %.0f cycles/element" % (nC, b.value, nC / b.value / 1e3, per, tot / per))
 for n, c in zip(names, cyc):

@@ -16,6 +16,11 @@ Dirichlet masking -> scatter into the global trace CSR + RHS) over the whole syn
               measured in this run (MEASURED_PEAKS.json holds no FP64 figure); HBM side reported alongside.
 * `cpu_baseline`: the oracle's C++ restatement of the reference path on all host cores, bounded sample.
 * --impl reference: the reference cannot be built here (Eigen/PETSc/MOAB/... absent) -> times the oracle port.
+* --config 4: BASELINE.json configs[3]: 3-D convection-diffusion (HDGConvectionDiffusionReactionSource, D = 1e-2, v = 4(-(y-1/2), x-1/2, 0),
+              tau = |v.n| + D / sqrt(D dt)) at order 4.  The named 7,986,000-tet mesh (Kuhn 110^3 x 6) needs 202 GB for the trace matrix alone, so it
+              exists on >= 2 GPUs only; the default keeps ~1 M tets per GPU (cubes 55 / 69 / 87 / 110 at 1 / 2 / 4 / 8 GPUs: the named mesh at 8), i.e.
+              "scaling": "weak".  --cubes 110 --recompute-recovery runs the named mesh on 2 or 4 GPUs (U, Q not stored).
+* --config 5: BASELINE.json configs[4]: order sweep p = 1..5 on 3-D tets at a fixed DOF count (one GPU): one JSON line, "sweep" holds the orders.
 """
 import argparse
 import ctypes as C
@@ -48,6 +53,25 @@ def poisson_inputs(nodes, cells, order, dim=3):
     dirv[b] = ana[tp["faces"][b]]
     tau = np.ones((nF, nNf))
     return tp, tau, dirv
+
+
+def convdiff_inputs(nodes, cells, order, dim=3, D=1e-2, dt=1e-2):
+    """BASELINE configs[3] fields (tests/parallel/TestParHDGConvectionDiffusionReactionSource.cpp; the same as tests/helpers.py::config4_fields)."""
+    from hyperfox_b200 import capi
+    tp = capi.host_compute_faces(dim, order, cells)
+    faces = tp["faces"]
+    nF, nNf = faces.shape
+    vel = np.zeros_like(nodes)
+    vel[:, 0] = -4.0 * (nodes[:, 1] - 0.5); vel[:, 1] = 4.0 * (nodes[:, 0] - 0.5)
+    fx = nodes[faces[:, :dim]]                       # the face's vertices come first in its node list
+    nrm = np.cross(fx[:, 1] - fx[:, 0], fx[:, 2] - fx[:, 0])
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    tau = np.abs(np.einsum("fad,fd->fa", vel[faces], nrm)) + D / np.sqrt(D * dt)
+    ana = np.sin(nodes[:, 0]) * np.exp(nodes[:, 1])
+    dirv = np.zeros((nF, nNf))
+    b = tp["boundary"]
+    dirv[b] = ana[faces[b]]
+    return tp, np.ascontiguousarray(tau), dirv, np.ascontiguousarray(vel), np.full((nodes.shape[0], 1), D)
 
 
 class ClockSampler:
@@ -90,7 +114,7 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline(order, cores, target_s=12.0, dim=3):
+def cpu_baseline(order, cores, target_s=12.0, dim=3, model="poisson"):
     """Oracle port of the reference path (HouseholderQR condensation as the reference) on `cores` workers."""
     from oracle import lib as O
     from oracle import meshgen          # the oracle's own mesh generator: this leg never touches the product package
@@ -105,10 +129,18 @@ def cpu_baseline(order, cores, target_s=12.0, dim=3):
     nF, nNf = topo["faces"].shape
     ana = np.sin(nodes[:, 0]) * np.exp(nodes[:, 1])
     dirv = np.zeros((nF, nNf, 1)); dirv[topo["boundary"], :, 0] = ana[topo["faces"][topo["boundary"]]]
-    h = O.HDGOracle(re, dict(nodes=nodes, cells=cells, **topo), O.make_model(1, O.OP_DIFFUSION), dict(Tau=np.ones((nF, nNf, 1)), Dirichlet=dirv))
+    if model == "cd":
+        vel = np.zeros_like(nodes); vel[:, 0] = -4.0 * (nodes[:, 1] - 0.5); vel[:, 1] = 4.0 * (nodes[:, 0] - 0.5)
+        fx = nodes[topo["faces"][:, :dim]]
+        nrm = np.cross(fx[:, 1] - fx[:, 0], fx[:, 2] - fx[:, 0]); nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+        tau = np.abs(np.einsum("fad,fd->fa", vel[topo["faces"]], nrm)) + 1e-2 / np.sqrt(1e-2 * 1e-2)
+        h = O.HDGOracle(re, dict(nodes=nodes, cells=cells, **topo), O.make_model(1, O.OP_DIFFUSION | O.OP_CONVECTION, 1),
+                        dict(Tau=tau[:, :, None].copy(), Dirichlet=dirv, Velocity=vel, DiffusionTensor=np.full((nodes.shape[0], 1), 1e-2)))
+    else:
+        h = O.HDGOracle(re, dict(nodes=nodes, cells=cells, **topo), O.make_model(1, O.OP_DIFFUSION), dict(Tau=np.ones((nF, nNf, 1)), Dirichlet=dirv))
     h.pattern()
     sec, _, _ = h.bench_assemble(cores, useLU=0)
-    return cells.shape[0] / sec, "Kuhn %d^3 x 6 = %d tets, order %d, %d threads, %.1f s" % (N, cells.shape[0], order, cores, sec), sec
+    return cells.shape[0] / sec, "Kuhn %d^3 x 6 = %d tets, order %d%s, %d threads, %.1f s" % (N, cells.shape[0], order, ", convection-diffusion" if model == "cd" else "", cores, sec), sec
 
 
 _REAL_STDOUT = None
@@ -128,8 +160,16 @@ def emit(line):
     out.flush()
 
 
-def workload_name(order, N):
+def workload_name(order, N, model="poisson"):
+    if model == "cd":
+        return ("3D convection-diffusion HDG order %d, synthetic Kuhn mesh %d^3 x 6 = %d tets (BASELINE configs[3]%s), HDGConvectionDiffusionReactionSource "
+                "(Velocity + DiffusionTensor) + DirichletModel, D=1e-2, v=4(-(y-1/2),x-1/2,0), tau=|v.n|+D/sqrt(D dt)"
+                % (order, N, 6 * N ** 3, ": the named 8M-tet mesh" if N == 110 else ", reduced to ~1M tets per GPU"))
     return "3D Poisson HDG order %d, synthetic Kuhn mesh %d^3 x 6 = %d tets (BASELINE configs[2]), HDGLaplaceModel + DirichletModel, tau=1" % (order, N, 6 * N ** 3)
+
+
+def metric_name(order, model):
+    return "HDG elements assembled+condensed/s (p=%d 3D tets%s)" % (order, ", convection-diffusion" if model == "cd" else "")
 
 
 def nAll_owned(nOwned, world, torch, dist):
@@ -175,15 +215,15 @@ def run_reference(args):
     vals = []
     sample = ""
     for i in range(args.warmup + args.steps):
-        v, sample, sec = cpu_baseline(args.order, cores, target_s=4.0)
+        v, sample, sec = cpu_baseline(args.order, cores, target_s=4.0, model=args.model)
         if i >= args.warmup:
             vals.append((v, sec))
     v = float(np.mean([x[0] for x in vals]))
     ms = float(np.mean([x[1] for x in vals])) * 1e3
-    line = {"impl": "reference", "metric": "HDG elements assembled+condensed/s (p=%d 3D tets)" % args.order, "value": v, "unit": "elements/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+    line = {"impl": "reference", "metric": metric_name(args.order, args.model), "value": v, "unit": "elements/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak" if args.config == 4 else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args.order, args.cubes), "sample_per_step": sample,
+            "config": {"workload": workload_name(args.order, args.cubes, args.model), "sample_per_step": sample,
                        "implementation": "oracle port of the reference CPU path, all host cores (the reference binary is not buildable here: it needs "
                                          "Eigen/Boost/PETSc/MOAB/Zoltan/HDF5/MPI); each step assembles+condenses a bounded sample of the workload's "
                                          "elements (same element type, order, model, fields), elements/s does not depend on the sample size"},
@@ -198,8 +238,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native")
-    ap.add_argument("--cubes", type=int, default=55, help="N: the unit cube is split into N^3 hexes x 6 Kuhn tets")
-    ap.add_argument("--order", type=int, default=3)
+    ap.add_argument("--cubes", type=int, default=None, help="N: the unit cube is split into N^3 hexes x 6 Kuhn tets (default 55; --config 4: ~1M tets per GPU)")
+    ap.add_argument("--order", type=int, default=None)
+    ap.add_argument("--config", type=int, default=3, choices=(3, 4, 5), help="BASELINE.json configs, 1-based: 3 = Poisson p=3 1M tets (default), "
+                    "4 = convection-diffusion p=4 (8M tets at 8 GPUs), 5 = order sweep p=1..5 at a fixed DOF count")
+    ap.add_argument("--recompute-recovery", action="store_true", help="HFX_RECOMPUTE_RECOVERY: do not store U, Q (order 4 only)")
+    ap.add_argument("--sweep-dofs", type=float, default=2.0e7, help="--config 5: nCells * nN(p) per order (SURVEY 8d: 2e7)")
     ap.add_argument("--partition-file", default=None, help="cell partition vector (.npy or text, one rank id per cell of the global mesh), "
                     "e.g. a Zoltan partition; default: recursive coordinate bisection")
     ap.add_argument("--partition", default="rcb", choices=("rcb", "slabs"), help="built-in stand-in for the Zoltan partition")
@@ -208,8 +252,16 @@ def main():
     ap.add_argument("--no-solve", action="store_true")
     args = ap.parse_args()
     protect_stdout()
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    args.model = "cd" if args.config == 4 else "poisson"
+    if args.order is None:
+        args.order = 4 if args.config == 4 else 3
+    if args.cubes is None:
+        args.cubes = {1: 55, 2: 69, 4: 87, 8: 110}.get(world_env, int(round(55 * world_env ** (1.0 / 3.0)))) if args.config == 4 else 55
     if args.impl == "reference":
         return run_reference(args)
+    if args.config == 5:
+        return run_order_sweep(args)
 
     import torch
     import torch.distributed as dist
@@ -246,7 +298,12 @@ def main():
     else:
         lverts, lcells = verts, lin
     nodes, cells = meshgen.high_order(lverts, lcells, order)
-    tp, tau, dirv = poisson_inputs(nodes, cells, order, dim)
+    cd = args.model == "cd"
+    vel = dten = None
+    if cd:
+        tp, tau, dirv, vel, dten = convdiff_inputs(nodes, cells, order, dim)
+    else:
+        tp, tau, dirv = poisson_inputs(nodes, cells, order, dim)
     # only faces on the true domain boundary carry the Dirichlet condition (partition cuts are interior faces of the global mesh)
     fc = nodes[tp["faces"][tp["boundary"]]].reshape(tp["boundary"].size, -1, dim)
     onb = np.zeros(tp["boundary"].size, dtype=bool)
@@ -265,10 +322,13 @@ def main():
     check(L.hfx_mesh_set(h, nodes.shape[0], pd(nodes), nC, pi(cells)), h)
     check(L.hfx_field_set(h, b"Tau", 2, nNf, 1, pd(tau), 0), h)
     check(L.hfx_field_set(h, b"Dirichlet", 2, nNf, 1, pd(dirv), 0), h)
-    md = capi.ModelDesc(1, 1, 0, 0.0)
+    if cd:
+        check(L.hfx_field_set(h, b"DiffusionTensor", 0, 1, 1, pd(dten), 0), h)
+        check(L.hfx_field_set(h, b"Velocity", 0, 1, dim, pd(vel), 0), h)
+    md = capi.ModelDesc(1, 1 | (2 if cd else 0), 0, 0.0)
     check(L.hfx_model_describe(h, C.byref(md)), h)
     check(L.hfx_boundary_describe(h, 0, bfaces.size, pi(bfaces)), h)
-    check(L.hfx_allocate(h, 0), h)
+    check(L.hfx_allocate(h, 2 if args.recompute_recovery else 0), h)
     nnz = C.c_longlong(0); nrows = C.c_longlong(0)
     check(L.hfx_get_csr(h, C.byref(nrows), C.byref(nnz), None, None, None, None), h)
 
@@ -302,8 +362,11 @@ def main():
                 ks.append(a.value)
         del os.environ[var]
         return float(np.mean(ks))
-    straight_ms = other_path("HFX_NO_REFPATH")
-    general_ms = other_path("HFX_NO_AFFINE")
+    kk = C.c_int(0)
+    L.hfx_last_assemble_kernel(h, C.byref(kk), None)
+    kernel_name = ("hdg_assemble_kernel (fused element groups)", "hdg_generic_kernel", "hdg_big_kernel (large elements, 512-thread CTA per SM)")[kk.value]
+    straight_ms = other_path("HFX_NO_REFPATH") if order <= 3 else my_ms
+    general_ms = other_path("HFX_NO_AFFINE") if order <= 3 else my_ms
     # the two other kernels of the path, timed separately from the headline: GMRES(30) on the assembled trace system (not to
     # convergence: the difference of a 90- and a 30-iteration solve, device time from CUDA events inside hfx_solve) and the local recovery.
     # On several GPUs this is the product's distributed solve: ghost-face trace blocks over NCCL send/recv overlapped with the interior rows
@@ -365,13 +428,18 @@ def main():
         fm = {"Solution": hfox.Field(m, hfox.Cell, re.getNumNodes(), 1), "Flux": hfox.Field(m, hfox.Cell, re.getNumNodes(), dim),
               "Trace": hfox.Field(m, hfox.Face, nNf, 1), "Tau": hfox.Field(m, hfox.Face, nNf, 1), "Dirichlet": hfox.Field(m, hfox.Face, nNf, 1)}
         # pinned host storage for the fields that cross PCIe every step
-        pin = {k: torch.empty(fm[k].values.size, dtype=torch.float64).pin_memory() for k in ("Tau", "Dirichlet")}
-        for k, src in (("Tau", tau), ("Dirichlet", dirv)):
+        host_fields = [("Tau", tau), ("Dirichlet", dirv)]
+        if cd:
+            fm["Velocity"] = hfox.Field(m, hfox.Node, 1, dim); fm["DiffusionTensor"] = hfox.Field(m, hfox.Node, 1, 1)
+            host_fields += [("Velocity", vel), ("DiffusionTensor", dten)]
+        pin = {k: torch.empty(fm[k].values.size, dtype=torch.float64).pin_memory() for k, _ in host_fields}
+        for k, src in host_fields:
             fm[k].values = pin[k].numpy()
             fm[k].values[:] = src.ravel()
-        s = hfox.HDGSolver(device=lrank)
+        s = hfox.HDGSolver(device=lrank, recomputeRecovery=args.recompute_recovery)
         s.setMesh(m); s.setFieldMap(fm); s.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts(), device=lrank))
-        s.setModel(hfox.HDGLaplaceModel(re)); s.setBoundaryCondition(hfox.DirichletModel(re.getFaceElement()), bfaces.tolist())
+        s.setModel(hfox.HDGConvectionDiffusionReactionSource(re) if cd else hfox.HDGLaplaceModel(re))
+        s.setBoundaryCondition(hfox.DirichletModel(re.getFaceElement()), bfaces.tolist())
         s.initialize(); s.allocate()
         status = np.zeros(4)
         for _ in range(max(1, args.warmup)):
@@ -382,7 +450,7 @@ def main():
             s.assemble()                      # H2D: Tau + Dirichlet ; kernel ; D2H: status word (inside hfx_assemble)
         barrier()
         e2e_ms = (time.time() - t2) * 1e3 / args.steps
-        h2d = int(fm["Tau"].values.nbytes + fm["Dirichlet"].values.nbytes)
+        h2d = int(sum(fm[k].values.nbytes for k, _ in host_fields))
         d2h = 4
 
     # ---- max over ranks ---------------------------------------------------------------------------------------------
@@ -409,22 +477,24 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_ach = BYTES_STORE[order] * nC / (my_k * 1e-3) / 1e9
     line = {
-        "metric": "HDG elements assembled+condensed/s (p=%d 3D tets)" % order,
+        "metric": metric_name(order, args.model),
         "value": nAll / (ms_step * 1e-3), "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(order, N), "elements_per_rank": nC, "owned_elements_rank0": nOwned, "partition": ((("file " + os.path.basename(args.partition_file)) if args.partition_file else ("recursive coordinate bisection of the cell centroids" if args.partition == "rcb" else "slabs of the lexicographic Kuhn mesh")) + ", overlap-1 ghost cells recomputed by the face owner" if world > 1 else "single rank"), "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if args.config == 4 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(order, N, args.model), "kernel": kernel_name, "recovery": "by recomputation (U, Q not stored)" if args.recompute_recovery else "stored U, Q", "elements_per_rank": nC, "owned_elements_rank0": nOwned, "partition": ((("file " + os.path.basename(args.partition_file)) if args.partition_file else ("recursive coordinate bisection of the cell centroids" if args.partition == "rcb" else "slabs of the lexicographic Kuhn mesh")) + ", overlap-1 ghost cells recomputed by the face owner" if world > 1 else "single rank"), "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
                    "l2": "inputs+outputs per step (%.1f GB) far larger than the 126 MB L2" % ((BYTES_STORE[order] * nC) / 1e9),
                    "timing": "CUDA events on the library stream around memset+kernel, max over ranks; wall-clock per step %.2f ms" % ms_wall,
                    "setup_s": round(t_setup, 1),
-                   "element_paths": "every element of this mesh is straight-sided with a face-constant tau and takes the all-reference path "
-                                    "(every block from staged reference matrices, DESIGN.md 4.1); the same mesh through the straight-sided path "
-                                    "(tau varying along faces / other operators) runs at %.3g elements/s and through the general path "
-                                    "(curved elements) at %.3g elements/s on rank 0" % (nC / (straight_ms * 1e-3), nC / (general_ms * 1e-3))},
+                   "element_paths": ("every element of this mesh is straight-sided with a face-constant tau and takes the all-reference path "
+                                     "(every block from staged reference matrices, DESIGN.md 4.1); the same mesh through the straight-sided path "
+                                     "(tau varying along faces / other operators) runs at %.3g elements/s and through the general path "
+                                     "(curved elements) at %.3g elements/s on rank 0" % (nC / (straight_ms * 1e-3), nC / (general_ms * 1e-3))) if order <= 3 else
+                                    "every element is straight-sided (large-element kernel, DESIGN.md 4.1c); tau and v.n vary along the faces: weighted face masses by cubature"},
         "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4 + DFMA share one 64 FMA/clk/SM pipe; tcgen05 has no FP64 kind)", "achieved": ach, "peak": peak["tflops"], "unit": "TFLOP/s", "frac": ach / peak["tflops"] if peak["tflops"] else None,
                      "traffic": (NCU_TRAFFIC_PER_ELEM[order] * nC if order in NCU_TRAFFIC_PER_ELEM else None),
-                     "traffic_source": "ncu --set full capture at 82,944 tets scaled per element (profiles/r1_assemble_p3_ncu_full_summary.txt); algorithmic bytes %d/element" % BYTES_STORE[order],
+                     "traffic_source": ("ncu --set full capture at 82,944 tets scaled per element (profiles/r1_assemble_p3_ncu_full_summary.txt); algorithmic bytes %d/element" % BYTES_STORE[order]) if order in NCU_TRAFFIC_PER_ELEM else "not captured for this order; algorithmic bytes %d/element" % BYTES_STORE[order],
                      "peak_source": peak["how"], "kernel_ms": my_k,
                      "algorithmic_flops_per_element": FLOPS_PER_ELEM[order],
+                     "flop_count": "SURVEY 8(d) LU-based dense count of the Laplace element at this order (convection adds the Suu contraction: counted as zero)",
                      "hbm": {"achieved_GBs": hbm_ach, "peak_GBs": hbm_peak, "frac": hbm_ach / hbm_peak, "bytes_per_element": BYTES_STORE[order],
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
         "solve_and_recovery": extra,
@@ -437,11 +507,71 @@ def main():
                        "api": "hyperfox_b200.hfox.HDGSolver.assemble (host Fields, pinned Tau/Dirichlet)"}
     if not args.no_cpu_baseline and world >= 1:
         cores = os.cpu_count() or 1
-        v, sample, _ = cpu_baseline(order, cores)
+        v, sample, _ = cpu_baseline(order, cores, model=args.model)
         line["cpu_baseline"] = {"value": v, "unit": "elements/s", "cores": cores, "kind": "port", "sample": sample}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_order_sweep(args):
+    """BASELINE configs[4]: p = 1..5 on 3-D tets at a fixed DOF count, Laplace, straight-sided Kuhn meshes, one GPU (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from hyperfox_b200 import capi, meshgen
+    from hyperfox_b200.capi import check, lib, pd, pi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    L = lib()
+    peak = fp64_peak(0)
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0)
+    except Exception:
+        hbm_peak = 6650.0
+    NN = {1: 4, 2: 10, 3: 20, 4: 35, 5: 56}
+    sampler = ClockSampler(0); sampler.start()
+    rows = []
+    for order in (1, 2, 3, 4, 5):
+        N = max(2, int(round((args.sweep_dofs / NN[order] / 6.0) ** (1.0 / 3.0))))
+        nodes, cells = meshgen.kuhn_mesh(N, order, 3)
+        tp, tau, dirv = poisson_inputs(nodes, cells, order, 3)
+        nF, nNf = tp["faces"].shape
+        h = C.c_void_p()
+        check(L.hfx_ctx_create(0, C.byref(h)))
+        check(L.hfx_refel_set(h, 3, order, 0), h)
+        check(L.hfx_mesh_set(h, nodes.shape[0], pd(nodes), cells.shape[0], pi(cells)), h)
+        check(L.hfx_field_set(h, b"Tau", 2, nNf, 1, pd(tau), 0), h)
+        check(L.hfx_field_set(h, b"Dirichlet", 2, nNf, 1, pd(dirv), 0), h)
+        md = capi.ModelDesc(1, 1, 0, 0.0)
+        check(L.hfx_model_describe(h, C.byref(md)), h)
+        check(L.hfx_boundary_describe(h, 0, 0, None), h)
+        check(L.hfx_allocate(h, 0), h)
+        a, b = C.c_float(0), C.c_float(0)
+        ms = []
+        for i in range(args.warmup + args.steps):
+            check(L.hfx_assemble(h), h)
+            L.hfx_last_assemble_ms(h, C.byref(a), C.byref(b))
+            if i >= args.warmup:
+                ms.append(a.value)
+        kk = C.c_int(0)
+        L.hfx_last_assemble_kernel(h, C.byref(kk), None)
+        t = float(np.mean(ms)) * 1e-3
+        nC = cells.shape[0]
+        tf = FLOPS_PER_ELEM[order] * nC / t / 1e12
+        gbs = BYTES_STORE[order] * nC / t / 1e9
+        rows.append({"order": order, "cubes": N, "elements": nC, "dofs": nC * NN[order], "kernel": ("fused", "general", "big")[kk.value], "ms_per_step": t * 1e3,
+                     "elements_per_s": nC / t, "tflops_algorithmic": tf, "frac_fp64_peak": tf / peak["tflops"], "hbm_GBs_algorithmic": gbs, "frac_hbm_peak": gbs / hbm_peak})
+        check(L.hfx_ctx_destroy(h))
+    clocks = sampler.stop()
+    r3 = rows[2]
+    emit({"metric": "HDG elements assembled+condensed/s, order sweep p=1..5 on 3D tets at %.3g DOFs (value: p=3)" % args.sweep_dofs, "value": r3["elements_per_s"], "unit": "elements/s",
+          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r3["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+          "dtype": "f64", "data": "synthetic", "config": {"workload": "BASELINE configs[4]: order sweep p=1..5, 3D Poisson HDG on synthetic Kuhn meshes, nCells*nN(p) ~ %.3g per order" % args.sweep_dofs,
+                                                          "l2": "every order's inputs+outputs exceed the 126 MB L2", "timing": "CUDA events on the library stream around memset+kernel"},
+          "sweep": rows, "roofline": {"bound": "tensor", "achieved": r3["tflops_algorithmic"], "peak": peak["tflops"], "unit": "TFLOP/s", "frac": r3["frac_fp64_peak"], "traffic": None,
+                                      "peak_source": peak["how"], "hbm_peak_GBs": hbm_peak},
+          "gpu_launches": args.steps * 5, "clocks": clocks})
 
 
 def fp64_peak(device):

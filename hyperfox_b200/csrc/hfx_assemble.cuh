@@ -65,6 +65,9 @@ struct AsmParams {
   double* vals; double* rhs;
   int* status;                // bit 0: (near) zero pivot met in a local inverse
   long long* prof;            // optional [16] per-phase cycle counters (block 0 only), NULL in production
+  // recovery by recomputation (hfx_allocate flag HFX_RECOMPUTE_RECOVERY: U, Q are not stored; hfx_recover re-condenses the element and applies
+  // u_e = U lambda_e + U0, q_e = Q lambda_e + Q0 (HDGSolver.cpp:741-775) out of shared memory).  Served by hfx_big.cuh.
+  int recover; const double* recTrace; double* recSol; double* recFlux;
 };
 
 template <int DIM, int P> struct ElemCfg;

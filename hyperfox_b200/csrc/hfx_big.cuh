@@ -538,8 +538,24 @@ __global__ void __launch_bounds__(kBigThreads, 1) hdg_big_kernel(const AsmParams
     fence_proxy_async();
     __syncthreads();
     HFX_PROF(8);
+    if (p.recover) {   // recovery by recomputation: u_e = U lambda_e + U0, q_e = Q lambda_e + Q0 straight out of shared memory; nothing else leaves
+      constexpr int q = DIM * nN;
+      double* const LAM = SJ;   // (dead since PD)
+      if (tid < l) LAM[tid] = p.recTrace[(size_t)ISM[tid / t] * t + PERM[tid]];
+      __syncthreads();
+      if (tid < nN + q) {
+        const int rq = tid - nN;
+        const double* row = tid < nN ? UU + tid * ldc : QQ + ((rq % DIM) * nN + rq / DIM) * ldc;
+        double s0 = row[l], s1 = 0.0;
+#pragma unroll 4
+        for (int c2 = 0; c2 < l; c2 += 2) { s0 = fma(row[c2], LAM[c2], s0); s1 = fma(row[c2 + 1], LAM[c2 + 1], s1); }
+        if (tid < nN) p.recSol[(size_t)e * nN + tid] = s0 + s1; else p.recFlux[(size_t)e * q + rq] = s0 + s1;
+      }
+      __syncthreads();
+      continue;
+    }
     // U, Q leave as whole rows (row-major per element in HBM): one bulk copy (TMA) per row, in flight during the S phase
-    {
+    if (p.U) {
       constexpr int q = DIM * nN;
       if (tid < nN + q) {
         const int row = tid;
@@ -668,8 +684,8 @@ __global__ void __launch_bounds__(kBigThreads, 1) hdg_big_kernel(const AsmParams
         if (p.S0) p.S0[(size_t)e * l + r] = s0;
         const int rowDof = F * t + PERM[r];
         if (INTF[f]) atomicAdd(p.rhs + rowDof, s0); else p.rhs[rowDof] = s0;
-      } else if (tid >= 128 && tid < 128 + nN) p.U0[(size_t)e * nN + (tid - 128)] = UU[(tid - 128) * ldc + l];
-      else if (tid >= 192 && tid < 192 + q) { const int rq = tid - 192; p.Q0[(size_t)e * q + rq] = QQ[((rq % DIM) * nN + rq / DIM) * ldc + l]; }
+      } else if (p.U && tid >= 128 && tid < 128 + nN) p.U0[(size_t)e * nN + (tid - 128)] = UU[(tid - 128) * ldc + l];
+      else if (p.U && tid >= 192 && tid < 192 + q) { const int rq = tid - 192; p.Q0[(size_t)e * q + rq] = QQ[((rq % DIM) * nN + rq / DIM) * ldc + l]; }
       bulk_wait_read();   // U, Q rows have left shared memory: the regions are rewritten by the next element pass
     }
     __syncthreads();

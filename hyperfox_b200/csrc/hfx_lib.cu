@@ -857,7 +857,7 @@ struct hfx_ctx {
   bool modelSet = false, bcSet = false;
   DBuf<uint8_t> dFaceBC;
   // allocation
-  bool allocated = false, assembled = false, keepS = false, pivotFallback = false; int lastKernel = 0;
+  bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false; int lastKernel = 0;
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
   DBuf<long long> dFaceRowStart, dBlockCount, dTotal;
   long long nnz = 0;
@@ -1423,7 +1423,7 @@ int hfx_allocate(hfx_ctx* c, int flags) {
     DField* dir = find_field(c, "Dirichlet");
     need(dir != nullptr, "DirichletModel", "setFieldMap", "need to give a field named Dirichlet to the DirichletModel");
     need(dir->type == HFX_FIELD_FACE && dir->nObj == c->nNf && dir->nVal == nD, "DirichletModel", "setFieldMap", "the Dirichlet field must be a face field with one object per face node");
-    c->keepS = flags & HFX_KEEP_LOCAL_S;
+    c->keepS = flags & HFX_KEEP_LOCAL_S; c->recompute = flags & HFX_RECOMPUTE_RECOVERY;
     const int nF = c->nFaces, nC = c->nCells;
     // The scatter stores every off-diagonal (face, neighbour face) block with a plain copy: a block must have ONE contributing element, i.e.
     // two cells may share at most one face and a cell may not list a face twice (true for every conforming mesh; checked, not assumed).
@@ -1469,7 +1469,11 @@ int hfx_allocate(hfx_ctx* c, int flags) {
       c->nNonAffine = na;
     }
     // element blocks (HDGSolver.cpp:93-104) and the global system (linSystem->allocate :81)
-    c->dU.alloc((size_t)nC * u * l); c->dQ.alloc((size_t)nC * q * l); c->dU0.alloc((size_t)nC * u); c->dQ0.alloc((size_t)nC * q);
+    if (c->recompute) {
+      need(c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && c->nNonAffine == 0, "hfx", "allocate",
+           "recovery by recomputation is served by the large-element kernel: straight-sided 3-D order-4 cells, one DOF per node");
+      c->dU.release(); c->dQ.release(); c->dU0.release(); c->dQ0.release();
+    } else { c->dU.alloc((size_t)nC * u * l); c->dQ.alloc((size_t)nC * q * l); c->dU0.alloc((size_t)nC * u); c->dQ0.alloc((size_t)nC * q); }
     if (c->keepS) { c->dS.alloc((size_t)nC * l * l); c->dS0.alloc((size_t)nC * l); } else { c->dS.release(); c->dS0.release(); }
     c->dVals.alloc((size_t)c->nnz); c->dRhs.alloc((size_t)nF * t); c->valsCleared = false;
     {   // element chunks for the pipelined assemble (hfx_field_set_async): faces are numbered in order of first appearance over ascending
@@ -1487,11 +1491,13 @@ int hfx_allocate(hfx_ctx* c, int flags) {
   });
 }
 
-int hfx_assemble(hfx_ctx* c) {
+// recoverMode: the element kernels are run again for hfx_recover (HFX_RECOMPUTE_RECOVERY): same inputs, nothing is written but Solution and Flux
+static int assemble_impl(hfx_ctx* c, bool recoverMode) {
   return guard(c, [&] {
     HFX_CUDA(cudaSetDevice(c->device));
     need(c->allocated, "HDGSolver", "assemble", "the solver must be initialized and allocated before assembling.");
     AsmParams p{};
+    if (recoverMode) { p.recover = 1; p.recTrace = find_field(c, "Trace")->d.p; p.recSol = find_field(c, "Solution")->d.p; p.recFlux = find_field(c, "Flux")->d.p; }
     p.nCells = c->nCells; p.diffConst = 1.0;
     p.elemX = c->dElemX.p; p.cells = c->dCells.p; p.cell2face = c->dC2F.p;
     p.fperm = c->dFperm.p; p.tauSide = c->dTauSide.p; p.elemPos = c->dElemPos.p;
@@ -1542,9 +1548,9 @@ int hfx_assemble(hfx_ctx* c) {
       }
       c->dRhs.zero(c->st); c->dStatus.zero(c->st);
     };
-    clearSystem();
+    if (!recoverMode) clearSystem();
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
-    bool fused = c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
+    bool fused = !recoverMode && c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
     // fields still crossing PCIe (hfx_field_set_async): the element chunks start as their face-id prefix has arrived
     std::vector<DField*> pend;
     for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) pend.push_back(&kv.second);
@@ -1574,6 +1580,11 @@ int hfx_assemble(hfx_ctx* c) {
       if (!pend.empty()) waitPieces(0, -1);
       HFX_CUDA((launch_big<3, 4>(p, c->nSM, c->st)));
       big = true;
+    }
+    if (recoverMode) {
+      need(big && !c->pivotFallback, "hfx", "recover", "recovery by recomputation is served by the large-element kernel (straight-sided 3-D order-4 cells, D = c I) only");
+      HFX_CUDA(cudaStreamSynchronize(c->st));
+      return;
     }
     if (!fused && !big && !pend.empty()) waitPieces(0, -1);
     for (DField* f : pend) f->pendingPieces = 0;
@@ -1654,6 +1665,8 @@ int hfx_assemble(hfx_ctx* c) {
   });
 }
 
+int hfx_assemble(hfx_ctx* c) { return assemble_impl(c, false); }
+
 int hfx_assemble_profile(hfx_ctx* c, long long* cycles16) {   // dev aid: per-phase clock64 deltas of CTA 0 (see hfx_assemble.cuh HFX_PROF)
   int rc = guard(c, [&] { HFX_CUDA(cudaSetDevice(c->device)); c->dProf.alloc(16); c->dProf.zero(c->st); c->profOn = true; });
   if (rc) return rc;
@@ -1679,6 +1692,7 @@ int hfx_recover(hfx_ctx* c) {
   return guard(c, [&] {
     HFX_CUDA(cudaSetDevice(c->device));
     need(c->assembled, "HDGSolver", "solve", "system must be assembled before solving");
+    if (c->recompute) { if (assemble_impl(c, true)) throw std::runtime_error(c->err); return; }
     const int nD = c->md.nDOF, t = c->nNf * nD, u = c->nN * nD, q = u * c->dim, l = c->nFc * t;
     int grid = std::min(c->nCells, c->nSM * 32);
     int bs = getenv("HFX_REC_BS") ? atoi(getenv("HFX_REC_BS")) : 128;   // 128 threads: 16 elements in flight per SM (thread- and shared-memory-limited)
@@ -1857,6 +1871,7 @@ int hfx_get_local(hfx_ctx* c, int iEl, int nEl, double* S, double* S0, double* U
     need(c->assembled, "hfx", "get_local", "the system must be assembled first");
     need(iEl >= 0 && nEl >= 0 && iEl + nEl <= c->nCells, "hfx", "get_local", "element range out of bounds");
     const int nD = c->md.nDOF, t = c->nNf * nD, u = c->nN * nD, q = u * c->dim, l = c->nFc * t;
+    need(!c->recompute || !(U || U0 || Q || Q0), "hfx", "get_local", "U, Q are not stored under HFX_RECOMPUTE_RECOVERY");
     if (S || S0) need(c->keepS, "hfx", "get_local", "allocate with HFX_KEEP_LOCAL_S to keep the per-element S, S0 blocks");
     if (S) c->dS.download(S, (size_t)nEl * l * l, c->st, (size_t)iEl * l * l);
     if (S0) c->dS0.download(S0, (size_t)nEl * l, c->st, (size_t)iEl * l);

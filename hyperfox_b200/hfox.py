@@ -474,12 +474,13 @@ class HDGSolver:
 
     INPUT_FIELDS = ("Tau", "Dirichlet", "DiffusionTensor", "Velocity")
 
-    def __init__(self, device=0, keepLocalS=False):
+    def __init__(self, device=0, keepLocalS=False, recomputeRecovery=False):
         self.myMesh = self.fieldMap = self.linSystem = self.model = None
         self.boundaries = []
         self.initialized = self.allocated = self.assembled = False
         self.device = device
         self.keepLocalS = keepLocalS
+        self.recomputeRecovery = recomputeRecovery   # HFX_RECOMPUTE_RECOVERY: U, Q are not stored, the recovery re-condenses each element
         self.ctx = None
         self.verbose = False
         self.stats = capi.SolveStats()
@@ -562,7 +563,7 @@ class HDGSolver:
         for bm, faces in self.boundaries:
             bm.allocate(self.nDOFsPerNode)
             check(L.hfx_boundary_describe(h, bm.kind, 0 if faces is None else faces.size, None if faces is None else pi(faces)), h)
-        check(L.hfx_allocate(h, 1 if self.keepLocalS else 0), h)
+        check(L.hfx_allocate(h, (1 if self.keepLocalS else 0) | (2 if self.recomputeRecovery else 0)), h)
         self.allocated = True
 
     def _input_fields(self):

@@ -102,7 +102,9 @@ enum { HFX_BC_DIRICHLET = 0, HFX_BC_INTEGRATED_DIRICHLET = 1 };
 int hfx_boundary_describe(hfx_ctx* ctx, int kind, int nFaces, const int* faceIds /* NULL: mesh boundary */);
 
 /* ---- solver: HDGSolver::allocate / assemble / solve  src/solver/HDGSolver.cpp:5-106,166-174,677-779 ----------- */
-enum { HFX_KEEP_LOCAL_S = 1 }; /* also store the per-element S,S0 Fields the reference keeps (HDGSolver.cpp:101-104) */
+enum { HFX_KEEP_LOCAL_S = 1,        /* also store the per-element S,S0 Fields the reference keeps (HDGSolver.cpp:101-104) */
+       HFX_RECOMPUTE_RECOVERY = 2 /* do NOT store the recovery operators U,Q,U0,Q0 (HDGSolver.cpp:93-100; 67 KB per order-4 tet): hfx_recover re-condenses each
+                                     element and applies them out of shared memory.  Straight-sided 3-D order-4 meshes (the large-element kernel) only. */ };
 int hfx_allocate(hfx_ctx* ctx, int flags);
 int hfx_assemble(hfx_ctx* ctx);
 typedef struct {

@@ -727,6 +727,7 @@ class HDGSolver : public Solver {
   }
   void setDevice(int d) { device = d; }
   void keepLocalS(bool k) { keepS = k; }
+  void recomputeRecovery(bool r) { recompute = r; }   // HFX_RECOMPUTE_RECOVERY: U, Q are not stored (large meshes of order-4 tets)
 
   void allocate() override {   // src/solver/HDGSolver.cpp:5-106
     if (!initialized) throw ErrorHandle("HDGSolver", "allocate", "must initialize the solver before allocating.");
@@ -773,7 +774,7 @@ class HDGSolver : public Solver {
       static const int none = 0;
       detail::check(hfx_boundary_describe(h, bm->cKind(), (int)ids.size(), ids.empty() ? &none : ids.data()), h);
     }
-    detail::check(hfx_allocate(h, keepS ? HFX_KEEP_LOCAL_S : 0), h);
+    detail::check(hfx_allocate(h, (keepS ? HFX_KEEP_LOCAL_S : 0) | (recompute ? HFX_RECOMPUTE_RECOVERY : 0)), h);
     allocated = 1;
   }
 
@@ -890,7 +891,7 @@ class HDGSolver : public Solver {
   HDGSolverOpts myOpts;
   detail::Context* ownCtx = nullptr;
   int device = 0, mask = 0;
-  bool keepS = false;
+  bool keepS = false, recompute = false;
   std::vector<double> xip;
   hfx_solve_stats stats{0, 0.0, 0.0, 0};
 };

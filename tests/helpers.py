@@ -135,7 +135,7 @@ def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
     return h
 
 
-def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True):
+def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True, recompute=False):
     dim, order = case["dim"], case["order"]
     m = hfox.Mesh(dim, order, case.get("geom", "simplex"))
     m.setMesh(case["nodes"], case["cells"])
@@ -181,7 +181,7 @@ def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True):
     bm = hfox.DirichletModel(re.getFaceElement()) if case["bc"] == "dirichlet" else hfox.IntegratedDirichletModel(re.getFaceElement())
     opts = hfox.PetscOpts(rtol=rtol, maxits=maxits, verbose=False)
     lai = hfox.CudaLinAlgebraInterface(opts)
-    s = hfox.HDGSolver(keepLocalS=keepS)
+    s = hfox.HDGSolver(keepLocalS=keepS, recomputeRecovery=recompute)
     s.setVerbosity(False)
     s.setMesh(m)
     s.setFieldMap(fm)

@@ -59,3 +59,20 @@ def test_big_kernel_reassembly_is_bit_reproducible():
     v1 = s.getCSR()[2].copy(); r1 = s.getCSR()[3].copy()
     s.assemble()
     assert np.array_equal(v1, s.getCSR()[2]) and np.array_equal(r1, s.getCSR()[3])
+
+
+@pytest.mark.parametrize("model", ["laplace", "cdrs", "euler"])
+def test_recovery_by_recomputation(model):
+    """HFX_RECOMPUTE_RECOVERY: U, Q are never stored; hfx_recover re-condenses each element and applies them out of shared memory.
+    Same solution fields as the stored-operator recovery (to rounding: the sums run in another order) and as the oracle."""
+    case = H.make_case(3, 4, N=2, perturb=0.1, model=model, tau_double=model == "cdrs", seed=41)
+    o = H.run_oracle(case)
+    s1, fm1, _ = H.run_device(case)
+    s2, fm2, _ = H.run_device(case, recompute=True)
+    assert s2.lastAssembleKernel() == "big"
+    for name in ("Trace", "Solution", "Flux"):
+        assert H.rel_err(fm2[name].values, fm1[name].values) < 1e-12, name
+    assert H.rel_err(fm2["Solution"].values, o.sol.ravel()) < TOL_SOLUTION
+    assert H.rel_err(fm2["Flux"].values, o.flux.ravel()) < TOL_SOLUTION
+    with pytest.raises(Exception):
+        s2.getLocal()

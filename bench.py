@@ -188,7 +188,7 @@ def dist_gate(rank, world, lrank):
     from hyperfox_b200.dist import DistributedPoisson
     g = np.load(os.path.join(ROOT, "tests", "golden", "dist_gate_kuhn6_p3.npz"))
     verts, lin, order = g["verts"], g["lin"], int(g["order"])
-    part = partition.rcb_partition_vector(verts, lin, world) if world > 1 else np.zeros(lin.shape[0], dtype=np.int32)
+    part = partition.rcb_partition_vector_c(verts, lin, world) if world > 1 else np.zeros(lin.shape[0], dtype=np.int32)
     dp = DistributedPoisson(verts, lin, part, rank, world, order, device=lrank, rtol=1e-13)
     dp.assemble(); dp.solve()
     ids, sol = dp.owned_solution()
@@ -292,8 +292,8 @@ def main():
     if world > 1:
         # recursive coordinate bisection of the cell centroids, balanced by cell count (a third of the slabs' cut at 8 ranks)
         part = partition.load_partition_vector(args.partition_file, nTot, world) if args.partition_file else \
-            (partition.rcb_partition_vector(verts, lin, world) if args.partition == "rcb" else partition.partition_vector(nTot, world))
-        prob = partition.rank_problem(verts, lin, part, rank, dim)
+            (partition.rcb_partition_vector_c(verts, lin, world) if args.partition == "rcb" else partition.partition_vector(nTot, world))
+        prob = partition.Plan(dim, lin, part, rank, world).as_problem(verts)      # partition + halo plan: host C++ behind the C ABI (hfx_plan_create)
         lverts, lcells, nOwned = prob["verts"], prob["lin_cells"], int(prob["owned_cells"].size)
     else:
         lverts, lcells = verts, lin
@@ -381,8 +381,8 @@ def main():
             check(L.hfx_comm_init(h, world, rank, uid), h)
             gv = np.full(nodes.shape[0], -1, dtype=np.int64)      # global vertex id of the vertex nodes of the local high-order mesh
             gv[cells[:, :dim + 1]] = prob["vertex_ids"][prob["lin_cells"]]
-            canon = partition.face_canonical_positions(dim, order, tp["faces"], gv)
-            partition.set_halo(h, prob, canon)
+            canon = partition.face_canonical_positions_c(dim, order, tp["faces"], gv)
+            prob["plan"].set_halo(h, canon)
         if world == 1 or gate["ok"]:
             check(L.hfx_assemble(h), h)
             info = capi.SolveInfo()

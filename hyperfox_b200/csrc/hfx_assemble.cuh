@@ -67,6 +67,7 @@ struct AsmParams {
   long long* prof;            // optional [16] per-phase cycle counters (block 0 only), NULL in production
   // recovery by recomputation (hfx_allocate flag HFX_RECOMPUTE_RECOVERY: U, Q are not stored; hfx_recover re-condenses the element and applies
   // u_e = U lambda_e + U0, q_e = Q lambda_e + Q0 (HDGSolver.cpp:741-775) out of shared memory).  Served by hfx_big.cuh.
+  int gjThreads;              // hfx_big.cuh: threads of the K^-1 Gauss-Jordan (experiments: HFX_BIG_GJ)
   int recover; const double* recTrace; double* recSol; double* recFlux;
 };
 
@@ -329,7 +330,7 @@ __device__ __forceinline__ int grab1(int* ctr, int lane) {   // warp-granular dy
 // pivot block raises bit 0 of *flag.  np = n rounded up to even: the caller provides pad row/column = 0, pad diagonal = 1.
 // The inverse ends in ((np/2) odd ? b1 : b0).
 constexpr int kGJThreads = 128;
-template <int np, int ld, int GT>
+template <int np, int ld, int GT, bool kWholeCTA = (GT == kAsmThreads)>
 __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* flag, int barId) {
   // not inlined on purpose: inside the big kernel the register allocator rematerialises every address of this latency-bound loop
   constexpr int MT = np / 2, NS = MT * np, NQ = (NS + GT - 1) / GT;
@@ -377,7 +378,7 @@ __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* 
         *reinterpret_cast<double2*>(dst + offA[q]) = make_double2(r0, r1);
       }
     }
-    if (GT == kAsmThreads) __syncthreads(); else if (GT == 32) __syncwarp(); else bar_sync_named(barId, GT);
+    if (kWholeCTA) __syncthreads(); else if (GT == 32) __syncwarp(); else bar_sync_named(barId, GT);
   };
 #pragma unroll 1
   for (int k = 0; k + 2 < np; k += 4) { step(b0, b1, k); step(b1, b0, k + 2); }

@@ -452,7 +452,9 @@ __global__ void __launch_bounds__(kBigThreads, 1) hdg_big_kernel(const AsmParams
     HFX_PROF(5);
 
     // ---- PE: K^-1 (2x2-block-pivot Gauss-Jordan, all warps; the inverse ends in KA or KB) ------------------------------------------------------
-    group_invert<npe, nNp, NT>(KA, KB, tid, p.status, 1);
+    // (the pivot chain is serial and every thread redoes the pivot-block determinant / reciprocal: fewer threads = less redundant FP64 issue)
+    if (p.gjThreads == 256) { if (tid < 256) group_invert<npe, nNp, 256, false>(KA, KB, tid, p.status, 1); __syncthreads(); }
+    else group_invert<npe, nNp, NT, true>(KA, KB, tid, p.status, 1);
     double* const KI = ((npe / 2) & 1) ? KB : KA;
     HFX_PROF(6);
 

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -20,6 +21,7 @@
 #include "hfx_krylov.cuh"
 #include "host/hfx_refel.h"
 #include "host/hfx_topology.h"
+#include "host/hfx_partition.h"
 #include "host/hfx_meshio.h"
 
 namespace hfx {
@@ -1578,6 +1580,7 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode) {
     if (!fused && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA
         && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_BIG")) {
       if (!pend.empty()) waitPieces(0, -1);
+      p.gjThreads = getenv("HFX_BIG_GJ") ? atoi(getenv("HFX_BIG_GJ")) : 512;
       HFX_CUDA((launch_big<3, 4>(p, c->nSM, c->st)));
       big = true;
     }
@@ -1825,6 +1828,53 @@ int hfx_comm_set_halo(hfx_ctx* c, int nNbr, const int* nbrRank, const int* sendC
     HFX_CUDA(cudaStreamSynchronize(c->st));
     H.planned = true;
   });
+}
+
+struct hfx_plan { hfx::PartitionPlan p; };
+namespace { thread_local std::string g_plan_err; }
+const char* hfx_plan_last_error(void) { return g_plan_err.c_str(); }
+static int plan_guard(const std::function<void()>& f) { try { f(); return 0; } catch (const std::exception& e) { g_plan_err = e.what(); return 1; } }
+
+int hfx_host_rcb_partition(int dim, int geom, long long nVerts, const double* verts, long long nCells, const int* linCells, int world, int* part) {
+  return plan_guard([&] {
+    RefElement lin(dim, 1, geom == HFX_SIMPLEX ? kSimplex : kOrthotope);
+    rcb_partition(dim, nVerts, verts, nCells, lin.numNodes(), linCells, world, part);
+  });
+}
+int hfx_plan_create(int dim, int geom, long long nCells, const int* linCells, const int* part, int rank, int world, hfx_plan** plan) {
+  return plan_guard([&] {
+    if (!plan) throw std::runtime_error("Partitioner : update : no plan handle");
+    if (rank < 0 || rank >= world) throw std::runtime_error("Partitioner : initialize : the rank must lie in [0, nPartitions)");
+    std::unique_ptr<hfx_plan> P(new hfx_plan);
+    build_partition_plan(dim, geom == HFX_SIMPLEX ? 0 : 1, nCells, linCells, part, rank, world, &P->p);
+    *plan = P.release();
+  });
+}
+void hfx_plan_destroy(hfx_plan* plan) { delete plan; }
+int hfx_plan_sizes(const hfx_plan* plan, long long sizes[8]) {
+  if (!plan || !sizes) return 1;
+  const PartitionPlan& P = plan->p;
+  sizes[0] = P.nOwned; sizes[1] = P.nGhost; sizes[2] = (long long)P.vertexIds.size(); sizes[3] = (long long)P.faceGlobal.size(); sizes[4] = (long long)P.nbrs.size();
+  sizes[5] = (long long)P.sendFaces.size(); sizes[6] = (long long)P.recvFaces.size(); sizes[7] = (long long)P.sharedFaceList.size() / 3;
+  return 0;
+}
+int hfx_plan_get(const hfx_plan* plan, long long* cellsGlobal, long long* vertexIds, int* localCells, long long* faceGlobal, int* faceOwner, unsigned char* ownedFace,
+                 int* nbrRank, int* sendCount, int* recvCount, int* sendFaces, int* recvFaces, long long* sharedFaceList) {
+  if (!plan) return 1;
+  const PartitionPlan& P = plan->p;
+  auto cp = [](const auto& v, auto* dst) { if (dst) std::copy(v.begin(), v.end(), dst); };
+  cp(P.cellsGlobal, cellsGlobal); cp(P.vertexIds, vertexIds); cp(P.localCells, localCells); cp(P.faceGlobal, faceGlobal); cp(P.faceOwner, faceOwner); cp(P.ownedFace, ownedFace);
+  cp(P.nbrs, nbrRank); cp(P.sendCount, sendCount); cp(P.recvCount, recvCount); cp(P.sendFaces, sendFaces); cp(P.recvFaces, recvFaces); cp(P.sharedFaceList, sharedFaceList);
+  return 0;
+}
+int hfx_host_face_canonical_positions(int dim, int order, long long nFaces, int nNf, const int* faces, const long long* nodeVertexGid, unsigned char* canonPos) {
+  return plan_guard([&] { face_canonical_positions(dim, order, nFaces, nNf, faces, nodeVertexGid, canonPos); });
+}
+int hfx_comm_set_halo_plan(hfx_ctx* c, const hfx_plan* plan, const unsigned char* canonPos) {
+  if (!plan) return 1;
+  const PartitionPlan& P = plan->p;
+  if (c && (long long)P.faceGlobal.size() != c->nFaces) { c->err = "Partitioner : computeSharedFaces : the plan's local mesh is not the mesh of this context"; return 1; }
+  return hfx_comm_set_halo(c, (int)P.nbrs.size(), P.nbrs.data(), P.sendCount.data(), P.sendFaces.data(), P.recvCount.data(), P.recvFaces.data(), P.ownedFace.data(), canonPos);
 }
 
 int hfx_comm_halo_field(hfx_ctx* c, const char* name) {

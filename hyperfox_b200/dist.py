@@ -1,7 +1,7 @@
 """One process per GPU: distributed HDG solve of the reference-shaped problem.
 
 The mesh is partitioned by a cell partition vector (the reference: Zoltan, src/parallel/ZoltanPartitioner.cpp); every rank builds its
-local problem deterministically from the global linear mesh (partition.rank_problem), assembles its owned + ghost elements with no
+local problem deterministically from the global linear mesh (hfx_plan_create, host C++), assembles its owned + ghost elements with no
 exchange, and the Krylov solve exchanges only ghost-face trace blocks (NCCL send/recv) and dot products (NCCL all-reduce) inside
 libhfx.so.  torch.distributed is used for plumbing only: broadcasting the ncclUniqueId and gathering results.
 """
@@ -32,12 +32,11 @@ class DistributedPoisson:
                  topology=None):
         self.rank, self.world, self.dim, self.order = rank, world, dim, order
         c2f, f2c = topology if topology is not None else partition.global_linear_topology(lin_cells, dim)
-        self.prob = p = partition.rank_problem(verts, lin_cells, part, rank, dim, c2f, f2c)
+        self.plan = partition.Plan(dim, lin_cells, part, rank, world)          # host C++ behind the C ABI (hfx_plan_create)
+        self.prob = p = self.plan.as_problem(verts)
         nodes, cells = meshgen.high_order(p["verts"], p["lin_cells"], order)
         self.mesh = m = hfox.Mesh(dim, order, "simplex")
         m.setMesh(nodes, cells)
-        if not np.array_equal(m.cell2FaceMap, p["local_topology"]["cell2face"]):
-            raise capi.ErrorHandle("Partitioner : computeSharedFaces : local face numbering of the high-order mesh differs from its linear skeleton")
         re = m.getReferenceElement()
         nN, nNf = re.getNumNodes(), re.getFaceElement().getNumNodes()
         self.fm = fm = {"Solution": hfox.Field(m, hfox.Cell, nN, 1), "Flux": hfox.Field(m, hfox.Cell, nN, dim), "Trace": hfox.Field(m, hfox.Face, nNf, 1),
@@ -58,8 +57,8 @@ class DistributedPoisson:
         check(lib().hfx_comm_init(s._h(), world, rank, uid), s._h())
         gv = np.full(nodes.shape[0], -1, dtype=np.int64)          # global vertex id of the vertex nodes of the local high-order mesh
         gv[cells[:, :dim + 1]] = p["vertex_ids"][p["lin_cells"]]
-        self.canon = partition.face_canonical_positions(dim, order, m.faces, gv)
-        partition.set_halo(s._h(), p, self.canon)
+        self.canon = partition.face_canonical_positions_c(dim, order, m.faces, gv)
+        self.plan.set_halo(s._h(), self.canon)      # hfx_comm_set_halo_plan checks that the plan's local mesh is the context's mesh
         self.nodes, self.cells = nodes, cells
 
     def assemble(self): self.solver.assemble()

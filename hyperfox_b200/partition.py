@@ -231,3 +231,80 @@ def set_halo(ctx_handle, prob, canon):
     own = np.ascontiguousarray(prob["owned_face"], dtype=np.uint8)
     check(lib().hfx_comm_set_halo(ctx_handle, int(prob["nbrs"].size), pi(prob["nbrs"]), pi(sc), pi(np.ascontiguousarray(sf)), pi(rc), pi(np.ascontiguousarray(rf)),
                                   own.ctypes.data_as(C.POINTER(C.c_ubyte)), np.ascontiguousarray(canon, dtype=np.uint8).ctypes.data_as(C.POINTER(C.c_ubyte))), ctx_handle)
+
+
+# ---- the same plan through the C ABI (host C++: csrc/host/hfx_partition.cpp) -- what bench.py, dist.py and the C++ mirror use -----------------
+def rcb_partition_vector_c(verts, lin_cells, world, geom=0):
+    """hfx_host_rcb_partition: recursive coordinate bisection in host C++ (same cuts as rcb_partition_vector)."""
+    import ctypes as C
+    from .capi import lib, pd, pi, ErrorHandle
+    verts = np.ascontiguousarray(verts, dtype=np.float64); cells = np.ascontiguousarray(lin_cells, dtype=np.int32)
+    part = np.zeros(cells.shape[0], dtype=np.int32)
+    L = lib()
+    L.hfx_plan_last_error.restype = C.c_char_p
+    if L.hfx_host_rcb_partition(verts.shape[1], geom, C.c_longlong(verts.shape[0]), pd(verts), C.c_longlong(cells.shape[0]), pi(cells), world, pi(part)):
+        raise ErrorHandle(L.hfx_plan_last_error().decode())
+    return part
+
+
+class Plan:
+    """hfx_plan handle: the partition / halo plan of one rank, built in host C++ (hfx_plan_create)."""
+
+    def __init__(self, dim, lin_cells, part, rank, world, geom=0):
+        import ctypes as C
+        from .capi import lib, pi, ErrorHandle
+        self.L = lib()
+        self.L.hfx_plan_last_error.restype = C.c_char_p
+        self.L.hfx_plan_destroy.restype = None
+        cells = np.ascontiguousarray(lin_cells, dtype=np.int32); part = np.ascontiguousarray(part, dtype=np.int32)
+        self.h = C.c_void_p()
+        if self.L.hfx_plan_create(dim, geom, C.c_longlong(cells.shape[0]), pi(cells), pi(part), rank, world, C.byref(self.h)):
+            raise ErrorHandle(self.L.hfx_plan_last_error().decode())
+        sz = (C.c_longlong * 8)()
+        self.L.hfx_plan_sizes(self.h, sz)
+        nO, nG, nV, nF, nN, nS, nR, nSh = [int(x) for x in sz]
+        nv = cells.shape[1]
+        lp = C.POINTER(C.c_longlong)
+        self.cells_global = np.zeros(nO + nG, dtype=np.int64); self.vertex_ids = np.zeros(nV, dtype=np.int64); self.lin_cells = np.zeros((nO + nG, nv), dtype=np.int32)
+        self.face_global = np.zeros(nF, dtype=np.int64); self.face_owner = np.zeros(nF, dtype=np.int32); self.owned_face = np.zeros(nF, dtype=np.uint8)
+        self.nbrs = np.zeros(nN, dtype=np.int32); sc = np.zeros(nN, dtype=np.int32); rc = np.zeros(nN, dtype=np.int32)
+        sf = np.zeros(nS, dtype=np.int32); rf = np.zeros(nR, dtype=np.int32); self.shared_face_list = np.zeros((nSh, 3), dtype=np.int64)
+        self.L.hfx_plan_get(self.h, self.cells_global.ctypes.data_as(lp), self.vertex_ids.ctypes.data_as(lp), pi(self.lin_cells), self.face_global.ctypes.data_as(lp),
+                            pi(self.face_owner), self.owned_face.ctypes.data_as(C.POINTER(C.c_ubyte)), pi(self.nbrs), pi(sc), pi(rc), pi(sf), pi(rf),
+                            self.shared_face_list.ctypes.data_as(lp))
+        self.n_owned, self.n_ghost = nO, nG
+        self.owned_cells, self.ghost_cells = self.cells_global[:nO], self.cells_global[nO:]
+        so, ro = np.r_[0, np.cumsum(sc)], np.r_[0, np.cumsum(rc)]
+        self.send = [sf[so[k]:so[k + 1]] for k in range(nN)]; self.recv = [rf[ro[k]:ro[k + 1]] for k in range(nN)]
+
+    def as_problem(self, verts):
+        """The dict rank_problem() returns (same keys), from the C++ plan."""
+        return dict(owned_cells=self.owned_cells, ghost_cells=self.ghost_cells, cells_global=self.cells_global, verts=np.asarray(verts)[self.vertex_ids],
+                    lin_cells=self.lin_cells, vertex_ids=self.vertex_ids, face_global=self.face_global, face_owner=self.face_owner, owned_face=self.owned_face,
+                    nbrs=self.nbrs, send=self.send, recv=self.recv, plan=self)
+
+    def set_halo(self, ctx_handle, canon):
+        import ctypes as C
+        from .capi import check
+        check(self.L.hfx_comm_set_halo_plan(ctx_handle, self.h, np.ascontiguousarray(canon, dtype=np.uint8).ctypes.data_as(C.POINTER(C.c_ubyte))), ctx_handle)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.hfx_plan_destroy(self.h); self.h = None
+        except Exception:
+            pass
+
+
+def face_canonical_positions_c(dim, order, faces, node_vertex_gid):
+    """hfx_host_face_canonical_positions (host C++): same result as face_canonical_positions."""
+    import ctypes as C
+    from .capi import lib, pi, ErrorHandle
+    faces = np.ascontiguousarray(faces, dtype=np.int32); gv = np.ascontiguousarray(node_vertex_gid, dtype=np.int64)
+    out = np.zeros(faces.shape, dtype=np.uint8)
+    L = lib()
+    L.hfx_plan_last_error.restype = C.c_char_p
+    if L.hfx_host_face_canonical_positions(dim, order, C.c_longlong(faces.shape[0]), faces.shape[1], pi(faces), gv.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                           out.ctypes.data_as(C.POINTER(C.c_ubyte))):
+        raise ErrorHandle(L.hfx_plan_last_error().decode())
+    return out

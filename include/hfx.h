@@ -146,6 +146,30 @@ int hfx_comm_set_halo(hfx_ctx* ctx, int nNbr, const int* nbrRank, const int* sen
                       const int* recvFaces, const unsigned char* ownedFace, const unsigned char* canonPos);
 int hfx_comm_halo_field(hfx_ctx* ctx, const char* faceFieldName); /* Partitioner::updateSharedInformation for one face field */
 
+/* ---- element partition and halo plan on the host (C++, csrc/host/hfx_partition.cpp): what the reference negotiates over MPI in
+   src/parallel/Partitioner.cpp:42-107 (computeSharedFaces), :565-826 (updateSharedInformation) and ZoltanPartitioner.cpp:35-167, as a pure
+   function of (global linear mesh, cell partition vector, rank): every rank derives its plan without communication. -------------------- */
+/* recursive coordinate bisection of the cell centroids: deterministic stand-in for the Zoltan PHG partition (ZoltanPartitioner.cpp:14-32);
+   verts [nVerts][dim], linCells [nCells][verticesPerCell], part [nCells] out.  A Zoltan partition vector can be passed to hfx_plan_create instead. */
+int hfx_host_rcb_partition(int dim, int geom, long long nVerts, const double* verts, long long nCells, const int* linCells, int world, int* part);
+typedef struct hfx_plan hfx_plan;
+/* plan of `rank`: owned cells + the ghost cells across the faces it owns (a face travels with its first adjacent cell, ZoltanPartitioner.cpp:83-133),
+   local vertex / cell / face numbering, face ownership, send / receive lists per neighbour rank, the reference's sharedFaceList */
+int hfx_plan_create(int dim, int geom, long long nCells, const int* linCells, const int* part, int rank, int world, hfx_plan** plan);
+void hfx_plan_destroy(hfx_plan* plan);
+const char* hfx_plan_last_error(void);
+/* sizes[8] = nOwnedCells, nGhostCells, nLocalVertices, nLocalFaces, nNeighbours, nSendFaces, nRecvFaces, nSharedFaces */
+int hfx_plan_sizes(const hfx_plan* plan, long long sizes[8]);
+/* any pointer may be NULL.  cellsGlobal [nOwned+nGhost] (owned first), vertexIds [nLocalVertices], localCells [(nOwned+nGhost)][verticesPerCell],
+   faceGlobal / faceOwner / ownedFace [nLocalFaces], nbrRank / sendCount / recvCount [nNeighbours], sendFaces [nSendFaces], recvFaces [nRecvFaces]
+   (LOCAL face ids, per neighbour in ascending global face id), sharedFaceList [3 nSharedFaces] = [global face, other rank, global adjacent cell] (Partitioner.h:223) */
+int hfx_plan_get(const hfx_plan* plan, long long* cellsGlobal, long long* vertexIds, int* localCells, long long* faceGlobal, int* faceOwner, unsigned char* ownedFace,
+                 int* nbrRank, int* sendCount, int* recvCount, int* sendFaces, int* recvFaces, long long* sharedFaceList);
+/* canonPos of hfx_comm_set_halo from the local high-order face connectivity and the global vertex id of every vertex node (-1 for the other nodes) */
+int hfx_host_face_canonical_positions(int dim, int order, long long nFaces, int nNf, const int* faces, const long long* nodeVertexGid, unsigned char* canonPos);
+/* hfx_comm_set_halo with the lists of a plan (the local mesh of ctx must be the plan's local cells at the context's order) */
+int hfx_comm_set_halo_plan(hfx_ctx* ctx, const hfx_plan* plan, const unsigned char* canonPos);
+
 /* ---- parity hooks ----------------------------------------------------------------------------------------------- */
 /* CSR of the global trace system: sorted columns, explicit zeros (PetscInterface.cpp:99-103).  nnz query with NULLs. */
 int hfx_get_csr(hfx_ctx* ctx, long long* nrows, long long* nnz, long long* rowptr, int* colidx, double* vals, double* rhs);

@@ -25,6 +25,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <exception>
 #include <functional>
 #include <iostream>
@@ -333,6 +336,186 @@ class Field {
   FieldType type = None;
   int numEntities = 0, numObjPerEnt = 0, numValsPerObj = 0;
   bool doubleValued = false;
+};
+
+// ---- src/parallel/Partitioner.h, ZoltanPartitioner.h ----------------------------------------------------------------------------------
+// One process per GPU.  The reference reads rank / size from MPI_COMM_WORLD, lets Zoltan cut the cell graph and MIGRATES cells, nodes, faces and
+// field values between the ranks (Partitioner.cpp:203-563), then negotiates the shared faces over MPI (:42-107).  Here every process starts
+// from the same global mesh, so the same end state is a pure function of (global mesh, cell partition vector, rank): update() replaces the
+// mesh and the fields by this rank's part -- the owned cells followed by the ghost cells across the faces it owns (overlap 1: the face owner
+// recomputes the element on the other side, so assembly needs no exchange) -- through the host C++ plan behind the C ABI (hfx_plan_create).
+// Difference kept on purpose: the partitioned Mesh holds LOCAL ids in its connectivity (the device path indexes with them); the reference keeps
+// global ids there and translates with global2Local*.  local2Global* / global2Local* / getSharedFaceList have the reference's meaning.
+class Partitioner {
+ public:
+  Partitioner() {}
+  explicit Partitioner(Mesh* pmesh) { setMesh(pmesh); }
+  virtual ~Partitioner() { if (plan) hfx_plan_destroy(plan); }
+  virtual void initialize() {   // Partitioner.cpp:5-11 with the launcher's RANK / WORLD_SIZE (torchrun, mpirun wrappers) instead of MPI_Comm_rank / size
+    const char* r = std::getenv("RANK"); const char* w = std::getenv("WORLD_SIZE");
+    initialize(r ? std::atoi(r) : 0, w ? std::atoi(w) : 1);
+  }
+  virtual void initialize(int rank_, int nPartitions_) {
+    if (nPartitions_ < 1 || rank_ < 0 || rank_ >= nPartitions_) throw ErrorHandle("Partitioner", "initialize", "the rank must lie in [0, nPartitions)");
+    rank = rank_; nPartitions = nPartitions_; initialized = 1;
+  }
+  virtual void computePartition() = 0;   // fills partitionVector: one rank id per cell of the global mesh
+  virtual void setMesh(Mesh* pmesh) { myMesh = pmesh; if (pmesh) pmesh->setPartitioner(this); }
+  virtual void setFields(std::vector<Field*> fieldList) { fields = fieldList; }
+  virtual void update() {   // Partitioner.cpp:203-563: afterwards the mesh and the fields are this rank's part
+    if (!initialized) throw ErrorHandle("Partitioner", "update", "must initialize the partitioner before updating.");
+    if (!myMesh || !myMesh->getReferenceElement()) throw ErrorHandle("Partitioner", "update", "must set the mesh before updating.");
+    const ReferenceElement* re = myMesh->getReferenceElement();
+    const int dim = re->getDimension(), geom = re->getGeometry() == simplex ? HFX_SIMPLEX : HFX_ORTHOTOPE;
+    const int nN = re->getNumNodes(), nv = geom == HFX_SIMPLEX ? dim + 1 : (1 << dim), nC = myMesh->getNumberCells(), dsp = myMesh->getNodeSpaceDimension();
+    if ((int)partitionVector.size() != nC) throw ErrorHandle("Partitioner", "update", "must compute the partition before updating (one rank id per cell).");
+    totNodes = myMesh->getNumberPoints(); totCells = nC; totFaces = myMesh->getNumberFaces();
+    const std::vector<int>& gc = *myMesh->getCells();
+    std::vector<int> lin((size_t)nC * nv);   // linear skeleton: the vertices come first in the node list of a cell
+    for (int c = 0; c < nC; c++) for (int k = 0; k < nv; k++) lin[(size_t)c * nv + k] = gc[(size_t)c * nN + k];
+    if (plan) { hfx_plan_destroy(plan); plan = nullptr; }
+    if (hfx_plan_create(dim, geom, nC, lin.data(), partitionVector.data(), rank, nPartitions, &plan)) throw ErrorHandle(hfx_plan_last_error());
+    long long sz[8];
+    hfx_plan_sizes(plan, sz);
+    nOwned = (int)sz[0];
+    const int nL = (int)(sz[0] + sz[1]), nFl = (int)sz[3];
+    std::vector<long long> cg((size_t)nL), fg((size_t)nFl), sfl((size_t)sz[7] * 3);
+    hfx_plan_get(plan, cg.data(), 0, 0, fg.data(), 0, 0, 0, 0, 0, 0, 0, sfl.data());
+    elementIDs.assign(cg.begin(), cg.end()); faceIDs.assign(fg.begin(), fg.end()); sharedFaceList.assign(sfl.begin(), sfl.end());
+    // local nodes: ascending global id over the nodes of the local cells
+    std::vector<int> used; used.reserve((size_t)nL * nN);
+    for (int i = 0; i < nL; i++) for (int k = 0; k < nN; k++) used.push_back(gc[(size_t)elementIDs[i] * nN + k]);
+    std::sort(used.begin(), used.end()); used.erase(std::unique(used.begin(), used.end()), used.end());
+    nodeIDs = used;
+    computeGlobal2LocalMaps();
+    std::vector<double> pts((size_t)nodeIDs.size() * dsp);
+    const std::vector<double>& gp = *myMesh->getPoints();
+    for (size_t i = 0; i < nodeIDs.size(); i++) for (int d = 0; d < dsp; d++) pts[i * dsp + d] = gp[(size_t)nodeIDs[i] * dsp + d];
+    std::vector<int> lc((size_t)nL * nN);
+    for (int i = 0; i < nL; i++) for (int k = 0; k < nN; k++) lc[(size_t)i * nN + k] = glob2LocNodeIDs[gc[(size_t)elementIDs[i] * nN + k]];
+    // global vertex id of the vertex nodes (the rank-independent order in which face blocks travel is defined with them)
+    std::vector<long long> gv(nodeIDs.size(), -1);
+    for (int i = 0; i < nL; i++) for (int k = 0; k < nv; k++) gv[(size_t)lc[(size_t)i * nN + k]] = gc[(size_t)elementIDs[i] * nN + k];
+    // fields first (they still refer to the global mesh), then the mesh
+    std::vector<std::vector<double> > newVals(fields.size());
+    for (size_t f = 0; f < fields.size(); f++) {
+      Field* F = fields[f];
+      const std::vector<int>* ids = *F->getFieldType() == Node ? &nodeIDs : *F->getFieldType() == Face ? &faceIDs : *F->getFieldType() == Cell ? &elementIDs : nullptr;
+      if (!ids) throw ErrorHandle("Partitioner", "update", "the field type is not supported");
+      const size_t n = (size_t)(*F->getNumObjPerEnt()) * (*F->getNumValsPerObj());
+      newVals[f].resize(ids->size() * n);
+      for (size_t i = 0; i < ids->size(); i++) std::copy(F->getValues()->begin() + (size_t)(*ids)[i] * n, F->getValues()->begin() + ((size_t)(*ids)[i] + 1) * n, newVals[f].begin() + i * n);
+    }
+    myMesh->setMesh(dsp, pts, lc);
+    myMesh->setPartitioner(this);
+    if (myMesh->getNumberFaces() != nFl) throw ErrorHandle("Partitioner", "update", "the local face numbering of the mesh differs from the plan's");
+    for (size_t f = 0; f < fields.size(); f++) { fields[f]->computeNumEntities(); *fields[f]->getValues() = newVals[f]; }
+    const int nNf = re->getFaceElement()->getNumNodes();
+    canon.assign((size_t)nFl * nNf, 0);
+    if (hfx_host_face_canonical_positions(dim, re->getOrder(), nFl, nNf, myMesh->getFaces()->data(), gv.data(), canon.data())) throw ErrorHandle(hfx_plan_last_error());
+    // faces of the true domain boundary: a local face with one local cell is either on the boundary or on a cut of the partition
+    updated = true;
+  }
+  // Partitioner.cpp:565-826 exchanges the values of cell / face fields on the shared entities over MPI.  On the device path the only shared values
+  // are the traces of ghost faces: HDGSolver::solve exchanges them over NCCL (hfx_comm_halo_field) before the local recovery.
+  virtual void updateSharedInformation() {
+    if (!updated) throw ErrorHandle("Partitioner", "updateSharedInformation", "must update the partition before sharing information.");
+  }
+  virtual int getNumPartitions() const { return nPartitions; }
+  virtual int getRank() const { return rank; }
+  virtual int getTotalNumberNodes() const { return totNodes; }
+  virtual int getTotalNumberEls() const { return totCells; }
+  virtual int getTotalNumberFaces() const { return totFaces; }
+  virtual int getNumberOwnedCells() const { return nOwned; }   // the local cells [0, nOwned) are owned, the rest are ghosts
+  virtual const std::vector<int>* getSharedFaceList() const { return &sharedFaceList; }
+  virtual int local2GlobalNode(int loc) const { return nodeIDs[loc]; }
+  virtual int local2GlobalFace(int loc) const { return faceIDs[loc]; }
+  virtual int local2GlobalEl(int loc) const { return elementIDs[loc]; }
+  virtual void local2GlobalNodeSlice(const std::vector<int>& loc, std::vector<int>* glob) const { slice(loc, glob, nodeIDs); }
+  virtual void local2GlobalFaceSlice(const std::vector<int>& loc, std::vector<int>* glob) const { slice(loc, glob, faceIDs); }
+  virtual void local2GlobalElementSlice(const std::vector<int>& loc, std::vector<int>* glob) const { slice(loc, glob, elementIDs); }
+  virtual int global2LocalNode(int glob) const { return find(glob2LocNodeIDs, glob); }
+  virtual int global2LocalFace(int glob) const { return find(glob2LocFaceIDs, glob); }
+  virtual int global2LocalElement(int glob) const { return find(glob2LocElementIDs, glob); }
+  virtual void global2LocalNodeSlice(const std::vector<int>& glob, std::vector<int>* loc) const { loc->resize(glob.size()); for (size_t i = 0; i < glob.size(); i++) (*loc)[i] = global2LocalNode(glob[i]); }
+  virtual void global2LocalFaceSlice(const std::vector<int>& glob, std::vector<int>* loc) const { loc->resize(glob.size()); for (size_t i = 0; i < glob.size(); i++) (*loc)[i] = global2LocalFace(glob[i]); }
+  virtual void global2LocalElementSlice(const std::vector<int>& glob, std::vector<int>* loc) const { loc->resize(glob.size()); for (size_t i = 0; i < glob.size(); i++) (*loc)[i] = global2LocalElement(glob[i]); }
+  virtual const std::vector<int>* getNodeIds() const { return &nodeIDs; }
+  virtual const std::vector<int>* getFaceIds() const { return &faceIDs; }
+  virtual const std::vector<int>* getCellIds() const { return &elementIDs; }
+  const std::vector<int>* getPartitionVector() const { return &partitionVector; }
+  // device side: the halo plan HDGSolver::allocate hands to the library, and the NCCL id every rank must share (created by rank 0 with
+  // hfx_comm_unique_id and distributed by the host program, e.g. MPI_Bcast or exchangeCommunicatorId below)
+  const hfx_plan* getPlan() const { return plan; }
+  const std::vector<unsigned char>* getCanonicalFacePositions() const { return &canon; }
+  void setCommunicatorId(const char id128[128]) { commId.assign(id128, id128 + 128); }
+  bool hasCommunicatorId() const { return commId.size() == 128; }
+  const char* getCommunicatorId() const { return commId.data(); }
+  void exchangeCommunicatorId(const std::string& path) {   // rank 0 writes the id to `path` (atomically), the other ranks wait for it: for launchers without MPI
+    char id[128];
+    if (rank == 0) {
+      detail::check(hfx_comm_unique_id(id), nullptr);
+      const std::string tmp = path + ".tmp";
+      FILE* f = std::fopen(tmp.c_str(), "wb");
+      if (!f || std::fwrite(id, 1, 128, f) != 128) throw ErrorHandle("Partitioner", "exchangeCommunicatorId", "cannot write " + tmp);
+      std::fclose(f);
+      if (std::rename(tmp.c_str(), path.c_str())) throw ErrorHandle("Partitioner", "exchangeCommunicatorId", "cannot publish " + path);
+    } else {
+      for (int tries = 0;; tries++) {
+        FILE* f = std::fopen(path.c_str(), "rb");
+        if (f) { const size_t n = std::fread(id, 1, 128, f); std::fclose(f); if (n == 128) break; }
+        if (tries > 6000) throw ErrorHandle("Partitioner", "exchangeCommunicatorId", "timed out waiting for " + path);
+        struct timespec ts = {0, 10000000}; nanosleep(&ts, nullptr);
+      }
+    }
+    setCommunicatorId(id);
+  }
+
+ protected:
+  static void slice(const std::vector<int>& loc, std::vector<int>* glob, const std::vector<int>& ids) { glob->resize(loc.size()); for (size_t i = 0; i < loc.size(); i++) (*glob)[i] = ids[loc[i]]; }
+  static int find(const std::map<int, int>& m, int g) { std::map<int, int>::const_iterator it = m.find(g); return it == m.end() ? -1 : it->second; }
+  void computeGlobal2LocalMaps() {   // Partitioner.cpp:109-125
+    glob2LocNodeIDs.clear(); glob2LocFaceIDs.clear(); glob2LocElementIDs.clear();
+    for (size_t i = 0; i < nodeIDs.size(); i++) glob2LocNodeIDs[nodeIDs[i]] = (int)i;
+    for (size_t i = 0; i < faceIDs.size(); i++) glob2LocFaceIDs[faceIDs[i]] = (int)i;
+    for (size_t i = 0; i < elementIDs.size(); i++) glob2LocElementIDs[elementIDs[i]] = (int)i;
+  }
+  Mesh* myMesh = NULL;
+  std::vector<Field*> fields;
+  std::vector<int> nodeIDs, faceIDs, elementIDs, sharedFaceList, partitionVector;
+  std::map<int, int> glob2LocNodeIDs, glob2LocFaceIDs, glob2LocElementIDs;
+  int nPartitions = 1, rank = 0, totNodes = 0, totCells = 0, totFaces = 0, nOwned = 0;
+  bool initialized = 0, updated = false;
+  hfx_plan* plan = nullptr;
+  std::vector<unsigned char> canon;
+  std::vector<char> commId;
+};
+
+// Recursive coordinate bisection of the cell centroids: the deterministic stand-in for ZoltanPartitioner (Zoltan PHG is not available; its cuts are
+// not pinned by any reference test, and solution fields do not depend on them).
+class RcbPartitioner : public Partitioner {
+ public:
+  using Partitioner::Partitioner;
+  void computePartition() override {
+    if (!initialized) throw ErrorHandle("RcbPartitioner", "computePartition", "must initialize the partitioner before computing the partition.");
+    if (!myMesh || !myMesh->getReferenceElement()) throw ErrorHandle("RcbPartitioner", "computePartition", "must set the mesh before computing the partition.");
+    const ReferenceElement* re = myMesh->getReferenceElement();
+    const int dim = re->getDimension(), geom = re->getGeometry() == simplex ? HFX_SIMPLEX : HFX_ORTHOTOPE, nN = re->getNumNodes(), nv = geom == HFX_SIMPLEX ? dim + 1 : (1 << dim);
+    if (myMesh->getNodeSpaceDimension() != dim) throw ErrorHandle("RcbPartitioner", "computePartition", "the node space dimension must equal the dimension of the reference element");
+    const int nC = myMesh->getNumberCells();
+    std::vector<int> lin((size_t)nC * nv);
+    for (int c = 0; c < nC; c++) for (int k = 0; k < nv; k++) lin[(size_t)c * nv + k] = (*myMesh->getCells())[(size_t)c * nN + k];
+    partitionVector.assign((size_t)nC, 0);
+    if (hfx_host_rcb_partition(dim, geom, myMesh->getNumberPoints(), myMesh->getPoints()->data(), nC, lin.data(), nPartitions, partitionVector.data())) throw ErrorHandle(hfx_plan_last_error());
+  }
+};
+// A partition computed elsewhere (e.g. the reference's Zoltan run: ZoltanPartitioner.cpp:35-167), one rank id per global cell.
+class VectorPartitioner : public Partitioner {
+ public:
+  VectorPartitioner(Mesh* pmesh, const std::vector<int>& cellRanks) : Partitioner(pmesh), given(cellRanks) {}
+  void computePartition() override { partitionVector = given; }
+ protected:
+  std::vector<int> given;
 };
 
 // ---- src/resolution/PetscOpts.h ------------------------------------------------------------------------------------------
@@ -775,6 +958,14 @@ class HDGSolver : public Solver {
       detail::check(hfx_boundary_describe(h, bm->cKind(), (int)ids.size(), ids.empty() ? &none : ids.data()), h);
     }
     detail::check(hfx_allocate(h, (keepS ? HFX_KEEP_LOCAL_S : 0) | (recompute ? HFX_RECOMPUTE_RECOVERY : 0)), h);
+    // several GPUs (src/solver/HDGSolver.cpp:64-76 asks the Partitioner for the shared faces): NCCL communicator + halo plan of the partitioned mesh
+    Partitioner* pp = myMesh->getPartitioner();
+    if (pp && pp->getNumPartitions() > 1) {
+      if (!pp->getPlan()) throw ErrorHandle("HDGSolver", "allocate", "the partitioner of the mesh must be updated before allocating.");
+      if (!pp->hasCommunicatorId()) throw ErrorHandle("HDGSolver", "allocate", "the partitioner needs the communicator id shared by all ranks (setCommunicatorId / exchangeCommunicatorId).");
+      detail::check(hfx_comm_init(h, pp->getNumPartitions(), pp->getRank(), pp->getCommunicatorId()), h);
+      detail::check(hfx_comm_set_halo_plan(h, pp->getPlan(), pp->getCanonicalFacePositions()->data()), h);
+    }
     allocated = 1;
   }
 

@@ -374,6 +374,100 @@ static void testNonLinearWrapper(const std::string& dir) {
   }
 }
 
+// tests/parallel/TestZoltanPartitioner.cpp ("Test initialization", "Test a mesh partition", "Testing a field partition") restated for the one-process-per-GPU
+// Partitioner of the mirror: every rank of a `world`-way partition is built in this one process (the plan is a pure function of mesh, partition vector and
+// rank), so the reference's MPI_Bcast / MPI_Allreduce checks become loops over the ranks.  The partitioned Mesh holds LOCAL ids (see hyperfox.h), hence the
+// local2Global* translations where the reference compares ids directly.
+static void testPartitioner(const std::string& meshFile, int dim, int order, int world) {
+  Mesh seqMesh(dim, order, "simplex");
+  loadMesh(meshFile, &seqMesh, dim);
+  const int nN = seqMesh.getReferenceElement()->getNumNodes(), nNf = seqMesh.getReferenceElement()->getFaceElement()->getNumNodes(), nFc = dim + 1;
+  {
+    Mesh m0(dim, order, "simplex");
+    RcbPartitioner p0(&m0);
+    CHECK_THROWS(p0.update());
+    CHECK_THROWS(p0.computePartition());
+    CHECK_NOTHROW(p0.initialize(1, 4));
+    CHECK(p0.getNumPartitions() == 4);
+    CHECK(p0.getRank() == 1);
+    CHECK_THROWS(p0.initialize(4, 4));
+  }
+  std::vector<int> ownerOfCell(seqMesh.getNumberCells(), -1), faceOwners(seqMesh.getNumberFaces(), 0);
+  int sumOwned = 0, sumBFaces = 0;
+  std::vector<std::vector<int> > shared(world);
+  for (int rank = 0; rank < world; rank++) {
+    Mesh parMesh(dim, order, "simplex");
+    loadMesh(meshFile, &parMesh, dim);
+    Field nodeField(&parMesh, Node, 1, 1), cellField(&parMesh, Cell, 1, 1), faceField(&parMesh, Face, 1, 1);
+    for (size_t i = 0; i < nodeField.getValues()->size(); i++) (*nodeField.getValues())[i] = (double)i;
+    for (size_t i = 0; i < cellField.getValues()->size(); i++) (*cellField.getValues())[i] = (double)i;
+    for (size_t i = 0; i < faceField.getValues()->size(); i++) (*faceField.getValues())[i] = (double)i;
+    RcbPartitioner zPart(&parMesh);
+    zPart.initialize(rank, world);
+    zPart.setFields({&nodeField, &cellField, &faceField});
+    zPart.computePartition();
+    zPart.update();
+    CHECK(zPart.getTotalNumberNodes() == seqMesh.getNumberPoints());
+    CHECK(zPart.getTotalNumberEls() == seqMesh.getNumberCells());
+    CHECK(zPart.getTotalNumberFaces() == seqMesh.getNumberFaces());
+    const std::vector<int>& pv = *zPart.getPartitionVector();
+    std::vector<double> point; std::vector<int> cell;
+    for (int i = 0; i < parMesh.getNumberPoints(); i++) {
+      parMesh.getPoint(i, &point);
+      const int g = zPart.local2GlobalNode(i);
+      for (int k = 0; k < dim; k++) CHECK(point[k] == (*seqMesh.getPoints())[(size_t)g * dim + k]);
+      CHECK(zPart.global2LocalNode(g) == i);
+      CHECK((*nodeField.getValues())[i] == (double)g);
+    }
+    for (int i = 0; i < parMesh.getNumberCells(); i++) {
+      parMesh.getCell(i, &cell);
+      const int g = zPart.local2GlobalEl(i);
+      for (int k = 0; k < nN; k++) CHECK(zPart.local2GlobalNode(cell[k]) == (*seqMesh.getCells())[(size_t)g * nN + k]);
+      parMesh.getCell2Face(i, &cell);
+      for (int k = 0; k < nFc; k++) CHECK(zPart.local2GlobalFace(cell[k]) == (*seqMesh.getCell2FaceMap())[(size_t)g * nFc + k]);
+      CHECK((*cellField.getValues())[i] == (double)g);
+      CHECK((i < zPart.getNumberOwnedCells()) == (pv[g] == rank));      // owned cells first, then the ghosts
+      if (i < zPart.getNumberOwnedCells()) { CHECK(ownerOfCell[g] == -1); ownerOfCell[g] = rank; sumOwned++; }
+    }
+    for (int i = 0; i < parMesh.getNumberFaces(); i++) {
+      parMesh.getFace(i, &cell);
+      const int g = zPart.local2GlobalFace(i);
+      // same node SET as the global face; the order is that of the face's first LOCAL cell, which is why blocks travel in the canonical order
+      std::vector<int> a(nNf), b(nNf);
+      for (int k = 0; k < nNf; k++) { a[k] = zPart.local2GlobalNode(cell[k]); b[k] = (*seqMesh.getFaces())[(size_t)g * nNf + k]; }
+      std::sort(a.begin(), a.end()); std::sort(b.begin(), b.end());
+      CHECK(a == b);
+      CHECK((*faceField.getValues())[i] == (double)g);
+      CHECK(zPart.global2LocalFace(g) == i);
+      parMesh.getFace2Cell(i, &cell);
+      for (size_t k = 0; k < cell.size(); k++) { const int gc = zPart.local2GlobalEl(cell[k]); CHECK(gc == (*seqMesh.getFace2CellMap())[(size_t)g * 2] || gc == (*seqMesh.getFace2CellMap())[(size_t)g * 2 + 1]); }
+      // a face of the true boundary is a boundary face of the local mesh; the owner of a face holds both of its cells
+      const bool ownedFace = pv[(*seqMesh.getFace2CellMap())[(size_t)g * 2]] == rank;
+      if (ownedFace) { faceOwners[g]++; CHECK((int)cell.size() == ((*seqMesh.getFace2CellMap())[(size_t)g * 2 + 1] >= 0 ? 2 : 1)); }
+      if (seqMesh.getBoundaryFaces()->count(g)) { CHECK(parMesh.getBoundaryFaces()->count(i) == 1); if (ownedFace) sumBFaces++; }
+    }
+    for (int g = 0; g < seqMesh.getNumberCells(); g++) { const int l = zPart.global2LocalElement(g); if (l != -1) CHECK(zPart.local2GlobalEl(l) == g); }
+    // sharedFaceList: [global face, rank of the other partition, global id of the adjacent cell there] (Partitioner.h:223)
+    const std::vector<int>& sfl = *zPart.getSharedFaceList();
+    CHECK(sfl.size() % 3 == 0);
+    for (size_t i = 0; i < sfl.size() / 3; i++) {
+      const int F = sfl[3 * i], orank = sfl[3 * i + 1], ocell = sfl[3 * i + 2];
+      const int c0 = (*seqMesh.getFace2CellMap())[(size_t)F * 2], c1 = (*seqMesh.getFace2CellMap())[(size_t)F * 2 + 1];
+      CHECK(orank != rank); CHECK(pv[ocell] == orank); CHECK(ocell == c0 || ocell == c1); CHECK(pv[ocell == c0 ? c1 : c0] == rank);
+      shared[rank].push_back(F);
+    }
+    CHECK_NOTHROW(zPart.updateSharedInformation());
+  }
+  CHECK(sumOwned == seqMesh.getNumberCells());                                   // every cell is owned exactly once
+  for (size_t F = 0; F < faceOwners.size(); F++) CHECK(faceOwners[F] == 1);      // every face is owned exactly once
+  CHECK(sumBFaces == (int)seqMesh.getBoundaryFaces()->size());
+  // a shared face appears in the lists of exactly two ranks
+  std::map<int, int> cnt;
+  for (int r = 0; r < world; r++) for (size_t i = 0; i < shared[r].size(); i++) cnt[shared[r][i]]++;
+  for (std::map<int, int>::const_iterator it = cnt.begin(); it != cnt.end(); ++it) CHECK(it->second == 2);
+  CHECK(world == 1 || !cnt.empty());
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { std::printf("usage: %s <mesh dir> [contract|meshio|nlw|solver|lai|laplace|diffsrc|rk]\n", argv[0]); return 2; }
   const std::string dir = argv[1], sec = argc > 2 ? argv[2] : "all";
@@ -383,6 +477,11 @@ int main(int argc, char** argv) {
     if (sec == "meshio" || sec == "all") {
       testGmshIo(dir, "regression_dim-2_h-2e-1", 2, 2);
       testGmshIo(dir, "regression_dim-3_h-2e-1", 3, 3);
+    }
+    if (sec == "partitioner" || sec == "all") {
+      testPartitioner(dir + "/regression_dim-2_h-1e-1_ord-3.txt", 2, 3, 3);
+      testPartitioner(dir + "/regression_dim-3_h-2e-1_ord-3.txt", 3, 3, 4);
+      testPartitioner(dir + "/regression_dim-2_h-2e-1_ord-2.txt", 2, 2, 1);
     }
     if (sec == "solver" || sec == "all") testHDGSolver(dir, true);
     if (sec == "lai" || sec == "all") testLinAlgebraInterface();

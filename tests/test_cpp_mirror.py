@@ -66,6 +66,12 @@ def test_cpp_mirror_non_linear_wrapper(mesh_dir):
     assert " 0 failed" in out, out
 
 
+def test_cpp_mirror_partitioner(mesh_dir):
+    """tests/parallel/TestZoltanPartitioner.cpp restated against the mirror's Partitioner (host C++ plan behind the C ABI; every rank built in one process)."""
+    out = run(mesh_dir, "partitioner")
+    assert " 0 failed" in out, out
+
+
 @pytest.mark.gpu
 def test_cpp_mirror_reference_tests(mesh_dir):
     out = run(mesh_dir, "all")

@@ -105,3 +105,47 @@ def test_rcb_on_an_unstructured_reference_mesh(world):
             q = probs[s]
             ks = list(q["nbrs"]).index(r)
             assert np.array_equal(p["face_global"][p["send"][k]], q["face_global"][q["recv"][ks]])
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_host_cpp_plan_equals_the_numpy_plan(world):
+    """The plan behind the C ABI (hfx_plan_create, host C++) against the numpy restatement above: same partition vector, same local numbering,
+    same ownership, same send / receive lists -- and the reference's sharedFaceList triples [global face, other rank, global adjacent cell]."""
+    v, c = meshgen.kuhn_linear(5, 3)
+    v = v + 0.01 * np.sin(7.0 * v[:, ::-1])            # break the lattice symmetry: the bisection cuts must not depend on ties
+    part = P.rcb_partition_vector(v, c, world)
+    assert np.array_equal(P.rcb_partition_vector_c(v, c, world), part)
+    c2f, f2c = P.global_linear_topology(c, 3)
+    for r in range(world):
+        ref = P.rank_problem(v, c, part, r, 3, c2f, f2c)
+        pl = P.Plan(3, c, part, r, world)
+        q = pl.as_problem(v)
+        for k in ("owned_cells", "ghost_cells", "cells_global", "lin_cells", "vertex_ids", "face_global", "face_owner", "owned_face", "nbrs", "verts"):
+            assert np.array_equal(np.asarray(ref[k]), np.asarray(q[k])), k
+        for k in range(len(ref["nbrs"])):
+            assert np.array_equal(ref["send"][k], q["send"][k]) and np.array_equal(ref["recv"][k], q["recv"][k])
+        # sharedFaceList: every cut face of this rank once, with the rank and the cell on the other side
+        keys, other = P.shared_faces(c, part, r, 3)
+        sfl = pl.shared_face_list
+        assert sfl.shape[0] == keys.shape[0]
+        for F, orank, ocell in sfl:
+            cc = f2c[F]
+            assert part[ocell] == orank != r and ocell in cc and part[cc[0] if cc[1] == ocell else cc[1]] == r
+
+
+@pytest.mark.parametrize("dim,order", [(2, 3), (3, 1), (3, 3), (3, 4)])
+def test_host_cpp_canonical_positions_equal_numpy(dim, order):
+    v, c = meshgen.kuhn_linear(2, dim)
+    nodes, cells = meshgen.high_order(v, c, order)
+    tp = capi.host_compute_faces(dim, order, cells)
+    gv = np.full(nodes.shape[0], -1, dtype=np.int64)
+    gv[cells[:, :dim + 1]] = np.random.default_rng(3).permutation(v.shape[0])[c]     # arbitrary global vertex ids
+    assert np.array_equal(P.face_canonical_positions_c(dim, order, tp["faces"], gv), P.face_canonical_positions(dim, order, tp["faces"], gv))
+
+
+def test_plan_errors_are_reported():
+    v, c = meshgen.kuhn_linear(2, 3)
+    with pytest.raises(Exception, match="Partitioner"):
+        P.Plan(3, c, np.full(c.shape[0], 5, dtype=np.int32), 0, 2)
+    with pytest.raises(Exception, match="Partitioner"):
+        P.Plan(3, c, np.zeros(c.shape[0], dtype=np.int32), 1, 2)          # rank 1 owns nothing

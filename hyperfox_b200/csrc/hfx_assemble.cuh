@@ -386,6 +386,90 @@ __device__ __noinline__ void group_invert(double* b0, double* b1, int tid, int* 
   if (bad) atomicOr(flag, 1);
 }
 
+// ---- Gauss-Jordan inverse with 4x4 block pivots and tensor-core updates ----------------------------------------------------------------
+// In-place-form block Gauss-Jordan, ping-pong b0 -> b1 -> b0 ... (column-major, leading dimension ld, np a multiple of 4).  Step s, pivot rows /
+// columns K = [4s, 4s+4):  T = P^-1 src'[K, :],  dst = base - A' T  with the substitutions that make every entry of the inverse-so-far fall out of
+// the same product:  src'[K, K] = I,  A'[K, :] = -I (so the pivot rows become T),  A'[i, :] = src[i, K],  base = src outside the pivot rows / columns, 0 inside.
+// P^-1 comes from the adjugate: lane (lr, lc) forms the cofactor it needs as its DMMA operand, det(P) is a quad reduction, ONE reciprocal per four
+// pivots (the serial pivot chain, not the flops, is what an inverse costs: 18 barrier steps of ~700 cycles for the 2x2-block version at np = 36).
+// Warp w < ceil(np/8) owns the columns [8w, 8w+8) of every step: 1 + ceil(np/8) DMMAs per step.  Unpivoted, like group_invert; the callers refine U.
+// The inverse ends in ((np/4) odd ? b1 : b0).  Must be called by whole warps; warps >= ceil(np/8) return at once (the caller synchronises the CTA).
+template <int np, int ld>
+__device__ __noinline__ void block4_invert(double* b0, double* b1, int tid, int* flag, int barId) {
+  static_assert(np % 4 == 0, "4x4 pivot blocks");
+  constexpr int NS = np / 4, NCT = (np + 7) / 8;
+  const int warp = tid >> 5, lane = tid & 31, lr = lane >> 2, lc = lane & 3;
+  if (warp >= NCT) return;
+  const double* src = b0; double* dst = b1;
+  const double s00 = b0[0];
+  const double scale = (s00 * s00) * (s00 * s00);
+  bool bad = false;
+  // cofactor geometry of this lane: entry (r, c) = (lr & 3, lc) of P^-1 is (-1)^(r+c) det(P without row c and column r) / det P
+  const int r = lr & 3, c = lc;
+  const int R0 = c == 0 ? 1 : 0, R1 = c <= 1 ? 2 : 1, R2 = c <= 2 ? 3 : 2;      // rows of the minor
+  const int C0 = r == 0 ? 1 : 0, C1 = r <= 1 ? 2 : 1, C2 = r <= 2 ? 3 : 2;      // columns of the minor
+  const double sgn = ((r + c) & 1) ? -1.0 : 1.0;
+  const int n0 = warp * 8;
+  const int jb = imin(n0 + lr, np - 1);            // column this lane fetches for T (B fragment)
+#pragma unroll 1
+  for (int s = 0; s < NS; s++) {
+    const int k = 4 * s;
+    const double* P = src + k + ld * k;
+    const double m00 = P[R0 + ld * C0], m01 = P[R0 + ld * C1], m02 = P[R0 + ld * C2];
+    const double m10 = P[R1 + ld * C0], m11 = P[R1 + ld * C1], m12 = P[R1 + ld * C2];
+    const double m20 = P[R2 + ld * C0], m21 = P[R2 + ld * C1], m22 = P[R2 + ld * C2];
+    // det P from the 2x2 minors of its two row pairs (every lane, no shuffles: the chain is six dependent FP64 operations, and a dependent FP64
+    // operation costs ~40 cycles on this part)
+    double2 q0[4], q1[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { q0[j] = *reinterpret_cast<const double2*>(P + ld * j); q1[j] = *reinterpret_cast<const double2*>(P + ld * j + 2); }
+    // rows 0,1: a0j = q0[j].x, a1j = q0[j].y ; rows 2,3: a2j = q1[j].x, a3j = q1[j].y
+    const double s0 = fma(q0[0].x, q0[1].y, -q0[0].y * q0[1].x), s1 = fma(q0[0].x, q0[2].y, -q0[0].y * q0[2].x), s2 = fma(q0[0].x, q0[3].y, -q0[0].y * q0[3].x);
+    const double s3 = fma(q0[1].x, q0[2].y, -q0[1].y * q0[2].x), s4 = fma(q0[1].x, q0[3].y, -q0[1].y * q0[3].x), s5 = fma(q0[2].x, q0[3].y, -q0[2].y * q0[3].x);
+    const double c5 = fma(q1[2].x, q1[3].y, -q1[2].y * q1[3].x), c4 = fma(q1[1].x, q1[3].y, -q1[1].y * q1[3].x), c3 = fma(q1[1].x, q1[2].y, -q1[1].y * q1[2].x);
+    const double c2 = fma(q1[0].x, q1[3].y, -q1[0].y * q1[3].x), c1 = fma(q1[0].x, q1[2].y, -q1[0].y * q1[2].x), c0 = fma(q1[0].x, q1[1].y, -q1[0].y * q1[1].x);
+    const double det = fma(s0, c5, fma(-s1, c4, s2 * c3)) + fma(s3, c2, fma(-s4, c1, s5 * c0));
+    // operands that do not depend on P^-1 are fetched while the cofactor chain runs
+    const bool jInK = (unsigned)(jb - k) < 4u;
+    const double tsrc = jInK ? ((jb - k) == lc ? 1.0 : 0.0) : src[(k + lc) + ld * jb];
+    const double d0 = fma(m11, m22, -m12 * m21), d1 = fma(m10, m22, -m12 * m20), d2 = fma(m10, m21, -m11 * m20);
+    const double adj = sgn * fma(m00, d0, fma(-m01, d1, m02 * d2));
+    if (!(fabs(det) > 1e-56 * scale)) bad = true;
+    // one Newton step on the reciprocal seed (relative error ~1e-12): the callers refine U = -K^-1 R with one step of iterative refinement, which
+    // squares what an inexact K^-1 leaves behind
+    double rd;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd) : "d"(det));
+    rd = fma(fma(-det, rd, 1.0), rd, rd);
+    const double pinv = lr < 4 ? adj * rd : 0.0;
+    double t[2] = {0.0, 0.0};
+    dmma(t, pinv, tsrc);                           // T[lr][n0 + 2 lc + {0,1}], rows lr < 4
+    // T as the right operand of the update: B[kk = lc][n = lr] = T[lc][n0 + lr], held by lane 4 lc + (lr >> 1), component lr & 1
+    const int sl = 4 * lc + (lr >> 1);
+    const double t0 = __shfl_sync(0xffffffffu, t[0], sl), t1 = __shfl_sync(0xffffffffu, t[1], sl);
+    const double bt = (lr & 1) ? t1 : t0;
+#pragma unroll
+    for (int mt = 0; mt < NCT; mt++) {
+      const int i = mt * 8 + lr, ic = imin(i, np - 1);
+      const bool iInK = (unsigned)(i - k) < 4u;
+      const double a = iInK ? ((i - k) == lc ? 1.0 : 0.0) : -src[ic + ld * (k + lc)];      // -A'
+      double cc[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int j = n0 + 2 * lc + h, jc = imin(j, np - 1);
+        cc[h] = (iInK || (unsigned)(j - k) < 4u) ? 0.0 : src[ic + ld * jc];
+      }
+      dmma(cc, a, bt);
+      if (i < np) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) { const int j = n0 + 2 * lc + h; if (j < np) dst[i + ld * j] = cc[h]; }
+      }
+    }
+    bar_sync_named(barId, NCT * 32);
+    const double* tsw = dst; dst = const_cast<double*>(src); src = tsw;
+  }
+  if (bad) atomicOr(flag, 1);
+}
+
 __device__ __forceinline__ double det_only(const double (&J)[2][2]) { return J[0][0] * J[1][1] - J[0][1] * J[1][0]; }
 __device__ __forceinline__ double det_only(const double (&J)[3][3]) {
   const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2], c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
@@ -1429,7 +1513,9 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     //      A warp task = one column tile x every row tile: the right operand is fetched once per reduction step and feeds MTN
     //      independent accumulator chains (operand traffic, not the DMMA pipe, is what limits these skinny products).
     double* const KB = (W == Mm) ? Wb : Mm;          // the buffer that does not hold W (W is dead once A and B exist)
-    double* const KI = ((nNp / 2) & 1) ? KB : SUU;
+    constexpr bool kBlock4 = (TPE == kAsmThreads) && (nNp % 4 == 0) && (nNp >= 16);   // 4x4-block pivots with tensor-core updates (block4_invert)
+    const bool useB4 = kBlock4 && p.gjThreads != 512;
+    double* const KI = useB4 ? (((nNp / 4) & 1) ? KB : SUU) : (((nNp / 2) & 1) ? KB : SUU);
     double* const KC = W;                            // copy of K for the refinement step of U (P7r); the Gauss-Jordan consumes SUU and KB
     {
       const int lr = lane >> 2, lc = lane & 3;
@@ -1481,7 +1567,8 @@ __global__ void __launch_bounds__(kAsmThreads, 2) hdg_assemble_kernel(const AsmP
     HFX_PROF(9);
     // ---- P6: K^-1 (2x2-block-pivot Gauss-Jordan on all eight warps: the pivot chain is serial, measured variants that ran it on
     //      four warps or on one warp beside the R tiles were slower) ------------------------------------------------
-    group_invert<nNp, nNp, NT>(SUU, KB, tid, p.status, 1 + grp);
+    if (kBlock4 && useB4) { block4_invert<kBlock4 ? nNp : 4, nNp>(SUU, KB, tid, p.status, 1 + grp); gsync(); }
+    else group_invert<nNp, nNp, NT>(SUU, KB, tid, p.status, 1 + grp);
     HFX_PROF(10);
 
     // ---- P7: U = -K^-1 R ; U0 = K^-1 Fu (column l), then one step of iterative refinement, U <- U - K^-1 (K U + R).

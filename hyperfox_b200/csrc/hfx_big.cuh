@@ -453,9 +453,9 @@ __global__ void __launch_bounds__(kBigThreads, 1) hdg_big_kernel(const AsmParams
 
     // ---- PE: K^-1 (2x2-block-pivot Gauss-Jordan, all warps; the inverse ends in KA or KB) ------------------------------------------------------
     // (the pivot chain is serial and every thread redoes the pivot-block determinant / reciprocal: fewer threads = less redundant FP64 issue)
-    if (p.gjThreads == 256) { if (tid < 256) group_invert<npe, nNp, 256, false>(KA, KB, tid, p.status, 1); __syncthreads(); }
-    else group_invert<npe, nNp, NT, true>(KA, KB, tid, p.status, 1);
-    double* const KI = ((npe / 2) & 1) ? KB : KA;
+    double* KI;
+    if (p.gjThreads == 512) { group_invert<npe, nNp, NT, true>(KA, KB, tid, p.status, 1); KI = ((npe / 2) & 1) ? KB : KA; }   // (2x2-block pivots on CUDA cores: HFX_BIG_GJ=512)
+    else { block4_invert<npe, nNp>(KA, KB, tid, p.status, 1); __syncthreads(); KI = ((npe / 4) & 1) ? KB : KA; }               // 4x4-block pivots, tensor-core updates
     HFX_PROF(6);
 
     // ---- PF: U = -K^-1 R, one refinement step U -= K^-1 (K U + R) (see hfx_assemble.cuh P7); a warp owns (row tile, column tile) -------------------

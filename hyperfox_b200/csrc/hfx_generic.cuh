@@ -32,7 +32,9 @@ struct GenParams {
   int rkStage, rkNumStages;
   double rkRow[8];           // Butcher row of the current stage (a_s0 .. a_s,nStages-1)
   const double* oldSol; const double* oldFlux; const double* oldTrace;          // OldSolution / OldFlux (cell), OldTrace (face)
-  const double* rkSol[8]; const double* rkFlux[8]; const double* rkTrace[8];   // RKStage_k, RKStage_Flux_k (cell), RKStage_Trace_k (face)
+  const double* rkSol[8]; const double* rkFlux[8]; const double* rkTrace[8];   // RKStage_k, RKStage_Flux_k (cell), RKStage_Trace_k (face)  // per-element Model surface (FEModel::compute / getLocalMatrix / getLocalRHS, src/model/FEModel.h:43-78): build the local system of ONE element,
+  // write it out dense (column-major n x n, S_qq = M (x) I included) with its right-hand side, and stop before the condensation
+  int dumpElem; double* dumpA; double* dumpF;
 };
 
 // scratch layout (offsets in doubles), identical on host and device
@@ -214,7 +216,8 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
   __syncthreads();
 
   long long tprev = clock64();
-  for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
+  const bool dump = P.dumpA != nullptr;
+  for (int e = dump ? P.dumpElem : blockIdx.x; e < (dump ? P.dumpElem + 1 : p.nCells); e += gridDim.x) {
     // ---- gather (HDGSolver.cpp:231-326) ----------------------------------------------------------------------------------------
     const int* cell = p.cells + (size_t)e * nN;
     for (int i = tid; i < nN * dim; i += NT) X[i] = p.elemX[(size_t)e * nN * dim + i];
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
     // reference-to-physical mass matrix (Mass.cpp:5-38): read by the time schemes and, for curved elements, inverted for Sqq^-1 = M^-1 (x) I;
     // a straight-sided element without time scheme never reads it (Sqq itself is not stored: the condensation only needs W)
     const bool affW = affE && p.mhinv;
-    if (!affW || euler || p.timeScheme == 2) {
+    if (!affW || euler || p.timeScheme == 2 || dump) {
       const int lane = tid & 31, warp = tid >> 5, NWARP = NT / 32, MT = (nN + 7) / 8, NG = (nN + 23) / 24;
       for (int task = warp; task < MT * NG; task += NWARP) {
         mma_task_rt<3>(task % MT, (task / MT) * 3, lane, nN, nN, nIP,
@@ -608,6 +611,18 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
       __syncthreads();
     }
 
+    if (dump) {   // the local system as Model::compute leaves it (operators + time scheme), S_qq = M (x) I_{dim nDOF} (HDGBase.cpp:152)
+      const int sd = dim * nD;
+      for (int idx = tid; idx < n * n; idx += NT) {
+        const int c = idx / n, r = idx - c * n;
+        double v;
+        if (r >= sQ && r < sL && c >= sQ && c < sL) { const int rq = r - sQ, cq = c - sQ; v = (rq % sd) == (cq % sd) ? MM[(rq / sd) * nN + cq / sd] : 0.0; }
+        else v = Lm[idx];
+        P.dumpA[idx] = v;
+      }
+      for (int i = tid; i < n; i += NT) P.dumpF[i] = Fv[i];
+      return;
+    }
     HFX_GPROF(5);
     // ---- static condensation (HDGSolver.cpp:331-348) -------------------------------------------------------------------------------
     // W = M^-1: a straight-sided element has M = det J * M_ref (constant det J), so W = M_ref^-1 / det J comes from the reference table;

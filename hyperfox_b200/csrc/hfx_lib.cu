@@ -842,6 +842,7 @@ struct hfx_ctx {
   std::unique_ptr<RefElement> re;
   int dim = 0, order = 0, geom = HFX_SIMPLEX, nN = 0, nNf = 0, nFc = 0, nIP = 0, nIPf = 0;
   DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv, dSRef, dSRefT, dERef, dARef, dMFRef, dBRef, dBary;
+  DBuf<double> dDumpA, dDumpF;   // hfx_get_local_matrix
   DBuf<uint8_t> dAffine; long long nNonAffine = 0;   // cells that are not the affine image of the reference element (curved / multilinear)
   DBuf<int> dFaceNodes; DBuf<int8_t> dNodeInFace;
   // mesh
@@ -1494,7 +1495,7 @@ int hfx_allocate(hfx_ctx* c, int flags) {
 }
 
 // recoverMode: the element kernels are run again for hfx_recover (HFX_RECOMPUTE_RECOVERY): same inputs, nothing is written but Solution and Flux
-static int assemble_impl(hfx_ctx* c, bool recoverMode) {
+static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double* dumpA = nullptr, double* dumpF = nullptr) {
   return guard(c, [&] {
     HFX_CUDA(cudaSetDevice(c->device));
     need(c->allocated, "HDGSolver", "assemble", "the solver must be initialized and allocated before assembling.");
@@ -1537,6 +1538,7 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode) {
     p.faceNodes = c->dFaceNodes.p; p.nodeInFace = c->dNodeInFace.p; p.mhinv = c->dMHInv.p;
     p.sref = c->dSRef.p; p.srefT = c->dSRefT.p; p.eref = c->dERef.p; p.noRef = getenv("HFX_NO_REFPATH") ? 1 : 0; p.aref = c->dARef.p; p.mfref = c->dMFRef.p; p.bref = c->dBRef.p;
     p.affine = getenv("HFX_NO_AFFINE") ? nullptr : c->dAffine.p;
+    p.gjThreads = getenv("HFX_GJ") ? atoi(getenv("HFX_GJ")) : 0;   // experiments: 512 = the 2x2-block Gauss-Jordan on CUDA cores
     p.U = c->dU.p; p.Q = c->dQ.p; p.U0 = c->dU0.p; p.Q0 = c->dQ0.p; p.S = c->dS.p; p.S0 = c->dS0.p;
     p.vals = c->dVals.p; p.rhs = c->dRhs.p; p.status = c->dStatus.p;
     p.prof = c->profOn ? c->dProf.p : nullptr;
@@ -1550,9 +1552,10 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode) {
       }
       c->dRhs.zero(c->st); c->dStatus.zero(c->st);
     };
-    if (!recoverMode) clearSystem();
+    const bool dumpMode = dumpA != nullptr;
+    if (!recoverMode && !dumpMode) clearSystem();
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
-    bool fused = !recoverMode && c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
+    bool fused = !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
     // fields still crossing PCIe (hfx_field_set_async): the element chunks start as their face-id prefix has arrived
     std::vector<DField*> pend;
     for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) pend.push_back(&kv.second);
@@ -1577,10 +1580,9 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode) {
     }
     // 3-D order 4: the large-element kernel (one 512-thread CTA per SM, operands resident in shared memory) when every cell is straight-sided and D = c I
     bool big = false;
-    if (!fused && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA
+    if (!fused && !dumpMode && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA
         && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_BIG")) {
       if (!pend.empty()) waitPieces(0, -1);
-      p.gjThreads = getenv("HFX_BIG_GJ") ? atoi(getenv("HFX_BIG_GJ")) : 512;
       HFX_CUDA((launch_big<3, 4>(p, c->nSM, c->st)));
       big = true;
     }
@@ -1594,6 +1596,7 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode) {
     auto launchGeneric = [&](bool pivot) {   // general kernel: 3-D orders 4-5, nDOFsPerNode > 1, HDGUNabU, orthotopes; pivot: partial pivoting in K^-1
       GenParams g{};
       g.forcePivot = pivot ? 1 : 0;
+      g.dumpElem = dumpElem; g.dumpA = dumpA; g.dumpF = dumpF;
       g.a = p; g.dim = c->dim; g.nN = c->nN; g.nNf = c->nNf; g.nFc = c->nFc; g.nIP = c->nIP; g.nIPf = c->nIPf; g.nD = c->md.nDOF;
       g.nSrc = 1;
       g.frameV[0] = 0; g.frameV[1] = 1; g.frameV[2] = c->geom == HFX_SIMPLEX ? 2 : 3; g.frameV[3] = c->geom == HFX_SIMPLEX ? 3 : 4;
@@ -1639,13 +1642,14 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode) {
       if (perSM < 1) perSM = 1;
       if (perSM > 4) perSM = 4;
       long long grid = std::min<long long>((long long)c->nSM * perSM, c->nCells);
-      if (grid < 1) grid = 1;
+      if (grid < 1 || dumpMode) grid = 1;
       if (c->genGrid != grid || c->genStride != z.total) { c->dGenWs.alloc((size_t)grid * z.total); c->genGrid = (int)grid; c->genStride = z.total; }
       g.ws = c->dGenWs.p; g.wsStride = z.total;
       hdg_generic_kernel<<<(int)grid, kGenThreads, smem, c->st>>>(g);
       HFX_CUDA(cudaGetLastError());
     };
     if (!fused && !big) launchGeneric(getenv("HFX_FORCE_PIVOT") != nullptr);
+    if (dumpMode) { HFX_CUDA(cudaStreamSynchronize(c->st)); return; }
     c->lastKernel = fused ? 0 : (big ? 2 : 1);
     HFX_CUDA(cudaEventRecord(c->ev2, c->st));
     int status = 0;
@@ -1669,6 +1673,20 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode) {
 }
 
 int hfx_assemble(hfx_ctx* c) { return assemble_impl(c, false); }
+
+int hfx_get_local_matrix(hfx_ctx* c, int iEl, double* A, double* F) {
+  int rc = guard(c, [&] {
+    need(c->allocated, "FEModel", "compute", "the solver must be initialized and allocated before computing a local matrix.");
+    need(iEl >= 0 && iEl < c->nCells, "FEModel", "compute", "element index out of range");
+    need(A != nullptr && F != nullptr, "FEModel", "getLocalMatrix", "no storage for the local matrix / right-hand side");
+    const int nD = c->md.nDOF, n = c->nN * nD * (1 + c->dim) + c->nFc * c->nNf * nD;
+    c->dDumpA.alloc((size_t)n * n); c->dDumpF.alloc((size_t)n);
+  });
+  if (rc) return rc;
+  rc = assemble_impl(c, false, iEl, c->dDumpA.p, c->dDumpF.p);
+  if (rc) return rc;
+  return guard(c, [&] { c->dDumpA.download(A, c->dDumpA.n, c->st); c->dDumpF.download(F, c->dDumpF.n, c->st); });
+}
 
 int hfx_assemble_profile(hfx_ctx* c, long long* cycles16) {   // dev aid: per-phase clock64 deltas of CTA 0 (see hfx_assemble.cuh HFX_PROF)
   int rc = guard(c, [&] { HFX_CUDA(cudaSetDevice(c->device)); c->dProf.alloc(16); c->dProf.zero(c->st); c->profOn = true; });

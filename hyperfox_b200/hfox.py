@@ -265,6 +265,55 @@ class _HDGModel:
     def _mask(self, fieldNames, strict=True):
         return self.opmask
 
+    # ---- the per-element surface of the reference (src/model/FEModel.h:43-78): setElementNodes / setFieldMap(local values) / compute /
+    #      getLocalMatrix / getLocalRHS.  compute() runs the DEVICE operators on a one-element mesh (hfx_get_local_matrix: the general kernel's
+    #      dense local system before the condensation), so the reference's model tests (TestHDGLaplaceModel, TestHDGBase identities, ...) can
+    #      be run against what the GPU actually assembles.
+    def setElementNodes(self, nodes):
+        self.elementNodes = f64(np.asarray(nodes, dtype=np.float64))
+        if self.elementNodes.ndim != 2 or self.elementNodes.shape[0] != self.refEl.getNumNodes():
+            raise ErrorHandle("FEModel : setElementNodes : the number of nodes does not match the reference element")
+
+    def setFieldMap(self, fm):
+        """Element-local field values (std::map<std::string, std::vector<double>>): Tau [nFaces x nNodesPerFace x nDOF^2 (x 2 never: one side)],
+        DiffusionTensor [nNodes x (1 | dim^2)], Velocity [nNodes x dim], BufferSolution / Solution [nNodes x nDOF], Trace [nFaces x nNodesPerFace x nDOF]."""
+        if "Tau" not in fm:
+            raise ErrorHandle("HDGModel : setFieldMap : must provide a Tau field")
+        self.localFieldMap = {k: np.asarray(v, dtype=np.float64).ravel() for k, v in fm.items()}
+
+    def compute(self, device=0):
+        if not self.allocated:
+            raise ErrorHandle("FEModel : compute : the model must be allocated before computing")
+        if getattr(self, "elementNodes", None) is None:
+            raise ErrorHandle("FEModel : compute : the nodes have not been set")
+        if getattr(self, "localFieldMap", None) is None:
+            raise ErrorHandle("FEModel : compute : the field map has not been set")
+        re, nD, lf = self.refEl, self.nDOF, self.localFieldMap
+        dim, nN, nFc, nNf = re.getDimension(), re.getNumNodes(), re.getNumFaces(), re.getFaceElement().getNumNodes()
+        m = Mesh(dim, re.getOrder(), "simplex" if re._geom == 0 else "orthotope")
+        m.setMesh(self.elementNodes, np.arange(nN, dtype=np.int32)[None, :])
+        # the faces of a one-element mesh are its local faces, their node lists the element's face nodes: local field values map one to one
+        if not np.array_equal(m.cell2FaceMap[0], np.arange(nFc)) or not np.array_equal(m.faces, np.asarray(re.getFaceNodes())):
+            raise ErrorHandle("FEModel : compute : unexpected face numbering of the one-element mesh")
+        fm = {"Solution": Field(m, Cell, nN, nD), "Flux": Field(m, Cell, nN, nD * dim), "Trace": Field(m, Face, nNf, nD), "Dirichlet": Field(m, Face, nNf, nD)}
+        tau = lf["Tau"]
+        if tau.size != nFc * nNf * nD * nD:
+            raise ErrorHandle("HDGModel : setFieldMap : the Tau field does not have the right size")
+        fm["Tau"] = Field(m, Face, nNf, nD * nD); fm["Tau"].values[:] = tau
+        for name, ftype, nObj in (("DiffusionTensor", Node, 1), ("Velocity", Node, 1), ("BufferSolution", Cell, nN), ("Solution", Cell, nN), ("Trace", Face, nNf)):
+            if name in lf:
+                ents = {Node: nN, Cell: 1, Face: nFc}[ftype]
+                if lf[name].size % (ents * nObj) != 0:
+                    raise ErrorHandle("HDGModel : setFieldMap : the %s field does not have the right size" % name)
+                fm[name] = Field(m, ftype, nObj, lf[name].size // (ents * nObj)); fm[name].values[:] = lf[name]
+        s = HDGSolver(device=device)
+        s.setVerbosity(False); s.setMesh(m); s.setFieldMap(fm); s.setLinSystem(CudaLinAlgebraInterface(PetscOpts(), device=device))
+        s.setModel(self); s.setBoundaryModel(DirichletModel(re.getFaceElement())); s.initialize(); s.allocate()
+        self.localMatrix, self.localRHS = s.getLocalMatrix(0)
+
+    def getLocalMatrix(self): return self.localMatrix
+    def getLocalRHS(self): return self.localRHS
+
 
 class HDGLaplaceModel(_HDGModel):
     """Base + Diffusion(D = I) (src/model/HDGLaplaceModel.cpp:18-30)."""
@@ -657,6 +706,21 @@ class HDGSolver:
             out.update(S=np.zeros((nEl, l * l)), S0=np.zeros((nEl, l)))
         check(lib().hfx_get_local(self._h(), iEl, nEl, pd(out.get("S")), pd(out.get("S0")), pd(out["U"]), pd(out["U0"]), pd(out["Q"]), pd(out["Q0"])), self._h())
         return out
+
+    def getLocalMatrix(self, iEl):
+        """(A [n, n], F [n]): the dense local system of element iEl as Model::compute leaves it (operators + time scheme, before the condensation),
+        from the device (hfx_get_local_matrix).  Unknown order [u | q | lambda] as in the reference."""
+        if not (self.initialized and self.allocated):
+            raise ErrorHandle("HDGSolver : assemble : the solver must be initialized and allocated before assembling.")
+        for name in self._input_fields():
+            self._upload_field(name)
+        self._describe_model()
+        self._eval_callbacks()
+        re, nD = self.myMesh.getReferenceElement(), self.nDOFsPerNode
+        n = re.getNumNodes() * nD * (1 + self.myMesh.dim) + re.getNumFaces() * re.getFaceElement().getNumNodes() * nD
+        A = np.zeros((n, n)); F = np.zeros(n)
+        check(lib().hfx_get_local_matrix(self._h(), int(iEl), pd(A), pd(F)), self._h())
+        return np.ascontiguousarray(A.T), F          # the library writes column-major
 
     def getElemDofs(self):
         mesh, re = self.myMesh, self.myMesh.getReferenceElement()

@@ -179,6 +179,11 @@ int hfx_get_csr(hfx_ctx* ctx, long long* nrows, long long* nnz, long long* rowpt
    device; lets a test check the global system at sizes where hfx_get_csr is too large to bring back) */
 int hfx_residual(hfx_ctx* ctx, double* rnorm, double* bnorm);
 int hfx_get_local(hfx_ctx* ctx, int iEl, int nEl, double* S, double* S0, double* U, double* U0, double* Q, double* Q0);
+/* The per-element Model surface (FEModel::compute / getLocalMatrix / getLocalRHS, src/model/FEModel.h:43-78; Operator::assemble / getMatrix,
+   src/operator/Operator.h:27-41): the dense local system of element iEl as Model::compute leaves it -- operators + time scheme, BEFORE the static
+   condensation -- computed on the device by the general kernel.  A: n x n column-major, n = nN nDOF (1 + dim) + nFc nNf nDOF, unknown order
+   [u | q | lambda] as the reference (q index = (node * dim + d) * nDOF + dof); F: n.  Needs hfx_allocate; uses the current fields. */
+int hfx_get_local_matrix(hfx_ctx* ctx, int iEl, double* A, double* F);
 /* element -> global trace dof ids (matRowCols, HDGSolver.cpp:596) */
 int hfx_get_elem_dofs(hfx_ctx* ctx, int iEl, int nEl, int* dofs);
 

@@ -410,6 +410,7 @@ def main():
             extra = {"gmres_ms_per_iteration": t_it_max * 1e3, "gmres_ms_per_iteration_rank0": t_it * 1e3, "gmres_iterations_timed": i90 - i30,
                      "timing": "CUDA events around hfx_solve on the library stream, (90-iteration solve - 30-iteration solve) / 60, max over ranks",
                      "phases_ms_rank0": {"operator (SpMV + halo + Jacobi)": info.msPhase[0], "dots": info.msPhase[1], "reduce + all-reduce + Hessenberg step": info.msPhase[2], "Gram-Schmidt update": info.msPhase[3]},
+                     "transport": ("single GPU", "NCCL: ncclSend/Recv + ncclAllReduce", "NVLink peer memory (CUDA IPC): ghost blocks stored straight into the neighbours' buffers, one-shot all-reduce")[info.transport],
                      "all_reduces_per_iteration": (info.allReduces / max(i90, 1)) if world > 1 else 0,
                      "halo_exchanges_per_iteration": (info.haloExchanges / max(i90, 1)) if world > 1 else 0,
                      "halo_bytes_per_exchange_rank0": int(info.haloBytesPerExchange), "neighbours_rank0": int(info.nNeighbours),

@@ -31,7 +31,7 @@ class SolveStats(C.Structure):
 
 class SolveInfo(C.Structure):
     _fields_ = [("msPerIteration", C.c_float), ("allReduces", C.c_longlong), ("haloExchanges", C.c_longlong), ("haloBytesPerExchange", C.c_longlong),
-                ("ownedFaces", C.c_longlong), ("interiorFaces", C.c_longlong), ("boundaryFaces", C.c_longlong), ("nNeighbours", C.c_int), ("msPhase", C.c_float * 4)]
+                ("ownedFaces", C.c_longlong), ("interiorFaces", C.c_longlong), ("boundaryFaces", C.c_longlong), ("nNeighbours", C.c_int), ("msPhase", C.c_float * 4), ("transport", C.c_int)]
 
 
 # every symbol include/hfx.h declares (tests/test_capi_symbols.py checks the header against this list and the .so)

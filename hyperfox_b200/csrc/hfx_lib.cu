@@ -529,6 +529,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -543,6 +544,7 @@ struct NcclApi {
       auto sym = [&](const char* n) { void* p = dlsym(a.h, n); if (!p) throw Err("hfx", "comm", std::string("missing NCCL symbol ") + n); return p; };
       a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId"); a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
       a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy"); a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+      a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
       a.Send = (decltype(a.Send))sym("ncclSend"); a.Recv = (decltype(a.Recv))sym("ncclRecv");
       a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart"); a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
       a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
@@ -574,6 +576,29 @@ struct Halo {
   cudaStream_t stComm = nullptr;            // the exchange runs beside the interior rows
   cudaEvent_t evPack = nullptr, evHalo = nullptr;
   long long bytesPerExchangePerDof = 0;     // (send + recv faces) * 8: bytes per exchange = this * t
+  // ---- NVLink peer memory (one process per GPU: CUDA IPC).  Every rank exposes one buffer -- all-reduce slots + flags, halo flags, two receive
+  //      buffers -- and maps the buffers of all the others: ghost-face blocks are STORED straight into the owner-to-ghost slots of the neighbour and the
+  //      Gram-Schmidt dots are summed by a one-shot all-reduce (every rank writes its partial sums to every peer, then adds the slots in rank order), so
+  //      an iteration has no NCCL call on its critical path.  HFX_P2P=0 keeps the NCCL transport (ncclSend/Recv + ncclAllReduce).
+  bool p2p = false;
+  int tmaxP = 0;                            // doubles per face slot in the peer buffers
+  char* box = nullptr;                      // this rank's shared buffer (cudaMalloc + cudaIpcGetMemHandle)
+  size_t boxBytes = 0;
+  std::vector<char*> peerBox;               // [nRanks] mapped base addresses (own entry = box)
+  std::vector<long long> peerRecvFaces;     // [nRanks] receive faces of every rank (size of its receive buffers)
+  std::vector<long long> remoteOff;         // [nNbr] face offset of this rank's block inside neighbour k's receive buffer
+  DBuf<char*> dPeerBox;                     // device copy of peerBox
+  DBuf<int> dSendNbr;                       // [send faces] neighbour index of every send slot
+  DBuf<double*> dNbrRbuf;                   // [2][nNbr] remote receive buffer (parity, neighbour), already offset to this rank's block
+  DBuf<unsigned long long*> dNbrFlag;       // [nNbr] remote halo flag of this rank in neighbour k's box
+  DBuf<int> dNbrRank;                       // [nNbr]
+  DBuf<unsigned int> dTicket;               // last-block ticket of the push kernel
+  DBuf<int> dP2PStatus;                     // bit 0: a wait timed out
+  unsigned long long redEpoch = 0, haloEpoch = 0;
+  static constexpr int kRedMax = 40;        // doubles per all-reduce (restart + 2 <= 40)
+  size_t offRedFlag() const { return (size_t)2 * nRanks * kRedMax * sizeof(double); }
+  size_t offHaloFlag() const { return offRedFlag() + (size_t)2 * nRanks * sizeof(unsigned long long); }
+  size_t offRbuf() const { return (offHaloFlag() + (size_t)nRanks * sizeof(unsigned long long) + 255) & ~(size_t)255; }
 };
 
 // Blocks travel in a rank-independent node order: canon[F][a] = position of local face node a in the canonical order of face F (the
@@ -595,6 +620,108 @@ __global__ void halo_unpack_kernel(long long n, int nNf, int nD, const int* __re
   const long long slot = i / t; const int r = (int)(i % t), a = r / nD, k = r - a * nD, F = faces[slot];
   x[(size_t)F * t + r] = buf[slot * t + canon[(size_t)F * nNf + a] * nD + k];
 }
+// ---- peer-memory transport ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+constexpr unsigned long long kP2PTimeoutNs = 20ull * 1000ull * 1000ull * 1000ull;   // a peer that never arrives: give up instead of hanging the GPU
+
+// Ghost-face blocks straight into the neighbours' receive buffers (canonical node order), then -- by the last block to finish -- this rank's halo flag in
+// every neighbour's box.  rbuf[k]: neighbour k's receive buffer of this exchange's parity, already offset to this rank's block.
+__global__ void halo_push_kernel(long long n, int nNf, int nD, int tmax, const int* __restrict__ faces, const int* __restrict__ slotNbr, const int* __restrict__ nbrStart,
+                                 const uint8_t* __restrict__ canon, const double* __restrict__ x, double* const* __restrict__ rbuf, unsigned long long* const* __restrict__ flag,
+                                 int nNbr, unsigned long long epoch, unsigned int* ticket) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = nNf * nD;
+  if (i < n) {
+    const long long slot = i / t; const int r = (int)(i % t), a = r / nD, k = r - a * nD, F = faces[slot], nb = slotNbr[slot];
+    rbuf[nb][(slot - nbrStart[nb]) * tmax + canon[(size_t)F * nNf + a] * nD + k] = x[(size_t)F * t + r];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    __threadfence_system();
+    if (threadIdx.x < nNbr) st_release_sys(flag[threadIdx.x], epoch);
+    if (threadIdx.x == 0) *ticket = 0;
+  }
+}
+// wait for the blocks of all neighbours of this exchange, then scatter them into the ghost rows of x
+__global__ void halo_pull_kernel(long long n, int nNf, int nD, int tmax, const int* __restrict__ faces, const uint8_t* __restrict__ canon, const double* __restrict__ buf,
+                                 double* __restrict__ x, const unsigned long long* __restrict__ myFlags, const int* __restrict__ nbrRank, int nNbr, unsigned long long epoch, int* status) {
+  if (threadIdx.x < nNbr) {
+    const unsigned long long* f = myFlags + nbrRank[threadIdx.x];
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < epoch) { if (global_ns() - t0 > kP2PTimeoutNs) { atomicOr(status, 1); break; } }
+  }
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int t = nNf * nD;
+  const long long slot = i / t; const int r = (int)(i % t), a = r / nD, k = r - a * nD, F = faces[slot];
+  x[(size_t)F * t + r] = buf[slot * tmax + canon[(size_t)F * nNf + a] * nD + k];
+}
+// One-shot all-reduce (sum) of cnt <= kRedMax doubles over all ranks: this rank's values go to slot [parity][rank] of EVERY box, a flag per writer says the
+// slot is complete, and every rank adds the slots in rank order (the same order everywhere: bitwise identical results, which the device-side
+// convergence logic of the Krylov solver relies on).  One block of max(cnt, nRanks) <= 64 threads.
+__global__ void p2p_allreduce_kernel(double* red, int cnt, char* const* __restrict__ boxes, int nRanks, int rank, size_t offFlag, unsigned long long epoch, int* status) {
+  const int par = (int)(epoch & 1ull), j = threadIdx.x;
+  const double v = j < cnt ? red[j] : 0.0;
+  if (j < cnt) for (int r = 0; r < nRanks; r++) reinterpret_cast<double*>(boxes[r])[((size_t)par * nRanks + rank) * Halo::kRedMax + j] = v;
+  __threadfence_system();
+  __syncthreads();
+  if (j < nRanks) st_release_sys(reinterpret_cast<unsigned long long*>(boxes[j] + offFlag) + (size_t)par * nRanks + rank, epoch);
+  if (j < nRanks) {
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(boxes[rank] + offFlag) + (size_t)par * nRanks + j;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < epoch) { if (global_ns() - t0 > kP2PTimeoutNs) { atomicOr(status, 1); break; } }
+  }
+  __syncthreads();
+  if (j < cnt) {
+    const double* slots = reinterpret_cast<const double*>(boxes[rank]) + (size_t)par * nRanks * Halo::kRedMax;
+    double s2 = 0.0;
+    for (int r = 0; r < nRanks; r++) s2 += slots[(size_t)r * Halo::kRedMax + j];
+    red[j] = s2;
+  }
+}
+
+// The per-iteration reduction of the distributed Krylov solver in ONE launch: warp j sums row j of the partial dot products (fixed order), the sums go to
+// every peer's slot, and the slots are added in rank order (see p2p_allreduce_kernel).  nvals = nv + 1 <= 32 rows: <z, V_j> (j < nv) and ||.||^2 (row nv).
+__global__ void __launch_bounds__(1024) p2p_reduce_allreduce_kernel(int nv, int nb, const double* __restrict__ partial, const double* __restrict__ npart, double* red,
+                                                                    char* const* __restrict__ boxes, int nRanks, int rank, size_t offFlag, unsigned long long epoch, int* status) {
+  const int par = (int)(epoch & 1ull), j = threadIdx.x >> 5, lane = threadIdx.x & 31, nvals = nv + 1;
+  if (j < nvals) {
+    const double* src = j < nv ? partial + (size_t)j * nb : npart;
+    double s2 = 0.0;
+    for (int i = lane; i < nb; i += 32) s2 += src[i];
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    for (int r = lane; r < nRanks; r += 32) reinterpret_cast<double*>(boxes[r])[((size_t)par * nRanks + rank) * Halo::kRedMax + j] = s2;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < nRanks) {
+    st_release_sys(reinterpret_cast<unsigned long long*>(boxes[threadIdx.x] + offFlag) + (size_t)par * nRanks + rank, epoch);
+    const unsigned long long* f = reinterpret_cast<const unsigned long long*>(boxes[rank] + offFlag) + (size_t)par * nRanks + threadIdx.x;
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(f) < epoch) { if (global_ns() - t0 > kP2PTimeoutNs) { atomicOr(status, 1); break; } }
+  }
+  __syncthreads();
+  if (threadIdx.x < nvals) {
+    const double* slots = reinterpret_cast<const double*>(boxes[rank]) + (size_t)par * nRanks * Halo::kRedMax;
+    double s2 = 0.0;
+    for (int r = 0; r < nRanks; r++) s2 += slots[(size_t)r * Halo::kRedMax + threadIdx.x];
+    red[threadIdx.x] = s2;
+  }
+}
+
 __global__ void mask_rows_kernel(long long n, int t, const uint8_t* __restrict__ owned, const double* __restrict__ src, double* __restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = owned[i / t] ? src[i] : 0.0;
@@ -611,6 +738,25 @@ inline void halo_begin(Halo& H, int nNf, int nD, double* x, cudaStream_t st) {
   NcclApi& N = NcclApi::get();
   const int t = nNf * nD;
   const long long ns = (long long)H.sendOff.back() * t, nr = (long long)H.recvOff.back() * t;
+  if (H.p2p) {
+    const unsigned long long ep = ++H.haloEpoch;
+    const int par = (int)(ep & 1ull), nNbr = (int)H.nbr.size();
+    if (nNbr) {
+      const long long nsg = std::max<long long>(ns, 1);
+      halo_push_kernel<<<nblk(nsg, 256), 256, 0, st>>>(ns, nNf, nD, H.tmaxP, H.dSend.p, H.dSendNbr.p, H.dNbrRank.p + nNbr, H.dCanon.p, x, H.dNbrRbuf.p + (size_t)par * nNbr,
+                                                     H.dNbrFlag.p, nNbr, ep, H.dTicket.p);
+    }
+    HFX_CUDA(cudaEventRecord(H.evPack, st));
+    HFX_CUDA(cudaStreamWaitEvent(H.stComm, H.evPack, 0));
+    if (nNbr) {
+      const double* rb = reinterpret_cast<const double*>(H.box + H.offRbuf()) + (size_t)par * H.recvOff.back() * H.tmaxP;
+      const long long nrg = std::max<long long>(nr, 1);
+      halo_pull_kernel<<<nblk(nrg, 256), 256, 0, H.stComm>>>(nr, nNf, nD, H.tmaxP, H.dRecv.p, H.dCanon.p, rb, x, reinterpret_cast<const unsigned long long*>(H.box + H.offHaloFlag()),
+                                                            H.dNbrRank.p, nNbr, ep, H.dP2PStatus.p);
+    }
+    HFX_CUDA(cudaEventRecord(H.evHalo, H.stComm));
+    return;
+  }
   if (ns) halo_pack_kernel<<<nblk(ns, 256), 256, 0, st>>>(ns, nNf, nD, H.dSend.p, H.dCanon.p, x, H.sbuf.p);
   HFX_CUDA(cudaEventRecord(H.evPack, st));
   HFX_CUDA(cudaStreamWaitEvent(H.stComm, H.evPack, 0));
@@ -706,7 +852,23 @@ struct Krylov {
     HFX_CUDA(cudaMemsetAsync(w.p, 0, n * sizeof(double), st));
     HFX_CUDA(cudaMemsetAsync(tmp.p, 0, n * sizeof(double), st));
     const int* done = &state.p->done;
-    auto all_reduce = [&](int cnt) { if (dist) { HFX_NCCL(NcclApi::get().AllReduce(red.p, red.p, cnt, ncclDouble, ncclSum, halo->comm, st)); allReduces++; } };
+    auto all_reduce = [&](int cnt) {
+      if (!dist) return;
+      if (halo->p2p && cnt <= Halo::kRedMax) {
+        const unsigned long long ep = ++halo->redEpoch;
+        p2p_allreduce_kernel<<<1, 64, 0, st>>>(red.p, cnt, halo->dPeerBox.p, halo->nRanks, halo->rank, halo->offRedFlag(), ep, halo->dP2PStatus.p);
+      } else HFX_NCCL(NcclApi::get().AllReduce(red.p, red.p, cnt, ncclDouble, ncclSum, halo->comm, st));
+      allReduces++;
+    };
+    // red[0..nv] = the nv dot products and the squared norm, summed over the block partials and over the ranks: one fused launch over peer memory, or
+    // the reduction kernel followed by ncclAllReduce
+    auto reduce_all = [&](int nv) {
+      if (dist && halo->p2p) {
+        const unsigned long long ep = ++halo->redEpoch;
+        p2p_reduce_allreduce_kernel<<<1, 1024, 0, st>>>(nv, kDotBlocks, partial.p, npart.p, red.p, halo->dPeerBox.p, halo->nRanks, halo->rank, halo->offRedFlag(), ep, halo->dP2PStatus.p);
+        allReduces++;
+      } else { kry_reduce_kernel<<<nv + 1, 256, 0, st>>>(nv, kDotBlocks, partial.p, npart.p, red.p, done); all_reduce(nv + 1); }
+    };
     // z = M^-1 A v: point Jacobi inside the SpMV; face-block Jacobi as its own pass
     auto op = [&](double* v, double* zv) {
       if (blockPC) { A.apply(v, tmp.p, nullptr, done, st); A.block_pc_apply(tmp.p, nullptr, zv, st); }
@@ -742,8 +904,7 @@ struct Krylov {
         HFX_CUDA(cudaEventRecord(evPh[k][1], st));
         dots_dev(n, k + 1, V.p, ldv, w.p, partial.p, done, st);
         HFX_CUDA(cudaEventRecord(evPh[k][2], st));
-        kry_reduce_kernel<<<k + 2, 256, 0, st>>>(k + 1, kDotBlocks, partial.p, npart.p, red.p, done);
-        all_reduce(k + 2);
+        reduce_all(k + 1);
         kry_step_kernel<<<1, 32, 0, st>>>(state.p, k, k + 1, 0, red.p);
         HFX_CUDA(cudaEventRecord(evPh[k][3], st));
         lincomb_dev(n, k + 1, V.p, ldv, w.p, state.p->c, -1.0, V.p + (size_t)(k + 1) * ldv, mask, npart.p, done, st);
@@ -754,8 +915,7 @@ struct Krylov {
         }
       }
       // tail: close the last column (needs ||V_mm||), solve the small triangular system, update x
-      kry_reduce_kernel<<<1, 256, 0, st>>>(0, kDotBlocks, partial.p, npart.p, red.p, done);
-      all_reduce(1);
+      reduce_all(0);
       kry_step_kernel<<<1, 32, 0, st>>>(state.p, k, 0, 1, red.p);
       kry_backsolve_kernel<<<1, 32, 0, st>>>(state.p);
       lincomb_dev(n, m, V.p, ldv, x, state.p->c, 1.0, x, nullptr, nullptr, nullptr, st);
@@ -1042,6 +1202,8 @@ int hfx_ctx_destroy(hfx_ctx* c) {
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->ev2) cudaEventDestroy(c->ev2);
+  for (int r = 0; r < (int)c->halo.peerBox.size(); r++) if (c->halo.peerBox[(size_t)r] && r != c->halo.rank) cudaIpcCloseMemHandle(c->halo.peerBox[(size_t)r]);
+  if (c->halo.box) { cudaFree(c->halo.box); c->halo.box = nullptr; }
   if (c->halo.comm) { try { NcclApi::get().CommDestroy(c->halo.comm); } catch (...) {} c->halo.comm = nullptr; }
   if (c->halo.stComm) { cudaStreamSynchronize(c->halo.stComm); cudaStreamDestroy(c->halo.stComm); cudaEventDestroy(c->halo.evPack); cudaEventDestroy(c->halo.evHalo); }
   cudaStream_t st = c->st;
@@ -1747,6 +1909,11 @@ int hfx_solve(hfx_ctx* c, const hfx_solve_opts* opts, hfx_solve_stats* stats) {
     }
     c->krylov.allReduces = 0; c->krylov.haloExchanges = 0;
     c->krylov.solve(A, b, x, o, stats, c->st);
+    if (dist && c->halo.p2p) {   // a peer that never arrived (the wait kernels give up after 20 s instead of hanging the device)
+      int pst = 0;
+      c->halo.dP2PStatus.download(&pst, 1, c->st);
+      need(!(pst & 1), "Partitioner", "updateSharedInformation", "timed out waiting for a neighbour's trace blocks or partial sums over NVLink peer memory");
+    }
     if (dist) { halo_exchange(c->halo, c->nNf, c->md.nDOF, x, c->st); HFX_CUDA(cudaStreamSynchronize(c->st)); }   // recovery needs the ghost traces (HDGSolver.cpp:730-732)
   });
   if (rc) return rc;
@@ -1763,6 +1930,7 @@ int hfx_solve_info(const hfx_ctx* c, hfx_solve_info_t* info) {
   info->ownedFaces = H.planned ? H.nOwnedFaces : c->nFaces;
   info->interiorFaces = H.planned ? H.nInterior : c->nFaces; info->boundaryFaces = H.planned ? H.nBoundary : 0;
   info->nNeighbours = H.planned ? (int)H.nbr.size() : 0;
+  info->transport = H.planned ? (H.p2p ? 2 : 1) : 0;
   for (int ph = 0; ph < 4; ph++) info->msPhase[ph] = c->krylov.phaseIts > 0 ? c->krylov.msPhase[ph] / (float)c->krylov.phaseIts : 0.f;
   return 0;
 }
@@ -1807,6 +1975,86 @@ int hfx_comm_init(hfx_ctx* c, int nRanks, int rank, const char* id128) {
   });
 }
 
+// Maps every rank's shared buffer into this process (CUDA IPC) and derives the remote addresses the halo push needs.  Collective.  Falls back to the
+// NCCL transport (H.p2p = false) when HFX_P2P=0, when there are more than 64 ranks, or when a peer cannot be mapped (no NVLink / PCIe peer access).
+static void setup_peer_memory(hfx_ctx* c) {
+  Halo& H = c->halo;
+  H.p2p = false;
+  if (!H.comm || H.nRanks < 2) return;
+  NcclApi& N = NcclApi::get();
+  const int W = H.nRanks, nNbr = (int)H.nbr.size();
+  struct Rec { cudaIpcMemHandle_t h; long long nRecv; int want; int off[64]; };
+  Rec mine{};
+  const bool want = !(getenv("HFX_P2P") && atoi(getenv("HFX_P2P")) == 0) && W <= 64;
+  mine.want = want ? 1 : 0;
+  H.tmaxP = c->nNf * 3;
+  mine.nRecv = H.recvOff.back();
+  for (int r = 0; r < 64; r++) mine.off[r] = -1;
+  for (int k = 0; k < nNbr; k++) mine.off[H.nbr[k]] = H.recvOff[k];
+  // (re)allocate the box: sizes depend on the plan
+  for (int r = 0; r < (int)H.peerBox.size(); r++) if (H.peerBox[r] && r != H.rank) cudaIpcCloseMemHandle(H.peerBox[r]);
+  H.peerBox.clear();
+  if (H.box) { cudaFree(H.box); H.box = nullptr; }
+  H.boxBytes = H.offRbuf() + (size_t)2 * std::max<long long>(1, mine.nRecv) * H.tmaxP * sizeof(double);
+  HFX_CUDA(cudaMalloc(&H.box, H.boxBytes));
+  HFX_CUDA(cudaMemset(H.box, 0, H.boxBytes));
+  H.redEpoch = 0; H.haloEpoch = 0;
+  if (want && cudaIpcGetMemHandle(&mine.h, H.box) != cudaSuccess) { cudaGetLastError(); mine.want = 0; }
+  DBuf<char> dMine, dAll;
+  dMine.upload(reinterpret_cast<const char*>(&mine), sizeof(Rec), c->st);
+  dAll.alloc(sizeof(Rec) * (size_t)W);
+  HFX_NCCL(N.AllGather(dMine.p, dAll.p, sizeof(Rec), ncclChar, H.comm, c->st));
+  std::vector<Rec> all((size_t)W);
+  dAll.download(reinterpret_cast<char*>(all.data()), sizeof(Rec) * (size_t)W, c->st);
+  bool ok = true;
+  for (int r = 0; r < W; r++) ok = ok && all[(size_t)r].want;
+  H.peerBox.assign((size_t)W, nullptr);
+  H.peerRecvFaces.assign((size_t)W, 0);
+  if (ok) {
+    for (int r = 0; r < W && ok; r++) {
+      H.peerRecvFaces[(size_t)r] = all[(size_t)r].nRecv;
+      if (r == H.rank) { H.peerBox[(size_t)r] = H.box; continue; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      H.peerBox[(size_t)r] = static_cast<char*>(ptr);
+    }
+  }
+  // every rank must take the same decision: agree through one more gather of the outcome
+  int myOk = ok ? 1 : 0;
+  DBuf<char> dOk, dOks;
+  dOk.upload(reinterpret_cast<const char*>(&myOk), sizeof(int), c->st);
+  dOks.alloc(sizeof(int) * (size_t)W);
+  HFX_NCCL(N.AllGather(dOk.p, dOks.p, sizeof(int), ncclChar, H.comm, c->st));
+  std::vector<int> oks((size_t)W);
+  dOks.download(reinterpret_cast<char*>(oks.data()), sizeof(int) * (size_t)W, c->st);
+  for (int r = 0; r < W; r++) ok = ok && oks[(size_t)r];
+  if (!ok) {
+    for (int r = 0; r < W; r++) if (H.peerBox[(size_t)r] && r != H.rank) cudaIpcCloseMemHandle(H.peerBox[(size_t)r]);
+    H.peerBox.clear();
+    return;
+  }
+  H.dPeerBox.upload(H.peerBox, c->st);
+  // remote addresses of this rank's blocks: neighbour k keeps them at face offset off_k[rank] of its receive buffers
+  std::vector<double*> rb((size_t)2 * std::max(1, nNbr), nullptr);
+  std::vector<unsigned long long*> fl((size_t)std::max(1, nNbr), nullptr);
+  std::vector<int> nbrInfo((size_t)2 * std::max(1, nNbr), 0), slotNbr((size_t)std::max(1, H.sendOff.back()), 0);
+  for (int k = 0; k < nNbr; k++) {
+    const int r = H.nbr[k];
+    const int off = all[(size_t)r].off[H.rank];
+    if ((H.sendOff[k + 1] - H.sendOff[k]) > 0 && off < 0) throw Err("Partitioner", "computeSharedFaces", "a neighbour does not expect the faces this rank sends");
+    char* base = H.peerBox[(size_t)r] + H.offRbuf();
+    for (int par = 0; par < 2; par++)
+      rb[(size_t)par * nNbr + k] = reinterpret_cast<double*>(base) + ((size_t)par * all[(size_t)r].nRecv + (size_t)std::max(off, 0)) * H.tmaxP;
+    fl[(size_t)k] = reinterpret_cast<unsigned long long*>(H.peerBox[(size_t)r] + H.offHaloFlag()) + H.rank;
+    nbrInfo[(size_t)k] = r; nbrInfo[(size_t)nNbr + k] = H.sendOff[k];
+    for (int i2 = H.sendOff[k]; i2 < H.sendOff[k + 1]; i2++) slotNbr[(size_t)i2] = k;
+  }
+  H.dNbrRbuf.upload(rb, c->st); H.dNbrFlag.upload(fl, c->st); H.dNbrRank.upload(nbrInfo, c->st); H.dSendNbr.upload(slotNbr, c->st);
+  H.dTicket.alloc(1); H.dTicket.zero(c->st); H.dP2PStatus.alloc(1); H.dP2PStatus.zero(c->st);
+  HFX_CUDA(cudaStreamSynchronize(c->st));
+  H.p2p = true;
+}
+
 int hfx_comm_set_halo(hfx_ctx* c, int nNbr, const int* nbrRank, const int* sendCount, const int* sendFaces, const int* recvCount, const int* recvFaces,
                       const unsigned char* ownedFace, const unsigned char* canonPos) {
   return guard(c, [&] {
@@ -1845,6 +2093,7 @@ int hfx_comm_set_halo(hfx_ctx* c, int nNbr, const int* nbrRank, const int* sendC
     H.bytesPerExchangePerDof = 8LL * ((long long)H.sendOff.back() + H.recvOff.back());
     HFX_CUDA(cudaStreamSynchronize(c->st));
     H.planned = true;
+    setup_peer_memory(c);   // collective over the communicator (every rank calls hfx_comm_set_halo)
   });
 }
 

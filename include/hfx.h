@@ -120,7 +120,9 @@ int hfx_recover(hfx_ctx* ctx);                                                  
 /* what the last hfx_solve cost: device time per Krylov iteration (CUDA events around the whole solve / iterations), and on several GPUs the
    collectives it issued (replaces the MPI_Allreduce / VecScatter counts of KSPSolve's -log_view) */
 typedef struct { float msPerIteration; long long allReduces, haloExchanges, haloBytesPerExchange, ownedFaces, interiorFaces, boundaryFaces; int nNeighbours;
-                 float msPhase[4]; /* mean ms per iteration: operator (SpMV + halo + preconditioner), dots, reduction (+ all-reduce) + Hessenberg step, Gram-Schmidt update */ } hfx_solve_info_t;
+                 float msPhase[4]; /* mean ms per iteration: operator (SpMV + halo + preconditioner), dots, reduction (+ all-reduce) + Hessenberg step, Gram-Schmidt update */
+                 int transport;    /* 0 single GPU, 1 NCCL (ncclSend/Recv + ncclAllReduce), 2 NVLink peer memory (CUDA IPC: direct stores into the neighbours' ghost
+                                      buffers + one-shot all-reduce; HFX_P2P=0 selects 1) */ } hfx_solve_info_t;
 int hfx_solve_info(const hfx_ctx* ctx, hfx_solve_info_t* info);
 int hfx_sync(hfx_ctx* ctx);
 /* timing of the last hfx_assemble (CUDA events on the library's stream), milliseconds */

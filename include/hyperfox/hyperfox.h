@@ -773,9 +773,103 @@ class HDGModel : public FEModel {
   const ScalarFunction& reactionFunction() const { return reaction; }
   int getNumDOFsPerNode() const { return nDOFsPNode; }
 
+  // ---- the per-element surface of the reference (src/model/FEModel.h:43-78) ------------------------------------------------------------------
+  // compute() runs the DEVICE operators on a one-element mesh (hfx_get_local_matrix: the general kernel's dense local system before the
+  // condensation), so the reference's model tests run against what the GPU assembles.  Field values are element-local, as the reference hands them
+  // to a Model: Tau [nFaces x nNodesPerFace x nDOF^2], DiffusionTensor [nNodes x (1 | dim^2)], Velocity [nNodes x dim], BufferSolution / Solution
+  // [nNodes x nDOF], Trace [nFaces x nNodesPerFace x nDOF].  Runge-Kutta models need the solver's stage fields and are served by HDGSolver only.
+  struct LocalMatrix {
+    int n = 0; std::vector<double> a;   // column-major n x n, unknown order [u | q | lambda]
+    double operator()(int i, int j) const { return a[(size_t)i + (size_t)n * j]; }
+    int rows() const { return n; } int cols() const { return n; }
+  };
+  void setElementNodes(const std::vector<std::vector<double> >* ns) {
+    if (!ns || (int)ns->size() != refEl->getNumNodes()) throw ErrorHandle("FEModel", "setElementNodes", "the number of nodes does not match the reference element");
+    elementNodes = ns;
+  }
+  virtual void setFieldMap(const std::map<std::string, std::vector<double> >* fm) {
+    if (!fm || !fm->count("Tau")) throw ErrorHandle("HDGModel", "setFieldMap", "must provide a Tau field");
+    localFieldMap = fm;
+  }
+  void setDevice(int d) { device = d; }
+  virtual void compute() {
+    if (!allocated) throw ErrorHandle("FEModel", "compute", "the model must be allocated before computing");
+    if (!elementNodes) throw ErrorHandle("FEModel", "compute", "the nodes have not been set");
+    if (!localFieldMap) throw ErrorHandle("FEModel", "compute", "the field map has not been set");
+    if (timeScheme && timeScheme->cKind() != HFX_TS_EULER_IMPLICIT) throw ErrorHandle("FEModel", "compute", "a Runge-Kutta model needs the stage fields of the solver: use HDGSolver");
+    const int dim = refEl->getDimension(), nN = refEl->getNumNodes(), nFc = refEl->getNumFaces(), nNf = refEl->getFaceElement()->getNumNodes(), nD = nDOFsPNode;
+    const int dsp = (int)(*elementNodes)[0].size();
+    struct Ctx { hfx_ctx* h = nullptr; ~Ctx() { if (h) hfx_ctx_destroy(h); } } C;
+    detail::check(hfx_ctx_create(device, &C.h), nullptr);
+    hfx_ctx* h = C.h;
+    std::vector<double> pts((size_t)nN * dsp);
+    for (int i = 0; i < nN; i++) for (int d = 0; d < dsp; d++) pts[(size_t)i * dsp + d] = (*elementNodes)[i][d];
+    std::vector<int> cell(nN);
+    for (int i = 0; i < nN; i++) cell[i] = i;
+    detail::check(hfx_refel_set(h, dim, refEl->getOrder(), refEl->getGeometry() == simplex ? HFX_SIMPLEX : HFX_ORTHOTOPE), h);
+    detail::check(hfx_mesh_set(h, nN, pts.data(), 1, cell.data()), h);
+    // the faces of a one-element mesh are its local faces and their node lists the element's face nodes: local values map one to one
+    const std::map<std::string, std::vector<double> >& lf = *localFieldMap;
+    std::set<std::string> names;
+    auto put = [&](const char* name, int type, int ents, int nObj, int nValsDefault) {
+      std::map<std::string, std::vector<double> >::const_iterator it = lf.find(name);
+      std::vector<double> zeros;
+      const std::vector<double>* v = nullptr;
+      int nVals = nValsDefault;
+      if (it != lf.end()) {
+        v = &it->second;
+        if (v->size() % ((size_t)ents * nObj) != 0) throw ErrorHandle("HDGModel", "setFieldMap", std::string("the ") + name + " field does not have the right size");
+        nVals = (int)(v->size() / ((size_t)ents * nObj));
+        names.insert(name);
+      } else if (nValsDefault > 0) { zeros.assign((size_t)ents * nObj * nValsDefault, 0.0); v = &zeros; }
+      if (v) detail::check(hfx_field_set(h, name, type, nObj, nVals, v->data(), 0), h);
+    };
+    if (lf.at("Tau").size() != (size_t)nFc * nNf * nD * nD) throw ErrorHandle("HDGModel", "setFieldMap", "the Tau field does not have the right size");
+    put("Tau", Face, nFc, nNf, nD * nD);
+    put("Dirichlet", Face, nFc, nNf, nD);
+    put("Trace", Face, nFc, nNf, nD);
+    put("Solution", Cell, 1, nN, nD);
+    put("Flux", Cell, 1, nN, nD * dim);
+    if (usesDiffusionField()) put("DiffusionTensor", Node, nN, 1, 0);
+    put("Velocity", Node, nN, 1, 0);
+    put("BufferSolution", Cell, 1, nN, 0);
+    hfx_model_desc md;
+    md.nDOF = nD; md.opmask = opmask(names, true);
+    md.timeScheme = timeScheme ? timeScheme->cKind() : HFX_TS_NONE; md.dt = timeScheme ? timeScheme->getTimeStep() : 0.0;
+    detail::check(hfx_model_describe(h, &md), h);
+    static const int none = 0;
+    detail::check(hfx_boundary_describe(h, 0, 0, &none), h);
+    detail::check(hfx_allocate(h, 0), h);
+    if (md.opmask & (HFX_OP_SOURCE | HFX_OP_REACTION)) {
+      const int nIP = refEl->getNumIPs();
+      std::vector<double> xip((size_t)nIP * dsp), pt(dsp);
+      detail::check(hfx_ip_coords(h, xip.data()), h);
+      evalLocalCallbacks(h, md.opmask, xip, nIP, dsp);
+    }
+    const int n = nN * nD * (1 + dim) + nFc * nNf * nD;
+    localMatrix.n = n; localMatrix.a.assign((size_t)n * n, 0.0); localRHS.assign((size_t)n, 0.0);
+    detail::check(hfx_get_local_matrix(h, 0, localMatrix.a.data(), localRHS.data()), h);
+  }
+  virtual const LocalMatrix* getLocalMatrix() const { return &localMatrix; }
+  virtual const std::vector<double>* getLocalRHS() const { return &localRHS; }
+
  protected:
-  int nDOFsPNode = 1;
+  virtual void evalLocalCallbacks(hfx_ctx* h, int mask, const std::vector<double>& xip, int nIP, int d) {
+    std::vector<double> v((size_t)nIP), pt(d);
+    for (int pass = 0; pass < 2; pass++) {
+      const bool src = pass == 0;
+      if (!(mask & (src ? HFX_OP_SOURCE : HFX_OP_REACTION))) continue;
+      const ScalarFunction& fn = src ? source : reaction;
+      for (int k = 0; k < nIP; k++) { pt.assign(xip.begin() + (size_t)k * d, xip.begin() + (size_t)(k + 1) * d); v[k] = fn(pt); }
+      detail::check(src ? hfx_source_values(h, v.data()) : hfx_reaction_values(h, v.data()), h);
+    }
+  }
+  int nDOFsPNode = 1, device = 0;
   ScalarFunction source, reaction;
+  const std::vector<std::vector<double> >* elementNodes = nullptr;
+  const std::map<std::string, std::vector<double> >* localFieldMap = nullptr;
+  LocalMatrix localMatrix;
+  std::vector<double> localRHS;
 };
 
 class HDGLaplaceModel : public HDGModel {   // Base + Diffusion(D = I)  (src/model/HDGLaplaceModel.cpp:18-30)
@@ -832,6 +926,12 @@ class HDGBurgersModel : public HDGModel {
   }
   const ComponentFunction& componentSourceFunction() const { return componentSource; }
   bool isBurgers() const override { return true; }
+  void evalLocalCallbacks(hfx_ctx* h, int mask, const std::vector<double>& xip, int nIP, int d) override {   // one scalar Source per component
+    if (!(mask & HFX_OP_SOURCE)) return;
+    std::vector<double> vc((size_t)d * nIP), pt(d);
+    for (int c = 0; c < d; c++) for (int ip = 0; ip < nIP; ip++) { pt.assign(xip.begin() + (size_t)ip * d, xip.begin() + (size_t)(ip + 1) * d); vc[(size_t)c * nIP + ip] = componentSource(pt, c); }
+    detail::check(hfx_source_values_n(h, d, vc.data()), h);
+  }
   int opmask(const std::set<std::string>& names, bool) const override {
     if (!names.count("BufferSolution")) throw ErrorHandle("HDGBurgersModel", "setFieldMap", "must provide a BufferSolution field for the Newton-Raphson iterations");
     return HFX_OP_UNABU | (names.count("DiffusionTensor") ? HFX_OP_DIFFUSION : 0) | (componentSource ? HFX_OP_SOURCE : 0);

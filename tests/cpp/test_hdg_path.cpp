@@ -468,11 +468,54 @@ static void testPartitioner(const std::string& meshFile, int dim, int order, int
   CHECK(world == 1 || !cnt.empty());
 }
 
+// tests/unittests/model/TestHDGLaplaceModel.cpp: the call-order contract of the per-element surface (host only), and -- on the GPU -- the block identities
+// the reference pins in tests/unittests/operator/TestHDGBase.cpp:26-135, checked on the DEVICE's local matrix of the reference element (tau = 1):
+// S_qq = M (x) I_dim with the reference mass matrix, S_ul = -S_lu^T, S_ll symmetric, zero right-hand side.
+static void testHDGLaplaceModel(int dim, int order, bool compute) {
+  ReferenceElement refEl(dim, order, "simplex");
+  HDGLaplaceModel mod(&refEl);
+  CHECK_THROWS(mod.compute());
+  std::map<std::string, std::vector<double> > fm;
+  CHECK_THROWS(mod.setFieldMap(&fm));
+  std::vector<double> taus((size_t)refEl.getNumFaces() * refEl.getFaceElement()->getNumNodes(), 1.0);
+  fm["Tau"] = taus;
+  CHECK_NOTHROW(mod.setFieldMap(&fm));
+  CHECK_THROWS(mod.compute());
+  CHECK_NOTHROW(mod.setElementNodes(refEl.getNodes()));
+  CHECK_THROWS(mod.compute());
+  CHECK_NOTHROW(mod.allocate(1));
+  if (!compute) return;
+  CHECK_NOTHROW(mod.compute());
+  const HDGModel::LocalMatrix& A = *mod.getLocalMatrix();
+  const int nN = refEl.getNumNodes(), u = nN, q = nN * dim, l = refEl.getNumFaces() * refEl.getFaceElement()->getNumNodes();
+  CHECK(A.rows() == u + q + l);
+  double rhs = 0.0;
+  for (size_t i = 0; i < mod.getLocalRHS()->size(); i++) rhs += (*mod.getLocalRHS())[i];
+  CHECK(std::fabs(rhs) < 1e-12);
+  // reference mass matrix from the mirror's own tables
+  const std::vector<std::vector<double> >& phi = *refEl.getIPShapeFunctions();
+  const std::vector<double>& w = *refEl.getIPWeights();
+  double worst = 0.0;
+  for (int i = 0; i < nN; i++) for (int j = 0; j < nN; j++) {
+    double m = 0.0;
+    for (int ip = 0; ip < refEl.getNumIPs(); ip++) m += w[ip] * phi[ip][i] * phi[ip][j];
+    for (int d = 0; d < dim; d++) for (int e = 0; e < dim; e++)
+      worst = std::max(worst, std::fabs(A(u + i * dim + d, u + j * dim + e) - (d == e ? m : 0.0)));
+  }
+  CHECK(worst < 1e-12);
+  worst = 0.0;
+  for (int i = 0; i < u; i++) for (int j = 0; j < l; j++) worst = std::max(worst, std::fabs(A(i, u + q + j) + A(u + q + j, i)));
+  CHECK(worst < 1e-12);
+  for (int i = 0; i < l; i++) for (int j = 0; j < l; j++) worst = std::max(worst, std::fabs(A(u + q + i, u + q + j) - A(u + q + j, u + q + i)));
+  CHECK(worst < 1e-12);
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { std::printf("usage: %s <mesh dir> [contract|meshio|nlw|solver|lai|laplace|diffsrc|rk]\n", argv[0]); return 2; }
   const std::string dir = argv[1], sec = argc > 2 ? argv[2] : "all";
   try {
-    if (sec == "contract") testHDGSolver(dir, false);
+    if (sec == "contract") { testHDGSolver(dir, false); testHDGLaplaceModel(2, 3, false); testHDGLaplaceModel(3, 2, false); }
+    if (sec == "model" || sec == "all") { for (int dim = 2; dim <= 3; dim++) for (int order = 1; order <= (dim == 2 ? 5 : 4); order++) testHDGLaplaceModel(dim, order, true); }
     if (sec == "nlw" || sec == "all") testNonLinearWrapper(dir);
     if (sec == "meshio" || sec == "all") {
       testGmshIo(dir, "regression_dim-2_h-2e-1", 2, 2);

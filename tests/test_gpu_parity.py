@@ -333,11 +333,15 @@ def test_distributed_solve_single_rank_communicator():
     _run_dist(1)
 
 
-def test_distributed_solve_two_gpus():
-    """Trace-halo exchange + all-reduced dots over NCCL on two GPUs: solution fields within 1e-10 of the single-process oracle."""
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_distributed_solve_two_gpus(transport, monkeypatch):
+    """Trace-halo exchange + summed dots on two GPUs -- over NVLink peer memory (direct stores into the neighbour's ghost buffers, one-shot all-reduce;
+    the default) and over NCCL (HFX_P2P=0): solution fields within 1e-10 of the single-process oracle, same GMRES iteration count."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    if transport == "nccl":
+        monkeypatch.setenv("HFX_P2P", "0")
     _run_dist(2, cubes=4)
 
 

@@ -722,6 +722,27 @@ __global__ void __launch_bounds__(1024) p2p_reduce_allreduce_kernel(int nv, int 
   }
 }
 
+// dst = sum_k coef[k] * src[k] (up to 8 terms, dst may alias a source): RungeKutta::computeStage / computeSolution (RungeKutta.cpp:145-213), Newton damping
+struct LinCombArgs { const double* src[8]; double coef[8]; int n; };
+__global__ void field_lincomb_kernel(long long len, LinCombArgs a, double* __restrict__ dst) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) {
+    double s2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < a.n) s2 = fma(a.coef[k], a.src[k][i], s2);
+    dst[i] = s2;
+  }
+}
+// out[0] += sum (a - b)^2, out[1] += sum b^2 over the first len entries (per-block partial sums in fixed order, then atomics: two doubles)
+__global__ void field_diff_norm2_kernel(long long len, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ partial) {
+  double d2 = 0.0, r2 = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (long long)gridDim.x * blockDim.x) { const double d = a[i] - b[i]; d2 = fma(d, d, d2); r2 = fma(b[i], b[i], r2); }
+  __shared__ double sd[256], sr[256];
+  sd[threadIdx.x] = d2; sr[threadIdx.x] = r2;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) { if (threadIdx.x < o) { sd[threadIdx.x] += sd[threadIdx.x + o]; sr[threadIdx.x] += sr[threadIdx.x + o]; } __syncthreads(); }
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sd[0]; partial[2 * blockIdx.x + 1] = sr[0]; }
+}
+
 __global__ void mask_rows_kernel(long long n, int t, const uint8_t* __restrict__ owned, const double* __restrict__ src, double* __restrict__ dst) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = owned[i / t] ? src[i] : 0.0;
@@ -1003,6 +1024,8 @@ struct hfx_ctx {
   int dim = 0, order = 0, geom = HFX_SIMPLEX, nN = 0, nNf = 0, nFc = 0, nIP = 0, nIPf = 0;
   DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv, dSRef, dSRefT, dERef, dARef, dMFRef, dBRef, dBary;
   DBuf<double> dDumpA, dDumpF;   // hfx_get_local_matrix
+  DBuf<double> dNormPartial;     // hfx_field_diff_norm2
+  long long nOwnedCells = -1;    // partitioned mesh: the local cells [0, nOwnedCells) are owned (hfx_comm_set_halo_plan); -1: all
   DBuf<uint8_t> dAffine; long long nNonAffine = 0;   // cells that are not the affine image of the reference element (curved / multilinear)
   DBuf<int> dFaceNodes; DBuf<int8_t> dNodeInFace;
   // mesh
@@ -1490,6 +1513,59 @@ int hfx_field_get(hfx_ctx* c, const char* name, double* vals) {
     DField* f = find_field(c, name);
     need(f != nullptr, "Field", "getValues", "no such field");
     f->d.download(vals, f->d.n, c->st);
+  });
+}
+
+int hfx_field_lincomb(hfx_ctx* c, const char* dst, int nTerms, const double* coefs, const char* const* names) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    need(nTerms >= 1 && nTerms <= 8, "RungeKutta", "computeStage", "a linear combination takes between one and eight fields");
+    LinCombArgs a{}; a.n = nTerms;
+    DField* f0 = nullptr;
+    for (int k = 0; k < nTerms; k++) {
+      DField* f = find_field(c, names[k]);
+      need(f != nullptr && f->d.p, "RungeKutta", "setFieldMap", (std::string("the field map must provide the field ") + names[k]).c_str());
+      if (f->pendingPieces > 0) { for (int q = 0; q < 2; q++) HFX_CUDA(cudaStreamSynchronize(c->stCopy[q])); f->pendingPieces = 0; }
+      if (!f0) f0 = f;
+      need(f->d.n == f0->d.n, "RungeKutta", "computeStage", "the fields of a linear combination must have the same length");
+      a.src[k] = f->d.p; a.coef[k] = coefs[k];
+    }
+    const int type = f0->type, nObj = f0->nObj, nVal = f0->nVal; const size_t len = f0->d.n;
+    DField& d = c->fields[dst];          // (may insert: references to other map entries stay valid)
+    if (!d.d.p || d.d.n != len) { d.type = type; d.nObj = nObj; d.nVal = nVal; d.dbl = 0; d.d.alloc(len); }
+    if (d.pendingPieces > 0) { for (int q = 0; q < 2; q++) HFX_CUDA(cudaStreamSynchronize(c->stCopy[q])); d.pendingPieces = 0; }
+    field_lincomb_kernel<<<std::min(nblk((long long)len, 256), c->nSM * 8), 256, 0, c->st>>>((long long)len, a, d.d.p);
+    HFX_CUDA(cudaGetLastError());
+  });
+}
+
+int hfx_field_diff_norm2(hfx_ctx* c, const char* aName, const char* bName, double* diff2, double* ref2) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    DField* a = find_field(c, aName); DField* b = find_field(c, bName);
+    need(a && b && a->d.p && b->d.p && a->d.n == b->d.n, "NonLinearWrapper", "solve", "the current and previous Solutions should be set before attempting to solve");
+    // a partitioned mesh keeps its owned cells first (hfx_plan): ghost cells are somebody else's and must not be counted twice
+    long long len = (long long)a->d.n;
+    const bool dist = c->halo.comm && c->halo.planned && c->halo.nRanks > 1;
+    if (dist && a->type == HFX_FIELD_CELL && c->nOwnedCells >= 0) len = (long long)c->nOwnedCells * a->nObj * a->nVal;
+    const int nb = std::min(nblk(std::max<long long>(len, 1), 256), c->nSM * 4);
+    c->dNormPartial.alloc((size_t)2 * nb);
+    field_diff_norm2_kernel<<<nb, 256, 0, c->st>>>(len, a->d.p, b->d.p, c->dNormPartial.p);
+    HFX_CUDA(cudaGetLastError());
+    std::vector<double> h((size_t)2 * nb);
+    c->dNormPartial.download(h.data(), h.size(), c->st);
+    double d2 = 0.0, r2 = 0.0;
+    for (int i = 0; i < nb; i++) { d2 += h[(size_t)2 * i]; r2 += h[(size_t)2 * i + 1]; }
+    if (dist) {   // NonLinearWrapper.cpp:26-27: two MPI_Allreduce(SUM)
+      c->dNormPartial.alloc(std::max<size_t>(c->dNormPartial.n, 2));
+      const double loc[2] = {d2, r2};
+      HFX_CUDA(cudaMemcpyAsync(c->dNormPartial.p, loc, sizeof(loc), cudaMemcpyHostToDevice, c->st));
+      HFX_NCCL(NcclApi::get().AllReduce(c->dNormPartial.p, c->dNormPartial.p, 2, ncclDouble, ncclSum, c->halo.comm, c->st));
+      double glob[2];
+      c->dNormPartial.download(glob, 2, c->st);
+      d2 = glob[0]; r2 = glob[1];
+    }
+    if (diff2) *diff2 = d2; if (ref2) *ref2 = r2;
   });
 }
 
@@ -2141,6 +2217,7 @@ int hfx_comm_set_halo_plan(hfx_ctx* c, const hfx_plan* plan, const unsigned char
   if (!plan) return 1;
   const PartitionPlan& P = plan->p;
   if (c && (long long)P.faceGlobal.size() != c->nFaces) { c->err = "Partitioner : computeSharedFaces : the plan's local mesh is not the mesh of this context"; return 1; }
+  if (c) c->nOwnedCells = P.nOwned;
   return hfx_comm_set_halo(c, (int)P.nbrs.size(), P.nbrs.data(), P.sendCount.data(), P.sendFaces.data(), P.recvCount.data(), P.recvFaces.data(), P.ownedFace.data(), canonPos);
 }
 

@@ -13,6 +13,7 @@ Host Fields hold the values (as in the reference); HDGSolver.assemble() copies t
 copies Trace / Solution / Flux back.  The C++ mirror with the same names lives in include/hyperfox/.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -138,8 +139,28 @@ class Field:
     def __init__(self, mesh, ftype, nObjPerEnt, nValsPerObj):
         self.mesh, self.type, self.nObj, self.nVals = mesh, ftype, nObjPerEnt, nValsPerObj
         nEnt = {Node: mesh.getNumberPoints(), Cell: mesh.getNumberCells(), Face: mesh.getNumberFaces()}[ftype]
+        self._dev = self._devName = None      # the HDGSolver whose device context holds a copy of this field, and its name there
+        self._deviceNewer = False             # the device copy is ahead of the host array (solve / device field arithmetic wrote it)
         self.values = np.zeros(nEnt * nObjPerEnt * nValsPerObj)
         self.doubleValued = False
+
+    # The host array is the user's view.  Results the device produces (HDGSolver.solve, RungeKutta.computeStage / computeSolution, NonLinearWrapper) stay
+    # on the device until somebody looks: reading `values` brings them back (into the SAME array object), and from then on the host copy is
+    # authoritative again (it may be modified in place, which cannot be observed), so the next assemble uploads it.
+    @property
+    def values(self):
+        if self._deviceNewer:
+            self._deviceNewer = False
+            check(lib().hfx_field_get(self._dev._h(), self._devName.encode(), pd(self._values)), self._dev._h())
+        return self._values
+
+    @values.setter
+    def values(self, v):
+        self._values = v
+        self._deviceNewer = False
+
+    def _on_device(self, solver):
+        return self._dev is solver and self._devName is not None
 
     def getValues(self): return self.values
     def getFieldType(self): return self.type
@@ -210,6 +231,15 @@ class RungeKutta:
     def getNumStages(self): return self.bTable.shape[1] - 1
     def stageRow(self): return np.ascontiguousarray(self.bTable[self.stageCounter, 1:])
 
+    def _device_solver(self, fm):
+        """The HDGSolver on whose device the solution fields of `fm` live (after its solve()), if its field map is `fm`: the stage arithmetic then
+        runs there.  None: host arithmetic (numpy), e.g. for fields that never met a solver.  At most 8 terms per combination (7 stages)."""
+        sol = fm.get("Solution")
+        s = getattr(sol, "_dev", None)
+        if s is None or getattr(s, "fieldMap", None) is not fm or self.getNumStages() > 7 or os.environ.get("HFX_HOST_FIELD_ARITHMETIC"):
+            return None
+        return s
+
     def fieldNames(self):
         """Everything RungeKutta::setFieldMap requires (:44-88) for the current stage."""
         names = ["OldSolution"] + ["Old" + a for a in self.auxiliaryFields]
@@ -221,6 +251,14 @@ class RungeKutta:
         if self.stageCounter >= self.getNumStages():
             raise ErrorHandle("RungeKutta : computeStage : cannot compute more stages than the method allows, think about computing the solution")
         row, s = self.bTable[self.stageCounter, 1:], self.stageCounter
+        solver = self._device_solver(fm)
+        if solver is not None:     # RungeKutta.cpp:145-179 as device AXPYs: the fields do not leave the GPU between the stages
+            for base in ["Solution"] + self.auxiliaryFields:
+                sname = lambda k: "RKStage_%d" % k if base == "Solution" else "RKStage_%s_%d" % (base, k)
+                solver.fieldLinComb(sname(s), [1.0 / self.dt, -1.0 / self.dt], [base, "Old" + base])
+                solver.fieldLinComb(base, [1.0] + [self.dt * row[j] for j in range(s + 1)], ["Old" + base] + [sname(j) for j in range(s + 1)])
+            self.stageCounter += 1
+            return
         for base in ["Solution"] + self.auxiliaryFields:
             stage = lambda k: fm["RKStage_%d" % k if base == "Solution" else "RKStage_%s_%d" % (base, k)]
             sol, old = fm[base].values, fm["Old" + base].values
@@ -232,6 +270,14 @@ class RungeKutta:
         if self.stageCounter != self.getNumStages():
             raise ErrorHandle("RungeKutta : computeSolution : all stages must be computed before computing the solution")
         bs = self.bTable[self.stageCounter, 1:]
+        solver = self._device_solver(fm)
+        if solver is not None:     # RungeKutta.cpp:181-213
+            nSt = self.getNumStages()
+            for base in ["Solution"] + self.auxiliaryFields:
+                sname = lambda k: "RKStage_%d" % k if base == "Solution" else "RKStage_%s_%d" % (base, k)
+                solver.fieldLinComb(base, [1.0] + [self.dt * bs[k] for k in range(nSt)], ["Old" + base] + [sname(k) for k in range(nSt)])
+            self.stageCounter = 0
+            return
         for base in ["Solution"] + self.auxiliaryFields:
             stage = lambda k: fm["RKStage_%d" % k if base == "Solution" else "RKStage_%s_%d" % (base, k)]
             fm[base].values[:] = fm["Old" + base].values + self.dt * sum(bs[k] * stage(k).values for k in range(self.getNumStages()))
@@ -563,7 +609,10 @@ class HDGSolver:
 
     def _upload_field(self, name, asynchronous=False):
         f = self.fieldMap[name]
+        if f._deviceNewer and f._dev is self and f._devName == name:
+            return                             # produced on the device and not looked at since: nothing to upload
         v = f64(f.values)
+        f._dev, f._devName = self, name
         if asynchronous:   # the copy overlaps the assembly; the field's storage is not touched before hfx_assemble returns
             self._keep = getattr(self, "_keep", {}); self._keep[name] = v
             check(lib().hfx_field_set_async(self._h(), name.encode(), f.type, f.nObj, f.nVals, pd(v), int(f.doubleValued)), self._h())
@@ -681,9 +730,37 @@ class HDGSolver:
             raise ErrorHandle("HDGSolver : solve : system must be assembled before solving")
         o = self.linSystem.opts.c() if hasattr(self.linSystem, "opts") else PetscOpts().c()
         check(lib().hfx_solve(self._h(), C.byref(o), C.byref(self.stats)), self._h())
-        for name in ("Trace", "Solution", "Flux"):
+        for name in ("Trace", "Solution", "Flux"):      # left on the device; Field.values fetches them when somebody looks
             f = self.fieldMap[name]
-            check(lib().hfx_field_get(self._h(), name.encode(), pd(f.values)), self._h())
+            f._values = f64(f._values)
+            f._dev, f._devName, f._deviceNewer = self, name, True
+
+    # ---- device field arithmetic (hfx_field_lincomb / hfx_field_diff_norm2) ---------------------------------------------------------------
+    def _ensure_on_device(self, name):
+        f = self.fieldMap[name]
+        if not (f._on_device(self) and f._devName == name) or not f._deviceNewer:
+            v = f64(f._values)
+            check(lib().hfx_field_set(self._h(), name.encode(), f.type, f.nObj, f.nVals, pd(v), int(f.doubleValued)), self._h())
+            f._dev, f._devName = self, name
+
+    def fieldLinComb(self, dst, coefs, names):
+        """fieldMap[dst] <- sum_k coefs[k] * fieldMap[names[k]] on the device; the result stays there until its `values` are read."""
+        for n in names:
+            self._ensure_on_device(n)
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        cf = f64(np.asarray(coefs, dtype=np.float64))
+        check(lib().hfx_field_lincomb(self._h(), dst.encode(), len(names), pd(cf), arr), self._h())
+        f = self.fieldMap[dst]
+        f._values = f64(f._values)
+        f._dev, f._devName, f._deviceNewer = self, dst, True
+
+    def fieldDiffNorm2(self, a, b):
+        """(||a - b||^2, ||b||^2) of two fields of the field map, on the device (owned cells + all-reduce on a partitioned mesh)."""
+        for n in (a, b):
+            self._ensure_on_device(n)
+        d2, r2 = C.c_double(0), C.c_double(0)
+        check(lib().hfx_field_diff_norm2(self._h(), a.encode(), b.encode(), C.byref(d2), C.byref(r2)), self._h())
+        return d2.value, r2.value
 
     # ---- parity hooks -------------------------------------------------------------------------------------------
     def getCSR(self, with_cols=True):
@@ -755,7 +832,13 @@ class NonLinearWrapper:
         solver.solve()
 
     @staticmethod
-    def vanillaResidualComputer(cur, prev):       # NonLinearWrapper.cpp:12-34 (single process: the two all-reduces are identities)
+    def vanillaResidualComputer(cur, prev):       # NonLinearWrapper.cpp:12-34: ||cur - prev|| / ||prev||, the two sums all-reduced over the ranks
+        s = getattr(cur, "_dev", None)
+        if s is not None and not os.environ.get("HFX_HOST_FIELD_ARITHMETIC"):
+            names = {id(f): n for n, f in s.fieldMap.items()}
+            if id(cur) in names and id(prev) in names:      # on the device: one fused pass, owned cells + ncclAllReduce on a partitioned mesh
+                diff, ref = s.fieldDiffNorm2(names[id(cur)], names[id(prev)])
+                return np.sqrt(diff / ref) if ref != 0 else np.sqrt(diff)
         diff, ref = float(np.sum((cur.values - prev.values) ** 2)), float(np.sum(prev.values ** 2))
         return np.sqrt(diff / ref) if ref != 0 else np.sqrt(diff)
 
@@ -775,12 +858,20 @@ class NonLinearWrapper:
             raise ErrorHandle("NonLinearWrapper : solve : the Solver must be set before attempting to solve")
         if self.currentSolution is None:
             raise ErrorHandle("NonLinearWrapper : solve : the current and previous Solutions should be set before attempting to solve")
-        cur, prev = self.currentSolution.values, self.previousSolution.values
+        s = self.mySolver
+        names = {id(f): n for n, f in getattr(s, "fieldMap", {}).items()} if hasattr(s, "fieldLinComb") else {}
+        onDevice = id(self.currentSolution) in names and id(self.previousSolution) in names and not os.environ.get("HFX_HOST_FIELD_ARITHMETIC")
         for _ in range(self.maxIters):
             self.linearizedSolver(self.mySolver)
             self.residual = self.residualComputer(self.currentSolution, self.previousSolution)
             if self.residual < self.resTol:
                 break
+            if onDevice:      # NonLinearWrapper.cpp:55-70 as device AXPYs
+                c, p_ = names[id(self.currentSolution)], names[id(self.previousSolution)]
+                s.fieldLinComb(c, [1.0 - self.dampening, self.dampening], [c, p_])
+                s.fieldLinComb(p_, [1.0], [c])
+                continue
+            cur, prev = self.currentSolution.values, self.previousSolution.values
             val = (1.0 - self.dampening) * cur + self.dampening * prev
             cur[:] = val
             prev[:] = val

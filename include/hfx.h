@@ -74,6 +74,13 @@ int hfx_field_set(hfx_ctx* ctx, const char* name, int type, int nObjPerEnt, int 
    hfx_assemble / hfx_sync returns.  hfx_assemble starts on the first elements while the rest of a Face field is still in flight. */
 int hfx_field_set_async(hfx_ctx* ctx, const char* name, int type, int nObjPerEnt, int nValsPerObj, const double* vals, int doubleValued);
 int hfx_field_get(hfx_ctx* ctx, const char* name, double* vals); /* device -> host */
+/* dst <- sum_k coefs[k] * field names[k] on the device (1 <= nTerms <= 8, equal lengths, dst may be one of the sources and is created with the
+   layout of the first source if it does not exist): RungeKutta::computeStage / computeSolution (src/operator/RungeKutta.cpp:145-213) and the
+   damped update of NonLinearWrapper (src/solver/NonLinearWrapper.cpp:55-70) without a host round trip of the fields */
+int hfx_field_lincomb(hfx_ctx* ctx, const char* dst, int nTerms, const double* coefs, const char* const* names);
+/* ||a - b||_2^2 and ||b||_2^2 of two device fields: the residual of NonLinearWrapper (NonLinearWrapper.cpp:12-34).  On a partitioned mesh cell fields count
+   the owned cells only and the two sums are all-reduced over the ranks (the reference's two MPI_Allreduce) */
+int hfx_field_diff_norm2(hfx_ctx* ctx, const char* a, const char* b, double* diff2, double* ref2);
 int hfx_field_size(const hfx_ctx* ctx, const char* name, long long* n);
 
 /* ---- model: the four HDG models as an operator descriptor  src/model/*.cpp (computeLocalMatrix/RHS) ----------- */

@@ -825,14 +825,14 @@ class HDGModel : public FEModel {
       if (v) detail::check(hfx_field_set(h, name, type, nObj, nVals, v->data(), 0), h);
     };
     if (lf.at("Tau").size() != (size_t)nFc * nNf * nD * nD) throw ErrorHandle("HDGModel", "setFieldMap", "the Tau field does not have the right size");
-    put("Tau", Face, nFc, nNf, nD * nD);
-    put("Dirichlet", Face, nFc, nNf, nD);
-    put("Trace", Face, nFc, nNf, nD);
-    put("Solution", Cell, 1, nN, nD);
-    put("Flux", Cell, 1, nN, nD * dim);
-    if (usesDiffusionField()) put("DiffusionTensor", Node, nN, 1, 0);
-    put("Velocity", Node, nN, 1, 0);
-    put("BufferSolution", Cell, 1, nN, 0);
+    put("Tau", HFX_FIELD_FACE, nFc, nNf, nD * nD);
+    put("Dirichlet", HFX_FIELD_FACE, nFc, nNf, nD);
+    put("Trace", HFX_FIELD_FACE, nFc, nNf, nD);
+    put("Solution", HFX_FIELD_CELL, 1, nN, nD);
+    put("Flux", HFX_FIELD_CELL, 1, nN, nD * dim);
+    if (usesDiffusionField()) put("DiffusionTensor", HFX_FIELD_NODE, nN, 1, 0);
+    put("Velocity", HFX_FIELD_NODE, nN, 1, 0);
+    put("BufferSolution", HFX_FIELD_CELL, 1, nN, 0);
     hfx_model_desc md;
     md.nDOF = nD; md.opmask = opmask(names, true);
     md.timeScheme = timeScheme ? timeScheme->cKind() : HFX_TS_NONE; md.dt = timeScheme ? timeScheme->getTimeStep() : 0.0;

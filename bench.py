@@ -364,7 +364,7 @@ def main():
         return float(np.mean(ks))
     kk = C.c_int(0)
     L.hfx_last_assemble_kernel(h, C.byref(kk), None)
-    kernel_name = ("hdg_assemble_kernel (fused element groups)", "hdg_generic_kernel", "hdg_big_kernel (large elements, 512-thread CTA per SM)")[kk.value]
+    kernel_name = ("hdg_assemble_kernel (fused element groups)", "hdg_generic_kernel", "hdg_big_kernel (large elements, 512-thread CTA per SM)", "hdg_p1_kernel (one thread per element)")[kk.value]
     straight_ms = other_path("HFX_NO_REFPATH") if order <= 3 else my_ms
     general_ms = other_path("HFX_NO_AFFINE") if order <= 3 else my_ms
     # the two other kernels of the path, timed separately from the headline: GMRES(30) on the assembled trace system (not to
@@ -561,7 +561,7 @@ def run_order_sweep(args):
         nC = cells.shape[0]
         tf = FLOPS_PER_ELEM[order] * nC / t / 1e12
         gbs = BYTES_STORE[order] * nC / t / 1e9
-        rows.append({"order": order, "cubes": N, "elements": nC, "dofs": nC * NN[order], "kernel": ("fused", "general", "big")[kk.value], "ms_per_step": t * 1e3,
+        rows.append({"order": order, "cubes": N, "elements": nC, "dofs": nC * NN[order], "kernel": ("fused", "general", "big", "p1")[kk.value], "ms_per_step": t * 1e3,
                      "elements_per_s": nC / t, "tflops_algorithmic": tf, "frac_fp64_peak": tf / peak["tflops"], "hbm_GBs_algorithmic": gbs, "frac_hbm_peak": gbs / hbm_peak})
         check(L.hfx_ctx_destroy(h))
     clocks = sampler.stop()

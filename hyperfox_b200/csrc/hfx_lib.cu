@@ -18,6 +18,7 @@
 #include "hfx_assemble.cuh"
 #include "hfx_generic.cuh"
 #include "hfx_big.cuh"
+#include "hfx_p1.cuh"
 #include "hfx_krylov.cuh"
 #include "host/hfx_refel.h"
 #include "host/hfx_topology.h"
@@ -1043,7 +1044,7 @@ struct hfx_ctx {
   bool modelSet = false, bcSet = false;
   DBuf<uint8_t> dFaceBC;
   // allocation
-  bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false; int lastKernel = 0;
+  bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false, p1Ready = false; int lastKernel = 0;
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
   DBuf<long long> dFaceRowStart, dBlockCount, dTotal;
   long long nnz = 0;
@@ -1391,6 +1392,28 @@ int hfx_refel_set(hfx_ctx* c, int dim, int order, int geom) {
         bary[(size_t)i * (dim + 1)] = s0;
       }
       c->dBary.upload(bary, c->st);
+      // linear tetrahedra: constant-memory tables of the one-thread-per-element kernel (hfx_p1.cuh); its face-node map is compiled in
+      c->p1Ready = false;
+      if (dim == 3 && order == 1 && geom == HFX_SIMPLEX && n == 4 && t == 3 && nip == 4 && nipf == 3) {
+        static const int fn[4][3] = {{3, 1, 0}, {2, 1, 3}, {2, 3, 0}, {0, 1, 2}};
+        bool same = true;
+        for (int f = 0; f < 4; f++) for (int a = 0; a < 3; a++) same = same && re.faceNodes()[(size_t)f * 3 + a] == fn[f][a];
+        if (same) {
+          P1Tables T{};
+          for (int r = 0; r < 3; r++) for (int m = 0; m < 4; m++) for (int k = 0; k < 4; k++) { T.A[r][m][k] = aref[((size_t)r * n + k) * np + m]; T.S[r][m][k] = sref[((size_t)r * n + m) * np + k]; }
+          for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) T.MF[a][b] = mf[(size_t)a + (size_t)tp * b];
+          for (int f = 0; f < 4; f++) for (int m = 0; m < 4; m++) for (int b = 0; b < 3; b++) T.BH[f][m][b] = bref[((size_t)f * n + m) * t + b];
+          for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) for (int cc = 0; cc < 3; cc++) {
+            double s2 = 0.0;
+            for (int ip = 0; ip < nipf; ip++) s2 += fe->ipWeights()[ip] * fe->ipShape()[(size_t)ip * t + a] * fe->ipShape()[(size_t)ip * t + b] * fe->ipShape()[(size_t)ip * t + cc];
+            T.T3[a][b][cc] = s2;
+          }
+          for (int ip = 0; ip < nip; ip++) for (int i = 0; i < 4; i++) T.PHIW[ip][i] = re.ipWeights()[ip] * re.ipShape()[(size_t)ip * n + i];
+          HFX_CUDA(cudaMemcpyToSymbolAsync(c_p1, &T, sizeof(T), 0, cudaMemcpyHostToDevice, c->st));
+          HFX_CUDA(cudaStreamSynchronize(c->st));
+          c->p1Ready = true;
+        }
+      }
     }
     std::vector<int8_t> nif((size_t)c->nFc * c->nN, -1);
     for (int f = 0; f < c->nFc; f++) for (int a = 0; a < t; a++) nif[(size_t)f * c->nN + re.faceNodes()[(size_t)f * t + a]] = (int8_t)a;
@@ -1793,7 +1816,17 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     const bool dumpMode = dumpA != nullptr;
     if (!recoverMode && !dumpMode) clearSystem();
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
-    bool fused = !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
+    // linear tets, Laplace-type model, straight-sided cells: one thread per element (hfx_p1.cuh).  Opt-in (HFX_P1=1): measured at 134 M el/s against the
+    // 186 M el/s of the element-group kernel -- 255 registers + spills and 8 warps per SM leave it latency bound
+    bool p1 = false;
+    if (getenv("HFX_P1") && atoi(getenv("HFX_P1")) != 0 && !recoverMode && !dumpMode && c->p1Ready && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 1 && c->md.nDOF == 1 && (c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE)) == 0
+        && c->md.timeScheme == HFX_TS_NONE && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_P1")) {
+      for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) { for (DField* f : {&kv.second}) for (int k = 0; k < f->pendingPieces; k++) HFX_CUDA(cudaStreamWaitEvent(c->st, f->ev[k], 0)); kv.second.pendingPieces = 0; }
+      p.eBegin = 0; p.eEnd = c->nCells;
+      HFX_CUDA(launch_p1(p, c->nSM, c->st));
+      p1 = true;
+    }
+    bool fused = !p1 && !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
     // fields still crossing PCIe (hfx_field_set_async): the element chunks start as their face-id prefix has arrived
     std::vector<DField*> pend;
     for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) pend.push_back(&kv.second);
@@ -1818,7 +1851,7 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     }
     // 3-D order 4: the large-element kernel (one 512-thread CTA per SM, operands resident in shared memory) when every cell is straight-sided and D = c I
     bool big = false;
-    if (!fused && !dumpMode && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA
+    if (!fused && !p1 && !dumpMode && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA
         && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_BIG")) {
       if (!pend.empty()) waitPieces(0, -1);
       HFX_CUDA((launch_big<3, 4>(p, c->nSM, c->st)));
@@ -1829,7 +1862,7 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
       HFX_CUDA(cudaStreamSynchronize(c->st));
       return;
     }
-    if (!fused && !big && !pend.empty()) waitPieces(0, -1);
+    if (!fused && !big && !p1 && !pend.empty()) waitPieces(0, -1);
     for (DField* f : pend) f->pendingPieces = 0;
     auto launchGeneric = [&](bool pivot) {   // general kernel: 3-D orders 4-5, nDOFsPerNode > 1, HDGUNabU, orthotopes; pivot: partial pivoting in K^-1
       GenParams g{};
@@ -1886,9 +1919,9 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
       hdg_generic_kernel<<<(int)grid, kGenThreads, smem, c->st>>>(g);
       HFX_CUDA(cudaGetLastError());
     };
-    if (!fused && !big) launchGeneric(getenv("HFX_FORCE_PIVOT") != nullptr);
+    if (!fused && !big && !p1) launchGeneric(getenv("HFX_FORCE_PIVOT") != nullptr);
     if (dumpMode) { HFX_CUDA(cudaStreamSynchronize(c->st)); return; }
-    c->lastKernel = fused ? 0 : (big ? 2 : 1);
+    c->lastKernel = p1 ? 3 : (fused ? 0 : (big ? 2 : 1));
     HFX_CUDA(cudaEventRecord(c->ev2, c->st));
     int status = 0;
     c->dStatus.download(&status, 1, c->st);

@@ -135,7 +135,7 @@ int hfx_sync(hfx_ctx* ctx);
 /* timing of the last hfx_assemble (CUDA events on the library's stream), milliseconds */
 int hfx_last_assemble_ms(const hfx_ctx* ctx, float* msTotal, float* msKernel);
 /* which device kernel served the last hfx_assemble: 0 fused element-group kernel (hfx_assemble.cuh), 1 general kernel (hfx_generic.cuh),
-   2 large-element kernel (hfx_big.cuh); pivotFallback = 1 if the assembly was redone with partial pivoting after a vanishing pivot */
+   2 large-element kernel (hfx_big.cuh), 3 linear-tet kernel, one thread per element (hfx_p1.cuh); pivotFallback = 1 if the assembly was redone with partial pivoting after a vanishing pivot */
 int hfx_last_assemble_kernel(const hfx_ctx* ctx, int* kernel, int* pivotFallback);
 /* development aid: one assemble with per-phase clock64 counters of CTA 0 (cycles16[16]) */
 int hfx_assemble_profile(hfx_ctx* ctx, long long* cycles16);

@@ -352,8 +352,8 @@ def main():
     # transparency: the same workload through the two slower paths of the fused kernel, three steps each outside the headline:
     #   HFX_NO_REFPATH: straight-sided path (what affine elements with a tau that varies along a face, or a convection / reaction /
     #                   time-scheme model, take);  HFX_NO_AFFINE: general path (curved elements)
-    def other_path(var):
-        os.environ[var] = "1"
+    def other_path(var, val="1"):
+        os.environ[var] = val
         ks = []
         for i in range(3):
             check(L.hfx_assemble(h), h)
@@ -365,7 +365,8 @@ def main():
     kk = C.c_int(0)
     L.hfx_last_assemble_kernel(h, C.byref(kk), None)
     kernel_name = ("hdg_assemble_kernel (fused element groups)", "hdg_generic_kernel", "hdg_big_kernel (large elements, 512-thread CTA per SM)", "hdg_p1_kernel (one thread per element)")[kk.value]
-    straight_ms = other_path("HFX_NO_REFPATH") if order <= 3 else my_ms
+    # (order 3: a mesh whose tau varies along faces, or a convection / reaction / time-scheme model, takes the SJ_r formulation of hfx_big.cuh since round 2)
+    straight_ms = (other_path("HFX_BIG_P3", "2") if order == 3 else other_path("HFX_NO_REFPATH")) if order <= 3 else my_ms
     general_ms = other_path("HFX_NO_AFFINE") if order <= 3 else my_ms
     # the two other kernels of the path, timed separately from the headline: GMRES(30) on the assembled trace system (not to
     # convergence: the difference of a 90- and a 30-iteration solve, device time from CUDA events inside hfx_solve) and the local recovery.
@@ -486,8 +487,8 @@ def main():
                    "timing": "CUDA events on the library stream around memset+kernel, max over ranks; wall-clock per step %.2f ms" % ms_wall,
                    "setup_s": round(t_setup, 1),
                    "element_paths": ("every element of this mesh is straight-sided with a face-constant tau and takes the all-reference path "
-                                     "(every block from staged reference matrices, DESIGN.md 4.1); the same mesh through the straight-sided path "
-                                     "(tau varying along faces / other operators) runs at %.3g elements/s and through the general path "
+                                     "(every block from staged reference matrices, DESIGN.md 4.1); the same mesh through the path that straight-sided cells with "
+                                     "a tau varying along faces / other operators take (order 3: hdg_big_kernel<3,3,256>) runs at %.3g elements/s and through the general path "
                                      "(curved elements) at %.3g elements/s on rank 0" % (nC / (straight_ms * 1e-3), nC / (general_ms * 1e-3))) if order <= 3 else
                                     "every element is straight-sided (large-element kernel, DESIGN.md 4.1c); tau and v.n vary along the faces: weighted face masses by cubature"},
         "roofline": {"bound": "tensor", "pipe": "fp64 (DMMA m8n8k4 + DFMA share one 64 FMA/clk/SM pipe; tcgen05 has no FP64 kind)", "achieved": ach, "peak": peak["tflops"], "unit": "TFLOP/s", "frac": ach / peak["tflops"] if peak["tflops"] else None,

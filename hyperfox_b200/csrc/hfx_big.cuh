@@ -21,7 +21,6 @@
 
 namespace hfx {
 
-constexpr int kBigThreads = 512;
 
 template <int DIM, int P>
 struct BigSmem {
@@ -33,9 +32,9 @@ struct BigSmem {
   static constexpr int KSN = nNp / 4;                      // reduction steps over the element nodes
   static constexpr int MTN = (nN + 7) / 8;                 // 8-row tiles over the element nodes
   static constexpr int ldc = ((l + 2 + 11) / 16) * 16 + 4; // R, U, Q, Zq rows: >= l + 2, = 4 mod 16
-  static constexpr int ldb = ev(l);                        // resident B^ rows
+  static constexpr int ldb = (l % 16 == 4 || l % 16 == 12) ? l : ev(l) + 4 - (ev(l) % 4 == 0 ? 0 : 2);   // resident B^ rows (= 4 or 12 mod 16 where that is cheap)
   static constexpr int tq = ((t + 3) / 4) * 4;             // face reduction pad
-  static constexpr int ldf = tq + 4;                       // face matrices, column-major [b][a]
+  static constexpr int ldf = (tq % 16 == 4 || tq % 16 == 12) ? tq : tq + 4;   // face matrices, column-major [b][a], leading dimension = 4 or 12 mod 16
   static constexpr int FSZ = ldf * tq;
   static constexpr int nIPp = ((nIP + 3) / 4) * 4, nIPfp = ((nIPf + 3) / 4) * 4;
   static constexpr int ldw = 12;                           // face weights [ip][(f, kind)], 2 nFc <= 8 columns
@@ -68,22 +67,25 @@ struct BigSmem {
   static constexpr int oPHI = oQQ, oCG = oPHI + nIPp * nNp, oKC = oCG + nIPp * nNp;
   static_assert(oKC + nNp * nNp <= oEnd, "PHI, CG and the K copy live in the Q region");
   static constexpr int oZQ = oSJ;                          // Zq_f [nFc][tq][ldc]
-  static constexpr int oST = oZQ + nFc * tq * ldc;         // S staging: nFc^2 blocks of t x t (face-node positions), then S0 [l]
-  static_assert(oST + ev(l * l + l) <= oUU, "the S phase reuses the SJ / K / R span");
-  static constexpr int nDoubles = oEnd;
+  static constexpr int szZQ = nFc * tq * ldc, szST = ev(l * l + l);
+  // S staging (nFc^2 blocks of t x t in face-node positions, then S0 [l]): behind Zq inside the span when it fits (order 4), else in its own area
+  static constexpr bool stInSpan = oZQ + szZQ + szST <= oUU;
+  static_assert(oZQ + szZQ <= oUU, "Zq reuses the SJ / K / R span");
+  static constexpr int oST = stInSpan ? oZQ + szZQ : oEnd;
+  static constexpr int nDoubles = stInSpan ? oEnd : oEnd + szST;
   static constexpr int nInts = 2 * nFc * t + nFc * nN + nFc * nFc + 6 * nFc + (l + 2) + 8;
   static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * (size_t)nFc + 4 * (size_t)nInts + 16;
 };
 
-template <int DIM, int P>
-__global__ void __launch_bounds__(kBigThreads, 1) hdg_big_kernel(const AsmParams p) {
+template <int DIM, int P, int NT_>
+__global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const AsmParams p) {
   using L = BigSmem<DIM, P>;
   constexpr int nN = L::nN, t = L::t, nFc = L::nFc, nIP = L::nIP, nIPf = L::nIPf, l = L::l;
   constexpr int nNp = L::nNp, npe = L::npe, KSN = L::KSN, MTN = L::MTN, ldc = L::ldc, ldb = L::ldb, tq = L::tq, ldf = L::ldf, FSZ = L::FSZ;
   constexpr int nIPp = L::nIPp, nIPfp = L::nIPfp, ldw = L::ldw, D2 = DIM * DIM;
-  constexpr int NT = kBigThreads, NWARP = NT / 32;
+  constexpr int NT = NT_, NWARP = NT / 32;
   constexpr int L1T = (l + 1 + 7) / 8, LT = (l + 7) / 8;
-  static_assert(l + 1 <= NT && nFc * nIPf <= 64 && nIP <= 64, "thread roles");
+  static_assert(l + 1 <= 128 && nFc * nIPf <= 64 && nIP <= 64 && 160 + nFc * nFc <= NT && 192 + DIM * nN <= NT && 64 + nIP <= NT, "thread roles");
   extern __shared__ __align__(16) double sm[];
   double* const AR = sm + L::oAR; double* const BH = sm + L::oBH; double* const MF = sm + L::oMF;
   double* const X = sm + L::oX; double* const TAU = sm + L::oTAU; double* const VN = sm + L::oVN; double* const GEO = sm + L::oGEO;
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kBigThreads, 1) hdg_big_kernel(const AsmParams
     } else if (tid >= 160 && tid < 160 + nFc * nFc) POS[tid - 160] = p.elemPos[(size_t)e * nFc * nFc + (tid - 160)];
     if (hasConv) { const int* cell = p.cells + (size_t)e * nN; for (int i = tid; i < nN * DIM; i += NT) VN[i] = p.vel[(size_t)cell[i / DIM] * DIM + (i % DIM)]; }
     if (needPhi) for (int i = tid; i < nIP * nN; i += NT) PHI[(i / nN) * nNp + (i % nN)] = p.shape[i];
-    if (euler && tid >= 256 && tid < 256 + nN) SOLD[tid - 256] = p.solOld[(size_t)e * nN + (tid - 256)];
+    if (euler) for (int i = tid; i < nN; i += NT) SOLD[i] = p.solOld[(size_t)e * nN + i];
     __syncthreads();
     HFX_PROF(0);
 
@@ -698,15 +700,18 @@ __global__ void __launch_bounds__(kBigThreads, 1) hdg_big_kernel(const AsmParams
   }
 }
 
-template <int DIM, int P>
+template <int DIM, int P, int NT_>
 inline cudaError_t launch_big(const AsmParams& p, int nSM, cudaStream_t st) {
   using L = BigSmem<DIM, P>;
-  cudaError_t e = cudaFuncSetAttribute(hdg_big_kernel<DIM, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  cudaError_t e = cudaFuncSetAttribute(hdg_big_kernel<DIM, P, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (e != cudaSuccess) return e;
-  long long grid = nSM;
+  int perSM = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_big_kernel<DIM, P, NT_>, NT_, L::bytes);
+  if (perSM < 1) perSM = 1;
+  long long grid = (long long)nSM * perSM;
   if (grid > p.eEnd - p.eBegin) grid = p.eEnd - p.eBegin;
   if (grid < 1) grid = 1;
-  hdg_big_kernel<DIM, P><<<(int)grid, kBigThreads, L::bytes, st>>>(p);
+  hdg_big_kernel<DIM, P, NT_><<<(int)grid, NT_, L::bytes, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -505,6 +505,16 @@ __global__ void field_is_const_kernel(long long n, const double* __restrict__ v,
   if (__syncthreads_or(diff) && threadIdx.x == 0) out[1] = 1.0;   // (benign race: every writer stores the same value)
 }
 
+// out[0] = 1 if tau varies along some face (per side): such meshes leave the all-reference path of the element-group kernel (HDGBase.cpp:18-32: tau is a nodal face field)
+__global__ void tau_varies_kernel(long long nFaces, int t, int tauVals, const double* __restrict__ tau, int* __restrict__ out) {
+  bool diff = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nFaces * t * tauVals; i += (long long)gridDim.x * blockDim.x) {
+    const long long F = i / ((long long)t * tauVals); const int side = (int)(i % tauVals);
+    diff |= (tau[i] != tau[F * t * tauVals + side]);
+  }
+  if (__syncthreads_or(diff) && threadIdx.x == 0) out[0] = 1;   // (benign race: every writer stores the same value)
+}
+
 // FP64 FMA peak probe: 8 independent register-resident DFMA chains per thread
 __global__ void dfma_peak_kernel(int iters, double* out) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
@@ -1026,6 +1036,7 @@ struct hfx_ctx {
   DBuf<double> dShape, dDShape, dW, dFShape, dFDShape, dFW, dFFS, dMHInv, dSRef, dSRefT, dERef, dARef, dMFRef, dBRef, dBary;
   DBuf<double> dDumpA, dDumpF;   // hfx_get_local_matrix
   DBuf<double> dNormPartial;     // hfx_field_diff_norm2
+  DBuf<int> dTauFlag;            // tau_varies_kernel
   long long nOwnedCells = -1;    // partitioned mesh: the local cells [0, nOwnedCells) are owned (hfx_comm_set_halo_plan); -1: all
   DBuf<uint8_t> dAffine; long long nNonAffine = 0;   // cells that are not the affine image of the reference element (curved / multilinear)
   DBuf<int> dFaceNodes; DBuf<int8_t> dNodeInFace;
@@ -1826,7 +1837,24 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
       HFX_CUDA(launch_p1(p, c->nSM, c->st));
       p1 = true;
     }
-    bool fused = !p1 && !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
+    // 3-D order 3 with convection / reaction / a time scheme on straight-sided cells: the SJ_r formulation of hfx_big.cuh (two 256-thread CTAs per SM) instead of the
+    // straight-sided path of the element-group kernel.  HFX_BIG_P3=0 disables, HFX_BIG_P3=2 routes the Laplace-type models through it as well.
+    const int bigP3Mode = getenv("HFX_BIG_P3") ? atoi(getenv("HFX_BIG_P3")) : 1;
+    const bool needSuuModel = (c->md.opmask & (HFX_OP_CONVECTION | HFX_OP_REACTION)) || c->md.timeScheme == HFX_TS_EULER_IMPLICIT;
+    bool tauVaries = false;
+    if (!needSuuModel && bigP3Mode == 1 && !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 3 && c->md.nDOF == 1 && tau->nVal <= 2 && !p.diff && p.affine
+        && c->nNonAffine == 0 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme == HFX_TS_NONE) {
+      // Laplace-type model: the all-reference path of the element-group kernel is the fastest when tau is constant on every face; one pass over Tau decides
+      if (tau->pendingPieces > 0) { for (int k = 0; k < 2; k++) HFX_CUDA(cudaStreamSynchronize(c->stCopy[k])); }
+      c->dTauFlag.alloc(1); c->dTauFlag.zero(c->st);
+      tau_varies_kernel<<<c->nSM * 4, 256, 0, c->st>>>((long long)c->nFaces, c->nNf, tau->nVal, tau->d.p, c->dTauFlag.p);
+      int tv = 0;
+      c->dTauFlag.download(&tv, 1, c->st);
+      tauVaries = tv != 0;
+    }
+    const bool bigP3 = !p1 && !recoverMode && !dumpMode && bigP3Mode > 0 && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 3 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU)
+        && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && (needSuuModel || bigP3Mode == 2 || tauVaries);
+    bool fused = !p1 && !bigP3 && !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
     // fields still crossing PCIe (hfx_field_set_async): the element chunks start as their face-id prefix has arrived
     std::vector<DField*> pend;
     for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) pend.push_back(&kv.second);
@@ -1854,7 +1882,12 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     if (!fused && !p1 && !dumpMode && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA
         && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_BIG")) {
       if (!pend.empty()) waitPieces(0, -1);
-      HFX_CUDA((launch_big<3, 4>(p, c->nSM, c->st)));
+      HFX_CUDA((launch_big<3, 4, 512>(p, c->nSM, c->st)));
+      big = true;
+    }
+    if (bigP3) {
+      if (!pend.empty()) waitPieces(0, -1);
+      HFX_CUDA((launch_big<3, 3, 256>(p, c->nSM, c->st)));
       big = true;
     }
     if (recoverMode) {

@@ -76,3 +76,12 @@ def test_recovery_by_recomputation(model):
     assert H.rel_err(fm2["Flux"].values, o.flux.ravel()) < TOL_SOLUTION
     with pytest.raises(Exception):
         s2.getLocal()
+
+
+@pytest.mark.parametrize("model,diff,tau_double,expect", [("laplace", "none", False, "fused"), ("diffsrc", "none", True, "big"), ("cdrs", "none", True, "big"),
+                                                          ("euler", "const", False, "big"), ("cdrs", "scalar", False, "fused")])
+def test_order_3_dispatch_and_parity(model, diff, tau_double, expect):
+    """3-D order 3 on straight-sided cells: Laplace-type models with a face-constant tau keep the all-reference path of the element-group kernel; a tau that varies
+    along faces (tau_double draws random nodal values), convection, reaction or implicit Euler take hdg_big_kernel<3,3,256>; a diffusion FIELD keeps the element-group kernel."""
+    o, s, fm = compare(H.make_case(3, 3, N=2, perturb=0.1, model=model, diff=diff, tau_double=tau_double, seed=61))
+    assert s.lastAssembleKernel() == expect

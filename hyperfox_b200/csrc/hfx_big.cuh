@@ -133,22 +133,43 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
   if ((nN & 1) && tid == 0) KA[nN + nNp * nN] = 1.0;      // odd size: unit pad diagonal of K for the 2x2-block Gauss-Jordan (pad row / column stay zero)
   __syncthreads();
 
-  long long tprev = clock64();
-  for (int e = p.eBegin + blockIdx.x; e < p.eEnd; e += gridDim.x) {
-    // ---- P0: gather (HDGSolver.cpp:231-326) --------------------------------------------------------------------------------------------
-    for (int i = tid; i < nN * DIM; i += NT) X[i] = p.elemX[(size_t)e * nN * DIM + i];
+  // ---- software prefetch of the next element's gather (registers): the two dependent levels (face ids -> tau / row starts) are issued in two stages
+  //      behind the S phase of the current element, so their DRAM latency never sits on the critical path -----------------------------------------------
+  static_assert(nN * DIM <= NT, "one thread per coordinate");
+  double pfX = 0.0, pfTau = 0.0;
+  int pfF = 0, pfPerm = 0, pfSide = 0, pfPos = 0, pfBc = 0, pfInt = 0;
+  long long pfRow = 0;
+  auto prefetchA = [&](int e) {
+    if (e >= p.eEnd) return;
+    if (tid < nN * DIM) pfX = p.elemX[(size_t)e * nN * DIM + tid];
     if (tid < l) {
       const int f = tid / t;
-      const int F = p.cell2face[(size_t)e * nFc + f];
-      const int pos = p.fperm[(size_t)e * l + tid];
-      PERM[tid] = pos; CMAP[f * t + pos] = tid;
-      const int side = (p.tauVals == 2) ? p.tauSide[(size_t)e * nFc + f] : 0;
-      TAU[tid] = p.tau[((size_t)F * t + pos) * p.tauVals + side];
+      pfF = p.cell2face[(size_t)e * nFc + f];
+      pfPerm = p.fperm[(size_t)e * l + tid];
+      pfSide = (p.tauVals == 2) ? p.tauSide[(size_t)e * nFc + f] : 0;
+    } else if (tid >= 128 && tid < 128 + nFc) pfF = p.cell2face[(size_t)e * nFc + (tid - 128)];
+    else if (tid >= 160 && tid < 160 + nFc * nFc) pfPos = p.elemPos[(size_t)e * nFc * nFc + (tid - 160)];
+  };
+  auto prefetchB = [&](int e) {
+    if (e >= p.eEnd) return;
+    if (tid < l) pfTau = p.tau[((size_t)pfF * t + pfPerm) * p.tauVals + pfSide];
+    else if (tid >= 128 && tid < 128 + nFc) { pfRow = p.faceRowStart[pfF]; pfBc = p.faceBC[pfF]; pfInt = p.faceInterior[pfF]; }
+  };
+  prefetchA(p.eBegin + blockIdx.x);
+  prefetchB(p.eBegin + blockIdx.x);
+
+  long long tprev = clock64();
+  for (int e = p.eBegin + blockIdx.x; e < p.eEnd; e += gridDim.x) {
+    // ---- P0: commit the prefetched gather (HDGSolver.cpp:231-326) ----------------------------------------------------------------------------
+    if (tid < nN * DIM) X[tid] = pfX;
+    if (tid < l) {
+      PERM[tid] = pfPerm; CMAP[(tid / t) * t + pfPerm] = tid;
+      TAU[tid] = pfTau;
     } else if (tid == l) CMAP[l] = l;
     else if (tid >= 128 && tid < 128 + nFc) {
-      const int f = tid - 128, F = p.cell2face[(size_t)e * nFc + f];
-      ISM[f] = F; ROWS[f] = p.faceRowStart[F]; BCF[f] = p.faceBC[F]; INTF[f] = p.faceInterior[F];
-    } else if (tid >= 160 && tid < 160 + nFc * nFc) POS[tid - 160] = p.elemPos[(size_t)e * nFc * nFc + (tid - 160)];
+      const int f = tid - 128;
+      ISM[f] = pfF; ROWS[f] = pfRow; BCF[f] = pfBc; INTF[f] = pfInt;
+    } else if (tid >= 160 && tid < 160 + nFc * nFc) POS[tid - 160] = pfPos;
     if (hasConv) { const int* cell = p.cells + (size_t)e * nN; for (int i = tid; i < nN * DIM; i += NT) VN[i] = p.vel[(size_t)cell[i / DIM] * DIM + (i % DIM)]; }
     if (needPhi) for (int i = tid; i < nIP * nN; i += NT) PHI[(i / nN) * nNp + (i % nN)] = p.shape[i];
     if (euler) for (int i = tid; i < nN; i += NT) SOLD[i] = p.solOld[(size_t)e * nN + i];
@@ -524,17 +545,32 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
           double bh[2] = {0.0, 0.0}; int fc[2] = {0, 0};
 #pragma unroll
           for (int h = 0; h < 2; h++) if (n + h < l) { bh[h] = BH[m * ldb + n + h]; fc[h] = (n + h) / t; }
+          double qv[DIM][2];
 #pragma unroll
           for (int d = 0; d < DIM; d++) {
-            double v[2];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
               double s = 0.0;
 #pragma unroll
               for (int r = 0; r < DIM; r++) s = fma(-Ii[d][r], c[r][h], s);
-              v[h] = fma(GEO[G_F + fc[h] * GF + GF_CQ + d], bh[h], s);
+              qv[d][h] = fma(GEO[G_F + fc[h] * GF + GF_CQ + d], bh[h], s);
             }
-            *reinterpret_cast<double2*>(QQ + (d * nN + m) * ldc + n) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(QQ + (d * nN + m) * ldc + n) = make_double2(qv[d][0], qv[d][1]);
+          }
+          // Zq_f[b][:] = -c sum_d n_fd Q_d[faceNodes_f(b)][:] for the faces this node lies on (straight face, D = c I: Slq_d = -c area n_fd M^f): the S phase reads
+          // it instead of the (1 + dim) t long reduction.  The span that held SJ / K / R is free since the refinement of U.
+          if (!p.recover) {
+#pragma unroll
+            for (int f = 0; f < nFc; f++) {
+              const int b = NIF[f * nN + m];
+              if (b >= 0) {
+                const double* g = GEO + G_F + f * GF + GF_N;
+                double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+                for (int d = 0; d < DIM; d++) { const double w = -dsc * g[d]; z0 = fma(w, qv[d][0], z0); z1 = fma(w, qv[d][1], z1); }
+                *reinterpret_cast<double2*>(ZQ + (f * tq + b) * ldc + n) = make_double2(z0, z1);
+              }
+            }
           }
         }
       }
@@ -542,6 +578,7 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
     fence_proxy_async();
     __syncthreads();
     HFX_PROF(8);
+    prefetchA(e + gridDim.x);
     if (p.recover) {   // recovery by recomputation: u_e = U lambda_e + U0, q_e = Q lambda_e + Q0 straight out of shared memory; nothing else leaves
       constexpr int q = DIM * nN;
       double* const LAM = SJ;   // (dead since PD)
@@ -555,37 +592,33 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
         for (int c2 = 0; c2 < l; c2 += 2) { s0 = fma(row[c2], LAM[c2], s0); s1 = fma(row[c2 + 1], LAM[c2 + 1], s1); }
         if (tid < nN) p.recSol[(size_t)e * nN + tid] = s0 + s1; else p.recFlux[(size_t)e * q + rq] = s0 + s1;
       }
+      prefetchB(e + gridDim.x);
       __syncthreads();
       continue;
     }
     // U, Q leave as whole rows (row-major per element in HBM): one bulk copy (TMA) per row, in flight during the S phase
     if (p.U) {
       constexpr int q = DIM * nN;
-      if (tid < nN + q) {
-        const int row = tid;
-        if (row < nN) bulk_store(p.U + ((size_t)e * nN + row) * l, UU + row * ldc, l * 8);
-        else { const int rq = row - nN; bulk_store(p.Q + ((size_t)e * q + rq) * l, QQ + ((rq % DIM) * nN + rq / DIM) * ldc, l * 8); }
-        bulk_commit();
+      if (p.gjThreads != 2) {   // one TMA row copy per thread: the issuing warps spend ~3 k cycles at order 4 (140 serialised issues) while the others start the S phase
+        if (tid < nN + q) {
+          const int row = tid;
+          if (row < nN) bulk_store(p.U + ((size_t)e * nN + row) * l, UU + row * ldc, l * 8);
+          else { const int rq = row - nN; bulk_store(p.Q + ((size_t)e * q + rq) * l, QQ + ((rq % DIM) * nN + rq / DIM) * ldc, l * 8); }
+          bulk_commit();
+        }
+      } else {                  // (experiment HFX_GJ=2: coalesced 16-byte stores by the whole CTA: same time, the store path is the limit either way)
+        static_assert(l % 2 == 0, "16-byte pieces");
+        constexpr int L2 = l / 2;
+        double2* const gU = reinterpret_cast<double2*>(p.U + (size_t)e * nN * l);
+        double2* const gQ = reinterpret_cast<double2*>(p.Q + (size_t)e * q * l);
+        for (int idx = tid; idx < (nN + q) * L2; idx += NT) {
+          const int row = idx / L2, c2 = idx - row * L2;
+          if (row < nN) gU[idx] = *reinterpret_cast<const double2*>(UU + row * ldc + 2 * c2);
+          else { const int rq = row - nN; gQ[rq * L2 + c2] = *reinterpret_cast<const double2*>(QQ + ((rq % DIM) * nN + rq / DIM) * ldc + 2 * c2); }
+        }
       }
     }
 
-    // ---- PZ: Zq_f[b][:] = -c sum_d n_fd Q_d[faceNodes_f(b)][:] (straight face, D = c I: Slq_d = -c area n_fd M^f) ----------------------------------
-    for (int item = tid; item < l * (ldc / 2); item += NT) {
-      const int fb = item / (ldc / 2), c2 = 2 * (item - fb * (ldc / 2)), f = fb / t, b = fb - f * t;
-      if (c2 <= l) {
-        const int nd = FN[fb];
-        const double* g = GEO + G_F + f * GF + GF_N;
-        double zx = 0.0, zy = 0.0;
-#pragma unroll
-        for (int d = 0; d < DIM; d++) {
-          const double2 qq = *reinterpret_cast<const double2*>(QQ + (d * nN + nd) * ldc + c2);
-          const double w = -dsc * g[d];
-          zx = fma(w, qq.x, zx); zy = fma(w, qq.y, zy);
-        }
-        *reinterpret_cast<double2*>(ZQ + (f * tq + b) * ldc + c2) = make_double2(zx, zy);
-      }
-    }
-    __syncthreads();
     HFX_PROF(9);
 
     // ---- PS: S_f = FT_f (U_f - I_f) + (area_f M^f) Zq_f (+ FC_f on the diagonal block: convection part of Sll) ; S0 = -(column l) (:347-348);
@@ -657,6 +690,7 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
     }
     __syncthreads();
     HFX_PROF(10);
+    prefetchB(e + gridDim.x);
 
     // ---- PW: write-out.  Block (f, f2) of the element is one contiguous t x t block of the global block CSR (face-node order): coalesced copy,
     //      atomic add where the second element of an interior face adds to the same diagonal block (two contributors on zeroed storage: order independent).

@@ -246,7 +246,8 @@ def main():
     ap.add_argument("--sweep-dofs", type=float, default=2.0e7, help="--config 5: nCells * nN(p) per order (SURVEY 8d: 2e7)")
     ap.add_argument("--partition-file", default=None, help="cell partition vector (.npy or text, one rank id per cell of the global mesh), "
                     "e.g. a Zoltan partition; default: recursive coordinate bisection")
-    ap.add_argument("--partition", default="rcb", choices=("rcb", "slabs"), help="built-in stand-in for the Zoltan partition")
+    ap.add_argument("--partition", default="rcb", choices=("rcb", "graph", "slabs"), help="built-in stand-in for the Zoltan partition: recursive coordinate bisection, "
+                    "recursive bisection of the dual graph (greedy graph growing), or slabs of the lexicographic mesh")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-solve", action="store_true")
@@ -292,7 +293,8 @@ def main():
     if world > 1:
         # recursive coordinate bisection of the cell centroids, balanced by cell count (a third of the slabs' cut at 8 ranks)
         part = partition.load_partition_vector(args.partition_file, nTot, world) if args.partition_file else \
-            (partition.rcb_partition_vector_c(verts, lin, world) if args.partition == "rcb" else partition.partition_vector(nTot, world))
+            (partition.rcb_partition_vector_c(verts, lin, world) if args.partition == "rcb" else
+             (partition.graph_partition_vector_c(lin, world, dim) if args.partition == "graph" else partition.partition_vector(nTot, world)))
         prob = partition.Plan(dim, lin, part, rank, world).as_problem(verts)      # partition + halo plan: host C++ behind the C ABI (hfx_plan_create)
         lverts, lcells, nOwned = prob["verts"], prob["lin_cells"], int(prob["owned_cells"].size)
     else:
@@ -482,7 +484,7 @@ def main():
         "metric": metric_name(order, args.model),
         "value": nAll / (ms_step * 1e-3), "unit": "elements/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak" if args.config == 4 else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(order, N, args.model), "kernel": kernel_name, "recovery": "by recomputation (U, Q not stored)" if args.recompute_recovery else "stored U, Q", "elements_per_rank": nC, "owned_elements_rank0": nOwned, "partition": ((("file " + os.path.basename(args.partition_file)) if args.partition_file else ("recursive coordinate bisection of the cell centroids" if args.partition == "rcb" else "slabs of the lexicographic Kuhn mesh")) + ", overlap-1 ghost cells recomputed by the face owner" if world > 1 else "single rank"), "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
+        "config": {"workload": workload_name(order, N, args.model), "kernel": kernel_name, "recovery": "by recomputation (U, Q not stored)" if args.recompute_recovery else "stored U, Q", "elements_per_rank": nC, "owned_elements_rank0": nOwned, "partition": ((("file " + os.path.basename(args.partition_file)) if args.partition_file else ("recursive coordinate bisection of the cell centroids" if args.partition == "rcb" else ("recursive bisection of the dual graph (greedy graph growing)" if args.partition == "graph" else "slabs of the lexicographic Kuhn mesh"))) + ", overlap-1 ghost cells recomputed by the face owner" if world > 1 else "single rank"), "trace_dofs_rank0": int(nrows.value), "csr_nnz_rank0": int(nnz.value),
                    "l2": "inputs+outputs per step (%.1f GB) far larger than the 126 MB L2" % ((BYTES_STORE[order] * nC) / 1e9),
                    "timing": "CUDA events on the library stream around memset+kernel, max over ranks; wall-clock per step %.2f ms" % ms_wall,
                    "setup_s": round(t_setup, 1),

@@ -2250,6 +2250,9 @@ int hfx_host_rcb_partition(int dim, int geom, long long nVerts, const double* ve
     rcb_partition(dim, nVerts, verts, nCells, lin.numNodes(), linCells, world, part);
   });
 }
+int hfx_host_graph_partition(int dim, int geom, long long nCells, const int* linCells, int world, int* part) {
+  return plan_guard([&] { graph_partition(dim, geom == HFX_SIMPLEX ? 0 : 1, nCells, linCells, world, part); });
+}
 int hfx_plan_create(int dim, int geom, long long nCells, const int* linCells, const int* part, int rank, int world, hfx_plan** plan) {
   return plan_guard([&] {
     if (!plan) throw std::runtime_error("Partitioner : update : no plan handle");

@@ -56,6 +56,66 @@ void rcb_partition(int dim, long long nVerts, const double* verts, long long nCe
   }
 }
 
+void graph_partition(int dim, int geom, long long nCells, const int* cells, int world, int* part) {
+  if (world < 1) throw std::runtime_error("Partitioner : computePartition : the number of partitions must be positive");
+  if (nCells < world) throw std::runtime_error("Partitioner : computePartition : every rank must own at least one cell");
+  RefElement lin(dim, 1, geom == 0 ? kSimplex : kOrthotope);
+  const int nFc = lin.numFaces();
+  MeshTopology G;
+  compute_faces(lin, (int)nCells, cells, &G);
+  // dual graph in CSR form: neighbours of a cell in ascending local face order
+  std::vector<int> adj((size_t)nCells * nFc, -1);
+  for (long long c = 0; c < nCells; c++)
+    for (int f = 0; f < nFc; f++) {
+      const int F = G.cell2face[(size_t)c * nFc + f];
+      const int a = G.face2cell[(size_t)F * 2], b = G.face2cell[(size_t)F * 2 + 1];
+      adj[(size_t)c * nFc + f] = a == c ? b : a;
+    }
+  std::vector<int> mark((size_t)nCells, -1);          // id of the job a cell currently belongs to
+  std::vector<int> level((size_t)nCells, 0);
+  struct Job { std::vector<int> ids; int r0, k; };
+  std::vector<Job> stack;
+  { Job j; j.ids.resize((size_t)nCells); std::iota(j.ids.begin(), j.ids.end(), 0); j.r0 = 0; j.k = world; stack.push_back(std::move(j)); }
+  int jobId = 0;
+  std::vector<int> order, queue;
+  while (!stack.empty()) {
+    Job job = std::move(stack.back());
+    stack.pop_back();
+    if (job.k == 1) { for (int id : job.ids) part[id] = job.r0; continue; }
+    const int me = jobId++;
+    for (int id : job.ids) mark[(size_t)id] = me;
+    // breadth-first order of the subset from `start` (components that are not reached are appended from their lowest remaining id)
+    auto bfs = [&](int start) {
+      order.clear();
+      const int visited = -2 - me;                     // (distinct from every job id)
+      auto run = [&](int s0) {
+        queue.assign(1, s0); mark[(size_t)s0] = visited; level[(size_t)s0] = 0;
+        for (size_t h = 0; h < queue.size(); h++) {
+          const int c = queue[h];
+          order.push_back(c);
+          for (int f = 0; f < nFc; f++) {
+            const int nb = adj[(size_t)c * nFc + f];
+            if (nb >= 0 && mark[(size_t)nb] == me) { mark[(size_t)nb] = visited; level[(size_t)nb] = level[(size_t)c] + 1; queue.push_back(nb); }
+          }
+        }
+      };
+      run(start);
+      for (int id : job.ids) if (mark[(size_t)id] == me) run(id);
+      for (int id : job.ids) mark[(size_t)id] = me;    // restore for the next sweep
+    };
+    bfs(job.ids.front());
+    const int far = order.back();                      // a cell of the last shell: pseudo-peripheral start
+    bfs(far);
+    const int kl = job.k / 2;
+    const long long n = (long long)job.ids.size(), nl = (n * kl + job.k / 2) / job.k;
+    Job L, R;
+    L.ids.assign(order.begin(), order.begin() + nl); R.ids.assign(order.begin() + nl, order.end());
+    std::sort(L.ids.begin(), L.ids.end()); std::sort(R.ids.begin(), R.ids.end());
+    L.r0 = job.r0; L.k = kl; R.r0 = job.r0 + kl; R.k = job.k - kl;
+    stack.push_back(std::move(L)); stack.push_back(std::move(R));
+  }
+}
+
 void build_partition_plan(int dim, int geom, long long nCells, const int* cells, const int* part, int rank, int world, PartitionPlan* P) {
   RefElement lin(dim, 1, geom == 0 ? kSimplex : kOrthotope);
   const int nv = lin.numNodes(), nFc = lin.numFaces();

@@ -12,6 +12,11 @@ namespace hfx {
 // partition vector can be used instead).  verts [nVerts][dim], cells [nCells][nv] (vertex ids), part [nCells] out.
 void rcb_partition(int dim, long long nVerts, const double* verts, long long nCells, int nv, const int* cells, int world, int* part);
 
+// Graph partition of the dual graph (cells adjacent through a face -- the graph the reference hands to Zoltan GRAPH / PHG, ZoltanPartitioner.cpp:169-260) by
+// recursive bisection with greedy graph growing: breadth-first from a pseudo-peripheral cell of the subset, the first floor(k/2)/k of the cells in BFS order
+// (ties by cell id) form one side; every part of a connected mesh is a union of at most a few BFS shells, balanced to one cell.  Deterministic; needs no coordinates.
+void graph_partition(int dim, int geom, long long nCells, const int* cells, int world, int* part);
+
 struct PartitionPlan {
   int dim = 0, geom = 0, rank = 0, world = 1, nv = 0, nFc = 0;
   long long nOwned = 0, nGhost = 0;

@@ -247,6 +247,19 @@ def rcb_partition_vector_c(verts, lin_cells, world, geom=0):
     return part
 
 
+def graph_partition_vector_c(lin_cells, world, dim=3, geom=0):
+    """hfx_host_graph_partition: recursive bisection of the dual graph by greedy graph growing (host C++; the stand-in closest to Zoltan GRAPH)."""
+    import ctypes as C
+    from .capi import lib, pi, ErrorHandle
+    cells = np.ascontiguousarray(lin_cells, dtype=np.int32)
+    part = np.zeros(cells.shape[0], dtype=np.int32)
+    L = lib()
+    L.hfx_plan_last_error.restype = C.c_char_p
+    if L.hfx_host_graph_partition(dim, geom, C.c_longlong(cells.shape[0]), pi(cells), world, pi(part)):
+        raise ErrorHandle(L.hfx_plan_last_error().decode())
+    return part
+
+
 class Plan:
     """hfx_plan handle: the partition / halo plan of one rank, built in host C++ (hfx_plan_create)."""
 

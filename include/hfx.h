@@ -161,6 +161,9 @@ int hfx_comm_halo_field(hfx_ctx* ctx, const char* faceFieldName); /* Partitioner
 /* recursive coordinate bisection of the cell centroids: deterministic stand-in for the Zoltan PHG partition (ZoltanPartitioner.cpp:14-32);
    verts [nVerts][dim], linCells [nCells][verticesPerCell], part [nCells] out.  A Zoltan partition vector can be passed to hfx_plan_create instead. */
 int hfx_host_rcb_partition(int dim, int geom, long long nVerts, const double* verts, long long nCells, const int* linCells, int world, int* part);
+/* graph partition of the dual graph of the mesh (cells adjacent through a face: the graph ZoltanPartitioner.cpp:169-260 hands to Zoltan GRAPH / PHG) by recursive
+   bisection with greedy graph growing from a pseudo-peripheral cell; deterministic, balanced to one cell, needs no coordinates */
+int hfx_host_graph_partition(int dim, int geom, long long nCells, const int* linCells, int world, int* part);
 typedef struct hfx_plan hfx_plan;
 /* plan of `rank`: owned cells + the ghost cells across the faces it owns (a face travels with its first adjacent cell, ZoltanPartitioner.cpp:83-133),
    local vertex / cell / face numbering, face ownership, send / receive lists per neighbour rank, the reference's sharedFaceList */

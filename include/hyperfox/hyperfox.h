@@ -509,6 +509,22 @@ class RcbPartitioner : public Partitioner {
     if (hfx_host_rcb_partition(dim, geom, myMesh->getNumberPoints(), myMesh->getPoints()->data(), nC, lin.data(), nPartitions, partitionVector.data())) throw ErrorHandle(hfx_plan_last_error());
   }
 };
+// Recursive bisection of the dual graph (cells adjacent through a face: what ZoltanPartitioner.cpp:169-260 gives Zoltan) by greedy graph growing.
+class GraphPartitioner : public Partitioner {
+ public:
+  using Partitioner::Partitioner;
+  void computePartition() override {
+    if (!initialized) throw ErrorHandle("GraphPartitioner", "computePartition", "must initialize the partitioner before computing the partition.");
+    if (!myMesh || !myMesh->getReferenceElement()) throw ErrorHandle("GraphPartitioner", "computePartition", "must set the mesh before computing the partition.");
+    const ReferenceElement* re = myMesh->getReferenceElement();
+    const int dim = re->getDimension(), geom = re->getGeometry() == simplex ? HFX_SIMPLEX : HFX_ORTHOTOPE, nN = re->getNumNodes(), nv = geom == HFX_SIMPLEX ? dim + 1 : (1 << dim);
+    const int nC = myMesh->getNumberCells();
+    std::vector<int> lin((size_t)nC * nv);
+    for (int c = 0; c < nC; c++) for (int k = 0; k < nv; k++) lin[(size_t)c * nv + k] = (*myMesh->getCells())[(size_t)c * nN + k];
+    partitionVector.assign((size_t)nC, 0);
+    if (hfx_host_graph_partition(dim, geom, nC, lin.data(), nPartitions, partitionVector.data())) throw ErrorHandle(hfx_plan_last_error());
+  }
+};
 // A partition computed elsewhere (e.g. the reference's Zoltan run: ZoltanPartitioner.cpp:35-167), one rank id per global cell.
 class VectorPartitioner : public Partitioner {
  public:

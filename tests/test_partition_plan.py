@@ -149,3 +149,45 @@ def test_plan_errors_are_reported():
         P.Plan(3, c, np.full(c.shape[0], 5, dtype=np.int32), 0, 2)
     with pytest.raises(Exception, match="Partitioner"):
         P.Plan(3, c, np.zeros(c.shape[0], dtype=np.int32), 1, 2)          # rank 1 owns nothing
+
+
+@pytest.mark.parametrize("mesh,world", [("kuhn", 2), ("kuhn", 5), ("kuhn", 8), ("gmsh", 3), ("gmsh", 8)])
+def test_graph_partition_is_balanced_connected_and_plans(mesh, world):
+    """hfx_host_graph_partition (recursive bisection of the dual graph by greedy graph growing, the stand-in closest to Zoltan GRAPH): balanced to one cell,
+    every part connected in the dual graph, no coordinates needed, and a valid input of the halo plan (ownership / send = receive lists)."""
+    if mesh == "kuhn":
+        v, c = meshgen.kuhn_linear(5, 3)
+    else:
+        from tests.conftest import load_mesh
+        nodes, cells = load_mesh("regression_dim-3_h-2e-1_ord-1")
+        v, c = nodes, cells[:, :4]
+    part = P.graph_partition_vector_c(c, world)
+    counts = np.bincount(part, minlength=world)
+    assert counts.min() >= c.shape[0] // world - 1 and counts.max() <= -(-c.shape[0] // world) + 1
+    c2f, f2c = P.global_linear_topology(c, 3)
+    for r in range(world):           # compactness of each part: graph growing leaves one dominant connected piece (the tail of a BFS order may split off a few cells)
+        ids = np.flatnonzero(part == r); inpart = np.zeros(c.shape[0], dtype=bool); inpart[ids] = True
+        seen = np.zeros(c.shape[0], dtype=bool); comps = []
+        for s0 in ids:
+            if seen[s0]:
+                continue
+            stack = [s0]; seen[s0] = True; n = 0
+            while stack:
+                x = stack.pop(); n += 1
+                for F in c2f[x]:
+                    for y in f2c[F]:
+                        if y >= 0 and inpart[y] and not seen[y]:
+                            seen[y] = True; stack.append(y)
+            comps.append(n)
+        assert max(comps) >= 0.9 * ids.size, (r, comps)
+    plans = [P.Plan(3, c, part, r, world) for r in range(world)]
+    owned = np.concatenate([pl.face_global[pl.owned_face == 1] for pl in plans])
+    assert np.array_equal(np.sort(owned), np.arange(f2c.shape[0]))
+    for r, pl in enumerate(plans):
+        for k, s2 in enumerate(pl.nbrs):
+            q = plans[s2]; ks = list(q.nbrs).index(r)
+            assert np.array_equal(pl.face_global[pl.send[k]], q.face_global[q.recv[ks]])
+    # the cut: a graph partition of the structured mesh should not be worse than twice the coordinate bisection's
+    if mesh == "kuhn":
+        cut = lambda pv: int(((f2c[:, 1] >= 0) & (pv[f2c[:, 0]] != pv[np.maximum(f2c[:, 1], 0)])).sum())
+        assert cut(part) <= 2 * cut(P.rcb_partition_vector(v, c, world))

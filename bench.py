@@ -497,6 +497,8 @@ def main():
                      "traffic": (NCU_TRAFFIC_PER_ELEM[order] * nC if order in NCU_TRAFFIC_PER_ELEM else None),
                      "traffic_source": ("ncu --set full capture at 82,944 tets scaled per element (profiles/r1_assemble_p3_ncu_full_summary.txt); algorithmic bytes %d/element" % BYTES_STORE[order]) if order in NCU_TRAFFIC_PER_ELEM else "not captured for this order; algorithmic bytes %d/element" % BYTES_STORE[order],
                      "peak_source": peak["how"], "kernel_ms": my_k,
+                     "dmma_issue_peak_tflops": peak.get("dmma_tflops"),   # the tensor sub-pipe's own ceiling, measured in this run (DMMA m8n8k4 chains); shares the FP64 datapath
+
                      "algorithmic_flops_per_element": FLOPS_PER_ELEM[order],
                      "flop_count": "SURVEY 8(d) LU-based dense count of the Laplace element at this order (convection adds the Suu contraction: counted as zero)",
                      "hbm": {"achieved_GBs": hbm_ach, "peak_GBs": hbm_peak, "frac": hbm_ach / hbm_peak, "bytes_per_element": BYTES_STORE[order],
@@ -586,7 +588,15 @@ def fp64_peak(device):
         L.hfx_fp64_peak.restype = C.c_double
         tf = L.hfx_fp64_peak(device)
         if tf > 0:
-            return {"tflops": tf, "how": "measured in this run: DFMA chain microbenchmark (hfx_fp64_peak), best of 5"}
+            out = {"tflops": tf, "how": "measured in this run: DFMA chain microbenchmark (hfx_fp64_peak), best of 5"}
+            try:
+                L.hfx_dmma_peak.restype = C.c_double
+                dm = L.hfx_dmma_peak(device)
+                if dm > 0:
+                    out["dmma_tflops"] = dm
+            except Exception:
+                pass
+            return out
     except Exception:
         pass
     return {"tflops": 37.0, "how": "fallback: nominal B200 FP64 (148 SM x 64 DFMA/clk x 1.965 GHz)"}

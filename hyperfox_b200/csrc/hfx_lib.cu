@@ -1184,6 +1184,46 @@ int hfx_device_count(void) {
   return n;
 }
 
+// FP64 tensor-core issue peak: 8 independent DMMA (m8n8k4) accumulator chains per warp
+__global__ void dmma_peak_kernel(int iters, double* out) {
+  double c[8][2];
+#pragma unroll
+  for (int k = 0; k < 8; k++) { c[k][0] = threadIdx.x * 1e-9; c[k][1] = k; }
+  const double a = 1.0000001, b = 1e-9 * (threadIdx.x & 3);
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) dmma(c[k], a, b);
+  }
+  double s2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) s2 += c[k][0] + c[k][1];
+  if (s2 == 123.456) out[0] = s2;
+}
+
+double hfx_dmma_peak(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+  double* d = nullptr;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int iters = 4096, blocks = prop.multiProcessorCount * 4, threads = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0);
+    dmma_peak_kernel<<<blocks, threads>>>(iters, d);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double fl = 2.0 * 8 * 8 * 4 * 8 * (double)iters * blocks * (threads / 32);   // 512 flop per DMMA, 8 chains per warp
+    if (rep > 0 && ms > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return cudaGetLastError() == cudaSuccess ? best : -1.0;
+}
+
 double hfx_fp64_peak(int device) {
   if (cudaSetDevice(device) != cudaSuccess) return -1.0;
   cudaDeviceProp prop;
@@ -2281,6 +2321,9 @@ int hfx_plan_get(const hfx_plan* plan, long long* cellsGlobal, long long* vertex
 }
 int hfx_host_face_canonical_positions(int dim, int order, long long nFaces, int nNf, const int* faces, const long long* nodeVertexGid, unsigned char* canonPos) {
   return plan_guard([&] { face_canonical_positions(dim, order, nFaces, nNf, faces, nodeVertexGid, canonPos); });
+}
+int hfx_host_face_canonical_positions_geom(int dim, int order, int geom, long long nFaces, int nNf, const int* faces, const long long* nodeVertexGid, unsigned char* canonPos) {
+  return plan_guard([&] { face_canonical_positions_geom(dim, order, geom == HFX_SIMPLEX ? 0 : 1, nFaces, nNf, faces, nodeVertexGid, canonPos); });
 }
 int hfx_comm_set_halo_plan(hfx_ctx* c, const hfx_plan* plan, const unsigned char* canonPos) {
   if (!plan) return 1;

@@ -267,4 +267,52 @@ void face_canonical_positions(int dim, int order, long long nFaces, int nNf, con
   }
 }
 
+void face_canonical_positions_geom(int dim, int order, int geom, long long nFaces, int nNf, const int* faces, const long long* gv, uint8_t* canon) {
+  if (geom == 0 || dim <= 2) { face_canonical_positions(dim, order, nFaces, nNf, faces, gv, canon); return; }   // (a line has the same two symmetries either way)
+  if (dim != 3) throw std::runtime_error("Partitioner : update : unsupported face type");
+  RefElement fe(2, order, kOrthotope);
+  if (fe.numNodes() != nNf) throw std::runtime_error("Partitioner : update : the face connectivity does not match the face element");
+  const std::vector<double>& ref = fe.nodes();   // [nNf][2] on [-1,1]^2; the four corners come first
+  double cx[4][2];
+  for (int k = 0; k < 4; k++) for (int d = 0; d < 2; d++) {
+    cx[k][d] = ref[(size_t)k * 2 + d];
+    if (std::fabs(std::fabs(cx[k][d]) - 1.0) > 1e-12) throw std::runtime_error("Partitioner : update : the corners of the face element do not come first");
+  }
+  auto adjacent = [&](int a, int b) { return (cx[a][0] == cx[b][0]) != (cx[a][1] == cx[b][1]); };
+  // tables[A][s]: A = corner with the smallest global id, s = 0 / 1: the lower-id neighbour is the first / second neighbour of A (in corner order)
+  std::vector<int> tables((size_t)4 * 2 * nNf, -1);
+  for (int A = 0; A < 4; A++) {
+    int nb[2], nn = 0, D = -1;
+    for (int k = 0; k < 4; k++) { if (k == A) continue; if (adjacent(A, k)) nb[nn++] = k; else D = k; }
+    if (nn != 2 || D < 0) throw std::runtime_error("Partitioner : update : unexpected corner layout of the face element");
+    for (int s2 = 0; s2 < 2; s2++) {
+      const int B = nb[s2], C = nb[1 - s2];
+      double w[4][2];
+      w[A][0] = -1; w[A][1] = -1; w[B][0] = 1; w[B][1] = -1; w[C][0] = -1; w[C][1] = 1; w[D][0] = 1; w[D][1] = 1;
+      for (int a = 0; a < nNf; a++) {
+        double eta[2] = {0, 0};
+        for (int k = 0; k < 4; k++) {
+          const double N = 0.25 * (1.0 + ref[(size_t)a * 2] * cx[k][0]) * (1.0 + ref[(size_t)a * 2 + 1] * cx[k][1]);
+          eta[0] += N * w[k][0]; eta[1] += N * w[k][1];
+        }
+        int best = -1; double bd = 1e300;
+        for (int b = 0; b < nNf; b++) { const double d = std::max(std::fabs(ref[(size_t)b * 2] - eta[0]), std::fabs(ref[(size_t)b * 2 + 1] - eta[1])); if (d < bd) { bd = d; best = b; } }
+        if (bd > 1e-10) throw std::runtime_error("Partitioner : update : the face node set is not symmetric under the symmetries of the square");
+        tables[((size_t)A * 2 + s2) * nNf + a] = best;
+      }
+    }
+  }
+  for (long long F = 0; F < nFaces; F++) {
+    long long g[4];
+    for (int k = 0; k < 4; k++) { g[k] = gv[faces[(size_t)F * nNf + k]]; if (g[k] < 0) throw std::runtime_error("Partitioner : update : a face vertex has no global vertex id"); }
+    int A = 0;
+    for (int k = 1; k < 4; k++) if (g[k] < g[A]) A = k;
+    int nb[2], nn = 0;
+    for (int k = 0; k < 4; k++) if (k != A && adjacent(A, k)) nb[nn++] = k;
+    const int s2 = g[nb[0]] < g[nb[1]] ? 0 : 1;
+    if (g[nb[0]] == g[nb[1]]) throw std::runtime_error("Partitioner : update : repeated global vertex id on a face");
+    for (int a = 0; a < nNf; a++) canon[(size_t)F * nNf + a] = (uint8_t)tables[((size_t)A * 2 + s2) * nNf + a];
+  }
+}
+
 }  // namespace hfx

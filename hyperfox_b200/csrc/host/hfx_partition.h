@@ -39,5 +39,8 @@ void build_partition_plan(int dim, int geom, long long nCells, const int* cells,
 // face's vertices are taken in ascending GLOBAL vertex id (the local order of a face comes from its first LOCAL cell and differs between ranks).
 // faces [nFaces][nNf] local high-order face connectivity (vertices first); nodeVertexGid [nNodes]: global vertex id of the vertex nodes (-1 elsewhere).
 void face_canonical_positions(int dim, int order, long long nFaces, int nNf, const int* faces, const long long* nodeVertexGid, uint8_t* canon);
+// same for the faces of orthotope cells (lines in 2-D: as above; quadrilaterals in 3-D): the canonical frame of a quadrilateral puts the corner with the smallest global
+// id at (-1,-1) and, of its two neighbours, the one with the smaller id at (1,-1); a node keeps its bilinear weights on the corners
+void face_canonical_positions_geom(int dim, int order, int geom, long long nFaces, int nNf, const int* faces, const long long* nodeVertexGid, uint8_t* canon);
 
 }  // namespace hfx

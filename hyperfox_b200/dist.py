@@ -29,13 +29,30 @@ class DistributedPoisson:
     """HDGLaplaceModel + DirichletModel (g = analytic function of x) on a partitioned simplex mesh; rank-local hfox objects."""
 
     def __init__(self, verts, lin_cells, part, rank, world, order, dim=3, device=0, g=lambda x: np.sin(x[:, 0]) * np.exp(x[:, 1]), rtol=1e-12, maxits=20000,
-                 topology=None):
+                 topology=None, geom="simplex", global_mesh=None):
+        """geom = "orthotope" (quads / hexes): pass the global order-p mesh as global_mesh = (nodes, cells); verts / lin_cells are then its nodes and the
+        vertex columns of its cells (global node ids), and the local mesh is cut out of it (simplices are raised to order p from the local linear cells)."""
         self.rank, self.world, self.dim, self.order = rank, world, dim, order
-        c2f, f2c = topology if topology is not None else partition.global_linear_topology(lin_cells, dim)
-        self.plan = partition.Plan(dim, lin_cells, part, rank, world)          # host C++ behind the C ABI (hfx_plan_create)
+        gcode = 0 if geom == "simplex" else 1
+        if topology is not None:
+            c2f, f2c = topology
+        else:
+            tpg = capi.host_compute_faces(dim, 1, lin_cells, gcode)
+            c2f, f2c = tpg["cell2face"], tpg["face2cell"]
+        self.plan = partition.Plan(dim, lin_cells, part, rank, world, geom=gcode)          # host C++ behind the C ABI (hfx_plan_create)
         self.prob = p = self.plan.as_problem(verts)
-        nodes, cells = meshgen.high_order(p["verts"], p["lin_cells"], order)
-        self.mesh = m = hfox.Mesh(dim, order, "simplex")
+        nv = lin_cells.shape[1]
+        if global_mesh is None:
+            nodes, cells = meshgen.high_order(p["verts"], p["lin_cells"], order)
+            vgid = p["vertex_ids"][p["lin_cells"]]
+        else:                     # cut the local cells (owned first, then ghosts) out of the global order-p mesh: local nodes in ascending global id
+            gnodes, gcells = global_mesh
+            loc = gcells[p["cells_global"]]
+            used = np.unique(loc)
+            remap = -np.ones(gnodes.shape[0], dtype=np.int64); remap[used] = np.arange(used.size)
+            nodes, cells = np.ascontiguousarray(gnodes[used]), remap[loc].astype(np.int32)
+            vgid = loc[:, :nv]     # any globally consistent id of the vertices defines the canonical face-node order: the global node id
+        self.mesh = m = hfox.Mesh(dim, order, geom)
         m.setMesh(nodes, cells)
         re = m.getReferenceElement()
         nN, nNf = re.getNumNodes(), re.getFaceElement().getNumNodes()
@@ -56,8 +73,8 @@ class DistributedPoisson:
         uid = broadcast_unique_id(rank, world)
         check(lib().hfx_comm_init(s._h(), world, rank, uid), s._h())
         gv = np.full(nodes.shape[0], -1, dtype=np.int64)          # global vertex id of the vertex nodes of the local high-order mesh
-        gv[cells[:, :dim + 1]] = p["vertex_ids"][p["lin_cells"]]
-        self.canon = partition.face_canonical_positions_c(dim, order, m.faces, gv)
+        gv[cells[:, :nv]] = vgid
+        self.canon = partition.face_canonical_positions_c(dim, order, m.faces, gv, geom=gcode)
         self.plan.set_halo(s._h(), self.canon)      # hfx_comm_set_halo_plan checks that the plan's local mesh is the context's mesh
         self.nodes, self.cells = nodes, cells
 

@@ -309,15 +309,15 @@ class Plan:
             pass
 
 
-def face_canonical_positions_c(dim, order, faces, node_vertex_gid):
-    """hfx_host_face_canonical_positions (host C++): same result as face_canonical_positions."""
+def face_canonical_positions_c(dim, order, faces, node_vertex_gid, geom=0):
+    """hfx_host_face_canonical_positions[_geom] (host C++): same result as face_canonical_positions; geom = 1: faces of orthotope cells."""
     import ctypes as C
     from .capi import lib, pi, ErrorHandle
     faces = np.ascontiguousarray(faces, dtype=np.int32); gv = np.ascontiguousarray(node_vertex_gid, dtype=np.int64)
     out = np.zeros(faces.shape, dtype=np.uint8)
     L = lib()
     L.hfx_plan_last_error.restype = C.c_char_p
-    if L.hfx_host_face_canonical_positions(dim, order, C.c_longlong(faces.shape[0]), faces.shape[1], pi(faces), gv.ctypes.data_as(C.POINTER(C.c_longlong)),
-                                           out.ctypes.data_as(C.POINTER(C.c_ubyte))):
+    if L.hfx_host_face_canonical_positions_geom(dim, order, geom, C.c_longlong(faces.shape[0]), faces.shape[1], pi(faces), gv.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                                out.ctypes.data_as(C.POINTER(C.c_ubyte))):
         raise ErrorHandle(L.hfx_plan_last_error().decode())
     return out

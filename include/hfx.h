@@ -23,6 +23,7 @@ int hfx_ctx_destroy(hfx_ctx* ctx);
 const char* hfx_last_error(const hfx_ctx* ctx); /* ctx may be NULL: last error of a failed hfx_ctx_create */
 int hfx_device_count(void);                     /* 0 when no CUDA device is usable: the product has no CPU fallback */
 double hfx_fp64_peak(int device);               /* measured DFMA peak of the device in TFLOP/s (roofline denominator; <0 on error) */
+double hfx_dmma_peak(int device);               /* measured DMMA (mma.sync.m8n8k4.f64) issue peak in TFLOP/s: the tensor sub-pipe's own ceiling (<0 on error) */
 
 /* ---- reference element: ReferenceElement(dim, order, geom)  src/element/ReferenceElement.cpp:5-26 ------------ */
 enum { HFX_SIMPLEX = 0, HFX_ORTHOTOPE = 1 };
@@ -179,6 +180,8 @@ int hfx_plan_get(const hfx_plan* plan, long long* cellsGlobal, long long* vertex
                  int* nbrRank, int* sendCount, int* recvCount, int* sendFaces, int* recvFaces, long long* sharedFaceList);
 /* canonPos of hfx_comm_set_halo from the local high-order face connectivity and the global vertex id of every vertex node (-1 for the other nodes) */
 int hfx_host_face_canonical_positions(int dim, int order, long long nFaces, int nNf, const int* faces, const long long* nodeVertexGid, unsigned char* canonPos);
+/* the same for any cell geometry (HFX_SIMPLEX / HFX_ORTHOTOPE: quadrilateral faces of hexahedra keep their bilinear weights on the corners) */
+int hfx_host_face_canonical_positions_geom(int dim, int order, int geom, long long nFaces, int nNf, const int* faces, const long long* nodeVertexGid, unsigned char* canonPos);
 /* hfx_comm_set_halo with the lists of a plan (the local mesh of ctx must be the plan's local cells at the context's order) */
 int hfx_comm_set_halo_plan(hfx_ctx* ctx, const hfx_plan* plan, const unsigned char* canonPos);
 

@@ -191,3 +191,49 @@ def test_graph_partition_is_balanced_connected_and_plans(mesh, world):
     if mesh == "kuhn":
         cut = lambda pv: int(((f2c[:, 1] >= 0) & (pv[f2c[:, 0]] != pv[np.maximum(f2c[:, 1], 0)])).sum())
         assert cut(part) <= 2 * cut(P.rcb_partition_vector(v, c, world))
+
+
+@pytest.mark.parametrize("dim,order", [(2, 2), (2, 4), (3, 1), (3, 2)])
+def test_canonical_face_node_order_of_orthotope_faces(dim, order):
+    """Quadrilateral faces of hexahedra (and the edges of quads): the two cells of an interior face order its nodes differently (any of the 8 symmetries of the square);
+    the canonical positions must put the same physical node in the same slot -- with arbitrary global vertex ids."""
+    nodes, cells = meshgen.box_mesh(2, order, dim, perturb=0.1)
+    tp = capi.host_compute_faces(dim, order, cells, 1)
+    nv = 2 ** dim
+    gv = np.full(nodes.shape[0], -1, dtype=np.int64)
+    vids = np.unique(cells[:, :nv])
+    gv[vids] = np.random.default_rng(5).permutation(10 * vids.size)[:vids.size]
+    fn = capi.host_refel_tables(dim, order, 1)["faceNodes"]
+    canon1 = P.face_canonical_positions_c(dim, order, tp["faces"], gv, geom=1)
+    assert all(np.array_equal(np.sort(r), np.arange(r.size)) for r in canon1)
+    checked = 0
+    for F in range(tp["faces"].shape[0]):
+        c2 = tp["face2cell"][F, 1]
+        if c2 < 0:
+            continue
+        k = list(tp["cell2face"][c2]).index(F)
+        f2 = np.ascontiguousarray(cells[c2][fn[k]][None, :])
+        canon2 = P.face_canonical_positions_c(dim, order, f2, gv, geom=1)[0]
+        a = np.empty(f2.shape[1], dtype=int); a[canon1[F]] = tp["faces"][F]
+        b = np.empty(f2.shape[1], dtype=int); b[canon2] = f2[0]
+        assert np.array_equal(a, b)
+        checked += 1
+    assert checked > 0
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_plan_of_a_hexahedral_mesh(world):
+    nodes, cells = meshgen.box_mesh(4, 1, 3)
+    part = P.rcb_partition_vector_c(nodes, cells, world, geom=1)
+    assert np.bincount(part, minlength=world).tolist() == [cells.shape[0] // world] * world
+    tp = capi.host_compute_faces(3, 1, cells, 1)
+    plans = [P.Plan(3, cells, part, r, world, geom=1) for r in range(world)]
+    owned = np.concatenate([pl.face_global[pl.owned_face == 1] for pl in plans])
+    assert np.array_equal(np.sort(owned), np.arange(tp["faces"].shape[0]))
+    for r, pl in enumerate(plans):
+        for k, s2 in enumerate(pl.nbrs):
+            q = plans[s2]; ks = list(q.nbrs).index(r)
+            assert np.array_equal(pl.face_global[pl.send[k]], q.face_global[q.recv[ks]])
+        ghosts = np.flatnonzero(pl.owned_face == 0)
+        recv = np.concatenate(pl.recv) if pl.recv else np.zeros(0, dtype=int)
+        assert np.array_equal(np.sort(recv), ghosts)

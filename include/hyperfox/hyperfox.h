@@ -312,17 +312,31 @@ class Field {
       default: throw ErrorHandle("Field", "computeNumEntities", "the field type is not supported");
     }
   }
-  void allocate() { computeNumEntities(); values.assign((size_t)numEntities * numObjPerEnt * numValsPerObj, 0.0); }
-  std::vector<double>* getValues() { return &values; }
+  void allocate() { computeNumEntities(); values.assign((size_t)numEntities * numObjPerEnt * numValsPerObj, 0.0); deviceNewer = false; }
+  // Results the device produces (HDGSolver::solve, RungeKutta::computeStage / computeSolution) stay there until somebody looks: getValues() brings them back, and from then
+  // on the host vector is authoritative again (it may be modified in place), so the next assemble uploads it.
+  std::vector<double>* getValues() { syncFromDevice(); return &values; }
+  void syncFromDevice() {
+    if (!deviceNewer) return;
+    deviceNewer = false;
+    detail::check(hfx_field_get(devCtx, devName.c_str(), values.data()), devCtx);
+  }
+  void markOnDevice(hfx_ctx* c, const std::string& name, bool newer) { devCtx = c; devName = name; deviceNewer = newer; }
+  bool isDeviceNewer(const hfx_ctx* c, const std::string& name) const { return deviceNewer && devCtx == c && devName == name; }
+  hfx_ctx* deviceContext() const { return devCtx; }
+  const std::string& deviceName() const { return devName; }
+  std::vector<double>* hostValues() { return &values; }   // no synchronisation: for code that is about to overwrite or upload
   FieldType* getFieldType() { return &type; }
   int* getNumEntities() { return &numEntities; }
   int* getNumObjPerEnt() { return &numObjPerEnt; }
   int* getNumValsPerObj() { return &numValsPerObj; }
   void getValues(int i, std::vector<double>* vals) {
+    syncFromDevice();
     const size_t n = (size_t)numObjPerEnt * numValsPerObj;
     vals->assign(values.begin() + i * n, values.begin() + (i + 1) * n);
   }
   void getSliceValues(std::vector<int>& is, std::vector<double>* vals) {
+    syncFromDevice();
     const size_t n = (size_t)numObjPerEnt * numValsPerObj;
     vals->resize(is.size() * n);
     for (size_t k = 0; k < is.size(); k++) std::copy(values.begin() + is[k] * n, values.begin() + (is[k] + 1) * n, vals->begin() + k * n);
@@ -336,6 +350,9 @@ class Field {
   FieldType type = None;
   int numEntities = 0, numObjPerEnt = 0, numValsPerObj = 0;
   bool doubleValued = false;
+  hfx_ctx* devCtx = nullptr;   // device context that holds a copy of this field (under devName) ...
+  std::string devName;
+  bool deviceNewer = false;    // ... which is ahead of `values`
 };
 
 // ---- src/parallel/Partitioner.h, ZoltanPartitioner.h ----------------------------------------------------------------------------------
@@ -714,6 +731,17 @@ class RungeKutta : public TimeScheme {
   void computeStage(std::map<std::string, Field*>* fm) {   // RungeKutta.cpp:145-180
     if (stageCounter >= getNumStages()) throw ErrorHandle("RungeKutta", "computeStage", "cannot compute more stages than the method allows, think about computing the solution");
     const double invdt = 1.0 / deltat;
+    if (hfx_ctx* h = deviceOf(fm)) {   // device AXPYs (hfx_field_lincomb): the fields do not leave the GPU between the stages
+      for (size_t b = 0; b <= auxiliaryFields.size(); b++) {
+        const std::string base = b == 0 ? "Solution" : auxiliaryFields[b - 1];
+        lincomb(h, fm, stageName(base, stageCounter), {invdt, -invdt}, {base, "Old" + base});
+        std::vector<double> cf(1, 1.0); std::vector<std::string> nm(1, "Old" + base);
+        for (int j = 0; j < stageCounter + 1; j++) { cf.push_back(deltat * bTable[stageCounter * nT + 1 + j]); nm.push_back(stageName(base, j)); }
+        lincomb(h, fm, base, cf, nm);
+      }
+      stageCounter += 1;
+      return;
+    }
     for (size_t b = 0; b <= auxiliaryFields.size(); b++) {
       const std::string base = b == 0 ? "Solution" : auxiliaryFields[b - 1];
       std::vector<double>& sol = *fm->at(base)->getValues();
@@ -730,6 +758,16 @@ class RungeKutta : public TimeScheme {
   }
   void computeSolution(std::map<std::string, Field*>* fm) {   // RungeKutta.cpp:182-213
     if (stageCounter != getNumStages()) throw ErrorHandle("RungeKutta", "computeSolution", "all stages must be computed before computing the solution");
+    if (hfx_ctx* h = deviceOf(fm)) {
+      for (size_t b = 0; b <= auxiliaryFields.size(); b++) {
+        const std::string base = b == 0 ? "Solution" : auxiliaryFields[b - 1];
+        std::vector<double> cf(1, 1.0); std::vector<std::string> nm(1, "Old" + base);
+        for (int k = 0; k < getNumStages(); k++) { cf.push_back(deltat * bTable[stageCounter * nT + 1 + k]); nm.push_back(stageName(base, k)); }
+        lincomb(h, fm, base, cf, nm);
+      }
+      stageCounter = 0;
+      return;
+    }
     for (size_t b = 0; b <= auxiliaryFields.size(); b++) {
       const std::string base = b == 0 ? "Solution" : auxiliaryFields[b - 1];
       std::vector<double>& sol = *fm->at(base)->getValues();
@@ -745,6 +783,26 @@ class RungeKutta : public TimeScheme {
 
  protected:
   static std::string stageName(const std::string& base, int k) { return base == "Solution" ? "RKStage_" + std::to_string(k) : "RKStage_" + base + "_" + std::to_string(k); }
+  // the device context on which the solution fields of `fm` live (after HDGSolver::solve), or NULL: host arithmetic.  At most 8 terms per combination (7 stages).
+  hfx_ctx* deviceOf(std::map<std::string, Field*>* fm) const {
+    if (std::getenv("HFX_HOST_FIELD_ARITHMETIC") || getNumStages() > 7) return nullptr;
+    std::map<std::string, Field*>::iterator it = fm->find("Solution");
+    return it == fm->end() ? nullptr : it->second->deviceContext();
+  }
+  static void lincomb(hfx_ctx* h, std::map<std::string, Field*>* fm, const std::string& dst, const std::vector<double>& cf, const std::vector<std::string>& nm) {
+    std::vector<const char*> names(nm.size());
+    for (size_t k = 0; k < nm.size(); k++) {
+      Field* f = fm->at(nm[k]);
+      if (!f->isDeviceNewer(h, nm[k])) {   // the host copy is the newest (or the field never met the device): upload it
+        detail::check(hfx_field_set(h, nm[k].c_str(), *f->getFieldType() == Node ? HFX_FIELD_NODE : (*f->getFieldType() == Face ? HFX_FIELD_FACE : HFX_FIELD_CELL), *f->getNumObjPerEnt(),
+                                    *f->getNumValsPerObj(), f->getValues()->data(), f->isDoubleValued() ? 1 : 0), h);
+        f->markOnDevice(h, nm[k], false);
+      }
+      names[k] = nm[k].c_str();
+    }
+    detail::check(hfx_field_lincomb(h, dst.c_str(), (int)nm.size(), cf.data(), names.data()), h);
+    fm->at(dst)->markOnDevice(h, dst, true);
+  }
   void tab(int n, std::initializer_list<double> v) { nT = n; bTable.assign(v.begin(), v.end()); }
   std::vector<double> bTable;
   int nT = 0;
@@ -1019,7 +1077,11 @@ class Solver {
 class HDGSolver : public Solver {
  public:
   using Solver::Solver;
-  ~HDGSolver() { delete ownCtx; }
+  ~HDGSolver() {   // fields whose newest copy lives in this solver's context come home before the context goes away
+    if (fieldMap) for (std::map<std::string, Field*>::iterator it = fieldMap->begin(); it != fieldMap->end(); ++it)
+      if (it->second && it->second->deviceContext() && ownCtx && it->second->deviceContext() == ownCtx->h) { try { it->second->syncFromDevice(); } catch (...) {} it->second->markOnDevice(nullptr, "", false); }
+    delete ownCtx;
+  }
   void setOptions(HDGSolverOpts opts) {
     if (opts.type != IMPLICIT) throw ErrorHandle("HDGSolver", "setOptions", "only the IMPLICIT solver type has a device path");
     myOpts = opts;
@@ -1101,8 +1163,8 @@ class HDGSolver : public Solver {
     if (cl) o = cl->cOpts();
     detail::check(hfx_solve(ctx(), &o, &stats), ctx());
     if (cl) cl->stats = stats;
-    const char* out[3] = {"Trace", "Solution", "Flux"};
-    for (int k = 0; k < 3; k++) detail::check(hfx_field_get(ctx(), out[k], fieldMap->at(out[k])->getValues()->data()), ctx());
+    const char* out[3] = {"Trace", "Solution", "Flux"};   // left on the device; Field::getValues() fetches them when somebody looks
+    for (int k = 0; k < 3; k++) fieldMap->at(out[k])->markOnDevice(ctx(), out[k], true);
   }
 
   // parity hooks
@@ -1147,7 +1209,9 @@ class HDGSolver : public Solver {
     const std::set<std::string> names = inputNames();
     for (std::set<std::string>::const_iterator it = names.begin(); it != names.end(); ++it) {
       Field* f = fieldMap->at(*it);
+      if (f->isDeviceNewer(ctx(), *it)) continue;   // produced on the device and not looked at since
       detail::check(hfx_field_set(ctx(), it->c_str(), cType(*f->getFieldType()), *f->getNumObjPerEnt(), *f->getNumValsPerObj(), f->getValues()->data(), f->isDoubleValued() ? 1 : 0), ctx());
+      f->markOnDevice(ctx(), *it, false);
     }
   }
   void describeModel(bool strict) {

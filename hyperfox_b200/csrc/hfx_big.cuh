@@ -22,9 +22,29 @@
 namespace hfx {
 
 
-template <int DIM, int P>
+// Element descriptions: sizes (Cubature.cpp nIP map), the vertices that span the affine frame of a straight-sided cell (origin + one per
+// reference axis) and of a face.  Simplices: 0,1,2,3; orthotopes: 0,1,3,4 and 0,1,3 (vertex order of ReferenceElement.cpp:885-943).
+template <int DIM_, int P>
+struct BigSimplex {
+  using E = ElemCfg<DIM_, P>;
+  static constexpr int DIM = DIM_, nN = E::nN, nNf = E::nNf, nFc = E::nFc, nIP = E::nIP, nIPf = E::nIPf;
+  __host__ __device__ static constexpr int fv(int i) { return i; }
+  __host__ __device__ static constexpr int ff(int i) { return i; }
+};
+struct BigHexP2 {   // 27-node hexahedron (the reference element's maximum order for orthotopes in 3-D)
+  static constexpr int DIM = 3, nN = 27, nNf = 9, nFc = 6, nIP = 58, nIPf = 20;
+  __host__ __device__ static constexpr int fv(int i) { return i == 0 ? 0 : (i == 1 ? 1 : (i == 2 ? 3 : 4)); }
+  __host__ __device__ static constexpr int ff(int i) { return i == 0 ? 0 : (i == 1 ? 1 : 3); }
+};
+__host__ __device__ constexpr int big_ld(int x) {   // smallest even leading dimension >= x that is 4 or 12 mod 16 (both DMMA fragment patterns conflict free)
+  int v = (x + 3) & ~3;
+  while (v % 16 != 4 && v % 16 != 12) v += 4;
+  return v;
+}
+
+template <class C>
 struct BigSmem {
-  using C = ElemCfg<DIM, P>;
+  static constexpr int DIM = C::DIM;
   static constexpr int nN = C::nN, t = C::nNf, nFc = C::nFc, nIP = C::nIP, nIPf = C::nIPf, l = nFc * t;
   static constexpr int nNp = ((nN + 3) / 4) * 4;           // reduction pad (zeros) up to a multiple of 4
   static constexpr int npe = ev(nN);                       // size of the Gauss-Jordan (even), and the leading dimension of the global reference tables
@@ -32,13 +52,13 @@ struct BigSmem {
   static constexpr int KSN = nNp / 4;                      // reduction steps over the element nodes
   static constexpr int MTN = (nN + 7) / 8;                 // 8-row tiles over the element nodes
   static constexpr int ldc = ((l + 2 + 11) / 16) * 16 + 4; // R, U, Q, Zq rows: >= l + 2, = 4 mod 16
-  static constexpr int ldb = (l % 16 == 4 || l % 16 == 12) ? l : ev(l) + 4 - (ev(l) % 4 == 0 ? 0 : 2);   // resident B^ rows (= 4 or 12 mod 16 where that is cheap)
+  static constexpr int ldb = big_ld(l);                    // resident B^ rows
   static constexpr int tq = ((t + 3) / 4) * 4;             // face reduction pad
-  static constexpr int ldf = (tq % 16 == 4 || tq % 16 == 12) ? tq : tq + 4;   // face matrices, column-major [b][a], leading dimension = 4 or 12 mod 16
+  static constexpr int ldf = big_ld(tq);                   // face matrices, column-major [b][a]
   static constexpr int FSZ = ldf * tq;
   static constexpr int nIPp = ((nIP + 3) / 4) * 4, nIPfp = ((nIPf + 3) / 4) * 4;
-  static constexpr int ldw = 12;                           // face weights [ip][(f, kind)], 2 nFc <= 8 columns
-  static_assert(2 * nFc <= 8, "one column tile of face weights");
+  static constexpr int NWT = (2 * nFc + 7) / 8;            // column tiles of the face weights [ip][(f, kind)]
+  static constexpr int ldw = big_ld(8 * NWT);
   // resident tables
   static constexpr int oAR = 0;                            // A^_r row-major [DIM][nNp][nNp]
   static constexpr int oBH = oAR + DIM * nNp * nNp;        // B^ row-major [nNp][ldb], column (f, b)
@@ -77,15 +97,18 @@ struct BigSmem {
   static constexpr size_t bytes = (size_t)nDoubles * 8 + 8 * (size_t)nFc + 4 * (size_t)nInts + 16;
 };
 
-template <int DIM, int P, int NT_>
+template <class C, int NT_>
 __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const AsmParams p) {
-  using L = BigSmem<DIM, P>;
+  using L = BigSmem<C>;
+  constexpr int DIM = C::DIM;
   constexpr int nN = L::nN, t = L::t, nFc = L::nFc, nIP = L::nIP, nIPf = L::nIPf, l = L::l;
   constexpr int nNp = L::nNp, npe = L::npe, KSN = L::KSN, MTN = L::MTN, ldc = L::ldc, ldb = L::ldb, tq = L::tq, ldf = L::ldf, FSZ = L::FSZ;
   constexpr int nIPp = L::nIPp, nIPfp = L::nIPfp, ldw = L::ldw, D2 = DIM * DIM;
   constexpr int NT = NT_, NWARP = NT / 32;
   constexpr int L1T = (l + 1 + 7) / 8, LT = (l + 7) / 8;
-  static_assert(l + 1 <= 128 && nFc * nIPf <= 64 && nIP <= 64 && 160 + nFc * nFc <= NT && 192 + DIM * nN <= NT && 64 + nIP <= NT, "thread roles");
+  constexpr int kIPBase = ((nFc * nIPf + 31) / 32) * 32;   // threads [0, nFc nIPf): face cubature points; [kIPBase, kIPBase + nIP): bulk cubature points
+  static_assert(l + 1 <= 128 && 160 + nFc * nFc <= NT && kIPBase + nIP <= NT && 128 + nN + DIM * nN <= NT && nFc <= 32, "thread roles");
+  static_assert(L::bytes <= 232448, "shared memory of one CTA");
   extern __shared__ __align__(16) double sm[];
   double* const AR = sm + L::oAR; double* const BH = sm + L::oBH; double* const MF = sm + L::oMF;
   double* const X = sm + L::oX; double* const TAU = sm + L::oTAU; double* const VN = sm + L::oVN; double* const GEO = sm + L::oGEO;
@@ -184,7 +207,7 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
 #pragma unroll
       for (int r = 0; r < DIM; r++)
 #pragma unroll
-        for (int m = 0; m < DIM; m++) J[r][m] = 0.5 * (X[(r + 1) * DIM + m] - X[m]);
+        for (int m = 0; m < DIM; m++) J[r][m] = 0.5 * (X[C::fv(r + 1) * DIM + m] - X[C::fv(0) * DIM + m]);
       det_inv(J, det, I);
       const double rdet = fast_rcp(det);
       const int* fn = FN + f * t;
@@ -192,7 +215,7 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
 #pragma unroll
       for (int r = 0; r < DIM - 1; r++)
 #pragma unroll
-        for (int m = 0; m < DIM; m++) Jf[r][m] = 0.5 * (X[fn[r + 1] * DIM + m] - X[fn[0] * DIM + m]);
+        for (int m = 0; m < DIM; m++) Jf[r][m] = 0.5 * (X[fn[C::ff(r + 1)] * DIM + m] - X[fn[C::ff(0)] * DIM + m]);
       double nv[DIM];
       if (DIM == 2) { nv[0] = -Jf[0][1]; nv[1] = Jf[0][0]; }
       else {
@@ -226,7 +249,7 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
 #pragma unroll
       for (int r = 0; r < DIM; r++)
 #pragma unroll
-        for (int m = 0; m < DIM; m++) J[r][m] = 0.5 * (X[(r + 1) * DIM + m] - X[m]);
+        for (int m = 0; m < DIM; m++) J[r][m] = 0.5 * (X[C::fv(r + 1) * DIM + m] - X[C::fv(0) * DIM + m]);
       det_inv(J, det, I);
 #pragma unroll
       for (int m = 0; m < DIM; m++)
@@ -281,8 +304,8 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
         FT[f * FSZ + a + ldf * b] = GEO[G_F + f * GF + GF_TA] * MF[a + ldf * b];
       }
     }
-    if (needPhi && tid >= 64 && tid < 64 + nIP) {   // bulk cubature points: weights of the Suu / Fu contractions, convective velocity
-      const int ip = tid - 64;
+    if (needPhi && tid >= kIPBase && tid < kIPBase + nIP) {   // bulk cubature points: weights of the Suu / Fu contractions, convective velocity
+      const int ip = tid - kIPBase;
       const double dv = __ldg(p.w + ip) * det;
       double lw = 0.0;
       if (hasReac) lw += ts * p.reacIP[(size_t)e * nIP + ip] * dv;
@@ -351,14 +374,18 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
         constexpr int MR = t * t, FW_MT = (MR + 7) / 8, KSF = nIPfp / 4;
         for (int task = warp; task < FW_MT; task += NWARP) {
           const int m = task * 8 + lr, mc = imin(m, MR - 1);
-          double a[KSF], c[2] = {0.0, 0.0};
+          double a[KSF], c[L::NWT][2];
+          zero_c(c);
 #pragma unroll
           for (int ks = 0; ks < KSF; ks++) { const int k = ks * 4 + lc; a[ks] = k < nIPf ? __ldg(p.ffs + (size_t)k * MR + mc) : 0.0; }
 #pragma unroll
-          for (int ks = 0; ks < KSF; ks++) dmma(c, a[ks], FWT[(ks * 4 + lc) * ldw + lr]);
-          if (m < MR) {   // lane lc holds (f = lc, kind 0 | 1); row m = b * t + a
+          for (int ks = 0; ks < KSF; ks++)
+#pragma unroll
+            for (int j = 0; j < L::NWT; j++) dmma(c[j], a[ks], FWT[(ks * 4 + lc) * ldw + 8 * j + lr]);
+          if (m < MR) {   // column tile j, lane lc holds (f = 4 j + lc, kind 0 | 1); row m = b * t + a
             const int b = m / t, a2 = m - b * t;
-            if (lc < nFc) { FT[lc * FSZ + a2 + ldf * b] = c[0]; FC[lc * FSZ + a2 + ldf * b] = c[1]; }
+#pragma unroll
+            for (int j = 0; j < L::NWT; j++) { const int f = 4 * j + lc; if (f < nFc) { FT[f * FSZ + a2 + ldf * b] = c[j][0]; FC[f * FSZ + a2 + ldf * b] = c[j][1]; } }
           }
         }
       }
@@ -722,8 +749,11 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
         if (p.S0) p.S0[(size_t)e * l + r] = s0;
         const int rowDof = F * t + PERM[r];
         if (INTF[f]) atomicAdd(p.rhs + rowDof, s0); else p.rhs[rowDof] = s0;
-      } else if (p.U && tid >= 128 && tid < 128 + nN) p.U0[(size_t)e * nN + (tid - 128)] = UU[(tid - 128) * ldc + l];
-      else if (p.U && tid >= 192 && tid < 192 + q) { const int rq = tid - 192; p.Q0[(size_t)e * q + rq] = QQ[((rq % DIM) * nN + rq / DIM) * ldc + l]; }
+      } else if (p.U && tid >= 128 && tid < 128 + nN + q) {
+        const int row = tid - 128;
+        if (row < nN) p.U0[(size_t)e * nN + row] = UU[row * ldc + l];
+        else { const int rq = row - nN; p.Q0[(size_t)e * q + rq] = QQ[((rq % DIM) * nN + rq / DIM) * ldc + l]; }
+      }
       bulk_wait_read();   // U, Q rows have left shared memory: the regions are rewritten by the next element pass
     }
     __syncthreads();
@@ -734,18 +764,18 @@ __global__ void __launch_bounds__(NT_, NT_ >= 512 ? 1 : 2) hdg_big_kernel(const 
   }
 }
 
-template <int DIM, int P, int NT_>
+template <class C, int NT_>
 inline cudaError_t launch_big(const AsmParams& p, int nSM, cudaStream_t st) {
-  using L = BigSmem<DIM, P>;
-  cudaError_t e = cudaFuncSetAttribute(hdg_big_kernel<DIM, P, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
+  using L = BigSmem<C>;
+  cudaError_t e = cudaFuncSetAttribute(hdg_big_kernel<C, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
   if (e != cudaSuccess) return e;
   int perSM = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_big_kernel<DIM, P, NT_>, NT_, L::bytes);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_big_kernel<C, NT_>, NT_, L::bytes);
   if (perSM < 1) perSM = 1;
   long long grid = (long long)nSM * perSM;
   if (grid > p.eEnd - p.eBegin) grid = p.eEnd - p.eBegin;
   if (grid < 1) grid = 1;
-  hdg_big_kernel<DIM, P, NT_><<<(int)grid, NT_, L::bytes, st>>>(p);
+  hdg_big_kernel<C, NT_><<<(int)grid, NT_, L::bytes, st>>>(p);
   return cudaGetLastError();
 }
 

@@ -1922,12 +1922,19 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     if (!fused && !p1 && !dumpMode && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA
         && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_BIG")) {
       if (!pend.empty()) waitPieces(0, -1);
-      HFX_CUDA((launch_big<3, 4, 512>(p, c->nSM, c->st)));
+      HFX_CUDA((launch_big<BigSimplex<3, 4>, 512>(p, c->nSM, c->st)));
+      big = true;
+    }
+    // structured hexahedra of order 2 (parallelepiped cells, flagged affine): the same formulation with the orthotope frame
+    if (!fused && !p1 && !big && !dumpMode && !recoverMode && c->geom == HFX_ORTHOTOPE && c->dim == 3 && c->order == 2 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU)
+        && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_BIG")) {
+      if (!pend.empty()) waitPieces(0, -1);
+      HFX_CUDA((launch_big<BigHexP2, 512>(p, c->nSM, c->st)));
       big = true;
     }
     if (bigP3) {
       if (!pend.empty()) waitPieces(0, -1);
-      HFX_CUDA((launch_big<3, 3, 256>(p, c->nSM, c->st)));
+      HFX_CUDA((launch_big<BigSimplex<3, 3>, 256>(p, c->nSM, c->st)));
       big = true;
     }
     if (recoverMode) {

@@ -35,3 +35,21 @@ def test_constant_solution_on_orthotopes(dim, order):
     assert np.abs(fm["Solution"].values - 3.0).max() < 1e-12
     assert np.abs(fm["Flux"].values).max() < 1e-11
     assert np.abs(fm["Trace"].values - 3.0).max() < 1e-12
+
+
+@pytest.mark.parametrize("model,diff,bc,tau_double", [("laplace", "none", "dirichlet", False), ("laplace", "none", "integrated", False), ("diffsrc", "const", "dirichlet", True),
+                                                      ("cdrs", "none", "dirichlet", True), ("euler", "none", "dirichlet", False)])
+def test_structured_hexahedra_take_the_large_element_kernel(model, diff, bc, tau_double, monkeypatch):
+    """Parallelepiped hexahedra of order 2 (every cell of a structured mesh) with D = c I: hdg_big_kernel<BigHexP2, 512> (hfx_big.cuh with the orthotope frame) against the
+    oracle and against the general kernel; a perturbed (trilinear) mesh keeps the general kernel."""
+    case = H.make_case(3, 2, N=3, perturb=0.0, model=model, diff=diff, bc=bc, tau_double=tau_double, seed=67, geom="orthotope")
+    o, s, fm = compare(case)
+    assert s.lastAssembleKernel() == "big"
+    l1 = s.getLocal(); v1 = s.getCSR()[2].copy()
+    monkeypatch.setenv("HFX_NO_BIG", "1")
+    s2, fm2, _ = H.run_device(case)
+    assert s2.lastAssembleKernel() == "general"
+    assert H.rel_err(l1["S"], s2.getLocal()["S"]) < 1e-12 and H.rel_err(v1, s2.getCSR()[2]) < 1e-12
+    monkeypatch.delenv("HFX_NO_BIG")
+    s3, _, _ = H.run_device(H.make_case(3, 2, N=2, perturb=0.15, geom="orthotope"), solve=False)
+    assert s3.lastAssembleKernel() == "general"

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Hex variant of the headline (SURVEY.md section 8d "Hex variant: the N^3 hexes directly"; north_star: "synthetic structured tet/hex meshes ... at 1, 2, 4 and 8 GPUs"):
 3-D Poisson HDG on N^3 order-2 hexahedra (the reference element's maximum order for hexes), assemble + condense throughput and the distributed GMRES iteration.
-One process per GPU (torchrun for N > 1), strong scaling on the fixed mesh, rank 0 prints one JSON line.  Orthotope cells run through the general kernel (hfx_generic.cuh).
+One process per GPU (torchrun for N > 1), strong scaling on the fixed mesh, rank 0 prints one JSON line.  Structured (parallelepiped) order-2 hexahedra take hdg_big_kernel<BigHexP2, 512>; everything else on orthotopes the general kernel.
   python tools/bench_hex.py [--cubes 48] [--order 2] [--steps 5] [--warmup 3]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 tools/bench_hex.py --gpus 2"""
 import argparse, ctypes as C, json, os, sys, time
@@ -43,10 +43,13 @@ def main():
     tot = torch.tensor([float(dp.prob["owned_cells"].size)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    kk = C.c_int(0)
+    L.hfx_last_assemble_kernel(h, C.byref(kk), None)
+    kname = ("hdg_assemble_kernel", "hdg_generic_kernel (general kernel)", "hdg_big_kernel<BigHexP2, 512> (large-element formulation with the orthotope frame)", "hdg_p1_kernel")[kk.value]
     if rank == 0:
         print(json.dumps({"metric": "HDG elements assembled+condensed/s (p=%d 3D hexes)" % a.order, "value": float(tot.item()) / (float(red[0]) * 1e-3), "unit": "elements/s", "n_gpus": world,
                           "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(red[0]), "higher_is_better": True, "scaling": "strong", "dtype": "f64", "data": "synthetic",
-                          "config": {"workload": "3D Poisson HDG order %d on %d^3 = %d structured hexahedra, HDGLaplaceModel + DirichletModel, tau = 1; general kernel (hfx_generic.cuh)" % (a.order, a.cubes, a.cubes ** 3),
+                          "config": {"workload": "3D Poisson HDG order %d on %d^3 = %d structured hexahedra, HDGLaplaceModel + DirichletModel, tau = 1; %s" % (a.order, a.cubes, a.cubes ** 3, kname),
                                      "partition": "recursive coordinate bisection, plan in host C++ (hfx_plan_create, orthotope cells)" if world > 1 else "single rank",
                                      "elements_rank0": int(dp.mesh.getNumberCells()), "owned_elements_rank0": int(dp.prob["owned_cells"].size)},
                           "gmres_ms_per_iteration": float(red[1]), "transport": int(info.transport), "halo_bytes_per_exchange_rank0": int(info.haloBytesPerExchange)}), flush=True)

@@ -229,20 +229,19 @@ __global__ void spmv_face_kernel(int nList, const int* __restrict__ faceList /*N
   }
 }
 
-// Streaming variant for block rows of at most kSpmvStage doubles (p <= 3 tets, every 2-D order): the warp first copies the face's whole
+// Streaming variant (block rows that fit the shared-memory staging of eight warps: up to order-4 tets, order-2 hexes, every 2-D order): the warp first copies the face's whole
 // contiguous run into shared memory with 16-byte asynchronous copies -- every byte of the matrix crosses the SM exactly once, fully
 // coalesced, with the whole run in flight per warp -- then a few lanes per row reduce it against the gathered x.
-constexpr int kSpmvStage = 768, kSpmvMaxLen = 80;
 __global__ void __launch_bounds__(256) spmv_block_kernel(int nList, const int* __restrict__ faceList /*NULL: faces 0..nList-1*/, int t, int nFc2,
                                                          const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
                                                          const int* __restrict__ nbr, const double* __restrict__ vals, const double* __restrict__ x,
                                                          double* __restrict__ y, const double* __restrict__ dinv /*NULL or row scaling (Jacobi)*/,
-                                                         const int* __restrict__ done) {
+                                                         const int* __restrict__ done, int stage /*doubles per warp: an even bound on the block row*/, int maxLen) {
   if (done && *done) return;
   extern __shared__ __align__(16) double spmv_sm[];
-  double (*sv)[kSpmvStage] = reinterpret_cast<double (*)[kSpmvStage]>(spmv_sm);
-  double (*sx)[kSpmvMaxLen] = reinterpret_cast<double (*)[kSpmvMaxLen]>(spmv_sm + 8 * kSpmvStage);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* const svw = spmv_sm + (size_t)w * stage;                       // this warp's copy of the block row
+  double* const sxw = spmv_sm + (size_t)8 * stage + (size_t)w * maxLen;  // and of the entries of x it multiplies
   const int LPR = t > 16 ? 1 : (t > 8 ? 2 : (t > 4 ? 4 : 8));   // lanes per row (power of two), 32 / LPR rows per pass
   const int a = lane / LPR, part = lane - a * LPR;
   for (int li = blockIdx.x * 8 + w; li < nList; li += gridDim.x * 8) {
@@ -252,11 +251,11 @@ __global__ void __launch_bounds__(256) spmv_block_kernel(int nList, const int* _
     const bool al = ((rowStart[F] & 1) == 0);
     const int n2 = al ? tot >> 1 : 0;
     for (int i = lane; i < n2; i += 32) {
-      const unsigned sa = (unsigned)__cvta_generic_to_shared(&sv[w][2 * i]);
+      const unsigned sa = (unsigned)__cvta_generic_to_shared(&svw[2 * i]);
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(v + 2 * i) : "memory");
     }
-    for (int i = 2 * n2 + lane; i < tot; i += 32) sv[w][i] = v[i];
-    for (int k = lane; k < len; k += 32) { const int g = k / t, b = k - g * t; sx[w][k] = x[(size_t)nbr[(size_t)F * nFc2 + g] * t + b]; }
+    for (int i = 2 * n2 + lane; i < tot; i += 32) svw[i] = v[i];
+    for (int k = lane; k < len; k += 32) { const int g = k / t, b = k - g * t; sxw[k] = x[(size_t)nbr[(size_t)F * nFc2 + g] * t + b]; }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
     for (int a0 = 0; a0 < t; a0 += 32 / LPR) {
@@ -264,8 +263,8 @@ __global__ void __launch_bounds__(256) spmv_block_kernel(int nList, const int* _
       double s = 0.0;
       if (row < t) {
         for (int g = 0; g < m; g++) {
-          const double* vr = &sv[w][(g * t + row) * t];
-          const double* xr = &sx[w][g * t];
+          const double* vr = &svw[(g * t + row) * t];
+          const double* xr = &sxw[g * t];
           for (int b = part; b < t; b += LPR) s = fma(vr[b], xr[b], s);
         }
       }
@@ -1087,10 +1086,15 @@ struct FaceOp : LinOp {
     const int t = c->nNf * c->md.nDOF;
     const int len = 2 * c->nFc * t, nb = nblk((long long)nList * 32, 256);   // at most 2 nFc - 1 neighbour faces per row
     const int lenMax = (2 * c->nFc - 1) * t;   // a face has at most 2 nFc - 1 neighbour faces (itself included)
-    if (lenMax * t <= kSpmvStage && lenMax <= kSpmvMaxLen && !getenv("HFX_SPMV_V1")) {
-      constexpr int shm = 8 * (kSpmvStage + kSpmvMaxLen) * (int)sizeof(double);
+    // staging sized by the mesh, up to 6 KB per warp (order-3 tets: 5.6 KB).  Larger block rows keep the register-only kernel: measured at order 4 (12.6 KB per row,
+    // two CTAs per SM) the staged kernel takes 6.1 ms against 3.4 ms per SpMV (HFX_SPMV_STAGE_MAX raises the limit for experiments)
+    const int stage = (lenMax * t + 1) & ~1, maxLen = (lenMax + 1) & ~1;
+    const int shm = 8 * (stage + maxLen) * (int)sizeof(double);
+    const int stageMax = getenv("HFX_SPMV_STAGE_MAX") ? atoi(getenv("HFX_SPMV_STAGE_MAX")) : 768;
+    if (stage <= stageMax && shm <= 113 * 1024 && !getenv("HFX_SPMV_V1")) {
       HFX_CUDA(cudaFuncSetAttribute(spmv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shm));   // per device: set every time (cheap)
-      spmv_block_kernel<<<std::min(nblk(nList, 8), c->nSM * 4), 256, shm, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);
+      const int perSM = std::max(1, std::min(4, (227 * 1024) / (shm + 1024)));
+      spmv_block_kernel<<<std::min(nblk(nList, 8), c->nSM * perSM), 256, shm, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done, stage, maxLen);
     } else if (len <= 96) spmv_face_kernel<3><<<nb, 256, 0, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);
     else if (len <= 256) spmv_face_kernel<8><<<nb, 256, 0, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);
     else spmv_face_kernel<16><<<nb, 256, 0, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);

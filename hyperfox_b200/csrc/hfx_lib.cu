@@ -275,6 +275,75 @@ __global__ void __launch_bounds__(256) spmv_block_kernel(int nList, const int* _
   }
 }
 
+// The same for block rows beyond the staging of one warp (order-4 tets: 12.6 KB, order-2 hexes): the row is streamed in chunks of whole t x t blocks, the next chunk
+// issued as soon as the previous one has been reduced; global and shared addresses keep the same 16-byte phase (t odd: a row may start on an odd double).
+__global__ void __launch_bounds__(256) spmv_block_chunk_kernel(int nList, const int* __restrict__ faceList /*NULL: faces 0..nList-1*/, int t, int nFc2,
+                                                         const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
+                                                         const int* __restrict__ nbr, const double* __restrict__ vals, const double* __restrict__ x,
+                                                         double* __restrict__ y, const double* __restrict__ dinv /*NULL or row scaling (Jacobi)*/,
+                                                         const int* __restrict__ done, int stage /*doubles per warp: an even bound on the block row*/, int maxLen) {
+  if (done && *done) return;
+  extern __shared__ __align__(16) double spmv_sm[];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* const svw = spmv_sm + (size_t)w * stage;                       // this warp's copy of the block row
+  double* const sxw = spmv_sm + (size_t)8 * stage + (size_t)w * maxLen;  // and of the entries of x it multiplies
+  const int LPR = t > 16 ? 1 : (t > 8 ? 2 : (t > 4 ? 4 : 8));   // lanes per row (power of two), 32 / LPR rows per pass
+  const int a = lane / LPR, part = lane - a * LPR;
+  const int tt = t * t, CB = max(1, (stage - 2) / tt);          // blocks per staged chunk (the whole row when it fits: order <= 3)
+  const int NPASS = (t * LPR + 31) / 32;                        // row passes (1 unless t > 32 / LPR)
+  for (int li = blockIdx.x * 8 + w; li < nList; li += gridDim.x * 8) {
+    const int F = faceList ? faceList[li] : li;
+    const int m = nnb[F], len = m * t;
+    const long long base = rowStart[F];
+    // chunk g0: asynchronous 16-byte copies of nb whole blocks; d0 keeps the 16-byte phase of the global and the shared addresses equal
+    auto issue = [&](int g0) -> int {
+      const int nb = min(CB, m - g0), tot = nb * tt;
+      const long long ofs = base + (long long)g0 * tt;
+      const double* v = vals + ofs;
+      const int d0 = (int)(ofs & 1);
+      if (d0 && lane == 0) svw[1] = v[0];
+      const int n2 = (tot - d0) >> 1;
+      for (int i = lane; i < n2; i += 32) {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(&svw[2 * d0 + 2 * i]);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(v + d0 + 2 * i) : "memory");
+      }
+      if (lane == 0 && ((tot - d0) & 1)) svw[d0 + tot - 1] = v[tot - 1];
+      return d0;
+    };
+    int d0 = issue(0);                                           // the matrix stream is in flight while x is gathered
+    for (int k = lane; k < len; k += 32) { const int g = k / t, b2 = k - g * t; sxw[k] = x[(size_t)nbr[(size_t)F * nFc2 + g] * t + b2]; }
+    double acc[2] = {0.0, 0.0};                                  // (NPASS <= 2: t <= 32)
+    for (int g0 = 0; g0 < m; g0 += CB) {
+      const int nb = min(CB, m - g0);
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      __syncwarp();
+#pragma unroll
+      for (int ps = 0; ps < 2; ps++) {
+        const int row = ps * (32 / LPR) + a;
+        if (ps < NPASS && row < t) {
+          double s2 = 0.0;
+          for (int g = 0; g < nb; g++) {
+            const double* vr = &svw[d0 + (g * t + row) * t];
+            const double* xr = &sxw[(g0 + g) * t];
+            for (int b2 = part; b2 < t; b2 += LPR) s2 = fma(vr[b2], xr[b2], s2);
+          }
+          acc[ps] += s2;
+        }
+      }
+      __syncwarp();
+      if (g0 + CB < m) d0 = issue(g0 + CB);
+    }
+#pragma unroll
+    for (int ps = 0; ps < 2; ps++) {
+      if (ps >= NPASS) break;                                      // (warp-uniform)
+      const int row = ps * (32 / LPR) + a;
+      double s2 = acc[ps];
+      for (int o = 1; o < LPR; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      if (row < t && part == 0) { const size_t r = (size_t)F * t + row; y[r] = dinv ? dinv[r] * s2 : s2; }
+    }
+  }
+}
+
 // generic CSR SpMV (LinAlgebraInterface mirror)
 __global__ void spmv_csr_kernel(long long n, const long long* __restrict__ rowptr, const int* __restrict__ colidx, const double* __restrict__ vals,
                                 const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ dinv, const int* __restrict__ done) {
@@ -1088,13 +1157,21 @@ struct FaceOp : LinOp {
     const int lenMax = (2 * c->nFc - 1) * t;   // a face has at most 2 nFc - 1 neighbour faces (itself included)
     // staging sized by the mesh, up to 6 KB per warp (order-3 tets: 5.6 KB).  Larger block rows keep the register-only kernel: measured at order 4 (12.6 KB per row,
     // two CTAs per SM) the staged kernel takes 6.1 ms against 3.4 ms per SpMV (HFX_SPMV_STAGE_MAX raises the limit for experiments)
-    const int stage = (lenMax * t + 1) & ~1, maxLen = (lenMax + 1) & ~1;
-    const int shm = 8 * (stage + maxLen) * (int)sizeof(double);
+    // (whole rows up to 6 KB per warp -- order-3 tets: 5.6 KB; longer rows are staged in chunks of whole t x t blocks: staging the 12.6 KB rows of order 4 at once
+    // halves the occupancy and was measured at 6.1 ms against 3.4 ms for the register-only kernel)
     const int stageMax = getenv("HFX_SPMV_STAGE_MAX") ? atoi(getenv("HFX_SPMV_STAGE_MAX")) : 768;
-    if (stage <= stageMax && shm <= 113 * 1024 && !getenv("HFX_SPMV_V1")) {
+    const int whole = (lenMax * t + 1) & ~1, maxLen = (lenMax + 1) & ~1;
+    if (whole <= stageMax && !getenv("HFX_SPMV_V1")) {            // the whole block row in one piece (order <= 3 tets: 5.6 KB)
+      const int shm = 8 * (whole + maxLen) * (int)sizeof(double);
       HFX_CUDA(cudaFuncSetAttribute(spmv_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shm));   // per device: set every time (cheap)
       const int perSM = std::max(1, std::min(4, (227 * 1024) / (shm + 1024)));
-      spmv_block_kernel<<<std::min(nblk(nList, 8), c->nSM * perSM), 256, shm, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done, stage, maxLen);
+      spmv_block_kernel<<<std::min(nblk(nList, 8), c->nSM * perSM), 256, shm, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done, whole, maxLen);
+    } else if (t <= 32 && 8 * (std::max(stageMax, t * t + 4) + maxLen) * 8 <= 227 * 1024 && !getenv("HFX_SPMV_V1")) {   // longer rows in chunks of whole blocks (order 4: 1.95 ms against 3.45 ms register-only at 384 000 tets)
+      const int stage = std::max(stageMax, t * t + 2 + ((t * t) & 1));
+      const int shm = 8 * (stage + maxLen) * (int)sizeof(double);
+      HFX_CUDA(cudaFuncSetAttribute(spmv_block_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, shm));
+      const int perSM = std::max(1, std::min(4, (227 * 1024) / (shm + 1024)));
+      spmv_block_chunk_kernel<<<std::min(nblk(nList, 8), c->nSM * perSM), 256, shm, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done, stage, maxLen);
     } else if (len <= 96) spmv_face_kernel<3><<<nb, 256, 0, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);
     else if (len <= 256) spmv_face_kernel<8><<<nb, 256, 0, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);
     else spmv_face_kernel<16><<<nb, 256, 0, st>>>(nList, list, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dVals.p, x, y, dinv, done);

@@ -566,7 +566,7 @@ def run_order_sweep(args):
         nC = cells.shape[0]
         tf = FLOPS_PER_ELEM[order] * nC / t / 1e12
         gbs = BYTES_STORE[order] * nC / t / 1e9
-        rows.append({"order": order, "cubes": N, "elements": nC, "dofs": nC * NN[order], "kernel": ("fused", "general", "big", "p1")[kk.value], "ms_per_step": t * 1e3,
+        rows.append({"order": order, "cubes": N, "elements": nC, "dofs": nC * NN[order], "kernel": ("fused", "general", "big", "p1", "col")[kk.value], "ms_per_step": t * 1e3,
                      "elements_per_s": nC / t, "tflops_algorithmic": tf, "frac_fp64_peak": tf / peak["tflops"], "hbm_GBs_algorithmic": gbs, "frac_hbm_peak": gbs / hbm_peak})
         check(L.hfx_ctx_destroy(h))
     clocks = sampler.stop()

@@ -60,6 +60,7 @@ struct AsmParams {
   const double* mfref;        // M^f [ev(t) x t]: face reference mass
   const double* bref;         // B^_f [nFc][nN][t] = M_ref^-1[:, faceNodes_f] M^f: W Sql_d = -(area n_d / detJ) B^_f
   const uint8_t* affine;      // [nCells] or NULL (shortcut disabled)
+  const double* colTab;       // tables of the column-per-lane kernel (hfx_col.cuh) or NULL
   // outputs
   double* U; double* Q; double* U0; double* Q0; double* S; double* S0;  // S,S0 may be NULL
   double* vals; double* rhs;

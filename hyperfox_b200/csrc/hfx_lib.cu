@@ -19,6 +19,7 @@
 #include "hfx_generic.cuh"
 #include "hfx_big.cuh"
 #include "hfx_p1.cuh"
+#include "hfx_col.cuh"
 #include "hfx_krylov.cuh"
 #include "host/hfx_refel.h"
 #include "host/hfx_topology.h"
@@ -1123,7 +1124,8 @@ struct hfx_ctx {
   bool modelSet = false, bcSet = false;
   DBuf<uint8_t> dFaceBC;
   // allocation
-  bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false, p1Ready = false; int lastKernel = 0;
+  bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false, p1Ready = false, colReady = false; int lastKernel = 0;
+  DBuf<double> dColTab;
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
   DBuf<long long> dFaceRowStart, dBlockCount, dTotal;
   long long nnz = 0;
@@ -1546,6 +1548,14 @@ int hfx_refel_set(hfx_ctx* c, int dim, int order, int geom) {
           c->p1Ready = true;
         }
       }
+      // order-2 tetrahedra: tables of the column-per-lane kernel (hfx_col.cuh); its face-node map is compiled in
+      c->colReady = false;
+      if (dim == 3 && order == 2 && geom == HFX_SIMPLEX && n == 10 && t == 6 && nip == ColEl<2>::nIP && nipf == ColEl<2>::nIPf && col_face_nodes_match<2>(re.faceNodes().data())) {
+        std::vector<double> T;
+        col_fill_tables<2>(T, aref.data(), sref.data(), np, mf.data(), tp, bref.data(), fe->ipWeights().data(), fe->ipShape().data(), re.ipWeights().data(), re.ipShape().data());
+        c->dColTab.upload(T, c->st);
+        c->colReady = true;
+      }
     }
     std::vector<int8_t> nif((size_t)c->nFc * c->nN, -1);
     for (int f = 0; f < c->nFc; f++) for (int a = 0; a < t; a++) nif[(size_t)f * c->nN + re.faceNodes()[(size_t)f * t + a]] = (int8_t)a;
@@ -1948,15 +1958,26 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     const bool dumpMode = dumpA != nullptr;
     if (!recoverMode && !dumpMode) clearSystem();
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
-    // linear tets, Laplace-type model, straight-sided cells: one thread per element (hfx_p1.cuh).  Opt-in (HFX_P1=1): measured at 134 M el/s against the
-    // 186 M el/s of the element-group kernel -- 255 registers + spills and 8 warps per SM leave it latency bound
-    bool p1 = false;
-    if (getenv("HFX_P1") && atoi(getenv("HFX_P1")) != 0 && !recoverMode && !dumpMode && c->p1Ready && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 1 && c->md.nDOF == 1 && (c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE)) == 0
+    // linear tets, Laplace-type model, straight-sided cells: sixteen lanes per element, one trace column per lane (hfx_p1.cuh): 552 M el/s against the 206 M el/s of
+    // the element-group kernel and the 142 M el/s of the one-thread-per-element variant (255 registers + spills, scattered 8-byte stores; HFX_P1=2)
+    bool p1 = false, col = false;
+    const int p1Mode = getenv("HFX_P1") ? atoi(getenv("HFX_P1")) : 1;   // 1 (default): sixteen lanes per element; 2: one thread per element; 0: element-group kernel
+    if (p1Mode != 0 && !recoverMode && !dumpMode && c->p1Ready && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 1 && c->md.nDOF == 1 && (c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE)) == 0
         && c->md.timeScheme == HFX_TS_NONE && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_P1")) {
       for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) { for (DField* f : {&kv.second}) for (int k = 0; k < f->pendingPieces; k++) HFX_CUDA(cudaStreamWaitEvent(c->st, f->ev[k], 0)); kv.second.pendingPieces = 0; }
       p.eBegin = 0; p.eEnd = c->nCells;
-      HFX_CUDA(launch_p1(p, c->nSM, c->st));
+      if (p1Mode == 2) HFX_CUDA(launch_p1(p, c->nSM, c->st));   // one thread per element
+      else HFX_CUDA(launch_p1g(p, c->nSM, c->st));                                   // sixteen lanes per element
       p1 = true;
+    }
+    // order-2 tets, same eligibility: one warp per element, one trace column per lane (hfx_col.cuh).  HFX_COL=0 keeps the element-group kernel
+    if (!p1 && (!getenv("HFX_COL") || atoi(getenv("HFX_COL")) != 0) && !recoverMode && !dumpMode && c->colReady && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 2 && c->md.nDOF == 1
+        && (c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE)) == 0 && c->md.timeScheme == HFX_TS_NONE && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC")) {
+      for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) { for (int k = 0; k < kv.second.pendingPieces; k++) HFX_CUDA(cudaStreamWaitEvent(c->st, kv.second.ev[k], 0)); kv.second.pendingPieces = 0; }
+      p.eBegin = 0; p.eEnd = c->nCells; p.colTab = c->dColTab.p;
+      const int nw = getenv("HFX_COL_NW") ? atoi(getenv("HFX_COL_NW")) : 4;
+      if (nw == 8) HFX_CUDA((launch_col<2, 8>(p, c->nSM, c->st))); else if (nw == 2) HFX_CUDA((launch_col<2, 2>(p, c->nSM, c->st))); else HFX_CUDA((launch_col<2, 4>(p, c->nSM, c->st)));
+      p1 = col = true;
     }
     // 3-D order 3 with convection / reaction / a time scheme on straight-sided cells: the SJ_r formulation of hfx_big.cuh (two 256-thread CTAs per SM) instead of the
     // straight-sided path of the element-group kernel.  HFX_BIG_P3=0 disables, HFX_BIG_P3=2 routes the Laplace-type models through it as well.
@@ -2082,7 +2103,7 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     };
     if (!fused && !big && !p1) launchGeneric(getenv("HFX_FORCE_PIVOT") != nullptr);
     if (dumpMode) { HFX_CUDA(cudaStreamSynchronize(c->st)); return; }
-    c->lastKernel = p1 ? 3 : (fused ? 0 : (big ? 2 : 1));
+    c->lastKernel = col ? 4 : (p1 ? 3 : (fused ? 0 : (big ? 2 : 1)));
     HFX_CUDA(cudaEventRecord(c->ev2, c->st));
     int status = 0;
     c->dStatus.download(&status, 1, c->st);

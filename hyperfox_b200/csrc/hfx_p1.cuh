@@ -312,4 +312,300 @@ inline cudaError_t launch_p1(const AsmParams& p, int nSM, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------------------------------
+// SIXTEEN LANES PER ELEMENT (two elements per warp).  The columns of the condensation are independent once K^-1 is known: lane c < 12 owns trace column
+// c = (face, face node) -- its column of R, U, Q and S -- lane 12 the right-hand-side column (U0, Q0, S0); the shared part of the element (geometry, tau masses,
+// SJ_r, K, K^-1: one entry per lane) lives in a 1.7 KB shared-memory slice.  A lane holds one column (about 45 doubles) instead of the whole element, the rows of
+// U and Q leave as 96-byte runs, and 32 elements are in flight per SM.  Same algebra, tables and eligibility as hdg_p1_kernel above.
+constexpr int kPGThreads = 256, kPGElems = kPGThreads / 16;
+constexpr int PG_X = 0, PG_N = 12, PG_AR = 24, PG_FT = 28, PG_SJ = 64, PG_CR = 112, PG_CQ = 124, PG_K = 136, PG_KI = 152, PG_FU = 168, PG_TAU = 172, PG_HF = 184, PG_RS = 196,
+              PG_INT = 200, PG_STRIDE = 224;   // ints at PG_INT: F[4], BC[4], INTR[4], SIDE[4], PERM[12], POS[16]
+constexpr int PGI_F = 0, PGI_BC = 4, PGI_IN = 8, PGI_SD = 12, PGI_PERM = 16, PGI_POS = 28;
+constexpr int kPGTab = (int)(sizeof(P1Tables) / sizeof(double)), kPGTabAll = kPGTab + 64;   // + EF[(m,k)][f] = MF[nif(f,m)][nif(f,k)] or 0
+constexpr int kHNIF[4][4] = {{2, 1, -1, 0}, {-1, 1, 0, 2}, {2, -1, 0, 1}, {0, 1, 2, -1}};
+__host__ __device__ constexpr unsigned long long p1_nif_bits() {
+  unsigned long long b = 0ull;
+  for (int f = 0; f < 4; f++) for (int m = 0; m < 4; m++) b |= (unsigned long long)(kHNIF[f][m] & 15) << (4 * (f * 4 + m));
+  return b;
+}
+constexpr unsigned long long kNifBits = p1_nif_bits();
+constexpr int kHFN[4][3] = {{3, 1, 0}, {2, 1, 3}, {2, 3, 0}, {0, 1, 2}};
+constexpr int kHOPP[4] = {2, 0, 1, 3};
+__host__ __device__ constexpr unsigned p1_fn_bits() {   // two bits per (f, b), then two bits per opposite node
+  unsigned b = 0u;
+  for (int f = 0; f < 4; f++) for (int a = 0; a < 3; a++) b |= (unsigned)kHFN[f][a] << (2 * (f * 3 + a));
+  for (int f = 0; f < 4; f++) b |= (unsigned)kHOPP[f] << (24 + 2 * f);
+  return b;
+}
+constexpr unsigned kFnBits = p1_fn_bits();
+
+template <int MINB>
+__global__ void __launch_bounds__(kPGThreads, MINB) hdg_p1g_kernel(const AsmParams p) {
+  extern __shared__ __align__(16) double smg[];
+  const int tid = threadIdx.x, g = tid >> 4, j = tid & 15;
+  double* const TB = smg;                                             // tables (CTA-wide)
+  double* const E = smg + ((kPGTabAll + 1) & ~1) + g * PG_STRIDE;     // this element's slice
+  int* const EI = reinterpret_cast<int*>(E + PG_INT);
+  long long* const RS = reinterpret_cast<long long*>(E + PG_RS);
+  {
+    const double* cp = reinterpret_cast<const double*>(&c_p1);
+    for (int i = tid; i < kPGTab; i += kPGThreads) TB[i] = cp[i];
+    if (tid < 64) {
+      const int mk = tid >> 2, f = tid & 3, m = mk >> 2, k = mk & 3;
+      const int a = (int)((kNifBits >> (4 * (f * 4 + m))) & 15ull), b = (int)((kNifBits >> (4 * (f * 4 + k))) & 15ull);
+      TB[kPGTab + tid] = (a != 15 && b != 15) ? c_p1.MF[a][b] : 0.0;
+    }
+  }
+  __syncthreads();
+  const P1Tables& T = *reinterpret_cast<const P1Tables*>(TB);
+  const double* const EF = TB + kPGTab;
+  auto nif = [](int f, int m) { return (int)((kNifBits >> (4 * (f * 4 + m))) & 15ull); };   // 15: the node is not on the face
+  const bool hasDiff = p.opmask & 1, hasSrc = (p.opmask & 8) && p.srcIP;
+  const double dsc = hasDiff ? p.diffConst : 0.0;
+  const int tv = p.tauVals;
+  for (long long e0 = (long long)p.eBegin + (long long)blockIdx.x * kPGElems; e0 < p.eEnd; e0 += (long long)gridDim.x * kPGElems) {
+    const bool live = e0 + g < p.eEnd;
+    const long long e = live ? e0 + g : (long long)p.eEnd - 1;
+    // ---- stage 1: gather ---------------------------------------------------------------------------------------------------------------------------------
+    if (j < 12) { E[PG_X + j] = p.elemX[(size_t)e * 12 + j]; EI[PGI_PERM + j] = p.fperm[(size_t)e * 12 + j]; }
+    EI[PGI_POS + j] = p.elemPos[(size_t)e * 16 + j];
+    if (j >= 12) {
+      const int f = j - 12, Ff = p.cell2face[(size_t)e * 4 + f];
+      EI[PGI_F + f] = Ff; EI[PGI_BC + f] = p.faceBC[Ff]; EI[PGI_IN + f] = p.faceInterior[Ff]; RS[f] = p.faceRowStart[Ff];
+      EI[PGI_SD + f] = tv == 2 ? p.tauSide[(size_t)e * 4 + f] : 0;
+    }
+    __syncwarp();
+    // ---- stage 2: geometry (every lane keeps Jinv and det), per-face data by lanes 0-3, tau by lanes 0-11, source by lane 12 --------------------------------
+    double J[3][3], det, I[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int m = 0; m < 3; m++) J[r][m] = 0.5 * (E[PG_X + (r + 1) * 3 + m] - E[PG_X + m]);
+    det_inv(J, det, I);
+    if (j < 4) {
+      const int f = j;
+      const int v0 = (kFnBits >> (2 * (f * 3))) & 3, v1 = (kFnBits >> (2 * (f * 3 + 1))) & 3, v2 = (kFnBits >> (2 * (f * 3 + 2))) & 3, vo = (kFnBits >> (24 + 2 * f)) & 3;
+      double a0[3], a1[3], xo[3];
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        const double x0 = E[PG_X + v0 * 3 + m];
+        a0[m] = 0.5 * (E[PG_X + v1 * 3 + m] - x0); a1[m] = 0.5 * (E[PG_X + v2 * 3 + m] - x0); xo[m] = E[PG_X + vo * 3 + m] - x0;
+      }
+      const double nv[3] = {a0[1] * a1[2] - a0[2] * a1[1], a0[2] * a1[0] - a0[0] * a1[2], a0[0] * a1[1] - a0[1] * a1[0]};
+      const double nn = nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2];
+      const double ar = sqrt(nn), inv = 1.0 / ar;
+      const double prod = fma(xo[2], nv[2], fma(xo[1], nv[1], xo[0] * nv[0]));
+      const double sg = prod > 0.0 ? -inv : inv;
+      const double n0 = sg * nv[0], n1 = sg * nv[1], n2 = sg * nv[2], rdet = 1.0 / det;
+      E[PG_N + f * 3] = n0; E[PG_N + f * 3 + 1] = n1; E[PG_N + f * 3 + 2] = n2; E[PG_AR + f] = ar;
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        E[PG_HF + f * 3 + r] = -ar * (I[0][r] * n0 + I[1][r] * n1 + I[2][r] * n2);
+        E[PG_CR + f * 3 + r] = ar * rdet * (J[r][0] * n0 + J[r][1] * n1 + J[r][2] * n2);
+      }
+      E[PG_CQ + f * 3] = ar * rdet * n0; E[PG_CQ + f * 3 + 1] = ar * rdet * n1; E[PG_CQ + f * 3 + 2] = ar * rdet * n2;
+    }
+    if (j < 12) {
+      const int f = j / 3;
+      E[PG_TAU + j] = p.tau[((size_t)EI[PGI_F + f] * 3 + EI[PGI_PERM + j]) * tv + EI[PGI_SD + f]];
+    } else if (j == 12) {
+      double Fu[4] = {0.0, 0.0, 0.0, 0.0};
+      if (hasSrc) {
+#pragma unroll
+        for (int ip = 0; ip < 4; ip++) {
+          const double sv = p.srcIP[(size_t)e * 4 + ip] * det;
+#pragma unroll
+          for (int i = 0; i < 4; i++) Fu[i] = fma(T.PHIW[ip][i], sv, Fu[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) E[PG_FU + i] = Fu[i];
+    }
+    __syncwarp();
+    // ---- stage 3: tau masses (lanes 0-11: row (f, a)) and SJ_r (lane = (m, k)) --------------------------------------------------------------------------------
+    if (j < 12) {
+      const int f = j / 3, a = j - 3 * f;
+      const double ar = E[PG_AR + f], t0 = E[PG_TAU + f * 3], t1 = E[PG_TAU + f * 3 + 1], t2 = E[PG_TAU + f * 3 + 2];
+#pragma unroll
+      for (int b = 0; b < 3; b++) E[PG_FT + j * 3 + b] = ar * (T.T3[a][b][0] * t0 + T.T3[a][b][1] * t1 + T.T3[a][b][2] * t2);
+    }
+    {
+      const int m = j >> 2, k = j & 3;
+      const double e0f = EF[j * 4], e1f = EF[j * 4 + 1], e2f = EF[j * 4 + 2], e3f = EF[j * 4 + 3];
+      const double s0 = T.S[0][m][k], s1 = T.S[1][m][k], s2 = T.S[2][m][k];
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const double g0 = I[0][r] * I[0][0] + I[1][r] * I[1][0] + I[2][r] * I[2][0], g1 = I[0][r] * I[0][1] + I[1][r] * I[1][1] + I[2][r] * I[2][1],
+                     g2 = I[0][r] * I[0][2] + I[1][r] * I[1][2] + I[2][r] * I[2][2];
+        const double v = g0 * s0 + g1 * s1 + g2 * s2;
+        const double w = E[PG_HF + r] * e0f + E[PG_HF + 3 + r] * e1f + E[PG_HF + 6 + r] * e2f + E[PG_HF + 9 + r] * e3f;
+        E[PG_SJ + (r * 4 + m) * 4 + k] = dsc * fma(det, v, w);
+      }
+    }
+    __syncwarp();
+    // ---- stage 4: K (lane = (m, n)) ------------------------------------------------------------------------------------------------------------------------------
+    {
+      const int m = j >> 2, n = j & 3;
+      double v = 0.0;
+#pragma unroll
+      for (int f = 0; f < 4; f++) { const int a = nif(f, m), b = nif(f, n); if (a != 15 && b != 15) v += E[PG_FT + (f * 3 + a) * 3 + b]; }
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const double* sj = E + PG_SJ + (r * 4 + m) * 4;
+        v -= sj[0] * T.A[r][0][n] + sj[1] * T.A[r][1][n] + sj[2] * T.A[r][2][n] + sj[3] * T.A[r][3][n];
+      }
+      E[PG_K + j] = v;
+    }
+    __syncwarp();
+    // ---- stage 5: K^-1 by cofactors, lane (i, c) forms Ki[i][c] = cof(c, i) / det K; det K = sum_i K[c][i] cof(c, i) over the four lanes of a column c --------------
+    {
+      const int i = j >> 2, c = j & 3;
+      const int r0 = c <= 0 ? 1 : 0, r1 = c <= 1 ? 2 : 1, r2 = c <= 2 ? 3 : 2;      // rows without c
+      const int c0 = i <= 0 ? 1 : 0, c1 = i <= 1 ? 2 : 1, c2 = i <= 2 ? 3 : 2;      // columns without i
+      const double* Kp = E + PG_K;
+      const double a00 = Kp[r0 * 4 + c0], a01 = Kp[r0 * 4 + c1], a02 = Kp[r0 * 4 + c2], a10 = Kp[r1 * 4 + c0], a11 = Kp[r1 * 4 + c1], a12 = Kp[r1 * 4 + c2],
+                   a20 = Kp[r2 * 4 + c0], a21 = Kp[r2 * 4 + c1], a22 = Kp[r2 * 4 + c2];
+      double cof = a00 * (a11 * a22 - a12 * a21) - a01 * (a10 * a22 - a12 * a20) + a02 * (a10 * a21 - a11 * a20);
+      if ((i + c) & 1) cof = -cof;
+      double dK = Kp[c * 4 + i] * cof;
+      dK += __shfl_xor_sync(0xffffffffu, dK, 4);
+      dK += __shfl_xor_sync(0xffffffffu, dK, 8);
+      if (!(fabs(dK) > 1e-300) && live) atomicOr(p.status, 1);
+      E[PG_KI + j] = cof / dK;
+    }
+    __syncwarp();
+    // ---- stage 6: one column per lane ----------------------------------------------------------------------------------------------------------------------------
+    if (j < 13 && live) {
+      const bool rhsCol = j == 12;
+      const int c = rhsCol ? 0 : j, fc = c / 3, bcol = c - 3 * fc;
+      const double b0 = T.BH[fc][0][bcol], b1 = T.BH[fc][1][bcol], b2 = T.BH[fc][2][bcol], b3 = T.BH[fc][3][bcol];
+      double R[4];
+      if (!rhsCol) {
+        const double cr0 = E[PG_CR + fc * 3], cr1 = E[PG_CR + fc * 3 + 1], cr2 = E[PG_CR + fc * 3 + 2];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const double2* s0 = reinterpret_cast<const double2*>(E + PG_SJ + m * 4);
+          const double2* s1 = reinterpret_cast<const double2*>(E + PG_SJ + (4 + m) * 4);
+          const double2* s2 = reinterpret_cast<const double2*>(E + PG_SJ + (8 + m) * 4);
+          const double2 p0 = s0[0], p1 = s0[1], q0 = s1[0], q1 = s1[1], w0 = s2[0], w1 = s2[1];
+          double v = cr0 * (p0.x * b0 + p0.y * b1 + p1.x * b2 + p1.y * b3);
+          v = fma(cr1, q0.x * b0 + q0.y * b1 + q1.x * b2 + q1.y * b3, v);
+          v = fma(cr2, w0.x * b0 + w0.y * b1 + w1.x * b2 + w1.y * b3, v);
+          const int a = nif(fc, m);
+          if (a != 15) v -= E[PG_FT + (fc * 3 + a) * 3 + bcol];      // Sul = -tau mass
+          R[m] = v;
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 4; m++) R[m] = -E[PG_FU + m];
+      }
+      double U[4], V[4];
+      const double2* Ki2 = reinterpret_cast<const double2*>(E + PG_KI);
+      const double2* K2 = reinterpret_cast<const double2*>(E + PG_K);
+#pragma unroll
+      for (int m = 0; m < 4; m++) { const double2 x = Ki2[2 * m], y = Ki2[2 * m + 1]; U[m] = -(x.x * R[0] + x.y * R[1] + y.x * R[2] + y.y * R[3]); }
+#pragma unroll
+      for (int m = 0; m < 4; m++) { const double2 x = K2[2 * m], y = K2[2 * m + 1]; V[m] = R[m] + x.x * U[0] + x.y * U[1] + y.x * U[2] + y.y * U[3]; }
+#pragma unroll
+      for (int m = 0; m < 4; m++) { const double2 x = Ki2[2 * m], y = Ki2[2 * m + 1]; U[m] -= x.x * V[0] + x.y * V[1] + y.x * V[2] + y.y * V[3]; }
+      double Q[3][4];
+      {
+        double Pr[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int m = 0; m < 4; m++) Pr[r][m] = T.A[r][m][0] * U[0] + T.A[r][m][1] * U[1] + T.A[r][m][2] * U[2] + T.A[r][m][3] * U[3];
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          const double cq = rhsCol ? 0.0 : E[PG_CQ + fc * 3 + d];
+#pragma unroll
+          for (int m = 0; m < 4; m++) {
+            const double bm = m == 0 ? b0 : (m == 1 ? b1 : (m == 2 ? b2 : b3));
+            Q[d][m] = fma(cq, bm, -(I[d][0] * Pr[0][m] + I[d][1] * Pr[1][m] + I[d][2] * Pr[2][m]));
+          }
+        }
+      }
+      if (!rhsCol) {
+        double* const gU = p.U + (size_t)e * 48;
+        double* const gQ = p.Q + (size_t)e * 144;
+#pragma unroll
+        for (int m = 0; m < 4; m++) gU[m * 12 + c] = U[m];
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+          for (int d = 0; d < 3; d++) gQ[(m * 3 + d) * 12 + c] = Q[d][m];
+      } else {
+#pragma unroll
+        for (int m = 0; m < 4; m++) p.U0[(size_t)e * 4 + m] = U[m];
+#pragma unroll
+        for (int m = 0; m < 4; m++)
+#pragma unroll
+          for (int d = 0; d < 3; d++) p.Q0[(size_t)e * 12 + m * 3 + d] = Q[d][m];
+      }
+      const int permC = rhsCol ? 0 : EI[PGI_PERM + c];
+      double* const gS = p.S ? p.S + (size_t)e * 144 : nullptr;
+#pragma unroll
+      for (int f = 0; f < 4; f++) {
+        const double n0 = E[PG_N + f * 3], n1 = E[PG_N + f * 3 + 1], n2 = E[PG_N + f * 3 + 2], ar = E[PG_AR + f];
+        double zq[3], uf[3];
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+          const int nd = kP1FN[f][b];
+          zq[b] = -dsc * (n0 * Q[0][nd] + n1 * Q[1][nd] + n2 * Q[2][nd]);
+          uf[b] = U[nd] - ((!rhsCol && f == fc && b == bcol) ? 1.0 : 0.0);
+        }
+        const int bcf = EI[PGI_BC + f], Ff = EI[PGI_F + f];
+        const bool inter = EI[PGI_IN + f] != 0;
+        double* const blk = p.vals + RS[f] + (long long)EI[PGI_POS + f * 4 + fc] * 9 + permC;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          const double* ft = E + PG_FT + (f * 3 + a) * 3;
+          double s2 = ft[0] * uf[0] + ft[1] * uf[1] + ft[2] * uf[2] + ar * (T.MF[a][0] * zq[0] + T.MF[a][1] * zq[1] + T.MF[a][2] * zq[2]);
+          const int r = f * 3 + a, pr = EI[PGI_PERM + r];
+          if (!rhsCol) {
+            if (bcf == 1) s2 = (r == c) ? 1.0 : 0.0;                                          // DirichletModel row (Set)
+            else if (bcf == 2) s2 = (f == fc) ? ar * T.MF[a][bcol] : 0.0;                      // IntegratedDirichletModel row: face mass
+            if (gS) gS[r + 12 * c] = s2;
+            double* dst = blk + pr * 3;
+            if (f == fc && inter) atomicAdd(dst, s2); else *dst = s2;
+          } else {
+            double s0 = -s2;
+            if (bcf == 1) s0 = p.dirichlet[(size_t)Ff * 3 + a];
+            else if (bcf == 2) {
+              s0 = 0.0;
+#pragma unroll
+              for (int b = 0; b < 3; b++) s0 = fma(ar * T.MF[a][b], p.dirichlet[(size_t)Ff * 3 + b], s0);
+            }
+            if (p.S0) p.S0[(size_t)e * 12 + r] = s0;
+            double* dst = p.rhs + (size_t)Ff * 3 + pr;
+            if (inter) atomicAdd(dst, s0); else *dst = s0;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int MINB>
+inline cudaError_t launch_p1g_t(const AsmParams& p, int nSM, cudaStream_t st) {
+  const size_t bytes = (size_t)(((kPGTabAll + 1) & ~1) + kPGElems * PG_STRIDE) * sizeof(double);
+  cudaError_t e = cudaFuncSetAttribute(hdg_p1g_kernel<MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  int perSM = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, hdg_p1g_kernel<MINB>, kPGThreads, bytes);
+  if (perSM < 1) perSM = 1;
+  long long grid = (long long)nSM * perSM;
+  const long long need = ((long long)(p.eEnd - p.eBegin) + kPGElems - 1) / kPGElems;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  hdg_p1g_kernel<MINB><<<(int)grid, kPGThreads, bytes, st>>>(p);
+  return cudaGetLastError();
+}
+inline cudaError_t launch_p1g(const AsmParams& p, int nSM, cudaStream_t st) {
+  const int minb = getenv("HFX_P1_MINB") ? atoi(getenv("HFX_P1_MINB")) : 2;
+  return minb == 3 ? launch_p1g_t<3>(p, nSM, st) : (minb == 4 ? launch_p1g_t<4>(p, nSM, st) : launch_p1g_t<2>(p, nSM, st));
+}
+
 }  // namespace hfx

@@ -812,10 +812,10 @@ class HDGSolver:
         return a.value, b.value
 
     def lastAssembleKernel(self):
-        """Which device kernel served the last assemble: "fused" (hfx_assemble.cuh), "general" (hfx_generic.cuh), "big" (hfx_big.cuh) or "p1" (hfx_p1.cuh)."""
+        """Which device kernel served the last assemble: "fused" (hfx_assemble.cuh), "general" (hfx_generic.cuh), "big" (hfx_big.cuh), "p1" (hfx_p1.cuh) or "col" (hfx_col.cuh)."""
         k, pf = C.c_int(0), C.c_int(0)
         lib().hfx_last_assemble_kernel(self._h(), C.byref(k), C.byref(pf))
-        return ("fused", "general", "big", "p1")[k.value]
+        return ("fused", "general", "big", "p1", "col")[k.value]
 
 
 class NonLinearWrapper:

@@ -1,5 +1,5 @@
-"""Linear-tet kernel (hfx_p1.cuh: one thread per element, Laplace-type models on straight-sided cells; opt-in with HFX_P1=1) against the
-oracle and against the element-group kernel."""
+"""Linear-tet kernels (hfx_p1.cuh; Laplace-type models on straight-sided cells) against the oracle and against the element-group kernel:
+HFX_P1=1 (the default) = sixteen lanes per element, one trace column per lane; HFX_P1=2 = one thread per element (kept for comparison)."""
 import numpy as np
 import pytest
 
@@ -12,9 +12,23 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("model,diff,bc,tau_double", [("laplace", "none", "dirichlet", False), ("laplace", "none", "integrated", False),
                                                       ("diffsrc", "none", "dirichlet", True), ("diffsrc", "const", "integrated", True),
                                                       ("diffsrc", "const", "dirichlet", False)])
-def test_p1_kernel_matches_oracle(model, diff, bc, tau_double, monkeypatch):
-    monkeypatch.setenv("HFX_P1", "1")
+@pytest.mark.parametrize("variant", ["1", "2"])
+def test_p1_kernel_matches_oracle(model, diff, bc, tau_double, variant, monkeypatch):
+    monkeypatch.setenv("HFX_P1", variant)
     o, s, fm = compare(H.make_case(3, 1, N=3, perturb=0.12, model=model, diff=diff, bc=bc, tau_double=tau_double, seed=43))
+    assert s.lastAssembleKernel() == "p1"
+
+
+def test_p1_kernel_is_the_default_on_linear_tets():
+    o, s, fm = compare(H.make_case(3, 1, N=4, perturb=0.1, model="laplace", seed=61))
+    assert s.lastAssembleKernel() == "p1"
+
+
+def test_p1_kernel_ragged_tail():
+    """the reference's own Gmsh tets (729 cells: neither a multiple of the sixteen elements of a CTA nor of the two of a warp)"""
+    case = H.make_case(3, 1, mesh="regression_dim-3_h-2e-1_ord-1", model="diffsrc", bc="integrated", tau_double=True, seed=67)
+    assert case["cells"].shape[0] % 2 == 1
+    o, s, fm = compare(case)
     assert s.lastAssembleKernel() == "p1"
 
 

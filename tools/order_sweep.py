@@ -13,7 +13,8 @@ L = lib()
 L.hfx_fp64_peak.restype = C.c_double
 peak = L.hfx_fp64_peak(0)
 out = []
-for order in (1, 2, 3, 4, 5):
+orders = tuple(int(x) for x in sys.argv[2].split(",")) if len(sys.argv) > 2 else (1, 2, 3, 4, 5)
+for order in orders:
     N = max(2, int(round((target / NN[order] / 6.0) ** (1.0 / 3.0))))
     nodes, cells = meshgen.kuhn_mesh(N, order, 3)
     tp = capi.host_compute_faces(3, order, cells)
@@ -37,7 +38,9 @@ for order in (1, 2, 3, 4, 5):
             ms.append(b.value)
     t = float(np.mean(ms)) * 1e-3
     nC = cells.shape[0]
-    row = dict(order=order, cubes=N, elements=nC, dofs=nC * NN[order], kernel="fused" if order <= 3 else "general", ms=t * 1e3, elements_per_s=nC / t,
+    kk = C.c_int(0)
+    L.hfx_last_assemble_kernel(h, C.byref(kk), None)
+    row = dict(order=order, cubes=N, elements=nC, dofs=nC * NN[order], kernel=("fused", "general", "big", "p1", "col")[kk.value], ms=t * 1e3, elements_per_s=nC / t,
                tflops_algorithmic=FLOPS[order] * nC / t / 1e12, frac_fp64_peak=FLOPS[order] * nC / t / 1e12 / peak)
     out.append(row)
     print(json.dumps(row))

@@ -35,6 +35,8 @@ struct GenParams {
   const double* rkSol[8]; const double* rkFlux[8]; const double* rkTrace[8];   // RKStage_k, RKStage_Flux_k (cell), RKStage_Trace_k (face)  // per-element Model surface (FEModel::compute / getLocalMatrix / getLocalRHS, src/model/FEModel.h:43-78): build the local system of ONE element,
   // write it out dense (column-major n x n, S_qq = M (x) I included) with its right-hand side, and stop before the condensation
   int dumpElem; double* dumpA; double* dumpF;
+  // HDGSolverOpts.type = WEXPLICIT / SEXPLICIT (HDGSolver.cpp:346-354): S = S_ll, S0 = F_l - S_lu sol - S_lq flux with the element's current Solution / Flux (cell fields)
+  int explicitS; const double* solCur; const double* fluxCur;
 };
 
 // scratch layout (offsets in doubles), identical on host and device
@@ -784,7 +786,9 @@ __global__ void __launch_bounds__(kGenThreads, HFX_GEN_MINBLOCKS) hdg_generic_ke
         const int mt = task % MT, ng = task / MT;
         mma_task_rt<3>(mt, ng * 3, lane, l, l + 1, u + q,
             [&](int r, int k) { return Lm[(sL + r) + n * k]; },
-            [&](int k, int c) { const double* pc = k < u ? Um + u * c + k : Qm + q * c + (k - u); return *pc; },
+            [&](int k, int c) {
+              if (P.explicitS) return c >= l ? (k < u ? P.solCur[(size_t)e * u + k] : P.fluxCur[(size_t)e * q + (k - u)]) : 0.0;   // explicit trace problem (:349-353)
+              const double* pc = k < u ? Um + u * c + k : Qm + q * c + (k - u); return *pc; },
             [&](int r, int c, double v0, double v1) {
               if (r < l) { if (c <= l) emitS(r, c, v0); if (c + 1 <= l) emitS(r, c + 1, v1); }
             });

@@ -1125,6 +1125,7 @@ struct hfx_ctx {
   DBuf<uint8_t> dFaceBC;
   // allocation
   bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false, p1Ready = false, colReady = false; int lastKernel = 0;
+  int solverType = 0;   // HDGSolverOpts.type: 0 IMPLICIT, 1 WEXPLICIT, 2 SEXPLICIT (HDGSolverOpts.h:6-10)
   DBuf<double> dColTab;
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
   DBuf<long long> dFaceRowStart, dBlockCount, dTotal;
@@ -1956,6 +1957,7 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
       c->dRhs.zero(c->st); c->dStatus.zero(c->st);
     };
     const bool dumpMode = dumpA != nullptr;
+    const bool forceGeneric = getenv("HFX_FORCE_GENERIC") != nullptr || c->solverType != 0;   // the explicit solver types live in the general kernel
     if (!recoverMode && !dumpMode) clearSystem();
     HFX_CUDA(cudaEventRecord(c->ev1, c->st));
     // linear tets, Laplace-type model, straight-sided cells: sixteen lanes per element, one trace column per lane (hfx_p1.cuh): 552 M el/s against the 206 M el/s of
@@ -1963,7 +1965,7 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     bool p1 = false, col = false;
     const int p1Mode = getenv("HFX_P1") ? atoi(getenv("HFX_P1")) : 1;   // 1 (default): sixteen lanes per element; 2: one thread per element; 0: element-group kernel
     if (p1Mode != 0 && !recoverMode && !dumpMode && c->p1Ready && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 1 && c->md.nDOF == 1 && (c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE)) == 0
-        && c->md.timeScheme == HFX_TS_NONE && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_P1")) {
+        && c->md.timeScheme == HFX_TS_NONE && !p.diff && p.affine && c->nNonAffine == 0 && !forceGeneric && !getenv("HFX_NO_P1")) {
       for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) { for (DField* f : {&kv.second}) for (int k = 0; k < f->pendingPieces; k++) HFX_CUDA(cudaStreamWaitEvent(c->st, f->ev[k], 0)); kv.second.pendingPieces = 0; }
       p.eBegin = 0; p.eEnd = c->nCells;
       if (p1Mode == 2) HFX_CUDA(launch_p1(p, c->nSM, c->st));   // one thread per element
@@ -1972,7 +1974,7 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     }
     // order-2 tets, same eligibility: one warp per element, one trace column per lane (hfx_col.cuh).  HFX_COL=0 keeps the element-group kernel
     if (!p1 && (!getenv("HFX_COL") || atoi(getenv("HFX_COL")) != 0) && !recoverMode && !dumpMode && c->colReady && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 2 && c->md.nDOF == 1
-        && (c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE)) == 0 && c->md.timeScheme == HFX_TS_NONE && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC")) {
+        && (c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE)) == 0 && c->md.timeScheme == HFX_TS_NONE && !p.diff && p.affine && c->nNonAffine == 0 && !forceGeneric) {
       for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) { for (int k = 0; k < kv.second.pendingPieces; k++) HFX_CUDA(cudaStreamWaitEvent(c->st, kv.second.ev[k], 0)); kv.second.pendingPieces = 0; }
       p.eBegin = 0; p.eEnd = c->nCells; p.colTab = c->dColTab.p;
       const int nw = getenv("HFX_COL_NW") ? atoi(getenv("HFX_COL_NW")) : 4;
@@ -1995,8 +1997,8 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
       tauVaries = tv != 0;
     }
     const bool bigP3 = !p1 && !recoverMode && !dumpMode && bigP3Mode > 0 && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 3 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU)
-        && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && (needSuuModel || bigP3Mode == 2 || tauVaries);
-    bool fused = !p1 && !bigP3 && !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !getenv("HFX_FORCE_GENERIC");
+        && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !p.diff && p.affine && c->nNonAffine == 0 && !forceGeneric && (needSuuModel || bigP3Mode == 2 || tauVaries);
+    bool fused = !p1 && !bigP3 && !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !forceGeneric;
     // fields still crossing PCIe (hfx_field_set_async): the element chunks start as their face-id prefix has arrived
     std::vector<DField*> pend;
     for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) pend.push_back(&kv.second);
@@ -2022,14 +2024,14 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     // 3-D order 4: the large-element kernel (one 512-thread CTA per SM, operands resident in shared memory) when every cell is straight-sided and D = c I
     bool big = false;
     if (!fused && !p1 && !dumpMode && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 4 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme != HFX_TS_RUNGE_KUTTA
-        && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_BIG")) {
+        && !p.diff && p.affine && c->nNonAffine == 0 && !forceGeneric && !getenv("HFX_NO_BIG")) {
       if (!pend.empty()) waitPieces(0, -1);
       HFX_CUDA((launch_big<BigSimplex<3, 4>, 512>(p, c->nSM, c->st)));
       big = true;
     }
     // structured hexahedra of order 2 (parallelepiped cells, flagged affine): the same formulation with the orthotope frame
     if (!fused && !p1 && !big && !dumpMode && !recoverMode && c->geom == HFX_ORTHOTOPE && c->dim == 3 && c->order == 2 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU)
-        && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !p.diff && p.affine && c->nNonAffine == 0 && !getenv("HFX_FORCE_GENERIC") && !getenv("HFX_NO_BIG")) {
+        && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !p.diff && p.affine && c->nNonAffine == 0 && !forceGeneric && !getenv("HFX_NO_BIG")) {
       if (!pend.empty()) waitPieces(0, -1);
       HFX_CUDA((launch_big<BigHexP2, 512>(p, c->nSM, c->st)));
       big = true;
@@ -2052,6 +2054,11 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
       g.dumpElem = dumpElem; g.dumpA = dumpA; g.dumpF = dumpF;
       g.a = p; g.dim = c->dim; g.nN = c->nN; g.nNf = c->nNf; g.nFc = c->nFc; g.nIP = c->nIP; g.nIPf = c->nIPf; g.nD = c->md.nDOF;
       g.nSrc = 1;
+      if (c->solverType != 0) {   // HDGSolver.cpp:349-353
+        DField* so = find_field(c, "Solution"); DField* fl = find_field(c, "Flux");
+        need(so && fl, "HDGSolver", "calcElementalMatrices", "the explicit solver types need the Solution and Flux fields");
+        g.explicitS = 1; g.solCur = so->d.p; g.fluxCur = fl->d.p;
+      }
       g.frameV[0] = 0; g.frameV[1] = 1; g.frameV[2] = c->geom == HFX_SIMPLEX ? 2 : 3; g.frameV[3] = c->geom == HFX_SIMPLEX ? 3 : 4;
       if (p.opmask & HFX_OP_UNABU) {
         DField* bs = find_field(c, "BufferSolution");
@@ -2125,6 +2132,13 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
   });
 }
 
+int hfx_solver_type(hfx_ctx* c, int type) {
+  return guard(c, [&] {
+    need(type >= 0 && type <= 2, "HDGSolver", "setOptions", "solver types: IMPLICIT (0), WEXPLICIT (1), SEXPLICIT (2)");
+    c->solverType = type;
+  });
+}
+
 int hfx_assemble(hfx_ctx* c) { return assemble_impl(c, false); }
 
 int hfx_get_local_matrix(hfx_ctx* c, int iEl, double* A, double* F) {
@@ -2191,6 +2205,15 @@ int hfx_solve(hfx_ctx* c, const hfx_solve_opts* opts, hfx_solve_stats* stats) {
     const double* b = c->dRhs.p;
     double* x = find_field(c, "Trace")->d.p;
     const bool dist = c->halo.comm && c->halo.planned;
+    if (c->solverType == 2) {   // SEXPLICIT (HDGSolver.cpp:709-729): S = S_ll couples the nodes of one face only; every face block is inverted and applied on its own
+      need(!dist, "HDGSolver", "allocate", "the SEXPLICIT mode is currently unsuported in parallel, please use the WEXPLICIT mode instead.");
+      need(A.has_block_pc(), "HDGSolver", "solve", "face blocks beyond 32 x 32 are not supported by the SEXPLICIT face solve");
+      A.block_pc_setup(c->st);
+      A.block_pc_apply(b, nullptr, x, c->st);
+      HFX_CUDA(cudaGetLastError());
+      if (stats) { stats->iterations = 0; stats->resnorm = 0.0; stats->bnorm = 0.0; stats->converged = 1; }
+      return;
+    }
     c->krylov.halo = dist ? &c->halo : nullptr;
     if (dist) {   // every Krylov vector is zero on the rows this rank does not own, so plain dots + all-reduce give the global dots
       const int t = c->nNf * c->md.nDOF;

@@ -24,7 +24,7 @@ Node, Cell, Face = 0, 1, 2      # FieldType (src/field/FieldTypes.h); C ABI: HFX
 Add, Set = 0, 1                 # AssemblyType.h
 KSPGMRES, KSPCG = 0, 1
 PCNONE, PCJACOBI, PCBJACOBI = 0, 1, 2   # PCBJACOBI: Jacobi on the t x t diagonal blocks of the faces (the block structure of the trace system)
-IMPLICIT = 0
+IMPLICIT, WEXPLICIT, SEXPLICIT = 0, 1, 2    # HDGSolverType (src/solver/HDGSolverOpts.h:6-10)
 
 OP_DIFFUSION, OP_CONVECTION, OP_REACTION, OP_SOURCE, OP_UNABU = 1, 2, 4, 8, 16
 
@@ -412,6 +412,21 @@ class HDGConvectionDiffusionReactionSource(_HDGModel):
         return m
 
 
+class HDGTransport(_HDGModel):
+    """HDGTransport (src/model/HDGTransport.cpp:5-69): localMatrix = Base + Convection, zero right-hand side; a Velocity field is required."""
+    usesDiffusionField = False
+
+    def setFieldMap(self, fm):
+        if "Velocity" not in fm:
+            raise ErrorHandle("HDGTransport : setFieldMap : one must provide a Velocity field to use the Transport model.")
+        super().setFieldMap(fm)
+
+    def _mask(self, fieldNames, strict=True):
+        if strict and "Velocity" not in fieldNames:
+            raise ErrorHandle("HDGTransport : setFieldMap : one must provide a Velocity field to use the Transport model.")
+        return OP_CONVECTION
+
+
 class HDGBurgersModel(_HDGModel):
     """Base + HDGUNabU (Newton-linearised convection, needs BufferSolution and Trace) [+ Diffusion if DiffusionTensor] ; rhs = UNabU
     rhs [+ one scalar Source per component]  (src/model/HDGBurgersModel.cpp:5-124)."""
@@ -580,11 +595,15 @@ class HDGSolver:
         self.verbose = False
         self.stats = capi.SolveStats()
         self._meshUploaded = False
+        self.myOpts = HDGSolverOpts()
 
     def setVerbosity(self, v): self.verbose = bool(v)
     def setOptions(self, opts):
-        if opts.type != IMPLICIT:
-            raise ErrorHandle("HDGSolver : setOptions : only the IMPLICIT solver type has a device path")
+        """HDGSolver::setOptions (HDGSolver.h:41).  WEXPLICIT / SEXPLICIT: the trace problem is explicit in the current Solution / Flux (HDGSolver.cpp:346-354)."""
+        if opts.type not in (IMPLICIT, WEXPLICIT, SEXPLICIT):
+            raise ErrorHandle("HDGSolver : setOptions : unknown solver type")
+        self.myOpts = opts
+        self.verbose = bool(opts.verbosity)
     def setMesh(self, m): self.myMesh = m; self._meshUploaded = False
     def setFieldMap(self, fm): self.fieldMap = fm
     def setLinSystem(self, lai): self.linSystem = lai
@@ -624,7 +643,7 @@ class HDGSolver:
             raise ErrorHandle("HDGSolver : allocate : must initialize the solver before allocating.")
         if self.myMesh is None:
             raise ErrorHandle("HDGSolver : allocate : must set the Mesh before allocating.")
-        if self.linSystem is None:
+        if self.linSystem is None and self.myOpts.type != SEXPLICIT:      # HDGSolver.cpp:12-14
             raise ErrorHandle("HDGSolver : allocate : must set the linear system before allocating.")
         if self.model is None:
             raise ErrorHandle("HDGSolver : allocate : must set the model before allocating.")
@@ -661,6 +680,7 @@ class HDGSolver:
         for bm, faces in self.boundaries:
             bm.allocate(self.nDOFsPerNode)
             check(L.hfx_boundary_describe(h, bm.kind, 0 if faces is None else faces.size, None if faces is None else pi(faces)), h)
+        check(L.hfx_solver_type(h, self.myOpts.type), h)
         check(L.hfx_allocate(h, (1 if self.keepLocalS else 0) | (2 if self.recomputeRecovery else 0)), h)
         self.allocated = True
 
@@ -676,6 +696,8 @@ class HDGSolver:
             names.append("Solution")
         if getattr(self.model, "isBurgers", False):
             names += [n for n in ("BufferSolution", "Trace") if n in self.fieldMap]
+        if self.myOpts.type != IMPLICIT and self.allocated:
+            names += [n for n in ("Solution", "Flux") if n not in names]
         return names
 
     def _describe_model(self, strict=True):
@@ -729,6 +751,7 @@ class HDGSolver:
         if not self.assembled:
             raise ErrorHandle("HDGSolver : solve : system must be assembled before solving")
         o = self.linSystem.opts.c() if hasattr(self.linSystem, "opts") else PetscOpts().c()
+        check(lib().hfx_solver_type(self._h(), self.myOpts.type), self._h())
         check(lib().hfx_solve(self._h(), C.byref(o), C.byref(self.stats)), self._h())
         for name in ("Trace", "Solution", "Flux"):      # left on the device; Field.values fetches them when somebody looks
             f = self.fieldMap[name]

@@ -123,6 +123,11 @@ typedef struct {
   double rtol;   /* PetscOpts.h:20: 1e-6                                                */
 } hfx_solve_opts;
 typedef struct { int iterations; double resnorm; double bnorm; int converged; } hfx_solve_stats;
+/* HDGSolver::setOptions (src/solver/HDGSolver.h:41, HDGSolverOpts.h:6-15): IMPLICIT (0, default), WEXPLICIT (1), SEXPLICIT (2).  The explicit types keep U, Q, U0, Q0
+   but make the trace problem explicit in the current Solution / Flux fields (HDGSolver.cpp:346-354: S = S_ll, S0 = F_l - S_lu u - S_lq q); WEXPLICIT assembles and
+   solves the (face-block-diagonal) global system as usual (:605-624), SEXPLICIT solves every face on its own in hfx_solve (:626-667,709-729) */
+enum { HFX_SOLVER_IMPLICIT = 0, HFX_SOLVER_WEXPLICIT = 1, HFX_SOLVER_SEXPLICIT = 2 };
+int hfx_solver_type(hfx_ctx* ctx, int type);
 int hfx_solve(hfx_ctx* ctx, const hfx_solve_opts* opts, hfx_solve_stats* stats); /* Trace <- solution; then recovery */
 int hfx_recover(hfx_ctx* ctx);                                                    /* HDGSolver.cpp:741-775 */
 /* what the last hfx_solve cost: device time per Krylov iteration (CUDA events around the whole solve / iterations), and on several GPUs the

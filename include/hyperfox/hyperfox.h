@@ -984,6 +984,16 @@ class HDGConvectionDiffusionReactionSource : public HDGModel {   // src/model/HD
   }
 };
 
+class HDGTransport : public HDGModel {   // Base + Convection, zero right-hand side  (src/model/HDGTransport.cpp:5-69)
+ public:
+  using HDGModel::HDGModel;
+  bool usesDiffusionField() const override { return false; }
+  int opmask(const std::set<std::string>& names, bool strict) const override {
+    if (strict && !names.count("Velocity")) throw ErrorHandle("HDGTransport", "setFieldMap", "one must provide a Velocity field to use the Transport model.");
+    return HFX_OP_CONVECTION;
+  }
+};
+
 // Base + HDGUNabU [+ Diffusion if DiffusionTensor] ; rhs = UNabU rhs [+ one scalar Source per component]  (src/model/HDGBurgersModel.cpp:5-124)
 class HDGBurgersModel : public HDGModel {
  public:
@@ -1082,10 +1092,8 @@ class HDGSolver : public Solver {
       if (it->second && it->second->deviceContext() && ownCtx && it->second->deviceContext() == ownCtx->h) { try { it->second->syncFromDevice(); } catch (...) {} it->second->markOnDevice(nullptr, "", false); }
     delete ownCtx;
   }
-  void setOptions(HDGSolverOpts opts) {
-    if (opts.type != IMPLICIT) throw ErrorHandle("HDGSolver", "setOptions", "only the IMPLICIT solver type has a device path");
-    myOpts = opts;
-  }
+  // HDGSolver.h:41.  WEXPLICIT / SEXPLICIT: the trace problem is explicit in the current Solution / Flux (HDGSolver.cpp:346-354, hfx_solver_type)
+  void setOptions(HDGSolverOpts opts) { myOpts = opts; verbose = opts.verbosity; }
   void setDevice(int d) { device = d; }
   void keepLocalS(bool k) { keepS = k; }
   void recomputeRecovery(bool r) { recompute = r; }   // HFX_RECOMPUTE_RECOVERY: U, Q are not stored (large meshes of order-4 tets)
@@ -1093,7 +1101,7 @@ class HDGSolver : public Solver {
   void allocate() override {   // src/solver/HDGSolver.cpp:5-106
     if (!initialized) throw ErrorHandle("HDGSolver", "allocate", "must initialize the solver before allocating.");
     if (myMesh == NULL) throw ErrorHandle("HDGSolver", "allocate", "must set the Mesh before allocating.");
-    if (linSystem == NULL) throw ErrorHandle("HDGSolver", "allocate", "must set the linear system before allocating.");
+    if (linSystem == NULL && myOpts.type != SEXPLICIT) throw ErrorHandle("HDGSolver", "allocate", "must set the linear system before allocating.");   // HDGSolver.cpp:12-14
     if (model == NULL) throw ErrorHandle("HDGSolver", "allocate", "must set the model before allocating.");
     if (boundaryList.empty()) throw ErrorHandle("HDGSolver", "allocate", "must set the boundary model before allocating.");
     if (fieldMap == NULL || fieldMap->size() == 0) throw ErrorHandle("HDGSolver", "allocate", "must set the fields before allocating.");
@@ -1135,6 +1143,7 @@ class HDGSolver : public Solver {
       static const int none = 0;
       detail::check(hfx_boundary_describe(h, bm->cKind(), (int)ids.size(), ids.empty() ? &none : ids.data()), h);
     }
+    detail::check(hfx_solver_type(h, (int)myOpts.type), h);
     detail::check(hfx_allocate(h, (keepS ? HFX_KEEP_LOCAL_S : 0) | (recompute ? HFX_RECOMPUTE_RECOVERY : 0)), h);
     // several GPUs (src/solver/HDGSolver.cpp:64-76 asks the Partitioner for the shared faces): NCCL communicator + halo plan of the partitioned mesh
     Partitioner* pp = myMesh->getPartitioner();
@@ -1161,6 +1170,7 @@ class HDGSolver : public Solver {
     hfx_solve_opts o{0, 1, 30, 1000, 1e-6};
     CudaLinAlgebraInterface* cl = dynamic_cast<CudaLinAlgebraInterface*>(linSystem);
     if (cl) o = cl->cOpts();
+    detail::check(hfx_solver_type(ctx(), (int)myOpts.type), ctx());
     detail::check(hfx_solve(ctx(), &o, &stats), ctx());
     if (cl) cl->stats = stats;
     const char* out[3] = {"Trace", "Solution", "Flux"};   // left on the device; Field::getValues() fetches them when somebody looks
@@ -1203,6 +1213,7 @@ class HDGSolver : public Solver {
       if (allocated) { const std::vector<std::string> nm = rk->fieldNames(); for (size_t k = 0; k < nm.size(); k++) if (fieldMap->count(nm[k])) s.insert(nm[k]); }
     } else if (model->getTimeScheme() && allocated) s.insert("Solution");
     if (hm && hm->isBurgers()) { if (fieldMap->count("BufferSolution")) s.insert("BufferSolution"); s.insert("Trace"); }
+    if (myOpts.type != IMPLICIT && allocated) { s.insert("Solution"); s.insert("Flux"); }   // the explicit data of HDGSolver.cpp:349-353
     return s;
   }
   void uploadInputs() {

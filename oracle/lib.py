@@ -217,8 +217,13 @@ class HDGOracle:
         nC, u, q, l = self.nCells, self.u, self.q, self.l
         self.U = np.zeros((nC, u * l)); self.Q = np.zeros((nC, q * l)); self.S = np.zeros((nC, l * l))
         self.U0 = np.zeros((nC, u)); self.Q0 = np.zeros((nC, q)); self.S0 = np.zeros((nC, l))
-        lib().orc_assemble_local(C.byref(self.rc.c), C.byref(self.model), C.byref(self.cm), C.byref(self.cf), 0, nC, self.useLU,
-                                 _d(self.U), _d(self.Q), _d(self.S), _d(self.U0), _d(self.Q0), _d(self.S0))
+        if getattr(self, "solverType", 0) != 0:   # HDGSolverOpts.type = WEXPLICIT (1) / SEXPLICIT (2): explicit in the current Solution / Flux (HDGSolver.cpp:346-354)
+            self._sol = _c64(self.f["Solution"]).reshape(nC, u); self._flux = _c64(self.f["Flux"]).reshape(nC, q)
+            lib().orc_assemble_local_explicit(C.byref(self.rc.c), C.byref(self.model), C.byref(self.cm), C.byref(self.cf), 0, nC, self.useLU,
+                                              _d(self._sol), _d(self._flux), _d(self.U), _d(self.Q), _d(self.S), _d(self.U0), _d(self.Q0), _d(self.S0))
+        else:
+            lib().orc_assemble_local(C.byref(self.rc.c), C.byref(self.model), C.byref(self.cm), C.byref(self.cf), 0, nC, self.useLU,
+                                     _d(self.U), _d(self.Q), _d(self.S), _d(self.U0), _d(self.Q0), _d(self.S0))
         lib().orc_apply_bc(C.byref(self.rc.c), C.byref(self.model), C.byref(self.cm), C.byref(self.cf), _d(self.S), _d(self.S0))
 
     def pattern(self):
@@ -242,6 +247,29 @@ class HDGOracle:
         self.rhs = np.zeros(self.ndofs)
         lib().orc_scatter(C.byref(self.rc.c), self.nDOF, C.byref(self.cm), _d(self.S), _d(self.S0),
                           self.rowptr.ctypes.data_as(_lp), _i(self.colidx), _d(self.vals), _d(self.rhs))
+
+    def solve_faces(self):
+        """HDGSolverOpts.type = SEXPLICIT (HDGSolver.cpp:626-667,709-729): the element blocks S_ll / S0 are accumulated per FACE (face-node order) and every
+        face is solved on its own (HouseholderQR there, LAPACK here); then the usual local recovery."""
+        t = self.t
+        Sf = np.zeros((self.nFaces, t, t)); S0f = np.zeros((self.nFaces, t))
+        dofs = self.elem_dofs()
+        for e in range(self.nCells):
+            Se = self.S[e].reshape(self.l, self.l).T      # column-major element block -> [row, col]
+            for i in range(self.rc.nFc):
+                d = dofs[e, i * t:(i + 1) * t]; F = d[0] // t; loc = d - F * t
+                Sf[F][np.ix_(loc, loc)] += Se[i * t:(i + 1) * t, i * t:(i + 1) * t]
+                S0f[F][loc] += self.S0[e, i * t:(i + 1) * t]
+        x = np.concatenate([np.linalg.solve(Sf[F], S0f[F]) for F in range(self.nFaces)])
+        self.its, self.resnorm = 0, 0.0
+        return self._recover(x)
+
+    def _recover(self, x):
+        self.trace = x
+        self.sol = np.zeros((self.nCells, self.u)); self.flux = np.zeros((self.nCells, self.q))
+        lib().orc_recover(C.byref(self.rc.c), self.nDOF, C.byref(self.cm), _d(x), _d(self.U), _d(self.Q), _d(self.U0), _d(self.Q0),
+                          _d(self.sol), _d(self.flux))
+        return self.trace, self.sol, self.flux
 
     def solve(self, rtol=1e-6, maxits=1000, restart=30, pc=1, bs=0):
         x = np.zeros(self.ndofs)

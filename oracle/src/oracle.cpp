@@ -790,6 +790,31 @@ void orc_assemble_local(const orc_refel* re, const orc_model* md, const orc_mesh
   }
 }
 
+// HDGSolver::calcElementalMatrices with myOpts.type = WEXPLICIT / SEXPLICIT (HDGSolver.cpp:346-354): U, Q, U0, Q0 as in the implicit case, but the trace problem
+// is explicit in the element's CURRENT Solution / Flux fields:  S = S_ll,  S0 = F_l - S_lu sol - S_lq flux
+void orc_assemble_local_explicit(const orc_refel* re, const orc_model* md, const orc_mesh* m, const orc_fields* f, int e0, int e1, int useLU,
+                                 const double* solCur, const double* fluxCur, double* U, double* Q, double* S, double* U0, double* Q0, double* S0) {
+  Sizes z(re, md->nDOF);
+  ElGather G; Mat A; std::vector<double> F;
+  const int sL = z.u + z.q;
+  for (int e = e0; e < e1; e++) {
+    gather_element(re, md, m, f, e, G);
+    local_system(re, md, &G.ef, A, F);
+    size_t k = (size_t)e;
+    double* locS = S + k * z.l * z.l; double* locS0 = S0 + k * z.l;
+    if (useLU) condense_t<PLU>(z.u, z.q, z.l, A, F.data(), U + k * z.u * z.l, Q + k * z.q * z.l, locS, U0 + k * z.u, Q0 + k * z.q, locS0);
+    else condense_t<HQR>(z.u, z.q, z.l, A, F.data(), U + k * z.u * z.l, Q + k * z.q * z.l, locS, U0 + k * z.u, Q0 + k * z.q, locS0);
+    const double* sol = solCur + k * z.u; const double* flux = fluxCur + k * z.q;
+    for (int i = 0; i < z.l; i++) {
+      double s0 = F[sL + i];
+      for (int j = 0; j < z.u; j++) s0 -= A(sL + i, j) * sol[j];
+      for (int j = 0; j < z.q; j++) s0 -= A(sL + i, z.u + j) * flux[j];
+      locS0[i] = s0;
+      for (int j = 0; j < z.l; j++) locS[(size_t)j * z.l + i] = A(sL + i, sL + j);
+    }
+  }
+}
+
 // HDGSolver::applyBoundaryConditions :361-529 (serial, CGType boundary models: DirichletModel / IntegratedDirichletModel)
 void orc_apply_bc(const orc_refel* re, const orc_model* md, const orc_mesh* m, const orc_fields* f, double* S, double* S0) {
   Sizes z(re, md->nDOF);

@@ -107,6 +107,9 @@ typedef struct {
 /* HDGSolver::calcElementalMatrices + applyBoundaryConditions for elements [e0,e1): writes per-element col-major blocks. */
 void orc_assemble_local(const orc_refel* re, const orc_model* md, const orc_mesh* m, const orc_fields* f, int e0, int e1, int useLU,
                         double* U, double* Q, double* S, double* U0, double* Q0, double* S0);
+/* the same for HDGSolverOpts.type = WEXPLICIT / SEXPLICIT (HDGSolver.cpp:346-354): S = S_ll, S0 = F_l - S_lu sol - S_lq flux (cell fields Solution [nCells][u], Flux [nCells][q]) */
+void orc_assemble_local_explicit(const orc_refel* re, const orc_model* md, const orc_mesh* m, const orc_fields* f, int e0, int e1, int useLU,
+                                 const double* solCur, const double* fluxCur, double* U, double* Q, double* S, double* U0, double* Q0, double* S0);
 void orc_apply_bc(const orc_refel* re, const orc_model* md, const orc_mesh* m, const orc_fields* f, double* S, double* S0);
 
 /* CSR pattern (sorted columns, explicit zeros) HDGSolver.cpp:117-164 + PETSc AIJ; returns nnz; pass NULL colidx to count */

@@ -65,7 +65,7 @@ def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="di
         A = rng.standard_normal((nodes.shape[0], dim, dim)) * 0.2
         D = np.eye(dim)[None] + A @ A.transpose(0, 2, 1) + 0.1 * A    # not symmetric on purpose: exercises the col-major layout
         fields["DiffusionTensor"] = D.transpose(0, 2, 1).reshape(nodes.shape[0], dim * dim)   # col-major per node
-    if model in ("cdrs", "cd"):
+    if model in ("cdrs", "cd", "transport", "transport_euler"):
         c = nodes - 0.5
         vel = np.zeros_like(nodes)
         vel[:, 0], vel[:, 1] = -4 * c[:, 1], 4 * c[:, 0]
@@ -75,7 +75,7 @@ def make_case(dim, order, mesh="kuhn", N=3, perturb=0.1, model="laplace", bc="di
     if model == "burgers":
         case["source"] = lambda x, c: (c + 1.0) * np.exp(-3 * sum((xi - 0.4) ** 2 for xi in x))
     case["reaction"] = (lambda x: 1.0 + x[0]) if model == "cdrs" else None
-    if model == "euler":
+    if model in ("euler", "transport_euler"):
         case["solOld"] = rng.random((cells.shape[0], nN))
     return case
 
@@ -100,7 +100,7 @@ def config4_fields(case, D=1e-2, dt=1e-2):
     return case
 
 
-def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
+def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True, solverType=0):
     ore, topo = case["ore"], case["topo"]
     rc = O.RefElC(ore)
     model = case["model"]
@@ -112,6 +112,8 @@ def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
         diffComps = f["DiffusionTensor"].shape[1]
     if model in ("cdrs", "cd"):
         mask = O.OP_CONVECTION | (O.OP_DIFFUSION if "DiffusionTensor" in f else 0)
+    if model in ("transport", "transport_euler"):      # HDGTransport.cpp:47-61: Base + Convection
+        mask = O.OP_CONVECTION
     xip = np.einsum("pi,cid->cpd", ore.ipShape, case["nodes"][case["cells"]])
     nD = case.get("nD", 1)
     if model == "burgers":
@@ -123,19 +125,26 @@ def run_oracle(case, useLU=0, rtol=1e-13, maxits=20000, solve=True):
     if case["reaction"] is not None:
         mask |= O.OP_REACTION
         f["reacIP"] = np.array([[case["reaction"](p) for p in el] for el in xip])
-    if model == "euler":
+    if model in ("euler", "transport_euler"):
         ts = O.TS_EULER_IMPLICIT
         f["solOld"] = case["solOld"]
+    if solverType != 0:      # WEXPLICIT / SEXPLICIT: explicit in the current Solution / Flux (HDGSolver.cpp:346-354)
+        f["Solution"] = case["solOld"] if "solOld" in case else case["solCur"]
+        f["Flux"] = case["fluxCur"]
     md = O.make_model(nD, mask, diffComps, ts, 0.1)
     mesh = dict(nodes=case["nodes"], cells=case["cells"], **topo)
     h = O.HDGOracle(rc, mesh, md, f, bcKind=O.BC_DIRICHLET if case["bc"] == "dirichlet" else O.BC_INTEGRATED_DIRICHLET, useLU=useLU)
+    h.solverType = solverType
     h.assemble()
     if solve:
-        h.solve(rtol=rtol, maxits=maxits)
+        if solverType == 2:
+            h.solve_faces()
+        else:
+            h.solve(rtol=rtol, maxits=maxits)
     return h
 
 
-def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True, recompute=False):
+def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True, recompute=False, solverType=0):
     dim, order = case["dim"], case["order"]
     m = hfox.Mesh(dim, order, case.get("geom", "simplex"))
     m.setMesh(case["nodes"], case["cells"])
@@ -171,9 +180,14 @@ def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True, recompute
         mod = hfox.HDGDiffusionSource(re)
     elif model == "burgers":
         mod = hfox.HDGBurgersModel(re)
+    elif model in ("transport", "transport_euler"):
+        mod = hfox.HDGTransport(re)
     else:
         mod = hfox.HDGConvectionDiffusionReactionSource(re)
-    if model == "euler":
+    if solverType != 0:
+        fm["Solution"].values[:] = case.get("solCur", np.zeros(0)).ravel() if "solOld" not in case else case["solOld"].ravel()
+        fm["Flux"].values[:] = case["fluxCur"].ravel()
+    if model in ("euler", "transport_euler"):
         ts = hfox.Euler(re)
         ts.setTimeStep(0.1)
         mod.setTimeScheme(ts)
@@ -183,6 +197,8 @@ def run_device(case, rtol=1e-13, maxits=20000, solve=True, keepS=True, recompute
     lai = hfox.CudaLinAlgebraInterface(opts)
     s = hfox.HDGSolver(keepLocalS=keepS, recomputeRecovery=recompute)
     s.setVerbosity(False)
+    if solverType != 0:
+        s.setOptions(hfox.HDGSolverOpts(type=solverType, verbosity=False))
     s.setMesh(m)
     s.setFieldMap(fm)
     s.setLinSystem(lai)

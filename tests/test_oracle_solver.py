@@ -135,3 +135,26 @@ def test_boundary_model_rows_of_the_global_system(dim, order, bc):
             M = Mref * meas / 2.0                                           # reference measure of the face element: 2 (segment and triangle)
             assert np.abs(diag - M).max() < 1e-13 * np.abs(M).max()
             assert np.abs(o.rhs[F * t:(F + 1) * t] - M @ g[F]).max() < 1e-13 * max(1.0, np.abs(g[F]).max()) * np.abs(M).max() * t
+
+
+def test_explicit_solver_types_of_the_oracle():
+    """HDGSolverOpts.type = WEXPLICIT / SEXPLICIT (HDGSolver.cpp:346-354,626-667,709-729).  The reference holds no known answers for them, so the restatement is
+    pinned through what the algebra implies: (i) with the converged implicit Solution / Flux as data, the explicit trace problem returns the implicit trace (the
+    l rows of the local systems summed over the elements ARE the global equations, and S_ll couples one face only); (ii) the global solve of WEXPLICIT and the
+    per-face solves of SEXPLICIT agree."""
+    from tests import helpers as H
+    case = H.make_case(2, 3, N=3, perturb=0.1, model="diffsrc", tau_double=True, seed=9)
+    o = H.run_oracle(case)
+    case["solCur"], case["fluxCur"] = o.sol.copy(), o.flux.copy()
+    w = H.run_oracle(case, solverType=1)
+    s = H.run_oracle(case, solverType=2)
+    assert H.rel_err(w.trace, o.trace) < 1e-10 and H.rel_err(s.trace, o.trace) < 1e-10
+    assert H.rel_err(s.trace, w.trace) < 1e-10
+    assert H.rel_err(w.sol, o.sol) < 1e-9
+    # S = S_ll: no coupling between different faces of an element
+    l, t = w.l, w.t
+    S = w.S.reshape(w.nCells, l, l)
+    for f in range(l // t):
+        for g in range(l // t):
+            if f != g:
+                assert np.abs(S[:, g * t:(g + 1) * t, f * t:(f + 1) * t]).max() == 0.0

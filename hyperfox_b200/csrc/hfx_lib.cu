@@ -1431,6 +1431,49 @@ int hfx_host_read_h5_mesh(const char* path, int* nNodes, int* dimNodeSpace, int*
   });
 }
 
+// HDF5Io::write / loadFields without libhdf5 (csrc/host/hfx_meshio.cpp)
+int hfx_host_write_h5(const char* path, unsigned mtime, int dimNodeSpace, long long nNodes, const double* nodes, long long nCells, int nodesPerCell, const int* cells,
+                      int nFields, const char* const* names, const int* ftypes, const long long* shapes, const double* const* vals) {
+  return guard(nullptr, [&] {
+    H5Mesh m; const H5Mesh* pm = nullptr;
+    if (nodes && cells) {
+      m.dimNodeSpace = dimNodeSpace; m.nodesPerCell = nodesPerCell;
+      m.nodes.assign(nodes, nodes + (size_t)nNodes * dimNodeSpace); m.cells.assign(cells, cells + (size_t)nCells * nodesPerCell);
+      pm = &m;
+    }
+    std::vector<H5Field> fs((size_t)std::max(0, nFields));
+    for (int k = 0; k < nFields; k++) {
+      fs[k].name = names[k]; fs[k].ftype = ftypes[k];
+      for (int d = 0; d < 3; d++) fs[k].shape[d] = shapes[3 * k + d];
+      const size_t n = (size_t)(shapes[3 * k] * shapes[3 * k + 1] * shapes[3 * k + 2]);
+      fs[k].vals.assign(vals[k], vals[k] + n);
+    }
+    write_h5(path, pm, fs, mtime);
+  });
+}
+int hfx_host_h5_info(const char* path, int* hasMesh, int* nFields, char* names, int namesCap) {
+  return guard(nullptr, [&] {
+    if (hasMesh) *hasMesh = h5_has_mesh(path) ? 1 : 0;
+    const std::vector<std::string> nm = h5_field_names(path);
+    if (nFields) *nFields = (int)nm.size();
+    if (names && namesCap > 0) {   // '\n'-separated list
+      std::string all;
+      for (const std::string& s : nm) { all += s; all += '\n'; }
+      if ((int)all.size() + 1 > namesCap) throw std::runtime_error("HDF5Io : loadFields : name buffer too small");
+      std::memcpy(names, all.c_str(), all.size() + 1);
+    }
+  });
+}
+int hfx_host_read_h5_field(const char* path, const char* name, long long shape[3], int* ftype, double* vals) {
+  return guard(nullptr, [&] {
+    H5Field f;
+    read_h5_field(path, name, &f);
+    for (int d = 0; d < 3; d++) shape[d] = f.shape[d];
+    if (ftype) *ftype = f.ftype;
+    if (vals && !f.vals.empty()) std::memcpy(vals, f.vals.data(), f.vals.size() * sizeof(double));
+  });
+}
+
 int hfx_host_high_order_mesh(int dim, int order, int nLin, const double* lin, int nCells, const int* cells, int nExisting1, const int* existing1,
                              int nExisting2, const int* existing2, int* nNodesOut, double* nodesOut, int* cellsOut) {
   return guard(nullptr, [&] {

@@ -336,4 +336,238 @@ void read_h5_mesh(const std::string& path, H5Mesh* out) {
   for (size_t i = 0; i < nc; i++) out->cells[i] = (int)(int64_t)f.u(addr + i * size, size);
 }
 
+
+namespace {
+H5File open_h5(const std::string& path, const char* who) {
+  H5File f;
+  std::ifstream in(path, std::ios::binary);
+  if (!in) throw std::runtime_error(std::string("HDF5Io : ") + who + " : could not open " + path);
+  f.b.assign(std::istreambuf_iterator<char>(in), std::istreambuf_iterator<char>());
+  static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+  if (f.b.size() < 96 || !std::equal(sig, sig + 8, f.b.begin())) throw std::runtime_error(std::string("HDF5Io : ") + who + " : the file " + path + " is not an hdf5 file.");
+  if (f.b[8] != 0 || f.b[13] != 8 || f.b[14] != 8) H5File::bad("only superblock version 0 with 8-byte offsets is supported");
+  return f;
+}
+}  // namespace
+
+bool h5_has_mesh(const std::string& path) {
+  H5File f = open_h5(path, "load");
+  return f.children(f.entry(24 + 4 * 8)).count("Mesh") > 0;
+}
+
+std::vector<std::string> h5_field_names(const std::string& path) {
+  H5File f = open_h5(path, "loadFields");
+  auto top = f.children(f.entry(24 + 4 * 8));
+  std::vector<std::string> out;
+  if (!top.count("FieldData")) return out;
+  for (const auto& kv : f.children(top["FieldData"])) out.push_back(kv.first);
+  return out;
+}
+
+void read_h5_field(const std::string& path, const std::string& name, H5Field* out) {
+  auto fail = [&](const std::string& m) { throw std::runtime_error("HDF5Io : loadFields : " + m); };
+  H5File f = open_h5(path, "loadFields");
+  auto top = f.children(f.entry(24 + 4 * 8));
+  if (!top.count("FieldData")) fail("the file has no FieldData group");
+  auto fd = f.children(top["FieldData"]);
+  if (!fd.count(name)) fail("field with name " + name + " was not found in FieldData");
+  std::vector<uint64_t> shape;
+  int cls = -1, size = 0;
+  size_t addr = 0;
+  f.dataset(fd[name], &shape, &cls, &size, &addr);
+  if (shape.size() != 3 || cls != 1 || size != 8) fail("a field must be a three-dimensional float64 dataset");
+  for (int k = 0; k < 3; k++) if (shape[k] > f.b.size()) fail("could not get shape of field dataspace");
+  const uint64_t n01 = shape[0] * shape[1];
+  if ((shape[1] && n01 / shape[1] != shape[0]) || n01 > f.b.size() || (shape[2] && n01 * shape[2] > f.b.size() / 8)) fail("truncated field dataset");
+  const size_t n = (size_t)(n01 * shape[2]);
+  if (!f.inside(addr, (uint64_t)n * 8)) fail("could not load field values into field");
+  out->name = name;
+  for (int k = 0; k < 3; k++) out->shape[k] = (long long)shape[k];
+  out->vals.resize(n);
+  if (n) std::memcpy(out->vals.data(), f.b.data() + addr, n * 8);
+  // attribute "ftype" (version-1 attribute message: name, datatype, dataspace, each padded to 8 bytes, then the value; any integer width)
+  bool found = false;
+  for (const H5File::Msg& m : f.messages(fd[name].ohdr)) {
+    if (m.type != 0xc || m.size < 8) continue;
+    if (f.u(m.data, 1) != 1) fail("only version-1 attribute messages are supported");
+    const size_t ns = f.u(m.data + 2, 2), ts = f.u(m.data + 4, 2), ss = f.u(m.data + 6, 2);
+    auto pad8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+    const size_t pn = m.data + 8, pt = pn + pad8(ns), ps = pt + pad8(ts), pv = ps + pad8(ss);
+    if (!f.inside(pn, ns) || ns < 1 || pv > m.data + m.size) fail("corrupt attribute message");
+    std::string an(reinterpret_cast<const char*>(f.b.data() + pn), ns - 1);
+    if (an != "ftype") continue;
+    if ((f.u(pt, 1) & 0x0F) != 0) fail("attribute ftype must be an integer");
+    const int isz = (int)f.u(pt + 4, 4);
+    if ((isz != 1 && isz != 2 && isz != 4 && isz != 8) || pv + isz > m.data + m.size) fail("corrupt attribute message");
+    const uint64_t raw = f.u(pv, isz);
+    out->ftype = (int)(int64_t)(isz == 8 ? raw : (isz == 4 ? (uint64_t)(int64_t)(int32_t)raw : (isz == 2 ? (uint64_t)(int64_t)(int16_t)raw : (uint64_t)(int64_t)(int8_t)raw)));
+    found = true;
+  }
+  if (!found) fail("attribute ftype could not be found for field: " + name);
+}
+
+// ---- HDF5 subset writer ------------------------------------------------------------------------------------------------------------------------------------
+namespace {
+struct H5Writer {
+  std::vector<unsigned char> b;
+  uint64_t eoa = 96;                                   // the superblock
+  struct Aggr { uint64_t addr = 0, end = 0; bool open = false; } meta, sdata;
+  static constexpr uint64_t kBlock = 2048;
+  void put(uint64_t off, uint64_t v, int n) { if (b.size() < off + n) b.resize(off + n, 0); for (int i = 0; i < n; i++) b[off + i] = (unsigned char)(v >> (8 * i)); }
+  void bytes(uint64_t off, const void* p, size_t n) { if (b.size() < off + n) b.resize(off + n, 0); if (n) std::memcpy(b.data() + off, p, n); }
+  // libhdf5's block aggregators (H5MFaggr.c) as far as these files exercise them: bump inside the block; a block that ends at the end of the file grows by what is
+  // missing; otherwise a new block of max(2 KB, size) starts at the end of the file
+  uint64_t aggr(Aggr& a, uint64_t size) {
+    if (a.open && a.addr + size <= a.end) { const uint64_t r = a.addr; a.addr += size; return r; }
+    if (a.open && a.end == eoa) { eoa += size - (a.end - a.addr); a.end = eoa; const uint64_t r = a.addr; a.addr += size; return r; }
+    a.open = true; a.addr = eoa; a.end = eoa + std::max(kBlock, size); eoa = a.end;
+    const uint64_t r = a.addr; a.addr += size; return r;
+  }
+  uint64_t allocMeta(uint64_t size) { return aggr(meta, size); }
+  uint64_t allocRaw(uint64_t size) { if (size < kBlock) return aggr(sdata, size); const uint64_t r = eoa; eoa += size; return r; }
+  void close() {   // blocks that end at the end of the file give their unused tail back
+    for (int pass = 0; pass < 2; pass++) {
+      if (sdata.open && sdata.end == eoa) { eoa = sdata.addr; sdata.end = sdata.addr; }
+      if (meta.open && meta.end == eoa) { eoa = meta.addr; meta.end = meta.addr; }
+    }
+  }
+  struct Group {
+    uint64_t ohdr = 0, btree = 0, heap = 0, heapData = 0, heapSize = 0, heapUsed = 8;
+    std::vector<uint64_t> snods;
+    struct Child { std::string name; uint64_t nameOff, ohdr; bool isGroup; uint64_t btree, heap; };
+    std::vector<Child> children;
+  };
+  // H5Gcreate: object header (one symbol-table message), B-tree node of the group (K = 16: 544 bytes), local heap (32-byte header + data segment)
+  Group makeGroup(size_t nameBytes) {
+    Group g;
+    g.ohdr = allocMeta(40);
+    g.btree = allocMeta(544);
+    g.heapSize = std::max<uint64_t>(88, ((8 + nameBytes + 16 + 7) / 8) * 8);     // libhdf5 starts with 88 bytes and would grow the segment; sized at once here
+    g.heap = allocMeta(32 + g.heapSize);
+    g.heapData = g.heap + 32;
+    return g;
+  }
+  void link(Group& g, const std::string& name, uint64_t ohdr, bool isGroup, uint64_t btree, uint64_t heap) {
+    if (g.children.size() % 8 == 0) g.snods.push_back(allocMeta(328));        // symbol-table nodes hold 2K = 8 entries
+    const uint64_t len = ((name.size() + 1 + 7) / 8) * 8;
+    g.children.push_back({name, g.heapUsed, ohdr, isGroup, btree, heap});
+    g.heapUsed += len;
+  }
+  void finishGroup(const Group& g) {
+    put(g.ohdr, 1, 1); put(g.ohdr + 2, 1, 2); put(g.ohdr + 4, 1, 4); put(g.ohdr + 8, 24, 4);
+    put(g.ohdr + 16, 0x11, 2); put(g.ohdr + 18, 16, 2); put(g.ohdr + 24, g.btree, 8); put(g.ohdr + 32, g.heap, 8);
+    // heap: names, then one free block
+    bytes(g.heap, "HEAP", 4); put(g.heap + 8, g.heapSize, 8); put(g.heap + 24, g.heapData, 8);
+    put(g.heapData + g.heapSize - 1, 0, 1);
+    for (const auto& c : g.children) bytes(g.heapData + c.nameOff, c.name.c_str(), c.name.size() + 1);
+    if (g.heapSize - g.heapUsed >= 16) { put(g.heap + 16, g.heapUsed, 8); put(g.heapData + g.heapUsed, 1, 8); put(g.heapData + g.heapUsed + 8, g.heapSize - g.heapUsed, 8); }
+    else put(g.heap + 16, 1, 8);    // H5HL_FREE_NULL
+    // children sorted by name over the symbol-table nodes (eight per node), one leaf B-tree node above them
+    std::vector<Group::Child> cs = g.children;
+    std::sort(cs.begin(), cs.end(), [](const Group::Child& a, const Group::Child& c) { return a.name < c.name; });
+    bytes(g.btree, "TREE", 4); put(g.btree + 4, 0, 1); put(g.btree + 5, 0, 1); put(g.btree + 6, g.snods.size(), 2);
+    put(g.btree + 8, ~0ull, 8); put(g.btree + 16, ~0ull, 8);
+    put(g.btree + 544 - 1, 0, 1);
+    put(g.btree + 24, 0, 8);
+    for (size_t k = 0; k < g.snods.size(); k++) {
+      const uint64_t sn = g.snods[k];
+      const size_t lo = k * 8, hi = std::min(cs.size(), lo + 8);
+      bytes(sn, "SNOD", 4); put(sn + 4, 1, 1); put(sn + 6, hi - lo, 2);
+      put(sn + 328 - 1, 0, 1);
+      for (size_t i = lo; i < hi; i++) {
+        const uint64_t e = sn + 8 + (i - lo) * 40;
+        put(e, cs[i].nameOff, 8); put(e + 8, cs[i].ohdr, 8);
+        if (cs[i].isGroup) { put(e + 16, 1, 4); put(e + 24, cs[i].btree, 8); put(e + 32, cs[i].heap, 8); }
+      }
+      put(g.btree + 24 + 8 + k * 16, sn, 8);                       // child k
+      put(g.btree + 24 + 16 + k * 16, cs[hi - 1].nameOff, 8);      // key k+1: the largest name of the node
+    }
+  }
+  // H5Dcreate + H5Dwrite (+ H5Acreate "ftype"): version-1 object header of 16 + 256 bytes
+  void datasetBody(uint64_t oh, uint64_t dataAddr, int rank, const long long* dims, bool isFloat, uint64_t nbytes, unsigned mtime, const int* ftype) {
+    put(oh, 1, 1); put(oh + 2, ftype ? 7 : 6, 2); put(oh + 4, 1, 4); put(oh + 8, 256, 4);
+    uint64_t p = oh + 16;
+    auto hdr = [&](int type, int size, int flags) { put(p, type, 2); put(p + 2, size, 2); put(p + 4, flags, 1); p += 8; };
+    // dataspace, version 1, maximum dimensions present (= the dimensions)
+    hdr(0x1, 8 + 16 * rank, 0);
+    put(p, 1, 1); put(p + 1, rank, 1); put(p + 2, 1, 1);
+    for (int k = 0; k < rank; k++) { put(p + 8 + 8 * k, (uint64_t)dims[k], 8); put(p + 8 + 8 * rank + 8 * k, (uint64_t)dims[k], 8); }
+    p += 8 + 16 * rank;
+    static const unsigned char f8[24] = {0x11, 0x20, 0x3f, 0x00, 0x08, 0, 0, 0, 0, 0, 0x40, 0, 0x34, 0x0b, 0x00, 0x34, 0xff, 0x03, 0, 0, 0, 0, 0, 0};   // IEEE little-endian binary64
+    static const unsigned char i4[16] = {0x10, 0x08, 0x00, 0x00, 0x04, 0, 0, 0, 0, 0, 0x20, 0, 0, 0, 0, 0};                                           // signed little-endian 32 bits
+    if (isFloat) { hdr(0x3, 24, 1); bytes(p, f8, 24); p += 24; } else { hdr(0x3, 16, 1); bytes(p, i4, 16); p += 16; }
+    hdr(0x5, 8, 1); put(p, 2, 1); put(p + 1, 2, 1); put(p + 2, 2, 1); put(p + 3, 1, 1); p += 8;                  // fill value, version 2: late allocation, no value
+    hdr(0x8, 24, 0); put(p, 3, 1); put(p + 1, 1, 1); put(p + 2, dataAddr, 8); put(p + 10, nbytes, 8); p += 24;  // contiguous layout, version 3
+    hdr(0x12, 8, 0); put(p, 1, 1); put(p + 4, mtime, 4); p += 8;                                                 // modification time, version 1
+    if (ftype) {   // attribute, version 1: "ftype", int32, simple dataspace [1]
+      hdr(0xc, 64, 0);
+      put(p, 1, 1); put(p + 2, 6, 2); put(p + 4, 12, 2); put(p + 6, 24, 2);
+      bytes(p + 8, "ftype", 6);
+      bytes(p + 16, i4, 12);
+      put(p + 32, 1, 1); put(p + 33, 1, 1); put(p + 34, 1, 1); put(p + 40, 1, 8); put(p + 48, 1, 8);
+      put(p + 56, (uint64_t)(uint32_t)*ftype, 4);
+      p += 64;
+    }
+    const uint64_t rest = oh + 272 - p;
+    if (rest < 8) throw std::runtime_error("HDF5Io : write : object header overflow");
+    hdr(0x0, (int)(rest - 8), 0);
+    put(oh + 272 - 1, 0, 1);
+  }
+};
+}  // namespace
+
+void write_h5(const std::string& path, const H5Mesh* mesh, const std::vector<H5Field>& fields, unsigned mtime) {
+  if (!mesh && fields.empty()) throw std::runtime_error("HDFIo : write : could not find anything to write");
+  H5Writer w;
+  size_t rootNames = (mesh ? 8 : 0) + (fields.empty() ? 0 : 16);
+  H5Writer::Group root = w.makeGroup(rootNames);
+  std::vector<std::pair<H5Writer::Group, std::string>> groups;
+  auto writeSet = [&](H5Writer::Group& g, const std::string& name, int rank, const long long* dims, bool isFloat, const void* data, uint64_t nbytes, const int* ftype) {
+    const uint64_t oh = w.allocMeta(272);            // H5Dcreate: the header, then the link in the group
+    w.link(g, name, oh, false, 0, 0);
+    const uint64_t addr = nbytes ? w.allocRaw(nbytes) : ~0ull;   // H5Dwrite: late allocation of the contiguous storage
+    w.datasetBody(oh, addr, rank, dims, isFloat, nbytes, mtime, ftype);
+    if (nbytes) w.bytes(addr, data, (size_t)nbytes);
+  };
+  if (mesh) {
+    if (mesh->dimNodeSpace < 1 || mesh->nodesPerCell < 1) throw std::runtime_error("HDF5Io : writeMesh : the mesh has no nodes or cells");
+    H5Writer::Group g = w.makeGroup(16);
+    w.link(root, "Mesh", g.ohdr, true, g.btree, g.heap);
+    const long long nd[2] = {(long long)(mesh->nodes.size() / mesh->dimNodeSpace), mesh->dimNodeSpace};
+    const long long cd[2] = {(long long)(mesh->cells.size() / mesh->nodesPerCell), mesh->nodesPerCell};
+    writeSet(g, "Nodes", 2, nd, true, mesh->nodes.data(), (uint64_t)mesh->nodes.size() * 8, nullptr);      // HDF5Io.cpp:283-301
+    writeSet(g, "Cells", 2, cd, false, mesh->cells.data(), (uint64_t)mesh->cells.size() * 4, nullptr);
+    w.finishGroup(g);
+  }
+  if (!fields.empty()) {
+    size_t nb = 0;
+    for (const H5Field& f : fields) nb += ((f.name.size() + 1 + 7) / 8) * 8;
+    if (fields.size() > 256) throw std::runtime_error("HDF5Io : writeFields : more than 256 fields in one file are not supported");
+    H5Writer::Group g = w.makeGroup(nb);
+    w.link(root, "FieldData", g.ohdr, true, g.btree, g.heap);
+    std::vector<const H5Field*> order;
+    for (const H5Field& f : fields) order.push_back(&f);
+    std::sort(order.begin(), order.end(), [](const H5Field* a, const H5Field* c) { return a->name < c->name; });   // std::map order (HDF5Io.cpp:311)
+    for (const H5Field* f : order) {
+      const uint64_t n = (uint64_t)f->shape[0] * (uint64_t)f->shape[1] * (uint64_t)f->shape[2];
+      if (n != f->vals.size()) throw std::runtime_error("HDF5Io : writeFields : problem writing values of field: " + f->name);
+      writeSet(g, f->name, 3, f->shape, true, f->vals.data(), n * 8, &f->ftype);
+    }
+    w.finishGroup(g);
+  }
+  w.finishGroup(root);
+  w.close();
+  // superblock, version 0 (root symbol-table entry with cached B-tree / heap addresses)
+  static const unsigned char sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
+  w.bytes(0, sig, 8);
+  w.put(13, 8, 1); w.put(14, 8, 1); w.put(16, 4, 2); w.put(18, 16, 2);
+  w.put(24, 0, 8); w.put(32, ~0ull, 8); w.put(40, w.eoa, 8); w.put(48, ~0ull, 8);
+  w.put(56, 0, 8); w.put(64, root.ohdr, 8); w.put(72, 1, 4); w.put(80, root.btree, 8); w.put(88, root.heap, 8);
+  w.b.resize((size_t)w.eoa, 0);
+  std::ofstream out(path, std::ios::binary | std::ios::trunc);
+  if (!out) throw std::runtime_error("HDF5Io : write : could not open " + path + " for writing");
+  out.write(reinterpret_cast<const char*>(w.b.data()), (std::streamsize)w.b.size());
+  if (!out) throw std::runtime_error("HDF5Io : write : could not write " + path);
+}
+
 }  // namespace hfx

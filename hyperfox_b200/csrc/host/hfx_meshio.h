@@ -30,4 +30,21 @@ struct H5Mesh {
 };
 void read_h5_mesh(const std::string& path, H5Mesh* out);
 
+// Field datasets of the reference's files (HDF5Io::loadFields / writeFields, src/io/HDF5Io.cpp:154-187,304-391): /FieldData/<name>, f8 [nEntities][nObjPerEnt][nValsPerObj]
+// with an integer attribute "ftype" (FieldTypes.h: Node 0, Edge 1, Face 2, Cell 3).
+struct H5Field {
+  std::string name;
+  int ftype = -1;
+  long long shape[3] = {0, 0, 0};
+  std::vector<double> vals;
+};
+bool h5_has_mesh(const std::string& path);
+std::vector<std::string> h5_field_names(const std::string& path);
+void read_h5_field(const std::string& path, const std::string& name, H5Field* out);   // throws std::runtime_error("HDF5Io : loadFields : ...")
+
+// HDF5Io::write (src/io/HDF5Io.cpp:66-109, writeMesh :189-302, writeFields :304-391) without libhdf5: the same subset of the format, laid out the way libhdf5 1.10 lays
+// out the files of the reference's tools (2 KB metadata / small-data aggregator blocks), so that a mesh-only file is byte-identical to the one convertGmsh2H5HO wrote
+// for the same mesh, up to the modification times.  mesh may be NULL (fields only); mtime: seconds since the epoch stored in the dataset headers.
+void write_h5(const std::string& path, const H5Mesh* mesh, const std::vector<H5Field>& fields, unsigned mtime);
+
 }  // namespace hfx

@@ -101,7 +101,7 @@ class Io:
     def setMesh(self, mesh): self.myMesh = mesh
     def setField(self, name, field): self.fieldMap[name] = field
     def load(self, filename): raise NotImplementedError
-    def write(self, filename): raise ErrorHandle("%s : write : writing is not supported by this build" % type(self).__name__)
+    def write(self, filename): raise ErrorHandle("%s : write : writing is not supported by this format" % type(self).__name__)
 
     def _need_mesh(self, filename, ext):
         if self.myMesh is None:
@@ -111,13 +111,44 @@ class Io:
 
 
 class HDF5Io(Io):
-    """HDF5Io::load, mesh part (src/io/HDF5Io.cpp:111-152), without libhdf5 (hfx_host_read_h5_mesh)."""
+    """HDF5Io (src/io/HDF5Io.cpp) without libhdf5: load = Mesh group (:111-152) + the fields registered with setField (:154-187), write = Mesh group (:189-302) +
+    FieldData group (:304-391).  The files carry the reference's FieldType values (FieldTypes.h: Node 0, Face 2, Cell 3)."""
+    _TO_FILE = {Node: 0, Face: 2, Cell: 3}
+    _FROM_FILE = {0: Node, 2: Face, 3: Cell}
 
     def load(self, filename):
         from . import meshio
-        self._need_mesh(filename, ".h5")
-        nodes, cells = meshio.read_h5_mesh(filename)
-        self.myMesh.setMesh(nodes, cells)
+        if self.myMesh is None:
+            raise ErrorHandle("HDF5Io : load : must enter a mesh into the io before loading a file.")
+        hasMesh, names = meshio.h5_info(filename)
+        if not hasMesh and not names:
+            raise ErrorHandle("HDFIo : load : could not find Mesh or FieldData groups in file")
+        if hasMesh:
+            nodes, cells = meshio.read_h5_mesh(filename)
+            self.myMesh.setMesh(nodes, cells)
+        if names:
+            for name, f in self.fieldMap.items():
+                if name not in names:
+                    raise ErrorHandle("HDF5Io : loadFields : field with name " + name + " was not found in FieldData")
+                ft, vals = meshio.read_h5_field(filename, name)
+                if ft not in self._FROM_FILE:
+                    raise ErrorHandle("HDF5Io : loadFields : edge fields are not supported yet.")
+                f.type, f.nObj, f.nVals = self._FROM_FILE[ft], vals.shape[1], vals.shape[2]
+                f._deviceNewer = False
+                f._values = np.ascontiguousarray(vals.ravel())
+
+    def write(self, filename):
+        from . import meshio
+        if self.myMesh is None and not self.fieldMap:
+            raise ErrorHandle("HDFIo : write : could not find anything to write")
+        fields = {}
+        for name, f in self.fieldMap.items():
+            v = f.values
+            nEnt = v.size // max(1, f.nObj * f.nVals)
+            fields[name] = (self._TO_FILE[f.type], v.reshape(nEnt, f.nObj, f.nVals))
+        m = self.myMesh
+        hasMesh = m is not None and getattr(m, "nodes", None) is not None
+        meshio.write_h5(filename, m.nodes if hasMesh else None, m.cells if hasMesh else None, fields, mtime=int(__import__("time").time()))
 
 
 class GmshIo(Io):

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import capi
-from .capi import check, lib, pd, pi
+from .capi import ErrorHandle, check, lib, pd, pi
 
 
 def read_msh(path):
@@ -53,3 +53,49 @@ def read_h5_mesh(path):
     nodes, cells = np.zeros((nn.value, d.value)), np.zeros((nc.value, npc.value), dtype=np.int32)
     check(L.hfx_host_read_h5_mesh(str(path).encode(), C.byref(nn), C.byref(d), C.byref(nc), C.byref(npc), pd(nodes), pi(cells)))
     return nodes, cells
+
+
+# FieldType values stored in the files: the reference's enum (src/field/FieldTypes.h)
+H5_NODE, H5_EDGE, H5_FACE, H5_CELL = 0, 1, 2, 3
+
+
+def write_h5(path, nodes=None, cells=None, fields=None, mtime=0):
+    """HDF5Io::write (src/io/HDF5Io.cpp:66-109) without libhdf5.  fields: {name: (ftype, values[nEntities, nObjPerEnt, nValsPerObj])} with the reference's
+    FieldType values (H5_NODE / H5_FACE / H5_CELL)."""
+    L = lib()
+    fields = fields or {}
+    names = sorted(fields)
+    arrs = [np.ascontiguousarray(fields[n][1], dtype=np.float64) for n in names]
+    for n, a in zip(names, arrs):
+        if a.ndim != 3:
+            raise ErrorHandle("HDF5Io : writeFields : problem writing values of field: " + n)
+    cn = (C.c_char_p * max(1, len(names)))(*[n.encode() for n in names])
+    ft = np.array([int(fields[n][0]) for n in names] or [0], dtype=np.int32)
+    sh = np.array([a.shape for a in arrs] or [[0, 0, 0]], dtype=np.int64)
+    vp = (C.c_void_p * max(1, len(names)))(*[a.ctypes.data for a in arrs])
+    if nodes is not None:
+        nodes = np.ascontiguousarray(nodes, dtype=np.float64); cells = np.ascontiguousarray(cells, dtype=np.int32)
+        check(L.hfx_host_write_h5(str(path).encode(), C.c_uint(int(mtime)), nodes.shape[1], C.c_longlong(nodes.shape[0]), pd(nodes), C.c_longlong(cells.shape[0]), cells.shape[1],
+                                  pi(cells), len(names), cn, pi(ft), sh.ctypes.data_as(C.POINTER(C.c_longlong)), vp))
+    else:
+        check(L.hfx_host_write_h5(str(path).encode(), C.c_uint(int(mtime)), 0, C.c_longlong(0), None, C.c_longlong(0), 0, None, len(names), cn, pi(ft),
+                                  sh.ctypes.data_as(C.POINTER(C.c_longlong)), vp))
+
+
+def h5_info(path):
+    """(has a Mesh group, names of the datasets of the FieldData group)"""
+    L = lib()
+    hm, nf = C.c_int(0), C.c_int(0)
+    buf = C.create_string_buffer(1 << 16)
+    check(L.hfx_host_h5_info(str(path).encode(), C.byref(hm), C.byref(nf), buf, len(buf)))
+    return bool(hm.value), [s for s in buf.value.decode().split("\n") if s]
+
+
+def read_h5_field(path, name):
+    """HDF5Io::loadFields (src/io/HDF5Io.cpp:154-187): (ftype, values [nEntities, nObjPerEnt, nValsPerObj]) of /FieldData/<name>"""
+    L = lib()
+    sh = (C.c_longlong * 3)(); ft = C.c_int(-1)
+    check(L.hfx_host_read_h5_field(str(path).encode(), name.encode(), sh, C.byref(ft), None))
+    vals = np.zeros(tuple(sh))
+    check(L.hfx_host_read_h5_field(str(path).encode(), name.encode(), sh, C.byref(ft), pd(vals)))
+    return ft.value, vals

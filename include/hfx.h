@@ -60,6 +60,16 @@ int hfx_host_read_msh(const char* path, int* nNodes, int counts[4], double* node
    [nCells][nodesPerCell] (i4 / i8) of the reference's mesh files (superblock 0, symbol-table groups, contiguous datasets).  First call
    with NULL arrays for the sizes. */
 int hfx_host_read_h5_mesh(const char* path, int* nNodes, int* dimNodeSpace, int* nCells, int* nodesPerCell, double* nodes, int* cells);
+/* HDF5Io::write (src/io/HDF5Io.cpp:66-109; writeMesh :189-302, writeFields :304-391) without libhdf5: group Mesh (Nodes f8, Cells i4; nodes / cells NULL: no Mesh group)
+   and group FieldData with one f8 dataset [nEntities][nObjPerEnt][nValsPerObj] per field (shapes[3k..3k+2]) carrying the int attribute "ftype" (the reference's
+   FieldTypes.h values: Node 0, Edge 1, Face 2, Cell 3).  Same subset of the format as the reader, laid out as libhdf5 lays out the reference's files: a mesh-only file is
+   byte-identical to the one tools/convertGmsh2H5HO.cpp wrote for that mesh, up to the modification times (mtime: seconds since the epoch). */
+int hfx_host_write_h5(const char* path, unsigned mtime, int dimNodeSpace, long long nNodes, const double* nodes, long long nCells, int nodesPerCell, const int* cells,
+                      int nFields, const char* const* names, const int* ftypes, const long long* shapes, const double* const* vals);
+/* HDF5Io::load (src/io/HDF5Io.cpp:13-64): which groups a file holds; names: '\n'-separated field names (may be NULL) */
+int hfx_host_h5_info(const char* path, int* hasMesh, int* nFields, char* names, int namesCap);
+/* HDF5Io::loadFields (src/io/HDF5Io.cpp:154-187): shape, ftype attribute and values of /FieldData/<name>; vals NULL: sizes only */
+int hfx_host_read_h5_field(const char* path, const char* name, long long shape[3], int* ftype, double* vals);
 /* generateHigherOrderMesh (convertGmsh2H5HO.cpp:117-257): straight-sided order-p simplex mesh from a linear one, the reference's node
    numbering.  lin[nLin][dim], cells[nCells][dim+1]; existing1 / existing2: edges / triangles already present in the input file
    (they precede the generated ones, as in MOAB).  Pass NULL output arrays to only count; nodesOut[nNodesOut][dim], cellsOut[nCells][nN]. */

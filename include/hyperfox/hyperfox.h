@@ -245,24 +245,14 @@ class Io {
   std::map<std::string, Field*> fieldMap;
 };
 
-// src/io/HDF5Io.h: load() of the mesh part (loadMesh, HDF5Io.cpp:111-152) without libhdf5; field I/O and write() are out of scope.
+// src/io/HDF5Io.h without libhdf5 (hfx_host_read_h5_mesh / hfx_host_read_h5_field / hfx_host_write_h5): load = Mesh group (HDF5Io.cpp:111-152) + the fields registered
+// with setField (:154-187); write = Mesh group (:189-302) + FieldData group (:304-391).  Bodies after the Field class below.
 class HDF5Io : public Io {
  public:
   HDF5Io() {}
   explicit HDF5Io(Mesh* mesh) { setMesh(mesh); }
-  void load(std::string filename) override {
-    if (!myMesh) throw ErrorHandle("HDF5Io", "load", "the mesh must be set before loading");
-    if (getExtension(filename) != ".h5") throw ErrorHandle("HDF5Io", "load", "the file extension must be .h5");
-    int nNodes = 0, dimSpace = 0, nCells = 0, nPerCell = 0;
-    detail::check(hfx_host_read_h5_mesh(filename.c_str(), &nNodes, &dimSpace, &nCells, &nPerCell, 0, 0), nullptr);
-    if (!myMesh->getReferenceElement() || myMesh->getReferenceElement()->getNumNodes() != nPerCell)
-      throw ErrorHandle("HDF5Io", "loadMesh", "the cells of the file do not have the number of nodes of the reference element of the mesh");
-    std::vector<double> pts((size_t)nNodes * dimSpace);
-    std::vector<int> cells((size_t)nCells * nPerCell);
-    detail::check(hfx_host_read_h5_mesh(filename.c_str(), &nNodes, &dimSpace, &nCells, &nPerCell, pts.data(), cells.data()), nullptr);
-    myMesh->setMesh(dimSpace, pts, cells);
-  }
-  void write(std::string) override { throw ErrorHandle("HDF5Io", "write", "writing HDF5 files is not supported by this build"); }
+  void load(std::string filename) override;
+  void write(std::string filename) override;
 };
 
 class GmshIo : public Io {
@@ -354,6 +344,52 @@ class Field {
   std::string devName;
   bool deviceNewer = false;    // ... which is ahead of `values`
 };
+
+inline void HDF5Io::load(std::string filename) {
+  if (!myMesh) throw ErrorHandle("HDF5Io", "load", "must enter a mesh into the io before loading a file.");
+  int hasMesh = 0, nFields = 0;
+  std::vector<char> names(1 << 16);
+  detail::check(hfx_host_h5_info(filename.c_str(), &hasMesh, &nFields, names.data(), (int)names.size()), nullptr);
+  if (!hasMesh && nFields == 0) throw ErrorHandle("HDFIo", "load", "could not find Mesh or FieldData groups in file");
+  if (hasMesh) {
+    int nNodes = 0, dimSpace = 0, nCells = 0, nPerCell = 0;
+    detail::check(hfx_host_read_h5_mesh(filename.c_str(), &nNodes, &dimSpace, &nCells, &nPerCell, 0, 0), nullptr);
+    if (!myMesh->getReferenceElement() || myMesh->getReferenceElement()->getNumNodes() != nPerCell)
+      throw ErrorHandle("HDF5Io", "loadMesh", "the cells of the file do not have the number of nodes of the reference element of the mesh");
+    std::vector<double> pts((size_t)nNodes * dimSpace);
+    std::vector<int> cells((size_t)nCells * nPerCell);
+    detail::check(hfx_host_read_h5_mesh(filename.c_str(), &nNodes, &dimSpace, &nCells, &nPerCell, pts.data(), cells.data()), nullptr);
+    myMesh->setMesh(dimSpace, pts, cells);
+  }
+  if (nFields > 0) {
+    for (std::map<std::string, Field*>::iterator it = fieldMap.begin(); it != fieldMap.end(); ++it) {
+      long long shape[3] = {0, 0, 0};
+      int ft = -1;
+      detail::check(hfx_host_read_h5_field(filename.c_str(), it->first.c_str(), shape, &ft, 0), nullptr);
+      Field* f = it->second;
+      *f->getFieldType() = (FieldType)ft; *f->getNumEntities() = (int)shape[0]; *f->getNumObjPerEnt() = (int)shape[1]; *f->getNumValsPerObj() = (int)shape[2];
+      f->getValues()->assign((size_t)(shape[0] * shape[1] * shape[2]), 0.0);
+      detail::check(hfx_host_read_h5_field(filename.c_str(), it->first.c_str(), shape, &ft, f->getValues()->data()), nullptr);
+    }
+  }
+}
+inline void HDF5Io::write(std::string filename) {
+  const bool meshExists = myMesh != NULL && myMesh->getNumberPoints() > 0;
+  if (!meshExists && fieldMap.empty()) throw ErrorHandle("HDFIo", "write", "could not find anything to write");
+  std::vector<const char*> names; std::vector<int> ftypes; std::vector<long long> shapes; std::vector<const double*> vals;
+  for (std::map<std::string, Field*>::iterator it = fieldMap.begin(); it != fieldMap.end(); ++it) {
+    Field* f = it->second;
+    const std::vector<double>* v = f->getValues();
+    const long long per = (long long)*f->getNumObjPerEnt() * *f->getNumValsPerObj();
+    names.push_back(it->first.c_str()); ftypes.push_back((int)*f->getFieldType());
+    shapes.push_back(per ? (long long)v->size() / per : 0); shapes.push_back(*f->getNumObjPerEnt()); shapes.push_back(*f->getNumValsPerObj());
+    vals.push_back(v->data());
+  }
+  const int nPerCell = meshExists ? myMesh->getReferenceElement()->getNumNodes() : 0;
+  detail::check(hfx_host_write_h5(filename.c_str(), (unsigned)std::time(nullptr), meshExists ? myMesh->getNodeSpaceDimension() : 0, meshExists ? myMesh->getNumberPoints() : 0,
+                                  meshExists ? myMesh->getPoints()->data() : nullptr, meshExists ? myMesh->getNumberCells() : 0, nPerCell,
+                                  meshExists ? myMesh->getCells()->data() : nullptr, (int)names.size(), names.data(), ftypes.data(), shapes.data(), vals.data()), nullptr);
+}
 
 // ---- src/parallel/Partitioner.h, ZoltanPartitioner.h ----------------------------------------------------------------------------------
 // One process per GPU.  The reference reads rank / size from MPI_COMM_WORLD, lets Zoltan cut the cell graph and MIGRATES cells, nodes, faces and

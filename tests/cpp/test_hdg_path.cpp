@@ -3,7 +3,7 @@
 //   tests/unittests/resolution/TestLinAlgebraInterfaces.cpp:29-170 (state machine + three stock systems)
 //   tests/regression/HDG/TestHDGLaplace.cpp:110-139            (u = sin x e^y on the reference's regression meshes, l2 ceiling 1e-2)
 //   tests/regression/HDG/TestHDGDiffusionSource.cpp            (HDGDiffusionSource + source callback: manufactured Poisson)
-// Only differences: meshes come from text exports of the reference's .h5 fixtures (HDF5Io is out of scope), PetscInterface ->
+// Only differences: meshes come from text exports of the reference's .h5 fixtures (the HDF5Io mirror is tested on its own), PetscInterface ->
 // CudaLinAlgebraInterface, Catch2's CHECK -> the four-line macros below.
 // usage: test_hdg_path <mesh dir> [section]   sections: contract | solver | lai | laplace | diffsrc | rk
 #include <cstdio>
@@ -345,6 +345,53 @@ static void testGmshIo(const std::string& dir, const std::string& name, int dim,
   CHECK_THROWS(h5.load(dir + "/missing.h5"));
 }
 
+// tests/unittests/io/TestHDF5Io.cpp:163-209 ("Load test field", "Write test field") on the reference's fieldTest.h5 and lightTri2.h5 (verbatim copies), plus the mesh round
+// trip of "Test write mesh file": HDF5Io::write then HDF5Io::load.  Host only.
+static void testHDF5IoFields(const std::string& dir) {
+  std::vector<double> nodeFieldData(9), cellFieldData(8 * 2);
+  for (int i = 0; i < 9; i++) nodeFieldData[i] = i;
+  for (int i = 0; i < 8; i++) { cellFieldData[i * 2] = i; cellFieldData[i * 2 + 1] = -i; }
+  Mesh m(2, 2, "simplex");
+  HDF5Io meshIo(&m);
+  CHECK_NOTHROW(meshIo.load(dir + "/lightTri2.h5"));
+  {   // load
+    Io* tmpIo = new HDF5Io(&m);
+    Field nodeField(&m, Node, 1, 1), cellField(&m, Cell, 2, 1);
+    tmpIo->setField("NodeField", &nodeField); tmpIo->setField("CellField", &cellField);
+    tmpIo->load(dir + "/fieldTest.h5");
+    CHECK(*nodeField.getValues() == nodeFieldData);
+    CHECK(*cellField.getValues() == cellFieldData);
+    CHECK(*cellField.getFieldType() == Cell && *cellField.getNumEntities() == 8 && *cellField.getNumObjPerEnt() == 2);
+    Field missing(&m, Node, 1, 1);
+    tmpIo->setField("NoSuchField", &missing);
+    CHECK_THROWS(tmpIo->load(dir + "/fieldTest.h5"));
+    delete tmpIo;
+  }
+  {   // write, then load into fresh objects
+    Io* tmpIo = new HDF5Io(&m);
+    Field nodeField(&m, Node, 1, 1), cellField(&m, Cell, 2, 1);
+    *nodeField.getValues() = nodeFieldData;
+    for (size_t i = 0; i < cellField.getValues()->size(); i++) (*cellField.getValues())[i] = cellFieldData[i];
+    tmpIo->setField("NodeField", &nodeField); tmpIo->setField("CellField", &cellField);
+    const std::string out = dir + "/tmp.h5";
+    tmpIo->write(out);
+    Mesh m2(2, 2, "simplex");
+    HDF5Io io2(&m2);
+    Field n2(&m, Node, 1, 1), c2(&m, Cell, 1, 1);
+    io2.setField("NodeField", &n2); io2.setField("CellField", &c2);
+    io2.load(out);
+    CHECK(*m2.getCells() == *m.getCells());
+    CHECK(*m2.getPoints() == *m.getPoints());
+    CHECK(*n2.getValues() == *nodeField.getValues());
+    CHECK(*c2.getValues() == *cellField.getValues());
+    CHECK(*c2.getNumObjPerEnt() == 2);
+    std::remove(out.c_str());
+    delete tmpIo;
+  }
+  HDF5Io nothing;
+  CHECK_THROWS(nothing.write(dir + "/nothing.h5"));
+}
+
 // tests/unittests/solver/TestNonLinearWrapper.cpp:11-46: Newton on x^2 = 0 through setLinearizedSolver, Node fields on lightTri.  Host only.
 static void testNonLinearWrapper(const std::string& dir) {
   Mesh m(2, 1, "simplex");
@@ -521,6 +568,7 @@ int main(int argc, char** argv) {
     if (sec == "meshio" || sec == "all") {
       testGmshIo(dir, "regression_dim-2_h-2e-1", 2, 2);
       testGmshIo(dir, "regression_dim-3_h-2e-1", 3, 3);
+      testHDF5IoFields(dir);
     }
     if (sec == "partitioner" || sec == "all") {
       testPartitioner(dir + "/regression_dim-2_h-1e-1_ord-3.txt", 2, 3, 3);

@@ -37,7 +37,7 @@ def mesh_dir(tmp_path_factory):
     from tests.conftest import unpacked_fixtures
     for name in ("regression_dim-2_h-2e-1", "regression_dim-3_h-2e-1"):
         shutil.copyfile(os.path.join(unpacked_fixtures("msh"), name + ".msh"), os.path.join(d, name + ".msh"))
-    for name in ("regression_dim-2_h-2e-1_ord-2", "regression_dim-3_h-2e-1_ord-3"):
+    for name in ("regression_dim-2_h-2e-1_ord-2", "regression_dim-3_h-2e-1_ord-3", "lightTri2", "fieldTest"):
         shutil.copyfile(os.path.join(unpacked_fixtures("h5"), name + ".h5"), os.path.join(d, name + ".h5"))
     return str(d)
 

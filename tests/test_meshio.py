@@ -187,14 +187,14 @@ def test_python_io_mirrors():
     assert a.getNumberCells() == b.getNumberCells() == 729 and a.getNumberPoints() == b.getNumberPoints() == 4249
     assert np.array_equal(a.cells, b.cells) and np.array_equal(a.faces, b.faces) and np.array_equal(a.face2CellMap, b.face2CellMap)
     assert np.abs(a.nodes - b.nodes).max() < 1e-15
-    with pytest.raises(hfox.ErrorHandle, match="extension"):
+    with pytest.raises(hfox.ErrorHandle, match="is not an hdf5 file"):
         hfox.HDF5Io(a).load(os.path.join(MSH, "regression_dim-3_h-2e-1.msh"))
     with pytest.raises(hfox.ErrorHandle, match="mesh must be set"):
         hfox.GmshIo().load(os.path.join(MSH, "regression_dim-3_h-2e-1.msh"))
     with pytest.raises(hfox.ErrorHandle, match="connectivity does not match"):
         hfox.HDF5Io(hfox.Mesh(3, 2, "simplex")).load(os.path.join(H5, "regression_dim-3_h-2e-1_ord-3.h5"))
     with pytest.raises(hfox.ErrorHandle, match="write"):
-        hfox.HDF5Io(a).write("out.h5")
+        io.write("out.msh")
 
 
 @pytest.mark.parametrize("dim,order,N", [(2, 5, 6), (3, 3, 5), (3, 4, 3)])
@@ -211,3 +211,90 @@ def test_generator_agrees_with_the_synthetic_mesh_generator(dim, order, N):
     perm = np.full(n1.shape[0], -1, dtype=np.int64)
     perm[c1.ravel()] = c2.ravel()
     assert perm.min() >= 0 and np.unique(perm).size == perm.size and np.array_equal(perm[c1], c2)
+
+
+@pytest.mark.parametrize("name", ["lightTri2", "regression_dim-2_h-2e-1_ord-2", "regression_dim-3_h-2e-1_ord-3", "regression_dim-3_h-3e-1_ord-5"])
+def test_h5_writer_reproduces_the_reference_files_byte_for_byte(name, tmp_path):
+    """hfx_host_write_h5 (HDF5Io::write without libhdf5) against the files the reference's own writer produced (tools/convertGmsh2H5HO.cpp -> HDF5Io::write ->
+    libhdf5): written from the same mesh, the file is IDENTICAL to the reference's up to the two 4-byte modification times -- superblock, group B-trees, local
+    heaps, symbol-table nodes, object headers and the placement of every block included."""
+    ref = open(os.path.join(H5, name + ".h5"), "rb").read()
+    nodes, cells = product.read_h5_mesh(os.path.join(H5, name + ".h5"))
+    out = str(tmp_path / "out.h5")
+    product.write_h5(out, nodes, cells, mtime=12345)
+    got = open(out, "rb").read()
+    assert len(got) == len(ref)
+    diff = [i for i in range(len(ref)) if ref[i] != got[i]]
+    # the modification-time messages of the two datasets: 4 bytes each, 148 bytes into a 272-byte object header that starts at 1832 (Nodes) / after the Nodes data (Cells)
+    assert len(diff) <= 8 and all(1988 <= i < 1992 or i > 4000 for i in diff)
+    mt = int.from_bytes(ref[1988:1992], "little")
+    product.write_h5(out, nodes, cells, mtime=mt)
+    got = open(out, "rb").read()
+    rest = [i for i in range(len(ref)) if ref[i] != got[i]]
+    assert all(i > 4000 for i in rest) and len(rest) <= 4        # only the second dataset's time stamp can still differ
+    n2, c2 = product.read_h5_mesh(out)
+    assert np.array_equal(n2, nodes) and np.array_equal(c2, cells)
+
+
+def test_h5_field_reader_on_the_reference_file():
+    """tests/unittests/io/TestHDF5Io.cpp "Load test field": ressources/meshes/fieldTest.h5 holds NodeField = 0..8 (Node, 1 x 1) and CellField = (i, -i) (Cell, 2 x 1);
+    that file was written by h5py (scalar int64 ftype attribute), the reference's own writer stores an int32 [1] attribute: both are read."""
+    path = os.path.join(H5, "fieldTest.h5")
+    hasMesh, names = product.h5_info(path)
+    assert not hasMesh and names == ["CellField", "NodeField"]
+    ft, v = product.read_h5_field(path, "NodeField")
+    assert ft == product.H5_NODE and v.shape == (9, 1, 1) and np.array_equal(v.ravel(), np.arange(9.0))
+    ft, v = product.read_h5_field(path, "CellField")
+    assert ft == product.H5_CELL and v.shape == (8, 2, 1) and np.array_equal(v.ravel(), np.array([[i, -i] for i in range(8)], dtype=float).ravel())
+    err = Exception
+    with pytest.raises(err, match="was not found in FieldData"):
+        product.read_h5_field(path, "Nope")
+    with pytest.raises(err, match="no FieldData group"):
+        product.read_h5_field(os.path.join(H5, "lightTri2.h5"), "NodeField")
+
+
+def test_h5_write_then_load_fields_and_mesh(tmp_path):
+    """TestHDF5Io.cpp "Write test field" through the Python mirror: HDF5Io.write (Mesh + FieldData) then HDF5Io.load into fresh objects; and a file with more
+    fields than one symbol-table node holds (8), names longer than the initial heap."""
+    from hyperfox_b200 import hfox
+    m = hfox.Mesh(2, 2, "simplex")
+    hfox.HDF5Io(m).load(os.path.join(H5, "lightTri2.h5"))
+    nodeField, cellField, faceField = hfox.Field(m, hfox.Node, 1, 1), hfox.Field(m, hfox.Cell, 2, 1), hfox.Field(m, hfox.Face, 3, 2)
+    nodeField.values[:] = np.arange(9.0)
+    cellField.values[:] = np.array([[i, -i] for i in range(2)], dtype=float).ravel()
+    faceField.values[:] = np.random.default_rng(1).standard_normal(faceField.values.size)
+    io = hfox.HDF5Io(m)
+    io.setField("NodeField", nodeField); io.setField("CellField", cellField); io.setField("FaceField", faceField)
+    out = str(tmp_path / "tmp.h5")
+    io.write(out)
+    m2 = hfox.Mesh(2, 2, "simplex")
+    io2 = hfox.HDF5Io(m2)
+    hfox.HDF5Io(m2).load(os.path.join(H5, "lightTri2.h5"))
+    n2, c2, f2 = hfox.Field(m2, hfox.Node, 1, 1), hfox.Field(m2, hfox.Cell, 1, 1), hfox.Field(m2, hfox.Face, 1, 1)
+    io2.setField("NodeField", n2); io2.setField("CellField", c2); io2.setField("FaceField", f2)
+    io2.load(out)
+    assert np.array_equal(m2.nodes, m.nodes) and np.array_equal(m2.cells, m.cells)
+    assert np.array_equal(n2.values, nodeField.values) and np.array_equal(c2.values, cellField.values) and np.array_equal(f2.values, faceField.values)
+    assert (c2.type, c2.nObj, c2.nVals) == (hfox.Cell, 2, 1) and (f2.type, f2.nObj, f2.nVals) == (hfox.Face, 3, 2)
+    # the independent dev-time reader (tools/mini_h5.py, written against libhdf5's own files) parses the written file as well
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from mini_h5 import MiniH5
+    f = MiniH5(out)
+    assert np.array_equal(f.read("/Mesh/Nodes"), m.nodes) and np.array_equal(f.read("/Mesh/Cells"), m.cells)
+    assert np.array_equal(f.read("/FieldData/FaceField").ravel(), faceField.values)
+    # many fields, long names
+    rng = np.random.default_rng(3)
+    fields = {"RKStage_Flux_%d_with_a_rather_long_name" % k: (product.H5_CELL, rng.standard_normal((5, 3, 2))) for k in range(21)}
+    big = str(tmp_path / "many.h5")
+    product.write_h5(big, fields=fields)
+    hasMesh, names = product.h5_info(big)
+    assert not hasMesh and names == sorted(fields)
+    for k in names:
+        ft, v = product.read_h5_field(big, k)
+        assert ft == product.H5_CELL and np.array_equal(v, fields[k][1])
+    g = MiniH5(big)
+    for k in names:
+        assert np.array_equal(g.read("/FieldData/" + k), fields[k][1])
+    with pytest.raises(Exception, match="could not find anything to write"):
+        product.write_h5(str(tmp_path / "empty.h5"))

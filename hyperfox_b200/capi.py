@@ -39,7 +39,7 @@ SYMBOLS = [
     "hfx_ctx_create", "hfx_ctx_destroy", "hfx_last_error", "hfx_device_count", "hfx_fp64_peak", "hfx_dmma_peak", "hfx_refel_set", "hfx_refel_info", "hfx_refel_tables",
     "hfx_refel_host_tables", "hfx_mesh_set", "hfx_mesh_set_topology", "hfx_mesh_sizes", "hfx_mesh_get_topology", "hfx_host_compute_faces", "hfx_host_read_msh", "hfx_host_read_h5_mesh", "hfx_host_write_h5", "hfx_host_h5_info", "hfx_host_read_h5_field", "hfx_host_high_order_mesh",
     "hfx_field_set", "hfx_field_set_async", "hfx_field_get", "hfx_field_size", "hfx_field_lincomb", "hfx_field_diff_norm2", "hfx_model_describe", "hfx_time_scheme_rk", "hfx_ip_coords", "hfx_source_values", "hfx_source_values_n", "hfx_reaction_values",
-    "hfx_boundary_describe", "hfx_allocate", "hfx_assemble", "hfx_solver_type", "hfx_solve", "hfx_solve_info", "hfx_recover", "hfx_sync", "hfx_last_assemble_ms", "hfx_last_assemble_kernel", "hfx_assemble_profile", "hfx_get_csr",
+    "hfx_boundary_describe", "hfx_allocate", "hfx_assemble", "hfx_cg_allocate", "hfx_cg_assemble", "hfx_cg_solve", "hfx_cg_get_csr", "hfx_solver_type", "hfx_solve", "hfx_solve_info", "hfx_recover", "hfx_sync", "hfx_last_assemble_ms", "hfx_last_assemble_kernel", "hfx_assemble_profile", "hfx_get_csr",
     "hfx_get_local", "hfx_get_local_matrix", "hfx_residual", "hfx_get_elem_dofs", "hfx_comm_unique_id", "hfx_comm_init", "hfx_comm_set_halo", "hfx_comm_halo_field", "hfx_host_rcb_partition", "hfx_host_graph_partition", "hfx_plan_create", "hfx_plan_destroy", "hfx_plan_last_error", "hfx_plan_sizes", "hfx_plan_get", "hfx_host_face_canonical_positions", "hfx_host_face_canonical_positions_geom", "hfx_comm_set_halo_plan", "hfx_lai_create", "hfx_lai_destroy", "hfx_lai_last_error", "hfx_lai_set_opts", "hfx_lai_initialize",
     "hfx_lai_configure", "hfx_lai_allocate", "hfx_lai_add_val_matrix", "hfx_lai_add_vals_matrix", "hfx_lai_add_val_rhs", "hfx_lai_add_vals_rhs",
     "hfx_lai_set_val_matrix", "hfx_lai_set_vals_matrix", "hfx_lai_set_val_rhs", "hfx_lai_set_vals_rhs", "hfx_lai_zero_out_rows",

@@ -1,0 +1,130 @@
+// Continuous-Galerkin path: CGSolver::assemble (src/solver/CGSolver.cpp:42-246) for the Laplace-type models -- LaplaceModel (src/model/LaplaceModel.cpp:
+// Diffusion) and DiffusionSource without a time scheme (Diffusion + Source) -- with DirichletModel boundaries, on the device.  Node-based CSR (sorted columns, explicit
+// zeros: CGSolver::calcSparsityPattern :261-335 + PETSc AIJ), one CTA per element pass:
+//   J(ip) = sum_i dphi_i/dxi x_i, dV = w det J            (Operator.cpp:14-84)
+//   G(ip, i) = J^-1 grad^ phi_i                            (Diffusion.cpp:33-36)
+//   A_ij = sum_ip dV (D(ip) G(ip, i)) . G(ip, j)           (Diffusion.cpp:37-45; D interpolated from the nodes, scalar or dim x dim column-major: setDiffTensor :65-73)
+//   F_i  = sum_ip dV f(x_ip) phi_i(ip)                     (Source.cpp:24-48; f evaluated by the host callback at hfx_ip_coords)
+// and the element block is added into the global rows of its nodes (linSystem->addValsMatrix / addValsRHS): floating-point atomics -- a CG entry has as many
+// contributors as cells share the node pair, so unlike the HDG trace system the sum order is not fixed.  Any element the reference element supports (runtime sizes,
+// curved or multilinear geometry: the Jacobian is evaluated at every cubature point).
+#pragma once
+#include "hfx_assemble.cuh"
+
+namespace hfx {
+
+struct CgParams {
+  int nCells, dim, nN, nIP;
+  const double* nodes; const int* cells;
+  const double* shape; const double* dshape; const double* w;
+  const double* diff; int diffComps;      // DiffusionTensor node field [nNodes][1 | dim^2] or NULL (identity)
+  const double* srcIP;                    // [nCells][nIP] or NULL
+  const long long* rowptr; const int* colidx;
+  double* vals; double* rhs; int* status;
+};
+
+__device__ __forceinline__ long long cg_find(const long long* __restrict__ rowptr, const int* __restrict__ colidx, int row, int col) {
+  long long lo = rowptr[row], hi = rowptr[row + 1] - 1;
+  while (lo < hi) { const long long mid = (lo + hi) >> 1; if (colidx[mid] < col) lo = mid + 1; else hi = mid; }
+  return lo;   // the pattern holds every node pair of every cell
+}
+
+__global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
+  extern __shared__ __align__(16) double smcg[];
+  const int dim = p.dim, nN = p.nN, nIP = p.nIP, D2 = dim * dim, tid = threadIdx.x, NT = blockDim.x;
+  double* const X = smcg;                               // [nN][dim]
+  double* const JI = X + ((nN * dim + 1) & ~1);         // [nIP][dim][dim]
+  double* const DP = JI + ((nIP * D2 + 1) & ~1);        // [nIP][dim][dim] row-major D(a, b)
+  double* const DV = DP + ((nIP * D2 + 1) & ~1);        // [nIP]
+  double* const G = DV + ((nIP + 1) & ~1);              // [nIP][nN][dim]
+  int* const ID = reinterpret_cast<int*>(G + (size_t)nIP * nN * dim);
+  for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
+    for (int i = tid; i < nN; i += NT) {
+      const int n = p.cells[(size_t)e * nN + i];
+      ID[i] = n;
+      for (int m = 0; m < dim; m++) X[i * dim + m] = p.nodes[(size_t)n * dim + m];
+    }
+    __syncthreads();
+    for (int ip = tid; ip < nIP; ip += NT) {
+      double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+      for (int r = 0; r < dim; r++)
+        for (int m = 0; m < dim; m++) {
+          double s = 0.0;
+          for (int i = 0; i < nN; i++) s = fma(p.dshape[((size_t)ip * nN + i) * dim + r], X[i * dim + m], s);
+          J[r][m] = s;
+        }
+      double det, I[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+      if (dim == 1) { det = J[0][0]; I[0][0] = 1.0 / det; }
+      else if (dim == 2) {
+        det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        const double id = 1.0 / det;
+        I[0][0] = J[1][1] * id; I[0][1] = -J[0][1] * id; I[1][0] = -J[1][0] * id; I[1][1] = J[0][0] * id;
+      } else det_inv(J, det, I);
+      if (!(fabs(det) > 1e-300)) atomicOr(p.status, 1);
+      for (int a = 0; a < dim; a++) for (int b = 0; b < dim; b++) JI[ip * D2 + a * dim + b] = I[a][b];
+      DV[ip] = p.w[ip] * det;
+      if (p.diff) {
+        for (int a = 0; a < dim; a++)
+          for (int b = 0; b < dim; b++) {
+            double s = 0.0;
+            if (p.diffComps == 1) { if (a == b) for (int i = 0; i < nN; i++) s = fma(p.shape[(size_t)ip * nN + i], p.diff[ID[i]], s); }
+            else for (int i = 0; i < nN; i++) s = fma(p.shape[(size_t)ip * nN + i], p.diff[(size_t)ID[i] * D2 + a + dim * b], s);   // column-major per node
+            DP[ip * D2 + a * dim + b] = s;
+          }
+      }
+    }
+    __syncthreads();
+    for (int k = tid; k < nIP * nN; k += NT) {
+      const int ip = k / nN;
+      const double* ds = p.dshape + (size_t)k * dim;
+      for (int a = 0; a < dim; a++) {
+        double s = 0.0;
+        for (int b = 0; b < dim; b++) s = fma(JI[ip * D2 + a * dim + b], ds[b], s);
+        G[(size_t)k * dim + a] = s;
+      }
+    }
+    __syncthreads();
+    for (int idx = tid; idx < nN * nN; idx += NT) {
+      const int i = idx / nN, j = idx - i * nN;
+      double acc = 0.0;
+      for (int ip = 0; ip < nIP; ip++) {
+        const double* gi = G + ((size_t)ip * nN + i) * dim; const double* gj = G + ((size_t)ip * nN + j) * dim;
+        double s = 0.0;
+        if (p.diff) {
+          const double* Dm = DP + ip * D2;
+          for (int a = 0; a < dim; a++) { double t = 0.0; for (int b = 0; b < dim; b++) t = fma(Dm[a * dim + b], gi[b], t); s = fma(t, gj[a], s); }
+        } else for (int a = 0; a < dim; a++) s = fma(gi[a], gj[a], s);
+        acc = fma(DV[ip], s, acc);
+      }
+      atomicAdd(p.vals + cg_find(p.rowptr, p.colidx, ID[i], ID[j]), acc);
+    }
+    if (p.srcIP)
+      for (int i = tid; i < nN; i += NT) {
+        double s = 0.0;
+        for (int ip = 0; ip < nIP; ip++) s = fma(DV[ip] * p.srcIP[(size_t)e * nIP + ip], p.shape[(size_t)ip * nN + i], s);
+        atomicAdd(p.rhs + ID[i], s);
+      }
+    __syncthreads();
+  }
+}
+
+inline size_t cg_smem_bytes(int dim, int nN, int nIP) {
+  const size_t D2 = (size_t)dim * dim;
+  const size_t d = (((size_t)nN * dim + 1) & ~(size_t)1) + 2 * (((size_t)nIP * D2 + 1) & ~(size_t)1) + (((size_t)nIP + 1) & ~(size_t)1) + (size_t)nIP * nN * dim;
+  return d * 8 + (size_t)((nN + 1) & ~1) * 4 + 16;
+}
+
+// DirichletModel through CGSolver (CGSolver.cpp:139-243): the rows of the nodes of every boundary face are zeroed (zeroOutRows), then the face's identity block and its
+// Dirichlet values (face-node order) are Set
+__global__ void cg_dirichlet_kernel(int nFaces, int nNf, const uint8_t* __restrict__ faceBC, const int* __restrict__ faces, const double* __restrict__ dirichlet,
+                                    const long long* __restrict__ rowptr, const int* __restrict__ colidx, double* __restrict__ vals, double* __restrict__ rhs) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= (long long)nFaces * nNf) return;
+  const int F = (int)(k / nNf);
+  if (faceBC[F] != 1) return;
+  const int n = faces[k];
+  for (long long q = rowptr[n]; q < rowptr[n + 1]; q++) vals[q] = colidx[q] == n ? 1.0 : 0.0;
+  rhs[n] = dirichlet[k];
+}
+
+}  // namespace hfx

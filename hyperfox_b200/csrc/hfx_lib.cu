@@ -20,6 +20,7 @@
 #include "hfx_big.cuh"
 #include "hfx_p1.cuh"
 #include "hfx_col.cuh"
+#include "hfx_cg.cuh"
 #include "hfx_krylov.cuh"
 #include "host/hfx_refel.h"
 #include "host/hfx_topology.h"
@@ -1125,6 +1126,9 @@ struct hfx_ctx {
   DBuf<uint8_t> dFaceBC;
   // allocation
   bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false, p1Ready = false, colReady = false; int lastKernel = 0;
+  // continuous-Galerkin path (hfx_cg_*): node-based CSR
+  DBuf<long long> dCgRowptr; DBuf<int> dCgCol; DBuf<double> dCgVals, dCgRhs; long long cgNnz = 0; bool cgAllocated = false, cgAssembled = false;
+  std::vector<long long> hCgRowptr; std::vector<int> hCgCol;
   int solverType = 0;   // HDGSolverOpts.type: 0 IMPLICIT, 1 WEXPLICIT, 2 SEXPLICIT (HDGSolverOpts.h:6-10)
   DBuf<double> dColTab;
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
@@ -2275,6 +2279,121 @@ int hfx_solve(hfx_ctx* c, const hfx_solve_opts* opts, hfx_solve_stats* stats) {
   });
   if (rc) return rc;
   return hfx_recover(c);
+}
+
+// ---- continuous-Galerkin path: CGSolver (src/solver/CGSolver.cpp) for LaplaceModel / DiffusionSource + DirichletModel ---------------------------------------------
+namespace {
+struct CsrDevOp : LinOp {
+  const long long* rowptr; const int* colidx; const double* vals;
+  CsrDevOp(long long n_, const long long* rp, const int* ci, const double* va) : rowptr(rp), colidx(ci), vals(va) { n = n_; }
+  void apply(double* x, double* y, const double* dinv, const int* done, cudaStream_t st) override {
+    spmv_csr_kernel<<<nblk(n * 32, 256), 256, 0, st>>>(n, rowptr, colidx, vals, x, y, dinv, done);
+  }
+  void diag_inverse(double* dinv, cudaStream_t st) override { diag_csr_kernel<<<nblk(n, 256), 256, 0, st>>>(n, rowptr, colidx, vals, dinv); }
+};
+}  // namespace
+
+int hfx_cg_allocate(hfx_ctx* c) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    // CGSolver::allocate checks (CGSolver.cpp:5-40)
+    need(c->topoSet, "CGSolver", "allocate", "must set the Mesh before allocating.");
+    need(c->modelSet, "CGSolver", "allocate", "must set the model before allocating.");
+    need(c->bcSet, "CGSolver", "allocate", "must set the boundary model before allocating.");
+    DField* sol = find_field(c, "Solution");
+    need(sol != nullptr, "CGSolver", "allocate", "the field map must have a Solution field.");
+    need(sol->type == HFX_FIELD_NODE, "CGSolver", "allocate", "the Solution field must be a nodal field.");
+    need(sol->nObj * sol->nVal == 1 && c->md.nDOF == 1, "CGSolver", "allocate", "the device CG path serves one degree of freedom per node (LaplaceModel, DiffusionSource)");
+    // CGSolver::calcSparsityPattern (:261-335): row of a node = the nodes of every cell it belongs to; sorted columns (PETSc AIJ)
+    const int nN = c->nN, nC = c->nCells, nNodes = c->nNodes;
+    std::vector<int> cells((size_t)nC * nN);
+    c->dCells.download(cells.data(), cells.size(), c->st);
+    HFX_CUDA(cudaStreamSynchronize(c->st));
+    std::vector<long long> n2c(nNodes + 1, 0);
+    for (size_t k = 0; k < cells.size(); k++) n2c[cells[k] + 1]++;
+    for (int i = 0; i < nNodes; i++) n2c[i + 1] += n2c[i];
+    std::vector<int> n2cList((size_t)n2c[nNodes]);
+    { std::vector<long long> pos(n2c.begin(), n2c.end() - 1); for (int e = 0; e < nC; e++) for (int i = 0; i < nN; i++) n2cList[(size_t)pos[cells[(size_t)e * nN + i]]++] = e; }
+    c->hCgRowptr.assign(nNodes + 1, 0); c->hCgCol.clear();
+    std::vector<int> row;
+    for (int n = 0; n < nNodes; n++) {
+      row.clear();
+      for (long long k = n2c[n]; k < n2c[n + 1]; k++) { const int e = n2cList[(size_t)k]; row.insert(row.end(), cells.begin() + (size_t)e * nN, cells.begin() + (size_t)(e + 1) * nN); }
+      std::sort(row.begin(), row.end());
+      row.erase(std::unique(row.begin(), row.end()), row.end());
+      c->hCgCol.insert(c->hCgCol.end(), row.begin(), row.end());
+      c->hCgRowptr[n + 1] = (long long)c->hCgCol.size();
+    }
+    c->cgNnz = (long long)c->hCgCol.size();
+    c->dCgRowptr.upload(c->hCgRowptr, c->st); c->dCgCol.upload(c->hCgCol, c->st);
+    c->dCgVals.alloc((size_t)c->cgNnz); c->dCgRhs.alloc((size_t)nNodes);
+    HFX_CUDA(cudaStreamSynchronize(c->st));
+    c->cgAllocated = true; c->cgAssembled = false;
+  });
+}
+
+int hfx_cg_assemble(hfx_ctx* c) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    need(c->cgAllocated, "CGSolver", "assemble", "must initialize and allocate the solver before allocating.");
+    need((c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE)) == 0 && (c->md.opmask & HFX_OP_DIFFUSION) && c->md.timeScheme == HFX_TS_NONE, "CGSolver", "assemble",
+         "the device CG path serves LaplaceModel and DiffusionSource without a time scheme (Diffusion [+ Source])");
+    for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) { for (int k = 0; k < kv.second.pendingPieces; k++) HFX_CUDA(cudaStreamWaitEvent(c->st, kv.second.ev[k], 0)); kv.second.pendingPieces = 0; }
+    CgParams p{};
+    p.nCells = c->nCells; p.dim = c->dim; p.nN = c->nN; p.nIP = c->nIP;
+    p.nodes = c->dNodes.p; p.cells = c->dCells.p; p.shape = c->dShape.p; p.dshape = c->dDShape.p; p.w = c->dW.p;
+    DField* df = find_field(c, "DiffusionTensor");
+    if (df) {
+      need(df->type == HFX_FIELD_NODE && (df->nObj * df->nVal == 1 || df->nObj * df->nVal == c->dim * c->dim), "LaplaceModel", "computeLocalMatrix", "the DiffusionTensor field must hold a scalar or a dim x dim tensor per node");
+      p.diff = df->d.p; p.diffComps = df->nObj * df->nVal;
+    }
+    if (c->md.opmask & HFX_OP_SOURCE) { need(c->dSrc.n >= (size_t)c->nCells * c->nIP, "Source", "calcSource", "must set a source function before calculating the source."); p.srcIP = c->dSrc.p; }
+    p.rowptr = c->dCgRowptr.p; p.colidx = c->dCgCol.p; p.vals = c->dCgVals.p; p.rhs = c->dCgRhs.p; p.status = c->dStatus.p;
+    if (c->dStatus.n < 1) c->dStatus.alloc(1);
+    p.status = c->dStatus.p;
+    c->dStatus.zero(c->st); c->dCgVals.zero(c->st); c->dCgRhs.zero(c->st);      // linSystem->clearSystem()
+    const size_t shm = cg_smem_bytes(c->dim, c->nN, c->nIP);
+    need(shm <= 227 * 1024, "CGSolver", "assemble", "the element does not fit the shared memory of an SM");
+    HFX_CUDA(cudaFuncSetAttribute(cg_element_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+    const int perSM = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (shm + 1024)));
+    cg_element_kernel<<<std::max(1, std::min(c->nCells, c->nSM * perSM)), 128, shm, c->st>>>(p);
+    HFX_CUDA(cudaGetLastError());
+    DField* dir = find_field(c, "Dirichlet");
+    need(dir && dir->type == HFX_FIELD_FACE && dir->nObj == c->nNf && dir->nVal == 1, "DirichletModel", "setFieldMap", "must give a field named Dirichlet to the DirichletModel");
+    cg_dirichlet_kernel<<<nblk((long long)c->nFaces * c->nNf, 256), 256, 0, c->st>>>(c->nFaces, c->nNf, c->dFaceBC.p, c->dFaces.p, dir->d.p, c->dCgRowptr.p, c->dCgCol.p, c->dCgVals.p, c->dCgRhs.p);
+    HFX_CUDA(cudaGetLastError());
+    int status = 0;
+    c->dStatus.download(&status, 1, c->st);
+    need(!(status & 1), "Operator", "calcInvJacobians", "singular element Jacobian met during the assembly");
+    c->cgAssembled = true;
+  });
+}
+
+int hfx_cg_solve(hfx_ctx* c, const hfx_solve_opts* opts, hfx_solve_stats* stats) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    need(c->cgAssembled, "CGSolver", "solve", "system must be assembled before solving");
+    hfx_solve_opts o = opts ? *opts : hfx_solve_opts{0, 1, 30, 1000, 1e-6};
+    if (o.pc == 2) o.pc = 1;
+    CsrDevOp A(c->nNodes, c->dCgRowptr.p, c->dCgCol.p, c->dCgVals.p);
+    c->krylov.halo = nullptr; c->krylov.allReduces = 0; c->krylov.haloExchanges = 0;
+    c->krylov.solve(A, c->dCgRhs.p, find_field(c, "Solution")->d.p, o, stats, c->st);
+    HFX_CUDA(cudaStreamSynchronize(c->st));
+  });
+}
+
+int hfx_cg_get_csr(hfx_ctx* c, long long* nrows, long long* nnz, long long* rowptr, int* colidx, double* vals, double* rhs) {
+  return guard(c, [&] {
+    HFX_CUDA(cudaSetDevice(c->device));
+    need(c->cgAllocated, "CGSolver", "assemble", "must initialize and allocate the solver before allocating.");
+    if (nrows) *nrows = c->nNodes;
+    if (nnz) *nnz = c->cgNnz;
+    if (rowptr) std::copy(c->hCgRowptr.begin(), c->hCgRowptr.end(), rowptr);
+    if (colidx) std::copy(c->hCgCol.begin(), c->hCgCol.end(), colidx);
+    if (vals) c->dCgVals.download(vals, (size_t)c->cgNnz, c->st);
+    if (rhs) c->dCgRhs.download(rhs, (size_t)c->nNodes, c->st);
+    HFX_CUDA(cudaStreamSynchronize(c->st));
+  });
 }
 
 int hfx_solve_info(const hfx_ctx* c, hfx_solve_info_t* info) {

@@ -872,6 +872,147 @@ class HDGSolver:
         return ("fused", "general", "big", "p1", "col")[k.value]
 
 
+class LaplaceModel:
+    """LaplaceModel (src/model/LaplaceModel.cpp:15-52): localMatrix = Diffusion (DiffusionTensor field if given), no right-hand side; assembly = {Add, None}."""
+    isCG = True
+
+    def __init__(self, refEl):
+        self.refEl, self.allocated, self.sourceFunc, self.timeScheme = refEl, False, None, None
+
+    def allocate(self, nDOFsPerNode):
+        self.nDOF, self.allocated = nDOFsPerNode, True
+
+    def _mask(self):
+        return OP_DIFFUSION
+
+
+class DiffusionSource(LaplaceModel):
+    """DiffusionSource without a time scheme (src/model/DiffusionSource.cpp): Diffusion + Source right-hand side."""
+
+    def setSourceFunction(self, s):
+        if not self.allocated:
+            raise ErrorHandle("DiffusionSource : setSourceFunction : the model must be allocated before setting the source function")
+        self.sourceFunc = s
+
+    def setTimeScheme(self, ts):
+        raise ErrorHandle("DiffusionSource : setTimeScheme : the device CG path has no time schemes")
+
+    def _mask(self):
+        if self.sourceFunc is None:
+            raise ErrorHandle("Source : calcSource : must set a source function before calculating the source.")
+        return OP_DIFFUSION | OP_SOURCE
+
+
+class CGSolver:
+    """CGSolver (src/solver/CGSolver.cpp) on the device (hfx_cg_*): node-based CSR, element loop, DirichletModel rows, Krylov solve into the nodal Solution field.
+    Same call-order contract as the reference (tests/unittests/solver/TestCGSolver.cpp:37-66)."""
+
+    def __init__(self, device=0):
+        self.myMesh = self.fieldMap = self.linSystem = self.model = None
+        self.boundaries = []
+        self.initialized = self.allocated = self.assembled = False
+        self.device, self.ctx, self.verbose = device, None, False
+        self.stats = capi.SolveStats()
+
+    def setVerbosity(self, v): self.verbose = bool(v)
+    def setMesh(self, m): self.myMesh = m
+    def setFieldMap(self, fm): self.fieldMap = fm
+    def setLinSystem(self, lai): self.linSystem = lai
+    def setModel(self, m): self.model = m
+
+    def setBoundaryModel(self, bm):
+        if self.myMesh is None:
+            raise ErrorHandle("Solver : setBoundaryModel : must set the Mesh before the boundary model.")
+        self.boundaries.append((bm, None))
+
+    def setBoundaryCondition(self, bm, faces):
+        self.boundaries.append((bm, np.array(sorted(faces), dtype=np.int32)))
+
+    def initialize(self):
+        if self.linSystem is not None:
+            self.linSystem.destroySystem(); self.linSystem.initialize(); self.linSystem.configure()
+        self.initialized = True
+
+    def _h(self): return self.ctx.h
+
+    def allocate(self):
+        if not self.initialized:
+            raise ErrorHandle("CGSolver : allocate : must initialize the solver before allocating.")
+        if self.myMesh is None:
+            raise ErrorHandle("CGSolver : allocate : must set the Mesh before allocating.")
+        if self.linSystem is None:
+            raise ErrorHandle("CGSolver : allocate : must set the linear system before allocating.")
+        if self.model is None:
+            raise ErrorHandle("CGSolver : allocate : must set the model before allocating.")
+        if not self.boundaries:
+            raise ErrorHandle("CGSolver : allocate : must set the boundary model before allocating.")
+        if not self.fieldMap:
+            raise ErrorHandle("CGSolver : allocate : must set the fields before allocating.")
+        if "Solution" not in self.fieldMap:
+            raise ErrorHandle("CGSolver : allocate : the field map must have a Solution field.")
+        sol, mesh, re = self.fieldMap["Solution"], self.myMesh, self.myMesh.getReferenceElement()
+        if sol.type != Node:
+            raise ErrorHandle("CGSolver : allocate : the Solution field must be a nodal field.")
+        self.nDOFsPerNode = sol.nObj * sol.nVals
+        self.ctx = getattr(self.linSystem, "ctx", None) or Context(self.device)
+        L, h = lib(), self._h()
+        check(L.hfx_refel_set(h, mesh.dim, mesh.order, re._geom), h)
+        check(L.hfx_mesh_set(h, mesh.getNumberPoints(), pd(mesh.nodes), mesh.getNumberCells(), pi(mesh.cells)), h)
+        self.model.allocate(self.nDOFsPerNode)
+        self._upload("Solution")
+        md = capi.ModelDesc(self.nDOFsPerNode, OP_DIFFUSION, 0, 0.0)
+        check(L.hfx_model_describe(h, C.byref(md)), h)
+        for bm, faces in self.boundaries:
+            bm.allocate(self.nDOFsPerNode)
+            if getattr(bm, "kind", None) != 0:
+                raise ErrorHandle("CGSolver : allocate : the device CG path serves DirichletModel boundaries")
+            check(L.hfx_boundary_describe(h, 0, 0 if faces is None else faces.size, None if faces is None else pi(faces)), h)
+        check(L.hfx_cg_allocate(h), h)
+        self.allocated = True
+
+    def _upload(self, name):
+        f = self.fieldMap[name]
+        v = f64(f.values)
+        check(lib().hfx_field_set(self._h(), name.encode(), f.type, f.nObj, f.nVals, pd(v), int(f.doubleValued)), self._h())
+
+    def assemble(self):
+        if not (self.initialized and self.allocated):
+            raise ErrorHandle("CGSolver : assemble : must initialize and allocate the solver before allocating.")
+        L, h, mesh = lib(), self._h(), self.myMesh
+        for name in ("Dirichlet", "DiffusionTensor"):
+            if name in self.fieldMap:
+                self._upload(name)
+        if "Dirichlet" not in self.fieldMap:
+            raise ErrorHandle("DirichletModel : setFieldMap : must give a field named Dirichlet to the DirichletModel")
+        mask = self.model._mask()
+        md = capi.ModelDesc(self.nDOFsPerNode, mask, 0, 0.0)
+        check(L.hfx_model_describe(h, C.byref(md)), h)
+        if mask & OP_SOURCE:
+            nC, nIP, d = mesh.getNumberCells(), mesh.getReferenceElement().getNumIPs(), mesh.dim
+            xip = np.zeros((nC, nIP, d))
+            check(L.hfx_ip_coords(h, pd(xip)), h)
+            v = f64([self.model.sourceFunc(list(p)) for p in xip.reshape(-1, d)])
+            check(L.hfx_source_values(h, pd(v)), h)
+        check(L.hfx_cg_assemble(h), h)
+        self.assembled = True
+
+    def solve(self):
+        if not self.assembled:
+            raise ErrorHandle("CGSolver : solve : system must be assembled before solving")
+        o = self.linSystem.opts.c() if hasattr(self.linSystem, "opts") else PetscOpts().c()
+        check(lib().hfx_cg_solve(self._h(), C.byref(o), C.byref(self.stats)), self._h())
+        f = self.fieldMap["Solution"]
+        f._deviceNewer = False
+        check(lib().hfx_field_get(self._h(), b"Solution", pd(f._values)), self._h())
+
+    def getCSR(self):
+        n, nnz = C.c_longlong(0), C.c_longlong(0)
+        check(lib().hfx_cg_get_csr(self._h(), C.byref(n), C.byref(nnz), None, None, None, None), self._h())
+        rowptr, col, vals, rhs = np.zeros(n.value + 1, dtype=np.int64), np.zeros(nnz.value, dtype=np.int32), np.zeros(nnz.value), np.zeros(n.value)
+        check(lib().hfx_cg_get_csr(self._h(), C.byref(n), C.byref(nnz), rowptr.ctypes.data_as(C.POINTER(C.c_longlong)), pi(col), pd(vals), pd(rhs)), self._h())
+        return rowptr, col, vals, rhs
+
+
 class NonLinearWrapper:
     """Fixed-point / Newton driver with damping (src/solver/NonLinearWrapper.cpp:41-79)."""
 

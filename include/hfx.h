@@ -147,6 +147,19 @@ typedef struct { float msPerIteration; long long allReduces, haloExchanges, halo
                  int transport;    /* 0 single GPU, 1 NCCL (ncclSend/Recv + ncclAllReduce), 2 NVLink peer memory (CUDA IPC: direct stores into the neighbours' ghost
                                       buffers + one-shot all-reduce; HFX_P2P=0 selects 1) */ } hfx_solve_info_t;
 int hfx_solve_info(const hfx_ctx* ctx, hfx_solve_info_t* info);
+
+/* ---- continuous-Galerkin path: CGSolver (src/solver/CGSolver.h, CGSolver.cpp) for the Laplace-type models on the same device backend ----------
+   Models: LaplaceModel (src/model/LaplaceModel.cpp: Diffusion with an optional DiffusionTensor node field) and DiffusionSource without a time scheme (Diffusion +
+   Source; hfx_model_describe with HFX_OP_DIFFUSION [| HFX_OP_SOURCE], nDOF = 1, source values through hfx_source_values at hfx_ip_coords); boundary: DirichletModel
+   (hfx_boundary_describe kind HFX_BC_DIRICHLET, values in the Face field "Dirichlet", face-node order).  Needs hfx_refel_set, hfx_mesh_set and a Node field "Solution".
+   hfx_cg_allocate  = CGSolver::allocate (:5-40) + calcSparsityPattern (:261-335): node-based CSR, sorted columns, explicit zeros
+   hfx_cg_assemble  = CGSolver::assemble (:42-246): element loop (Add), zeroOutRows + Set of the boundary rows
+   hfx_cg_solve     = CGSolver::solve (:248-259): Krylov on the device CSR, result in the "Solution" field (hfx_field_get)
+   hfx_cg_get_csr   = parity hook (NULL arrays: sizes only) */
+int hfx_cg_allocate(hfx_ctx* ctx);
+int hfx_cg_assemble(hfx_ctx* ctx);
+int hfx_cg_solve(hfx_ctx* ctx, const hfx_solve_opts* opts, hfx_solve_stats* stats);
+int hfx_cg_get_csr(hfx_ctx* ctx, long long* nrows, long long* nnz, long long* rowptr, int* colidx, double* vals, double* rhs);
 int hfx_sync(hfx_ctx* ctx);
 /* timing of the last hfx_assemble (CUDA events on the library's stream), milliseconds */
 int hfx_last_assemble_ms(const hfx_ctx* ctx, float* msTotal, float* msKernel);

@@ -1315,6 +1315,120 @@ class HDGSolver : public Solver {
 };
 
 // ---- src/solver/NonLinearWrapper.h / .cpp:41-79 -----------------------------------------------------------------------------
+// ---- continuous Galerkin: src/model/LaplaceModel.h, DiffusionSource.h, src/solver/CGSolver.h (hfx_cg_*) --------------------------------------------------------
+class LaplaceModel : public FEModel {   // localMatrix = Diffusion (DiffusionTensor field if given), assembly = {Add, None}  (src/model/LaplaceModel.cpp:15-52)
+ public:
+  using FEModel::FEModel;
+  void allocate(int nDOFsPerNode) override { nDOFsPNode = nDOFsPerNode; allocated = 1; assembly.matrix = Add; }
+  virtual int cgMask() const { return HFX_OP_DIFFUSION; }
+  virtual const ScalarFunction* sourceFunction() const { return nullptr; }
+
+ protected:
+  int nDOFsPNode = 1;
+};
+class DiffusionSource : public LaplaceModel {   // Diffusion + Source, no time scheme on the device CG path  (src/model/DiffusionSource.cpp)
+ public:
+  using LaplaceModel::LaplaceModel;
+  void setSourceFunction(ScalarFunction s) {
+    if (!allocated) throw ErrorHandle("DiffusionSource", "setSourceFunction", "the model must be allocated before setting the source function");
+    source = s;
+  }
+  int cgMask() const override {
+    if (!source) throw ErrorHandle("Source", "calcSource", "must set a source function before calculating the source.");
+    return HFX_OP_DIFFUSION | HFX_OP_SOURCE;
+  }
+  const ScalarFunction* sourceFunction() const override { return &source; }
+
+ protected:
+  ScalarFunction source;
+};
+
+class CGSolver : public Solver {   // src/solver/CGSolver.cpp: allocate :5-40 (+ calcSparsityPattern :261-335), assemble :42-246, solve :248-259
+ public:
+  using Solver::Solver;
+  ~CGSolver() { delete ownCtx; }
+  void setDevice(int d) { device = d; }
+  void allocate() override {
+    if (!initialized) throw ErrorHandle("CGSolver", "allocate", "must initialize the solver before allocating.");
+    if (myMesh == NULL) throw ErrorHandle("CGSolver", "allocate", "must set the Mesh before allocating.");
+    if (linSystem == NULL) throw ErrorHandle("CGSolver", "allocate", "must set the linear system before allocating.");
+    if (model == NULL) throw ErrorHandle("CGSolver", "allocate", "must set the model before allocating.");
+    if (boundaryList.empty()) throw ErrorHandle("CGSolver", "allocate", "must set the boundary model before allocating.");
+    if (fieldMap == NULL || fieldMap->size() == 0) throw ErrorHandle("CGSolver", "allocate", "must set the fields before allocating.");
+    std::map<std::string, Field*>::iterator it = fieldMap->find("Solution");
+    if (it == fieldMap->end()) throw ErrorHandle("CGSolver", "allocate", "the field map must have a Solution field.");
+    if (*it->second->getFieldType() != Node) throw ErrorHandle("CGSolver", "allocate", "the Solution field must be a nodal field.");
+    nDOFsPerNode = *it->second->getNumObjPerEnt() * *it->second->getNumValsPerObj();
+    if (!dynamic_cast<LaplaceModel*>(model)) throw ErrorHandle("CGSolver", "allocate", "the device CG path serves LaplaceModel and DiffusionSource");
+    const ReferenceElement* re = myMesh->getReferenceElement();
+    hfx_ctx* h = ctx();
+    detail::check(hfx_refel_set(h, re->getDimension(), re->getOrder(), re->getGeometry() == simplex ? HFX_SIMPLEX : HFX_ORTHOTOPE), h);
+    detail::check(hfx_mesh_set(h, myMesh->getNumberPoints(), myMesh->getPoints()->data(), myMesh->getNumberCells(), myMesh->getCells()->data()), h);
+    detail::check(hfx_mesh_set_topology(h, myMesh->getNumberFaces(), myMesh->getFaces()->data(), myMesh->getCell2FaceMap()->data(), myMesh->getFace2CellMap()->data()), h);
+    model->allocate(nDOFsPerNode);
+    upload("Solution");
+    hfx_model_desc md; md.nDOF = nDOFsPerNode; md.opmask = HFX_OP_DIFFUSION; md.timeScheme = HFX_TS_NONE; md.dt = 0.0;
+    detail::check(hfx_model_describe(h, &md), h);
+    for (size_t i = 0; i < boundaryList.size(); i++) {
+      BoundaryModel* bm = std::get<0>(boundaryList[i]);
+      bm->allocate(nDOFsPerNode);
+      if (bm->cKind() != HFX_BC_DIRICHLET) throw ErrorHandle("CGSolver", "allocate", "the device CG path serves DirichletModel boundaries");
+      std::vector<int> ids(std::get<1>(boundaryList[i])->begin(), std::get<1>(boundaryList[i])->end());
+      static const int none = 0;
+      detail::check(hfx_boundary_describe(h, HFX_BC_DIRICHLET, (int)ids.size(), ids.empty() ? &none : ids.data()), h);
+    }
+    detail::check(hfx_cg_allocate(h), h);
+    allocated = 1;
+  }
+  void assemble() override {
+    if (!(initialized && allocated)) throw ErrorHandle("CGSolver", "assemble", "must initialize and allocate the solver before allocating.");
+    hfx_ctx* h = ctx();
+    if (!fieldMap->count("Dirichlet")) throw ErrorHandle("DirichletModel", "setFieldMap", "must give a field named Dirichlet to the DirichletModel");
+    upload("Dirichlet");
+    if (fieldMap->count("DiffusionTensor")) upload("DiffusionTensor");
+    const LaplaceModel* lm = static_cast<const LaplaceModel*>(model);
+    hfx_model_desc md; md.nDOF = nDOFsPerNode; md.opmask = lm->cgMask(); md.timeScheme = HFX_TS_NONE; md.dt = 0.0;
+    detail::check(hfx_model_describe(h, &md), h);
+    if (md.opmask & HFX_OP_SOURCE) {
+      const int nC = myMesh->getNumberCells(), nIP = myMesh->getReferenceElement()->getNumIPs(), d = myMesh->getNodeSpaceDimension();
+      std::vector<double> xip((size_t)nC * nIP * d), v((size_t)nC * nIP), pt(d);
+      detail::check(hfx_ip_coords(h, xip.data()), h);
+      for (size_t k = 0; k < v.size(); k++) { pt.assign(xip.begin() + k * d, xip.begin() + (k + 1) * d); v[k] = (*lm->sourceFunction())(pt); }
+      detail::check(hfx_source_values(h, v.data()), h);
+    }
+    detail::check(hfx_cg_assemble(h), h);
+    assembled = 1;
+  }
+  void solve() override {
+    if (!assembled) throw ErrorHandle("CGSolver", "solve", "system must be assembled before solving");
+    hfx_solve_opts o{0, 1, 30, 1000, 1e-6};
+    CudaLinAlgebraInterface* cl = dynamic_cast<CudaLinAlgebraInterface*>(linSystem);
+    if (cl) o = cl->cOpts();
+    detail::check(hfx_cg_solve(ctx(), &o, &stats), ctx());
+    if (cl) cl->stats = stats;
+    Field* f = fieldMap->at("Solution");
+    f->markOnDevice(nullptr, "", false);
+    detail::check(hfx_field_get(ctx(), "Solution", f->getValues()->data()), ctx());
+  }
+  const hfx_solve_stats& getStats() const { return stats; }
+
+ private:
+  static int cType(FieldType t) { return t == Node ? HFX_FIELD_NODE : (t == Face ? HFX_FIELD_FACE : HFX_FIELD_CELL); }
+  void upload(const char* name) {
+    Field* f = fieldMap->at(name);
+    detail::check(hfx_field_set(ctx(), name, cType(*f->getFieldType()), *f->getNumObjPerEnt(), *f->getNumValsPerObj(), f->getValues()->data(), f->isDoubleValued() ? 1 : 0), ctx());
+  }
+  hfx_ctx* ctx() {
+    CudaLinAlgebraInterface* cl = dynamic_cast<CudaLinAlgebraInterface*>(linSystem);
+    if (cl) return cl->context();
+    if (!ownCtx) ownCtx = new detail::Context(device);
+    return ownCtx->h;
+  }
+  detail::Context* ownCtx = nullptr;
+  int device = 0;
+  hfx_solve_stats stats{0, 0.0, 0.0, 0};
+};
+
 class NonLinearWrapper {
  public:
   NonLinearWrapper() : mySolver(NULL), previousSolution(NULL), currentSolution(NULL), residual(0.0) {

@@ -17,6 +17,8 @@
 #include "HDGLaplaceModel.h"
 #include "GmshIo.h"
 #include "HDF5Io.h"
+#include "CGSolver.h"
+#include "LaplaceModel.h"
 #include "HDGSolver.h"
 #include "Mesh.h"
 #include "RungeKutta.h"
@@ -392,6 +394,67 @@ static void testHDF5IoFields(const std::string& dir) {
   CHECK_THROWS(nothing.write(dir + "/nothing.h5"));
 }
 
+// tests/unittests/solver/TestCGSolver.cpp:14-68 on lightTri (order 1): the call-order contract (every step throws before its prerequisite) and, with Dirichlet = 3 on
+// every boundary face, Solution = 3 at every node (1e-12); then tests/regression/CG/TestCGLaplace.cpp's harmonic solution on a regression mesh.
+static void testCGSolver(const std::string& dir, bool compute) {
+  Mesh m(2, 1, "simplex");
+  loadMesh(dir + "/lightTri.txt", &m, 2);
+  std::map<std::string, Field*> fieldMap;
+  Field sol(&m, Node, 1, 1);
+  fieldMap["Solution"] = &sol;
+  Field dir3(&m, Face, m.getReferenceElement()->getFaceElement()->getNumNodes(), 1);
+  fieldMap["Dirichlet"] = &dir3;
+  std::fill(dir3.getValues()->begin(), dir3.getValues()->end(), 3.0);
+  DirichletModel dirMod(m.getReferenceElement()->getFaceElement());
+  LaplaceModel lapMod(m.getReferenceElement());
+  PetscOpts myOpts;
+  myOpts.verbose = false; myOpts.rtol = 1e-14;
+  CudaLinAlgebraInterface lai(myOpts);
+  CGSolver cgSolve;
+  CHECK_NOTHROW(cgSolve.setVerbosity(0));
+  CHECK_THROWS(cgSolve.solve()); CHECK_THROWS(cgSolve.assemble()); CHECK_THROWS(cgSolve.allocate());
+  CHECK_NOTHROW(cgSolve.setMesh(&m));
+  CHECK_THROWS(cgSolve.solve()); CHECK_THROWS(cgSolve.assemble()); CHECK_THROWS(cgSolve.allocate());
+  CHECK_NOTHROW(cgSolve.setFieldMap(&fieldMap));
+  CHECK_THROWS(cgSolve.solve()); CHECK_THROWS(cgSolve.assemble()); CHECK_THROWS(cgSolve.allocate());
+  if (!compute) return;
+  CHECK_NOTHROW(cgSolve.setLinSystem(&lai));
+  CHECK_THROWS(cgSolve.solve()); CHECK_THROWS(cgSolve.assemble()); CHECK_THROWS(cgSolve.allocate());
+  CHECK_NOTHROW(cgSolve.setModel(&lapMod));
+  CHECK_THROWS(cgSolve.solve()); CHECK_THROWS(cgSolve.assemble()); CHECK_THROWS(cgSolve.allocate());
+  CHECK_NOTHROW(cgSolve.setBoundaryModel(&dirMod));
+  CHECK_THROWS(cgSolve.solve()); CHECK_THROWS(cgSolve.assemble()); CHECK_THROWS(cgSolve.allocate());
+  CHECK_NOTHROW(cgSolve.initialize());
+  CHECK_NOTHROW(cgSolve.allocate());
+  CHECK_THROWS(cgSolve.solve());
+  CHECK_NOTHROW(cgSolve.assemble());
+  CHECK_NOTHROW(cgSolve.solve());
+  const std::vector<double>* vals = sol.getValues();
+  for (int i = 0; i < m.getNumberPoints(); i++) CHECK(std::fabs((*vals)[i] - 3.0) < 1e-12);
+  // TestCGLaplace: u = sin x e^y
+  Mesh m2(2, 2, "simplex");
+  loadMesh(dir + "/regression_dim-2_h-1e-1_ord-2.txt", &m2, 2);
+  const int nNf = m2.getReferenceElement()->getFaceElement()->getNumNodes();
+  Field sol2(&m2, Node, 1, 1), dirichlet(&m2, Face, nNf, 1);
+  std::vector<int> face; std::vector<double> pt;
+  for (std::set<int>::const_iterator it = m2.getBoundaryFaces()->begin(); it != m2.getBoundaryFaces()->end(); ++it) {
+    m2.getFace(*it, &face);
+    for (int j = 0; j < nNf; j++) { m2.getPoint(face[j], &pt); (*dirichlet.getValues())[(size_t)*it * nNf + j] = anaLaplace(pt); }
+  }
+  std::map<std::string, Field*> fm2;
+  fm2["Solution"] = &sol2; fm2["Dirichlet"] = &dirichlet;
+  LaplaceModel lap2(m2.getReferenceElement());
+  DirichletModel dir2(m2.getReferenceElement()->getFaceElement());
+  CudaLinAlgebraInterface lai2(myOpts);
+  CGSolver s2;
+  s2.setVerbosity(false); s2.setMesh(&m2); s2.setFieldMap(&fm2); s2.setLinSystem(&lai2); s2.setModel(&lap2); s2.setBoundaryModel(&dir2);
+  s2.initialize(); s2.allocate(); s2.assemble(); s2.solve();
+  double num = 0.0, den = 0.0;
+  for (int i = 0; i < m2.getNumberPoints(); i++) { m2.getPoint(i, &pt); const double a = anaLaplace(pt), e = (*sol2.getValues())[i] - a; num += e * e; den += a * a; }
+  std::printf("  CG laplace: %d nodes, gmres its %d, nodal relative l2 error %.3e\n", m2.getNumberPoints(), s2.getStats().iterations, std::sqrt(num / den));
+  CHECK(std::sqrt(num / den) < 1e-2);
+}
+
 // tests/unittests/solver/TestNonLinearWrapper.cpp:11-46: Newton on x^2 = 0 through setLinearizedSolver, Node fields on lightTri.  Host only.
 static void testNonLinearWrapper(const std::string& dir) {
   Mesh m(2, 1, "simplex");
@@ -576,6 +639,8 @@ int main(int argc, char** argv) {
       testPartitioner(dir + "/regression_dim-2_h-2e-1_ord-2.txt", 2, 2, 1);
     }
     if (sec == "solver" || sec == "all") testHDGSolver(dir, true);
+    if (sec == "contract") testCGSolver(dir, false);
+    if (sec == "cg" || sec == "all") testCGSolver(dir, true);
     if (sec == "lai" || sec == "all") testLinAlgebraInterface();
     if (sec == "laplace" || sec == "all") {
       testLaplace(dir + "/regression_dim-2_h-1e-1_ord-2.txt", 2, 2);

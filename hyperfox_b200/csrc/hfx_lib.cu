@@ -382,14 +382,15 @@ __global__ void diag_csr_kernel(long long n, const long long* __restrict__ rowpt
 // block is written exactly once per assemble by a plain copy.  Clearing the system (HDGSolver.cpp:532-536) therefore only has to zero
 // those diagonal blocks: 1/7 of the matrix at p=3.
 __global__ void zero_diag_blocks_kernel(int nFaces, int t, int nFc2, const long long* __restrict__ rowStart, const uint8_t* __restrict__ nnb,
-                                        const int* __restrict__ nbr, const uint8_t* __restrict__ interior, double* __restrict__ vals) {
-  const int F = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+                                        const int* __restrict__ nbr, const uint8_t* __restrict__ interior, double* __restrict__ vals, int lpf /*lanes per face: 8, 16 or 32*/) {
+  const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int F = (int)(gt / lpf), lane = (int)(gt - (long long)F * lpf);
   if (F >= nFaces || !interior[F]) return;
   const int m = nnb[F];
   int g = 0;
   for (int k = 0; k < m; k++) if (nbr[(size_t)F * nFc2 + k] == F) g = k;
   double* blk = vals + rowStart[F] + (long long)g * t * t;
-  for (int i = lane; i < t * t; i += 32) blk[i] = 0.0;
+  for (int i = lane; i < t * t; i += lpf) blk[i] = 0.0;
 }
 
 // Face-block Jacobi (pc = 2): inverse of the t x t diagonal block of every face, one warp per face, unpivoted Gauss-Jordan in the warp's
@@ -1999,7 +2000,8 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
       if (!c->valsCleared || getenv("HFX_FULL_MEMSET")) { c->dVals.zero(c->st); c->valsCleared = true; }   // first assemble after allocate: everything
       else {
         const int t = c->nNf * c->md.nDOF;
-        zero_diag_blocks_kernel<<<nblk((long long)c->nFaces * 32, 256), 256, 0, c->st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dInterior.p, c->dVals.p);
+        const int lpf = t * t <= 8 ? 8 : (t * t <= 16 ? 16 : 32);   // small blocks (linear elements: 3 x 3) do not need a whole warp
+        zero_diag_blocks_kernel<<<nblk((long long)c->nFaces * lpf, 256), 256, 0, c->st>>>(c->nFaces, t, 2 * c->nFc, c->dFaceRowStart.p, c->dNnb.p, c->dNbr.p, c->dInterior.p, c->dVals.p, lpf);
       }
       c->dRhs.zero(c->st); c->dStatus.zero(c->st);
     };

@@ -340,6 +340,8 @@ __host__ __device__ constexpr unsigned p1_fn_bits() {   // two bits per (f, b), 
 }
 constexpr unsigned kFnBits = p1_fn_bits();
 
+__device__ __forceinline__ int lane_base16(int tid) { return (tid & 31) & 16; }
+
 template <int MINB>
 __global__ void __launch_bounds__(kPGThreads, MINB) hdg_p1g_kernel(const AsmParams p) {
   extern __shared__ __align__(16) double smg[];
@@ -364,16 +366,37 @@ __global__ void __launch_bounds__(kPGThreads, MINB) hdg_p1g_kernel(const AsmPara
   const bool hasDiff = p.opmask & 1, hasSrc = (p.opmask & 8) && p.srcIP;
   const double dsc = hasDiff ? p.diffConst : 0.0;
   const int tv = p.tauVals;
-  for (long long e0 = (long long)p.eBegin + (long long)blockIdx.x * kPGElems; e0 < p.eEnd; e0 += (long long)gridDim.x * kPGElems) {
+  // The gather of an element (coordinates, face ids -> row starts / flags, permutations, then tau through them) is two dependent trips to global memory: it is
+  // issued one element ahead into registers, behind the column stage of the previous element.
+  double nX = 0.0, nTau = 0.0; int nPerm = 0, nPos = 0, nF = 0, nBC = 0, nIN = 0, nSD = 0; long long nRS = 0;
+  const unsigned full = 0xffffffffu;
+  const int half = lane_base16(tid);
+  auto loadElem = [&](long long e) {
+    if (j < 12) { nX = p.elemX[(size_t)e * 12 + j]; nPerm = p.fperm[(size_t)e * 12 + j]; }
+    nPos = p.elemPos[(size_t)e * 16 + j];
+    if (j >= 12) {
+      const int f = j - 12;
+      nF = p.cell2face[(size_t)e * 4 + f]; nBC = p.faceBC[nF]; nIN = p.faceInterior[nF]; nRS = p.faceRowStart[nF];
+      nSD = tv == 2 ? p.tauSide[(size_t)e * 4 + f] : 0;
+    }
+  };
+  auto loadTau = [&]() {   // lanes 0-11: tau of face j / 3 at face node j % 3; the face id and the side sit in lane 12 + j / 3 of the same half warp
+    const int src = half + 12 + (j < 12 ? j / 3 : 0);
+    const int Ff = __shfl_sync(full, nF, src), sd = __shfl_sync(full, nSD, src);
+    if (j < 12) nTau = p.tau[((size_t)Ff * 3 + nPerm) * tv + sd];
+  };
+  const long long eFirst = (long long)p.eBegin + (long long)blockIdx.x * kPGElems;
+  if (eFirst < p.eEnd) { loadElem(eFirst + g < p.eEnd ? eFirst + g : (long long)p.eEnd - 1); loadTau(); }
+  for (long long e0 = eFirst; e0 < p.eEnd; e0 += (long long)gridDim.x * kPGElems) {
     const bool live = e0 + g < p.eEnd;
     const long long e = live ? e0 + g : (long long)p.eEnd - 1;
-    // ---- stage 1: gather ---------------------------------------------------------------------------------------------------------------------------------
-    if (j < 12) { E[PG_X + j] = p.elemX[(size_t)e * 12 + j]; EI[PGI_PERM + j] = p.fperm[(size_t)e * 12 + j]; }
-    EI[PGI_POS + j] = p.elemPos[(size_t)e * 16 + j];
-    if (j >= 12) {
-      const int f = j - 12, Ff = p.cell2face[(size_t)e * 4 + f];
-      EI[PGI_F + f] = Ff; EI[PGI_BC + f] = p.faceBC[Ff]; EI[PGI_IN + f] = p.faceInterior[Ff]; RS[f] = p.faceRowStart[Ff];
-      EI[PGI_SD + f] = tv == 2 ? p.tauSide[(size_t)e * 4 + f] : 0;
+    // ---- stage 1: the prefetched gather goes to the element's slice ------------------------------------------------------------------------------------------
+    if (j < 12) { E[PG_X + j] = nX; EI[PGI_PERM + j] = nPerm; E[PG_TAU + j] = nTau; }
+    EI[PGI_POS + j] = nPos;
+    if (j >= 12) { const int f = j - 12; EI[PGI_F + f] = nF; EI[PGI_BC + f] = nBC; EI[PGI_IN + f] = nIN; RS[f] = nRS; EI[PGI_SD + f] = nSD; }
+    {
+      const long long en0 = e0 + (long long)gridDim.x * kPGElems;
+      if (en0 < p.eEnd) loadElem(en0 + g < p.eEnd ? en0 + g : (long long)p.eEnd - 1);      // (CTA-uniform condition)
     }
     __syncwarp();
     // ---- stage 2: geometry (every lane keeps Jinv and det), per-face data by lanes 0-3, tau by lanes 0-11, source by lane 12 --------------------------------
@@ -406,10 +429,7 @@ __global__ void __launch_bounds__(kPGThreads, MINB) hdg_p1g_kernel(const AsmPara
       }
       E[PG_CQ + f * 3] = ar * rdet * n0; E[PG_CQ + f * 3 + 1] = ar * rdet * n1; E[PG_CQ + f * 3 + 2] = ar * rdet * n2;
     }
-    if (j < 12) {
-      const int f = j / 3;
-      E[PG_TAU + j] = p.tau[((size_t)EI[PGI_F + f] * 3 + EI[PGI_PERM + j]) * tv + EI[PGI_SD + f]];
-    } else if (j == 12) {
+    if (j == 12) {
       double Fu[4] = {0.0, 0.0, 0.0, 0.0};
       if (hasSrc) {
 #pragma unroll
@@ -584,6 +604,7 @@ __global__ void __launch_bounds__(kPGThreads, MINB) hdg_p1g_kernel(const AsmPara
         }
       }
     }
+    if (e0 + (long long)gridDim.x * kPGElems < p.eEnd) loadTau();   // the next element's face ids have arrived by now
     __syncwarp();
   }
 }

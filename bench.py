@@ -197,6 +197,8 @@ def dist_gate(rank, world, lrank):
         dist.all_gather_object(out, (ids, sol, int(dp.solver.stats.iterations), int(dp.solver.stats.converged)))
     else:
         out = [(ids, sol, int(dp.solver.stats.iterations), int(dp.solver.stats.converged))]
+    its_conv = (int(dp.solver.stats.iterations), int(dp.solver.stats.converged))
+    dp.close()   # collective, at the same point on every rank (never left to the garbage collector: see DistributedPoisson.close)
     full = np.zeros_like(g["solution"]); seen = np.zeros(lin.shape[0], dtype=int)
     for ids_r, sol_r, _, _ in out:
         full[ids_r] = sol_r; seen[ids_r] += 1
@@ -233,6 +235,10 @@ def run_reference(args):
 
 
 def main():
+    # watchdog: a rank that is stuck (a peer that never arrives, a collective that never completes) dumps the Python stack of every thread and exits instead of
+    # hanging the job (HFX_BENCH_WATCHDOG seconds, default 1500)
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ.get("HFX_BENCH_WATCHDOG", "1500")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -423,8 +429,11 @@ def main():
     # ---- end-to-end arm: reference-shaped API, host fields, H2D + D2H inside the timed region ---------------------------
     e2e_ms = None
     h2d = d2h = 0
+    # the product context of the timed section goes away here, at the same point on every rank (its peers map its halo buffers)
+    barrier()
+    check(L.hfx_ctx_destroy(h)); h = None
+    barrier()
     if not args.no_e2e:
-        check(L.hfx_ctx_destroy(h)); h = None
         m = hfox.Mesh(dim, order, "simplex")
         m.nodes, m.cells = capi.f64(nodes), capi.i32(cells)
         m.faces, m.cell2FaceMap, m.face2CellMap, m.boundaryFaces = tp["faces"], tp["cell2face"], tp["face2cell"], tp["boundary"]
@@ -456,6 +465,7 @@ def main():
         e2e_ms = (time.time() - t2) * 1e3 / args.steps
         h2d = int(sum(fm[k].values.nbytes for k, _ in host_fields))
         d2h = 4
+        s.ctx.close()
 
     # ---- max over ranks ---------------------------------------------------------------------------------------------
     red = torch.tensor([my_ms, my_k, e2e_ms if e2e_ms is not None else 0.0, wall_ms], dtype=torch.float64, device="cuda")

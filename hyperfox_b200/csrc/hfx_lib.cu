@@ -617,6 +617,7 @@ struct NcclApi {
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;   // optional
   static NcclApi& get() {
     static NcclApi a;
     if (!a.h) {
@@ -630,6 +631,7 @@ struct NcclApi {
       a.Send = (decltype(a.Send))sym("ncclSend"); a.Recv = (decltype(a.Recv))sym("ncclRecv");
       a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart"); a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
       a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+      a.CommAbort = (decltype(a.CommAbort))dlsym(a.h, "ncclCommAbort");
     }
     return a;
   }
@@ -1368,7 +1370,12 @@ int hfx_ctx_destroy(hfx_ctx* c) {
   if (c->ev2) cudaEventDestroy(c->ev2);
   for (int r = 0; r < (int)c->halo.peerBox.size(); r++) if (c->halo.peerBox[(size_t)r] && r != c->halo.rank) cudaIpcCloseMemHandle(c->halo.peerBox[(size_t)r]);
   if (c->halo.box) { cudaFree(c->halo.box); c->halo.box = nullptr; }
-  if (c->halo.comm) { try { NcclApi::get().CommDestroy(c->halo.comm); } catch (...) {} c->halo.comm = nullptr; }
+  // The communicator goes with ncclCommAbort: every operation this context enqueued has completed (stream synchronised above), and unlike ncclCommDestroy it never
+  // waits for the peers -- a context may be destroyed by a garbage collector at a moment the other ranks do not share (HFX_NCCL_DESTROY=1: the collective teardown)
+  if (c->halo.comm) {
+    try { NcclApi& na = NcclApi::get(); if (na.CommAbort && !getenv("HFX_NCCL_DESTROY")) na.CommAbort(c->halo.comm); else na.CommDestroy(c->halo.comm); } catch (...) {}
+    c->halo.comm = nullptr;
+  }
   if (c->halo.stComm) { cudaStreamSynchronize(c->halo.stComm); cudaStreamDestroy(c->halo.stComm); cudaEventDestroy(c->halo.evPack); cudaEventDestroy(c->halo.evHalo); }
   cudaStream_t st = c->st;
   delete c;

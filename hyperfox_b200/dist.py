@@ -81,6 +81,21 @@ class DistributedPoisson:
     def assemble(self): self.solver.assemble()
     def solve(self): self.solver.solve()
 
+    def close(self):
+        """Collective teardown: every rank calls it at the same point (a barrier first: the peers map this rank's halo buffers over CUDA IPC and must be done with them
+        before they are freed); the device context is destroyed here and not by the garbage collector."""
+        import torch
+        torch.cuda.synchronize()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        ctx = getattr(self.solver, "ctx", None)
+        if ctx is not None:
+            ctx.close()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+
     def owned_solution(self):
         """(global cell ids, Solution values [nOwned, nN]) of the cells this rank owns."""
         nO = self.prob["owned_cells"].size

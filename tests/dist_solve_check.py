@@ -48,6 +48,7 @@ def main():
         dist.all_gather_object(out, (ids, sol, dp.solver.stats.iterations))
     else:
         out = [(ids, sol, dp.solver.stats.iterations)]
+    dp.close()   # collective teardown at the same point on every rank
     if rank == 0:
         from oracle import lib as O
         from oracle.mesh import compute_faces

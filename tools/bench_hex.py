@@ -45,13 +45,15 @@ def main():
         dist.all_reduce(red, op=dist.ReduceOp.MAX); dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     kk = C.c_int(0)
     L.hfx_last_assemble_kernel(h, C.byref(kk), None)
+    nCellsLocal, nOwnedLocal = int(dp.mesh.getNumberCells()), int(dp.prob["owned_cells"].size)
+    dp.close()   # collective teardown at the same point on every rank
     kname = ("hdg_assemble_kernel", "hdg_generic_kernel (general kernel)", "hdg_big_kernel<BigHexP2, 512> (large-element formulation with the orthotope frame)", "hdg_p1_kernel")[kk.value]
     if rank == 0:
         print(json.dumps({"metric": "HDG elements assembled+condensed/s (p=%d 3D hexes)" % a.order, "value": float(tot.item()) / (float(red[0]) * 1e-3), "unit": "elements/s", "n_gpus": world,
                           "steps": a.steps, "warmup": a.warmup, "ms_per_step": float(red[0]), "higher_is_better": True, "scaling": "strong", "dtype": "f64", "data": "synthetic",
                           "config": {"workload": "3D Poisson HDG order %d on %d^3 = %d structured hexahedra, HDGLaplaceModel + DirichletModel, tau = 1; %s" % (a.order, a.cubes, a.cubes ** 3, kname),
                                      "partition": "recursive coordinate bisection, plan in host C++ (hfx_plan_create, orthotope cells)" if world > 1 else "single rank",
-                                     "elements_rank0": int(dp.mesh.getNumberCells()), "owned_elements_rank0": int(dp.prob["owned_cells"].size)},
+                                     "elements_rank0": nCellsLocal, "owned_elements_rank0": nOwnedLocal},
                           "gmres_ms_per_iteration": float(red[1]), "transport": int(info.transport), "halo_bytes_per_exchange_rank0": int(info.haloBytesPerExchange)}), flush=True)
     if world > 1:
         dist.barrier(); dist.destroy_process_group()

@@ -1,10 +1,13 @@
-// Continuous-Galerkin path: CGSolver::assemble (src/solver/CGSolver.cpp:42-246) for the Laplace-type models -- LaplaceModel (src/model/LaplaceModel.cpp:
-// Diffusion) and DiffusionSource without a time scheme (Diffusion + Source) -- with DirichletModel boundaries, on the device.  Node-based CSR (sorted columns, explicit
+// Continuous-Galerkin path: CGSolver::assemble (src/solver/CGSolver.cpp:42-246) for the scalar models -- LaplaceModel (src/model/LaplaceModel.cpp:
+// Diffusion), DiffusionSource (Diffusion + Source) and Transport (src/model/Transport.cpp: Convection), each optionally under an implicit Euler step (FEModel::compute,
+// src/model/FEModel.cpp:22-33 + Euler.cpp:18-37) -- with DirichletModel boundaries, on the device.  Node-based CSR (sorted columns, explicit
 // zeros: CGSolver::calcSparsityPattern :261-335 + PETSc AIJ), one CTA per element pass:
 //   J(ip) = sum_i dphi_i/dxi x_i, dV = w det J            (Operator.cpp:14-84)
 //   G(ip, i) = J^-1 grad^ phi_i                            (Diffusion.cpp:33-36)
 //   A_ij = sum_ip dV (D(ip) G(ip, i)) . G(ip, j)           (Diffusion.cpp:37-45; D interpolated from the nodes, scalar or dim x dim column-major: setDiffTensor :65-73)
 //   F_i  = sum_ip dV f(x_ip) phi_i(ip)                     (Source.cpp:24-48; f evaluated by the host callback at hfx_ip_coords)
+//   C_kl = sum_ip dV (v(ip) . G(ip, l)) phi_k(ip)          (Convection.cpp:5-49; v interpolated from the Velocity node field)
+//   Euler: A <- dt A + M, F <- dt F + M u_old,  M_jk = sum_ip dV phi_j phi_k   (Mass.cpp:5-38, Euler.cpp:28-32)
 // and the element block is added into the global rows of its nodes (linSystem->addValsMatrix / addValsRHS): floating-point atomics -- a CG entry has as many
 // contributors as cells share the node pair, so unlike the HDG trace system the sum order is not fixed.  Any element the reference element supports (runtime sizes,
 // curved or multilinear geometry: the Jacobian is evaluated at every cubature point).
@@ -19,6 +22,10 @@ struct CgParams {
   const double* shape; const double* dshape; const double* w;
   const double* diff; int diffComps;      // DiffusionTensor node field [nNodes][1 | dim^2] or NULL (identity)
   const double* srcIP;                    // [nCells][nIP] or NULL
+  const double* vel;                      // Velocity node field [nNodes][dim] or NULL (Convection, src/operator/Convection.cpp)
+  int hasDiffusion;                       // 0: Transport (Convection only)
+  double eulerDt;                         // > 0: implicit Euler (Euler.cpp:18-37): A <- dt A + M, F <- dt F + M u_old
+  const double* solOld;                   // Solution node field [nNodes] (the old state of the Euler step)
   const long long* rowptr; const int* colidx;
   double* vals; double* rhs; int* status;
 };
@@ -36,7 +43,9 @@ __global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
   double* const JI = X + ((nN * dim + 1) & ~1);         // [nIP][dim][dim]
   double* const DP = JI + ((nIP * D2 + 1) & ~1);        // [nIP][dim][dim] row-major D(a, b)
   double* const DV = DP + ((nIP * D2 + 1) & ~1);        // [nIP]
-  double* const G = DV + ((nIP + 1) & ~1);              // [nIP][nN][dim]
+  double* const VP = DV + ((nIP + 1) & ~1);             // [nIP][dim] velocity at the cubature points
+  double* const UO = VP + ((nIP * dim + 1) & ~1);       // [nIP] old solution at the cubature points
+  double* const G = UO + ((nIP + 1) & ~1);              // [nIP][nN][dim]
   int* const ID = reinterpret_cast<int*>(G + (size_t)nIP * nN * dim);
   for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
     for (int i = tid; i < nN; i += NT) {
@@ -63,6 +72,17 @@ __global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
       if (!(fabs(det) > 1e-300)) atomicOr(p.status, 1);
       for (int a = 0; a < dim; a++) for (int b = 0; b < dim; b++) JI[ip * D2 + a * dim + b] = I[a][b];
       DV[ip] = p.w[ip] * det;
+      if (p.vel)
+        for (int a = 0; a < dim; a++) {
+          double s = 0.0;
+          for (int i = 0; i < nN; i++) s = fma(p.shape[(size_t)ip * nN + i], p.vel[(size_t)ID[i] * dim + a], s);
+          VP[ip * dim + a] = s;
+        }
+      if (p.eulerDt > 0.0) {
+        double s = 0.0;
+        for (int i = 0; i < nN; i++) s = fma(p.shape[(size_t)ip * nN + i], p.solOld[ID[i]], s);
+        UO[ip] = s;
+      }
       if (p.diff) {
         for (int a = 0; a < dim; a++)
           for (int b = 0; b < dim; b++) {
@@ -86,23 +106,37 @@ __global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
     __syncthreads();
     for (int idx = tid; idx < nN * nN; idx += NT) {
       const int i = idx / nN, j = idx - i * nN;
-      double acc = 0.0;
+      double acc = 0.0, mss = 0.0;
       for (int ip = 0; ip < nIP; ip++) {
         const double* gi = G + ((size_t)ip * nN + i) * dim; const double* gj = G + ((size_t)ip * nN + j) * dim;
         double s = 0.0;
-        if (p.diff) {
-          const double* Dm = DP + ip * D2;
-          for (int a = 0; a < dim; a++) { double t = 0.0; for (int b = 0; b < dim; b++) t = fma(Dm[a * dim + b], gi[b], t); s = fma(t, gj[a], s); }
-        } else for (int a = 0; a < dim; a++) s = fma(gi[a], gj[a], s);
+        if (p.hasDiffusion) {
+          if (p.diff) {
+            const double* Dm = DP + ip * D2;
+            for (int a = 0; a < dim; a++) { double t = 0.0; for (int b = 0; b < dim; b++) t = fma(Dm[a * dim + b], gi[b], t); s = fma(t, gj[a], s); }
+          } else for (int a = 0; a < dim; a++) s = fma(gi[a], gj[a], s);
+        }
+        const double pi_ = p.shape[(size_t)ip * nN + i];
+        if (p.vel) {   // Convection.cpp:36-44: op(k, l) += dV (v . grad phi_l) phi_k
+          double vg = 0.0;
+          for (int a = 0; a < dim; a++) vg = fma(VP[ip * dim + a], gj[a], vg);
+          s = fma(vg, pi_, s);
+        }
         acc = fma(DV[ip], s, acc);
+        if (p.eulerDt > 0.0) mss = fma(DV[ip] * pi_, p.shape[(size_t)ip * nN + j], mss);   // Mass.cpp:5-38
       }
+      if (p.eulerDt > 0.0) acc = fma(p.eulerDt, acc, mss);                                    // Euler.cpp:28-32
       atomicAdd(p.vals + cg_find(p.rowptr, p.colidx, ID[i], ID[j]), acc);
     }
-    if (p.srcIP)
+    if (p.srcIP || p.eulerDt > 0.0)
       for (int i = tid; i < nN; i += NT) {
-        double s = 0.0;
-        for (int ip = 0; ip < nIP; ip++) s = fma(DV[ip] * p.srcIP[(size_t)e * nIP + ip], p.shape[(size_t)ip * nN + i], s);
-        atomicAdd(p.rhs + ID[i], s);
+        double s = 0.0, mu = 0.0;
+        for (int ip = 0; ip < nIP; ip++) {
+          const double wphi = DV[ip] * p.shape[(size_t)ip * nN + i];
+          if (p.srcIP) s = fma(wphi, p.srcIP[(size_t)e * nIP + ip], s);
+          if (p.eulerDt > 0.0) mu = fma(wphi, UO[ip], mu);            // (M u_old)_i = sum_ip dV phi_i u_old(ip)
+        }
+        atomicAdd(p.rhs + ID[i], p.eulerDt > 0.0 ? fma(p.eulerDt, s, mu) : s);
       }
     __syncthreads();
   }
@@ -110,7 +144,7 @@ __global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
 
 inline size_t cg_smem_bytes(int dim, int nN, int nIP) {
   const size_t D2 = (size_t)dim * dim;
-  const size_t d = (((size_t)nN * dim + 1) & ~(size_t)1) + 2 * (((size_t)nIP * D2 + 1) & ~(size_t)1) + (((size_t)nIP + 1) & ~(size_t)1) + (size_t)nIP * nN * dim;
+  const size_t d = (((size_t)nN * dim + 1) & ~(size_t)1) + 2 * (((size_t)nIP * D2 + 1) & ~(size_t)1) + 2 * (((size_t)nIP + 1) & ~(size_t)1) + (((size_t)nIP * dim + 1) & ~(size_t)1) + (size_t)nIP * nN * dim;
   return d * 8 + (size_t)((nN + 1) & ~1) * 4 + 16;
 }
 

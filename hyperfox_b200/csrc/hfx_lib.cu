@@ -2345,8 +2345,9 @@ int hfx_cg_assemble(hfx_ctx* c) {
   return guard(c, [&] {
     HFX_CUDA(cudaSetDevice(c->device));
     need(c->cgAllocated, "CGSolver", "assemble", "must initialize and allocate the solver before allocating.");
-    need((c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE)) == 0 && (c->md.opmask & HFX_OP_DIFFUSION) && c->md.timeScheme == HFX_TS_NONE, "CGSolver", "assemble",
-         "the device CG path serves LaplaceModel and DiffusionSource without a time scheme (Diffusion [+ Source])");
+    need((c->md.opmask & ~(HFX_OP_DIFFUSION | HFX_OP_SOURCE | HFX_OP_CONVECTION)) == 0 && (c->md.opmask & (HFX_OP_DIFFUSION | HFX_OP_CONVECTION))
+         && (c->md.timeScheme == HFX_TS_NONE || c->md.timeScheme == HFX_TS_EULER_IMPLICIT), "CGSolver", "assemble",
+         "the device CG path serves LaplaceModel, DiffusionSource and Transport (Diffusion / Convection [+ Source]), steady or under an implicit Euler step");
     for (auto& kv : c->fields) if (kv.second.pendingPieces > 0) { for (int k = 0; k < kv.second.pendingPieces; k++) HFX_CUDA(cudaStreamWaitEvent(c->st, kv.second.ev[k], 0)); kv.second.pendingPieces = 0; }
     CgParams p{};
     p.nCells = c->nCells; p.dim = c->dim; p.nN = c->nN; p.nIP = c->nIP;
@@ -2357,6 +2358,18 @@ int hfx_cg_assemble(hfx_ctx* c) {
       p.diff = df->d.p; p.diffComps = df->nObj * df->nVal;
     }
     if (c->md.opmask & HFX_OP_SOURCE) { need(c->dSrc.n >= (size_t)c->nCells * c->nIP, "Source", "calcSource", "must set a source function before calculating the source."); p.srcIP = c->dSrc.p; }
+    p.hasDiffusion = (c->md.opmask & HFX_OP_DIFFUSION) ? 1 : 0;
+    if (!p.hasDiffusion) p.diff = nullptr;
+    if (c->md.opmask & HFX_OP_CONVECTION) {
+      DField* vf = find_field(c, "Velocity");
+      need(vf && vf->type == HFX_FIELD_NODE, "Transport", "setFieldMap", "one must provide a Velocity field to use the Transport model.");
+      need(vf->nObj * vf->nVal == c->dim, "Transport", "parseVelocityVals", "the dimension of the velocity vector does not correspond to the dimension of the reference element");
+      p.vel = vf->d.p;
+    }
+    if (c->md.timeScheme == HFX_TS_EULER_IMPLICIT) {
+      need(c->md.dt != 0.0, "Euler", "apply", "the time step needs to be set before applying and it should not be 0");
+      p.eulerDt = c->md.dt; p.solOld = find_field(c, "Solution")->d.p;
+    }
     p.rowptr = c->dCgRowptr.p; p.colidx = c->dCgCol.p; p.vals = c->dCgVals.p; p.rhs = c->dCgRhs.p; p.status = c->dStatus.p;
     if (c->dStatus.n < 1) c->dStatus.alloc(1);
     p.status = c->dStatus.p;

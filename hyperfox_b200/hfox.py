@@ -875,6 +875,7 @@ class HDGSolver:
 class LaplaceModel:
     """LaplaceModel (src/model/LaplaceModel.cpp:15-52): localMatrix = Diffusion (DiffusionTensor field if given), no right-hand side; assembly = {Add, None}."""
     isCG = True
+    usesDiffusionField = True
 
     def __init__(self, refEl):
         self.refEl, self.allocated, self.sourceFunc, self.timeScheme = refEl, False, None, None
@@ -882,12 +883,15 @@ class LaplaceModel:
     def allocate(self, nDOFsPerNode):
         self.nDOF, self.allocated = nDOFsPerNode, True
 
-    def _mask(self):
+    def setTimeScheme(self, ts):
+        raise ErrorHandle("LaplaceModel : setTimeScheme : the Laplace model is stationary")
+
+    def _mask(self, fieldNames=()):
         return OP_DIFFUSION
 
 
 class DiffusionSource(LaplaceModel):
-    """DiffusionSource without a time scheme (src/model/DiffusionSource.cpp): Diffusion + Source right-hand side."""
+    """DiffusionSource (src/model/DiffusionSource.cpp): Diffusion + Source right-hand side, optionally under an implicit Euler step (FEModel::compute, FEModel.cpp:22-33)."""
 
     def setSourceFunction(self, s):
         if not self.allocated:
@@ -895,12 +899,29 @@ class DiffusionSource(LaplaceModel):
         self.sourceFunc = s
 
     def setTimeScheme(self, ts):
-        raise ErrorHandle("DiffusionSource : setTimeScheme : the device CG path has no time schemes")
+        if self.allocated:
+            raise ErrorHandle("FEModel : setTimeScheme : the time scheme must be set before allocation or field setting")
+        if getattr(ts, "isRK", False) or getattr(ts, "isExplicit", False):
+            raise ErrorHandle("DiffusionSource : setTimeScheme : the device CG path serves the implicit Euler scheme")
+        self.timeScheme = ts
 
-    def _mask(self):
+    def _mask(self, fieldNames=()):
         if self.sourceFunc is None:
             raise ErrorHandle("Source : calcSource : must set a source function before calculating the source.")
         return OP_DIFFUSION | OP_SOURCE
+
+
+class Transport(DiffusionSource):
+    """Transport (src/model/Transport.cpp): localMatrix = Convection (Velocity node field), zero right-hand side, optionally under an implicit Euler step."""
+    usesDiffusionField = False
+
+    def setSourceFunction(self, s):
+        raise ErrorHandle("Transport : setSourceFunction : the transport model has no source")
+
+    def _mask(self, fieldNames=()):
+        if "Velocity" not in fieldNames:
+            raise ErrorHandle("Transport : setFieldMap : one must provide a Velocity field to use the Transport model.")
+        return OP_CONVECTION
 
 
 class CGSolver:
@@ -979,13 +1000,17 @@ class CGSolver:
         if not (self.initialized and self.allocated):
             raise ErrorHandle("CGSolver : assemble : must initialize and allocate the solver before allocating.")
         L, h, mesh = lib(), self._h(), self.myMesh
-        for name in ("Dirichlet", "DiffusionTensor"):
+        names = ["Dirichlet"] + (["DiffusionTensor"] if self.model.usesDiffusionField else []) + ["Velocity"]
+        ts = self.model.timeScheme
+        if ts is not None:
+            names.append("Solution")            # the old state of the Euler step (Euler.cpp:31)
+        for name in names:
             if name in self.fieldMap:
                 self._upload(name)
         if "Dirichlet" not in self.fieldMap:
             raise ErrorHandle("DirichletModel : setFieldMap : must give a field named Dirichlet to the DirichletModel")
-        mask = self.model._mask()
-        md = capi.ModelDesc(self.nDOFsPerNode, mask, 0, 0.0)
+        mask = self.model._mask(set(self.fieldMap))
+        md = capi.ModelDesc(self.nDOFsPerNode, mask, 1 if ts is not None else 0, ts.dt if ts is not None else 0.0)
         check(L.hfx_model_describe(h, C.byref(md)), h)
         if mask & OP_SOURCE:
             nC, nIP, d = mesh.getNumberCells(), mesh.getReferenceElement().getNumIPs(), mesh.dim

@@ -1320,8 +1320,9 @@ class LaplaceModel : public FEModel {   // localMatrix = Diffusion (DiffusionTen
  public:
   using FEModel::FEModel;
   void allocate(int nDOFsPerNode) override { nDOFsPNode = nDOFsPerNode; allocated = 1; assembly.matrix = Add; }
-  virtual int cgMask() const { return HFX_OP_DIFFUSION; }
+  virtual int cgMask(const std::map<std::string, Field*>&) const { return HFX_OP_DIFFUSION; }
   virtual const ScalarFunction* sourceFunction() const { return nullptr; }
+  virtual bool usesDiffusionField() const { return true; }
 
  protected:
   int nDOFsPNode = 1;
@@ -1333,7 +1334,7 @@ class DiffusionSource : public LaplaceModel {   // Diffusion + Source, no time s
     if (!allocated) throw ErrorHandle("DiffusionSource", "setSourceFunction", "the model must be allocated before setting the source function");
     source = s;
   }
-  int cgMask() const override {
+  int cgMask(const std::map<std::string, Field*>&) const override {
     if (!source) throw ErrorHandle("Source", "calcSource", "must set a source function before calculating the source.");
     return HFX_OP_DIFFUSION | HFX_OP_SOURCE;
   }
@@ -1341,6 +1342,15 @@ class DiffusionSource : public LaplaceModel {   // Diffusion + Source, no time s
 
  protected:
   ScalarFunction source;
+};
+class Transport : public LaplaceModel {   // Convection (Velocity node field), zero right-hand side  (src/model/Transport.cpp)
+ public:
+  using LaplaceModel::LaplaceModel;
+  int cgMask(const std::map<std::string, Field*>& fm) const override {
+    if (!fm.count("Velocity")) throw ErrorHandle("Transport", "setFieldMap", "one must provide a Velocity field to use the Transport model.");
+    return HFX_OP_CONVECTION;
+  }
+  bool usesDiffusionField() const override { return false; }
 };
 
 class CGSolver : public Solver {   // src/solver/CGSolver.cpp: allocate :5-40 (+ calcSparsityPattern :261-335), assemble :42-246, solve :248-259
@@ -1385,9 +1395,13 @@ class CGSolver : public Solver {   // src/solver/CGSolver.cpp: allocate :5-40 (+
     hfx_ctx* h = ctx();
     if (!fieldMap->count("Dirichlet")) throw ErrorHandle("DirichletModel", "setFieldMap", "must give a field named Dirichlet to the DirichletModel");
     upload("Dirichlet");
-    if (fieldMap->count("DiffusionTensor")) upload("DiffusionTensor");
     const LaplaceModel* lm = static_cast<const LaplaceModel*>(model);
-    hfx_model_desc md; md.nDOF = nDOFsPerNode; md.opmask = lm->cgMask(); md.timeScheme = HFX_TS_NONE; md.dt = 0.0;
+    if (lm->usesDiffusionField() && fieldMap->count("DiffusionTensor")) upload("DiffusionTensor");
+    if (fieldMap->count("Velocity")) upload("Velocity");
+    TimeScheme* ts = model->getTimeScheme();   // FEModel::compute (FEModel.cpp:22-33): implicit Euler on the device CG path, the nodal Solution is the old state
+    if (ts && ts->cKind() != HFX_TS_EULER_IMPLICIT) throw ErrorHandle("CGSolver", "assemble", "the device CG path serves the implicit Euler scheme");
+    if (ts) upload("Solution");
+    hfx_model_desc md; md.nDOF = nDOFsPerNode; md.opmask = lm->cgMask(*fieldMap); md.timeScheme = ts ? HFX_TS_EULER_IMPLICIT : HFX_TS_NONE; md.dt = ts ? ts->getTimeStep() : 0.0;
     detail::check(hfx_model_describe(h, &md), h);
     if (md.opmask & HFX_OP_SOURCE) {
       const int nC = myMesh->getNumberCells(), nIP = myMesh->getReferenceElement()->getNumIPs(), d = myMesh->getNodeSpaceDimension();

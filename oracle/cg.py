@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE -- CPU restatement (numpy) of the reference's continuous-Galerkin path: Diffusion (src/operator/Diffusion.cpp:5-47, setDiffTensor :65-73),
-Source (src/operator/Source.cpp:5-48), LaplaceModel (src/model/LaplaceModel.cpp:15-52), DiffusionSource without a time scheme (src/model/DiffusionSource.cpp),
+Source (src/operator/Source.cpp:5-48), Convection (src/operator/Convection.cpp), Mass (src/operator/Mass.cpp), Euler (src/operator/Euler.cpp:18-37), LaplaceModel (src/model/LaplaceModel.cpp:15-52), DiffusionSource (src/model/DiffusionSource.cpp), Transport (src/model/Transport.cpp),
 DirichletModel (src/model/DirichletModel.cpp:19-44) and CGSolver (src/solver/CGSolver.cpp: calcSparsityPattern :261-335, assemble :42-246, solve :248-259).
 Only tests/ may import it.  Pinned by tests/test_oracle_cg.py on the reference's own known answers: TestDiffusion.cpp's monomial energies
-(v^T A v = 2 p^2 / (2 p - 1) per direction), TestCGSolver.cpp (lightTri, Dirichlet = 3 => Solution = 3 to 1e-12), and the regression ceilings of
+(v^T A v = 2 p^2 / (2 p - 1) per direction), TestConvection.cpp / TestMass.cpp (w^T C u = int x^2n, 1^T M 1 = volume, x^n^T M x^n = int x^2n), TestCGSolver.cpp (lightTri, Dirichlet = 3 => Solution = 3 to 1e-12), and the regression ceilings of
 tests/regression/CG/TestCGLaplace.cpp."""
 import numpy as np
 import scipy.sparse as sp
@@ -40,13 +40,33 @@ def source_vector(ore, X, fIP):
     return ore.ipShape.T @ (dV * fIP)
 
 
+def convection_matrix(ore, X, vel):
+    """Convection::setVelocity / assemble (src/operator/Convection.cpp:5-49): op(k, l) += dV (v(ip)^T invJ) . dShape_l  phi_k, v interpolated from the nodes"""
+    invJ, dV = element_geometry(ore, X)
+    G = np.einsum("pab,pib->pia", invJ, ore.ipDShape)
+    v = ore.ipShape @ np.asarray(vel, dtype=np.float64).reshape(ore.nNodes, ore.dim)
+    return np.einsum("p,pa,pla,pk->kl", dV, v, G, ore.ipShape)
+
+
+def mass_matrix(ore, X):
+    """Mass::assemble (src/operator/Mass.cpp:5-38): op(j, k) = sum_ip dV phi_j phi_k"""
+    _, dV = element_geometry(ore, X)
+    return np.einsum("p,pj,pk->jk", dV, ore.ipShape, ore.ipShape)
+
+
+def euler_apply(A, F, M, uOld, dt):
+    """FEModel::compute + Euler::apply, implicit (src/model/FEModel.cpp:22-33, src/operator/Euler.cpp:18-37): stiffness *= dt; rhs *= dt; stiffness += M; rhs += M u_old"""
+    return dt * A + M, dt * F + M @ uOld
+
+
 class CGOracle:
     """CGSolver on a whole mesh: node-based CSR with sorted columns and explicit zeros (calcSparsityPattern + PETSc AIJ), element loop (Add), then per boundary
     model zero rows + Set of the DirichletModel's identity / Dirichlet values (face-node order)."""
 
-    def __init__(self, ore, nodes, cells, faces, boundary, diff=None, source=None):
+    def __init__(self, ore, nodes, cells, faces, boundary, diff=None, source=None, vel=None, diffusion=True, dt=0.0, solOld=None):
+        """diffusion=False + vel: Transport (src/model/Transport.cpp: Convection only); dt > 0: implicit Euler with the nodal Solution solOld as the old state"""
         self.ore, self.nodes, self.cells, self.faces, self.boundary = ore, nodes, cells, faces, np.asarray(boundary)
-        self.diff, self.source = diff, source
+        self.diff, self.source, self.vel, self.diffusion, self.dt, self.solOld = diff, source, vel, diffusion, dt, solOld
         self.n = nodes.shape[0]
 
     def pattern(self):
@@ -71,10 +91,14 @@ class CGOracle:
         xipAll = np.einsum("pi,cid->cpd", self.ore.ipShape, self.nodes[self.cells])
         for e, c in enumerate(self.cells):
             X = self.nodes[c]
-            Ae = diffusion_matrix(self.ore, X, None if self.diff is None else self.diff[c])
+            Ae = diffusion_matrix(self.ore, X, None if self.diff is None else self.diff[c]) if self.diffusion else np.zeros((c.size, c.size))
+            if self.vel is not None:
+                Ae = Ae + convection_matrix(self.ore, X, self.vel[c])
+            Fe = source_vector(self.ore, X, np.array([self.source(p) for p in xipAll[e]])) if self.source is not None else np.zeros(c.size)
+            if self.dt > 0.0:
+                Ae, Fe = euler_apply(Ae, Fe, mass_matrix(self.ore, X), self.solOld[c], self.dt)
             A[np.ix_(c, c)] = A[np.ix_(c, c)].toarray() + Ae
-            if self.source is not None:
-                b[c] += source_vector(self.ore, X, np.array([self.source(p) for p in xipAll[e]]))
+            b[c] += Fe
         A = A.tocsr()
         bn = np.unique(self.faces[self.boundary])
         mask = np.zeros(self.n, dtype=bool); mask[bn] = True

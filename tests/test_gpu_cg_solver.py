@@ -128,3 +128,76 @@ def test_cg_reassembly_and_unsupported_models():
         s2 = hfox.CGSolver(); s2.setMesh(m); s2.setFieldMap(fm2); s2.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts()))
         s2.setModel(hfox.LaplaceModel(m.getReferenceElement())); s2.setBoundaryModel(hfox.DirichletModel(m.getReferenceElement().getFaceElement()))
         s2.initialize(); s2.allocate()
+
+
+def _compare_time(dim, order, model, nSteps=3, dt=0.05):
+    """implicit Euler steps through the mirror (Solution is the old state and receives the new one) against the oracle running the same steps"""
+    nodes, cells = meshgen.kuhn_mesh(3, order, dim, perturb=0.1)
+    m = hfox.Mesh(dim, order, "simplex"); m.setMesh(nodes, cells)
+    re = m.getReferenceElement()
+    nNf = re.getFaceElement().getNumNodes()
+    fm = {"Solution": hfox.Field(m, hfox.Node, 1, 1), "Dirichlet": hfox.Field(m, hfox.Face, nNf, 1)}
+    rng = np.random.default_rng(4)
+    vel = diff = src = None
+    if model == "transport":
+        vel = np.zeros_like(nodes); vel[:, 0], vel[:, 1] = -(nodes[:, 1] - 0.5), nodes[:, 0] - 0.5
+        fm["Velocity"] = hfox.Field(m, hfox.Node, 1, dim); fm["Velocity"].values[:] = vel.ravel()
+        mod = hfox.Transport(re)
+    else:
+        diff = 0.5 + rng.random((nodes.shape[0], 1))
+        fm["DiffusionTensor"] = hfox.Field(m, hfox.Node, 1, 1); fm["DiffusionTensor"].values[:] = diff.ravel()
+        src = lambda x: np.exp(-10 * sum((xi - 0.5) ** 2 for xi in x))
+        mod = hfox.DiffusionSource(re)
+    ts = hfox.Euler(re); ts.setTimeStep(dt)
+    mod.setTimeScheme(ts)
+    s = hfox.CGSolver()
+    s.setVerbosity(False); s.setMesh(m); s.setFieldMap(fm); s.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts(rtol=1e-14, maxits=20000)))
+    s.setModel(mod); s.setBoundaryModel(hfox.DirichletModel(re.getFaceElement())); s.initialize(); s.allocate()
+    if src is not None:
+        mod.setSourceFunction(src)
+    ore = OracleRefEl(dim, order)
+    topo = compute_faces(cells, ore)
+    u0 = np.sin(3 * nodes[:, 0]) * np.cos(2 * nodes[:, 1])
+    fm["Solution"].values[:] = u0
+    dirv = np.zeros(topo["faces"].shape); dirv[topo["boundary"]] = u0[topo["faces"][topo["boundary"]]]
+    fm["Dirichlet"].values[:] = dirv.ravel()
+    uo = u0.copy()
+    for step in range(nSteps):
+        s.assemble(); s.solve()
+        o = cg.CGOracle(ore, nodes, cells, topo["faces"], topo["boundary"], diff=diff, source=src, vel=vel, diffusion=model != "transport", dt=dt, solOld=uo)
+        o.assemble(dirv); uo = o.solve()
+        if step == 0:
+            rowptr, col, vals, rhs = s.getCSR()
+            assert np.array_equal(rowptr, o.rowptr) and np.array_equal(col, o.colidx)
+            assert H.rel_err(vals, o.vals) < 1e-12 and H.rel_err(rhs, o.b) < 1e-12
+    assert s.stats.converged == 1
+    assert H.rel_err(fm["Solution"].values, uo) < 1e-10
+
+
+@pytest.mark.parametrize("dim,order,model", [(2, 2, "diffsrc"), (3, 2, "diffsrc"), (2, 3, "transport"), (3, 1, "transport")])
+def test_cg_implicit_euler_steps_match_oracle(dim, order, model):
+    """DiffusionSource / Transport (src/model/DiffusionSource.cpp, Transport.cpp) + Euler (FEModel::compute, Euler.cpp:18-37) through CGSolver: dt A + M, dt F + M u_old"""
+    _compare_time(dim, order, model)
+
+
+def test_cg_steady_convection_diffusion_terms_match_oracle():
+    """the Convection entries on their own (steady Transport is singular: assembled entries only)"""
+    dim, order = 2, 3
+    nodes, cells = meshgen.kuhn_mesh(3, order, dim, perturb=0.1)
+    m = hfox.Mesh(dim, order, "simplex"); m.setMesh(nodes, cells)
+    re = m.getReferenceElement()
+    fm = {"Solution": hfox.Field(m, hfox.Node, 1, 1), "Dirichlet": hfox.Field(m, hfox.Face, re.getFaceElement().getNumNodes(), 1), "Velocity": hfox.Field(m, hfox.Node, 1, dim)}
+    vel = np.stack([1.0 + nodes[:, 1], 0.5 - nodes[:, 0]], axis=1)
+    fm["Velocity"].values[:] = vel.ravel()
+    s = hfox.CGSolver()
+    s.setVerbosity(False); s.setMesh(m); s.setFieldMap(fm); s.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts()))
+    s.setModel(hfox.Transport(re)); s.setBoundaryModel(hfox.DirichletModel(re.getFaceElement())); s.initialize(); s.allocate()
+    s.assemble()
+    ore = OracleRefEl(dim, order); topo = compute_faces(cells, ore)
+    o = cg.CGOracle(ore, nodes, cells, topo["faces"], topo["boundary"], vel=vel, diffusion=False)
+    o.assemble(np.zeros(topo["faces"].shape))
+    assert H.rel_err(s.getCSR()[2], o.vals) < 1e-12
+    with pytest.raises(hfox.ErrorHandle, match="Velocity"):
+        fm2 = {k: v for k, v in fm.items() if k != "Velocity"}
+        s2 = hfox.CGSolver(); s2.setVerbosity(False); s2.setMesh(m); s2.setFieldMap(fm2); s2.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts()))
+        s2.setModel(hfox.Transport(re)); s2.setBoundaryModel(hfox.DirichletModel(re.getFaceElement())); s2.initialize(); s2.allocate(); s2.assemble()

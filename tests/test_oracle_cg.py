@@ -54,3 +54,38 @@ def test_cg_laplace_regression(dim, order, name):
     A = o.A.toarray()
     assert np.abs(A[inner].sum(axis=1)).max() < 1e-11
     assert np.abs(A[np.ix_(inner, inner)] - A[np.ix_(inner, inner)].T).max() < 1e-12
+
+
+def _intx2n(dim, n):
+    """tests/TestUtils.h.in:88-96"""
+    return 2.0 / (2.0 * n + 1) if dim < 3 else 1.0 / (2.0 * n + 3.0) + 1.0 / (2.0 * n + 1.0)
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_convection_and_mass_known_answers(dim, order):
+    """tests/unittests/operator/TestConvection.cpp:26-48 (v = e_d, u = x_d^(p) / p ... : w^T C u = int x^(2(p-1))) and TestMass.cpp:24-41 (1^T M 1 = volume of the
+    reference simplex, (x^p)^T M x^p = int x^2p) on the reference element"""
+    ore = ReferenceElement(dim, order, "simplex")
+    X = ore.nodes
+    j = order - 1
+    for d in range(dim):
+        vel = np.zeros((ore.nNodes, dim)); vel[:, d] = 1.0
+        u = X[:, d] ** (j + 1) / (j + 1.0); w = X[:, d] ** j
+        assert abs(w @ cg.convection_matrix(ore, X, vel) @ u - _intx2n(dim, j)) < 1e-12
+    M = cg.mass_matrix(ore, X)
+    one = np.ones(ore.nNodes)
+    assert abs(one @ M @ one - [2.0, 2.0, 4.0 / 3.0][dim - 1]) < 1e-12
+    xn = X[:, 0] ** order
+    assert abs(xn @ M @ xn - _intx2n(dim, order)) < 1e-12
+
+
+def test_euler_apply_identity():
+    """tests/unittests/operator/TestEuler.cpp: stiffness -> M + dt K, rhs -> M u_old + dt f"""
+    ore = ReferenceElement(2, 2, "simplex")
+    X = ore.nodes * 0.3 + 1.0
+    K = cg.diffusion_matrix(ore, X); M = cg.mass_matrix(ore, X)
+    rng = np.random.default_rng(0)
+    f, u = rng.standard_normal(ore.nNodes), rng.standard_normal(ore.nNodes)
+    A, F = cg.euler_apply(K, f, M, u, 0.01)
+    assert np.abs(A - (M + 0.01 * K)).max() < 1e-15 and np.abs(F - (M @ u + 0.01 * f)).max() < 1e-15

@@ -27,6 +27,11 @@ struct CgParams {
   double eulerDt;                         // > 0: implicit Euler (Euler.cpp:18-37): A <- dt A + M, F <- dt F + M u_old
   const double* solOld;                   // Solution node field [nNodes] (the old state of the Euler step)
   const long long* rowptr; const int* colidx;
+  const unsigned char* affine;            // [nCells] 1: the cell is the affine image of the reference element (served by cg_affine_kernel when skipAffine is set) or NULL
+  int skipAffine;
+  const double* refTab;                   // cg_affine_kernel: K^_rs [dim*dim][nN*nN], M^ [nN*nN], w phi [nIP][nN]
+  int fv[4];                              // vertices spanning the affine frame (0,1,2,3 simplices; 0,1,3,4 orthotopes)
+  const unsigned short* pos;              // [nCells][nN][nN] position of column cells[e][j] inside row cells[e][i] (built once by cg_positions_kernel) or NULL
   double* vals; double* rhs; int* status;
 };
 
@@ -48,6 +53,7 @@ __global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
   double* const G = UO + ((nIP + 1) & ~1);              // [nIP][nN][dim]
   int* const ID = reinterpret_cast<int*>(G + (size_t)nIP * nN * dim);
   for (int e = blockIdx.x; e < p.nCells; e += gridDim.x) {
+    if (p.skipAffine && p.affine[e]) continue;      // (block-uniform)
     for (int i = tid; i < nN; i += NT) {
       const int n = p.cells[(size_t)e * nN + i];
       ID[i] = n;
@@ -126,7 +132,8 @@ __global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
         if (p.eulerDt > 0.0) mss = fma(DV[ip] * pi_, p.shape[(size_t)ip * nN + j], mss);   // Mass.cpp:5-38
       }
       if (p.eulerDt > 0.0) acc = fma(p.eulerDt, acc, mss);                                    // Euler.cpp:28-32
-      atomicAdd(p.vals + cg_find(p.rowptr, p.colidx, ID[i], ID[j]), acc);
+      const long long at = p.pos ? p.rowptr[ID[i]] + p.pos[(size_t)e * nN * nN + idx] : cg_find(p.rowptr, p.colidx, ID[i], ID[j]);
+      atomicAdd(p.vals + at, acc);
     }
     if (p.srcIP || p.eulerDt > 0.0)
       for (int i = tid; i < nN; i += NT) {
@@ -140,6 +147,87 @@ __global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
       }
     __syncthreads();
   }
+}
+
+// scatter map of the element blocks (once per hfx_cg_allocate): the binary search of every (row, column) pair is done here, not in every assembly
+__global__ void cg_positions_kernel(long long nEntries, int nN, const int* __restrict__ cells, const long long* __restrict__ rowptr, const int* __restrict__ colidx,
+                                    unsigned short* __restrict__ pos) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nEntries) return;
+  const long long e = k / (nN * nN);
+  const int ij = (int)(k - e * nN * nN), i = ij / nN, j = ij - i * nN;
+  const int row = cells[e * nN + i], col = cells[e * nN + j];
+  pos[k] = (unsigned short)(cg_find(rowptr, colidx, row, col) - rowptr[row]);
+}
+
+// Cells that are the affine image of the reference element, D = I, no convection: the Jacobian is constant, so
+//   A = sum_rs C_rs K^_rs,  C = detJ Jinv^T Jinv,  K^_rs[i][j] = sum_ip w d_r phi_i d_s phi_j   (reference stiffness matrices, resident in shared memory)
+//   M = detJ M^,  F_i = detJ sum_ip w phi_i f(x_ip)
+// -- dim^2 multiply-adds per entry instead of a loop over the cubature points.  One warp per element, no barrier.
+__global__ void __launch_bounds__(256) cg_affine_kernel(const CgParams p) {
+  extern __shared__ __align__(16) double smca[];
+  const int dim = p.dim, nN = p.nN, nIP = p.nIP, D2 = dim * dim, NN = nN * nN;
+  const int nTab = D2 * NN + NN + nIP * nN;
+  for (int i = threadIdx.x; i < nTab; i += blockDim.x) smca[i] = p.refTab[i];
+  __syncthreads();
+  const double* const KH = smca; const double* const MH = smca + D2 * NN; const double* const PW = MH + NN;
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int e = blockIdx.x * wpb + (threadIdx.x >> 5); e < p.nCells; e += gridDim.x * wpb) {
+    if (!p.affine[e]) continue;
+    const int* cell = p.cells + (size_t)e * nN;
+    double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    {
+      const double* x0 = p.nodes + (size_t)cell[p.fv[0]] * dim;
+      for (int r = 0; r < dim; r++) { const double* xr = p.nodes + (size_t)cell[p.fv[r + 1]] * dim; for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (xr[m] - x0[m]); }
+    }
+    double det, I[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    if (dim == 1) { det = J[0][0]; I[0][0] = 1.0 / det; }
+    else if (dim == 2) {
+      det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+      const double id = 1.0 / det;
+      I[0][0] = J[1][1] * id; I[0][1] = -J[0][1] * id; I[1][0] = -J[1][0] * id; I[1][1] = J[0][0] * id;
+    } else det_inv(J, det, I);
+    if (!(fabs(det) > 1e-300) && lane == 0) atomicOr(p.status, 1);
+    double Cm[9];
+    for (int r = 0; r < dim; r++) for (int s2 = 0; s2 < dim; s2++) { double a = 0.0; for (int k = 0; k < dim; k++) a = fma(I[k][r], I[k][s2], a); Cm[r * dim + s2] = det * a; }
+    const double dt = p.eulerDt;
+    for (int idx = lane; idx < NN; idx += 32) {
+      double acc = 0.0;
+      for (int q = 0; q < D2; q++) acc = fma(Cm[q], KH[q * NN + idx], acc);
+      if (dt > 0.0) acc = fma(dt, acc, det * MH[idx]);
+      const int i = idx / nN;
+      const long long at = p.pos ? p.rowptr[cell[i]] + p.pos[(size_t)e * NN + idx] : cg_find(p.rowptr, p.colidx, cell[i], cell[idx - i * nN]);
+      atomicAdd(p.vals + at, acc);
+    }
+    if (p.srcIP || dt > 0.0)
+      for (int i = lane; i < nN; i += 32) {
+        double s = 0.0, mu = 0.0;
+        if (p.srcIP) for (int ip = 0; ip < nIP; ip++) s = fma(PW[ip * nN + i], p.srcIP[(size_t)e * nIP + ip], s);
+        if (dt > 0.0) for (int j = 0; j < nN; j++) mu = fma(MH[i * nN + j], p.solOld[cell[j]], mu);
+        atomicAdd(p.rhs + cell[i], det * (dt > 0.0 ? fma(dt, s, mu) : s));
+      }
+  }
+}
+
+// affine image of the reference element? (same test as elem_affine_kernel of the HDG path, on the node-based mesh)
+__global__ void cg_affine_flags_kernel(int nCells, int nN, int dim, int fv0, int fv1, int fv2, int fv3, const double* __restrict__ nodes, const int* __restrict__ cells,
+                                       const double* __restrict__ bary, unsigned char* __restrict__ affine) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nCells) return;
+  const int fv[4] = {fv0, fv1, fv2, fv3};
+  const int* cell = cells + (size_t)e * nN;
+  double V[4][3];
+  for (int v = 0; v <= dim; v++) for (int m = 0; m < dim; m++) V[v][m] = nodes[(size_t)cell[fv[v]] * dim + m];
+  double h = 0.0;
+  for (int v = 1; v <= dim; v++) for (int m = 0; m < dim; m++) h = fmax(h, fabs(V[v][m] - V[0][m]));
+  bool ok = true;
+  for (int i = 0; i < nN && ok; i++)
+    for (int m = 0; m < dim; m++) {
+      double s = 0.0;
+      for (int v = 0; v <= dim; v++) s = fma(bary[i * (dim + 1) + v], V[v][m], s);
+      if (!(fabs(s - nodes[(size_t)cell[i] * dim + m]) <= 1e-13 * h)) ok = false;
+    }
+  affine[e] = ok ? 1 : 0;
 }
 
 inline size_t cg_smem_bytes(int dim, int nN, int nIP) {

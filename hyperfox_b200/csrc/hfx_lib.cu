@@ -1130,7 +1130,7 @@ struct hfx_ctx {
   // allocation
   bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false, p1Ready = false, colReady = false; int lastKernel = 0;
   // continuous-Galerkin path (hfx_cg_*): node-based CSR
-  DBuf<long long> dCgRowptr; DBuf<int> dCgCol; DBuf<double> dCgVals, dCgRhs; long long cgNnz = 0; bool cgAllocated = false, cgAssembled = false;
+  DBuf<long long> dCgRowptr; DBuf<int> dCgCol; DBuf<double> dCgVals, dCgRhs, dCgRefTab; DBuf<unsigned short> dCgPos; DBuf<unsigned char> dCgAffine; long long cgNonAffine = 0; long long cgNnz = 0; bool cgAllocated = false, cgAssembled = false;
   std::vector<long long> hCgRowptr; std::vector<int> hCgCol;
   int solverType = 0;   // HDGSolverOpts.type: 0 IMPLICIT, 1 WEXPLICIT, 2 SEXPLICIT (HDGSolverOpts.h:6-10)
   DBuf<double> dColTab;
@@ -2336,6 +2336,42 @@ int hfx_cg_allocate(hfx_ctx* c) {
     c->cgNnz = (long long)c->hCgCol.size();
     c->dCgRowptr.upload(c->hCgRowptr, c->st); c->dCgCol.upload(c->hCgCol, c->st);
     c->dCgVals.alloc((size_t)c->cgNnz); c->dCgRhs.alloc((size_t)nNodes);
+    // scatter map: position of every element entry inside its row (rows longer than 65535 entries keep the search in the kernel)
+    long long maxRow = 0;
+    for (int n = 0; n < nNodes; n++) maxRow = std::max(maxRow, c->hCgRowptr[n + 1] - c->hCgRowptr[n]);
+    c->dCgPos.alloc(0);
+    if (maxRow <= 65535 && !getenv("HFX_CG_SEARCH")) {
+      const long long nEnt = (long long)nC * nN * nN;
+      c->dCgPos.alloc((size_t)nEnt);
+      cg_positions_kernel<<<nblk(nEnt, 256), 256, 0, c->st>>>(nEnt, nN, c->dCells.p, c->dCgRowptr.p, c->dCgCol.p, c->dCgPos.p);
+      HFX_CUDA(cudaGetLastError());
+    }
+    // cells that are the affine image of the reference element + the reference matrices their fast path combines (cg_affine_kernel)
+    {
+      const RefElement& re = *c->re;
+      const int dim = c->dim, nIP = c->nIP, NN = nN * nN;
+      std::vector<double> tab((size_t)dim * dim * NN + NN + (size_t)nIP * nN, 0.0);
+      for (int r = 0; r < dim; r++) for (int s2 = 0; s2 < dim; s2++) for (int i = 0; i < nN; i++) for (int j = 0; j < nN; j++) {
+        double a = 0.0;
+        for (int ip = 0; ip < nIP; ip++) a += re.ipWeights()[ip] * re.ipDShape()[((size_t)ip * nN + i) * dim + r] * re.ipDShape()[((size_t)ip * nN + j) * dim + s2];
+        tab[(size_t)(r * dim + s2) * NN + i * nN + j] = a;
+      }
+      for (int i = 0; i < nN; i++) for (int j = 0; j < nN; j++) {
+        double a = 0.0;
+        for (int ip = 0; ip < nIP; ip++) a += re.ipWeights()[ip] * re.ipShape()[(size_t)ip * nN + i] * re.ipShape()[(size_t)ip * nN + j];
+        tab[(size_t)dim * dim * NN + i * nN + j] = a;
+      }
+      for (int ip = 0; ip < nIP; ip++) for (int i = 0; i < nN; i++) tab[(size_t)dim * dim * NN + NN + (size_t)ip * nN + i] = re.ipWeights()[ip] * re.ipShape()[(size_t)ip * nN + i];
+      c->dCgRefTab.upload(tab, c->st);
+      c->dCgAffine.alloc((size_t)nC);
+      const bool sx = c->geom == HFX_SIMPLEX;
+      cg_affine_flags_kernel<<<nblk(nC, 128), 128, 0, c->st>>>(nC, nN, dim, 0, 1, sx ? 2 : 3, sx ? 3 : 4, c->dNodes.p, c->dCells.p, c->dBary.p, c->dCgAffine.p);
+      HFX_CUDA(cudaGetLastError());
+      std::vector<unsigned char> fl((size_t)nC);
+      c->dCgAffine.download(fl.data(), fl.size(), c->st);
+      c->cgNonAffine = 0;
+      for (unsigned char f : fl) c->cgNonAffine += f ? 0 : 1;
+    }
     HFX_CUDA(cudaStreamSynchronize(c->st));
     c->cgAllocated = true; c->cgAssembled = false;
   });
@@ -2371,15 +2407,29 @@ int hfx_cg_assemble(hfx_ctx* c) {
       p.eulerDt = c->md.dt; p.solOld = find_field(c, "Solution")->d.p;
     }
     p.rowptr = c->dCgRowptr.p; p.colidx = c->dCgCol.p; p.vals = c->dCgVals.p; p.rhs = c->dCgRhs.p; p.status = c->dStatus.p;
+    p.pos = c->dCgPos.n ? c->dCgPos.p : nullptr;
     if (c->dStatus.n < 1) c->dStatus.alloc(1);
     p.status = c->dStatus.p;
     c->dStatus.zero(c->st); c->dCgVals.zero(c->st); c->dCgRhs.zero(c->st);      // linSystem->clearSystem()
-    const size_t shm = cg_smem_bytes(c->dim, c->nN, c->nIP);
-    need(shm <= 227 * 1024, "CGSolver", "assemble", "the element does not fit the shared memory of an SM");
-    HFX_CUDA(cudaFuncSetAttribute(cg_element_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
-    const int perSM = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (shm + 1024)));
-    cg_element_kernel<<<std::max(1, std::min(c->nCells, c->nSM * perSM)), 128, shm, c->st>>>(p);
-    HFX_CUDA(cudaGetLastError());
+    // affine cells with D = I and no convection: reference-matrix combinations (cg_affine_kernel); everything else: cubature loop (cg_element_kernel)
+    const size_t shmA = ((size_t)c->dim * c->dim * c->nN * c->nN + (size_t)c->nN * c->nN + (size_t)c->nIP * c->nN) * sizeof(double);
+    const bool fast = p.hasDiffusion && !p.diff && !p.vel && shmA <= 200 * 1024 && c->cgNonAffine < c->nCells && !getenv("HFX_CG_NO_AFFINE");
+    p.affine = c->dCgAffine.p; p.skipAffine = fast ? 1 : 0; p.refTab = c->dCgRefTab.p;
+    p.fv[0] = 0; p.fv[1] = 1; p.fv[2] = c->geom == HFX_SIMPLEX ? 2 : 3; p.fv[3] = c->geom == HFX_SIMPLEX ? 3 : 4;
+    if (fast) {
+      HFX_CUDA(cudaFuncSetAttribute(cg_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmA));
+      const int perSM = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (shmA + 1024)));
+      cg_affine_kernel<<<std::max(1, std::min(nblk(c->nCells, 8), c->nSM * perSM)), 256, shmA, c->st>>>(p);
+      HFX_CUDA(cudaGetLastError());
+    }
+    if (!fast || c->cgNonAffine > 0) {
+      const size_t shm = cg_smem_bytes(c->dim, c->nN, c->nIP);
+      need(shm <= 227 * 1024, "CGSolver", "assemble", "the element does not fit the shared memory of an SM");
+      HFX_CUDA(cudaFuncSetAttribute(cg_element_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+      const int perSM = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (shm + 1024)));
+      cg_element_kernel<<<std::max(1, std::min(c->nCells, c->nSM * perSM)), 128, shm, c->st>>>(p);
+      HFX_CUDA(cudaGetLastError());
+    }
     DField* dir = find_field(c, "Dirichlet");
     need(dir && dir->type == HFX_FIELD_FACE && dir->nObj == c->nNf && dir->nVal == 1, "DirichletModel", "setFieldMap", "must give a field named Dirichlet to the DirichletModel");
     cg_dirichlet_kernel<<<nblk((long long)c->nFaces * c->nNf, 256), 256, 0, c->st>>>(c->nFaces, c->nNf, c->dFaceBC.p, c->dFaces.p, dir->d.p, c->dCgRowptr.p, c->dCgCol.p, c->dCgVals.p, c->dCgRhs.p);

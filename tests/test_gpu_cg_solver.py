@@ -201,3 +201,47 @@ def test_cg_steady_convection_diffusion_terms_match_oracle():
         fm2 = {k: v for k, v in fm.items() if k != "Velocity"}
         s2 = hfox.CGSolver(); s2.setVerbosity(False); s2.setMesh(m); s2.setFieldMap(fm2); s2.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts()))
         s2.setModel(hfox.Transport(re)); s2.setBoundaryModel(hfox.DirichletModel(re.getFaceElement())); s2.initialize(); s2.allocate(); s2.assemble()
+
+
+def test_cg_affine_fast_path_and_mixed_meshes(monkeypatch):
+    """cells that are the affine image of the reference element take cg_affine_kernel (reference stiffness matrices), the others the cubature loop: a mesh with a few
+    curved cells against the oracle, and the fast path against the cubature loop on the same straight-sided mesh"""
+    nodes, cells = meshgen.kuhn_mesh(3, 3, 3, perturb=0.1)
+    isv = np.zeros(nodes.shape[0], dtype=bool); isv[np.unique(cells[:, :4])] = True
+    bend = np.setdiff1d(np.unique(cells[:7]), np.nonzero(isv)[0])           # the high-order nodes of the first seven cells
+    mixed = nodes.copy(); mixed[bend] += 0.004 * np.random.default_rng(8).uniform(-1, 1, size=(bend.size, 3))
+    _compare(3, 3, mixed, cells)
+    m, fm, s = _setup(3, 3, nodes, cells)
+    fm["Dirichlet"].values[:] = 1.5
+    s.assemble(); v1 = s.getCSR()[2].copy()
+    monkeypatch.setenv("HFX_CG_NO_AFFINE", "1")
+    s.assemble(); v2 = s.getCSR()[2].copy()
+    assert H.rel_err(v1, v2) < 1e-13 and np.abs(v1).max() > 0
+
+
+@pytest.mark.parametrize("dim,order,geom", [(2, 4, "simplex"), (3, 2, "simplex"), (3, 2, "orthotope")])
+def test_cg_affine_fast_path_with_source_and_euler(dim, order, geom):
+    """DiffusionSource without a DiffusionTensor field (D = I) + source + implicit Euler on straight-sided cells: every term of the fast path (C_rs K^_rs, detJ M^,
+    detJ w phi f) against the oracle"""
+    nodes, cells = (meshgen.kuhn_mesh(3, order, dim, perturb=0.1) if geom == "simplex" else meshgen.box_mesh(3, order, dim))
+    m = hfox.Mesh(dim, order, geom); m.setMesh(nodes, cells)
+    re = m.getReferenceElement()
+    fm = {"Solution": hfox.Field(m, hfox.Node, 1, 1), "Dirichlet": hfox.Field(m, hfox.Face, re.getFaceElement().getNumNodes(), 1)}
+    src = lambda x: 1.0 + x[0] * x[1]
+    mod = hfox.DiffusionSource(re)
+    ts = hfox.Euler(re); ts.setTimeStep(0.03); mod.setTimeScheme(ts)
+    s = hfox.CGSolver()
+    s.setVerbosity(False); s.setMesh(m); s.setFieldMap(fm); s.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts(rtol=1e-14, maxits=20000)))
+    s.setModel(mod); s.setBoundaryModel(hfox.DirichletModel(re.getFaceElement())); s.initialize(); s.allocate()
+    mod.setSourceFunction(src)
+    ore = OracleRefEl(dim, order, geom); topo = compute_faces(cells, ore)
+    u0 = np.cos(2 * nodes[:, 0]) + nodes[:, 1] ** 2
+    fm["Solution"].values[:] = u0
+    dirv = np.zeros(topo["faces"].shape); dirv[topo["boundary"]] = u0[topo["faces"][topo["boundary"]]]
+    fm["Dirichlet"].values[:] = dirv.ravel()
+    s.assemble(); s.solve()
+    o = cg.CGOracle(ore, nodes, cells, topo["faces"], topo["boundary"], source=src, dt=0.03, solOld=u0)
+    o.assemble(dirv); o.solve()
+    rowptr, col, vals, rhs = s.getCSR()
+    assert H.rel_err(vals, o.vals) < 1e-12 and H.rel_err(rhs, o.b) < 1e-12
+    assert H.rel_err(fm["Solution"].values, o.sol) < 1e-10

@@ -2044,13 +2044,16 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     bool tauVaries = false;
     if (!needSuuModel && bigP3Mode == 1 && !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 3 && c->md.nDOF == 1 && tau->nVal <= 2 && !p.diff && p.affine
         && c->nNonAffine == 0 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme == HFX_TS_NONE) {
-      // Laplace-type model: the all-reference path of the element-group kernel is the fastest when tau is constant on every face; one pass over Tau decides
-      if (tau->pendingPieces > 0) { for (int k = 0; k < 2; k++) HFX_CUDA(cudaStreamSynchronize(c->stCopy[k])); }
-      c->dTauFlag.alloc(1); c->dTauFlag.zero(c->st);
-      tau_varies_kernel<<<c->nSM * 4, 256, 0, c->st>>>((long long)c->nFaces, c->nNf, tau->nVal, tau->d.p, c->dTauFlag.p);
-      int tv = 0;
-      c->dTauFlag.download(&tv, 1, c->st);
-      tauVaries = tv != 0;
+      // Laplace-type model: the all-reference path of the element-group kernel is the fastest when tau is constant on every face; one pass over Tau decides.
+      // While Tau is still crossing PCIe (hfx_field_set_async) the pass is skipped -- waiting for the whole field would serialise the upload and the first element
+      // chunks -- and the element-group kernel, which checks tau face by face anyway, serves every element.
+      if (tau->pendingPieces == 0) {
+        c->dTauFlag.alloc(1); c->dTauFlag.zero(c->st);
+        tau_varies_kernel<<<c->nSM * 4, 256, 0, c->st>>>((long long)c->nFaces, c->nNf, tau->nVal, tau->d.p, c->dTauFlag.p);
+        int tv = 0;
+        c->dTauFlag.download(&tv, 1, c->st);
+        tauVaries = tv != 0;
+      }
     }
     const bool bigP3 = !p1 && !recoverMode && !dumpMode && bigP3Mode > 0 && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 3 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU)
         && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !p.diff && p.affine && c->nNonAffine == 0 && !forceGeneric && (needSuuModel || bigP3Mode == 2 || tauVaries);

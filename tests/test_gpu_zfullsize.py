@@ -26,11 +26,21 @@ TOL_FLUX = 1e-10         # the same bar for the flux, measured against the flux 
 
 
 def test_full_size_constant_state_polynomial_exactness_and_reproducibility():
+    _full_size(3, 55, (998250, 20), 20146500, 1399365000, "fused")
+
+
+@pytest.mark.parametrize("order,N,shape,kernel", [(1, 94, (4983504, 4), "p1"), (2, 69, (1971054, 10), "col")])
+def test_full_size_properties_at_the_order_sweep_sizes(order, N, shape, kernel):
+    """the same properties on the order-1 and order-2 meshes of BASELINE configs[4] (2e7 dofs per order), through the column-per-lane kernels"""
+    _full_size(order, N, shape, None, None, kernel)
+
+
+def _full_size(order, N, shape, nrowsWant, nnzWant, kernelWant):
     from hyperfox_b200 import capi, meshgen
     from hyperfox_b200.capi import check, lib, pd, pi
-    dim, order, N = 3, 3, 55
+    dim = 3
     nodes, cells = meshgen.kuhn_mesh(N, order, dim)
-    assert cells.shape == (998250, 20)
+    assert cells.shape == shape
     tp = capi.host_compute_faces(dim, order, cells)
     faces, bnd = tp["faces"], tp["boundary"]
     nF, nNf = faces.shape
@@ -72,19 +82,29 @@ def test_full_size_constant_state_polynomial_exactness_and_reproducibility():
 
         # ---- constant state ---------------------------------------------------------------------------------------------------
         rn, bn, sol, flux, rhs, nrows, nnz = run(np.full((nF, nNf), 3.0))
-        assert nrows == nF * nNf == 20146500 and nnz == 1399365000
+        assert nrows == nF * nNf and (nrowsWant is None or (nrows == nrowsWant and nnz == nnzWant))
+        kk = C.c_int(-1)
+        L.hfx_last_assemble_kernel(h, C.byref(kk), None)
+        assert ("fused", "general", "big", "p1", "col")[kk.value] == kernelWant
         assert bn > 0.0 and rn <= 1e-12 * bn, (rn, bn)
-        obs = {"const_residual_rel": rn / bn, "const_solution_rel": float(np.abs(sol - 3.0).max() / 3.0), "const_flux_abs": float(np.abs(flux).max())}
+        obs = {"order": order, "elements": int(nC), "kernel": kernelWant, "const_residual_rel": rn / bn, "const_solution_rel": float(np.abs(sol - 3.0).max() / 3.0), "const_flux_abs": float(np.abs(flux).max())}
         assert obs["const_solution_rel"] < TOL_SOLUTION                      # north-star bar for solution fields
         assert obs["const_flux_abs"] < TOL_FLUX * 3.0 * N                    # flux scale of the problem: |u| / h
         # ---- bit-reproducible re-assembly ---------------------------------------------------------------------------------------
         rn2, bn2, sol2, flux2, rhs2, _, _ = run(np.full((nF, nNf), 3.0))
         assert np.array_equal(rhs, rhs2) and np.array_equal(sol, sol2) and np.array_equal(flux, flux2)
         del sol2, flux2, rhs2
-        # ---- harmonic polynomial of degree 3 <= p: u = x^3 - 3 x y^2 + 2 y z - x + 0.5 ------------------------------------------
+        # ---- harmonic polynomial of degree <= p: u = x^3 - 3 x y^2 + 2 y z - x + 0.5 (order 3), x^2 - y^2 + 2 y z - x + 0.5 (order 2), 1 + x - 2 y + z / 2 (order 1)
         x, y, z = nodes[:, 0], nodes[:, 1], nodes[:, 2]
-        u = x ** 3 - 3.0 * x * y ** 2 + 2.0 * y * z - x + 0.5
-        grad = np.stack([3.0 * x ** 2 - 3.0 * y ** 2 - 1.0, -6.0 * x * y + 2.0 * z, 2.0 * y], axis=1)
+        if order >= 3:
+            u = x ** 3 - 3.0 * x * y ** 2 + 2.0 * y * z - x + 0.5
+            grad = np.stack([3.0 * x ** 2 - 3.0 * y ** 2 - 1.0, -6.0 * x * y + 2.0 * z, 2.0 * y], axis=1)
+        elif order == 2:
+            u = x ** 2 - y ** 2 + 2.0 * y * z - x + 0.5
+            grad = np.stack([2.0 * x - 1.0, -2.0 * y + 2.0 * z, 2.0 * y], axis=1)
+        else:
+            u = 1.0 + x - 2.0 * y + 0.5 * z
+            grad = np.stack([np.ones_like(x), -2.0 * np.ones_like(x), 0.5 * np.ones_like(x)], axis=1)
         rn, bn, sol, flux, rhs, _, _ = run(u[faces])
         g = grad[cells]                                          # [nC, nN, dim]; the flux is +grad u or -grad u (sign convention of the model)
         sgn = 1.0 if np.abs(flux - g).max() < np.abs(flux + g).max() else -1.0
@@ -94,7 +114,7 @@ def test_full_size_constant_state_polynomial_exactness_and_reproducibility():
         print("full-size observed:", json.dumps(obs))
         out = os.environ.get("HFX_FULLSIZE_LOG")
         if out:
-            with open(out, "w") as f:
+            with open(out, "a") as f:
                 f.write(json.dumps(obs) + "\n")
         assert rn <= 1e-12 * bn, (rn, bn)
         assert obs["poly_solution_rel"] < TOL_SOLUTION

@@ -31,6 +31,8 @@ struct CgParams {
   int skipAffine;
   const double* refTab;                   // cg_affine_kernel: K^_rs [dim*dim][nN*nN], M^ [nN*nN], w phi [nIP][nN]
   int fv[4];                              // vertices spanning the affine frame (0,1,2,3 simplices; 0,1,3,4 orthotopes)
+  // gather form of the fast path (cg_gather_kernel): per node the cells it belongs to (ascending) with its local index there, per cell C = detJ Jinv^T Jinv and detJ
+  const long long* n2c; const int* n2cCell; const unsigned char* n2cLoc; const double* cellGeo; int nNodes; int maxRow;
   const unsigned short* pos;              // [nCells][nN][nN] position of column cells[e][j] inside row cells[e][i] (built once by cg_positions_kernel) or NULL
   double* vals; double* rhs; int* status;
 };
@@ -206,6 +208,81 @@ __global__ void __launch_bounds__(256) cg_affine_kernel(const CgParams p) {
         if (dt > 0.0) for (int j = 0; j < nN; j++) mu = fma(MH[i * nN + j], p.solOld[cell[j]], mu);
         atomicAdd(p.rhs + cell[i], det * (dt > 0.0 ? fma(dt, s, mu) : s));
       }
+  }
+}
+
+// C = detJ Jinv^T Jinv (row-major dim x dim) and detJ of every affine cell: the geometry does not change between assemblies (once per hfx_cg_allocate)
+__global__ void cg_cell_geometry_kernel(int nCells, int nN, int dim, int fv0, int fv1, int fv2, int fv3, const double* __restrict__ nodes, const int* __restrict__ cells,
+                                        const unsigned char* __restrict__ affine, double* __restrict__ geo /*[nCells][10]*/, int* __restrict__ status) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nCells || !affine[e]) return;
+  const int fv[4] = {fv0, fv1, fv2, fv3};
+  const int* cell = cells + (size_t)e * nN;
+  double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  const double* x0 = nodes + (size_t)cell[fv[0]] * dim;
+  for (int r = 0; r < dim; r++) { const double* xr = nodes + (size_t)cell[fv[r + 1]] * dim; for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (xr[m] - x0[m]); }
+  double det, I[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  if (dim == 1) { det = J[0][0]; I[0][0] = 1.0 / det; }
+  else if (dim == 2) {
+    det = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double id = 1.0 / det;
+    I[0][0] = J[1][1] * id; I[0][1] = -J[0][1] * id; I[1][0] = -J[1][0] * id; I[1][1] = J[0][0] * id;
+  } else det_inv(J, det, I);
+  if (!(fabs(det) > 1e-300)) atomicOr(status, 1);
+  double* g = geo + (size_t)e * 10;
+  for (int q = 0; q < 9; q++) g[q] = 0.0;
+  for (int r = 0; r < dim; r++) for (int s2 = 0; s2 < dim; s2++) { double a = 0.0; for (int k = 0; k < dim; k++) a = fma(I[k][r], I[k][s2], a); g[r * dim + s2] = det * a; }
+  g[9] = det;
+}
+
+// Gather form of the fast path: ONE WARP PER ROW (node).  The warp walks the cells the node belongs to in ascending order and adds each cell's row of
+// sum_rs C_rs K^_rs (+ the Euler mass) into the row's image in shared memory at the precomputed positions, then stores the row once: no atomics, every entry summed in
+// a fixed order (bit-reproducible), the matrix written exactly once.  The right-hand side entry of the node is reduced the same way.
+__global__ void __launch_bounds__(256) cg_gather_kernel(const CgParams p) {
+  extern __shared__ __align__(16) double smcq[];
+  const int dim = p.dim, nN = p.nN, nIP = p.nIP, D2 = dim * dim, NN = nN * nN;
+  const int nTab = D2 * NN + NN + nIP * nN;
+  for (int i = threadIdx.x; i < nTab; i += blockDim.x) smcq[i] = p.refTab[i];
+  __syncthreads();
+  const double* const KH = smcq; const double* const MH = smcq + D2 * NN; const double* const PW = MH + NN;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  double* const buf = smcq + ((nTab + 1) & ~1) + (size_t)w * p.maxRow;
+  const double dt = p.eulerDt;
+  for (int r = blockIdx.x * wpb + w; r < p.nNodes; r += gridDim.x * wpb) {
+    const long long r0 = p.rowptr[r];
+    const int len = (int)(p.rowptr[r + 1] - r0);
+    for (int k = lane; k < len; k += 32) buf[k] = 0.0;
+    __syncwarp();
+    double frhs = 0.0;
+    for (long long k = p.n2c[r]; k < p.n2c[r + 1]; k++) {
+      const int e = p.n2cCell[k];
+      if (!p.affine[e]) continue;                                  // (warp-uniform) curved cells come afterwards, through cg_element_kernel
+      const int i = p.n2cLoc[k];
+      const double* g = p.cellGeo + (size_t)e * 10;
+      double Cm[9];
+      for (int q = 0; q < D2; q++) Cm[q] = g[q];
+      const double det = g[9];
+      const unsigned short* ps = p.pos + (size_t)e * NN + i * nN;
+      for (int j = lane; j < nN; j += 32) {
+        double acc = 0.0;
+        for (int q = 0; q < D2; q++) acc = fma(Cm[q], KH[q * NN + i * nN + j], acc);
+        if (dt > 0.0) acc = fma(dt, acc, det * MH[i * nN + j]);
+        buf[ps[j]] += acc;                                           // the nodes of a cell are distinct: no two lanes share a position
+      }
+      if (p.srcIP || dt > 0.0) {
+        const int* cell = p.cells + (size_t)e * nN;
+        double s = 0.0, mu = 0.0;
+        if (p.srcIP) for (int ip = lane; ip < nIP; ip += 32) s = fma(PW[ip * nN + i], p.srcIP[(size_t)e * nIP + ip], s);
+        if (dt > 0.0) for (int j = lane; j < nN; j += 32) mu = fma(MH[i * nN + j], p.solOld[cell[j]], mu);
+        double v = det * (dt > 0.0 ? fma(dt, s, mu) : s);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        frhs += v;
+      }
+      __syncwarp();
+    }
+    for (int k = lane; k < len; k += 32) p.vals[r0 + k] = buf[k];
+    if (lane == 0 && (p.srcIP || dt > 0.0)) p.rhs[r] = frhs;
+    __syncwarp();
   }
 }
 

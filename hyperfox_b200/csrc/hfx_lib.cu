@@ -1130,7 +1130,7 @@ struct hfx_ctx {
   // allocation
   bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false, p1Ready = false, colReady = false; int lastKernel = 0;
   // continuous-Galerkin path (hfx_cg_*): node-based CSR
-  DBuf<long long> dCgRowptr; DBuf<int> dCgCol; DBuf<double> dCgVals, dCgRhs, dCgRefTab; DBuf<unsigned short> dCgPos; DBuf<unsigned char> dCgAffine; long long cgNonAffine = 0; long long cgNnz = 0; bool cgAllocated = false, cgAssembled = false;
+  DBuf<long long> dCgRowptr; DBuf<int> dCgCol; DBuf<double> dCgVals, dCgRhs, dCgRefTab; DBuf<unsigned short> dCgPos; DBuf<unsigned char> dCgAffine, dCgN2cLoc; long long cgNonAffine = 0; DBuf<long long> dCgN2c; DBuf<int> dCgN2cCell; DBuf<double> dCgGeo; int cgMaxRow = 0; long long cgNnz = 0; bool cgAllocated = false, cgAssembled = false;
   std::vector<long long> hCgRowptr; std::vector<int> hCgCol;
   int solverType = 0;   // HDGSolverOpts.type: 0 IMPLICIT, 1 WEXPLICIT, 2 SEXPLICIT (HDGSolverOpts.h:6-10)
   DBuf<double> dColTab;
@@ -2325,7 +2325,9 @@ int hfx_cg_allocate(hfx_ctx* c) {
     for (size_t k = 0; k < cells.size(); k++) n2c[cells[k] + 1]++;
     for (int i = 0; i < nNodes; i++) n2c[i + 1] += n2c[i];
     std::vector<int> n2cList((size_t)n2c[nNodes]);
-    { std::vector<long long> pos(n2c.begin(), n2c.end() - 1); for (int e = 0; e < nC; e++) for (int i = 0; i < nN; i++) n2cList[(size_t)pos[cells[(size_t)e * nN + i]]++] = e; }
+    std::vector<unsigned char> n2cLoc((size_t)n2c[nNodes]);
+    { std::vector<long long> pos(n2c.begin(), n2c.end() - 1); for (int e = 0; e < nC; e++) for (int i = 0; i < nN; i++) { const size_t at = (size_t)pos[cells[(size_t)e * nN + i]]++; n2cList[at] = e; n2cLoc[at] = (unsigned char)i; } }
+    c->dCgN2c.upload(n2c, c->st); c->dCgN2cCell.upload(n2cList, c->st); c->dCgN2cLoc.upload(n2cLoc, c->st);
     c->hCgRowptr.assign(nNodes + 1, 0); c->hCgCol.clear();
     std::vector<int> row;
     for (int n = 0; n < nNodes; n++) {
@@ -2342,6 +2344,7 @@ int hfx_cg_allocate(hfx_ctx* c) {
     // scatter map: position of every element entry inside its row (rows longer than 65535 entries keep the search in the kernel)
     long long maxRow = 0;
     for (int n = 0; n < nNodes; n++) maxRow = std::max(maxRow, c->hCgRowptr[n + 1] - c->hCgRowptr[n]);
+    c->cgMaxRow = (int)std::min<long long>(maxRow, 1 << 30);
     c->dCgPos.alloc(0);
     if (maxRow <= 65535 && !getenv("HFX_CG_SEARCH")) {
       const long long nEnt = (long long)nC * nN * nN;
@@ -2374,6 +2377,13 @@ int hfx_cg_allocate(hfx_ctx* c) {
       c->dCgAffine.download(fl.data(), fl.size(), c->st);
       c->cgNonAffine = 0;
       for (unsigned char f : fl) c->cgNonAffine += f ? 0 : 1;
+      c->dCgGeo.alloc((size_t)nC * 10);
+      c->dStatus.zero(c->st);
+      cg_cell_geometry_kernel<<<nblk(nC, 128), 128, 0, c->st>>>(nC, nN, dim, 0, 1, sx ? 2 : 3, sx ? 3 : 4, c->dNodes.p, c->dCells.p, c->dCgAffine.p, c->dCgGeo.p, c->dStatus.p);
+      HFX_CUDA(cudaGetLastError());
+      int st0 = 0;
+      c->dStatus.download(&st0, 1, c->st);
+      need(!(st0 & 1), "Operator", "calcInvJacobians", "singular element Jacobian met while preparing the mesh");
     }
     HFX_CUDA(cudaStreamSynchronize(c->st));
     c->cgAllocated = true; c->cgAssembled = false;
@@ -2419,7 +2429,17 @@ int hfx_cg_assemble(hfx_ctx* c) {
     const bool fast = p.hasDiffusion && !p.diff && !p.vel && shmA <= 200 * 1024 && c->cgNonAffine < c->nCells && !getenv("HFX_CG_NO_AFFINE");
     p.affine = c->dCgAffine.p; p.skipAffine = fast ? 1 : 0; p.refTab = c->dCgRefTab.p;
     p.fv[0] = 0; p.fv[1] = 1; p.fv[2] = c->geom == HFX_SIMPLEX ? 2 : 3; p.fv[3] = c->geom == HFX_SIMPLEX ? 3 : 4;
-    if (fast) {
+    // HFX_CG_GATHER=1: gather form -- one warp per row, no atomics, bit-reproducible.  Measured slower than the element-wise scatter with atomics at orders >= 2
+    // (80.6 against 182.6 M el/s at order 3: a row walks its cells one after the other through dependent loads), so the scatter stays the default
+    const size_t shmG = shmA + 16 + (size_t)8 * c->cgMaxRow * sizeof(double);
+    const bool gather = fast && p.pos && shmG <= 220 * 1024 && c->nN <= 255 && getenv("HFX_CG_GATHER") && atoi(getenv("HFX_CG_GATHER")) != 0;
+    if (gather) {
+      p.n2c = c->dCgN2c.p; p.n2cCell = c->dCgN2cCell.p; p.n2cLoc = c->dCgN2cLoc.p; p.cellGeo = c->dCgGeo.p; p.nNodes = c->nNodes; p.maxRow = c->cgMaxRow;
+      HFX_CUDA(cudaFuncSetAttribute(cg_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmG));
+      const int perSM = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (shmG + 1024)));
+      cg_gather_kernel<<<std::max(1, std::min(nblk(c->nNodes, 8), c->nSM * perSM)), 256, shmG, c->st>>>(p);
+      HFX_CUDA(cudaGetLastError());
+    } else if (fast) {
       HFX_CUDA(cudaFuncSetAttribute(cg_affine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmA));
       const int perSM = (int)std::max<size_t>(1, std::min<size_t>(4, (227 * 1024) / (shmA + 1024)));
       cg_affine_kernel<<<std::max(1, std::min(nblk(c->nCells, 8), c->nSM * perSM)), 256, shmA, c->st>>>(p);

@@ -122,7 +122,7 @@ def test_cg_reassembly_and_unsupported_models():
     s.assemble()
     v1 = s.getCSR()[2].copy()
     s.assemble()
-    assert H.rel_err(s.getCSR()[2], v1) < 1e-14          # clearSystem between assemblies (atomics: equal to rounding, not bitwise)
+    assert H.rel_err(s.getCSR()[2], v1) < 1e-14          # clearSystem between assemblies (atomics: equal to rounding, not bitwise; HFX_CG_GATHER=1 for bitwise)
     with pytest.raises(hfox.ErrorHandle, match="nodal field"):
         fm2 = dict(fm); fm2["Solution"] = hfox.Field(m, hfox.Cell, m.getReferenceElement().getNumNodes(), 1)
         s2 = hfox.CGSolver(); s2.setMesh(m); s2.setFieldMap(fm2); s2.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts()))
@@ -245,3 +245,28 @@ def test_cg_affine_fast_path_with_source_and_euler(dim, order, geom):
     rowptr, col, vals, rhs = s.getCSR()
     assert H.rel_err(vals, o.vals) < 1e-12 and H.rel_err(rhs, o.b) < 1e-12
     assert H.rel_err(fm["Solution"].values, o.sol) < 1e-10
+
+
+def test_cg_gather_form_matches_the_atomic_scatter_and_is_bit_reproducible(monkeypatch):
+    """the gather form (HFX_CG_GATHER=1: one warp per row, fixed summation order) against the default element-wise scatter with atomics, matrix and right-hand side,
+    with a source and an implicit Euler step; two assemblies of the gather form agree bit for bit"""
+    monkeypatch.setenv("HFX_CG_GATHER", "1")
+    dim, order = 3, 2
+    nodes, cells = meshgen.kuhn_mesh(4, order, dim, perturb=0.1)
+    m = hfox.Mesh(dim, order, "simplex"); m.setMesh(nodes, cells)
+    re = m.getReferenceElement()
+    fm = {"Solution": hfox.Field(m, hfox.Node, 1, 1), "Dirichlet": hfox.Field(m, hfox.Face, re.getFaceElement().getNumNodes(), 1)}
+    mod = hfox.DiffusionSource(re)
+    ts = hfox.Euler(re); ts.setTimeStep(0.02); mod.setTimeScheme(ts)
+    s = hfox.CGSolver()
+    s.setVerbosity(False); s.setMesh(m); s.setFieldMap(fm); s.setLinSystem(hfox.CudaLinAlgebraInterface(hfox.PetscOpts(rtol=1e-12)))
+    s.setModel(mod); s.setBoundaryModel(hfox.DirichletModel(re.getFaceElement())); s.initialize(); s.allocate()
+    mod.setSourceFunction(lambda x: x[0] - x[2] ** 2)
+    u0 = np.sin(nodes[:, 0] + 2 * nodes[:, 1])
+    fm["Solution"].values[:] = u0; fm["Dirichlet"].values[:] = 0.7
+    s.assemble(); _, _, v1, r1 = s.getCSR()
+    s._upload("Solution"); s.assemble(); _, _, v2, r2 = s.getCSR()
+    assert np.array_equal(v1, v2) and np.array_equal(r1, r2)
+    monkeypatch.setenv("HFX_CG_GATHER", "0")
+    s.assemble(); _, _, v3, r3 = s.getCSR()
+    assert H.rel_err(v1, v3) < 1e-13 and H.rel_err(r1, r3) < 1e-13 and np.abs(r1).max() > 0

@@ -1132,6 +1132,7 @@ struct hfx_ctx {
   // continuous-Galerkin path (hfx_cg_*): node-based CSR
   DBuf<long long> dCgRowptr; DBuf<int> dCgCol; DBuf<double> dCgVals, dCgRhs, dCgRefTab; DBuf<unsigned short> dCgPos; DBuf<unsigned char> dCgAffine, dCgN2cLoc; long long cgNonAffine = 0; DBuf<long long> dCgN2c; DBuf<int> dCgN2cCell; DBuf<double> dCgGeo; int cgMaxRow = 0; long long cgNnz = 0; bool cgAllocated = false, cgAssembled = false;
   std::vector<long long> hCgRowptr; std::vector<int> hCgCol;
+  int tauVariesCached = -1;   // outcome of the last pass over Tau (kernel choice at order 3); -1: never looked
   int solverType = 0;   // HDGSolverOpts.type: 0 IMPLICIT, 1 WEXPLICIT, 2 SEXPLICIT (HDGSolverOpts.h:6-10)
   DBuf<double> dColTab;
   DBuf<int> dNbr; DBuf<uint8_t> dNnb, dInterior, dFperm, dTauSide, dElemPos;
@@ -1869,6 +1870,7 @@ int hfx_allocate(hfx_ctx* c, int flags) {
   return guard(c, [&] {
     HFX_CUDA(cudaSetDevice(c->device));
     // HDGSolver::allocate checks (HDGSolver.cpp:5-73)
+    c->tauVariesCached = -1;
     need(c->topoSet, "HDGSolver", "allocate", "must set the Mesh before allocating.");
     need(c->modelSet, "HDGSolver", "allocate", "must set the model before allocating.");
     need(c->bcSet, "HDGSolver", "allocate", "must set the boundary model before allocating.");
@@ -2041,19 +2043,21 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     // straight-sided path of the element-group kernel.  HFX_BIG_P3=0 disables, HFX_BIG_P3=2 routes the Laplace-type models through it as well.
     const int bigP3Mode = getenv("HFX_BIG_P3") ? atoi(getenv("HFX_BIG_P3")) : 1;
     const bool needSuuModel = (c->md.opmask & (HFX_OP_CONVECTION | HFX_OP_REACTION)) || c->md.timeScheme == HFX_TS_EULER_IMPLICIT;
-    bool tauVaries = false;
+    bool tauVaries = false, tauEligible = false, tauSpeculated = false;
     if (!needSuuModel && bigP3Mode == 1 && !recoverMode && !dumpMode && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 3 && c->md.nDOF == 1 && tau->nVal <= 2 && !p.diff && p.affine
         && c->nNonAffine == 0 && !(c->md.opmask & HFX_OP_UNABU) && c->md.timeScheme == HFX_TS_NONE) {
       // Laplace-type model: the all-reference path of the element-group kernel is the fastest when tau is constant on every face; one pass over Tau decides.
       // While Tau is still crossing PCIe (hfx_field_set_async) the pass is skipped -- waiting for the whole field would serialise the upload and the first element
-      // chunks -- and the element-group kernel, which checks tau face by face anyway, serves every element.
-      if (tau->pendingPieces == 0) {
+      // chunks: the outcome of the previous pass is used instead, and the pass runs at the end of this assemble, when the field has arrived.
+      tauEligible = true;
+      if (tau->pendingPieces == 0 || c->tauVariesCached < 0) {
+        if (tau->pendingPieces > 0) { for (int k = 0; k < 2; k++) HFX_CUDA(cudaStreamSynchronize(c->stCopy[k])); }   // first assemble only
         c->dTauFlag.alloc(1); c->dTauFlag.zero(c->st);
         tau_varies_kernel<<<c->nSM * 4, 256, 0, c->st>>>((long long)c->nFaces, c->nNf, tau->nVal, tau->d.p, c->dTauFlag.p);
         int tv = 0;
         c->dTauFlag.download(&tv, 1, c->st);
-        tauVaries = tv != 0;
-      }
+        tauVaries = tv != 0; c->tauVariesCached = tv != 0 ? 1 : 0;
+      } else { tauVaries = c->tauVariesCached != 0; tauSpeculated = true; }   // both kernels serve any tau: the choice is a matter of speed only; refreshed below
     }
     const bool bigP3 = !p1 && !recoverMode && !dumpMode && bigP3Mode > 0 && c->geom == HFX_SIMPLEX && c->dim == 3 && c->order == 3 && c->md.nDOF == 1 && !(c->md.opmask & HFX_OP_UNABU)
         && c->md.timeScheme != HFX_TS_RUNGE_KUTTA && !p.diff && p.affine && c->nNonAffine == 0 && !forceGeneric && (needSuuModel || bigP3Mode == 2 || tauVaries);
@@ -2186,6 +2190,13 @@ static int assemble_impl(hfx_ctx* c, bool recoverMode, int dumpElem = -1, double
     }
     HFX_CUDA(cudaEventElapsedTime(&c->msTotal, c->ev0, c->ev2));
     HFX_CUDA(cudaEventElapsedTime(&c->msKernel, c->ev1, c->ev2));
+    if (tauEligible && tauSpeculated) {   // the field is resident now: look at it for the next assemble
+      c->dTauFlag.zero(c->st);
+      tau_varies_kernel<<<c->nSM * 4, 256, 0, c->st>>>((long long)c->nFaces, c->nNf, tau->nVal, tau->d.p, c->dTauFlag.p);
+      int tv = 0;
+      c->dTauFlag.download(&tv, 1, c->st);
+      c->tauVariesCached = tv != 0 ? 1 : 0;
+    }
     need(!(status & 1), "HDGSolver", "calcElementalMatrices", "singular local matrix met during static condensation");
     c->assembled = true;
   });

@@ -1450,12 +1450,18 @@ int hfx_host_write_h5(const char* path, unsigned mtime, int dimNodeSpace, long l
   return guard(nullptr, [&] {
     H5Mesh m; const H5Mesh* pm = nullptr;
     if (nodes && cells) {
+      if (dimNodeSpace < 1 || dimNodeSpace > 3 || nodesPerCell < 1 || nNodes < 0 || nCells < 0) throw std::runtime_error("HDF5Io : writeMesh : the mesh has no nodes or cells");
       m.dimNodeSpace = dimNodeSpace; m.nodesPerCell = nodesPerCell;
       m.nodes.assign(nodes, nodes + (size_t)nNodes * dimNodeSpace); m.cells.assign(cells, cells + (size_t)nCells * nodesPerCell);
       pm = &m;
     }
     std::vector<H5Field> fs((size_t)std::max(0, nFields));
+    if (!path) throw std::runtime_error("HDF5Io : write : no file name");
+    if (nFields > 0 && (!names || !ftypes || !shapes || !vals)) throw std::runtime_error("HDF5Io : writeFields : missing field arrays");
     for (int k = 0; k < nFields; k++) {
+      if (!names[k] || !names[k][0] || std::strchr(names[k], '/')) throw std::runtime_error("HDF5Io : writeFields : a field needs a non-empty name without '/'");
+      for (int d = 0; d < 3; d++) if (shapes[3 * k + d] < 0 || shapes[3 * k + d] > (1ll << 40)) throw std::runtime_error(std::string("HDF5Io : writeFields : problem writing values of field: ") + names[k]);
+      if (shapes[3 * k] * shapes[3 * k + 1] * shapes[3 * k + 2] > 0 && !vals[k]) throw std::runtime_error(std::string("HDF5Io : writeFields : problem writing values of field: ") + names[k]);
       fs[k].name = names[k]; fs[k].ftype = ftypes[k];
       for (int d = 0; d < 3; d++) fs[k].shape[d] = shapes[3 * k + d];
       const size_t n = (size_t)(shapes[3 * k] * shapes[3 * k + 1] * shapes[3 * k + 2]);

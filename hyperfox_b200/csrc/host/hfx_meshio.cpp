@@ -292,7 +292,7 @@ struct H5File {
       } else if (m.type == 0x8) {
         if (u(m.data, 1) != 3 || u(m.data + 1, 1) != 1) bad("only contiguous dataset layouts are supported");
         *addr = (size_t)u(m.data + 2, 8); haveL = true;
-        if (u(m.data + 2, 8) == UINT64_MAX) bad("dataset without allocated storage (HADDR_UNDEF)");
+        // (HADDR_UNDEF: no storage allocated -- legal for an empty dataset; the callers check the address against the bytes they need)
       }
     }
     if (!haveS || !haveT || !haveL) bad("incomplete dataset header");
@@ -322,7 +322,7 @@ void read_h5_mesh(const std::string& path, H5Mesh* out) {
   if (shape.size() != 2 || cls != 1 || size != 8) H5File::bad("Nodes must be a two-dimensional float64 dataset");
   if (shape[1] == 0 || shape[1] > 3 || shape[0] > f.b.size() / (8 * shape[1])) H5File::bad("truncated Nodes dataset");
   const size_t nn = (size_t)(shape[0] * shape[1]);
-  if (!f.inside(addr, (uint64_t)nn * 8)) H5File::bad("truncated Nodes dataset");
+  if (!f.inside(addr, (uint64_t)nn * 8)) H5File::bad(addr == UINT64_MAX ? "dataset without allocated storage (HADDR_UNDEF)" : "truncated Nodes dataset");
   out->dimNodeSpace = (int)shape[1];
   out->nodes.resize(nn);
   std::memcpy(out->nodes.data(), f.b.data() + addr, nn * 8);
@@ -330,7 +330,7 @@ void read_h5_mesh(const std::string& path, H5Mesh* out) {
   if (shape.size() != 2 || cls != 0 || (size != 4 && size != 8)) H5File::bad("Cells must be a two-dimensional integer dataset");
   if (shape[1] == 0 || shape[1] > 4096 || shape[0] > f.b.size() / ((uint64_t)size * shape[1])) H5File::bad("truncated Cells dataset");
   const size_t nc = (size_t)(shape[0] * shape[1]);
-  if (!f.inside(addr, (uint64_t)nc * size)) H5File::bad("truncated Cells dataset");
+  if (!f.inside(addr, (uint64_t)nc * size)) H5File::bad(addr == UINT64_MAX ? "dataset without allocated storage (HADDR_UNDEF)" : "truncated Cells dataset");
   out->nodesPerCell = (int)shape[1];
   out->cells.resize(nc);
   for (size_t i = 0; i < nc; i++) out->cells[i] = (int)(int64_t)f.u(addr + i * size, size);
@@ -380,7 +380,7 @@ void read_h5_field(const std::string& path, const std::string& name, H5Field* ou
   const uint64_t n01 = shape[0] * shape[1];
   if ((shape[1] && n01 / shape[1] != shape[0]) || n01 > f.b.size() || (shape[2] && n01 * shape[2] > f.b.size() / 8)) fail("truncated field dataset");
   const size_t n = (size_t)(n01 * shape[2]);
-  if (!f.inside(addr, (uint64_t)n * 8)) fail("could not load field values into field");
+  if (n && !f.inside(addr, (uint64_t)n * 8)) fail("could not load field values into field");
   out->name = name;
   for (int k = 0; k < 3; k++) out->shape[k] = (long long)shape[k];
   out->vals.resize(n);

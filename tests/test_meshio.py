@@ -298,3 +298,17 @@ def test_h5_write_then_load_fields_and_mesh(tmp_path):
         assert np.array_equal(g.read("/FieldData/" + k), fields[k][1])
     with pytest.raises(Exception, match="could not find anything to write"):
         product.write_h5(str(tmp_path / "empty.h5"))
+
+
+def test_h5_writer_rejects_bad_input(tmp_path):
+    out = str(tmp_path / "bad.h5")
+    with pytest.raises(Exception, match="non-empty name"):
+        product.write_h5(out, fields={"a/b": (product.H5_NODE, np.zeros((2, 1, 1)))})
+    with pytest.raises(Exception, match="problem writing values"):
+        product.write_h5(out, fields={"f": (product.H5_NODE, np.zeros((2, 1)))})
+    # an empty field is legal (zero entities): written and read back
+    product.write_h5(out, fields={"empty": (product.H5_CELL, np.zeros((0, 3, 1))), "one": (product.H5_FACE, np.ones((1, 1, 1)))})
+    ft, v = product.read_h5_field(out, "empty")
+    assert ft == product.H5_CELL and v.shape == (0, 3, 1)
+    ft, v = product.read_h5_field(out, "one")
+    assert ft == product.H5_FACE and v.ravel().tolist() == [1.0]

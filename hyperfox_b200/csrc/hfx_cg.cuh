@@ -64,12 +64,15 @@ __global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
     __syncthreads();
     for (int ip = tid; ip < nIP; ip += NT) {
       double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-      for (int r = 0; r < dim; r++)
-        for (int m = 0; m < dim; m++) {
-          double s = 0.0;
-          for (int i = 0; i < nN; i++) s = fma(p.dshape[((size_t)ip * nN + i) * dim + r], X[i * dim + m], s);
-          J[r][m] = s;
-        }
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+          if (r < dim && m < dim) {   // (compile-time indices: J and I stay in registers)
+            double s = 0.0;
+            for (int i = 0; i < nN; i++) s = fma(p.dshape[((size_t)ip * nN + i) * dim + r], X[i * dim + m], s);
+            J[r][m] = s;
+          }
       double det, I[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
       if (dim == 1) { det = J[0][0]; I[0][0] = 1.0 / det; }
       else if (dim == 2) {
@@ -78,7 +81,10 @@ __global__ void __launch_bounds__(128) cg_element_kernel(const CgParams p) {
         I[0][0] = J[1][1] * id; I[0][1] = -J[0][1] * id; I[1][0] = -J[1][0] * id; I[1][1] = J[0][0] * id;
       } else det_inv(J, det, I);
       if (!(fabs(det) > 1e-300)) atomicOr(p.status, 1);
-      for (int a = 0; a < dim; a++) for (int b = 0; b < dim; b++) JI[ip * D2 + a * dim + b] = I[a][b];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) if (a < dim && b < dim) JI[ip * D2 + a * dim + b] = I[a][b];
       DV[ip] = p.w[ip] * det;
       if (p.vel)
         for (int a = 0; a < dim; a++) {
@@ -178,9 +184,15 @@ __global__ void __launch_bounds__(256) cg_affine_kernel(const CgParams p) {
     if (!p.affine[e]) continue;
     const int* cell = p.cells + (size_t)e * nN;
     double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    {
+    {   // (loops with compile-time bounds: J, I and C stay in registers)
       const double* x0 = p.nodes + (size_t)cell[p.fv[0]] * dim;
-      for (int r = 0; r < dim; r++) { const double* xr = p.nodes + (size_t)cell[p.fv[r + 1]] * dim; for (int m = 0; m < dim; m++) J[r][m] = 0.5 * (xr[m] - x0[m]); }
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+        if (r < dim) {
+          const double* xr = p.nodes + (size_t)cell[p.fv[r + 1]] * dim;
+#pragma unroll
+          for (int m = 0; m < 3; m++) if (m < dim) J[r][m] = 0.5 * (xr[m] - x0[m]);
+        }
     }
     double det, I[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     if (dim == 1) { det = J[0][0]; I[0][0] = 1.0 / det; }
@@ -190,12 +202,23 @@ __global__ void __launch_bounds__(256) cg_affine_kernel(const CgParams p) {
       I[0][0] = J[1][1] * id; I[0][1] = -J[0][1] * id; I[1][0] = -J[1][0] * id; I[1][1] = J[0][0] * id;
     } else det_inv(J, det, I);
     if (!(fabs(det) > 1e-300) && lane == 0) atomicOr(p.status, 1);
-    double Cm[9];
-    for (int r = 0; r < dim; r++) for (int s2 = 0; s2 < dim; s2++) { double a = 0.0; for (int k = 0; k < dim; k++) a = fma(I[k][r], I[k][s2], a); Cm[r * dim + s2] = det * a; }
+    double Cm[9];   // C(r, s) at Cm[3 r + s]
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int s2 = 0; s2 < 3; s2++) {
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) if (k < dim) a = fma(I[k][r], I[k][s2], a);
+        Cm[r * 3 + s2] = det * a;
+      }
     const double dt = p.eulerDt;
     for (int idx = lane; idx < NN; idx += 32) {
       double acc = 0.0;
-      for (int q = 0; q < D2; q++) acc = fma(Cm[q], KH[q * NN + idx], acc);
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; s2++) if (r < dim && s2 < dim) acc = fma(Cm[r * 3 + s2], KH[(r * dim + s2) * NN + idx], acc);
       if (dt > 0.0) acc = fma(dt, acc, det * MH[idx]);
       const int i = idx / nN;
       const long long at = p.pos ? p.rowptr[cell[i]] + p.pos[(size_t)e * NN + idx] : cg_find(p.rowptr, p.colidx, cell[i], cell[idx - i * nN]);
@@ -259,13 +282,19 @@ __global__ void __launch_bounds__(256) cg_gather_kernel(const CgParams p) {
       if (!p.affine[e]) continue;                                  // (warp-uniform) curved cells come afterwards, through cg_element_kernel
       const int i = p.n2cLoc[k];
       const double* g = p.cellGeo + (size_t)e * 10;
-      double Cm[9];
-      for (int q = 0; q < D2; q++) Cm[q] = g[q];
+      double Cm[9];   // C(r, s) at Cm[3 r + s] (compile-time indices: registers)
+#pragma unroll
+      for (int r2 = 0; r2 < 3; r2++)
+#pragma unroll
+        for (int s2 = 0; s2 < 3; s2++) Cm[r2 * 3 + s2] = (r2 < dim && s2 < dim) ? g[r2 * dim + s2] : 0.0;
       const double det = g[9];
       const unsigned short* ps = p.pos + (size_t)e * NN + i * nN;
       for (int j = lane; j < nN; j += 32) {
         double acc = 0.0;
-        for (int q = 0; q < D2; q++) acc = fma(Cm[q], KH[q * NN + i * nN + j], acc);
+#pragma unroll
+        for (int r2 = 0; r2 < 3; r2++)
+#pragma unroll
+          for (int s2 = 0; s2 < 3; s2++) if (r2 < dim && s2 < dim) acc = fma(Cm[r2 * 3 + s2], KH[(r2 * dim + s2) * NN + i * nN + j], acc);
         if (dt > 0.0) acc = fma(dt, acc, det * MH[i * nN + j]);
         buf[ps[j]] += acc;                                           // the nodes of a cell are distinct: no two lanes share a position
       }

@@ -1125,7 +1125,7 @@ struct hfx_ctx {
   int rkStage = 0, rkNumStages = 0; double rkRow[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // model / boundary
   hfx_model_desc md{1, HFX_OP_DIFFUSION, HFX_TS_NONE, 0.0};
-  bool modelSet = false, bcSet = false;
+  bool modelSet = false, bcSet = false; int bcKindsSeen = 0;   // bit k: a boundary model of kind k has been described
   DBuf<uint8_t> dFaceBC;
   // allocation
   bool allocated = false, assembled = false, keepS = false, pivotFallback = false, recompute = false, p1Ready = false, colReady = false; int lastKernel = 0;
@@ -1868,7 +1868,7 @@ int hfx_boundary_describe(hfx_ctx* c, int kind, int nFaces, const int* faceIds) 
     if (!ids->empty()) mark_bc_kernel<<<nblk((long long)ids->size(), 256), 256, 0, c->st>>>((int)ids->size(), d.p, (uint8_t)(kind + 1), c->dFaceBC.p);
     HFX_CUDA(cudaGetLastError());
     HFX_CUDA(cudaStreamSynchronize(c->st));
-    c->bcSet = true;
+    c->bcSet = true; c->bcKindsSeen |= 1 << kind;
   });
 }
 
@@ -2332,7 +2332,8 @@ int hfx_cg_allocate(hfx_ctx* c) {
     DField* sol = find_field(c, "Solution");
     need(sol != nullptr, "CGSolver", "allocate", "the field map must have a Solution field.");
     need(sol->type == HFX_FIELD_NODE, "CGSolver", "allocate", "the Solution field must be a nodal field.");
-    need(sol->nObj * sol->nVal == 1 && c->md.nDOF == 1, "CGSolver", "allocate", "the device CG path serves one degree of freedom per node (LaplaceModel, DiffusionSource)");
+    need(sol->nObj * sol->nVal == 1 && c->md.nDOF == 1, "CGSolver", "allocate", "the device CG path serves one degree of freedom per node (LaplaceModel, DiffusionSource, Transport)");
+    need((c->bcKindsSeen & ~(1 << HFX_BC_DIRICHLET)) == 0, "CGSolver", "allocate", "the device CG path serves DirichletModel boundaries");
     // CGSolver::calcSparsityPattern (:261-335): row of a node = the nodes of every cell it belongs to; sorted columns (PETSc AIJ)
     const int nN = c->nN, nC = c->nCells, nNodes = c->nNodes;
     std::vector<int> cells((size_t)nC * nN);

@@ -238,3 +238,26 @@ def test_burgers_model_is_the_sum_of_its_operators(dim, order):
     assert ((exp - F2) ** 2).sum() < 1e-12
     # the reference's test compares the u-segment with M sol alone: true because the HDGUNabU right-hand side of a constant state vanishes
     assert np.abs(rhs[:u]).max() < 1e-12
+
+
+@pytest.mark.parametrize("dim,order", DIMS_ORDERS)
+def test_transport_model_is_base_plus_convection(dim, order):
+    """tests/unittests/model/TestHDGTransport.cpp (src/model/HDGTransport.cpp:47-69): localMatrix = Base + Convection, zero right-hand side -- the operator
+    descriptor HFX_OP_CONVECTION of the product's HDGTransport; with an implicit Euler step the u rows are scaled by dt and the mass terms added."""
+    re, rc = setup(dim, order)
+    rng = np.random.default_rng(dim * 100 + order)
+    nN, nNf, nFc = rc.nN, rc.nNf, rc.nFc
+    nodes = re.nodes * 0.3 + 0.01 * rng.standard_normal(re.nodes.shape)
+    tau = 0.5 + rng.random(nFc * nNf); vel = rng.standard_normal((nN, dim)); sold = rng.random(nN)
+    base = O.op_base(rc, 1, nodes, tau); conv = O.op_convection(rc, 1, nodes, vel)
+    A, F = O.local_system(rc, O.make_model(1, O.OP_CONVECTION), nodes=nodes, tau=tau, vel=vel)
+    assert ((A - base - conv) ** 2).sum() < 1e-12 and np.abs(F).max() == 0
+    dt = 0.05
+    AE, FE = O.local_system(rc, O.make_model(1, O.OP_CONVECTION, timeScheme=O.TS_EULER_IMPLICIT, dt=dt), nodes=nodes, tau=tau, vel=vel, solOld=sold)
+    jac, inv, dV, nrm = O.element_geometry(rc, nodes)
+    M = O.op_mass(re.ipShape, dV[:rc.nIP])
+    ref = base + conv
+    ref[:nN, :] *= dt
+    ref[:nN, :nN] += M
+    assert ((AE - ref) ** 2).sum() < 1e-12
+    assert np.abs(FE[:nN] - M @ sold).max() < 1e-12 and np.abs(FE[nN:]).max() == 0
